@@ -1,0 +1,266 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of ``oracle/libpvo_oracle.so`` (the CPU restatement of PanoVLM's hot path, see
+``pvo_math.hpp``).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module; nothing under ``panovlm_b200/`` does.
+Parity status: unpinned by the reference's own tests (it has none) — pinned against scipy / numpy /
+torch-autograd in ``tests/test_oracle_*.py``.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+P2PLANE_METER, P2PLANE_ANGLE, P2LINE_METER, P2LINE_ANGLE, PLANE2PLANE_GLOBAL, PLANE_IOU = range(6)
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libpvo_oracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.pvo_normal_equations.restype = C.c_double
+        _LIB.pvo_kdtree_build.restype = C.c_void_p
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def num_threads():
+    return lib().pvo_num_threads()
+
+
+def aa_to_R(aa):
+    """Rotation matrix (row-major numpy 3x3) of an angle-axis vector."""
+    out = np.zeros(9)
+    lib().pvo_aa_to_R(_p(_f64(aa)), _p(out))
+    return out.reshape(3, 3).T.copy()  # library buffer is column-major
+
+
+def R_to_aa(R):
+    out = np.zeros(3)
+    lib().pvo_R_to_aa(_p(_f64(np.asarray(R).T)), _p(out))
+    return out
+
+
+def aa_rotate(aa, p):
+    out = np.zeros(3)
+    lib().pvo_aa_rotate(_p(_f64(aa)), _p(_f64(p)), _p(out))
+    return out
+
+
+def form_plane(pts, tol):
+    pts = _f64(pts)
+    out = np.zeros(4)
+    lib().pvo_form_plane(C.c_int(len(pts)), _p(pts), C.c_double(tol), _p(out))
+    return out
+
+
+def form_line(pts, tol, dis_thr=0.0):
+    pts = _f64(pts)
+    out = np.zeros(6)
+    ok = lib().pvo_form_line(C.c_int(len(pts)), _p(pts), C.c_double(tol), C.c_double(dis_thr), _p(out))
+    return bool(ok), out
+
+
+def sym_eig3(A):
+    ev, vec = np.zeros(3), np.zeros(9)
+    lib().pvo_sym_eig3(_p(_f64(A)), _p(ev), _p(vec))
+    return ev, vec.reshape(3, 3)
+
+
+def fast_atan2(y, x):
+    y = np.ascontiguousarray(y)
+    x = np.ascontiguousarray(x)
+    out = np.empty_like(y)
+    fn = lib().pvo_fast_atan2_f if y.dtype == np.float32 else lib().pvo_fast_atan2_d
+    fn(C.c_long(y.size), _p(y), _p(x), _p(out))
+    return out
+
+
+def image_to_cam(rows, cols, px):
+    px = _f64(px).reshape(-1, 2)
+    out = np.zeros((len(px), 3))
+    lib().pvo_image_to_cam_d(C.c_int(rows), C.c_int(cols), C.c_long(len(px)), _p(px), _p(out))
+    return out
+
+
+def cam_to_image(rows, cols, cam):
+    cam = np.ascontiguousarray(cam).reshape(-1, 3)
+    out = np.zeros((len(cam), 2), dtype=cam.dtype)
+    fn = lib().pvo_cam_to_image_f if cam.dtype == np.float32 else lib().pvo_cam_to_image_d
+    fn(C.c_int(rows), C.c_int(cols), C.c_long(len(cam)), _p(cam), _p(out))
+    return out
+
+
+class Blocks:
+    """Parallel-array residual-block list (mirrors util/Optimization.cpp's AddResidualBlock calls)."""
+
+    def __init__(self, type, ref, nei, consts, huber, normalize=None):
+        self.type = _i32(type)
+        n = len(self.type)
+        self.ref = _i32(np.broadcast_to(ref, n))
+        self.nei = _i32(np.broadcast_to(nei, n))
+        self.consts = _f64(consts).reshape(n, 12)
+        self.huber = _f64(np.broadcast_to(huber, n))
+        self.normalize = _i32(np.broadcast_to(1 if normalize is None else normalize, n))
+        self.n = n
+
+    def _args(self):
+        return (C.c_long(self.n), _p(self.type), _p(self.ref), _p(self.nei), _p(self.normalize), _p(self.huber), _p(self.consts))
+
+    def evaluate(self, poses, apply_loss=True, jac=True):
+        poses = _f64(poses)
+        r, cost = np.zeros(self.n), np.zeros(self.n)
+        J = np.zeros((self.n, 12)) if jac else None
+        lib().pvo_eval_blocks(*self._args(), _p(poses), C.c_int(int(apply_loss)), _p(r), _p(J), _p(cost))
+        return r, J, cost
+
+    def normal_equations(self, poses):
+        poses = _f64(poses)
+        nb = poses.size // 6
+        H, g = np.zeros((6 * nb, 6 * nb)), np.zeros(6 * nb)
+        cost = lib().pvo_normal_equations(*self._args(), _p(poses), C.c_int(nb), _p(H), _p(g))
+        return H, g, cost
+
+    def solve_lm(self, poses, is_const=None, max_iter=20):
+        poses = _f64(poses).copy()
+        nb = poses.size // 6
+        mask = np.zeros(nb, dtype=np.uint8) if is_const is None else np.ascontiguousarray(is_const, dtype=np.uint8)
+        summ = np.zeros(6)
+        lib().pvo_solve_lm(*self._args(), _p(poses), C.c_int(nb), _p(mask), C.c_int(max_iter), _p(summ))
+        keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
+        return poses, dict(zip(keys, summ.tolist()))
+
+
+def transform_cloud(R, t, cloud):
+    cloud = _f32(cloud).reshape(-1, 4)
+    out = np.empty_like(cloud)
+    lib().pvo_transform_cloud(_p(_f64(R)), _p(_f64(t)), _p(cloud), C.c_int(len(cloud)), _p(out))
+    return out
+
+
+def world2local(R, t, pw):
+    pw = _f64(pw).reshape(-1, 3)
+    out = np.empty_like(pw)
+    lib().pvo_world2local(_p(_f64(R)), _p(_f64(t)), C.c_long(len(pw)), _p(pw), _p(out))
+    return out
+
+
+def knn(pts, queries, k, use_kdtree=True):
+    pts, queries = _f32(pts).reshape(-1, 4), _f32(queries).reshape(-1, 4)
+    idx = np.empty((len(queries), k), dtype=np.int32)
+    d2 = np.empty((len(queries), k), dtype=np.float32)
+    lib().pvo_knn(_p(pts), C.c_int(len(pts)), _p(queries), C.c_int(len(queries)), C.c_int(k), C.c_int(int(use_kdtree)), _p(idx), _p(d2))
+    return idx, d2
+
+
+def associate_p2plane(ref_world, R_ref, t_ref, nei_world, R_nei, t_nei, plane_tol, dist_thr, k=10, use_kdtree=True):
+    ref_world, nei_world = _f32(ref_world).reshape(-1, 4), _f32(nei_world).reshape(-1, 4)
+    n = len(nei_world)
+    q, pt, pl = np.empty(n, dtype=np.int32), np.empty((n, 3)), np.empty((n, 4))
+    m = lib().pvo_associate_p2plane(_p(ref_world), C.c_int(len(ref_world)), _p(_f64(R_ref)), _p(_f64(t_ref)),
+                                    _p(nei_world), C.c_int(n), _p(_f64(R_nei)), _p(_f64(t_nei)),
+                                    C.c_double(plane_tol), C.c_float(dist_thr), C.c_int(k), C.c_int(int(use_kdtree)), _p(q), _p(pt), _p(pl))
+    return q[:m].copy(), pt[:m].copy(), pl[:m].copy()
+
+
+def transform_lines(R, t, lines):
+    lines = _f64(lines).reshape(-1, 6)
+    out = np.empty_like(lines)
+    lib().pvo_transform_lines(_p(_f64(R)), _p(_f64(t)), C.c_int(len(lines)), _p(lines), _p(out))
+    return out
+
+
+def line_votes(ref_lines_world, nei_corner_world, p2s_off, p2s_ids, S_nei, dist_thr):
+    ref_lines_world = _f64(ref_lines_world).reshape(-1, 6)
+    pts = _f32(nei_corner_world).reshape(-1, 4)
+    M = np.zeros((S_nei, len(ref_lines_world)), dtype=np.int32)
+    lib().pvo_line_votes(_p(ref_lines_world), C.c_int(len(ref_lines_world)), _p(pts), C.c_int(len(pts)), _p(_i32(p2s_off)), _p(_i32(p2s_ids)),
+                         C.c_int(S_nei), C.c_double(dist_thr), _p(M))
+    return M
+
+
+def find_associations(ref_coeffs_local, ref_lines_world, nei_lines_world, seg_sizes_nei, M):
+    S_ref, S_nei = len(ref_lines_world), len(nei_lines_world)
+    on, orf = np.empty(S_nei, dtype=np.int32), np.empty(S_nei, dtype=np.int32)
+    oa, ob = np.empty((S_nei, 3)), np.empty((S_nei, 3))
+    m = lib().pvo_find_associations(_p(_f64(ref_coeffs_local)), _p(_f64(ref_lines_world)), C.c_int(S_ref), _p(_f64(nei_lines_world)), C.c_int(S_nei),
+                                    _p(_i32(seg_sizes_nei)), _p(_i32(M)), _p(on), _p(orf), _p(oa), _p(ob))
+    return on[:m].copy(), orf[:m].copy(), oa[:m].copy(), ob[:m].copy()
+
+
+def angle_votes(rows, cols, lines, cloud_local, p2s_off, p2s_ids, S, T_cl):
+    lines, cloud = _f32(lines).reshape(-1, 4), _f32(cloud_local).reshape(-1, 4)
+    counts = np.zeros((len(lines), S), dtype=np.int32)
+    lib().pvo_angle_votes(C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), _p(cloud), C.c_int(len(cloud)), _p(_i32(p2s_off)), _p(_i32(p2s_ids)),
+                          C.c_int(S), _p(_f64(T_cl)), _p(counts))
+    return counts
+
+
+def associate_by_angle(rows, cols, lines, cloud_local, p2s_off, p2s_ids, seg_sizes, end_points, T_cl, filter_by_length=True):
+    lines, cloud = _f32(lines).reshape(-1, 4), _f32(cloud_local).reshape(-1, 4)
+    S = len(seg_sizes)
+    cap = max(1, len(lines) * S)
+    oi, ol = np.empty(cap, dtype=np.int32), np.empty(cap, dtype=np.int32)
+    os_, oe, oa = np.empty((cap, 3)), np.empty((cap, 3)), np.empty(cap, dtype=np.float32)
+    m = lib().pvo_associate_by_angle(C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), _p(cloud), C.c_int(len(cloud)), _p(_i32(p2s_off)), _p(_i32(p2s_ids)),
+                                     C.c_int(S), _p(_i32(seg_sizes)), _p(_f64(end_points)), _p(_f64(T_cl)), C.c_int(int(filter_by_length)), C.c_int(cap),
+                                     _p(oi), _p(ol), _p(os_), _p(oe), _p(oa))
+    return oi[:m].copy(), ol[:m].copy(), os_[:m].copy(), oe[:m].copy(), oa[:m].copy()
+
+
+def project_depth(cloud, rows, cols, T_cl, size=3, want_image=True):
+    cloud = _f32(cloud).reshape(-1, 4)
+    img = np.zeros((rows, cols), dtype=np.uint16) if want_image else None
+    uvd = np.zeros((len(cloud), 3), dtype=np.float32)
+    lib().pvo_project_depth(_p(cloud), C.c_int(len(cloud)), C.c_int(rows), C.c_int(cols), _p(_f64(T_cl)), C.c_int(size), _p(img), _p(uvd))
+    return img, uvd
+
+
+class KdTreeHandle:
+    def __init__(self, pts):
+        self.pts = _f32(pts).reshape(-1, 4)
+        self.h = C.c_void_p(lib().pvo_kdtree_build(_p(self.pts), C.c_int(len(self.pts))))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().pvo_kdtree_free(self.h)
+            self.h = None
+
+
+def dense_icp_eval(target_world, src_local, src_off, poses_lw, plane_tol, dist_thr, k=10, huber=0.2, weight=1.0, mode=1, tree=None):
+    """One Gauss-Newton evaluation of the dense ICP sweep (configs[4]); returns (sys[n_frames,29], times[3], n_assoc)."""
+    target_world, src_local = _f32(target_world).reshape(-1, 4), _f32(src_local).reshape(-1, 4)
+    src_off = _i32(src_off)
+    nf = len(src_off) - 1
+    poses_lw = _f64(poses_lw).reshape(nf, 6)
+    out, times, nassoc = np.zeros((nf, 29)), np.zeros(3), C.c_long(0)
+    lib().pvo_dense_icp_eval(_p(target_world), C.c_int(len(target_world)), _p(src_local), _p(src_off), C.c_int(nf), _p(poses_lw),
+                             C.c_double(plane_tol), C.c_float(dist_thr), C.c_int(k), C.c_double(huber), C.c_double(weight), C.c_int(mode),
+                             tree.h if tree is not None else None, _p(out), _p(times), C.byref(nassoc))
+    return out, times, nassoc.value

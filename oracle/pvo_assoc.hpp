@@ -1,0 +1,399 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see pvo_math.hpp header).  Parity status: unpinned by the
+// reference's own tests; pinned against scipy cKDTree / numpy in tests/test_oracle_assoc.py.
+//
+// CPU restatement of the association code on the hot path:
+//   sensors/Velodyne.cpp:1773-1859        Transform2LidarWorld / World2Local
+//   lidar_mapping/LidarFeatureAssociate.cpp:120-197,219-236,442-476,550-630
+//   joint_optimization/CameraLidarLineAssociate.cpp:340-475,628-715
+//   sensors/Equirectangular.{h,cpp}, util/Visualization.h:408-441
+// PCL/FLANN behaviour restated from their documentation: KdTreeFLANN = exact k-NN on
+// float32 squared L2 (accumulated x,y,z in float), ascending; ties here are broken by lower index
+// (FLANN's tie order is implementation-defined).
+#pragma once
+#include <map>
+#include <numeric>
+#include <set>
+#include "pvo_math.hpp"
+
+namespace pvo {
+
+// ---- pcl::transformPointCloud(cloud, out, Matrix4d): double arithmetic, float32 store -----------
+// (PCL common/impl/transforms.hpp Transformer<double>::se3; called from Velodyne.cpp:1790-1806)
+inline void TransformCloud(const double R[9] /*row-major*/, const double t[3], const float* in, int n, float* out, int stride = 4) {
+  for (int i = 0; i < n; ++i) {
+    const double p[3] = {in[i * stride], in[i * stride + 1], in[i * stride + 2]};
+    for (int r = 0; r < 3; ++r)
+      out[i * stride + r] = static_cast<float>(R[r * 3 + 0] * p[0] + R[r * 3 + 1] * p[1] + R[r * 3 + 2] * p[2] + t[r]);
+    for (int c = 3; c < stride; ++c) out[i * stride + c] = in[i * stride + c];
+  }
+}
+
+// Velodyne::World2Local (Velodyne.cpp:1850-1853): R_wl^T * p - R_wl^T * t_wl
+inline void World2Local(const double R[9], const double t[3], const double pw[3], double out[3]) {
+  for (int r = 0; r < 3; ++r) {
+    const double a = R[0 * 3 + r] * pw[0] + R[1 * 3 + r] * pw[1] + R[2 * 3 + r] * pw[2];
+    const double b = R[0 * 3 + r] * t[0] + R[1 * 3 + r] * t[1] + R[2 * 3 + r] * t[2];
+    out[r] = a - b;
+  }
+}
+
+// ---- exact k-NN on float32 squared distances ------------------------------------------------
+inline float SqDistF32(const float* a, const float* b) {  // flann::L2_Simple<float>
+  float r = 0.f;
+  const float dx = a[0] - b[0]; r += dx * dx;
+  const float dy = a[1] - b[1]; r += dy * dy;
+  const float dz = a[2] - b[2]; r += dz * dz;
+  return r;
+}
+
+struct KnnResult { std::vector<int> idx; std::vector<float> d2; };
+
+struct KnnHeap {  // keeps the k smallest (d2, idx) lexicographically; worst at front of a sorted array
+  int k; int n = 0; std::vector<float> d; std::vector<int> id;
+  explicit KnnHeap(int k_) : k(k_), d(k_), id(k_) {}
+  inline bool full() const { return n == k; }
+  inline float worst() const { return d[n - 1]; }
+  inline bool accepts(float dd, int ii) const { return n < k || dd < d[n - 1] || (dd == d[n - 1] && ii < id[n - 1]); }
+  inline void push(float dd, int ii) {
+    if (!accepts(dd, ii)) return;
+    int pos = (n < k) ? n : k - 1;
+    while (pos > 0 && (d[pos - 1] > dd || (d[pos - 1] == dd && id[pos - 1] > ii))) { d[pos] = d[pos - 1]; id[pos] = id[pos - 1]; --pos; }
+    d[pos] = dd; id[pos] = ii;
+    if (n < k) ++n;
+  }
+};
+
+inline void KnnBrute(const float* pts, int n, int stride, const float* q, int k, KnnResult& out) {
+  KnnHeap h(k);
+  for (int i = 0; i < n; ++i) h.push(SqDistF32(q, pts + (size_t)i * stride), i);
+  out.idx.assign(h.id.begin(), h.id.begin() + h.n);
+  out.d2.assign(h.d.begin(), h.d.begin() + h.n);
+}
+
+// Exact kd-tree (leaf size 15 like pcl::KdTreeFLANN's KDTreeSingleIndexParams(15)); returns the same
+// set/order as KnnBrute.  Used for the timed CPU baseline so that it is a fair "reference-like" cost.
+struct KdTree {
+  struct Node { int lo, hi, left, right, dim; float split_lo, split_hi; };
+  const float* pts = nullptr; int stride = 4;
+  std::vector<int> order; std::vector<Node> nodes;
+  std::vector<float> leaf_xyz;  // points copied in leaf order for locality
+  void Build(const float* p, int n, int stride_) {
+    pts = p; stride = stride_; order.resize(n); std::iota(order.begin(), order.end(), 0);
+    nodes.clear(); nodes.reserve(2 * (n / 8 + 1));
+    if (n > 0) BuildRec(0, n);
+    leaf_xyz.resize((size_t)n * 3);
+    for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) leaf_xyz[(size_t)i * 3 + c] = pts[(size_t)order[i] * stride + c];
+  }
+  int BuildRec(int lo, int hi) {
+    const int id = (int)nodes.size(); nodes.push_back(Node{lo, hi, -1, -1, -1, 0.f, 0.f});
+    if (hi - lo <= 15) return id;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = lo; i < hi; ++i) for (int c = 0; c < 3; ++c) { const float v = pts[(size_t)order[i] * stride + c]; mn[c] = std::min(mn[c], v); mx[c] = std::max(mx[c], v); }
+    int dim = 0; for (int c = 1; c < 3; ++c) if (mx[c] - mn[c] > mx[dim] - mn[dim]) dim = c;
+    if (mx[dim] == mn[dim]) return id;  // all identical: keep as a (large) leaf
+    const int mid = (lo + hi) / 2;
+    std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi,
+                     [&](int a, int b) { return pts[(size_t)a * stride + dim] < pts[(size_t)b * stride + dim]; });
+    float left_max = -FLT_MAX; for (int i = lo; i < mid; ++i) left_max = std::max(left_max, pts[(size_t)order[i] * stride + dim]);
+    const float right_min = pts[(size_t)order[mid] * stride + dim];
+    nodes[id].dim = dim; nodes[id].split_lo = left_max; nodes[id].split_hi = right_min;
+    const int l = BuildRec(lo, mid); const int r = BuildRec(mid, hi);
+    nodes[id].left = l; nodes[id].right = r;
+    return id;
+  }
+  void SearchRec(int nid, const float* q, KnnHeap& h, double mind2) const {
+    const Node& nd = nodes[nid];
+    if (nd.left < 0) {
+      for (int i = nd.lo; i < nd.hi; ++i) h.push(SqDistF32(q, &leaf_xyz[(size_t)i * 3]), order[i]);
+      return;
+    }
+    const double v = q[nd.dim];
+    int first = nd.left, second = nd.right; double cut;
+    if (v <= 0.5 * ((double)nd.split_lo + nd.split_hi)) { cut = std::max(0.0, (double)nd.split_hi - v); }
+    else { first = nd.right; second = nd.left; cut = std::max(0.0, v - (double)nd.split_lo); }
+    SearchRec(first, q, h, mind2);
+    const double bound = cut * cut * (1.0 - 1e-6);  // conservative vs float32 rounding of the distances
+    if (!h.full() || bound <= (double)h.worst()) SearchRec(second, q, h, bound);
+  }
+  void Knn(const float* q, int k, KnnResult& out) const {
+    KnnHeap h(k);
+    if (!nodes.empty()) SearchRec(0, q, h, 0.0);
+    out.idx.assign(h.id.begin(), h.id.begin() + h.n);
+    out.d2.assign(h.d.begin(), h.d.begin() + h.n);
+  }
+};
+
+// ---- AssociatePoint2Plane (LidarFeatureAssociate.cpp:550-630) ---------------------------------
+struct P2PlaneAssoc { int query_idx; double point[3]; double plane[4]; };
+
+// ref_world / nei_world: n x 4 float32 (x,y,z,intensity) already in world coordinates (float32, as
+// produced by TransformCloud).  R/t are the frames' R_wl, t_wl.  k is 10 in the reference (:574).
+// Quirk C.6: the reference indexes [k-1] even when PCL returns < k results; here such queries are
+// rejected (documented difference).
+inline void AssociatePoint2Plane(const float* ref_world, int n_ref, const double R_ref[9], const double t_ref[3],
+                                 const float* nei_world, int n_nei, const double R_nei[9], const double t_nei[3],
+                                 double plane_tolerance, float dist_threshold, int k, bool use_kdtree,
+                                 std::vector<P2PlaneAssoc>& out, const KdTree* prebuilt = nullptr) {
+  const float sq_thr = dist_threshold * dist_threshold;
+  KdTree local_tree;
+  const KdTree* tree = prebuilt;
+  if (use_kdtree && !tree) { local_tree.Build(ref_world, n_ref, 4); tree = &local_tree; }  // rebuilt per call (:566-567)
+  KnnResult res;
+  std::vector<double> pl((size_t)k * 3);
+  for (int idx = 0; idx < n_nei; ++idx) {
+    const float* q = nei_world + (size_t)idx * 4;
+    if (use_kdtree) tree->Knn(q, k, res); else KnnBrute(ref_world, n_ref, 4, q, k, res);
+    if ((int)res.idx.size() < k) continue;
+    if (res.d2[k - 1] > sq_thr) continue;
+    int same = 0;
+    for (int j = 0; j < k; ++j) {
+      const float* pt = ref_world + (size_t)res.idx[j] * 4;
+      same += (pt[3] == q[3]);
+      const double pw[3] = {pt[0], pt[1], pt[2]};
+      World2Local(R_ref, t_ref, pw, &pl[(size_t)j * 3]);
+    }
+    if (same < k) continue;
+    double plane[4], line[6];
+    FormPlaneLSQ(k, pl.data(), plane_tolerance, plane);
+    const bool is_line = FormLinePCA(k, pl.data(), 3.0, 0.0, line);
+    if ((plane[0] == 0 && plane[1] == 0 && plane[2] == 0 && plane[3] == 0) || is_line) continue;
+    P2PlaneAssoc a; a.query_idx = idx;
+    const double qw[3] = {q[0], q[1], q[2]};
+    World2Local(R_nei, t_nei, qw, a.point);
+    for (int c = 0; c < 4; ++c) a.plane[c] = plane[c];
+    out.push_back(a);
+  }
+}
+
+// ---- line-to-line (LidarFeatureAssociate.cpp:219-236, 442-476, 120-197) --------------------------
+inline void TransformLine(const double R[9], const double t[3], const double in[6], double out[6]) {  // :219-236
+  for (int r = 0; r < 3; ++r) {
+    out[r] = R[r * 3] * in[0] + R[r * 3 + 1] * in[1] + R[r * 3 + 2] * in[2] + t[r];
+    out[3 + r] = R[r * 3] * in[3] + R[r * 3 + 1] * in[4] + R[r * 3 + 2] * in[5];
+  }
+}
+
+struct L2LAssoc { int nei_line, ref_line; double a[3], b[3]; };
+
+// Vote matrix (row = nei segment, col = ref segment), AssociateLine2Line :459-473.
+inline void Line2LineVotes(const double* ref_lines_world, int S_ref, const float* nei_corner_world, int n_pts,
+                           const int* p2s_off, const int* p2s_ids, int S_nei, double dist_threshold, std::vector<int>& M) {
+  M.assign((size_t)S_nei * S_ref, 0);
+  for (int i = 0; i < n_pts; ++i) {
+    const double p[3] = {nei_corner_world[i * 4], nei_corner_world[i * 4 + 1], nei_corner_world[i * 4 + 2]};
+    for (int s = 0; s < S_ref; ++s) {
+      const double d = PointToLineDistance3D(p, ref_lines_world + s * 6);
+      if (d > dist_threshold) continue;
+      for (int e = p2s_off[i]; e < p2s_off[i + 1]; ++e) M[(size_t)p2s_ids[e] * S_ref + s] += 1;
+    }
+  }
+}
+
+// FindAssociations (:120-197).  seg_sizes_nei[s] = nei.edge_segmented[s].size().
+inline void FindAssociations(const double* ref_coeffs_local, const double* ref_lines_world, int S_ref,
+                             const double* nei_lines_world, int S_nei, const int* seg_sizes_nei,
+                             const std::vector<int>& M, std::vector<L2LAssoc>& out) {
+  std::map<int, L2LAssoc> m;
+  for (int s = 0; s < S_nei; ++s) {
+    if (S_ref == 0) break;
+    int max_col = 0, max_count = M[(size_t)s * S_ref];
+    for (int c = 1; c < S_ref; ++c) if (M[(size_t)s * S_ref + c] > max_count) { max_count = M[(size_t)s * S_ref + c]; max_col = c; }
+    if ((size_t)max_count < (size_t)seg_sizes_nei[s] / 2) continue;
+    const double* dr = ref_lines_world + max_col * 6 + 3;
+    const double* dn = nei_lines_world + s * 6 + 3;
+    if (PlaneAngle(dr, dn) * 180.0 / M_PI > 7) continue;
+    const double* cl = ref_coeffs_local + max_col * 6;
+    L2LAssoc a; a.nei_line = s; a.ref_line = max_col;
+    for (int c = 0; c < 3; ++c) { a.a[c] = 0.1 * cl[3 + c] + cl[c]; a.b[c] = -0.1 * cl[3 + c] + cl[c]; }
+    auto it = m.find(max_col);
+    if (it == m.end()) m.insert({max_col, a});
+    else {
+      const double d1 = PointToLineDistance3D(nei_lines_world + it->second.nei_line * 6, ref_lines_world + max_col * 6);
+      const double d2 = PointToLineDistance3D(nei_lines_world + s * 6, ref_lines_world + max_col * 6);
+      if (d2 < d1) it->second = a;
+    }
+  }
+  for (auto& kv : m) out.push_back(kv.second);
+}
+
+// ---- Equirectangular (sensors/Equirectangular.h) ------------------------------------------------
+struct Equirect {
+  int rows, cols;
+  template <typename T> void CamToSphere(const T p[3], T s[2]) const {  // :41-72 (USE_FAST_ATAN2 is defined, :6)
+    s[0] = FastAtan2(p[0], p[2]);
+    s[1] = -FastAtan2(p[1], (T)std::sqrt(Square(p[0]) + Square(p[2])));
+  }
+  template <typename T> void SphereToImage(const T s[2], T px[2]) const {  // :80-96
+    px[0] = cols * (0.5 + s[0] / (2.0 * M_PI));
+    px[1] = rows * (0.5 - s[1] / M_PI);
+  }
+  template <typename T> void ImageToSphere(const T px[2], T s[2]) const {  // :98-114
+    s[0] = (2 * px[0] / cols - 1) * M_PI;
+    s[1] = (0.5 - px[1] / rows) * M_PI;
+  }
+  template <typename T> void SphereToCam(const T s[2], T r, T cam[3]) const {  // :116-146
+    T cy = std::cos(s[1]);
+    cam[0] = r * cy * std::sin(s[0]);
+    cam[1] = -r * std::sin(s[1]);
+    cam[2] = r * cy * std::cos(s[0]);
+  }
+  template <typename T> void ImageToCam(const T px[2], T r, T cam[3]) const { T s[2]; ImageToSphere(px, s); SphereToCam(s, r, cam); }  // :148-170
+  template <typename T> void CamToImage(const T cam[3], T px[2]) const { T s[2]; CamToSphere(cam, s); SphereToImage(s, px); }      // :172-182
+  bool IsInsideI(int x, int y) const { return x >= 0 && y >= 0 && x + 1 <= cols && y + 1 <= rows; }                               // :184-187
+
+  // BreakToSegments (Equirectangular.cpp:20-58)
+  std::vector<std::pair<float, float>> BreakToSegments(const float start[2], const float end[2], float seg_length) const {
+    float p1[3], p2[3];
+    ImageToCam(start, 5.0f, p1); ImageToCam(end, 5.0f, p2);
+    const float sl[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+    const float length = std::sqrt((start[0] - end[0]) * (start[0] - end[0]) + (start[1] - end[1]) * (start[1] - end[1]));
+    const int count = length / seg_length + 1;
+    std::vector<std::pair<float, float>> seg = {{start[0], start[1]}};
+    for (int i = 1; i < count; ++i) {
+      const float f = i * 1.f / count;
+      float p[3] = {p1[0] + f * sl[0], p1[1] + f * sl[1], p1[2] + f * sl[2]};
+      float px[2]; CamToImage(p, px);
+      if (std::abs(px[0] - seg.back().first) > 0.8 * cols) {
+        const float g = p1[0] / (p1[0] - p2[0]);
+        float pb[3] = {p1[0] + g * sl[0], p1[1] + g * sl[1], p1[2] + g * sl[2]};
+        float left[2]; CamToImage(pb, left); left[0] = 0;
+        const std::pair<float, float> L{left[0], left[1]}, Rr{float(cols - 1), left[1]};
+        if (px[0] > seg.back().first) { seg.push_back(L); seg.push_back(Rr); }
+        else { seg.push_back(Rr); seg.push_back(L); }
+      }
+      seg.push_back({px[0], px[1]});
+    }
+    seg.push_back({end[0], end[1]});
+    return seg;
+  }
+};
+
+// ---- AssociateByAngle (CameraLidarLineAssociate.cpp:340-475) + Filter(false,true) (:628-715) ----------
+struct CamLidarPair { int image_line, lidar_line; double start[3], end[3]; float angle; };
+
+inline void Transform4(const double T[16], const double p[3], double out[3]) {  // (T * p.homogeneous()).hnormalized(), affine
+  for (int r = 0; r < 3; ++r) out[r] = T[r * 4] * p[0] + T[r * 4 + 1] * p[1] + T[r * 4 + 2] * p[2] + T[r * 4 + 3];
+}
+
+// Per (image line, LiDAR segment) vote counts of AssociateByAngle's inner loop (:389-414); exposed so
+// the device counters can be compared directly.  counts is L x S.
+inline void AngleVotes(const Equirect& eq, const float* lines /*L x 4*/, int L, const float* cloud_local /*P x 4*/, int P,
+                       const int* p2s_off, const int* p2s_ids, int S, const double T_cl[16], std::vector<int>& counts) {
+  counts.assign((size_t)L * S, 0);
+  std::vector<float> range(P), cam((size_t)P * 4);
+  for (int i = 0; i < P; ++i) { const float* p = cloud_local + i * 4; range[i] = p[0] * p[0] + p[1] * p[1] + p[2] * p[2]; }
+  double R[9], t[3];
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[r * 3 + c] = T_cl[r * 4 + c]; t[r] = T_cl[r * 4 + 3]; }
+  TransformCloud(R, t, cloud_local, P, cam.data(), 4);
+  const double thr = 3.0 / 180.0 * M_PI;
+  for (int l = 0; l < L; ++l) {
+    const double px1[2] = {lines[l * 4], lines[l * 4 + 1]}, px2[2] = {lines[l * 4 + 2], lines[l * 4 + 3]};
+    double p1[3], p2[3]; eq.ImageToCam(px1, 1.0, p1); eq.ImageToCam(px2, 1.0, p2);
+    const double zero[3] = {0, 0, 0}; double plane[4];
+    FormPlane3(p1, p2, zero, plane);
+    const double nn = std::sqrt(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2] + plane[3] * plane[3]);
+    for (int c = 0; c < 4; ++c) plane[c] /= nn;
+    const double p4[3] = {(p1[0] + p2[0]) / 2.0, (p1[1] + p2[1]) / 2.0, (p1[2] + p2[2]) / 2.0};
+    const double scope = VectorAngle3D(p1, p4);
+    for (int i = 0; i < P; ++i) {
+      if (range[i] > 15 * 15) continue;
+      const double p[3] = {cam[i * 4], cam[i * 4 + 1], cam[i * 4 + 2]};
+      double pp[3]; ProjectPointToPlane(p, plane, pp, true);
+      if (VectorAngle3D(p, pp) >= thr) continue;
+      if (VectorAngle3D(p4, pp) >= scope + thr) continue;
+      for (int e = p2s_off[i]; e < p2s_off[i + 1]; ++e) counts[(size_t)l * S + p2s_ids[e]]++;
+    }
+  }
+}
+
+inline void AssociateByAngle(const Equirect& eq, const float* lines, int L, const float* cloud_local, int P,
+                             const int* p2s_off, const int* p2s_ids, int S, const int* seg_sizes,
+                             const double* end_points /*S x 2 x 3, lidar frame*/, const double T_cl[16],
+                             bool filter_by_length, std::vector<CamLidarPair>& out) {
+  std::vector<int> counts;
+  AngleVotes(eq, lines, L, cloud_local, P, p2s_off, p2s_ids, S, T_cl, counts);
+  const double thr = 3.0 / 180.0 * M_PI;
+  std::vector<double> ep((size_t)S * 6), lplane((size_t)S * 4);
+  const double zero[3] = {0, 0, 0};
+  for (int s = 0; s < S; ++s) {
+    Transform4(T_cl, end_points + s * 6, &ep[s * 6]);
+    Transform4(T_cl, end_points + s * 6 + 3, &ep[s * 6 + 3]);
+    double pl[4]; FormPlane3(&ep[s * 6], &ep[s * 6 + 3], zero, pl);
+    const double nn = std::sqrt(pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2] + pl[3] * pl[3]);
+    for (int c = 0; c < 4; ++c) lplane[s * 4 + c] = pl[c] / nn;
+  }
+  std::vector<CamLidarPair> pairs;
+  for (int l = 0; l < L; ++l) {
+    const double px1[2] = {lines[l * 4], lines[l * 4 + 1]}, px2[2] = {lines[l * 4 + 2], lines[l * 4 + 3]};
+    double p1[3], p2[3]; eq.ImageToCam(px1, 1.0, p1); eq.ImageToCam(px2, 1.0, p2);
+    double plane[4]; FormPlane3(p1, p2, zero, plane);
+    const double nn = std::sqrt(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2] + plane[3] * plane[3]);
+    for (int c = 0; c < 4; ++c) plane[c] /= nn;
+    const double p4[3] = {(p1[0] + p2[0]) / 2.0, (p1[1] + p2[1]) / 2.0, (p1[2] + p2[2]) / 2.0};
+    const double scope = VectorAngle3D(p1, p4);
+    for (int s = 0; s < S; ++s) {  // std::map iteration = ascending segment id, only segments with votes
+      const int cnt = counts[(size_t)l * S + s];
+      if (cnt == 0) continue;
+      if ((size_t)cnt < (size_t)seg_sizes[s] / 2) continue;
+      const double angle = PlaneAngle(plane, &lplane[s * 4], true);
+      if (angle > thr) continue;
+      double mid[3], midp[3];
+      for (int c = 0; c < 3; ++c) mid[c] = (ep[s * 6 + c] + ep[s * 6 + 3 + c]) / 2.f;
+      ProjectPointToPlane(mid, plane, midp, true);
+      if (VectorAngle3D(midp, p4) > scope) continue;
+      const float angle2 = VectorAngle3D(mid, midp);
+      if (angle2 > thr / 2.0) continue;
+      CamLidarPair pr; pr.image_line = l; pr.lidar_line = s; pr.angle = angle + angle2;
+      for (int c = 0; c < 3; ++c) { pr.start[c] = ep[s * 6 + c]; pr.end[c] = ep[s * 6 + 3 + c]; }
+      pairs.push_back(pr);
+    }
+  }
+  // Filter(false, true): projected LiDAR line length in [100, 2000] px (:676-692)
+  for (const CamLidarPair& p : pairs) {
+    if (filter_by_length) {
+      const float a[3] = {(float)p.start[0], (float)p.start[1], (float)p.start[2]};
+      const float b[3] = {(float)p.end[0], (float)p.end[1], (float)p.end[2]};
+      float pa[2], pb[2]; eq.CamToImage(a, pa); eq.CamToImage(b, pb);
+      auto seg = eq.BreakToSegments(pa, pb, 100);
+      float len = 0;
+      for (size_t i = 0; i + 1 < seg.size(); ++i) {
+        if (std::abs(seg[i].first - seg[i + 1].first) > 0.8 * eq.cols) continue;
+        const float dx = seg[i].first - seg[i + 1].first, dy = seg[i].second - seg[i + 1].second;
+        len += std::sqrt(dx * dx + dy * dy);
+      }
+      if (len < 100.f || len > 2000.f) continue;
+    }
+    out.push_back(p);
+  }
+  // back to the LiDAR frame (:469-474): T_lc = T_cl^-1 (rigid)
+  double Tlc[16] = {0};
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Tlc[r * 4 + c] = T_cl[c * 4 + r];
+  for (int r = 0; r < 3; ++r) Tlc[r * 4 + 3] = -(Tlc[r * 4] * T_cl[3] + Tlc[r * 4 + 1] * T_cl[7] + Tlc[r * 4 + 2] * T_cl[11]);
+  Tlc[15] = 1;
+  for (CamLidarPair& p : out) { double s[3], e[3]; Transform4(Tlc, p.start, s); Transform4(Tlc, p.end, e); for (int c = 0; c < 3; ++c) { p.start[c] = s[c]; p.end[c] = e[c]; } }
+}
+
+// ---- ProjectLidar2PanoramaDepth (util/Visualization.h:408-441) ----------------------------------
+// uvd (optional, n x 3): per-point pixel.x, pixel.y (float, FastAtan2 path) and depth (float).
+inline void ProjectLidar2PanoramaDepth(const float* cloud, int n, int stride, int rows, int cols, const double T_cl[16],
+                                       int size, uint16_t* img /*rows*cols, zeroed by caller*/, float* uvd) {
+  Equirect eq{rows, cols};
+  double R[9], t[3];
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[r * 3 + c] = T_cl[r * 4 + c]; t[r] = T_cl[r * 4 + 3]; }
+  for (int i = 0; i < n; ++i) {
+    float p[4] = {0, 0, 0, 0}, in4[4] = {cloud[(size_t)i * stride], cloud[(size_t)i * stride + 1], cloud[(size_t)i * stride + 2], 0};
+    TransformCloud(R, t, in4, 1, p, 4);
+    float s[2], px[2];
+    eq.CamToSphere(p, s); eq.SphereToImage(s, px);
+    const float depth = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    if (uvd) { uvd[(size_t)i * 3] = px[0]; uvd[(size_t)i * 3 + 1] = px[1]; uvd[(size_t)i * 3 + 2] = depth; }
+    if (!img) continue;
+    const int rbx = (int)std::ceil(px[0]) + size / 2, rby = (int)std::ceil(px[1]) + size / 2;
+    const int ltx = (int)std::floor(px[0]) - size / 2, lty = (int)std::floor(px[1]) - size / 2;
+    if (!eq.IsInsideI(rbx, rby) || !eq.IsInsideI(ltx, lty)) continue;
+    const uint16_t rel = static_cast<uint16_t>(depth * 256.0);
+    for (int u = lty; u <= rby; ++u) for (int v = ltx; v <= rbx; ++v) img[(size_t)u * cols + v] = rel;
+  }
+}
+
+}  // namespace pvo
