@@ -1,0 +1,145 @@
+/* panovlm_b200 — C ABI of the B200-native correspondence-and-residual hot path of PanoVLM.
+ *
+ * The reference (3dv-casia/PanoVLM) has no plugin/FFI interface; the surface this library drops in behind is
+ * Ceres' (SURVEY.md §8b):
+ *   - ceres::EvaluationCallback::PrepareForEvaluation(evaluate_jacobians, new_point)  ->  pvb_blocks_evaluate()
+ *   - ceres::CostFunction::Evaluate(parameters, residuals, jacobians) for the functors of
+ *     base/CostFunction.h:567-1022 (one AutoDiffCostFunction<F,1,3,3,3,3> per correspondence, built by
+ *     util/Optimization.cpp:329-441, 506-607)                                         ->  pvb_blocks_residuals()/
+ *                                                                                          pvb_blocks_jacobians() rows
+ *   - the association loops those builders call (lidar_mapping/LidarFeatureAssociate.cpp:442-476, 550-630,
+ *     joint_optimization/CameraLidarLineAssociate.cpp:340-475)                        ->  pvb_frames_* / pvb_*_votes
+ *   - the bulk SE(3) + equirectangular projection util/Visualization.h:408-441       ->  pvb_project_*
+ *   - the solve the reduced system feeds (lidar_mapping/LidarOdometry.cpp:78-80)       ->  pvb_blocks_solve_lm(),
+ *                                                                                          pvb_dense_*
+ * Conventions: every function returns 0 on success and a negative code on error (no exceptions cross the ABI);
+ * pvb_last_error() gives the message.  The caller owns every host array it passes; the context owns device and
+ * pinned buffers; pointers returned by getters stay valid until the next evaluate call on the same context.
+ * Pose blocks are 6 doubles (angle-axis aa_lw[3], t_lw[3]) = the parameter blocks of
+ * lidar_mapping/LidarOdometry.cpp:23-33 (world -> sensor).  Rotation matrices are row-major.
+ * There is no CPU fallback: every entry point needs a CUDA device (sm_100a build).
+ */
+#ifndef PANOVLM_B200_H_
+#define PANOVLM_B200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pvb_ctx pvb_ctx;
+
+enum { PVB_OK = 0, PVB_ERR_CUDA = -1, PVB_ERR_ARG = -2, PVB_ERR_STATE = -3, PVB_ERR_NOMEM = -4 };
+
+/* residual types = the reference functors (base/CostFunction.h) */
+enum {
+  PVB_P2PLANE_METER = 0,      /* Point2Plane_Meter   :567-619   consts: p[0..2] plane[3..6] weight[7]                      */
+  PVB_P2PLANE_ANGLE = 1,      /* Point2Plane_Angle   :630-729   consts: p[0..2] plane[3..6] (weight ignored, as upstream)   */
+  PVB_P2LINE_METER = 2,       /* Point2Line_Meter    :769-829   consts: p[0..2] a[3..5] dir[6..8] weight[9]                */
+  PVB_P2LINE_ANGLE = 3,       /* Point2Line_Angle    :836-934   consts: p[0..2] a[3..5] dir[6..8] (dir = (a-b)/|a-b|)       */
+  PVB_PLANE2PLANE_GLOBAL = 4, /* Plane2Plane_Global  :350-425   consts: n[0..2] a[3..5] b[6..8] weight[9]                  */
+  PVB_PLANE_IOU = 5           /* PlaneIOUResidual    :433-507   consts: plane[0..3] mid_nei[4..6] mid_ref[7..9] angle[10] weight[11] */
+};
+
+/* ---- lifecycle --------------------------------------------------------------------------------------------- */
+int pvb_create(int device, pvb_ctx** out);
+void pvb_destroy(pvb_ctx* ctx);
+const char* pvb_last_error(const pvb_ctx* ctx);
+int pvb_set_stream(pvb_ctx* ctx, void* cuda_stream); /* run on a caller-owned cudaStream_t (NULL: own stream)  */
+int pvb_synchronize(pvb_ctx* ctx);
+long pvb_kernel_launches(const pvb_ctx* ctx);        /* kernels this context has launched so far                */
+void* pvb_stream(const pvb_ctx* ctx);                 /* the cudaStream_t work is enqueued on                    */
+
+/* ---- A. correspondence-list mode: the ceres::CostFunction / EvaluationCallback surface -------------------- */
+/* Registers n residual blocks (== n problem.AddResidualBlock calls, util/Optimization.cpp:417,549,555,592,602).
+ * ref/nei index pose blocks; huber <= 0 means loss == nullptr; consts is n x 12 (layout per type above).        */
+int pvb_blocks_set(pvb_ctx* ctx, long n, const int* type, const int* ref, const int* nei, const int* normalize,
+                   const double* huber, const double* consts, int n_pose_blocks);
+/* == PrepareForEvaluation: evaluates every block at `poses` (n_pose_blocks x 6, host).  want_rows: per-block
+ * residual + 1x12 Jacobian rows are brought back to pinned host mirrors (original block order);
+ * want_system: the per-edge normal equations (12x12 upper + gradient, 92 doubles) are reduced on the device.    */
+int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int want_system);
+const double* pvb_blocks_residuals(const pvb_ctx* ctx); /* n doubles, loss-corrected                             */
+const double* pvb_blocks_jacobians(const pvb_ctx* ctx); /* n x 12 row-major [d aa_ref | d t_ref | d aa_nei | d t_nei] */
+int pvb_blocks_cost(const pvb_ctx* ctx, double* cost, long* n_residuals);
+int pvb_blocks_num_edges(const pvb_ctx* ctx);
+int pvb_blocks_edges(const pvb_ctx* ctx, int* ref, int* nei);
+/* per edge: H upper-triangular row-major (78) | g (12) | cost | n_residuals  (parameter order aa_r,t_r,aa_n,t_n) */
+int pvb_blocks_edge_systems(const pvb_ctx* ctx, double* out92);
+/* dense 6nb x 6nb J^T J, J^T r assembled on the host from the edge systems of the last evaluate                 */
+int pvb_blocks_dense_system(const pvb_ctx* ctx, double* H, double* g, double* cost);
+/* the ceres::Solve(SetOptionsLidar(...)) step (LidarOdometry.cpp:78-80): trust-region LM over the registered
+ * blocks, evaluation on the device, linear algebra on the host.  summary6 = initial_cost, final_cost, iterations,
+ * successful, unsuccessful, termination (0 max-iter, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure) */
+int pvb_blocks_solve_lm(pvb_ctx* ctx, double* poses, const unsigned char* is_const, int max_iterations, double* summary6);
+
+/* ---- B. frames: transform to world + point-to-plane association per pose-graph edge ------------------------ */
+typedef struct {
+  const float* surf_target; int n_target; /* ref side: surfLessFlat, n x 4 (x,y,z,intensity=class), sensor frame */
+  const float* surf_query; int n_query;   /* nei side: surfFlat                                                   */
+} pvb_frame;
+
+typedef struct {
+  double plane_tolerance; /* lidar_plane_tolerance (base/Config.h:117)                                           */
+  float dist_threshold;   /* point_to_plane_dis_threshold (Config.h:116), compared squared in float32             */
+  int k;                  /* 10 in the reference (LidarFeatureAssociate.cpp:574); 5 and 10 are built              */
+  double cell_size;       /* uniform-grid cell (m); <= 0: chosen per cloud from its extent and point count        */
+} pvb_assoc_params;
+
+int pvb_frames_set(pvb_ctx* ctx, int n_frames, const pvb_frame* frames);
+/* AssociatePoint2Plane for every edge (ref[e], nei[e]) at the given poses (n_frames x 6): clouds -> world
+ * (float32), cell-sorted targets, exact k-NN + plane fit.  *n_assoc = number of accepted correspondences.      */
+int pvb_frames_associate_point2plane(pvb_ctx* ctx, const double* poses, int n_edges, const int* ref, const int* nei,
+                                     const pvb_assoc_params* prm, long* n_assoc);
+/* correspondences of the last association, edge-major, query order within an edge (the reference's push_back
+ * order): edge index, query index in nei.surfFlat, point in the nei sensor frame, plane in the ref sensor frame */
+int pvb_frames_get_point2plane(const pvb_ctx* ctx, long cap, int* edge, int* query, double* point3, double* plane4);
+/* debug/parity view of the k-NN itself for one edge: indices into ref.surfLessFlat and float32 squared distances */
+int pvb_frames_knn(pvb_ctx* ctx, const double* poses, int ref, int nei, const pvb_assoc_params* prm, int* idx, float* d2);
+
+/* ---- C. dense ICP sweep (BASELINE.json configs[4]): fused transform + k-NN + plane fit + residual + reduce --- */
+typedef struct {
+  double plane_tolerance;
+  float dist_threshold;
+  int k;
+  int residual_type; /* PVB_P2PLANE_METER or PVB_P2PLANE_ANGLE                                                    */
+  int normalize;     /* normalize_distance (Config.h:113)                                                         */
+  double huber;      /* 0.2 (metre) / 2 deg (angle), util/Optimization.cpp:513-517; <= 0: none                    */
+  double weight;     /* lidar_weight                                                                              */
+} pvb_dense_params;
+
+/* target cloud in the world frame (n x 4 float32: x,y,z,class); builds the cell-sorted layout in HBM             */
+int pvb_dense_set_target(pvb_ctx* ctx, const float* xyzc, long n, double cell_size);
+/* source frames in their sensor frames, concatenated; frame f = [offsets[f], offsets[f+1]).  Points of a frame
+ * are re-ordered along a Morton curve on upload so that a thread block works on a compact patch.              */
+int pvb_dense_set_sources(pvb_ctx* ctx, const float* xyzc, const int* offsets, int n_frames);
+/* one Gauss-Newton evaluation at poses_lw (n_frames x 6): per frame 29 doubles = H upper 6x6 (21) | g (6) | cost |
+ * n_residuals w.r.t. the frame's own pose (the target/reference pose is constant = identity).                  */
+int pvb_dense_evaluate(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, double* out_sys29);
+/* same, but leaves the reduced systems on the device (for an on-stream allreduce); pointer to n_frames x 29     */
+int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, double** dev_sys29);
+/* Gauss-Newton/LM step per frame from the reduced 6x6 systems (host, 64 tiny solves): poses updated in place.   */
+int pvb_dense_gauss_newton_step(const double* sys29, int n_frames, double lambda, double* poses_lw);
+/* per-query view of the last evaluate for parity: valid flag, point (nei frame), plane, residual, 6 Jacobian cols */
+int pvb_dense_get_rows(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, unsigned char* valid,
+                       double* point3, double* plane4, double* residual, double* jac6);
+
+/* ---- D. bulk SE(3) + equirectangular projection (util/Visualization.h:408-441) -------------------------- */
+/* uvd: n x 3 float32 = pixel.x, pixel.y (FastAtan2 path, base/Math.h:15-29), depth = |p|                          */
+int pvb_project_equirect(pvb_ctx* ctx, const float* xyzi, long n, const double* T_cl16, int rows, int cols, float* uvd);
+/* the sparse depth image itself: uint16(depth*256) splatted over (size+1)^2 windows, last point wins             */
+int pvb_project_depth_image(pvb_ctx* ctx, const float* xyzi, long n, const double* T_cl16, int rows, int cols, int size, uint16_t* image);
+
+/* ---- E. line-to-line vote matrix (LidarFeatureAssociate.cpp:459-473) ------------------------------------- */
+/* M[nei_seg][ref_seg] += 1 for every nei corner point (world, float32) within dist_threshold of the ref line     */
+int pvb_line_votes(pvb_ctx* ctx, const double* ref_lines_world6, int n_ref_lines, const float* nei_corner_world, int n_points,
+                   const int* p2s_off, const int* p2s_ids, int n_nei_lines, double dist_threshold, int* M);
+
+/* ---- F. camera-LiDAR line association votes (CameraLidarLineAssociate.cpp:389-414) ------------------------ */
+/* counts[image_line][lidar_segment] of AssociateByAngle's inner loop; cloud is cornerLessSharp in the LiDAR frame */
+int pvb_angle_votes(pvb_ctx* ctx, int rows, int cols, const float* lines4, int n_lines, const float* cloud_local, int n_points,
+                    const int* p2s_off, const int* p2s_ids, int n_segments, const double* T_cl16, int* counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANOVLM_B200_H_ */

@@ -1,0 +1,278 @@
+"""ctypes mirror of include/panovlm_b200.h (same names, argument meaning and error behaviour).
+
+Every method forwards to one ``pvb_*`` entry point; errors (negative return codes) raise :class:`PvbError` with
+``pvb_last_error``.  numpy arrays are the host buffers; nothing here computes on the CPU.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+P2PLANE_METER, P2PLANE_ANGLE, P2LINE_METER, P2LINE_ANGLE, PLANE2PLANE_GLOBAL, PLANE_IOU = range(6)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class PvbError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libpanovlm_b200.so")
+
+
+def build_library():
+    """nvcc -gencode arch=compute_100a,code=sm_100a (cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "csrc")])
+
+
+class _Frame(C.Structure):
+    _fields_ = [("surf_target", C.c_void_p), ("n_target", C.c_int), ("surf_query", C.c_void_p), ("n_query", C.c_int)]
+
+
+class _AssocParams(C.Structure):
+    _fields_ = [("plane_tolerance", C.c_double), ("dist_threshold", C.c_float), ("k", C.c_int), ("cell_size", C.c_double)]
+
+
+class _DenseParams(C.Structure):
+    _fields_ = [("plane_tolerance", C.c_double), ("dist_threshold", C.c_float), ("k", C.c_int), ("residual_type", C.c_int),
+                ("normalize", C.c_int), ("huber", C.c_double), ("weight", C.c_double)]
+
+
+def load_library():
+    """Loads libpanovlm_b200.so; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise PvbError(f"{path} is missing: build it with panovlm_b200.build_library() / __graft_entry__.build() "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    L.pvb_last_error.restype = C.c_char_p
+    L.pvb_kernel_launches.restype = C.c_long
+    L.pvb_stream.restype = C.c_void_p
+    L.pvb_blocks_residuals.restype = C.POINTER(C.c_double)
+    L.pvb_blocks_jacobians.restype = C.POINTER(C.c_double)
+    _LIB = L
+    return L
+
+
+EXPORTS = [
+    "pvb_create", "pvb_destroy", "pvb_last_error", "pvb_set_stream", "pvb_synchronize", "pvb_kernel_launches", "pvb_stream",
+    "pvb_blocks_set", "pvb_blocks_evaluate", "pvb_blocks_residuals", "pvb_blocks_jacobians", "pvb_blocks_cost", "pvb_blocks_num_edges",
+    "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_dense_system", "pvb_blocks_solve_lm",
+    "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn",
+    "pvb_dense_set_target", "pvb_dense_set_sources", "pvb_dense_evaluate", "pvb_dense_evaluate_device", "pvb_dense_gauss_newton_step",
+    "pvb_dense_get_rows", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
+]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _arr(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Context:
+    """One GPU + one stream (pvb_create / pvb_destroy)."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        rc = self._L.pvb_create(C.c_int(device), C.byref(self._h))
+        if rc != 0:
+            raise PvbError(f"pvb_create(device={device}) failed with code {rc}: a CUDA device is required (no CPU fallback)")
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.pvb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PvbError(f"code {rc}: {self._L.pvb_last_error(self._h).decode()}")
+
+    # ---- lifecycle
+    def set_stream(self, cuda_stream):
+        self._ck(self._L.pvb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self._L.pvb_synchronize(self._h))
+
+    @property
+    def kernel_launches(self):
+        return self._L.pvb_kernel_launches(self._h)
+
+    @property
+    def stream(self):
+        return self._L.pvb_stream(self._h)
+
+    # ---- A. correspondence-list mode
+    def blocks_set(self, type, ref, nei, consts, huber, normalize, n_pose_blocks):
+        t = _arr(type, np.int32)
+        n = len(t)
+        r = _arr(np.broadcast_to(ref, n), np.int32)
+        m = _arr(np.broadcast_to(nei, n), np.int32)
+        nz = _arr(np.broadcast_to(normalize, n), np.int32)
+        h = _arr(np.broadcast_to(huber, n), np.float64)
+        c = _arr(consts, np.float64).reshape(n, 12)
+        self._n_blocks, self._nb = n, int(n_pose_blocks)
+        self._ck(self._L.pvb_blocks_set(self._h, C.c_long(n), _p(t), _p(r), _p(m), _p(nz), _p(h), _p(c), C.c_int(n_pose_blocks)))
+
+    def blocks_evaluate(self, poses, want_rows=True, want_system=True):
+        poses = _arr(poses, np.float64)
+        self._ck(self._L.pvb_blocks_evaluate(self._h, _p(poses), C.c_int(int(want_rows)), C.c_int(int(want_system))))
+
+    def blocks_rows(self):
+        n = self._n_blocks
+        rp, jp = self._L.pvb_blocks_residuals(self._h), self._L.pvb_blocks_jacobians(self._h)
+        if not rp or not jp:
+            raise PvbError("no rows: call blocks_evaluate(want_rows=True) first")
+        return np.ctypeslib.as_array(rp, shape=(n,)).copy(), np.ctypeslib.as_array(jp, shape=(n, 12)).copy()
+
+    def blocks_cost(self):
+        c, n = C.c_double(), C.c_long()
+        self._ck(self._L.pvb_blocks_cost(self._h, C.byref(c), C.byref(n)))
+        return c.value, n.value
+
+    def blocks_edges(self):
+        ne = self._L.pvb_blocks_num_edges(self._h)
+        r, m = np.zeros(ne, np.int32), np.zeros(ne, np.int32)
+        self._ck(self._L.pvb_blocks_edges(self._h, _p(r), _p(m)))
+        s = np.zeros((ne, 92))
+        self._ck(self._L.pvb_blocks_edge_systems(self._h, _p(s)))
+        return r, m, s
+
+    def blocks_dense_system(self):
+        D = 6 * self._nb
+        H, g, c = np.zeros((D, D)), np.zeros(D), C.c_double()
+        self._ck(self._L.pvb_blocks_dense_system(self._h, _p(H), _p(g), C.byref(c)))
+        return H, g, c.value
+
+    def blocks_solve_lm(self, poses, is_const=None, max_iterations=20):
+        poses = _arr(poses, np.float64).copy()
+        mask = np.zeros(self._nb, np.uint8) if is_const is None else _arr(is_const, np.uint8)
+        s = np.zeros(6)
+        self._ck(self._L.pvb_blocks_solve_lm(self._h, _p(poses), _p(mask), C.c_int(max_iterations), _p(s)))
+        keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
+        return poses, dict(zip(keys, s.tolist()))
+
+    # ---- B. frames
+    def frames_set(self, targets, queries):
+        """targets[f] / queries[f]: (n,4) float32 arrays in the sensor frame (surfLessFlat / surfFlat)."""
+        self._keep = [[_arr(t, np.float32).reshape(-1, 4) for t in targets], [_arr(q, np.float32).reshape(-1, 4) for q in queries]]
+        n = len(targets)
+        arr = (_Frame * n)()
+        for f in range(n):
+            t, q = self._keep[0][f], self._keep[1][f]
+            arr[f] = _Frame(t.ctypes.data if len(t) else None, len(t), q.ctypes.data if len(q) else None, len(q))
+        self._n_frames = n
+        self._ck(self._L.pvb_frames_set(self._h, C.c_int(n), arr))
+
+    def frames_associate_point2plane(self, poses, ref, nei, plane_tolerance, dist_threshold, k=10, cell_size=0.0):
+        poses = _arr(poses, np.float64)
+        ref, nei = _arr(ref, np.int32), _arr(nei, np.int32)
+        prm = _AssocParams(plane_tolerance, dist_threshold, k, cell_size)
+        n = C.c_long()
+        self._ck(self._L.pvb_frames_associate_point2plane(self._h, _p(poses), C.c_int(len(ref)), _p(ref), _p(nei), C.byref(prm), C.byref(n)))
+        m = n.value
+        e, q, pt, pl = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros((m, 3)), np.zeros((m, 4))
+        self._ck(self._L.pvb_frames_get_point2plane(self._h, C.c_long(m), _p(e), _p(q), _p(pt), _p(pl)))
+        return e, q, pt, pl
+
+    def frames_knn(self, poses, ref, nei, n_query, dist_threshold, k=10, cell_size=0.0):
+        poses = _arr(poses, np.float64)
+        prm = _AssocParams(0.05, dist_threshold, k, cell_size)
+        idx, d2 = np.zeros((n_query, k), np.int32), np.zeros((n_query, k), np.float32)
+        self._ck(self._L.pvb_frames_knn(self._h, _p(poses), C.c_int(ref), C.c_int(nei), C.byref(prm), _p(idx), _p(d2)))
+        return idx, d2
+
+    # ---- C. dense
+    @staticmethod
+    def dense_params(plane_tolerance=0.05, dist_threshold=1.0, k=10, residual_type=P2PLANE_METER, normalize=1, huber=0.2, weight=1.0):
+        return _DenseParams(plane_tolerance, dist_threshold, k, residual_type, normalize, huber, weight)
+
+    def dense_set_target(self, xyzc, cell_size=0.0):
+        a = _arr(xyzc, np.float32).reshape(-1, 4)
+        self._ck(self._L.pvb_dense_set_target(self._h, _p(a), C.c_long(len(a)), C.c_double(cell_size)))
+
+    def dense_set_sources(self, xyzc, offsets):
+        a = xyzc if (isinstance(xyzc, np.ndarray) and xyzc.dtype == np.float32 and xyzc.flags.c_contiguous) else _arr(xyzc, np.float32)
+        off = _arr(offsets, np.int32)
+        self._dense_frames, self._dense_n = len(off) - 1, int(off[-1])
+        self._ck(self._L.pvb_dense_set_sources(self._h, _p(a), _p(off), C.c_int(len(off) - 1)))
+
+    def dense_set_sources_ptr(self, ptr, offsets):
+        """Same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
+        off = _arr(offsets, np.int32)
+        self._dense_frames, self._dense_n = len(off) - 1, int(off[-1])
+        self._ck(self._L.pvb_dense_set_sources(self._h, C.c_void_p(ptr), _p(off), C.c_int(len(off) - 1)))
+
+    def dense_evaluate(self, poses_lw, prm):
+        poses = _arr(poses_lw, np.float64)
+        out = np.zeros((self._dense_frames, 29))
+        self._ck(self._L.pvb_dense_evaluate(self._h, _p(poses), C.byref(prm), _p(out)))
+        return out
+
+    def dense_evaluate_device(self, poses_lw, prm):
+        """Enqueues the evaluation; returns the device pointer of the (n_frames x 29) reduced systems."""
+        poses = _arr(poses_lw, np.float64)
+        ptr = C.c_void_p()
+        self._ck(self._L.pvb_dense_evaluate_device(self._h, _p(poses), C.byref(prm), C.byref(ptr)))
+        return ptr.value
+
+    def dense_gauss_newton_step(self, sys29, poses_lw, lam=0.0):
+        poses = _arr(poses_lw, np.float64).copy()
+        s = _arr(sys29, np.float64)
+        rc = self._L.pvb_dense_gauss_newton_step(_p(s), C.c_int(len(s)), C.c_double(lam), _p(poses))
+        if rc != 0:
+            raise PvbError(f"pvb_dense_gauss_newton_step: code {rc}")
+        return poses
+
+    def dense_get_rows(self, poses_lw, prm):
+        poses = _arr(poses_lw, np.float64)
+        n = self._dense_n
+        v, pt, pl, r, j = np.zeros(n, np.uint8), np.zeros((n, 3)), np.zeros((n, 4)), np.zeros(n), np.zeros((n, 6))
+        self._ck(self._L.pvb_dense_get_rows(self._h, _p(poses), C.byref(prm), _p(v), _p(pt), _p(pl), _p(r), _p(j)))
+        return v.astype(bool), pt, pl, r, j
+
+    # ---- D/E/F
+    def project_equirect(self, xyzi, T_cl, rows, cols):
+        a = _arr(xyzi, np.float32).reshape(-1, 4)
+        out = np.zeros((len(a), 3), np.float32)
+        self._ck(self._L.pvb_project_equirect(self._h, _p(a), C.c_long(len(a)), _p(_arr(T_cl, np.float64)), C.c_int(rows), C.c_int(cols), _p(out)))
+        return out
+
+    def project_depth_image(self, xyzi, T_cl, rows, cols, size=3):
+        a = _arr(xyzi, np.float32).reshape(-1, 4)
+        img = np.zeros((rows, cols), np.uint16)
+        self._ck(self._L.pvb_project_depth_image(self._h, _p(a), C.c_long(len(a)), _p(_arr(T_cl, np.float64)), C.c_int(rows), C.c_int(cols), C.c_int(size), _p(img)))
+        return img
+
+    def line_votes(self, ref_lines_world, nei_corner_world, p2s_off, p2s_ids, n_nei_lines, dist_threshold):
+        rl = _arr(ref_lines_world, np.float64).reshape(-1, 6)
+        pts = _arr(nei_corner_world, np.float32).reshape(-1, 4)
+        M = np.zeros((n_nei_lines, len(rl)), np.int32)
+        self._ck(self._L.pvb_line_votes(self._h, _p(rl), C.c_int(len(rl)), _p(pts), C.c_int(len(pts)), _p(_arr(p2s_off, np.int32)), _p(_arr(p2s_ids, np.int32)),
+                                        C.c_int(n_nei_lines), C.c_double(dist_threshold), _p(M)))
+        return M
+
+    def angle_votes(self, rows, cols, lines, cloud_local, p2s_off, p2s_ids, n_segments, T_cl):
+        ln = _arr(lines, np.float32).reshape(-1, 4)
+        cl = _arr(cloud_local, np.float32).reshape(-1, 4)
+        counts = np.zeros((len(ln), n_segments), np.int32)
+        self._ck(self._L.pvb_angle_votes(self._h, C.c_int(rows), C.c_int(cols), _p(ln), C.c_int(len(ln)), _p(cl), C.c_int(len(cl)), _p(_arr(p2s_off, np.int32)),
+                                         _p(_arr(p2s_ids, np.int32)), C.c_int(n_segments), _p(_arr(T_cl, np.float64)), _p(counts)))
+        return counts

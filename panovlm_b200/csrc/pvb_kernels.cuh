@@ -1,0 +1,369 @@
+// panovlm_b200 — sm_100a kernels of the hot path.  HBM-bound integer/float/double work: no tensor cores.
+//   k_transform_world      T1  Velodyne::Transform2LidarWorld per cloud (float32 store) + per-cloud AABB
+//   k_cell_hist/k_scatter      cell-sorted target layout (uniform grid, x fastest)
+//   k_associate<K,...>     K2p fused: query -> world, exact k-NN on the grid, class test, plane fit, collinearity,
+//                              [emit correspondence] [residual + Jacobian rows] [per-tile 6x6 normal-equation partial]
+//   k_eval_blocks          K3  residual + analytic Jacobian over a correspondence list (+ per-tile 12x12 partial)
+//   k_sum_partials         K4  deterministic (fixed order) assembly of the per-edge / per-frame normal equations
+//   k_project / k_splat    K1  SE(3) + equirectangular projection, sparse depth image
+//   k_line_votes           K2l AssociateLine2Line vote matrix
+//   k_angle_votes          K2c AssociateByAngle vote counts
+#pragma once
+#include <cuda_runtime.h>
+#include "pvb_knn.cuh"
+
+namespace pvb {
+
+constexpr int kTile = 128;   // queries / residual rows per thread block
+
+struct WorldPose { double R[9]; double t[3]; };   // T_wl of a pose block (row-major R)
+
+struct CloudTile { int cloud; int start; int count; int pad; };          // points [start, start+count) of `cloud`
+struct Pair { int target_cloud; int query_cloud; int ref_block; int nei_block; };
+struct QueryTile { int pair; int start; int count; int out_base; };       // queries [start, start+count) (global index); output slot of the first
+
+PVB_HD uint32_t ordered_f32(float f) { const uint32_t u = f2u(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+PVB_HD float unordered_f32(uint32_t u) { return u2f((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ F4 ldg_f4(const F4* p) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+}
+
+// ---- T1: local -> world (float32) for every point of every cloud; w = (index in cloud << 5) | class ----------
+__global__ void __launch_bounds__(256) k_transform_world(const F4* __restrict__ local, const CloudTile* __restrict__ tiles,
+                                                         const int* __restrict__ cloud_block, const WorldPose* __restrict__ wpose,
+                                                         const int* __restrict__ cloud_off, F4* __restrict__ world, uint32_t* __restrict__ aabb /*[cloud][6]*/) {
+  const CloudTile t = tiles[blockIdx.x];
+  const WorldPose& wp = wpose[cloud_block[t.cloud]];
+  const int i = threadIdx.x;
+  float x = 0, y = 0, z = 0;
+  const bool act = i < t.count;
+  if (act) {
+    const F4 p = ldg_f4(local + t.start + i);
+    transform_point_f32(wp.R, wp.t, p.x, p.y, p.z, x, y, z);
+    F4 o; o.x = x; o.y = y; o.z = z;
+    o.w = u2f(((uint32_t)(t.start + i - cloud_off[t.cloud]) << 5) | ((uint32_t)p.w & 31u));
+    reinterpret_cast<float4*>(world)[t.start + i] = make_float4(o.x, o.y, o.z, o.w);
+  }
+  if (aabb) {
+    uint32_t lo[3] = {act ? ordered_f32(x) : 0xFFFFFFFFu, act ? ordered_f32(y) : 0xFFFFFFFFu, act ? ordered_f32(z) : 0xFFFFFFFFu};
+    uint32_t hi[3] = {act ? ordered_f32(x) : 0u, act ? ordered_f32(y) : 0u, act ? ordered_f32(z) : 0u};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o)); hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o)); }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { atomicMin(aabb + t.cloud * 6 + c, lo[c]); atomicMax(aabb + t.cloud * 6 + 3 + c, hi[c]); }
+    }
+  }
+}
+
+// ---- grid build -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_keys(const F4* __restrict__ world, const CloudTile* __restrict__ tiles, const GridDesc* __restrict__ grids,
+                                                   unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist) {
+  const CloudTile t = tiles[blockIdx.x];
+  const int i = threadIdx.x;
+  if (i >= t.count) return;
+  const GridDesc& g = grids[t.cloud];
+  const F4 p = ldg_f4(world + t.start + i);
+  const int cx = cell_coord((double)p.x, g.origin[0], g.inv_h, g.dims[0]);
+  const int cy = cell_coord((double)p.y, g.origin[1], g.inv_h, g.dims[1]);
+  const int cz = cell_coord((double)p.z, g.origin[2], g.inv_h, g.dims[2]);
+  const unsigned long long cell = (unsigned long long)g.cell_base + ((unsigned long long)cz * g.dims[1] + cy) * g.dims[0] + cx;
+  keys[t.start + i] = cell;
+  vals[t.start + i] = (uint32_t)(t.start + i);
+  atomicAdd(hist + cell, 1u);
+}
+
+__global__ void __launch_bounds__(256) k_gather_f4(const F4* __restrict__ src, const uint32_t* __restrict__ idx, long long n, F4* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + idx[i]);
+}
+
+// Morton key of a source point in its own sensor frame (0.25 m cells, +-512 m), frame id in the high bits.
+__device__ __forceinline__ unsigned long long spread3(uint32_t v) {
+  unsigned long long x = v & 0xFFFull;
+  x = (x | (x << 16)) & 0x0000FF0000FFull; x = (x | (x << 8)) & 0x00F00F00F00Full;
+  x = (x | (x << 4)) & 0x0C30C30C30C3ull;  x = (x | (x << 2)) & 0x249249249249ull;
+  return x;
+}
+__global__ void __launch_bounds__(256) k_morton_keys(const F4* __restrict__ local, const CloudTile* __restrict__ tiles, unsigned long long* __restrict__ keys,
+                                                     uint32_t* __restrict__ vals) {
+  const CloudTile t = tiles[blockIdx.x];
+  const int i = threadIdx.x;
+  if (i >= t.count) return;
+  const F4 p = ldg_f4(local + t.start + i);
+  auto q = [](float v) { const float f = floorf((v + 512.f) * 4.f); return (uint32_t)(f < 0.f ? 0.f : (f > 4095.f ? 4095.f : f)); };
+  const unsigned long long m = spread3(q(p.x)) | (spread3(q(p.y)) << 1) | (spread3(q(p.z)) << 2);
+  keys[t.start + i] = ((unsigned long long)t.cloud << 36) | m;
+  vals[t.start + i] = (uint32_t)(t.start + i);
+}
+
+// ---- K2p: fused associate (+ residual + reduce) --------------------------------------------------------------------
+struct AssocArgs {
+  const F4* q_local;            // query records, local frame: x,y,z,intensity(class)  (dense mode: Morton order)
+  const uint32_t* q_orig;       // original index of each (re-ordered) query, or null (identity)
+  const QueryTile* tiles;
+  const Pair* pairs;
+  const GridDesc* grids;
+  const uint32_t* cell_start;
+  const F4* sorted;             // cell-sorted world target records
+  const WorldPose* wpose;       // per pose block
+  const PosePrep* prep;         // per pose block
+  AssocParams prm;              // rmax is derived per target grid in the kernel
+  double thr;                   // distance threshold (m)
+  // residual
+  int residual_type, normalize; double huber, weight;
+  // outputs (any may be null)
+  unsigned char* out_valid; double* out_point; double* out_plane;   // indexed by output slot: q_orig[query] (dense) or tile.out_base + lane
+  double* out_res; double* out_jac6;                                 // idem
+  int* out_nn_idx; float* out_nn_d2;                                 // idem, K per query (debug / parity)
+  double* partials;                                                  // [tile][29]
+};
+
+template <int K, bool REDUCE>
+__global__ void __launch_bounds__(kTile) k_associate(const AssocArgs a) {
+  __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
+  const QueryTile t = a.tiles[blockIdx.x];
+  const Pair pr = a.pairs[t.pair];
+  const int i = threadIdx.x;
+  const bool act = i < t.count;
+  bool valid = false;
+  double p_local[3] = {0, 0, 0}, plane[4] = {0, 0, 0, 0};
+  double r = 0.0, cost = 0.0, J[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) J[k] = 0.0;
+  uint32_t qi = 0;
+  if (act) {
+    const int gq = t.start + i;
+    qi = a.q_orig ? a.q_orig[gq] : (uint32_t)(t.out_base + i);
+    const F4 q = ldg_f4(a.q_local + gq);
+    const WorldPose& wn = a.wpose[pr.nei_block];
+    const WorldPose& wr = a.wpose[pr.ref_block];
+    float qx, qy, qz;
+    transform_point_f32(wn.R, wn.t, q.x, q.y, q.z, qx, qy, qz);
+    const GridDesc& g = a.grids[pr.target_cloud];
+    const uint32_t* cs = a.cell_start + g.cell_base;
+    const F4* srt = a.sorted;
+    auto cells = [cs](long long c) { return (long long)__ldg(cs + c); };
+    auto load = [srt](long long p) { return ldg_f4(srt + p); };
+    unsigned long long keys[K];
+    AssocParams prm = a.prm;
+    prm.rmax = (int)ceil(a.thr / g.h);
+    valid = associate_point2plane<K>(g, cells, load, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, keys);
+    if (a.out_nn_idx) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const bool ok = (keys[j] & kKeyEmptyLow) != kKeyEmptyLow;
+        a.out_nn_idx[(size_t)qi * K + j] = ok ? (int)(f2u(load((long long)(uint32_t)(keys[j] & kKeyEmptyLow)).w) >> 5) : -1;
+        a.out_nn_d2[(size_t)qi * K + j] = ok ? u2f((uint32_t)(keys[j] >> 32)) : INFINITY;
+      }
+    }
+    if (valid && (REDUCE || a.out_res)) {
+      double c[12];
+      c[0] = p_local[0]; c[1] = p_local[1]; c[2] = p_local[2];
+      c[3] = plane[0]; c[4] = plane[1]; c[5] = plane[2]; c[6] = plane[3]; c[7] = a.weight;
+      c[8] = c[9] = c[10] = c[11] = 0.0;
+      r = eval_block(a.residual_type, a.normalize != 0, c, a.prep[pr.ref_block], a.prep[pr.nei_block], J);
+      cost = huber_correct(a.huber, r, J, 12);
+    }
+    if (a.out_valid) a.out_valid[qi] = valid ? 1 : 0;
+    if (a.out_point && valid) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) a.out_point[(size_t)qi * 3 + k] = p_local[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a.out_plane[(size_t)qi * 4 + k] = plane[k];
+    }
+    if (a.out_res) {
+      a.out_res[qi] = r;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a.out_jac6[(size_t)qi * 6 + k] = J[6 + k];
+    }
+  }
+  if (REDUCE) {
+    // stage rows in shared memory, then 29 threads each own one entry of (H upper 21 | g 6 | cost | count):
+    // fixed summation order => run-to-run identical results.
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sJ[i][k] = valid ? J[6 + k] : 0.0;
+    sJ[i][6] = valid ? r : 0.0;
+    sJ[i][7] = valid ? cost : 0.0;
+    __syncthreads();
+    if (i < 28) {
+      int ia = 0, ib = 0; double acc = 0.0;
+      if (i < 21) { int o = i; ia = 0; while (o >= 6 - ia) { o -= 6 - ia; ++ia; } ib = ia + o; }
+      else if (i < 27) { ia = i - 21; ib = 6; }
+      if (i < 27) { for (int row = 0; row < kTile; ++row) acc += sJ[row][ia] * sJ[row][ib]; }
+      else { for (int row = 0; row < kTile; ++row) acc += sJ[row][7]; }
+      a.partials[(size_t)blockIdx.x * 29 + i] = acc;
+    }
+    // residual count: ballot of valid flags (exact integer)
+    const unsigned b = __ballot_sync(0xffffffffu, valid);
+    __shared__ int scount[kTile / 32];
+    if ((i & 31) == 0) scount[i >> 5] = __popc(b);
+    __syncthreads();
+    if (i == 0) { int n = 0; for (int w = 0; w < kTile / 32; ++w) n += scount[w]; a.partials[(size_t)blockIdx.x * 29 + 28] = (double)n; }
+  }
+}
+
+// ---- K3: residual + analytic Jacobian over a correspondence list sorted by pose-graph edge --------------------------
+struct BlockTile { int edge; int start; int count; int pad; };
+struct EvalArgs {
+  const BlockTile* tiles;
+  const int* edge_ref; const int* edge_nei;
+  const int* type; const int* normalize; const double* huber;
+  const double* consts;        // SoA: consts[k * n + row]
+  const uint32_t* orig;        // original block index of each sorted row
+  long long n;
+  const PosePrep* prep;
+  double* out_r; double* out_J;   // original order (may be null)
+  double* partials;               // [tile][92] (may be null)
+};
+
+__global__ void __launch_bounds__(kTile) k_eval_blocks(const EvalArgs a) {
+  __shared__ double sJ[kTile][14];   // J12 | r | cost  (stride 14 doubles)
+  const BlockTile t = a.tiles[blockIdx.x];
+  const int i = threadIdx.x;
+  const bool act = i < t.count;
+  double J[12], r = 0.0, cost = 0.0;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) J[k] = 0.0;
+  if (act) {
+    const long long row = (long long)t.start + i;
+    double c[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) c[k] = __ldg(a.consts + (size_t)k * a.n + row);
+    r = eval_block(a.type[row], a.normalize[row] != 0, c, a.prep[a.edge_ref[t.edge]], a.prep[a.edge_nei[t.edge]], J);
+    cost = huber_correct(a.huber[row], r, J, 12);
+    if (a.out_r) {
+      const uint32_t o = a.orig[row];
+      a.out_r[o] = r;
+      double2* dst = reinterpret_cast<double2*>(a.out_J + (size_t)o * 12);   // 96-byte rows, 16-byte aligned: 128-bit stores
+#pragma unroll
+      for (int k = 0; k < 6; ++k) dst[k] = make_double2(J[2 * k], J[2 * k + 1]);
+    }
+  }
+  if (a.partials) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) sJ[i][k] = J[k];
+    sJ[i][12] = r; sJ[i][13] = cost;
+    __syncthreads();
+    if (i < 92) {
+      int ia = 0, ib = 0; double acc = 0.0;
+      if (i < 78) { int o = i; while (o >= 12 - ia) { o -= 12 - ia; ++ia; } ib = ia + o; }
+      else if (i < 90) { ia = i - 78; ib = 12; }
+      if (i < 90) { for (int row = 0; row < kTile; ++row) acc += sJ[row][ia] * sJ[row][ib]; }
+      else if (i == 90) { for (int row = 0; row < kTile; ++row) acc += sJ[row][13]; }
+      else acc = (double)t.count;
+      a.partials[(size_t)blockIdx.x * 92 + i] = acc;
+    }
+  }
+}
+
+// ---- K4: sum the per-tile partials of each edge / frame in tile order --------------------------------------------------
+template <int NV>
+__global__ void k_sum_partials(const double* __restrict__ partials, const int* __restrict__ tile_begin /*[n_groups+1]*/, double* __restrict__ out) {
+  const int gidx = blockIdx.x, v = threadIdx.x;
+  if (v >= NV) return;
+  double acc = 0.0;
+  for (int t = tile_begin[gidx]; t < tile_begin[gidx + 1]; ++t) acc += partials[(size_t)t * NV + v];
+  out[(size_t)gidx * NV + v] = acc;
+}
+
+// ---- K1: SE(3) + equirectangular projection (float32 FastAtan2 path) --------------------------------------------------
+__global__ void __launch_bounds__(256) k_project(const F4* __restrict__ pts, long long n, WorldPose T, int rows, int cols, float* __restrict__ uvd,
+                                                 unsigned long long* __restrict__ splat, int size) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const F4 p = ldg_f4(pts + i);
+  float x, y, z, u, v;
+  transform_point_f32(T.R, T.t, p.x, p.y, p.z, x, y, z);
+  cam_to_image_f32(x, y, z, rows, cols, u, v);
+  const float depth = sqrtf(fadd(fadd(fmul(x, x), fmul(y, y)), fmul(z, z)));
+  if (uvd) { uvd[i * 3] = u; uvd[i * 3 + 1] = v; uvd[i * 3 + 2] = depth; }
+  if (splat) {
+    const int h = size / 2;
+    const int rbx = (int)ceilf(u) + h, rby = (int)ceilf(v) + h, ltx = (int)floorf(u) - h, lty = (int)floorf(v) - h;
+    const bool in_rb = rbx >= 0 && rby >= 0 && rbx + 1 <= cols && rby + 1 <= rows;
+    const bool in_lt = ltx >= 0 && lty >= 0 && ltx + 1 <= cols && lty + 1 <= rows;
+    if (in_rb && in_lt) {
+      const uint32_t rel = (uint32_t)((int)((double)depth * 256.0)) & 0xFFFFu;
+      const unsigned long long key = ((unsigned long long)(i + 1) << 16) | rel;     // "last writer wins" == largest point index
+      for (int yy = lty; yy <= rby; ++yy) for (int xx = ltx; xx <= rbx; ++xx) atomicMax(splat + (size_t)yy * cols + xx, key);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_splat_finalize(const unsigned long long* __restrict__ splat, long long n, uint16_t* __restrict__ img) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) img[i] = (uint16_t)(splat[i] & 0xFFFFull);
+}
+
+// ---- non-fused double helpers for threshold-critical vote kernels (bit-identical to the -ffp-contract=off CPU) ----------
+__device__ __forceinline__ double dot3_nf(const double* a, const double* b) { return dadd(dadd(dmul(a[0], b[0]), dmul(a[1], b[1])), dmul(a[2], b[2])); }
+__device__ __forceinline__ double vector_angle_nf(const double* a, const double* b) {   // Geometry.hpp:450-466
+  double c = dot3_nf(a, b);
+  const double n1 = sqrt(dot3_nf(a, a)), n2 = sqrt(dot3_nf(b, b));
+  c = c / dmul(n1, n2);
+  if (c >= 1.0) return 0.0;
+  if (c <= -1.0) return M_PI;
+  return acos(c);
+}
+
+// ---- K2l: line-to-line vote matrix ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_line_votes(const double* __restrict__ ref_lines, int S_ref, const F4* __restrict__ pts, int n_pts,
+                                                    const int* __restrict__ p2s_off, const int* __restrict__ p2s_ids, double thr, int* __restrict__ M) {
+  extern __shared__ double s_lines[];
+  for (int k = threadIdx.x; k < S_ref * 6; k += blockDim.x) s_lines[k] = ref_lines[k];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const F4 p = ldg_f4(pts + i);
+  const double P[3] = {(double)p.x, (double)p.y, (double)p.z};
+  const int e0 = p2s_off[i], e1 = p2s_off[i + 1];
+  if (e0 == e1) return;
+  for (int s = 0; s < S_ref; ++s) {
+    const double* l = s_lines + s * 6;   // PointToLineDistance3D (Geometry.hpp:198-211)
+    const double d0 = dsub(P[0], l[0]), d1 = dsub(P[1], l[1]), d2 = dsub(P[2], l[2]);
+    const double k = dadd(dadd(dmul(l[3], d0), dmul(l[4], d1)), dmul(l[5], d2)) / dadd(dadd(dmul(l[3], l[3]), dmul(l[4], l[4])), dmul(l[5], l[5]));
+    const double e[3] = {dsub(dadd(dmul(k, l[3]), l[0]), P[0]), dsub(dadd(dmul(k, l[4]), l[1]), P[1]), dsub(dadd(dmul(k, l[5]), l[2]), P[2])};
+    const double dist = sqrt(dadd(dadd(dmul(e[0], e[0]), dmul(e[1], e[1])), dmul(e[2], e[2])));
+    if (dist > thr) continue;
+    for (int q = e0; q < e1; ++q) atomicAdd(M + (size_t)p2s_ids[q] * S_ref + s, 1);
+  }
+}
+
+// ---- K2c: camera-LiDAR AssociateByAngle vote counts ------------------------------------------------------------------------
+struct ImageLinePlane { double n[4]; double p4[3]; double scope; };   // unit plane through the origin, arc midpoint, half-arc angle
+__global__ void __launch_bounds__(128) k_angle_votes(const ImageLinePlane* __restrict__ lines, int L, const F4* __restrict__ cloud_local, int P, WorldPose T,
+                                                     const int* __restrict__ p2s_off, const int* __restrict__ p2s_ids, int S, int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y;
+  if (i >= P) return;
+  const int e0 = p2s_off[i], e1 = p2s_off[i + 1];
+  if (e0 == e1) return;
+  const F4 pl = ldg_f4(cloud_local + i);
+  const float range = fadd(fadd(fmul(pl.x, pl.x), fmul(pl.y, pl.y)), fmul(pl.z, pl.z));
+  if (range > 15 * 15) return;                                           // CameraLidarLineAssociate.cpp:395
+  float x, y, z;
+  transform_point_f32(T.R, T.t, pl.x, pl.y, pl.z, x, y, z);
+  const double p[3] = {(double)x, (double)y, (double)z};
+  const ImageLinePlane ln = lines[l];
+  // ProjectPointToPlane(p, plane, normalized = true)  (Geometry.hpp:301-316)
+  const double s = dadd(dadd(dadd(dmul(ln.n[0], p[0]), dmul(ln.n[1], p[1])), dmul(ln.n[2], p[2])), ln.n[3]);
+  const double dis = fabs(s);
+  double pp[3] = {dsub(p[0], dmul(dis, ln.n[0])), dsub(p[1], dmul(dis, ln.n[1])), dsub(p[2], dmul(dis, ln.n[2]))};
+  if (fabs(dadd(dadd(dadd(dmul(ln.n[0], pp[0]), dmul(ln.n[1], pp[1])), dmul(ln.n[2], pp[2])), ln.n[3])) > 1e-4) {
+    pp[0] = dadd(p[0], dmul(dis, ln.n[0])); pp[1] = dadd(p[1], dmul(dis, ln.n[1])); pp[2] = dadd(p[2], dmul(dis, ln.n[2]));
+  }
+  const double thr = 3.0 / 180.0 * M_PI;
+  if (vector_angle_nf(p, pp) >= thr) return;                             // :402
+  if (vector_angle_nf(ln.p4, pp) >= ln.scope + thr) return;              // :405
+  for (int q = e0; q < e1; ++q) atomicAdd(counts + (size_t)l * S + p2s_ids[q], 1);
+}
+
+#endif  // __CUDACC__
+}  // namespace pvb

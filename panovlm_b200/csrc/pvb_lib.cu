@@ -1,0 +1,774 @@
+// panovlm_b200 — context, device-memory management and the extern "C" ABI (include/panovlm_b200.h).
+// One context = one GPU + one stream.  Host code is C++ (the reference's host is C++); no torch types here.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/panovlm_b200.h"
+#include "pvb_host.hpp"
+#include "pvb_kernels.cuh"
+
+using namespace pvb;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct CloudSet {
+  int n_clouds = 0; long long n_points = 0; int n_tiles = 0;
+  std::vector<int> off;           // n_clouds + 1
+  DevBuf local, d_off, tiles, cloud_block;
+  void release() { local.release(); d_off.release(); tiles.release(); cloud_block.release(); }
+};
+
+struct TargetIndex {
+  DevBuf world, sorted, keys, keys_alt, vals, vals_alt, hist, cell_start, grids, aabb, tmp;
+  std::vector<GridDesc> h_grids;
+  long long total_cells = 0;
+  bool built = false;
+  void release() { world.release(); sorted.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release(); hist.release(); cell_start.release(); grids.release(); aabb.release(); tmp.release(); }
+};
+
+}  // namespace
+
+struct pvb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr; bool own_stream = true;
+  std::string err;
+  long launches = 0;
+  // pose staging
+  PinBuf h_pose; DevBuf d_prep, d_wpose;
+  // ---- blocks mode
+  long long bn = 0; int nb = 0; int b_tiles = 0;
+  std::vector<int> edge_ref, edge_nei, edge_tile_begin;
+  std::vector<uint32_t> b_orig;
+  DevBuf b_tile, b_eref, b_enei, b_type, b_norm, b_huber, b_consts, b_orig_d, b_r, b_J, b_part, b_esys, b_tbegin;
+  PinBuf h_r, h_J, h_esys;
+  bool b_has_rows = false, b_has_sys = false;
+  // ---- frames mode
+  CloudSet f_tgt, f_qry; TargetIndex f_index; int n_frames = 0;
+  DevBuf f_pairs, f_qtiles, f_valid, f_point, f_plane, f_nn_idx, f_nn_d2;
+  PinBuf fh_valid, fh_point, fh_plane;
+  std::vector<int> a_edge, a_query; std::vector<double> a_point, a_plane;
+  // ---- dense mode
+  CloudSet d_tgt, d_src; TargetIndex d_index; int d_frames = 0;
+  DevBuf d_q_sorted, d_q_orig, d_pairs, d_qtiles, d_part, d_sys, d_tbegin, d_valid, d_point, d_plane, d_res, d_jac;
+  PinBuf dh_sys;
+  int d_ntiles = 0; double d_cell = 0;
+  // ---- misc
+  DevBuf m_a, m_b, m_c, m_d, m_e;
+  PinBuf mh_a;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    err = buf; return code;
+  }
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->fail(PVB_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define CKL() do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return ctx->fail(PVB_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+namespace {
+
+int upload_poses(pvb_ctx* ctx, const double* poses, int nb, bool block0_identity_prefix) {
+  // layout in pinned staging: PosePrep[nb'] then WorldPose[nb'] where nb' = nb (+1 if an identity block is prefixed)
+  const int n = nb + (block0_identity_prefix ? 1 : 0);
+  const size_t bytes = (size_t)n * (sizeof(PosePrep) + sizeof(WorldPose));
+  CK(ctx->h_pose.ensure(bytes));
+  CK(ctx->d_prep.ensure((size_t)n * sizeof(PosePrep)));
+  CK(ctx->d_wpose.ensure((size_t)n * sizeof(WorldPose)));
+  CK(cudaStreamSynchronize(ctx->stream));   // staging buffer may still be in flight from the previous call
+  PosePrep* hp = ctx->h_pose.as<PosePrep>();
+  WorldPose* hw = reinterpret_cast<WorldPose*>(hp + n);
+  int o = 0;
+  const double zero6[6] = {0, 0, 0, 0, 0, 0};
+  if (block0_identity_prefix) { prepare_pose(zero6, hp[0]); world_pose(hp[0], hw[0].R, hw[0].t); o = 1; }
+  for (int b = 0; b < nb; ++b) { prepare_pose(poses + 6 * b, hp[o + b]); world_pose(hp[o + b], hw[o + b].R, hw[o + b].t); }
+  CK(cudaMemcpyAsync(ctx->d_prep.p, hp, (size_t)n * sizeof(PosePrep), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_wpose.p, hw, (size_t)n * sizeof(WorldPose), cudaMemcpyHostToDevice, ctx->stream));
+  return PVB_OK;
+}
+
+int set_cloudset(pvb_ctx* ctx, CloudSet& cs, const std::vector<const float*>& ptrs, const std::vector<int>& counts, const std::vector<int>& blocks, int tile) {
+  cs.n_clouds = (int)counts.size();
+  cs.off.assign(cs.n_clouds + 1, 0);
+  for (int c = 0; c < cs.n_clouds; ++c) cs.off[c + 1] = cs.off[c] + counts[c];
+  cs.n_points = cs.off[cs.n_clouds];
+  CK(cs.local.ensure(std::max<size_t>(16, (size_t)cs.n_points * sizeof(F4))));
+  for (int c = 0; c < cs.n_clouds; ++c)
+    if (counts[c] > 0) CK(cudaMemcpyAsync(cs.local.as<F4>() + cs.off[c], ptrs[c], (size_t)counts[c] * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<CloudTile> tiles;
+  for (int c = 0; c < cs.n_clouds; ++c)
+    for (int s = 0; s < counts[c]; s += tile) tiles.push_back(CloudTile{c, cs.off[c] + s, std::min(tile, counts[c] - s), 0});
+  cs.n_tiles = (int)tiles.size();
+  CK(cs.tiles.ensure(std::max<size_t>(16, tiles.size() * sizeof(CloudTile))));
+  CK(cs.d_off.ensure((size_t)(cs.n_clouds + 1) * sizeof(int)));
+  CK(cs.cloud_block.ensure(std::max<size_t>(16, (size_t)cs.n_clouds * sizeof(int))));
+  if (!tiles.empty()) CK(cudaMemcpyAsync(cs.tiles.p, tiles.data(), tiles.size() * sizeof(CloudTile), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(cs.d_off.p, cs.off.data(), (size_t)(cs.n_clouds + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (cs.n_clouds) CK(cudaMemcpyAsync(cs.cloud_block.p, blocks.data(), (size_t)cs.n_clouds * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+  return PVB_OK;
+}
+
+// world transform + cell-sorted layout of every cloud of `cs` (poses already uploaded to ctx->d_wpose)
+int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_hint) {
+  const long long n = cs.n_points;
+  ti.built = false;
+  if (n == 0 || cs.n_clouds == 0) { ti.h_grids.assign(cs.n_clouds, GridDesc{}); ti.built = true; return PVB_OK; }
+  CK(ti.world.ensure((size_t)n * sizeof(F4)));
+  CK(ti.sorted.ensure((size_t)n * sizeof(F4)));
+  CK(ti.aabb.ensure((size_t)cs.n_clouds * 6 * sizeof(uint32_t)));
+  std::vector<uint32_t> init((size_t)cs.n_clouds * 6);
+  for (int c = 0; c < cs.n_clouds; ++c) for (int k = 0; k < 6; ++k) init[(size_t)c * 6 + k] = k < 3 ? 0xFFFFFFFFu : 0u;
+  CK(cudaMemcpyAsync(ti.aabb.p, init.data(), init.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_transform_world<<<cs.n_tiles, 256, 0, ctx->stream>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>(), cs.cloud_block.as<int>(), ctx->d_wpose.as<WorldPose>(),
+                                                         cs.d_off.as<int>(), ti.world.as<F4>(), ti.aabb.as<uint32_t>());
+  CKL();
+  CK(cudaMemcpyAsync(init.data(), ti.aabb.p, init.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ti.h_grids.assign(cs.n_clouds, GridDesc{});
+  long long cells = 0;
+  for (int c = 0; c < cs.n_clouds; ++c) {
+    GridDesc& g = ti.h_grids[c];
+    const int cnt = cs.off[c + 1] - cs.off[c];
+    g.n_points = cnt; g.point_base = cs.off[c]; g.cell_base = cells;
+    if (cnt == 0) { g.dims[0] = g.dims[1] = g.dims[2] = 1; g.h = 1.0; g.inv_h = 1.0; g.origin[0] = g.origin[1] = g.origin[2] = 0; cells += 2; continue; }
+    double lo[3], ext[3];
+    for (int k = 0; k < 3; ++k) { lo[k] = unordered_f32(init[(size_t)c * 6 + k]); ext[k] = std::max(1e-3, (double)unordered_f32(init[(size_t)c * 6 + 3 + k]) - lo[k]); }
+    double h = cell_hint > 0 ? cell_hint : std::cbrt(ext[0] * ext[1] * ext[2] / (double)cnt);
+    h = std::max(h, 0.02);
+    for (;;) {
+      double nc = 1; for (int k = 0; k < 3; ++k) nc *= std::floor(ext[k] / h) + 1;
+      if (nc <= 4.0 * cnt + 4096.0 && nc < 1.5e9) break;
+      h *= 1.25;
+    }
+    g.h = h; g.inv_h = 1.0 / h;
+    for (int k = 0; k < 3; ++k) { g.origin[k] = lo[k]; g.dims[k] = (int)std::floor(ext[k] / h) + 1; }
+    cells += (long long)g.dims[0] * g.dims[1] * g.dims[2] + 1;   // +1: the row-end lookup cells(row + x1 + 1) of the last row
+  }
+  ti.total_cells = cells;
+  if (cells >= (1ll << 32)) return ctx->fail(PVB_ERR_ARG, "grid too large (%lld cells)", cells);
+  CK(ti.grids.ensure((size_t)cs.n_clouds * sizeof(GridDesc)));
+  CK(cudaMemcpyAsync(ti.grids.p, ti.h_grids.data(), (size_t)cs.n_clouds * sizeof(GridDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ti.hist.ensure((size_t)(cells + 1) * 4));
+  CK(ti.cell_start.ensure((size_t)(cells + 1) * 4));
+  CK(ti.keys.ensure((size_t)n * 8)); CK(ti.keys_alt.ensure((size_t)n * 8));
+  CK(ti.vals.ensure((size_t)n * 4)); CK(ti.vals_alt.ensure((size_t)n * 4));
+  CK(cudaMemsetAsync(ti.hist.p, 0, (size_t)(cells + 1) * 4, ctx->stream));
+  k_cell_keys<<<cs.n_tiles, 256, 0, ctx->stream>>>(ti.world.as<F4>(), cs.tiles.as<CloudTile>(), ti.grids.as<GridDesc>(), ti.keys.as<unsigned long long>(),
+                                                   ti.vals.as<uint32_t>(), ti.hist.as<uint32_t>());
+  CKL();
+  int end_bit = 1; while ((1ll << end_bit) < cells + 1 && end_bit < 63) ++end_bit;
+  size_t tmp1 = 0, tmp2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp1, ti.keys.as<unsigned long long>(), ti.keys_alt.as<unsigned long long>(), ti.vals.as<uint32_t>(), ti.vals_alt.as<uint32_t>(),
+                                  (int)n, 0, end_bit, ctx->stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ti.hist.as<uint32_t>(), ti.cell_start.as<uint32_t>(), (int)(cells + 1), ctx->stream);
+  CK(ti.tmp.ensure(std::max(tmp1, tmp2)));
+  size_t tb = ti.tmp.cap;
+  CK(cub::DeviceRadixSort::SortPairs(ti.tmp.p, tb, ti.keys.as<unsigned long long>(), ti.keys_alt.as<unsigned long long>(), ti.vals.as<uint32_t>(), ti.vals_alt.as<uint32_t>(),
+                                     (int)n, 0, end_bit, ctx->stream));
+  tb = ti.tmp.cap;
+  CK(cub::DeviceScan::ExclusiveSum(ti.tmp.p, tb, ti.hist.as<uint32_t>(), ti.cell_start.as<uint32_t>(), (int)(cells + 1), ctx->stream));
+  k_gather_f4<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ti.world.as<F4>(), ti.vals_alt.as<uint32_t>(), n, ti.sorted.as<F4>());
+  CKL();
+  ti.built = true;
+  return PVB_OK;
+}
+
+template <bool REDUCE>
+int launch_associate(pvb_ctx* ctx, int k, int n_tiles, const AssocArgs& a) {
+  if (n_tiles == 0) return PVB_OK;
+  if (k == 10) k_associate<10, REDUCE><<<n_tiles, kTile, 0, ctx->stream>>>(a);
+  else if (k == 5) k_associate<5, REDUCE><<<n_tiles, kTile, 0, ctx->stream>>>(a);
+  else return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
+  CKL();
+  return PVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ================================================================ lifecycle
+int pvb_create(int device, pvb_ctx** out) {
+  if (!out) return PVB_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return PVB_ERR_CUDA;   // no CPU fallback by design
+  if (device < 0 || device >= n) return PVB_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return PVB_ERR_CUDA;
+  pvb_ctx* ctx = new pvb_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PVB_ERR_CUDA; }
+  *out = ctx;
+  return PVB_OK;
+}
+
+void pvb_destroy(pvb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* dbs[] = {&ctx->d_prep, &ctx->d_wpose, &ctx->b_tile, &ctx->b_eref, &ctx->b_enei, &ctx->b_type, &ctx->b_norm, &ctx->b_huber, &ctx->b_consts, &ctx->b_orig_d, &ctx->b_r, &ctx->b_J,
+                   &ctx->b_part, &ctx->b_esys, &ctx->b_tbegin, &ctx->f_pairs, &ctx->f_qtiles, &ctx->f_valid, &ctx->f_point, &ctx->f_plane, &ctx->f_nn_idx, &ctx->f_nn_d2,
+                   &ctx->d_q_sorted, &ctx->d_q_orig, &ctx->d_pairs, &ctx->d_qtiles, &ctx->d_part, &ctx->d_sys, &ctx->d_tbegin, &ctx->d_valid, &ctx->d_point, &ctx->d_plane,
+                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e};
+  for (DevBuf* b : dbs) b->release();
+  PinBuf* pbs[] = {&ctx->h_pose, &ctx->h_r, &ctx->h_J, &ctx->h_esys, &ctx->fh_valid, &ctx->fh_point, &ctx->fh_plane, &ctx->dh_sys, &ctx->mh_a};
+  for (PinBuf* b : pbs) b->release();
+  ctx->f_tgt.release(); ctx->f_qry.release(); ctx->f_index.release(); ctx->d_tgt.release(); ctx->d_src.release(); ctx->d_index.release();
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* pvb_last_error(const pvb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pvb_set_stream(pvb_ctx* ctx, void* s) {
+  if (!ctx) return PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (s == nullptr) {
+    if (!ctx->own_stream) { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    return PVB_OK;
+  }
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)s; ctx->own_stream = false;
+  return PVB_OK;
+}
+
+int pvb_synchronize(pvb_ctx* ctx) { if (!ctx) return PVB_ERR_ARG; CK(cudaStreamSynchronize(ctx->stream)); return PVB_OK; }
+long pvb_kernel_launches(const pvb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* pvb_stream(const pvb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ================================================================ A. correspondence-list mode
+int pvb_blocks_set(pvb_ctx* ctx, long n, const int* type, const int* ref, const int* nei, const int* normalize, const double* huber, const double* consts, int nb) {
+  if (!ctx) return PVB_ERR_ARG;
+  if (n < 0 || nb <= 0 || (n > 0 && (!type || !ref || !nei || !normalize || !huber || !consts))) return ctx->fail(PVB_ERR_ARG, "pvb_blocks_set: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  for (long i = 0; i < n; ++i) {
+    if (ref[i] < 0 || ref[i] >= nb || nei[i] < 0 || nei[i] >= nb) return ctx->fail(PVB_ERR_ARG, "block %ld: pose index out of range", i);
+    if (type[i] < 0 || type[i] > PVB_PLANE_IOU) return ctx->fail(PVB_ERR_ARG, "block %ld: unknown residual type %d", i, type[i]);
+  }
+  ctx->bn = n; ctx->nb = nb; ctx->b_has_rows = ctx->b_has_sys = false;
+  // group rows by pose-graph edge (stable: rows of an edge keep their registration order)
+  std::vector<uint32_t> order(n);
+  for (long i = 0; i < n; ++i) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    const long long ka = (long long)ref[a] * nb + nei[a], kb = (long long)ref[b] * nb + nei[b];
+    return ka < kb;
+  });
+  ctx->b_orig = order;
+  ctx->edge_ref.clear(); ctx->edge_nei.clear(); ctx->edge_tile_begin.clear();
+  std::vector<BlockTile> tiles;
+  std::vector<int> s_type(n), s_norm(n); std::vector<double> s_huber(n), s_consts((size_t)n * 12);
+  long i = 0;
+  while (i < n) {
+    long j = i;
+    const int er = ref[order[i]], en = nei[order[i]];
+    while (j < n && ref[order[j]] == er && nei[order[j]] == en) ++j;
+    const int e = (int)ctx->edge_ref.size();
+    ctx->edge_ref.push_back(er); ctx->edge_nei.push_back(en); ctx->edge_tile_begin.push_back((int)tiles.size());
+    for (long s = i; s < j; s += kTile) tiles.push_back(BlockTile{e, (int)s, (int)std::min<long>(kTile, j - s), 0});
+    i = j;
+  }
+  ctx->edge_tile_begin.push_back((int)tiles.size());
+  ctx->b_tiles = (int)tiles.size();
+  for (long r = 0; r < n; ++r) {
+    const uint32_t o = order[r];
+    s_type[r] = type[o]; s_norm[r] = normalize[o]; s_huber[r] = huber[o];
+    for (int k = 0; k < 12; ++k) s_consts[(size_t)k * n + r] = consts[(size_t)o * 12 + k];
+  }
+  const int ne = (int)ctx->edge_ref.size();
+  CK(ctx->b_tile.ensure(std::max<size_t>(16, tiles.size() * sizeof(BlockTile))));
+  CK(ctx->b_eref.ensure(std::max<size_t>(16, (size_t)ne * 4))); CK(ctx->b_enei.ensure(std::max<size_t>(16, (size_t)ne * 4)));
+  CK(ctx->b_tbegin.ensure((size_t)(ne + 1) * 4));
+  CK(ctx->b_type.ensure(std::max<size_t>(16, (size_t)n * 4))); CK(ctx->b_norm.ensure(std::max<size_t>(16, (size_t)n * 4)));
+  CK(ctx->b_huber.ensure(std::max<size_t>(16, (size_t)n * 8))); CK(ctx->b_consts.ensure(std::max<size_t>(16, (size_t)n * 96)));
+  CK(ctx->b_orig_d.ensure(std::max<size_t>(16, (size_t)n * 4)));
+  CK(ctx->b_r.ensure(std::max<size_t>(16, (size_t)n * 8))); CK(ctx->b_J.ensure(std::max<size_t>(16, (size_t)n * 96)));
+  CK(ctx->b_part.ensure(std::max<size_t>(16, tiles.size() * 92 * 8))); CK(ctx->b_esys.ensure(std::max<size_t>(16, (size_t)ne * 92 * 8)));
+  CK(ctx->h_esys.ensure(std::max<size_t>(16, (size_t)ne * 92 * 8)));
+  if (n > 0) {
+    CK(cudaMemcpyAsync(ctx->b_tile.p, tiles.data(), tiles.size() * sizeof(BlockTile), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_eref.p, ctx->edge_ref.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_enei.p, ctx->edge_nei.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_type.p, s_type.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_norm.p, s_norm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_huber.p, s_huber.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_consts.p, s_consts.data(), (size_t)n * 96, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_orig_d.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(ctx->b_tbegin.p, ctx->edge_tile_begin.data(), (size_t)(ne + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int want_system) {
+  if (!ctx || !poses) return PVB_ERR_ARG;
+  if (ctx->nb <= 0) return ctx->fail(PVB_ERR_STATE, "pvb_blocks_set has not been called");
+  CK(cudaSetDevice(ctx->device));
+  int rc = upload_poses(ctx, poses, ctx->nb, false);
+  if (rc) return rc;
+  const long long n = ctx->bn;
+  const int ne = (int)ctx->edge_ref.size();
+  ctx->b_has_rows = ctx->b_has_sys = false;
+  if (n > 0) {
+    EvalArgs a;
+    a.tiles = ctx->b_tile.as<BlockTile>(); a.edge_ref = ctx->b_eref.as<int>(); a.edge_nei = ctx->b_enei.as<int>();
+    a.type = ctx->b_type.as<int>(); a.normalize = ctx->b_norm.as<int>(); a.huber = ctx->b_huber.as<double>(); a.consts = ctx->b_consts.as<double>();
+    a.orig = ctx->b_orig_d.as<uint32_t>(); a.n = n; a.prep = ctx->d_prep.as<PosePrep>();
+    a.out_r = want_rows ? ctx->b_r.as<double>() : nullptr; a.out_J = want_rows ? ctx->b_J.as<double>() : nullptr;
+    a.partials = want_system ? ctx->b_part.as<double>() : nullptr;
+    k_eval_blocks<<<ctx->b_tiles, kTile, 0, ctx->stream>>>(a);
+    CKL();
+    if (want_system) {
+      k_sum_partials<92><<<ne, 96, 0, ctx->stream>>>(ctx->b_part.as<double>(), ctx->b_tbegin.as<int>(), ctx->b_esys.as<double>());
+      CKL();
+      CK(cudaMemcpyAsync(ctx->h_esys.p, ctx->b_esys.p, (size_t)ne * 92 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (want_rows) {
+      CK(ctx->h_r.ensure((size_t)n * 8)); CK(ctx->h_J.ensure((size_t)n * 96));
+      CK(cudaMemcpyAsync(ctx->h_r.p, ctx->b_r.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->h_J.p, ctx->b_J.p, (size_t)n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->b_has_rows = want_rows != 0; ctx->b_has_sys = want_system != 0;
+  return PVB_OK;
+}
+
+const double* pvb_blocks_residuals(const pvb_ctx* ctx) { return (ctx && ctx->b_has_rows) ? ctx->h_r.as<double>() : nullptr; }
+const double* pvb_blocks_jacobians(const pvb_ctx* ctx) { return (ctx && ctx->b_has_rows) ? ctx->h_J.as<double>() : nullptr; }
+
+int pvb_blocks_cost(const pvb_ctx* ctx, double* cost, long* nres) {
+  if (!ctx || !ctx->b_has_sys) return PVB_ERR_STATE;
+  double c = 0, n = 0;
+  const double* s = ctx->h_esys.as<double>();
+  for (size_t e = 0; e < ctx->edge_ref.size(); ++e) { c += s[e * 92 + 90]; n += s[e * 92 + 91]; }
+  if (cost) *cost = c;
+  if (nres) *nres = (long)n;
+  return PVB_OK;
+}
+
+int pvb_blocks_num_edges(const pvb_ctx* ctx) { return ctx ? (int)ctx->edge_ref.size() : PVB_ERR_ARG; }
+int pvb_blocks_edges(const pvb_ctx* ctx, int* ref, int* nei) {
+  if (!ctx) return PVB_ERR_ARG;
+  for (size_t e = 0; e < ctx->edge_ref.size(); ++e) { ref[e] = ctx->edge_ref[e]; nei[e] = ctx->edge_nei[e]; }
+  return PVB_OK;
+}
+int pvb_blocks_edge_systems(const pvb_ctx* ctx, double* out) {
+  if (!ctx || !ctx->b_has_sys) return PVB_ERR_STATE;
+  memcpy(out, ctx->h_esys.p, ctx->edge_ref.size() * 92 * 8);
+  return PVB_OK;
+}
+
+static double assemble_dense(const pvb_ctx* ctx, double* H, double* g) {
+  const int D = 6 * ctx->nb;
+  if (H) std::fill(H, H + (size_t)D * D, 0.0);
+  if (g) std::fill(g, g + D, 0.0);
+  double cost = 0;
+  const double* s = ctx->h_esys.as<double>();
+  for (size_t e = 0; e < ctx->edge_ref.size(); ++e) {
+    const double* S = s + e * 92;
+    cost += S[90];
+    if (!H && !g) continue;
+    const int o[2] = {6 * ctx->edge_ref[e], 6 * ctx->edge_nei[e]};
+    int q = 0;
+    for (int a = 0; a < 12; ++a)
+      for (int b = a; b < 12; ++b, ++q) {
+        const int ia = o[a / 6] + a % 6, ib = o[b / 6] + b % 6;
+        if (H) {
+          if (ia == ib) H[(size_t)ia * D + ib] += S[q] * (a == b ? 1.0 : 2.0);   // ref == nei edge: both (a,b) and (b,a) land on the diagonal
+          else { H[(size_t)ia * D + ib] += S[q]; H[(size_t)ib * D + ia] += S[q]; }
+        }
+      }
+    if (g) for (int a = 0; a < 12; ++a) g[o[a / 6] + a % 6] += S[78 + a];
+  }
+  return cost;
+}
+
+int pvb_blocks_dense_system(const pvb_ctx* ctx, double* H, double* g, double* cost) {
+  if (!ctx || !ctx->b_has_sys) return PVB_ERR_STATE;
+  const double c = assemble_dense(ctx, H, g);
+  if (cost) *cost = c;
+  return PVB_OK;
+}
+
+int pvb_blocks_solve_lm(pvb_ctx* ctx, double* poses, const unsigned char* is_const, int max_iterations, double* summary6) {
+  if (!ctx || !poses) return PVB_ERR_ARG;
+  if (ctx->nb <= 0) return ctx->fail(PVB_ERR_STATE, "pvb_blocks_set has not been called");
+  int rc_inner = PVB_OK;
+  EvalFn eval = [&](const double* x, double* H, double* g) -> double {
+    const int rc = pvb_blocks_evaluate(ctx, x, 0, 1);
+    if (rc) { rc_inner = rc; return 0.0; }
+    return assemble_dense(ctx, H, g);
+  };
+  LMOptions opt; opt.max_iterations = max_iterations;
+  const LMSummary S = solve_lm(eval, poses, ctx->nb, is_const, opt);
+  if (rc_inner) return rc_inner;
+  if (summary6) { summary6[0] = S.initial_cost; summary6[1] = S.final_cost; summary6[2] = S.iterations; summary6[3] = S.successful; summary6[4] = S.unsuccessful; summary6[5] = S.termination; }
+  return PVB_OK;
+}
+
+// ================================================================ B. frames
+int pvb_frames_set(pvb_ctx* ctx, int n_frames, const pvb_frame* frames) {
+  if (!ctx || n_frames <= 0 || !frames) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_frames_set: bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<const float*> tp(n_frames), qp(n_frames); std::vector<int> tc(n_frames), qc(n_frames), blocks(n_frames);
+  for (int f = 0; f < n_frames; ++f) { tp[f] = frames[f].surf_target; tc[f] = frames[f].n_target; qp[f] = frames[f].surf_query; qc[f] = frames[f].n_query; blocks[f] = f; }
+  int rc = set_cloudset(ctx, ctx->f_tgt, tp, tc, blocks, 256); if (rc) return rc;
+  rc = set_cloudset(ctx, ctx->f_qry, qp, qc, blocks, 256); if (rc) return rc;
+  ctx->n_frames = n_frames; ctx->f_index.built = false;
+  return PVB_OK;
+}
+
+static int frames_run(pvb_ctx* ctx, const double* poses, int n_edges, const int* ref, const int* nei, const pvb_assoc_params* prm, bool want_nn, long long* total_slots,
+                      std::vector<int>* slot_edge_begin) {
+  if (ctx->n_frames <= 0) return ctx->fail(PVB_ERR_STATE, "pvb_frames_set has not been called");
+  if (!prm || (prm->k != 5 && prm->k != 10)) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10");
+  for (int e = 0; e < n_edges; ++e)
+    if (ref[e] < 0 || ref[e] >= ctx->n_frames || nei[e] < 0 || nei[e] >= ctx->n_frames) return ctx->fail(PVB_ERR_ARG, "edge %d out of range", e);
+  int rc = upload_poses(ctx, poses, ctx->n_frames, false); if (rc) return rc;
+  rc = build_target_index(ctx, ctx->f_tgt, ctx->f_index, prm->cell_size); if (rc) return rc;
+  std::vector<Pair> pairs(n_edges); std::vector<QueryTile> tiles; slot_edge_begin->assign(n_edges + 1, 0);
+  long long slots = 0;
+  for (int e = 0; e < n_edges; ++e) {
+    pairs[e] = Pair{ref[e], nei[e], ref[e], nei[e]};
+    (*slot_edge_begin)[e] = (int)slots;
+    const int q0 = ctx->f_qry.off[nei[e]], qn = ctx->f_qry.off[nei[e] + 1] - q0;
+    const bool has_target = ctx->f_tgt.off[ref[e] + 1] > ctx->f_tgt.off[ref[e]];
+    if (has_target) for (int s = 0; s < qn; s += kTile) tiles.push_back(QueryTile{e, q0 + s, std::min(kTile, qn - s), (int)(slots + s)});
+    slots += qn;
+  }
+  (*slot_edge_begin)[n_edges] = (int)slots;
+  *total_slots = slots;
+  CK(ctx->f_pairs.ensure(std::max<size_t>(16, pairs.size() * sizeof(Pair)))); CK(ctx->f_qtiles.ensure(std::max<size_t>(16, tiles.size() * sizeof(QueryTile))));
+  CK(ctx->f_valid.ensure(std::max<size_t>(16, (size_t)slots))); CK(ctx->f_point.ensure(std::max<size_t>(16, (size_t)slots * 24))); CK(ctx->f_plane.ensure(std::max<size_t>(16, (size_t)slots * 32)));
+  if (want_nn) { CK(ctx->f_nn_idx.ensure(std::max<size_t>(16, (size_t)slots * prm->k * 4))); CK(ctx->f_nn_d2.ensure(std::max<size_t>(16, (size_t)slots * prm->k * 4))); }
+  if (!pairs.empty()) CK(cudaMemcpyAsync(ctx->f_pairs.p, pairs.data(), pairs.size() * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->f_qtiles.p, tiles.data(), tiles.size() * sizeof(QueryTile), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->f_valid.p, 0, std::max<size_t>(16, (size_t)slots), ctx->stream));
+  AssocArgs a{};
+  a.q_local = ctx->f_qry.local.as<F4>(); a.q_orig = nullptr; a.tiles = ctx->f_qtiles.as<QueryTile>(); a.pairs = ctx->f_pairs.as<Pair>();
+  a.grids = ctx->f_index.grids.as<GridDesc>(); a.cell_start = ctx->f_index.cell_start.as<uint32_t>(); a.sorted = ctx->f_index.sorted.as<F4>();
+  a.wpose = ctx->d_wpose.as<WorldPose>(); a.prep = ctx->d_prep.as<PosePrep>();
+  a.prm.sq_thr = prm->dist_threshold * prm->dist_threshold; a.prm.rmax = 1; a.prm.plane_tol = prm->plane_tolerance; a.prm.collinear_tol = 3.0;
+  a.thr = (double)prm->dist_threshold;
+  a.residual_type = PVB_P2PLANE_METER; a.normalize = 0; a.huber = 0; a.weight = 1;
+  a.out_valid = ctx->f_valid.as<unsigned char>(); a.out_point = ctx->f_point.as<double>(); a.out_plane = ctx->f_plane.as<double>();
+  a.out_nn_idx = want_nn ? ctx->f_nn_idx.as<int>() : nullptr; a.out_nn_d2 = want_nn ? ctx->f_nn_d2.as<float>() : nullptr;
+  rc = launch_associate<false>(ctx, prm->k, (int)tiles.size(), a); if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));   // pairs/tiles vectors go out of scope
+  return PVB_OK;
+}
+
+int pvb_frames_associate_point2plane(pvb_ctx* ctx, const double* poses, int n_edges, const int* ref, const int* nei, const pvb_assoc_params* prm, long* n_assoc) {
+  if (!ctx || !poses || n_edges < 0 || (n_edges > 0 && (!ref || !nei))) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  long long slots = 0; std::vector<int> sb;
+  int rc = frames_run(ctx, poses, n_edges, ref, nei, prm, false, &slots, &sb); if (rc) return rc;
+  CK(ctx->fh_valid.ensure(std::max<size_t>(16, (size_t)slots))); CK(ctx->fh_point.ensure(std::max<size_t>(16, (size_t)slots * 24))); CK(ctx->fh_plane.ensure(std::max<size_t>(16, (size_t)slots * 32)));
+  if (slots > 0) {
+    CK(cudaMemcpyAsync(ctx->fh_valid.p, ctx->f_valid.p, (size_t)slots, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->fh_point.p, ctx->f_point.p, (size_t)slots * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->fh_plane.p, ctx->f_plane.p, (size_t)slots * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->a_edge.clear(); ctx->a_query.clear(); ctx->a_point.clear(); ctx->a_plane.clear();
+  const unsigned char* v = ctx->fh_valid.as<unsigned char>(); const double* pt = ctx->fh_point.as<double>(); const double* pl = ctx->fh_plane.as<double>();
+  for (int e = 0; e < n_edges; ++e)
+    for (int s = sb[e]; s < sb[e + 1]; ++s)
+      if (v[s]) {
+        ctx->a_edge.push_back(e); ctx->a_query.push_back(s - sb[e]);
+        ctx->a_point.insert(ctx->a_point.end(), pt + (size_t)s * 3, pt + (size_t)s * 3 + 3);
+        ctx->a_plane.insert(ctx->a_plane.end(), pl + (size_t)s * 4, pl + (size_t)s * 4 + 4);
+      }
+  if (n_assoc) *n_assoc = (long)ctx->a_edge.size();
+  return PVB_OK;
+}
+
+int pvb_frames_get_point2plane(const pvb_ctx* ctx, long cap, int* edge, int* query, double* point3, double* plane4) {
+  if (!ctx) return PVB_ERR_ARG;
+  const long n = std::min<long>(cap, (long)ctx->a_edge.size());
+  for (long i = 0; i < n; ++i) { if (edge) edge[i] = ctx->a_edge[i]; if (query) query[i] = ctx->a_query[i]; }
+  if (point3) memcpy(point3, ctx->a_point.data(), (size_t)n * 24);
+  if (plane4) memcpy(plane4, ctx->a_plane.data(), (size_t)n * 32);
+  return PVB_OK;
+}
+
+int pvb_frames_knn(pvb_ctx* ctx, const double* poses, int ref, int nei, const pvb_assoc_params* prm, int* idx, float* d2) {
+  if (!ctx || !poses || !idx || !d2) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  long long slots = 0; std::vector<int> sb;
+  int rc = frames_run(ctx, poses, 1, &ref, &nei, prm, true, &slots, &sb); if (rc) return rc;
+  if (slots > 0) {
+    CK(cudaMemcpyAsync(idx, ctx->f_nn_idx.p, (size_t)slots * prm->k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(d2, ctx->f_nn_d2.p, (size_t)slots * prm->k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+// ================================================================ C. dense ICP sweep
+int pvb_dense_set_target(pvb_ctx* ctx, const float* xyzc, long n, double cell_size) {
+  if (!ctx || !xyzc || n <= 0) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_dense_set_target: bad arguments") : PVB_ERR_ARG;
+  if (n >= (1l << 27)) return ctx->fail(PVB_ERR_ARG, "target cloud too large (%ld >= 2^27 points)", n);
+  CK(cudaSetDevice(ctx->device));
+  int rc = set_cloudset(ctx, ctx->d_tgt, {xyzc}, {(int)n}, {0}, 256); if (rc) return rc;
+  const double zero6[6] = {0, 0, 0, 0, 0, 0};
+  rc = upload_poses(ctx, zero6, 1, false); if (rc) return rc;      // target frame == world
+  ctx->d_cell = cell_size;
+  rc = build_target_index(ctx, ctx->d_tgt, ctx->d_index, cell_size); if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  // the unsorted world copy and sort scratch are not needed after the build
+  ctx->d_index.world.release(); ctx->d_index.keys.release(); ctx->d_index.keys_alt.release(); ctx->d_index.vals.release(); ctx->d_index.vals_alt.release(); ctx->d_index.hist.release();
+  return PVB_OK;
+}
+
+int pvb_dense_set_sources(pvb_ctx* ctx, const float* xyzc, const int* offsets, int n_frames) {
+  if (!ctx || !xyzc || !offsets || n_frames <= 0) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_dense_set_sources: bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<const float*> ptrs(n_frames); std::vector<int> cnt(n_frames), blocks(n_frames);
+  for (int f = 0; f < n_frames; ++f) { ptrs[f] = xyzc + (size_t)offsets[f] * 4; cnt[f] = offsets[f + 1] - offsets[f]; blocks[f] = f + 1; if (cnt[f] < 0) return ctx->fail(PVB_ERR_ARG, "offsets not monotone"); }
+  CloudSet& cs = ctx->d_src;
+  int rc = set_cloudset(ctx, cs, ptrs, cnt, blocks, 256); if (rc) return rc;
+  ctx->d_frames = n_frames;
+  const long long n = cs.n_points;
+  // Morton re-ordering per frame (keys = frame << 36 | morton36)
+  DevBuf &k0 = ctx->m_a, &k1 = ctx->m_b, &v0 = ctx->m_c, &v1 = ctx->m_d, &tmp = ctx->m_e;
+  CK(k0.ensure((size_t)n * 8)); CK(k1.ensure((size_t)n * 8)); CK(v0.ensure((size_t)n * 4)); CK(v1.ensure((size_t)n * 4));
+  CK(ctx->d_q_sorted.ensure((size_t)n * sizeof(F4))); CK(ctx->d_q_orig.ensure((size_t)n * 4));
+  if (n > 0) {
+    k_morton_keys<<<cs.n_tiles, 256, 0, ctx->stream>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>(), k0.as<unsigned long long>(), v0.as<uint32_t>());
+    CKL();
+    int frame_bits = 1; while ((1 << frame_bits) < n_frames + 1) ++frame_bits;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.as<unsigned long long>(), k1.as<unsigned long long>(), v0.as<uint32_t>(), v1.as<uint32_t>(), (int)n, 0, 36 + frame_bits, ctx->stream);
+    CK(tmp.ensure(tb)); tb = tmp.cap;
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k0.as<unsigned long long>(), k1.as<unsigned long long>(), v0.as<uint32_t>(), v1.as<uint32_t>(), (int)n, 0, 36 + frame_bits, ctx->stream));
+    k_gather_f4<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(cs.local.as<F4>(), v1.as<uint32_t>(), n, ctx->d_q_sorted.as<F4>());
+    CKL();
+    CK(cudaMemcpyAsync(ctx->d_q_orig.p, v1.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  // tiles: frames keep their contiguous ranges after the sort (frame id is the most significant key part)
+  std::vector<Pair> pairs(n_frames); std::vector<QueryTile> tiles; std::vector<int> tbegin(n_frames + 1, 0);
+  for (int f = 0; f < n_frames; ++f) {
+    pairs[f] = Pair{0, f, 0, f + 1};
+    tbegin[f] = (int)tiles.size();
+    for (int s = 0; s < cnt[f]; s += kTile) tiles.push_back(QueryTile{f, cs.off[f] + s, std::min(kTile, cnt[f] - s), 0});
+  }
+  tbegin[n_frames] = (int)tiles.size();
+  ctx->d_ntiles = (int)tiles.size();
+  CK(ctx->d_pairs.ensure(pairs.size() * sizeof(Pair))); CK(ctx->d_qtiles.ensure(std::max<size_t>(16, tiles.size() * sizeof(QueryTile)))); CK(ctx->d_tbegin.ensure(tbegin.size() * 4));
+  CK(ctx->d_part.ensure(std::max<size_t>(16, tiles.size() * 29 * 8))); CK(ctx->d_sys.ensure((size_t)n_frames * 29 * 8)); CK(ctx->dh_sys.ensure((size_t)n_frames * 29 * 8));
+  CK(cudaMemcpyAsync(ctx->d_pairs.p, pairs.data(), pairs.size() * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->d_qtiles.p, tiles.data(), tiles.size() * sizeof(QueryTile), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_tbegin.p, tbegin.data(), tbegin.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+static int dense_args(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, AssocArgs& a) {
+  if (!ctx->d_index.built) return ctx->fail(PVB_ERR_STATE, "pvb_dense_set_target has not been called");
+  if (ctx->d_frames <= 0) return ctx->fail(PVB_ERR_STATE, "pvb_dense_set_sources has not been called");
+  if (!prm || (prm->k != 5 && prm->k != 10)) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10");
+  if (prm->residual_type != PVB_P2PLANE_METER && prm->residual_type != PVB_P2PLANE_ANGLE) return ctx->fail(PVB_ERR_ARG, "residual_type must be a point-to-plane type");
+  int rc = upload_poses(ctx, poses_lw, ctx->d_frames, true); if (rc) return rc;
+  a = AssocArgs{};
+  a.q_local = ctx->d_q_sorted.as<F4>(); a.q_orig = ctx->d_q_orig.as<uint32_t>(); a.tiles = ctx->d_qtiles.as<QueryTile>(); a.pairs = ctx->d_pairs.as<Pair>();
+  a.grids = ctx->d_index.grids.as<GridDesc>(); a.cell_start = ctx->d_index.cell_start.as<uint32_t>(); a.sorted = ctx->d_index.sorted.as<F4>();
+  a.wpose = ctx->d_wpose.as<WorldPose>(); a.prep = ctx->d_prep.as<PosePrep>();
+  a.prm.sq_thr = prm->dist_threshold * prm->dist_threshold; a.prm.rmax = 1; a.prm.plane_tol = prm->plane_tolerance; a.prm.collinear_tol = 3.0;
+  a.thr = (double)prm->dist_threshold;
+  a.residual_type = prm->residual_type; a.normalize = prm->normalize; a.huber = prm->huber; a.weight = prm->weight;
+  return PVB_OK;
+}
+
+int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, double** dev_sys) {
+  if (!ctx || !poses_lw) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  AssocArgs a; int rc = dense_args(ctx, poses_lw, prm, a); if (rc) return rc;
+  a.partials = ctx->d_part.as<double>();
+  rc = launch_associate<true>(ctx, prm->k, ctx->d_ntiles, a); if (rc) return rc;
+  k_sum_partials<29><<<ctx->d_frames, 32, 0, ctx->stream>>>(ctx->d_part.as<double>(), ctx->d_tbegin.as<int>(), ctx->d_sys.as<double>());
+  CKL();
+  if (dev_sys) *dev_sys = ctx->d_sys.as<double>();
+  return PVB_OK;
+}
+
+int pvb_dense_evaluate(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, double* out_sys) {
+  if (!ctx || !out_sys) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  int rc = pvb_dense_evaluate_device(ctx, poses_lw, prm, nullptr); if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->dh_sys.p, ctx->d_sys.p, (size_t)ctx->d_frames * 29 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_sys, ctx->dh_sys.p, (size_t)ctx->d_frames * 29 * 8);
+  return PVB_OK;
+}
+
+int pvb_dense_get_rows(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, unsigned char* valid, double* point3, double* plane4, double* residual, double* jac6) {
+  if (!ctx || !poses_lw) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  AssocArgs a; int rc = dense_args(ctx, poses_lw, prm, a); if (rc) return rc;
+  const size_t n = (size_t)ctx->d_src.n_points;
+  CK(ctx->d_valid.ensure(n)); CK(ctx->d_point.ensure(n * 24)); CK(ctx->d_plane.ensure(n * 32)); CK(ctx->d_res.ensure(n * 8)); CK(ctx->d_jac.ensure(n * 48));
+  CK(cudaMemsetAsync(ctx->d_valid.p, 0, n, ctx->stream)); CK(cudaMemsetAsync(ctx->d_point.p, 0, n * 24, ctx->stream)); CK(cudaMemsetAsync(ctx->d_plane.p, 0, n * 32, ctx->stream));
+  a.out_valid = ctx->d_valid.as<unsigned char>(); a.out_point = ctx->d_point.as<double>(); a.out_plane = ctx->d_plane.as<double>();
+  a.out_res = ctx->d_res.as<double>(); a.out_jac6 = ctx->d_jac.as<double>();
+  rc = launch_associate<false>(ctx, prm->k, ctx->d_ntiles, a); if (rc) return rc;
+  if (valid) CK(cudaMemcpyAsync(valid, ctx->d_valid.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (point3) CK(cudaMemcpyAsync(point3, ctx->d_point.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  if (plane4) CK(cudaMemcpyAsync(plane4, ctx->d_plane.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (residual) CK(cudaMemcpyAsync(residual, ctx->d_res.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (jac6) CK(cudaMemcpyAsync(jac6, ctx->d_jac.p, n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+int pvb_dense_gauss_newton_step(const double* sys29, int n_frames, double lambda, double* poses_lw) {
+  if (!sys29 || !poses_lw || n_frames <= 0) return PVB_ERR_ARG;
+  for (int f = 0; f < n_frames; ++f) {
+    const double* S = sys29 + (size_t)f * 29;
+    if (S[28] < 6) continue;
+    std::vector<double> A(36), b(6);
+    int q = 0;
+    for (int a = 0; a < 6; ++a) for (int c = a; c < 6; ++c, ++q) { A[a * 6 + c] = S[q]; A[c * 6 + a] = S[q]; }
+    for (int a = 0; a < 6; ++a) { A[a * 6 + a] += lambda * std::max(A[a * 6 + a], 1e-6); b[a] = -S[21 + a]; }
+    if (!cholesky_solve(A, 6, b)) continue;
+    for (int a = 0; a < 6; ++a) poses_lw[6 * f + a] += b[a];
+  }
+  return PVB_OK;
+}
+
+// ================================================================ D. projection
+static void T16_to_pose(const double* T, WorldPose& w) { for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) w.R[r * 3 + c] = T[r * 4 + c]; w.t[r] = T[r * 4 + 3]; } }
+
+int pvb_project_equirect(pvb_ctx* ctx, const float* xyzi, long n, const double* T, int rows, int cols, float* uvd) {
+  if (!ctx || !xyzi || !T || !uvd || n < 0) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  if (n == 0) return PVB_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->m_a.ensure((size_t)n * 16)); CK(ctx->m_b.ensure((size_t)n * 12));
+  CK(cudaMemcpyAsync(ctx->m_a.p, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  WorldPose w; T16_to_pose(T, w);
+  k_project<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->m_a.as<F4>(), n, w, rows, cols, ctx->m_b.as<float>(), nullptr, 0);
+  CKL();
+  CK(cudaMemcpyAsync(uvd, ctx->m_b.p, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+int pvb_project_depth_image(pvb_ctx* ctx, const float* xyzi, long n, const double* T, int rows, int cols, int size, uint16_t* image) {
+  if (!ctx || !xyzi || !T || !image || n < 0 || rows <= 0 || cols <= 0) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t px = (size_t)rows * cols;
+  CK(ctx->m_a.ensure(std::max<size_t>(16, (size_t)n * 16))); CK(ctx->m_c.ensure(px * 8)); CK(ctx->m_d.ensure(px * 2));
+  CK(cudaMemsetAsync(ctx->m_c.p, 0, px * 8, ctx->stream));
+  if (n > 0) {
+    CK(cudaMemcpyAsync(ctx->m_a.p, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    WorldPose w; T16_to_pose(T, w);
+    k_project<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->m_a.as<F4>(), n, w, rows, cols, nullptr, ctx->m_c.as<unsigned long long>(), size);
+    CKL();
+  }
+  k_splat_finalize<<<(unsigned)((px + 255) / 256), 256, 0, ctx->stream>>>(ctx->m_c.as<unsigned long long>(), (long long)px, ctx->m_d.as<uint16_t>());
+  CKL();
+  CK(cudaMemcpyAsync(image, ctx->m_d.p, px * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+// ================================================================ E. line votes
+int pvb_line_votes(pvb_ctx* ctx, const double* ref_lines, int S_ref, const float* pts, int n_pts, const int* p2s_off, const int* p2s_ids, int S_nei, double thr, int* M) {
+  if (!ctx || !M || S_ref < 0 || S_nei < 0 || n_pts < 0) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  const size_t msz = (size_t)S_ref * S_nei;
+  if (msz == 0) return PVB_OK;
+  if (n_pts == 0) { memset(M, 0, msz * 4); return PVB_OK; }
+  if (!ref_lines || !pts || !p2s_off || !p2s_ids) return ctx->fail(PVB_ERR_ARG, "null input");
+  CK(cudaSetDevice(ctx->device));
+  const int n_ids = p2s_off[n_pts];
+  CK(ctx->m_a.ensure((size_t)S_ref * 48)); CK(ctx->m_b.ensure((size_t)n_pts * 16)); CK(ctx->m_c.ensure((size_t)(n_pts + 1) * 4)); CK(ctx->m_d.ensure(std::max<size_t>(16, (size_t)n_ids * 4))); CK(ctx->m_e.ensure(msz * 4));
+  CK(cudaMemcpyAsync(ctx->m_a.p, ref_lines, (size_t)S_ref * 48, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_b.p, pts, (size_t)n_pts * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_c.p, p2s_off, (size_t)(n_pts + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_ids) CK(cudaMemcpyAsync(ctx->m_d.p, p2s_ids, (size_t)n_ids * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->m_e.p, 0, msz * 4, ctx->stream));
+  k_line_votes<<<(n_pts + 127) / 128, 128, (size_t)S_ref * 48, ctx->stream>>>(ctx->m_a.as<double>(), S_ref, ctx->m_b.as<F4>(), n_pts, ctx->m_c.as<int>(), ctx->m_d.as<int>(), thr, ctx->m_e.as<int>());
+  CKL();
+  CK(cudaMemcpyAsync(M, ctx->m_e.p, msz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+// ================================================================ F. camera-LiDAR angle votes
+int pvb_angle_votes(pvb_ctx* ctx, int rows, int cols, const float* lines4, int L, const float* cloud_local, int P, const int* p2s_off, const int* p2s_ids, int S, const double* T_cl, int* counts) {
+  if (!ctx || !counts || L < 0 || P < 0 || S < 0) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  const size_t csz = (size_t)L * S;
+  if (csz == 0) return PVB_OK;
+  if (P == 0) { memset(counts, 0, csz * 4); return PVB_OK; }
+  if (!lines4 || !cloud_local || !p2s_off || !p2s_ids || !T_cl) return ctx->fail(PVB_ERR_ARG, "null input");
+  CK(cudaSetDevice(ctx->device));
+  // image-line planes on the host (CameraLidarLineAssociate.cpp:381-387): ImageToCam uses exact sin/cos
+  std::vector<ImageLinePlane> lp(L);
+  for (int l = 0; l < L; ++l) {
+    double p1[3], p2[3];
+    image_to_cam_f64(lines4[l * 4], lines4[l * 4 + 1], rows, cols, p1);
+    image_to_cam_f64(lines4[l * 4 + 2], lines4[l * 4 + 3], rows, cols, p2);
+    // FormPlane(p1, p2, 0): (p2-p1) x (0-p1)
+    const double a = (p2[1] - p1[1]) * (0 - p1[2]) - (p2[2] - p1[2]) * (0 - p1[1]);
+    const double b = (p2[2] - p1[2]) * (0 - p1[0]) - (p2[0] - p1[0]) * (0 - p1[2]);
+    const double c = (p2[0] - p1[0]) * (0 - p1[1]) - (p2[1] - p1[1]) * (0 - p1[0]);
+    const double d = -(a * p1[0] + b * p1[1] + c * p1[2]);
+    const double nn = std::sqrt(a * a + b * b + c * c + d * d);
+    lp[l].n[0] = a / nn; lp[l].n[1] = b / nn; lp[l].n[2] = c / nn; lp[l].n[3] = d / nn;
+    for (int k = 0; k < 3; ++k) lp[l].p4[k] = (p1[k] + p2[k]) / 2.0;
+    double cs = p1[0] * lp[l].p4[0] + p1[1] * lp[l].p4[1] + p1[2] * lp[l].p4[2];
+    const double n1 = std::sqrt(p1[0] * p1[0] + p1[1] * p1[1] + p1[2] * p1[2]);
+    const double n2 = std::sqrt(lp[l].p4[0] * lp[l].p4[0] + lp[l].p4[1] * lp[l].p4[1] + lp[l].p4[2] * lp[l].p4[2]);
+    cs /= (n1 * n2);
+    lp[l].scope = cs >= 1.0 ? 0.0 : (cs <= -1.0 ? M_PI : std::acos(cs));
+  }
+  const int n_ids = p2s_off[P];
+  CK(ctx->m_a.ensure(lp.size() * sizeof(ImageLinePlane))); CK(ctx->m_b.ensure((size_t)P * 16)); CK(ctx->m_c.ensure((size_t)(P + 1) * 4)); CK(ctx->m_d.ensure(std::max<size_t>(16, (size_t)n_ids * 4))); CK(ctx->m_e.ensure(csz * 4));
+  CK(cudaMemcpyAsync(ctx->m_a.p, lp.data(), lp.size() * sizeof(ImageLinePlane), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_b.p, cloud_local, (size_t)P * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_c.p, p2s_off, (size_t)(P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_ids) CK(cudaMemcpyAsync(ctx->m_d.p, p2s_ids, (size_t)n_ids * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->m_e.p, 0, csz * 4, ctx->stream));
+  WorldPose w; T16_to_pose(T_cl, w);
+  dim3 grid((P + 127) / 128, L);
+  k_angle_votes<<<grid, 128, 0, ctx->stream>>>(ctx->m_a.as<ImageLinePlane>(), L, ctx->m_b.as<F4>(), P, w, ctx->m_c.as<int>(), ctx->m_d.as<int>(), S, ctx->m_e.as<int>());
+  CKL();
+  CK(cudaMemcpyAsync(counts, ctx->m_e.p, csz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,452 @@
+// panovlm_b200 — device math for the correspondence-and-residual hot path (sm_100a).
+//
+// Everything here is `__host__ __device__` so that tests/host_harness.cpp can exercise the exact same
+// arithmetic on the CPU (test infrastructure only; the shipped library has no CPU path).
+//
+// What the reference does (base/CostFunction.h:567-1022, one ceres::AutoDiffCostFunction<F,1,3,3,3,3> at a
+// time with Jet<double,12>) is re-derived here analytically:
+//   P = R_r R_n^T (p - t_n) + t_r                                  (CostFunction.h:584-604 via angle-axis detour)
+//   dP/da_r = -[R_r u]x J_l(a_r)   dP/dt_r = I   dP/da_n = R_r R_n^T [q]x J_l(a_n)   dP/dt_n = -R_r R_n^T
+// with q = p - t_n, u = R_n^T q and J_l the SO(3) left Jacobian (Ceres differentiates w.r.t. the raw
+// angle-axis vector, no manifold).  The scalar tail r(P) is evaluated with a 3-wide (6-wide for the two
+// point Plane2Plane_Global) forward dual so every autodiff branch (zero rows below 1e-3, abs' = +-1,
+// clamped acos) is reproduced exactly.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define PVB_HD __host__ __device__ __forceinline__
+#else
+#define PVB_HD inline
+#endif
+
+namespace pvb {
+
+enum BlockType : int { P2PLANE_METER = 0, P2PLANE_ANGLE = 1, P2LINE_METER = 2, P2LINE_ANGLE = 3, PLANE2PLANE_GLOBAL = 4, PLANE_IOU = 5 };
+
+// ---- rounding-exact float/double helpers (no FMA contraction: the reference's PCL/FLANN/OpenCV float paths
+//      are plain mul+add; the host build uses -ffp-contract=off) ------------------------------------------
+PVB_HD float fmul(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+PVB_HD float fadd(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+PVB_HD float fsub(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+PVB_HD double dmul(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+PVB_HD double dadd(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+PVB_HD double dsub(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+
+// ---- per pose-block quantities prepared on the host once per evaluation -----------------------------------
+struct PosePrep {
+  double R[9];    // R_lw (world -> frame), row-major
+  double Jl[9];   // SO(3) left Jacobian of aa_lw, row-major
+  double t[3];    // t_lw
+};
+
+// pcl::transformPointCloud(cloud, out, Matrix4d) (sensors/Velodyne.cpp:1790-1806): double math, float32 store.
+PVB_HD void transform_point_f32(const double* R_rowmajor, const double* t, float x, float y, float z, float& ox, float& oy, float& oz) {
+  const double px = x, py = y, pz = z;
+  ox = (float)dadd(dadd(dadd(dmul(R_rowmajor[0], px), dmul(R_rowmajor[1], py)), dmul(R_rowmajor[2], pz)), t[0]);
+  oy = (float)dadd(dadd(dadd(dmul(R_rowmajor[3], px), dmul(R_rowmajor[4], py)), dmul(R_rowmajor[5], pz)), t[1]);
+  oz = (float)dadd(dadd(dadd(dmul(R_rowmajor[6], px), dmul(R_rowmajor[7], py)), dmul(R_rowmajor[8], pz)), t[2]);
+}
+
+// Velodyne::World2Local (sensors/Velodyne.cpp:1850-1853): R_wl^T p - R_wl^T t_wl, each product summed x,y,z.
+PVB_HD void world2local(const double* R_wl, const double* t_wl, const double pw[3], double out[3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double a = dadd(dadd(dmul(R_wl[0 * 3 + r], pw[0]), dmul(R_wl[1 * 3 + r], pw[1])), dmul(R_wl[2 * 3 + r], pw[2]));
+    const double b = dadd(dadd(dmul(R_wl[0 * 3 + r], t_wl[0]), dmul(R_wl[1 * 3 + r], t_wl[1])), dmul(R_wl[2 * 3 + r], t_wl[2]));
+    out[r] = dsub(a, b);
+  }
+}
+
+// flann::L2_Simple<float> squared distance (the metric behind pcl::KdTreeFLANN::nearestKSearch)
+PVB_HD float sqdist_f32(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = fsub(ax, bx), dy = fsub(ay, by), dz = fsub(az, bz);
+  return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+}
+
+// ---- forward dual number (N = 3: d/dP, N = 6: d/d(A,B)) ---------------------------------------------------
+template <int N>
+struct Dual {
+  double v;
+  double d[N];
+};
+template <int N> PVB_HD Dual<N> mk(double v) { Dual<N> r; r.v = v; for (int i = 0; i < N; ++i) r.d[i] = 0.0; return r; }
+template <int N> PVB_HD Dual<N> seed(double v, int k) { Dual<N> r = mk<N>(v); r.d[k] = 1.0; return r; }
+template <int N> PVB_HD Dual<N> operator+(const Dual<N>& a, const Dual<N>& b) { Dual<N> r; r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+template <int N> PVB_HD Dual<N> operator-(const Dual<N>& a, const Dual<N>& b) { Dual<N> r; r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+template <int N> PVB_HD Dual<N> operator-(const Dual<N>& a) { Dual<N> r; r.v = -a.v; for (int i = 0; i < N; ++i) r.d[i] = -a.d[i]; return r; }
+template <int N> PVB_HD Dual<N> operator*(const Dual<N>& a, const Dual<N>& b) { Dual<N> r; r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.v * b.d[i] + a.d[i] * b.v; return r; }
+template <int N> PVB_HD Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) {
+  Dual<N> r; const double inv = 1.0 / b.v; r.v = a.v * inv;
+  for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
+  return r;
+}
+template <int N> PVB_HD Dual<N> operator+(const Dual<N>& a, double s) { Dual<N> r = a; r.v += s; return r; }
+template <int N> PVB_HD Dual<N> operator-(const Dual<N>& a, double s) { Dual<N> r = a; r.v -= s; return r; }
+template <int N> PVB_HD Dual<N> operator*(const Dual<N>& a, double s) { Dual<N> r; r.v = a.v * s; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * s; return r; }
+template <int N> PVB_HD Dual<N> operator*(double s, const Dual<N>& a) { return a * s; }
+template <int N> PVB_HD Dual<N> dsqrt(const Dual<N>& a) { Dual<N> r; r.v = sqrt(a.v); const double k = 1.0 / (2.0 * r.v); for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * k; return r; }
+template <int N> PVB_HD Dual<N> dacos(const Dual<N>& a) { Dual<N> r; r.v = acos(a.v); const double k = -1.0 / sqrt(1.0 - a.v * a.v); for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * k; return r; }
+template <int N> PVB_HD Dual<N> dabs(const Dual<N>& a) { return a.v < 0.0 ? -a : a; }   // ceres::abs(Jet): +1 slope at 0
+
+// base/Geometry.hpp:450-466
+template <int N> PVB_HD Dual<N> vector_angle(const Dual<N> a[3], const Dual<N> b[3]) {
+  Dual<N> c = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+  const Dual<N> n1 = dsqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  const Dual<N> n2 = dsqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+  c = c / (n1 * n2);
+  if (c.v >= 1.0) return mk<N>(0.0);
+  if (c.v <= -1.0) return mk<N>(M_PI);
+  return dacos(c);
+}
+
+// normalize_distance tail of Point2Plane_Angle / Point2Line_Angle (CostFunction.h:699-715, 901-917)
+template <int N> PVB_HD Dual<N> angle_tail(const Dual<N> P[3], const Dual<N> Pp[3], bool normalize) {
+  if (normalize) {
+    const Dual<N> nrm = dsqrt(Pp[0] * Pp[0] + Pp[1] * Pp[1] + Pp[2] * Pp[2]);
+    const Dual<N> ratio = (nrm - 1.0) / nrm;
+    Dual<N> c[3], v1[3], v2[3];
+    for (int k = 0; k < 3; ++k) { c[k] = ratio * Pp[k]; v1[k] = Pp[k] - c[k]; v2[k] = P[k] - c[k]; }
+    return vector_angle(v1, v2);
+  }
+  return vector_angle(P, Pp);
+}
+
+// ---- residual tails: r and g = dr/dP (before the robust loss) ---------------------------------------------
+// consts layout per type: see include/panovlm_b200.h (identical to the reference functors' members).
+PVB_HD double tail_point_plane(int type, bool normalize, const double* c, const double P[3], double g[3]) {
+  typedef Dual<3> D;
+  D p[3] = {seed<3>(P[0], 0), seed<3>(P[1], 1), seed<3>(P[2], 2)};
+  const double n0 = c[3], n1 = c[4], n2 = c[5], d = c[6];
+  D s = p[0] * n0 + p[1] * n1 + p[2] * n2 + d;
+  D dis = dabs(s);                                              // PointToPlaneDistance(..., normalized=true)
+  D r;
+  if (type == P2PLANE_METER) {
+    r = dis * c[7];                                             // CostFunction.h:607
+  } else {
+    if (dis.v < 1e-3) { g[0] = g[1] = g[2] = 0.0; return 0.0; }  // :680-684 zero residual AND zero row
+    D pp[3] = {p[0] - dis * n0, p[1] - dis * n1, p[2] - dis * n2};
+    const double chk = n0 * pp[0].v + n1 * pp[1].v + n2 * pp[2].v + d;
+    if (fabs(chk) > 1e-4) { pp[0] = p[0] + dis * n0; pp[1] = p[1] + dis * n1; pp[2] = p[2] + dis * n2; }   // :688-693
+    r = angle_tail(p, pp, normalize);
+  }
+  g[0] = r.d[0]; g[1] = r.d[1]; g[2] = r.d[2];
+  return r.v;
+}
+
+PVB_HD double tail_point_line(int type, bool normalize, const double* c, const double P[3], double g[3]) {
+  typedef Dual<3> D;
+  D p[3] = {seed<3>(P[0], 0), seed<3>(P[1], 1), seed<3>(P[2], 2)};
+  const double x0 = c[3], y0 = c[4], z0 = c[5], nx = c[6], ny = c[7], nz = c[8];
+  D k = (p[0] - x0) * nx + (p[1] - y0) * ny + (p[2] - z0) * nz;
+  if (type == P2LINE_METER) k = k / mk<3>(nx * nx + ny * ny + nz * nz);   // PointToLineDistance3D divides by |n|^2 (Geometry.hpp:207)
+  D pp[3] = {k * nx + x0, k * ny + y0, k * nz + z0};
+  D dx = p[0] - pp[0], dy = p[1] - pp[1], dz = p[2] - pp[2];
+  D r;
+  if (type == P2LINE_METER) {
+    D ex = pp[0] - p[0], ey = pp[1] - p[1], ez = pp[2] - p[2];
+    r = dsqrt(ex * ex + ey * ey + ez * ez) * c[9];              // CostFunction.h:815
+  } else {
+    D dis = dsqrt(dx * dx + dy * dy + dz * dz);                 // :889-891
+    if (dis.v < 1e-3) { g[0] = g[1] = g[2] = 0.0; return 0.0; }
+    r = angle_tail(p, pp, normalize);
+  }
+  g[0] = r.d[0]; g[1] = r.d[1]; g[2] = r.d[2];
+  return r.v;
+}
+
+// Plane2Plane_Global (CostFunction.h:350-425): r = w * PlaneAngle(n_ref, A x B); gA/gB = dr/dA, dr/dB
+PVB_HD double tail_plane2plane(const double* c, const double A[3], const double B[3], double gA[3], double gB[3]) {
+  typedef Dual<6> D;
+  D a[3] = {seed<6>(A[0], 0), seed<6>(A[1], 1), seed<6>(A[2], 2)};
+  D b[3] = {seed<6>(B[0], 3), seed<6>(B[1], 4), seed<6>(B[2], 5)};
+  D n1[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+  D cs = dabs(n1[0] * c[0] + n1[1] * c[1] + n1[2] * c[2]);      // PlaneAngle(plane2, plane1): |dot|
+  const double nr = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  D nn = dsqrt(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
+  cs = cs / (nn * nr);                                          // Geometry.hpp:477-480 (norm1 * norm2, plane2 first)
+  D r;
+  if (cs.v >= 1.0) r = mk<6>(0.0); else r = dacos(cs);
+  r = r * c[9];
+  for (int k = 0; k < 3; ++k) { gA[k] = r.d[k]; gB[k] = r.d[3 + k]; }
+  return r.v;
+}
+
+// PlaneIOUResidual (CostFunction.h:433-507)
+PVB_HD double tail_plane_iou(const double* c, const double M[3], double g[3]) {
+  typedef Dual<3> D;
+  D m[3] = {seed<3>(M[0], 0), seed<3>(M[1], 1), seed<3>(M[2], 2)};
+  const double n0 = c[0], n1 = c[1], n2 = c[2], d = c[3];
+  D dis = dabs(m[0] * n0 + m[1] * n1 + m[2] * n2 + d);          // ProjectPointToPlane(normalized=true)
+  D pp[3] = {m[0] - dis * n0, m[1] - dis * n1, m[2] - dis * n2};
+  if (fabs(n0 * pp[0].v + n1 * pp[1].v + n2 * pp[2].v + d) > 1e-4) { pp[0] = m[0] + dis * n0; pp[1] = m[1] + dis * n1; pp[2] = m[2] + dis * n2; }
+  D ip[3] = {mk<3>(c[7]), mk<3>(c[8]), mk<3>(c[9])};
+  D ang = vector_angle(pp, ip);
+  if (ang.v < c[10]) { g[0] = g[1] = g[2] = 0.0; return 0.0; }
+  D r = (ang - c[10]) * c[11];
+  g[0] = r.d[0]; g[1] = r.d[1]; g[2] = r.d[2];
+  return r.v;
+}
+
+// ---- the common transform + analytic Jacobian row --------------------------------------------------------
+PVB_HD void transform_nei_to_ref(const PosePrep& pr, const PosePrep& pn, const double p[3], double q[3], double P[3]) {
+  q[0] = p[0] - pn.t[0]; q[1] = p[1] - pn.t[1]; q[2] = p[2] - pn.t[2];
+  double u[3];
+  for (int k = 0; k < 3; ++k) u[k] = pn.R[0 * 3 + k] * q[0] + pn.R[1 * 3 + k] * q[1] + pn.R[2 * 3 + k] * q[2];   // R_n^T q
+  for (int k = 0; k < 3; ++k) P[k] = pr.R[k * 3 + 0] * u[0] + pr.R[k * 3 + 1] * u[1] + pr.R[k * 3 + 2] * u[2] + pr.t[k];
+}
+
+// accumulate J += g^T dP/d(params) for one transformed point (q = p - t_n, P = transformed)
+PVB_HD void accumulate_row(const PosePrep& pr, const PosePrep& pn, const double q[3], const double P[3], const double g[3], double J[12]) {
+  const double v[3] = {P[0] - pr.t[0], P[1] - pr.t[1], P[2] - pr.t[2]};
+  const double a[3] = {v[1] * g[2] - v[2] * g[1], v[2] * g[0] - v[0] * g[2], v[0] * g[1] - v[1] * g[0]};          // v x g
+  double w[3], h[3];
+  for (int k = 0; k < 3; ++k) w[k] = pr.R[0 * 3 + k] * g[0] + pr.R[1 * 3 + k] * g[1] + pr.R[2 * 3 + k] * g[2];    // R_r^T g
+  for (int k = 0; k < 3; ++k) h[k] = pn.R[k * 3 + 0] * w[0] + pn.R[k * 3 + 1] * w[1] + pn.R[k * 3 + 2] * w[2];    // R_n R_r^T g
+  const double b[3] = {h[1] * q[2] - h[2] * q[1], h[2] * q[0] - h[0] * q[2], h[0] * q[1] - h[1] * q[0]};          // h x q
+  for (int j = 0; j < 3; ++j) {
+    J[j] += a[0] * pr.Jl[0 * 3 + j] + a[1] * pr.Jl[1 * 3 + j] + a[2] * pr.Jl[2 * 3 + j];
+    J[3 + j] += g[j];
+    J[6 + j] += b[0] * pn.Jl[0 * 3 + j] + b[1] * pn.Jl[1 * 3 + j] + b[2] * pn.Jl[2 * 3 + j];
+    J[9 + j] -= h[j];
+  }
+}
+
+// One residual block: raw residual + 1x12 Jacobian row [d/daa_r | d/dt_r | d/daa_n | d/dt_n].
+PVB_HD double eval_block(int type, bool normalize, const double* c, const PosePrep& pr, const PosePrep& pn, double J[12]) {
+  for (int k = 0; k < 12; ++k) J[k] = 0.0;
+  double q[3], P[3], g[3], r;
+  switch (type) {
+    case P2PLANE_METER:
+    case P2PLANE_ANGLE:
+      transform_nei_to_ref(pr, pn, c, q, P);
+      r = tail_point_plane(type, normalize, c, P, g);
+      accumulate_row(pr, pn, q, P, g, J);
+      return r;
+    case P2LINE_METER:
+    case P2LINE_ANGLE:
+      transform_nei_to_ref(pr, pn, c, q, P);
+      r = tail_point_line(type, normalize, c, P, g);
+      accumulate_row(pr, pn, q, P, g, J);
+      return r;
+    case PLANE2PLANE_GLOBAL: {
+      double qb[3], A[3], B[3], gA[3], gB[3];
+      transform_nei_to_ref(pr, pn, c + 3, q, A);
+      transform_nei_to_ref(pr, pn, c + 6, qb, B);
+      r = tail_plane2plane(c, A, B, gA, gB);
+      accumulate_row(pr, pn, q, A, gA, J);
+      accumulate_row(pr, pn, qb, B, gB, J);
+      return r;
+    }
+    case PLANE_IOU:
+      transform_nei_to_ref(pr, pn, c + 4, q, P);
+      r = tail_plane_iou(c, P, g);
+      accumulate_row(pr, pn, q, P, g, J);
+      return r;
+    default:
+      return 0.0;
+  }
+}
+
+// ceres::HuberLoss + Corrector (rho'' <= 0 branch): scales r and the row by sqrt(rho'); returns 0.5*rho(r^2).
+PVB_HD double huber_correct(double a, double& r, double* J, int n) {
+  const double s = r * r;
+  if (a <= 0.0 || s <= a * a) return 0.5 * s;
+  const double sq = sqrt(s);
+  const double k = sqrt(a / sq);
+  r *= k;
+  for (int i = 0; i < n; ++i) J[i] *= k;
+  return 0.5 * (2.0 * a * sq - a * a);
+}
+
+// ---- plane fit / collinearity test of AssociatePoint2Plane (LidarFeatureAssociate.cpp:593-596) -------------
+// Least-squares A x = -1 over K points by Householder QR with column pivoting (what Geometry.hpp:361's
+// colPivHouseholderQr().solve does), then d = 1/|x|, n = x/|x| and the tolerance test (:364-371).
+template <int K>
+PVB_HD bool form_plane_lsq(const double (*pts)[3], double tol, double plane[4]) {
+  double A[K][3], b[K];
+  for (int i = 0; i < K; ++i) { A[i][0] = pts[i][0]; A[i][1] = pts[i][1]; A[i][2] = pts[i][2]; b[i] = -1.0; }
+  int perm[3] = {0, 1, 2};
+  double diag[3] = {0, 0, 0};
+  int rank = 0;
+  double maxpivot = 0.0;
+  bool stop = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (stop) continue;
+    double cn[3] = {0, 0, 0};
+#pragma unroll
+    for (int c = k; c < 3; ++c) { double s = 0; for (int r = k; r < K; ++r) s += A[r][c] * A[r][c]; cn[c] = s; }
+    int best = k; double bn = cn[k];
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c) if (cn[c] > bn) { bn = cn[c]; best = c; }
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c) {          // static column indices keep A[][] in registers
+      if (best == c) {
+        for (int r = 0; r < K; ++r) { const double tmp = A[r][k]; A[r][k] = A[r][c]; A[r][c] = tmp; }
+        const int tp = perm[k]; perm[k] = perm[c]; perm[c] = tp;
+      }
+    }
+    const double norm = sqrt(bn);
+    if (k == 0) maxpivot = norm;
+    if (norm <= maxpivot * DBL_EPSILON * 3.0) { stop = true; continue; }
+    ++rank;
+    const double alpha = (A[k][k] > 0) ? -norm : norm;
+    const double vk = A[k][k] - alpha;
+    double vtv = vk * vk;
+    for (int r = k + 1; r < K; ++r) vtv += A[r][k] * A[r][k];
+    if (vtv > 0) {
+      const double inv = 2.0 / vtv;
+#pragma unroll
+      for (int c = k + 1; c < 3; ++c) {
+        double dot = vk * A[k][c];
+        for (int r = k + 1; r < K; ++r) dot += A[r][k] * A[r][c];
+        const double f = dot * inv;
+        A[k][c] -= f * vk;
+        for (int r = k + 1; r < K; ++r) A[r][c] -= f * A[r][k];
+      }
+      double dot = vk * b[k];
+      for (int r = k + 1; r < K; ++r) dot += A[r][k] * b[r];
+      const double f = dot * inv;
+      b[k] -= f * vk;
+      for (int r = k + 1; r < K; ++r) b[r] -= f * A[r][k];
+    }
+    diag[k] = alpha;
+  }
+  double y[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    if (k >= rank) continue;
+    double s = b[k];
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c) if (c < rank) s -= A[k][c] * y[c];
+    y[k] = s / diag[k];
+  }
+  double x[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) { if (perm[k] == 0) x[0] = y[k]; else if (perm[k] == 1) x[1] = y[k]; else x[2] = y[k]; }
+  const double nrm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  const double d = 1.0 / nrm;
+  const double n0 = x[0] / nrm, n1 = x[1] / nrm, n2 = x[2] / nrm;
+  if (tol > 0) {
+    for (int i = 0; i < K; ++i)
+      if (fabs(n0 * pts[i][0] + n1 * pts[i][1] + n2 * pts[i][2] + d) > tol) return false;
+  }
+  plane[0] = n0; plane[1] = n1; plane[2] = n2; plane[3] = d;
+  return true;
+}
+
+// FormLine(points, tolerance) collinearity test (Geometry.hpp:220-246): true when lambda_max > tol * lambda_mid.
+// Eigenvalues of the symmetric 3x3 scatter matrix by the trigonometric closed form.
+template <int K>
+PVB_HD bool points_collinear(const double (*pts)[3], double tol) {
+  double c[3] = {0, 0, 0};
+  for (int i = 0; i < K; ++i) { c[0] = c[0] + pts[i][0]; c[1] = c[1] + pts[i][1]; c[2] = c[2] + pts[i][2]; }
+  c[0] = c[0] / double(K); c[1] = c[1] / double(K); c[2] = c[2] / double(K);
+  double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+  for (int i = 0; i < K; ++i) {
+    const double x = pts[i][0] - c[0], y = pts[i][1] - c[1], z = pts[i][2] - c[2];
+    a00 += x * x; a01 += x * y; a02 += x * z; a11 += y * y; a12 += y * z; a22 += z * z;
+  }
+  const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+  const double qm = (a00 + a11 + a22) / 3.0;
+  const double p2 = (a00 - qm) * (a00 - qm) + (a11 - qm) * (a11 - qm) + (a22 - qm) * (a22 - qm) + 2.0 * p1;
+  double l0, l1, l2;   // ascending
+  if (p2 <= 0.0) { l0 = l1 = l2 = qm; }
+  else {
+    const double p = sqrt(p2 / 6.0), ip = 1.0 / p;
+    const double b00 = (a00 - qm) * ip, b11 = (a11 - qm) * ip, b22 = (a22 - qm) * ip, b01 = a01 * ip, b02 = a02 * ip, b12 = a12 * ip;
+    double r = 0.5 * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+    r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+    const double phi = acos(r) / 3.0;
+    l2 = qm + 2.0 * p * cos(phi);
+    l0 = qm + 2.0 * p * cos(phi + 2.0943951023931953);
+    l1 = 3.0 * qm - l0 - l2;
+  }
+  return l2 > tol * l1;
+}
+
+// ---- Equirectangular float path (sensors/Equirectangular.h:41-96 with USE_FAST_ATAN2, base/Math.h:15-29) ----
+PVB_HD float fast_atan2_f32(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = mn / fadd(mx, (float)DBL_EPSILON);
+  const float s = fmul(a, a);
+  const double sd = s, ad = a;
+  // ((c3*s + c2)*s - c1)*s*a + c0*a evaluated in double (the literals are double), rounded once to float
+  double r = dmul(dmul(dsub(dmul(dadd(dmul(-0.04432655554792128, sd), 0.1555786518463281), sd), 0.3258083974640975), sd), ad);
+  r = dadd(r, dmul(0.9997878412794807, ad));
+  float rf = (float)r;
+  if (ay > ax) rf = (float)dsub(M_PI_2, (double)rf);
+  if (x < 0) rf = (float)dsub(M_PI, (double)rf);
+  if (y < 0) rf = -rf;
+  return rf;
+}
+
+PVB_HD double fast_atan2_f64(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const double a = fmin(ax, ay) / dadd(fmax(ax, ay), DBL_EPSILON);
+  const double s = dmul(a, a);
+  double r = dadd(dmul(dmul(dsub(dmul(dadd(dmul(-0.04432655554792128, s), 0.1555786518463281), s), 0.3258083974640975), s), a), dmul(0.9997878412794807, a));
+  if (ay > ax) r = dsub(M_PI_2, r);
+  if (x < 0) r = dsub(M_PI, r);
+  if (y < 0) r = -r;
+  return r;
+}
+
+// CamToImage in float (CamToSphere + SphereToImage): pixel of a camera-frame point
+PVB_HD void cam_to_image_f32(float x, float y, float z, int rows, int cols, float& u, float& v) {
+  const float lon = fast_atan2_f32(x, z);
+  const float lat = -fast_atan2_f32(y, sqrtf(fadd(fmul(x, x), fmul(z, z))));
+  u = (float)dmul((double)cols, dadd(0.5, (double)lon / (2.0 * M_PI)));
+  v = (float)dmul((double)rows, dsub(0.5, (double)lat / M_PI));
+}
+
+// ImageToCam in double, exact sin/cos (Equirectangular.h:98-170)
+PVB_HD void image_to_cam_f64(double px, double py, int rows, int cols, double cam[3]) {
+  const double lon = (2 * px / cols - 1) * M_PI;
+  const double lat = (0.5 - py / rows) * M_PI;
+  const double cy = cos(lat);
+  cam[0] = cy * sin(lon);
+  cam[1] = -sin(lat);
+  cam[2] = cy * cos(lon);
+}
+
+}  // namespace pvb

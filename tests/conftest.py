@@ -1,0 +1,45 @@
+"""pytest configuration: `gpu` marker, in-tree build of the oracle and of the host harness of the device math."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def build_host_harness():
+    out = os.path.join(ROOT, "tests", "libpvb_host_harness.so")
+    src = os.path.join(ROOT, "tests", "host_harness.cpp")
+    deps = [src] + [os.path.join(ROOT, "panovlm_b200", "csrc", f) for f in ("pvb_math.cuh", "pvb_knn.cuh", "pvb_host.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-std=c++17", "-x", "c++", "-shared", "-o", out, src])
+    return out
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import pvo
+    pvo.build()
+    pvo.lib()
+    return pvo
+
+
+@pytest.fixture(scope="session")
+def harness():
+    import ctypes
+    return ctypes.CDLL(build_host_harness())
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    import panovlm_b200
+    ctx = panovlm_b200.Context(0)   # raises loudly if the extension or the GPU is missing
+    yield ctx
+    ctx.close()

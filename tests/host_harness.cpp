@@ -1,0 +1,116 @@
+// TEST INFRASTRUCTURE ONLY — compiles the product's `__host__ __device__` math (panovlm_b200/csrc/*.cuh,
+// pvb_host.hpp) with g++ so the not-gpu tests can check the exact device arithmetic against the oracle on the
+// CPU.  It is never linked into libpanovlm_b200.so and the product has no CPU path.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../panovlm_b200/csrc/pvb_host.hpp"
+#include "../panovlm_b200/csrc/pvb_knn.cuh"
+
+using namespace pvb;
+
+// per-query association on a host-built grid (counting sort), K = 10 or 5
+template <int K>
+static void associate_all(const float* tgt, int n, const double* R_ref, const double* t_ref, const float* qry, int m, const double* R_nei, const double* t_nei,
+                          double h, float thr, double plane_tol, unsigned char* valid, double* p_local, double* plane, int* nn_idx, float* nn_d2) {
+  GridDesc g;
+  float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+  for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) { mn[c] = std::min(mn[c], tgt[i * 4 + c]); mx[c] = std::max(mx[c], tgt[i * 4 + c]); }
+  for (int c = 0; c < 3; ++c) { g.origin[c] = mn[c]; g.dims[c] = std::max(1, (int)std::floor(((double)mx[c] - mn[c]) / h) + 1); }
+  g.h = h; g.inv_h = 1.0 / h; g.n_points = n; g.cell_base = 0; g.point_base = 0;
+  const long long ncell = (long long)g.dims[0] * g.dims[1] * g.dims[2];
+  std::vector<int> start(ncell + 1, 0), cell(n);
+  for (int i = 0; i < n; ++i) {
+    const int cx = cell_coord(tgt[i * 4], g.origin[0], g.inv_h, g.dims[0]), cy = cell_coord(tgt[i * 4 + 1], g.origin[1], g.inv_h, g.dims[1]),
+              cz = cell_coord(tgt[i * 4 + 2], g.origin[2], g.inv_h, g.dims[2]);
+    cell[i] = (int)(((long long)cz * g.dims[1] + cy) * g.dims[0] + cx);
+    start[cell[i] + 1]++;
+  }
+  for (long long c = 0; c < ncell; ++c) start[c + 1] += start[c];
+  std::vector<int> fill(start.begin(), start.end() - 1);
+  std::vector<F4> sorted(n);
+  for (int i = 0; i < n; ++i) {
+    F4 r; r.x = tgt[i * 4]; r.y = tgt[i * 4 + 1]; r.z = tgt[i * 4 + 2];
+    r.w = u2f(((uint32_t)i << 5) | ((uint32_t)tgt[i * 4 + 3] & 31u));
+    sorted[fill[cell[i]]++] = r;
+  }
+  auto cells = [&](long long c) { return (long long)start[c]; };
+  auto load = [&](long long i) { return sorted[i]; };
+  AssocParams prm; prm.sq_thr = thr * thr; prm.rmax = (int)std::ceil((double)thr / h); prm.plane_tol = plane_tol; prm.collinear_tol = 3.0;
+  for (int i = 0; i < m; ++i) {
+    unsigned long long keys[K];
+    const uint32_t qcls = (uint32_t)qry[i * 4 + 3] & 31u;
+    valid[i] = associate_point2plane<K>(g, cells, load, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei,
+                                        p_local + 3 * i, plane + 4 * i, keys) ? 1 : 0;
+    for (int j = 0; j < K; ++j) {
+      const bool ok = (keys[j] & kKeyEmptyLow) != kKeyEmptyLow;
+      nn_idx[i * K + j] = ok ? (int)(f2u(sorted[(uint32_t)(keys[j] & kKeyEmptyLow)].w) >> 5) : -1;
+      nn_d2[i * K + j] = ok ? u2f((uint32_t)(keys[j] >> 32)) : INFINITY;
+    }
+  }
+}
+
+extern "C" {
+
+void pvbh_pose_prep(const double* pose6, double* out21) {
+  PosePrep p; prepare_pose(pose6, p);
+  memcpy(out21, p.R, 72); memcpy(out21 + 9, p.Jl, 72); memcpy(out21 + 18, p.t, 24);
+}
+
+void pvbh_eval_blocks(long n, const int* type, const int* ref, const int* nei, const int* normalize, const double* huber, const double* consts,
+                      const double* poses, int nb, int apply_loss, double* out_r, double* out_J, double* out_cost) {
+  std::vector<PosePrep> pp(nb);
+  for (int b = 0; b < nb; ++b) prepare_pose(poses + 6 * b, pp[b]);
+  for (long i = 0; i < n; ++i) {
+    double J[12];
+    double r = eval_block(type[i], normalize[i] != 0, consts + 12 * i, pp[ref[i]], pp[nei[i]], J);
+    const double c = huber_correct(apply_loss ? huber[i] : 0.0, r, J, 12);
+    out_r[i] = r; out_cost[i] = c;
+    if (out_J) memcpy(out_J + 12 * i, J, 96);
+  }
+}
+
+// dense LM through the product's host solver, residuals evaluated with the device math on the CPU
+void pvbh_solve_lm(long n, const int* type, const int* ref, const int* nei, const int* normalize, const double* huber, const double* consts,
+                   double* poses, int nb, const unsigned char* is_const, int max_iter, double* summary) {
+  EvalFn eval = [&](const double* x, double* H, double* g) {
+    std::vector<PosePrep> pp(nb);
+    for (int b = 0; b < nb; ++b) prepare_pose(x + 6 * b, pp[b]);
+    const int D = 6 * nb;
+    if (H) std::fill(H, H + (size_t)D * D, 0.0);
+    if (g) std::fill(g, g + D, 0.0);
+    double cost = 0;
+    for (long i = 0; i < n; ++i) {
+      double J[12];
+      double r = eval_block(type[i], normalize[i] != 0, consts + 12 * i, pp[ref[i]], pp[nei[i]], J);
+      cost += huber_correct(huber[i], r, J, 12);
+      if (!H) continue;
+      const int o[2] = {6 * ref[i], 6 * nei[i]};
+      for (int a = 0; a < 12; ++a) {
+        const int ia = o[a / 6] + a % 6;
+        g[ia] += J[a] * r;
+        for (int c = 0; c < 12; ++c) H[(size_t)ia * D + o[c / 6] + c % 6] += J[a] * J[c];
+      }
+    }
+    return cost;
+  };
+  LMOptions opt; opt.max_iterations = max_iter;
+  LMSummary S = solve_lm(eval, poses, nb, is_const, opt);
+  summary[0] = S.initial_cost; summary[1] = S.final_cost; summary[2] = S.iterations; summary[3] = S.successful; summary[4] = S.unsuccessful; summary[5] = S.termination;
+}
+
+void pvbh_associate(const float* tgt, int n, const double* R_ref, const double* t_ref, const float* qry, int m, const double* R_nei, const double* t_nei,
+                    double h, float thr, double plane_tol, int K, unsigned char* valid, double* p_local, double* plane, int* nn_idx, float* nn_d2) {
+  if (K == 10) associate_all<10>(tgt, n, R_ref, t_ref, qry, m, R_nei, t_nei, h, thr, plane_tol, valid, p_local, plane, nn_idx, nn_d2);
+  else associate_all<5>(tgt, n, R_ref, t_ref, qry, m, R_nei, t_nei, h, thr, plane_tol, valid, p_local, plane, nn_idx, nn_d2);
+}
+
+void pvbh_transform_cloud(const double* R, const double* t, const float* in, int n, float* out) {
+  for (int i = 0; i < n; ++i) { transform_point_f32(R, t, in[i * 4], in[i * 4 + 1], in[i * 4 + 2], out[i * 4], out[i * 4 + 1], out[i * 4 + 2]); out[i * 4 + 3] = in[i * 4 + 3]; }
+}
+void pvbh_fast_atan2_f(long n, const float* y, const float* x, float* out) { for (long i = 0; i < n; ++i) out[i] = fast_atan2_f32(y[i], x[i]); }
+void pvbh_fast_atan2_d(long n, const double* y, const double* x, double* out) { for (long i = 0; i < n; ++i) out[i] = fast_atan2_f64(y[i], x[i]); }
+void pvbh_cam_to_image_f(int rows, int cols, long n, const float* cam, float* px) { for (long i = 0; i < n; ++i) cam_to_image_f32(cam[3 * i], cam[3 * i + 1], cam[3 * i + 2], rows, cols, px[2 * i], px[2 * i + 1]); }
+void pvbh_image_to_cam_d(int rows, int cols, long n, const double* px, double* cam) { for (long i = 0; i < n; ++i) image_to_cam_f64(px[2 * i], px[2 * i + 1], rows, cols, cam + 3 * i); }
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+"""The C-ABI library loads (no GPU needed for dlopen) and exports every symbol include/panovlm_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "panovlm_b200.h")).read()
+    return sorted(set(re.findall(r"\b(pvb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import panovlm_b200
+    if not os.path.exists(panovlm_b200.lib_path()):
+        panovlm_b200.build_library()
+    lib = ctypes.CDLL(panovlm_b200.lib_path())
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"missing export {n}"
+    assert sorted(panovlm_b200.api.EXPORTS) == names
+
+
+def test_no_cpu_fallback_without_a_device():
+    import panovlm_b200
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(panovlm_b200.PvbError):
+        panovlm_b200.Context(0)
+
+
+def test_product_never_touches_the_oracle():
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "panovlm_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")) or f == "Makefile":
+                if re.search(r"oracle|pvo_", open(os.path.join(dp, f), errors="ignore").read()):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -1,0 +1,95 @@
+"""The product's `__host__ __device__` math (panovlm_b200/csrc/pvb_math.cuh, pvb_knn.cuh, pvb_host.hpp) compiled
+with g++ (tests/host_harness.cpp) and compared with the oracle on the CPU — catches arithmetic/parity bugs before any
+GPU time is spent.  The same functions run inside the CUDA kernels; `-m gpu` tests then check the kernels proper."""
+import ctypes as C
+import os
+
+import numpy as np
+
+import cases
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None  # noqa: E731
+
+
+def _eval(h, c, loss):
+    n = len(c["type"])
+    r, J, cost = np.zeros(n), np.zeros((n, 12)), np.zeros(n)
+    h.pvbh_eval_blocks(C.c_long(n), p(c["type"]), p(c["ref"]), p(c["nei"]), p(c["normalize"]), p(c["huber"]), p(np.ascontiguousarray(c["consts"])),
+                       p(np.ascontiguousarray(c["poses"])), C.c_int(c["nb"]), C.c_int(loss), p(r), p(J), p(cost))
+    return r, J, cost
+
+
+def test_analytic_jacobian_matches_jet_oracle(oracle, harness):
+    c = cases.random_blocks(1, 6000)
+    b = oracle.Blocks(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"])
+    for loss in (0, 1):
+        r, J, cost = b.evaluate(c["poses"], apply_loss=bool(loss))
+        r2, J2, c2 = _eval(harness, c, loss)
+        assert (np.abs(r - r2) / np.maximum(1e-9, np.abs(r))).max() < 1e-8           # gate: 1e-5 relative
+        assert (np.abs(J - J2).max(1) / np.maximum(1e-12, np.abs(J).max(1))).max() < 1e-7   # gate: 1e-6 relative
+        assert np.abs(cost - c2).max() < 1e-10
+
+
+def test_zero_rows_and_golden_functors(harness):
+    c = cases.on_plane_blocks()
+    r, J, _ = _eval(harness, c, 0)
+    assert np.all(r == 0) and np.all(J == 0)
+    g = dict(np.load(os.path.join(G, "functors.npz")))
+    g["nb"] = int(g["nb"])
+    r, J, _ = _eval(harness, g, 0)
+    assert np.abs(r - g["residual"]).max() < 1e-8
+    assert (np.abs(J - g["jacobian"]) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1, keepdims=True))).max() < 1e-7
+
+
+def test_grid_knn_and_association_equal_oracle(oracle, harness):
+    g = np.load(os.path.join(G, "assoc_pair.npz"))
+    refw, neiw = np.ascontiguousarray(g["ref_world"]), np.ascontiguousarray(g["nei_world"])
+    R_ref, t_ref, R_nei, t_nei = (np.ascontiguousarray(g[k]) for k in ("R_ref", "t_ref", "R_nei", "t_nei"))
+    for (h, thr, tol, K) in [(0.5, 1.0, 0.05, 10), (0.17, 1.0, 0.05, 10), (1.3, 1.0, 0.01, 10), (0.3, 0.3, 0.05, 5), (0.07, 0.3, 0.05, 5)]:
+        q, pt, pl = oracle.associate_p2plane(refw, R_ref, t_ref, neiw, R_nei, t_nei, tol, thr, K, True)
+        m = len(neiw)
+        valid, pl2, pt2 = np.zeros(m, np.uint8), np.zeros((m, 4)), np.zeros((m, 3))
+        ni, nd = np.zeros((m, K), np.int32), np.zeros((m, K), np.float32)
+        harness.pvbh_associate(p(refw), C.c_int(len(refw)), p(R_ref), p(t_ref), p(neiw), C.c_int(m), p(R_nei), p(t_nei), C.c_double(h), C.c_float(thr),
+                               C.c_double(tol), C.c_int(K), p(valid), p(pt2), p(pl2), p(ni), p(nd))
+        q2 = np.nonzero(valid)[0]
+        assert np.array_equal(q, q2)
+        assert np.abs(pl - pl2[q2]).max() < 1e-12 and np.abs(pt - pt2[q2]).max() == 0.0
+        idx, d2 = oracle.knn(refw, neiw, K, False)
+        full = d2[:, K - 1] <= np.float32(thr) * np.float32(thr)
+        assert np.array_equal(d2[full], nd[full]) and np.array_equal(idx[full], ni[full])       # bit-exact float32 distances
+        assert np.all(ni[~full][:, K - 1] == -1)                                                  # fewer than K within the threshold
+
+
+def test_host_lm_matches_oracle_lm(oracle, harness):
+    g = np.load(os.path.join(G, "assoc_pair.npz"))
+    n = len(g["query"])
+    consts = np.zeros((n, 12)); consts[:, :3] = g["point"]; consts[:, 3:7] = g["plane"]; consts[:, 7] = 1.0
+    for bt, hub in ((1, 2 * np.pi / 180), (0, 0.2)):
+        blk = oracle.Blocks(np.full(n, bt), 0, 1, consts, hub, 1)
+        P1, s1 = blk.solve_lm(np.zeros((2, 6)), is_const=[1, 0], max_iter=20)
+        P2, summ, mask = np.zeros((2, 6)), np.zeros(6), np.array([1, 0], np.uint8)
+        harness.pvbh_solve_lm(C.c_long(n), p(blk.type), p(blk.ref), p(blk.nei), p(blk.normalize), p(blk.huber), p(blk.consts), p(P2), C.c_int(2), p(mask), C.c_int(20), p(summ))
+        assert summ[2] == s1["iterations"] and summ[3] == s1["successful"]
+        assert np.abs(P1[1] - P2[1]).max() / np.abs(P1[1]).max() < 1e-8                           # gate: 1e-4 relative on pose deltas
+
+
+def test_float_paths_are_bit_exact(oracle, harness):
+    g = np.load(os.path.join(G, "fast_atan2.npz"))
+    yf, xf = g["y"].astype(np.float32), g["x"].astype(np.float32)
+    out = np.zeros_like(yf)
+    harness.pvbh_fast_atan2_f(C.c_long(len(yf)), p(yf), p(xf), p(out))
+    assert np.array_equal(out, oracle.fast_atan2(yf, xf))
+    outd = np.zeros_like(g["y"])
+    harness.pvbh_fast_atan2_d(C.c_long(len(outd)), p(np.ascontiguousarray(g["y"])), p(np.ascontiguousarray(g["x"])), p(outd))
+    assert np.array_equal(outd, oracle.fast_atan2(g["y"], g["x"]))
+    rng = np.random.default_rng(0)
+    cam = rng.normal(0, 5, (5000, 3)).astype(np.float32)
+    px = np.zeros((5000, 2), np.float32)
+    harness.pvbh_cam_to_image_f(C.c_int(2880), C.c_int(5760), C.c_long(5000), p(cam), p(px))
+    assert np.array_equal(px, oracle.cam_to_image(2880, 5760, cam))
+    a = np.load(os.path.join(G, "assoc_pair.npz"))
+    out = np.empty_like(a["ref_local"])
+    harness.pvbh_transform_cloud(p(np.ascontiguousarray(a["R_ref"])), p(np.ascontiguousarray(a["t_ref"])), p(np.ascontiguousarray(a["ref_local"])), C.c_int(len(out)), p(out))
+    assert np.array_equal(out, a["ref_world"])

@@ -1,0 +1,155 @@
+"""Pins the CPU oracle against the committed golden vectors (tests/golden/, produced by INDEPENDENT implementations:
+torch autograd twin, scipy, numpy) and against closed-form / finite-difference checks.
+The reference has no tests of its own for this path, so this file is what "oracle checked" means here."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_rotation_helpers_match_scipy_golden(oracle):
+    g = np.load(os.path.join(G, "rotations.npz"))
+    for aa, R in zip(g["aa"], g["R"]):
+        assert np.abs(oracle.aa_to_R(aa) - R).max() < 5e-15
+        back = oracle.R_to_aa(R)
+        # rotation vectors are unique below pi
+        if np.linalg.norm(aa) < 3.14:
+            assert np.abs(back - aa).max() < 1e-9 * max(1.0, 1.0 / (np.pi - np.linalg.norm(aa)))
+        p = np.array([0.3, -1.2, 2.0])
+        assert np.abs(oracle.aa_rotate(aa, p) - R @ p).max() < 5e-15
+
+
+def test_functors_match_autograd_twin_golden(oracle):
+    g = np.load(os.path.join(G, "functors.npz"))
+    b = oracle.Blocks(g["type"], g["ref"], g["nei"], g["consts"], g["huber"], g["normalize"])
+    r, J, _ = b.evaluate(g["poses"], apply_loss=False)
+    assert np.abs(r - g["residual"]).max() < 1e-12
+    scale = np.maximum(1e-9, np.abs(g["jacobian"]).max(axis=1, keepdims=True))
+    assert (np.abs(J - g["jacobian"]) / scale).max() < 1e-7    # first-order branch at |aa| = 1e-10 differs at O(theta)
+
+
+def test_jet_jacobian_matches_central_differences(oracle):
+    c = cases.random_blocks(11, 120)
+    b = oracle.Blocks(c["type"], c["ref"], c["nei"], c["consts"], 0.0, c["normalize"])
+    poses = c["poses"].copy()
+    poses[:3] = np.random.default_rng(5).normal(0, 0.3, (3, 6))     # keep away from the theta ~ 0 / pi branch switches
+    r0, J, _ = b.evaluate(poses, apply_loss=False)
+    h = 1e-6
+    for blk, cols in ((c["ref"], 0), (c["nei"], 6)):
+        for k in range(6):
+            num = np.zeros(len(r0))
+            for sgn in (1, -1):
+                # perturb per-block: evaluate with every pose block shifted, pick rows per their block (independent rows)
+                rr = np.zeros(len(r0))
+                for pb in range(c["nb"]):
+                    P = poses.copy(); P[pb, k] += sgn * h
+                    rk, _, _ = b.evaluate(P, apply_loss=False, jac=False)
+                    rr[blk == pb] = rk[blk == pb]
+                num += sgn * rr
+            num /= 2 * h
+            same = c["ref"] == c["nei"]                      # ref == nei rows: the two partials add up
+            ana = J[:, cols + k] + np.where(same, J[:, (6 - cols) + k], 0.0)
+            ok = np.abs(r0) > 1e-6                             # skip the clamped / zeroed branches
+            assert np.abs(num[ok] - ana[ok]).max() < 2e-5 * max(1.0, np.abs(ana[ok]).max())
+
+
+def test_zero_residual_branches_give_zero_rows(oracle):
+    c = cases.on_plane_blocks()
+    b = oracle.Blocks(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"])
+    r, J, _ = b.evaluate(c["poses"], apply_loss=False)
+    assert np.all(r == 0.0) and np.all(J == 0.0)
+
+
+def test_identity_poses_leave_points_unchanged(oracle):
+    consts = np.zeros((1, 12)); consts[0, :3] = [1, 2, 3]; consts[0, 3:7] = [0, 0, 1, -1.0]; consts[0, 7] = 1.0
+    b = oracle.Blocks([0], 0, 1, consts, 0.0, 1)
+    r, _, _ = b.evaluate(np.zeros((2, 6)), apply_loss=False)
+    assert abs(r[0] - 2.0) < 1e-15
+
+
+def test_huber_corrector(oracle):
+    consts = np.zeros((2, 12)); consts[:, :3] = [[0, 0, 1.05], [0, 0, 3.0]]; consts[:, 3:7] = [0, 0, 1, -1.0]; consts[:, 7] = 1.0
+    b = oracle.Blocks([0, 0], 0, 1, consts, 0.2, 1)
+    r, J, cost = b.evaluate(np.zeros((2, 6)), apply_loss=True)
+    assert abs(r[0] - 0.05) < 1e-15 and abs(cost[0] - 0.5 * 0.05 ** 2) < 1e-15          # inlier: untouched
+    s = 2.0 ** 2
+    assert abs(cost[1] - 0.5 * (2 * 0.2 * 2.0 - 0.04)) < 1e-14 and abs(r[1] - 2.0 * np.sqrt(0.2 / 2.0)) < 1e-14
+    assert abs(J[1, 11] - (-1.0) * np.sqrt(0.2 / np.sqrt(s))) < 1e-14                     # d/dt_n = -R_rn^T n scaled by sqrt(rho')
+
+
+def test_form_plane_and_line_match_numpy(oracle):
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        base = rng.normal(0, 5, 3) + 4 * n
+        u = np.cross(n, [1, 0, 0]); u /= np.linalg.norm(u); v = np.cross(n, u)
+        pts = base + rng.normal(0, 0.3, (10, 1)) * u + rng.normal(0, 0.3, (10, 1)) * v + rng.normal(0, 0.005, (10, 1)) * n
+        x = np.linalg.lstsq(pts, -np.ones(10), rcond=None)[0]
+        pl = oracle.form_plane(pts, 0.0)
+        assert np.abs(pl[:3] - x / np.linalg.norm(x)).max() < 1e-10 and abs(pl[3] - 1 / np.linalg.norm(x)) < 1e-10
+        assert np.all(oracle.form_plane(pts, 1e-6) == 0.0)      # tolerance violated -> zero vector
+        c = pts - pts.mean(0)
+        w, vec = np.linalg.eigh(c.T @ c)
+        ev, evec = oracle.sym_eig3(c.T @ c)
+        assert np.abs(ev - w).max() < 1e-10 * max(1.0, w.max())
+        ok, line = oracle.form_line(pts, 3.0)
+        assert ok == bool(w[2] > 3.0 * w[1])
+    line_pts = np.array([[0, 0, 0.0], [1, 1, 1], [2, 2, 2.001], [3, 3, 3]])
+    ok, line = oracle.form_line(line_pts, 10.0, 0.05)
+    assert ok and abs(abs(line[3:] @ np.ones(3) / np.sqrt(3)) - 1) < 1e-6
+
+
+def test_fast_atan2_error_bound_and_branches(oracle):
+    g = np.load(os.path.join(G, "fast_atan2.npz"))
+    got = oracle.fast_atan2(g["y"], g["x"])
+    assert np.abs(got - g["atan2"]).max() < 1.7e-4                 # measured max error 1.67e-4 rad
+    gotf = oracle.fast_atan2(g["y"].astype(np.float32), g["x"].astype(np.float32))
+    assert gotf.dtype == np.float32 and np.abs(gotf - g["atan2"]).max() < 1.8e-4
+
+
+def test_knn_kdtree_equals_brute_force_and_ckdtree_golden(oracle):
+    g = np.load(os.path.join(G, "assoc_pair.npz"))
+    idx_b, d2_b = oracle.knn(g["ref_world"], g["nei_world"], 10, use_kdtree=False)
+    idx_k, d2_k = oracle.knn(g["ref_world"], g["nei_world"], 10, use_kdtree=True)
+    assert np.array_equal(idx_b, idx_k) and np.array_equal(d2_b, d2_k)
+    assert np.all(np.diff(d2_b, axis=1) >= 0)
+    same = [set(a) == set(b) for a, b in zip(idx_b, g["knn_idx"])]
+    assert np.mean(same) == 1.0
+
+
+def test_transform_cloud_is_double_math_float_store(oracle):
+    g = np.load(os.path.join(G, "assoc_pair.npz"))
+    assert np.array_equal(oracle.transform_cloud(g["R_ref"], g["t_ref"], g["ref_local"]), g["ref_world"])
+    assert np.array_equal(oracle.transform_cloud(g["R_nei"], g["t_nei"], g["nei_local"]), g["nei_world"])
+
+
+def test_associate_point2plane_matches_golden(oracle):
+    g = np.load(os.path.join(G, "assoc_pair.npz"))
+    for kd in (True, False):
+        q, pt, pl = oracle.associate_p2plane(g["ref_world"], g["R_ref"], g["t_ref"], g["nei_world"], g["R_nei"], g["t_nei"], float(g["tol"]), float(g["thr"]), int(g["k"]), kd)
+        assert np.array_equal(q, g["query"])
+        assert np.abs(pl - g["plane"]).max() < 1e-9 and np.abs(pt - g["point"]).max() < 1e-12
+
+
+def test_lm_recovers_relative_pose(oracle):
+    from panovlm_b200 import synth
+    from scipy.spatial.transform import Rotation
+    A, B = synth.make_pair(seed=5, n_az=900)
+    refw = oracle.transform_cloud(A["R_wl"], A["t_wl"], A["surfLessFlat"])
+    poses = np.zeros((2, 6))
+    for it in range(4):                                            # re-associate like LidarOdometry.cpp:166-183
+        R_nei = oracle.aa_to_R(poses[1, :3]).T
+        t_nei = -R_nei @ poses[1, 3:]
+        neiw = oracle.transform_cloud(R_nei, t_nei, B["surfFlat"])
+        q, pt, pl = oracle.associate_p2plane(refw, A["R_wl"], A["t_wl"], neiw, R_nei, t_nei, 0.05, 1.0, 10, True)
+        consts = np.zeros((len(q), 12)); consts[:, :3] = pt; consts[:, 3:7] = pl; consts[:, 7] = 1.0
+        blk = oracle.Blocks(np.full(len(q), oracle.P2PLANE_METER), 0, 1, consts, 0.2, 1)
+        poses, s = blk.solve_lm(poses, is_const=[1, 0], max_iter=20)
+        assert s["final_cost"] <= s["initial_cost"]
+    R_lw = B["R_wl"].T
+    assert np.abs(poses[1, :3] - Rotation.from_matrix(R_lw).as_rotvec()).max() < 3e-3
+    assert np.abs(poses[1, 3:] - (-R_lw @ B["t_wl"])).max() < 2e-2
