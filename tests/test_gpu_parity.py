@@ -1,0 +1,362 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C ABI (ctypes mirror) and is
+compared with the CPU oracle on the same seeded inputs; bars: bit-exact for integer / index / float32 work,
+1e-5 relative on residuals, 1e-6 on Jacobian rows, 1e-4 on pose deltas (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+RES_RTOL, JAC_RTOL, POSE_RTOL = 1e-5, 1e-6, 1e-4
+
+
+def _rel(a, b, floor):
+    return np.abs(a - b) / np.maximum(floor, np.abs(b))
+
+
+# ---------------------------------------------------------------- A. correspondence-list mode (K3 + K4)
+def test_blocks_rows_match_oracle(gpu_ctx, oracle):
+    c = cases.random_blocks(1, 20000)
+    b = oracle.Blocks(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"])
+    r, J, cost = b.evaluate(c["poses"], apply_loss=True)
+    gpu_ctx.blocks_set(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"], c["nb"])
+    gpu_ctx.blocks_evaluate(c["poses"], want_rows=True, want_system=True)
+    r2, J2 = gpu_ctx.blocks_rows()
+    assert _rel(r2, r, 1e-9).max() < RES_RTOL
+    assert (np.abs(J2 - J).max(1) / np.maximum(1e-12, np.abs(J).max(1))).max() < JAC_RTOL
+    c2, n2 = gpu_ctx.blocks_cost()
+    assert n2 == len(r) and abs(c2 - cost.sum()) < 1e-9 * cost.sum()
+    H, g, cst = b.normal_equations(c["poses"])
+    H2, g2, cst2 = gpu_ctx.blocks_dense_system()
+    assert np.abs(H2 - H).max() < 1e-9 * np.abs(H).max() and np.abs(g2 - g).max() < 1e-9 * np.abs(g).max()
+    assert np.allclose(H2, H2.T)
+
+
+def test_blocks_golden_functors_and_zero_rows(gpu_ctx):
+    g = np.load(os.path.join(G, "functors.npz"))
+    gpu_ctx.blocks_set(g["type"], g["ref"], g["nei"], g["consts"], 0.0, g["normalize"], int(g["nb"]))
+    gpu_ctx.blocks_evaluate(g["poses"], True, False)
+    r, J = gpu_ctx.blocks_rows()
+    assert _rel(r, g["residual"], 1e-9).max() < RES_RTOL
+    assert (np.abs(J - g["jacobian"]).max(1) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1))).max() < JAC_RTOL
+    c = cases.on_plane_blocks()
+    gpu_ctx.blocks_set(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"], c["nb"])
+    gpu_ctx.blocks_evaluate(c["poses"], True, True)
+    r, J = gpu_ctx.blocks_rows()
+    assert np.all(r == 0) and np.all(J == 0)
+
+
+def test_blocks_deterministic_and_edge_grouping(gpu_ctx):
+    c = cases.random_blocks(3, 5000, nb=5)
+    gpu_ctx.blocks_set(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"], c["nb"])
+    gpu_ctx.blocks_evaluate(c["poses"], False, True)
+    er, en, s1 = gpu_ctx.blocks_edges()
+    gpu_ctx.blocks_evaluate(c["poses"], False, True)
+    _, _, s2 = gpu_ctx.blocks_edges()
+    assert np.array_equal(s1, s2)                                          # fixed reduction order: run-to-run identical
+    assert len(set(zip(er.tolist(), en.tolist()))) == len(er)
+    assert s1[:, 91].sum() == 5000
+
+
+def test_blocks_empty_and_bad_arguments(gpu_ctx):
+    import panovlm_b200
+    gpu_ctx.blocks_set(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 12)), np.zeros(0), np.zeros(0, np.int32), 2)
+    gpu_ctx.blocks_evaluate(np.zeros((2, 6)), True, True)
+    assert gpu_ctx.blocks_cost() == (0.0, 0)
+    with pytest.raises(panovlm_b200.PvbError):
+        gpu_ctx.blocks_set([0], [0], [7], np.zeros((1, 12)), [0.0], [1], 2)      # pose index out of range
+    with pytest.raises(panovlm_b200.PvbError):
+        gpu_ctx.blocks_set([9], [0], [1], np.zeros((1, 12)), [0.0], [1], 2)      # unknown functor
+
+
+def test_lm_pose_deltas_match_oracle(gpu_ctx, oracle):
+    g = np.load(os.path.join(G, "assoc_pair.npz"))
+    n = len(g["query"])
+    consts = np.zeros((n, 12)); consts[:, :3] = g["point"]; consts[:, 3:7] = g["plane"]; consts[:, 7] = 1.0
+    for bt, hub in ((1, 2 * np.pi / 180), (0, 0.2)):
+        blk = oracle.Blocks(np.full(n, bt), 0, 1, consts, hub, 1)
+        P1, s1 = blk.solve_lm(np.zeros((2, 6)), is_const=[1, 0], max_iter=20)
+        gpu_ctx.blocks_set(blk.type, blk.ref, blk.nei, blk.consts, blk.huber, blk.normalize, 2)
+        P2, s2 = gpu_ctx.blocks_solve_lm(np.zeros((2, 6)), is_const=[1, 0], max_iterations=20)
+        assert s2["iterations"] == s1["iterations"] and s2["successful"] == s1["successful"]
+        assert abs(s2["final_cost"] - s1["final_cost"]) < 1e-8 * s1["final_cost"]
+        assert (np.abs(P1[1] - P2[1]) / np.abs(P1[1]).max()).max() < POSE_RTOL
+
+
+def test_lm_multi_frame_pose_graph(gpu_ctx, oracle):
+    """4-frame pose graph, first frame constant (LidarOdometry.cpp:59-66), mixed plane + line residuals."""
+    rng = np.random.default_rng(4)
+    nb, n = 4, 4000
+    truth = np.concatenate([rng.normal(0, 0.05, (nb, 3)), rng.normal(0, 0.3, (nb, 3))], axis=1); truth[0] = 0
+    ref = rng.integers(0, nb, n).astype(np.int32); nei = ((ref + rng.integers(1, nb, n)) % nb).astype(np.int32)
+    typ = rng.choice([0, 1, 2, 3], n).astype(np.int32)
+    consts = np.zeros((n, 12))
+    from scipy.spatial.transform import Rotation
+    for i in range(n):
+        pw = rng.normal(0, 4, 3)                                    # a world point seen from both frames
+        Rr, tr = Rotation.from_rotvec(truth[ref[i], :3]).as_matrix(), truth[ref[i], 3:]
+        Rn, tn = Rotation.from_rotvec(truth[nei[i], :3]).as_matrix(), truth[nei[i], 3:]
+        p_ref, p_nei = Rr @ pw + tr, Rn @ pw + tn
+        consts[i, :3] = p_nei + rng.normal(0, 0.01, 3)
+        if typ[i] < 2:
+            nrm = rng.normal(size=3); nrm /= np.linalg.norm(nrm)
+            d = -nrm @ p_ref
+            if d < 0: nrm, d = -nrm, -d
+            consts[i, 3:6] = nrm; consts[i, 6] = d; consts[i, 7] = 1.0
+        else:
+            dr = rng.normal(size=3); dr /= np.linalg.norm(dr)
+            consts[i, 3:6] = p_ref + 0.3 * dr; consts[i, 6:9] = dr; consts[i, 9] = 1.0
+    hub = np.where(typ % 2 == 1, 2 * np.pi / 180, 0.2)
+    blk = oracle.Blocks(typ, ref, nei, consts, hub, 1)
+    start = truth + np.concatenate([rng.normal(0, 0.01, (nb, 3)), rng.normal(0, 0.03, (nb, 3))], axis=1); start[0] = 0
+    mask = [1, 0, 0, 0]
+    P1, s1 = blk.solve_lm(start, is_const=mask, max_iter=20)
+    gpu_ctx.blocks_set(typ, ref, nei, consts, hub, 1, nb)
+    P2, s2 = gpu_ctx.blocks_solve_lm(start, is_const=mask, max_iterations=20)
+    assert s1["final_cost"] < 0.2 * s1["initial_cost"]
+    assert abs(s2["final_cost"] - s1["final_cost"]) < 1e-7 * s1["final_cost"]
+    d1, d2 = P1 - start, P2 - start
+    assert np.abs(d1 - d2).max() < POSE_RTOL * np.abs(d1).max()
+
+
+# ---------------------------------------------------------------- B. frames: T1 + K2p (emit)
+def _pair_frames(seed=20260925, n_az=900, ground=True):
+    from panovlm_b200 import synth
+    return synth.make_pair(seed=seed, n_az=n_az, ground_class=ground)
+
+
+def test_frames_knn_bit_exact(gpu_ctx, oracle):
+    g = np.load(os.path.join(G, "assoc_pair.npz"))
+    from scipy.spatial.transform import Rotation
+    poses = np.zeros((2, 6))                                       # frame 0 = A (identity pose in the fixture), frame 1 = B at identity
+    R_lw = g["R_ref"].T
+    poses[0, :3] = Rotation.from_matrix(R_lw).as_rotvec(); poses[0, 3:] = -R_lw @ g["t_ref"]
+    gpu_ctx.frames_set([g["ref_local"], g["nei_local"]], [g["nei_local"], g["nei_local"]])
+    for k, thr, cell in ((10, 1.0, 0.0), (10, 1.0, 0.25), (5, 0.3, 0.11)):
+        idx, d2 = gpu_ctx.frames_knn(poses, 0, 1, len(g["nei_local"]), thr, k, cell)
+        oi, od = oracle.knn(g["ref_world"], g["nei_world"], k, False)
+        full = od[:, k - 1] <= np.float32(thr) * np.float32(thr)
+        assert np.array_equal(d2[full], od[full])                  # float32 squared distances, bit for bit
+        assert np.array_equal(idx[full], oi[full])
+        assert np.all(idx[~full][:, k - 1] == -1)
+
+
+def test_frames_associate_matches_golden_and_oracle(gpu_ctx, oracle):
+    g = np.load(os.path.join(G, "assoc_pair.npz"))
+    poses = np.zeros((2, 6))
+    gpu_ctx.frames_set([g["ref_local"], g["nei_local"]], [g["nei_local"], g["nei_local"]])
+    e, q, pt, pl = gpu_ctx.frames_associate_point2plane(poses, [0], [1], float(g["tol"]), float(g["thr"]), int(g["k"]))
+    assert np.array_equal(q, g["query"]) and np.all(e == 0)
+    assert np.abs(pl - g["plane"]).max() < 1e-9 and np.abs(pt - g["point"]).max() < 1e-12
+
+
+def test_frames_pose_graph_edges(gpu_ctx, oracle):
+    """6 frames with non-trivial poses, all ordered edges: same correspondences as the reference loop
+    (util/Optimization.cpp:521-557) builds one pair at a time."""
+    from panovlm_b200 import synth
+    from scipy.spatial.transform import Rotation
+    frames = synth.make_sequence(6, n_az=600)
+    rng = np.random.default_rng(0)
+    poses = np.zeros((6, 6))
+    Rs, ts = [], []
+    for f, fr in enumerate(frames):
+        R = fr["R_wl"] @ Rotation.from_rotvec(rng.normal(0, 0.01, 3)).as_matrix()      # perturbed estimate
+        t = fr["t_wl"] + rng.normal(0, 0.03, 3)
+        R_lw = R.T
+        poses[f, :3] = Rotation.from_matrix(R_lw).as_rotvec(); poses[f, 3:] = -R_lw @ t
+    for f in range(6):                                            # what the library derives from the blocks
+        R_wl = oracle.aa_to_R(poses[f, :3]).T
+        Rs.append(R_wl); ts.append(-R_wl @ poses[f, 3:])
+    gpu_ctx.frames_set([f["surfLessFlat"] for f in frames], [f["surfFlat"] for f in frames])
+    ref = np.array([i for i in range(6) for j in range(6) if i != j], np.int32)
+    nei = np.array([j for i in range(6) for j in range(6) if i != j], np.int32)
+    e, q, pt, pl = gpu_ctx.frames_associate_point2plane(poses, ref, nei, 0.05, 1.0, 10)
+    world_t = [oracle.transform_cloud(Rs[f], ts[f], frames[f]["surfLessFlat"]) for f in range(6)]
+    world_q = [oracle.transform_cloud(Rs[f], ts[f], frames[f]["surfFlat"]) for f in range(6)]
+    total = 0
+    for ei, (i, j) in enumerate(zip(ref, nei)):
+        oq, opt, opl = oracle.associate_p2plane(world_t[i], Rs[i], ts[i], world_q[j], Rs[j], ts[j], 0.05, 1.0, 10, True)
+        m = e == ei
+        assert np.array_equal(q[m], oq)
+        if len(oq):
+            assert np.abs(pl[m] - opl).max() < 1e-9 and np.abs(pt[m] - opt).max() < 1e-9
+        total += len(oq)
+    assert total == len(e) and total > 500
+
+
+def test_frames_edge_cases(gpu_ctx):
+    import panovlm_b200
+    few = np.array([[0, 0, 1, 1], [0.1, 0, 1, 1], [0, 0.1, 1, 1]], np.float32)              # fewer than k targets (quirk C.6 guard)
+    qs = np.array([[0, 0, 1.01, 1]], np.float32)
+    gpu_ctx.frames_set([few, np.zeros((0, 4), np.float32)], [qs, qs])
+    e, q, pt, pl = gpu_ctx.frames_associate_point2plane(np.zeros((2, 6)), [0, 1], [1, 0], 0.05, 1.0, 10)
+    assert len(e) == 0
+    with pytest.raises(panovlm_b200.PvbError):
+        gpu_ctx.frames_associate_point2plane(np.zeros((2, 6)), [0], [5], 0.05, 1.0, 10)
+    with pytest.raises(panovlm_b200.PvbError):
+        gpu_ctx.frames_associate_point2plane(np.zeros((2, 6)), [0], [1], 0.05, 1.0, 7)
+
+
+# ---------------------------------------------------------------- C. dense fused sweep (K2p reduce + K4)
+@pytest.fixture(scope="module")
+def dense_small():
+    from panovlm_b200 import synth
+    return synth.make_dense_sweep(n_target=200_000, n_frames=4, pts_per_frame=5000, seed=11)
+
+
+def test_dense_rows_and_systems_match_oracle(gpu_ctx, oracle, dense_small):
+    d = dense_small
+    gpu_ctx.dense_set_target(d["target"])
+    gpu_ctx.dense_set_sources(d["src_local"], d["src_off"])
+    for rtype, hub, k, thr in ((0, 0.2, 10, 1.0), (1, 2 * np.pi / 180, 10, 0.3), (0, 0.2, 5, 0.3)):
+        prm = gpu_ctx.dense_params(plane_tolerance=0.05, dist_threshold=thr, k=k, residual_type=rtype, normalize=1, huber=hub, weight=1.0)
+        sys_gpu = gpu_ctx.dense_evaluate(d["poses_lw_init"], prm)
+        valid, pt, pl, r, j6 = gpu_ctx.dense_get_rows(d["poses_lw_init"], prm)
+        nf = len(d["src_off"]) - 1
+        tot = 0
+        for f in range(nf):
+            lo, hi = d["src_off"][f], d["src_off"][f + 1]
+            R_wl = oracle.aa_to_R(d["poses_lw_init"][f, :3]).T
+            t_wl = -R_wl @ d["poses_lw_init"][f, 3:]
+            w = oracle.transform_cloud(R_wl, t_wl, d["src_local"][lo:hi])
+            oq, opt, opl = oracle.associate_p2plane(d["target"], np.eye(3), np.zeros(3), w, R_wl, t_wl, 0.05, thr, k, True)
+            gq = np.nonzero(valid[lo:hi])[0]
+            assert np.array_equal(gq, oq)                                             # identical association sets
+            assert np.abs(pl[lo:hi][gq] - opl).max() < 1e-9 and np.abs(pt[lo:hi][gq] - opt).max() < 1e-9
+            consts = np.zeros((len(oq), 12)); consts[:, :3] = opt; consts[:, 3:7] = opl; consts[:, 7] = 1.0
+            blk = oracle.Blocks(np.full(len(oq), rtype), 0, 1, consts, hub, 1)
+            poses2 = np.stack([np.zeros(6), d["poses_lw_init"][f]])
+            ro, Jo, co = blk.evaluate(poses2, apply_loss=True)
+            assert _rel(r[lo:hi][gq], ro, 1e-9).max() < RES_RTOL
+            assert (np.abs(j6[lo:hi][gq] - Jo[:, 6:]).max(1) / np.maximum(1e-12, np.abs(Jo[:, 6:]).max(1))).max() < JAC_RTOL
+            H = Jo[:, 6:].T @ Jo[:, 6:]; gvec = Jo[:, 6:].T @ ro
+            iu = np.triu_indices(6)
+            assert np.abs(sys_gpu[f, :21] - H[iu]).max() < 1e-9 * np.abs(H).max()
+            assert np.abs(sys_gpu[f, 21:27] - gvec).max() < 1e-9 * max(1e-30, np.abs(gvec).max())
+            assert abs(sys_gpu[f, 27] - co.sum()) < 1e-9 * co.sum() and sys_gpu[f, 28] == len(oq)
+            tot += len(oq)
+        assert tot > 0.25 * len(valid)      # FormLine's 3:1 elongation test rejects a large share of random 10-NN sets
+
+
+def test_dense_matches_oracle_sweep_entry_point(gpu_ctx, oracle, dense_small):
+    """The timed CPU baseline (pvo_dense_icp_eval) and the fused GPU sweep produce the same reduced systems."""
+    d = dense_small
+    gpu_ctx.dense_set_target(d["target"])
+    gpu_ctx.dense_set_sources(d["src_local"], d["src_off"])
+    prm = gpu_ctx.dense_params(0.05, 1.0, 10, 0, 1, 0.2, 1.0)
+    s_gpu = gpu_ctx.dense_evaluate(d["poses_lw_init"], prm)
+    for mode in (0, 1):
+        s_cpu, times, n = oracle.dense_icp_eval(d["target"], d["src_local"], d["src_off"], d["poses_lw_init"], 0.05, 1.0, 10, 0.2, 1.0, mode)
+        assert np.array_equal(s_cpu[:, 28], s_gpu[:, 28]) and n == s_gpu[:, 28].sum()
+        assert np.abs(s_cpu - s_gpu).max() < 1e-8 * np.abs(s_cpu).max()
+    s_again = gpu_ctx.dense_evaluate(d["poses_lw_init"], prm)
+    assert np.array_equal(s_gpu, s_again)                                             # deterministic reduction
+
+
+def test_dense_gauss_newton_converges_to_true_poses(gpu_ctx, dense_small):
+    d = dense_small
+    gpu_ctx.dense_set_target(d["target"])
+    gpu_ctx.dense_set_sources(d["src_local"], d["src_off"])
+    prm = gpu_ctx.dense_params(0.05, 1.0, 10, 0, 1, 0.2, 1.0)
+    poses = d["poses_lw_init"].copy()
+    costs = []
+    for it in range(8):
+        s = gpu_ctx.dense_evaluate(poses, prm)
+        costs.append(s[:, 27].sum())
+        poses = gpu_ctx.dense_gauss_newton_step(s, poses, 1e-6)
+    assert costs[-1] < 0.2 * costs[0]
+    err0 = np.abs(d["poses_lw_init"] - d["poses_lw_true"]).max(0)
+    err = np.abs(poses - d["poses_lw_true"]).max(0)
+    assert err[:3].max() < 2e-3 and err[3:].max() < 2e-2 and err.max() < err0.max()
+
+
+def test_dense_full_size_properties(gpu_ctx):
+    """Size-independent properties at a large size the CPU oracle cannot sweep in seconds: every source point is an
+    exact copy of a target point moved by a known rigid transform => at the true pose the point-to-plane residual of
+    every accepted query is ~0 and the reduced gradient vanishes; counts are invariant to the tile decomposition."""
+    from panovlm_b200 import synth
+    rng = np.random.default_rng(5)
+    n_t, nf, per = 2_000_000, 8, 100_000
+    tgt = np.concatenate([synth.sample_floor_plan(n_t, rng, xlim=(0, 40.0)), np.ones((n_t, 1))], axis=1).astype(np.float32)
+    from scipy.spatial.transform import Rotation
+    src, off, poses = [], [0], []
+    for f in range(nf):
+        pick = rng.choice(n_t, per, replace=False)
+        R, t = Rotation.from_rotvec(rng.normal(0, 0.05, 3)).as_matrix(), np.array([20.0, 25, 2]) + rng.normal(0, 1, 3)
+        pl = (tgt[pick, :3].astype(np.float64) - t) @ R
+        src.append(np.concatenate([pl, np.ones((per, 1))], axis=1).astype(np.float32)); off.append(off[-1] + per)
+        poses.append(np.concatenate([Rotation.from_matrix(R.T).as_rotvec(), -R.T @ t]))
+    src, poses = np.concatenate(src), np.array(poses)
+    gpu_ctx.dense_set_target(tgt)
+    gpu_ctx.dense_set_sources(src, np.array(off, np.int32))
+    prm = gpu_ctx.dense_params(0.05, 0.3, 10, 0, 1, 0.0, 1.0)
+    s = gpu_ctx.dense_evaluate(poses, prm)
+    assert s[:, 28].sum() > 0.25 * nf * per
+    rms = np.sqrt(2 * s[:, 27] / s[:, 28])
+    assert rms.max() < 2e-3                                                            # float32 round trip of the copies only
+    H = np.zeros((nf, 6, 6)); iu = np.triu_indices(6)
+    for f in range(nf):
+        H[f][iu] = s[f, :21]
+        w = np.linalg.eigvalsh(H[f] + H[f].T - np.diag(np.diag(H[f])))
+        assert w.min() > 0                                                             # J^T J is positive definite
+    # a rigid shift of ALL inputs leaves the association counts unchanged only if the search is exact:
+    s2 = gpu_ctx.dense_evaluate(poses, gpu_ctx.dense_params(0.05, 0.3, 5, 0, 1, 0.0, 1.0))
+    assert np.all(s2[:, 28] >= s[:, 28] * 0.9)
+
+
+# ---------------------------------------------------------------- D/E/F. projection and vote kernels (bit-exact)
+def test_projection_bit_exact(gpu_ctx, oracle):
+    from panovlm_b200 import synth
+    from scipy.spatial.transform import Rotation
+    A, _ = _pair_frames(n_az=1800)
+    T = np.eye(4); T[:3, :3] = Rotation.from_rotvec([0.02, -1.3, 0.01]).as_matrix(); T[:3, 3] = [0.05, -0.1, 0.02]
+    uvd = gpu_ctx.project_equirect(A["cloud"], T, 2880, 5760)
+    img_o, uvd_o = oracle.project_depth(A["cloud"], 2880, 5760, T, size=3)
+    assert np.array_equal(uvd, uvd_o)                                                  # FastAtan2 float path, bit for bit
+    img = gpu_ctx.project_depth_image(A["cloud"], T, 2880, 5760, 3)
+    assert np.array_equal(img, img_o) and (img > 0).sum() > 10000
+    img4 = gpu_ctx.project_depth_image(A["cloud"], T, 1440, 2880, 4)                   # SfM::ComputeDepthImage: half-res, size 4
+    img4_o, _ = oracle.project_depth(A["cloud"], 1440, 2880, T, size=4)
+    assert np.array_equal(img4, img4_o)
+    assert gpu_ctx.project_equirect(np.zeros((0, 4), np.float32), T, 100, 200).shape == (0, 3)
+
+
+def test_line_votes_and_associations(gpu_ctx, oracle):
+    A, B = _pair_frames(n_az=1800)
+    RB, tB = np.eye(3), np.zeros(3)
+    ref_lines_w = oracle.transform_lines(A["R_wl"], A["t_wl"], A["segment_coeffs"])
+    nei_lines_w = oracle.transform_lines(RB, tB, B["segment_coeffs"])
+    nei_w = oracle.transform_cloud(RB, tB, B["cornerLessSharp"])
+    for thr in (0.3, 0.4, 0.05):
+        M = gpu_ctx.line_votes(ref_lines_w, nei_w, B["p2s_off"], B["p2s_ids"], len(B["segment_coeffs"]), thr)
+        Mo = oracle.line_votes(ref_lines_w, nei_w, B["p2s_off"], B["p2s_ids"], len(B["segment_coeffs"]), thr)
+        assert np.array_equal(M, Mo)
+    assert Mo.shape == (len(B["segment_coeffs"]), len(A["segment_coeffs"]))
+    M = gpu_ctx.line_votes(ref_lines_w, nei_w, B["p2s_off"], B["p2s_ids"], len(B["segment_coeffs"]), 0.3)
+    sizes = np.diff(B["seg_off"])
+    on, orf, oa, ob = oracle.find_associations(A["segment_coeffs"], ref_lines_w, nei_lines_w, sizes, M)
+    assert len(on) >= 5 and len(set(orf.tolist())) == len(orf)
+
+
+def test_angle_votes_bit_exact(gpu_ctx, oracle):
+    from scipy.spatial.transform import Rotation
+    A, _ = _pair_frames(n_az=1800)
+    rows, cols = 2880, 5760
+    T = np.eye(4); T[:3, :3] = Rotation.from_rotvec([0.01, 0.02, -0.01]).as_matrix(); T[:3, 3] = [0.03, -0.05, 0.02]
+    # image lines = projections of the LiDAR segments' end points (+ noise) plus random clutter lines
+    rng = np.random.default_rng(9)
+    ends_cam = A["end_points"].reshape(-1, 3) @ T[:3, :3].T + T[:3, 3]
+    px = oracle.cam_to_image(rows, cols, ends_cam).reshape(-1, 4) + rng.normal(0, 2, (len(A["end_points"]), 4))
+    clutter = np.stack([rng.uniform(0, cols, 30), rng.uniform(0, rows, 30), rng.uniform(0, cols, 30), rng.uniform(0, rows, 30)], axis=1)
+    lines = np.concatenate([px, clutter]).astype(np.float32)
+    S = len(A["segment_coeffs"])
+    cnt = gpu_ctx.angle_votes(rows, cols, lines, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], S, T)
+    cnt_o = oracle.angle_votes(rows, cols, lines, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], S, T)
+    assert np.array_equal(cnt, cnt_o) and cnt.sum() > 50
+    sizes = np.diff(A["seg_off"])
+    oi, ol, s, e, ang = oracle.associate_by_angle(rows, cols, lines, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], sizes, A["end_points"], T, True)
+    assert len(oi) >= 3 and np.all(oi < len(px))                                        # true lines pair up, clutter does not
