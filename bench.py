@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — residual-evaluations/sec of the fused correspondence-and-residual hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[4], the dense ICP sweep the metric's 1/2/4/8-GPU clause and the
+HBM-roofline target are quoted on: a 10,000,000-point target cloud (float32, 200x50x4 m multi-room floor plan) and
+64 source frames x 156,250 points per GPU; one *step* = one Gauss-Newton iteration = for every source point: SE(3)
+transform (float32 store) -> exact 10-NN on the cell-sorted target -> class test -> LSQ plane fit + collinearity test
+-> Point2Plane_Meter residual + analytic Jacobian + Huber -> per-frame 6x6 normal equations -> (N>1: one NCCL
+allreduce of the packed 6x6/6x1 blocks) -> 64 tiny solves + pose update on the host.
+One residual evaluation = one source point at one pose estimate (points x iterations).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm   (torchrun for N>1)
+  python bench.py --impl reference ...                           the reference algorithm on the host cores (oracle port)
+
+Multi-GPU: source frames shard across ranks (each rank owns 64 frames: weak scaling), the target is replicated, the
+only exchange is the allreduce of the reduced systems.  Synthetic data, seeds fixed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG_PER_QUERY = {10: 176.0, 5: 96.0}   # bytes: query 16 + k*16 target records, reduced-output mode
+HBM_FALLBACK_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-target", type=int, default=10_000_000)
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--pts-per-frame", type=int, default=156_250)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--radius", type=float, default=1.0)
+    ap.add_argument("--cpu-sample-frames", type=int, default=2, help="source frames in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (recipe's clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_data(args, rank):
+    from panovlm_b200 import synth
+    # the target is identical on every rank (same seed); each rank owns its own source frames
+    return synth.make_dense_sweep(n_target=args.n_target, n_frames=args.frames, pts_per_frame=args.pts_per_frame, seed=20260929,
+                                  source_seed=20260930 + 1000 * rank)
+
+
+def cpu_baseline(args, d, steps=1, mode=1, tree=None, build_s=0.0):
+    """The oracle port of the reference algorithm on a bounded sample of the same workload (same target, first
+    `cpu_sample_frames` source frames), kd-tree prebuilt (the GPU path also builds its grid once, outside the step)."""
+    from oracle import pvo
+    nf = min(args.cpu_sample_frames, args.frames)
+    off = d["src_off"][: nf + 1]
+    if tree is None:
+        t0 = time.time()
+        tree = pvo.KdTreeHandle(d["target"])
+        build_s = time.time() - t0
+    times, n_assoc = [], 0
+    for _ in range(steps):
+        t0 = time.time()
+        _, tt, n_assoc = pvo.dense_icp_eval(d["target"], d["src_local"][: off[-1]], off, d["poses_lw_init"][:nf], 0.05, args.radius, args.k, 0.2, 1.0, mode, tree)
+        times.append(time.time() - t0)
+    evals = int(off[-1])
+    return {"evals": evals, "seconds": float(np.median(times)), "per_step": times, "kdtree_build_s": build_s, "n_assoc": int(n_assoc),
+            "threads": pvo.num_threads(), "frames": nf, "tree": tree}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d = make_data(args, 0)
+    from oracle import pvo
+    nf = min(args.cpu_sample_frames, args.frames)
+    off = d["src_off"][: nf + 1]
+    tree = pvo.KdTreeHandle(d["target"])
+    per = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.time()
+        pvo.dense_icp_eval(d["target"], d["src_local"][: off[-1]], off, d["poses_lw_init"][:nf], 0.05, args.radius, args.k, 0.2, 1.0, 1, tree)
+        if it >= args.warmup:
+            per.append(time.time() - t0)
+    total = sum(per)
+    value = int(off[-1]) * args.steps / total
+    sample = f"{nf} of {args.frames} source frames ({int(off[-1])} points) per step against the full {args.n_target}-point target, kd-tree prebuilt"
+    line = {"impl": "reference", "metric": "residual_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args),
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": pvo.num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args):
+    return {"workload": f"configs[4]: dense ICP sweep, {args.n_target}-pt target, {args.frames} source frames x {args.pts_per_frame} pts per GPU, "
+                        f"k={args.k}, radius={args.radius} m, plane_tol=0.05, Point2Plane_Meter + Huber(0.2), per-frame 6x6 reduce",
+            "n_target": args.n_target, "frames_per_gpu": args.frames, "pts_per_frame": args.pts_per_frame, "k": args.k, "radius_m": args.radius,
+            "l2": "inputs (160 MB target records + 160 MB queries + cell table) exceed the 126 MB L2; no explicit flush",
+            "parallelism": "frames sharded across GPUs (weak), target replicated, one allreduce of the packed 6x6/6x1 blocks per step"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import panovlm_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    d = make_data(args, rank)
+    nq = int(d["src_off"][-1])
+
+    ctx = panovlm_b200.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)          # library work, torch events and NCCL all on one stream
+    ctx.dense_set_target(d["target"])
+    src_pinned = torch.from_numpy(d["src_local"]).pin_memory()
+    ctx.dense_set_sources_ptr(src_pinned.data_ptr(), d["src_off"])
+    prm = ctx.dense_params(0.05, args.radius, args.k, panovlm_b200.P2PLANE_METER, 1, 0.2, 1.0)
+    nf = args.frames
+    sys_all = torch.zeros((world * nf, 29), dtype=torch.float64, device="cuda")     # packed normal-equation blocks of ALL ranks
+    my_ptr = sys_all.data_ptr() + rank * nf * 29 * 8
+    sys_host = torch.zeros((world * nf, 29), dtype=torch.float64).pin_memory()
+
+    def gn_step(poses):
+        """one Gauss-Newton iteration, inputs resident in HBM"""
+        if world > 1:
+            sys_all.zero_()
+        ctx.dense_evaluate_device(poses, prm, my_ptr)
+        if world > 1:
+            dist.all_reduce(sys_all)                  # the single exchange step: 6x6/6x1 blocks of every frame
+        sys_host.copy_(sys_all, non_blocking=True)
+        stream.synchronize()
+        mine = sys_host[rank * nf:(rank + 1) * nf].numpy()
+        return ctx.dense_gauss_newton_step(mine, poses, 1e-6), mine
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident value: W warm-up + K timed GN iterations
+    poses = d["poses_lw_init"].copy()
+    for _ in range(args.warmup):
+        poses, _ = gn_step(poses)
+    poses = d["poses_lw_init"].copy()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    l0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, costs = [], []
+    e0.record()
+    for _ in range(args.steps):
+        poses, mine = gn_step(poses)
+        kernel_ms.append(ctx.dense_kernel_time_ms())
+        costs.append(float(mine[:, 27].sum()))
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    if rank == 0:
+        sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * nq * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: the same iteration through the C ABI with HOST buffers (source clouds + poses H2D, systems D2H)
+    e2e = None
+    if not args.no_e2e:
+        poses_e = d["poses_lw_init"].copy()
+
+        def e2e_step(p):
+            ctx.dense_set_sources_ptr(src_pinned.data_ptr(), d["src_off"])       # H2D of this step's source clouds + re-ordering
+            return gn_step(p)
+        for _ in range(max(1, args.warmup // 2)):
+            poses_e, _ = e2e_step(poses_e)
+        poses_e = d["poses_lw_init"].copy()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            poses_e, _ = e2e_step(poses_e)
+        f1.record()
+        barrier()
+        te = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * nq * args.steps / (float(te.item()) * 1e-3), "unit": "evals/s",
+               "h2d_bytes_per_step": int(nq * 16 + nf * (21 + 12) * 8 * 1 + (nf + 1) * 4), "d2h_bytes_per_step": int(world * nf * 29 * 8),
+               "ms_per_step": float(te.item()) / args.steps,
+               "note": "per step: source clouds (pinned host) -> device + Morton re-order, poses H2D, fused kernel, allreduce, reduced systems D2H; target map resident"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused associate+residual), CUDA-event time measured inside the library
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = HBM_FALLBACK_GBS, "fallback"
+    if os.path.exists(peaks_path):
+        try:
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    k_ms = float(np.mean(kernel_ms))
+    alg_bytes = nq * B_ALG_PER_QUERY[args.k]
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("k_associate_dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "k_associate<10,true>", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "kernel_share_of_step": k_ms * args.steps / ms}
+
+    line = {"metric": "residual_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "gn_cost_first_last": [costs[0], costs[-1]], "ms_per_gauss_newton_iter": ms_max / args.steps}
+
+    # ---- CPU baseline: the oracle port timed on this box's host cores (bounded sample), N=1 only
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import pvo
+        cb = cpu_baseline(args, d, steps=1, mode=1)
+        v = cb["evals"] / cb["seconds"]
+        sample = (f"{cb['frames']} of {args.frames} source frames ({cb['evals']} points, {cb['n_assoc']} accepted) against the full {args.n_target}-point target, "
+                  f"kd-tree prebuilt ({cb['kdtree_build_s']:.1f} s, not counted), association + Jet<12> residuals on all threads")
+        line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": cb["threads"], "kind": "port", "sample": sample, "seconds": cb["seconds"]}
+        cb0 = cpu_baseline(argparse.Namespace(**{**vars(args), "cpu_sample_frames": 1}), d, steps=1, mode=0, tree=cb["tree"])
+        line["cpu_baseline"]["reference_faithful"] = {"value": cb0["evals"] / cb0["seconds"], "unit": "evals/s",
+                                                      "note": "association serial on 1 core (util/Optimization.cpp:506-562 has no omp), evaluation on all threads; 1 frame"}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

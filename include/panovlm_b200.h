@@ -115,8 +115,12 @@ int pvb_dense_set_sources(pvb_ctx* ctx, const float* xyzc, const int* offsets, i
 /* one Gauss-Newton evaluation at poses_lw (n_frames x 6): per frame 29 doubles = H upper 6x6 (21) | g (6) | cost |
  * n_residuals w.r.t. the frame's own pose (the target/reference pose is constant = identity).                  */
 int pvb_dense_evaluate(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, double* out_sys29);
-/* same, but leaves the reduced systems on the device (for an on-stream allreduce); pointer to n_frames x 29     */
+/* same, but leaves the reduced systems on the device (for an on-stream allreduce).  If *dev_sys29 is non-NULL on entry
+ * it is a caller-owned device buffer (n_frames x 29 doubles) the result is written to; otherwise it receives the
+ * context's own buffer.                                                                                            */
 int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, double** dev_sys29);
+/* device time (CUDA events on the context's stream) of the fused associate+residual kernel of the last dense evaluate */
+int pvb_dense_kernel_time_ms(pvb_ctx* ctx, float* ms);
 /* Gauss-Newton/LM step per frame from the reduced 6x6 systems (host, 64 tiny solves): poses updated in place.   */
 int pvb_dense_gauss_newton_step(const double* sys29, int n_frames, double lambda, double* poses_lw);
 /* per-query view of the last evaluate for parity: valid flag, point (nei frame), plane, residual, 6 Jacobian cols */

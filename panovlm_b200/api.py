@@ -66,7 +66,7 @@ EXPORTS = [
     "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_dense_system", "pvb_blocks_solve_lm",
     "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn",
     "pvb_dense_set_target", "pvb_dense_set_sources", "pvb_dense_evaluate", "pvb_dense_evaluate_device", "pvb_dense_gauss_newton_step",
-    "pvb_dense_get_rows", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
+    "pvb_dense_get_rows", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
 ]
 
 
@@ -226,12 +226,18 @@ class Context:
         self._ck(self._L.pvb_dense_evaluate(self._h, _p(poses), C.byref(prm), _p(out)))
         return out
 
-    def dense_evaluate_device(self, poses_lw, prm):
-        """Enqueues the evaluation; returns the device pointer of the (n_frames x 29) reduced systems."""
+    def dense_evaluate_device(self, poses_lw, prm, out_ptr=None):
+        """Enqueues the evaluation; returns the device pointer of the (n_frames x 29) reduced systems
+        (out_ptr: caller-owned device buffer to write them to, e.g. a slice of an allreduce buffer)."""
         poses = _arr(poses_lw, np.float64)
-        ptr = C.c_void_p()
+        ptr = C.c_void_p(out_ptr)
         self._ck(self._L.pvb_dense_evaluate_device(self._h, _p(poses), C.byref(prm), C.byref(ptr)))
         return ptr.value
+
+    def dense_kernel_time_ms(self):
+        ms = C.c_float()
+        self._ck(self._L.pvb_dense_kernel_time_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def dense_gauss_newton_step(self, sys29, poses_lw, lam=0.0):
         poses = _arr(poses_lw, np.float64).copy()

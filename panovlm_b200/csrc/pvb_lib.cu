@@ -85,6 +85,7 @@ struct pvb_ctx {
   DevBuf d_q_sorted, d_q_orig, d_pairs, d_qtiles, d_part, d_sys, d_tbegin, d_valid, d_point, d_plane, d_res, d_jac;
   PinBuf dh_sys;
   int d_ntiles = 0; double d_cell = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;   // brackets the fused associate kernel of the last dense evaluate
   // ---- misc
   DevBuf m_a, m_b, m_c, m_d, m_e;
   PinBuf mh_a;
@@ -231,6 +232,7 @@ int pvb_create(int device, pvb_ctx** out) {
   pvb_ctx* ctx = new pvb_ctx();
   ctx->device = device;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PVB_ERR_CUDA; }
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   *out = ctx;
   return PVB_OK;
 }
@@ -247,6 +249,8 @@ void pvb_destroy(pvb_ctx* ctx) {
   PinBuf* pbs[] = {&ctx->h_pose, &ctx->h_r, &ctx->h_J, &ctx->h_esys, &ctx->fh_valid, &ctx->fh_point, &ctx->fh_plane, &ctx->dh_sys, &ctx->mh_a};
   for (PinBuf* b : pbs) b->release();
   ctx->f_tgt.release(); ctx->f_qry.release(); ctx->f_index.release(); ctx->d_tgt.release(); ctx->d_src.release(); ctx->d_index.release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -619,16 +623,29 @@ int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_de
   CK(cudaSetDevice(ctx->device));
   AssocArgs a; int rc = dense_args(ctx, poses_lw, prm, a); if (rc) return rc;
   a.partials = ctx->d_part.as<double>();
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
   rc = launch_associate<true>(ctx, prm->k, ctx->d_ntiles, a); if (rc) return rc;
-  k_sum_partials<29><<<ctx->d_frames, 32, 0, ctx->stream>>>(ctx->d_part.as<double>(), ctx->d_tbegin.as<int>(), ctx->d_sys.as<double>());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  double* dst = (dev_sys && *dev_sys) ? *dev_sys : ctx->d_sys.as<double>();   // caller-provided device buffer (e.g. a slice of an allreduce buffer)
+  k_sum_partials<29><<<ctx->d_frames, 32, 0, ctx->stream>>>(ctx->d_part.as<double>(), ctx->d_tbegin.as<int>(), dst);
   CKL();
-  if (dev_sys) *dev_sys = ctx->d_sys.as<double>();
+  if (dev_sys) *dev_sys = dst;
+  return PVB_OK;
+}
+
+int pvb_dense_kernel_time_ms(pvb_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return PVB_ERR_ARG;
+  if (!ctx->ev_valid) return ctx->fail(PVB_ERR_STATE, "no dense evaluate has run");
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
   return PVB_OK;
 }
 
 int pvb_dense_evaluate(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, double* out_sys) {
   if (!ctx || !out_sys) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
-  int rc = pvb_dense_evaluate_device(ctx, poses_lw, prm, nullptr); if (rc) return rc;
+  double* none = nullptr;
+  int rc = pvb_dense_evaluate_device(ctx, poses_lw, prm, &none); if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->dh_sys.p, ctx->d_sys.p, (size_t)ctx->d_frames * 29 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   memcpy(out_sys, ctx->dh_sys.p, (size_t)ctx->d_frames * 29 * 8);

@@ -268,17 +268,18 @@ def sample_floor_plan(n, rng, xlim=None, noise=0.0, L=200.0, W=50.0, H=4.0):
     return out
 
 
-def make_dense_sweep(n_target=10_000_000, n_frames=64, pts_per_frame=156_250, seed=20260929, L=200.0):
+def make_dense_sweep(n_target=10_000_000, n_frames=64, pts_per_frame=156_250, seed=20260929, L=200.0, source_seed=None):
     """configs[4]: target cloud (world == target frame) + n_frames source frames, each a local scan of a
     slab of the building (like a LiDAR at that position), expressed in its own sensor frame whose true pose is
     a small perturbation; the initial guess handed to the optimiser is the unperturbed slab pose.
     Returns dict(target[n,4] f32, src_local[m,4] f32, src_off[n_frames+1] i32, poses_lw_init[n_frames,6],
     poses_lw_true[n_frames,6])."""
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(seed)                    # target cloud
     scale = n_target / 10_000_000.0
     Lx = max(10.0, L * scale)                          # keep the surface density (~400 pts/m^2) when scaled down
     tgt = sample_floor_plan(n_target, rng, xlim=(0, Lx), L=L)
     target = np.concatenate([tgt, np.ones((n_target, 1))], axis=1).astype(np.float32)
+    rng = np.random.default_rng(seed + 1 if source_seed is None else source_seed)   # source frames (per-rank seed in bench.py)
     src, off, init, true = [], [0], [], []
     from scipy.spatial.transform import Rotation
     slab = Lx / n_frames
