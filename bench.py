@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=2, help="source frames in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cell", type=float, default=0.0, help="target grid cell size in metres (0: library default)")
     return ap.parse_args()
 
 
@@ -148,7 +149,7 @@ def run_reference(args):
 def config_dict(args):
     return {"workload": f"configs[4]: dense ICP sweep, {args.n_target}-pt target, {args.frames} source frames x {args.pts_per_frame} pts per GPU, "
                         f"k={args.k}, radius={args.radius} m, plane_tol=0.05, Point2Plane_Meter + Huber(0.2), per-frame 6x6 reduce",
-            "n_target": args.n_target, "frames_per_gpu": args.frames, "pts_per_frame": args.pts_per_frame, "k": args.k, "radius_m": args.radius,
+            "cell_m": args.cell, "n_target": args.n_target, "frames_per_gpu": args.frames, "pts_per_frame": args.pts_per_frame, "k": args.k, "radius_m": args.radius,
             "l2": "inputs (160 MB target records + 160 MB queries + cell table) exceed the 126 MB L2; no explicit flush",
             "parallelism": "frames sharded across GPUs (weak), target replicated, one allreduce of the packed 6x6/6x1 blocks per step"}
 
@@ -173,9 +174,10 @@ def main():
     nq = int(d["src_off"][-1])
 
     ctx = panovlm_b200.Context(local)
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)          # library work, torch events and NCCL all on one stream
-    ctx.dense_set_target(d["target"])
+    stream = torch.cuda.Stream()                # a real (non-legacy) stream: library work, torch events, copies and NCCL all on it
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.dense_set_target(d["target"], args.cell)
     src_pinned = torch.from_numpy(d["src_local"]).pin_memory()
     ctx.dense_set_sources_ptr(src_pinned.data_ptr(), d["src_off"])
     prm = ctx.dense_params(0.05, args.radius, args.k, panovlm_b200.P2PLANE_METER, 1, 0.2, 1.0)

@@ -129,6 +129,7 @@ struct AssocArgs {
 template <int K, bool REDUCE>
 __global__ void __launch_bounds__(kTile) k_associate(const AssocArgs a) {
   __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
+  __shared__ uint32_t s_win[K][kTile];           // record positions of each query's K neighbours
   const QueryTile t = a.tiles[blockIdx.x];
   const Pair pr = a.pairs[t.pair];
   const int i = threadIdx.x;
@@ -152,16 +153,31 @@ __global__ void __launch_bounds__(kTile) k_associate(const AssocArgs a) {
     const F4* srt = a.sorted;
     auto cells = [cs](long long c) { return (long long)__ldg(cs + c); };
     auto load = [srt](long long p) { return ldg_f4(srt + p); };
-    unsigned long long keys[K];
+    auto win = [&](int j) { return s_win[j][i]; };
+    auto set_win = [&](int j, uint32_t pos) { s_win[j][i] = pos; };
     AssocParams prm = a.prm;
     prm.rmax = (int)ceil(a.thr / g.h);
-    valid = associate_point2plane<K>(g, cells, load, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, keys);
     if (a.out_nn_idx) {
 #pragma unroll
+      for (int j = 0; j < K; ++j) s_win[j][i] = 0xFFFFFFFFu;
+    }
+    valid = associate_point2plane<K>(g, cells, load, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win);
+    if (a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
       for (int j = 0; j < K; ++j) {
-        const bool ok = (keys[j] & kKeyEmptyLow) != kKeyEmptyLow;
-        a.out_nn_idx[(size_t)qi * K + j] = ok ? (int)(f2u(load((long long)(uint32_t)(keys[j] & kKeyEmptyLow)).w) >> 5) : -1;
-        a.out_nn_d2[(size_t)qi * K + j] = ok ? u2f((uint32_t)(keys[j] >> 32)) : INFINITY;
+        const uint32_t pj = s_win[j][i];
+        if (pj == 0xFFFFFFFFu) { a.out_nn_idx[(size_t)qi * K + (K - 1 - j)] = -1; a.out_nn_d2[(size_t)qi * K + (K - 1 - j)] = INFINITY; continue; }
+        const F4 rj = load((long long)pj);
+        const float dj = sqdist_f32(qx, qy, qz, rj.x, rj.y, rj.z);
+        int rank = 0;
+        for (int m = 0; m < K; ++m) {
+          const uint32_t pm = s_win[m][i];
+          if (pm == 0xFFFFFFFFu || m == j) continue;
+          const F4 rm = load((long long)pm);
+          const float dm = sqdist_f32(qx, qy, qz, rm.x, rm.y, rm.z);
+          rank += (dm < dj || (dm == dj && pm < pj)) ? 1 : 0;
+        }
+        a.out_nn_idx[(size_t)qi * K + rank] = (int)(f2u(rj.w) >> 5);
+        a.out_nn_d2[(size_t)qi * K + rank] = dj;
       }
     }
     if (valid && (REDUCE || a.out_res)) {

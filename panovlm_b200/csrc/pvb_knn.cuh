@@ -46,71 +46,106 @@ PVB_HD int cell_coord(double v, double origin, double inv_h, int n) {
   return c;
 }
 
-constexpr unsigned long long kKeyEmptyLow = 0xFFFFFFFFull;
-
+// ---- exact k-NN selection, two passes over the candidate cells ------------------------------------------------
+// Pass 1 keeps only the K smallest squared distances: float32 bit patterns of non-negative floats order like
+// unsigned integers, so the sorted list is maintained with a branch-free min/max chain (2 ALU ops per slot, no
+// payload, no divergence).  Pass 2 re-scans the same cells and hands every candidate that belongs to the K smallest
+// (d2 < tau, plus as many d2 == tau as needed, in scan order) to `sink(j, position)`.
 template <int K>
-PVB_HD void topk_insert(unsigned long long (&keys)[K], unsigned long long key) {
-  unsigned long long k = key;
+PVB_HD void topk_values_insert(uint32_t (&keys)[K], uint32_t key) {
+  uint32_t k = key;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    const unsigned long long a = keys[j];
-    const bool lt = k < a;
-    keys[j] = lt ? k : a;
-    k = lt ? a : k;
+    const uint32_t a = keys[j];
+    const uint32_t lo = a < k ? a : k;
+    k = a < k ? k : a;
+    keys[j] = lo;
   }
 }
 
-// scan one contiguous record range, inserting candidates (d2 <= thr^2 is encoded in the initial keys)
 template <int K, typename PointLoader>
-PVB_HD void scan_range(const PointLoader& load, long long lo, long long hi, float qx, float qy, float qz, unsigned long long (&keys)[K]) {
+PVB_HD void scan_values(const PointLoader& load, long long lo, long long hi, float qx, float qy, float qz, uint32_t (&keys)[K]) {
   for (long long i = lo; i < hi; ++i) {
     const F4 p = load(i);
-    const float d2 = sqdist_f32(qx, qy, qz, p.x, p.y, p.z);
-    const unsigned long long key = ((unsigned long long)f2u(d2) << 32) | (unsigned long long)(uint32_t)i;
-    if (key < keys[K - 1]) topk_insert<K>(keys, key);
+    topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, p.x, p.y, p.z)));
   }
 }
 
-// Exact K-NN of (qx,qy,qz) within sqrt(sq_thr).  keys[] come back ascending by (d2, record position);
-// returns the number of valid neighbours (== K when the K-th is within the threshold).
-// `pos` in the keys is relative to g.point_base.  CellLoader: cell_start value; PointLoader: record.
-template <int K, typename CellLoader, typename PointLoader>
-PVB_HD int knn_search(const GridDesc& g, const CellLoader& cells, const PointLoader& load, float qx, float qy, float qz, float sq_thr, int rmax,
-                      unsigned long long (&keys)[K]) {
-  const unsigned long long init = ((unsigned long long)f2u(sq_thr) << 32) | kKeyEmptyLow;
+template <typename PointLoader, typename Sink>
+PVB_HD void scan_collect(const PointLoader& load, long long lo, long long hi, float qx, float qy, float qz, uint32_t tau, int eq_needed, int& eq_taken, int& n_out,
+                         const Sink& sink) {
+  for (long long i = lo; i < hi; ++i) {
+    const F4 p = load(i);
+    const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, p.x, p.y, p.z));
+    bool take = kb < tau;
+    if (kb == tau && eq_taken < eq_needed) { take = true; ++eq_taken; }
+    if (take) { sink(n_out, (uint32_t)i, kb); ++n_out; }
+  }
+}
+
+// visits the cells of ring `r` (r == 0: the whole (2R+1)^3 block of radius R) row by row; f(range_lo, range_hi)
+template <typename CellLoader, typename F>
+PVB_HD void for_each_range(const GridDesc& g, const CellLoader& cells, int cx, int cy, int cz, int r, bool whole_block, const F& f) {
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  const int z0 = cz - r < 0 ? 0 : cz - r, z1 = cz + r > nz - 1 ? nz - 1 : cz + r;
+  const int y0 = cy - r < 0 ? 0 : cy - r, y1 = cy + r > ny - 1 ? ny - 1 : cy + r;
+  const int x0 = cx - r < 0 ? 0 : cx - r, x1 = cx + r > nx - 1 ? nx - 1 : cx + r;
+  for (int z = z0; z <= z1; ++z) {
+    const bool zshell = (z == cz - r) || (z == cz + r);
+    for (int y = y0; y <= y1; ++y) {
+      const long long row = ((long long)z * ny + y) * nx;
+      const bool full = whole_block || (r == 1) || zshell || (y == cy - r) || (y == cy + r);
+      if (full) {
+        f(cells(row + x0), cells(row + x1 + 1));
+      } else {
+        if (cx - r >= 0) f(cells(row + cx - r), cells(row + cx - r + 1));
+        if (cx + r <= nx - 1) f(cells(row + cx + r), cells(row + cx + r + 1));
+      }
+    }
+  }
+}
+
+// Exact K-NN of (qx,qy,qz) within sqrt(sq_thr).  Returns the number of neighbours handed to sink (K, or 0 when the
+// K-th nearest is beyond the threshold / fewer than K points are in reach).  sink(j, record position, d2 bits).
+template <int K, typename CellLoader, typename PointLoader, typename Sink>
+PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoader& load, float qx, float qy, float qz, float sq_thr, int rmax, const Sink& sink) {
+  const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
+  uint32_t keys[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) keys[j] = init;
+  const double fx = ((double)qx - g.origin[0]) * g.inv_h, fy = ((double)qy - g.origin[1]) * g.inv_h, fz = ((double)qz - g.origin[2]) * g.inv_h;
   const int cx = cell_coord((double)qx, g.origin[0], g.inv_h, g.dims[0]);
   const int cy = cell_coord((double)qy, g.origin[1], g.inv_h, g.dims[1]);
   const int cz = cell_coord((double)qz, g.origin[2], g.inv_h, g.dims[2]);
-  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
-  for (int r = 1; r <= rmax; ++r) {
-    const int z0 = cz - r < 0 ? 0 : cz - r, z1 = cz + r > nz - 1 ? nz - 1 : cz + r;
-    const int y0 = cy - r < 0 ? 0 : cy - r, y1 = cy + r > ny - 1 ? ny - 1 : cy + r;
-    const int x0 = cx - r < 0 ? 0 : cx - r, x1 = cx + r > nx - 1 ? nx - 1 : cx + r;
-    for (int z = z0; z <= z1; ++z) {
-      const bool zshell = (z == cz - r) || (z == cz + r);
-      for (int y = y0; y <= y1; ++y) {
-        const long long row = ((long long)z * ny + y) * nx;
-        const bool full = (r == 1) || zshell || (y == cy - r) || (y == cy + r);
-        if (full) {
-          scan_range<K>(load, cells(row + x0), cells(row + x1 + 1), qx, qy, qz, keys);
-        } else {
-          if (cx - r >= 0) scan_range<K>(load, cells(row + cx - r), cells(row + cx - r + 1), qx, qy, qz, keys);
-          if (cx + r <= nx - 1) scan_range<K>(load, cells(row + cx + r), cells(row + cx + r + 1), qx, qy, qz, keys);
-        }
-      }
-    }
-    // all points closer than r*h have been seen
-    if ((keys[K - 1] & kKeyEmptyLow) != kKeyEmptyLow) {
-      const double reach = (double)r * g.h;
-      if ((double)u2f((uint32_t)(keys[K - 1] >> 32)) < reach * reach * (1.0 - 1e-6)) break;
+  // distance from the query to the nearest face of its own cell (0 when the query was clamped into the grid)
+  double slack = 0.5;
+  {
+    const double f[3] = {fx - cx, fy - cy, fz - cz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double m = f[a] < 1.0 - f[a] ? f[a] : 1.0 - f[a];
+      m = m < 0.0 ? 0.0 : m;
+      slack = m < slack ? m : slack;
     }
   }
-  int n = 0;
+  int r = 1;
+  for (; r <= rmax; ++r) {
+    for_each_range(g, cells, cx, cy, cz, r, false, [&](long long lo, long long hi) { scan_values<K>(load, lo, hi, qx, qy, qz, keys); });
+    if (keys[K - 1] != init) {      // ring r covers every point closer than (r + slack) * h
+      const double reach = ((double)r + slack) * g.h;
+      if ((double)u2f(keys[K - 1]) < reach * reach * (1.0 - 1e-6)) break;
+    }
+  }
+  if (keys[K - 1] == init) return 0;
+  if (r > rmax) r = rmax;
+  const uint32_t tau = keys[K - 1];
+  int n_lt = 0;
 #pragma unroll
-  for (int j = 0; j < K; ++j) n += ((keys[j] & kKeyEmptyLow) != kKeyEmptyLow) ? 1 : 0;
-  return n;
+  for (int j = 0; j < K; ++j) n_lt += keys[j] < tau ? 1 : 0;
+  int eq_taken = 0, n_out = 0;
+  const int eq_needed = K - n_lt;
+  for_each_range(g, cells, cx, cy, cz, r, true, [&](long long lo, long long hi) { scan_collect(load, lo, hi, qx, qy, qz, tau, eq_needed, eq_taken, n_out, sink); });
+  return n_out;
 }
 
 struct AssocParams {
@@ -122,26 +157,44 @@ struct AssocParams {
 
 // Per-query body of AssociatePoint2Plane.  qw = query in world (float32), qcls = class label.
 // R_ref/t_ref, R_nei/t_nei = R_wl, t_wl of the two frames.  On success: p_local (query in the neighbour's
-// sensor frame, double) and plane (n, d) in the reference sensor frame.
-template <int K, typename CellLoader, typename PointLoader>
+// sensor frame, double) and plane (n, d) in the reference sensor frame.  win(j) / set_win(j, pos) access the
+// caller's per-query neighbour slots (shared memory on the device).
+template <int K, typename CellLoader, typename PointLoader, typename WinGet, typename WinSet>
 PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const PointLoader& load, const AssocParams& prm,
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
-                                  double p_local[3], double plane[4], unsigned long long (&keys)[K]) {
-  const int found = knn_search<K>(g, cells, load, qx, qy, qz, prm.sq_thr, prm.rmax, keys);
+                                  double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win) {
+  const int found = knn_select<K>(g, cells, load, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); });
   if (found < K) return false;                                   // :578 (k-th beyond the threshold) + quirk C.6 guard
   double pts[K][3];
   int same = 0;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    const F4 p = load((long long)(uint32_t)(keys[j] & kKeyEmptyLow));
+    const F4 p = load((long long)win(j));
     same += ((f2u(p.w) & 31u) == qcls) ? 1 : 0;                  // :586 pt.intensity == point.intensity
     const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
     world2local(R_ref, t_ref, pw, pts[j]);                       // :587
   }
   if (same < K) return false;                                    // :590
-  if (!form_plane_lsq<K>(pts, prm.plane_tol, plane)) return false;   // :593
-  if (points_collinear<K>(pts, prm.collinear_tol)) return false;     // :594-596
+  if (points_collinear<K>(pts, prm.collinear_tol)) return false; // :594-596 (evaluated first: the QR below works in place)
+  double x[3];
+  lstsq_minus_one_inplace<K>(pts, x);                            // :593 FormPlane: A x = -1 (destroys pts)
+  const double nrm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  const double d = 1.0 / nrm;
+  const double n0 = x[0] / nrm, n1 = x[1] / nrm, n2 = x[2] / nrm;
+  if (prm.plane_tol > 0) {                                       // Geometry.hpp:364-371 (points re-read: L1-resident)
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const F4 p = load((long long)win(j));
+      const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
+      double pl[3];
+      world2local(R_ref, t_ref, pw, pl);
+      ok = ok && !(fabs(n0 * pl[0] + n1 * pl[1] + n2 * pl[2] + d) > prm.plane_tol);
+    }
+    if (!ok) return false;
+  }
+  plane[0] = n0; plane[1] = n1; plane[2] = n2; plane[3] = d;
   const double qw[3] = {(double)qx, (double)qy, (double)qz};
   world2local(R_nei, t_nei, qw, p_local);                        // :598-599
   return true;

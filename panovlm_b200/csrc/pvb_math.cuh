@@ -300,10 +300,12 @@ PVB_HD double huber_correct(double a, double& r, double* J, int n) {
 // ---- plane fit / collinearity test of AssociatePoint2Plane (LidarFeatureAssociate.cpp:593-596) -------------
 // Least-squares A x = -1 over K points by Householder QR with column pivoting (what Geometry.hpp:361's
 // colPivHouseholderQr().solve does), then d = 1/|x|, n = x/|x| and the tolerance test (:364-371).
+// In-place core: A (K x 3, destroyed) x = -1 in the least-squares sense.
 template <int K>
-PVB_HD bool form_plane_lsq(const double (*pts)[3], double tol, double plane[4]) {
-  double A[K][3], b[K];
-  for (int i = 0; i < K; ++i) { A[i][0] = pts[i][0]; A[i][1] = pts[i][1]; A[i][2] = pts[i][2]; b[i] = -1.0; }
+PVB_HD void lstsq_minus_one_inplace(double (*A)[3], double x[3]) {
+  double b[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) b[i] = -1.0;
   int perm[3] = {0, 1, 2};
   double diag[3] = {0, 0, 0};
   int rank = 0;
@@ -360,8 +362,16 @@ PVB_HD bool form_plane_lsq(const double (*pts)[3], double tol, double plane[4]) 
     for (int c = k + 1; c < 3; ++c) if (c < rank) s -= A[k][c] * y[c];
     y[k] = s / diag[k];
   }
-  double x[3] = {0, 0, 0};
+  x[0] = x[1] = x[2] = 0.0;
+#pragma unroll
   for (int k = 0; k < 3; ++k) { if (perm[k] == 0) x[0] = y[k]; else if (perm[k] == 1) x[1] = y[k]; else x[2] = y[k]; }
+}
+
+template <int K>
+PVB_HD bool form_plane_lsq(const double (*pts)[3], double tol, double plane[4]) {
+  double A[K][3], x[3];
+  for (int i = 0; i < K; ++i) { A[i][0] = pts[i][0]; A[i][1] = pts[i][1]; A[i][2] = pts[i][2]; }
+  lstsq_minus_one_inplace<K>(A, x);
   const double nrm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
   const double d = 1.0 / nrm;
   const double n0 = x[0] / nrm, n1 = x[1] / nrm, n2 = x[2] / nrm;

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY — compiles the product's `__host__ __device__` math (panovlm_b200/csrc/*.cuh,
 // pvb_host.hpp) with g++ so the not-gpu tests can check the exact device arithmetic against the oracle on the
 // CPU.  It is never linked into libpanovlm_b200.so and the product has no CPU path.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -38,14 +39,23 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
   auto load = [&](long long i) { return sorted[i]; };
   AssocParams prm; prm.sq_thr = thr * thr; prm.rmax = (int)std::ceil((double)thr / h); prm.plane_tol = plane_tol; prm.collinear_tol = 3.0;
   for (int i = 0; i < m; ++i) {
-    unsigned long long keys[K];
+    uint32_t wpos[K];
+    for (int j = 0; j < K; ++j) wpos[j] = 0xFFFFFFFFu;
     const uint32_t qcls = (uint32_t)qry[i * 4 + 3] & 31u;
+    auto win = [&](int j) { return wpos[j]; };
+    auto set_win = [&](int j, uint32_t pos) { wpos[j] = pos; };
     valid[i] = associate_point2plane<K>(g, cells, load, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei,
-                                        p_local + 3 * i, plane + 4 * i, keys) ? 1 : 0;
+                                        p_local + 3 * i, plane + 4 * i, win, set_win) ? 1 : 0;
+    std::vector<std::pair<std::pair<float, uint32_t>, int>> nn;
     for (int j = 0; j < K; ++j) {
-      const bool ok = (keys[j] & kKeyEmptyLow) != kKeyEmptyLow;
-      nn_idx[i * K + j] = ok ? (int)(f2u(sorted[(uint32_t)(keys[j] & kKeyEmptyLow)].w) >> 5) : -1;
-      nn_d2[i * K + j] = ok ? u2f((uint32_t)(keys[j] >> 32)) : INFINITY;
+      if (wpos[j] == 0xFFFFFFFFu) continue;
+      const F4 r = sorted[wpos[j]];
+      nn.push_back({{sqdist_f32(qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], r.x, r.y, r.z), wpos[j]}, (int)(f2u(r.w) >> 5)});
+    }
+    std::sort(nn.begin(), nn.end());
+    for (int j = 0; j < K; ++j) {
+      nn_idx[i * K + j] = j < (int)nn.size() ? nn[j].second : -1;
+      nn_d2[i * K + j] = j < (int)nn.size() ? nn[j].first.first : INFINITY;
     }
   }
 }
