@@ -126,8 +126,8 @@ struct AssocArgs {
   double* partials;                                                  // [tile][29]
 };
 
-template <int K, bool REDUCE>
-__global__ void __launch_bounds__(kTile) k_associate(const AssocArgs a) {
+template <int K, bool REDUCE, int MINB>
+__global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
   __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
   __shared__ uint32_t s_win[K][kTile];           // record positions of each query's K neighbours
   const QueryTile t = a.tiles[blockIdx.x];

@@ -53,30 +53,39 @@ PVB_HD int cell_coord(double v, double origin, double inv_h, int n) {
 // (d2 < tau, plus as many d2 == tau as needed, in scan order) to `sink(j, position)`.
 template <int K>
 PVB_HD void topk_values_insert(uint32_t (&keys)[K], uint32_t key) {
-  uint32_t k = key;
+  // sorted ascending; inserting `key` and dropping the largest: new[j] = median(old[j-1], key, old[j])
+  //                                                                   = min(old[j], max(old[j-1], key))
+  // every slot is computed from the OLD values only: 2 independent min/max per slot, dependency depth 2.
+  uint32_t prev = 0u;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     const uint32_t a = keys[j];
-    const uint32_t lo = a < k ? a : k;
-    k = a < k ? k : a;
-    keys[j] = lo;
+    const uint32_t m = prev > key ? prev : key;
+    keys[j] = a < m ? a : m;
+    prev = a;
   }
 }
 
 template <int K, typename PointLoader>
 PVB_HD void scan_values(const PointLoader& load, long long lo, long long hi, float qx, float qy, float qz, uint32_t (&keys)[K]) {
+  if (lo >= hi) return;
+  F4 p = load(lo);
   for (long long i = lo; i < hi; ++i) {
-    const F4 p = load(i);
-    topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, p.x, p.y, p.z)));
+    const F4 c = p;
+    if (i + 1 < hi) p = load(i + 1);        // software prefetch: the next record is in flight while this one is ranked
+    topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
   }
 }
 
 template <typename PointLoader, typename Sink>
 PVB_HD void scan_collect(const PointLoader& load, long long lo, long long hi, float qx, float qy, float qz, uint32_t tau, int eq_needed, int& eq_taken, int& n_out,
                          const Sink& sink) {
+  if (lo >= hi) return;
+  F4 p = load(lo);
   for (long long i = lo; i < hi; ++i) {
-    const F4 p = load(i);
-    const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, p.x, p.y, p.z));
+    const F4 c = p;
+    if (i + 1 < hi) p = load(i + 1);
+    const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
     bool take = kb < tau;
     if (kb == tau && eq_taken < eq_needed) { take = true; ++eq_taken; }
     if (take) { sink(n_out, (uint32_t)i, kb); ++n_out; }

@@ -4,6 +4,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -66,6 +67,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
+  int tune_minb = 3;
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
@@ -210,8 +212,11 @@ int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_
 template <bool REDUCE>
 int launch_associate(pvb_ctx* ctx, int k, int n_tiles, const AssocArgs& a) {
   if (n_tiles == 0) return PVB_OK;
-  if (k == 10) k_associate<10, REDUCE><<<n_tiles, kTile, 0, ctx->stream>>>(a);
-  else if (k == 5) k_associate<5, REDUCE><<<n_tiles, kTile, 0, ctx->stream>>>(a);
+  const int minb = ctx->tune_minb;   // register budget of the fused kernel: 3 (<=168 regs) or 4 (<=128 regs) resident blocks per SM
+  if (k == 10 && minb == 4) k_associate<10, REDUCE, 4><<<n_tiles, kTile, 0, ctx->stream>>>(a);
+  else if (k == 10) k_associate<10, REDUCE, 3><<<n_tiles, kTile, 0, ctx->stream>>>(a);
+  else if (k == 5 && minb == 4) k_associate<5, REDUCE, 4><<<n_tiles, kTile, 0, ctx->stream>>>(a);
+  else if (k == 5) k_associate<5, REDUCE, 3><<<n_tiles, kTile, 0, ctx->stream>>>(a);
   else return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
   CKL();
   return PVB_OK;
@@ -233,6 +238,7 @@ int pvb_create(int device, pvb_ctx** out) {
   ctx->device = device;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PVB_ERR_CUDA; }
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e) == 4 ? 4 : 3;
   *out = ctx;
   return PVB_OK;
 }

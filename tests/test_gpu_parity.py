@@ -294,9 +294,9 @@ def test_dense_full_size_properties(gpu_ctx):
     src, poses = np.concatenate(src), np.array(poses)
     gpu_ctx.dense_set_target(tgt)
     gpu_ctx.dense_set_sources(src, np.array(off, np.int32))
-    prm = gpu_ctx.dense_params(0.05, 0.3, 10, 0, 1, 0.0, 1.0)
+    prm = gpu_ctx.dense_params(1e-3, 0.3, 10, 0, 1, 0.0, 1.0)     # tight plane tolerance: only truly coplanar neighbour sets
     s = gpu_ctx.dense_evaluate(poses, prm)
-    assert s[:, 28].sum() > 0.25 * nf * per
+    assert s[:, 28].sum() > 0.2 * nf * per
     rms = np.sqrt(2 * s[:, 27] / s[:, 28])
     assert rms.max() < 2e-3                                                            # float32 round trip of the copies only
     H = np.zeros((nf, 6, 6)); iu = np.triu_indices(6)
@@ -305,7 +305,7 @@ def test_dense_full_size_properties(gpu_ctx):
         w = np.linalg.eigvalsh(H[f] + H[f].T - np.diag(np.diag(H[f])))
         assert w.min() > 0                                                             # J^T J is positive definite
     # a rigid shift of ALL inputs leaves the association counts unchanged only if the search is exact:
-    s2 = gpu_ctx.dense_evaluate(poses, gpu_ctx.dense_params(0.05, 0.3, 5, 0, 1, 0.0, 1.0))
+    s2 = gpu_ctx.dense_evaluate(poses, gpu_ctx.dense_params(1e-3, 0.3, 5, 0, 1, 0.0, 1.0))
     assert np.all(s2[:, 28] >= s[:, 28] * 0.9)
 
 
