@@ -126,7 +126,7 @@ struct AssocArgs {
   double* partials;                                                  // [tile][29]
 };
 
-template <int K, bool REDUCE, int MINB>
+template <int K, bool REDUCE, int MINB, bool DEBUG_NN>
 __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
   __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
   __shared__ uint32_t s_win[K][kTile];           // record positions of each query's K neighbours
@@ -157,12 +157,12 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
     auto set_win = [&](int j, uint32_t pos) { s_win[j][i] = pos; };
     AssocParams prm = a.prm;
     prm.rmax = (int)ceil(a.thr / g.h);
-    if (a.out_nn_idx) {
+    if (DEBUG_NN && a.out_nn_idx) {
 #pragma unroll
       for (int j = 0; j < K; ++j) s_win[j][i] = 0xFFFFFFFFu;
     }
     valid = associate_point2plane<K>(g, cells, load, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win);
-    if (a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
+    if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
       for (int j = 0; j < K; ++j) {
         const uint32_t pj = s_win[j][i];
         if (pj == 0xFFFFFFFFu) { a.out_nn_idx[(size_t)qi * K + (K - 1 - j)] = -1; a.out_nn_d2[(size_t)qi * K + (K - 1 - j)] = INFINITY; continue; }
@@ -181,11 +181,11 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
       }
     }
     if (valid && (REDUCE || a.out_res)) {
-      double c[12];
-      c[0] = p_local[0]; c[1] = p_local[1]; c[2] = p_local[2];
-      c[3] = plane[0]; c[4] = plane[1]; c[5] = plane[2]; c[6] = plane[3]; c[7] = a.weight;
-      c[8] = c[9] = c[10] = c[11] = 0.0;
-      r = eval_block(a.residual_type, a.normalize != 0, c, a.prep[pr.ref_block], a.prep[pr.nei_block], J);
+      double c[8] = {p_local[0], p_local[1], p_local[2], plane[0], plane[1], plane[2], plane[3], a.weight};
+      double q[3], P[3], g[3];
+      transform_nei_to_ref(a.prep[pr.ref_block], a.prep[pr.nei_block], c, q, P);
+      r = tail_point_plane(a.residual_type, a.normalize != 0, c, P, g);
+      accumulate_row(a.prep[pr.ref_block], a.prep[pr.nei_block], q, P, g, J);
       cost = huber_correct(a.huber, r, J, 12);
     }
     if (a.out_valid) a.out_valid[qi] = valid ? 1 : 0;
@@ -202,27 +202,28 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
     }
   }
   if (REDUCE) {
-    // stage rows in shared memory, then 29 threads each own one entry of (H upper 21 | g 6 | cost | count):
-    // fixed summation order => run-to-run identical results.
+    // Per-WARP reduction (no block barrier: warps of a tile finish their searches at different times).  Rows are
+    // staged in shared memory, then 28 lanes each own one entry of (H upper 21 | g 6 | cost); fixed summation
+    // order => run-to-run identical results.  partials: [tile][warp][29].
+    const int w = i >> 5, lane = i & 31;
 #pragma unroll
     for (int k = 0; k < 6; ++k) sJ[i][k] = valid ? J[6 + k] : 0.0;
     sJ[i][6] = valid ? r : 0.0;
     sJ[i][7] = valid ? cost : 0.0;
-    __syncthreads();
-    if (i < 28) {
-      int ia = 0, ib = 0; double acc = 0.0;
-      if (i < 21) { int o = i; ia = 0; while (o >= 6 - ia) { o -= 6 - ia; ++ia; } ib = ia + o; }
-      else if (i < 27) { ia = i - 21; ib = 6; }
-      if (i < 27) { for (int row = 0; row < kTile; ++row) acc += sJ[row][ia] * sJ[row][ib]; }
-      else { for (int row = 0; row < kTile; ++row) acc += sJ[row][7]; }
-      a.partials[(size_t)blockIdx.x * 29 + i] = acc;
-    }
-    // residual count: ballot of valid flags (exact integer)
     const unsigned b = __ballot_sync(0xffffffffu, valid);
-    __shared__ int scount[kTile / 32];
-    if ((i & 31) == 0) scount[i >> 5] = __popc(b);
-    __syncthreads();
-    if (i == 0) { int n = 0; for (int w = 0; w < kTile / 32; ++w) n += scount[w]; a.partials[(size_t)blockIdx.x * 29 + 28] = (double)n; }
+    __syncwarp();
+    double* out = a.partials + ((size_t)blockIdx.x * (kTile / 32) + w) * 29;
+    if (lane < 28) {
+      int ia = 0, ib = 0; double acc = 0.0;
+      if (lane < 21) { int o = lane; ia = 0; while (o >= 6 - ia) { o -= 6 - ia; ++ia; } ib = ia + o; }
+      else if (lane < 27) { ia = lane - 21; ib = 6; }
+      const double (*rows)[8] = &sJ[w * 32];
+      if (lane < 27) { for (int row = 0; row < 32; ++row) acc += rows[row][ia] * rows[row][ib]; }
+      else { for (int row = 0; row < 32; ++row) acc += rows[row][7]; }
+      out[lane] = acc;
+    } else if (lane == 28) {
+      out[28] = (double)__popc(b);
+    }
   }
 }
 

@@ -68,11 +68,9 @@ PVB_HD void topk_values_insert(uint32_t (&keys)[K], uint32_t key) {
 
 template <int K, typename PointLoader>
 PVB_HD void scan_values(const PointLoader& load, long long lo, long long hi, float qx, float qy, float qz, uint32_t (&keys)[K]) {
-  if (lo >= hi) return;
-  F4 p = load(lo);
+#pragma unroll 2
   for (long long i = lo; i < hi; ++i) {
-    const F4 c = p;
-    if (i + 1 < hi) p = load(i + 1);        // software prefetch: the next record is in flight while this one is ranked
+    const F4 c = load(i);
     topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
   }
 }
@@ -80,11 +78,9 @@ PVB_HD void scan_values(const PointLoader& load, long long lo, long long hi, flo
 template <typename PointLoader, typename Sink>
 PVB_HD void scan_collect(const PointLoader& load, long long lo, long long hi, float qx, float qy, float qz, uint32_t tau, int eq_needed, int& eq_taken, int& n_out,
                          const Sink& sink) {
-  if (lo >= hi) return;
-  F4 p = load(lo);
+#pragma unroll 2
   for (long long i = lo; i < hi; ++i) {
-    const F4 c = p;
-    if (i + 1 < hi) p = load(i + 1);
+    const F4 c = load(i);
     const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
     bool take = kb < tau;
     if (kb == tau && eq_taken < eq_needed) { take = true; ++eq_taken; }
@@ -104,11 +100,14 @@ PVB_HD void for_each_range(const GridDesc& g, const CellLoader& cells, int cx, i
     for (int y = y0; y <= y1; ++y) {
       const long long row = ((long long)z * ny + y) * nx;
       const bool full = whole_block || (r == 1) || zshell || (y == cy - r) || (y == cy + r);
-      if (full) {
-        f(cells(row + x0), cells(row + x1 + 1));
-      } else {
-        if (cx - r >= 0) f(cells(row + cx - r), cells(row + cx - r + 1));
-        if (cx + r <= nx - 1) f(cells(row + cx + r), cells(row + cx + r + 1));
+      // one call site of f (keeps the inlined scan loop single: instruction-cache footprint)
+      const int nparts = full ? 1 : 2;
+      for (int part = 0; part < nparts; ++part) {
+        long long c0, c1;
+        if (full) { c0 = row + x0; c1 = row + x1 + 1; }
+        else if (part == 0) { if (cx - r < 0) continue; c0 = row + cx - r; c1 = c0 + 1; }
+        else { if (cx + r > nx - 1) continue; c0 = row + cx + r; c1 = c0 + 1; }
+        f(cells(c0), cells(c1));
       }
     }
   }
@@ -175,25 +174,45 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
                                   double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win) {
   const int found = knn_select<K>(g, cells, load, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); });
   if (found < K) return false;                                   // :578 (k-th beyond the threshold) + quirk C.6 guard
-  double pts[K][3];
+  // neighbours -> reference sensor frame (:587), streamed: Gram matrix for the LSQ plane and the scatter matrix
+  PlaneAcc acc; plane_acc_clear(acc);
   int same = 0;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < K; ++j) {
     const F4 p = load((long long)win(j));
     same += ((f2u(p.w) & 31u) == qcls) ? 1 : 0;                  // :586 pt.intensity == point.intensity
     const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
-    world2local(R_ref, t_ref, pw, pts[j]);                       // :587
+    double pl[3];
+    world2local(R_ref, t_ref, pw, pl);
+    plane_acc_add(acc, pl);
   }
   if (same < K) return false;                                    // :590
-  if (points_collinear<K>(pts, prm.collinear_tol)) return false; // :594-596 (evaluated first: the QR below works in place)
+  if (collinear_from_gram(acc, K, prm.collinear_tol)) return false;   // :594-596
+  Chol3 L;
+  if (!chol3_factor(acc, L)) return false;
   double x[3];
-  lstsq_minus_one_inplace<K>(pts, x);                            // :593 FormPlane: A x = -1 (destroys pts)
+  { const double rhs[3] = {-acc.h0, -acc.h1, -acc.h2}; chol3_solve(L, rhs, x); }   // :593 FormPlane: A x = -1
+  {                                                              // one refinement step: t = A^T (b - A x)
+    double t[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int j = 0; j < K; ++j) {
+      const F4 p = load((long long)win(j));
+      const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
+      double pl[3];
+      world2local(R_ref, t_ref, pw, pl);
+      const double rj = -1.0 - (pl[0] * x[0] + pl[1] * x[1] + pl[2] * x[2]);
+      t[0] += pl[0] * rj; t[1] += pl[1] * rj; t[2] += pl[2] * rj;
+    }
+    double dx[3];
+    chol3_solve(L, t, dx);
+    x[0] += dx[0]; x[1] += dx[1]; x[2] += dx[2];
+  }
   const double nrm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
   const double d = 1.0 / nrm;
   const double n0 = x[0] / nrm, n1 = x[1] / nrm, n2 = x[2] / nrm;
-  if (prm.plane_tol > 0) {                                       // Geometry.hpp:364-371 (points re-read: L1-resident)
+  if (prm.plane_tol > 0) {                                       // Geometry.hpp:364-371
     bool ok = true;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < K; ++j) {
       const F4 p = load((long long)win(j));
       const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};

@@ -212,12 +212,14 @@ int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_
 template <bool REDUCE>
 int launch_associate(pvb_ctx* ctx, int k, int n_tiles, const AssocArgs& a) {
   if (n_tiles == 0) return PVB_OK;
-  const int minb = ctx->tune_minb;   // register budget of the fused kernel: 3 (<=168 regs) or 4 (<=128 regs) resident blocks per SM
-  if (k == 10 && minb == 4) k_associate<10, REDUCE, 4><<<n_tiles, kTile, 0, ctx->stream>>>(a);
-  else if (k == 10) k_associate<10, REDUCE, 3><<<n_tiles, kTile, 0, ctx->stream>>>(a);
-  else if (k == 5 && minb == 4) k_associate<5, REDUCE, 4><<<n_tiles, kTile, 0, ctx->stream>>>(a);
-  else if (k == 5) k_associate<5, REDUCE, 3><<<n_tiles, kTile, 0, ctx->stream>>>(a);
-  else return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
+  const int minb = ctx->tune_minb;   // register budget of the fused kernel: 3 or 4 resident blocks per SM
+  const bool dbg = a.out_nn_idx != nullptr;
+  if (k != 5 && k != 10) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
+#define PVB_LAUNCH(KK, MB, DBG) k_associate<KK, REDUCE, MB, DBG><<<n_tiles, kTile, 0, ctx->stream>>>(a)
+  if (dbg) { if (k == 10) PVB_LAUNCH(10, 3, true); else PVB_LAUNCH(5, 3, true); }
+  else if (k == 10) { if (minb == 4) PVB_LAUNCH(10, 4, false); else PVB_LAUNCH(10, 3, false); }
+  else { if (minb == 4) PVB_LAUNCH(5, 4, false); else PVB_LAUNCH(5, 3, false); }
+#undef PVB_LAUNCH
   CKL();
   return PVB_OK;
 }
@@ -594,13 +596,13 @@ int pvb_dense_set_sources(pvb_ctx* ctx, const float* xyzc, const int* offsets, i
   std::vector<Pair> pairs(n_frames); std::vector<QueryTile> tiles; std::vector<int> tbegin(n_frames + 1, 0);
   for (int f = 0; f < n_frames; ++f) {
     pairs[f] = Pair{0, f, 0, f + 1};
-    tbegin[f] = (int)tiles.size();
+    tbegin[f] = (int)tiles.size() * (kTile / 32);      // partials are per warp: kTile/32 entries per tile
     for (int s = 0; s < cnt[f]; s += kTile) tiles.push_back(QueryTile{f, cs.off[f] + s, std::min(kTile, cnt[f] - s), 0});
   }
-  tbegin[n_frames] = (int)tiles.size();
+  tbegin[n_frames] = (int)tiles.size() * (kTile / 32);
   ctx->d_ntiles = (int)tiles.size();
   CK(ctx->d_pairs.ensure(pairs.size() * sizeof(Pair))); CK(ctx->d_qtiles.ensure(std::max<size_t>(16, tiles.size() * sizeof(QueryTile)))); CK(ctx->d_tbegin.ensure(tbegin.size() * 4));
-  CK(ctx->d_part.ensure(std::max<size_t>(16, tiles.size() * 29 * 8))); CK(ctx->d_sys.ensure((size_t)n_frames * 29 * 8)); CK(ctx->dh_sys.ensure((size_t)n_frames * 29 * 8));
+  CK(ctx->d_part.ensure(std::max<size_t>(16, tiles.size() * (kTile / 32) * 29 * 8))); CK(ctx->d_sys.ensure((size_t)n_frames * 29 * 8)); CK(ctx->dh_sys.ensure((size_t)n_frames * 29 * 8));
   CK(cudaMemcpyAsync(ctx->d_pairs.p, pairs.data(), pairs.size() * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->d_qtiles.p, tiles.data(), tiles.size() * sizeof(QueryTile), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_tbegin.p, tbegin.data(), tbegin.size() * 4, cudaMemcpyHostToDevice, ctx->stream));

@@ -413,6 +413,58 @@ PVB_HD bool points_collinear(const double (*pts)[3], double tol) {
   return l2 > tol * l1;
 }
 
+// ---- streaming plane fit (registers: 9 doubles instead of a K x 3 matrix) ------------------------------------------
+// Same least-squares problem as Geometry.hpp:345-373 (A x = -1): Gram matrix G = A^T A and h = A^T 1 are accumulated
+// point by point, G x = -h is solved by a 3x3 Cholesky and corrected by one step of iterative refinement with the
+// residual evaluated from the points (corrected semi-normal equations), which restores QR-level accuracy for the
+// conditioning met here (cond(A) ~ range / neighbourhood size ~ 1e3..1e4).  The scatter matrix of the collinearity
+// test (Geometry.hpp:229-235) is G - h h^T / n.
+struct PlaneAcc { double g00, g01, g02, g11, g12, g22, h0, h1, h2; };
+PVB_HD void plane_acc_clear(PlaneAcc& a) { a.g00 = a.g01 = a.g02 = a.g11 = a.g12 = a.g22 = a.h0 = a.h1 = a.h2 = 0.0; }
+PVB_HD void plane_acc_add(PlaneAcc& a, const double p[3]) {
+  a.g00 += p[0] * p[0]; a.g01 += p[0] * p[1]; a.g02 += p[0] * p[2]; a.g11 += p[1] * p[1]; a.g12 += p[1] * p[2]; a.g22 += p[2] * p[2];
+  a.h0 += p[0]; a.h1 += p[1]; a.h2 += p[2];
+}
+struct Chol3 { double l00, l10, l11, l20, l21, l22; };
+PVB_HD bool chol3_factor(const PlaneAcc& a, Chol3& L) {
+  if (!(a.g00 > 0.0)) return false;
+  L.l00 = sqrt(a.g00); L.l10 = a.g01 / L.l00; L.l20 = a.g02 / L.l00;
+  const double d1 = a.g11 - L.l10 * L.l10;
+  if (!(d1 > 0.0)) return false;
+  L.l11 = sqrt(d1); L.l21 = (a.g12 - L.l20 * L.l10) / L.l11;
+  const double d2 = a.g22 - L.l20 * L.l20 - L.l21 * L.l21;
+  if (!(d2 > 0.0)) return false;
+  L.l22 = sqrt(d2);
+  return true;
+}
+PVB_HD void chol3_solve(const Chol3& L, const double b[3], double x[3]) {
+  const double y0 = b[0] / L.l00;
+  const double y1 = (b[1] - L.l10 * y0) / L.l11;
+  const double y2 = (b[2] - L.l20 * y0 - L.l21 * y1) / L.l22;
+  x[2] = y2 / L.l22;
+  x[1] = (y1 - L.l21 * x[2]) / L.l11;
+  x[0] = (y0 - L.l10 * x[1] - L.l20 * x[2]) / L.l00;
+}
+// lambda_max > tol * lambda_mid of the scatter matrix (FormLine's "is a line" test)
+PVB_HD bool collinear_from_gram(const PlaneAcc& a, int n, double tol) {
+  const double inv = 1.0 / (double)n;
+  const double a00 = a.g00 - a.h0 * a.h0 * inv, a01 = a.g01 - a.h0 * a.h1 * inv, a02 = a.g02 - a.h0 * a.h2 * inv;
+  const double a11 = a.g11 - a.h1 * a.h1 * inv, a12 = a.g12 - a.h1 * a.h2 * inv, a22 = a.g22 - a.h2 * a.h2 * inv;
+  const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+  const double qm = (a00 + a11 + a22) / 3.0;
+  const double p2 = (a00 - qm) * (a00 - qm) + (a11 - qm) * (a11 - qm) + (a22 - qm) * (a22 - qm) + 2.0 * p1;
+  if (p2 <= 0.0) return 1.0 > tol;      // all eigenvalues equal
+  const double p = sqrt(p2 / 6.0), ip = 1.0 / p;
+  const double b00 = (a00 - qm) * ip, b11 = (a11 - qm) * ip, b22 = (a22 - qm) * ip, b01 = a01 * ip, b02 = a02 * ip, b12 = a12 * ip;
+  double r = 0.5 * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+  r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+  const double phi = acos(r) / 3.0;
+  const double l2 = qm + 2.0 * p * cos(phi);
+  const double l0 = qm + 2.0 * p * cos(phi + 2.0943951023931953);
+  const double l1 = 3.0 * qm - l0 - l2;
+  return l2 > tol * l1;
+}
+
 // ---- Equirectangular float path (sensors/Equirectangular.h:41-96 with USE_FAST_ATAN2, base/Math.h:15-29) ----
 PVB_HD float fast_atan2_f32(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
