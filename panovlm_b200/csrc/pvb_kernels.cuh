@@ -130,6 +130,7 @@ template <int K, bool REDUCE, int MINB, bool DEBUG_NN>
 __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
   __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
   __shared__ uint32_t s_win[K][kTile];           // record positions of each query's K neighbours
+  __shared__ uint32_t s_rng[18][kTile];          // the <= 9 (lo, hi) row ranges of each query's 3x3x3 cell block
   const QueryTile t = a.tiles[blockIdx.x];
   const Pair pr = a.pairs[t.pair];
   const int i = threadIdx.x;
@@ -155,13 +156,15 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
     auto load = [srt](long long p) { return ldg_f4(srt + p); };
     auto win = [&](int j) { return s_win[j][i]; };
     auto set_win = [&](int j, uint32_t pos) { s_win[j][i] = pos; };
+    auto range_set = [&](int k, uint32_t lo, uint32_t hi) { s_rng[2 * k][i] = lo; s_rng[2 * k + 1][i] = hi; };
+    auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = s_rng[2 * k][i]; hi = s_rng[2 * k + 1][i]; };
     AssocParams prm = a.prm;
     prm.rmax = (int)ceil(a.thr / g.h);
     if (DEBUG_NN && a.out_nn_idx) {
 #pragma unroll
       for (int j = 0; j < K; ++j) s_win[j][i] = 0xFFFFFFFFu;
     }
-    valid = associate_point2plane<K>(g, cells, load, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win);
+    valid = associate_point2plane<K>(g, cells, load, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set, range_get);
     if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
       for (int j = 0; j < K; ++j) {
         const uint32_t pj = s_win[j][i];
@@ -283,12 +286,24 @@ __global__ void __launch_bounds__(kTile) k_eval_blocks(const EvalArgs a) {
 
 // ---- K4: sum the per-tile partials of each edge / frame in tile order --------------------------------------------------
 template <int NV>
-__global__ void k_sum_partials(const double* __restrict__ partials, const int* __restrict__ tile_begin /*[n_groups+1]*/, double* __restrict__ out) {
-  const int gidx = blockIdx.x, v = threadIdx.x;
-  if (v >= NV) return;
-  double acc = 0.0;
-  for (int t = tile_begin[gidx]; t < tile_begin[gidx + 1]; ++t) acc += partials[(size_t)t * NV + v];
-  out[(size_t)gidx * NV + v] = acc;
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partials, const int* __restrict__ tile_begin /*[n_groups+1]*/, double* __restrict__ out) {
+  // 8 slices x 32 value lanes; slice s sums rows begin+s, begin+s+8, ... ; slices are then added in order 0..7
+  // (fixed order => deterministic).  NV <= 96: values are handled in chunks of 32 lanes.
+  __shared__ double sm[8][96];
+  const int gidx = blockIdx.x, lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int t0 = tile_begin[gidx], t1 = tile_begin[gidx + 1];
+  for (int v = lane; v < NV; v += 32) {
+    double acc = 0.0;
+    for (int t = t0 + slice; t < t1; t += 8) acc += partials[(size_t)t * NV + v];
+    sm[slice][v] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double acc = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) acc += sm[sl][threadIdx.x];
+    out[(size_t)gidx * NV + threadIdx.x] = acc;
+  }
 }
 
 // ---- K1: SE(3) + equirectangular projection (float32 FastAtan2 path) --------------------------------------------------

@@ -113,10 +113,30 @@ PVB_HD void for_each_range(const GridDesc& g, const CellLoader& cells, int cx, i
   }
 }
 
+// Flattened walk over a list of record ranges: every lane advances through ITS candidates back to back, so the
+// trip count of a warp is the longest lane's total (not the sum over rows of the longest row).
+template <typename RangeGet, typename Body>
+PVB_HD void walk_ranges(int n_ranges, const RangeGet& range, const Body& body) {
+  int row = 0;
+  uint32_t i = 0, hi = 0;
+  for (;;) {
+    while (i >= hi) {
+      if (row >= n_ranges) return;
+      range(row, i, hi);
+      ++row;
+    }
+    body((long long)i);
+    ++i;
+  }
+}
+
 // Exact K-NN of (qx,qy,qz) within sqrt(sq_thr).  Returns the number of neighbours handed to sink (K, or 0 when the
 // K-th nearest is beyond the threshold / fewer than K points are in reach).  sink(j, record position, d2 bits).
-template <int K, typename CellLoader, typename PointLoader, typename Sink>
-PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoader& load, float qx, float qy, float qz, float sq_thr, int rmax, const Sink& sink) {
+// range_set(idx, lo, hi) / range_get(idx, lo&, hi&): caller-provided storage for the <= 9 row ranges of the 3x3x3
+// block (shared memory on the device).
+template <int K, typename CellLoader, typename PointLoader, typename Sink, typename RangeSet, typename RangeGet>
+PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoader& load, float qx, float qy, float qz, float sq_thr, int rmax, const Sink& sink,
+                      const RangeSet& range_set, const RangeGet& range_get) {
   const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
   uint32_t keys[K];
 #pragma unroll
@@ -136,23 +156,47 @@ PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoa
       slack = m < slack ? m : slack;
     }
   }
+  // ---- ring 1: the 3x3x3 block = up to 9 contiguous row ranges, looked up once and walked twice
+  int n_ranges = 0;
+  for_each_range(g, cells, cx, cy, cz, 1, true, [&](long long lo, long long hi) { if (hi > lo) { range_set(n_ranges, (uint32_t)lo, (uint32_t)hi); ++n_ranges; } });
+  walk_ranges(n_ranges, range_get, [&](long long i) {
+    const F4 c = load(i);
+    topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
+  });
   int r = 1;
-  for (; r <= rmax; ++r) {
-    for_each_range(g, cells, cx, cy, cz, r, false, [&](long long lo, long long hi) { scan_values<K>(load, lo, hi, qx, qy, qz, keys); });
-    if (keys[K - 1] != init) {      // ring r covers every point closer than (r + slack) * h
-      const double reach = ((double)r + slack) * g.h;
-      if ((double)u2f(keys[K - 1]) < reach * reach * (1.0 - 1e-6)) break;
+  bool done = false;
+  if (keys[K - 1] != init) {
+    const double reach = (1.0 + slack) * g.h;
+    done = (double)u2f(keys[K - 1]) < reach * reach * (1.0 - 1e-6);
+  }
+  if (!done) {        // rare: widen ring by ring (generic nested loops)
+    for (r = 2; r <= rmax; ++r) {
+      for_each_range(g, cells, cx, cy, cz, r, false, [&](long long lo, long long hi) { scan_values<K>(load, lo, hi, qx, qy, qz, keys); });
+      if (keys[K - 1] != init) {      // ring r covers every point closer than (r + slack) * h
+        const double reach = ((double)r + slack) * g.h;
+        if ((double)u2f(keys[K - 1]) < reach * reach * (1.0 - 1e-6)) break;
+      }
     }
+    if (r > rmax) r = rmax;
   }
   if (keys[K - 1] == init) return 0;
-  if (r > rmax) r = rmax;
   const uint32_t tau = keys[K - 1];
   int n_lt = 0;
 #pragma unroll
   for (int j = 0; j < K; ++j) n_lt += keys[j] < tau ? 1 : 0;
   int eq_taken = 0, n_out = 0;
   const int eq_needed = K - n_lt;
-  for_each_range(g, cells, cx, cy, cz, r, true, [&](long long lo, long long hi) { scan_collect(load, lo, hi, qx, qy, qz, tau, eq_needed, eq_taken, n_out, sink); });
+  if (r == 1) {
+    walk_ranges(n_ranges, range_get, [&](long long i) {
+      const F4 c = load(i);
+      const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
+      bool take = kb < tau;
+      if (kb == tau && eq_taken < eq_needed) { take = true; ++eq_taken; }
+      if (take) { sink(n_out, (uint32_t)i, kb); ++n_out; }
+    });
+  } else {
+    for_each_range(g, cells, cx, cy, cz, r, true, [&](long long lo, long long hi) { scan_collect(load, lo, hi, qx, qy, qz, tau, eq_needed, eq_taken, n_out, sink); });
+  }
   return n_out;
 }
 
@@ -167,12 +211,12 @@ struct AssocParams {
 // R_ref/t_ref, R_nei/t_nei = R_wl, t_wl of the two frames.  On success: p_local (query in the neighbour's
 // sensor frame, double) and plane (n, d) in the reference sensor frame.  win(j) / set_win(j, pos) access the
 // caller's per-query neighbour slots (shared memory on the device).
-template <int K, typename CellLoader, typename PointLoader, typename WinGet, typename WinSet>
+template <int K, typename CellLoader, typename PointLoader, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
 PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const PointLoader& load, const AssocParams& prm,
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
-                                  double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win) {
-  const int found = knn_select<K>(g, cells, load, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); });
+                                  double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get) {
+  const int found = knn_select<K>(g, cells, load, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get);
   if (found < K) return false;                                   // :578 (k-th beyond the threshold) + quirk C.6 guard
   // neighbours -> reference sensor frame (:587), streamed: Gram matrix for the LSQ plane and the scatter matrix
   PlaneAcc acc; plane_acc_clear(acc);

@@ -364,7 +364,7 @@ int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int wa
     k_eval_blocks<<<ctx->b_tiles, kTile, 0, ctx->stream>>>(a);
     CKL();
     if (want_system) {
-      k_sum_partials<92><<<ne, 96, 0, ctx->stream>>>(ctx->b_part.as<double>(), ctx->b_tbegin.as<int>(), ctx->b_esys.as<double>());
+      k_sum_partials<92><<<ne, 256, 0, ctx->stream>>>(ctx->b_part.as<double>(), ctx->b_tbegin.as<int>(), ctx->b_esys.as<double>());
       CKL();
       CK(cudaMemcpyAsync(ctx->h_esys.p, ctx->b_esys.p, (size_t)ne * 92 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -636,7 +636,7 @@ int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_de
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;
   double* dst = (dev_sys && *dev_sys) ? *dev_sys : ctx->d_sys.as<double>();   // caller-provided device buffer (e.g. a slice of an allreduce buffer)
-  k_sum_partials<29><<<ctx->d_frames, 32, 0, ctx->stream>>>(ctx->d_part.as<double>(), ctx->d_tbegin.as<int>(), dst);
+  k_sum_partials<29><<<ctx->d_frames, 256, 0, ctx->stream>>>(ctx->d_part.as<double>(), ctx->d_tbegin.as<int>(), dst);
   CKL();
   if (dev_sys) *dev_sys = dst;
   return PVB_OK;
