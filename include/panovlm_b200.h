@@ -143,6 +143,53 @@ int pvb_line_votes(pvb_ctx* ctx, const double* ref_lines_world6, int n_ref_lines
 int pvb_angle_votes(pvb_ctx* ctx, int rows, int cols, const float* lines4, int n_lines, const float* cloud_local, int n_points,
                     const int* p2s_off, const int* p2s_ids, int n_segments, const double* T_cl16, int* counts);
 
+/* ---- G. host-side builders around the kernels (C++ in the library, no device math of their own) ----------- */
+/* FindNeighbors (lidar_mapping/LidarFeatureAssociate.cpp:19-111): k nearest frame centres (float32, self excluded),
+ * previous / next frame with a valid pose, loop candidates within 20 m more than 200 frames away from all but one of
+ * the current neighbours; frames without a pose get their temporal neighbours.  t_wl: n x 3 frame positions.
+ * out_offsets: n+1, out_neighbors: up to cap entries.  Returns the number of neighbour entries or < 0.          */
+int pvb_find_neighbors(int n_frames, const double* t_wl, const unsigned char* pose_valid, const unsigned char* frame_valid,
+                       int neighbor_size, int* out_offsets, int* out_neighbors, int cap);
+
+typedef struct {
+  const float* corner_local; int n_corner;      /* cornerLessSharp, n x 4, sensor frame                                 */
+  const int* p2s_off; const int* p2s_ids;       /* point_to_segment as CSR (sensors/Velodyne.h:89)                       */
+  int n_segments;
+  const double* segment_coeffs;                 /* n_segments x 6: point + unit direction, sensor frame (Velodyne.h:87)   */
+  const double* end_points;                     /* n_segments x 2 x 3, sensor frame (Velodyne.h:88); may be NULL for A2   */
+  const double* R_wl; const double* t_wl;       /* pose (row-major R)                                                      */
+} pvb_line_frame;
+
+/* AssociateLine2Line (LidarFeatureAssociate.cpp:442-476) + FindAssociations (:120-197): vote matrix on the device, the
+ * per-segment arg-max / 7 degree / many-to-one tail on the host.  Outputs sized for nei->n_segments entries:
+ * neighbour line, reference line, and the two synthetic end points c +- 0.1 d of the reference line (its sensor frame). */
+int pvb_line2line_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, double dist_threshold,
+                            int* n_out, int* nei_line, int* ref_line, double* point_a3, double* point_b3);
+
+/* CameraLidarLineAssociate::AssociateByAngle (joint_optimization/CameraLidarLineAssociate.cpp:340-475) followed by
+ * Filter(false, filter_by_length) (:628-715): per (image line, LiDAR segment) vote counts on the device, acceptance tests,
+ * projected-length filter and the transform back to the LiDAR frame on the host.  Outputs sized for cap pairs.        */
+int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* lines4, int n_lines, const pvb_line_frame* lidar,
+                               const double* T_cl16, int filter_by_length, int cap, int* n_out, int* image_line, int* lidar_line,
+                               double* start3, double* end3, float* angle);
+
+/* Residual-block builders == the AddResidualBlock loops of util/Optimization.cpp.  Each appends to caller arrays
+ * (type, ref, nei, normalize: int; huber: double; consts: 12 doubles per block) starting at index `at` and returns the new
+ * count (or < 0).  Angle residuals use HuberLoss(2 deg) for planes and no loss for line-to-line (Optimization.cpp:417).  */
+int pvb_build_point2plane_blocks(long n, const double* point3, const double* plane4, int ref_block, int nei_block, int angle_residual,
+                                 int normalize_distance, double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize,
+                                 double* huber, double* consts);           /* Optimization.cpp:506-562 */
+/* one block per point of the neighbour segment (world float32 -> neighbour sensor frame, Optimization.cpp:403-431) */
+int pvb_build_line2line_blocks(const pvb_line_frame* nei, const float* nei_corner_world, int nei_line, const double* point_a3,
+                               const double* point_b3, int ref_block, int nei_block, int angle_residual, int normalize_distance, double weight,
+                               long at, long cap, int* type, int* ref, int* nei_out, int* normalize, double* huber, double* consts);
+/* two blocks per pair: Plane2Plane_Global + PlaneIOUResidual, HuberLoss(3 deg) (Optimization.cpp:564-607) */
+int pvb_build_camera_lidar_blocks(int rows, int cols, int n_pairs, const float* image_line4, const double* start3, const double* end3,
+                                  const float* pair_weight, int cam_block, int lidar_block, double weight, long at, long cap, int* type, int* ref,
+                                  int* nei, int* normalize, double* huber, double* consts);
+/* pcl::transformPointCloud of one cloud on the device (sensors/Velodyne.cpp:1790-1806): n x 4 float32 in, n x 4 out     */
+int pvb_transform_cloud(pvb_ctx* ctx, const float* xyzi, long n, const double* R9, const double* t3, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,41 @@ class _Frame(C.Structure):
     _fields_ = [("surf_target", C.c_void_p), ("n_target", C.c_int), ("surf_query", C.c_void_p), ("n_query", C.c_int)]
 
 
+class _LineFrame(C.Structure):
+    _fields_ = [("corner_local", C.c_void_p), ("n_corner", C.c_int), ("p2s_off", C.c_void_p), ("p2s_ids", C.c_void_p), ("n_segments", C.c_int),
+                ("segment_coeffs", C.c_void_p), ("end_points", C.c_void_p), ("R_wl", C.c_void_p), ("t_wl", C.c_void_p)]
+
+
+class LineFrame:
+    """Host arrays of one frame's corner features (pvb_line_frame); keeps the numpy buffers alive."""
+
+    def __init__(self, corner_local, p2s_off, p2s_ids, segment_coeffs, end_points, R_wl, t_wl):
+        self.corner = _arr(corner_local, np.float32).reshape(-1, 4)
+        self.p2s_off, self.p2s_ids = _arr(p2s_off, np.int32), _arr(p2s_ids, np.int32)
+        self.coeffs = _arr(segment_coeffs, np.float64).reshape(-1, 6)
+        self.ends = None if end_points is None else _arr(end_points, np.float64).reshape(-1, 6)
+        self.R, self.t = _arr(R_wl, np.float64).reshape(3, 3), _arr(t_wl, np.float64).reshape(3)
+        self.c = _LineFrame(self.corner.ctypes.data, len(self.corner), self.p2s_off.ctypes.data, self.p2s_ids.ctypes.data if len(self.p2s_ids) else None,
+                            len(self.coeffs), self.coeffs.ctypes.data if len(self.coeffs) else None, None if self.ends is None else self.ends.ctypes.data,
+                            self.R.ctypes.data, self.t.ctypes.data)
+
+
+class BlockList:
+    """Growable parallel arrays of residual blocks filled by the pvb_build_* entry points."""
+
+    def __init__(self, cap):
+        self.cap, self.n = cap, 0
+        self.type, self.ref, self.nei, self.normalize = (np.zeros(cap, np.int32) for _ in range(4))
+        self.huber, self.consts = np.zeros(cap), np.zeros((cap, 12))
+
+    def args(self):
+        return (C.c_long(self.n), C.c_long(self.cap), _p(self.type), _p(self.ref), _p(self.nei), _p(self.normalize), _p(self.huber), _p(self.consts))
+
+    def view(self):
+        n = self.n
+        return dict(type=self.type[:n], ref=self.ref[:n], nei=self.nei[:n], normalize=self.normalize[:n], huber=self.huber[:n], consts=self.consts[:n])
+
+
 class _AssocParams(C.Structure):
     _fields_ = [("plane_tolerance", C.c_double), ("dist_threshold", C.c_float), ("k", C.c_int), ("cell_size", C.c_double)]
 
@@ -67,6 +102,8 @@ EXPORTS = [
     "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn",
     "pvb_dense_set_target", "pvb_dense_set_sources", "pvb_dense_evaluate", "pvb_dense_evaluate_device", "pvb_dense_gauss_newton_step",
     "pvb_dense_get_rows", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
+    "pvb_find_neighbors", "pvb_line2line_associate", "pvb_camera_lidar_associate", "pvb_build_point2plane_blocks", "pvb_build_line2line_blocks",
+    "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
 ]
 
 
@@ -253,6 +290,72 @@ class Context:
         v, pt, pl, r, j = np.zeros(n, np.uint8), np.zeros((n, 3)), np.zeros((n, 4)), np.zeros(n), np.zeros((n, 6))
         self._ck(self._L.pvb_dense_get_rows(self._h, _p(poses), C.byref(prm), _p(v), _p(pt), _p(pl), _p(r), _p(j)))
         return v.astype(bool), pt, pl, r, j
+
+    # ---- G. host builders
+    @staticmethod
+    def find_neighbors(t_wl, pose_valid=None, frame_valid=None, neighbor_size=6):
+        t = _arr(t_wl, np.float64).reshape(-1, 3)
+        n = len(t)
+        pv = None if pose_valid is None else _arr(pose_valid, np.uint8)
+        fv = None if frame_valid is None else _arr(frame_valid, np.uint8)
+        off, out = np.zeros(n + 1, np.int32), np.zeros(n * (neighbor_size + 64), np.int32)
+        m = load_library().pvb_find_neighbors(C.c_int(n), _p(t), _p(pv), _p(fv), C.c_int(neighbor_size), _p(off), _p(out), C.c_int(len(out)))
+        if m < 0:
+            raise PvbError(f"pvb_find_neighbors: code {m}")
+        return [out[off[i]:off[i + 1]].tolist() for i in range(n)]
+
+    def transform_cloud(self, xyzi, R, t):
+        a = _arr(xyzi, np.float32).reshape(-1, 4)
+        out = np.empty_like(a)
+        self._ck(self._L.pvb_transform_cloud(self._h, _p(a), C.c_long(len(a)), _p(_arr(R, np.float64)), _p(_arr(t, np.float64)), _p(out)))
+        return out
+
+    def line2line_associate(self, ref, nei, dist_threshold):
+        S = max(1, nei.c.n_segments)
+        nl, rl, a, b, n = np.zeros(S, np.int32), np.zeros(S, np.int32), np.zeros((S, 3)), np.zeros((S, 3)), C.c_int()
+        self._ck(self._L.pvb_line2line_associate(self._h, C.byref(ref.c), C.byref(nei.c), C.c_double(dist_threshold), C.byref(n), _p(nl), _p(rl), _p(a), _p(b)))
+        m = n.value
+        return nl[:m].copy(), rl[:m].copy(), a[:m].copy(), b[:m].copy()
+
+    def camera_lidar_associate(self, rows, cols, lines, lidar, T_cl, filter_by_length=True):
+        ln = _arr(lines, np.float32).reshape(-1, 4)
+        cap = max(1, len(ln) * max(1, lidar.c.n_segments))
+        il, ll, s, e, ang, n = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros(cap, np.float32), C.c_int()
+        self._ck(self._L.pvb_camera_lidar_associate(self._h, C.c_int(rows), C.c_int(cols), _p(ln), C.c_int(len(ln)), C.byref(lidar.c), _p(_arr(T_cl, np.float64)),
+                                                     C.c_int(int(filter_by_length)), C.c_int(cap), C.byref(n), _p(il), _p(ll), _p(s), _p(e), _p(ang)))
+        m = n.value
+        return il[:m].copy(), ll[:m].copy(), s[:m].copy(), e[:m].copy(), ang[:m].copy()
+
+    @staticmethod
+    def build_point2plane_blocks(bl, point, plane, ref_block, nei_block, angle_residual, normalize_distance, weight):
+        pt, pl = _arr(point, np.float64).reshape(-1, 3), _arr(plane, np.float64).reshape(-1, 4)
+        n, cap, *arrs = bl.args()
+        m = load_library().pvb_build_point2plane_blocks(C.c_long(len(pt)), _p(pt), _p(pl), C.c_int(ref_block), C.c_int(nei_block), C.c_int(int(angle_residual)),
+                                                        C.c_int(int(normalize_distance)), C.c_double(weight), n, cap, *arrs)
+        if m < 0:
+            raise PvbError(f"pvb_build_point2plane_blocks: code {m}")
+        bl.n = m
+
+    @staticmethod
+    def build_line2line_blocks(bl, nei, nei_corner_world, nei_line, a, b, ref_block, nei_block, angle_residual, normalize_distance, weight):
+        w = _arr(nei_corner_world, np.float32).reshape(-1, 4)
+        n, cap, *arrs = bl.args()
+        m = load_library().pvb_build_line2line_blocks(C.byref(nei.c), _p(w), C.c_int(int(nei_line)), _p(_arr(a, np.float64)), _p(_arr(b, np.float64)), C.c_int(ref_block),
+                                                      C.c_int(nei_block), C.c_int(int(angle_residual)), C.c_int(int(normalize_distance)), C.c_double(weight), n, cap, *arrs)
+        if m < 0:
+            raise PvbError(f"pvb_build_line2line_blocks: code {m}")
+        bl.n = m
+
+    @staticmethod
+    def build_camera_lidar_blocks(bl, rows, cols, image_lines, start, end, pair_weight, cam_block, lidar_block, weight):
+        ln, s, e = _arr(image_lines, np.float32).reshape(-1, 4), _arr(start, np.float64).reshape(-1, 3), _arr(end, np.float64).reshape(-1, 3)
+        pw = None if pair_weight is None else _arr(pair_weight, np.float32)
+        n, cap, *arrs = bl.args()
+        m = load_library().pvb_build_camera_lidar_blocks(C.c_int(rows), C.c_int(cols), C.c_int(len(ln)), _p(ln), _p(s), _p(e), _p(pw), C.c_int(cam_block), C.c_int(lidar_block),
+                                                         C.c_double(weight), n, cap, *arrs)
+        if m < 0:
+            raise PvbError(f"pvb_build_camera_lidar_blocks: code {m}")
+        bl.n = m
 
     # ---- D/E/F
     def project_equirect(self, xyzi, T_cl, rows, cols):

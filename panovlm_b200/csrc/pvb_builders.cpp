@@ -1,0 +1,340 @@
+// panovlm_b200 — host-side builders around the kernels (C++ because the reference's host is C++).
+// Mirrors the serial loops of util/Optimization.cpp:329-607 and the tails of the association functions that stay on
+// the host (small integer / per-segment work): lidar_mapping/LidarFeatureAssociate.cpp:19-111, 120-197 and
+// joint_optimization/CameraLidarLineAssociate.cpp:415-475, 628-715.  Only public pvb_* entry points are used for the
+// device work (vote matrices, cloud transforms).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <set>
+#include <vector>
+#include "../../include/panovlm_b200.h"
+#include "pvb_math.cuh"
+
+using namespace pvb;
+
+namespace {
+
+// base/Geometry.hpp helpers in plain double (host).  The build uses -ffp-contract=off like the reference's distro libs.
+inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline double sq(double a) { return a * a; }
+inline double vector_angle(const double* a, const double* b, bool normalized = false) {   // :450-466
+  double c = dot3(a, b);
+  if (!normalized) c /= (std::sqrt(sq(a[0]) + sq(a[1]) + sq(a[2])) * std::sqrt(sq(b[0]) + sq(b[1]) + sq(b[2])));
+  if (c >= 1.0) return 0.0;
+  if (c <= -1.0) return M_PI;
+  return std::acos(c);
+}
+inline double plane_angle(const double* a, const double* b, bool normalized = false) {   // :471-485
+  double c = std::fabs(dot3(a, b));
+  if (!normalized) c /= (std::sqrt(sq(a[0]) + sq(a[1]) + sq(a[2])) * std::sqrt(sq(b[0]) + sq(b[1]) + sq(b[2])));
+  if (c >= 1.0) return 0.0;
+  return std::acos(c);
+}
+inline double point_to_line(const double* p, const double* l) {   // :198-211
+  const double k = (l[3] * (p[0] - l[0]) + l[4] * (p[1] - l[1]) + l[5] * (p[2] - l[2])) / (sq(l[3]) + sq(l[4]) + sq(l[5]));
+  const double q[3] = {k * l[3] + l[0], k * l[4] + l[1], k * l[5] + l[2]};
+  return std::sqrt(sq(q[0] - p[0]) + sq(q[1] - p[1]) + sq(q[2] - p[2]));
+}
+inline void project_to_plane(const double* p, const double* pl, double* out) {   // :301-316, normalized == true
+  const double t = std::fabs(pl[0] * p[0] + pl[1] * p[1] + pl[2] * p[2] + pl[3]);
+  for (int k = 0; k < 3; ++k) out[k] = p[k] - t * pl[k];
+  if (std::fabs(pl[0] * out[0] + pl[1] * out[1] + pl[2] * out[2] + pl[3]) > 1e-4)
+    for (int k = 0; k < 3; ++k) out[k] = p[k] + t * pl[k];
+}
+inline void plane_through_origin(const double* p1, const double* p2, double* pl) {   // FormPlane(p1, p2, 0) :328-336, then 4-vector normalize
+  const double z[3] = {0, 0, 0};
+  pl[0] = (p2[1] - p1[1]) * (z[2] - p1[2]) - (p2[2] - p1[2]) * (z[1] - p1[1]);
+  pl[1] = (p2[2] - p1[2]) * (z[0] - p1[0]) - (p2[0] - p1[0]) * (z[2] - p1[2]);
+  pl[2] = (p2[0] - p1[0]) * (z[1] - p1[1]) - (p2[1] - p1[1]) * (z[0] - p1[0]);
+  pl[3] = -(pl[0] * p1[0] + pl[1] * p1[1] + pl[2] * p1[2]);
+}
+inline void normalize4(double* pl) { const double n = std::sqrt(sq(pl[0]) + sq(pl[1]) + sq(pl[2]) + sq(pl[3])); for (int k = 0; k < 4; ++k) pl[k] /= n; }
+inline void transform4(const double* T, const double* p, double* out) {   // (T * p.homogeneous()).hnormalized() for a rigid T
+  for (int r = 0; r < 3; ++r) out[r] = T[r * 4] * p[0] + T[r * 4 + 1] * p[1] + T[r * 4 + 2] * p[2] + T[r * 4 + 3];
+}
+inline void transform_line(const double* R, const double* t, const double* in, double* out) {   // TransformLines :219-236
+  for (int r = 0; r < 3; ++r) {
+    out[r] = R[r * 3] * in[0] + R[r * 3 + 1] * in[1] + R[r * 3 + 2] * in[2] + t[r];
+    out[3 + r] = R[r * 3] * in[3] + R[r * 3 + 1] * in[4] + R[r * 3 + 2] * in[5];
+  }
+}
+
+// float image -> camera ray of radius r (Equirectangular.h:98-146 with T = float)
+inline void image_to_cam_f32(float px, float py, int rows, int cols, float r, float* cam) {
+  const float lon = (2 * px / cols - 1) * M_PI;
+  const float lat = (0.5 - py / rows) * M_PI;
+  const float cy = std::cos(lat);
+  cam[0] = r * cy * std::sin(lon);
+  cam[1] = -r * std::sin(lat);
+  cam[2] = r * cy * std::cos(lon);
+}
+
+// Equirectangular::BreakToSegments (sensors/Equirectangular.cpp:20-58)
+std::vector<std::pair<float, float>> break_to_segments(int rows, int cols, const float* start, const float* end, float seg_length) {
+  float p1[3], p2[3];
+  image_to_cam_f32(start[0], start[1], rows, cols, 5.0f, p1);
+  image_to_cam_f32(end[0], end[1], rows, cols, 5.0f, p2);
+  const float sl[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  const float length = std::sqrt((start[0] - end[0]) * (start[0] - end[0]) + (start[1] - end[1]) * (start[1] - end[1]));
+  const int count = length / seg_length + 1;
+  std::vector<std::pair<float, float>> seg = {{start[0], start[1]}};
+  for (int i = 1; i < count; ++i) {
+    const float f = i * 1.f / count;
+    float u, v;
+    cam_to_image_f32(p1[0] + f * sl[0], p1[1] + f * sl[1], p1[2] + f * sl[2], rows, cols, u, v);
+    if (std::abs(u - seg.back().first) > 0.8 * cols) {
+      const float g = p1[0] / (p1[0] - p2[0]);
+      float lu, lv;
+      cam_to_image_f32(p1[0] + g * sl[0], p1[1] + g * sl[1], p1[2] + g * sl[2], rows, cols, lu, lv);
+      const std::pair<float, float> L{0.f, lv}, R{float(cols - 1), lv};
+      if (u > seg.back().first) { seg.push_back(L); seg.push_back(R); }
+      else { seg.push_back(R); seg.push_back(L); }
+    }
+    seg.push_back({u, v});
+  }
+  seg.push_back({end[0], end[1]});
+  return seg;
+}
+
+struct BlockOut { long at, cap; int* type; int* ref; int* nei; int* normalize; double* huber; double* consts; };
+inline bool push_block(BlockOut& o, int type, int ref, int nei, int normalize, double huber, const double c[12]) {
+  if (o.at >= o.cap) return false;
+  o.type[o.at] = type; o.ref[o.at] = ref; o.nei[o.at] = nei; o.normalize[o.at] = normalize; o.huber[o.at] = huber;
+  std::memcpy(o.consts + 12 * o.at, c, 96);
+  ++o.at;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pvb_find_neighbors(int n, const double* t_wl, const unsigned char* pose_valid, const unsigned char* frame_valid, int neighbor_size,
+                       int* out_offsets, int* out_neighbors, int cap) {
+  if (n <= 0 || !t_wl || !out_offsets || !out_neighbors || neighbor_size < 1) return PVB_ERR_ARG;
+  auto pv = [&](int i) { return !pose_valid || pose_valid[i]; };
+  auto fv = [&](int i) { return !frame_valid || frame_valid[i]; };
+  std::vector<int> centre_frame;             // lidar_center cloud: frames with a valid pose AND valid data (:25-38)
+  std::vector<float> centre;
+  for (int i = 0; i < n; ++i)
+    if (pv(i) && fv(i)) { centre_frame.push_back(i); for (int k = 0; k < 3; ++k) centre.push_back((float)t_wl[3 * i + k]); }
+  const int m = (int)centre_frame.size();
+  int total = 0;
+  out_offsets[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    std::vector<int> neighbors;
+    if (pv(i)) {
+      const float q[3] = {(float)t_wl[3 * i], (float)t_wl[3 * i + 1], (float)t_wl[3 * i + 2]};
+      std::vector<std::pair<float, int>> d(m);
+      for (int j = 0; j < m; ++j) d[j] = {sqdist_f32(q[0], q[1], q[2], centre[3 * j], centre[3 * j + 1], centre[3 * j + 2]), j};
+      std::sort(d.begin(), d.end());
+      const int k = std::min(neighbor_size, m);
+      for (int j = 0; j < k; ++j) neighbors.push_back(d[j].second);
+      if (!neighbors.empty()) neighbors.erase(neighbors.begin());              // the first is the frame itself (:52)
+      for (int& v : neighbors) v = centre_frame[v];
+      std::set<int> nset(neighbors.begin(), neighbors.end());
+      int p = i - 1;
+      while (p >= 0 && !pv(p)) --p;
+      if (p >= 0 && nset.count(p) == 0) neighbors.push_back(p);
+      p = i + 1;
+      while (p < n && !pv(p)) ++p;
+      if (p < n && nset.count(p) == 0) neighbors.push_back(p);
+      const float r2 = 20.0f * 20.0f;                                          // loop candidates (:79-98), sorted by distance
+      for (int j = 0; j < m && d[j].first < r2; ++j) {
+        const int cand = centre_frame[d[j].second];
+        int same_loop = 0;
+        for (int it : nset) { if (std::abs(cand - it) <= 200) ++same_loop; if (same_loop >= 2) break; }
+        if (same_loop < 2 && nset.count(cand) == 0) { neighbors.push_back(cand); nset.insert(cand); }
+      }
+    } else {
+      for (int j = -neighbor_size / 2; j <= neighbor_size / 2; ++j) neighbors.push_back(i - j);   // :103-106 (may be out of range; callers filter)
+    }
+    for (int v : neighbors) { if (total >= cap) return PVB_ERR_ARG; out_neighbors[total++] = v; }
+    out_offsets[i + 1] = total;
+  }
+  return total;
+}
+
+int pvb_line2line_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, double dist_threshold, int* n_out, int* nei_line, int* ref_line,
+                            double* point_a3, double* point_b3) {
+  if (!ctx || !ref || !nei || !n_out) return PVB_ERR_ARG;
+  *n_out = 0;
+  const int Sr = ref->n_segments, Sn = nei->n_segments;
+  if (Sr == 0 || Sn == 0) return PVB_OK;                                       // CheckLidarSegment (:208-216)
+  std::vector<double> ref_w((size_t)Sr * 6), nei_w((size_t)Sn * 6);
+  for (int s = 0; s < Sr; ++s) transform_line(ref->R_wl, ref->t_wl, ref->segment_coeffs + 6 * s, &ref_w[6 * s]);
+  for (int s = 0; s < Sn; ++s) transform_line(nei->R_wl, nei->t_wl, nei->segment_coeffs + 6 * s, &nei_w[6 * s]);
+  std::vector<float> world((size_t)std::max(1, nei->n_corner) * 4);
+  int rc = pvb_transform_cloud(ctx, nei->corner_local, nei->n_corner, nei->R_wl, nei->t_wl, world.data());
+  if (rc) return rc;
+  std::vector<int> M((size_t)Sn * Sr, 0);
+  rc = pvb_line_votes(ctx, ref_w.data(), Sr, world.data(), nei->n_corner, nei->p2s_off, nei->p2s_ids, Sn, dist_threshold, M.data());
+  if (rc) return rc;
+  std::vector<int> seg_size(Sn, 0);                                            // edge_segmented[s].size()
+  for (int i = 0; i < nei->n_corner; ++i) for (int e = nei->p2s_off[i]; e < nei->p2s_off[i + 1]; ++e) seg_size[nei->p2s_ids[e]]++;
+  struct A { int nl, rl; double a[3], b[3]; };
+  std::map<int, A> assoc;                                                      // eigen_map<int, Line2Line> keyed by the reference line
+  for (int s = 0; s < Sn; ++s) {
+    int max_col = 0, max_count = M[(size_t)s * Sr];
+    for (int c = 1; c < Sr; ++c) if (M[(size_t)s * Sr + c] > max_count) { max_count = M[(size_t)s * Sr + c]; max_col = c; }
+    if ((size_t)max_count < (size_t)seg_size[s] / 2) continue;                 // :132
+    if (plane_angle(&ref_w[6 * max_col + 3], &nei_w[6 * s + 3]) * 180.0 / M_PI > 7) continue;   // :138
+    const double* cl = ref->segment_coeffs + 6 * max_col;
+    A a; a.nl = s; a.rl = max_col;
+    for (int k = 0; k < 3; ++k) { a.a[k] = 0.1 * cl[3 + k] + cl[k]; a.b[k] = -0.1 * cl[3 + k] + cl[k]; }   // :144-145
+    auto it = assoc.find(max_col);
+    if (it == assoc.end()) assoc.insert({max_col, a});
+    else {
+      const double d1 = point_to_line(&nei_w[6 * it->second.nl], &ref_w[6 * max_col]);
+      const double d2 = point_to_line(&nei_w[6 * s], &ref_w[6 * max_col]);
+      if (d2 < d1) it->second = a;
+    }
+  }
+  int n = 0;
+  for (auto& kv : assoc) {
+    nei_line[n] = kv.second.nl; ref_line[n] = kv.second.rl;
+    std::memcpy(point_a3 + 3 * n, kv.second.a, 24); std::memcpy(point_b3 + 3 * n, kv.second.b, 24);
+    ++n;
+  }
+  *n_out = n;
+  return PVB_OK;
+}
+
+int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* lines4, int L, const pvb_line_frame* lidar, const double* T, int filter_by_length,
+                               int cap, int* n_out, int* image_line, int* lidar_line, double* start3, double* end3, float* angle_out) {
+  if (!ctx || !lidar || !T || !n_out || !lidar->end_points) return PVB_ERR_ARG;
+  *n_out = 0;
+  const int S = lidar->n_segments;
+  if (L == 0 || S == 0) return PVB_OK;
+  std::vector<int> counts((size_t)L * S, 0);
+  int rc = pvb_angle_votes(ctx, rows, cols, lines4, L, lidar->corner_local, lidar->n_corner, lidar->p2s_off, lidar->p2s_ids, S, T, counts.data());
+  if (rc) return rc;
+  std::vector<int> seg_size(S, 0);
+  for (int i = 0; i < lidar->n_corner; ++i) for (int e = lidar->p2s_off[i]; e < lidar->p2s_off[i + 1]; ++e) seg_size[lidar->p2s_ids[e]]++;
+  std::vector<double> ep((size_t)S * 6), lplane((size_t)S * 4);
+  for (int s = 0; s < S; ++s) {                                                // :373-386
+    transform4(T, lidar->end_points + 6 * s, &ep[6 * s]);
+    transform4(T, lidar->end_points + 6 * s + 3, &ep[6 * s + 3]);
+    plane_through_origin(&ep[6 * s], &ep[6 * s + 3], &lplane[4 * s]);
+    normalize4(&lplane[4 * s]);
+  }
+  const double thr = 3.0 / 180.0 * M_PI;
+  struct P { int il, ll; double s[3], e[3]; float ang; };
+  std::vector<P> pairs;
+  for (int l = 0; l < L; ++l) {
+    double p1[3], p2[3], plane[4];
+    image_to_cam_f64(lines4[l * 4], lines4[l * 4 + 1], rows, cols, p1);
+    image_to_cam_f64(lines4[l * 4 + 2], lines4[l * 4 + 3], rows, cols, p2);
+    plane_through_origin(p1, p2, plane);
+    normalize4(plane);
+    const double p4[3] = {(p1[0] + p2[0]) / 2.0, (p1[1] + p2[1]) / 2.0, (p1[2] + p2[2]) / 2.0};
+    const double scope = vector_angle(p1, p4);
+    for (int s = 0; s < S; ++s) {                                              // std::map order = ascending segment id (:415)
+      const int cnt = counts[(size_t)l * S + s];
+      if (cnt == 0) continue;
+      if ((size_t)cnt < (size_t)seg_size[s] / 2) continue;                     // :417
+      const double ang = plane_angle(plane, &lplane[4 * s], true);
+      if (ang > thr) continue;                                                 // :422-424
+      double mid[3], midp[3];
+      for (int k = 0; k < 3; ++k) mid[k] = (ep[6 * s + k] + ep[6 * s + 3 + k]) / 2.f;
+      project_to_plane(mid, plane, midp);
+      if (vector_angle(midp, p4) > scope) continue;                            // :433
+      const float ang2 = vector_angle(mid, midp);
+      if (ang2 > thr / 2.0) continue;                                          // :436
+      P pr; pr.il = l; pr.ll = s; pr.ang = ang + ang2;
+      std::memcpy(pr.s, &ep[6 * s], 24); std::memcpy(pr.e, &ep[6 * s + 3], 24);
+      pairs.push_back(pr);
+    }
+  }
+  double Tlc[16] = {0};                                                         // T_cl^-1 (rigid), :469
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Tlc[r * 4 + c] = T[c * 4 + r];
+  for (int r = 0; r < 3; ++r) Tlc[r * 4 + 3] = -(Tlc[r * 4] * T[3] + Tlc[r * 4 + 1] * T[7] + Tlc[r * 4 + 2] * T[11]);
+  Tlc[15] = 1;
+  int n = 0;
+  for (const P& p : pairs) {
+    if (filter_by_length) {                                                    // Filter(false, true): :676-692
+      float ua, va, ub, vb;
+      cam_to_image_f32((float)p.s[0], (float)p.s[1], (float)p.s[2], rows, cols, ua, va);
+      cam_to_image_f32((float)p.e[0], (float)p.e[1], (float)p.e[2], rows, cols, ub, vb);
+      const float a[2] = {ua, va}, b[2] = {ub, vb};
+      const auto seg = break_to_segments(rows, cols, a, b, 100);
+      float len = 0;
+      for (size_t i = 0; i + 1 < seg.size(); ++i) {
+        if (std::abs(seg[i].first - seg[i + 1].first) > 0.8 * cols) continue;
+        const float dx = seg[i].first - seg[i + 1].first, dy = seg[i].second - seg[i + 1].second;
+        len += std::sqrt(dx * dx + dy * dy);
+      }
+      if (len < 100.f || len > 2000.f) continue;
+    }
+    if (n >= cap) return PVB_ERR_ARG;
+    image_line[n] = p.il; lidar_line[n] = p.ll; angle_out[n] = p.ang;
+    transform4(Tlc, p.s, start3 + 3 * n); transform4(Tlc, p.e, end3 + 3 * n);
+    ++n;
+  }
+  *n_out = n;
+  return PVB_OK;
+}
+
+int pvb_build_point2plane_blocks(long n, const double* point3, const double* plane4, int ref_block, int nei_block, int angle_residual, int normalize_distance,
+                                 double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize, double* huber, double* consts) {
+  if (n < 0 || (n > 0 && (!point3 || !plane4)) || !type || !ref || !nei || !normalize || !huber || !consts) return PVB_ERR_ARG;
+  BlockOut o{at, cap, type, ref, nei, normalize, huber, consts};
+  const double hub = angle_residual ? 2 * M_PI / 180.0 : 0.2;                  // Optimization.cpp:513-517
+  for (long i = 0; i < n; ++i) {
+    double c[12] = {point3[3 * i], point3[3 * i + 1], point3[3 * i + 2], plane4[4 * i], plane4[4 * i + 1], plane4[4 * i + 2], plane4[4 * i + 3], weight, 0, 0, 0, 0};
+    if (!push_block(o, angle_residual ? PVB_P2PLANE_ANGLE : PVB_P2PLANE_METER, ref_block, nei_block, normalize_distance, hub, c)) return PVB_ERR_ARG;
+  }
+  return (int)o.at;
+}
+
+int pvb_build_line2line_blocks(const pvb_line_frame* nf, const float* world, int nei_line, const double* a, const double* b, int ref_block, int nei_block,
+                               int angle_residual, int normalize_distance, double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize,
+                               double* huber, double* consts) {
+  if (!nf || !world || !a || !b || !type) return PVB_ERR_ARG;
+  BlockOut o{at, cap, type, ref, nei, normalize, huber, consts};
+  double d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};                       // Point2Line_*: line_direction = (a - b).normalized()
+  const double nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  for (int k = 0; k < 3; ++k) d[k] /= nn;
+  for (int i = 0; i < nf->n_corner; ++i) {
+    bool member = false;
+    for (int e = nf->p2s_off[i]; e < nf->p2s_off[i + 1]; ++e) member = member || nf->p2s_ids[e] == nei_line;
+    if (!member) continue;
+    const double pw[3] = {world[4 * i], world[4 * i + 1], world[4 * i + 2]};
+    double pl[3];
+    world2local(nf->R_wl, nf->t_wl, pw, pl);                                   // Optimization.cpp:407 / :422
+    double c[12] = {pl[0], pl[1], pl[2], a[0], a[1], a[2], d[0], d[1], d[2], weight, 0, 0};
+    // angle residuals are added with loss == nullptr (:417), metre residuals with HuberLoss(0.2) (:430)
+    if (!push_block(o, angle_residual ? PVB_P2LINE_ANGLE : PVB_P2LINE_METER, ref_block, nei_block, normalize_distance, angle_residual ? 0.0 : 0.2, c)) return PVB_ERR_ARG;
+  }
+  return (int)o.at;
+}
+
+int pvb_build_camera_lidar_blocks(int rows, int cols, int n_pairs, const float* line4, const double* start3, const double* end3, const float* pair_weight,
+                                  int cam_block, int lidar_block, double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize, double* huber,
+                                  double* consts) {
+  if (n_pairs < 0 || (n_pairs > 0 && (!line4 || !start3 || !end3)) || !type) return PVB_ERR_ARG;
+  BlockOut o{at, cap, type, ref, nei, normalize, huber, consts};
+  const double hub = 3.0 * M_PI / 180.0;
+  for (int i = 0; i < n_pairs; ++i) {
+    double p1[3], p2[3], plane[4];
+    image_to_cam_f64(line4[4 * i], line4[4 * i + 1], rows, cols, p1);           // Optimization.cpp:587-589
+    image_to_cam_f64(line4[4 * i + 2], line4[4 * i + 3], rows, cols, p2);
+    plane_through_origin(p1, p2, plane);
+    const double nn = std::sqrt(sq(plane[0]) + sq(plane[1]) + sq(plane[2]));
+    const double w = (pair_weight ? (double)pair_weight[i] : 1.0) * weight;
+    const double* s = start3 + 3 * i; const double* e = end3 + 3 * i;
+    // Plane2Plane_Global::Create(plane.head(3), lidar_line_end, lidar_line_start, w): ctor normalises the normal (CostFunction.h:362)
+    double c1[12] = {plane[0] / nn, plane[1] / nn, plane[2] / nn, e[0], e[1], e[2], s[0], s[1], s[2], w, 0, 0};
+    if (!push_block(o, PVB_PLANE2PLANE_GLOBAL, cam_block, lidar_block, 1, hub, c1)) return PVB_ERR_ARG;
+    // PlaneIOUResidual::Create(plane, (end + start)/2, (p1 + p2)/2, VectorAngle3D(p1, p2, true), 2 w): plane / |n| (CostFunction.h:457)
+    const double ang = vector_angle(p1, p2, true);
+    double c2[12] = {plane[0] / nn, plane[1] / nn, plane[2] / nn, plane[3] / nn, (e[0] + s[0]) / 2.0, (e[1] + s[1]) / 2.0, (e[2] + s[2]) / 2.0,
+                     (p1[0] + p2[0]) / 2.0, (p1[1] + p2[1]) / 2.0, (p1[2] + p2[2]) / 2.0, ang, 2.0 * weight};
+    if (!push_block(o, PVB_PLANE_IOU, cam_block, lidar_block, 1, hub, c2)) return PVB_ERR_ARG;
+  }
+  return (int)o.at;
+}
+
+}  // extern "C"

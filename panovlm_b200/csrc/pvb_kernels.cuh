@@ -63,6 +63,15 @@ __global__ void __launch_bounds__(256) k_transform_world(const F4* __restrict__ 
   }
 }
 
+__global__ void __launch_bounds__(256) k_transform_simple(const F4* __restrict__ in, long long n, WorldPose wp, F4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const F4 p = ldg_f4(in + i);
+  float x, y, z;
+  transform_point_f32(wp.R, wp.t, p.x, p.y, p.z, x, y, z);
+  reinterpret_cast<float4*>(out)[i] = make_float4(x, y, z, p.w);
+}
+
 // ---- grid build -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cell_keys(const F4* __restrict__ world, const CloudTile* __restrict__ tiles, const GridDesc* __restrict__ grids,
                                                    unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist) {

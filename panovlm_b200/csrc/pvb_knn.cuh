@@ -130,6 +130,17 @@ PVB_HD void walk_ranges(int n_ranges, const RangeGet& range, const Body& body) {
   }
 }
 
+// Nested variant (per-row loops): fewer dependent instructions per candidate, more lane idling at row ends.
+template <typename RangeGet, typename Body>
+PVB_HD void walk_ranges_nested(int n_ranges, const RangeGet& range, const Body& body) {
+  for (int row = 0; row < n_ranges; ++row) {
+    uint32_t lo, hi;
+    range(row, lo, hi);
+#pragma unroll 2
+    for (uint32_t i = lo; i < hi; ++i) body((long long)i);
+  }
+}
+
 // Exact K-NN of (qx,qy,qz) within sqrt(sq_thr).  Returns the number of neighbours handed to sink (K, or 0 when the
 // K-th nearest is beyond the threshold / fewer than K points are in reach).  sink(j, record position, d2 bits).
 // range_set(idx, lo, hi) / range_get(idx, lo&, hi&): caller-provided storage for the <= 9 row ranges of the 3x3x3
@@ -159,7 +170,7 @@ PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoa
   // ---- ring 1: the 3x3x3 block = up to 9 contiguous row ranges, looked up once and walked twice
   int n_ranges = 0;
   for_each_range(g, cells, cx, cy, cz, 1, true, [&](long long lo, long long hi) { if (hi > lo) { range_set(n_ranges, (uint32_t)lo, (uint32_t)hi); ++n_ranges; } });
-  walk_ranges(n_ranges, range_get, [&](long long i) {
+  walk_ranges_nested(n_ranges, range_get, [&](long long i) {
     const F4 c = load(i);
     topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
   });
@@ -187,7 +198,7 @@ PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoa
   int eq_taken = 0, n_out = 0;
   const int eq_needed = K - n_lt;
   if (r == 1) {
-    walk_ranges(n_ranges, range_get, [&](long long i) {
+    walk_ranges_nested(n_ranges, range_get, [&](long long i) {
       const F4 c = load(i);
       const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
       bool take = kb < tau;
@@ -233,10 +244,10 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
   if (same < K) return false;                                    // :590
   if (collinear_from_gram(acc, K, prm.collinear_tol)) return false;   // :594-596
   Chol3 L;
-  if (!chol3_factor(acc, L)) return false;
   double x[3];
-  { const double rhs[3] = {-acc.h0, -acc.h1, -acc.h2}; chol3_solve(L, rhs, x); }   // :593 FormPlane: A x = -1
-  {                                                              // one refinement step: t = A^T (b - A x)
+  if (chol3_factor(acc, L)) {
+    { const double rhs[3] = {-acc.h0, -acc.h1, -acc.h2}; chol3_solve(L, rhs, x); }   // :593 FormPlane: A x = -1
+    // one refinement step: t = A^T (b - A x)
     double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll 1
     for (int j = 0; j < K; ++j) {
@@ -250,6 +261,15 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
     double dx[3];
     chol3_solve(L, t, dx);
     x[0] += dx[0]; x[1] += dx[1]; x[2] += dx[2];
+  } else {                                                       // rank-deficient neighbour set: Eigen's basic solution
+    double A[K * 3];
+#pragma unroll 1
+    for (int j = 0; j < K; ++j) {
+      const F4 p = load((long long)win(j));
+      const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
+      world2local(R_ref, t_ref, pw, &A[j * 3]);
+    }
+    lstsq_minus_one_rolled(K, A, x);
   }
   const double nrm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
   const double d = 1.0 / nrm;

@@ -730,6 +730,20 @@ int pvb_project_depth_image(pvb_ctx* ctx, const float* xyzi, long n, const doubl
   return PVB_OK;
 }
 
+int pvb_transform_cloud(pvb_ctx* ctx, const float* xyzi, long n, const double* R, const double* t, float* out) {
+  if (!ctx || n < 0 || (n > 0 && (!xyzi || !out)) || !R || !t) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  if (n == 0) return PVB_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->m_a.ensure((size_t)n * 16)); CK(ctx->m_b.ensure((size_t)n * 16));
+  CK(cudaMemcpyAsync(ctx->m_a.p, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  WorldPose w; for (int k = 0; k < 9; ++k) w.R[k] = R[k]; for (int k = 0; k < 3; ++k) w.t[k] = t[k];
+  k_transform_simple<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->m_a.as<F4>(), n, w, ctx->m_b.as<F4>());
+  CKL();
+  CK(cudaMemcpyAsync(out, ctx->m_b.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
 // ================================================================ E. line votes
 int pvb_line_votes(pvb_ctx* ctx, const double* ref_lines, int S_ref, const float* pts, int n_pts, const int* p2s_off, const int* p2s_ids, int S_nei, double thr, int* M) {
   if (!ctx || !M || S_ref < 0 || S_nei < 0 || n_pts < 0) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;

@@ -465,6 +465,68 @@ PVB_HD bool collinear_from_gram(const PlaneAcc& a, int n, double tol) {
   return l2 > tol * l1;
 }
 
+// Rank-deficient fallback of the plane fit (Cholesky of the Gram matrix failed: e.g. every neighbour has one
+// coordinate exactly 0).  Eigen's colPivHouseholderQr().solve (Geometry.hpp:361) then returns the basic solution of
+// the leading rank x rank block with the remaining components 0; this rolled-loop version (local memory, few
+// registers, rare path) reproduces it.  A: K x 3 row-major, destroyed.
+PVB_HD void lstsq_minus_one_rolled(int K, double* A, double x[3]) {
+  double b[16];
+  for (int i = 0; i < K; ++i) b[i] = -1.0;
+  int perm[3] = {0, 1, 2};
+  double diag[3] = {0, 0, 0};
+  int rank = 0;
+  double maxpivot = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) {
+    int best = k; double bn = -1.0;
+#pragma unroll 1
+    for (int c = k; c < 3; ++c) {
+      double s = 0;
+      for (int r = k; r < K; ++r) s += A[r * 3 + c] * A[r * 3 + c];
+      if (s > bn) { bn = s; best = c; }
+    }
+    if (best != k) {
+      for (int r = 0; r < K; ++r) { const double tmp = A[r * 3 + k]; A[r * 3 + k] = A[r * 3 + best]; A[r * 3 + best] = tmp; }
+      const int tp = perm[k]; perm[k] = perm[best]; perm[best] = tp;
+    }
+    const double norm = sqrt(bn);
+    if (k == 0) maxpivot = norm;
+    if (norm <= maxpivot * DBL_EPSILON * 3.0) break;
+    ++rank;
+    const double akk = A[k * 3 + k];
+    const double alpha = (akk > 0) ? -norm : norm;
+    const double vk = akk - alpha;
+    double vtv = vk * vk;
+    for (int r = k + 1; r < K; ++r) vtv += A[r * 3 + k] * A[r * 3 + k];
+    if (vtv > 0) {
+      const double inv = 2.0 / vtv;
+#pragma unroll 1
+      for (int c = k + 1; c < 3; ++c) {
+        double dot = vk * A[k * 3 + c];
+        for (int r = k + 1; r < K; ++r) dot += A[r * 3 + k] * A[r * 3 + c];
+        const double f = dot * inv;
+        A[k * 3 + c] -= f * vk;
+        for (int r = k + 1; r < K; ++r) A[r * 3 + c] -= f * A[r * 3 + k];
+      }
+      double dot = vk * b[k];
+      for (int r = k + 1; r < K; ++r) dot += A[r * 3 + k] * b[r];
+      const double f = dot * inv;
+      b[k] -= f * vk;
+      for (int r = k + 1; r < K; ++r) b[r] -= f * A[r * 3 + k];
+    }
+    diag[k] = alpha;
+  }
+  double y[3] = {0, 0, 0};
+#pragma unroll 1
+  for (int k = rank - 1; k >= 0; --k) {
+    double s = b[k];
+    for (int c = k + 1; c < rank; ++c) s -= A[k * 3 + c] * y[c];
+    y[k] = s / diag[k];
+  }
+  x[0] = x[1] = x[2] = 0.0;
+  for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
+}
+
 // ---- Equirectangular float path (sensors/Equirectangular.h:41-96 with USE_FAST_ATAN2, base/Math.h:15-29) ----
 PVB_HD float fast_atan2_f32(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);

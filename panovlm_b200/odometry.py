@@ -1,0 +1,91 @@
+"""Host loop the hot path drops into: a Python mirror of LidarOdometry::RefinePose / EstimatePose
+(lidar_mapping/LidarOdometry.cpp:15-114, 116-187) driving the C ABI.  Every numeric step runs in the library:
+FindNeighbors (host C++), point-to-plane association of all pose-graph edges (fused kNN kernel), line-to-line vote
+matrices (kernel) + tails (host C++), residual-block builders (host C++), Levenberg-Marquardt with device evaluation.
+
+Not reproduced here ("next"): the LidarLineMatch track gate of AddLidarLineToLineResidual2
+(util/Optimization.cpp:383-400) — every associated line pair contributes residuals.
+"""
+import numpy as np
+
+from .api import BlockList, Context, LineFrame
+
+
+class OdometryConfig:
+    def __init__(self, point_to_plane=True, line_to_line=True, angle_residual=True, normalize_distance=True, plane_dis_threshold=1.0,
+                 line_dis_threshold=0.3, plane_tolerance=0.05, lidar_weight=0.01, neighbor_size=6, max_lm_iterations=20):
+        self.point_to_plane, self.line_to_line = point_to_plane, line_to_line
+        self.angle_residual, self.normalize_distance = angle_residual, normalize_distance          # config/Room.txt:67-74
+        self.plane_dis_threshold, self.line_dis_threshold, self.plane_tolerance = plane_dis_threshold, line_dis_threshold, plane_tolerance
+        self.lidar_weight, self.neighbor_size, self.max_lm_iterations = lidar_weight, neighbor_size, max_lm_iterations
+
+
+def pose_blocks_from_world(R_wl, t_wl, R_to_aa):
+    """T_wl -> (aa_lw, t_lw) blocks (LidarOdometry.cpp:25-33)."""
+    out = np.zeros((len(R_wl), 6))
+    for i, (R, t) in enumerate(zip(R_wl, t_wl)):
+        R_lw = R.T
+        out[i, :3] = R_to_aa(R_lw)
+        out[i, 3:] = -R_lw @ t
+    return out
+
+
+def world_from_pose_blocks(poses, aa_to_R):
+    R_wl, t_wl = [], []
+    for p in poses:
+        R = aa_to_R(p[:3]).T
+        R_wl.append(R); t_wl.append(-R @ p[3:])
+    return R_wl, t_wl
+
+
+def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
+    """One outer iteration's residual blocks (the Add*Residual calls of RefinePose); returns a BlockList."""
+    n = len(frames)
+    R_wl, t_wl = world_from_pose_blocks(poses, aa_to_R)
+    neighbors = Context.find_neighbors(np.array(t_wl), None, None, cfg.neighbor_size)
+    edges = [(i, j) for i in range(n) for j in neighbors[i] if 0 <= j < n and j != i]
+    cap = sum(len(frames[j]["surfFlat"]) for _, j in edges) + sum(len(frames[j]["cornerLessSharp"]) for _, j in edges) * 2 + 16
+    bl = BlockList(cap)
+    if cfg.line_to_line:                                            # AddLidarLineToLineResidual2 (Optimization.cpp:329-441)
+        lf = [LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], R_wl[i], t_wl[i]) for i, f in enumerate(frames)]
+        world = [ctx.transform_cloud(f["cornerLessSharp"], R_wl[i], t_wl[i]) for i, f in enumerate(frames)]
+        for (i, j) in edges:
+            nl, rl, a, b = ctx.line2line_associate(lf[i], lf[j], cfg.line_dis_threshold)
+            for k in range(len(nl)):
+                Context.build_line2line_blocks(bl, lf[j], world[j], nl[k], a[k], b[k], i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
+    if cfg.point_to_plane:                                          # AddLidarPointToPlaneResidual (Optimization.cpp:506-562)
+        ctx.frames_set([f["surfLessFlat"] for f in frames], [f["surfFlat"] for f in frames])
+        ref = np.array([e[0] for e in edges], np.int32)
+        nei = np.array([e[1] for e in edges], np.int32)
+        e, q, pt, pl = ctx.frames_associate_point2plane(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, 10)
+        for ei in range(len(edges)):
+            m = e == ei
+            if m.any():
+                Context.build_point2plane_blocks(bl, pt[m], pl[m], int(ref[ei]), int(nei[ei]), cfg.angle_residual, cfg.normalize_distance, 1.0)
+    return bl, edges
+
+
+def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
+    """RefinePose: build the problem at `poses`, fix the first frame, solve (LidarOdometry.cpp:15-114)."""
+    bl, edges = build_problem(ctx, frames, poses, cfg, aa_to_R)
+    v = bl.view()
+    ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
+    mask = np.zeros(len(frames), np.uint8); mask[0] = 1
+    new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
+    summary["n_blocks"], summary["n_edges"] = bl.n, len(edges)
+    return new_poses, summary
+
+
+def estimate_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, max_iteration=7):
+    """EstimatePose's outer loop with its early exits (LidarOdometry.cpp:166-183)."""
+    last_cost, small_steps, log = None, 0, []
+    for it in range(max_iteration):
+        poses, s = refine_pose(ctx, frames, poses, cfg, aa_to_R)
+        log.append(s)
+        if last_cost is not None and abs(last_cost - s["final_cost"]) / max(s["final_cost"], 1e-300) < 0.01:
+            break
+        small_steps = small_steps + 1 if s["successful"] < 5 else 0
+        if small_steps >= 2:
+            break
+        last_cost = s["final_cost"]
+    return poses, log

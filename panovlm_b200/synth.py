@@ -277,7 +277,10 @@ def make_dense_sweep(n_target=10_000_000, n_frames=64, pts_per_frame=156_250, se
     rng = np.random.default_rng(seed)                    # target cloud
     scale = n_target / 10_000_000.0
     Lx = max(10.0, L * scale)                          # keep the surface density (~400 pts/m^2) when scaled down
-    tgt = sample_floor_plan(n_target, rng, xlim=(0, Lx), L=L)
+    # world origin inside the building, above the floor (a plane through the origin is degenerate for the reference's
+    # 'A x = -1' plane parameterisation, Geometry.hpp:345-373; real sensor-frame data never has it)
+    origin = np.array([0.37 * Lx, 23.3, 1.6])
+    tgt = sample_floor_plan(n_target, rng, xlim=(0, Lx), L=L) - origin
     target = np.concatenate([tgt, np.ones((n_target, 1))], axis=1).astype(np.float32)
     rng = np.random.default_rng(seed + 1 if source_seed is None else source_seed)   # source frames (per-rank seed in bench.py)
     src, off, init, true = [], [0], [], []
@@ -285,9 +288,9 @@ def make_dense_sweep(n_target=10_000_000, n_frames=64, pts_per_frame=156_250, se
     slab = Lx / n_frames
     for f in range(n_frames):
         x0, x1 = f * slab, (f + 1) * slab
-        pw = sample_floor_plan(pts_per_frame, rng, xlim=(x0, x1), noise=0.01, L=L)
+        pw = sample_floor_plan(pts_per_frame, rng, xlim=(x0, x1), noise=0.01, L=L) - origin
         # sensor pose: centre of the slab, true pose = nominal o small perturbation
-        c = np.array([(x0 + x1) / 2, 25.0, 2.0])
+        c = np.array([(x0 + x1) / 2, 25.0, 2.0]) - origin
         R_nom = Rotation.from_rotvec([0, 0, 0.3 * np.sin(f)]).as_matrix()
         dR = Rotation.from_rotvec(rng.normal(0, 0.004, 3)).as_matrix()
         dt = rng.normal(0, 0.02, 3)

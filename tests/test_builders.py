@@ -1,0 +1,118 @@
+"""Host-side builders of the library (pvb_find_neighbors, pvb_build_*_blocks): pure C++ host code, no GPU needed.
+Expected values are rebuilt here in Python from the reference's description with the oracle's primitives."""
+import numpy as np
+
+import panovlm_b200
+from panovlm_b200 import BlockList, Context, LineFrame, synth
+
+
+def py_find_neighbors(t_wl, pose_valid, frame_valid, k):
+    """lidar_mapping/LidarFeatureAssociate.cpp:19-111 restated in Python (float32 centres, brute-force k-NN)."""
+    n = len(t_wl)
+    cf = [i for i in range(n) if pose_valid[i] and frame_valid[i]]
+    c = t_wl[cf].astype(np.float32)
+    out = []
+    for i in range(n):
+        if not pose_valid[i]:
+            out.append([i - j for j in range(-(k // 2), k // 2 + 1)])
+            continue
+        q = t_wl[i].astype(np.float32)
+        d = ((q - c) ** 2).astype(np.float32)
+        d2 = (d[:, 0] + d[:, 1]) + d[:, 2]
+        order = sorted(range(len(cf)), key=lambda j: (d2[j], j))
+        nb = [cf[j] for j in order[:k]][1:]
+        s = set(nb)
+        p = i - 1
+        while p >= 0 and not pose_valid[p]:
+            p -= 1
+        if p >= 0 and p not in s:
+            nb.append(p)
+        p = i + 1
+        while p < n and not pose_valid[p]:
+            p += 1
+        if p < n and p not in s:
+            nb.append(p)
+        for j in order:
+            if not d2[j] < np.float32(400.0):
+                break
+            cand, same = cf[j], 0
+            for it in sorted(s):
+                if abs(cand - it) <= 200:
+                    same += 1
+                if same >= 2:
+                    break
+            if same < 2 and cand not in s:
+                nb.append(cand); s.add(cand)
+        out.append(nb)
+    return out
+
+
+def test_find_neighbors_matches_reference_rules():
+    rng = np.random.default_rng(0)
+    n = 700                                                     # long enough for loop closures (> 200 frames apart)
+    a = np.linspace(0, 4 * np.pi, n)
+    t = np.stack([30 * np.cos(a), rng.normal(0, 0.05, n), 30 * np.sin(a)], axis=1) + rng.normal(0, 0.2, (n, 3))
+    pv = np.ones(n, np.uint8); pv[[5, 6, 300]] = 0
+    fv = np.ones(n, np.uint8); fv[[10, 11]] = 0
+    got = Context.find_neighbors(t, pv, fv, 6)
+    exp = py_find_neighbors(t, pv, fv, 6)
+    assert got == exp
+    assert any(abs(i - j) > 200 for i, nb in enumerate(got) for j in nb if pv[i])   # loop closures are found
+    assert got[5] == [5 - j for j in range(-3, 4)]
+
+
+def test_point2plane_and_line_blocks(oracle):
+    A, B = synth.make_pair(seed=3, n_az=900)
+    bl = BlockList(10000)
+    pts, pls = np.random.default_rng(1).normal(size=(7, 3)), np.random.default_rng(2).normal(size=(7, 4))
+    Context.build_point2plane_blocks(bl, pts, pls, 2, 5, True, True, 0.01)
+    Context.build_point2plane_blocks(bl, pts, pls, 2, 5, False, False, 0.1)
+    v = bl.view()
+    assert np.all(v["type"][:7] == 1) and np.all(v["type"][7:] == 0) and np.all(v["ref"] == 2) and np.all(v["nei"] == 5)
+    assert np.allclose(v["huber"][:7], 2 * np.pi / 180) and np.allclose(v["huber"][7:], 0.2)
+    assert np.array_equal(v["consts"][:7, :3], pts) and np.array_equal(v["consts"][:7, 3:7], pls) and np.all(v["consts"][7:, 7] == 0.1)
+    assert np.all(v["normalize"][:7] == 1) and np.all(v["normalize"][7:] == 0)
+    # line-to-line: one block per point of the neighbour segment, point taken from the float32 WORLD cloud back to the sensor frame
+    fr = LineFrame(B["cornerLessSharp"], B["p2s_off"], B["p2s_ids"], B["segment_coeffs"], B["end_points"], B["R_wl"], B["t_wl"])
+    world = oracle.transform_cloud(B["R_wl"], B["t_wl"], B["cornerLessSharp"])
+    a, b = np.array([1.0, 2.0, 3.0]), np.array([1.1, 2.0, 2.5])
+    bl2 = BlockList(1000)
+    Context.build_line2line_blocks(bl2, fr, world, 4, a, b, 0, 1, True, True, 1.0)
+    v = bl2.view()
+    members = [i for i in range(len(world)) if 4 in B["p2s_ids"][B["p2s_off"][i]:B["p2s_off"][i + 1]]]
+    assert len(v["type"]) == len(members) > 4 and np.all(v["type"] == 3) and np.all(v["huber"] == 0.0)     # angle line residuals: loss == nullptr
+    pl = oracle.world2local(B["R_wl"], B["t_wl"], world[members, :3].astype(np.float64))
+    assert np.array_equal(v["consts"][:, :3], pl)
+    d = (a - b) / np.linalg.norm(a - b)
+    assert np.allclose(v["consts"][:, 3:6], a) and np.abs(v["consts"][:, 6:9] - d).max() < 1e-15
+    Context.build_line2line_blocks(bl2, fr, world, 4, a, b, 0, 1, False, True, 0.5)
+    v = bl2.view()
+    assert np.all(v["type"][len(members):] == 2) and np.all(v["huber"][len(members):] == 0.2) and np.all(v["consts"][len(members):, 9] == 0.5)
+
+
+def test_camera_lidar_blocks_evaluate_like_the_reference_construction(oracle):
+    rows, cols = 2880, 5760
+    rng = np.random.default_rng(5)
+    lines = np.stack([rng.uniform(0, cols, 12), rng.uniform(0, rows, 12), rng.uniform(0, cols, 12), rng.uniform(0, rows, 12)], axis=1).astype(np.float32)
+    start, end = rng.normal(0, 3, (12, 3)), rng.normal(0, 3, (12, 3))
+    pw = rng.uniform(0.5, 2, 12).astype(np.float32)
+    bl = BlockList(100)
+    Context.build_camera_lidar_blocks(bl, rows, cols, lines, start, end, pw, 0, 1, 25.0)
+    v = bl.view()
+    assert len(v["type"]) == 24 and np.all(v["type"][0::2] == 4) and np.all(v["type"][1::2] == 5) and np.allclose(v["huber"], 3 * np.pi / 180)
+    p1 = oracle.image_to_cam(rows, cols, lines[:, :2].astype(np.float64))
+    p2 = oracle.image_to_cam(rows, cols, lines[:, 2:].astype(np.float64))
+    nrm = np.cross(p2 - p1, -p1)                                   # FormPlane(p1, p2, 0)
+    d = -(nrm * p1).sum(1)
+    nn = np.linalg.norm(nrm, axis=1, keepdims=True)
+    c1, c2 = v["consts"][0::2], v["consts"][1::2]
+    assert np.abs(c1[:, :3] - nrm / nn).max() < 1e-12 and np.array_equal(c1[:, 3:6], end) and np.array_equal(c1[:, 6:9], start)
+    assert np.allclose(c1[:, 9], pw.astype(np.float64) * 25.0)
+    assert np.abs(c2[:, :3] - nrm / nn).max() < 1e-12 and np.abs(c2[:, 3] - d / nn[:, 0]).max() < 1e-12
+    assert np.allclose(c2[:, 4:7], (end + start) / 2) and np.allclose(c2[:, 7:10], (p1 + p2) / 2)
+    ang = np.arccos(np.clip((p1 * p2).sum(1), -1, 1))
+    assert np.abs(c2[:, 10] - ang).max() < 1e-12 and np.all(c2[:, 11] == 50.0)
+    # the blocks evaluate (oracle functors) to finite residuals with the camera / LiDAR pose blocks
+    blk = oracle.Blocks(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"])
+    r, J, _ = blk.evaluate(np.concatenate([rng.normal(0, 0.1, (2, 3)), rng.normal(0, 0.5, (2, 3))], axis=1))
+    assert np.all(np.isfinite(r)) and np.all(np.isfinite(J))

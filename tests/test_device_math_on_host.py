@@ -93,3 +93,26 @@ def test_float_paths_are_bit_exact(oracle, harness):
     out = np.empty_like(a["ref_local"])
     harness.pvbh_transform_cloud(p(np.ascontiguousarray(a["R_ref"])), p(np.ascontiguousarray(a["t_ref"])), p(np.ascontiguousarray(a["ref_local"])), C.c_int(len(out)), p(out))
     assert np.array_equal(out, a["ref_world"])
+
+
+def test_rank_deficient_neighbour_sets_follow_the_qr_basic_solution(oracle, harness):
+    """Neighbours with one coordinate exactly 0 in the reference frame (a floor through the origin): Eigen's rank-revealing
+    QR returns a basic solution that may still pass the tolerance test; the streaming plane fit must fall back to it."""
+    from panovlm_b200 import synth
+    rng = np.random.default_rng(12)
+    n = 60000
+    tgt = np.concatenate([synth.sample_floor_plan(n, rng, xlim=(0, 12.0)), np.ones((n, 1))], axis=1).astype(np.float32)   # floor at z == 0, walls at x == 0 / y == 0
+    qry = tgt[rng.choice(n, 3000, replace=False)].copy()
+    qry[:, :3] += rng.normal(0, 0.01, (3000, 3)).astype(np.float32)
+    I, z = np.eye(3), np.zeros(3)
+    oq, opt, opl = oracle.associate_p2plane(tgt, I, z, qry, I, z, 0.05, 1.0, 10, True)
+    m = len(qry)
+    valid, pl2, pt2 = np.zeros(m, np.uint8), np.zeros((m, 4)), np.zeros((m, 3))
+    ni, nd = np.zeros((m, 10), np.int32), np.zeros((m, 10), np.float32)
+    harness.pvbh_associate(p(tgt), C.c_int(n), p(I.copy()), p(z), p(np.ascontiguousarray(qry)), C.c_int(m), p(I.copy()), p(z), C.c_double(0.3), C.c_float(1.0),
+                           C.c_double(0.05), C.c_int(10), p(valid), p(pt2), p(pl2), p(ni), p(nd))
+    q2 = np.nonzero(valid)[0]
+    assert np.array_equal(oq, q2)
+    degenerate = np.abs(opl[:, 2]) < 1e-12                       # bogus vertical planes through floor points (n_z == 0)
+    assert degenerate.sum() > 50
+    assert np.abs(opl - pl2[q2]).max() < 1e-9

@@ -362,3 +362,99 @@ def test_angle_votes_bit_exact(gpu_ctx, oracle):
     sizes = np.diff(A["seg_off"])
     oi, ol, s, e, ang = oracle.associate_by_angle(rows, cols, lines, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], sizes, A["end_points"], T, True)
     assert len(oi) >= 3 and np.all(oi < len(px))                                        # true lines pair up, clutter does not
+
+
+# ---------------------------------------------------------------- G. builders on the device + the odometry loop
+def _line_frame(f, R=None, t=None):
+    from panovlm_b200 import LineFrame
+    return LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], f["R_wl"] if R is None else R, f["t_wl"] if t is None else t)
+
+
+def test_transform_cloud_and_line2line_associate(gpu_ctx, oracle):
+    A, B = _pair_frames(n_az=1800)
+    assert np.array_equal(gpu_ctx.transform_cloud(A["cloud"], A["R_wl"], A["t_wl"]), oracle.transform_cloud(A["R_wl"], A["t_wl"], A["cloud"]))
+    RB, tB = np.eye(3), np.zeros(3)
+    for thr in (0.3, 0.1):
+        nl, rl, a, b = gpu_ctx.line2line_associate(_line_frame(A), _line_frame(B, RB, tB), thr)
+        ref_w = oracle.transform_lines(A["R_wl"], A["t_wl"], A["segment_coeffs"]); nei_w = oracle.transform_lines(RB, tB, B["segment_coeffs"])
+        M = oracle.line_votes(ref_w, oracle.transform_cloud(RB, tB, B["cornerLessSharp"]), B["p2s_off"], B["p2s_ids"], len(B["segment_coeffs"]), thr)
+        on, orf, oa, ob = oracle.find_associations(A["segment_coeffs"], ref_w, nei_w, np.diff(B["seg_off"]), M)
+        assert np.array_equal(nl, on) and np.array_equal(rl, orf) and np.array_equal(a, oa) and np.array_equal(b, ob)
+    assert len(on) >= 3
+
+
+def test_camera_lidar_associate_matches_oracle(gpu_ctx, oracle):
+    from scipy.spatial.transform import Rotation
+    A, _ = _pair_frames(n_az=1800)
+    rows, cols = 2880, 5760
+    T = np.eye(4); T[:3, :3] = Rotation.from_rotvec([0.01, 0.02, -0.01]).as_matrix(); T[:3, 3] = [0.03, -0.05, 0.02]
+    rng = np.random.default_rng(9)
+    ends_cam = A["end_points"].reshape(-1, 3) @ T[:3, :3].T + T[:3, 3]
+    px = oracle.cam_to_image(rows, cols, ends_cam).reshape(-1, 4) + rng.normal(0, 2, (len(A["end_points"]), 4))
+    clutter = np.stack([rng.uniform(0, cols, 30), rng.uniform(0, rows, 30), rng.uniform(0, cols, 30), rng.uniform(0, rows, 30)], axis=1)
+    lines = np.concatenate([px, clutter]).astype(np.float32)
+    sizes = np.diff(A["seg_off"])
+    for flt in (True, False):
+        il, ll, s, e, ang = gpu_ctx.camera_lidar_associate(rows, cols, lines, _line_frame(A), T, flt)
+        oi, ol, os_, oe, oa = oracle.associate_by_angle(rows, cols, lines, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], sizes, A["end_points"], T, flt)
+        assert np.array_equal(il, oi) and np.array_equal(ll, ol) and np.array_equal(ang, oa)
+        assert np.abs(s - os_).max() < 1e-12 and np.abs(e - oe).max() < 1e-12
+    assert len(oi) >= 3
+
+
+def _oracle_refine(oracle, frames, poses, cfg):
+    """The same outer iteration as panovlm_b200.odometry.refine_pose, built from oracle primitives only."""
+    from panovlm_b200 import Context
+    n = len(frames)
+    R_wl = [oracle.aa_to_R(p[:3]).T for p in poses]
+    t_wl = [-R @ p[3:] for R, p in zip(R_wl, poses)]
+    from test_builders import py_find_neighbors
+    neighbors = py_find_neighbors(np.array(t_wl), np.ones(n, np.uint8), np.ones(n, np.uint8), cfg.neighbor_size)
+    edges = [(i, j) for i in range(n) for j in neighbors[i] if 0 <= j < n and j != i]
+    T, Rf, Nf, C, Hb, Nz = [], [], [], [], [], []
+    corner_w = [oracle.transform_cloud(R_wl[i], t_wl[i], f["cornerLessSharp"]) for i, f in enumerate(frames)]
+    tgt_w = [oracle.transform_cloud(R_wl[i], t_wl[i], f["surfLessFlat"]) for i, f in enumerate(frames)]
+    qry_w = [oracle.transform_cloud(R_wl[i], t_wl[i], f["surfFlat"]) for i, f in enumerate(frames)]
+    lines_w = [oracle.transform_lines(R_wl[i], t_wl[i], f["segment_coeffs"]) for i, f in enumerate(frames)]
+    for (i, j) in edges:
+        fj = frames[j]
+        M = oracle.line_votes(lines_w[i], corner_w[j], fj["p2s_off"], fj["p2s_ids"], len(fj["segment_coeffs"]), cfg.line_dis_threshold)
+        on, orf, oa, ob = oracle.find_associations(frames[i]["segment_coeffs"], lines_w[i], lines_w[j], np.diff(fj["seg_off"]), M)
+        for k in range(len(on)):
+            d = (oa[k] - ob[k]) / np.linalg.norm(oa[k] - ob[k])
+            for pi in range(len(corner_w[j])):
+                if on[k] in fj["p2s_ids"][fj["p2s_off"][pi]:fj["p2s_off"][pi + 1]]:
+                    pl = oracle.world2local(R_wl[j], t_wl[j], corner_w[j][pi, :3].astype(np.float64))[0]
+                    c = np.zeros(12); c[:3] = pl; c[3:6] = oa[k]; c[6:9] = d; c[9] = 1.0
+                    T.append(3); Rf.append(i); Nf.append(j); C.append(c); Hb.append(0.0); Nz.append(1)
+    for (i, j) in edges:
+        oq, opt, opl = oracle.associate_p2plane(tgt_w[i], R_wl[i], t_wl[i], qry_w[j], R_wl[j], t_wl[j], cfg.plane_tolerance, cfg.plane_dis_threshold, 10, True)
+        for k in range(len(oq)):
+            c = np.zeros(12); c[:3] = opt[k]; c[3:7] = opl[k]; c[7] = 1.0
+            T.append(1); Rf.append(i); Nf.append(j); C.append(c); Hb.append(2 * np.pi / 180); Nz.append(1)
+    blk = oracle.Blocks(np.array(T), np.array(Rf), np.array(Nf), np.array(C), np.array(Hb), np.array(Nz))
+    mask = np.zeros(n, np.uint8); mask[0] = 1
+    return blk.solve_lm(poses, mask, cfg.max_lm_iterations), blk.n
+
+
+def test_odometry_outer_iteration_matches_oracle_loop(gpu_ctx, oracle):
+    """configs[1]-shaped (small): 6 frames, line-to-line + point-to-plane angle residuals, first frame fixed;
+    two outer iterations of RefinePose through the C ABI vs the same loop on the oracle: pose deltas <= 1e-4 relative."""
+    from panovlm_b200 import odometry, synth
+    from scipy.spatial.transform import Rotation
+    frames = synth.make_sequence(6, n_az=600)
+    rng = np.random.default_rng(1)
+    R0 = [f["R_wl"] @ Rotation.from_rotvec(rng.normal(0, 0.01, 3) * (i > 0)).as_matrix() for i, f in enumerate(frames)]
+    t0 = [f["t_wl"] + rng.normal(0, 0.03, 3) * (i > 0) for i, f in enumerate(frames)]
+    start = odometry.pose_blocks_from_world(R0, t0, oracle.R_to_aa)
+    cfg = odometry.OdometryConfig()
+    p_gpu, p_cpu = start.copy(), start.copy()
+    for it in range(2):
+        p_gpu, s_gpu = odometry.refine_pose(gpu_ctx, frames, p_gpu, cfg, oracle.aa_to_R)
+        (p_cpu, s_cpu), n_cpu = _oracle_refine(oracle, frames, p_cpu, cfg)
+        assert s_gpu["n_blocks"] == n_cpu
+        assert abs(s_gpu["final_cost"] - s_cpu["final_cost"]) < 1e-6 * s_cpu["final_cost"]
+        d_gpu, d_cpu = p_gpu - start, p_cpu - start
+        assert np.abs(d_gpu - d_cpu).max() < POSE_RTOL * np.abs(d_cpu).max()
+    truth = odometry.pose_blocks_from_world([f["R_wl"] for f in frames], [f["t_wl"] for f in frames], oracle.R_to_aa)
+    assert np.abs(p_gpu - truth).max() < np.abs(start - truth).max()
