@@ -1,0 +1,88 @@
+// panovlm_b200 — header-only adapter that plugs the C ABI (panovlm_b200.h) into an existing ceres::Problem.
+//
+// NOT compiled in this repository (Ceres is not installed in the build image); it is the reference-side binding a
+// PanoVLM maintainer adds.  It keeps the surface the reference uses today:
+//   * util/Optimization.cpp:549,555,417,430,592,602  problem.AddResidualBlock(cost, loss, aa_rw, t_rw, aa_nw, t_nw)
+//   * lidar_mapping/LidarOdometry.cpp:78-80           ceres::Solve(options, &problem, &summary)
+// and replaces the per-correspondence AutoDiffCostFunction<F,1,3,3,3,3> evaluation (base/CostFunction.h:567-1022) by
+// one device evaluation per ceres evaluation point, driven by a ceres::EvaluationCallback (Ceres >= 2.0).
+//
+// Usage (inside LidarOdometry::RefinePose, replacing the Add*Residual calls):
+//
+//   pvb::CeresBridge bridge(ctx, angleAxis_lw_list, t_lw_list);        // pose arrays stay where they are
+//   ceres::Problem::Options popt; popt.evaluation_callback = &bridge;
+//   ceres::Problem problem(popt);
+//   ...                                                                  // associations via pvb_frames_* / pvb_line2line_*
+//   bridge.AddBlocks(n, type, ref, nei, normalize, huber, consts, &problem);   // one thin CostFunction per correspondence
+//   problem.SetParameterBlockConstant(...first valid frame...);         // unchanged (LidarOdometry.cpp:59-66)
+//   ceres::Solve(SetOptionsLidar(threads, n), &problem, &summary);     // unchanged
+//
+// The robust loss is applied on the device (per correspondence, before any reduction), so blocks are added with
+// loss == nullptr; Ceres therefore sees already-corrected residuals/Jacobians, which is exactly what its Corrector
+// would have produced (rho'' <= 0 for HuberLoss).
+#pragma once
+#include <ceres/ceres.h>
+#include <Eigen/Core>
+#include <memory>
+#include <vector>
+#include "panovlm_b200.h"
+
+namespace pvb {
+
+class CeresBridge : public ceres::EvaluationCallback {
+ public:
+  // pose arrays: the eigen_vector<Eigen::Vector3d> lists of lidar_mapping/LidarOdometry.cpp:23-24 (stable addresses)
+  CeresBridge(pvb_ctx* ctx, std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>>& aa,
+              std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>>& t)
+      : ctx_(ctx), aa_(aa), t_(t), poses_(6 * aa.size()) {}
+
+  // Called once, single-threaded, before Ceres evaluates all residual blocks at a point.
+  void PrepareForEvaluation(bool evaluate_jacobians, bool /*new_evaluation_point*/) override {
+    for (size_t i = 0; i < aa_.size(); ++i) {
+      for (int k = 0; k < 3; ++k) { poses_[6 * i + k] = aa_[i][k]; poses_[6 * i + 3 + k] = t_[i][k]; }
+    }
+    ok_ = pvb_blocks_evaluate(ctx_, poses_.data(), /*want_rows=*/1, /*want_system=*/0) == PVB_OK;
+    r_ = pvb_blocks_residuals(ctx_);
+    J_ = evaluate_jacobians ? pvb_blocks_jacobians(ctx_) : nullptr;
+  }
+
+  // Thin per-correspondence cost function: copies one device-computed row.  Thread-safe (read-only).
+  class Row : public ceres::SizedCostFunction<1, 3, 3, 3, 3> {
+   public:
+    Row(const CeresBridge* b, long i) : b_(b), i_(i) {}
+    bool Evaluate(double const* const*, double* residuals, double** jacobians) const override {
+      if (!b_->ok_) return false;
+      residuals[0] = b_->r_[i_];
+      if (jacobians) {
+        const double* row = b_->Jrow(i_);
+        for (int blk = 0; blk < 4; ++blk)
+          if (jacobians[blk]) for (int k = 0; k < 3; ++k) jacobians[blk][k] = row ? row[3 * blk + k] : 0.0;
+      }
+      return true;
+    }
+   private:
+    const CeresBridge* b_; long i_;
+  };
+
+  // Registers the blocks with the library and adds one Row per block to the problem (loss == nullptr, see above).
+  bool AddBlocks(long n, const int* type, const int* ref, const int* nei, const int* normalize, const double* huber, const double* consts,
+                 ceres::Problem* problem) {
+    if (pvb_blocks_set(ctx_, n, type, ref, nei, normalize, huber, consts, (int)aa_.size()) != PVB_OK) return false;
+    for (long i = 0; i < n; ++i)
+      problem->AddResidualBlock(new Row(this, i), nullptr, aa_[ref[i]].data(), t_[ref[i]].data(), aa_[nei[i]].data(), t_[nei[i]].data());
+    return true;
+  }
+
+ private:
+  friend class Row;
+  const double* Jrow(long i) const { return J_ ? J_ + 12 * i : nullptr; }
+  pvb_ctx* ctx_;
+  std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>>& aa_;
+  std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>>& t_;
+  std::vector<double> poses_;
+  const double* r_ = nullptr;
+  const double* J_ = nullptr;
+  bool ok_ = false;
+};
+
+}  // namespace pvb
