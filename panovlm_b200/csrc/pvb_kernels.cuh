@@ -135,7 +135,7 @@ struct AssocArgs {
   double* partials;                                                  // [tile][29]
 };
 
-template <int K, bool REDUCE, int MINB, bool DEBUG_NN>
+template <int K, bool REDUCE, int MINB, bool DEBUG_NN, bool FLAT>
 __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
   __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
   __shared__ uint32_t s_win[K][kTile];           // record positions of each query's K neighbours
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
 #pragma unroll
       for (int j = 0; j < K; ++j) s_win[j][i] = 0xFFFFFFFFu;
     }
-    valid = associate_point2plane<K>(g, cells, load, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set, range_get);
+    valid = associate_point2plane<K, FLAT>(g, cells, load, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set, range_get);
     if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
       for (int j = 0; j < K; ++j) {
         const uint32_t pj = s_win[j][i];

@@ -115,8 +115,9 @@ PVB_HD void for_each_range(const GridDesc& g, const CellLoader& cells, int cx, i
 
 // Flattened walk over a list of record ranges: every lane advances through ITS candidates back to back, so the
 // trip count of a warp is the longest lane's total (not the sum over rows of the longest row).
-template <typename RangeGet, typename Body>
-PVB_HD void walk_ranges(int n_ranges, const RangeGet& range, const Body& body) {
+template <typename RangeGet, typename Body2>
+PVB_HD void walk_ranges(int n_ranges, const RangeGet& range, const Body2& body2) {
+  // two records per trip (both loads in flight before either is ranked); body2(i, n) handles n in {1, 2} records
   int row = 0;
   uint32_t i = 0, hi = 0;
   for (;;) {
@@ -125,8 +126,9 @@ PVB_HD void walk_ranges(int n_ranges, const RangeGet& range, const Body& body) {
       range(row, i, hi);
       ++row;
     }
-    body((long long)i);
-    ++i;
+    const int n = (hi - i) >= 2u ? 2 : 1;
+    body2((long long)i, n);
+    i += (uint32_t)n;
   }
 }
 
@@ -145,7 +147,7 @@ PVB_HD void walk_ranges_nested(int n_ranges, const RangeGet& range, const Body& 
 // K-th nearest is beyond the threshold / fewer than K points are in reach).  sink(j, record position, d2 bits).
 // range_set(idx, lo, hi) / range_get(idx, lo&, hi&): caller-provided storage for the <= 9 row ranges of the 3x3x3
 // block (shared memory on the device).
-template <int K, typename CellLoader, typename PointLoader, typename Sink, typename RangeSet, typename RangeGet>
+template <int K, bool FLAT, typename CellLoader, typename PointLoader, typename Sink, typename RangeSet, typename RangeGet>
 PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoader& load, float qx, float qy, float qz, float sq_thr, int rmax, const Sink& sink,
                       const RangeSet& range_set, const RangeGet& range_get) {
   const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
@@ -170,10 +172,20 @@ PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoa
   // ---- ring 1: the 3x3x3 block = up to 9 contiguous row ranges, looked up once and walked twice
   int n_ranges = 0;
   for_each_range(g, cells, cx, cy, cz, 1, true, [&](long long lo, long long hi) { if (hi > lo) { range_set(n_ranges, (uint32_t)lo, (uint32_t)hi); ++n_ranges; } });
-  walk_ranges_nested(n_ranges, range_get, [&](long long i) {
-    const F4 c = load(i);
-    topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
-  });
+  if (FLAT) {
+    walk_ranges(n_ranges, range_get, [&](long long i, int n) {
+      const F4 c0 = load(i);
+      F4 c1 = c0;
+      if (n == 2) c1 = load(i + 1);
+      topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c0.x, c0.y, c0.z)));
+      if (n == 2) topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c1.x, c1.y, c1.z)));
+    });
+  } else {
+    walk_ranges_nested(n_ranges, range_get, [&](long long i) {
+      const F4 c = load(i);
+      topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
+    });
+  }
   int r = 1;
   bool done = false;
   if (keys[K - 1] != init) {
@@ -198,13 +210,23 @@ PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoa
   int eq_taken = 0, n_out = 0;
   const int eq_needed = K - n_lt;
   if (r == 1) {
-    walk_ranges_nested(n_ranges, range_get, [&](long long i) {
-      const F4 c = load(i);
+    auto collect = [&](const F4& c, long long i) {
       const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
       bool take = kb < tau;
       if (kb == tau && eq_taken < eq_needed) { take = true; ++eq_taken; }
       if (take) { sink(n_out, (uint32_t)i, kb); ++n_out; }
-    });
+    };
+    if (FLAT) {
+      walk_ranges(n_ranges, range_get, [&](long long i, int n) {
+        const F4 c0 = load(i);
+        F4 c1 = c0;
+        if (n == 2) c1 = load(i + 1);
+        collect(c0, i);
+        if (n == 2) collect(c1, i + 1);
+      });
+    } else {
+      walk_ranges_nested(n_ranges, range_get, [&](long long i) { collect(load(i), i); });
+    }
   } else {
     for_each_range(g, cells, cx, cy, cz, r, true, [&](long long lo, long long hi) { scan_collect(load, lo, hi, qx, qy, qz, tau, eq_needed, eq_taken, n_out, sink); });
   }
@@ -222,12 +244,12 @@ struct AssocParams {
 // R_ref/t_ref, R_nei/t_nei = R_wl, t_wl of the two frames.  On success: p_local (query in the neighbour's
 // sensor frame, double) and plane (n, d) in the reference sensor frame.  win(j) / set_win(j, pos) access the
 // caller's per-query neighbour slots (shared memory on the device).
-template <int K, typename CellLoader, typename PointLoader, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+template <int K, bool FLAT, typename CellLoader, typename PointLoader, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
 PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const PointLoader& load, const AssocParams& prm,
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
                                   double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get) {
-  const int found = knn_select<K>(g, cells, load, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get);
+  const int found = knn_select<K, FLAT>(g, cells, load, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get);
   if (found < K) return false;                                   // :578 (k-th beyond the threshold) + quirk C.6 guard
   // neighbours -> reference sensor frame (:587), streamed: Gram matrix for the LSQ plane and the scatter matrix
   PlaneAcc acc; plane_acc_clear(acc);

@@ -67,7 +67,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 3;
+  int tune_minb = 4, tune_walk = 0;
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
@@ -212,13 +212,18 @@ int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_
 template <bool REDUCE>
 int launch_associate(pvb_ctx* ctx, int k, int n_tiles, const AssocArgs& a) {
   if (n_tiles == 0) return PVB_OK;
-  const int minb = ctx->tune_minb;   // register budget of the fused kernel: 3 or 4 resident blocks per SM
+  // tuning knobs (PVB_MINB: resident blocks per SM the register allocation targets; PVB_WALK: 0 nested row loops,
+  // 1 flattened two-records-per-trip walk).  Defaults are the fastest measured on B200.
+  const int minb = ctx->tune_minb, flat = ctx->tune_walk;
   const bool dbg = a.out_nn_idx != nullptr;
   if (k != 5 && k != 10) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
-#define PVB_LAUNCH(KK, MB, DBG) k_associate<KK, REDUCE, MB, DBG><<<n_tiles, kTile, 0, ctx->stream>>>(a)
-  if (dbg) { if (k == 10) PVB_LAUNCH(10, 3, true); else PVB_LAUNCH(5, 3, true); }
-  else if (k == 10) { if (minb == 4) PVB_LAUNCH(10, 4, false); else PVB_LAUNCH(10, 3, false); }
-  else { if (minb == 4) PVB_LAUNCH(5, 4, false); else PVB_LAUNCH(5, 3, false); }
+#define PVB_LAUNCH(KK, MB, DBG, FL) k_associate<KK, REDUCE, MB, DBG, FL><<<n_tiles, kTile, 0, ctx->stream>>>(a)
+#define PVB_DISPATCH(KK)                                                                                   \
+  if (dbg) PVB_LAUNCH(KK, 4, true, false);                                                                 \
+  else if (flat) { if (minb >= 6) PVB_LAUNCH(KK, 6, false, true); else if (minb == 5) PVB_LAUNCH(KK, 5, false, true); else PVB_LAUNCH(KK, 4, false, true); } \
+  else { if (minb >= 6) PVB_LAUNCH(KK, 6, false, false); else if (minb == 5) PVB_LAUNCH(KK, 5, false, false); else PVB_LAUNCH(KK, 4, false, false); }
+  if (k == 10) { PVB_DISPATCH(10) } else { PVB_DISPATCH(5) }
+#undef PVB_DISPATCH
 #undef PVB_LAUNCH
   CKL();
   return PVB_OK;
@@ -240,7 +245,8 @@ int pvb_create(int device, pvb_ctx** out) {
   ctx->device = device;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PVB_ERR_CUDA; }
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
-  if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e) == 4 ? 4 : 3;
+  if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e);
+  if (const char* e = getenv("PVB_WALK")) ctx->tune_walk = atoi(e) != 0;
   *out = ctx;
   return PVB_OK;
 }
