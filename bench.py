@@ -282,7 +282,17 @@ def main():
             traffic = json.load(open(tp)).get("k_associate_dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = {"bound": "hbm", "kernel": "k_associate<10,true>", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+    # instruction-issue view of the same launch (the kernel is issue-bound): executed warp instructions per
+    # launch from the committed ncu capture vs 4 schedulers x 148 SMs x SM clock
+    issue = None
+    if os.path.exists(tp):
+        try:
+            wi = json.load(open(tp)).get("k_associate_warp_instructions_per_launch")
+            if wi:
+                issue = {"warp_instructions": wi, "achieved_ginst_s": wi / (k_ms * 1e-3) / 1e9, "peak_ginst_s": 4 * 148 * 1.965, "frac": wi / (k_ms * 1e-3) / 1e9 / (4 * 148 * 1.965)}
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "k_associate<10,true>", "issue": issue, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "kernel_share_of_step": k_ms * args.steps / ms}
 
     line = {"metric": "residual_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

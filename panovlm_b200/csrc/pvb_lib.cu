@@ -67,7 +67,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 4, tune_walk = 0;
+  int tune_minb = 6, tune_walk = 0;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
