@@ -100,6 +100,19 @@ def make_data(args, rank):
                                   source_seed=20260930 + 1000 * rank)
 
 
+def use_physical_cores():
+    """The kd-tree search is memory-latency bound: one thread per physical core is faster than all hyper-threads."""
+    from oracle import pvo
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            pvo.set_num_threads(n)
+    except Exception:
+        pass
+    return pvo.num_threads()
+
+
 def cpu_baseline(args, d, steps=1, mode=1, tree=None, build_s=0.0):
     """The oracle port of the reference algorithm on a bounded sample of the same workload (same target, first
     `cpu_sample_frames` source frames), kd-tree prebuilt (the GPU path also builds its grid once, outside the step)."""
@@ -126,6 +139,7 @@ def run_reference(args):
         return
     d = make_data(args, 0)
     from oracle import pvo
+    use_physical_cores()
     nf = min(args.cpu_sample_frames, args.frames)
     off = d["src_off"][: nf + 1]
     tree = pvo.KdTreeHandle(d["target"])
@@ -303,6 +317,7 @@ def main():
     # ---- CPU baseline: the oracle port timed on this box's host cores (bounded sample), N=1 only
     if world == 1 and not args.no_cpu_baseline:
         from oracle import pvo
+        use_physical_cores()
         cb = cpu_baseline(args, d, steps=1, mode=1)
         v = cb["evals"] / cb["seconds"]
         sample = (f"{cb['frames']} of {args.frames} source frames ({cb['evals']} points, {cb['n_assoc']} accepted) against the full {args.n_target}-point target, "

@@ -54,6 +54,10 @@ def num_threads():
     return lib().pvo_num_threads()
 
 
+def set_num_threads(n):
+    lib().pvo_set_num_threads(C.c_int(int(n)))
+
+
 def aa_to_R(aa):
     """Rotation matrix (row-major numpy 3x3) of an angle-axis vector."""
     out = np.zeros(9)

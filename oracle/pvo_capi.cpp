@@ -22,6 +22,12 @@ int pvo_num_threads() {
 #endif
 }
 
+void pvo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 // ---- rotation / geometry primitives (for pinning against scipy / numpy) --------------------------------
 void pvo_aa_to_R(const double* aa, double* R_colmajor) { AngleAxisToRotationMatrix(aa, R_colmajor); }
 void pvo_R_to_aa(const double* R_colmajor, double* aa) { RotationMatrixToAngleAxis(R_colmajor, aa); }

@@ -294,13 +294,17 @@ __global__ void __launch_bounds__(kTile) k_eval_blocks(const EvalArgs a) {
 }
 
 // ---- K4: sum the per-tile partials of each edge / frame in tile order --------------------------------------------------
+// Stage 1: block (group, chunk) sums its share of the group's partial rows (8 slices x 32 value lanes, slices added in
+// order) into chunk_out[group][chunk][NV]; stage 2 (k_sum_chunks) adds the chunks in order.  Every order is fixed =>
+// deterministic.  NV <= 96.
+constexpr int kSumChunks = 16;
 template <int NV>
-__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partials, const int* __restrict__ tile_begin /*[n_groups+1]*/, double* __restrict__ out) {
-  // 8 slices x 32 value lanes; slice s sums rows begin+s, begin+s+8, ... ; slices are then added in order 0..7
-  // (fixed order => deterministic).  NV <= 96: values are handled in chunks of 32 lanes.
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partials, const int* __restrict__ tile_begin /*[n_groups+1]*/, double* __restrict__ chunk_out) {
   __shared__ double sm[8][96];
-  const int gidx = blockIdx.x, lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int t0 = tile_begin[gidx], t1 = tile_begin[gidx + 1];
+  const int gidx = blockIdx.x, chunk = blockIdx.y, lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int g0 = tile_begin[gidx], g1 = tile_begin[gidx + 1];
+  const int per = (g1 - g0 + kSumChunks - 1) / kSumChunks;
+  const int t0 = g0 + chunk * per, t1 = min(g1, t0 + per);
   for (int v = lane; v < NV; v += 32) {
     double acc = 0.0;
     for (int t = t0 + slice; t < t1; t += 8) acc += partials[(size_t)t * NV + v];
@@ -311,8 +315,17 @@ __global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__
     double acc = 0.0;
 #pragma unroll
     for (int sl = 0; sl < 8; ++sl) acc += sm[sl][threadIdx.x];
-    out[(size_t)gidx * NV + threadIdx.x] = acc;
+    chunk_out[((size_t)gidx * kSumChunks + chunk) * NV + threadIdx.x] = acc;
   }
+}
+template <int NV>
+__global__ void k_sum_chunks(const double* __restrict__ chunk_out, double* __restrict__ out) {
+  const int gidx = blockIdx.x, v = threadIdx.x;
+  if (v >= NV) return;
+  double acc = 0.0;
+#pragma unroll
+  for (int c = 0; c < kSumChunks; ++c) acc += chunk_out[((size_t)gidx * kSumChunks + c) * NV + v];
+  out[(size_t)gidx * NV + v] = acc;
 }
 
 // ---- K1: SE(3) + equirectangular projection (float32 FastAtan2 path) --------------------------------------------------

@@ -74,6 +74,7 @@ struct pvb_ctx {
   long long bn = 0; int nb = 0; int b_tiles = 0;
   std::vector<int> edge_ref, edge_nei, edge_tile_begin;
   std::vector<uint32_t> b_orig;
+  DevBuf b_chunk, d_chunk;
   DevBuf b_tile, b_eref, b_enei, b_type, b_norm, b_huber, b_consts, b_orig_d, b_r, b_J, b_part, b_esys, b_tbegin;
   PinBuf h_r, h_J, h_esys;
   bool b_has_rows = false, b_has_sys = false;
@@ -258,7 +259,7 @@ void pvb_destroy(pvb_ctx* ctx) {
   DevBuf* dbs[] = {&ctx->d_prep, &ctx->d_wpose, &ctx->b_tile, &ctx->b_eref, &ctx->b_enei, &ctx->b_type, &ctx->b_norm, &ctx->b_huber, &ctx->b_consts, &ctx->b_orig_d, &ctx->b_r, &ctx->b_J,
                    &ctx->b_part, &ctx->b_esys, &ctx->b_tbegin, &ctx->f_pairs, &ctx->f_qtiles, &ctx->f_valid, &ctx->f_point, &ctx->f_plane, &ctx->f_nn_idx, &ctx->f_nn_d2,
                    &ctx->d_q_sorted, &ctx->d_q_orig, &ctx->d_pairs, &ctx->d_qtiles, &ctx->d_part, &ctx->d_sys, &ctx->d_tbegin, &ctx->d_valid, &ctx->d_point, &ctx->d_plane,
-                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e};
+                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e, &ctx->b_chunk, &ctx->d_chunk};
   for (DevBuf* b : dbs) b->release();
   PinBuf* pbs[] = {&ctx->h_pose, &ctx->h_r, &ctx->h_J, &ctx->h_esys, &ctx->fh_valid, &ctx->fh_point, &ctx->fh_plane, &ctx->dh_sys, &ctx->mh_a};
   for (PinBuf* b : pbs) b->release();
@@ -370,7 +371,10 @@ int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int wa
     k_eval_blocks<<<ctx->b_tiles, kTile, 0, ctx->stream>>>(a);
     CKL();
     if (want_system) {
-      k_sum_partials<92><<<ne, 256, 0, ctx->stream>>>(ctx->b_part.as<double>(), ctx->b_tbegin.as<int>(), ctx->b_esys.as<double>());
+      CK(ctx->b_chunk.ensure((size_t)ne * kSumChunks * 92 * 8));
+      k_sum_partials<92><<<dim3(ne, kSumChunks), 256, 0, ctx->stream>>>(ctx->b_part.as<double>(), ctx->b_tbegin.as<int>(), ctx->b_chunk.as<double>());
+      CKL();
+      k_sum_chunks<92><<<ne, 96, 0, ctx->stream>>>(ctx->b_chunk.as<double>(), ctx->b_esys.as<double>());
       CKL();
       CK(cudaMemcpyAsync(ctx->h_esys.p, ctx->b_esys.p, (size_t)ne * 92 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -642,7 +646,10 @@ int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_de
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;
   double* dst = (dev_sys && *dev_sys) ? *dev_sys : ctx->d_sys.as<double>();   // caller-provided device buffer (e.g. a slice of an allreduce buffer)
-  k_sum_partials<29><<<ctx->d_frames, 256, 0, ctx->stream>>>(ctx->d_part.as<double>(), ctx->d_tbegin.as<int>(), dst);
+  CK(ctx->d_chunk.ensure((size_t)ctx->d_frames * kSumChunks * 29 * 8));
+  k_sum_partials<29><<<dim3(ctx->d_frames, kSumChunks), 256, 0, ctx->stream>>>(ctx->d_part.as<double>(), ctx->d_tbegin.as<int>(), ctx->d_chunk.as<double>());
+  CKL();
+  k_sum_chunks<29><<<ctx->d_frames, 32, 0, ctx->stream>>>(ctx->d_chunk.as<double>(), dst);
   CKL();
   if (dev_sys) *dev_sys = dst;
   return PVB_OK;
