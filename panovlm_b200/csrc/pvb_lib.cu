@@ -88,7 +88,9 @@ struct pvb_ctx {
   DevBuf d_q_sorted, d_q_orig, d_pairs, d_qtiles, d_part, d_sys, d_tbegin, d_valid, d_point, d_plane, d_res, d_jac;
   PinBuf dh_sys;
   int d_ntiles = 0; double d_cell = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;   // brackets the fused associate kernel of the last dense evaluate
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t eval_done = nullptr; std::vector<cudaEvent_t> chunk_ev;
+  std::vector<int> d_chunk_frame, d_chunk_ctile, d_chunk_qtile; bool d_chunks_pending = false;   // brackets the fused associate kernel of the last dense evaluate
   // ---- misc
   DevBuf m_a, m_b, m_c, m_d, m_e;
   PinBuf mh_a;
@@ -103,6 +105,12 @@ struct pvb_ctx {
 #define CKL() do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return ctx->fail(PVB_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
 
 namespace {
+
+// scratch buffers m_a..m_e are shared with the source-upload pipeline: wait for it before reusing them elsewhere
+int quiesce_copy(pvb_ctx* ctx) {
+  if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+  return PVB_OK;
+}
 
 int upload_poses(pvb_ctx* ctx, const double* poses, int nb, bool block0_identity_prefix) {
   // layout in pinned staging: PosePrep[nb'] then WorldPose[nb'] where nb' = nb (+1 if an identity block is prefixed)
@@ -264,6 +272,9 @@ void pvb_destroy(pvb_ctx* ctx) {
   PinBuf* pbs[] = {&ctx->h_pose, &ctx->h_r, &ctx->h_J, &ctx->h_esys, &ctx->fh_valid, &ctx->fh_point, &ctx->fh_plane, &ctx->dh_sys, &ctx->mh_a};
   for (PinBuf* b : pbs) b->release();
   ctx->f_tgt.release(); ctx->f_qry.release(); ctx->f_index.release(); ctx->d_tgt.release(); ctx->d_src.release(); ctx->d_index.release();
+  for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+  if (ctx->eval_done) cudaEventDestroy(ctx->eval_done);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -577,46 +588,89 @@ int pvb_dense_set_target(pvb_ctx* ctx, const float* xyzc, long n, double cell_si
   return PVB_OK;
 }
 
-int pvb_dense_set_sources(pvb_ctx* ctx, const float* xyzc, const int* offsets, int n_frames) {
-  if (!ctx || !xyzc || !offsets || n_frames <= 0) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_dense_set_sources: bad arguments") : PVB_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  std::vector<const float*> ptrs(n_frames); std::vector<int> cnt(n_frames), blocks(n_frames);
-  for (int f = 0; f < n_frames; ++f) { ptrs[f] = xyzc + (size_t)offsets[f] * 4; cnt[f] = offsets[f + 1] - offsets[f]; blocks[f] = f + 1; if (cnt[f] < 0) return ctx->fail(PVB_ERR_ARG, "offsets not monotone"); }
+// Source upload is pipelined against the next evaluate: the frames are split into chunks; every chunk is copied,
+// Morton-keyed, sorted and gathered on a copy stream and signals an event; pvb_dense_evaluate* then launches the fused
+// kernel chunk by chunk, each launch waiting only for its own chunk, so the H2D copy and the re-ordering of chunk c+1
+// overlap the association of chunk c.  (With a pinned host buffer the copies are truly asynchronous.)
+static int dense_prepare_layout(pvb_ctx* ctx, const int* offsets, int n_frames) {
   CloudSet& cs = ctx->d_src;
-  int rc = set_cloudset(ctx, cs, ptrs, cnt, blocks, 256); if (rc) return rc;
-  ctx->d_frames = n_frames;
+  cs.n_clouds = n_frames;
+  cs.off.assign(offsets, offsets + n_frames + 1);
+  if (cs.off[0] != 0) return ctx->fail(PVB_ERR_ARG, "offsets must start at 0");
+  for (int f = 0; f < n_frames; ++f) if (cs.off[f + 1] < cs.off[f]) return ctx->fail(PVB_ERR_ARG, "offsets not monotone");
+  cs.n_points = cs.off[n_frames];
   const long long n = cs.n_points;
-  // Morton re-ordering per frame (keys = frame << 36 | morton36)
-  DevBuf &k0 = ctx->m_a, &k1 = ctx->m_b, &v0 = ctx->m_c, &v1 = ctx->m_d, &tmp = ctx->m_e;
-  CK(k0.ensure((size_t)n * 8)); CK(k1.ensure((size_t)n * 8)); CK(v0.ensure((size_t)n * 4)); CK(v1.ensure((size_t)n * 4));
-  CK(ctx->d_q_sorted.ensure((size_t)n * sizeof(F4))); CK(ctx->d_q_orig.ensure((size_t)n * 4));
-  if (n > 0) {
-    k_morton_keys<<<cs.n_tiles, 256, 0, ctx->stream>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>(), k0.as<unsigned long long>(), v0.as<uint32_t>());
-    CKL();
-    int frame_bits = 1; while ((1 << frame_bits) < n_frames + 1) ++frame_bits;
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.as<unsigned long long>(), k1.as<unsigned long long>(), v0.as<uint32_t>(), v1.as<uint32_t>(), (int)n, 0, 36 + frame_bits, ctx->stream);
-    CK(tmp.ensure(tb)); tb = tmp.cap;
-    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k0.as<unsigned long long>(), k1.as<unsigned long long>(), v0.as<uint32_t>(), v1.as<uint32_t>(), (int)n, 0, 36 + frame_bits, ctx->stream));
-    k_gather_f4<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(cs.local.as<F4>(), v1.as<uint32_t>(), n, ctx->d_q_sorted.as<F4>());
-    CKL();
-    CK(cudaMemcpyAsync(ctx->d_q_orig.p, v1.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-  }
-  // tiles: frames keep their contiguous ranges after the sort (frame id is the most significant key part)
+  std::vector<CloudTile> ctiles; std::vector<int> blocks(n_frames);
   std::vector<Pair> pairs(n_frames); std::vector<QueryTile> tiles; std::vector<int> tbegin(n_frames + 1, 0);
+  const int n_chunks = std::min(n_frames, 8);
+  ctx->d_chunk_frame.assign(n_chunks + 1, 0); ctx->d_chunk_ctile.assign(n_chunks + 1, 0); ctx->d_chunk_qtile.assign(n_chunks + 1, 0);
+  for (int c = 0; c <= n_chunks; ++c) ctx->d_chunk_frame[c] = (int)((long long)n_frames * c / n_chunks);
+  int chunk = 0;
   for (int f = 0; f < n_frames; ++f) {
+    while (chunk < n_chunks && ctx->d_chunk_frame[chunk] == f) { ctx->d_chunk_ctile[chunk] = (int)ctiles.size(); ctx->d_chunk_qtile[chunk] = (int)tiles.size(); ++chunk; }
+    const int cnt = cs.off[f + 1] - cs.off[f];
+    blocks[f] = f + 1;
     pairs[f] = Pair{0, f, 0, f + 1};
     tbegin[f] = (int)tiles.size() * (kTile / 32);      // partials are per warp: kTile/32 entries per tile
-    for (int s = 0; s < cnt[f]; s += kTile) tiles.push_back(QueryTile{f, cs.off[f] + s, std::min(kTile, cnt[f] - s), 0});
+    for (int s0 = 0; s0 < cnt; s0 += 256) ctiles.push_back(CloudTile{f, cs.off[f] + s0, std::min(256, cnt - s0), 0});
+    for (int s0 = 0; s0 < cnt; s0 += kTile) tiles.push_back(QueryTile{f, cs.off[f] + s0, std::min(kTile, cnt - s0), 0});
   }
+  ctx->d_chunk_ctile[n_chunks] = (int)ctiles.size(); ctx->d_chunk_qtile[n_chunks] = (int)tiles.size();
   tbegin[n_frames] = (int)tiles.size() * (kTile / 32);
+  cs.n_tiles = (int)ctiles.size();
   ctx->d_ntiles = (int)tiles.size();
+  ctx->d_frames = n_frames;
+  CK(cs.local.ensure(std::max<size_t>(16, (size_t)n * sizeof(F4))));
+  CK(cs.tiles.ensure(std::max<size_t>(16, ctiles.size() * sizeof(CloudTile))));
+  CK(ctx->m_a.ensure(std::max<size_t>(16, (size_t)n * 8))); CK(ctx->m_b.ensure(std::max<size_t>(16, (size_t)n * 8)));
+  CK(ctx->m_c.ensure(std::max<size_t>(16, (size_t)n * 4))); CK(ctx->m_d.ensure(std::max<size_t>(16, (size_t)n * 4)));
+  CK(ctx->d_q_sorted.ensure(std::max<size_t>(16, (size_t)n * sizeof(F4)))); CK(ctx->d_q_orig.ensure(std::max<size_t>(16, (size_t)n * 4)));
   CK(ctx->d_pairs.ensure(pairs.size() * sizeof(Pair))); CK(ctx->d_qtiles.ensure(std::max<size_t>(16, tiles.size() * sizeof(QueryTile)))); CK(ctx->d_tbegin.ensure(tbegin.size() * 4));
   CK(ctx->d_part.ensure(std::max<size_t>(16, tiles.size() * (kTile / 32) * 29 * 8))); CK(ctx->d_sys.ensure((size_t)n_frames * 29 * 8)); CK(ctx->dh_sys.ensure((size_t)n_frames * 29 * 8));
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->m_a.as<unsigned long long>(), ctx->m_b.as<unsigned long long>(), ctx->m_c.as<uint32_t>(), ctx->m_d.as<uint32_t>(), (int)std::max<long long>(1, n), 0, 64, ctx->stream);
+  CK(ctx->m_e.ensure(tb));
+  if (!ctiles.empty()) CK(cudaMemcpyAsync(cs.tiles.p, ctiles.data(), ctiles.size() * sizeof(CloudTile), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_pairs.p, pairs.data(), pairs.size() * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->d_qtiles.p, tiles.data(), tiles.size() * sizeof(QueryTile), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_tbegin.p, tbegin.data(), tbegin.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  while ((int)ctx->chunk_ev.size() < n_chunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+  return PVB_OK;
+}
+
+int pvb_dense_set_sources(pvb_ctx* ctx, const float* xyzc, const int* offsets, int n_frames) {
+  if (!ctx || !xyzc || !offsets || n_frames <= 0) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_dense_set_sources: bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CloudSet& cs = ctx->d_src;
+  const bool same = ctx->d_frames == n_frames && (int)cs.off.size() == n_frames + 1 && std::equal(offsets, offsets + n_frames + 1, cs.off.begin());
+  if (!same) { int rc = dense_prepare_layout(ctx, offsets, n_frames); if (rc) return rc; }
+  if (!ctx->copy_stream) { CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->eval_done, cudaEventDisableTiming)); }
+  cudaStream_t cp = ctx->copy_stream;
+  // the previous evaluate may still be reading the query buffers
+  CK(cudaEventRecord(ctx->eval_done, ctx->stream));
+  CK(cudaStreamWaitEvent(cp, ctx->eval_done, 0));
+  const int n_chunks = (int)ctx->d_chunk_frame.size() - 1;
+  int frame_bits = 1; while ((1 << frame_bits) < n_frames + 1) ++frame_bits;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int f0 = ctx->d_chunk_frame[c], f1 = ctx->d_chunk_frame[c + 1];
+    const long long p0 = cs.off[f0], cnt = (long long)cs.off[f1] - p0;
+    if (cnt > 0) {
+      CK(cudaMemcpyAsync(cs.local.as<F4>() + p0, xyzc + (size_t)p0 * 4, (size_t)cnt * sizeof(F4), cudaMemcpyHostToDevice, cp));
+      const int t0 = ctx->d_chunk_ctile[c], t1 = ctx->d_chunk_ctile[c + 1];
+      // Morton re-ordering per frame (keys = frame << 36 | morton36); vals are global point indices
+      k_morton_keys<<<t1 - t0, 256, 0, cp>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, ctx->m_a.as<unsigned long long>(), ctx->m_c.as<uint32_t>());
+      CKL();
+      size_t tb = ctx->m_e.cap;
+      CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<unsigned long long>() + p0, ctx->m_b.as<unsigned long long>() + p0, ctx->m_c.as<uint32_t>() + p0,
+                                         ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, 36 + frame_bits, cp));
+      k_gather_f4<<<(unsigned)((cnt + 255) / 256), 256, 0, cp>>>(cs.local.as<F4>(), ctx->m_d.as<uint32_t>() + p0, cnt, ctx->d_q_sorted.as<F4>() + p0);
+      CKL();
+      CK(cudaMemcpyAsync(ctx->d_q_orig.as<uint32_t>() + p0, ctx->m_d.as<uint32_t>() + p0, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cp));
+    }
+    CK(cudaEventRecord(ctx->chunk_ev[c], cp));
+  }
+  ctx->d_chunks_pending = true;
   return PVB_OK;
 }
 
@@ -642,7 +696,20 @@ int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_de
   AssocArgs a; int rc = dense_args(ctx, poses_lw, prm, a); if (rc) return rc;
   a.partials = ctx->d_part.as<double>();
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  rc = launch_associate<true>(ctx, prm->k, ctx->d_ntiles, a); if (rc) return rc;
+  if (ctx->d_chunks_pending) {            // fresh upload: consume it chunk by chunk as the copy stream delivers
+    const int n_chunks = (int)ctx->d_chunk_frame.size() - 1;
+    for (int c = 0; c < n_chunks; ++c) {
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+      const int t0 = ctx->d_chunk_qtile[c], t1 = ctx->d_chunk_qtile[c + 1];
+      AssocArgs ac = a;
+      ac.tiles = a.tiles + t0;
+      ac.partials = a.partials + (size_t)t0 * (kTile / 32) * 29;
+      rc = launch_associate<true>(ctx, prm->k, t1 - t0, ac); if (rc) return rc;
+    }
+    ctx->d_chunks_pending = false;
+  } else {
+    rc = launch_associate<true>(ctx, prm->k, ctx->d_ntiles, a); if (rc) return rc;
+  }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;
   double* dst = (dev_sys && *dev_sys) ? *dev_sys : ctx->d_sys.as<double>();   // caller-provided device buffer (e.g. a slice of an allreduce buffer)
@@ -682,6 +749,7 @@ int pvb_dense_get_rows(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_par
   CK(cudaMemsetAsync(ctx->d_valid.p, 0, n, ctx->stream)); CK(cudaMemsetAsync(ctx->d_point.p, 0, n * 24, ctx->stream)); CK(cudaMemsetAsync(ctx->d_plane.p, 0, n * 32, ctx->stream));
   a.out_valid = ctx->d_valid.as<unsigned char>(); a.out_point = ctx->d_point.as<double>(); a.out_plane = ctx->d_plane.as<double>();
   a.out_res = ctx->d_res.as<double>(); a.out_jac6 = ctx->d_jac.as<double>();
+  if (ctx->d_chunks_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->d_chunks_pending = false; }
   rc = launch_associate<false>(ctx, prm->k, ctx->d_ntiles, a); if (rc) return rc;
   if (valid) CK(cudaMemcpyAsync(valid, ctx->d_valid.p, n, cudaMemcpyDeviceToHost, ctx->stream));
   if (point3) CK(cudaMemcpyAsync(point3, ctx->d_point.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
@@ -714,6 +782,7 @@ int pvb_project_equirect(pvb_ctx* ctx, const float* xyzi, long n, const double* 
   if (!ctx || !xyzi || !T || !uvd || n < 0) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
   if (n == 0) return PVB_OK;
   CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
   CK(ctx->m_a.ensure((size_t)n * 16)); CK(ctx->m_b.ensure((size_t)n * 12));
   CK(cudaMemcpyAsync(ctx->m_a.p, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
   WorldPose w; T16_to_pose(T, w);
@@ -727,6 +796,7 @@ int pvb_project_equirect(pvb_ctx* ctx, const float* xyzi, long n, const double* 
 int pvb_project_depth_image(pvb_ctx* ctx, const float* xyzi, long n, const double* T, int rows, int cols, int size, uint16_t* image) {
   if (!ctx || !xyzi || !T || !image || n < 0 || rows <= 0 || cols <= 0) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
   const size_t px = (size_t)rows * cols;
   CK(ctx->m_a.ensure(std::max<size_t>(16, (size_t)n * 16))); CK(ctx->m_c.ensure(px * 8)); CK(ctx->m_d.ensure(px * 2));
   CK(cudaMemsetAsync(ctx->m_c.p, 0, px * 8, ctx->stream));
@@ -747,6 +817,7 @@ int pvb_transform_cloud(pvb_ctx* ctx, const float* xyzi, long n, const double* R
   if (!ctx || n < 0 || (n > 0 && (!xyzi || !out)) || !R || !t) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
   if (n == 0) return PVB_OK;
   CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
   CK(ctx->m_a.ensure((size_t)n * 16)); CK(ctx->m_b.ensure((size_t)n * 16));
   CK(cudaMemcpyAsync(ctx->m_a.p, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
   WorldPose w; for (int k = 0; k < 9; ++k) w.R[k] = R[k]; for (int k = 0; k < 3; ++k) w.t[k] = t[k];
@@ -765,6 +836,7 @@ int pvb_line_votes(pvb_ctx* ctx, const double* ref_lines, int S_ref, const float
   if (n_pts == 0) { memset(M, 0, msz * 4); return PVB_OK; }
   if (!ref_lines || !pts || !p2s_off || !p2s_ids) return ctx->fail(PVB_ERR_ARG, "null input");
   CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
   const int n_ids = p2s_off[n_pts];
   CK(ctx->m_a.ensure((size_t)S_ref * 48)); CK(ctx->m_b.ensure((size_t)n_pts * 16)); CK(ctx->m_c.ensure((size_t)(n_pts + 1) * 4)); CK(ctx->m_d.ensure(std::max<size_t>(16, (size_t)n_ids * 4))); CK(ctx->m_e.ensure(msz * 4));
   CK(cudaMemcpyAsync(ctx->m_a.p, ref_lines, (size_t)S_ref * 48, cudaMemcpyHostToDevice, ctx->stream));
@@ -787,6 +859,7 @@ int pvb_angle_votes(pvb_ctx* ctx, int rows, int cols, const float* lines4, int L
   if (P == 0) { memset(counts, 0, csz * 4); return PVB_OK; }
   if (!lines4 || !cloud_local || !p2s_off || !p2s_ids || !T_cl) return ctx->fail(PVB_ERR_ARG, "null input");
   CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
   // image-line planes on the host (CameraLidarLineAssociate.cpp:381-387): ImageToCam uses exact sin/cos
   std::vector<ImageLinePlane> lp(L);
   for (int l = 0; l < L; ++l) {
