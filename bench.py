@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=64, help="source frames in the bounded CPU-baseline sample (64 = the whole step, ~4 s on 64 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--cell", type=float, default=0.0, help="target grid cell size in metres (0: library default)")
     return ap.parse_args()
 
@@ -158,6 +159,32 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "evals/s", "cores": pvo.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def bench_blocks(ctx, peak_gbs, n=1_400_000, nb=454, seed=5):
+    """Room-shaped residual-block list: every frame linked to 7 neighbours, 440 plane correspondences per edge."""
+    rng = np.random.default_rng(seed)
+    ref = np.repeat(np.arange(nb), 7)
+    nei = (ref + np.tile(np.array([-3, -2, -1, 1, 2, 3, 40]), nb)) % nb
+    per = n // len(ref)
+    ref, nei = np.repeat(ref, per).astype(np.int32), np.repeat(nei, per).astype(np.int32)
+    n = len(ref)
+    consts = np.zeros((n, 12))
+    consts[:, :3] = rng.normal(0, 4, (n, 3))
+    nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    consts[:, 3:6] = nrm; consts[:, 6] = np.abs(rng.normal(2, 1, n)); consts[:, 7] = 1.0
+    poses = np.concatenate([rng.normal(0, 0.2, (nb, 3)), rng.normal(0, 1.0, (nb, 3))], axis=1)
+    ctx.blocks_set(np.full(n, 1, np.int32), ref, nei, consts, 2 * np.pi / 180, 1, nb)
+    out = {"n_blocks": n, "n_pose_blocks": nb, "n_edges": int(len(set(zip(ref.tolist(), nei.tolist()))))}
+    for name, rows, sysm, balg in (("reduced", False, True, 64.0), ("rows", True, False, 168.0)):
+        ms = []
+        for _ in range(6):
+            ctx.blocks_evaluate(poses, want_rows=rows, want_system=sysm)
+            ms.append(ctx.blocks_kernel_time_ms())
+        k = float(np.median(ms[2:]))
+        out[name] = {"kernel_ms": k, "evals_per_s": n / (k * 1e-3), "algorithmic_bytes_per_row": balg, "achieved_GBs": n * balg / (k * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": n * balg / (k * 1e-3) / 1e9 / peak_gbs}
+    return out
 
 
 def config_dict(args):
@@ -313,6 +340,14 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "gn_cost_first_last": [costs[0], costs[-1]], "ms_per_gauss_newton_iter": ms_max / args.steps}
+
+    # ---- secondary kernel: K3/K4 over a Room-shaped correspondence list (configs[1] sizes: 454 pose blocks, ~3.2 k edges,
+    #      1.4 M residual blocks = Point2Plane_Angle + Huber 2 deg), device time of k_eval_blocks per evaluation
+    if world == 1 and not args.no_extra:
+        try:
+            line["extra"] = {"k_eval_blocks": bench_blocks(ctx, peak)}
+        except Exception as e:                                   # never lose the headline line
+            line["extra"] = {"k_eval_blocks": {"error": str(e)}}
 
     # ---- CPU baseline: the oracle port timed on this box's host cores (bounded sample), N=1 only
     if world == 1 and not args.no_cpu_baseline:

@@ -61,6 +61,8 @@ int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int wa
 const double* pvb_blocks_residuals(const pvb_ctx* ctx); /* n doubles, loss-corrected                             */
 const double* pvb_blocks_jacobians(const pvb_ctx* ctx); /* n x 12 row-major [d aa_ref | d t_ref | d aa_nei | d t_nei] */
 int pvb_blocks_cost(const pvb_ctx* ctx, double* cost, long* n_residuals);
+/* device time (CUDA events) of the residual+Jacobian kernel of the last pvb_blocks_evaluate                          */
+int pvb_blocks_kernel_time_ms(pvb_ctx* ctx, float* ms);
 int pvb_blocks_num_edges(const pvb_ctx* ctx);
 int pvb_blocks_edges(const pvb_ctx* ctx, int* ref, int* nei);
 /* per edge: H upper-triangular row-major (78) | g (12) | cost | n_residuals  (parameter order aa_r,t_r,aa_n,t_n) */

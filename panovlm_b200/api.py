@@ -97,7 +97,7 @@ def load_library():
 
 EXPORTS = [
     "pvb_create", "pvb_destroy", "pvb_last_error", "pvb_set_stream", "pvb_synchronize", "pvb_kernel_launches", "pvb_stream",
-    "pvb_blocks_set", "pvb_blocks_evaluate", "pvb_blocks_residuals", "pvb_blocks_jacobians", "pvb_blocks_cost", "pvb_blocks_num_edges",
+    "pvb_blocks_set", "pvb_blocks_evaluate", "pvb_blocks_residuals", "pvb_blocks_jacobians", "pvb_blocks_cost", "pvb_blocks_kernel_time_ms", "pvb_blocks_num_edges",
     "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_dense_system", "pvb_blocks_solve_lm",
     "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn",
     "pvb_dense_set_target", "pvb_dense_set_sources", "pvb_dense_evaluate", "pvb_dense_evaluate_device", "pvb_dense_gauss_newton_step",
@@ -183,6 +183,11 @@ class Context:
         c, n = C.c_double(), C.c_long()
         self._ck(self._L.pvb_blocks_cost(self._h, C.byref(c), C.byref(n)))
         return c.value, n.value
+
+    def blocks_kernel_time_ms(self):
+        ms = C.c_float()
+        self._ck(self._L.pvb_blocks_kernel_time_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def blocks_edges(self):
         ne = self._L.pvb_blocks_num_edges(self._h)

@@ -89,6 +89,7 @@ struct pvb_ctx {
   PinBuf dh_sys;
   int d_ntiles = 0; double d_cell = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
+  cudaEvent_t bev0 = nullptr, bev1 = nullptr; bool bev_valid = false;     // brackets k_eval_blocks of the last blocks evaluate
   cudaStream_t copy_stream = nullptr; cudaEvent_t eval_done = nullptr; std::vector<cudaEvent_t> chunk_ev;
   std::vector<int> d_chunk_frame, d_chunk_ctile, d_chunk_qtile; bool d_chunks_pending = false;   // brackets the fused associate kernel of the last dense evaluate
   // ---- misc
@@ -253,7 +254,7 @@ int pvb_create(int device, pvb_ctx** out) {
   pvb_ctx* ctx = new pvb_ctx();
   ctx->device = device;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PVB_ERR_CUDA; }
-  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->bev0); cudaEventCreate(&ctx->bev1);
   if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e);
   if (const char* e = getenv("PVB_WALK")) ctx->tune_walk = atoi(e) != 0;
   *out = ctx;
@@ -275,6 +276,8 @@ void pvb_destroy(pvb_ctx* ctx) {
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
   if (ctx->eval_done) cudaEventDestroy(ctx->eval_done);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->bev0) cudaEventDestroy(ctx->bev0);
+  if (ctx->bev1) cudaEventDestroy(ctx->bev1);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -379,8 +382,11 @@ int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int wa
     a.orig = ctx->b_orig_d.as<uint32_t>(); a.n = n; a.prep = ctx->d_prep.as<PosePrep>();
     a.out_r = want_rows ? ctx->b_r.as<double>() : nullptr; a.out_J = want_rows ? ctx->b_J.as<double>() : nullptr;
     a.partials = want_system ? ctx->b_part.as<double>() : nullptr;
+    CK(cudaEventRecord(ctx->bev0, ctx->stream));
     k_eval_blocks<<<ctx->b_tiles, kTile, 0, ctx->stream>>>(a);
     CKL();
+    CK(cudaEventRecord(ctx->bev1, ctx->stream));
+    ctx->bev_valid = true;
     if (want_system) {
       CK(ctx->b_chunk.ensure((size_t)ne * kSumChunks * 92 * 8));
       k_sum_partials<92><<<dim3(ne, kSumChunks), 256, 0, ctx->stream>>>(ctx->b_part.as<double>(), ctx->b_tbegin.as<int>(), ctx->b_chunk.as<double>());
@@ -397,6 +403,14 @@ int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int wa
   }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->b_has_rows = want_rows != 0; ctx->b_has_sys = want_system != 0;
+  return PVB_OK;
+}
+
+int pvb_blocks_kernel_time_ms(pvb_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return PVB_ERR_ARG;
+  if (!ctx->bev_valid) return ctx->fail(PVB_ERR_STATE, "no blocks evaluate has run");
+  CK(cudaEventSynchronize(ctx->bev1));
+  CK(cudaEventElapsedTime(ms, ctx->bev0, ctx->bev1));
   return PVB_OK;
 }
 

@@ -297,122 +297,6 @@ PVB_HD double huber_correct(double a, double& r, double* J, int n) {
   return 0.5 * (2.0 * a * sq - a * a);
 }
 
-// ---- plane fit / collinearity test of AssociatePoint2Plane (LidarFeatureAssociate.cpp:593-596) -------------
-// Least-squares A x = -1 over K points by Householder QR with column pivoting (what Geometry.hpp:361's
-// colPivHouseholderQr().solve does), then d = 1/|x|, n = x/|x| and the tolerance test (:364-371).
-// In-place core: A (K x 3, destroyed) x = -1 in the least-squares sense.
-template <int K>
-PVB_HD void lstsq_minus_one_inplace(double (*A)[3], double x[3]) {
-  double b[K];
-#pragma unroll
-  for (int i = 0; i < K; ++i) b[i] = -1.0;
-  int perm[3] = {0, 1, 2};
-  double diag[3] = {0, 0, 0};
-  int rank = 0;
-  double maxpivot = 0.0;
-  bool stop = false;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    if (stop) continue;
-    double cn[3] = {0, 0, 0};
-#pragma unroll
-    for (int c = k; c < 3; ++c) { double s = 0; for (int r = k; r < K; ++r) s += A[r][c] * A[r][c]; cn[c] = s; }
-    int best = k; double bn = cn[k];
-#pragma unroll
-    for (int c = k + 1; c < 3; ++c) if (cn[c] > bn) { bn = cn[c]; best = c; }
-#pragma unroll
-    for (int c = k + 1; c < 3; ++c) {          // static column indices keep A[][] in registers
-      if (best == c) {
-        for (int r = 0; r < K; ++r) { const double tmp = A[r][k]; A[r][k] = A[r][c]; A[r][c] = tmp; }
-        const int tp = perm[k]; perm[k] = perm[c]; perm[c] = tp;
-      }
-    }
-    const double norm = sqrt(bn);
-    if (k == 0) maxpivot = norm;
-    if (norm <= maxpivot * DBL_EPSILON * 3.0) { stop = true; continue; }
-    ++rank;
-    const double alpha = (A[k][k] > 0) ? -norm : norm;
-    const double vk = A[k][k] - alpha;
-    double vtv = vk * vk;
-    for (int r = k + 1; r < K; ++r) vtv += A[r][k] * A[r][k];
-    if (vtv > 0) {
-      const double inv = 2.0 / vtv;
-#pragma unroll
-      for (int c = k + 1; c < 3; ++c) {
-        double dot = vk * A[k][c];
-        for (int r = k + 1; r < K; ++r) dot += A[r][k] * A[r][c];
-        const double f = dot * inv;
-        A[k][c] -= f * vk;
-        for (int r = k + 1; r < K; ++r) A[r][c] -= f * A[r][k];
-      }
-      double dot = vk * b[k];
-      for (int r = k + 1; r < K; ++r) dot += A[r][k] * b[r];
-      const double f = dot * inv;
-      b[k] -= f * vk;
-      for (int r = k + 1; r < K; ++r) b[r] -= f * A[r][k];
-    }
-    diag[k] = alpha;
-  }
-  double y[3] = {0, 0, 0};
-#pragma unroll
-  for (int k = 2; k >= 0; --k) {
-    if (k >= rank) continue;
-    double s = b[k];
-#pragma unroll
-    for (int c = k + 1; c < 3; ++c) if (c < rank) s -= A[k][c] * y[c];
-    y[k] = s / diag[k];
-  }
-  x[0] = x[1] = x[2] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { if (perm[k] == 0) x[0] = y[k]; else if (perm[k] == 1) x[1] = y[k]; else x[2] = y[k]; }
-}
-
-template <int K>
-PVB_HD bool form_plane_lsq(const double (*pts)[3], double tol, double plane[4]) {
-  double A[K][3], x[3];
-  for (int i = 0; i < K; ++i) { A[i][0] = pts[i][0]; A[i][1] = pts[i][1]; A[i][2] = pts[i][2]; }
-  lstsq_minus_one_inplace<K>(A, x);
-  const double nrm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-  const double d = 1.0 / nrm;
-  const double n0 = x[0] / nrm, n1 = x[1] / nrm, n2 = x[2] / nrm;
-  if (tol > 0) {
-    for (int i = 0; i < K; ++i)
-      if (fabs(n0 * pts[i][0] + n1 * pts[i][1] + n2 * pts[i][2] + d) > tol) return false;
-  }
-  plane[0] = n0; plane[1] = n1; plane[2] = n2; plane[3] = d;
-  return true;
-}
-
-// FormLine(points, tolerance) collinearity test (Geometry.hpp:220-246): true when lambda_max > tol * lambda_mid.
-// Eigenvalues of the symmetric 3x3 scatter matrix by the trigonometric closed form.
-template <int K>
-PVB_HD bool points_collinear(const double (*pts)[3], double tol) {
-  double c[3] = {0, 0, 0};
-  for (int i = 0; i < K; ++i) { c[0] = c[0] + pts[i][0]; c[1] = c[1] + pts[i][1]; c[2] = c[2] + pts[i][2]; }
-  c[0] = c[0] / double(K); c[1] = c[1] / double(K); c[2] = c[2] / double(K);
-  double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
-  for (int i = 0; i < K; ++i) {
-    const double x = pts[i][0] - c[0], y = pts[i][1] - c[1], z = pts[i][2] - c[2];
-    a00 += x * x; a01 += x * y; a02 += x * z; a11 += y * y; a12 += y * z; a22 += z * z;
-  }
-  const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
-  const double qm = (a00 + a11 + a22) / 3.0;
-  const double p2 = (a00 - qm) * (a00 - qm) + (a11 - qm) * (a11 - qm) + (a22 - qm) * (a22 - qm) + 2.0 * p1;
-  double l0, l1, l2;   // ascending
-  if (p2 <= 0.0) { l0 = l1 = l2 = qm; }
-  else {
-    const double p = sqrt(p2 / 6.0), ip = 1.0 / p;
-    const double b00 = (a00 - qm) * ip, b11 = (a11 - qm) * ip, b22 = (a22 - qm) * ip, b01 = a01 * ip, b02 = a02 * ip, b12 = a12 * ip;
-    double r = 0.5 * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
-    r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-    const double phi = acos(r) / 3.0;
-    l2 = qm + 2.0 * p * cos(phi);
-    l0 = qm + 2.0 * p * cos(phi + 2.0943951023931953);
-    l1 = 3.0 * qm - l0 - l2;
-  }
-  return l2 > tol * l1;
-}
-
 // ---- streaming plane fit (registers: 9 doubles instead of a K x 3 matrix) ------------------------------------------
 // Same least-squares problem as Geometry.hpp:345-373 (A x = -1): Gram matrix G = A^T A and h = A^T 1 are accumulated
 // point by point, G x = -h is solved by a 3x3 Cholesky and corrected by one step of iterative refinement with the
