@@ -98,6 +98,14 @@ int pvb_frames_get_point2plane(const pvb_ctx* ctx, long cap, int* edge, int* que
 /* debug/parity view of the k-NN itself for one edge: indices into ref.surfLessFlat and float32 squared distances */
 int pvb_frames_knn(pvb_ctx* ctx, const double* poses, int ref, int nei, const pvb_assoc_params* prm, int* idx, float* d2);
 
+/* AssociatePoint2Line (LidarFeatureAssociate.cpp:478-548) on the frames' cornerLessSharp clouds (n x 4 float32, sensor frame):
+ * 5 nearest reference corner points, PCA line test (FormLine(pts, 10, 0.05)) in the world frame; per correspondence the query in the
+ * neighbour's sensor frame and the two synthetic line points c +- 0.1 d in the reference sensor frame.                           */
+int pvb_frames_set_corners(pvb_ctx* ctx, int n_frames, const float* const* corner, const int* n_corner);
+int pvb_frames_associate_point2line(pvb_ctx* ctx, const double* poses, int n_edges, const int* ref, const int* nei, float dist_threshold,
+                                    double cell_size, long* n_assoc);
+int pvb_frames_get_point2line(const pvb_ctx* ctx, long cap, int* edge, int* query, double* point3, double* a3, double* b3);
+
 /* ---- C. dense ICP sweep (BASELINE.json configs[4]): fused transform + k-NN + plane fit + residual + reduce --- */
 typedef struct {
   double plane_tolerance;
@@ -181,6 +189,10 @@ int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* li
 int pvb_build_point2plane_blocks(long n, const double* point3, const double* plane4, int ref_block, int nei_block, int angle_residual,
                                  int normalize_distance, double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize,
                                  double* huber, double* consts);           /* Optimization.cpp:506-562 */
+/* AddLidarPointToLineResidual (Optimization.cpp:443-504): Point2Line_Angle / _Meter with HuberLoss(2 deg / 0.2) */
+int pvb_build_point2line_blocks(long n, const double* point3, const double* a3, const double* b3, int ref_block, int nei_block, int angle_residual,
+                                int normalize_distance, double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize,
+                                double* huber, double* consts);
 /* one block per point of the neighbour segment (world float32 -> neighbour sensor frame, Optimization.cpp:403-431) */
 int pvb_build_line2line_blocks(const pvb_line_frame* nei, const float* nei_corner_world, int nei_line, const double* point_a3,
                                const double* point_b3, int ref_block, int nei_block, int angle_residual, int normalize_distance, double weight,

@@ -193,6 +193,15 @@ def associate_p2plane(ref_world, R_ref, t_ref, nei_world, R_nei, t_nei, plane_to
     return q[:m].copy(), pt[:m].copy(), pl[:m].copy()
 
 
+def associate_p2line(ref_world, R_ref, t_ref, nei_world, R_nei, t_nei, dist_thr, use_kdtree=True):
+    ref_world, nei_world = _f32(ref_world).reshape(-1, 4), _f32(nei_world).reshape(-1, 4)
+    n = len(nei_world)
+    q, pt, a, b = np.empty(n, dtype=np.int32), np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 3))
+    m = lib().pvo_associate_p2line(_p(ref_world), C.c_int(len(ref_world)), _p(_f64(R_ref)), _p(_f64(t_ref)), _p(nei_world), C.c_int(n), _p(_f64(R_nei)), _p(_f64(t_nei)),
+                                   C.c_float(dist_thr), C.c_int(int(use_kdtree)), _p(q), _p(pt), _p(a), _p(b))
+    return q[:m].copy(), pt[:m].copy(), a[:m].copy(), b[:m].copy()
+
+
 def transform_lines(R, t, lines):
     lines = _f64(lines).reshape(-1, 6)
     out = np.empty_like(lines)

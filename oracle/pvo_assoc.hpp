@@ -165,6 +165,37 @@ inline void AssociatePoint2Plane(const float* ref_world, int n_ref, const double
   }
 }
 
+// ---- AssociatePoint2Line (LidarFeatureAssociate.cpp:478-548): 5-NN on the corner clouds, PCA line test in WORLD frame
+struct P2LineAssoc { int query_idx; double point[3]; double a[3], b[3]; };
+
+inline void AssociatePoint2Line(const float* ref_world, int n_ref, const double R_ref[9], const double t_ref[3],
+                                const float* nei_world, int n_nei, const double R_nei[9], const double t_nei[3],
+                                float dist_threshold, bool use_kdtree, std::vector<P2LineAssoc>& out) {
+  const int k = 5;
+  const float sq_thr = dist_threshold * dist_threshold;
+  KdTree tree;
+  if (use_kdtree) tree.Build(ref_world, n_ref, 4);
+  KnnResult res;
+  for (int idx = 0; idx < n_nei; ++idx) {
+    const float* q = nei_world + (size_t)idx * 4;
+    if (use_kdtree) tree.Knn(q, k, res); else KnnBrute(ref_world, n_ref, 4, q, k, res);
+    if ((int)res.idx.size() < k) continue;                     // quirk C.6 guard
+    if (res.d2[k - 1] > sq_thr) continue;                      // :497
+    double pts[15];
+    for (int j = 0; j < k; ++j) for (int c = 0; c < 3; ++c) pts[j * 3 + c] = ref_world[(size_t)res.idx[j] * 4 + c];   // :503 world coordinates
+    double line[6];
+    if (!FormLinePCA(k, pts, 10.0, 0.05, line)) continue;      // :506-509
+    double aw[3], bw[3];
+    for (int c = 0; c < 3; ++c) { aw[c] = 0.1 * line[3 + c] + line[c]; bw[c] = -0.1 * line[3 + c] + line[c]; }   // :514-515
+    P2LineAssoc a; a.query_idx = idx;
+    const double qw[3] = {q[0], q[1], q[2]};
+    World2Local(R_nei, t_nei, qw, a.point);                    // :517
+    World2Local(R_ref, t_ref, aw, a.a);                        // :518-519
+    World2Local(R_ref, t_ref, bw, a.b);
+    out.push_back(a);
+  }
+}
+
 // ---- line-to-line (LidarFeatureAssociate.cpp:219-236, 442-476, 120-197) --------------------------
 inline void TransformLine(const double R[9], const double t[3], const double in[6], double out[6]) {  // :219-236
   for (int r = 0; r < 3; ++r) {

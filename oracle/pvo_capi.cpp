@@ -106,6 +106,14 @@ int pvo_associate_p2plane(const float* ref_world, int n_ref, const double* R_ref
   return (int)v.size();
 }
 
+int pvo_associate_p2line(const float* ref_world, int n_ref, const double* R_ref, const double* t_ref, const float* nei_world, int n_nei,
+                          const double* R_nei, const double* t_nei, float dist_thr, int use_kdtree, int* out_query, double* out_point, double* out_a, double* out_b) {
+  std::vector<P2LineAssoc> v;
+  AssociatePoint2Line(ref_world, n_ref, R_ref, t_ref, nei_world, n_nei, R_nei, t_nei, dist_thr, use_kdtree != 0, v);
+  for (size_t i = 0; i < v.size(); ++i) { out_query[i] = v[i].query_idx; std::memcpy(out_point + 3 * i, v[i].point, 24); std::memcpy(out_a + 3 * i, v[i].a, 24); std::memcpy(out_b + 3 * i, v[i].b, 24); }
+  return (int)v.size();
+}
+
 void pvo_transform_lines(const double* R, const double* t, int S, const double* in, double* out) { for (int s = 0; s < S; ++s) TransformLine(R, t, in + 6 * s, out + 6 * s); }
 
 void pvo_line_votes(const double* ref_lines_world, int S_ref, const float* nei_corner_world, int n_pts, const int* p2s_off, const int* p2s_ids,

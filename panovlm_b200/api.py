@@ -99,10 +99,10 @@ EXPORTS = [
     "pvb_create", "pvb_destroy", "pvb_last_error", "pvb_set_stream", "pvb_synchronize", "pvb_kernel_launches", "pvb_stream",
     "pvb_blocks_set", "pvb_blocks_evaluate", "pvb_blocks_residuals", "pvb_blocks_jacobians", "pvb_blocks_cost", "pvb_blocks_kernel_time_ms", "pvb_blocks_num_edges",
     "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_dense_system", "pvb_blocks_solve_lm",
-    "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn",
+    "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn", "pvb_frames_set_corners", "pvb_frames_associate_point2line", "pvb_frames_get_point2line",
     "pvb_dense_set_target", "pvb_dense_set_sources", "pvb_dense_evaluate", "pvb_dense_evaluate_device", "pvb_dense_gauss_newton_step",
     "pvb_dense_get_rows", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
-    "pvb_find_neighbors", "pvb_line2line_associate", "pvb_camera_lidar_associate", "pvb_build_point2plane_blocks", "pvb_build_line2line_blocks",
+    "pvb_find_neighbors", "pvb_line2line_associate", "pvb_camera_lidar_associate", "pvb_build_point2plane_blocks", "pvb_build_point2line_blocks", "pvb_build_line2line_blocks",
     "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
 ]
 
@@ -241,6 +241,23 @@ class Context:
         self._ck(self._L.pvb_frames_knn(self._h, _p(poses), C.c_int(ref), C.c_int(nei), C.byref(prm), _p(idx), _p(d2)))
         return idx, d2
 
+    def frames_set_corners(self, corners):
+        self._keep_c = [_arr(c, np.float32).reshape(-1, 4) for c in corners]
+        n = len(corners)
+        ptrs = (C.c_void_p * n)(*[c.ctypes.data if len(c) else None for c in self._keep_c])
+        cnt = np.array([len(c) for c in self._keep_c], np.int32)
+        self._ck(self._L.pvb_frames_set_corners(self._h, C.c_int(n), ptrs, _p(cnt)))
+
+    def frames_associate_point2line(self, poses, ref, nei, dist_threshold, cell_size=0.0):
+        poses = _arr(poses, np.float64)
+        ref, nei = _arr(ref, np.int32), _arr(nei, np.int32)
+        n = C.c_long()
+        self._ck(self._L.pvb_frames_associate_point2line(self._h, _p(poses), C.c_int(len(ref)), _p(ref), _p(nei), C.c_float(dist_threshold), C.c_double(cell_size), C.byref(n)))
+        m = n.value
+        e, q, pt, a, b = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros((m, 3)), np.zeros((m, 3)), np.zeros((m, 3))
+        self._ck(self._L.pvb_frames_get_point2line(self._h, C.c_long(m), _p(e), _p(q), _p(pt), _p(a), _p(b)))
+        return e, q, pt, a, b
+
     # ---- C. dense
     @staticmethod
     def dense_params(plane_tolerance=0.05, dist_threshold=1.0, k=10, residual_type=P2PLANE_METER, normalize=1, huber=0.2, weight=1.0):
@@ -339,6 +356,16 @@ class Context:
                                                         C.c_int(int(normalize_distance)), C.c_double(weight), n, cap, *arrs)
         if m < 0:
             raise PvbError(f"pvb_build_point2plane_blocks: code {m}")
+        bl.n = m
+
+    @staticmethod
+    def build_point2line_blocks(bl, point, a, b, ref_block, nei_block, angle_residual, normalize_distance, weight):
+        pt, pa, pb = (_arr(x, np.float64).reshape(-1, 3) for x in (point, a, b))
+        n, cap, *arrs = bl.args()
+        m = load_library().pvb_build_point2line_blocks(C.c_long(len(pt)), _p(pt), _p(pa), _p(pb), C.c_int(ref_block), C.c_int(nei_block), C.c_int(int(angle_residual)),
+                                                       C.c_int(int(normalize_distance)), C.c_double(weight), n, cap, *arrs)
+        if m < 0:
+            raise PvbError(f"pvb_build_point2line_blocks: code {m}")
         bl.n = m
 
     @staticmethod

@@ -289,6 +289,21 @@ int pvb_build_point2plane_blocks(long n, const double* point3, const double* pla
   return (int)o.at;
 }
 
+int pvb_build_point2line_blocks(long n, const double* point3, const double* a3, const double* b3, int ref_block, int nei_block, int angle_residual, int normalize_distance,
+                                double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize, double* huber, double* consts) {
+  if (n < 0 || (n > 0 && (!point3 || !a3 || !b3)) || !type || !ref || !nei || !normalize || !huber || !consts) return PVB_ERR_ARG;
+  BlockOut o{at, cap, type, ref, nei, normalize, huber, consts};
+  const double hub = angle_residual ? 2 * M_PI / 180.0 : 0.2;                  // Optimization.cpp:449-453 (a loss in both modes)
+  for (long i = 0; i < n; ++i) {
+    const double* a = a3 + 3 * i; const double* b = b3 + 3 * i;
+    double d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+    const double nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    double c[12] = {point3[3 * i], point3[3 * i + 1], point3[3 * i + 2], a[0], a[1], a[2], d[0] / nn, d[1] / nn, d[2] / nn, weight, 0, 0};
+    if (!push_block(o, angle_residual ? PVB_P2LINE_ANGLE : PVB_P2LINE_METER, ref_block, nei_block, normalize_distance, hub, c)) return PVB_ERR_ARG;
+  }
+  return (int)o.at;
+}
+
 int pvb_build_line2line_blocks(const pvb_line_frame* nf, const float* world, int nei_line, const double* a, const double* b, int ref_block, int nei_block,
                                int angle_residual, int normalize_distance, double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize,
                                double* huber, double* consts) {

@@ -239,6 +239,46 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
   }
 }
 
+// ---- A3: point-to-line association (5-NN + PCA line) --------------------------------------------------------------------
+struct LineAssocArgs {
+  const F4* q_local; const QueryTile* tiles; const Pair* pairs; const GridDesc* grids; const uint32_t* cell_start; const F4* sorted;
+  const WorldPose* wpose; float sq_thr; double thr;
+  unsigned char* out_valid; double* out_point; double* out_a; double* out_b;     // indexed by tile.out_base + lane
+};
+template <int K>
+__global__ void __launch_bounds__(kTile) k_associate_line(const LineAssocArgs a) {
+  __shared__ uint32_t s_win[K][kTile];
+  __shared__ uint32_t s_rng[18][kTile];
+  const QueryTile t = a.tiles[blockIdx.x];
+  const Pair pr = a.pairs[t.pair];
+  const int i = threadIdx.x;
+  if (i >= t.count) return;
+  const int gq = t.start + i;
+  const uint32_t slot = (uint32_t)(t.out_base + i);
+  const F4 q = ldg_f4(a.q_local + gq);
+  const WorldPose& wn = a.wpose[pr.nei_block];
+  const WorldPose& wr = a.wpose[pr.ref_block];
+  float qx, qy, qz;
+  transform_point_f32(wn.R, wn.t, q.x, q.y, q.z, qx, qy, qz);
+  const GridDesc& g = a.grids[pr.target_cloud];
+  const uint32_t* cs = a.cell_start + g.cell_base;
+  const F4* srt = a.sorted;
+  auto cells = [cs](long long c) { return (long long)__ldg(cs + c); };
+  auto load = [srt](long long p) { return ldg_f4(srt + p); };
+  auto win = [&](int j) { return s_win[j][i]; };
+  auto set_win = [&](int j, uint32_t pos) { s_win[j][i] = pos; };
+  auto range_set = [&](int k, uint32_t lo, uint32_t hi) { s_rng[2 * k][i] = lo; s_rng[2 * k + 1][i] = hi; };
+  auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = s_rng[2 * k][i]; hi = s_rng[2 * k + 1][i]; };
+  double p_local[3], pa[3], pb[3];
+  const bool valid = associate_point2line<K>(g, cells, load, a.sq_thr, (int)ceil(a.thr / g.h), qx, qy, qz, wr.R, wr.t, wn.R, wn.t, p_local, pa, pb, win, set_win,
+                                             range_set, range_get);
+  a.out_valid[slot] = valid ? 1 : 0;
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a.out_point[(size_t)slot * 3 + k] = p_local[k]; a.out_a[(size_t)slot * 3 + k] = pa[k]; a.out_b[(size_t)slot * 3 + k] = pb[k]; }
+  }
+}
+
 // ---- K3: residual + analytic Jacobian over a correspondence list sorted by pose-graph edge --------------------------
 struct BlockTile { int edge; int start; int count; int pad; };
 struct EvalArgs {

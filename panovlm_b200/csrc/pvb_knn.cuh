@@ -314,4 +314,31 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
   return true;
 }
 
+// Per-query body of AssociatePoint2Line (lidar_mapping/LidarFeatureAssociate.cpp:478-548): 5 nearest corner points of
+// the reference frame (world, float32), PCA line test in the WORLD frame, synthetic end points c +- 0.1 d moved to the
+// reference sensor frame, query moved to the neighbour's sensor frame.
+template <int K, typename CellLoader, typename PointLoader, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+PVB_HD bool associate_point2line(const GridDesc& g, const CellLoader& cells, const PointLoader& load, float sq_thr, int rmax, float qx, float qy, float qz,
+                                 const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
+                                 double p_local[3], double a_local[3], double b_local[3], const WinGet& win, const WinSet& set_win, const RangeSet& range_set,
+                                 const RangeGet& range_get) {
+  const int found = knn_select<K, false>(g, cells, load, qx, qy, qz, sq_thr, rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get);
+  if (found < K) return false;                                   // :497 + quirk C.6 guard
+  double pts[K][3];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const F4 p = load((long long)win(j));
+    pts[j][0] = (double)p.x; pts[j][1] = (double)p.y; pts[j][2] = (double)p.z;   // :503 (world coordinates)
+  }
+  double line[6];
+  if (!form_line_pca<K>(pts, 10.0, 0.05, line)) return false;    // :506-509
+  const double aw[3] = {0.1 * line[3] + line[0], 0.1 * line[4] + line[1], 0.1 * line[5] + line[2]};      // :514-515
+  const double bw[3] = {-0.1 * line[3] + line[0], -0.1 * line[4] + line[1], -0.1 * line[5] + line[2]};
+  const double qw[3] = {(double)qx, (double)qy, (double)qz};
+  world2local(R_nei, t_nei, qw, p_local);                        // :517
+  world2local(R_ref, t_ref, aw, a_local);                        // :518-519
+  world2local(R_ref, t_ref, bw, b_local);
+  return true;
+}
+
 }  // namespace pvb

@@ -80,6 +80,9 @@ struct pvb_ctx {
   bool b_has_rows = false, b_has_sys = false;
   // ---- frames mode
   CloudSet f_tgt, f_qry; TargetIndex f_index; int n_frames = 0;
+  CloudSet f_corner; TargetIndex f_cindex; int n_corner_frames = 0;
+  DevBuf f_la, f_lb; PinBuf fh_la, fh_lb;
+  std::vector<int> l_edge, l_query; std::vector<double> l_point, l_a, l_b;
   DevBuf f_pairs, f_qtiles, f_valid, f_point, f_plane, f_nn_idx, f_nn_d2;
   PinBuf fh_valid, fh_point, fh_plane;
   std::vector<int> a_edge, a_query; std::vector<double> a_point, a_plane;
@@ -272,7 +275,8 @@ void pvb_destroy(pvb_ctx* ctx) {
   for (DevBuf* b : dbs) b->release();
   PinBuf* pbs[] = {&ctx->h_pose, &ctx->h_r, &ctx->h_J, &ctx->h_esys, &ctx->fh_valid, &ctx->fh_point, &ctx->fh_plane, &ctx->dh_sys, &ctx->mh_a};
   for (PinBuf* b : pbs) b->release();
-  ctx->f_tgt.release(); ctx->f_qry.release(); ctx->f_index.release(); ctx->d_tgt.release(); ctx->d_src.release(); ctx->d_index.release();
+  ctx->f_tgt.release(); ctx->f_qry.release(); ctx->f_index.release(); ctx->f_corner.release(); ctx->f_cindex.release(); ctx->f_la.release(); ctx->f_lb.release();
+  ctx->fh_la.release(); ctx->fh_lb.release(); ctx->d_tgt.release(); ctx->d_src.release(); ctx->d_index.release();
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
   if (ctx->eval_done) cudaEventDestroy(ctx->eval_done);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -583,6 +587,85 @@ int pvb_frames_knn(pvb_ctx* ctx, const double* poses, int ref, int nei, const pv
     CK(cudaMemcpyAsync(d2, ctx->f_nn_d2.p, (size_t)slots * prm->k * 4, cudaMemcpyDeviceToHost, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+// ---- point-to-line association on the corner clouds (A3) ------------------------------------------------------------
+int pvb_frames_set_corners(pvb_ctx* ctx, int n_frames, const float* const* corner, const int* n_corner) {
+  if (!ctx || n_frames <= 0 || !corner || !n_corner) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_frames_set_corners: bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<const float*> p(corner, corner + n_frames); std::vector<int> c(n_corner, n_corner + n_frames), blocks(n_frames);
+  for (int f = 0; f < n_frames; ++f) blocks[f] = f;
+  int rc = set_cloudset(ctx, ctx->f_corner, p, c, blocks, 256); if (rc) return rc;
+  ctx->n_corner_frames = n_frames; ctx->f_cindex.built = false;
+  return PVB_OK;
+}
+
+int pvb_frames_associate_point2line(pvb_ctx* ctx, const double* poses, int n_edges, const int* ref, const int* nei, float dist_threshold, double cell_size, long* n_assoc) {
+  if (!ctx || !poses || n_edges < 0 || (n_edges > 0 && (!ref || !nei))) return ctx ? ctx->fail(PVB_ERR_ARG, "bad arguments") : PVB_ERR_ARG;
+  if (ctx->n_corner_frames <= 0) return ctx->fail(PVB_ERR_STATE, "pvb_frames_set_corners has not been called");
+  CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
+  const int nfr = ctx->n_corner_frames;
+  for (int e = 0; e < n_edges; ++e) if (ref[e] < 0 || ref[e] >= nfr || nei[e] < 0 || nei[e] >= nfr) return ctx->fail(PVB_ERR_ARG, "edge %d out of range", e);
+  int rc = upload_poses(ctx, poses, nfr, false); if (rc) return rc;
+  CloudSet& cs = ctx->f_corner;
+  rc = build_target_index(ctx, cs, ctx->f_cindex, cell_size); if (rc) return rc;
+  std::vector<Pair> pairs(n_edges); std::vector<QueryTile> tiles; std::vector<int> sb(n_edges + 1, 0);
+  long long slots = 0;
+  for (int e = 0; e < n_edges; ++e) {
+    pairs[e] = Pair{ref[e], nei[e], ref[e], nei[e]};
+    sb[e] = (int)slots;
+    const int q0 = cs.off[nei[e]], qn = cs.off[nei[e] + 1] - q0;
+    if (cs.off[ref[e] + 1] > cs.off[ref[e]]) for (int s0 = 0; s0 < qn; s0 += kTile) tiles.push_back(QueryTile{e, q0 + s0, std::min(kTile, qn - s0), (int)(slots + s0)});
+    slots += qn;
+  }
+  sb[n_edges] = (int)slots;
+  CK(ctx->f_pairs.ensure(std::max<size_t>(16, pairs.size() * sizeof(Pair)))); CK(ctx->f_qtiles.ensure(std::max<size_t>(16, tiles.size() * sizeof(QueryTile))));
+  const size_t S = std::max<size_t>(16, (size_t)slots);
+  CK(ctx->f_valid.ensure(S)); CK(ctx->f_point.ensure(S * 24)); CK(ctx->f_la.ensure(S * 24)); CK(ctx->f_lb.ensure(S * 24));
+  CK(ctx->fh_valid.ensure(S)); CK(ctx->fh_point.ensure(S * 24)); CK(ctx->fh_la.ensure(S * 24)); CK(ctx->fh_lb.ensure(S * 24));
+  if (!pairs.empty()) CK(cudaMemcpyAsync(ctx->f_pairs.p, pairs.data(), pairs.size() * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->f_qtiles.p, tiles.data(), tiles.size() * sizeof(QueryTile), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->f_valid.p, 0, S, ctx->stream));
+  if (!tiles.empty()) {
+    LineAssocArgs a{};
+    a.q_local = cs.local.as<F4>(); a.tiles = ctx->f_qtiles.as<QueryTile>(); a.pairs = ctx->f_pairs.as<Pair>(); a.grids = ctx->f_cindex.grids.as<GridDesc>();
+    a.cell_start = ctx->f_cindex.cell_start.as<uint32_t>(); a.sorted = ctx->f_cindex.sorted.as<F4>(); a.wpose = ctx->d_wpose.as<WorldPose>();
+    a.sq_thr = dist_threshold * dist_threshold; a.thr = (double)dist_threshold;
+    a.out_valid = ctx->f_valid.as<unsigned char>(); a.out_point = ctx->f_point.as<double>(); a.out_a = ctx->f_la.as<double>(); a.out_b = ctx->f_lb.as<double>();
+    k_associate_line<5><<<(int)tiles.size(), kTile, 0, ctx->stream>>>(a);
+    CKL();
+  }
+  if (slots > 0) {
+    CK(cudaMemcpyAsync(ctx->fh_valid.p, ctx->f_valid.p, (size_t)slots, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->fh_point.p, ctx->f_point.p, (size_t)slots * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->fh_la.p, ctx->f_la.p, (size_t)slots * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->fh_lb.p, ctx->f_lb.p, (size_t)slots * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->l_edge.clear(); ctx->l_query.clear(); ctx->l_point.clear(); ctx->l_a.clear(); ctx->l_b.clear();
+  const unsigned char* v = ctx->fh_valid.as<unsigned char>();
+  const double *pt = ctx->fh_point.as<double>(), *pa = ctx->fh_la.as<double>(), *pb = ctx->fh_lb.as<double>();
+  for (int e = 0; e < n_edges; ++e)
+    for (int sl = sb[e]; sl < sb[e + 1]; ++sl)
+      if (v[sl]) {
+        ctx->l_edge.push_back(e); ctx->l_query.push_back(sl - sb[e]);
+        ctx->l_point.insert(ctx->l_point.end(), pt + (size_t)sl * 3, pt + (size_t)sl * 3 + 3);
+        ctx->l_a.insert(ctx->l_a.end(), pa + (size_t)sl * 3, pa + (size_t)sl * 3 + 3);
+        ctx->l_b.insert(ctx->l_b.end(), pb + (size_t)sl * 3, pb + (size_t)sl * 3 + 3);
+      }
+  if (n_assoc) *n_assoc = (long)ctx->l_edge.size();
+  return PVB_OK;
+}
+
+int pvb_frames_get_point2line(const pvb_ctx* ctx, long cap, int* edge, int* query, double* point3, double* a3, double* b3) {
+  if (!ctx) return PVB_ERR_ARG;
+  const long n = std::min<long>(cap, (long)ctx->l_edge.size());
+  for (long i = 0; i < n; ++i) { if (edge) edge[i] = ctx->l_edge[i]; if (query) query[i] = ctx->l_query[i]; }
+  if (point3) memcpy(point3, ctx->l_point.data(), (size_t)n * 24);
+  if (a3) memcpy(a3, ctx->l_a.data(), (size_t)n * 24);
+  if (b3) memcpy(b3, ctx->l_b.data(), (size_t)n * 24);
   return PVB_OK;
 }
 

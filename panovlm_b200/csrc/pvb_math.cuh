@@ -349,6 +349,58 @@ PVB_HD bool collinear_from_gram(const PlaneAcc& a, int n, double tol) {
   return l2 > tol * l1;
 }
 
+// FormLine(points, tolerance, dis_threshold) (Geometry.hpp:220-260) for the k = 5 neighbours of AssociatePoint2Line:
+// centroid + unit direction (eigenvector of the largest eigenvalue of the scatter matrix) when lambda_max > tolerance *
+// lambda_mid and every point is within dis_threshold of the line.  Eigenvalues by the trigonometric closed form, the
+// eigenvector as the largest cross product of two rows of (S - lambda_max I) (well conditioned: the test guarantees
+// a spectral gap of 10x).  The sign of the direction is arbitrary (the residuals only use the line).
+template <int K>
+PVB_HD bool form_line_pca(const double (*pts)[3], double tolerance, double dis_threshold, double line6[6]) {
+  double c[3] = {0, 0, 0};
+  for (int i = 0; i < K; ++i) { c[0] = c[0] + pts[i][0]; c[1] = c[1] + pts[i][1]; c[2] = c[2] + pts[i][2]; }
+  c[0] = c[0] / double(K); c[1] = c[1] / double(K); c[2] = c[2] / double(K);
+  double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+  for (int i = 0; i < K; ++i) {
+    const double x = pts[i][0] - c[0], y = pts[i][1] - c[1], z = pts[i][2] - c[2];
+    a00 += x * x; a01 += x * y; a02 += x * z; a11 += y * y; a12 += y * z; a22 += z * z;
+  }
+  const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+  const double qm = (a00 + a11 + a22) / 3.0;
+  const double p2 = (a00 - qm) * (a00 - qm) + (a11 - qm) * (a11 - qm) + (a22 - qm) * (a22 - qm) + 2.0 * p1;
+  if (p2 <= 0.0) return false;                         // isotropic scatter: lambda_max == lambda_mid
+  const double p = sqrt(p2 / 6.0), ip = 1.0 / p;
+  const double b00 = (a00 - qm) * ip, b11 = (a11 - qm) * ip, b22 = (a22 - qm) * ip, b01 = a01 * ip, b02 = a02 * ip, b12 = a12 * ip;
+  double r = 0.5 * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+  r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+  const double phi = acos(r) / 3.0;
+  const double l2 = qm + 2.0 * p * cos(phi);
+  const double l0 = qm + 2.0 * p * cos(phi + 2.0943951023931953);
+  const double l1 = 3.0 * qm - l0 - l2;
+  if (!(l2 > tolerance * l1)) return false;
+  const double r0[3] = {a00 - l2, a01, a02}, r1[3] = {a01, a11 - l2, a12}, r2[3] = {a02, a12, a22 - l2};
+  double v[3][3] = {{r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]},
+                    {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]},
+                    {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]}};
+  double n0 = v[0][0] * v[0][0] + v[0][1] * v[0][1] + v[0][2] * v[0][2];
+  const double n1 = v[1][0] * v[1][0] + v[1][1] * v[1][1] + v[1][2] * v[1][2];
+  const double n2 = v[2][0] * v[2][0] + v[2][1] * v[2][1] + v[2][2] * v[2][2];
+  double d[3] = {v[0][0], v[0][1], v[0][2]};
+  if (n1 > n0) { n0 = n1; d[0] = v[1][0]; d[1] = v[1][1]; d[2] = v[1][2]; }
+  if (n2 > n0) { n0 = n2; d[0] = v[2][0]; d[1] = v[2][1]; d[2] = v[2][2]; }
+  if (!(n0 > 0.0)) return false;
+  const double inv = 1.0 / sqrt(n0);
+  d[0] *= inv; d[1] *= inv; d[2] *= inv;
+  if (dis_threshold > 0.0) {
+    for (int i = 0; i < K; ++i) {                       // PointToLineDistance3D (Geometry.hpp:198-211)
+      const double k = d[0] * (pts[i][0] - c[0]) + d[1] * (pts[i][1] - c[1]) + d[2] * (pts[i][2] - c[2]);
+      const double ex = k * d[0] + c[0] - pts[i][0], ey = k * d[1] + c[1] - pts[i][1], ez = k * d[2] + c[2] - pts[i][2];
+      if (sqrt(ex * ex + ey * ey + ez * ez) > dis_threshold) return false;
+    }
+  }
+  line6[0] = c[0]; line6[1] = c[1]; line6[2] = c[2]; line6[3] = d[0]; line6[4] = d[1]; line6[5] = d[2];
+  return true;
+}
+
 // Rank-deficient fallback of the plane fit (Cholesky of the Gram matrix failed: e.g. every neighbour has one
 // coordinate exactly 0).  Eigen's colPivHouseholderQr().solve (Geometry.hpp:361) then returns the basic solution of
 // the leading rank x rank block with the remaining components 0; this rolled-loop version (local memory, few

@@ -63,7 +63,43 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
   }
 }
 
+static void associate_lines(const float* tgt, int n, const double* R_ref, const double* t_ref, const float* qry, int m, const double* R_nei, const double* t_nei,
+                            double h, float thr, unsigned char* valid, double* p_local, double* pa, double* pb) {
+  GridDesc g;
+  float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+  for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) { mn[c] = std::min(mn[c], tgt[i * 4 + c]); mx[c] = std::max(mx[c], tgt[i * 4 + c]); }
+  for (int c = 0; c < 3; ++c) { g.origin[c] = mn[c]; g.dims[c] = std::max(1, (int)std::floor(((double)mx[c] - mn[c]) / h) + 1); }
+  g.h = h; g.inv_h = 1.0 / h; g.n_points = n; g.cell_base = 0; g.point_base = 0;
+  const long long ncell = (long long)g.dims[0] * g.dims[1] * g.dims[2];
+  std::vector<int> start(ncell + 2, 0), cell(n);
+  for (int i = 0; i < n; ++i) {
+    cell[i] = (int)(((long long)cell_coord(tgt[i * 4 + 2], g.origin[2], g.inv_h, g.dims[2]) * g.dims[1] + cell_coord(tgt[i * 4 + 1], g.origin[1], g.inv_h, g.dims[1])) * g.dims[0] +
+                    cell_coord(tgt[i * 4], g.origin[0], g.inv_h, g.dims[0]));
+    start[cell[i] + 1]++;
+  }
+  for (long long c = 0; c <= ncell; ++c) start[c + 1] += start[c];
+  std::vector<int> fill(start.begin(), start.end() - 1);
+  std::vector<F4> sorted(n);
+  for (int i = 0; i < n; ++i) { F4 r; r.x = tgt[i * 4]; r.y = tgt[i * 4 + 1]; r.z = tgt[i * 4 + 2]; r.w = u2f((uint32_t)i << 5); sorted[fill[cell[i]]++] = r; }
+  auto cells = [&](long long c) { return (long long)start[c]; };
+  auto load = [&](long long i) { return sorted[i]; };
+  for (int i = 0; i < m; ++i) {
+    uint32_t wpos[5], rng[18];
+    auto win = [&](int j) { return wpos[j]; };
+    auto set_win = [&](int j, uint32_t pos) { wpos[j] = pos; };
+    auto range_set = [&](int k, uint32_t lo, uint32_t hi) { rng[2 * k] = lo; rng[2 * k + 1] = hi; };
+    auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = rng[2 * k]; hi = rng[2 * k + 1]; };
+    valid[i] = associate_point2line<5>(g, cells, load, thr * thr, (int)std::ceil((double)thr / h), qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], R_ref, t_ref, R_nei, t_nei,
+                                       p_local + 3 * i, pa + 3 * i, pb + 3 * i, win, set_win, range_set, range_get) ? 1 : 0;
+  }
+}
+
 extern "C" {
+
+void pvbh_associate_lines(const float* tgt, int n, const double* R_ref, const double* t_ref, const float* qry, int m, const double* R_nei, const double* t_nei,
+                          double h, float thr, unsigned char* valid, double* p_local, double* pa, double* pb) {
+  associate_lines(tgt, n, R_ref, t_ref, qry, m, R_nei, t_nei, h, thr, valid, p_local, pa, pb);
+}
 
 void pvbh_pose_prep(const double* pose6, double* out21) {
   PosePrep p; prepare_pose(pose6, p);

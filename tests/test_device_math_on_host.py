@@ -116,3 +116,26 @@ def test_rank_deficient_neighbour_sets_follow_the_qr_basic_solution(oracle, harn
     degenerate = np.abs(opl[:, 2]) < 1e-12                       # bogus vertical planes through floor points (n_z == 0)
     assert degenerate.sum() > 50
     assert np.abs(opl - pl2[q2]).max() < 1e-9
+
+
+def test_point2line_association_equals_oracle(oracle, harness):
+    """AssociatePoint2Line (5-NN + PCA line in the world frame): same accepted queries; end points equal up to the arbitrary sign
+    of the eigenvector (a <-> b swap), which leaves the line and therefore the residuals unchanged."""
+    from panovlm_b200 import synth
+    A, B = synth.make_pair(seed=20260925, n_az=1800)
+    I, z = np.eye(3), np.zeros(3)
+    refw = oracle.transform_cloud(A["R_wl"], A["t_wl"], A["cornerLessSharp"])
+    neiw = oracle.transform_cloud(I, z, B["cornerLessSharp"])
+    for thr, h in ((0.3, 0.3), (0.7, 0.25)):
+        oq, opt, oa, ob = oracle.associate_p2line(refw, A["R_wl"], A["t_wl"], neiw, I, z, thr, True)
+        m = len(neiw)
+        valid, pt, pa, pb = np.zeros(m, np.uint8), np.zeros((m, 3)), np.zeros((m, 3)), np.zeros((m, 3))
+        harness.pvbh_associate_lines(p(np.ascontiguousarray(refw)), C.c_int(len(refw)), p(np.ascontiguousarray(A["R_wl"])), p(np.ascontiguousarray(A["t_wl"])), p(np.ascontiguousarray(neiw)),
+                                     C.c_int(m), p(I.copy()), p(z), C.c_double(h), C.c_float(thr), p(valid), p(pt), p(pa), p(pb))
+        q = np.nonzero(valid)[0]
+        assert np.array_equal(q, oq) and len(q) > 100
+        assert np.abs(pt[q] - opt).max() == 0.0
+        same = np.abs(pa[q] - oa).max(1) < 1e-9
+        swapped = np.abs(pa[q] - ob).max(1) < 1e-9
+        assert np.all(same | swapped)
+        assert np.all(np.where(same, np.abs(pb[q] - ob).max(1), np.abs(pb[q] - oa).max(1)) < 1e-9)

@@ -465,3 +465,47 @@ def test_odometry_outer_iteration_matches_oracle_loop(gpu_ctx, oracle):
         assert np.abs(d_gpu - d_cpu).max() < POSE_RTOL * np.abs(d_cpu).max()
     truth = odometry.pose_blocks_from_world([f["R_wl"] for f in frames], [f["t_wl"] for f in frames], oracle.R_to_aa)
     assert np.abs(p_gpu - truth).max() < np.abs(start - truth).max()
+
+
+def test_frames_point2line_matches_oracle(gpu_ctx, oracle):
+    """AssociatePoint2Line (5-NN + PCA line) for consecutive frames, both directions, non-trivial poses."""
+    from panovlm_b200 import Context, BlockList, synth
+    from scipy.spatial.transform import Rotation
+    frames = synth.make_sequence(4, n_az=900)
+    rng = np.random.default_rng(2)
+    poses = np.zeros((4, 6)); Rs, ts = [], []
+    for f, fr in enumerate(frames):
+        R = fr["R_wl"] @ Rotation.from_rotvec(rng.normal(0, 0.01, 3)).as_matrix(); t = fr["t_wl"] + rng.normal(0, 0.03, 3)
+        poses[f, :3] = Rotation.from_matrix(R.T).as_rotvec(); poses[f, 3:] = -R.T @ t
+    for f in range(4):
+        R_wl = oracle.aa_to_R(poses[f, :3]).T
+        Rs.append(R_wl); ts.append(-R_wl @ poses[f, 3:])
+    gpu_ctx.frames_set_corners([f["cornerLessSharp"] for f in frames])
+    ref = np.array([0, 1, 1, 2, 2, 3], np.int32); nei = np.array([1, 0, 2, 1, 3, 2], np.int32)       # abs(n - i) <= 1 (Optimization.cpp:475)
+    world = [oracle.transform_cloud(Rs[f], ts[f], frames[f]["cornerLessSharp"]) for f in range(4)]
+    for thr in (0.3, 0.7):
+        e, q, pt, a, b = gpu_ctx.frames_associate_point2line(poses, ref, nei, thr)
+        total = 0
+        for ei, (i, j) in enumerate(zip(ref, nei)):
+            oq, opt, oa, ob = oracle.associate_p2line(world[i], Rs[i], ts[i], world[j], Rs[j], ts[j], thr, True)
+            m = e == ei
+            assert np.array_equal(q[m], oq)
+            if len(oq):
+                assert np.abs(pt[m] - opt).max() < 1e-12
+                same = np.abs(a[m] - oa).max(1) < 1e-9
+                assert np.all(same | (np.abs(a[m] - ob).max(1) < 1e-9))                               # eigenvector sign: a <-> b
+                assert np.all(np.where(same, np.abs(b[m] - ob).max(1), np.abs(b[m] - oa).max(1)) < 1e-9)
+            total += len(oq)
+        assert total == len(e) and total > 200
+    # the residual blocks built from them evaluate identically whichever end point order was chosen
+    bl = BlockList(len(e) + 8)
+    Context.build_point2line_blocks(bl, pt, a, b, 0, 1, True, True, 1.0)
+    v = bl.view()
+    assert np.all(v["type"] == 3) and np.allclose(v["huber"], 2 * np.pi / 180)
+    blk = oracle.Blocks(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"])
+    r1, _, _ = blk.evaluate(poses[:2])
+    bl2 = BlockList(len(e) + 8)
+    Context.build_point2line_blocks(bl2, pt, b, a, 0, 1, True, True, 1.0)
+    v2 = bl2.view()
+    r2, _, _ = oracle.Blocks(v2["type"], v2["ref"], v2["nei"], v2["consts"], v2["huber"], v2["normalize"]).evaluate(poses[:2])
+    assert np.abs(r1 - r2).max() < 1e-9
