@@ -68,16 +68,40 @@ constexpr int kFrameSys = 29;   // single-pose (ref constant) form: H upper 6x6 
 struct LMOptions { int max_iterations = 20; double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8; };
 struct LMSummary { double initial_cost = 0, final_cost = 0; int iterations = 0, successful = 0, unsuccessful = 0, termination = 0; };
 
+// In-place lower Cholesky + solve.  Right-looking blocked factorisation (64-wide panels, OpenMP over the rows of the panel
+// solve and of the trailing update) so that pose graphs of a few hundred frames (6 N unknowns) factor in well under a second.
 inline bool cholesky_solve(std::vector<double>& A, int n, std::vector<double>& b) {
-  for (int j = 0; j < n; ++j) {
-    double d = A[(size_t)j * n + j];
-    for (int k = 0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
-    if (!(d > 0.0)) return false;
-    d = std::sqrt(d); A[(size_t)j * n + j] = d;
-    for (int i = j + 1; i < n; ++i) {
-      double s = A[(size_t)i * n + j];
-      for (int k = 0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
-      A[(size_t)i * n + j] = s / d;
+  const int NB = 64;
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int k1 = std::min(n, k0 + NB);
+    for (int j = k0; j < k1; ++j) {                      // factor the diagonal block (unblocked, rows k0..k1)
+      double d = A[(size_t)j * n + j];
+      for (int k = k0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+      if (!(d > 0.0)) return false;
+      d = std::sqrt(d); A[(size_t)j * n + j] = d;
+      for (int i = j + 1; i < k1; ++i) {
+        double s = A[(size_t)i * n + j];
+        for (int k = k0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+        A[(size_t)i * n + j] = s / d;
+      }
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = k1; i < n; ++i) {                       // panel: L[i, k0:k1] = A[i, k0:k1] * L[k0:k1, k0:k1]^-T
+      for (int j = k0; j < k1; ++j) {
+        double s = A[(size_t)i * n + j];
+        for (int k = k0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+        A[(size_t)i * n + j] = s / A[(size_t)j * n + j];
+      }
+    }
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int i = k1; i < n; ++i) {                       // trailing update (lower part): A[i, j] -= L[i, k0:k1] . L[j, k0:k1]
+      const double* li = &A[(size_t)i * n + k0];
+      for (int j = k1; j <= i; ++j) {
+        const double* lj = &A[(size_t)j * n + k0];
+        double s = 0.0;
+        for (int k = 0; k < k1 - k0; ++k) s += li[k] * lj[k];
+        A[(size_t)i * n + j] -= s;
+      }
     }
   }
   for (int i = 0; i < n; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= A[(size_t)i * n + k] * b[k]; b[i] = s / A[(size_t)i * n + i]; }

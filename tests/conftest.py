@@ -19,7 +19,7 @@ def build_host_harness():
     src = os.path.join(ROOT, "tests", "host_harness.cpp")
     deps = [src] + [os.path.join(ROOT, "panovlm_b200", "csrc", f) for f in ("pvb_math.cuh", "pvb_knn.cuh", "pvb_host.hpp")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-std=c++17", "-x", "c++", "-shared", "-o", out, src])
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-fPIC", "-std=c++17", "-x", "c++", "-shared", "-o", out, src])
     return out
 
 
