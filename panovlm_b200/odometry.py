@@ -58,10 +58,11 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
         ref = np.array([e[0] for e in edges], np.int32)
         nei = np.array([e[1] for e in edges], np.int32)
         e, q, pt, pl = ctx.frames_associate_point2plane(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, 10)
+        bounds = np.searchsorted(e, np.arange(len(edges) + 1))         # correspondences come back edge-major
         for ei in range(len(edges)):
-            m = e == ei
-            if m.any():
-                Context.build_point2plane_blocks(bl, pt[m], pl[m], int(ref[ei]), int(nei[ei]), cfg.angle_residual, cfg.normalize_distance, 1.0)
+            lo, hi = bounds[ei], bounds[ei + 1]
+            if hi > lo:
+                Context.build_point2plane_blocks(bl, pt[lo:hi], pl[lo:hi], int(ref[ei]), int(nei[ei]), cfg.angle_residual, cfg.normalize_distance, 1.0)
     return bl, edges
 
 

@@ -47,8 +47,22 @@ for rep in range(3):
     out["associate_all_edges_s"] = time.time() - t
 out.update(n_edges=len(edges), n_queries=int(sum(len(frames[j]["surfFlat"]) for j in nei)), n_point2plane=int(len(e)))
 t = time.time()
-new_poses, s = odometry.refine_pose(ctx, frames, poses, cfg, aa_to_R)
-out["refine_pose_s"] = time.time() - t
+bl, _ = odometry.build_problem(ctx, frames, poses, cfg, aa_to_R)
+out["build_problem_s"] = time.time() - t
+v = bl.view()
+t = time.time()
+ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], n)
+out["blocks_set_s"] = time.time() - t
+t = time.time()
+for _ in range(5):
+    ctx.blocks_evaluate(poses, want_rows=False, want_system=True)
+out["evaluate_reduced_s"] = (time.time() - t) / 5
+out["k_eval_blocks_ms"] = ctx.blocks_kernel_time_ms()
+mask = np.zeros(n, np.uint8); mask[0] = 1
+t = time.time()
+new_poses, s = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
+out["solve_lm_s"] = time.time() - t
+s["n_blocks"] = bl.n
 out["lm"] = s
 truth = odometry.pose_blocks_from_world([f["R_wl"] for f in frames], [f["t_wl"] for f in frames], R_to_aa)
 out["pose_err_before_after"] = [float(np.abs(poses - truth).max()), float(np.abs(new_poses - truth).max())]
