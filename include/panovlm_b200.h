@@ -129,6 +129,8 @@ int pvb_dense_evaluate(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_par
  * it is a caller-owned device buffer (n_frames x 29 doubles) the result is written to; otherwise it receives the
  * context's own buffer.                                                                                            */
 int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, double** dev_sys29);
+/* debug: out2[0] = tiles of the fused kernel staged through TMA so far, out2[1] = tiles that used the global-memory path */
+int pvb_debug_counters(pvb_ctx* ctx, unsigned long long* out2);
 /* device time (CUDA events on the context's stream) of the fused associate+residual kernel of the last dense evaluate */
 int pvb_dense_kernel_time_ms(pvb_ctx* ctx, float* ms);
 /* Gauss-Newton/LM step per frame from the reduced 6x6 systems (host, 64 tiny solves): poses updated in place.   */

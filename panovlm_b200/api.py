@@ -101,7 +101,7 @@ EXPORTS = [
     "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_dense_system", "pvb_blocks_solve_lm",
     "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn", "pvb_frames_set_corners", "pvb_frames_associate_point2line", "pvb_frames_get_point2line",
     "pvb_dense_set_target", "pvb_dense_set_sources", "pvb_dense_evaluate", "pvb_dense_evaluate_device", "pvb_dense_gauss_newton_step",
-    "pvb_dense_get_rows", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
+    "pvb_dense_get_rows", "pvb_debug_counters", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
     "pvb_find_neighbors", "pvb_line2line_associate", "pvb_camera_lidar_associate", "pvb_build_point2plane_blocks", "pvb_build_point2line_blocks", "pvb_build_line2line_blocks",
     "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
 ]
@@ -292,6 +292,11 @@ class Context:
         ptr = C.c_void_p(out_ptr)
         self._ck(self._L.pvb_dense_evaluate_device(self._h, _p(poses), C.byref(prm), C.byref(ptr)))
         return ptr.value
+
+    def debug_counters(self):
+        out = (C.c_ulonglong * 2)()
+        self._ck(self._L.pvb_debug_counters(self._h, out))
+        return int(out[0]), int(out[1])
 
     def dense_kernel_time_ms(self):
         ms = C.c_float()

@@ -132,14 +132,44 @@ struct AssocArgs {
   unsigned char* out_valid; double* out_point; double* out_plane;   // indexed by output slot: q_orig[query] (dense) or tile.out_base + lane
   double* out_res; double* out_jac6;                                 // idem
   int* out_nn_idx; float* out_nn_d2;                                 // idem, K per query (debug / parity)
-  double* partials;                                                  // [tile][29]
+  double* partials;                                                  // [tile][warp][29]
+  unsigned long long* stats;                                         // optional: [0] tiles staged through TMA, [1] tiles on the global path
 };
 
-template <int K, bool REDUCE, int MINB, bool DEBUG_NN, bool FLAT>
+// ---- TMA staging helpers (sm_90+/sm_100a): 1-D bulk copies global -> shared completing on an mbarrier ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  }
+}
+
+constexpr int kStageRows = 64;     // (y,z) rows of a tile's cell box that can be staged
+constexpr int kStageCap = 768;     // staged records per tile (12 KB of shared memory)
+
+template <int K, bool REDUCE, int MINB, bool DEBUG_NN, bool STAGE>
 __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
   __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
   __shared__ uint32_t s_win[K][kTile];           // record positions of each query's K neighbours
   __shared__ uint32_t s_rng[18][kTile];          // the <= 9 (lo, hi) row ranges of each query's 3x3x3 cell block
+  __shared__ __align__(16) F4 s_pts[STAGE ? kStageCap : 1];          // the tile's candidate rows, copied by TMA
+  __shared__ uint32_t s_row_lo[STAGE ? kStageRows : 1], s_row_base[STAGE ? kStageRows : 1];
+  __shared__ int s_box[6];
+  __shared__ int s_staged;
+  __shared__ __align__(8) uint64_t s_bar;
   const QueryTile t = a.tiles[blockIdx.x];
   const Pair pr = a.pairs[t.pair];
   const int i = threadIdx.x;
@@ -150,19 +180,84 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
 #pragma unroll
   for (int k = 0; k < 12; ++k) J[k] = 0.0;
   uint32_t qi = 0;
+  const GridDesc& g = a.grids[pr.target_cloud];
+  const uint32_t* cs = a.cell_start + g.cell_base;
+  const F4* srt = a.sorted;
+  const WorldPose& wn = a.wpose[pr.nei_block];
+  const WorldPose& wr = a.wpose[pr.ref_block];
+  F4 q; q.x = q.y = q.z = q.w = 0.f;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (act) {
+    q = ldg_f4(a.q_local + t.start + i);
+    transform_point_f32(wn.R, wn.t, q.x, q.y, q.z, qx, qy, qz);
+  }
+  int nyb = 1, by0 = 0, bz0 = 0;
+  bool staged = false;
+  if (STAGE) {
+    // ---- stage the rows of the tile's cell box (its queries' cells +- 1) in shared memory with TMA bulk copies ------------
+    if (i == 0) { s_box[0] = s_box[1] = s_box[2] = 0x7fffffff; s_box[3] = s_box[4] = s_box[5] = -1; s_staged = 0; }
+    __syncthreads();
+    int c3[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, d3[3] = {-1, -1, -1};
+    if (act) {
+      c3[0] = d3[0] = cell_coord((double)qx, g.origin[0], g.inv_h, g.dims[0]);
+      c3[1] = d3[1] = cell_coord((double)qy, g.origin[1], g.inv_h, g.dims[1]);
+      c3[2] = d3[2] = cell_coord((double)qz, g.origin[2], g.inv_h, g.dims[2]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { c3[k] = min(c3[k], __shfl_xor_sync(0xffffffffu, c3[k], o)); d3[k] = max(d3[k], __shfl_xor_sync(0xffffffffu, d3[k], o)); }
+    }
+    if ((i & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { atomicMin(&s_box[k], c3[k]); atomicMax(&s_box[3 + k], d3[k]); }
+    }
+    __syncthreads();
+    const int bx0 = max(0, s_box[0] - 1), bx1 = min(g.dims[0] - 1, s_box[3] + 1);
+    by0 = max(0, s_box[1] - 1); const int by1 = min(g.dims[1] - 1, s_box[4] + 1);
+    bz0 = max(0, s_box[2] - 1); const int bz1 = min(g.dims[2] - 1, s_box[5] + 1);
+    nyb = by1 - by0 + 1;
+    const int rows = nyb * (bz1 - bz0 + 1);
+    if (s_box[3] >= 0 && rows <= kStageRows) {
+      if (i < rows) {
+        const int y = by0 + i % nyb, z = bz0 + i / nyb;
+        const long long row = ((long long)z * g.dims[1] + y) * g.dims[0];
+        const uint32_t lo = __ldg(cs + row + bx0), hi = __ldg(cs + row + bx1 + 1);
+        s_row_lo[i] = lo; s_row_base[i] = hi - lo;            // length for now
+      }
+      __syncthreads();
+      if (i == 0) {
+        uint32_t total = 0;
+        for (int k = 0; k < rows; ++k) { const uint32_t len = s_row_base[k]; s_row_base[k] = total; total += len; }
+        if (total > 0 && total <= (uint32_t)kStageCap) {
+          mbar_init(&s_bar, 1);
+          mbar_expect_tx(&s_bar, total * 16u);
+          for (int k = 0; k < rows; ++k) {
+            const uint32_t len = (k + 1 < rows ? s_row_base[k + 1] : total) - s_row_base[k];
+            if (len) tma_bulk_g2s(&s_pts[s_row_base[k]], srt + s_row_lo[k], len * 16u, &s_bar);
+          }
+          s_staged = 1;
+        }
+      }
+      __syncthreads();
+      staged = s_staged != 0;
+      if (staged) mbar_wait(&s_bar, 0);
+    }
+    if (a.stats && i == 0) atomicAdd(a.stats + (staged ? 0 : 1), 1ull);
+  }
   if (act) {
     const int gq = t.start + i;
     qi = a.q_orig ? a.q_orig[gq] : (uint32_t)(t.out_base + i);
-    const F4 q = ldg_f4(a.q_local + gq);
-    const WorldPose& wn = a.wpose[pr.nei_block];
-    const WorldPose& wr = a.wpose[pr.ref_block];
-    float qx, qy, qz;
-    transform_point_f32(wn.R, wn.t, q.x, q.y, q.z, qx, qy, qz);
-    const GridDesc& g = a.grids[pr.target_cloud];
-    const uint32_t* cs = a.cell_start + g.cell_base;
-    const F4* srt = a.sorted;
     auto cells = [cs](long long c) { return (long long)__ldg(cs + c); };
-    auto load = [srt](long long p) { return ldg_f4(srt + p); };
+    auto loadg = [srt](long long p) { return ldg_f4(srt + p); };
+    auto load1 = [&](long long p) { return (STAGE && staged) ? s_pts[p] : ldg_f4(srt + p); };
+    auto row_map = [&](int y, int z, uint32_t& lo, uint32_t& hi) {
+      if (STAGE && staged) {
+        const int rl = (z - bz0) * nyb + (y - by0);
+        const uint32_t nlo = s_row_base[rl] + (lo - s_row_lo[rl]);
+        hi = nlo + (hi - lo); lo = nlo;
+      }
+    };
     auto win = [&](int j) { return s_win[j][i]; };
     auto set_win = [&](int j, uint32_t pos) { s_win[j][i] = pos; };
     auto range_set = [&](int k, uint32_t lo, uint32_t hi) { s_rng[2 * k][i] = lo; s_rng[2 * k + 1][i] = hi; };
@@ -173,7 +268,9 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
 #pragma unroll
       for (int j = 0; j < K; ++j) s_win[j][i] = 0xFFFFFFFFu;
     }
-    valid = associate_point2plane<K, FLAT>(g, cells, load, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set, range_get);
+    valid = associate_point2plane<K>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
+                                     range_get);
+    auto load = loadg;     // the debug view below is only built without staging
     if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
       for (int j = 0; j < K; ++j) {
         const uint32_t pj = s_win[j][i];

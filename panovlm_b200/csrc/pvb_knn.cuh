@@ -4,6 +4,9 @@
 // (lidar_mapping/LidarFeatureAssociate.cpp:570-599): k nearest on float32 squared L2, k-th <= thr^2,
 // same-class test, neighbours -> reference sensor frame, LSQ plane + tolerance, collinearity reject.
 //
+// (Staging: a thread block may copy the rows its queries need into shared memory with TMA bulk copies; ring-1 ranges are
+// then translated into that staging area by `row_map` — see k_associate in pvb_kernels.cuh.)
+//
 // Data layout: the target cloud (world frame, float32) is bucketed into a uniform grid (cell size h, x fastest)
 // and stored sorted by cell as 16-byte records {x, y, z, (orig_idx << 5) | class}; cell_start[c] is the offset
 // of the first record of cell c.  All cells of one (y,z) row that a query needs are one contiguous range.
@@ -113,26 +116,7 @@ PVB_HD void for_each_range(const GridDesc& g, const CellLoader& cells, int cx, i
   }
 }
 
-// Flattened walk over a list of record ranges: every lane advances through ITS candidates back to back, so the
-// trip count of a warp is the longest lane's total (not the sum over rows of the longest row).
-template <typename RangeGet, typename Body2>
-PVB_HD void walk_ranges(int n_ranges, const RangeGet& range, const Body2& body2) {
-  // two records per trip (both loads in flight before either is ranked); body2(i, n) handles n in {1, 2} records
-  int row = 0;
-  uint32_t i = 0, hi = 0;
-  for (;;) {
-    while (i >= hi) {
-      if (row >= n_ranges) return;
-      range(row, i, hi);
-      ++row;
-    }
-    const int n = (hi - i) >= 2u ? 2 : 1;
-    body2((long long)i, n);
-    i += (uint32_t)n;
-  }
-}
-
-// Nested variant (per-row loops): fewer dependent instructions per candidate, more lane idling at row ends.
+// Walk over a list of record ranges (per-row loops).
 template <typename RangeGet, typename Body>
 PVB_HD void walk_ranges_nested(int n_ranges, const RangeGet& range, const Body& body) {
   for (int row = 0; row < n_ranges; ++row) {
@@ -145,11 +129,14 @@ PVB_HD void walk_ranges_nested(int n_ranges, const RangeGet& range, const Body& 
 
 // Exact K-NN of (qx,qy,qz) within sqrt(sq_thr).  Returns the number of neighbours handed to sink (K, or 0 when the
 // K-th nearest is beyond the threshold / fewer than K points are in reach).  sink(j, record position, d2 bits).
-// range_set(idx, lo, hi) / range_get(idx, lo&, hi&): caller-provided storage for the <= 9 row ranges of the 3x3x3
-// block (shared memory on the device).
-template <int K, bool FLAT, typename CellLoader, typename PointLoader, typename Sink, typename RangeSet, typename RangeGet>
-PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoader& load, float qx, float qy, float qz, float sq_thr, int rmax, const Sink& sink,
-                      const RangeSet& range_set, const RangeGet& range_get) {
+//  * ring 1 (the 3x3x3 cell block = up to 9 contiguous row ranges) is looked up once and walked twice through `load1`;
+//    row_map(y, z, lo, hi) may translate a row range into another index space (the tile's shared-memory staging area);
+//  * wider rings (rare) go through `loadg` with positions in the global sorted array.
+//  ring_out tells the caller which space the neighbour positions are in (1: load1's, > 1: loadg's).
+//  range_set(idx, lo, hi) / range_get(idx, lo&, hi&): caller-provided storage for the <= 9 row ranges.
+template <int K, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename Sink, typename RangeSet, typename RangeGet>
+PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const Load1& load1, const LoadG& loadg, const RowMap& row_map, float qx, float qy, float qz,
+                      float sq_thr, int rmax, const Sink& sink, const RangeSet& range_set, const RangeGet& range_get, int& ring_out) {
   const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
   uint32_t keys[K];
 #pragma unroll
@@ -169,32 +156,33 @@ PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoa
       slack = m < slack ? m : slack;
     }
   }
-  // ---- ring 1: the 3x3x3 block = up to 9 contiguous row ranges, looked up once and walked twice
+  // ---- ring 1
   int n_ranges = 0;
-  for_each_range(g, cells, cx, cy, cz, 1, true, [&](long long lo, long long hi) { if (hi > lo) { range_set(n_ranges, (uint32_t)lo, (uint32_t)hi); ++n_ranges; } });
-  if (FLAT) {
-    walk_ranges(n_ranges, range_get, [&](long long i, int n) {
-      const F4 c0 = load(i);
-      F4 c1 = c0;
-      if (n == 2) c1 = load(i + 1);
-      topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c0.x, c0.y, c0.z)));
-      if (n == 2) topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c1.x, c1.y, c1.z)));
-    });
-  } else {
-    walk_ranges_nested(n_ranges, range_get, [&](long long i) {
-      const F4 c = load(i);
-      topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
-    });
+  {
+    const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+    const int z0 = cz - 1 < 0 ? 0 : cz - 1, z1 = cz + 1 > nz - 1 ? nz - 1 : cz + 1;
+    const int y0 = cy - 1 < 0 ? 0 : cy - 1, y1 = cy + 1 > ny - 1 ? ny - 1 : cy + 1;
+    const int x0 = cx - 1 < 0 ? 0 : cx - 1, x1 = cx + 1 > nx - 1 ? nx - 1 : cx + 1;
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        const long long row = ((long long)z * ny + y) * nx;
+        uint32_t lo = (uint32_t)cells(row + x0), hi = (uint32_t)cells(row + x1 + 1);
+        if (hi > lo) { row_map(y, z, lo, hi); range_set(n_ranges, lo, hi); ++n_ranges; }
+      }
   }
+  walk_ranges_nested(n_ranges, range_get, [&](long long i) {
+    const F4 c = load1(i);
+    topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
+  });
   int r = 1;
   bool done = false;
   if (keys[K - 1] != init) {
     const double reach = (1.0 + slack) * g.h;
     done = (double)u2f(keys[K - 1]) < reach * reach * (1.0 - 1e-6);
   }
-  if (!done) {        // rare: widen ring by ring (generic nested loops)
+  if (!done) {        // rare: widen ring by ring (generic nested loops, global positions)
     for (r = 2; r <= rmax; ++r) {
-      for_each_range(g, cells, cx, cy, cz, r, false, [&](long long lo, long long hi) { scan_values<K>(load, lo, hi, qx, qy, qz, keys); });
+      for_each_range(g, cells, cx, cy, cz, r, false, [&](long long lo, long long hi) { scan_values<K>(loadg, lo, hi, qx, qy, qz, keys); });
       if (keys[K - 1] != init) {      // ring r covers every point closer than (r + slack) * h
         const double reach = ((double)r + slack) * g.h;
         if ((double)u2f(keys[K - 1]) < reach * reach * (1.0 - 1e-6)) break;
@@ -202,6 +190,7 @@ PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoa
     }
     if (r > rmax) r = rmax;
   }
+  ring_out = r;
   if (keys[K - 1] == init) return 0;
   const uint32_t tau = keys[K - 1];
   int n_lt = 0;
@@ -210,25 +199,15 @@ PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const PointLoa
   int eq_taken = 0, n_out = 0;
   const int eq_needed = K - n_lt;
   if (r == 1) {
-    auto collect = [&](const F4& c, long long i) {
+    walk_ranges_nested(n_ranges, range_get, [&](long long i) {
+      const F4 c = load1(i);
       const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
       bool take = kb < tau;
       if (kb == tau && eq_taken < eq_needed) { take = true; ++eq_taken; }
       if (take) { sink(n_out, (uint32_t)i, kb); ++n_out; }
-    };
-    if (FLAT) {
-      walk_ranges(n_ranges, range_get, [&](long long i, int n) {
-        const F4 c0 = load(i);
-        F4 c1 = c0;
-        if (n == 2) c1 = load(i + 1);
-        collect(c0, i);
-        if (n == 2) collect(c1, i + 1);
-      });
-    } else {
-      walk_ranges_nested(n_ranges, range_get, [&](long long i) { collect(load(i), i); });
-    }
+    });
   } else {
-    for_each_range(g, cells, cx, cy, cz, r, true, [&](long long lo, long long hi) { scan_collect(load, lo, hi, qx, qy, qz, tau, eq_needed, eq_taken, n_out, sink); });
+    for_each_range(g, cells, cx, cy, cz, r, true, [&](long long lo, long long hi) { scan_collect(loadg, lo, hi, qx, qy, qz, tau, eq_needed, eq_taken, n_out, sink); });
   }
   return n_out;
 }
@@ -244,13 +223,15 @@ struct AssocParams {
 // R_ref/t_ref, R_nei/t_nei = R_wl, t_wl of the two frames.  On success: p_local (query in the neighbour's
 // sensor frame, double) and plane (n, d) in the reference sensor frame.  win(j) / set_win(j, pos) access the
 // caller's per-query neighbour slots (shared memory on the device).
-template <int K, bool FLAT, typename CellLoader, typename PointLoader, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
-PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const PointLoader& load, const AssocParams& prm,
+template <int K, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const Load1& load1, const LoadG& loadg, const RowMap& row_map, const AssocParams& prm,
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
                                   double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get) {
-  const int found = knn_select<K, FLAT>(g, cells, load, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get);
-  if (found < K) return false;                                   // :578 (k-th beyond the threshold) + quirk C.6 guard
+  int ring = 1;
+  const int found = knn_select<K>(g, cells, load1, loadg, row_map, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
+  if (found < K) return false;                                   // :578
+  auto load = [&](long long pos) { return ring == 1 ? load1(pos) : loadg(pos); };   // neighbour positions live in the space they were found in (k-th beyond the threshold) + quirk C.6 guard
   // neighbours -> reference sensor frame (:587), streamed: Gram matrix for the LSQ plane and the scatter matrix
   PlaneAcc acc; plane_acc_clear(acc);
   int same = 0;
@@ -322,7 +303,8 @@ PVB_HD bool associate_point2line(const GridDesc& g, const CellLoader& cells, con
                                  const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
                                  double p_local[3], double a_local[3], double b_local[3], const WinGet& win, const WinSet& set_win, const RangeSet& range_set,
                                  const RangeGet& range_get) {
-  const int found = knn_select<K, false>(g, cells, load, qx, qy, qz, sq_thr, rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get);
+  int ring = 1;
+  const int found = knn_select<K>(g, cells, load, load, [](int, int, uint32_t&, uint32_t&) {}, qx, qy, qz, sq_thr, rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
   if (found < K) return false;                                   // :497 + quirk C.6 guard
   double pts[K][3];
 #pragma unroll

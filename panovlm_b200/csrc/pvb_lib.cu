@@ -67,7 +67,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 6, tune_walk = 0;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
+  int tune_minb = 6, tune_stage = 0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
@@ -223,17 +223,19 @@ int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_
 }
 
 template <bool REDUCE>
-int launch_associate(pvb_ctx* ctx, int k, int n_tiles, const AssocArgs& a) {
+int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a) {
   if (n_tiles == 0) return PVB_OK;
-  // tuning knobs (PVB_MINB: resident blocks per SM the register allocation targets; PVB_WALK: 0 nested row loops,
-  // 1 flattened two-records-per-trip walk).  Defaults are the fastest measured on B200.
-  const int minb = ctx->tune_minb, flat = ctx->tune_walk;
+  // tuning knobs (PVB_MINB: resident blocks per SM the register allocation targets; PVB_STAGE: 1 = stage each tile's candidate
+  // rows in shared memory with TMA bulk copies, 0 = read them through L1/L2).  Defaults: fastest measured on B200.
+  const int minb = ctx->tune_minb, stage = ctx->tune_stage;
   const bool dbg = a.out_nn_idx != nullptr;
   if (k != 5 && k != 10) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
-#define PVB_LAUNCH(KK, MB, DBG, FL) k_associate<KK, REDUCE, MB, DBG, FL><<<n_tiles, kTile, 0, ctx->stream>>>(a)
+  a.stats = nullptr;
+  if (stage && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
+#define PVB_LAUNCH(KK, MB, DBG, ST) k_associate<KK, REDUCE, MB, DBG, ST><<<n_tiles, kTile, 0, ctx->stream>>>(a)
 #define PVB_DISPATCH(KK)                                                                                   \
   if (dbg) PVB_LAUNCH(KK, 4, true, false);                                                                 \
-  else if (flat) { if (minb >= 6) PVB_LAUNCH(KK, 6, false, true); else if (minb == 5) PVB_LAUNCH(KK, 5, false, true); else PVB_LAUNCH(KK, 4, false, true); } \
+  else if (stage) { if (minb >= 6) PVB_LAUNCH(KK, 6, false, true); else if (minb == 5) PVB_LAUNCH(KK, 5, false, true); else PVB_LAUNCH(KK, 4, false, true); } \
   else { if (minb >= 6) PVB_LAUNCH(KK, 6, false, false); else if (minb == 5) PVB_LAUNCH(KK, 5, false, false); else PVB_LAUNCH(KK, 4, false, false); }
   if (k == 10) { PVB_DISPATCH(10) } else { PVB_DISPATCH(5) }
 #undef PVB_DISPATCH
@@ -259,7 +261,8 @@ int pvb_create(int device, pvb_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PVB_ERR_CUDA; }
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->bev0); cudaEventCreate(&ctx->bev1);
   if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e);
-  if (const char* e = getenv("PVB_WALK")) ctx->tune_walk = atoi(e) != 0;
+  if (const char* e = getenv("PVB_STAGE")) ctx->tune_stage = atoi(e) != 0;
+  if (ctx->d_stats.ensure(16) == cudaSuccess) cudaMemset(ctx->d_stats.p, 0, 16);
   *out = ctx;
   return PVB_OK;
 }
@@ -271,7 +274,7 @@ void pvb_destroy(pvb_ctx* ctx) {
   DevBuf* dbs[] = {&ctx->d_prep, &ctx->d_wpose, &ctx->b_tile, &ctx->b_eref, &ctx->b_enei, &ctx->b_type, &ctx->b_norm, &ctx->b_huber, &ctx->b_consts, &ctx->b_orig_d, &ctx->b_r, &ctx->b_J,
                    &ctx->b_part, &ctx->b_esys, &ctx->b_tbegin, &ctx->f_pairs, &ctx->f_qtiles, &ctx->f_valid, &ctx->f_point, &ctx->f_plane, &ctx->f_nn_idx, &ctx->f_nn_d2,
                    &ctx->d_q_sorted, &ctx->d_q_orig, &ctx->d_pairs, &ctx->d_qtiles, &ctx->d_part, &ctx->d_sys, &ctx->d_tbegin, &ctx->d_valid, &ctx->d_point, &ctx->d_plane,
-                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e, &ctx->b_chunk, &ctx->d_chunk};
+                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e, &ctx->b_chunk, &ctx->d_chunk, &ctx->d_stats};
   for (DevBuf* b : dbs) b->release();
   PinBuf* pbs[] = {&ctx->h_pose, &ctx->h_r, &ctx->h_J, &ctx->h_esys, &ctx->fh_valid, &ctx->fh_point, &ctx->fh_plane, &ctx->dh_sys, &ctx->mh_a};
   for (PinBuf* b : pbs) b->release();
@@ -816,6 +819,14 @@ int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_de
   k_sum_chunks<29><<<ctx->d_frames, 32, 0, ctx->stream>>>(ctx->d_chunk.as<double>(), dst);
   CKL();
   if (dev_sys) *dev_sys = dst;
+  return PVB_OK;
+}
+
+int pvb_debug_counters(pvb_ctx* ctx, unsigned long long* out2) {
+  if (!ctx || !out2) return PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out2, ctx->d_stats.p, 16, cudaMemcpyDeviceToHost));
   return PVB_OK;
 }
 

@@ -15,8 +15,8 @@ from panovlm_b200 import synth  # noqa: E402
 n_target = int(os.environ.get("SWEEP_TARGET", 10_000_000))
 d = synth.make_dense_sweep(n_target=n_target, n_frames=64, pts_per_frame=156_250 * n_target // 10_000_000, seed=20260929, source_seed=20260930)
 out = []
-for minb, walk, cell in itertools.product((4, 5, 6), (0, 1), (0.0, 0.14)):
-    os.environ["PVB_MINB"], os.environ["PVB_WALK"] = str(minb), str(walk)
+for minb, walk, cell in itertools.product((5, 6), (0, 1), (0.0,)):          # "walk" column = PVB_STAGE
+    os.environ["PVB_MINB"], os.environ["PVB_STAGE"] = str(minb), str(walk)
     ctx = panovlm_b200.Context(0)
     ctx.dense_set_target(d["target"], cell)
     ctx.dense_set_sources(d["src_local"], d["src_off"])
@@ -25,7 +25,7 @@ for minb, walk, cell in itertools.product((4, 5, 6), (0, 1), (0.0, 0.14)):
     for it in range(6):
         s = ctx.dense_evaluate(d["poses_lw_init"], prm)
         ms.append(ctx.dense_kernel_time_ms())
-    rec = {"minb": minb, "walk": walk, "cell": cell, "kernel_ms": float(np.median(ms[2:])), "cost": float(s[:, 27].sum()), "n": float(s[:, 28].sum())}
+    rec = {"minb": minb, "stage": walk, "staged_vs_global_tiles": ctx.debug_counters(), "cell": cell, "kernel_ms": float(np.median(ms[2:])), "cost": float(s[:, 27].sum()), "n": float(s[:, 28].sum())}
     print(json.dumps(rec), flush=True)
     out.append(rec)
     ctx.close()
