@@ -124,7 +124,10 @@ inline LMSummary solve_lm(const EvalFn& eval, double* poses, int nb, const unsig
   LMSummary S;
   double cost = eval(poses, H.data(), g.data());
   S.initial_cost = cost;
-  auto gather = [&]() { for (int i = 0; i < n; ++i) { gs[i] = g[fi[i]]; for (int j = 0; j < n; ++j) Hs[(size_t)i * n + j] = H[(size_t)fi[i] * D + fi[j]]; } };
+  auto gather = [&]() {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) { gs[i] = g[fi[i]]; for (int j = 0; j < n; ++j) Hs[(size_t)i * n + j] = H[(size_t)fi[i] * D + fi[j]]; }
+  };
   auto gmax = [&]() { double m = 0; for (int i = 0; i < n; ++i) m = std::max(m, std::fabs(gs[i])); return m; };
   gather();
   for (int i = 0; i < n; ++i) sc[i] = 1.0 / (1.0 + std::sqrt(Hs[(size_t)i * n + i]));
@@ -133,13 +136,16 @@ inline LMSummary solve_lm(const EvalFn& eval, double* poses, int nb, const unsig
   if (n == 0 || gmax() <= opt.gradient_tolerance) { S.final_cost = cost; S.termination = 2; return S; }
   for (int it = 1; it <= opt.max_iterations; ++it) {
     S.iterations = it;
-    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Hsc[(size_t)i * n + j] = Hs[(size_t)i * n + j] * sc[i] * sc[j];
-    A = Hsc;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { const double v = Hs[(size_t)i * n + j] * sc[i] * sc[j]; Hsc[(size_t)i * n + j] = v; A[(size_t)i * n + j] = v; }
     for (int i = 0; i < n; ++i) { y[i] = -gs[i] * sc[i]; A[(size_t)i * n + i] += std::min(std::max(A[(size_t)i * n + i], 1e-6), 1e32) / radius; }
     bool ok = cholesky_solve(A, n, y);
     double model = 0;
     if (ok) {
-      for (int i = 0; i < n; ++i) { double hy = 0; for (int j = 0; j < n; ++j) hy += Hsc[(size_t)i * n + j] * y[j]; model -= y[i] * (gs[i] * sc[i] + 0.5 * hy); }
+      std::vector<double> term(n);
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < n; ++i) { double hy = 0; for (int j = 0; j < n; ++j) hy += Hsc[(size_t)i * n + j] * y[j]; term[i] = y[i] * (gs[i] * sc[i] + 0.5 * hy); }
+      for (int i = 0; i < n; ++i) model -= term[i];        // fixed summation order
       ok = model > 0.0;
     }
     if (!ok) { radius *= 0.5; S.unsuccessful++; if (++invalid >= 5 || radius < 1e-32) { S.termination = 4; break; } continue; }
