@@ -49,7 +49,7 @@ for case in range(n_cases):
         consts = np.zeros((len(oq), 12)); consts[:, :3] = opt; consts[:, 3:7] = opl; consts[:, 7] = 1.0
         blk = pvo.Blocks(np.full(len(oq), rtype), 0, 1, consts, hub, 1)
         ro, Jo, co = blk.evaluate(np.stack([np.zeros(6), poses[f]]), apply_loss=True) if len(oq) else (np.zeros(0), np.zeros((0, 12)), np.zeros(0))
-        exp_sys.append((oq, opl, Jo[:, 6:], ro, co))
+        exp_sys.append((oq, opl, Jo[:, 6:], ro, co, opt))
     for stage, ctx in ctxs.items():
         ctx.dense_set_target(tgt, cell)
         ctx.dense_set_sources(d["src_local"], d["src_off"])
@@ -58,13 +58,19 @@ for case in range(n_cases):
         valid, pt, pl, r, j6 = ctx.dense_get_rows(poses, prm)
         for f in range(nf):
             lo, hi = d["src_off"][f], d["src_off"][f + 1]
-            oq, opl, J6, ro, co = exp_sys[f]
+            oq, opl, J6, ro, co, opt = exp_sys[f]
             gq = np.nonzero(valid[lo:hi])[0]
             if not np.array_equal(gq, oq):
                 print("MISMATCH association set", dict(case=case, stage=stage, frame=f, cell=cell, thr=thr, k=k, tol=tol, n_gpu=len(gq), n_cpu=len(oq)))
                 sys.exit(1)
             if len(oq):
-                dp = np.abs(pl[lo:hi][gq] - opl).max(); worst["plane"] = max(worst["plane"], dp)
+                # plane parity where it matters: the offset of the two planes at the query (coefficients of a plane far from the origin are
+                # individually ill-conditioned: d changes by |dn| * distance) + the residuals themselves
+                R_wl = pvo.aa_to_R(poses[f, :3]).T; t_wl = -R_wl @ poses[f, 3:]
+                pw = opt @ R_wl.T + t_wl
+                dpl = pl[lo:hi][gq] - opl
+                dp = max(np.abs((dpl[:, :3] * pw).sum(1) + dpl[:, 3]).max(), (np.abs(r[lo:hi][gq] - ro) / np.maximum(1e-9, np.abs(ro))).max() * 1e-3)
+                worst["plane"] = max(worst["plane"], dp)
                 H = J6.T @ J6; gv = J6.T @ ro
                 iu = np.triu_indices(6)
                 ds = max(np.abs(s[f, :21] - H[iu]).max() / max(1e-30, np.abs(H).max()), np.abs(s[f, 21:27] - gv).max() / max(1e-30, np.abs(gv).max(), 1e-9 * np.abs(H).max()))
