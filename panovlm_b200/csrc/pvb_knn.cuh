@@ -223,7 +223,9 @@ struct AssocParams {
 // R_ref/t_ref, R_nei/t_nei = R_wl, t_wl of the two frames.  On success: p_local (query in the neighbour's
 // sensor frame, double) and plane (n, d) in the reference sensor frame.  win(j) / set_win(j, pos) access the
 // caller's per-query neighbour slots (shared memory on the device).
-template <int K, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+// REF_ID: the reference frame's pose is exactly the identity (rigid target map): World2Local of a neighbour is then the
+// neighbour itself bit for bit (x*1 + y*0 + z*0 - 0), so the 3 x K matrix-vector products per query are skipped.
+template <int K, bool REF_ID, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
 PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const Load1& load1, const LoadG& loadg, const RowMap& row_map, const AssocParams& prm,
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
@@ -241,7 +243,7 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
     same += ((f2u(p.w) & 31u) == qcls) ? 1 : 0;                  // :586 pt.intensity == point.intensity
     const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
     double pl[3];
-    world2local(R_ref, t_ref, pw, pl);
+    if (REF_ID) { pl[0] = pw[0]; pl[1] = pw[1]; pl[2] = pw[2]; } else world2local(R_ref, t_ref, pw, pl);
     plane_acc_add(acc, pl);
   }
   if (same < K) return false;                                    // :590
@@ -257,7 +259,7 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
       const F4 p = load((long long)win(j));
       const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
       double pl[3];
-      world2local(R_ref, t_ref, pw, pl);
+      if (REF_ID) { pl[0] = pw[0]; pl[1] = pw[1]; pl[2] = pw[2]; } else world2local(R_ref, t_ref, pw, pl);
       const double rj = -1.0 - (pl[0] * x[0] + pl[1] * x[1] + pl[2] * x[2]);
       t[0] += pl[0] * rj; t[1] += pl[1] * rj; t[2] += pl[2] * rj;
     }
@@ -270,7 +272,7 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
     for (int j = 0; j < K; ++j) {
       const F4 p = load((long long)win(j));
       const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
-      world2local(R_ref, t_ref, pw, &A[j * 3]);
+      if (REF_ID) { A[j * 3] = pw[0]; A[j * 3 + 1] = pw[1]; A[j * 3 + 2] = pw[2]; } else world2local(R_ref, t_ref, pw, &A[j * 3]);
     }
     lstsq_minus_one_rolled(K, A, x);
   }
@@ -284,7 +286,7 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
       const F4 p = load((long long)win(j));
       const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
       double pl[3];
-      world2local(R_ref, t_ref, pw, pl);
+      if (REF_ID) { pl[0] = pw[0]; pl[1] = pw[1]; pl[2] = pw[2]; } else world2local(R_ref, t_ref, pw, pl);
       ok = ok && !(fabs(n0 * pl[0] + n1 * pl[1] + n2 * pl[2] + d) > prm.plane_tol);
     }
     if (!ok) return false;

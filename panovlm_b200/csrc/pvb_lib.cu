@@ -223,7 +223,7 @@ int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_
 }
 
 template <bool REDUCE>
-int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a) {
+int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_identity = false) {
   if (n_tiles == 0) return PVB_OK;
   // tuning knobs (PVB_MINB: resident blocks per SM the register allocation targets; PVB_STAGE: 1 = stage each tile's candidate
   // rows in shared memory with TMA bulk copies, 0 = read them through L1/L2).  Defaults: fastest measured on B200.
@@ -232,7 +232,7 @@ int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a) {
   if (k != 5 && k != 10) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
   a.stats = nullptr;
   if (stage && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
-#define PVB_LAUNCH(KK, MB, DBG, ST) k_associate<KK, REDUCE, MB, DBG, ST><<<n_tiles, kTile, 0, ctx->stream>>>(a)
+#define PVB_LAUNCH(KK, MB, DBG, ST) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, ST, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, ST, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
 #define PVB_DISPATCH(KK)                                                                                   \
   if (dbg) PVB_LAUNCH(KK, 4, true, false);                                                                 \
   else if (stage) { if (minb >= 6) PVB_LAUNCH(KK, 6, false, true); else if (minb == 5) PVB_LAUNCH(KK, 5, false, true); else PVB_LAUNCH(KK, 4, false, true); } \
@@ -804,11 +804,11 @@ int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_de
       AssocArgs ac = a;
       ac.tiles = a.tiles + t0;
       ac.partials = a.partials + (size_t)t0 * (kTile / 32) * 29;
-      rc = launch_associate<true>(ctx, prm->k, t1 - t0, ac); if (rc) return rc;
+      rc = launch_associate<true>(ctx, prm->k, t1 - t0, ac, true); if (rc) return rc;
     }
     ctx->d_chunks_pending = false;
   } else {
-    rc = launch_associate<true>(ctx, prm->k, ctx->d_ntiles, a); if (rc) return rc;
+    rc = launch_associate<true>(ctx, prm->k, ctx->d_ntiles, a, true); if (rc) return rc;   // the target frame is the world: identity reference pose
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;
@@ -858,7 +858,7 @@ int pvb_dense_get_rows(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_par
   a.out_valid = ctx->d_valid.as<unsigned char>(); a.out_point = ctx->d_point.as<double>(); a.out_plane = ctx->d_plane.as<double>();
   a.out_res = ctx->d_res.as<double>(); a.out_jac6 = ctx->d_jac.as<double>();
   if (ctx->d_chunks_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->d_chunks_pending = false; }
-  rc = launch_associate<false>(ctx, prm->k, ctx->d_ntiles, a); if (rc) return rc;
+  rc = launch_associate<false>(ctx, prm->k, ctx->d_ntiles, a, true); if (rc) return rc;
   if (valid) CK(cudaMemcpyAsync(valid, ctx->d_valid.p, n, cudaMemcpyDeviceToHost, ctx->stream));
   if (point3) CK(cudaMemcpyAsync(point3, ctx->d_point.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
   if (plane4) CK(cudaMemcpyAsync(plane4, ctx->d_plane.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));

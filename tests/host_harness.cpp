@@ -47,7 +47,7 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
     uint32_t rng[18];
     auto range_set = [&](int k, uint32_t lo, uint32_t hi) { rng[2 * k] = lo; rng[2 * k + 1] = hi; };
     auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = rng[2 * k]; hi = rng[2 * k + 1]; };
-    valid[i] = associate_point2plane<K>(g, cells, load, load, [](int, int, uint32_t&, uint32_t&) {}, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei,
+    valid[i] = associate_point2plane<K, false>(g, cells, load, load, [](int, int, uint32_t&, uint32_t&) {}, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei,
                                         p_local + 3 * i, plane + 4 * i, win, set_win, range_set, range_get) ? 1 : 0;
     std::vector<std::pair<std::pair<float, uint32_t>, int>> nn;
     for (int j = 0; j < K; ++j) {
