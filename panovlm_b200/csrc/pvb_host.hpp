@@ -85,7 +85,7 @@ inline bool cholesky_solve(std::vector<double>& A, int n, std::vector<double>& b
         A[(size_t)i * n + j] = s / d;
       }
     }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 512)
     for (int i = k1; i < n; ++i) {                       // panel: L[i, k0:k1] = A[i, k0:k1] * L[k0:k1, k0:k1]^-T
       for (int j = k0; j < k1; ++j) {
         double s = A[(size_t)i * n + j];
@@ -93,7 +93,7 @@ inline bool cholesky_solve(std::vector<double>& A, int n, std::vector<double>& b
         A[(size_t)i * n + j] = s / A[(size_t)j * n + j];
       }
     }
-#pragma omp parallel for schedule(dynamic, 8)
+#pragma omp parallel for schedule(dynamic, 8) if (n > 512)
     for (int i = k1; i < n; ++i) {                       // trailing update (lower part): A[i, j] -= L[i, k0:k1] . L[j, k0:k1]
       const double* li = &A[(size_t)i * n + k0];
       for (int j = k1; j <= i; ++j) {
@@ -125,7 +125,7 @@ inline LMSummary solve_lm(const EvalFn& eval, double* poses, int nb, const unsig
   double cost = eval(poses, H.data(), g.data());
   S.initial_cost = cost;
   auto gather = [&]() {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 512)
     for (int i = 0; i < n; ++i) { gs[i] = g[fi[i]]; for (int j = 0; j < n; ++j) Hs[(size_t)i * n + j] = H[(size_t)fi[i] * D + fi[j]]; }
   };
   auto gmax = [&]() { double m = 0; for (int i = 0; i < n; ++i) m = std::max(m, std::fabs(gs[i])); return m; };
@@ -136,14 +136,14 @@ inline LMSummary solve_lm(const EvalFn& eval, double* poses, int nb, const unsig
   if (n == 0 || gmax() <= opt.gradient_tolerance) { S.final_cost = cost; S.termination = 2; return S; }
   for (int it = 1; it <= opt.max_iterations; ++it) {
     S.iterations = it;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 512)
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { const double v = Hs[(size_t)i * n + j] * sc[i] * sc[j]; Hsc[(size_t)i * n + j] = v; A[(size_t)i * n + j] = v; }
     for (int i = 0; i < n; ++i) { y[i] = -gs[i] * sc[i]; A[(size_t)i * n + i] += std::min(std::max(A[(size_t)i * n + i], 1e-6), 1e32) / radius; }
     bool ok = cholesky_solve(A, n, y);
     double model = 0;
     if (ok) {
       std::vector<double> term(n);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 512)
       for (int i = 0; i < n; ++i) { double hy = 0; for (int j = 0; j < n; ++j) hy += Hsc[(size_t)i * n + j] * y[j]; term[i] = y[i] * (gs[i] * sc[i] + 0.5 * hy); }
       for (int i = 0; i < n; ++i) model -= term[i];        // fixed summation order
       ok = model > 0.0;
