@@ -37,7 +37,12 @@ enum {
   PVB_P2LINE_METER = 2,       /* Point2Line_Meter    :769-829   consts: p[0..2] a[3..5] dir[6..8] weight[9]                */
   PVB_P2LINE_ANGLE = 3,       /* Point2Line_Angle    :836-934   consts: p[0..2] a[3..5] dir[6..8] (dir = (a-b)/|a-b|)       */
   PVB_PLANE2PLANE_GLOBAL = 4, /* Plane2Plane_Global  :350-425   consts: n[0..2] a[3..5] b[6..8] weight[9]                  */
-  PVB_PLANE_IOU = 5           /* PlaneIOUResidual    :433-507   consts: plane[0..3] mid_nei[4..6] mid_ref[7..9] angle[10] weight[11] */
+  PVB_PLANE_IOU = 5,          /* PlaneIOUResidual    :433-507   consts: plane[0..3] mid_nei[4..6] mid_ref[7..9] angle[10] weight[11] */
+  /* calibration-mode functors (CameraLidarOptimizer.cpp:58-63, LidarOdometry_test.cpp:127): one relative pose = the `ref` block,
+     the `nei` block is ignored (zero Jacobian columns)                                                                          */
+  PVB_PLANE2PLANE_RELATIVE = 6, /* Plane2Plane_Relative :294-346  consts as PVB_PLANE2PLANE_GLOBAL; residual in DEGREES (:334)    */
+  PVB_PLANE_RELATIVE_IOU = 7,   /* PlaneRelativeIOUResidual :509-563  consts as PVB_PLANE_IOU                                      */
+  PVB_LINE2LINE_ANGLE = 8       /* Line2Line_Angle     :984-1022  consts: dir_ref[0..2] dir_nei[3..5] (unit); rotation blocks only */
 };
 
 /* ---- lifecycle --------------------------------------------------------------------------------------------- */

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 P2PLANE_METER, P2PLANE_ANGLE, P2LINE_METER, P2LINE_ANGLE, PLANE2PLANE_GLOBAL, PLANE_IOU = range(6)
+PLANE2PLANE_RELATIVE, PLANE_RELATIVE_IOU, LINE2LINE_ANGLE = 6, 7, 8
 
 
 def build():

@@ -522,6 +522,38 @@ struct PairWisePoint2Line_Meter {  // CostFunction.h:939-980 (2 blocks)
   }
 };
 
+struct Plane2Plane_Relative {  // CostFunction.h:294-346 (2 blocks aa_cl, t_cl; residual in DEGREES, :334)
+  double plane_ref[3], point_a[3], point_b[3], weight;
+  template <typename T> bool operator()(const T* aa_cl, const T* t_cl, T* residual) const {
+    T pa[3] = {T(point_a[0]), T(point_a[1]), T(point_a[2])}, pb[3] = {T(point_b[0]), T(point_b[1]), T(point_b[2])}, A[3], B[3];
+    AngleAxisRotatePoint(aa_cl, pa, A);
+    A[0] = A[0] + t_cl[0]; A[1] = A[1] + t_cl[1]; A[2] = A[2] + t_cl[2];
+    AngleAxisRotatePoint(aa_cl, pb, B);
+    B[0] = B[0] + t_cl[0]; B[1] = B[1] + t_cl[1]; B[2] = B[2] + t_cl[2];
+    T lidar_plane[3] = {A[1] * B[2] - A[2] * B[1], A[2] * B[0] - A[0] * B[2], A[0] * B[1] - A[1] * B[0]};
+    T img_plane[3] = {T(plane_ref[0]), T(plane_ref[1]), T(plane_ref[2])};
+    residual[0] = T(weight) * PlaneAngle<T>(img_plane, lidar_plane) * T(180.0) / T(M_PI);
+    return true;
+  }
+};
+
+struct PlaneRelativeIOUResidual {  // CostFunction.h:509-563 (2 blocks aa_cl, t_cl)
+  double ref_plane[4], middle_neighbor[3], middle_ref[3], angle, weight;
+  template <typename T> bool operator()(const T* aa_cl, const T* t_cl, T* residual) const {
+    T pn[3] = {T(middle_neighbor[0]), T(middle_neighbor[1]), T(middle_neighbor[2])}, mid[3];
+    AngleAxisRotatePoint(aa_cl, pn, mid);
+    mid[0] = mid[0] + t_cl[0]; mid[1] = mid[1] + t_cl[1]; mid[2] = mid[2] + t_cl[2];
+    T pc[4] = {T(ref_plane[0]), T(ref_plane[1]), T(ref_plane[2]), T(ref_plane[3])};
+    T ip[3] = {T(middle_ref[0]), T(middle_ref[1]), T(middle_ref[2])};
+    T proj[3];
+    ProjectPointToPlane(mid, pc, proj, true);
+    T curr = VectorAngle3D(proj, ip);
+    if (curr < T(angle)) residual[0] = T(0.0);
+    else residual[0] = T(weight) * (curr - T(angle));
+    return true;
+  }
+};
+
 struct Line2Line_Angle {  // CostFunction.h:984-1022 (2 rotation blocks; < 1e-3 => 0)
   double dir_ref[3], dir_nei[3];
   template <typename T> bool operator()(const T* aa_rw, const T* aa_nw, T* residual) const {

@@ -10,13 +10,17 @@
 
 namespace pvo {
 
-enum BlockType { P2PLANE_METER = 0, P2PLANE_ANGLE = 1, P2LINE_METER = 2, P2LINE_ANGLE = 3, PLANE2PLANE_GLOBAL = 4, PLANE_IOU = 5 };
+enum BlockType { P2PLANE_METER = 0, P2PLANE_ANGLE = 1, P2LINE_METER = 2, P2LINE_ANGLE = 3, PLANE2PLANE_GLOBAL = 4, PLANE_IOU = 5,
+                 PLANE2PLANE_RELATIVE = 6, PLANE_RELATIVE_IOU = 7, LINE2LINE_ANGLE = 8 };
 
 // consts layout (12 doubles):
 //  P2PLANE_*          : p[0..2] plane[3..6] weight[7]
 //  P2LINE_*           : p[0..2] a[3..5] dir[6..8] weight[9]        (dir already normalised (a-b)/|a-b|)
 //  PLANE2PLANE_GLOBAL : n[0..2] (normalised) a[3..5] b[6..8] weight[9]
 //  PLANE_IOU          : plane[0..3] (normalised) mid_nei[4..6] mid_ref[7..9] angle[10] weight[11]
+//  PLANE2PLANE_RELATIVE / PLANE_RELATIVE_IOU : consts as PLANE2PLANE_GLOBAL / PLANE_IOU; parameters = the `ref` block only
+//                       (aa_cl, t_cl); the `nei` block is ignored and its Jacobian columns are zero
+//  LINE2LINE_ANGLE    : dir_ref[0..2] dir_nei[3..5] (unit); parameters = aa of the ref block and aa of the nei block
 struct Block { int type, ref, nei, normalize; double huber; double c[12]; };
 
 inline void EvalBlockRaw(const Block& b, const double* pr, const double* pn, double* r, double* J) {
@@ -28,6 +32,13 @@ inline void EvalBlockRaw(const Block& b, const double* pr, const double* pn, dou
     case P2LINE_ANGLE: { Point2Line_Angle f; std::memcpy(f.p, b.c, 24); std::memcpy(f.line_point, b.c + 3, 24); std::memcpy(f.line_dir, b.c + 6, 24); f.weight = b.c[9]; f.normalize_distance = b.normalize != 0; EvaluateAutoDiff4(f, aa_r, t_r, aa_n, t_n, r, J); break; }
     case PLANE2PLANE_GLOBAL: { Plane2Plane_Global f; std::memcpy(f.plane_ref, b.c, 24); std::memcpy(f.point_a, b.c + 3, 24); std::memcpy(f.point_b, b.c + 6, 24); f.weight = b.c[9]; EvaluateAutoDiff4(f, aa_r, t_r, aa_n, t_n, r, J); break; }
     case PLANE_IOU: { PlaneIOUResidual f; std::memcpy(f.ref_plane, b.c, 32); std::memcpy(f.middle_neighbor, b.c + 4, 24); std::memcpy(f.middle_ref, b.c + 7, 24); f.angle = b.c[10]; f.weight = b.c[11]; EvaluateAutoDiff4(f, aa_r, t_r, aa_n, t_n, r, J); break; }
+    case PLANE2PLANE_RELATIVE: { Plane2Plane_Relative f; std::memcpy(f.plane_ref, b.c, 24); std::memcpy(f.point_a, b.c + 3, 24); std::memcpy(f.point_b, b.c + 6, 24); f.weight = b.c[9];
+      if (J) for (int i = 6; i < 12; ++i) J[i] = 0; EvaluateAutoDiff2(f, aa_r, t_r, r, J); break; }
+    case PLANE_RELATIVE_IOU: { PlaneRelativeIOUResidual f; std::memcpy(f.ref_plane, b.c, 32); std::memcpy(f.middle_neighbor, b.c + 4, 24); std::memcpy(f.middle_ref, b.c + 7, 24); f.angle = b.c[10]; f.weight = b.c[11];
+      if (J) for (int i = 6; i < 12; ++i) J[i] = 0; EvaluateAutoDiff2(f, aa_r, t_r, r, J); break; }
+    case LINE2LINE_ANGLE: { Line2Line_Angle f; std::memcpy(f.dir_ref, b.c, 24); std::memcpy(f.dir_nei, b.c + 3, 24);
+      double j6[6]; EvaluateAutoDiff2(f, aa_r, aa_n, r, J ? j6 : nullptr);
+      if (J) { for (int i = 0; i < 12; ++i) J[i] = 0; for (int i = 0; i < 3; ++i) { J[i] = j6[i]; J[6 + i] = j6[3 + i]; } } break; }
     default: *r = 0; if (J) for (int i = 0; i < 12; ++i) J[i] = 0;
   }
 }

@@ -10,6 +10,7 @@ import subprocess
 import numpy as np
 
 P2PLANE_METER, P2PLANE_ANGLE, P2LINE_METER, P2LINE_ANGLE, PLANE2PLANE_GLOBAL, PLANE_IOU = range(6)
+PLANE2PLANE_RELATIVE, PLANE_RELATIVE_IOU, LINE2LINE_ANGLE = 6, 7, 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None

@@ -317,7 +317,7 @@ int pvb_blocks_set(pvb_ctx* ctx, long n, const int* type, const int* ref, const 
   CK(cudaSetDevice(ctx->device));
   for (long i = 0; i < n; ++i) {
     if (ref[i] < 0 || ref[i] >= nb || nei[i] < 0 || nei[i] >= nb) return ctx->fail(PVB_ERR_ARG, "block %ld: pose index out of range", i);
-    if (type[i] < 0 || type[i] > PVB_PLANE_IOU) return ctx->fail(PVB_ERR_ARG, "block %ld: unknown residual type %d", i, type[i]);
+    if (type[i] < 0 || type[i] > PVB_LINE2LINE_ANGLE) return ctx->fail(PVB_ERR_ARG, "block %ld: unknown residual type %d", i, type[i]);
   }
   ctx->bn = n; ctx->nb = nb; ctx->b_has_rows = ctx->b_has_sys = false;
   // group rows by pose-graph edge (stable: rows of an edge keep their registration order)

@@ -24,7 +24,8 @@
 
 namespace pvb {
 
-enum BlockType : int { P2PLANE_METER = 0, P2PLANE_ANGLE = 1, P2LINE_METER = 2, P2LINE_ANGLE = 3, PLANE2PLANE_GLOBAL = 4, PLANE_IOU = 5 };
+enum BlockType : int { P2PLANE_METER = 0, P2PLANE_ANGLE = 1, P2LINE_METER = 2, P2LINE_ANGLE = 3, PLANE2PLANE_GLOBAL = 4, PLANE_IOU = 5,
+                       PLANE2PLANE_RELATIVE = 6, PLANE_RELATIVE_IOU = 7, LINE2LINE_ANGLE = 8 };
 
 // ---- rounding-exact float/double helpers (no FMA contraction: the reference's PCL/FLANN/OpenCV float paths
 //      are plain mul+add; the host build uses -ffp-contract=off) ------------------------------------------
@@ -250,6 +251,13 @@ PVB_HD void accumulate_row(const PosePrep& pr, const PosePrep& pn, const double 
   }
 }
 
+PVB_HD PosePrep identity_prep() {
+  PosePrep p;
+  for (int k = 0; k < 9; ++k) { p.R[k] = (k % 4 == 0) ? 1.0 : 0.0; p.Jl[k] = p.R[k]; }
+  p.t[0] = p.t[1] = p.t[2] = 0.0;
+  return p;
+}
+
 // One residual block: raw residual + 1x12 Jacobian row [d/daa_r | d/dt_r | d/daa_n | d/dt_n].
 PVB_HD double eval_block(int type, bool normalize, const double* c, const PosePrep& pr, const PosePrep& pn, double J[12]) {
   for (int k = 0; k < 12; ++k) J[k] = 0.0;
@@ -281,6 +289,45 @@ PVB_HD double eval_block(int type, bool normalize, const double* c, const PosePr
       r = tail_plane_iou(c, P, g);
       accumulate_row(pr, pn, q, P, g, J);
       return r;
+    // Calibration-mode functors (CostFunction.h:294-346, 509-563): one relative pose (aa_cl, t_cl) = the `ref` block,
+    // P = R p + t, i.e. the common transform with the neighbour block pinned at identity; its columns stay zero.
+    case PLANE2PLANE_RELATIVE: {
+      const PosePrep id = identity_prep();
+      double qb[3], A[3], B[3], gA[3], gB[3];
+      transform_nei_to_ref(pr, id, c + 3, q, A);
+      transform_nei_to_ref(pr, id, c + 6, qb, B);
+      r = tail_plane2plane(c, A, B, gA, gB);
+      accumulate_row(pr, id, q, A, gA, J);
+      accumulate_row(pr, id, qb, B, gB, J);
+      const double deg = 180.0 / M_PI;                          // :334 residual in degrees ((w * angle) * 180) / pi
+      r = r * 180.0 / M_PI;
+      for (int k = 0; k < 6; ++k) { J[k] *= deg; J[6 + k] = 0.0; }
+      return r;
+    }
+    case PLANE_RELATIVE_IOU: {
+      const PosePrep id = identity_prep();
+      transform_nei_to_ref(pr, id, c + 4, q, P);
+      r = tail_plane_iou(c, P, g);
+      accumulate_row(pr, id, q, P, g, J);
+      for (int k = 6; k < 12; ++k) J[k] = 0.0;
+      return r;
+    }
+    // Line2Line_Angle (CostFunction.h:984-1022): rotations only, r = PlaneAngle(R_r R_n^T d_nei, d_ref, normalized), < 1e-3 => 0
+    case LINE2LINE_ANGLE: {
+      PosePrep r0 = pr, n0 = pn;
+      r0.t[0] = r0.t[1] = r0.t[2] = 0.0; n0.t[0] = n0.t[1] = n0.t[2] = 0.0;
+      transform_nei_to_ref(r0, n0, c + 3, q, P);
+      const double dot = P[0] * c[0] + P[1] * c[1] + P[2] * c[2];
+      const double cs = fabs(dot);
+      if (cs >= 1.0) return 0.0;
+      r = acos(cs);
+      if (r < 1e-3) return 0.0;
+      const double k = (dot < 0.0 ? 1.0 : -1.0) / sqrt(1.0 - cs * cs);
+      g[0] = k * c[0]; g[1] = k * c[1]; g[2] = k * c[2];
+      accumulate_row(r0, n0, q, P, g, J);
+      for (int j = 0; j < 3; ++j) J[3 + j] = J[9 + j] = 0.0;
+      return r;
+    }
     default:
       return 0.0;
   }

@@ -33,6 +33,30 @@ def random_blocks(seed, n, nb=8):
     return dict(type=types, ref=ref, nei=nei, consts=consts, huber=huber, normalize=normalize, poses=poses, nb=nb)
 
 
+def random_blocks_f6(seed, n, nb=8):
+    """Calibration-mode functors (types 6, 7, 8: Plane2Plane_Relative, PlaneRelativeIOUResidual, Line2Line_Angle)."""
+    rng = np.random.default_rng(seed)
+    c = random_blocks(seed + 1, n, nb)
+    types = rng.integers(6, 9, n).astype(np.int32)
+    consts = np.zeros((n, 12))
+    for i, bt in enumerate(types):
+        k = consts[i]
+        nrm = rng.normal(size=3); nrm /= np.linalg.norm(nrm)
+        if bt == 6:
+            k[:3] = nrm; k[3:6] = rng.normal(0, 3, 3); k[6:9] = rng.normal(0, 3, 3); k[9] = 0.5
+        elif bt == 7:
+            m = rng.normal(size=3)
+            k[:3] = nrm; k[3] = 0.0; k[4:7] = rng.normal(0, 3, 3); k[7:10] = m / np.linalg.norm(m); k[10] = rng.uniform(0, 2); k[11] = 2.0
+        else:
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            k[:3] = nrm; k[3:6] = d
+    c["type"], c["consts"] = types, consts
+    same = rng.random(n) < 0.1                 # Line2Line_Angle with identical rotations and directions: the < 1e-3 => 0 branch
+    for i in np.nonzero(same & (types == 8))[0]:
+        c["nei"][i] = c["ref"][i]; consts[i, 3:6] = consts[i, :3] * (1 if i % 2 else -1)
+    return c
+
+
 def on_plane_blocks():
     """Closed-form cases: point on the plane => r = 0 and a zero Jacobian row (angle types)."""
     consts = np.zeros((2, 12))

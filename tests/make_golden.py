@@ -4,6 +4,7 @@ The reference ships no golden vectors and cannot be built here, 
 INDEPENDENT implementations, never from the oracle itself:
   functors.npz   residuals + 1x12 Jacobians of all six cost functors from tests/twin.py (torch float64 reverse-mode
                  autograd over the closed form P = R_r R_n^T (p - t_n) + t_r)
+  functors_f6.npz  same for the calibration-mode functors (Plane2Plane_Relative, PlaneRelativeIOUResidual, Line2Line_Angle)
   rotations.npz  scipy.spatial.transform.Rotation matrices / rotation vectors
   assoc_pair.npz a small 2-frame pair (feature clouds) with the expected point-to-plane associations computed with
                  scipy cKDTree (float64 on the float32 world points) + numpy lstsq / eigh
@@ -32,6 +33,15 @@ def golden_functors():
     for i in range(len(r)):
         r[i], J[i] = twin.residual_and_jacobian(int(c["type"][i]), c["consts"][i], bool(c["normalize"][i]), c["poses"][c["ref"][i]], c["poses"][c["nei"][i]])
     np.savez_compressed(os.path.join(OUT, "functors.npz"), residual=r, jacobian=J, **c)
+
+
+def golden_functors_f6():
+    c = cases.random_blocks_f6(20260926, 120)
+    r = np.zeros(len(c["type"]))
+    J = np.zeros((len(c["type"]), 12))
+    for i in range(len(r)):
+        r[i], J[i] = twin.residual_and_jacobian(int(c["type"][i]), c["consts"][i], bool(c["normalize"][i]), c["poses"][c["ref"][i]], c["poses"][c["nei"][i]])
+    np.savez_compressed(os.path.join(OUT, "functors_f6.npz"), residual=r, jacobian=J, **c)
 
 
 def golden_rotations():
@@ -90,6 +100,6 @@ def golden_atan2():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_rotations(); golden_assoc(); golden_atan2()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

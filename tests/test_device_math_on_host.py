@@ -5,6 +5,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import pytest
 
 import cases
 
@@ -20,8 +21,9 @@ def _eval(h, c, loss):
     return r, J, cost
 
 
-def test_analytic_jacobian_matches_jet_oracle(oracle, harness):
-    c = cases.random_blocks(1, 6000)
+@pytest.mark.parametrize("gen", [cases.random_blocks, cases.random_blocks_f6])
+def test_analytic_jacobian_matches_jet_oracle(oracle, harness, gen):
+    c = gen(1, 6000)
     b = oracle.Blocks(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"])
     for loss in (0, 1):
         r, J, cost = b.evaluate(c["poses"], apply_loss=bool(loss))
@@ -35,11 +37,12 @@ def test_zero_rows_and_golden_functors(harness):
     c = cases.on_plane_blocks()
     r, J, _ = _eval(harness, c, 0)
     assert np.all(r == 0) and np.all(J == 0)
-    g = dict(np.load(os.path.join(G, "functors.npz")))
-    g["nb"] = int(g["nb"])
-    r, J, _ = _eval(harness, g, 0)
-    assert np.abs(r - g["residual"]).max() < 1e-8
-    assert (np.abs(J - g["jacobian"]) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1, keepdims=True))).max() < 1e-7
+    for name in ("functors.npz", "functors_f6.npz"):
+        g = dict(np.load(os.path.join(G, name)))
+        g["nb"] = int(g["nb"])
+        r, J, _ = _eval(harness, g, 0)
+        assert np.abs(r - g["residual"]).max() < 1e-8
+        assert (np.abs(J - g["jacobian"]) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1, keepdims=True))).max() < 1e-7
 
 
 def test_grid_knn_and_association_equal_oracle(oracle, harness):

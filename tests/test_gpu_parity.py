@@ -19,8 +19,9 @@ def _rel(a, b, floor):
 
 
 # ---------------------------------------------------------------- A. correspondence-list mode (K3 + K4)
-def test_blocks_rows_match_oracle(gpu_ctx, oracle):
-    c = cases.random_blocks(1, 20000)
+@pytest.mark.parametrize("gen", [cases.random_blocks, cases.random_blocks_f6])
+def test_blocks_rows_match_oracle(gpu_ctx, oracle, gen):
+    c = gen(1, 20000)
     b = oracle.Blocks(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"])
     r, J, cost = b.evaluate(c["poses"], apply_loss=True)
     gpu_ctx.blocks_set(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"], c["nb"])
@@ -37,12 +38,13 @@ def test_blocks_rows_match_oracle(gpu_ctx, oracle):
 
 
 def test_blocks_golden_functors_and_zero_rows(gpu_ctx):
-    g = np.load(os.path.join(G, "functors.npz"))
-    gpu_ctx.blocks_set(g["type"], g["ref"], g["nei"], g["consts"], 0.0, g["normalize"], int(g["nb"]))
-    gpu_ctx.blocks_evaluate(g["poses"], True, False)
-    r, J = gpu_ctx.blocks_rows()
-    assert _rel(r, g["residual"], 1e-9).max() < RES_RTOL
-    assert (np.abs(J - g["jacobian"]).max(1) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1))).max() < JAC_RTOL
+    for name in ("functors.npz", "functors_f6.npz"):
+        g = np.load(os.path.join(G, name))
+        gpu_ctx.blocks_set(g["type"], g["ref"], g["nei"], g["consts"], 0.0, g["normalize"], int(g["nb"]))
+        gpu_ctx.blocks_evaluate(g["poses"], True, False)
+        r, J = gpu_ctx.blocks_rows()
+        assert _rel(r, g["residual"], 1e-9).max() < RES_RTOL
+        assert (np.abs(J - g["jacobian"]).max(1) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1))).max() < JAC_RTOL
     c = cases.on_plane_blocks()
     gpu_ctx.blocks_set(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"], c["nb"])
     gpu_ctx.blocks_evaluate(c["poses"], True, True)

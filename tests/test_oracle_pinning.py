@@ -23,8 +23,9 @@ def test_rotation_helpers_match_scipy_golden(oracle):
         assert np.abs(oracle.aa_rotate(aa, p) - R @ p).max() < 5e-15
 
 
-def test_functors_match_autograd_twin_golden(oracle):
-    g = np.load(os.path.join(G, "functors.npz"))
+@pytest.mark.parametrize("name", ["functors.npz", "functors_f6.npz"])
+def test_functors_match_autograd_twin_golden(oracle, name):
+    g = np.load(os.path.join(G, name))
     b = oracle.Blocks(g["type"], g["ref"], g["nei"], g["consts"], g["huber"], g["normalize"])
     r, J, _ = b.evaluate(g["poses"], apply_loss=False)
     assert np.abs(r - g["residual"]).max() < 1e-12

@@ -99,6 +99,30 @@ def residual(btype, c, normalize, aa_r, t_r, aa_n, t_n):
         if ang.item() < c[10].item():
             return ang * 0.0
         return c[11] * (ang - c[10])
+    if btype == 6:      # Plane2Plane_Relative: one relative pose (the ref block), degrees
+        R = exp_so3(aa_r)
+        A, B = R @ c[3:6] + t_r, R @ c[6:9] + t_r
+        return c[9] * plane_angle(c[0:3], torch.linalg.cross(A, B)) * 180.0 / math.pi
+    if btype == 7:      # PlaneRelativeIOUResidual
+        M = exp_so3(aa_r) @ c[4:7] + t_r
+        n, d = c[0:3], c[3]
+        dis = ((n * M).sum() + d).abs()
+        Pp = M - dis * n
+        if abs(((n * Pp).sum() + d).item()) > 1e-4:
+            Pp = M + dis * n
+        ang = vector_angle(Pp, c[7:10])
+        if ang.item() < c[10].item():
+            return ang * 0.0
+        return c[11] * (ang - c[10])
+    if btype == 8:      # Line2Line_Angle: rotations only, unit directions, no norm division
+        dr = exp_so3(aa_r) @ (exp_so3(aa_n).T @ c[3:6])
+        cs = (dr * c[0:3]).sum().abs()
+        if cs.item() >= 1.0:
+            return cs * 0.0
+        ang = torch.acos(cs)
+        if ang.item() < 1e-3:
+            return ang * 0.0
+        return ang
     raise ValueError(btype)
 
 
