@@ -183,6 +183,32 @@ typedef struct {
 int pvb_line2line_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, double dist_threshold,
                             int* n_out, int* nei_line, int* ref_line, double* point_a3, double* point_b3);
 
+/* ---- segment-based variants of the corner association (LidarFeatureAssociate.cpp:238-440; `point_to_line_residual` paths) ---- */
+/* pcl::KdTreeFLANN::nearestKSearch(k = 5) of every neighbour corner point in the reference's cornerLessSharp cloud, both moved to the
+ * world frame (float32) with the given T_wl: idx5 = n_nei x 5 indices into ref_local (unordered), a row of -1 when the 5th neighbour
+ * is beyond dist_threshold (:261, :416) or the reference cloud has fewer than 5 points.  cell_size <= 0: chosen from the cloud.     */
+int pvb_pair_knn5(pvb_ctx* ctx, const float* ref_local, int n_ref, const double* R_ref, const double* t_ref, const float* nei_local, int n_nei,
+                  const double* R_nei, const double* t_nei, float dist_threshold, double cell_size, int* idx5);
+/* arg-min / min over the infinite lines (point + direction, world) of PointToLineDistance3D for every point (world float32, n x 4);
+ * the first minimum wins (:335-341); line = -1 when there are no lines                                                             */
+int pvb_nearest_line(pvb_ctx* ctx, const double* lines_world6, int n_lines, const float* points_world, int n_points, int* line, double* dist);
+/* AssociatePoint2LineSegmentKNN (:238-317): a query whose 5 neighbours all belong to one reference segment is associated with that
+ * segment's line; outputs per association: query index in nei.cornerLessSharp, reference segment, the query in the neighbour's sensor
+ * frame and the synthetic line points c +- 0.1 d in the reference sensor frame.  The *_tail forms take the k-NN result as input.     */
+int pvb_point2line_segment_knn_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, float dist_threshold, long cap, long* n_out,
+                                         int* query, int* ref_line, double* point3, double* a3, double* b3);
+int pvb_point2line_segment_knn_tail(const pvb_line_frame* ref, const pvb_line_frame* nei, const int* idx5, long cap, long* n_out, int* query, int* ref_line,
+                                    double* point3, double* a3, double* b3);
+/* AssociatePoint2LineSegment (:319-383): nearest reference line, accepted within dist_threshold                                     */
+int pvb_point2line_segment_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, float dist_threshold, long cap, long* n_out,
+                                     int* query, int* ref_line, double* point3, double* a3, double* b3);
+/* AssociateLine2LineKNN (:385-440): votes from segments holding >= 3 of a point's 5 neighbours, then FindAssociations (:120-197);
+ * outputs as pvb_line2line_associate                                                                                                */
+int pvb_line2line_knn_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, float dist_threshold, int* n_out, int* nei_line,
+                                int* ref_line, double* point_a3, double* point_b3);
+int pvb_line2line_knn_tail(const pvb_line_frame* ref, const pvb_line_frame* nei, const int* idx5, int* n_out, int* nei_line, int* ref_line, double* point_a3,
+                           double* point_b3);
+
 /* CameraLidarLineAssociate::AssociateByAngle (joint_optimization/CameraLidarLineAssociate.cpp:340-475) followed by
  * Filter(false, filter_by_length) (:628-715): per (image line, LiDAR segment) vote counts on the device, acceptance tests,
  * projected-length filter and the transform back to the LiDAR frame on the host.  Outputs sized for cap pairs.        */

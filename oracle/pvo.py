@@ -203,6 +203,34 @@ def associate_p2line(ref_world, R_ref, t_ref, nei_world, R_nei, t_nei, dist_thr,
     return q[:m].copy(), pt[:m].copy(), a[:m].copy(), b[:m].copy()
 
 
+def associate_p2line_segment_knn(ref_world, ref_p2s_off, ref_p2s_ids, ref_coeffs_local, nei_world, R_nei, t_nei, dist_thr, use_kdtree=True):
+    ref_world, nei_world = _f32(ref_world).reshape(-1, 4), _f32(nei_world).reshape(-1, 4)
+    cap = max(1, len(nei_world) * 4)
+    q, ln, pt, a, b = np.empty(cap, dtype=np.int32), np.empty(cap, dtype=np.int32), np.empty((cap, 3)), np.empty((cap, 3)), np.empty((cap, 3))
+    m = lib().pvo_associate_p2line_segment_knn(_p(ref_world), C.c_int(len(ref_world)), _p(_i32(ref_p2s_off)), _p(_i32(ref_p2s_ids)), _p(_f64(ref_coeffs_local)),
+                                               _p(nei_world), C.c_int(len(nei_world)), _p(_f64(R_nei)), _p(_f64(t_nei)), C.c_float(dist_thr), C.c_int(int(use_kdtree)),
+                                               _p(q), _p(ln), _p(pt), _p(a), _p(b))
+    return q[:m].copy(), ln[:m].copy(), pt[:m].copy(), a[:m].copy(), b[:m].copy()
+
+
+def associate_p2line_segment(ref_lines_world, ref_coeffs_local, nei_world, R_nei, t_nei, dist_thr):
+    nei_world = _f32(nei_world).reshape(-1, 4)
+    lw = _f64(ref_lines_world).reshape(-1, 6)
+    cap = max(1, len(nei_world))
+    q, ln, pt, a, b = np.empty(cap, dtype=np.int32), np.empty(cap, dtype=np.int32), np.empty((cap, 3)), np.empty((cap, 3)), np.empty((cap, 3))
+    m = lib().pvo_associate_p2line_segment(_p(lw), _p(_f64(ref_coeffs_local)), C.c_int(len(lw)), _p(nei_world), C.c_int(len(nei_world)), _p(_f64(R_nei)), _p(_f64(t_nei)),
+                                           C.c_float(dist_thr), _p(q), _p(ln), _p(pt), _p(a), _p(b))
+    return q[:m].copy(), ln[:m].copy(), pt[:m].copy(), a[:m].copy(), b[:m].copy()
+
+
+def line2line_knn_votes(ref_world, ref_p2s_off, ref_p2s_ids, S_ref, nei_world, nei_p2s_off, nei_p2s_ids, S_nei, dist_thr, use_kdtree=True):
+    ref_world, nei_world = _f32(ref_world).reshape(-1, 4), _f32(nei_world).reshape(-1, 4)
+    M = np.zeros((S_nei, S_ref), dtype=np.int32)
+    lib().pvo_line2line_knn_votes(_p(ref_world), C.c_int(len(ref_world)), _p(_i32(ref_p2s_off)), _p(_i32(ref_p2s_ids)), C.c_int(S_ref), _p(nei_world), C.c_int(len(nei_world)),
+                                  _p(_i32(nei_p2s_off)), _p(_i32(nei_p2s_ids)), C.c_int(S_nei), C.c_float(dist_thr), C.c_int(int(use_kdtree)), _p(M))
+    return M
+
+
 def transform_lines(R, t, lines):
     lines = _f64(lines).reshape(-1, 6)
     out = np.empty_like(lines)

@@ -10,6 +10,7 @@
 // float32 squared L2 (accumulated x,y,z in float), ascending; ties here are broken by lower index
 // (FLANN's tie order is implementation-defined).
 #pragma once
+#include <limits>
 #include <map>
 #include <numeric>
 #include <set>
@@ -245,6 +246,82 @@ inline void FindAssociations(const double* ref_coeffs_local, const double* ref_l
     }
   }
   for (auto& kv : m) out.push_back(kv.second);
+}
+
+// ---- segment-based variants (LidarFeatureAssociate.cpp:238-440; off in the shipped configs) ---------------------
+struct P2SegAssoc { int query_idx, ref_line; double point[3], a[3], b[3]; };
+
+// per query: number of its 5 nearest reference corner points that belong to each segment (std::map<size_t,size_t> seg_count, :264-270)
+inline bool SegmentCounts(const KdTree* tree, const float* ref_world, int n_ref, const int* ref_p2s_off, const int* ref_p2s_ids,
+                          const float* q, float sq_thr, KnnResult& res, std::map<int, int>& seg_count) {
+  const int k = 5;
+  if (tree) tree->Knn(q, k, res); else KnnBrute(ref_world, n_ref, 4, q, k, res);
+  if ((int)res.idx.size() < k) return false;                   // quirk C.6 guard
+  if (res.d2[k - 1] > sq_thr) return false;                    // :261, :416
+  seg_count.clear();
+  for (int j = 0; j < k; ++j) for (int e = ref_p2s_off[res.idx[j]]; e < ref_p2s_off[res.idx[j] + 1]; ++e) seg_count[ref_p2s_ids[e]]++;
+  return true;
+}
+
+// AssociatePoint2LineSegmentKNN (:238-317): all 5 neighbours on one segment => point-to-line with that segment's coefficients
+inline void AssociatePoint2LineSegmentKNN(const float* ref_world, int n_ref, const int* ref_p2s_off, const int* ref_p2s_ids, const double* ref_coeffs_local,
+                                          const float* nei_world, int n_nei, const double R_nei[9], const double t_nei[3], float dist_threshold,
+                                          bool use_kdtree, std::vector<P2SegAssoc>& out) {
+  const float sq_thr = dist_threshold * dist_threshold;
+  KdTree tree;
+  if (use_kdtree) tree.Build(ref_world, n_ref, 4);
+  KnnResult res; std::map<int, int> cnt;
+  for (int idx = 0; idx < n_nei; ++idx) {
+    const float* q = nei_world + (size_t)idx * 4;
+    if (!SegmentCounts(use_kdtree ? &tree : nullptr, ref_world, n_ref, ref_p2s_off, ref_p2s_ids, q, sq_thr, res, cnt)) continue;
+    for (auto& kv : cnt) {
+      if (kv.second < 5 - 0) continue;                         // :276
+      const double* cl = ref_coeffs_local + 6 * kv.first;
+      P2SegAssoc a; a.query_idx = idx; a.ref_line = kv.first;
+      for (int c = 0; c < 3; ++c) { a.a[c] = 0.1 * cl[3 + c] + cl[c]; a.b[c] = -0.1 * cl[3 + c] + cl[c]; }   // :283-284
+      const double qw[3] = {q[0], q[1], q[2]};
+      World2Local(R_nei, t_nei, qw, a.point);                  // :286
+      out.push_back(a);
+    }
+  }
+}
+
+// AssociatePoint2LineSegment (:319-383): nearest infinite reference line (world), accepted when within dist_threshold
+inline void AssociatePoint2LineSegment(const double* ref_lines_world, const double* ref_coeffs_local, int S_ref, const float* nei_world, int n_nei,
+                                       const double R_nei[9], const double t_nei[3], float dist_threshold, std::vector<P2SegAssoc>& out) {
+  for (int idx = 0; idx < n_nei; ++idx) {
+    const double p[3] = {nei_world[(size_t)idx * 4], nei_world[(size_t)idx * 4 + 1], nei_world[(size_t)idx * 4 + 2]};
+    double min_distance = std::numeric_limits<double>::max();
+    int valid = -1;
+    for (int s = 0; s < S_ref; ++s) {
+      const double d = PointToLineDistance3D(p, ref_lines_world + 6 * s);
+      if (d < min_distance) { min_distance = d; valid = s; }
+    }
+    if (!(min_distance <= dist_threshold)) continue;           // :343 (float threshold promoted)
+    const double* cl = ref_coeffs_local + 6 * valid;
+    P2SegAssoc a; a.query_idx = idx; a.ref_line = valid;
+    for (int c = 0; c < 3; ++c) { a.a[c] = 0.1 * cl[3 + c] + cl[c]; a.b[c] = -0.1 * cl[3 + c] + cl[c]; }
+    World2Local(R_nei, t_nei, p, a.point);
+    out.push_back(a);
+  }
+}
+
+// AssociateLine2LineKNN vote matrix (:401-436): >= 3 of the 5 neighbours on a segment => one vote per segment of the query point
+inline void Line2LineKnnVotes(const float* ref_world, int n_ref, const int* ref_p2s_off, const int* ref_p2s_ids, int S_ref,
+                              const float* nei_world, int n_nei, const int* nei_p2s_off, const int* nei_p2s_ids, int S_nei, float dist_threshold,
+                              bool use_kdtree, std::vector<int>& M) {
+  M.assign((size_t)S_nei * S_ref, 0);
+  const float sq_thr = dist_threshold * dist_threshold;
+  KdTree tree;
+  if (use_kdtree) tree.Build(ref_world, n_ref, 4);
+  KnnResult res; std::map<int, int> cnt;
+  for (int idx = 0; idx < n_nei; ++idx) {
+    if (!SegmentCounts(use_kdtree ? &tree : nullptr, ref_world, n_ref, ref_p2s_off, ref_p2s_ids, nei_world + (size_t)idx * 4, sq_thr, res, cnt)) continue;
+    for (auto& kv : cnt) {
+      if (kv.second < 5 - 2) continue;                         // :428
+      for (int e = nei_p2s_off[idx]; e < nei_p2s_off[idx + 1]; ++e) M[(size_t)nei_p2s_ids[e] * S_ref + kv.first] += 1;   // :432-433
+    }
+  }
 }
 
 // ---- Equirectangular (sensors/Equirectangular.h) ------------------------------------------------

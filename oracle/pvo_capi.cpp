@@ -130,6 +130,30 @@ int pvo_find_associations(const double* ref_coeffs_local, const double* ref_line
   return (int)v.size();
 }
 
+int pvo_associate_p2line_segment_knn(const float* ref_world, int n_ref, const int* ref_p2s_off, const int* ref_p2s_ids, const double* ref_coeffs_local,
+                                     const float* nei_world, int n_nei, const double* R_nei, const double* t_nei, float dist_threshold, int use_kdtree,
+                                     int* out_query, int* out_line, double* out_point, double* out_a, double* out_b) {
+  std::vector<P2SegAssoc> v;
+  AssociatePoint2LineSegmentKNN(ref_world, n_ref, ref_p2s_off, ref_p2s_ids, ref_coeffs_local, nei_world, n_nei, R_nei, t_nei, dist_threshold, use_kdtree != 0, v);
+  for (size_t i = 0; i < v.size(); ++i) { out_query[i] = v[i].query_idx; out_line[i] = v[i].ref_line; std::memcpy(out_point + 3 * i, v[i].point, 24); std::memcpy(out_a + 3 * i, v[i].a, 24); std::memcpy(out_b + 3 * i, v[i].b, 24); }
+  return (int)v.size();
+}
+
+int pvo_associate_p2line_segment(const double* ref_lines_world, const double* ref_coeffs_local, int S_ref, const float* nei_world, int n_nei,
+                                 const double* R_nei, const double* t_nei, float dist_threshold, int* out_query, int* out_line, double* out_point, double* out_a, double* out_b) {
+  std::vector<P2SegAssoc> v;
+  AssociatePoint2LineSegment(ref_lines_world, ref_coeffs_local, S_ref, nei_world, n_nei, R_nei, t_nei, dist_threshold, v);
+  for (size_t i = 0; i < v.size(); ++i) { out_query[i] = v[i].query_idx; out_line[i] = v[i].ref_line; std::memcpy(out_point + 3 * i, v[i].point, 24); std::memcpy(out_a + 3 * i, v[i].a, 24); std::memcpy(out_b + 3 * i, v[i].b, 24); }
+  return (int)v.size();
+}
+
+void pvo_line2line_knn_votes(const float* ref_world, int n_ref, const int* ref_p2s_off, const int* ref_p2s_ids, int S_ref, const float* nei_world, int n_nei,
+                             const int* nei_p2s_off, const int* nei_p2s_ids, int S_nei, float dist_threshold, int use_kdtree, int* M) {
+  std::vector<int> m;
+  Line2LineKnnVotes(ref_world, n_ref, ref_p2s_off, ref_p2s_ids, S_ref, nei_world, n_nei, nei_p2s_off, nei_p2s_ids, S_nei, dist_threshold, use_kdtree != 0, m);
+  std::copy(m.begin(), m.end(), M);
+}
+
 void pvo_angle_votes(int rows, int cols, const float* lines, int L, const float* cloud_local, int P, const int* p2s_off, const int* p2s_ids, int S,
                      const double* T_cl, int* counts) {
   std::vector<int> c; AngleVotes(Equirect{rows, cols}, lines, L, cloud_local, P, p2s_off, p2s_ids, S, T_cl, c);

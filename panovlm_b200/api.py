@@ -105,6 +105,8 @@ EXPORTS = [
     "pvb_dense_get_rows", "pvb_debug_counters", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
     "pvb_find_neighbors", "pvb_line2line_associate", "pvb_camera_lidar_associate", "pvb_build_point2plane_blocks", "pvb_build_point2line_blocks", "pvb_build_line2line_blocks",
     "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
+    "pvb_pair_knn5", "pvb_nearest_line", "pvb_point2line_segment_knn_associate", "pvb_point2line_segment_knn_tail", "pvb_point2line_segment_associate",
+    "pvb_line2line_knn_associate", "pvb_line2line_knn_tail",
 ]
 
 
@@ -342,6 +344,61 @@ class Context:
         S = max(1, nei.c.n_segments)
         nl, rl, a, b, n = np.zeros(S, np.int32), np.zeros(S, np.int32), np.zeros((S, 3)), np.zeros((S, 3)), C.c_int()
         self._ck(self._L.pvb_line2line_associate(self._h, C.byref(ref.c), C.byref(nei.c), C.c_double(dist_threshold), C.byref(n), _p(nl), _p(rl), _p(a), _p(b)))
+        m = n.value
+        return nl[:m].copy(), rl[:m].copy(), a[:m].copy(), b[:m].copy()
+
+    def pair_knn5(self, ref_local, R_ref, t_ref, nei_local, R_nei, t_nei, dist_threshold, cell_size=0.0):
+        r, q = _arr(ref_local, np.float32).reshape(-1, 4), _arr(nei_local, np.float32).reshape(-1, 4)
+        idx = np.full((len(q), 5), -1, np.int32)
+        self._ck(self._L.pvb_pair_knn5(self._h, _p(r), C.c_int(len(r)), _p(_arr(R_ref, np.float64)), _p(_arr(t_ref, np.float64)), _p(q), C.c_int(len(q)),
+                                       _p(_arr(R_nei, np.float64)), _p(_arr(t_nei, np.float64)), C.c_float(dist_threshold), C.c_double(cell_size), _p(idx)))
+        return idx
+
+    def nearest_line(self, lines_world, points_world):
+        lw, pw = _arr(lines_world, np.float64).reshape(-1, 6), _arr(points_world, np.float32).reshape(-1, 4)
+        line, dist = np.full(len(pw), -1, np.int32), np.zeros(len(pw))
+        self._ck(self._L.pvb_nearest_line(self._h, _p(lw), C.c_int(len(lw)), _p(pw), C.c_int(len(pw)), _p(line), _p(dist)))
+        return line, dist
+
+    def _segment_assoc(self, fn, ref, nei, dist_threshold):
+        cap = max(1, nei.c.n_corner * 4)
+        q, ln, pt, a, b, n = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros((cap, 3)), C.c_long()
+        self._ck(fn(self._h, C.byref(ref.c), C.byref(nei.c), C.c_float(dist_threshold), C.c_long(cap), C.byref(n), _p(q), _p(ln), _p(pt), _p(a), _p(b)))
+        m = n.value
+        return q[:m].copy(), ln[:m].copy(), pt[:m].copy(), a[:m].copy(), b[:m].copy()
+
+    def point2line_segment_knn_associate(self, ref, nei, dist_threshold):
+        return self._segment_assoc(self._L.pvb_point2line_segment_knn_associate, ref, nei, dist_threshold)
+
+    def point2line_segment_associate(self, ref, nei, dist_threshold):
+        return self._segment_assoc(self._L.pvb_point2line_segment_associate, ref, nei, dist_threshold)
+
+    def line2line_knn_associate(self, ref, nei, dist_threshold):
+        S = max(1, nei.c.n_segments)
+        nl, rl, a, b, n = np.zeros(S, np.int32), np.zeros(S, np.int32), np.zeros((S, 3)), np.zeros((S, 3)), C.c_int()
+        self._ck(self._L.pvb_line2line_knn_associate(self._h, C.byref(ref.c), C.byref(nei.c), C.c_float(dist_threshold), C.byref(n), _p(nl), _p(rl), _p(a), _p(b)))
+        m = n.value
+        return nl[:m].copy(), rl[:m].copy(), a[:m].copy(), b[:m].copy()
+
+    @staticmethod
+    def point2line_segment_knn_tail(ref, nei, idx5):
+        idx = _arr(idx5, np.int32).reshape(-1, 5)
+        cap = max(1, len(idx) * 4)
+        q, ln, pt, a, b, n = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros((cap, 3)), C.c_long()
+        rc = load_library().pvb_point2line_segment_knn_tail(C.byref(ref.c), C.byref(nei.c), _p(idx), C.c_long(cap), C.byref(n), _p(q), _p(ln), _p(pt), _p(a), _p(b))
+        if rc:
+            raise PvbError(f"pvb_point2line_segment_knn_tail: code {rc}")
+        m = n.value
+        return q[:m].copy(), ln[:m].copy(), pt[:m].copy(), a[:m].copy(), b[:m].copy()
+
+    @staticmethod
+    def line2line_knn_tail(ref, nei, idx5):
+        idx = _arr(idx5, np.int32).reshape(-1, 5)
+        S = max(1, nei.c.n_segments)
+        nl, rl, a, b, n = np.zeros(S, np.int32), np.zeros(S, np.int32), np.zeros((S, 3)), np.zeros((S, 3)), C.c_int()
+        rc = load_library().pvb_line2line_knn_tail(C.byref(ref.c), C.byref(nei.c), _p(idx), C.byref(n), _p(nl), _p(rl), _p(a), _p(b))
+        if rc:
+            raise PvbError(f"pvb_line2line_knn_tail: code {rc}")
         m = n.value
         return nl[:m].copy(), rl[:m].copy(), a[:m].copy(), b[:m].copy()
 

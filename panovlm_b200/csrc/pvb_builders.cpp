@@ -107,6 +107,60 @@ inline bool push_block(BlockOut& o, int type, int ref, int nei, int normalize, d
   return true;
 }
 
+// FindAssociations (:120-197) on a vote matrix; shared by AssociateLine2Line and AssociateLine2LineKNN.
+int find_associations(const pvb_line_frame* ref, const pvb_line_frame* nei, const std::vector<int>& M, int* n_out, int* nei_line, int* ref_line,
+                             double* point_a3, double* point_b3) {
+  const int Sr = ref->n_segments, Sn = nei->n_segments;
+  std::vector<double> ref_w((size_t)Sr * 6), nei_w((size_t)Sn * 6);
+  for (int s = 0; s < Sr; ++s) transform_line(ref->R_wl, ref->t_wl, ref->segment_coeffs + 6 * s, &ref_w[6 * s]);
+  for (int s = 0; s < Sn; ++s) transform_line(nei->R_wl, nei->t_wl, nei->segment_coeffs + 6 * s, &nei_w[6 * s]);
+  std::vector<int> seg_size(Sn, 0);                                            // edge_segmented[s].size()
+  for (int i = 0; i < nei->n_corner; ++i) for (int e = nei->p2s_off[i]; e < nei->p2s_off[i + 1]; ++e) seg_size[nei->p2s_ids[e]]++;
+  struct A { int nl, rl; double a[3], b[3]; };
+  std::map<int, A> assoc;                                                      // eigen_map<int, Line2Line> keyed by the reference line
+  for (int s = 0; s < Sn; ++s) {
+    int max_col = 0, max_count = M[(size_t)s * Sr];
+    for (int c = 1; c < Sr; ++c) if (M[(size_t)s * Sr + c] > max_count) { max_count = M[(size_t)s * Sr + c]; max_col = c; }
+    if ((size_t)max_count < (size_t)seg_size[s] / 2) continue;                 // :132
+    if (plane_angle(&ref_w[6 * max_col + 3], &nei_w[6 * s + 3]) * 180.0 / M_PI > 7) continue;   // :138
+    const double* cl = ref->segment_coeffs + 6 * max_col;
+    A a; a.nl = s; a.rl = max_col;
+    for (int k = 0; k < 3; ++k) { a.a[k] = 0.1 * cl[3 + k] + cl[k]; a.b[k] = -0.1 * cl[3 + k] + cl[k]; }   // :144-145
+    auto it = assoc.find(max_col);
+    if (it == assoc.end()) assoc.insert({max_col, a});
+    else {
+      const double d1 = point_to_line(&nei_w[6 * it->second.nl], &ref_w[6 * max_col]);
+      const double d2 = point_to_line(&nei_w[6 * s], &ref_w[6 * max_col]);
+      if (d2 < d1) it->second = a;
+    }
+  }
+  int n = 0;
+  for (auto& kv : assoc) {
+    nei_line[n] = kv.second.nl; ref_line[n] = kv.second.rl;
+    std::memcpy(point_a3 + 3 * n, kv.second.a, 24); std::memcpy(point_b3 + 3 * n, kv.second.b, 24);
+    ++n;
+  }
+  *n_out = n;
+  return PVB_OK;
+}
+
+// std::map<size_t,size_t> seg_count of one query (:264-270, :419-425): ascending segment id, count of its 5 neighbours on it
+void segment_counts(const pvb_line_frame* ref, const int* nn5, std::map<int, int>& cnt) {
+  cnt.clear();
+  for (int j = 0; j < 5; ++j) for (int e = ref->p2s_off[nn5[j]]; e < ref->p2s_off[nn5[j] + 1]; ++e) cnt[ref->p2s_ids[e]]++;
+}
+
+void push_segment_assoc(const pvb_line_frame* ref, const pvb_line_frame* nei, int q, int seg, long at, int* query, int* ref_line, double* point3, double* a3, double* b3) {
+  const double* cl = ref->segment_coeffs + 6 * seg;
+  for (int k = 0; k < 3; ++k) { a3[3 * at + k] = 0.1 * cl[3 + k] + cl[k]; b3[3 * at + k] = -0.1 * cl[3 + k] + cl[k]; }   // :283-284, :349-350
+  float wx, wy, wz;                                                            // the neighbour's world cloud is float32 (Transform2LidarWorld)
+  const float* pl = nei->corner_local + 4 * (size_t)q;
+  transform_point_f32(nei->R_wl, nei->t_wl, pl[0], pl[1], pl[2], wx, wy, wz);
+  const double pw[3] = {(double)wx, (double)wy, (double)wz};
+  world2local(nei->R_wl, nei->t_wl, pw, point3 + 3 * at);                      // :286, :351
+  query[at] = q; ref_line[at] = seg;
+}
+
 }  // namespace
 
 extern "C" {
@@ -163,39 +217,99 @@ int pvb_line2line_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_l
   *n_out = 0;
   const int Sr = ref->n_segments, Sn = nei->n_segments;
   if (Sr == 0 || Sn == 0) return PVB_OK;                                       // CheckLidarSegment (:208-216)
-  std::vector<double> ref_w((size_t)Sr * 6), nei_w((size_t)Sn * 6);
+  std::vector<double> ref_w((size_t)Sr * 6);
   for (int s = 0; s < Sr; ++s) transform_line(ref->R_wl, ref->t_wl, ref->segment_coeffs + 6 * s, &ref_w[6 * s]);
-  for (int s = 0; s < Sn; ++s) transform_line(nei->R_wl, nei->t_wl, nei->segment_coeffs + 6 * s, &nei_w[6 * s]);
   std::vector<float> world((size_t)std::max(1, nei->n_corner) * 4);
   int rc = pvb_transform_cloud(ctx, nei->corner_local, nei->n_corner, nei->R_wl, nei->t_wl, world.data());
   if (rc) return rc;
   std::vector<int> M((size_t)Sn * Sr, 0);
   rc = pvb_line_votes(ctx, ref_w.data(), Sr, world.data(), nei->n_corner, nei->p2s_off, nei->p2s_ids, Sn, dist_threshold, M.data());
   if (rc) return rc;
-  std::vector<int> seg_size(Sn, 0);                                            // edge_segmented[s].size()
-  for (int i = 0; i < nei->n_corner; ++i) for (int e = nei->p2s_off[i]; e < nei->p2s_off[i + 1]; ++e) seg_size[nei->p2s_ids[e]]++;
-  struct A { int nl, rl; double a[3], b[3]; };
-  std::map<int, A> assoc;                                                      // eigen_map<int, Line2Line> keyed by the reference line
-  for (int s = 0; s < Sn; ++s) {
-    int max_col = 0, max_count = M[(size_t)s * Sr];
-    for (int c = 1; c < Sr; ++c) if (M[(size_t)s * Sr + c] > max_count) { max_count = M[(size_t)s * Sr + c]; max_col = c; }
-    if ((size_t)max_count < (size_t)seg_size[s] / 2) continue;                 // :132
-    if (plane_angle(&ref_w[6 * max_col + 3], &nei_w[6 * s + 3]) * 180.0 / M_PI > 7) continue;   // :138
-    const double* cl = ref->segment_coeffs + 6 * max_col;
-    A a; a.nl = s; a.rl = max_col;
-    for (int k = 0; k < 3; ++k) { a.a[k] = 0.1 * cl[3 + k] + cl[k]; a.b[k] = -0.1 * cl[3 + k] + cl[k]; }   // :144-145
-    auto it = assoc.find(max_col);
-    if (it == assoc.end()) assoc.insert({max_col, a});
-    else {
-      const double d1 = point_to_line(&nei_w[6 * it->second.nl], &ref_w[6 * max_col]);
-      const double d2 = point_to_line(&nei_w[6 * s], &ref_w[6 * max_col]);
-      if (d2 < d1) it->second = a;
+  return find_associations(ref, nei, M, n_out, nei_line, ref_line, point_a3, point_b3);
+}
+
+// ---- segment-based variants (LidarFeatureAssociate.cpp:238-440): 5-NN / nearest line on the device, membership counting here ---------
+int pvb_point2line_segment_knn_tail(const pvb_line_frame* ref, const pvb_line_frame* nei, const int* idx5, long cap, long* n_out, int* query, int* ref_line,
+                                    double* point3, double* a3, double* b3) {
+  if (!ref || !nei || !n_out || (nei->n_corner > 0 && !idx5)) return PVB_ERR_ARG;
+  *n_out = 0;
+  if (ref->n_segments == 0 || nei->n_segments == 0) return PVB_OK;             // CheckLidarSegment (:243-247)
+  std::map<int, int> cnt;
+  long n = 0;
+  for (int q = 0; q < nei->n_corner; ++q) {
+    if (idx5[5 * (size_t)q] < 0) continue;                                     // :261
+    segment_counts(ref, idx5 + 5 * (size_t)q, cnt);
+    for (auto& kv : cnt) {
+      if (kv.second < 5) continue;                                             // :276 all five neighbours on the segment
+      if (n >= cap) return PVB_ERR_NOMEM;
+      push_segment_assoc(ref, nei, q, kv.first, n, query, ref_line, point3, a3, b3);
+      ++n;
     }
   }
-  int n = 0;
-  for (auto& kv : assoc) {
-    nei_line[n] = kv.second.nl; ref_line[n] = kv.second.rl;
-    std::memcpy(point_a3 + 3 * n, kv.second.a, 24); std::memcpy(point_b3 + 3 * n, kv.second.b, 24);
+  *n_out = n;
+  return PVB_OK;
+}
+
+int pvb_line2line_knn_tail(const pvb_line_frame* ref, const pvb_line_frame* nei, const int* idx5, int* n_out, int* nei_line, int* ref_line, double* point_a3,
+                           double* point_b3) {
+  if (!ref || !nei || !n_out || (nei->n_corner > 0 && !idx5)) return PVB_ERR_ARG;
+  *n_out = 0;
+  const int Sr = ref->n_segments, Sn = nei->n_segments;
+  if (Sr == 0 || Sn == 0) return PVB_OK;
+  std::vector<int> M((size_t)Sn * Sr, 0);
+  std::map<int, int> cnt;
+  for (int q = 0; q < nei->n_corner; ++q) {
+    if (idx5[5 * (size_t)q] < 0) continue;                                     // :416
+    segment_counts(ref, idx5 + 5 * (size_t)q, cnt);
+    for (auto& kv : cnt) {
+      if (kv.second < 3) continue;                                             // :428 k_search_size - 2
+      for (int e = nei->p2s_off[q]; e < nei->p2s_off[q + 1]; ++e) M[(size_t)nei->p2s_ids[e] * Sr + kv.first] += 1;   // :432-433
+    }
+  }
+  return find_associations(ref, nei, M, n_out, nei_line, ref_line, point_a3, point_b3);
+}
+
+int pvb_point2line_segment_knn_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, float dist_threshold, long cap, long* n_out, int* query,
+                                         int* ref_line, double* point3, double* a3, double* b3) {
+  if (!ctx || !ref || !nei || !n_out) return PVB_ERR_ARG;
+  *n_out = 0;
+  if (ref->n_segments == 0 || nei->n_segments == 0 || nei->n_corner == 0) return PVB_OK;
+  std::vector<int> idx((size_t)nei->n_corner * 5);
+  int rc = pvb_pair_knn5(ctx, ref->corner_local, ref->n_corner, ref->R_wl, ref->t_wl, nei->corner_local, nei->n_corner, nei->R_wl, nei->t_wl, dist_threshold, 0.0, idx.data());
+  if (rc) return rc;
+  return pvb_point2line_segment_knn_tail(ref, nei, idx.data(), cap, n_out, query, ref_line, point3, a3, b3);
+}
+
+int pvb_line2line_knn_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, float dist_threshold, int* n_out, int* nei_line, int* ref_line,
+                                double* point_a3, double* point_b3) {
+  if (!ctx || !ref || !nei || !n_out) return PVB_ERR_ARG;
+  *n_out = 0;
+  if (ref->n_segments == 0 || nei->n_segments == 0) return PVB_OK;
+  std::vector<int> idx((size_t)std::max(1, nei->n_corner) * 5);
+  int rc = pvb_pair_knn5(ctx, ref->corner_local, ref->n_corner, ref->R_wl, ref->t_wl, nei->corner_local, nei->n_corner, nei->R_wl, nei->t_wl, dist_threshold, 0.0, idx.data());
+  if (rc) return rc;
+  return pvb_line2line_knn_tail(ref, nei, idx.data(), n_out, nei_line, ref_line, point_a3, point_b3);
+}
+
+int pvb_point2line_segment_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, float dist_threshold, long cap, long* n_out, int* query,
+                                     int* ref_line, double* point3, double* a3, double* b3) {
+  if (!ctx || !ref || !nei || !n_out) return PVB_ERR_ARG;
+  *n_out = 0;
+  const int Sr = ref->n_segments;
+  if (Sr == 0 || nei->n_segments == 0 || nei->n_corner == 0) return PVB_OK;
+  std::vector<double> ref_w((size_t)Sr * 6);
+  for (int s = 0; s < Sr; ++s) transform_line(ref->R_wl, ref->t_wl, ref->segment_coeffs + 6 * s, &ref_w[6 * s]);
+  std::vector<float> world((size_t)nei->n_corner * 4);
+  int rc = pvb_transform_cloud(ctx, nei->corner_local, nei->n_corner, nei->R_wl, nei->t_wl, world.data());
+  if (rc) return rc;
+  std::vector<int> line(nei->n_corner); std::vector<double> dist(nei->n_corner);
+  rc = pvb_nearest_line(ctx, ref_w.data(), Sr, world.data(), nei->n_corner, line.data(), dist.data());
+  if (rc) return rc;
+  long n = 0;
+  for (int q = 0; q < nei->n_corner; ++q) {
+    if (!(dist[q] <= (double)dist_threshold)) continue;                        // :343
+    if (n >= cap) return PVB_ERR_NOMEM;
+    push_segment_assoc(ref, nei, q, line[q], n, query, ref_line, point3, a3, b3);
     ++n;
   }
   *n_out = n;

@@ -341,6 +341,7 @@ struct LineAssocArgs {
   const F4* q_local; const QueryTile* tiles; const Pair* pairs; const GridDesc* grids; const uint32_t* cell_start; const F4* sorted;
   const WorldPose* wpose; float sq_thr; double thr;
   unsigned char* out_valid; double* out_point; double* out_a; double* out_b;     // indexed by tile.out_base + lane
+  int* out_nn;                                                                   // when set: neighbour indices only (K per slot, -1 = rejected), no line fit
 };
 template <int K>
 __global__ void __launch_bounds__(kTile) k_associate_line(const LineAssocArgs a) {
@@ -366,6 +367,13 @@ __global__ void __launch_bounds__(kTile) k_associate_line(const LineAssocArgs a)
   auto set_win = [&](int j, uint32_t pos) { s_win[j][i] = pos; };
   auto range_set = [&](int k, uint32_t lo, uint32_t hi) { s_rng[2 * k][i] = lo; s_rng[2 * k + 1][i] = hi; };
   auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = s_rng[2 * k][i]; hi = s_rng[2 * k + 1][i]; };
+  if (a.out_nn) {
+    int idx[K];
+    const bool ok = knn_indices<K>(g, cells, load, a.sq_thr, (int)ceil(a.thr / g.h), qx, qy, qz, idx, win, set_win, range_set, range_get);
+#pragma unroll
+    for (int j = 0; j < K; ++j) a.out_nn[(size_t)slot * K + j] = ok ? idx[j] : -1;
+    return;
+  }
   double p_local[3], pa[3], pb[3];
   const bool valid = associate_point2line<K>(g, cells, load, a.sq_thr, (int)ceil(a.thr / g.h), qx, qy, qz, wr.R, wr.t, wn.R, wn.t, p_local, pa, pb, win, set_win,
                                              range_set, range_get);
@@ -525,6 +533,28 @@ __global__ void __launch_bounds__(128) k_line_votes(const double* __restrict__ r
     if (dist > thr) continue;
     for (int q = e0; q < e1; ++q) atomicAdd(M + (size_t)p2s_ids[q] * S_ref + s, 1);
   }
+}
+
+// ---- AssociatePoint2LineSegment (LidarFeatureAssociate.cpp:319-383): nearest infinite line per point, first minimum wins --------
+__global__ void __launch_bounds__(128) k_nearest_line(const double* __restrict__ ref_lines, int S_ref, const F4* __restrict__ pts, int n_pts,
+                                                      int* __restrict__ out_line, double* __restrict__ out_dist) {
+  extern __shared__ double s_lines[];
+  for (int k = threadIdx.x; k < S_ref * 6; k += blockDim.x) s_lines[k] = ref_lines[k];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const F4 p = ldg_f4(pts + i);
+  const double P[3] = {(double)p.x, (double)p.y, (double)p.z};
+  double best = DBL_MAX; int arg = -1;
+  for (int s = 0; s < S_ref; ++s) {
+    const double* l = s_lines + s * 6;   // PointToLineDistance3D (Geometry.hpp:198-211)
+    const double d0 = dsub(P[0], l[0]), d1 = dsub(P[1], l[1]), d2 = dsub(P[2], l[2]);
+    const double k = dadd(dadd(dmul(l[3], d0), dmul(l[4], d1)), dmul(l[5], d2)) / dadd(dadd(dmul(l[3], l[3]), dmul(l[4], l[4])), dmul(l[5], l[5]));
+    const double e[3] = {dsub(dadd(dmul(k, l[3]), l[0]), P[0]), dsub(dadd(dmul(k, l[4]), l[1]), P[1]), dsub(dadd(dmul(k, l[5]), l[2]), P[2])};
+    const double dist = sqrt(dadd(dadd(dmul(e[0], e[0]), dmul(e[1], e[1])), dmul(e[2], e[2])));
+    if (dist < best) { best = dist; arg = s; }
+  }
+  out_line[i] = arg; out_dist[i] = best;
 }
 
 // ---- K2c: camera-LiDAR AssociateByAngle vote counts ------------------------------------------------------------------------

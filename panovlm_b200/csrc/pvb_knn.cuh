@@ -325,4 +325,17 @@ PVB_HD bool associate_point2line(const GridDesc& g, const CellLoader& cells, con
   return true;
 }
 
+// nearestKSearch alone (the segment-based variants, LidarFeatureAssociate.cpp:238-317, 385-440, only need the neighbour set):
+// indices into the reference cloud of the K nearest points, or false when the K-th is beyond the threshold / the cloud is smaller than K.
+template <int K, typename CellLoader, typename PointLoader, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+PVB_HD bool knn_indices(const GridDesc& g, const CellLoader& cells, const PointLoader& load, float sq_thr, int rmax, float qx, float qy, float qz, int out_idx[K],
+                        const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get) {
+  int ring = 1;
+  const int found = knn_select<K>(g, cells, load, load, [](int, int, uint32_t&, uint32_t&) {}, qx, qy, qz, sq_thr, rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
+  if (found < K) return false;                                   // :261 / :416 + quirk C.6 guard
+#pragma unroll
+  for (int j = 0; j < K; ++j) out_idx[j] = (int)(f2u(load((long long)win(j)).w) >> 5);
+  return true;
+}
+
 }  // namespace pvb

@@ -81,6 +81,7 @@ struct pvb_ctx {
   // ---- frames mode
   CloudSet f_tgt, f_qry; TargetIndex f_index; int n_frames = 0;
   CloudSet f_corner; TargetIndex f_cindex; int n_corner_frames = 0;
+  CloudSet p_cs; TargetIndex p_index;                                  // pair-level k-NN (pvb_pair_knn5)
   DevBuf f_la, f_lb; PinBuf fh_la, fh_lb;
   std::vector<int> l_edge, l_query; std::vector<double> l_point, l_a, l_b;
   DevBuf f_pairs, f_qtiles, f_valid, f_point, f_plane, f_nn_idx, f_nn_d2;
@@ -932,6 +933,62 @@ int pvb_transform_cloud(pvb_ctx* ctx, const float* xyzi, long n, const double* R
   k_transform_simple<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->m_a.as<F4>(), n, w, ctx->m_b.as<F4>());
   CKL();
   CK(cudaMemcpyAsync(out, ctx->m_b.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+// ================================================================ pair-level 5-NN and nearest line (segment-based variants of A3)
+int pvb_pair_knn5(pvb_ctx* ctx, const float* ref_local, int n_ref, const double* R_ref, const double* t_ref, const float* nei_local, int n_nei, const double* R_nei,
+                  const double* t_nei, float dist_threshold, double cell_size, int* idx5) {
+  if (!ctx || n_ref < 0 || n_nei < 0 || (n_nei > 0 && (!nei_local || !idx5)) || (n_ref > 0 && !ref_local) || !R_ref || !t_ref || !R_nei || !t_nei)
+    return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_pair_knn5: bad arguments") : PVB_ERR_ARG;
+  if (n_nei == 0) return PVB_OK;
+  if (n_ref < 5) { for (long i = 0; i < (long)n_nei * 5; ++i) idx5[i] = -1; return PVB_OK; }   // nearestKSearch returns < 5 neighbours (quirk C.6 guard)
+  CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
+  int rc = set_cloudset(ctx, ctx->p_cs, {ref_local, nei_local}, {n_ref, n_nei}, {0, 1}, 256); if (rc) return rc;
+  // the two T_wl go to the device as given (no angle-axis round trip)
+  CK(ctx->h_pose.ensure(2 * sizeof(WorldPose))); CK(ctx->d_wpose.ensure(2 * sizeof(WorldPose)));
+  CK(cudaStreamSynchronize(ctx->stream));
+  WorldPose* hw = ctx->h_pose.as<WorldPose>();
+  for (int k = 0; k < 9; ++k) { hw[0].R[k] = R_ref[k]; hw[1].R[k] = R_nei[k]; }
+  for (int k = 0; k < 3; ++k) { hw[0].t[k] = t_ref[k]; hw[1].t[k] = t_nei[k]; }
+  CK(cudaMemcpyAsync(ctx->d_wpose.p, hw, 2 * sizeof(WorldPose), cudaMemcpyHostToDevice, ctx->stream));
+  rc = build_target_index(ctx, ctx->p_cs, ctx->p_index, cell_size); if (rc) return rc;
+  const Pair pair{0, 1, 0, 1};
+  std::vector<QueryTile> tiles;
+  for (int s0 = 0; s0 < n_nei; s0 += kTile) tiles.push_back(QueryTile{0, n_ref + s0, std::min(kTile, n_nei - s0), s0});
+  CK(ctx->f_pairs.ensure(sizeof(Pair))); CK(ctx->f_qtiles.ensure(tiles.size() * sizeof(QueryTile))); CK(ctx->f_nn_idx.ensure((size_t)n_nei * 5 * 4));
+  CK(cudaMemcpyAsync(ctx->f_pairs.p, &pair, sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->f_qtiles.p, tiles.data(), tiles.size() * sizeof(QueryTile), cudaMemcpyHostToDevice, ctx->stream));
+  LineAssocArgs a{};
+  a.q_local = ctx->p_cs.local.as<F4>(); a.tiles = ctx->f_qtiles.as<QueryTile>(); a.pairs = ctx->f_pairs.as<Pair>(); a.grids = ctx->p_index.grids.as<GridDesc>();
+  a.cell_start = ctx->p_index.cell_start.as<uint32_t>(); a.sorted = ctx->p_index.sorted.as<F4>(); a.wpose = ctx->d_wpose.as<WorldPose>();
+  a.sq_thr = dist_threshold * dist_threshold; a.thr = (double)dist_threshold;
+  a.out_nn = ctx->f_nn_idx.as<int>();
+  k_associate_line<5><<<(int)tiles.size(), kTile, 0, ctx->stream>>>(a);
+  CKL();
+  CK(cudaMemcpyAsync(idx5, ctx->f_nn_idx.p, (size_t)n_nei * 5 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+int pvb_nearest_line(pvb_ctx* ctx, const double* lines_world6, int n_lines, const float* points_world, int n_points, int* line, double* dist) {
+  if (!ctx || n_lines < 0 || n_points < 0 || (n_points > 0 && (!points_world || !line || !dist)) || (n_lines > 0 && !lines_world6))
+    return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_nearest_line: bad arguments") : PVB_ERR_ARG;
+  if (n_points == 0) return PVB_OK;
+  if ((size_t)n_lines * 48 > 200 * 1024) return ctx->fail(PVB_ERR_ARG, "pvb_nearest_line: %d lines do not fit in shared memory", n_lines);
+  CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
+  CK(ctx->m_a.ensure(std::max<size_t>(16, (size_t)n_lines * 48))); CK(ctx->m_b.ensure((size_t)n_points * 16)); CK(ctx->m_c.ensure((size_t)n_points * 4)); CK(ctx->m_d.ensure((size_t)n_points * 8));
+  if (n_lines) CK(cudaMemcpyAsync(ctx->m_a.p, lines_world6, (size_t)n_lines * 48, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_b.p, points_world, (size_t)n_points * 16, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t smem = (size_t)n_lines * 48;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_nearest_line, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_nearest_line<<<(n_points + 127) / 128, 128, smem, ctx->stream>>>(ctx->m_a.as<double>(), n_lines, ctx->m_b.as<F4>(), n_points, ctx->m_c.as<int>(), ctx->m_d.as<double>());
+  CKL();
+  CK(cudaMemcpyAsync(line, ctx->m_c.p, (size_t)n_points * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(dist, ctx->m_d.p, (size_t)n_points * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return PVB_OK;
 }

@@ -116,3 +116,36 @@ def test_camera_lidar_blocks_evaluate_like_the_reference_construction(oracle):
     blk = oracle.Blocks(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"])
     r, J, _ = blk.evaluate(np.concatenate([rng.normal(0, 0.1, (2, 3)), rng.normal(0, 0.5, (2, 3))], axis=1))
     assert np.all(np.isfinite(r)) and np.all(np.isfinite(J))
+
+
+def _seg_pair(n_az=1800):
+    A, B = synth.make_pair(seed=20260925, n_az=n_az)
+    fa = LineFrame(A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], A["segment_coeffs"], A["end_points"], A["R_wl"], A["t_wl"])
+    fb = LineFrame(B["cornerLessSharp"], B["p2s_off"], B["p2s_ids"], B["segment_coeffs"], B["end_points"], np.eye(3), np.zeros(3))
+    return A, B, fa, fb
+
+
+def test_segment_knn_tails_match_oracle(oracle):
+    """pvb_point2line_segment_knn_tail / pvb_line2line_knn_tail (host tails of LidarFeatureAssociate.cpp:238-317, 385-440) fed with the oracle's own
+    5-NN: membership counting, the all-5 / >= 3 rules, World2Local and FindAssociations must reproduce the oracle's associations."""
+    A, B, fa, fb = _seg_pair()
+    ref_w = oracle.transform_cloud(A["R_wl"], A["t_wl"], A["cornerLessSharp"])
+    nei_w = oracle.transform_cloud(np.eye(3), np.zeros(3), B["cornerLessSharp"])
+    for thr in (0.3, 0.6):
+        idx, d2 = oracle.knn(ref_w, nei_w, 5, True)
+        idx = idx.copy(); idx[d2[:, 4] > np.float32(thr) * np.float32(thr)] = -1
+        q, ln, pt, a, b = Context.point2line_segment_knn_tail(fa, fb, idx)
+        oq, oln, opt, oa, ob = oracle.associate_p2line_segment_knn(ref_w, A["p2s_off"], A["p2s_ids"], A["segment_coeffs"], nei_w, np.eye(3), np.zeros(3), thr)
+        assert len(oq) > 20
+        assert np.array_equal(q, oq) and np.array_equal(ln, oln) and np.array_equal(pt, opt) and np.array_equal(a, oa) and np.array_equal(b, ob)
+        nl, rl, a2, b2 = Context.line2line_knn_tail(fa, fb, idx)
+        M = oracle.line2line_knn_votes(ref_w, A["p2s_off"], A["p2s_ids"], len(A["segment_coeffs"]), nei_w, B["p2s_off"], B["p2s_ids"], len(B["segment_coeffs"]), thr)
+        ref_lw = oracle.transform_lines(A["R_wl"], A["t_wl"], A["segment_coeffs"]); nei_lw = oracle.transform_lines(np.eye(3), np.zeros(3), B["segment_coeffs"])
+        on, orf, oa2, ob2 = oracle.find_associations(A["segment_coeffs"], ref_lw, nei_lw, np.diff(B["seg_off"]), M)
+        assert len(on) >= 3 and M.sum() > 50
+        assert np.array_equal(nl, on) and np.array_equal(rl, orf) and np.array_equal(a2, oa2) and np.array_equal(b2, ob2)
+    # nothing within reach => no association; a frame without segments => nothing (CheckLidarSegment)
+    q, *_ = Context.point2line_segment_knn_tail(fa, fb, np.full((len(B["cornerLessSharp"]), 5), -1, np.int32))
+    assert len(q) == 0
+    empty = LineFrame(B["cornerLessSharp"], np.zeros(len(B["cornerLessSharp"]) + 1, np.int32), np.zeros(0, np.int32), np.zeros((0, 6)), None, np.eye(3), np.zeros(3))
+    assert len(Context.line2line_knn_tail(fa, empty, idx)[0]) == 0

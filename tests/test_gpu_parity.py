@@ -392,6 +392,39 @@ def test_transform_cloud_and_line2line_associate(gpu_ctx, oracle):
     assert len(on) >= 3
 
 
+def test_segment_based_corner_associations_match_oracle(gpu_ctx, oracle):
+    """AssociatePoint2LineSegmentKNN / AssociatePoint2LineSegment / AssociateLine2LineKNN (LidarFeatureAssociate.cpp:238-440)."""
+    A, B = _pair_frames(n_az=1800)
+    RB, tB = np.eye(3), np.zeros(3)
+    fa, fb = _line_frame(A), _line_frame(B, RB, tB)
+    ref_w = oracle.transform_cloud(A["R_wl"], A["t_wl"], A["cornerLessSharp"]); nei_w = oracle.transform_cloud(RB, tB, B["cornerLessSharp"])
+    ref_lw = oracle.transform_lines(A["R_wl"], A["t_wl"], A["segment_coeffs"]); nei_lw = oracle.transform_lines(RB, tB, B["segment_coeffs"])
+    for thr in (0.3, 0.6, 0.05):
+        # the 5-NN itself: same neighbour sets as the exact search, -1 rows where the 5th neighbour is out of reach
+        idx = gpu_ctx.pair_knn5(A["cornerLessSharp"], A["R_wl"], A["t_wl"], B["cornerLessSharp"], RB, tB, thr)
+        oi, od = oracle.knn(ref_w, nei_w, 5, True)
+        ok = od[:, 4] <= np.float32(thr) * np.float32(thr)
+        assert np.array_equal(idx[:, 0] >= 0, ok)
+        assert np.array_equal(np.sort(idx[ok], axis=1), np.sort(oi[ok], axis=1))
+        got = gpu_ctx.point2line_segment_knn_associate(fa, fb, thr)
+        exp = oracle.associate_p2line_segment_knn(ref_w, A["p2s_off"], A["p2s_ids"], A["segment_coeffs"], nei_w, RB, tB, thr)
+        assert all(np.array_equal(g, e) for g, e in zip(got, exp))
+        got = gpu_ctx.point2line_segment_associate(fa, fb, thr)
+        exp = oracle.associate_p2line_segment(ref_lw, A["segment_coeffs"], nei_w, RB, tB, thr)
+        assert all(np.array_equal(g, e) for g, e in zip(got, exp))
+        nl, rl, a, b = gpu_ctx.line2line_knn_associate(fa, fb, thr)
+        M = oracle.line2line_knn_votes(ref_w, A["p2s_off"], A["p2s_ids"], len(A["segment_coeffs"]), nei_w, B["p2s_off"], B["p2s_ids"], len(B["segment_coeffs"]), thr)
+        on, orf, oa, ob = oracle.find_associations(A["segment_coeffs"], ref_lw, nei_lw, np.diff(B["seg_off"]), M)
+        assert np.array_equal(nl, on) and np.array_equal(rl, orf) and np.array_equal(a, oa) and np.array_equal(b, ob)
+    assert len(exp[0]) < len(B["cornerLessSharp"])
+    got = gpu_ctx.point2line_segment_associate(fa, fb, 0.3)
+    assert len(got[0]) > 50 and len(gpu_ctx.line2line_knn_associate(fa, fb, 0.3)[0]) >= 3
+    line, dist = gpu_ctx.nearest_line(ref_lw, nei_w)
+    assert line.min() >= 0 and np.all(dist >= 0)
+    # fewer than 5 reference corner points: every row rejected
+    assert np.all(gpu_ctx.pair_knn5(A["cornerLessSharp"][:4], A["R_wl"], A["t_wl"], B["cornerLessSharp"], RB, tB, 10.0) == -1)
+
+
 def test_camera_lidar_associate_matches_oracle(gpu_ctx, oracle):
     from scipy.spatial.transform import Rotation
     A, _ = _pair_frames(n_az=1800)
