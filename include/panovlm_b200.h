@@ -209,6 +209,21 @@ int pvb_line2line_knn_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const p
 int pvb_line2line_knn_tail(const pvb_line_frame* ref, const pvb_line_frame* nei, const int* idx5, int* n_out, int* nei_line, int* ref_line, double* point_a3,
                            double* point_b3);
 
+/* ---- LiDAR line tracks (lidar_mapping/LidarLineMatch.cpp:36-86, util/Tracks.cpp:58-186) --------------------------------------- */
+/* TrackBuilder::Build + Filter(min_track_length) + ExportTracks on line matches given as CSR: pair p = (frame pair_a[p], frame pair_b[p]),
+ * its matches match_off[p]..match_off[p+1] = (line of a, line of b).  Output CSR: track t = features track_off[t]..track_off[t+1] as
+ * (feat_frame, feat_line), ascending; tracks numbered as LidarLineMatch assigns ids (:80-81).  Host only.                            */
+int pvb_line_tracks_build(int n_pairs, const int* pair_a, const int* pair_b, const int* match_off, const int* match_a, const int* match_b, int min_track_length,
+                          int allow_multiple_map, int cap_features, int* n_tracks, int* track_off, int* feat_frame, int* feat_line);
+/* the gate of AddLidarLineToLineResidual2 (util/Optimization.cpp:343-400): keep[i] = the reference line and the neighbour line of
+ * association i share a track.  Host only.                                                                                          */
+int pvb_line_tracks_gate(int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int ref_frame, int nei_frame, int n, const int* ref_line,
+                         const int* nei_line, unsigned char* keep);
+/* LidarLineMatch::GenerateTracks: AssociateLine2Line(frames[nei], frames[i], dist_threshold = 0.3) for every frame i with a valid pose and
+ * every neighbour (CSR nbr_off / nbr_ids from pvb_find_neighbors), then pvb_line_tracks_build(allow_multiple_map = 1).              */
+int pvb_generate_line_tracks(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, const unsigned char* pose_valid, const int* nbr_off, const int* nbr_ids,
+                             double dist_threshold, int min_track_length, int cap_features, int* n_tracks, int* track_off, int* feat_frame, int* feat_line);
+
 /* CameraLidarLineAssociate::AssociateByAngle (joint_optimization/CameraLidarLineAssociate.cpp:340-475) followed by
  * Filter(false, filter_by_length) (:628-715): per (image line, LiDAR segment) vote counts on the device, acceptance tests,
  * projected-length filter and the transform back to the LiDAR frame on the host.  Outputs sized for cap pairs.        */

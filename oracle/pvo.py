@@ -231,6 +231,27 @@ def line2line_knn_votes(ref_world, ref_p2s_off, ref_p2s_ids, S_ref, nei_world, n
     return M
 
 
+def line_tracks(pair_a, pair_b, match_off, match_a, match_b, min_length=3, allow_multiple_map=True):
+    """TrackBuilder::Build + Filter + ExportTracks (util/Tracks.cpp:58-186): returns a list of tracks, each an (m, 2) array of (frame, line)."""
+    pair_a, pair_b, match_off, match_a, match_b = (_i32(x) for x in (pair_a, pair_b, match_off, match_a, match_b))
+    cap = 2 * len(match_a) + 1
+    off, ff, fl = np.zeros(cap + 1, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    n = lib().pvo_line_tracks(C.c_int(len(pair_a)), _p(pair_a), _p(pair_b), _p(match_off), _p(match_a), _p(match_b), C.c_int(min_length), C.c_int(int(allow_multiple_map)),
+                              _p(off), _p(ff), _p(fl))
+    return [np.stack([ff[off[t]:off[t + 1]], fl[off[t]:off[t + 1]]], axis=1) for t in range(n)]
+
+
+def line_track_gate(tracks, ref_frame, nei_frame, ref_line, nei_line):
+    off = np.zeros(len(tracks) + 1, np.int32)
+    off[1:] = np.cumsum([len(t) for t in tracks])
+    feats = np.concatenate(tracks) if tracks else np.zeros((0, 2), np.int32)
+    ff, fl = _i32(feats[:, 0]), _i32(feats[:, 1])
+    ref_line, nei_line = _i32(ref_line), _i32(nei_line)
+    keep = np.zeros(len(ref_line), np.uint8)
+    lib().pvo_line_track_gate(C.c_int(len(tracks)), _p(off), _p(ff), _p(fl), C.c_int(ref_frame), C.c_int(nei_frame), C.c_int(len(ref_line)), _p(ref_line), _p(nei_line), _p(keep))
+    return keep.astype(bool)
+
+
 def transform_lines(R, t, lines):
     lines = _f64(lines).reshape(-1, 6)
     out = np.empty_like(lines)

@@ -9,6 +9,7 @@
 #endif
 #include "pvo_assoc.hpp"
 #include "pvo_solver.hpp"
+#include "pvo_tracks.hpp"
 
 using namespace pvo;
 
@@ -152,6 +153,32 @@ void pvo_line2line_knn_votes(const float* ref_world, int n_ref, const int* ref_p
   std::vector<int> m;
   Line2LineKnnVotes(ref_world, n_ref, ref_p2s_off, ref_p2s_ids, S_ref, nei_world, n_nei, nei_p2s_off, nei_p2s_ids, S_nei, dist_threshold, use_kdtree != 0, m);
   std::copy(m.begin(), m.end(), M);
+}
+
+// line tracks: CSR in (pairs, matches), CSR out (track -> features), returns the number of tracks; keep[] = gate result per association
+int pvo_line_tracks(int n_pairs, const int* pair_a, const int* pair_b, const int* match_off, const int* match_a, const int* match_b, int min_length, int allow_multiple_map,
+                    int* track_off, int* feat_frame, int* feat_line) {
+  std::vector<std::pair<size_t, size_t>> pairs(n_pairs); std::vector<std::set<Feature>> matches(n_pairs);
+  for (int p = 0; p < n_pairs; ++p) {
+    pairs[p] = {(size_t)pair_a[p], (size_t)pair_b[p]};
+    for (int e = match_off[p]; e < match_off[p + 1]; ++e) matches[p].insert(Feature((uint32_t)match_a[e], (uint32_t)match_b[e]));
+  }
+  LineTracks T; BuildLineTracks(pairs, matches, (uint32_t)min_length, allow_multiple_map != 0, T);
+  int at = 0;
+  for (size_t t = 0; t < T.tracks.size(); ++t) {
+    track_off[t] = at;
+    for (const Feature& f : T.tracks[t]) { feat_frame[at] = (int)f.first; feat_line[at] = (int)f.second; ++at; }
+  }
+  track_off[T.tracks.size()] = at;
+  return (int)T.tracks.size();
+}
+
+void pvo_line_track_gate(int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int ref_frame, int nei_frame, int n, const int* ref_line,
+                         const int* nei_line, unsigned char* keep) {
+  LineTracks T; T.tracks.resize(n_tracks);
+  for (int t = 0; t < n_tracks; ++t) for (int e = track_off[t]; e < track_off[t + 1]; ++e) T.tracks[t].insert(Feature((uint32_t)feat_frame[e], (uint32_t)feat_line[e]));
+  const auto l2t = LinesToTrack(T);
+  for (int i = 0; i < n; ++i) keep[i] = TrackGate(T, l2t, Feature((uint32_t)ref_frame, (uint32_t)ref_line[i]), Feature((uint32_t)nei_frame, (uint32_t)nei_line[i])) ? 1 : 0;
 }
 
 void pvo_angle_votes(int rows, int cols, const float* lines, int L, const float* cloud_local, int P, const int* p2s_off, const int* p2s_ids, int S,

@@ -106,7 +106,7 @@ EXPORTS = [
     "pvb_find_neighbors", "pvb_line2line_associate", "pvb_camera_lidar_associate", "pvb_build_point2plane_blocks", "pvb_build_point2line_blocks", "pvb_build_line2line_blocks",
     "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
     "pvb_pair_knn5", "pvb_nearest_line", "pvb_point2line_segment_knn_associate", "pvb_point2line_segment_knn_tail", "pvb_point2line_segment_associate",
-    "pvb_line2line_knn_associate", "pvb_line2line_knn_tail",
+    "pvb_line2line_knn_associate", "pvb_line2line_knn_tail", "pvb_line_tracks_build", "pvb_line_tracks_gate", "pvb_generate_line_tracks",
 ]
 
 
@@ -379,6 +379,43 @@ class Context:
         self._ck(self._L.pvb_line2line_knn_associate(self._h, C.byref(ref.c), C.byref(nei.c), C.c_float(dist_threshold), C.byref(n), _p(nl), _p(rl), _p(a), _p(b)))
         m = n.value
         return nl[:m].copy(), rl[:m].copy(), a[:m].copy(), b[:m].copy()
+
+    @staticmethod
+    def line_tracks_build(pair_a, pair_b, match_off, match_a, match_b, min_track_length=3, allow_multiple_map=True):
+        pa, pb, mo, ma, mb = (_arr(x, np.int32) for x in (pair_a, pair_b, match_off, match_a, match_b))
+        cap = 2 * len(ma) + 1
+        off, ff, fl, n = np.zeros(cap + 1, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), C.c_int()
+        rc = load_library().pvb_line_tracks_build(C.c_int(len(pa)), _p(pa), _p(pb), _p(mo), _p(ma), _p(mb), C.c_int(min_track_length), C.c_int(int(allow_multiple_map)),
+                                                  C.c_int(cap), C.byref(n), _p(off), _p(ff), _p(fl))
+        if rc:
+            raise PvbError(f"pvb_line_tracks_build: code {rc}")
+        return [np.stack([ff[off[t]:off[t + 1]], fl[off[t]:off[t + 1]]], axis=1) for t in range(n.value)]
+
+    @staticmethod
+    def line_tracks_gate(tracks, ref_frame, nei_frame, ref_line, nei_line):
+        off = np.zeros(len(tracks) + 1, np.int32)
+        off[1:] = np.cumsum([len(t) for t in tracks])
+        feats = np.concatenate(tracks) if tracks else np.zeros((0, 2), np.int32)
+        ff, fl = _arr(feats[:, 0], np.int32), _arr(feats[:, 1], np.int32)
+        rl, nl = _arr(ref_line, np.int32), _arr(nei_line, np.int32)
+        keep = np.zeros(len(rl), np.uint8)
+        rc = load_library().pvb_line_tracks_gate(C.c_int(len(tracks)), _p(off), _p(ff), _p(fl), C.c_int(ref_frame), C.c_int(nei_frame), C.c_int(len(rl)), _p(rl), _p(nl), _p(keep))
+        if rc:
+            raise PvbError(f"pvb_line_tracks_gate: code {rc}")
+        return keep.astype(bool)
+
+    def generate_line_tracks(self, frames, neighbors, pose_valid=None, dist_threshold=0.3, min_track_length=3):
+        """frames: list of LineFrame; neighbors: list of lists (pvb_find_neighbors)."""
+        arr = (_LineFrame * len(frames))(*[f.c for f in frames])
+        off = np.zeros(len(frames) + 1, np.int32)
+        off[1:] = np.cumsum([len(nb) for nb in neighbors])
+        ids = _arr(np.concatenate([np.asarray(nb, np.int32) for nb in neighbors]) if off[-1] else np.zeros(0, np.int32), np.int32)
+        cap = 2 * sum(max(1, f.c.n_segments) for f in frames) * max(1, max((len(nb) for nb in neighbors), default=1)) + 1
+        toff, ff, fl, n = np.zeros(cap + 1, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), C.c_int()
+        pv = None if pose_valid is None else _arr(pose_valid, np.uint8)
+        self._ck(self._L.pvb_generate_line_tracks(self._h, C.c_int(len(frames)), arr, _p(pv) if pv is not None else None, _p(off), _p(ids), C.c_double(dist_threshold),
+                                                  C.c_int(min_track_length), C.c_int(cap), C.byref(n), _p(toff), _p(ff), _p(fl)))
+        return [np.stack([ff[toff[t]:toff[t + 1]], fl[toff[t]:toff[t + 1]]], axis=1) for t in range(n.value)]
 
     @staticmethod
     def point2line_segment_knn_tail(ref, nei, idx5):

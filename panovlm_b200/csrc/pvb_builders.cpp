@@ -316,6 +316,102 @@ int pvb_point2line_segment_associate(pvb_ctx* ctx, const pvb_line_frame* ref, co
   return PVB_OK;
 }
 
+// ---- LiDAR line tracks (lidar_mapping/LidarLineMatch.cpp:36-86, util/Tracks.cpp:58-186) and the track gate of
+//      AddLidarLineToLineResidual2 (util/Optimization.cpp:343-400) ------------------------------------------------------------------
+// A track is a connected component of the line-match graph whose lines come from >= min_track_length distinct frames (and, unless
+// allow_multiple_map, from pairwise distinct frames).  Tracks are numbered by their smallest (frame, line) feature and list their
+// features in ascending order — the order TrackBuilder::ExportTracks produces from its sorted feature index.
+int pvb_line_tracks_build(int n_pairs, const int* pair_a, const int* pair_b, const int* match_off, const int* match_a, const int* match_b, int min_track_length,
+                          int allow_multiple_map, int cap_features, int* n_tracks, int* track_off, int* feat_frame, int* feat_line) {
+  if (n_pairs < 0 || !n_tracks || (n_pairs > 0 && (!pair_a || !pair_b || !match_off))) return PVB_ERR_ARG;
+  *n_tracks = 0;
+  if (track_off) track_off[0] = 0;
+  const int n_matches = n_pairs ? match_off[n_pairs] : 0;
+  if (n_matches == 0) return PVB_OK;
+  if (!match_a || !match_b || !track_off || !feat_frame || !feat_line) return PVB_ERR_ARG;
+  typedef std::pair<int, int> F;
+  std::vector<F> feats; feats.reserve(2 * (size_t)n_matches);
+  for (int p = 0; p < n_pairs; ++p)
+    for (int e = match_off[p]; e < match_off[p + 1]; ++e) { feats.push_back(F(pair_a[p], match_a[e])); feats.push_back(F(pair_b[p], match_b[e])); }
+  std::sort(feats.begin(), feats.end());
+  feats.erase(std::unique(feats.begin(), feats.end()), feats.end());
+  const int nf = (int)feats.size();
+  auto id_of = [&](int frame, int line) { return (int)(std::lower_bound(feats.begin(), feats.end(), F(frame, line)) - feats.begin()); };
+  std::vector<int> parent(nf);
+  for (int i = 0; i < nf; ++i) parent[i] = i;
+  auto find = [&](int i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
+  for (int p = 0; p < n_pairs; ++p)
+    for (int e = match_off[p]; e < match_off[p + 1]; ++e) {
+      const int a = find(id_of(pair_a[p], match_a[e])), b = find(id_of(pair_b[p], match_b[e]));
+      if (a != b) parent[std::max(a, b)] = std::min(a, b);          // the root is the smallest feature of the component
+    }
+  // per component: number of distinct frames and whether a frame repeats (features are sorted by frame within a component)
+  std::vector<int> n_frames(nf, 0), last_frame(nf, -1), n_feat(nf, 0); std::vector<char> repeat(nf, 0);
+  for (int i = 0; i < nf; ++i) {
+    const int r = find(i);
+    n_feat[r]++;
+    if (last_frame[r] == feats[i].first && n_feat[r] > 1) repeat[r] = 1; else { n_frames[r]++; last_frame[r] = feats[i].first; }
+  }
+  std::vector<int> track_of(nf, -1);
+  int nt = 0, total = 0;
+  for (int i = 0; i < nf; ++i) {
+    if (parent[i] != i) continue;
+    if (n_frames[i] < min_track_length || (!allow_multiple_map && repeat[i]) || n_feat[i] < 2) continue;
+    track_of[i] = nt++; total += n_feat[i];
+  }
+  if (total > cap_features) return PVB_ERR_NOMEM;
+  std::vector<int> fill(nt + 1, 0);
+  for (int i = 0; i < nf; ++i) if (parent[i] == i && track_of[i] >= 0) fill[track_of[i] + 1] = n_feat[i];
+  for (int t = 0; t < nt; ++t) fill[t + 1] += fill[t];
+  for (int t = 0; t <= nt; ++t) track_off[t] = fill[t];
+  for (int i = 0; i < nf; ++i) {
+    const int t = track_of[find(i)];
+    if (t < 0) continue;
+    feat_frame[fill[t]] = feats[i].first; feat_line[fill[t]] = feats[i].second; fill[t]++;
+  }
+  *n_tracks = nt;
+  return PVB_OK;
+}
+
+// keep[i] = 1 iff the reference line (ref_frame, ref_line[i]) and the neighbour line (nei_frame, nei_line[i]) are in one track
+int pvb_line_tracks_gate(int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int ref_frame, int nei_frame, int n, const int* ref_line,
+                         const int* nei_line, unsigned char* keep) {
+  if (n < 0 || n_tracks < 0 || (n > 0 && (!ref_line || !nei_line || !keep)) || (n_tracks > 0 && (!track_off || !feat_frame || !feat_line))) return PVB_ERR_ARG;
+  std::map<std::pair<int, int>, int> track_of;                                 // a line belongs to at most one track (components are disjoint)
+  for (int t = 0; t < n_tracks; ++t) for (int e = track_off[t]; e < track_off[t + 1]; ++e) track_of[{feat_frame[e], feat_line[e]}] = t;
+  for (int i = 0; i < n; ++i) {
+    auto a = track_of.find({ref_frame, ref_line[i]});
+    auto b = track_of.find({nei_frame, nei_line[i]});
+    keep[i] = (a != track_of.end() && b != track_of.end() && a->second == b->second) ? 1 : 0;
+  }
+  return PVB_OK;
+}
+
+// LidarLineMatch::GenerateTracks (:36-86): AssociateLine2Line(lidars[nei], lidars[i], 0.3) over the frame graph, then the track builder.
+int pvb_generate_line_tracks(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, const unsigned char* pose_valid, const int* nbr_off, const int* nbr_ids,
+                             double dist_threshold, int min_track_length, int cap_features, int* n_tracks, int* track_off, int* feat_frame, int* feat_line) {
+  if (!ctx || n_frames < 0 || !n_tracks || (n_frames > 0 && (!frames || !nbr_off))) return PVB_ERR_ARG;
+  std::vector<int> pa, pb, off(1, 0), ma, mb;
+  std::vector<int> nl, rl; std::vector<double> a3, b3;
+  for (int i = 0; i < n_frames; ++i) {
+    if (pose_valid && !pose_valid[i]) continue;                                // :62
+    for (int e = nbr_off[i]; e < nbr_off[i + 1]; ++e) {
+      const int n = nbr_ids[e];
+      if (n < 0 || n >= n_frames) return PVB_ERR_ARG;
+      const int S = std::max(1, frames[i].n_segments);
+      nl.resize(S); rl.resize(S); a3.resize(3 * (size_t)S); b3.resize(3 * (size_t)S);
+      int m = 0;
+      const int rc = pvb_line2line_associate(ctx, &frames[n], &frames[i], dist_threshold, &m, nl.data(), rl.data(), a3.data(), b3.data());   // :66 roles swapped
+      if (rc) return rc;
+      std::set<std::pair<int, int>> uniq;                                      // set<pair<neighbor_line_idx, ref_line_idx>> (:67-69)
+      for (int k = 0; k < m; ++k) uniq.insert({nl[k], rl[k]});
+      for (auto& f : uniq) { ma.push_back(f.first); mb.push_back(f.second); }
+      pa.push_back(i); pb.push_back(n); off.push_back((int)ma.size());
+    }
+  }
+  return pvb_line_tracks_build((int)pa.size(), pa.data(), pb.data(), off.data(), ma.data(), mb.data(), min_track_length, 1, cap_features, n_tracks, track_off, feat_frame, feat_line);
+}
+
 int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* lines4, int L, const pvb_line_frame* lidar, const double* T, int filter_by_length,
                                int cap, int* n_out, int* image_line, int* lidar_line, double* start3, double* end3, float* angle_out) {
   if (!ctx || !lidar || !T || !n_out || !lidar->end_points) return PVB_ERR_ARG;

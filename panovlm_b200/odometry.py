@@ -1,10 +1,9 @@
 """Host loop the hot path drops into: a Python mirror of LidarOdometry::RefinePose / EstimatePose
 (lidar_mapping/LidarOdometry.cpp:15-114, 116-187) driving the C ABI.  Every numeric step runs in the library:
 FindNeighbors (host C++), point-to-plane association of all pose-graph edges (fused kNN kernel), line-to-line vote
-matrices (kernel) + tails (host C++), residual-block builders (host C++), Levenberg-Marquardt with device evaluation.
-
-Not reproduced here ("next"): the LidarLineMatch track gate of AddLidarLineToLineResidual2
-(util/Optimization.cpp:383-400) — every associated line pair contributes residuals.
+matrices (kernel) + tails (host C++), LiDAR line tracks and their gate (LidarLineMatch::GenerateTracks with neighbour size 4 /
+track length 3 as LidarOdometry.cpp:47-50, util/Optimization.cpp:383-400), residual-block builders (host C++), Levenberg-Marquardt
+with device evaluation.
 """
 import numpy as np
 
@@ -13,11 +12,13 @@ from .api import BlockList, Context, LineFrame
 
 class OdometryConfig:
     def __init__(self, point_to_plane=True, line_to_line=True, angle_residual=True, normalize_distance=True, plane_dis_threshold=1.0,
-                 line_dis_threshold=0.3, plane_tolerance=0.05, lidar_weight=0.01, neighbor_size=6, max_lm_iterations=20):
+                 line_dis_threshold=0.3, plane_tolerance=0.05, lidar_weight=0.01, neighbor_size=6, max_lm_iterations=20, line_tracks=True,
+                 track_neighbor_size=4, min_track_length=3):
         self.point_to_plane, self.line_to_line = point_to_plane, line_to_line
         self.angle_residual, self.normalize_distance = angle_residual, normalize_distance          # config/Room.txt:67-74
         self.plane_dis_threshold, self.line_dis_threshold, self.plane_tolerance = plane_dis_threshold, line_dis_threshold, plane_tolerance
         self.lidar_weight, self.neighbor_size, self.max_lm_iterations = lidar_weight, neighbor_size, max_lm_iterations
+        self.line_tracks, self.track_neighbor_size, self.min_track_length = line_tracks, track_neighbor_size, min_track_length   # LidarOdometry.cpp:47-50
 
 
 def pose_blocks_from_world(R_wl, t_wl, R_to_aa):
@@ -49,9 +50,13 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
     if cfg.line_to_line:                                            # AddLidarLineToLineResidual2 (Optimization.cpp:329-441)
         lf = [LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], R_wl[i], t_wl[i]) for i, f in enumerate(frames)]
         world = [ctx.transform_cloud(f["cornerLessSharp"], R_wl[i], t_wl[i]) for i, f in enumerate(frames)]
+        tracks = None
+        if cfg.line_tracks:                                         # LidarLineMatch::GenerateTracks (LidarLineMatch.cpp:36-86), threshold hard-coded 0.3
+            tracks = ctx.generate_line_tracks(lf, Context.find_neighbors(np.array(t_wl), None, None, cfg.track_neighbor_size), None, 0.3, cfg.min_track_length)
         for (i, j) in edges:
             nl, rl, a, b = ctx.line2line_associate(lf[i], lf[j], cfg.line_dis_threshold)
-            for k in range(len(nl)):
+            keep = Context.line_tracks_gate(tracks, i, j, rl, nl) if tracks is not None else np.ones(len(nl), bool)   # Optimization.cpp:383-400
+            for k in np.nonzero(keep)[0]:
                 Context.build_line2line_blocks(bl, lf[j], world[j], nl[k], a[k], b[k], i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
     if cfg.point_to_plane:                                          # AddLidarPointToPlaneResidual (Optimization.cpp:506-562)
         ctx.frames_set([f["surfLessFlat"] for f in frames], [f["surfFlat"] for f in frames])

@@ -149,3 +149,55 @@ def test_segment_knn_tails_match_oracle(oracle):
     assert len(q) == 0
     empty = LineFrame(B["cornerLessSharp"], np.zeros(len(B["cornerLessSharp"]) + 1, np.int32), np.zeros(0, np.int32), np.zeros((0, 6)), None, np.eye(3), np.zeros(3))
     assert len(Context.line2line_knn_tail(fa, empty, idx)[0]) == 0
+
+
+def _random_matches(rng, n_frames, n_lines, n_pairs, p_match):
+    pa, pb, off, ma, mb = [], [], [0], [], []
+    for _ in range(n_pairs):
+        a, b = rng.choice(n_frames, 2, replace=False)
+        m = {(int(x), int(y)) for x, y in zip(rng.integers(0, n_lines, 6), rng.integers(0, n_lines, 6)) if rng.random() < p_match}
+        pa.append(a); pb.append(b)
+        for x, y in sorted(m):
+            ma.append(x); mb.append(y)
+        off.append(len(ma))
+    return np.array(pa, np.int32), np.array(pb, np.int32), np.array(off, np.int32), np.array(ma, np.int32), np.array(mb, np.int32)
+
+
+def test_line_tracks_match_oracle_and_connected_components(oracle):
+    """pvb_line_tracks_build / pvb_line_tracks_gate vs the oracle's restatement of TrackBuilder (util/Tracks.cpp:58-186) and vs scipy's connected
+    components (independent pin: a track = a component spanning >= min_length distinct frames, numbered by its smallest feature)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    rng = np.random.default_rng(5)
+    for trial in range(30):
+        nfr, nl = int(rng.integers(3, 12)), int(rng.integers(2, 9))
+        pa, pb, off, ma, mb = _random_matches(rng, nfr, nl, int(rng.integers(1, 25)), rng.uniform(0.2, 0.9))
+        for min_len, multi in ((3, True), (2, True), (2, False), (1, True)):
+            got = Context.line_tracks_build(pa, pb, off, ma, mb, min_len, multi)
+            exp = oracle.line_tracks(pa, pb, off, ma, mb, min_len, multi)
+            assert len(got) == len(exp) and all(np.array_equal(g, e) for g, e in zip(got, exp))
+            # independent: connected components over feature ids frame * nl + line
+            if len(ma) == 0:
+                assert got == []
+                continue
+            u = np.concatenate([pa[p] * nl + ma[off[p]:off[p + 1]] for p in range(len(pa))]); v = np.concatenate([pb[p] * nl + mb[off[p]:off[p + 1]] for p in range(len(pa))])
+            ncomp, lab = connected_components(coo_matrix((np.ones(len(u)), (u, v)), shape=(nfr * nl, nfr * nl)), directed=False)
+            used = np.unique(np.concatenate([u, v]))
+            comps = {}
+            for f in used:
+                comps.setdefault(lab[f], []).append((f // nl, f % nl))
+            want = []
+            for feats in sorted(comps.values(), key=lambda fs: min(fs)):
+                frames = [f for f, _ in feats]
+                if len(set(frames)) < min_len or (not multi and len(set(frames)) != len(frames)) or len(feats) < 2:
+                    continue
+                want.append(np.array(sorted(feats), np.int32))
+            assert len(got) == len(want) and all(np.array_equal(g, w) for g, w in zip(got, want))
+            # gate: random candidate associations between two frames
+            rf, nf_ = int(rng.integers(0, nfr)), int(rng.integers(0, nfr))
+            rl, nln = rng.integers(0, nl, 20), rng.integers(0, nl, 20)
+            keep = Context.line_tracks_gate(got, rf, nf_, rl, nln)
+            assert np.array_equal(keep, oracle.line_track_gate(exp, rf, nf_, rl, nln))
+            tr = {(int(f), int(l)): t for t, fs in enumerate(got) for f, l in fs}
+            assert np.array_equal(keep, [tr.get((rf, int(a)), -1) == tr.get((nf_, int(b)), -2) for a, b in zip(rl, nln)])
+    assert Context.line_tracks_build(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32)) == []

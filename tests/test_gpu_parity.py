@@ -458,11 +458,26 @@ def _oracle_refine(oracle, frames, poses, cfg):
     tgt_w = [oracle.transform_cloud(R_wl[i], t_wl[i], f["surfLessFlat"]) for i, f in enumerate(frames)]
     qry_w = [oracle.transform_cloud(R_wl[i], t_wl[i], f["surfFlat"]) for i, f in enumerate(frames)]
     lines_w = [oracle.transform_lines(R_wl[i], t_wl[i], f["segment_coeffs"]) for i, f in enumerate(frames)]
+    def l2l(i, j, thr):          # AssociateLine2Line(ref = i, nei = j)
+        fj = frames[j]
+        M = oracle.line_votes(lines_w[i], corner_w[j], fj["p2s_off"], fj["p2s_ids"], len(fj["segment_coeffs"]), thr)
+        return oracle.find_associations(frames[i]["segment_coeffs"], lines_w[i], lines_w[j], np.diff(fj["seg_off"]), M)
+    tracks = None
+    if cfg.line_tracks:          # LidarLineMatch::GenerateTracks: pairs {i, nei} with matches {line of i (neighbour role), line of nei (reference role)}
+        tn = py_find_neighbors(np.array(t_wl), np.ones(n, np.uint8), np.ones(n, np.uint8), cfg.track_neighbor_size)
+        pa, pb, off, ma, mb = [], [], [0], [], []
+        for i in range(n):
+            for nb in tn[i]:
+                on, orf, _, _ = l2l(nb, i, 0.3)
+                for x, y in sorted(set(zip(on.tolist(), orf.tolist()))):
+                    ma.append(x); mb.append(y)
+                pa.append(i); pb.append(nb); off.append(len(ma))
+        tracks = oracle.line_tracks(pa, pb, off, ma, mb, cfg.min_track_length, True)
     for (i, j) in edges:
         fj = frames[j]
-        M = oracle.line_votes(lines_w[i], corner_w[j], fj["p2s_off"], fj["p2s_ids"], len(fj["segment_coeffs"]), cfg.line_dis_threshold)
-        on, orf, oa, ob = oracle.find_associations(frames[i]["segment_coeffs"], lines_w[i], lines_w[j], np.diff(fj["seg_off"]), M)
-        for k in range(len(on)):
+        on, orf, oa, ob = l2l(i, j, cfg.line_dis_threshold)
+        keep = oracle.line_track_gate(tracks, i, j, orf, on) if tracks is not None else np.ones(len(on), bool)
+        for k in np.nonzero(keep)[0]:
             d = (oa[k] - ob[k]) / np.linalg.norm(oa[k] - ob[k])
             for pi in range(len(corner_w[j])):
                 if on[k] in fj["p2s_ids"][fj["p2s_off"][pi]:fj["p2s_off"][pi + 1]]:
@@ -477,6 +492,38 @@ def _oracle_refine(oracle, frames, poses, cfg):
     blk = oracle.Blocks(np.array(T), np.array(Rf), np.array(Nf), np.array(C), np.array(Hb), np.array(Nz))
     mask = np.zeros(n, np.uint8); mask[0] = 1
     return blk.solve_lm(poses, mask, cfg.max_lm_iterations), blk.n
+
+
+def test_generate_line_tracks_matches_oracle(gpu_ctx, oracle):
+    """LidarLineMatch::GenerateTracks through the C ABI (device vote matrices + host union-find) vs the oracle pipeline."""
+    from panovlm_b200 import Context, synth
+    from test_builders import py_find_neighbors
+    frames = synth.make_sequence(8, n_az=600)
+    n = len(frames)
+    R_wl, t_wl = [f["R_wl"] for f in frames], [f["t_wl"] for f in frames]
+    lf = [_line_frame(f) for f in frames]
+    nbrs = Context.find_neighbors(np.array(t_wl), None, None, 4)
+    assert nbrs == py_find_neighbors(np.array(t_wl), np.ones(n, np.uint8), np.ones(n, np.uint8), 4)
+    corner_w = [oracle.transform_cloud(R_wl[i], t_wl[i], f["cornerLessSharp"]) for i, f in enumerate(frames)]
+    lines_w = [oracle.transform_lines(R_wl[i], t_wl[i], f["segment_coeffs"]) for i, f in enumerate(frames)]
+    pa, pb, off, ma, mb = [], [], [0], [], []
+    for i in range(n):
+        for nb in nbrs[i]:
+            M = oracle.line_votes(lines_w[nb], corner_w[i], frames[i]["p2s_off"], frames[i]["p2s_ids"], len(frames[i]["segment_coeffs"]), 0.3)
+            on, orf, _, _ = oracle.find_associations(frames[nb]["segment_coeffs"], lines_w[nb], lines_w[i], np.diff(frames[i]["seg_off"]), M)
+            for x, y in sorted(set(zip(on.tolist(), orf.tolist()))):
+                ma.append(x); mb.append(y)
+            pa.append(i); pb.append(nb); off.append(len(ma))
+    for min_len in (3, 2):
+        exp = oracle.line_tracks(pa, pb, off, ma, mb, min_len, True)
+        got = gpu_ctx.generate_line_tracks(lf, nbrs, None, 0.3, min_len)
+        assert len(got) == len(exp) and len(got) >= 3 and all(np.array_equal(g, e) for g, e in zip(got, exp))
+    pv = np.ones(n, np.uint8); pv[2] = 0                        # a frame without a valid pose contributes no pairs (:62)
+    got = gpu_ctx.generate_line_tracks(lf, nbrs, pv, 0.3, 2)
+    keep = [p for p in range(len(pa)) if pa[p] != 2]
+    exp = oracle.line_tracks([pa[p] for p in keep], [pb[p] for p in keep], np.concatenate([[0], np.cumsum([off[p + 1] - off[p] for p in keep])]),
+                             np.concatenate([ma[off[p]:off[p + 1]] for p in keep]), np.concatenate([mb[off[p]:off[p + 1]] for p in keep]), 2, True)
+    assert len(got) == len(exp) and all(np.array_equal(g, e) for g, e in zip(got, exp))
 
 
 def test_odometry_outer_iteration_matches_oracle_loop(gpu_ctx, oracle):
