@@ -75,9 +75,18 @@ int pvb_blocks_edge_systems(const pvb_ctx* ctx, double* out92);
 /* dense 6nb x 6nb J^T J, J^T r assembled on the host from the edge systems of the last evaluate                 */
 int pvb_blocks_dense_system(const pvb_ctx* ctx, double* H, double* g, double* cost);
 /* the ceres::Solve(SetOptionsLidar(...)) step (LidarOdometry.cpp:78-80): trust-region LM over the registered
- * blocks, evaluation on the device, linear algebra on the host.  summary6 = initial_cost, final_cost, iterations,
+ * blocks, evaluation on the device.  summary6 = initial_cost, final_cost, iterations,
  * successful, unsuccessful, termination (0 max-iter, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure) */
 int pvb_blocks_solve_lm(pvb_ctx* ctx, double* poses, const unsigned char* is_const, int max_iterations, double* summary6);
+/* where the linear algebra of the LM step runs — the analogue of SetOptionsLidar's linear_solver_type choice
+ * (util/Optimization.cpp:647-662): HOST = dense Cholesky on the host cores; DEVICE = the edge systems stay in HBM, dense assembly,
+ * Jacobi scaling, damping, blocked FP64 Cholesky and the triangular solves are kernels (pvb_solver.cuh), only 6N-vectors cross PCIe;
+ * AUTO (default) = DEVICE from 256 free unknowns.                                                                                   */
+enum { PVB_SOLVER_AUTO = 0, PVB_SOLVER_HOST = 1, PVB_SOLVER_DEVICE = 2 };
+int pvb_blocks_set_linear_solver(pvb_ctx* ctx, int kind);
+/* the device Cholesky solve alone: x = A^-1 b, A symmetric positive definite n x n row-major (parity / timing entry);
+ * factor_ms (may be NULL) = device time of factorisation + substitution                                                             */
+int pvb_cholesky_solve(pvb_ctx* ctx, const double* A, int n, const double* b, double* x, float* factor_ms);
 
 /* ---- B. frames: transform to world + point-to-plane association per pose-graph edge ------------------------ */
 typedef struct {

@@ -107,6 +107,7 @@ EXPORTS = [
     "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
     "pvb_pair_knn5", "pvb_nearest_line", "pvb_point2line_segment_knn_associate", "pvb_point2line_segment_knn_tail", "pvb_point2line_segment_associate",
     "pvb_line2line_knn_associate", "pvb_line2line_knn_tail", "pvb_line_tracks_build", "pvb_line_tracks_gate", "pvb_generate_line_tracks",
+    "pvb_blocks_set_linear_solver", "pvb_cholesky_solve",
 ]
 
 
@@ -213,6 +214,15 @@ class Context:
         self._ck(self._L.pvb_blocks_solve_lm(self._h, _p(poses), _p(mask), C.c_int(max_iterations), _p(s)))
         keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
         return poses, dict(zip(keys, s.tolist()))
+
+    def blocks_set_linear_solver(self, kind):
+        self._ck(self._L.pvb_blocks_set_linear_solver(self._h, C.c_int(kind)))
+
+    def cholesky_solve(self, A, b):
+        A, b = _arr(A, np.float64), _arr(b, np.float64)
+        x, ms = np.zeros(len(b)), C.c_float()
+        self._ck(self._L.pvb_cholesky_solve(self._h, _p(A), C.c_int(len(b)), _p(b), _p(x), C.byref(ms)))
+        return x, ms.value
 
     # ---- B. frames
     def frames_set(self, targets, queries):

@@ -11,6 +11,7 @@
 #include "../../include/panovlm_b200.h"
 #include "pvb_host.hpp"
 #include "pvb_kernels.cuh"
+#include "pvb_solver.cuh"
 
 using namespace pvb;
 
@@ -96,6 +97,10 @@ struct pvb_ctx {
   cudaEvent_t bev0 = nullptr, bev1 = nullptr; bool bev_valid = false;     // brackets k_eval_blocks of the last blocks evaluate
   cudaStream_t copy_stream = nullptr; cudaEvent_t eval_done = nullptr; std::vector<cudaEvent_t> chunk_ev;
   std::vector<int> d_chunk_frame, d_chunk_ctile, d_chunk_qtile; bool d_chunks_pending = false;   // brackets the fused associate kernel of the last dense evaluate
+  // ---- device linear solver of the LM loop (pvb_solver.cuh)
+  int solver_kind = 0;                                                  // PVB_SOLVER_AUTO
+  DevBuf s_H, s_A, s_g, s_sc, s_rhs, s_term, s_con, s_seg, s_gcon, s_gseg, s_fail; PinBuf sh_vec;
+  int s_n = 0, s_N = 0, s_ndest = 0, s_ngdest = 0; float s_last_factor_ms = 0.f;
   // ---- misc
   DevBuf m_a, m_b, m_c, m_d, m_e;
   PinBuf mh_a;
@@ -479,6 +484,188 @@ int pvb_blocks_dense_system(const pvb_ctx* ctx, double* H, double* g, double* co
   return PVB_OK;
 }
 
+// ---- device linear algebra of the trust-region step --------------------------------------------------------------------------------
+// factor the N x N matrix in ctx->s_A (lower triangle, in place) and solve with the right-hand side in ctx->s_rhs; *ok = 0 when a pivot fails
+constexpr size_t kTrsmSmem = 2 * kNB * (kNB + 1) * sizeof(double);
+static int device_factor_solve(pvb_ctx* ctx, int N, bool* ok) {
+  static bool attr_set = false;
+  if (!attr_set) { CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem)); attr_set = true; }
+  CK(cudaMemsetAsync(ctx->s_fail.p, 0, 4, ctx->stream));
+  for (int k0 = 0; k0 < N; k0 += kNB) {
+    k_potrf_diag<<<1, 256, 0, ctx->stream>>>(ctx->s_A.as<double>(), N, k0, ctx->s_fail.as<int>());
+    CKL();
+    const int T = (N - k0 - kNB) / kNB;
+    if (T > 0) {
+      k_trsm_panel<<<T, kNB, kTrsmSmem, ctx->stream>>>(ctx->s_A.as<double>(), N, k0);
+      CKL();
+      k_syrk_update<<<T * (T + 1) / 2, 256, 0, ctx->stream>>>(ctx->s_A.as<double>(), N, k0);
+      CKL();
+    }
+  }
+  k_chol_solve<<<1, 1024, 0, ctx->stream>>>(ctx->s_A.as<double>(), N, ctx->s_rhs.as<double>());
+  CKL();
+  int fail = 0;
+  CK(cudaMemcpyAsync(&fail, ctx->s_fail.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *ok = fail == 0;
+  return PVB_OK;
+}
+
+// free-block index map + contribution lists of every edge system to the dense matrix / gradient (sorted by destination, then edge)
+static int solver_prepare(pvb_ctx* ctx, const unsigned char* is_const) {
+  const int nb = ctx->nb, ne = (int)ctx->edge_ref.size();
+  std::vector<int> fidx(nb, -1);
+  int nf = 0;
+  for (int b = 0; b < nb; ++b) if (!is_const || !is_const[b]) fidx[b] = nf++;
+  ctx->s_n = 6 * nf; ctx->s_N = ((ctx->s_n + kNB - 1) / kNB) * kNB;
+  if (ctx->s_n == 0) return PVB_OK;
+  std::vector<HContrib> con, gcon;
+  for (int e = 0; e < ne; ++e) {
+    const int blk[2] = {fidx[ctx->edge_ref[e]], fidx[ctx->edge_nei[e]]};
+    for (int kr = 0; kr < 2; ++kr) {
+      if (blk[kr] < 0) continue;
+      gcon.push_back(HContrib{blk[kr], 0, e, kr});
+      for (int kc = 0; kc < 2; ++kc) if (blk[kc] >= 0) con.push_back(HContrib{blk[kr], blk[kc], e, kr * 2 + kc});
+    }
+  }
+  auto less = [](const HContrib& a, const HContrib& b) { if (a.dest_r != b.dest_r) return a.dest_r < b.dest_r; if (a.dest_c != b.dest_c) return a.dest_c < b.dest_c;
+                                                          if (a.edge != b.edge) return a.edge < b.edge; return a.kind < b.kind; };
+  std::sort(con.begin(), con.end(), less); std::sort(gcon.begin(), gcon.end(), less);
+  std::vector<int> seg, gseg;
+  for (size_t i = 0; i < con.size(); ++i) if (i == 0 || con[i].dest_r != con[i - 1].dest_r || con[i].dest_c != con[i - 1].dest_c) seg.push_back((int)i);
+  seg.push_back((int)con.size());
+  for (size_t i = 0; i < gcon.size(); ++i) if (i == 0 || gcon[i].dest_r != gcon[i - 1].dest_r) gseg.push_back((int)i);
+  gseg.push_back((int)gcon.size());
+  ctx->s_ndest = (int)seg.size() - 1; ctx->s_ngdest = (int)gseg.size() - 1;
+  const size_t N = (size_t)ctx->s_N;
+  CK(ctx->s_H.ensure(N * N * 8)); CK(ctx->s_A.ensure(N * N * 8));
+  CK(ctx->s_g.ensure(N * 8)); CK(ctx->s_sc.ensure(N * 8)); CK(ctx->s_rhs.ensure(N * 8)); CK(ctx->s_term.ensure(N * 8)); CK(ctx->s_fail.ensure(16));
+  CK(ctx->s_con.ensure(std::max<size_t>(16, con.size() * sizeof(HContrib)))); CK(ctx->s_seg.ensure(seg.size() * 4));
+  CK(ctx->s_gcon.ensure(std::max<size_t>(16, gcon.size() * sizeof(HContrib)))); CK(ctx->s_gseg.ensure(gseg.size() * 4));
+  CK(ctx->sh_vec.ensure(4 * N * 8));
+  if (!con.empty()) CK(cudaMemcpyAsync(ctx->s_con.p, con.data(), con.size() * sizeof(HContrib), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->s_seg.p, seg.data(), seg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!gcon.empty()) CK(cudaMemcpyAsync(ctx->s_gcon.p, gcon.data(), gcon.size() * sizeof(HContrib), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->s_gseg.p, gseg.data(), gseg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+// dense H (free unknowns) and gradient from the edge systems of the last evaluate, on the device; g also copied to the host (h_g)
+static int solver_assemble(pvb_ctx* ctx, double* h_g) {
+  const size_t N = (size_t)ctx->s_N;
+  CK(cudaMemsetAsync(ctx->s_H.p, 0, N * N * 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->s_g.p, 0, N * 8, ctx->stream));
+  if (ctx->s_ndest) { k_assemble_H<<<ctx->s_ndest, 64, 0, ctx->stream>>>(ctx->s_con.as<HContrib>(), ctx->s_seg.as<int>(), ctx->b_esys.as<double>(), ctx->s_N, ctx->s_H.as<double>()); CKL(); }
+  if (ctx->s_ngdest) { k_assemble_g<<<ctx->s_ngdest, 32, 0, ctx->stream>>>(ctx->s_gcon.as<HContrib>(), ctx->s_gseg.as<int>(), ctx->b_esys.as<double>(), ctx->s_g.as<double>()); CKL(); }
+  CK(cudaMemcpyAsync(h_g, ctx->s_g.p, (size_t)ctx->s_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+// The loop of pvb::solve_lm (pvb_host.hpp) with the linear algebra on the device.  Same control flow and constants; the candidate
+// evaluation already leaves the edge systems of the accepted point on the device, so an accepted step costs one evaluation, not two.
+static int solve_lm_device(pvb_ctx* ctx, double* poses, const unsigned char* is_const, const LMOptions& opt, LMSummary& S) {
+  const int nb = ctx->nb, D = 6 * nb;
+  int rc = solver_prepare(ctx, is_const); if (rc) return rc;
+  const int n = ctx->s_n, N = ctx->s_N;
+  std::vector<int> fi;
+  for (int b = 0; b < nb; ++b) if (!is_const || !is_const[b]) for (int k = 0; k < 6; ++k) fi.push_back(6 * b + k);
+  auto evaluate = [&](const double* x, double* cost) -> int {
+    const int r = pvb_blocks_evaluate(ctx, x, 0, 1); if (r) return r;
+    return pvb_blocks_cost(ctx, cost, nullptr);
+  };
+  double cost = 0;
+  rc = evaluate(poses, &cost); if (rc) return rc;
+  S = LMSummary(); S.initial_cost = cost;
+  if (n == 0) { S.final_cost = cost; S.termination = 2; return PVB_OK; }
+  double* hv = ctx->sh_vec.as<double>();
+  double *gs = hv, *sc = hv + N, *y = hv + 2 * N, *term = hv + 3 * N;
+  rc = solver_assemble(ctx, gs); if (rc) return rc;
+  k_jacobi_scale<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->s_H.as<double>(), n, N, ctx->s_sc.as<double>());
+  CKL();
+  CK(cudaMemcpyAsync(sc, ctx->s_sc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  auto gmax = [&]() { double m = 0; for (int i = 0; i < n; ++i) m = std::max(m, std::fabs(gs[i])); return m; };
+  double radius = 1e4, decrease = 2.0;
+  int invalid = 0;
+  std::vector<double> cand(D);
+  if (gmax() <= opt.gradient_tolerance) { S.final_cost = cost; S.termination = 2; return PVB_OK; }
+  for (int it = 1; it <= opt.max_iterations; ++it) {
+    S.iterations = it;
+    k_build_damped<<<dim3((N + 255) / 256, N), 256, 0, ctx->stream>>>(ctx->s_H.as<double>(), ctx->s_g.as<double>(), ctx->s_sc.as<double>(), n, N, radius, ctx->s_A.as<double>(),
+                                                                     ctx->s_rhs.as<double>());
+    CKL();
+    bool ok = false;
+    rc = device_factor_solve(ctx, N, &ok); if (rc) return rc;
+    double model = 0;
+    if (ok) {
+      k_model_terms<<<(n + 7) / 8, 256, 0, ctx->stream>>>(ctx->s_H.as<double>(), ctx->s_g.as<double>(), ctx->s_sc.as<double>(), ctx->s_rhs.as<double>(), n, N, ctx->s_term.as<double>());
+      CKL();
+      CK(cudaMemcpyAsync(y, ctx->s_rhs.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(term, ctx->s_term.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (int i = 0; i < n; ++i) model -= term[i];             // fixed summation order
+      ok = model > 0.0;
+    }
+    if (!ok) { radius *= 0.5; S.unsuccessful++; if (++invalid >= 5 || radius < 1e-32) { S.termination = 4; break; } continue; }
+    invalid = 0;
+    double sn = 0, xn = 0;
+    std::copy(poses, poses + D, cand.begin());
+    for (int i = 0; i < n; ++i) { const double d = y[i] * sc[i]; cand[fi[i]] += d; sn += d * d; xn += poses[fi[i]] * poses[fi[i]]; }
+    sn = std::sqrt(sn); xn = std::sqrt(xn);
+    double new_cost = 0;
+    rc = evaluate(cand.data(), &new_cost); if (rc) return rc;
+    if (sn <= opt.parameter_tolerance * (xn + opt.parameter_tolerance)) { S.termination = 3; break; }
+    const double change = cost - new_cost;
+    if (std::fabs(change) <= opt.function_tolerance * cost) { S.termination = 1; break; }
+    const double rho = change / model;
+    if (rho > 1e-3) {
+      std::copy(cand.begin(), cand.end(), poses);
+      cost = new_cost;
+      rc = solver_assemble(ctx, gs); if (rc) return rc;        // edge systems of the accepted point are already on the device
+      S.successful++;
+      radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
+      decrease = 2.0;
+      if (gmax() <= opt.gradient_tolerance) { S.termination = 2; break; }
+    } else {
+      radius /= decrease; decrease *= 2.0; S.unsuccessful++;
+      if (radius < 1e-32) { S.termination = 4; break; }
+    }
+  }
+  S.final_cost = cost;
+  return PVB_OK;
+}
+
+int pvb_blocks_set_linear_solver(pvb_ctx* ctx, int kind) {
+  if (!ctx || kind < PVB_SOLVER_AUTO || kind > PVB_SOLVER_DEVICE) return ctx ? ctx->fail(PVB_ERR_ARG, "unknown linear solver %d", kind) : PVB_ERR_ARG;
+  ctx->solver_kind = kind;
+  return PVB_OK;
+}
+
+// x = A^-1 b for a symmetric positive definite row-major A (n x n) with the device Cholesky of the LM loop (parity / benchmark entry)
+int pvb_cholesky_solve(pvb_ctx* ctx, const double* A, int n, const double* b, double* x, float* factor_ms) {
+  if (!ctx || !A || !b || !x || n <= 0) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_cholesky_solve: bad arguments") : PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const int N = ((n + kNB - 1) / kNB) * kNB;
+  CK(ctx->s_A.ensure((size_t)N * N * 8)); CK(ctx->s_rhs.ensure((size_t)N * 8)); CK(ctx->s_fail.ensure(16));
+  std::vector<double> pad((size_t)N * N, 0.0), rhs(N, 0.0);
+  for (int i = 0; i < N; ++i) { if (i < n) { memcpy(&pad[(size_t)i * N], A + (size_t)i * n, (size_t)n * 8); rhs[i] = b[i]; } else pad[(size_t)i * N + i] = 1.0; }
+  CK(cudaMemcpyAsync(ctx->s_A.p, pad.data(), pad.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->s_rhs.p, rhs.data(), rhs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->bev0, ctx->stream));
+  bool ok = false;
+  int rc = device_factor_solve(ctx, N, &ok); if (rc) return rc;
+  CK(cudaEventRecord(ctx->bev1, ctx->stream));
+  CK(cudaMemcpyAsync(rhs.data(), ctx->s_rhs.p, (size_t)N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->bev_valid = false;
+  if (factor_ms) CK(cudaEventElapsedTime(factor_ms, ctx->bev0, ctx->bev1));
+  if (!ok) return ctx->fail(PVB_ERR_ARG, "pvb_cholesky_solve: matrix is not positive definite");
+  memcpy(x, rhs.data(), (size_t)n * 8);
+  return PVB_OK;
+}
+
 int pvb_blocks_solve_lm(pvb_ctx* ctx, double* poses, const unsigned char* is_const, int max_iterations, double* summary6) {
   if (!ctx || !poses) return PVB_ERR_ARG;
   if (ctx->nb <= 0) return ctx->fail(PVB_ERR_STATE, "pvb_blocks_set has not been called");
@@ -489,7 +676,14 @@ int pvb_blocks_solve_lm(pvb_ctx* ctx, double* poses, const unsigned char* is_con
     return assemble_dense(ctx, H, g);
   };
   LMOptions opt; opt.max_iterations = max_iterations;
-  const LMSummary S = solve_lm(eval, poses, ctx->nb, is_const, opt);
+  int n_free = 0;
+  for (int b = 0; b < ctx->nb; ++b) if (!is_const || !is_const[b]) n_free += 6;
+  // SetOptionsLidar picks the linear solver by problem size (Optimization.cpp:647-662); here: device Cholesky once the dense host
+  // algebra would dominate (a 6x6 .. ~40-block system is faster on the host than ~3 launches per 64 columns)
+  const bool on_device = ctx->solver_kind == PVB_SOLVER_DEVICE || (ctx->solver_kind == PVB_SOLVER_AUTO && n_free >= 256);
+  LMSummary S;
+  if (on_device) { CK(cudaSetDevice(ctx->device)); const int rc = solve_lm_device(ctx, poses, is_const, opt, S); if (rc) return rc; }
+  else S = solve_lm(eval, poses, ctx->nb, is_const, opt);
   if (rc_inner) return rc_inner;
   if (summary6) { summary6[0] = S.initial_cost; summary6[1] = S.final_cost; summary6[2] = S.iterations; summary6[3] = S.successful; summary6[4] = S.unsuccessful; summary6[5] = S.termination; }
   return PVB_OK;

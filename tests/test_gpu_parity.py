@@ -89,10 +89,9 @@ def test_lm_pose_deltas_match_oracle(gpu_ctx, oracle):
         assert (np.abs(P1[1] - P2[1]) / np.abs(P1[1]).max()).max() < POSE_RTOL
 
 
-def test_lm_multi_frame_pose_graph(gpu_ctx, oracle):
-    """4-frame pose graph, first frame constant (LidarOdometry.cpp:59-66), mixed plane + line residuals."""
-    rng = np.random.default_rng(4)
-    nb, n = 4, 4000
+def _pose_graph_problem(nb, n, seed=4):
+    """nb-frame pose graph, mixed plane + line residuals between random frame pairs, noisy start."""
+    rng = np.random.default_rng(seed)
     truth = np.concatenate([rng.normal(0, 0.05, (nb, 3)), rng.normal(0, 0.3, (nb, 3))], axis=1); truth[0] = 0
     ref = rng.integers(0, nb, n).astype(np.int32); nei = ((ref + rng.integers(1, nb, n)) % nb).astype(np.int32)
     typ = rng.choice([0, 1, 2, 3], n).astype(np.int32)
@@ -113,16 +112,73 @@ def test_lm_multi_frame_pose_graph(gpu_ctx, oracle):
             dr = rng.normal(size=3); dr /= np.linalg.norm(dr)
             consts[i, 3:6] = p_ref + 0.3 * dr; consts[i, 6:9] = dr; consts[i, 9] = 1.0
     hub = np.where(typ % 2 == 1, 2 * np.pi / 180, 0.2)
-    blk = oracle.Blocks(typ, ref, nei, consts, hub, 1)
     start = truth + np.concatenate([rng.normal(0, 0.01, (nb, 3)), rng.normal(0, 0.03, (nb, 3))], axis=1); start[0] = 0
-    mask = [1, 0, 0, 0]
+    mask = np.zeros(nb, np.uint8); mask[0] = 1
+    return typ, ref, nei, consts, hub, start, mask
+
+
+def test_lm_multi_frame_pose_graph(gpu_ctx, oracle):
+    """4-frame pose graph, first frame constant (LidarOdometry.cpp:59-66), mixed plane + line residuals; host and device linear solver."""
+    from panovlm_b200 import api
+    nb = 4
+    typ, ref, nei, consts, hub, start, mask = _pose_graph_problem(nb, 4000)
+    blk = oracle.Blocks(typ, ref, nei, consts, hub, 1)
     P1, s1 = blk.solve_lm(start, is_const=mask, max_iter=20)
     gpu_ctx.blocks_set(typ, ref, nei, consts, hub, 1, nb)
-    P2, s2 = gpu_ctx.blocks_solve_lm(start, is_const=mask, max_iterations=20)
     assert s1["final_cost"] < 0.2 * s1["initial_cost"]
-    assert abs(s2["final_cost"] - s1["final_cost"]) < 1e-7 * s1["final_cost"]
-    d1, d2 = P1 - start, P2 - start
-    assert np.abs(d1 - d2).max() < POSE_RTOL * np.abs(d1).max()
+    try:
+        for kind in (api.SOLVER_HOST, api.SOLVER_DEVICE):
+            gpu_ctx.blocks_set_linear_solver(kind)
+            P2, s2 = gpu_ctx.blocks_solve_lm(start, is_const=mask, max_iterations=20)
+            assert s2["iterations"] == s1["iterations"] and s2["successful"] == s1["successful"] and s2["termination"] == s1["termination"]
+            assert abs(s2["final_cost"] - s1["final_cost"]) < 1e-7 * s1["final_cost"]
+            d1, d2 = P1 - start, P2 - start
+            assert np.abs(d1 - d2).max() < POSE_RTOL * np.abs(d1).max()
+    finally:
+        gpu_ctx.blocks_set_linear_solver(api.SOLVER_AUTO)
+
+
+def test_device_cholesky_matches_numpy(gpu_ctx):
+    """The blocked FP64 Cholesky + substitution of the device LM step alone, at sizes around the 64-wide panel boundaries."""
+    from panovlm_b200 import PvbError
+    rng = np.random.default_rng(8)
+    for n in (1, 6, 63, 64, 65, 200, 1000):
+        M = rng.normal(size=(n, n + 3))
+        A = M @ M.T + 0.1 * np.eye(n)
+        b = rng.normal(size=n)
+        x, ms = gpu_ctx.cholesky_solve(A, b)
+        xr = np.linalg.solve(A, b)
+        assert np.abs(x - xr).max() < 1e-9 * np.abs(xr).max(), n
+        x2, _ = gpu_ctx.cholesky_solve(A, b)
+        assert np.array_equal(x, x2)                               # fixed summation order: bit-reproducible
+    A = np.eye(5); A[3, 3] = -1.0
+    with pytest.raises(PvbError):
+        gpu_ctx.cholesky_solve(A, np.ones(5))
+
+
+def test_lm_device_solver_on_a_large_pose_graph(gpu_ctx, oracle):
+    """60 frames (354 free unknowns: AUTO picks the device solver): host and device linear algebra give the same LM trajectory;
+    both agree with the oracle's dense LM within the pose-delta gate."""
+    from panovlm_b200 import api
+    nb = 60
+    typ, ref, nei, consts, hub, start, mask = _pose_graph_problem(nb, 30000, seed=6)
+    gpu_ctx.blocks_set(typ, ref, nei, consts, hub, 1, nb)
+    out = {}
+    try:
+        for kind in (api.SOLVER_HOST, api.SOLVER_DEVICE, api.SOLVER_AUTO):
+            gpu_ctx.blocks_set_linear_solver(kind)
+            out[kind] = gpu_ctx.blocks_solve_lm(start, is_const=mask, max_iterations=8)
+    finally:
+        gpu_ctx.blocks_set_linear_solver(api.SOLVER_AUTO)
+    Ph, sh = out[api.SOLVER_HOST]; Pd, sd = out[api.SOLVER_DEVICE]; Pa, sa = out[api.SOLVER_AUTO]
+    assert sh["final_cost"] < 0.2 * sh["initial_cost"]
+    assert (sd["iterations"], sd["successful"], sd["termination"]) == (sh["iterations"], sh["successful"], sh["termination"])
+    assert abs(sd["final_cost"] - sh["final_cost"]) < 1e-9 * sh["final_cost"]
+    assert np.abs((Pd - start) - (Ph - start)).max() < 1e-7 * np.abs(Ph - start).max()
+    assert np.array_equal(Pa, Pd)                                  # AUTO == DEVICE at this size, and the device path is deterministic
+    blk = oracle.Blocks(typ, ref, nei, consts, hub, 1)
+    P1, s1 = blk.solve_lm(start, is_const=mask, max_iter=8)
+    assert np.abs((Pd - start) - (P1 - start)).max() < POSE_RTOL * np.abs(P1 - start).max()
 
 
 # ---------------------------------------------------------------- B. frames: T1 + K2p (emit)

@@ -59,11 +59,24 @@ for _ in range(5):
 out["evaluate_reduced_s"] = (time.time() - t) / 5
 out["k_eval_blocks_ms"] = ctx.blocks_kernel_time_ms()
 mask = np.zeros(n, np.uint8); mask[0] = 1
-t = time.time()
-new_poses, s = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
-out["solve_lm_s"] = time.time() - t
-s["n_blocks"] = bl.n
-out["lm"] = s
+from panovlm_b200 import api  # noqa: E402
+for name, kind in (("device", api.SOLVER_DEVICE), ("host", api.SOLVER_HOST)):
+    if name == "host" and os.environ.get("PVB_SKIP_HOST_LM"):
+        continue
+    ctx.blocks_set_linear_solver(kind)
+    t = time.time()
+    new_poses, s = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
+    out[f"solve_lm_{name}_s"] = time.time() - t
+    s["n_blocks"] = bl.n
+    out[f"lm_{name}"] = s
+    out[f"pose_err_after_{name}"] = float(np.abs(new_poses - odometry.pose_blocks_from_world([f["R_wl"] for f in frames], [f["t_wl"] for f in frames], R_to_aa)).max())
+# the device Cholesky alone at this size
+rng2 = np.random.default_rng(2)
+nn = 6 * (n - 1)
+M = rng2.normal(size=(nn, 64)); Amat = M @ M.T + np.eye(nn) * nn
+x, ms = ctx.cholesky_solve(Amat, rng2.normal(size=nn))
+x, ms = ctx.cholesky_solve(Amat, rng2.normal(size=nn))
+out["device_cholesky"] = {"n": nn, "factor_and_solve_ms": ms, "gflops": (nn ** 3 / 3) / (ms * 1e-3) / 1e9}
 truth = odometry.pose_blocks_from_world([f["R_wl"] for f in frames], [f["t_wl"] for f in frames], R_to_aa)
 out["pose_err_before_after"] = [float(np.abs(poses - truth).max()), float(np.abs(new_poses - truth).max())]
 print(json.dumps(out))
