@@ -11,6 +11,7 @@ import numpy as np
 
 P2PLANE_METER, P2PLANE_ANGLE, P2LINE_METER, P2LINE_ANGLE, PLANE2PLANE_GLOBAL, PLANE_IOU = range(6)
 PLANE2PLANE_RELATIVE, PLANE_RELATIVE_IOU, LINE2LINE_ANGLE = 6, 7, 8
+SOLVER_AUTO, SOLVER_HOST, SOLVER_DEVICE = 0, 1, 2   # pvb_blocks_set_linear_solver
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
