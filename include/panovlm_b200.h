@@ -234,11 +234,18 @@ int pvb_generate_line_tracks(pvb_ctx* ctx, int n_frames, const pvb_line_frame* f
                              double dist_threshold, int min_track_length, int cap_features, int* n_tracks, int* track_off, int* feat_frame, int* feat_line);
 
 /* CameraLidarLineAssociate::AssociateByAngle (joint_optimization/CameraLidarLineAssociate.cpp:340-475) followed by
- * Filter(false, filter_by_length) (:628-715): per (image line, LiDAR segment) vote counts on the device, acceptance tests,
- * projected-length filter and the transform back to the LiDAR frame on the host.  Outputs sized for cap pairs.        */
+ * Filter(false, filter_by_length) (:628-715) and, unless multiple_association, UniqueLinePair (:754-876): per (image line, LiDAR
+ * segment) vote counts on the device; acceptance tests, projected-length filter, one-to-one reduction and the transform back to the
+ * LiDAR frame on the host.  image_line_mask / lidar_line_mask (may be NULL = all lines take part, :351-366): 0 excludes a line.
+ * The reference's default is multiple_association = false (CameraLidarLineAssociate.h:109); the joint optimisation passes true with
+ * masks (CameraLidarOptimizer.cpp:362-364).  Outputs sized for cap pairs.                                                           */
 int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* lines4, int n_lines, const pvb_line_frame* lidar,
-                               const double* T_cl16, int filter_by_length, int cap, int* n_out, int* image_line, int* lidar_line,
+                               const double* T_cl16, int filter_by_length, int multiple_association, const unsigned char* image_line_mask,
+                               const unsigned char* lidar_line_mask, int cap, int* n_out, int* image_line, int* lidar_line,
                                double* start3, double* end3, float* angle);
+/* UniqueLinePair alone (host): candidates in input order -> one-to-one pairs, ascending image line                                  */
+int pvb_unique_line_pairs(int n, const int* image_line, const int* lidar_line, const float* score, int* n_out, int* out_image, int* out_lidar,
+                          float* out_score);
 
 /* Residual-block builders == the AddResidualBlock loops of util/Optimization.cpp.  Each appends to caller arrays
  * (type, ref, nei, normalize: int; huber: double; consts: 12 doubles per block) starting at index `at` and returns the new

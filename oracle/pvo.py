@@ -285,7 +285,15 @@ def angle_votes(rows, cols, lines, cloud_local, p2s_off, p2s_ids, S, T_cl):
     return counts
 
 
-def associate_by_angle(rows, cols, lines, cloud_local, p2s_off, p2s_ids, seg_sizes, end_points, T_cl, filter_by_length=True):
+def unique_line_pairs(image_line, lidar_line, score):
+    il, ll, sc = _i32(image_line), _i32(lidar_line), _f32(score)
+    oi, ol, os_ = np.empty(max(1, len(il)), np.int32), np.empty(max(1, len(il)), np.int32), np.empty(max(1, len(il)), np.float32)
+    m = lib().pvo_unique_line_pairs(C.c_int(len(il)), _p(il), _p(ll), _p(sc), _p(oi), _p(ol), _p(os_))
+    return oi[:m].copy(), ol[:m].copy(), os_[:m].copy()
+
+
+def associate_by_angle(rows, cols, lines, cloud_local, p2s_off, p2s_ids, seg_sizes, end_points, T_cl, filter_by_length=True, multiple_association=True,
+                       image_mask=None, lidar_mask=None):
     lines, cloud = _f32(lines).reshape(-1, 4), _f32(cloud_local).reshape(-1, 4)
     S = len(seg_sizes)
     cap = max(1, len(lines) * S)
@@ -293,7 +301,9 @@ def associate_by_angle(rows, cols, lines, cloud_local, p2s_off, p2s_ids, seg_siz
     os_, oe, oa = np.empty((cap, 3)), np.empty((cap, 3)), np.empty(cap, dtype=np.float32)
     m = lib().pvo_associate_by_angle(C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), _p(cloud), C.c_int(len(cloud)), _p(_i32(p2s_off)), _p(_i32(p2s_ids)),
                                      C.c_int(S), _p(_i32(seg_sizes)), _p(_f64(end_points)), _p(_f64(T_cl)), C.c_int(int(filter_by_length)), C.c_int(cap),
-                                     _p(oi), _p(ol), _p(os_), _p(oe), _p(oa))
+                                     _p(oi), _p(ol), _p(os_), _p(oe), _p(oa), C.c_int(int(multiple_association)),
+                                     _p(np.ascontiguousarray(image_mask, np.uint8)) if image_mask is not None else None,
+                                     _p(np.ascontiguousarray(lidar_mask, np.uint8)) if lidar_mask is not None else None)
     return oi[:m].copy(), ol[:m].copy(), os_[:m].copy(), oe[:m].copy(), oa[:m].copy()
 
 

@@ -414,10 +414,42 @@ inline void AngleVotes(const Equirect& eq, const float* lines /*L x 4*/, int L, 
   }
 }
 
+// UniqueLinePair (CameraLidarLineAssociate.cpp:754-876): one-to-one pairs, the smaller score (angle error) wins; processed in
+// input order, output ascending by image line.  The reference evaluates its cases 1-3 as consecutive `if`s on iterators that case 1
+// has just erased; with the strict inequalities those later conditions can never hold after case 1, so they are `else if` here.
+inline void UniqueLinePair(std::vector<CamLidarPair>& pairs) {
+  struct PS { int idx; float score; };
+  std::map<int, PS> i2l, l2i;
+  for (const CamLidarPair& pr : pairs) {
+    const int il = pr.image_line, ll = pr.lidar_line; const float sc = pr.angle;
+    auto a = i2l.find(il); auto b = l2i.find(ll);
+    const bool ha = a != i2l.end(), hb = b != l2i.end();
+    if (!ha && !hb) { i2l.insert({il, PS{ll, sc}}); l2i.insert({ll, PS{il, sc}}); }
+    else if (ha && !hb) {
+      if (sc < a->second.score) { l2i.erase(l2i.find(a->second.idx)); a->second = PS{ll, sc}; l2i.insert({ll, PS{il, sc}}); }
+    } else if (!ha && hb) {
+      if (sc < b->second.score) { i2l.erase(i2l.find(b->second.idx)); b->second = PS{il, sc}; i2l.insert({il, PS{ll, sc}}); }
+    } else {
+      if (sc < std::min(a->second.score, b->second.score)) {                      // case 1
+        i2l.erase(b->second.idx); l2i.erase(a->second.idx); i2l.erase(a); l2i.erase(b);
+        i2l.insert({il, PS{ll, sc}}); l2i.insert({ll, PS{il, sc}});
+      } else if (sc > a->second.score && sc < b->second.score) {                  // case 2
+        i2l.erase(i2l.find(b->second.idx)); l2i.erase(b);
+      } else if (sc < a->second.score && sc > b->second.score) {                  // case 3
+        l2i.erase(l2i.find(a->second.idx)); i2l.erase(a);
+      }
+    }
+  }
+  std::vector<CamLidarPair> out;
+  for (auto& kv : i2l) { CamLidarPair p{}; p.image_line = kv.first; p.lidar_line = kv.second.idx; p.angle = kv.second.score; out.push_back(p); }
+  pairs.swap(out);
+}
+
 inline void AssociateByAngle(const Equirect& eq, const float* lines, int L, const float* cloud_local, int P,
                              const int* p2s_off, const int* p2s_ids, int S, const int* seg_sizes,
                              const double* end_points /*S x 2 x 3, lidar frame*/, const double T_cl[16],
-                             bool filter_by_length, std::vector<CamLidarPair>& out) {
+                             bool filter_by_length, std::vector<CamLidarPair>& out, bool multiple_association = true,
+                             const unsigned char* image_mask = nullptr, const unsigned char* lidar_mask = nullptr) {
   std::vector<int> counts;
   AngleVotes(eq, lines, L, cloud_local, P, p2s_off, p2s_ids, S, T_cl, counts);
   const double thr = 3.0 / 180.0 * M_PI;
@@ -432,6 +464,7 @@ inline void AssociateByAngle(const Equirect& eq, const float* lines, int L, cons
   }
   std::vector<CamLidarPair> pairs;
   for (int l = 0; l < L; ++l) {
+    if (image_mask && !image_mask[l]) continue;               // :396
     const double px1[2] = {lines[l * 4], lines[l * 4 + 1]}, px2[2] = {lines[l * 4 + 2], lines[l * 4 + 3]};
     double p1[3], p2[3]; eq.ImageToCam(px1, 1.0, p1); eq.ImageToCam(px2, 1.0, p2);
     double plane[4]; FormPlane3(p1, p2, zero, plane);
@@ -443,6 +476,7 @@ inline void AssociateByAngle(const Equirect& eq, const float* lines, int L, cons
       const int cnt = counts[(size_t)l * S + s];
       if (cnt == 0) continue;
       if ((size_t)cnt < (size_t)seg_sizes[s] / 2) continue;
+      if (lidar_mask && !lidar_mask[s]) continue;             // :420
       const double angle = PlaneAngle(plane, &lplane[s * 4], true);
       if (angle > thr) continue;
       double mid[3], midp[3];
@@ -472,6 +506,10 @@ inline void AssociateByAngle(const Equirect& eq, const float* lines, int L, cons
       if (len < 100.f || len > 2000.f) continue;
     }
     out.push_back(p);
+  }
+  if (!multiple_association) {                                // :465-466; pairs are rebuilt from the unfiltered camera-frame end points (:866-875)
+    UniqueLinePair(out);
+    for (CamLidarPair& p : out) for (int c = 0; c < 3; ++c) { p.start[c] = ep[p.lidar_line * 6 + c]; p.end[c] = ep[p.lidar_line * 6 + 3 + c]; }
   }
   // back to the LiDAR frame (:469-474): T_lc = T_cl^-1 (rigid)
   double Tlc[16] = {0};

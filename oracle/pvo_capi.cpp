@@ -189,11 +189,21 @@ void pvo_angle_votes(int rows, int cols, const float* lines, int L, const float*
 
 int pvo_associate_by_angle(int rows, int cols, const float* lines, int L, const float* cloud_local, int P, const int* p2s_off, const int* p2s_ids, int S,
                            const int* seg_sizes, const double* end_points, const double* T_cl, int filter_by_length, int max_out,
-                           int* out_img, int* out_lidar, double* out_start, double* out_end, float* out_angle) {
+                           int* out_img, int* out_lidar, double* out_start, double* out_end, float* out_angle, int multiple_association,
+                           const unsigned char* image_mask, const unsigned char* lidar_mask) {
   std::vector<CamLidarPair> v;
-  AssociateByAngle(Equirect{rows, cols}, lines, L, cloud_local, P, p2s_off, p2s_ids, S, seg_sizes, end_points, T_cl, filter_by_length != 0, v);
+  AssociateByAngle(Equirect{rows, cols}, lines, L, cloud_local, P, p2s_off, p2s_ids, S, seg_sizes, end_points, T_cl, filter_by_length != 0, v, multiple_association != 0,
+                   image_mask, lidar_mask);
   const int n = std::min<int>((int)v.size(), max_out);
   for (int i = 0; i < n; ++i) { out_img[i] = v[i].image_line; out_lidar[i] = v[i].lidar_line; std::memcpy(out_start + 3 * i, v[i].start, 24); std::memcpy(out_end + 3 * i, v[i].end, 24); out_angle[i] = v[i].angle; }
+  return (int)v.size();
+}
+
+int pvo_unique_line_pairs(int n, const int* image_line, const int* lidar_line, const float* score, int* out_img, int* out_lidar, float* out_score) {
+  std::vector<CamLidarPair> v(n);
+  for (int i = 0; i < n; ++i) { v[i] = CamLidarPair{}; v[i].image_line = image_line[i]; v[i].lidar_line = lidar_line[i]; v[i].angle = score[i]; }
+  UniqueLinePair(v);
+  for (size_t i = 0; i < v.size(); ++i) { out_img[i] = v[i].image_line; out_lidar[i] = v[i].lidar_line; out_score[i] = v[i].angle; }
   return (int)v.size();
 }
 

@@ -108,7 +108,7 @@ EXPORTS = [
     "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
     "pvb_pair_knn5", "pvb_nearest_line", "pvb_point2line_segment_knn_associate", "pvb_point2line_segment_knn_tail", "pvb_point2line_segment_associate",
     "pvb_line2line_knn_associate", "pvb_line2line_knn_tail", "pvb_line_tracks_build", "pvb_line_tracks_gate", "pvb_generate_line_tracks",
-    "pvb_blocks_set_linear_solver", "pvb_cholesky_solve",
+    "pvb_blocks_set_linear_solver", "pvb_cholesky_solve", "pvb_unique_line_pairs",
 ]
 
 
@@ -450,12 +450,25 @@ class Context:
         m = n.value
         return nl[:m].copy(), rl[:m].copy(), a[:m].copy(), b[:m].copy()
 
-    def camera_lidar_associate(self, rows, cols, lines, lidar, T_cl, filter_by_length=True):
+    @staticmethod
+    def unique_line_pairs(image_line, lidar_line, score):
+        il, ll, sc = _arr(image_line, np.int32), _arr(lidar_line, np.int32), _arr(score, np.float32)
+        m = max(1, len(il))
+        oi, ol, os_, n = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros(m, np.float32), C.c_int()
+        rc = load_library().pvb_unique_line_pairs(C.c_int(len(il)), _p(il), _p(ll), _p(sc), C.byref(n), _p(oi), _p(ol), _p(os_))
+        if rc:
+            raise PvbError(f"pvb_unique_line_pairs: code {rc}")
+        return oi[:n.value].copy(), ol[:n.value].copy(), os_[:n.value].copy()
+
+    def camera_lidar_associate(self, rows, cols, lines, lidar, T_cl, filter_by_length=True, multiple_association=True, image_mask=None, lidar_mask=None):
         ln = _arr(lines, np.float32).reshape(-1, 4)
         cap = max(1, len(ln) * max(1, lidar.c.n_segments))
         il, ll, s, e, ang, n = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros(cap, np.float32), C.c_int()
+        im = None if image_mask is None else _arr(image_mask, np.uint8)
+        lm = None if lidar_mask is None else _arr(lidar_mask, np.uint8)
         self._ck(self._L.pvb_camera_lidar_associate(self._h, C.c_int(rows), C.c_int(cols), _p(ln), C.c_int(len(ln)), C.byref(lidar.c), _p(_arr(T_cl, np.float64)),
-                                                     C.c_int(int(filter_by_length)), C.c_int(cap), C.byref(n), _p(il), _p(ll), _p(s), _p(e), _p(ang)))
+                                                     C.c_int(int(filter_by_length)), C.c_int(int(multiple_association)), _p(im), _p(lm),
+                                                     C.c_int(cap), C.byref(n), _p(il), _p(ll), _p(s), _p(e), _p(ang)))
         m = n.value
         return il[:m].copy(), ll[:m].copy(), s[:m].copy(), e[:m].copy(), ang[:m].copy()
 

@@ -412,7 +412,37 @@ int pvb_generate_line_tracks(pvb_ctx* ctx, int n_frames, const pvb_line_frame* f
   return pvb_line_tracks_build((int)pa.size(), pa.data(), pb.data(), off.data(), ma.data(), mb.data(), min_track_length, 1, cap_features, n_tracks, track_off, feat_frame, feat_line);
 }
 
+// CameraLidarLineAssociate::UniqueLinePair (:754-876): reduce (image line, LiDAR line, score) candidates, processed in input order, to a
+// one-to-one matching in which a pair displaces an existing one only with a strictly smaller score; output ascending by image line.
+int pvb_unique_line_pairs(int n, const int* image_line, const int* lidar_line, const float* score, int* n_out, int* out_image, int* out_lidar, float* out_score) {
+  if (n < 0 || !n_out || (n > 0 && (!image_line || !lidar_line || !score || !out_image || !out_lidar || !out_score))) return PVB_ERR_ARG;
+  int max_i = -1, max_l = -1;
+  for (int k = 0; k < n; ++k) { if (image_line[k] < 0 || lidar_line[k] < 0) return PVB_ERR_ARG; max_i = std::max(max_i, image_line[k]); max_l = std::max(max_l, lidar_line[k]); }
+  std::vector<int> lidar_of(max_i + 1, -1), image_of(max_l + 1, -1);          // current partner (or -1) of every image / LiDAR line
+  std::vector<float> s_img(max_i + 1, 0.f);                                   // score of the pair an image line currently holds
+  auto drop_image = [&](int i) { image_of[lidar_of[i]] = -1; lidar_of[i] = -1; };
+  auto take = [&](int i, int l, float sc) { lidar_of[i] = l; image_of[l] = i; s_img[i] = sc; };
+  for (int k = 0; k < n; ++k) {
+    const int i = image_line[k], l = lidar_line[k]; const float sc = score[k];
+    const bool hi = lidar_of[i] >= 0, hl = image_of[l] >= 0;
+    if (!hi && !hl) take(i, l, sc);
+    else if (hi && !hl) { if (sc < s_img[i]) { drop_image(i); take(i, l, sc); } }
+    else if (!hi && hl) { if (sc < s_img[image_of[l]]) { drop_image(image_of[l]); take(i, l, sc); } }
+    else {
+      const float si = s_img[i], sl = s_img[image_of[l]];
+      if (sc < std::min(si, sl)) { drop_image(image_of[l]); drop_image(i); take(i, l, sc); }   // beats both: replaces both
+      else if (sc > si && sc < sl) drop_image(image_of[l]);                     // would displace l's pair but loses to i's: l's pair goes
+      else if (sc < si && sc > sl) drop_image(i);                               // symmetric
+    }
+  }
+  int m = 0;
+  for (int i = 0; i <= max_i; ++i) if (lidar_of[i] >= 0) { out_image[m] = i; out_lidar[m] = lidar_of[i]; out_score[m] = s_img[i]; ++m; }
+  *n_out = m;
+  return PVB_OK;
+}
+
 int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* lines4, int L, const pvb_line_frame* lidar, const double* T, int filter_by_length,
+                               int multiple_association, const unsigned char* image_line_mask, const unsigned char* lidar_line_mask,
                                int cap, int* n_out, int* image_line, int* lidar_line, double* start3, double* end3, float* angle_out) {
   if (!ctx || !lidar || !T || !n_out || !lidar->end_points) return PVB_ERR_ARG;
   *n_out = 0;
@@ -434,6 +464,7 @@ int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* li
   struct P { int il, ll; double s[3], e[3]; float ang; };
   std::vector<P> pairs;
   for (int l = 0; l < L; ++l) {
+    if (image_line_mask && !image_line_mask[l]) continue;                      // :396
     double p1[3], p2[3], plane[4];
     image_to_cam_f64(lines4[l * 4], lines4[l * 4 + 1], rows, cols, p1);
     image_to_cam_f64(lines4[l * 4 + 2], lines4[l * 4 + 3], rows, cols, p2);
@@ -445,6 +476,7 @@ int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* li
       const int cnt = counts[(size_t)l * S + s];
       if (cnt == 0) continue;
       if ((size_t)cnt < (size_t)seg_size[s] / 2) continue;                     // :417
+      if (lidar_line_mask && !lidar_line_mask[s]) continue;                    // :420
       const double ang = plane_angle(plane, &lplane[4 * s], true);
       if (ang > thr) continue;                                                 // :422-424
       double mid[3], midp[3];
@@ -462,7 +494,7 @@ int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* li
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Tlc[r * 4 + c] = T[c * 4 + r];
   for (int r = 0; r < 3; ++r) Tlc[r * 4 + 3] = -(Tlc[r * 4] * T[3] + Tlc[r * 4 + 1] * T[7] + Tlc[r * 4 + 2] * T[11]);
   Tlc[15] = 1;
-  int n = 0;
+  std::vector<P> kept;
   for (const P& p : pairs) {
     if (filter_by_length) {                                                    // Filter(false, true): :676-692
       float ua, va, ub, vb;
@@ -478,6 +510,20 @@ int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* li
       }
       if (len < 100.f || len > 2000.f) continue;
     }
+    kept.push_back(p);
+  }
+  if (!multiple_association && !kept.empty()) {                                // :465-466 UniqueLinePair; pairs rebuilt from the camera-frame end points (:866-875)
+    const int m = (int)kept.size();
+    std::vector<int> il(m), ll(m), oi(m), ol(m); std::vector<float> sc(m), os(m);
+    for (int k = 0; k < m; ++k) { il[k] = kept[k].il; ll[k] = kept[k].ll; sc[k] = kept[k].ang; }
+    int mu = 0;
+    const int rc2 = pvb_unique_line_pairs(m, il.data(), ll.data(), sc.data(), &mu, oi.data(), ol.data(), os.data());
+    if (rc2) return rc2;
+    kept.resize(mu);
+    for (int k = 0; k < mu; ++k) { kept[k].il = oi[k]; kept[k].ll = ol[k]; kept[k].ang = os[k]; std::memcpy(kept[k].s, &ep[6 * ol[k]], 24); std::memcpy(kept[k].e, &ep[6 * ol[k] + 3], 24); }
+  }
+  int n = 0;
+  for (const P& p : kept) {
     if (n >= cap) return PVB_ERR_ARG;
     image_line[n] = p.il; lidar_line[n] = p.ll; angle_out[n] = p.ang;
     transform4(Tlc, p.s, start3 + 3 * n); transform4(Tlc, p.e, end3 + 3 * n);

@@ -201,3 +201,27 @@ def test_line_tracks_match_oracle_and_connected_components(oracle):
             tr = {(int(f), int(l)): t for t, fs in enumerate(got) for f, l in fs}
             assert np.array_equal(keep, [tr.get((rf, int(a)), -1) == tr.get((nf_, int(b)), -2) for a, b in zip(rl, nln)])
     assert Context.line_tracks_build(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32)) == []
+
+
+def test_unique_line_pairs_matches_oracle_and_is_one_to_one(oracle):
+    """pvb_unique_line_pairs vs the oracle's restatement of UniqueLinePair (CameraLidarLineAssociate.cpp:754-876), incl. score ties (strict
+    inequalities: a tie never displaces) and the three-way cases."""
+    rng = np.random.default_rng(12)
+    for trial in range(200):
+        n = int(rng.integers(0, 40))
+        il, ll = rng.integers(0, 8, n), rng.integers(0, 8, n)
+        keep = np.unique(np.stack([il, ll], 1), axis=0, return_index=True)[1] if n else np.zeros(0, int)
+        keep.sort()
+        il, ll = il[keep], ll[keep]
+        sc = (rng.integers(0, 12, len(il)) * np.float32(0.01)).astype(np.float32)          # coarse scores => many ties
+        got = Context.unique_line_pairs(il, ll, sc)
+        exp = oracle.unique_line_pairs(il, ll, sc)
+        assert all(np.array_equal(g, e) for g, e in zip(got, exp))
+        assert len(set(got[0].tolist())) == len(got[0]) and len(set(got[1].tolist())) == len(got[1])
+        for i, l, s_ in zip(*got):                                                         # every surviving pair is one of the candidates
+            assert np.any((il == i) & (ll == l) & (sc == s_))
+    # hand cases from the reference's comment (:812-820): L1-A 0.3, L2-B 0.5, then L1-B
+    assert [x.tolist() for x in Context.unique_line_pairs([1, 2, 1], [0, 1, 1], [0.3, 0.5, 0.1])[:2]] == [[1], [1]]            # case 1: replaces both
+    assert [x.tolist() for x in Context.unique_line_pairs([1, 2, 1], [0, 1, 1], [0.3, 0.5, 0.4])[:2]] == [[1], [0]]            # case 2: L2-B dropped
+    assert [x.tolist() for x in Context.unique_line_pairs([1, 2, 1], [0, 1, 1], [0.5, 0.3, 0.4])[:2]] == [[2], [1]]            # case 3: L1-A dropped
+    assert [x.tolist() for x in Context.unique_line_pairs([1, 2, 1], [0, 1, 1], [0.3, 0.5, 0.9])[:2]] == [[1, 2], [0, 1]]      # case 4: unchanged

@@ -498,6 +498,21 @@ def test_camera_lidar_associate_matches_oracle(gpu_ctx, oracle):
         assert np.array_equal(il, oi) and np.array_equal(ll, ol) and np.array_equal(ang, oa)
         assert np.abs(s - os_).max() < 1e-12 and np.abs(e - oe).max() < 1e-12
     assert len(oi) >= 3
+    # duplicated image lines compete for the same LiDAR segments: UniqueLinePair (multiple_association = false, the reference default) keeps the best one
+    lines2 = np.concatenate([lines, px.astype(np.float32) + np.float32(1.5)])
+    many = gpu_ctx.camera_lidar_associate(rows, cols, lines2, _line_frame(A), T, True, True)
+    uniq = gpu_ctx.camera_lidar_associate(rows, cols, lines2, _line_frame(A), T, True, False)
+    exp = oracle.associate_by_angle(rows, cols, lines2, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], sizes, A["end_points"], T, True, False)
+    assert len(uniq[0]) < len(many[0]) and len(set(uniq[0].tolist())) == len(uniq[0]) and len(set(uniq[1].tolist())) == len(uniq[1])
+    assert np.array_equal(uniq[0], exp[0]) and np.array_equal(uniq[1], exp[1]) and np.array_equal(uniq[4], exp[4])
+    assert np.abs(uniq[2] - exp[2]).max() < 1e-12 and np.abs(uniq[3] - exp[3]).max() < 1e-12
+    # masks (CameraLidarOptimizer.cpp:362-364): excluded image lines / LiDAR segments never appear
+    im = np.ones(len(lines2), np.uint8); im[many[0][0]] = 0
+    lm = np.ones(len(sizes), np.uint8); lm[many[1][-1]] = 0
+    got = gpu_ctx.camera_lidar_associate(rows, cols, lines2, _line_frame(A), T, True, True, im, lm)
+    exp = oracle.associate_by_angle(rows, cols, lines2, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], sizes, A["end_points"], T, True, True, im, lm)
+    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]) and np.array_equal(got[4], exp[4])
+    assert many[0][0] not in got[0] and many[1][-1] not in got[1] and 0 < len(got[0]) < len(many[0])
 
 
 def _oracle_refine(oracle, frames, poses, cfg):
