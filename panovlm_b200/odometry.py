@@ -11,10 +11,11 @@ from .api import BlockList, Context, LineFrame
 
 
 class OdometryConfig:
-    def __init__(self, point_to_plane=True, line_to_line=True, angle_residual=True, normalize_distance=True, plane_dis_threshold=1.0,
+    def __init__(self, point_to_plane=True, line_to_line=True, point_to_line=False, use_segment=True, angle_residual=True, normalize_distance=True, plane_dis_threshold=1.0,
                  line_dis_threshold=0.3, plane_tolerance=0.05, lidar_weight=0.01, neighbor_size=6, max_lm_iterations=20, line_tracks=True,
                  track_neighbor_size=4, min_track_length=3):
         self.point_to_plane, self.line_to_line = point_to_plane, line_to_line
+        self.point_to_line, self.use_segment = point_to_line, use_segment                           # config point_to_line_residual (off in Room.txt:72)
         self.angle_residual, self.normalize_distance = angle_residual, normalize_distance          # config/Room.txt:67-74
         self.plane_dis_threshold, self.line_dis_threshold, self.plane_tolerance = plane_dis_threshold, line_dis_threshold, plane_tolerance
         self.lidar_weight, self.neighbor_size, self.max_lm_iterations = lidar_weight, neighbor_size, max_lm_iterations
@@ -45,10 +46,26 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
     R_wl, t_wl = world_from_pose_blocks(poses, aa_to_R)
     neighbors = Context.find_neighbors(np.array(t_wl), None, None, cfg.neighbor_size)
     edges = [(i, j) for i in range(n) for j in neighbors[i] if 0 <= j < n and j != i]
-    cap = sum(len(frames[j]["surfFlat"]) for _, j in edges) + sum(len(frames[j]["cornerLessSharp"]) for _, j in edges) * 2 + 16
+    cap = sum(len(frames[j]["surfFlat"]) for _, j in edges) + sum(len(frames[j]["cornerLessSharp"]) for _, j in edges) * 6 + 16
     bl = BlockList(cap)
-    if cfg.line_to_line:                                            # AddLidarLineToLineResidual2 (Optimization.cpp:329-441)
+    lf = None
+    if cfg.line_to_line or cfg.point_to_line:
         lf = [LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], R_wl[i], t_wl[i]) for i, f in enumerate(frames)]
+    if cfg.point_to_line:                                           # AddLidarPointToLineResidual (Optimization.cpp:443-504): consecutive frames only (:475)
+        near = [(i, j) for (i, j) in edges if abs(i - j) <= 1]
+        if cfg.use_segment:                                         # AssociatePoint2LineSegmentKNN (:482)
+            for (i, j) in near:
+                _, _, pt, a, b = ctx.point2line_segment_knn_associate(lf[i], lf[j], cfg.line_dis_threshold)
+                Context.build_point2line_blocks(bl, pt, a, b, i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
+        elif near:                                                  # AssociatePoint2Line (:484)
+            ctx.frames_set_corners([f["cornerLessSharp"] for f in frames])
+            e, _, pt, a, b = ctx.frames_associate_point2line(poses, np.array([x[0] for x in near], np.int32), np.array([x[1] for x in near], np.int32), cfg.line_dis_threshold)
+            bounds = np.searchsorted(e, np.arange(len(near) + 1))
+            for ei, (i, j) in enumerate(near):
+                lo, hi = bounds[ei], bounds[ei + 1]
+                if hi > lo:
+                    Context.build_point2line_blocks(bl, pt[lo:hi], a[lo:hi], b[lo:hi], i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
+    if cfg.line_to_line:                                            # AddLidarLineToLineResidual2 (Optimization.cpp:329-441)
         world = [ctx.transform_cloud(f["cornerLessSharp"], R_wl[i], t_wl[i]) for i, f in enumerate(frames)]
         tracks = None
         if cfg.line_tracks:                                         # LidarLineMatch::GenerateTracks (LidarLineMatch.cpp:36-86), threshold hard-coded 0.3

@@ -597,6 +597,35 @@ def test_generate_line_tracks_matches_oracle(gpu_ctx, oracle):
     assert len(got) == len(exp) and all(np.array_equal(g, e) for g, e in zip(got, exp))
 
 
+def test_odometry_point_to_line_blocks_match_oracle_associations(gpu_ctx, oracle):
+    """AddLidarPointToLineResidual (util/Optimization.cpp:443-504) through build_problem: consecutive frames only, both association branches."""
+    from panovlm_b200 import odometry, synth
+    frames = synth.make_sequence(5, n_az=900)
+    poses = odometry.pose_blocks_from_world([f["R_wl"] for f in frames], [f["t_wl"] for f in frames], oracle.R_to_aa)
+    R_wl = [oracle.aa_to_R(p[:3]).T for p in poses]; t_wl = [-R @ p[3:] for R, p in zip(R_wl, poses)]
+    cw = [oracle.transform_cloud(R_wl[i], t_wl[i], f["cornerLessSharp"]) for i, f in enumerate(frames)]
+    for use_segment in (True, False):
+        cfg = odometry.OdometryConfig(point_to_plane=False, line_to_line=False, point_to_line=True, use_segment=use_segment, line_dis_threshold=0.4)
+        bl, edges = odometry.build_problem(gpu_ctx, frames, poses, cfg, oracle.aa_to_R)
+        v = bl.view()
+        rows = []
+        for (i, j) in edges:
+            if abs(i - j) > 1:
+                continue
+            if use_segment:
+                _, _, pt, a, b = oracle.associate_p2line_segment_knn(cw[i], frames[i]["p2s_off"], frames[i]["p2s_ids"], frames[i]["segment_coeffs"], cw[j], R_wl[j], t_wl[j], 0.4)
+            else:
+                _, pt, a, b = oracle.associate_p2line(cw[i], R_wl[i], t_wl[i], cw[j], R_wl[j], t_wl[j], 0.4)
+            for k in range(len(pt)):
+                d = (a[k] - b[k]) / np.linalg.norm(a[k] - b[k])
+                rows.append((i, j, pt[k], a[k], d))
+        assert len(rows) == bl.n and bl.n > 50
+        assert np.array_equal(v["ref"], [r[0] for r in rows]) and np.array_equal(v["nei"], [r[1] for r in rows]) and np.all(v["type"] == 3)
+        assert np.abs(v["consts"][:, :3] - np.array([r[2] for r in rows])).max() < 1e-9 and np.abs(v["consts"][:, 3:6] - np.array([r[3] for r in rows])).max() < 1e-9
+        dd = np.abs(np.sum(v["consts"][:, 6:9] * np.array([r[4] for r in rows]), axis=1))        # PCA direction sign is free
+        assert np.abs(dd - 1).max() < 1e-9
+
+
 def test_odometry_outer_iteration_matches_oracle_loop(gpu_ctx, oracle):
     """configs[1]-shaped (small): 6 frames, line-to-line + point-to-plane angle residuals, first frame fixed;
     two outer iterations of RefinePose through the C ABI vs the same loop on the oracle: pose deltas <= 1e-4 relative."""
