@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
 #pragma unroll
       for (int j = 0; j < K; ++j) s_win[j][i] = 0xFFFFFFFFu;
     }
-    valid = associate_point2plane<K, REF_ID>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
+    valid = associate_point2plane<K, REF_ID, !STAGE>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
                                      range_get);
     auto load = loadg;     // the debug view below is only built without staging
     if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)

@@ -212,9 +212,115 @@ PVB_HD int knn_select(const GridDesc& g, const CellLoader& cells, const Load1& l
   return n_out;
 }
 
+// ---- pruned variant (default path): the 3x3x3 block is visited row by row, nearest rows first; a row - and, inside a row, each of
+// the two outer cells - is skipped when even its nearest face is farther than the current K-th distance (pass 1) / than tau (pass 2).
+// A skipped cell cannot hold one of the K nearest points (strict comparison with a 1e-5 relative safety margin on the bound for the
+// float rounding of d2), so the selected set is the same as that of the exhaustive walk; on surface-like clouds about half of the
+// candidates are never touched.  Row ranges are looked up when needed (no per-thread range storage).
+template <int K, typename CellLoader, typename F>
+PVB_HD void walk_block_pruned(const GridDesc& g, const CellLoader& cells, int cx, int cy, int cz, const double gap_lo[3], const double gap_hi[3], int R,
+                              const uint32_t& limit_key, const F& body) {
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  const int W = 2 * R + 1;
+  // distance from the query to the nearest face of the cells `d` steps away along axis a (d != 0)
+  auto gap = [&](int a, int d) { return d < 0 ? gap_lo[a] + (double)(-d - 1) * g.h : gap_hi[a] + (double)(d - 1) * g.h; };
+#pragma unroll 1
+  for (int o = 0; o < W * W; ++o) {
+    const int iz = o / W, iy = o - iz * W;
+    const int dz = (iz & 1) ? -((iz + 1) >> 1) : (iz >> 1);      // 0, -1, +1, -2, +2: nearest rows first
+    const int dy = (iy & 1) ? -((iy + 1) >> 1) : (iy >> 1);
+    const int y = cy + dy, z = cz + dz;
+    if (y < 0 || y >= ny || z < 0 || z >= nz) continue;
+    const double gy = dy == 0 ? 0.0 : gap(1, dy), gz = dz == 0 ? 0.0 : gap(2, dz);
+    const double b2 = (gy * gy + gz * gz) * (1.0 - 1e-5);
+    if (f2u((float)b2) > limit_key) continue;
+    int xa = cx, xb = cx;
+    for (int d = 1; d <= R; ++d) {
+      const double gx = gap(0, -d);
+      if (cx - d < 0 || f2u((float)(b2 + gx * gx * (1.0 - 1e-5))) > limit_key) break;
+      xa = cx - d;
+    }
+    for (int d = 1; d <= R; ++d) {
+      const double gx = gap(0, d);
+      if (cx + d > nx - 1 || f2u((float)(b2 + gx * gx * (1.0 - 1e-5))) > limit_key) break;
+      xb = cx + d;
+    }
+    const long long row = ((long long)z * ny + y) * nx;
+    const uint32_t lo = (uint32_t)cells(row + xa), hi = (uint32_t)cells(row + xb + 1);
+#pragma unroll 2
+    for (uint32_t i = lo; i < hi; ++i) body((long long)i);
+  }
+}
+
+template <int K, typename CellLoader, typename Load, typename Sink>
+PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const Load& load, float qx, float qy, float qz, float sq_thr, int r0, int rmax, const Sink& sink) {
+  const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
+  uint32_t keys[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) keys[j] = init;
+  const double fx = ((double)qx - g.origin[0]) * g.inv_h, fy = ((double)qy - g.origin[1]) * g.inv_h, fz = ((double)qz - g.origin[2]) * g.inv_h;
+  const int cx = cell_coord((double)qx, g.origin[0], g.inv_h, g.dims[0]);
+  const int cy = cell_coord((double)qy, g.origin[1], g.inv_h, g.dims[1]);
+  const int cz = cell_coord((double)qz, g.origin[2], g.inv_h, g.dims[2]);
+  // distances (m) from the query to the faces of its own cell: lower bounds for every point of the neighbouring cells on that side
+  // (0 when the query was clamped into the grid on that side)
+  double gap_lo[3], gap_hi[3], slack = 0.5;
+  {
+    const double f[3] = {fx - cx, fy - cy, fz - cz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double lo = f[a] < 0.0 ? 0.0 : f[a], hi = 1.0 - f[a] < 0.0 ? 0.0 : 1.0 - f[a];
+      gap_lo[a] = lo * g.h; gap_hi[a] = hi * g.h;
+      const double m = lo < hi ? lo : hi;
+      slack = m < slack ? m : slack;
+    }
+  }
+  walk_block_pruned<K>(g, cells, cx, cy, cz, gap_lo, gap_hi, r0, keys[K - 1], [&](long long i) {
+    const F4 c = load(i);
+    topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
+  });
+  int r = r0;
+  bool done = false;
+  if (keys[K - 1] != init) {
+    const double reach = ((double)r0 + slack) * g.h;
+    done = (double)u2f(keys[K - 1]) < reach * reach * (1.0 - 1e-6);
+  }
+  if (rmax < r0) rmax = r0;
+  if (!done) {        // rare: widen ring by ring (generic nested loops)
+    for (r = r0 + 1; r <= rmax; ++r) {
+      for_each_range(g, cells, cx, cy, cz, r, false, [&](long long lo, long long hi) { scan_values<K>(load, lo, hi, qx, qy, qz, keys); });
+      if (keys[K - 1] != init) {      // ring r covers every point closer than (r + slack) * h
+        const double reach = ((double)r + slack) * g.h;
+        if ((double)u2f(keys[K - 1]) < reach * reach * (1.0 - 1e-6)) break;
+      }
+    }
+    if (r > rmax) r = rmax;
+  }
+  if (keys[K - 1] == init) return 0;
+  const uint32_t tau = keys[K - 1];
+  int n_lt = 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) n_lt += keys[j] < tau ? 1 : 0;
+  int eq_taken = 0, n_out = 0;
+  const int eq_needed = K - n_lt;
+  if (r == r0) {
+    walk_block_pruned<K>(g, cells, cx, cy, cz, gap_lo, gap_hi, r0, tau, [&](long long i) {
+      const F4 c = load(i);
+      const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
+      bool take = kb < tau;
+      if (kb == tau && eq_taken < eq_needed) { take = true; ++eq_taken; }
+      if (take) { sink(n_out, (uint32_t)i, kb); ++n_out; }
+    });
+  } else {
+    for_each_range(g, cells, cx, cy, cz, r, true, [&](long long lo, long long hi) { scan_collect(load, lo, hi, qx, qy, qz, tau, eq_needed, eq_taken, n_out, sink); });
+  }
+  return n_out;
+}
+
 struct AssocParams {
   float sq_thr;           // point_to_plane_dis_threshold^2 computed in float (LidarFeatureAssociate.cpp:557)
   int rmax;               // ceil(thr / h)
+  int r0;                 // radius (cells) of the block the pruned walk starts with: 1 = 3x3x3, 2 = 5x5x5 (finer grids)
   double plane_tol;       // lidar_plane_tolerance
   double collinear_tol;   // 3.0 (LidarFeatureAssociate.cpp:594)
 };
@@ -225,13 +331,15 @@ struct AssocParams {
 // caller's per-query neighbour slots (shared memory on the device).
 // REF_ID: the reference frame's pose is exactly the identity (rigid target map): World2Local of a neighbour is then the
 // neighbour itself bit for bit (x*1 + y*0 + z*0 - 0), so the 3 x K matrix-vector products per query are skipped.
-template <int K, bool REF_ID, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+template <int K, bool REF_ID, bool PRUNE, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
 PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const Load1& load1, const LoadG& loadg, const RowMap& row_map, const AssocParams& prm,
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
                                   double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get) {
   int ring = 1;
-  const int found = knn_select<K>(g, cells, load1, loadg, row_map, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
+  int found;
+  if (PRUNE) { found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }); ring = 2; }
+  else found = knn_select<K>(g, cells, load1, loadg, row_map, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
   if (found < K) return false;                                   // :578
   auto load = [&](long long pos) { return ring == 1 ? load1(pos) : loadg(pos); };   // neighbour positions live in the space they were found in (k-th beyond the threshold) + quirk C.6 guard
   // neighbours -> reference sensor frame (:587), streamed: Gram matrix for the LSQ plane and the scatter matrix

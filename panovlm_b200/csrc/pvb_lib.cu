@@ -68,7 +68,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 6, tune_stage = 0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
+  int tune_minb = 6, tune_stage = 0, tune_r0 = 1; double tune_cellcap = 4.0, tune_hscale = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
@@ -188,11 +188,11 @@ int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_
     if (cnt == 0) { g.dims[0] = g.dims[1] = g.dims[2] = 1; g.h = 1.0; g.inv_h = 1.0; g.origin[0] = g.origin[1] = g.origin[2] = 0; cells += 2; continue; }
     double lo[3], ext[3];
     for (int k = 0; k < 3; ++k) { lo[k] = unordered_f32(init[(size_t)c * 6 + k]); ext[k] = std::max(1e-3, (double)unordered_f32(init[(size_t)c * 6 + 3 + k]) - lo[k]); }
-    double h = cell_hint > 0 ? cell_hint : std::cbrt(ext[0] * ext[1] * ext[2] / (double)cnt);
+    double h = cell_hint > 0 ? cell_hint : ctx->tune_hscale * std::cbrt(ext[0] * ext[1] * ext[2] / (double)cnt);
     h = std::max(h, 0.02);
     for (;;) {
       double nc = 1; for (int k = 0; k < 3; ++k) nc *= std::floor(ext[k] / h) + 1;
-      if (nc <= 4.0 * cnt + 4096.0 && nc < 1.5e9) break;
+      if (nc <= ctx->tune_cellcap * cnt + 4096.0 && nc < 1.5e9) break;
       h *= 1.25;
     }
     g.h = h; g.inv_h = 1.0 / h;
@@ -237,6 +237,7 @@ int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_ide
   const bool dbg = a.out_nn_idx != nullptr;
   if (k != 5 && k != 10) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
   a.stats = nullptr;
+  a.prm.r0 = ctx->tune_r0;
   if (stage && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
 #define PVB_LAUNCH(KK, MB, DBG, ST) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, ST, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, ST, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
 #define PVB_DISPATCH(KK)                                                                                   \
@@ -268,6 +269,9 @@ int pvb_create(int device, pvb_ctx** out) {
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->bev0); cudaEventCreate(&ctx->bev1);
   if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e);
   if (const char* e = getenv("PVB_STAGE")) ctx->tune_stage = atoi(e) != 0;
+  if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
+  if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
+  if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = std::max(0.1, atof(e));
   if (ctx->d_stats.ensure(16) == cudaSuccess) cudaMemset(ctx->d_stats.p, 0, 16);
   *out = ctx;
   return PVB_OK;

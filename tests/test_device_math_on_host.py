@@ -45,7 +45,11 @@ def test_zero_rows_and_golden_functors(harness):
         assert (np.abs(J - g["jacobian"]) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1, keepdims=True))).max() < 1e-7
 
 
-def test_grid_knn_and_association_equal_oracle(oracle, harness):
+@pytest.mark.parametrize("prune", [1, 2, 0])
+def test_grid_knn_and_association_equal_oracle(oracle, harness, prune):
+    """prune = 1 / 2: the pruned walk starting from a 3x3x3 / 5x5x5 block (rows / cells beyond the running K-th distance are skipped);
+    0: the exhaustive block walk."""
+    harness.pvbh_set_prune(C.c_int(prune))
     g = np.load(os.path.join(G, "assoc_pair.npz"))
     refw, neiw = np.ascontiguousarray(g["ref_world"]), np.ascontiguousarray(g["nei_world"])
     R_ref, t_ref, R_nei, t_nei = (np.ascontiguousarray(g[k]) for k in ("R_ref", "t_ref", "R_nei", "t_nei"))
@@ -142,3 +146,38 @@ def test_point2line_association_equals_oracle(oracle, harness):
         swapped = np.abs(pa[q] - ob).max(1) < 1e-9
         assert np.all(same | swapped)
         assert np.all(np.where(same, np.abs(pb[q] - ob).max(1), np.abs(pb[q] - oa).max(1)) < 1e-9)
+
+
+def test_pruned_block_walk_is_exact_on_random_surface_clouds(oracle, harness):
+    """Fuzz of the pruned walk (knn_select_pruned): planar clouds with duplicates, queries inside / outside the grid, cell sizes from far
+    below to far above the k-NN radius; the neighbour lists must equal the brute-force search bit for bit."""
+    I, z = np.eye(3), np.zeros(3)
+    rng = np.random.default_rng(21)
+    for trial in range(16):
+        harness.pvbh_set_prune(C.c_int(1 + trial % 2))
+        n = int(rng.integers(400, 3000))
+        uv = rng.uniform(-2, 2, (n, 2))
+        which = rng.integers(0, 3, n)
+        pts = np.zeros((n, 4), np.float32)
+        pts[:, 0] = np.where(which == 0, uv[:, 0], np.where(which == 1, 1.5, uv[:, 0]))
+        pts[:, 1] = np.where(which == 0, uv[:, 1], np.where(which == 1, uv[:, 0], -0.7))
+        pts[:, 2] = np.where(which == 0, 0.3, uv[:, 1])
+        pts[:, :3] += rng.normal(0, 0.005, (n, 3)).astype(np.float32)
+        pts[: n // 10, :3] = pts[n // 10: 2 * (n // 10), :3][: n // 10]                # exact duplicates => distance ties
+        m = 300
+        qry = np.zeros((m, 4), np.float32)
+        qry[:, :3] = pts[rng.integers(0, n, m), :3] + rng.normal(0, 0.02, (m, 3)).astype(np.float32)
+        qry[:20, :3] += rng.normal(0, 3.0, (20, 3)).astype(np.float32)                # far outside the grid: clamped cell coordinates
+        K = int(rng.choice([5, 10])); h = float(rng.choice([0.03, 0.08, 0.2, 0.6])); thr = float(rng.choice([0.25, 1.0]))
+        valid, pl2, pt2 = np.zeros(m, np.uint8), np.zeros((m, 4)), np.zeros((m, 3))
+        ni, nd = np.zeros((m, K), np.int32), np.zeros((m, K), np.float32)
+        harness.pvbh_associate(p(pts), C.c_int(n), p(I.copy()), p(z), p(qry), C.c_int(m), p(I.copy()), p(z), C.c_double(h), C.c_float(thr),
+                               C.c_double(0.05), C.c_int(K), p(valid), p(pt2), p(pl2), p(ni), p(nd))
+        idx, d2 = oracle.knn(pts, qry, K, False)
+        full = d2[:, K - 1] <= np.float32(thr) * np.float32(thr)
+        assert np.array_equal(d2[full], nd[full]), (trial, h, K)
+        # among exact ties the choice of equal-distance points is free; everything strictly inside tau must match
+        for r in np.nonzero(full)[0]:
+            inside = d2[r] < d2[r, K - 1]
+            assert set(idx[r][inside]) <= set(ni[r]), (trial, r)
+        assert np.all(ni[~full][:, K - 1] == -1)
