@@ -11,7 +11,7 @@
 using namespace pvb;
 
 // per-query association on a host-built grid (counting sort), K = 10 or 5
-static int g_prune = 1;   // 1: the pruned block walk of the default device path, 0: the exhaustive walk (the TMA-staged variant's)
+static int g_prune = 3;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned walk from a 3x3x3 / 5x5x5 block, 3: pruned + flattened (default device path)
 template <int K>
 static void associate_all(const float* tgt, int n, const double* R_ref, const double* t_ref, const float* qry, int m, const double* R_nei, const double* t_nei,
                           double h, float thr, double plane_tol, unsigned char* valid, double* p_local, double* plane, int* nn_idx, float* nn_d2) {
@@ -38,7 +38,7 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
   }
   auto cells = [&](long long c) { return (long long)start[c]; };
   auto load = [&](long long i) { return sorted[i]; };
-  AssocParams prm; prm.sq_thr = thr * thr; prm.rmax = (int)std::ceil((double)thr / h); prm.plane_tol = plane_tol; prm.collinear_tol = 3.0; prm.r0 = g_prune > 1 ? 2 : 1;
+  AssocParams prm; prm.sq_thr = thr * thr; prm.rmax = (int)std::ceil((double)thr / h); prm.plane_tol = plane_tol; prm.collinear_tol = 3.0; prm.r0 = g_prune == 2 ? 2 : 1;
   for (int i = 0; i < m; ++i) {
     uint32_t wpos[K];
     for (int j = 0; j < K; ++j) wpos[j] = 0xFFFFFFFFu;
@@ -49,10 +49,10 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
     auto range_set = [&](int k, uint32_t lo, uint32_t hi) { rng[2 * k] = lo; rng[2 * k + 1] = hi; };
     auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = rng[2 * k]; hi = rng[2 * k + 1]; };
     auto no_map = [](int, int, uint32_t&, uint32_t&) {};
-    valid[i] = (g_prune ? associate_point2plane<K, false, true>(g, cells, load, load, no_map, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei,
-                                                                p_local + 3 * i, plane + 4 * i, win, set_win, range_set, range_get)
-                        : associate_point2plane<K, false, false>(g, cells, load, load, no_map, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei,
-                                                                 p_local + 3 * i, plane + 4 * i, win, set_win, range_set, range_get)) ? 1 : 0;
+#define PVBH_ASSOC(MODE) associate_point2plane<K, false, MODE>(g, cells, load, load, no_map, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei, \
+                                                               p_local + 3 * i, plane + 4 * i, win, set_win, range_set, range_get)
+    valid[i] = (g_prune == 0 ? PVBH_ASSOC(0) : (g_prune == 3 ? PVBH_ASSOC(2) : PVBH_ASSOC(1))) ? 1 : 0;
+#undef PVBH_ASSOC
     std::vector<std::pair<std::pair<float, uint32_t>, int>> nn;
     for (int j = 0; j < K; ++j) {
       if (wpos[j] == 0xFFFFFFFFu) continue;
