@@ -160,9 +160,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 constexpr int kStageRows = 64;     // (y,z) rows of a tile's cell box that can be staged
 constexpr int kStageCap = 768;     // staged records per tile (12 KB of shared memory)
 
-template <int K, bool REDUCE, int MINB, bool DEBUG_NN, int MODE, bool REF_ID>   // MODE: 0 pruned rows, 1 exhaustive rows staged through TMA, 2 pruned rows + flattened list
+template <int K, bool REDUCE, int MINB, bool DEBUG_NN, bool STAGE, bool REF_ID>
 __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
-  constexpr bool STAGE = MODE == 1, FLAT = MODE == 2;
   __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
   __shared__ uint32_t s_win[K][kTile];           // record positions of each query's K neighbours
   __shared__ uint32_t s_rng[18][kTile];          // the <= 9 (lo, hi) row ranges of each query's 3x3x3 cell block
@@ -269,7 +268,7 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
 #pragma unroll
       for (int j = 0; j < K; ++j) s_win[j][i] = 0xFFFFFFFFu;
     }
-    valid = associate_point2plane<K, REF_ID, STAGE ? 0 : (FLAT ? 2 : 1)>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
+    valid = associate_point2plane<K, REF_ID, !STAGE>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
                                      range_get);
     auto load = loadg;     // the debug view below is only built without staging
     if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)

@@ -254,53 +254,8 @@ PVB_HD void walk_block_pruned(const GridDesc& g, const CellLoader& cells, int cx
   }
 }
 
-// ---- flattened variant of the pruned walk (3x3x3 start block): the surviving row ranges of a query are first written to a small
-// per-lane list (lock-step over the <= 9 rows, cheap), then ONE loop runs over all listed candidates with the next record prefetched.
-// Lanes of a warp no longer wait for the longest row of every step, only for the lane with the most candidates in total.
-template <typename CellLoader, typename RangeSet>
-PVB_HD int list_rows_pruned(const GridDesc& g, const CellLoader& cells, int cx, int cy, int cz, const FaceGaps& fg, int first_row, int last_row, uint32_t limit_key,
-                            const RangeSet& range_set) {
-  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
-  int n = 0;
-#pragma unroll 1
-  for (int o = first_row; o <= last_row; ++o) {
-    const int iz = o / 3, iy = o - iz * 3;
-    const int dz = (iz & 1) ? -1 : (iz >> 1), dy = (iy & 1) ? -1 : (iy >> 1);     // 0, -1, +1
-    const int y = cy + dy, z = cz + dz;
-    if (y < 0 || y >= ny || z < 0 || z >= nz) continue;
-    const float b2 = (dy == 0 ? 0.0f : (dy < 0 ? fg.lo[1] : fg.hi[1])) + (dz == 0 ? 0.0f : (dz < 0 ? fg.lo[2] : fg.hi[2]));
-    if (f2u(b2) > limit_key) continue;
-    const int xa = (cx - 1 < 0 || f2u(b2 + fg.lo[0]) > limit_key) ? cx : cx - 1;
-    const int xb = (cx + 1 > nx - 1 || f2u(b2 + fg.hi[0]) > limit_key) ? cx : cx + 1;
-    const long long row = ((long long)z * ny + y) * nx;
-    const uint32_t lo = (uint32_t)cells(row + xa), hi = (uint32_t)cells(row + xb + 1);
-    if (hi > lo) { range_set(n, lo, hi); ++n; }
-  }
-  return n;
-}
-
-template <typename Load, typename RangeGet, typename Body>
-PVB_HD void walk_list(int n, const Load& load, const RangeGet& range_get, const Body& body) {
-  if (n <= 0) return;
-  uint32_t i, hi;
-  range_get(0, i, hi);
-  int e = 0;
-  F4 c = load((long long)i);
-  bool alive = true;
-  while (alive) {
-    uint32_t ni = i + 1;
-    bool more = true;
-    if (ni >= hi) { ++e; if (e < n) range_get(e, ni, hi); else more = false; }
-    F4 cn = c;
-    if (more) cn = load((long long)ni);          // next record in flight while this one is processed
-    body(c, i);
-    c = cn; i = ni; alive = more;
-  }
-}
-
-template <int K, bool FLAT, typename CellLoader, typename Load, typename Sink, typename RangeSet, typename RangeGet>
-PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const Load& load, float qx, float qy, float qz, float sq_thr, int r0, int rmax, const Sink& sink,
-                             const RangeSet& range_set, const RangeGet& range_get) {
+template <int K, typename CellLoader, typename Load, typename Sink>
+PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const Load& load, float qx, float qy, float qz, float sq_thr, int r0, int rmax, const Sink& sink) {
   const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
   uint32_t keys[K];
 #pragma unroll
@@ -325,19 +280,10 @@ PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const L
   FaceGaps fg;
 #pragma unroll
   for (int a = 0; a < 3; ++a) { fg.lo[a] = (float)(gap_lo[a] * gap_lo[a] * (1.0 - 1e-5)); fg.hi[a] = (float)(gap_hi[a] * gap_hi[a] * (1.0 - 1e-5)); }
-  const bool flat = FLAT && r0 == 1;
-  if (flat) {
-    auto ins = [&](const F4& c, uint32_t) { topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z))); };
-    int n = list_rows_pruned(g, cells, cx, cy, cz, fg, 0, 0, init, range_set);          // the query's own row first ...
-    walk_list(n, load, range_get, ins);
-    n = list_rows_pruned(g, cells, cx, cy, cz, fg, 1, 8, keys[K - 1], range_set);       // ... then whatever the K-th distance so far still admits
-    walk_list(n, load, range_get, ins);
-  } else {
-    walk_block_pruned<K>(g, cells, cx, cy, cz, fg, gap_lo, gap_hi, r0, keys[K - 1], [&](long long i) {
-      const F4 c = load(i);
-      topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
-    });
-  }
+  walk_block_pruned<K>(g, cells, cx, cy, cz, fg, gap_lo, gap_hi, r0, keys[K - 1], [&](long long i) {
+    const F4 c = load(i);
+    topk_values_insert<K>(keys, f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z)));
+  });
   int r = r0;
   bool done = false;
   if (keys[K - 1] != init) {
@@ -362,15 +308,7 @@ PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const L
   for (int j = 0; j < K; ++j) n_lt += keys[j] < tau ? 1 : 0;
   int eq_taken = 0, n_out = 0;
   const int eq_needed = K - n_lt;
-  if (r == r0 && flat) {
-    const int n = list_rows_pruned(g, cells, cx, cy, cz, fg, 0, 8, tau, range_set);
-    walk_list(n, load, range_get, [&](const F4& c, uint32_t i) {
-      const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
-      bool take = kb < tau;
-      if (kb == tau && eq_taken < eq_needed) { take = true; ++eq_taken; }
-      if (take) { sink(n_out, i, kb); ++n_out; }
-    });
-  } else if (r == r0) {
+  if (r == r0) {
     walk_block_pruned<K>(g, cells, cx, cy, cz, fg, gap_lo, gap_hi, r0, tau, [&](long long i) {
       const F4 c = load(i);
       const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
@@ -398,14 +336,14 @@ struct AssocParams {
 // caller's per-query neighbour slots (shared memory on the device).
 // REF_ID: the reference frame's pose is exactly the identity (rigid target map): World2Local of a neighbour is then the
 // neighbour itself bit for bit (x*1 + y*0 + z*0 - 0), so the 3 x K matrix-vector products per query are skipped.
-template <int K, bool REF_ID, int PRUNE, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+template <int K, bool REF_ID, bool PRUNE, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
 PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const Load1& load1, const LoadG& loadg, const RowMap& row_map, const AssocParams& prm,
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
                                   double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get) {
   int ring = 1;
   int found;
-  if (PRUNE) { found = knn_select_pruned<K, PRUNE == 2>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get); ring = 2; }
+  if (PRUNE) { found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }); ring = 2; }
   else found = knn_select<K>(g, cells, load1, loadg, row_map, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
   if (found < K) return false;                                   // :578
   auto load = [&](long long pos) { return ring == 1 ? load1(pos) : loadg(pos); };   // neighbour positions live in the space they were found in (k-th beyond the threshold) + quirk C.6 guard

@@ -68,7 +68,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_flat = 1; double tune_cellcap = 4.0, tune_hscale = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
+  int tune_minb = 6, tune_stage = 0, tune_r0 = 1; double tune_cellcap = 4.0, tune_hscale = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
@@ -239,13 +239,12 @@ int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_ide
   a.stats = nullptr;
   a.prm.r0 = ctx->tune_r0;
   if (stage && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
-#define PVB_LAUNCH(KK, MB, DBG, MD) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, MD, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, MD, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
-#define PVB_MINB_SWITCH(KK, MD) do { if (minb >= 6) PVB_LAUNCH(KK, 6, false, MD); else if (minb == 5) PVB_LAUNCH(KK, 5, false, MD); else PVB_LAUNCH(KK, 4, false, MD); } while (0)
+#define PVB_LAUNCH(KK, MB, DBG, ST) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, ST, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, ST, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
+#define PVB_MINB_SWITCH(KK, ST) do { if (minb >= 6) PVB_LAUNCH(KK, 6, false, ST); else if (minb == 5) PVB_LAUNCH(KK, 5, false, ST); else PVB_LAUNCH(KK, 4, false, ST); } while (0)
 #define PVB_DISPATCH(KK)                                                                                   \
-  if (dbg) PVB_LAUNCH(KK, 4, true, 0);                                                                     \
-  else if (stage) PVB_MINB_SWITCH(KK, 1);                                                                  \
-  else if (ctx->tune_flat) PVB_MINB_SWITCH(KK, 2);                                                         \
-  else PVB_MINB_SWITCH(KK, 0);
+  if (dbg) PVB_LAUNCH(KK, 4, true, false);                                                                 \
+  else if (stage) PVB_MINB_SWITCH(KK, true);                                                               \
+  else PVB_MINB_SWITCH(KK, false);
   if (k == 10) { PVB_DISPATCH(10) } else { PVB_DISPATCH(5) }
 #undef PVB_DISPATCH
 #undef PVB_MINB_SWITCH
@@ -273,7 +272,6 @@ int pvb_create(int device, pvb_ctx** out) {
   if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e);
   if (const char* e = getenv("PVB_STAGE")) ctx->tune_stage = atoi(e) != 0;
   if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
-  if (const char* e = getenv("PVB_FLAT")) ctx->tune_flat = atoi(e) != 0;
   if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
   if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = std::max(0.1, atof(e));
   if (ctx->d_stats.ensure(16) == cudaSuccess) cudaMemset(ctx->d_stats.p, 0, 16);

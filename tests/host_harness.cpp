@@ -11,7 +11,7 @@
 using namespace pvb;
 
 // per-query association on a host-built grid (counting sort), K = 10 or 5
-static int g_prune = 3;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned walk from a 3x3x3 / 5x5x5 block, 3: pruned + flattened (default device path)
+static int g_prune = 1;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned walk from a 3x3x3 (default device path) / 5x5x5 block
 template <int K>
 static void associate_all(const float* tgt, int n, const double* R_ref, const double* t_ref, const float* qry, int m, const double* R_nei, const double* t_nei,
                           double h, float thr, double plane_tol, unsigned char* valid, double* p_local, double* plane, int* nn_idx, float* nn_d2) {
@@ -51,7 +51,7 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
     auto no_map = [](int, int, uint32_t&, uint32_t&) {};
 #define PVBH_ASSOC(MODE) associate_point2plane<K, false, MODE>(g, cells, load, load, no_map, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei, \
                                                                p_local + 3 * i, plane + 4 * i, win, set_win, range_set, range_get)
-    valid[i] = (g_prune == 0 ? PVBH_ASSOC(0) : (g_prune == 3 ? PVBH_ASSOC(2) : PVBH_ASSOC(1))) ? 1 : 0;
+    valid[i] = (g_prune == 0 ? PVBH_ASSOC(false) : PVBH_ASSOC(true)) ? 1 : 0;
 #undef PVBH_ASSOC
     std::vector<std::pair<std::pair<float, uint32_t>, int>> nn;
     for (int j = 0; j < K; ++j) {
