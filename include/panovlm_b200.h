@@ -268,6 +268,21 @@ int pvb_build_camera_lidar_blocks(int rows, int cols, int n_pairs, const float* 
 /* pcl::transformPointCloud of one cloud on the device (sensors/Velodyne.cpp:1790-1806): n x 4 float32 in, n x 4 out     */
 int pvb_transform_cloud(pvb_ctx* ctx, const float* xyzi, long n, const double* R9, const double* t3, float* out);
 
+/* ---- H. per-frame preprocessing either side of the path -------------------------------------------------- */
+/* SlerpPose (base/Geometry.hpp:572-583): poses are 4x4 row-major T_world<-local; ratio 0 -> pose_w1, 1 -> pose_w2. Host only.           */
+int pvb_slerp_pose(const double* pose_w1_16, const double* pose_w2_16, double ratio, double* out16);
+/* The pose of the END of every sweep as LidarOdometry::UndistortLidars chooses it (lidar_mapping/LidarOdometry.cpp:203-243, sweep 0.1 s
+ * + gap_time between sweeps): interpolated towards the next usable frame, extrapolated for the last frame; has_end[i] = 0 where the
+ * reference saves the raw cloud (`goto save_undistort`).  poses16: n x 16; pose_valid / frame_valid: IsPoseValid() / valid. Host only. */
+int pvb_undistort_end_poses(int n, const double* poses16, const unsigned char* pose_valid, const unsigned char* frame_valid, float gap_time,
+                            double* out_pose16, unsigned char* has_end);
+/* Velodyne::UndistortCloud (sensors/Velodyne.cpp:1642-1674) for a batch of frames in one launch: point i of a frame's n points (scan
+ * order) is moved by slerp(identity, q_se, float(i)/float(n)) and the same fraction of t_se, where (q_se, t_se) = T_wl^-1 T_we.
+ * xyzi / out: concatenated n x 4 float32 clouds, frame f = [offsets[f], offsets[f+1]); T_wl16 / T_we16: n_frames x 16 (start / end
+ * pose of the sweep); frames with has_end[f] == 0 (NULL: none) pass through unchanged.                                                 */
+int pvb_undistort_clouds(pvb_ctx* ctx, const float* xyzi, const int* offsets, int n_frames, const double* T_wl16, const double* T_we16,
+                         const unsigned char* has_end, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -169,6 +169,31 @@ def transform_cloud(R, t, cloud):
     return out
 
 
+def slerp_pose(pose_w1, pose_w2, ratio):
+    """SlerpPose (base/Geometry.hpp:572-583); poses 4x4 row-major."""
+    out = np.empty((4, 4))
+    lib().pvo_slerp_pose(_p(_f64(pose_w1)), _p(_f64(pose_w2)), C.c_double(ratio), _p(out))
+    return out
+
+
+def undistort_cloud(R_wl, t_wl, R_we, t_we, cloud):
+    """Velodyne::UndistortCloud (sensors/Velodyne.cpp:1642-1674); cloud n x 4 float32 in scan order."""
+    cloud = _f32(cloud).reshape(-1, 4)
+    out = np.empty_like(cloud)
+    lib().pvo_undistort_cloud(_p(_f64(R_wl)), _p(_f64(t_wl)), _p(_f64(R_we)), _p(_f64(t_we)), _p(cloud), C.c_long(len(cloud)), _p(out))
+    return out
+
+
+def undistort_end_poses(poses, pose_valid, frame_valid, gap_time):
+    """Sweep-end pose per frame as LidarOdometry::UndistortLidars picks it (lidar_mapping/LidarOdometry.cpp:203-243)."""
+    poses = _f64(poses).reshape(-1, 16)
+    n = len(poses)
+    pv, fv = np.ascontiguousarray(pose_valid, dtype=np.uint8), np.ascontiguousarray(frame_valid, dtype=np.uint8)
+    out, has = np.zeros((n, 16)), np.zeros(n, dtype=np.uint8)
+    lib().pvo_undistort_end_poses(C.c_int(n), _p(poses), _p(pv), _p(fv), C.c_float(gap_time), _p(out), _p(has))
+    return out.reshape(n, 4, 4), has.astype(bool)
+
+
 def world2local(R, t, pw):
     pw = _f64(pw).reshape(-1, 3)
     out = np.empty_like(pw)

@@ -10,6 +10,7 @@
 #include "pvo_assoc.hpp"
 #include "pvo_solver.hpp"
 #include "pvo_tracks.hpp"
+#include "pvo_undistort.hpp"
 
 using namespace pvo;
 
@@ -300,6 +301,16 @@ void pvo_dense_icp_eval(const float* target_world, int n_target, const float* sr
   out_times[1] = std::chrono::duration<double>(t2 - t1).count();
   out_times[2] = std::chrono::duration<double>(t3 - t2).count();
   *out_n_assoc = total;
+}
+
+// ---- pose interpolation / motion undistortion ------------------------------------------------
+void pvo_slerp_pose(const double* pose_w1, const double* pose_w2, double ratio, double* out16) { SlerpPose(pose_w1, pose_w2, ratio, out16); }
+void pvo_undistort_cloud(const double* R_wl, const double* t_wl, const double* R_we, const double* t_we, const float* in, long n, float* out) {
+  UndistortCloud(R_wl, t_wl, R_we, t_we, in, (size_t)n, out);
+}
+void pvo_undistort_end_poses(int n, const double* poses, const unsigned char* pose_valid, const unsigned char* frame_valid, float gap_time, double* out_pose,
+                             unsigned char* has) {
+  UndistortEndPoses(n, poses, pose_valid, frame_valid, gap_time, out_pose, has);
 }
 
 void* pvo_kdtree_build(const float* pts, int n) { KdTree* t = new KdTree(); t->Build(pts, n, 4); return t; }

@@ -109,6 +109,7 @@ EXPORTS = [
     "pvb_pair_knn5", "pvb_nearest_line", "pvb_point2line_segment_knn_associate", "pvb_point2line_segment_knn_tail", "pvb_point2line_segment_associate",
     "pvb_line2line_knn_associate", "pvb_line2line_knn_tail", "pvb_line_tracks_build", "pvb_line_tracks_gate", "pvb_generate_line_tracks",
     "pvb_blocks_set_linear_solver", "pvb_cholesky_solve", "pvb_unique_line_pairs",
+    "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
 ]
 
 
@@ -349,6 +350,32 @@ class Context:
         a = _arr(xyzi, np.float32).reshape(-1, 4)
         out = np.empty_like(a)
         self._ck(self._L.pvb_transform_cloud(self._h, _p(a), C.c_long(len(a)), _p(_arr(R, np.float64)), _p(_arr(t, np.float64)), _p(out)))
+        return out
+
+    @staticmethod
+    def slerp_pose(pose_w1, pose_w2, ratio):
+        out = np.empty((4, 4))
+        rc = load_library().pvb_slerp_pose(_p(_arr(pose_w1, np.float64)), _p(_arr(pose_w2, np.float64)), C.c_double(ratio), _p(out))
+        if rc < 0:
+            raise PvbError(f"pvb_slerp_pose: code {rc}")
+        return out
+
+    @staticmethod
+    def undistort_end_poses(poses, pose_valid, frame_valid, gap_time):
+        P = _arr(poses, np.float64).reshape(-1, 16)
+        n = len(P)
+        out, has = np.zeros((n, 16)), np.zeros(n, np.uint8)
+        rc = load_library().pvb_undistort_end_poses(C.c_int(n), _p(P), _p(_arr(pose_valid, np.uint8)), _p(_arr(frame_valid, np.uint8)), C.c_float(gap_time), _p(out), _p(has))
+        if rc < 0:
+            raise PvbError(f"pvb_undistort_end_poses: code {rc}")
+        return out.reshape(n, 4, 4), has.astype(bool)
+
+    def undistort_clouds(self, xyzi, offsets, T_wl, T_we, has_end=None):
+        a = _arr(xyzi, np.float32).reshape(-1, 4)
+        off = _arr(offsets, np.int32)
+        out = np.empty_like(a)
+        he = None if has_end is None else _arr(has_end, np.uint8)
+        self._ck(self._L.pvb_undistort_clouds(self._h, _p(a), _p(off), C.c_int(len(off) - 1), _p(_arr(T_wl, np.float64)), _p(_arr(T_we, np.float64)), _p(he), _p(out)))
         return out
 
     def line2line_associate(self, ref, nei, dist_threshold):

@@ -533,6 +533,91 @@ int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* li
   return PVB_OK;
 }
 
+// ---- pose interpolation around the sweep undistortion (base/Geometry.hpp:572-583, lidar_mapping/LidarOdometry.cpp:203-243) -------------
+namespace {
+// 4x4 inverse by Gauss-Jordan elimination with partial pivoting (the reference calls Eigen's general Matrix4d::inverse())
+bool inverse4(const double* M, double* out) {
+  double a[4][8];
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { a[r][c] = M[r * 4 + c]; a[r][4 + c] = r == c ? 1.0 : 0.0; }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 4; ++r) if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+    if (a[piv][c] == 0.0) return false;
+    if (piv != c) for (int k = 0; k < 8; ++k) std::swap(a[piv][k], a[c][k]);
+    const double inv = 1.0 / a[c][c];
+    for (int k = 0; k < 8; ++k) a[c][k] *= inv;
+    for (int r = 0; r < 4; ++r) {
+      if (r == c) continue;
+      const double f = a[r][c];
+      if (f != 0.0) for (int k = 0; k < 8; ++k) a[r][k] -= f * a[c][k];
+    }
+  }
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[r * 4 + c] = a[r][4 + c];
+  return true;
+}
+void mul4(const double* A, const double* B, double* C) {
+  double T[16];
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[r * 4 + c] = A[r * 4] * B[c] + A[r * 4 + 1] * B[4 + c] + A[r * 4 + 2] * B[8 + c] + A[r * 4 + 3] * B[12 + c];
+  memcpy(C, T, sizeof T);
+}
+bool slerp_pose(const double* pose_w1, const double* pose_w2, double ratio, double* out) {
+  double inv2[16], T21[16];
+  if (!inverse4(pose_w2, inv2)) return false;
+  mul4(inv2, pose_w1, T21);
+  double R21[9], q21[4], t21[3];
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R21[r * 3 + c] = T21[r * 4 + c]; t21[r] = T21[r * 4 + 3]; }
+  pvb::quat_from_matrix_eigen(R21, q21);
+  pvb::UndistortPrep u;
+  pvb::undistort_prepare(q21, t21, u);
+  double w_id, w_q;
+  pvb::slerp_weights(u, ratio, w_id, w_q);
+  const double qs[4] = {w_q * q21[0], w_q * q21[1], w_q * q21[2], w_id + w_q * q21[3]};
+  double Rs[9], Ts[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, invs[16];
+  pvb::quat_to_matrix_eigen(qs, Rs);
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) Ts[r * 4 + c] = Rs[r * 3 + c]; Ts[r * 4 + 3] = t21[r] * ratio; }
+  if (!inverse4(Ts, invs)) return false;
+  mul4(pose_w1, invs, out);
+  return true;
+}
+}  // namespace
+
+int pvb_slerp_pose(const double* pose_w1_16, const double* pose_w2_16, double ratio, double* out16) {
+  if (!pose_w1_16 || !pose_w2_16 || !out16) return PVB_ERR_ARG;
+  return slerp_pose(pose_w1_16, pose_w2_16, ratio, out16) ? PVB_OK : PVB_ERR_ARG;
+}
+
+int pvb_undistort_end_poses(int n, const double* poses16, const unsigned char* pose_valid, const unsigned char* frame_valid, float gap_time, double* out_pose16,
+                            unsigned char* has_end) {
+  if (n < 0 || (n > 0 && (!poses16 || !pose_valid || !frame_valid || !out_pose16 || !has_end))) return PVB_ERR_ARG;
+  const double sweep = 0.1;                                            // lidar_duration (LidarOdometry.cpp:203)
+  const double period = sweep + gap_time;
+  for (int i = 0; i < n; ++i) {
+    double* dst = out_pose16 + (size_t)i * 16;
+    std::fill(dst, dst + 16, 0.0);
+    has_end[i] = 0;
+    if (!pose_valid[i] || !frame_valid[i]) continue;
+    const double* cur = poses16 + (size_t)i * 16;
+    if (i + 1 < n) {
+      // the next frame that is not (pose-less AND invalid): the reference's loop condition joins the two tests with && (:220)
+      int nxt = i + 1;
+      while (nxt < n && !pose_valid[nxt] && !frame_valid[nxt]) ++nxt;
+      if (nxt == n) continue;
+      if (!slerp_pose(cur, poses16 + (size_t)nxt * 16, sweep / ((nxt - i) * period), dst)) return PVB_ERR_ARG;
+    } else {
+      // last frame: extrapolate from an earlier frame (:229-240); the loop tests frame i's own `valid` flag and index 0 is rejected (:232)
+      int prv = i - 1;
+      while (prv >= 0 && !pose_valid[prv] && !frame_valid[i]) --prv;
+      if (prv <= 0) continue;
+      double mid[16], inv_cur[16], rel[16];
+      if (!slerp_pose(poses16 + (size_t)prv * 16, cur, 1.0 - sweep / ((prv - i) * period), mid) || !inverse4(cur, inv_cur)) return PVB_ERR_ARG;
+      mul4(inv_cur, mid, rel);
+      mul4(cur, rel, dst);
+    }
+    has_end[i] = 1;
+  }
+  return PVB_OK;
+}
+
 int pvb_build_point2plane_blocks(long n, const double* point3, const double* plane4, int ref_block, int nei_block, int angle_residual, int normalize_distance,
                                  double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize, double* huber, double* consts) {
   if (n < 0 || (n > 0 && (!point3 || !plane4)) || !type || !ref || !nei || !normalize || !huber || !consts) return PVB_ERR_ARG;

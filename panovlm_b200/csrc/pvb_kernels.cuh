@@ -72,6 +72,19 @@ __global__ void __launch_bounds__(256) k_transform_simple(const F4* __restrict__
   reinterpret_cast<float4*>(out)[i] = make_float4(x, y, z, p.w);
 }
 
+// ---- sweep undistortion of a batch of frames (Velodyne::UndistortCloud): 16 B in, 16 B out per point, two FP64 sines --------------
+__global__ void __launch_bounds__(256) k_undistort(const F4* __restrict__ in, const CloudTile* __restrict__ tiles, const UndistortPrep* __restrict__ prep,
+                                                   const int* __restrict__ cloud_off, F4* __restrict__ out) {
+  const CloudTile t = tiles[blockIdx.x];
+  const int i = threadIdx.x;
+  if (i >= t.count) return;
+  const F4 p = ldg_f4(in + t.start + i);
+  const UndistortPrep& u = prep[t.cloud];
+  float x = p.x, y = p.y, z = p.z;
+  if (u.enabled) undistort_point_f32(u, (long long)(t.start + i - cloud_off[t.cloud]), (long long)(cloud_off[t.cloud + 1] - cloud_off[t.cloud]), p.x, p.y, p.z, x, y, z);
+  reinterpret_cast<float4*>(out)[t.start + i] = make_float4(x, y, z, p.w);
+}
+
 // ---- grid build -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cell_keys(const F4* __restrict__ world, const CloudTile* __restrict__ tiles, const GridDesc* __restrict__ grids,
                                                    unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist) {

@@ -1137,6 +1137,47 @@ int pvb_transform_cloud(pvb_ctx* ctx, const float* xyzi, long n, const double* R
   return PVB_OK;
 }
 
+// ================================================================ sweep undistortion
+int pvb_undistort_clouds(pvb_ctx* ctx, const float* xyzi, const int* offsets, int n_frames, const double* T_wl16, const double* T_we16, const unsigned char* has_end,
+                         float* out) {
+  if (!ctx || n_frames < 0 || (n_frames > 0 && (!offsets || !T_wl16 || !T_we16))) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_undistort_clouds: bad arguments") : PVB_ERR_ARG;
+  if (n_frames == 0) return PVB_OK;
+  const long long n = offsets[n_frames];
+  for (int f = 0; f < n_frames; ++f) if (offsets[f + 1] < offsets[f]) return ctx->fail(PVB_ERR_ARG, "pvb_undistort_clouds: offsets must ascend");
+  if (n == 0) return PVB_OK;
+  if (!xyzi || !out) return ctx->fail(PVB_ERR_ARG, "pvb_undistort_clouds: null cloud");
+  CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
+  std::vector<UndistortPrep> prep(n_frames);
+  std::vector<CloudTile> tiles;
+  for (int f = 0; f < n_frames; ++f) {
+    UndistortPrep& u = prep[f];
+    memset(&u, 0, sizeof(u));
+    if (!has_end || has_end[f]) {
+      const double* A = T_wl16 + (size_t)f * 16; const double* E = T_we16 + (size_t)f * 16;
+      double R_se[9], t_se[3], q[4];
+      for (int r = 0; r < 3; ++r) {                              // R_wl^T R_we, R_wl^T (t_we - t_wl)  (Velodyne.cpp:1647-1648)
+        for (int c = 0; c < 3; ++c) { double acc = 0.0; for (int k = 0; k < 3; ++k) acc += A[k * 4 + r] * E[k * 4 + c]; R_se[r * 3 + c] = acc; }
+        double acc = 0.0; for (int k = 0; k < 3; ++k) acc += A[k * 4 + r] * (E[k * 4 + 3] - A[k * 4 + 3]); t_se[r] = acc;
+      }
+      quat_from_matrix_eigen(R_se, q);
+      undistort_prepare(q, t_se, u);
+    }
+    for (int s0 = offsets[f]; s0 < offsets[f + 1]; s0 += 256) tiles.push_back(CloudTile{f, s0, std::min(256, offsets[f + 1] - s0), 0});
+  }
+  CK(ctx->m_a.ensure((size_t)n * 16)); CK(ctx->m_b.ensure((size_t)n * 16)); CK(ctx->m_c.ensure(tiles.size() * sizeof(CloudTile)));
+  CK(ctx->m_d.ensure(prep.size() * sizeof(UndistortPrep))); CK(ctx->m_e.ensure((size_t)(n_frames + 1) * 4));
+  CK(cudaMemcpyAsync(ctx->m_a.p, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_c.p, tiles.data(), tiles.size() * sizeof(CloudTile), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_d.p, prep.data(), prep.size() * sizeof(UndistortPrep), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_e.p, offsets, (size_t)(n_frames + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_undistort<<<(unsigned)tiles.size(), 256, 0, ctx->stream>>>(ctx->m_a.as<F4>(), ctx->m_c.as<CloudTile>(), ctx->m_d.as<UndistortPrep>(), ctx->m_e.as<int>(), ctx->m_b.as<F4>());
+  CKL();
+  CK(cudaMemcpyAsync(out, ctx->m_b.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // tiles / prep are host vectors: the copies above must have left them
+  return PVB_OK;
+}
+
 // ================================================================ pair-level 5-NN and nearest line (segment-based variants of A3)
 int pvb_pair_knn5(pvb_ctx* ctx, const float* ref_local, int n_ref, const double* R_ref, const double* t_ref, const float* nei_local, int n_nei, const double* R_nei,
                   const double* t_nei, float dist_threshold, double cell_size, int* idx5) {

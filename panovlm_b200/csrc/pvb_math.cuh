@@ -556,4 +556,74 @@ PVB_HD void image_to_cam_f64(double px, double py, int rows, int cols, double ca
   cam[2] = cy * cos(lon);
 }
 
+// ---- sweep undistortion (sensors/Velodyne.cpp:1642-1674) ------------------------------------------------------------------------
+// One sweep = one rigid motion (q_se, t_se) from the pose at the start to the pose at the end; point i of n is moved by the fraction
+// ratio = float(i) / float(n) of it: rotation = slerp(identity, q_se, ratio) (Eigen's formula, not renormalised), translation = ratio * t_se.
+// Everything that does not depend on the point is prepared once per frame on the host (UndistortPrep).
+struct UndistortPrep {
+  double q[4];          // q_se as x, y, z, w
+  double theta, sin_theta;
+  double t_se[3];
+  int linear;           // |w| >= 1 - eps: Eigen's slerp degenerates to linear weights
+  int enabled;          // 0: the frame has no usable end pose, points pass through unchanged (LidarOdometry.cpp:212-225 `goto save_undistort`)
+};
+
+PVB_HD void quat_from_matrix_eigen(const double R[9], double q[4]) {          // Eigen::Quaterniond(Matrix3d), R row-major
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0.0) {
+    const double s = sqrt(tr + 1.0), k = 0.5 / s;
+    q[3] = 0.5 * s; q[0] = (R[7] - R[5]) * k; q[1] = (R[2] - R[6]) * k; q[2] = (R[3] - R[1]) * k;
+    return;
+  }
+  int i = R[4] > R[0] ? 1 : 0;
+  if (R[8] > R[i * 4]) i = 2;
+  const int j = (i + 1) % 3, k = (j + 1) % 3;
+  const double s = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0), h = 0.5 / s;
+  q[i] = 0.5 * s;
+  q[3] = (R[k * 3 + j] - R[j * 3 + k]) * h;
+  q[j] = (R[j * 3 + i] + R[i * 3 + j]) * h;
+  q[k] = (R[k * 3 + i] + R[i * 3 + k]) * h;
+}
+
+PVB_HD void quat_to_matrix_eigen(const double q[4], double R[9]) {           // QuaternionBase::toRotationMatrix
+  const double tx = 2.0 * q[0], ty = 2.0 * q[1], tz = 2.0 * q[2];
+  const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3], txx = tx * q[0], txy = ty * q[0], txz = tz * q[0], tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
+}
+
+PVB_HD void undistort_prepare(const double q_se[4], const double t_se[3], UndistortPrep& u) {
+  for (int a = 0; a < 4; ++a) u.q[a] = q_se[a];
+  for (int a = 0; a < 3; ++a) u.t_se[a] = t_se[a];
+  const double ad = fabs(q_se[3]);
+  u.linear = ad >= 1.0 - 2.220446049250313e-16 ? 1 : 0;
+  u.theta = u.linear ? 0.0 : acos(ad);
+  u.sin_theta = u.linear ? 1.0 : sin(u.theta);
+  u.enabled = 1;
+}
+
+// weights of identity and q_se in the interpolated quaternion
+PVB_HD void slerp_weights(const UndistortPrep& u, double ratio, double& w_id, double& w_q) {
+  if (u.linear) { w_id = 1.0 - ratio; w_q = ratio; }
+  else { w_id = sin((1.0 - ratio) * u.theta) / u.sin_theta; w_q = sin(ratio * u.theta) / u.sin_theta; }
+  if (u.q[3] < 0.0) w_q = -w_q;
+}
+
+PVB_HD void undistort_point_f32(const UndistortPrep& u, long long i, long long n, float x, float y, float z, float& ox, float& oy, float& oz) {
+  const float ratio_f = (float)i / (float)n;                                 // `1.f * i / cloud.points.size()` (:1656) is float arithmetic
+  const double ratio = (double)ratio_f;
+  double w_id, w_q;
+  slerp_weights(u, ratio, w_id, w_q);
+  const double qx = dmul(w_q, u.q[0]), qy = dmul(w_q, u.q[1]), qz = dmul(w_q, u.q[2]), qw = dadd(w_id, dmul(w_q, u.q[3]));
+  const double vx = (double)x, vy = (double)y, vz = (double)z;
+  // Eigen's q * v: uv = 2 (q.vec x v); v + w uv + q.vec x uv  (products and sums kept un-fused like the host build of the reference)
+  double ux = dsub(dmul(qy, vz), dmul(qz, vy)), uy = dsub(dmul(qz, vx), dmul(qx, vz)), uz = dsub(dmul(qx, vy), dmul(qy, vx));
+  ux = dadd(ux, ux); uy = dadd(uy, uy); uz = dadd(uz, uz);
+  const double cx = dsub(dmul(qy, uz), dmul(qz, uy)), cy = dsub(dmul(qz, ux), dmul(qx, uz)), cz = dsub(dmul(qx, uy), dmul(qy, ux));
+  ox = (float)dadd(dadd(dadd(vx, dmul(qw, ux)), cx), dmul(ratio, u.t_se[0]));
+  oy = (float)dadd(dadd(dadd(vy, dmul(qw, uy)), cy), dmul(ratio, u.t_se[1]));
+  oz = (float)dadd(dadd(dadd(vz, dmul(qw, uz)), cz), dmul(ratio, u.t_se[2]));
+}
+
 }  // namespace pvb

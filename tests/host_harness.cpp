@@ -163,6 +163,17 @@ void pvbh_associate(const float* tgt, int n, const double* R_ref, const double* 
 void pvbh_transform_cloud(const double* R, const double* t, const float* in, int n, float* out) {
   for (int i = 0; i < n; ++i) { transform_point_f32(R, t, in[i * 4], in[i * 4 + 1], in[i * 4 + 2], out[i * 4], out[i * 4 + 1], out[i * 4 + 2]); out[i * 4 + 3] = in[i * 4 + 3]; }
 }
+// the per-point body of k_undistort on the host: frame prepared exactly like pvb_undistort_clouds does
+void pvbh_undistort_cloud(const double* R_wl, const double* t_wl, const double* R_we, const double* t_we, const float* in, long n, float* out) {
+  double R_se[9], t_se[3], q[4];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) { double acc = 0.0; for (int k = 0; k < 3; ++k) acc += R_wl[k * 3 + r] * R_we[k * 3 + c]; R_se[r * 3 + c] = acc; }
+    double acc = 0.0; for (int k = 0; k < 3; ++k) acc += R_wl[k * 3 + r] * (t_we[k] - t_wl[k]); t_se[r] = acc;
+  }
+  quat_from_matrix_eigen(R_se, q);
+  UndistortPrep u; undistort_prepare(q, t_se, u);
+  for (long i = 0; i < n; ++i) { undistort_point_f32(u, i, n, in[i * 4], in[i * 4 + 1], in[i * 4 + 2], out[i * 4], out[i * 4 + 1], out[i * 4 + 2]); out[i * 4 + 3] = in[i * 4 + 3]; }
+}
 void pvbh_fast_atan2_f(long n, const float* y, const float* x, float* out) { for (long i = 0; i < n; ++i) out[i] = fast_atan2_f32(y[i], x[i]); }
 void pvbh_fast_atan2_d(long n, const double* y, const double* x, double* out) { for (long i = 0; i < n; ++i) out[i] = fast_atan2_f64(y[i], x[i]); }
 void pvbh_cam_to_image_f(int rows, int cols, long n, const float* cam, float* px) { for (long i = 0; i < n; ++i) cam_to_image_f32(cam[3 * i], cam[3 * i + 1], cam[3 * i + 2], rows, cols, px[2 * i], px[2 * i + 1]); }
