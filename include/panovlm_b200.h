@@ -283,6 +283,39 @@ int pvb_undistort_end_poses(int n, const double* poses16, const unsigned char* p
 int pvb_undistort_clouds(pvb_ctx* ctx, const float* xyzi, const int* offsets, int n_frames, const double* T_wl16, const double* T_we16,
                          const unsigned char* has_end, float* out);
 
+/* ---- I. camera-camera reprojection residuals and their bundle adjustment -------------------------------------- */
+/* Registers the observation list of AddCameraResidual (util/Optimization.cpp:172-222, ANGLE_RESIDUAL_1): observation i = one
+ * problem.AddResidualBlock(PanoramaReprojResidual_1Angle(bearing_i, weight), HuberLoss(huber), aa_cw[cam_i], t_cw[cam_i], point_3d[point_i])
+ * (base/CostFunction.h:218-247).  bearing3: the key point on the unit sphere (eq.ImageToCam), normalised here like the functor's
+ * constructor does; huber <= 0: no loss (the reference passes 4 deg).  Camera blocks are 6 doubles (aa_cw, t_cw), points 3 doubles.   */
+int pvb_reproj_set(pvb_ctx* ctx, long n_obs, const int* cam, const int* point, const double* bearing3, double weight, double huber, int n_cams,
+                   long n_points);
+/* == PrepareForEvaluation for these blocks.  want_rows: residual + 1x9 Jacobian row [d aa_cw | d t_cw | d point] per observation in the
+ * caller's order (pinned host mirrors); want_system: the blocks of the normal equations are reduced on the device — per camera
+ * J_c^T J_c (upper 6x6, 21) and gradient (6), per point J_p^T J_p (upper 3x3, 6) and gradient (3), per observation the 6x3 coupling
+ * block J_c^T J_p.                                                                                                                  */
+int pvb_reproj_evaluate(pvb_ctx* ctx, const double* cams6, const double* points3, int want_rows, int want_system);
+const double* pvb_reproj_residuals(const pvb_ctx* ctx);   /* n_obs doubles, loss-corrected              */
+const double* pvb_reproj_jacobians(const pvb_ctx* ctx);   /* n_obs x 9 row-major                        */
+int pvb_reproj_cost(const pvb_ctx* ctx, double* cost);
+/* the reduced blocks of the last evaluate (any pointer may be NULL): cam_H21 n_cams x 21, cam_g6 n_cams x 6, pt_H6 n_points x 6,
+ * pt_g3 n_points x 3, obs_E18 n_obs x 18 (row-major 6x3, caller's observation order)                                                 */
+int pvb_reproj_blocks(pvb_ctx* ctx, double* cam_H21, double* cam_g6, double* pt_H6, double* pt_g3, double* obs_E18);
+int pvb_reproj_kernel_time_ms(pvb_ctx* ctx, float* ms);   /* device time of the residual + Jacobian kernel  */
+/* SfMGlobalBA (util/Optimization.cpp:10-82): ceres::Solve over cameras and structure with Ceres' trust-region defaults.  Each step
+ * eliminates the points on the device (Schur complement, the role of SetOptionsSfM's DENSE_SCHUR / SPARSE_SCHUR, :611-636), factors the
+ * reduced camera system with the blocked FP64 Cholesky and back-substitutes the points.  cam_param_const: n_cams x 6 flags (NULL: all
+ * free) — SetParameterBlockConstant on aa_cw / t_cw sets three of them (:40-43, :54-55); point_const: n_points flags (:45-47).
+ * cams6 / points3 are updated in place; summary6 as pvb_blocks_solve_lm.                                                            */
+int pvb_reproj_solve_lm(pvb_ctx* ctx, double* cams6, double* points3, const unsigned char* cam_param_const, const unsigned char* point_const,
+                        int max_iterations, double* summary6);
+/* The observation loop of AddCameraResidual (util/Optimization.cpp:187-219): tracks as CSR (track t = features track_off[t] ..
+ * track_off[t+1]: frame feat_frame[f], key point feat_xy[2f..2f+1] in pixels); features of frames without a valid pose are skipped;
+ * the key point is rounded to the pixel grid and mapped to the unit sphere in float32 exactly like Equirectangular::ImageToCam(cv::Point2i)
+ * (sensors/Equirectangular.h:155-164).  Returns the number of observations written (cam = frame, point = track) or < 0.  Host only.  */
+int pvb_build_reproj_observations(int rows, int cols, long n_tracks, const int* track_off, const int* feat_frame, const float* feat_xy,
+                                  const unsigned char* pose_valid, long cap, int* cam, int* point, double* bearing3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ def lib():
             build()
         _LIB = C.CDLL(path)
         _LIB.pvo_normal_equations.restype = C.c_double
+        _LIB.pvo_reproj_normal_equations.restype = C.c_double
         _LIB.pvo_kdtree_build.restype = C.c_void_p
     return _LIB
 
@@ -167,6 +168,40 @@ def transform_cloud(R, t, cloud):
     out = np.empty_like(cloud)
     lib().pvo_transform_cloud(_p(_f64(R)), _p(_f64(t)), _p(cloud), C.c_int(len(cloud)), _p(out))
     return out
+
+
+class Reproj:
+    """Observation list of the camera-camera term (AddCameraResidual, util/Optimization.cpp:172-222, ANGLE_RESIDUAL_1): observation i sees
+    point[i] from camera cam[i] along bearing[i] (unit-sphere direction of the key point)."""
+
+    def __init__(self, cam, point, bearing, weight=1.0, huber=4.0 * np.pi / 180.0):
+        self.cam, self.point, self.bearing = _i32(cam), _i32(point), _f64(bearing).reshape(-1, 3)
+        self.weight, self.huber, self.n = float(weight), float(huber), len(self.cam)
+
+    def _args(self):
+        return C.c_long(self.n), _p(self.cam), _p(self.point), _p(self.bearing), C.c_double(self.weight), C.c_double(self.huber)
+
+    def evaluate(self, cams, points, apply_loss=True, want_jacobian=True):
+        r, J, cost = np.zeros(self.n), np.zeros((self.n, 9)), np.zeros(self.n)
+        lib().pvo_reproj_eval(*self._args(), _p(_f64(cams)), _p(_f64(points)), C.c_int(int(apply_loss)), _p(r), _p(J) if want_jacobian else None, _p(cost))
+        return r, J, cost
+
+    def normal_equations(self, cams, points):
+        cams, points = _f64(cams).reshape(-1, 6), _f64(points).reshape(-1, 3)
+        x = np.concatenate([cams.ravel(), points.ravel()])
+        D = x.size
+        H, g = np.zeros((D, D)), np.zeros(D)
+        cost = lib().pvo_reproj_normal_equations(*self._args(), _p(x), C.c_int(len(cams)), C.c_long(len(points)), _p(H), _p(g))
+        return H, g, cost
+
+    def solve_lm(self, cams, points, param_const=None, max_iter=50):
+        cams, points = _f64(cams).reshape(-1, 6), _f64(points).reshape(-1, 3)
+        x = np.concatenate([cams.ravel(), points.ravel()])
+        mask = np.zeros(x.size, np.uint8) if param_const is None else np.ascontiguousarray(param_const, dtype=np.uint8)
+        summ = np.zeros(6)
+        lib().pvo_reproj_solve_lm(*self._args(), _p(x), C.c_int(len(cams)), C.c_long(len(points)), _p(mask), C.c_int(max_iter), _p(summ))
+        keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
+        return x[:cams.size].reshape(-1, 6), x[cams.size:].reshape(-1, 3), dict(zip(keys, summ.tolist()))
 
 
 def slerp_pose(pose_w1, pose_w2, ratio):

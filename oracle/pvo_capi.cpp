@@ -11,6 +11,7 @@
 #include "pvo_solver.hpp"
 #include "pvo_tracks.hpp"
 #include "pvo_undistort.hpp"
+#include "pvo_ba.hpp"
 
 using namespace pvo;
 
@@ -311,6 +312,37 @@ void pvo_undistort_cloud(const double* R_wl, const double* t_wl, const double* R
 void pvo_undistort_end_poses(int n, const double* poses, const unsigned char* pose_valid, const unsigned char* frame_valid, float gap_time, double* out_pose,
                              unsigned char* has) {
   UndistortEndPoses(n, poses, pose_valid, frame_valid, gap_time, out_pose, has);
+}
+
+// ---- camera reprojection residuals / bundle adjustment ---------------------------------------------
+static std::vector<ReprojObs> MakeObs(long n, const int* cam, const int* point, const double* bearing) {
+  std::vector<ReprojObs> v(n);
+  for (long i = 0; i < n; ++i) { v[i].cam = cam[i]; v[i].point = point[i]; std::memcpy(v[i].bearing, bearing + 3 * i, 24); }
+  return v;
+}
+void pvo_reproj_eval(long n, const int* cam, const int* point, const double* bearing, double weight, double huber, const double* cams, const double* points,
+                     int apply_loss, double* out_r, double* out_J9, double* out_cost) {
+  std::vector<ReprojObs> obs = MakeObs(n, cam, point, bearing);
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) {
+    double r, J[9];
+    const double c = EvalReproj(obs[i], weight, apply_loss ? huber : 0.0, cams, points, &r, out_J9 ? J : nullptr);
+    out_r[i] = r; if (out_cost) out_cost[i] = c;
+    if (out_J9) std::memcpy(out_J9 + 9 * i, J, 72);
+  }
+}
+double pvo_reproj_normal_equations(long n, const int* cam, const int* point, const double* bearing, double weight, double huber, const double* x, int nc, long np,
+                                   double* H, double* g) {
+  std::vector<ReprojObs> obs = MakeObs(n, cam, point, bearing);
+  return ReprojNormalEquations(obs.data(), n, weight, huber, x, nc, np, H, g);
+}
+// x = [cams (6 nc) | points (3 np)] updated in place; param_const per parameter
+void pvo_reproj_solve_lm(long n, const int* cam, const int* point, const double* bearing, double weight, double huber, double* x, int nc, long np,
+                         const unsigned char* param_const, int max_iter, double* summary) {
+  std::vector<ReprojObs> obs = MakeObs(n, cam, point, bearing);
+  auto eval = [&](const double* xx, double* H, double* g) { return ReprojNormalEquations(obs.data(), n, weight, huber, xx, nc, np, H, g); };
+  LMSummary S = SolveLMParams(eval, x, (int)(6L * nc + 3L * np), param_const, max_iter);
+  summary[0] = S.initial_cost; summary[1] = S.final_cost; summary[2] = S.iterations; summary[3] = S.successful; summary[4] = S.unsuccessful; summary[5] = S.termination;
 }
 
 void* pvo_kdtree_build(const float* pts, int n) { KdTree* t = new KdTree(); t->Build(pts, n, 4); return t; }

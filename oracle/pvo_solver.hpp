@@ -94,11 +94,11 @@ struct LMSummary { double initial_cost, final_cost; int iterations, successful, 
 // Ceres 2.0 TrustRegionMinimizer + LevenbergMarquardtStrategy defaults: initial radius 1e4, max 1e16,
 // min 1e-32, min_relative_decrease 1e-3, min/max_lm_diagonal 1e-6/1e32, jacobi_scaling (fixed from the
 // first Jacobian: 1/(1+sqrt(colnorm^2))), function/gradient/parameter tolerance 1e-6/1e-10/1e-8.
-template <typename EvalFn>  // double eval(const double* poses, double* H, double* g)  (H,g may be null)
-inline LMSummary SolveLM(EvalFn eval, double* poses, int nb, const unsigned char* is_const, int max_iter) {
-  const int D = 6 * nb;
+// Generic form: D parameters, param_const[i] != 0 pins parameter i (Problem::SetParameterBlockConstant on the block holding it).
+template <typename EvalFn>  // double eval(const double* x, double* H, double* g)  (H,g may be null; H is D x D, g is D)
+inline LMSummary SolveLMParams(EvalFn eval, double* poses, int D, const unsigned char* param_const, int max_iter) {
   std::vector<int> freeidx;
-  for (int b = 0; b < nb; ++b) if (!is_const || !is_const[b]) for (int k = 0; k < 6; ++k) freeidx.push_back(6 * b + k);
+  for (int i = 0; i < D; ++i) if (!param_const || !param_const[i]) freeidx.push_back(i);
   const int n = (int)freeidx.size();
   std::vector<double> H((size_t)D * D), g(D), Hs((size_t)n * n), gs(n), scale(n), A((size_t)n * n), step(n), cand(poses, poses + D);
   LMSummary S{}; S.termination = 0;
@@ -158,6 +158,14 @@ inline LMSummary SolveLM(EvalFn eval, double* poses, int nb, const unsigned char
   }
   S.final_cost = cost;
   return S;
+}
+
+// pose-block form used by the LiDAR problems: nb blocks of 6, is_const per block
+template <typename EvalFn>
+inline LMSummary SolveLM(EvalFn eval, double* poses, int nb, const unsigned char* is_const, int max_iter) {
+  std::vector<unsigned char> mask((size_t)6 * nb, 0);
+  if (is_const) for (int b = 0; b < nb; ++b) for (int k = 0; k < 6; ++k) mask[6 * b + k] = is_const[b];
+  return SolveLMParams(eval, poses, 6 * nb, mask.data(), max_iter);
 }
 
 }  // namespace pvo

@@ -93,6 +93,8 @@ def load_library():
     L.pvb_stream.restype = C.c_void_p
     L.pvb_blocks_residuals.restype = C.POINTER(C.c_double)
     L.pvb_blocks_jacobians.restype = C.POINTER(C.c_double)
+    L.pvb_reproj_residuals.restype = C.POINTER(C.c_double)
+    L.pvb_reproj_jacobians.restype = C.POINTER(C.c_double)
     _LIB = L
     return L
 
@@ -110,6 +112,8 @@ EXPORTS = [
     "pvb_line2line_knn_associate", "pvb_line2line_knn_tail", "pvb_line_tracks_build", "pvb_line_tracks_gate", "pvb_generate_line_tracks",
     "pvb_blocks_set_linear_solver", "pvb_cholesky_solve", "pvb_unique_line_pairs",
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
+    "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
+    "pvb_reproj_solve_lm", "pvb_build_reproj_observations",
 ]
 
 
@@ -351,6 +355,58 @@ class Context:
         out = np.empty_like(a)
         self._ck(self._L.pvb_transform_cloud(self._h, _p(a), C.c_long(len(a)), _p(_arr(R, np.float64)), _p(_arr(t, np.float64)), _p(out)))
         return out
+
+    # ---- camera-camera reprojection residuals / bundle adjustment
+    def reproj_set(self, cam, point, bearing, n_cams, n_points, weight=1.0, huber=4.0 * np.pi / 180.0):
+        cam, point, bearing = _arr(cam, np.int32), _arr(point, np.int32), _arr(bearing, np.float64).reshape(-1, 3)
+        self._reproj_n, self._reproj_nc, self._reproj_np = len(cam), int(n_cams), int(n_points)
+        self._ck(self._L.pvb_reproj_set(self._h, C.c_long(len(cam)), _p(cam), _p(point), _p(bearing), C.c_double(weight), C.c_double(huber), C.c_int(n_cams), C.c_long(n_points)))
+
+    def reproj_evaluate(self, cams, points, want_rows=True, want_system=True):
+        self._ck(self._L.pvb_reproj_evaluate(self._h, _p(_arr(cams, np.float64)), _p(_arr(points, np.float64)), C.c_int(int(want_rows)), C.c_int(int(want_system))))
+
+    def reproj_rows(self):
+        n = self._reproj_n
+        r = np.ctypeslib.as_array(self._L.pvb_reproj_residuals(self._h), shape=(n,)).copy() if n else np.zeros(0)
+        J = np.ctypeslib.as_array(self._L.pvb_reproj_jacobians(self._h), shape=(n, 9)).copy() if n else np.zeros((0, 9))
+        return r, J
+
+    def reproj_cost(self):
+        c = C.c_double()
+        self._ck(self._L.pvb_reproj_cost(self._h, C.byref(c)))
+        return c.value
+
+    def reproj_blocks(self):
+        nc, npt, n = self._reproj_nc, self._reproj_np, self._reproj_n
+        B, gc, Cp, gp, E = np.zeros((nc, 21)), np.zeros((nc, 6)), np.zeros((npt, 6)), np.zeros((npt, 3)), np.zeros((n, 18))
+        self._ck(self._L.pvb_reproj_blocks(self._h, _p(B), _p(gc), _p(Cp), _p(gp), _p(E)))
+        return B, gc, Cp, gp, E.reshape(n, 6, 3)
+
+    def reproj_kernel_time_ms(self):
+        ms = C.c_float()
+        self._ck(self._L.pvb_reproj_kernel_time_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def reproj_solve_lm(self, cams, points, cam_param_const=None, point_const=None, max_iterations=50):
+        cams, points = _arr(cams, np.float64).copy().reshape(-1, 6), _arr(points, np.float64).copy().reshape(-1, 3)
+        cc = None if cam_param_const is None else _arr(cam_param_const, np.uint8)
+        pc = None if point_const is None else _arr(point_const, np.uint8)
+        summ = np.zeros(6)
+        self._ck(self._L.pvb_reproj_solve_lm(self._h, _p(cams), _p(points), _p(cc), _p(pc), C.c_int(max_iterations), _p(summ)))
+        keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
+        return cams, points, dict(zip(keys, summ.tolist()))
+
+    @staticmethod
+    def build_reproj_observations(rows, cols, track_off, feat_frame, feat_xy, pose_valid=None):
+        track_off, feat_frame, feat_xy = _arr(track_off, np.int32), _arr(feat_frame, np.int32), _arr(feat_xy, np.float32).reshape(-1, 2)
+        cap = len(feat_frame)
+        cam, point, bearing = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros((cap, 3))
+        pv = None if pose_valid is None else _arr(pose_valid, np.uint8)
+        m = load_library().pvb_build_reproj_observations(C.c_int(rows), C.c_int(cols), C.c_long(len(track_off) - 1), _p(track_off), _p(feat_frame), _p(feat_xy), _p(pv),
+                                                         C.c_long(cap), _p(cam), _p(point), _p(bearing))
+        if m < 0:
+            raise PvbError(f"pvb_build_reproj_observations: code {m}")
+        return cam[:m].copy(), point[:m].copy(), bearing[:m].copy()
 
     @staticmethod
     def slerp_pose(pose_w1, pose_w2, ratio):

@@ -1,0 +1,117 @@
+// panovlm_b200 — the context behind the C ABI: device / pinned buffer holders, the per-mode state and the error macros.
+// Shared by the translation units of the library (pvb_lib.cu: association / residual / solver modes, pvb_ba.cu: reprojection mode).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/panovlm_b200.h"
+#include "pvb_knn.cuh"
+
+namespace pvb {
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct CloudSet {
+  int n_clouds = 0; long long n_points = 0; int n_tiles = 0;
+  std::vector<int> off;           // n_clouds + 1
+  DevBuf local, d_off, tiles, cloud_block;
+  void release() { local.release(); d_off.release(); tiles.release(); cloud_block.release(); }
+};
+
+struct TargetIndex {
+  DevBuf world, sorted, keys, keys_alt, vals, vals_alt, hist, cell_start, grids, aabb, tmp;
+  std::vector<GridDesc> h_grids;
+  long long total_cells = 0;
+  bool built = false;
+  void release() { world.release(); sorted.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release(); hist.release(); cell_start.release(); grids.release(); aabb.release(); tmp.release(); }
+};
+
+}  // namespace pvb
+
+struct pvb_ctx {
+  using DevBuf = pvb::DevBuf; using PinBuf = pvb::PinBuf; using CloudSet = pvb::CloudSet; using TargetIndex = pvb::TargetIndex; using GridDesc = pvb::GridDesc;
+  int device = 0;
+  cudaStream_t stream = nullptr; bool own_stream = true;
+  std::string err;
+  long launches = 0;
+  int tune_minb = 6, tune_stage = 0, tune_r0 = 1; double tune_cellcap = 4.0, tune_hscale = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
+  // pose staging
+  PinBuf h_pose; DevBuf d_prep, d_wpose;
+  // ---- blocks mode
+  long long bn = 0; int nb = 0; int b_tiles = 0;
+  std::vector<int> edge_ref, edge_nei, edge_tile_begin;
+  std::vector<uint32_t> b_orig;
+  DevBuf b_chunk, d_chunk;
+  DevBuf b_tile, b_eref, b_enei, b_type, b_norm, b_huber, b_consts, b_orig_d, b_r, b_J, b_part, b_esys, b_tbegin;
+  PinBuf h_r, h_J, h_esys;
+  bool b_has_rows = false, b_has_sys = false;
+  // ---- frames mode
+  CloudSet f_tgt, f_qry; TargetIndex f_index; int n_frames = 0;
+  CloudSet f_corner; TargetIndex f_cindex; int n_corner_frames = 0;
+  CloudSet p_cs; TargetIndex p_index;                                  // pair-level k-NN (pvb_pair_knn5)
+  DevBuf f_la, f_lb; PinBuf fh_la, fh_lb;
+  std::vector<int> l_edge, l_query; std::vector<double> l_point, l_a, l_b;
+  DevBuf f_pairs, f_qtiles, f_valid, f_point, f_plane, f_nn_idx, f_nn_d2;
+  PinBuf fh_valid, fh_point, fh_plane;
+  std::vector<int> a_edge, a_query; std::vector<double> a_point, a_plane;
+  // ---- dense mode
+  CloudSet d_tgt, d_src; TargetIndex d_index; int d_frames = 0;
+  DevBuf d_q_sorted, d_q_orig, d_pairs, d_qtiles, d_part, d_sys, d_tbegin, d_valid, d_point, d_plane, d_res, d_jac;
+  PinBuf dh_sys;
+  int d_ntiles = 0; double d_cell = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
+  cudaEvent_t bev0 = nullptr, bev1 = nullptr; bool bev_valid = false;     // brackets k_eval_blocks of the last blocks evaluate
+  cudaStream_t copy_stream = nullptr; cudaEvent_t eval_done = nullptr; std::vector<cudaEvent_t> chunk_ev;
+  std::vector<int> d_chunk_frame, d_chunk_ctile, d_chunk_qtile; bool d_chunks_pending = false;   // brackets the fused associate kernel of the last dense evaluate
+  // ---- device linear solver of the LM loop (pvb_solver.cuh)
+  int solver_kind = 0;                                                  // PVB_SOLVER_AUTO
+  DevBuf s_H, s_A, s_g, s_sc, s_rhs, s_term, s_con, s_seg, s_gcon, s_gseg, s_fail; PinBuf sh_vec;
+  int s_n = 0, s_N = 0, s_ndest = 0, s_ngdest = 0; float s_last_factor_ms = 0.f;
+  // ---- misc
+  DevBuf m_a, m_b, m_c, m_d, m_e;
+  PinBuf mh_a;
+  // ---- reprojection / bundle-adjustment mode (pvb_ba.cu owns the state; released through ba_free by pvb_destroy)
+  void* ba_state = nullptr; void (*ba_free)(void*) = nullptr;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    err = buf; return code;
+  }
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->fail(PVB_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define CKL() do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return ctx->fail(PVB_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+// ---- internal entry points shared between the translation units (not part of the ABI) ---------------------------------------------
+// blocked FP64 Cholesky + substitution of the LM step: factor the N x N matrix in ctx->s_A (lower triangle, N a multiple of 64) in place
+// and solve with the right-hand side in ctx->s_rhs; *ok = false when a pivot fails
+extern "C" __attribute__((visibility("hidden"))) int pvb_internal_factor_solve(pvb_ctx* ctx, int N, bool* ok);

@@ -303,3 +303,48 @@ def make_dense_sweep(n_target=10_000_000, n_frames=64, pts_per_frame=156_250, se
             dst.append(np.concatenate([Rotation.from_matrix(R_lw).as_rotvec(), -R_lw @ t]))
     return dict(target=target, src_local=np.concatenate(src), src_off=np.array(off, dtype=np.int32),
                 poses_lw_init=np.array(init), poses_lw_true=np.array(true), extent=(Lx, 50.0, 4.0))
+
+
+# ------------------------------------------------------------------------------------------------
+# panoramic structure-from-motion problem (the camera-camera term of the joint optimisation)
+# ------------------------------------------------------------------------------------------------
+def make_ba_problem(n_cams=12, n_points=300, track_len=(2, 8), pixel_noise_rad=2e-3, pose_noise=(0.01, 0.03), point_noise=0.03, seed=20261001, rows=2880, cols=5760):
+    """Cameras on a loop inside the box room, points on its walls, every point seen by `track_len` cameras (panoramas see all directions).
+    Returns the ground truth, perturbed initial values (camera blocks (aa_cw, t_cw), points) and the observation list with unit-sphere
+    bearings + the same key points as pixels (for the observation builder)."""
+    rng = np.random.default_rng(seed)
+    ang = np.linspace(0, 2 * np.pi, n_cams, endpoint=False)
+    cams_gt = np.zeros((n_cams, 6))
+    Rs = []
+    for c in range(n_cams):
+        R_wc = rotvec_to_R(np.array([0.0, ang[c] * 0.3, 0.0]) + rng.normal(size=3) * 0.05)
+        t_wc = np.array([1.5 * np.cos(ang[c]), rng.normal() * 0.05, 1.0 * np.sin(ang[c])])
+        R_cw = R_wc.T
+        # angle-axis of R_cw through the matrix logarithm
+        th = np.arccos(np.clip((np.trace(R_cw) - 1) / 2, -1, 1))
+        ax = np.array([R_cw[2, 1] - R_cw[1, 2], R_cw[0, 2] - R_cw[2, 0], R_cw[1, 0] - R_cw[0, 1]])
+        aa = ax / (2 * np.sin(th)) * th if th > 1e-9 else ax / 2
+        cams_gt[c, :3], cams_gt[c, 3:] = aa, -R_cw @ t_wc
+        Rs.append(rotvec_to_R(aa))
+    # points on the six faces of the room
+    face = rng.integers(0, 6, n_points)
+    pts = rng.uniform(ROOM_MIN, ROOM_MAX, size=(n_points, 3))
+    for a in range(3):
+        pts[face == 2 * a, a] = ROOM_MIN[a]
+        pts[face == 2 * a + 1, a] = ROOM_MAX[a]
+    cam, point, bearing, pix = [], [], [], []
+    for p in range(n_points):
+        L = int(rng.integers(track_len[0], min(track_len[1], n_cams) + 1))
+        for c in np.sort(rng.choice(n_cams, size=L, replace=False)):
+            Pc = Rs[c] @ pts[p] + cams_gt[c, 3:]
+            d = Pc / np.linalg.norm(Pc) + rng.normal(size=3) * pixel_noise_rad
+            d /= np.linalg.norm(d)
+            cam.append(c); point.append(p); bearing.append(d)
+            lon, lat = np.arctan2(d[0], d[2]), -np.arcsin(d[1])
+            pix.append([cols * (0.5 + lon / (2 * np.pi)), rows * (0.5 - lat / np.pi)])
+    cams0 = cams_gt.copy()
+    cams0[1:, :3] += rng.normal(size=(n_cams - 1, 3)) * pose_noise[0]
+    cams0[1:, 3:] += rng.normal(size=(n_cams - 1, 3)) * pose_noise[1]
+    pts0 = pts + rng.normal(size=pts.shape) * point_noise
+    return {"cams_gt": cams_gt, "points_gt": pts, "cams": cams0, "points": pts0, "cam": np.array(cam, np.int32), "point": np.array(point, np.int32),
+            "bearing": np.array(bearing), "pixels": np.array(pix, np.float32), "rows": rows, "cols": cols}
