@@ -309,6 +309,12 @@ int pvb_reproj_kernel_time_ms(pvb_ctx* ctx, float* ms);   /* device time of the 
  * cams6 / points3 are updated in place; summary6 as pvb_blocks_solve_lm.                                                            */
 int pvb_reproj_solve_lm(pvb_ctx* ctx, double* cams6, double* points3, const unsigned char* cam_param_const, const unsigned char* point_const,
                         int max_iterations, double* summary6);
+/* CameraLidarOptimizer::Optimize's solve (joint_optimization/CameraLidarOptimizer.cpp:387-548): ONE trust-region problem over the pose blocks
+ * [cameras | LiDARs] and the structure points with the reprojection observations (pvb_reproj_set; cam = index of the camera's pose block) and
+ * the LiDAR-LiDAR / camera-LiDAR residual blocks (pvb_blocks_set) together.  pose_param_const: n_pose_blocks x 6 flags (NULL: all free), e.g.
+ * camera 0 constant (:490-491) or the refine_* switches (:466-488); point_const as pvb_reproj_solve_lm (refine_structure, :462-465).        */
+int pvb_joint_solve_lm(pvb_ctx* ctx, double* poses6, double* points3, const unsigned char* pose_param_const, const unsigned char* point_const,
+                       int max_iterations, double* summary6);
 /* The observation loop of AddCameraResidual (util/Optimization.cpp:187-219): tracks as CSR (track t = features track_off[t] ..
  * track_off[t+1]: frame feat_frame[f], key point feat_xy[2f..2f+1] in pixels); features of frames without a valid pose are skipped;
  * the key point is rounded to the pixel grid and mapped to the unit sphere in float32 exactly like Equirectangular::ImageToCam(cv::Point2i)

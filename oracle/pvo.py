@@ -204,6 +204,17 @@ class Reproj:
         return x[:cams.size].reshape(-1, 6), x[cams.size:].reshape(-1, 3), dict(zip(keys, summ.tolist()))
 
 
+def joint_solve_lm(blocks, reproj, poses, points, param_const=None, max_iter=20):
+    """One LM over the pose blocks [cameras | LiDARs] and the points with both residual families (CameraLidarOptimizer::Optimize)."""
+    poses, points = _f64(poses).reshape(-1, 6), _f64(points).reshape(-1, 3)
+    x = np.concatenate([poses.ravel(), points.ravel()])
+    mask = np.zeros(x.size, np.uint8) if param_const is None else np.ascontiguousarray(param_const, dtype=np.uint8)
+    summ = np.zeros(6)
+    lib().pvo_joint_solve_lm(*blocks._args(), *reproj._args(), _p(x), C.c_int(len(poses)), C.c_long(len(points)), _p(mask), C.c_int(max_iter), _p(summ))
+    keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
+    return x[:poses.size].reshape(-1, 6), x[poses.size:].reshape(-1, 3), dict(zip(keys, summ.tolist()))
+
+
 def slerp_pose(pose_w1, pose_w2, ratio):
     """SlerpPose (base/Geometry.hpp:572-583); poses 4x4 row-major."""
     out = np.empty((4, 4))

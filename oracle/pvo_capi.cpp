@@ -345,6 +345,28 @@ void pvo_reproj_solve_lm(long n, const int* cam, const int* point, const double*
   summary[0] = S.initial_cost; summary[1] = S.final_cost; summary[2] = S.iterations; summary[3] = S.successful; summary[4] = S.unsuccessful; summary[5] = S.termination;
 }
 
+// joint problem of CameraLidarOptimizer::Optimize: pose blocks [cameras | LiDARs] (6 each) + structure points; the residual-block list
+// (LiDAR-LiDAR, camera-LiDAR) and the reprojection observations (camera index = pose block index) share the pose array.
+// x = [poses (6 nb) | points (3 np)] updated in place.
+void pvo_joint_solve_lm(long n, const int* type, const int* ref, const int* nei, const int* normalize, const double* huber, const double* consts,
+                        long n_obs, const int* cam, const int* point, const double* bearing, double weight, double obs_huber,
+                        double* x, int nb, long np, const unsigned char* param_const, int max_iter, double* summary) {
+  std::vector<Block> blocks(n);
+  for (long i = 0; i < n; ++i) blocks[i] = MakeBlock(i, type, ref, nei, normalize, huber, consts);
+  std::vector<ReprojObs> obs = MakeObs(n_obs, cam, point, bearing);
+  const long D = 6L * nb + 3L * np, Dp = 6L * nb;
+  std::vector<double> Hp((size_t)Dp * Dp), gp(Dp);
+  auto eval = [&](const double* xx, double* H, double* g) {
+    double cost = ReprojNormalEquations(obs.data(), n_obs, weight, obs_huber, xx, nb, np, H, g);
+    cost += NormalEquations(blocks.data(), n, xx, nb, H ? Hp.data() : nullptr, g ? gp.data() : nullptr);
+    if (H) for (long i = 0; i < Dp; ++i) for (long j = 0; j < Dp; ++j) H[(size_t)i * D + j] += Hp[(size_t)i * Dp + j];
+    if (g) for (long i = 0; i < Dp; ++i) g[i] += gp[i];
+    return cost;
+  };
+  LMSummary S = SolveLMParams(eval, x, (int)D, param_const, max_iter);
+  summary[0] = S.initial_cost; summary[1] = S.final_cost; summary[2] = S.iterations; summary[3] = S.successful; summary[4] = S.unsuccessful; summary[5] = S.termination;
+}
+
 void* pvo_kdtree_build(const float* pts, int n) { KdTree* t = new KdTree(); t->Build(pts, n, 4); return t; }
 void pvo_kdtree_free(void* t) { delete (KdTree*)t; }
 

@@ -113,7 +113,7 @@ EXPORTS = [
     "pvb_blocks_set_linear_solver", "pvb_cholesky_solve", "pvb_unique_line_pairs",
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
-    "pvb_reproj_solve_lm", "pvb_build_reproj_observations",
+    "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
 ]
 
 
@@ -395,6 +395,15 @@ class Context:
         self._ck(self._L.pvb_reproj_solve_lm(self._h, _p(cams), _p(points), _p(cc), _p(pc), C.c_int(max_iterations), _p(summ)))
         keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
         return cams, points, dict(zip(keys, summ.tolist()))
+
+    def joint_solve_lm(self, poses, points, pose_param_const=None, point_const=None, max_iterations=20):
+        poses, points = _arr(poses, np.float64).copy().reshape(-1, 6), _arr(points, np.float64).copy().reshape(-1, 3)
+        cc = None if pose_param_const is None else _arr(pose_param_const, np.uint8)
+        pc = None if point_const is None else _arr(point_const, np.uint8)
+        summ = np.zeros(6)
+        self._ck(self._L.pvb_joint_solve_lm(self._h, _p(poses), _p(points), _p(cc), _p(pc), C.c_int(max_iterations), _p(summ)))
+        keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
+        return poses, points, dict(zip(keys, summ.tolist()))
 
     @staticmethod
     def build_reproj_observations(rows, cols, track_off, feat_frame, feat_xy, pose_valid=None):

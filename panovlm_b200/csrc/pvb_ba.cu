@@ -197,16 +197,18 @@ __global__ void __launch_bounds__(128) k_schur_points(const double* __restrict__
   }
 }
 
-// one 6x6 block (c1 <= c2) of the reduced camera system: [c1 == c2] (S B S + damping) - sum_entries T_o1 E'_o2^T, entries in a fixed order
+// one 6x6 block (c1 <= c2) of the reduced camera system, added to the lower triangle of A:
+// [own_diag && c1 == c2] (S B S + damping) - sum_entries T_o1 E'_o2^T, entries in a fixed order
 __global__ void __launch_bounds__(64) k_schur_assemble(const PairDest* __restrict__ dest, const PairEntry* __restrict__ entries, const double* __restrict__ T,
                                                        const double* __restrict__ Es, const double* __restrict__ B, const double* __restrict__ scc, const int* __restrict__ fidx,
-                                                       double radius, int N, double* __restrict__ A) {
+                                                       double radius, int N, int own_diag, double* __restrict__ A) {
   const PairDest d = dest[blockIdx.x];
   const int tid = threadIdx.x;
   if (tid >= 36) return;
   const int i = tid / 6, j = tid - i * 6;
   const int fi = fidx[6 * d.c1 + i], fj = fidx[6 * d.c2 + j];
   if (fi < 0 || fj < 0) return;
+  if (d.c1 == d.c2 && fi < fj) return;                      // the diagonal block is symmetric: lower half only
   double acc = 0.0;
   for (int e = d.begin; e < d.end; ++e) {
     const PairEntry pe = entries[e];
@@ -215,20 +217,20 @@ __global__ void __launch_bounds__(64) k_schur_assemble(const PairDest* __restric
     acc += t[0] * es[0] + t[1] * es[1] + t[2] * es[2];
   }
   double v = -acc;
-  if (d.c1 == d.c2) {
+  if (own_diag && d.c1 == d.c2) {
     const int a = i < j ? i : j, b = i < j ? j : i;
     const double bs = B[(size_t)d.c1 * 21 + (a * 6 - a * (a - 1) / 2 + (b - a))] * scc[6 * (size_t)d.c1 + i] * scc[6 * (size_t)d.c1 + j];
     v += bs;
     if (i == j) v += fmin(fmax(bs, 1e-6), 1e32) / radius;
   }
-  A[(size_t)fi * N + fj] = v;
-  if (d.c1 != d.c2) A[(size_t)fj * N + fi] = v;
+  const int r = fi > fj ? fi : fj, c = fi > fj ? fj : fi;
+  A[(size_t)r * N + c] += v;
 }
 
-// right-hand side of the reduced system: -S g_c + sum_{o of c} T_o g'_p(o), fixed order per camera; identity on the padding rows
+// right-hand side of the reduced system, added to rhs: [own_gradient] -S g_c + sum_{o of c} T_o g'_p(o), fixed order per camera
 __global__ void __launch_bounds__(128) k_schur_rhs(const int* __restrict__ cam_off, const int* __restrict__ cam_obs, const int* __restrict__ pt, const double* __restrict__ T,
                                                    const double* __restrict__ gsp, const double* __restrict__ gc, const double* __restrict__ scc, const int* __restrict__ fidx,
-                                                   double* __restrict__ rhs) {
+                                                   int own_gradient, double* __restrict__ rhs) {
   __shared__ double part[6][129];
   const int c = blockIdx.x, tid = threadIdx.x;
   double acc[6] = {0, 0, 0, 0, 0, 0};
@@ -247,7 +249,30 @@ __global__ void __launch_bounds__(128) k_schur_rhs(const int* __restrict__ cam_o
     if (f < 0) return;
     double s = 0.0;
     for (int i = 0; i < 128; ++i) s += part[tid][i];
-    rhs[f] = s - gc[6 * (size_t)c + tid] * scc[6 * (size_t)c + tid];
+    if (own_gradient) s -= gc[6 * (size_t)c + tid] * scc[6 * (size_t)c + tid];
+    rhs[f] += s;
+  }
+}
+
+// joint solve: the cameras' own blocks J_c^T J_c and gradients join the dense pose-graph system (blk[c] = first unknown of camera c's block or -1)
+__global__ void __launch_bounds__(64) k_add_cam_blocks(const double* __restrict__ B, const double* __restrict__ gc, const int* __restrict__ blk, int N, double* __restrict__ H,
+                                                       double* __restrict__ g) {
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int f = blk[c];
+  if (f < 0 || tid >= 36) return;
+  const int i = tid / 6, j = tid - i * 6;
+  const int a = i < j ? i : j, b = i < j ? j : i;
+  H[(size_t)(f + i) * N + f + j] += B[(size_t)c * 21 + (a * 6 - a * (a - 1) / 2 + (b - a))];
+  if (j == 0) g[f + i] += gc[6 * (size_t)c + i];
+}
+
+// joint solve: a constant parameter inside a free block keeps its row, turned into the identity (step 0)
+__global__ void __launch_bounds__(128) k_pin_params(const int* __restrict__ pinned, int N, double* __restrict__ A, double* __restrict__ rhs) {
+  const int f = pinned[blockIdx.x];
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    if (j < f) A[(size_t)f * N + j] = 0.0;
+    else if (j > f) A[(size_t)j * N + f] = 0.0;
+    else { A[(size_t)f * N + f] = 1.0; rhs[f] = 0.0; }
   }
 }
 
@@ -535,10 +560,10 @@ int pvb_reproj_solve_lm(pvb_ctx* ctx, double* cams6, double* points3, const unsi
     CK(cudaMemsetAsync(ctx->s_A.p, 0, (size_t)N * N * 8, ctx->stream));
     CK(cudaMemsetAsync(ctx->s_rhs.p, 0, (size_t)N * 8, ctx->stream));
     k_schur_assemble<<<S->n_dest, 64, 0, ctx->stream>>>(S->d_dest.as<PairDest>(), S->d_entries.as<PairEntry>(), S->d_T.as<double>(), S->d_Es.as<double>(), S->d_B.as<double>(),
-                                                       S->d_scc.as<double>(), S->d_fidx.as<int>(), radius, N, ctx->s_A.as<double>());
+                                                       S->d_scc.as<double>(), S->d_fidx.as<int>(), radius, N, 1, ctx->s_A.as<double>());
     CKL();
     k_schur_rhs<<<nc, 128, 0, ctx->stream>>>(S->d_cam_off.as<int>(), S->d_cam_obs.as<int>(), S->d_pt.as<int>(), S->d_T.as<double>(), S->d_gsp.as<double>(), S->d_gc.as<double>(),
-                                             S->d_scc.as<double>(), S->d_fidx.as<int>(), ctx->s_rhs.as<double>());
+                                             S->d_scc.as<double>(), S->d_fidx.as<int>(), 1, ctx->s_rhs.as<double>());
     CKL();
     if (N > n) { k_pad_identity<<<(N - n + 63) / 64, 64, 0, ctx->stream>>>(ctx->s_A.as<double>(), ctx->s_rhs.as<double>(), n, N); CKL(); }
     bool ok = false;
@@ -603,6 +628,196 @@ int pvb_reproj_solve_lm(pvb_ctx* ctx, double* cams6, double* points3, const unsi
     if (stop) break;
     if (!accepted) {   // the candidate evaluation overwrote the blocks of the current point (device and host mirror): bring them back
       rc = evaluate(cams6, points3, &new_cost); if (rc) return rc;
+    }
+  }
+  return finish();
+}
+
+// CameraLidarOptimizer::Optimize's ceres::Solve (joint_optimization/CameraLidarOptimizer.cpp:387-548): camera-camera reprojection blocks
+// (AddCameraResidual, :431), LiDAR-LiDAR blocks and camera-LiDAR blocks (pvb_blocks_set: AddLidar*Residual / AddCameraLidarResidual,
+// :437-460) in ONE trust-region problem over the pose blocks [cameras | LiDARs] and the structure points.  The pose-graph part is reduced
+// per edge and assembled into the dense system by the LiDAR LM's kernels; the cameras' own blocks are added, the points are eliminated
+// (Schur complement) and the Cholesky of the LM loop solves for the poses.  Control flow = pvb::solve_lm (Ceres' defaults).
+int pvb_joint_solve_lm(pvb_ctx* ctx, double* poses6, double* points3, const unsigned char* pose_param_const, const unsigned char* point_const, int max_iterations,
+                       double* summary6) {
+  BAState* S = ctx ? ba_get(ctx, false) : nullptr;
+  if (!ctx || !poses6) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_joint_solve_lm: bad arguments") : PVB_ERR_ARG;
+  if (!S || ctx->nb <= 0) return ctx->fail(PVB_ERR_STATE, "pvb_joint_solve_lm needs pvb_blocks_set and pvb_reproj_set");
+  if (S->n_cam > ctx->nb) return ctx->fail(PVB_ERR_ARG, "pvb_joint_solve_lm: %d cameras but only %d pose blocks", S->n_cam, ctx->nb);
+  if (S->n_pts > 0 && !points3) return ctx->fail(PVB_ERR_ARG, "pvb_joint_solve_lm: null points");
+  CK(cudaSetDevice(ctx->device));
+  const int nb = ctx->nb, nc = S->n_cam; const long np = S->n_pts;
+  int rc = build_pairs(ctx, S); if (rc) return rc;
+  // a block whose six parameters are all constant leaves the system; a partly constant block stays and its constant rows are pinned
+  std::vector<unsigned char> blk_const(nb, 0);
+  for (int b = 0; b < nb; ++b) { bool all = pose_param_const != nullptr; for (int k = 0; k < 6 && all; ++k) all = pose_param_const[6 * b + k] != 0; blk_const[b] = all ? 1 : 0; }
+  rc = pvb_internal_solver_prepare(ctx, blk_const.data()); if (rc) return rc;
+  const int n = ctx->s_n, N = std::max(ctx->s_N, kPad);
+  std::vector<int> slot(6 * (size_t)nb, -1), fidx(6 * (size_t)nb, -1), cam_blk(nc, -1), pinned;
+  { int f = 0;
+    for (int b = 0; b < nb; ++b) {
+      if (blk_const[b]) continue;
+      for (int k = 0; k < 6; ++k) {
+        slot[6 * b + k] = f + k;
+        if (pose_param_const && pose_param_const[6 * b + k]) pinned.push_back(f + k); else fidx[6 * b + k] = f + k;
+      }
+      if (b < nc) cam_blk[b] = f;
+      f += 6;
+    } }
+  std::vector<unsigned char> ptc(std::max<long>(np, 1), 0);
+  long n_free_pts = 0;
+  for (long p = 0; p < np; ++p) { ptc[p] = point_const && point_const[p] ? 1 : 0; if (!ptc[p]) ++n_free_pts; }
+  DevBuf d_camblk, d_pinned, d_diag;
+  struct Guard { DevBuf *a, *b, *c; ~Guard() { a->release(); b->release(); c->release(); } } guard{&d_camblk, &d_pinned, &d_diag};
+  CK(d_camblk.ensure((size_t)nc * 4)); CK(d_pinned.ensure(std::max<size_t>(4, pinned.size() * 4))); CK(d_diag.ensure((size_t)N * 8));
+  CK(S->d_fidx.ensure(fidx.size() * 4)); CK(S->d_scc.ensure((size_t)nc * 48)); CK(S->d_scp.ensure(std::max<size_t>(8, (size_t)np * 24))); CK(S->d_ptconst.ensure(ptc.size()));
+  CK(S->d_Cinv.ensure(std::max<size_t>(8, (size_t)np * 48))); CK(S->d_gsp.ensure(std::max<size_t>(8, (size_t)np * 24))); CK(S->d_yp.ensure(std::max<size_t>(8, (size_t)np * 24)));
+  CK(S->d_T.ensure(std::max<size_t>(8, (size_t)S->n_obs * 144))); CK(S->d_Es.ensure(std::max<size_t>(8, (size_t)S->n_obs * 144)));
+  CK(cudaMemcpyAsync(S->d_fidx.p, fidx.data(), fidx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(S->d_ptconst.p, ptc.data(), ptc.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_camblk.p, cam_blk.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!pinned.empty()) CK(cudaMemcpyAsync(d_pinned.p, pinned.data(), pinned.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+
+  LMOptions opt; opt.max_iterations = max_iterations;
+  LMSummary R;
+  std::vector<double> g(std::max(n, 1)), hdiag(std::max(n, 1)), sc(std::max(n, 1), 1.0);
+  // evaluation of both parts at (poses, points) + the dense pose system of the free blocks with the cameras' own blocks added
+  auto evaluate = [&](const double* xp, const double* xs, double* out_cost) -> int {
+    int r = pvb_blocks_evaluate(ctx, xp, 0, 1); if (r) return r;
+    r = pvb_reproj_evaluate(ctx, xp, xs, 0, 1); if (r) return r;
+    double c1 = 0, c2 = 0;
+    r = pvb_blocks_cost(ctx, &c1, nullptr); if (r) return r;
+    r = pvb_reproj_cost(ctx, &c2); if (r) return r;
+    *out_cost = c1 + c2;
+    return PVB_OK;
+  };
+  auto assemble = [&]() -> int {
+    if (n == 0) return PVB_OK;
+    int r = pvb_internal_solver_assemble(ctx, g.data()); if (r) return r;
+    k_add_cam_blocks<<<nc, 64, 0, ctx->stream>>>(S->d_B.as<double>(), S->d_gc.as<double>(), d_camblk.as<int>(), ctx->s_N, ctx->s_H.as<double>(), ctx->s_g.as<double>());
+    CKL();
+    CK(cudaMemcpyAsync(g.data(), ctx->s_g.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpy2DAsync(hdiag.data(), 8, ctx->s_H.p, (size_t)(ctx->s_N + 1) * 8, 8, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PVB_OK;
+  };
+  double cost = 0.0;
+  rc = evaluate(poses6, points3, &cost); if (rc) return rc;
+  rc = assemble(); if (rc) return rc;
+  R.initial_cost = cost;
+  const double* hb = S->h_blocks.as<double>();
+  auto Cdiag = [&](long p, int k) { static const int di[3] = {0, 3, 5}; return hb[28 * (size_t)nc + 6 * (size_t)p + di[k]]; };
+  auto gpt = [&](long i) { return hb[28 * (size_t)nc + 6 * (size_t)np + i]; };
+  // Jacobi scaling, fixed from the first Jacobian: poses from the diagonal of the total dense system, points from their own blocks
+  std::vector<double> scc(6 * (size_t)nc, 1.0), scp(3 * (size_t)std::max<long>(np, 1), 1.0);
+  if (n) {
+    rc = pvb_internal_jacobi_scale(ctx); if (rc) return rc;
+    CK(cudaMemcpyAsync(sc.data(), ctx->s_sc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  for (int i = 0; i < 6 * nc; ++i) if (slot[i] >= 0) scc[i] = sc[slot[i]];
+  for (long p = 0; p < np; ++p) for (int k = 0; k < 3; ++k) scp[3 * p + k] = 1.0 / (1.0 + std::sqrt(Cdiag(p, k)));
+  CK(cudaMemcpyAsync(S->d_scc.p, scc.data(), (size_t)nc * 48, cudaMemcpyHostToDevice, ctx->stream));
+  if (np) CK(cudaMemcpyAsync(S->d_scp.p, scp.data(), (size_t)np * 24, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  auto gmax = [&]() {
+    double m = 0;
+    for (int i = 0; i < 6 * nb; ++i) if (fidx[i] >= 0) m = std::max(m, std::fabs(g[fidx[i]]));
+    for (long p = 0; p < np; ++p) if (!ptc[p]) for (int k = 0; k < 3; ++k) m = std::max(m, std::fabs(gpt(3 * p + k)));
+    return m;
+  };
+  auto finish = [&]() {
+    R.final_cost = cost;
+    if (summary6) { summary6[0] = R.initial_cost; summary6[1] = R.final_cost; summary6[2] = R.iterations; summary6[3] = R.successful; summary6[4] = R.unsuccessful; summary6[5] = R.termination; }
+    return PVB_OK;
+  };
+  const bool any_pose = (int)pinned.size() < n;
+  if ((!any_pose && n_free_pts == 0) || gmax() <= opt.gradient_tolerance) { R.termination = 2; return finish(); }
+  if (n == 0) return ctx->fail(PVB_ERR_ARG, "pvb_joint_solve_lm: every pose block is constant (use pvb_reproj_solve_lm for a structure-only refinement)");
+  std::vector<double> y(N), yp(3 * (size_t)std::max<long>(np, 1), 0.0), cand_x(6 * (size_t)nb), cand_p(3 * (size_t)std::max<long>(np, 1));
+  double radius = 1e4, decrease = 2.0;
+  int invalid = 0;
+  for (int it = 1; it <= opt.max_iterations; ++it) {
+    R.iterations = it;
+    rc = pvb_internal_build_damped(ctx, radius); if (rc) return rc;
+    if (np) {
+      k_schur_points<<<(unsigned)((np + 127) / 128), 128, 0, ctx->stream>>>(S->d_C.as<double>(), S->d_gp.as<double>(), S->d_E.as<double>(), S->d_pt_off.as<int>(), S->d_cam.as<int>(),
+                                                                            S->d_scc.as<double>(), S->d_scp.as<double>(), S->d_ptconst.as<unsigned char>(), np, radius,
+                                                                            S->d_Cinv.as<double>(), S->d_gsp.as<double>(), S->d_T.as<double>(), S->d_Es.as<double>());
+      CKL();
+      k_schur_assemble<<<S->n_dest, 64, 0, ctx->stream>>>(S->d_dest.as<PairDest>(), S->d_entries.as<PairEntry>(), S->d_T.as<double>(), S->d_Es.as<double>(), S->d_B.as<double>(),
+                                                         S->d_scc.as<double>(), S->d_fidx.as<int>(), radius, ctx->s_N, 0, ctx->s_A.as<double>());
+      CKL();
+      k_schur_rhs<<<nc, 128, 0, ctx->stream>>>(S->d_cam_off.as<int>(), S->d_cam_obs.as<int>(), S->d_pt.as<int>(), S->d_T.as<double>(), S->d_gsp.as<double>(), S->d_gc.as<double>(),
+                                               S->d_scc.as<double>(), S->d_fidx.as<int>(), 0, ctx->s_rhs.as<double>());
+      CKL();
+    }
+    if (!pinned.empty()) { k_pin_params<<<(unsigned)pinned.size(), 128, 0, ctx->stream>>>(d_pinned.as<int>(), ctx->s_N, ctx->s_A.as<double>(), ctx->s_rhs.as<double>()); CKL(); }
+    bool ok = false;
+    rc = pvb_internal_factor_solve(ctx, ctx->s_N, &ok); if (rc) return rc;
+    double model = 0.0;
+    if (ok) {
+      if (np) {
+        k_schur_backsub<<<(unsigned)((np + 127) / 128), 128, 0, ctx->stream>>>(S->d_Cinv.as<double>(), S->d_gsp.as<double>(), S->d_T.as<double>(), S->d_pt_off.as<int>(), S->d_cam.as<int>(),
+                                                                               S->d_fidx.as<int>(), ctx->s_rhs.as<double>(), np, S->d_yp.as<double>());
+        CKL();
+        CK(cudaMemcpyAsync(yp.data(), S->d_yp.p, (size_t)np * 24, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      CK(cudaMemcpyAsync(y.data(), ctx->s_rhs.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      // model cost change 0.5 (-y.g' + y^T D y) (see pvb_reproj_solve_lm), fixed order
+      for (int i = 0; i < 6 * nb; ++i) {
+        const int f = fidx[i];
+        if (f < 0) continue;
+        const double yi = y[f], s_ = sc[f], hd = hdiag[f] * s_ * s_;
+        model += 0.5 * (-yi * g[f] * s_ + std::min(std::max(hd, 1e-6), 1e32) / radius * yi * yi);
+      }
+      for (long p = 0; p < np; ++p) {
+        if (ptc[p]) continue;
+        for (int k = 0; k < 3; ++k) {
+          const double yi = yp[3 * p + k], s_ = scp[3 * p + k], hd = Cdiag(p, k) * s_ * s_;
+          model += 0.5 * (-yi * gpt(3 * p + k) * s_ + std::min(std::max(hd, 1e-6), 1e32) / radius * yi * yi);
+        }
+      }
+      ok = model > 0.0;
+    }
+    if (!ok) { radius *= 0.5; R.unsuccessful++; if (++invalid >= 5 || radius < 1e-32) { R.termination = 4; break; } continue; }
+    invalid = 0;
+    double sn = 0, xn = 0;
+    std::copy(poses6, poses6 + 6 * (size_t)nb, cand_x.begin());
+    if (np) std::copy(points3, points3 + 3 * (size_t)np, cand_p.begin());
+    for (int i = 0; i < 6 * nb; ++i) { const int f = fidx[i]; if (f < 0) continue; const double d = y[f] * sc[f]; cand_x[i] += d; sn += d * d; xn += poses6[i] * poses6[i]; }
+    for (long p = 0; p < np; ++p) { if (ptc[p]) continue; for (int k = 0; k < 3; ++k) { const double d = yp[3 * p + k] * scp[3 * p + k]; cand_p[3 * p + k] += d; sn += d * d; xn += points3[3 * p + k] * points3[3 * p + k]; } }
+    sn = std::sqrt(sn); xn = std::sqrt(xn);
+    double new_cost = 0.0;
+    rc = evaluate(cand_x.data(), cand_p.data(), &new_cost); if (rc) return rc;
+    bool accepted = false, stop = false;
+    if (sn <= opt.parameter_tolerance * (xn + opt.parameter_tolerance)) { R.termination = 3; stop = true; }
+    else {
+      const double change = cost - new_cost;
+      if (std::fabs(change) <= opt.function_tolerance * cost) { R.termination = 1; stop = true; }
+      else {
+        const double rho = change / model;
+        if (rho > 1e-3) {
+          accepted = true;
+          std::copy(cand_x.begin(), cand_x.end(), poses6);
+          if (np) std::copy(cand_p.begin(), cand_p.begin() + 3 * (size_t)np, points3);
+          cost = new_cost;
+          rc = assemble(); if (rc) return rc;
+          R.successful++;
+          radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
+          decrease = 2.0;
+          if (gmax() <= opt.gradient_tolerance) { R.termination = 2; stop = true; }
+        } else {
+          radius /= decrease; decrease *= 2.0; R.unsuccessful++;
+          if (radius < 1e-32) { R.termination = 4; stop = true; }
+        }
+      }
+    }
+    if (stop) break;
+    if (!accepted) {   // the candidate evaluation overwrote the reduced blocks of the current point: bring them back (the dense pose system is untouched)
+      rc = evaluate(poses6, points3, &new_cost); if (rc) return rc;
     }
   }
   return finish();

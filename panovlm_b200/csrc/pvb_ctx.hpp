@@ -115,3 +115,12 @@ struct pvb_ctx {
 // blocked FP64 Cholesky + substitution of the LM step: factor the N x N matrix in ctx->s_A (lower triangle, N a multiple of 64) in place
 // and solve with the right-hand side in ctx->s_rhs; *ok = false when a pivot fails
 extern "C" __attribute__((visibility("hidden"))) int pvb_internal_factor_solve(pvb_ctx* ctx, int N, bool* ok);
+// pieces of the device LM step of the pose-graph blocks (pvb_lib.cu), reused by the joint camera-LiDAR solve:
+//   prepare : free-block map and contribution lists for the given constant blocks (sets ctx->s_n, ctx->s_N)
+//   assemble: dense J^T J (ctx->s_H, N x N) and gradient (ctx->s_g) of the free blocks from the edge systems of the last pvb_blocks_evaluate;
+//             the gradient is also copied to h_g (s_n doubles)
+//   jacobi_scale: ctx->s_sc = 1 / (1 + sqrt(diag H));  build_damped: ctx->s_A (lower triangle) / ctx->s_rhs from s_H, s_g, s_sc and the radius
+extern "C" __attribute__((visibility("hidden"))) int pvb_internal_solver_prepare(pvb_ctx* ctx, const unsigned char* is_const_block);
+extern "C" __attribute__((visibility("hidden"))) int pvb_internal_solver_assemble(pvb_ctx* ctx, double* h_g);
+extern "C" __attribute__((visibility("hidden"))) int pvb_internal_jacobi_scale(pvb_ctx* ctx);
+extern "C" __attribute__((visibility("hidden"))) int pvb_internal_build_damped(pvb_ctx* ctx, double radius);

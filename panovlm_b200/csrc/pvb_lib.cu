@@ -550,6 +550,22 @@ static int solve_lm_device(pvb_ctx* ctx, double* poses, const unsigned char* is_
   return PVB_OK;
 }
 
+// ---- internal entry points for the joint camera-LiDAR solve (pvb_ba.cu); declared in pvb_ctx.hpp -------------------------------------
+int pvb_internal_solver_prepare(pvb_ctx* ctx, const unsigned char* is_const_block) { return solver_prepare(ctx, is_const_block); }
+int pvb_internal_solver_assemble(pvb_ctx* ctx, double* h_g) { return solver_assemble(ctx, h_g); }
+int pvb_internal_jacobi_scale(pvb_ctx* ctx) {
+  k_jacobi_scale<<<(ctx->s_N + 255) / 256, 256, 0, ctx->stream>>>(ctx->s_H.as<double>(), ctx->s_n, ctx->s_N, ctx->s_sc.as<double>());
+  CKL();
+  return PVB_OK;
+}
+int pvb_internal_build_damped(pvb_ctx* ctx, double radius) {
+  const int N = ctx->s_N;
+  k_build_damped<<<dim3((N + 255) / 256, N), 256, 0, ctx->stream>>>(ctx->s_H.as<double>(), ctx->s_g.as<double>(), ctx->s_sc.as<double>(), ctx->s_n, N, radius, ctx->s_A.as<double>(),
+                                                                   ctx->s_rhs.as<double>());
+  CKL();
+  return PVB_OK;
+}
+
 int pvb_blocks_set_linear_solver(pvb_ctx* ctx, int kind) {
   if (!ctx || kind < PVB_SOLVER_AUTO || kind > PVB_SOLVER_DEVICE) return ctx ? ctx->fail(PVB_ERR_ARG, "unknown linear solver %d", kind) : PVB_ERR_ARG;
   ctx->solver_kind = kind;

@@ -206,3 +206,69 @@ def test_reproj_room_scale_bundle_adjustment(gpu_ctx):
     assert np.array_equal(c1[0], d["cams"][0])
     # closer to the ground truth than the perturbed start (the gauge is pinned by camera 0 only up to scale: compare rotations)
     assert np.abs(c1[:, :3] - d["cams_gt"][:, :3]).mean() < 0.3 * np.abs(d["cams"][:, :3] - d["cams_gt"][:, :3]).mean()
+
+
+def _joint_problem(nc=6, npt=150, n_blocks=1500, seed=21):
+    """Pose blocks [cameras 0..nc) | LiDARs nc..2nc): a BA problem on the cameras plus plane / line residual blocks between random pairs of all pose
+    blocks (the LiDAR-LiDAR and camera-LiDAR families of the joint problem), consistent with one ground truth."""
+    from scipy.spatial.transform import Rotation
+    d = synth.make_ba_problem(n_cams=nc, n_points=npt, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    nb = 2 * nc
+    truth = np.concatenate([d["cams_gt"], np.concatenate([rng.normal(0, 0.3, (nc, 3)), rng.normal(0, 1.0, (nc, 3))], 1)])
+    typ = rng.integers(0, 4, n_blocks).astype(np.int32)
+    ref = rng.integers(0, nb, n_blocks).astype(np.int32)
+    nei = ((ref + rng.integers(1, nb, n_blocks)) % nb).astype(np.int32)
+    consts = np.zeros((n_blocks, 12))
+    for i in range(n_blocks):
+        pw = rng.normal(0, 4, 3)
+        Rr, tr = Rotation.from_rotvec(truth[ref[i], :3]).as_matrix(), truth[ref[i], 3:]
+        Rn, tn = Rotation.from_rotvec(truth[nei[i], :3]).as_matrix(), truth[nei[i], 3:]
+        p_ref, p_nei = Rr @ pw + tr, Rn @ pw + tn
+        consts[i, :3] = p_nei + rng.normal(0, 0.01, 3)
+        if typ[i] < 2:
+            nrm = rng.normal(size=3); nrm /= np.linalg.norm(nrm)
+            dd = -nrm @ p_ref
+            if dd < 0:
+                nrm, dd = -nrm, -dd
+            consts[i, 3:6] = nrm; consts[i, 6] = dd; consts[i, 7] = 0.05
+        else:
+            dr = rng.normal(size=3); dr /= np.linalg.norm(dr)
+            consts[i, 3:6] = p_ref + 0.3 * dr; consts[i, 6:9] = dr; consts[i, 9] = 0.05
+    hub = np.where(typ % 2 == 1, 2 * np.pi / 180, 0.2)
+    start = truth.copy()
+    start[:nc] = d["cams"]
+    start[nc:] += np.concatenate([rng.normal(0, 0.01, (nc, 3)), rng.normal(0, 0.03, (nc, 3))], axis=1)
+    return d, nb, (typ, ref, nei, consts, hub), start
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["all", "fixed_camera_rotations", "fixed_structure"])
+def test_joint_camera_lidar_lm_matches_dense_oracle_lm(gpu_ctx, oracle, mode):
+    """CameraLidarOptimizer::Optimize's solve: reprojection blocks + pose-graph blocks in one trust-region problem, points eliminated on the device."""
+    nc, npt = 6, 150
+    d, nb, (typ, ref, nei, consts, hub), start = _joint_problem(nc, npt)
+    pose_const = np.zeros((nb, 6), np.uint8)
+    pose_const[0] = 1                                             # camera 0 constant (CameraLidarOptimizer.cpp:490-491)
+    pt_const = np.zeros(npt, np.uint8)
+    if mode == "fixed_camera_rotations":
+        pose_const[:nc, :3] = 1                                   # refine_camera_rotation = false (:469-474)
+    if mode == "fixed_structure":
+        pt_const[:] = 1                                           # refine_structure = false (:462-465)
+    blk = oracle.Blocks(typ, ref, nei, consts, hub, 1)
+    rep = oracle.Reproj(d["cam"], d["point"], d["bearing"], huber=HUBER)
+    mask = np.concatenate([pose_const.ravel(), np.repeat(pt_const, 3)])
+    e_x, e_p, e_s = oracle.joint_solve_lm(blk, rep, start, d["points"], mask, max_iter=15)
+    gpu_ctx.blocks_set(typ, ref, nei, consts, hub, 1, nb)
+    gpu_ctx.reproj_set(d["cam"], d["point"], d["bearing"], nc, npt, huber=HUBER)
+    g_x, g_p, g_s = gpu_ctx.joint_solve_lm(start, d["points"], pose_const, pt_const, max_iterations=15)
+    for k in ("iterations", "successful", "unsuccessful", "termination"):
+        assert e_s[k] == g_s[k], (k, e_s, g_s)
+    assert abs(e_s["initial_cost"] - g_s["initial_cost"]) < 1e-10 * e_s["initial_cost"]
+    assert abs(e_s["final_cost"] - g_s["final_cost"]) < 1e-5 * e_s["final_cost"]
+    assert e_s["final_cost"] < 0.5 * e_s["initial_cost"]
+    assert np.abs(g_x - e_x).max() < 1e-4 * np.abs(e_x - start).max()          # pose deltas: 1e-4 relative (BASELINE.json)
+    if mode != "fixed_structure":
+        assert np.abs(g_p - e_p).max() < 1e-4 * np.abs(e_p - d["points"]).max()
+    assert np.array_equal(g_x[pose_const.astype(bool)], start[pose_const.astype(bool)])
+    assert np.array_equal(g_p[pt_const.astype(bool)], d["points"][pt_const.astype(bool)])
