@@ -243,6 +243,21 @@ int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* li
                                const double* T_cl16, int filter_by_length, int multiple_association, const unsigned char* image_line_mask,
                                const unsigned char* lidar_line_mask, int cap, int* n_out, int* image_line, int* lidar_line,
                                double* start3, double* end3, float* angle);
+/* ---- pixel-space CameraLidarLineAssociate::Associate, first stage (joint_optimization/CameraLidarLineAssociate.cpp:22-102): the fallback
+ * for frames without LiDAR line segments (CameraLidarOptimizer.cpp:360-367).  The RANSAC line fit that follows in the reference (:105-110) is
+ * PCL's randomised SACSegmentation and has no deterministic counterpart here; these entry points deliver its input.                        */
+/* image lines -> sub-line mid points (BreakToSegments(line, 70), seam pieces skipped, :38-54); returns their number.  Host only.            */
+int pvb_pixel_sub_lines(int rows, int cols, const float* lines4, int n_lines, int cap, float* mid2, int* sub_to_line);
+/* cv::flann knnSearch(k = 3) of every projected LiDAR point among the mid points (:74-79): cloud -> camera frame (float32) -> pixel (CamToImage
+ * with FastAtan2) -> idx3 = the 3 nearest mid points by ascending float squared L2 (-1 when there are fewer), d2_3 / pixel2 optional views   */
+int pvb_pixel_knn3(pvb_ctx* ctx, int rows, int cols, const float* mid2, int n_mid, const float* cloud_local, int n_points, const double* T_cl16,
+                   int* idx3, float* d2_3, float* pixel2);
+/* the two above + the 60 px gate (:81): line3 = n_points x 3 image-line index of the k-th nearest mid point, or -1                              */
+int pvb_pixel_line_neighbors(pvb_ctx* ctx, int rows, int cols, const float* lines4, int n_lines, const float* cloud_local, int n_points,
+                             const double* T_cl16, int* line3, float* d2_3, float* pixel2);
+/* `line_lidar` (:83-97) as CSR: per image line the LiDAR points that chose it (ascending, with multiplicity), emptied below min_points (6).
+ * Returns the number of entries.  Host only.                                                                                                */
+int pvb_pixel_line_candidates(int n_lines, int n_points, const int* line3, int min_points, int cap, int* line_off, int* lidar_idx);
 /* UniqueLinePair alone (host): candidates in input order -> one-to-one pairs, ascending image line                                  */
 int pvb_unique_line_pairs(int n, const int* image_line, const int* lidar_line, const float* score, int* n_out, int* out_image, int* out_lidar,
                           float* out_score);

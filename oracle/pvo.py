@@ -215,6 +215,24 @@ def joint_solve_lm(blocks, reproj, poses, points, param_const=None, max_iter=20)
     return x[:poses.size].reshape(-1, 6), x[poses.size:].reshape(-1, 3), dict(zip(keys, summ.tolist()))
 
 
+def pixel_line_neighbors(rows, cols, lines, cloud_local, T_cl):
+    """First stage of the pixel-space CameraLidarLineAssociate::Associate (joint_optimization/CameraLidarLineAssociate.cpp:22-91)."""
+    lines, cloud = _f32(lines).reshape(-1, 4), _f32(cloud_local).reshape(-1, 4)
+    n = len(cloud)
+    line3, d2, px = np.full((n, 3), -1, np.int32), np.zeros((n, 3), np.float32), np.zeros((n, 2), np.float32)
+    lib().pvo_pixel_line_neighbors(C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), _p(cloud), C.c_int(n), _p(_f64(T_cl)), _p(line3), _p(d2), _p(px))
+    return line3, d2, px
+
+
+def pixel_sub_lines(rows, cols, lines):
+    lines = _f32(lines).reshape(-1, 4)
+    cap = 64 + int(sum(np.hypot(l[0] - l[2], l[1] - l[3]) / 70 + 4 for l in lines))
+    mid, s2l = np.zeros((cap, 2), np.float32), np.zeros(cap, np.int32)
+    m = lib().pvo_pixel_sub_lines(C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), C.c_int(cap), _p(mid), _p(s2l))
+    assert m >= 0
+    return mid[:m].copy(), s2l[:m].copy()
+
+
 def slerp_pose(pose_w1, pose_w2, ratio):
     """SlerpPose (base/Geometry.hpp:572-583); poses 4x4 row-major."""
     out = np.empty((4, 4))

@@ -376,6 +376,57 @@ struct Equirect {
   }
 };
 
+// ---- pixel-space Associate, first stage (CameraLidarLineAssociate.cpp:22-91): the fallback for frames without LiDAR segments ----------
+// image lines -> sub-line mid points (BreakToSegments(line, 70), seam pieces skipped, :38-54); every LiDAR point -> camera frame
+// (pcl::transformPointCloud, float32) -> pixel (CamToImage, float + FastAtan2, :75-76) -> its 3 nearest mid points (cv::flann exact search,
+// float squared L2, :78), kept within 60 px (:81).  Output per point: image line of the k-th nearest mid point or -1, and the line -> LiDAR
+// point lists (`line_lidar`, :83) with lines holding fewer than `min_points` (6, :92) emptied.  The RANSAC line fit that follows (:105-110,
+// PCL's randomised SACSegmentation) has no deterministic answer and is not restated.
+inline void PixelSubLines(const Equirect& eq, const float* lines, int L, std::vector<float>& mid, std::vector<int>& sub_to_line) {
+  mid.clear(); sub_to_line.clear();
+  for (int l = 0; l < L; ++l) {
+    const float a[2] = {lines[l * 4], lines[l * 4 + 1]}, b[2] = {lines[l * 4 + 2], lines[l * 4 + 3]};
+    const auto seg = eq.BreakToSegments(a, b, 70);
+    for (size_t i = 0; i + 1 < seg.size(); ++i) {
+      if (std::abs(seg[i].first - seg[i + 1].first) > 0.8 * eq.cols) continue;                        // :44
+      mid.push_back((float)((seg[i + 1].first + seg[i].first) / 2.0));                                // :47-48
+      mid.push_back((float)((seg[i + 1].second + seg[i].second) / 2.0));
+      sub_to_line.push_back(l);
+    }
+  }
+}
+
+inline void PixelLineNeighbors(const Equirect& eq, const float* lines, int L, const float* cloud_local, int P, const double T_cl[16], int* line3, float* d2_3,
+                               float* pixel2) {
+  std::vector<float> mid; std::vector<int> s2l;
+  PixelSubLines(eq, lines, L, mid, s2l);
+  const int M = (int)s2l.size();
+  std::vector<float> cam((size_t)std::max(P, 1) * 4);
+  double R[9], t[3];
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[r * 3 + c] = T_cl[r * 4 + c]; t[r] = T_cl[r * 4 + 3]; }
+  TransformCloud(R, t, cloud_local, P, cam.data(), 4);
+  for (int i = 0; i < P; ++i) {
+    const float pc[3] = {cam[(size_t)i * 4], cam[(size_t)i * 4 + 1], cam[(size_t)i * 4 + 2]};
+    float px[2]; eq.CamToImage(pc, px);
+    if (pixel2) { pixel2[2 * i] = px[0]; pixel2[2 * i + 1] = px[1]; }
+    float bd[3] = {INFINITY, INFINITY, INFINITY}; int bi[3] = {-1, -1, -1};
+    for (int m = 0; m < M; ++m) {
+      const float dx = px[0] - mid[2 * m], dy = px[1] - mid[2 * m + 1];
+      const float d = dx * dx + dy * dy;                                                                // FLANN L2<float>
+      if (d < bd[2]) {
+        int k = 2;
+        while (k > 0 && d < bd[k - 1]) { bd[k] = bd[k - 1]; bi[k] = bi[k - 1]; --k; }
+        bd[k] = d; bi[k] = m;
+      }
+    }
+    for (int k = 0; k < 3; ++k) {
+      const bool keep = bi[k] >= 0 && !(bd[k] > 60 * 60);                                               // :81
+      line3[3 * i + k] = keep ? s2l[bi[k]] : -1;
+      if (d2_3) d2_3[3 * i + k] = bd[k];
+    }
+  }
+}
+
 // ---- AssociateByAngle (CameraLidarLineAssociate.cpp:340-475) + Filter(false,true) (:628-715) ----------
 struct CamLidarPair { int image_line, lidar_line; double start[3], end[3]; float angle; };
 

@@ -367,6 +367,19 @@ void pvo_joint_solve_lm(long n, const int* type, const int* ref, const int* nei,
   summary[0] = S.initial_cost; summary[1] = S.final_cost; summary[2] = S.iterations; summary[3] = S.successful; summary[4] = S.unsuccessful; summary[5] = S.termination;
 }
 
+void pvo_pixel_line_neighbors(int rows, int cols, const float* lines, int L, const float* cloud_local, int P, const double* T_cl, int* line3, float* d2_3, float* pixel2) {
+  Equirect eq{rows, cols};
+  PixelLineNeighbors(eq, lines, L, cloud_local, P, T_cl, line3, d2_3, pixel2);
+}
+int pvo_pixel_sub_lines(int rows, int cols, const float* lines, int L, int cap, float* mid2, int* sub_to_line) {
+  Equirect eq{rows, cols};
+  std::vector<float> mid; std::vector<int> s2l;
+  PixelSubLines(eq, lines, L, mid, s2l);
+  if ((int)s2l.size() > cap) return -1;
+  std::memcpy(mid2, mid.data(), mid.size() * 4); std::memcpy(sub_to_line, s2l.data(), s2l.size() * 4);
+  return (int)s2l.size();
+}
+
 void* pvo_kdtree_build(const float* pts, int n) { KdTree* t = new KdTree(); t->Build(pts, n, 4); return t; }
 void pvo_kdtree_free(void* t) { delete (KdTree*)t; }
 

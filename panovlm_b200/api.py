@@ -114,6 +114,7 @@ EXPORTS = [
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
+    "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates",
 ]
 
 
@@ -395,6 +396,34 @@ class Context:
         self._ck(self._L.pvb_reproj_solve_lm(self._h, _p(cams), _p(points), _p(cc), _p(pc), C.c_int(max_iterations), _p(summ)))
         keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
         return cams, points, dict(zip(keys, summ.tolist()))
+
+    # ---- pixel-space camera-LiDAR association (first stage)
+    @staticmethod
+    def pixel_sub_lines(rows, cols, lines):
+        lines = _arr(lines, np.float32).reshape(-1, 4)
+        cap = 64 + int(sum(np.hypot(float(l[0]) - float(l[2]), float(l[1]) - float(l[3])) / 70 + 4 for l in lines))
+        mid, s2l = np.zeros((cap, 2), np.float32), np.zeros(cap, np.int32)
+        m = load_library().pvb_pixel_sub_lines(C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), C.c_int(cap), _p(mid), _p(s2l))
+        if m < 0:
+            raise PvbError(f"pvb_pixel_sub_lines: code {m}")
+        return mid[:m].copy(), s2l[:m].copy()
+
+    def pixel_line_neighbors(self, rows, cols, lines, cloud_local, T_cl):
+        lines, cloud = _arr(lines, np.float32).reshape(-1, 4), _arr(cloud_local, np.float32).reshape(-1, 4)
+        n = len(cloud)
+        line3, d2, px = np.full((n, 3), -1, np.int32), np.zeros((n, 3), np.float32), np.zeros((n, 2), np.float32)
+        self._ck(self._L.pvb_pixel_line_neighbors(self._h, C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), _p(cloud), C.c_int(n), _p(_arr(T_cl, np.float64)),
+                                                  _p(line3), _p(d2), _p(px)))
+        return line3, d2, px
+
+    @staticmethod
+    def pixel_line_candidates(n_lines, line3, min_points=6):
+        line3 = _arr(line3, np.int32).reshape(-1, 3)
+        off, idx = np.zeros(n_lines + 1, np.int32), np.zeros(max(1, line3.size), np.int32)
+        m = load_library().pvb_pixel_line_candidates(C.c_int(n_lines), C.c_int(len(line3)), _p(line3), C.c_int(min_points), C.c_int(len(idx)), _p(off), _p(idx))
+        if m < 0:
+            raise PvbError(f"pvb_pixel_line_candidates: code {m}")
+        return off, idx[:m].copy()
 
     def joint_solve_lm(self, poses, points, pose_param_const=None, point_const=None, max_iterations=20):
         poses, points = _arr(poses, np.float64).copy().reshape(-1, 6), _arr(points, np.float64).copy().reshape(-1, 3)

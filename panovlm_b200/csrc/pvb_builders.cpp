@@ -533,6 +533,63 @@ int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* li
   return PVB_OK;
 }
 
+// ---- pixel-space Associate, first stage (joint_optimization/CameraLidarLineAssociate.cpp:22-102) -----------------------------------------
+// image lines -> sub-line mid points: BreakToSegments(line, 70), pieces across the +-pi seam skipped (:38-54)
+int pvb_pixel_sub_lines(int rows, int cols, const float* lines4, int n_lines, int cap, float* mid2, int* sub_to_line) {
+  if (rows <= 0 || cols <= 0 || n_lines < 0 || (n_lines > 0 && !lines4) || cap < 0 || (cap > 0 && (!mid2 || !sub_to_line))) return PVB_ERR_ARG;
+  int m = 0;
+  for (int l = 0; l < n_lines; ++l) {
+    const auto seg = break_to_segments(rows, cols, lines4 + 4 * l, lines4 + 4 * l + 2, 70);
+    for (size_t i = 0; i + 1 < seg.size(); ++i) {
+      if (std::abs(seg[i].first - seg[i + 1].first) > 0.8 * cols) continue;
+      if (m >= cap) return PVB_ERR_NOMEM;
+      mid2[2 * m] = (float)((seg[i + 1].first + seg[i].first) / 2.0);
+      mid2[2 * m + 1] = (float)((seg[i + 1].second + seg[i].second) / 2.0);
+      sub_to_line[m++] = l;
+    }
+  }
+  return m;
+}
+
+static int sub_line_cap(const float* lines4, int n_lines) {
+  double c = 64;
+  for (int l = 0; l < n_lines; ++l) c += std::hypot((double)lines4[4 * l] - lines4[4 * l + 2], (double)lines4[4 * l + 1] - lines4[4 * l + 3]) / 70.0 + 4.0;
+  return (int)c;
+}
+
+int pvb_pixel_line_neighbors(pvb_ctx* ctx, int rows, int cols, const float* lines4, int n_lines, const float* cloud_local, int n_points, const double* T_cl16,
+                             int* line3, float* d2_3, float* pixel2) {
+  if (!ctx || n_lines < 0 || n_points < 0 || (n_lines > 0 && !lines4) || (n_points > 0 && (!cloud_local || !line3)) || !T_cl16) return PVB_ERR_ARG;
+  const int cap = sub_line_cap(lines4, n_lines);
+  std::vector<float> mid((size_t)cap * 2); std::vector<int> s2l(cap);
+  const int M = pvb_pixel_sub_lines(rows, cols, lines4, n_lines, cap, mid.data(), s2l.data());
+  if (M < 0) return M;
+  std::vector<float> d2((size_t)std::max(n_points, 1) * 3);
+  const int rc = pvb_pixel_knn3(ctx, rows, cols, mid.data(), M, cloud_local, n_points, T_cl16, line3, d2.data(), pixel2);
+  if (rc) return rc;
+  for (long i = 0; i < (long)n_points * 3; ++i) {
+    const int m = line3[i];
+    line3[i] = (m >= 0 && !(d2[i] > 60 * 60)) ? s2l[m] : -1;                      // :81 vecDist > 60 * 60 is skipped
+    if (d2_3) d2_3[i] = d2[i];
+  }
+  return PVB_OK;
+}
+
+// line -> LiDAR point lists (`line_lidar`, :83): ascending point index, one entry per neighbouring sub-line (a point may appear up to three times
+// under the same line); lines with fewer than min_points entries (6, :92) are emptied
+int pvb_pixel_line_candidates(int n_lines, int n_points, const int* line3, int min_points, int cap, int* line_off, int* lidar_idx) {
+  if (n_lines < 0 || n_points < 0 || (n_points > 0 && !line3) || !line_off || (cap > 0 && !lidar_idx)) return PVB_ERR_ARG;
+  std::vector<int> count(n_lines + 1, 0);
+  for (long i = 0; i < (long)n_points * 3; ++i) if (line3[i] >= 0) { if (line3[i] >= n_lines) return PVB_ERR_ARG; count[line3[i]]++; }
+  line_off[0] = 0;
+  for (int l = 0; l < n_lines; ++l) line_off[l + 1] = line_off[l] + (count[l] >= min_points ? count[l] : 0);
+  if (line_off[n_lines] > cap) return PVB_ERR_NOMEM;
+  std::vector<int> fill(line_off, line_off + n_lines);
+  for (int i = 0; i < n_points; ++i)
+    for (int k = 0; k < 3; ++k) { const int l = line3[3 * i + k]; if (l >= 0 && count[l] >= min_points) lidar_idx[fill[l]++] = i; }
+  return line_off[n_lines];
+}
+
 // ---- pose interpolation around the sweep undistortion (base/Geometry.hpp:572-583, lidar_mapping/LidarOdometry.cpp:203-243) -------------
 namespace {
 // 4x4 inverse by Gauss-Jordan elimination with partial pivoting (the reference calls Eigen's general Matrix4d::inverse())
