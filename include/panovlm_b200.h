@@ -88,6 +88,17 @@ int pvb_blocks_set_linear_solver(pvb_ctx* ctx, int kind);
  * factor_ms (may be NULL) = device time of factorisation + substitution                                                             */
 int pvb_cholesky_solve(pvb_ctx* ctx, const double* A, int n, const double* b, double* x, float* factor_ms);
 
+/* ---- multi-GPU pose graphs: one process per GPU, edges sharded by reference frame -------------------------------------
+ * Every rank registers only ITS residual blocks but the GLOBAL edge list, so all ranks reduce into the same layout (n_edges x 92 doubles,
+ * edges of other ranks stay zero); the hook runs once per evaluation on the device buffer of edge systems, on the context's stream, before
+ * anything reads them: there the caller does ONE sum-allreduce (NCCL) and every rank continues with the complete normal equations -
+ * pvb_blocks_solve_lm then takes identical steps on all ranks.
+ * pvb_blocks_set_edge_list: edges sorted by (ref, nei), unique; must hold the edge of every block registered afterwards; n_edges = 0 returns
+ * to the single-GPU behaviour (edges derived from the blocks).  Call it before pvb_blocks_set.                                          */
+typedef void (*pvb_reduce_hook)(void* user, double* device_edge_systems, long n_doubles, void* cuda_stream);
+int pvb_blocks_set_edge_list(pvb_ctx* ctx, int n_edges, const int* ref, const int* nei);
+int pvb_blocks_set_reduce_hook(pvb_ctx* ctx, pvb_reduce_hook hook, void* user);
+
 /* ---- B. frames: transform to world + point-to-plane association per pose-graph edge ------------------------ */
 typedef struct {
   const float* surf_target; int n_target; /* ref side: surfLessFlat, n x 4 (x,y,z,intensity=class), sensor frame */

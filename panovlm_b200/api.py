@@ -114,6 +114,7 @@ EXPORTS = [
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
+    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook",
     "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates",
 ]
 
@@ -178,6 +179,14 @@ class Context:
         c = _arr(consts, np.float64).reshape(n, 12)
         self._n_blocks, self._nb = n, int(n_pose_blocks)
         self._ck(self._L.pvb_blocks_set(self._h, C.c_long(n), _p(t), _p(r), _p(m), _p(nz), _p(h), _p(c), C.c_int(n_pose_blocks)))
+
+    def blocks_set_edge_list(self, ref=None, nei=None):
+        """Global edge list of a sharded pose graph (sorted by (ref, nei), unique); None / empty: back to single-GPU behaviour."""
+        if ref is None or len(ref) == 0:
+            self._ck(self._L.pvb_blocks_set_edge_list(self._h, C.c_int(0), None, None))
+            return
+        ref, nei = _arr(ref, np.int32), _arr(nei, np.int32)
+        self._ck(self._L.pvb_blocks_set_edge_list(self._h, C.c_int(len(ref)), _p(ref), _p(nei)))
 
     def blocks_evaluate(self, poses, want_rows=True, want_system=True):
         poses = _arr(poses, np.float64)

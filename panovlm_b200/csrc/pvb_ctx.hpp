@@ -74,6 +74,9 @@ struct pvb_ctx {
   DevBuf b_tile, b_eref, b_enei, b_type, b_norm, b_huber, b_consts, b_orig_d, b_r, b_J, b_part, b_esys, b_tbegin;
   PinBuf h_r, h_J, h_esys;
   bool b_has_rows = false, b_has_sys = false;
+  // multi-GPU: the pose graph's GLOBAL edge list (every rank reduces into the same layout) and the exchange step of an evaluation
+  std::vector<int> g_edge_ref, g_edge_nei;
+  pvb_reduce_hook reduce_hook = nullptr; void* reduce_user = nullptr;
   // ---- frames mode
   CloudSet f_tgt, f_qry; TargetIndex f_index; int n_frames = 0;
   CloudSet f_corner; TargetIndex f_cindex; int n_corner_frames = 0;

@@ -250,15 +250,30 @@ int pvb_blocks_set(pvb_ctx* ctx, long n, const int* type, const int* ref, const 
   ctx->edge_ref.clear(); ctx->edge_nei.clear(); ctx->edge_tile_begin.clear();
   std::vector<BlockTile> tiles;
   std::vector<int> s_type(n), s_norm(n); std::vector<double> s_huber(n), s_consts((size_t)n * 12);
-  long i = 0;
-  while (i < n) {
-    long j = i;
-    const int er = ref[order[i]], en = nei[order[i]];
-    while (j < n && ref[order[j]] == er && nei[order[j]] == en) ++j;
-    const int e = (int)ctx->edge_ref.size();
-    ctx->edge_ref.push_back(er); ctx->edge_nei.push_back(en); ctx->edge_tile_begin.push_back((int)tiles.size());
-    for (long s = i; s < j; s += kTile) tiles.push_back(BlockTile{e, (int)s, (int)std::min<long>(kTile, j - s), 0});
-    i = j;
+  if (ctx->g_edge_ref.empty()) {
+    long i = 0;
+    while (i < n) {
+      long j = i;
+      const int er = ref[order[i]], en = nei[order[i]];
+      while (j < n && ref[order[j]] == er && nei[order[j]] == en) ++j;
+      const int e = (int)ctx->edge_ref.size();
+      ctx->edge_ref.push_back(er); ctx->edge_nei.push_back(en); ctx->edge_tile_begin.push_back((int)tiles.size());
+      for (long s = i; s < j; s += kTile) tiles.push_back(BlockTile{e, (int)s, (int)std::min<long>(kTile, j - s), 0});
+      i = j;
+    }
+  } else {
+    // multi-GPU: the global edge list gives the layout; edges without local blocks keep an empty tile range (their systems reduce to zero)
+    long i = 0;
+    for (size_t e = 0; e < ctx->g_edge_ref.size(); ++e) {
+      const int er = ctx->g_edge_ref[e], en = ctx->g_edge_nei[e];
+      if (er >= nb || en >= nb) return ctx->fail(PVB_ERR_ARG, "edge list entry %zu refers to a pose block beyond %d", e, nb);
+      long j = i;
+      while (j < n && ref[order[j]] == er && nei[order[j]] == en) ++j;
+      ctx->edge_ref.push_back(er); ctx->edge_nei.push_back(en); ctx->edge_tile_begin.push_back((int)tiles.size());
+      for (long s = i; s < j; s += kTile) tiles.push_back(BlockTile{(int)e, (int)s, (int)std::min<long>(kTile, j - s), 0});
+      i = j;
+    }
+    if (i != n) return ctx->fail(PVB_ERR_ARG, "block %u (edge %d -> %d) is not in the edge list set by pvb_blocks_set_edge_list", order[i], ref[order[i]], nei[order[i]]);
   }
   ctx->edge_tile_begin.push_back((int)tiles.size());
   ctx->b_tiles = (int)tiles.size();
@@ -313,22 +328,39 @@ int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int wa
     CKL();
     CK(cudaEventRecord(ctx->bev1, ctx->stream));
     ctx->bev_valid = true;
-    if (want_system) {
-      CK(ctx->b_chunk.ensure((size_t)ne * kSumChunks * 92 * 8));
-      k_sum_partials<92><<<dim3(ne, kSumChunks), 256, 0, ctx->stream>>>(ctx->b_part.as<double>(), ctx->b_tbegin.as<int>(), ctx->b_chunk.as<double>());
-      CKL();
-      k_sum_chunks<92><<<ne, 96, 0, ctx->stream>>>(ctx->b_chunk.as<double>(), ctx->b_esys.as<double>());
-      CKL();
-      CK(cudaMemcpyAsync(ctx->h_esys.p, ctx->b_esys.p, (size_t)ne * 92 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    }
     if (want_rows) {
       CK(ctx->h_r.ensure((size_t)n * 8)); CK(ctx->h_J.ensure((size_t)n * 96));
       CK(cudaMemcpyAsync(ctx->h_r.p, ctx->b_r.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaMemcpyAsync(ctx->h_J.p, ctx->b_J.p, (size_t)n * 96, cudaMemcpyDeviceToHost, ctx->stream));
     }
   }
+  if (want_system && ne > 0) {       // also with no local blocks (a rank of a sharded pose graph that owns no residual): its systems are zero
+    CK(ctx->b_chunk.ensure((size_t)ne * kSumChunks * 92 * 8));
+    k_sum_partials<92><<<dim3(ne, kSumChunks), 256, 0, ctx->stream>>>(ctx->b_part.as<double>(), ctx->b_tbegin.as<int>(), ctx->b_chunk.as<double>());
+    CKL();
+    k_sum_chunks<92><<<ne, 96, 0, ctx->stream>>>(ctx->b_chunk.as<double>(), ctx->b_esys.as<double>());
+    CKL();
+    if (ctx->reduce_hook) ctx->reduce_hook(ctx->reduce_user, ctx->b_esys.as<double>(), (long)ne * 92, (void*)ctx->stream);   // the ONE exchange step (allreduce) of an evaluation
+    CK(cudaMemcpyAsync(ctx->h_esys.p, ctx->b_esys.p, (size_t)ne * 92 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->b_has_rows = want_rows != 0; ctx->b_has_sys = want_system != 0;
+  return PVB_OK;
+}
+
+int pvb_blocks_set_edge_list(pvb_ctx* ctx, int n_edges, const int* ref, const int* nei) {
+  if (!ctx || n_edges < 0 || (n_edges > 0 && (!ref || !nei))) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_blocks_set_edge_list: bad arguments") : PVB_ERR_ARG;
+  for (int e = 0; e < n_edges; ++e) {
+    if (ref[e] < 0 || nei[e] < 0) return ctx->fail(PVB_ERR_ARG, "edge %d: negative pose index", e);
+    if (e > 0 && !(ref[e - 1] < ref[e] || (ref[e - 1] == ref[e] && nei[e - 1] < nei[e]))) return ctx->fail(PVB_ERR_ARG, "edge list must be sorted by (ref, nei) and unique (entry %d)", e);
+  }
+  ctx->g_edge_ref.assign(ref, ref + n_edges); ctx->g_edge_nei.assign(nei, nei + n_edges);
+  return PVB_OK;
+}
+
+int pvb_blocks_set_reduce_hook(pvb_ctx* ctx, pvb_reduce_hook hook, void* user) {
+  if (!ctx) return PVB_ERR_ARG;
+  ctx->reduce_hook = hook; ctx->reduce_user = user;
   return PVB_OK;
 }
 
