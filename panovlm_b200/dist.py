@@ -80,8 +80,8 @@ class _DevicePtr:
 
 
 def install_allreduce_hook(ctx, group=None):
-    """Registers the ONE exchange step of a sharded pose-graph evaluation: a sum-allreduce of the device buffer of edge systems, in place, on the
-    context's stream (which must be torch's current stream: ctx.set_stream(torch.cuda.current_stream().cuda_stream)).  NCCL reduces the aliased
+    """Registers the ONE exchange step of a sharded pose-graph evaluation: a sum-allreduce of the device buffer of edge systems, in place, enqueued on
+    the context's stream (the hook receives it and makes it torch's current stream for the duration of the call).  NCCL reduces the aliased
     device memory directly; with a gloo group (single-GPU tests) the buffer is staged through the host.  Returns a handle holding the callback
     (keep it alive while the hook is installed) and a call counter."""
     import ctypes as C
@@ -94,13 +94,15 @@ def install_allreduce_hook(ctx, group=None):
         calls["n"] += 1
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
-        t = torch.as_tensor(_DevicePtr(dev_ptr, n_doubles), device="cuda")
-        if dist.get_backend(group) == "nccl":
-            dist.all_reduce(t, group=group)
-        else:
-            h = t.cpu()
-            dist.all_reduce(h, group=group)
-            t.copy_(h)
+        # everything below is enqueued on the library's stream (the kernels that wrote the buffer precede it there, the readers follow)
+        with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+            t = torch.as_tensor(_DevicePtr(dev_ptr, n_doubles), device="cuda")
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(t, group=group)
+            else:
+                h = t.cpu()
+                dist.all_reduce(h, group=group)
+                t.copy_(h)
 
     cb = HOOK(_hook)
     ctx._ck(ctx._L.pvb_blocks_set_reduce_hook(ctx._h, cb, None))

@@ -111,7 +111,6 @@ def _gpu_worker(rank, world, port, out):
     from panovlm_b200 import api, dist as pd
     torch.cuda.set_device(0)
     ctx = panovlm_b200.Context(0)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     P = _problem()
     mine, bounds = _shard(P, world, rank)
     er, en = pd.global_edge_list(P["ref"], P["nei"])
