@@ -40,12 +40,22 @@ def world_from_pose_blocks(poses, aa_to_R):
     return R_wl, t_wl
 
 
-def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
-    """One outer iteration's residual blocks (the Add*Residual calls of RefinePose); returns a BlockList."""
+def pose_graph_edges(poses, cfg: OdometryConfig, aa_to_R):
+    """FindNeighbors (LidarFeatureAssociate.cpp:19-111) -> the (reference frame, neighbour frame) pairs of one outer iteration."""
+    n = len(poses)
+    _, t_wl = world_from_pose_blocks(poses, aa_to_R)
+    neighbors = Context.find_neighbors(np.array(t_wl), None, None, cfg.neighbor_size)
+    return [(i, j) for i in range(n) for j in neighbors[i] if 0 <= j < n and j != i]
+
+
+def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, frame_range=None):
+    """One outer iteration's residual blocks (the Add*Residual calls of RefinePose); returns a BlockList and the GLOBAL edge list.
+    frame_range = (lo, hi): only the edges whose reference frame lies in [lo, hi) are associated and turned into blocks (one rank's shard of a
+    pose graph split across GPUs); the clouds of all frames stay available as halo."""
     n = len(frames)
     R_wl, t_wl = world_from_pose_blocks(poses, aa_to_R)
-    neighbors = Context.find_neighbors(np.array(t_wl), None, None, cfg.neighbor_size)
-    edges = [(i, j) for i in range(n) for j in neighbors[i] if 0 <= j < n and j != i]
+    all_edges = pose_graph_edges(poses, cfg, aa_to_R)
+    edges = all_edges if frame_range is None else [(i, j) for (i, j) in all_edges if frame_range[0] <= i < frame_range[1]]
     cap = sum(len(frames[j]["surfFlat"]) for _, j in edges) + sum(len(frames[j]["cornerLessSharp"]) for _, j in edges) * 6 + 16
     bl = BlockList(cap)
     lf = None
@@ -77,6 +87,7 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
                 Context.build_line2line_blocks(bl, lf[j], world[j], nl[k], a[k], b[k], i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
     if cfg.point_to_plane:                                          # AddLidarPointToPlaneResidual (Optimization.cpp:506-562)
         ctx.frames_set([f["surfLessFlat"] for f in frames], [f["surfFlat"] for f in frames])
+    if cfg.point_to_plane and edges:
         ref = np.array([e[0] for e in edges], np.int32)
         nei = np.array([e[1] for e in edges], np.int32)
         e, q, pt, pl = ctx.frames_associate_point2plane(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, 10)
@@ -85,7 +96,7 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
             lo, hi = bounds[ei], bounds[ei + 1]
             if hi > lo:
                 Context.build_point2plane_blocks(bl, pt[lo:hi], pl[lo:hi], int(ref[ei]), int(nei[ei]), cfg.angle_residual, cfg.normalize_distance, 1.0)
-    return bl, edges
+    return bl, all_edges
 
 
 def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
@@ -96,6 +107,33 @@ def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
     mask = np.zeros(len(frames), np.uint8); mask[0] = 1
     new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
     summary["n_blocks"], summary["n_edges"] = bl.n, len(edges)
+    return new_poses, summary
+
+
+def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, world, rank, group=None):
+    """RefinePose on one rank of a pose graph sharded across GPUs (BASELINE.json configs[3]): contiguous ranges of reference frames
+    balanced by the query count of their edges, association + residual blocks of the rank's own edges only, the GLOBAL edge list as reduction layout
+    and ONE allreduce of the edge systems per evaluation (panovlm_b200.dist.install_allreduce_hook).  Every rank returns the same poses."""
+    from . import dist as pd
+    all_edges = pose_graph_edges(poses, cfg, aa_to_R)
+    weights = np.zeros(len(frames))
+    for (i, j) in all_edges:
+        weights[i] += len(frames[j]["surfFlat"]) + 4 * len(frames[j]["cornerLessSharp"])
+    bounds = pd.shard_frames_by_weight(weights, world)
+    bl, _ = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=(int(bounds[rank]), int(bounds[rank + 1])))
+    er, en = pd.global_edge_list([e[0] for e in all_edges], [e[1] for e in all_edges])
+    v = bl.view()
+    ctx.blocks_set_edge_list(er, en)
+    hook = pd.install_allreduce_hook(ctx, group)
+    try:
+        ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
+        mask = np.zeros(len(frames), np.uint8); mask[0] = 1
+        new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
+    finally:
+        pd.remove_allreduce_hook(ctx)
+        ctx.blocks_set_edge_list(None)
+    summary["n_blocks_local"], summary["n_edges"], summary["allreduces"] = bl.n, len(all_edges), hook["calls"]["n"]
+    summary["frame_range"] = [int(bounds[rank]), int(bounds[rank + 1])]
     return new_poses, summary
 
 
