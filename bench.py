@@ -187,6 +187,24 @@ def bench_blocks(ctx, peak_gbs, n=1_400_000, nb=454, seed=5):
     return out
 
 
+def bench_reproj(ctx, peak_gbs, n_cams=454, n_points=200_000, seed=7):
+    """Room-shaped camera-camera term (configs[2]): 454 panoramas, 200 k structure points, ~1.3 M observations of PanoramaReprojResidual_1Angle."""
+    from panovlm_b200 import synth
+    d = synth.make_ba_problem(n_cams=n_cams, n_points=n_points, track_len=(3, 10), seed=seed)
+    n = len(d["cam"])
+    ctx.reproj_set(d["cam"], d["point"], d["bearing"], n_cams, n_points, huber=4.0 * np.pi / 180.0)
+    out = {"n_observations": n, "n_cams": n_cams, "n_points": n_points}
+    for name, rows, sysm, balg in (("rows", True, False, 140.0), ("reduced", False, True, 144.0)):
+        ms = []
+        for _ in range(6):
+            ctx.reproj_evaluate(d["cams"], d["points"], rows, sysm)
+            ms.append(ctx.reproj_kernel_time_ms())
+        k = float(np.median(ms[2:]))
+        out[name] = {"kernel_ms": k, "evals_per_s": n / (k * 1e-3), "algorithmic_bytes_per_obs": balg, "achieved_GBs": n * balg / (k * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": n * balg / (k * 1e-3) / 1e9 / peak_gbs}
+    return out
+
+
 def config_dict(args):
     return {"workload": f"configs[4]: dense ICP sweep, {args.n_target}-pt target, {args.frames} source frames x {args.pts_per_frame} pts per GPU, "
                         f"k={args.k}, radius={args.radius} m, plane_tol=0.05, Point2Plane_Meter + Huber(0.2), per-frame 6x6 reduce",
@@ -348,6 +366,10 @@ def main():
             line["extra"] = {"k_eval_blocks": bench_blocks(ctx, peak)}
         except Exception as e:                                   # never lose the headline line
             line["extra"] = {"k_eval_blocks": {"error": str(e)}}
+        try:
+            line["extra"]["k_reproj_rows"] = bench_reproj(ctx, peak)
+        except Exception as e:
+            line["extra"]["k_reproj_rows"] = {"error": str(e)}
 
     # ---- CPU baseline: the oracle port timed on this box's host cores (bounded sample), N=1 only
     if world == 1 and not args.no_cpu_baseline:
