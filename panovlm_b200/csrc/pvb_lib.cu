@@ -202,7 +202,7 @@ void pvb_destroy(pvb_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   ctx->p_cs.release(); ctx->p_index.release();
-  DevBuf* sbs[] = {&ctx->s_H, &ctx->s_A, &ctx->s_g, &ctx->s_sc, &ctx->s_rhs, &ctx->s_term, &ctx->s_con, &ctx->s_seg, &ctx->s_gcon, &ctx->s_gseg, &ctx->s_fail};
+  DevBuf* sbs[] = {&ctx->s_H, &ctx->s_A, &ctx->s_g, &ctx->s_sc, &ctx->s_rhs, &ctx->s_y, &ctx->s_term, &ctx->s_con, &ctx->s_seg, &ctx->s_gcon, &ctx->s_gseg, &ctx->s_fail};
   for (DevBuf* b : sbs) b->release();
   ctx->sh_vec.release();
   if (ctx->ba_state && ctx->ba_free) ctx->ba_free(ctx->ba_state);
@@ -434,21 +434,33 @@ int pvb_blocks_dense_system(const pvb_ctx* ctx, double* H, double* g, double* co
 constexpr size_t kTrsmSmem = 2 * kNB * (kNB + 1) * sizeof(double);
 int pvb_internal_factor_solve(pvb_ctx* ctx, int N, bool* ok) {
   static bool attr_set = false;
-  if (!attr_set) { CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem)); attr_set = true; }
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+    CK(cudaFuncSetAttribute(k_syrk_update_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
+    attr_set = true;
+  }
   CK(cudaMemsetAsync(ctx->s_fail.p, 0, 4, ctx->stream));
+  CK(ctx->s_y.ensure((size_t)N * 8));
   for (int k0 = 0; k0 < N; k0 += kNB) {
     k_potrf_diag<<<1, 256, 0, ctx->stream>>>(ctx->s_A.as<double>(), N, k0, ctx->s_fail.as<int>());
     CKL();
     const int T = (N - k0 - kNB) / kNB;
     if (T > 0) {
-      k_trsm_panel<<<T, kNB, kTrsmSmem, ctx->stream>>>(ctx->s_A.as<double>(), N, k0);
+      k_trsm_panel<<<T, 256, kTrsmSmem, ctx->stream>>>(ctx->s_A.as<double>(), N, k0);
       CKL();
-      k_syrk_update<<<T * (T + 1) / 2, 256, 0, ctx->stream>>>(ctx->s_A.as<double>(), N, k0);
+    }
+    k_fwd_step<<<std::max(T, 1), 256, 0, ctx->stream>>>(ctx->s_A.as<double>(), N, k0, ctx->s_rhs.as<double>(), ctx->s_y.as<double>());   // L y = rhs, block by block
+    CKL();
+    if (T > 0) {
+      const int Ti = (T + 1) / 2;                                   // 128-row tiles; row tile ti owns 2 ti + 2 column tiles of 64
+      k_syrk_update_mma<<<Ti * (Ti + 1), 256, kSyrkSmem, ctx->stream>>>(ctx->s_A.as<double>(), N, k0);
       CKL();
     }
   }
-  k_chol_solve<<<1, 1024, 0, ctx->stream>>>(ctx->s_A.as<double>(), N, ctx->s_rhs.as<double>());
-  CKL();
+  for (int k0 = N - kNB; k0 >= 0; k0 -= kNB) {                     // L^T x = y; x lands in s_rhs
+    k_bwd_step<<<std::max(1, (k0 + 255) / 256), 256, 0, ctx->stream>>>(ctx->s_A.as<double>(), N, k0, ctx->s_y.as<double>(), ctx->s_rhs.as<double>());
+    CKL();
+  }
   int fail = 0;
   CK(cudaMemcpyAsync(&fail, ctx->s_fail.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

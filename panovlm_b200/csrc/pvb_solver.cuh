@@ -5,6 +5,8 @@
 //
 // Layout: matrices are row-major N x N with N = n rounded up to kNB (padding rows/columns are identity, so no kernel has an
 // edge case); the factor overwrites the lower triangle.  Every sum runs in a fixed order => bit-reproducible results.
+// Per 64-wide step: k_potrf_diag (1 block) -> k_trsm_panel (64 rows per block) -> k_fwd_step (forward substitution of this block, fused
+// into the factorisation sweep) -> k_syrk_update_mma (FP64 tensor cores); then one k_bwd_step per block from the last to the first.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -76,151 +78,211 @@ __global__ void __launch_bounds__(256) k_build_damped(const double* __restrict__
 }
 
 // ---- blocked right-looking Cholesky ---------------------------------------------------------------------------------------------
-// diagonal block: A[k0:k0+NB, k0:k0+NB] -> L11 (in place); *fail set when a pivot is not positive
+// diagonal block: A[k0:k0+NB, k0:k0+NB] -> L11 (in place); *fail set when a pivot is not positive.  Right-looking inside the block:
+// column j is scaled, then the whole trailing triangle takes its rank-1 update in parallel (256 threads); every element still
+// receives its subtractions in ascending j, the order of a left-looking loop.
 __global__ void __launch_bounds__(256) k_potrf_diag(double* __restrict__ A, int N, int k0, int* __restrict__ fail) {
   __shared__ double s[kNB][kNB + 1];
   const int t = threadIdx.x;
   for (int e = t; e < kNB * kNB; e += 256) { const int i = e / kNB, j = e % kNB; s[i][j] = j <= i ? A[(size_t)(k0 + i) * N + k0 + j] : 0.0; }
   __syncthreads();
+  const int ui = t >> 4, uk = t & 15;                  // update mapping: rows ui + 16 a, columns uk + 16 b
   for (int j = 0; j < kNB; ++j) {
-    // column j: every row i >= j subtracts its left part in ascending k (the order of the host's left-looking loop)
-    if (t < kNB && t >= j) {
-      double v = s[t][j];
-      for (int k = 0; k < j; ++k) v -= s[t][k] * s[j][k];
-      s[t][j] = v;
-    }
-    __syncthreads();
     const double d = s[j][j];
     if (!(d > 0.0)) { if (t == 0) *fail = 1; return; }
-    const double r = sqrt(d);
+    const double r = sqrt(d), rinv = 1.0 / r;
     __syncthreads();
-    if (t < kNB && t > j) s[t][j] /= r;
+    if (t < kNB && t > j) s[t][j] *= rinv;
     if (t == j) s[j][j] = r;
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = ui + 16 * a;
+      if (i <= j) continue;
+      const double sij = s[i][j];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int k = uk + 16 * b;
+        if (k > j && k <= i) s[i][k] -= sij * s[k][j];
+      }
+    }
     __syncthreads();
   }
   for (int e = t; e < kNB * kNB; e += 256) { const int i = e / kNB, j = e % kNB; if (j <= i) A[(size_t)(k0 + i) * N + k0 + j] = s[i][j]; }
 }
 
-// panel: rows below the diagonal block, L21 = A21 L11^-T; one thread per row, 64 rows per block
-__global__ void __launch_bounds__(kNB) k_trsm_panel(double* __restrict__ A, int N, int k0) {
+// panel: rows below the diagonal block, L21 = A21 L11^-T; 64 rows per block, 256 threads.  Column j is divided by L[j][j], then the
+// columns to its right take their update in parallel (thread = row x column group); per element the subtractions run in ascending j.
+__global__ void __launch_bounds__(256) k_trsm_panel(double* __restrict__ A, int N, int k0) {
   extern __shared__ double trsm_smem[];                         // 2 x 64 x 65 doubles (dynamic: above the 48 KB static limit)
   double (*L)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(trsm_smem);
   double (*R)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(trsm_smem + kNB * (kNB + 1));
   const int t = threadIdx.x;
   const int r0 = k0 + kNB + blockIdx.x * kNB;
-  for (int e = t; e < kNB * kNB; e += kNB) {
+  for (int e = t; e < kNB * kNB; e += 256) {
     const int i = e / kNB, j = e % kNB;
     L[i][j] = A[(size_t)(k0 + i) * N + k0 + j];
     R[i][j] = A[(size_t)(r0 + i) * N + k0 + j];
   }
   __syncthreads();
+  __shared__ double dinv[kNB];
+  if (t < kNB) dinv[t] = 1.0 / L[t][t];
+  __syncthreads();
+  const int row = t & (kNB - 1), cg = t >> 6;
   for (int j = 0; j < kNB; ++j) {
-    double v = R[t][j];
-    for (int k = 0; k < j; ++k) v -= R[t][k] * L[j][k];
-    R[t][j] = v / L[j][j];
+    if (t < kNB) R[t][j] *= dinv[j];
+    __syncthreads();
+    const double rj = R[row][j];
+    for (int k = j + 1 + cg; k < kNB; k += 4) R[row][k] -= rj * L[k][j];
+    __syncthreads();
+  }
+  for (int e = t; e < kNB * kNB; e += 256) { const int i = e / kNB, j = e % kNB; A[(size_t)(r0 + i) * N + k0 + j] = R[i][j]; }
+}
+
+// trailing update on the FP64 tensor cores (the one dense contraction of this library: C -= P P^T with the 64-wide panel P).
+// mma.sync.m8n8k4.f64: A fragment = P[row0 + (lane >> 2)][k + (lane & 3)], B fragment (col layout) = the same pattern on the column tile,
+// C fragment = 2 doubles per lane at [lane >> 2][2 (lane & 3) + {0, 1}].  Block = 128 rows x 64 columns of the lower triangle, 8 warps of
+// 32 x 32 (4 x 4 mma tiles); the two panel tiles are staged once in shared memory with a row stride of 68 doubles (conflict-free fragment
+// loads).  k runs ascending inside every accumulator => bit-reproducible.
+constexpr int kSyrkLd = kNB + 4;
+constexpr size_t kSyrkSmem = (size_t)(128 + 64) * kSyrkLd * sizeof(double);
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256) k_syrk_update_mma(double* __restrict__ A, int N, int k0) {
+  extern __shared__ double syrk_smem[];
+  double* Pa = syrk_smem;                       // 128 x 68
+  double* Pb = syrk_smem + 128 * kSyrkLd;       // 64 x 68
+  // linear block id -> (ti, tj): row tile ti of 128 rows owns the column tiles tj = 0 .. 2 ti + 1 of 64 columns
+  const int b = blockIdx.x;
+  int ti = (int)((sqrt(4.0 * (double)b + 1.0) - 1.0) * 0.5);
+  while ((long long)(ti + 1) * (ti + 2) <= b) ++ti;
+  while ((long long)ti * (ti + 1) > b) --ti;
+  const int tj = b - ti * (ti + 1);
+  const int base = k0 + kNB;
+  const int ra = base + ti * 128, rb = base + tj * 64;
+  if (rb >= N) return;                          // odd number of 64-tiles: the last row tile has one column tile less
+  const int t = threadIdx.x;
+  for (int e = t; e < 128 * kNB; e += 256) {
+    const int i = e / kNB, j = e % kNB;
+    Pa[i * kSyrkLd + j] = ra + i < N ? A[(size_t)(ra + i) * N + k0 + j] : 0.0;
+  }
+  for (int e = t; e < 64 * kNB; e += 256) {
+    const int i = e / kNB, j = e % kNB;
+    Pb[i * kSyrkLd + j] = A[(size_t)(rb + i) * N + k0 + j];
   }
   __syncthreads();
-  for (int e = t; e < kNB * kNB; e += kNB) { const int i = e / kNB, j = e % kNB; A[(size_t)(r0 + i) * N + k0 + j] = R[i][j]; }
-}
-
-// trailing update: for every lower-triangular tile (ti >= tj) of the rows/columns after the panel,
-// C[ti][tj] -= P[ti] P[tj]^T with P = the 64-wide panel; 256 threads, 4 x 4 outputs each, k ascending
-__global__ void __launch_bounds__(256) k_syrk_update(double* __restrict__ A, int N, int k0) {
-  constexpr int KH = 32;                                        // the 64-wide panel goes through shared memory in two halves
-  __shared__ double Pa[kNB][KH + 1];
-  __shared__ double Pb[kNB][KH + 1];
-  // linear block id -> (ti, tj), tj <= ti
-  const int b = blockIdx.x;
-  int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
-  while ((long long)(ti + 1) * (ti + 2) / 2 <= b) ++ti;
-  while ((long long)ti * (ti + 1) / 2 > b) --ti;
-  const int tj = b - ti * (ti + 1) / 2;
-  const int base = k0 + kNB;
-  const int ra = base + ti * kNB, rb = base + tj * kNB;
-  const int t = threadIdx.x;
-  const int ty = t / 16, tx = t % 16;
-  double acc[4][4];
+  const int w = t >> 5, lane = t & 31, g = lane >> 2, q = lane & 3;
+  const int wr = (w >> 1) * 32, wc = (w & 1) * 32;
+  if (rb + wc > ra + wr + 31) return;           // warp tile entirely above the diagonal
+  double c[4][4][2];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-  for (int kh = 0; kh < kNB; kh += KH) {
-    __syncthreads();
-    for (int e = t; e < kNB * KH; e += 256) {
-      const int i = e / KH, j = e % KH;
-      Pa[i][j] = A[(size_t)(ra + i) * N + k0 + kh + j];
-      Pb[i][j] = A[(size_t)(rb + i) * N + k0 + kh + j];
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < KH; ++k) {
-      double a[4], c[4];
+    for (int ni = 0; ni < 4; ++ni) c[mi][ni][0] = c[mi][ni][1] = 0.0;
+  const double* pa = Pa + (wr + g) * kSyrkLd + q;
+  const double* pb = Pb + (wc + g) * kSyrkLd + q;
+#pragma unroll 4
+  for (int k = 0; k < kNB; k += 4) {
+    double a[4], bb[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { a[u] = Pa[ty + 16 * u][k]; c[u] = Pb[tx + 16 * u][k]; }
+    for (int mi = 0; mi < 4; ++mi) a[mi] = pa[mi * 8 * kSyrkLd + k];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int ni = 0; ni < 4; ++ni) bb[ni] = pb[ni * 8 * kSyrkLd + k];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] += a[u] * c[v];
-    }
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(c[mi][ni][0], c[mi][ni][1], a[mi], bb[ni]);
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int mi = 0; mi < 4; ++mi) {
+    const int i = ra + wr + mi * 8 + g;
+    if (i >= N) continue;
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int i = ra + ty + 16 * u, j = rb + tx + 16 * v;
-      if (j <= i) A[(size_t)i * N + j] -= acc[u][v];
+    for (int ni = 0; ni < 4; ++ni) {
+      const int j = rb + wc + ni * 8 + 2 * q;
+      double* dst = A + (size_t)i * N + j;
+      if (j + 1 <= i) { double2 v = *reinterpret_cast<double2*>(dst); v.x -= c[mi][ni][0]; v.y -= c[mi][ni][1]; *reinterpret_cast<double2*>(dst) = v; }
+      else if (j <= i) dst[0] -= c[mi][ni][0];
     }
+  }
 }
 
-// forward + backward substitution with the factor, one thread block (1024 threads): x overwrites rhs
-__global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ A, int N, double* __restrict__ x) {
+// ---- substitution, one launch per 64-block and direction, spread over many thread blocks ----------------------------------------------
+// forward (L y = b), launched right after the panel of step k0 is final: every block solves the 64 x 64 diagonal system redundantly in shared
+// memory (no grid-wide barrier needed), block 0 stores y[k0 .. k0+63], and the blocks subtract L21 y from their 64 rows of b below
+// (one warp per row, coalesced, fixed-order shuffle reduction).  b is updated in place below the block; y is a separate vector.
+__global__ void __launch_bounds__(256) k_fwd_step(const double* __restrict__ A, int N, int k0, double* __restrict__ b, double* __restrict__ y) {
+  __shared__ double L[kNB][kNB + 1];
+  __shared__ double ys[kNB];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int e = t; e < kNB * kNB; e += 256) { const int i = e / kNB, j = e % kNB; L[i][j] = A[(size_t)(k0 + i) * N + k0 + j]; }
+  __syncthreads();
+  if (warp == 0) {                                     // 64 unknowns in one warp (two per lane): no block barrier inside the chain
+    double v0 = b[k0 + lane], v1 = b[k0 + 32 + lane];
+    const double d0 = 1.0 / L[lane][lane], d1 = 1.0 / L[lane + 32][lane + 32];
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const double yj = __shfl_sync(0xffffffffu, v0 * d0, j);
+      if (lane == j) v0 = yj;
+      if (lane > j) v0 -= L[lane][j] * yj;
+      v1 -= L[lane + 32][j] * yj;
+    }
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const double yj = __shfl_sync(0xffffffffu, v1 * d1, j);
+      if (lane == j) v1 = yj;
+      if (lane > j) v1 -= L[lane + 32][j + 32] * yj;
+    }
+    ys[lane] = v0; ys[lane + 32] = v1;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && t < kNB) y[k0 + t] = ys[t];
+  const int r0 = k0 + kNB + blockIdx.x * kNB;
+  for (int i = r0 + warp; i < r0 + kNB && i < N; i += 8) {
+    const double* row = A + (size_t)i * N + k0;
+    double s = row[lane] * ys[lane] + row[lane + 32] * ys[lane + 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) b[i] -= s;
+  }
+}
+
+// backward (L^T x = y), blocks visited from the last to the first: the diagonal system is again solved redundantly, block 0 stores
+// x[k0 .. k0+63] (a separate vector), and every block subtracts this block's contribution from its 256 entries of y to the left
+// (one thread per column, rows ascending).
+__global__ void __launch_bounds__(256) k_bwd_step(const double* __restrict__ A, int N, int k0, double* __restrict__ y, double* __restrict__ x) {
   __shared__ double L[kNB][kNB + 1];
   __shared__ double xs[kNB];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int nblk = N / kNB;
-  // L y = b
-  for (int b = 0; b < nblk; ++b) {
-    const int k0 = b * kNB;
-    for (int e = t; e < kNB * kNB; e += 1024) { const int i = e / kNB, j = e % kNB; L[i][j] = A[(size_t)(k0 + i) * N + k0 + j]; }
-    if (t < kNB) xs[t] = x[k0 + t];
-    __syncthreads();
-    for (int j = 0; j < kNB; ++j) {
-      if (t == j) xs[j] = xs[j] / L[j][j];
-      __syncthreads();
-      if (t < kNB && t > j) xs[t] -= L[t][j] * xs[j];
-      __syncthreads();
+  const int t = threadIdx.x;
+  for (int e = t; e < kNB * kNB; e += 256) { const int i = e / kNB, j = e % kNB; L[i][j] = A[(size_t)(k0 + i) * N + k0 + j]; }
+  __syncthreads();
+  if (t < 32) {                                        // one warp, two unknowns per lane, last to first
+    const int lane = t;
+    double v0 = y[k0 + lane], v1 = y[k0 + 32 + lane];
+    const double d0 = 1.0 / L[lane][lane], d1 = 1.0 / L[lane + 32][lane + 32];
+#pragma unroll 8
+    for (int j = 31; j >= 0; --j) {
+      const double xj = __shfl_sync(0xffffffffu, v1 * d1, j);
+      if (lane == j) v1 = xj;
+      if (lane < j) v1 -= L[j + 32][lane + 32] * xj;
+      v0 -= L[j + 32][lane] * xj;
     }
-    if (t < kNB) x[k0 + t] = xs[t];
-    // rows below: x[i] -= L[i, k0:k0+NB] . xs  (one warp per row)
-    for (int i = k0 + kNB + warp; i < N; i += 32) {
-      const double* row = A + (size_t)i * N + k0;
-      double s = row[lane] * xs[lane] + row[lane + 32] * xs[lane + 32];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) x[i] -= s;
+#pragma unroll 8
+    for (int j = 31; j >= 0; --j) {
+      const double xj = __shfl_sync(0xffffffffu, v0 * d0, j);
+      if (lane == j) v0 = xj;
+      if (lane < j) v0 -= L[j][lane] * xj;
     }
-    __syncthreads();
+    xs[lane] = v0; xs[lane + 32] = v1;
   }
-  // L^T x = y
-  for (int b = nblk - 1; b >= 0; --b) {
-    const int k0 = b * kNB;
-    for (int e = t; e < kNB * kNB; e += 1024) { const int i = e / kNB, j = e % kNB; L[i][j] = A[(size_t)(k0 + i) * N + k0 + j]; }
-    if (t < kNB) xs[t] = x[k0 + t];
-    __syncthreads();
-    for (int j = kNB - 1; j >= 0; --j) {
-      if (t == j) xs[j] = xs[j] / L[j][j];
-      __syncthreads();
-      if (t < j) xs[t] -= L[j][t] * xs[j];
-      __syncthreads();
-    }
-    if (t < kNB) x[k0 + t] = xs[t];
-    // columns to the left: x[c] -= sum_i L[k0 + i][c] xs[i]  (one thread per column, rows ascending)
-    for (int c = t; c < k0; c += 1024) {
-      double s = 0.0;
-      for (int i = 0; i < kNB; ++i) s += A[(size_t)(k0 + i) * N + c] * xs[i];
-      x[c] -= s;
-    }
-    __syncthreads();
+  __syncthreads();
+  if (blockIdx.x == 0 && t < kNB) x[k0 + t] = xs[t];
+  const int c = blockIdx.x * 256 + t;
+  if (c < k0) {
+    double s = 0.0;
+    for (int i = 0; i < kNB; ++i) s += A[(size_t)(k0 + i) * N + c] * xs[i];
+    y[c] -= s;
   }
 }
 
