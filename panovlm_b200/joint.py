@@ -1,0 +1,71 @@
+"""Host loop of the joint camera-LiDAR refinement: a Python mirror of CameraLidarOptimizer::Optimize / AssociateLineMulti
+(joint_optimization/CameraLidarOptimizer.cpp:330-548) driving the C ABI.  Pose blocks are laid out [cameras 0..n) | LiDARs n..2n):
+camera-camera reprojection observations (pvb_reproj_set), camera-LiDAR line pairs (AssociateByAngle on the device + builders) and the LiDAR-LiDAR
+blocks of RefinePose (panovlm_b200.odometry.build_problem) meet in ONE trust-region problem solved by pvb_joint_solve_lm."""
+import numpy as np
+
+from . import odometry
+from .api import BlockList, Context, LineFrame
+
+
+class JointConfig:
+    def __init__(self, camera_weight=1.0, camera_lidar_weight=1.0, lidar=None, refine_camera_rotation=True, refine_camera_trans=True, refine_lidar_rotation=True,
+                 refine_lidar_trans=True, refine_structure=True, max_lm_iterations=20):
+        self.camera_weight, self.camera_lidar_weight = camera_weight, camera_lidar_weight        # config/Room.txt:81-83
+        self.lidar = lidar or odometry.OdometryConfig(line_to_line=False)
+        self.refine_camera_rotation, self.refine_camera_trans = refine_camera_rotation, refine_camera_trans
+        self.refine_lidar_rotation, self.refine_lidar_trans, self.refine_structure = refine_lidar_rotation, refine_lidar_trans, refine_structure
+        self.max_lm_iterations = max_lm_iterations
+
+
+def _T_from_block(block, aa_to_R):
+    T = np.eye(4)
+    T[:3, :3] = aa_to_R(block[:3])
+    T[:3, 3] = block[3:]
+    return T
+
+
+def associate_lines(ctx: Context, frames, image_lines, cams, lidars, rows, cols, aa_to_R):
+    """AssociateLineMulti with neighbor_size_joint = 1 (CameraLidarOptimizer.cpp:330-384): image i against LiDAR i at T_cl = T_cw T_wl (:347-353)."""
+    pairs = {}
+    for i, f in enumerate(frames):
+        T_cl = _T_from_block(cams[i], aa_to_R) @ np.linalg.inv(_T_from_block(lidars[i], aa_to_R))
+        lf = LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], np.eye(3), np.zeros(3))
+        il, ll, s, e, ang = ctx.camera_lidar_associate(rows, cols, image_lines[i], lf, T_cl, True, True)
+        pairs[(i, i)] = (il, ll, s, e, ang)
+    return pairs
+
+
+def build_problem(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa_to_R):
+    """Steps 2-4 of Optimize (:418-460): returns the residual-block arrays over the pose blocks [cameras | LiDARs] and the line pairs."""
+    frames, n = data["frames"], len(data["frames"])
+    pairs = associate_lines(ctx, frames, data["image_lines"], cams, lidars, data["rows"], data["cols"], aa_to_R)
+    n_pairs = sum(len(p[0]) for p in pairs.values())
+    bl_cl = BlockList(2 * n_pairs + 16)
+    for (ci, li), (il, ll, s, e, ang) in pairs.items():                                    # AddCameraLidarResidual (util/Optimization.cpp:564-607)
+        if len(il):
+            Context.build_camera_lidar_blocks(bl_cl, data["rows"], data["cols"], data["image_lines"][ci][il], s, e, np.ones(len(il), np.float32), ci, n + li,
+                                              cfg.camera_lidar_weight)
+    bl_ll, _ = odometry.build_problem(ctx, frames, lidars, cfg.lidar, aa_to_R)            # steps 4: the LiDAR-LiDAR blocks of RefinePose
+    a, b = bl_cl.view(), bl_ll.view()
+    out = {k: np.concatenate([a[k], b[k] + n if k in ("ref", "nei") else b[k]]) for k in ("type", "ref", "nei", "normalize", "huber", "consts")}
+    return out, pairs, (bl_cl.n, bl_ll.n)
+
+
+def optimize(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa_to_R):
+    """One call of CameraLidarOptimizer::Optimize: build the three residual families at the current estimate and solve."""
+    n = len(data["frames"])
+    v, pairs, counts = build_problem(ctx, data, cams, lidars, points, cfg, aa_to_R)
+    poses = np.concatenate([cams, lidars])
+    ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], 2 * n)
+    ctx.reproj_set(data["cam"], data["point"], data["bearing"], n, len(points), weight=cfg.camera_weight, huber=4.0 * np.pi / 180.0)   # :431-432
+    const = np.zeros((2 * n, 6), np.uint8)
+    const[:n, :3] = 0 if cfg.refine_camera_rotation else 1                               # :466-476
+    const[:n, 3:] = 0 if cfg.refine_camera_trans else 1
+    const[n:, :3] = 0 if cfg.refine_lidar_rotation else 1                                # :478-488
+    const[n:, 3:] = 0 if cfg.refine_lidar_trans else 1
+    const[0] = 1                                                                         # :490-491 camera 0 constant
+    pt_const = None if cfg.refine_structure else np.ones(len(points), np.uint8)          # :462-465
+    new_poses, new_points, summary = ctx.joint_solve_lm(poses, points, const, pt_const, cfg.max_lm_iterations)
+    summary.update(n_camera_lidar_blocks=counts[0], n_lidar_blocks=counts[1], n_reproj=len(data["cam"]), n_line_pairs=sum(len(p[0]) for p in pairs.values()))
+    return new_poses[:n], new_poses[n:], new_points, summary, (v, const, pt_const)

@@ -348,3 +348,67 @@ def make_ba_problem(n_cams=12, n_points=300, track_len=(2, 8), pixel_noise_rad=2
     pts0 = pts + rng.normal(size=pts.shape) * point_noise
     return {"cams_gt": cams_gt, "points_gt": pts, "cams": cams0, "points": pts0, "cam": np.array(cam, np.int32), "point": np.array(point, np.int32),
             "bearing": np.array(bearing), "pixels": np.array(pix, np.float32), "rows": rows, "cols": cols}
+
+
+# ------------------------------------------------------------------------------------------------
+# joint camera-LiDAR problem (configs[2]: Room joint refinement)
+# ------------------------------------------------------------------------------------------------
+def _R_to_aa(R):
+    th = np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1))
+    ax = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return ax / (2 * np.sin(th)) * th if th > 1e-9 else ax / 2
+
+
+def pixel_of(cam_pts, rows, cols):
+    """Equirectangular projection (sensors/Equirectangular.h:41-96, exact atan2): camera-frame points -> pixels."""
+    p = np.asarray(cam_pts, dtype=np.float64).reshape(-1, 3)
+    lon = np.arctan2(p[:, 0], p[:, 2])
+    lat = -np.arctan2(p[:, 1], np.hypot(p[:, 0], p[:, 2]))
+    return np.stack([cols * (0.5 + lon / (2 * np.pi)), rows * (0.5 - lat / np.pi)], axis=1)
+
+
+def make_joint_problem(n_frames=8, n_points=400, n_az=600, seed=20261005, rows=2880, cols=5760, clutter=20, track_len=(2, 6), pixel_noise=2.0, bearing_noise=2e-3,
+                       pose_noise=(0.004, 0.02), point_noise=0.03):
+    """LiDAR frames on a loop (make_sequence) with a panoramic camera rigidly mounted on the sensor (T_cl), image lines = projections of the
+    LiDAR line segments (+ pixel noise) plus clutter, structure points on the room's faces seen by a few cameras each.  Returns ground truth and
+    perturbed initial pose blocks: cameras (aa_cw, t_cw) and LiDARs (aa_lw, t_lw)."""
+    rng = np.random.default_rng(seed)
+    frames = make_sequence(n_frames, seed=seed + 1, n_az=n_az)
+    T_cl = np.eye(4)
+    T_cl[:3, :3] = rotvec_to_R(np.array([0.01, 0.02, -0.01]))
+    T_cl[:3, 3] = [0.03, -0.05, 0.02]
+    T_lc = np.linalg.inv(T_cl)
+    cams_gt, lidars_gt, image_lines = np.zeros((n_frames, 6)), np.zeros((n_frames, 6)), []
+    Rcw, tcw = [], []
+    for i, f in enumerate(frames):
+        T_wl = np.eye(4); T_wl[:3, :3] = f["R_wl"]; T_wl[:3, 3] = f["t_wl"]
+        T_lw = np.linalg.inv(T_wl)
+        T_cw = T_cl @ T_lw
+        lidars_gt[i, :3], lidars_gt[i, 3:] = _R_to_aa(T_lw[:3, :3]), T_lw[:3, 3]
+        cams_gt[i, :3], cams_gt[i, 3:] = _R_to_aa(T_cw[:3, :3]), T_cw[:3, 3]
+        Rcw.append(rotvec_to_R(cams_gt[i, :3])); tcw.append(cams_gt[i, 3:].copy())
+        ends_cam = f["end_points"].reshape(-1, 3) @ T_cl[:3, :3].T + T_cl[:3, 3]
+        px = pixel_of(ends_cam, rows, cols).reshape(-1, 4) + rng.normal(0, pixel_noise, (len(f["end_points"]), 4))
+        cl = np.stack([rng.uniform(0, cols, clutter), rng.uniform(0, rows, clutter), rng.uniform(0, cols, clutter), rng.uniform(0, rows, clutter)], axis=1)
+        image_lines.append(np.concatenate([px, cl]).astype(np.float32))
+    face = rng.integers(0, 6, n_points)
+    pts = rng.uniform(ROOM_MIN, ROOM_MAX, size=(n_points, 3))
+    for a in range(3):
+        pts[face == 2 * a, a] = ROOM_MIN[a]
+        pts[face == 2 * a + 1, a] = ROOM_MAX[a]
+    cam, point, bearing = [], [], []
+    for p in range(n_points):
+        L = int(rng.integers(track_len[0], min(track_len[1], n_frames) + 1))
+        for c in np.sort(rng.choice(n_frames, size=L, replace=False)):
+            Pc = Rcw[c] @ pts[p] + tcw[c]
+            d = Pc / np.linalg.norm(Pc) + rng.normal(size=3) * bearing_noise
+            cam.append(c); point.append(p); bearing.append(d / np.linalg.norm(d))
+    cams0, lidars0 = cams_gt.copy(), lidars_gt.copy()
+    for arr in (cams0, lidars0):
+        arr[1:, :3] += rng.normal(size=(n_frames - 1, 3)) * pose_noise[0]
+        arr[1:, 3:] += rng.normal(size=(n_frames - 1, 3)) * pose_noise[1]
+    lidars0[0, :3] += rng.normal(size=3) * pose_noise[0]
+    lidars0[0, 3:] += rng.normal(size=3) * pose_noise[1]
+    return {"frames": frames, "T_cl": T_cl, "T_lc": T_lc, "image_lines": image_lines, "rows": rows, "cols": cols, "cams_gt": cams_gt, "lidars_gt": lidars_gt,
+            "cams": cams0, "lidars": lidars0, "points_gt": pts, "points": pts + rng.normal(size=pts.shape) * point_noise,
+            "cam": np.array(cam, np.int32), "point": np.array(point, np.int32), "bearing": np.array(bearing)}
