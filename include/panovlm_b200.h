@@ -302,6 +302,12 @@ int pvb_slerp_pose(const double* pose_w1_16, const double* pose_w2_16, double ra
  * reference saves the raw cloud (`goto save_undistort`).  poses16: n x 16; pose_valid / frame_valid: IsPoseValid() / valid. Host only. */
 int pvb_undistort_end_poses(int n, const double* poses16, const unsigned char* pose_valid, const unsigned char* frame_valid, float gap_time,
                             double* out_pose16, unsigned char* has_end);
+/* Pose text files (util/FileIO.cpp:11-73 ReadPoseT, :168-191 ExportPoseT): one line per frame, [name ]r00 r01 r02 tx r10 r11 r12 ty r20 r21 r22 tz
+ * with 6 significant digits (the reference's default ostream precision); inf / nan marks a frame without pose.  R9 row-major.  Host only.
+ * read: returns the number of poses (<= cap) or < 0; invalid lines are kept (valid = 0, R = 0, t = +inf) only when with_invalid; names may be NULL,
+ * else cap x name_len characters.                                                                                                          */
+int pvb_write_poses_text(const char* path, int n, const double* R9, const double* t3, const char* const* names);
+int pvb_read_poses_text(const char* path, int with_invalid, int cap, double* R9, double* t3, unsigned char* valid, char* names, int name_len);
 /* Velodyne::UndistortCloud (sensors/Velodyne.cpp:1642-1674) for a batch of frames in one launch: point i of a frame's n points (scan
  * order) is moved by slerp(identity, q_se, float(i)/float(n)) and the same fraction of t_se, where (q_se, t_se) = T_wl^-1 T_we.
  * xyzi / out: concatenated n x 4 float32 clouds, frame f = [offsets[f], offsets[f+1]); T_wl16 / T_we16: n_frames x 16 (start / end

@@ -114,7 +114,7 @@ EXPORTS = [
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
-    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook",
+    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text",
     "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates",
 ]
 
@@ -454,6 +454,26 @@ class Context:
         if m < 0:
             raise PvbError(f"pvb_build_reproj_observations: code {m}")
         return cam[:m].copy(), point[:m].copy(), bearing[:m].copy()
+
+    @staticmethod
+    def write_poses_text(path, R, t, names=None):
+        R, t = _arr(R, np.float64).reshape(-1, 9), _arr(t, np.float64).reshape(-1, 3)
+        arr = None
+        if names is not None:
+            arr = (C.c_char_p * len(R))(*[nm.encode() for nm in names])
+        rc = load_library().pvb_write_poses_text(str(path).encode(), C.c_int(len(R)), _p(R), _p(t), arr)
+        if rc < 0:
+            raise PvbError(f"pvb_write_poses_text: code {rc}")
+
+    @staticmethod
+    def read_poses_text(path, with_invalid=True, cap=100000, name_len=256):
+        R, t, valid = np.zeros((cap, 9)), np.zeros((cap, 3)), np.zeros(cap, np.uint8)
+        names = C.create_string_buffer(cap * name_len)
+        n = load_library().pvb_read_poses_text(str(path).encode(), C.c_int(int(with_invalid)), C.c_int(cap), _p(R), _p(t), _p(valid), names, C.c_int(name_len))
+        if n < 0:
+            raise PvbError(f"pvb_read_poses_text: code {n}")
+        nm = [names.raw[i * name_len:(i + 1) * name_len].split(b"\0", 1)[0].decode() for i in range(n)]
+        return R[:n].reshape(n, 3, 3).copy(), t[:n].copy(), valid[:n].astype(bool), nm
 
     @staticmethod
     def slerp_pose(pose_w1, pose_w2, ratio):

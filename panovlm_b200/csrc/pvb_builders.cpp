@@ -8,6 +8,8 @@
 #include <cstring>
 #include <map>
 #include <set>
+#include <cstdio>
+#include <string>
 #include <vector>
 #include "../../include/panovlm_b200.h"
 #include "pvb_math.cuh"
@@ -673,6 +675,53 @@ int pvb_undistort_end_poses(int n, const double* poses16, const unsigned char* p
     has_end[i] = 1;
   }
   return PVB_OK;
+}
+
+// ---- pose text files (util/FileIO.cpp:11-73 ReadPoseT, :168-191 ExportPoseT): the wire format either side of the path -----------------
+// One line per frame: [name ]r00 r01 r02 tx r10 r11 r12 ty r20 r21 r22 tz, written with the default ostream precision (6 significant digits,
+// "%g" - the reference's own precision loss, kept so that files stay interchangeable); a line holding "inf" / "nan" marks a frame without pose.
+int pvb_write_poses_text(const char* path, int n, const double* R9, const double* t3, const char* const* names) {
+  if (!path || n < 0 || (n > 0 && (!R9 || !t3))) return PVB_ERR_ARG;
+  FILE* f = std::fopen(path, "w");
+  if (!f) return PVB_ERR_STATE;
+  for (int i = 0; i < n; ++i) {
+    if (names && names[i]) std::fprintf(f, "%s ", names[i]);
+    const double* R = R9 + 9 * (size_t)i; const double* t = t3 + 3 * (size_t)i;
+    std::fprintf(f, "%g %g %g %g %g %g %g %g %g %g %g %g\n", R[0], R[1], R[2], t[0], R[3], R[4], R[5], t[1], R[6], R[7], R[8], t[2]);
+  }
+  std::fclose(f);
+  return PVB_OK;
+}
+
+// Returns the number of poses read (<= cap) or < 0.  valid[i] = 0: the line held inf / nan (R = 0, t = +inf as ReadPoseT leaves them); such
+// lines are skipped unless with_invalid.  names (may be NULL): cap x name_len characters, empty string when a line has no name.
+int pvb_read_poses_text(const char* path, int with_invalid, int cap, double* R9, double* t3, unsigned char* valid, char* names, int name_len) {
+  if (!path || cap < 0 || (cap > 0 && (!R9 || !t3))) return PVB_ERR_ARG;
+  FILE* f = std::fopen(path, "r");
+  if (!f) return PVB_ERR_STATE;
+  int n = 0;
+  char line[4096];
+  while (std::fgets(line, sizeof line, f)) {
+    std::vector<std::string> tok;
+    for (char* p = std::strtok(line, " \t\r\n"); p; p = std::strtok(nullptr, " \t\r\n")) tok.push_back(p);
+    std::string name;
+    if (tok.size() == 13) { name = tok[0]; tok.erase(tok.begin()); }                 // :31-35
+    if (tok.size() != 12) { if (tok.empty()) continue; }
+    bool ok = tok.size() == 12;
+    double v[12] = {0};
+    if (ok) for (const std::string& s : tok) if (s.find("inf") != std::string::npos || s.find("nan") != std::string::npos) { ok = false; break; }   // :41-48
+    if (ok) for (int k = 0; k < 12; ++k) v[k] = std::strtod(tok[k].c_str(), nullptr);
+    if (!ok && !with_invalid) continue;                                               // :67
+    if (n >= cap) { std::fclose(f); return PVB_ERR_NOMEM; }
+    double* R = R9 + 9 * (size_t)n; double* t = t3 + 3 * (size_t)n;
+    if (ok) { R[0] = v[0]; R[1] = v[1]; R[2] = v[2]; t[0] = v[3]; R[3] = v[4]; R[4] = v[5]; R[5] = v[6]; t[1] = v[7]; R[6] = v[8]; R[7] = v[9]; R[8] = v[10]; t[2] = v[11]; }
+    else { for (int k = 0; k < 9; ++k) R[k] = 0.0; t[0] = t[1] = t[2] = INFINITY; }   // :22-23
+    if (valid) valid[n] = ok ? 1 : 0;
+    if (names && name_len > 0) { std::snprintf(names + (size_t)n * name_len, name_len, "%s", name.c_str()); }
+    ++n;
+  }
+  std::fclose(f);
+  return n;
 }
 
 int pvb_build_point2plane_blocks(long n, const double* point3, const double* plane4, int ref_block, int nei_block, int angle_residual, int normalize_distance,

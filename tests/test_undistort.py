@@ -146,3 +146,31 @@ def test_undistort_exact_properties_at_full_size(gpu_ctx):
         a = cloud[off[f]:off[f + 1], :3].astype(np.float64)
         assert np.array_equal(out[off[f]:off[f + 1], :3], (a + ratio[:, None] * t_se[None, :]).astype(np.float32))
     assert np.array_equal(gpu_ctx.undistort_clouds(cloud, off, T_wl, T_wl), cloud)
+
+
+def test_pose_text_round_trip_and_format(tmp_path):
+    """ReadPoseT / ExportPoseT (util/FileIO.cpp:11-73, 168-191): 12 numbers per line with 6 significant digits, optional name, inf / nan lines."""
+    rng = np.random.default_rng(17)
+    n = 7
+    R = np.stack([Rot.from_rotvec(rng.normal(size=3)).as_matrix() for _ in range(n)])
+    t = rng.normal(size=(n, 3)) * 100
+    t[3] = np.inf                                                      # a frame without pose (ReadPoseT's marker)
+    names = [f"frame_{i:04d}.pcd" for i in range(n)]
+    path = tmp_path / "poses.txt"
+    panovlm_b200.Context.write_poses_text(path, R, t, names)
+    lines = path.read_text().splitlines()
+    assert len(lines) == n
+    for i, ln in enumerate(lines):                                     # exactly what `out << double` prints: "%g"
+        vals = [R[i, 0, 0], R[i, 0, 1], R[i, 0, 2], t[i, 0], R[i, 1, 0], R[i, 1, 1], R[i, 1, 2], t[i, 1], R[i, 2, 0], R[i, 2, 1], R[i, 2, 2], t[i, 2]]
+        assert ln == names[i] + " " + " ".join("%g" % v for v in vals)
+    R2, t2, valid, nm = panovlm_b200.Context.read_poses_text(path, with_invalid=True)
+    assert nm == names and valid.tolist() == [True, True, True, False, True, True, True]
+    ok = valid
+    assert np.abs(R2[ok] - R[ok]).max() < 5e-6 and np.abs(t2[ok] - t[ok]).max() < 5e-4     # the 6-digit precision of the format
+    assert np.all(R2[3] == 0) and np.all(np.isinf(t2[3]))
+    R3, t3, valid3, nm3 = panovlm_b200.Context.read_poses_text(path, with_invalid=False)
+    assert len(R3) == n - 1 and valid3.all() and nm3 == names[:3] + names[4:]
+    # files without names
+    panovlm_b200.Context.write_poses_text(path, R[:2], t[:2])
+    R4, t4, v4, nm4 = panovlm_b200.Context.read_poses_text(path)
+    assert len(R4) == 2 and nm4 == ["", ""] and np.abs(R4 - R[:2]).max() < 5e-6
