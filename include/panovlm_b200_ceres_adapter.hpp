@@ -85,4 +85,62 @@ class CeresBridge : public ceres::EvaluationCallback {
   bool ok_ = false;
 };
 
+// The camera-camera term: AddCameraResidual (util/Optimization.cpp:172-222, ANGLE_RESIDUAL_1) hands Ceres one
+// AutoDiffCostFunction<PanoramaReprojResidual_1Angle,1,3,3,3> per (track, observation) on the blocks (aa_cw, t_cw, point_3d).  This bridge evaluates
+// all of them in one launch per evaluation point (pvb_reproj_evaluate) and serves the 1x9 rows; HuberLoss(4 deg) is applied on the device.
+// The structure points are read where they live (PointTrack::point_3d): `points` holds their addresses in track order.
+// A ceres::Problem takes ONE evaluation callback: when both bridges are used (CameraLidarOptimizer::Optimize) register a small callback that forwards
+// PrepareForEvaluation to the two of them.
+class ReprojBridge : public ceres::EvaluationCallback {
+ public:
+  typedef std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>> Vec3List;
+  ReprojBridge(pvb_ctx* ctx, Vec3List& aa_cw, Vec3List& t_cw, std::vector<double*> points)
+      : ctx_(ctx), aa_(aa_cw), t_(t_cw), points_(std::move(points)), cams_(6 * aa_cw.size()), xyz_(3 * points_.size()) {}
+
+  void PrepareForEvaluation(bool evaluate_jacobians, bool /*new_evaluation_point*/) override {
+    for (size_t i = 0; i < aa_.size(); ++i)
+      for (int k = 0; k < 3; ++k) { cams_[6 * i + k] = aa_[i][k]; cams_[6 * i + 3 + k] = t_[i][k]; }
+    for (size_t p = 0; p < points_.size(); ++p)
+      for (int k = 0; k < 3; ++k) xyz_[3 * p + k] = points_[p][k];
+    ok_ = pvb_reproj_evaluate(ctx_, cams_.data(), xyz_.data(), /*want_rows=*/1, /*want_system=*/0) == PVB_OK;
+    r_ = pvb_reproj_residuals(ctx_);
+    J_ = evaluate_jacobians ? pvb_reproj_jacobians(ctx_) : nullptr;
+  }
+
+  class Row : public ceres::SizedCostFunction<1, 3, 3, 3> {
+   public:
+    Row(const ReprojBridge* b, long i) : b_(b), i_(i) {}
+    bool Evaluate(double const* const*, double* residuals, double** jacobians) const override {
+      if (!b_->ok_) return false;
+      residuals[0] = b_->r_[i_];
+      if (jacobians) {
+        const double* row = b_->J_ ? b_->J_ + 9 * i_ : nullptr;       // [d aa_cw | d t_cw | d point_3d]
+        for (int blk = 0; blk < 3; ++blk)
+          if (jacobians[blk]) for (int k = 0; k < 3; ++k) jacobians[blk][k] = row ? row[3 * blk + k] : 0.0;
+      }
+      return true;
+    }
+   private:
+    const ReprojBridge* b_; long i_;
+  };
+
+  // observation i: camera cam[i] sees point[i] along bearing[i] (unit sphere, eq.ImageToCam of the key point; see pvb_build_reproj_observations)
+  bool AddObservations(long n, const int* cam, const int* point, const double* bearing3, double weight, double huber, ceres::Problem* problem) {
+    if (pvb_reproj_set(ctx_, n, cam, point, bearing3, weight, huber, (int)aa_.size(), (long)points_.size()) != PVB_OK) return false;
+    for (long i = 0; i < n; ++i) problem->AddResidualBlock(new Row(this, i), nullptr, aa_[cam[i]].data(), t_[cam[i]].data(), points_[point[i]]);
+    return true;
+  }
+
+ private:
+  friend class Row;
+  pvb_ctx* ctx_;
+  Vec3List& aa_;
+  Vec3List& t_;
+  std::vector<double*> points_;
+  std::vector<double> cams_, xyz_;
+  const double* r_ = nullptr;
+  const double* J_ = nullptr;
+  bool ok_ = false;
+};
+
 }  // namespace pvb
