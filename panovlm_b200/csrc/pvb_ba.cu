@@ -63,48 +63,68 @@ struct ReprojArgs {
 };
 
 __global__ void __launch_bounds__(128) k_reproj_rows(ReprojArgs a) {
-  const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= a.n) return;
-  const PosePrep* pp = a.prep + a.cam[o];
-  double R[9], t[3];
+  __shared__ double stage[128 * kW];               // the tile's work rows {r, J[9], cost}: written out with coalesced stores
+  const int tid = threadIdx.x;
+  const long base = (long)blockIdx.x * blockDim.x;
+  const long o = base + tid;
+  const int count = (int)min((long)blockDim.x, a.n - base);
+  const bool act = tid < count;
+  double r = 0.0, cost = 0.0, J[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = __ldg(pp->R + k);
+  for (int j = 0; j < 9; ++j) J[j] = 0.0;
+  if (act) {
+    const PosePrep* pp = a.prep + a.cam[o];
+    double R[9], t[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) t[k] = __ldg(pp->t + k);
-  const double* Xp = a.X + 3 * (long)a.pt[o];
-  const double X[3] = {__ldg(Xp), __ldg(Xp + 1), __ldg(Xp + 2)};
-  const double s[3] = {a.bearing[3 * o], a.bearing[3 * o + 1], a.bearing[3 * o + 2]};
-  double v[3], P[3];
+    for (int k = 0; k < 9; ++k) R[k] = __ldg(pp->R + k);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { v[k] = R[k * 3] * X[0] + R[k * 3 + 1] * X[1] + R[k * 3 + 2] * X[2]; P[k] = v[k] + t[k]; }
-  const double n2 = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
-  const double n = sqrt(n2);
-  const double c = (P[0] * s[0] + P[1] * s[1] + P[2] * s[2]) / n;
-  double r = a.weight * acos(c);
-  // d r / d P = -w / sqrt(1 - c^2) * (s - c P / |P|) / |P|   (unguarded at c = 1 like the autodiff functor)
-  const double k = -a.weight / (sqrt(1.0 - c * c) * n);
-  const double g[3] = {k * (s[0] - c * P[0] / n), k * (s[1] - c * P[1] / n), k * (s[2] - c * P[2] / n)};
-  const double w[3] = {v[1] * g[2] - v[2] * g[1], v[2] * g[0] - v[0] * g[2], v[0] * g[1] - v[1] * g[0]};     // (R X) x g
-  double J[9];
+    for (int k = 0; k < 3; ++k) t[k] = __ldg(pp->t + k);
+    const double* Xp = a.X + 3 * (long)a.pt[o];
+    const double X[3] = {__ldg(Xp), __ldg(Xp + 1), __ldg(Xp + 2)};
+    const double s[3] = {a.bearing[3 * o], a.bearing[3 * o + 1], a.bearing[3 * o + 2]};
+    double v[3], P[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    J[j] = w[0] * __ldg(pp->Jl + j) + w[1] * __ldg(pp->Jl + 3 + j) + w[2] * __ldg(pp->Jl + 6 + j);             // d aa: through the left Jacobian of SO(3)
-    J[3 + j] = g[j];
-    J[6 + j] = g[0] * R[j] + g[1] * R[3 + j] + g[2] * R[6 + j];                                               // R^T g
+    for (int k = 0; k < 3; ++k) { v[k] = R[k * 3] * X[0] + R[k * 3 + 1] * X[1] + R[k * 3 + 2] * X[2]; P[k] = v[k] + t[k]; }
+    const double n2 = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+    const double n = sqrt(n2);
+    const double c = (P[0] * s[0] + P[1] * s[1] + P[2] * s[2]) / n;
+    r = a.weight * acos(c);
+    // d r / d P = -w / sqrt(1 - c^2) * (s - c P / |P|) / |P|   (unguarded at c = 1 like the autodiff functor)
+    const double k = -a.weight / (sqrt(1.0 - c * c) * n);
+    const double g[3] = {k * (s[0] - c * P[0] / n), k * (s[1] - c * P[1] / n), k * (s[2] - c * P[2] / n)};
+    const double w[3] = {v[1] * g[2] - v[2] * g[1], v[2] * g[0] - v[0] * g[2], v[0] * g[1] - v[1] * g[0]};     // (R X) x g
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      J[j] = w[0] * __ldg(pp->Jl + j) + w[1] * __ldg(pp->Jl + 3 + j) + w[2] * __ldg(pp->Jl + 6 + j);             // d aa: through the left Jacobian of SO(3)
+      J[3 + j] = g[j];
+      J[6 + j] = g[0] * R[j] + g[1] * R[3 + j] + g[2] * R[6 + j];                                               // R^T g
+    }
+    cost = huber_correct(a.huber, r, J, 9);
   }
-  const double cost = huber_correct(a.huber, r, J, 9);
-  if (a.W) {
-    double* w_ = a.W + (size_t)o * kW;
-    w_[0] = r;
+  double* mine = stage + tid * kW;
+  mine[0] = r;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) w_[1 + j] = J[j];
-    w_[10] = cost;
+  for (int j = 0; j < 9; ++j) mine[1 + j] = J[j];
+  mine[10] = cost;
+  // rows in the caller's order: when the tile maps to consecutive caller rows (point-major input, the reference's loop order) the 72-byte rows
+  // leave as one contiguous coalesced block, otherwise each thread scatters its own row
+  const long d0 = a.r_rows ? (long)a.orig[base] : 0;
+  const int contiguous = __syncthreads_and(!a.r_rows || !act || (long)a.orig[o] == d0 + tid);
+  if (a.W) {
+    double* dst = a.W + (size_t)base * kW;
+    for (int e = tid; e < count * kW; e += 128) dst[e] = stage[e];
   }
   if (a.r_rows) {
-    const long d = a.orig[o];
-    a.r_rows[d] = r;
+    if (contiguous) {
+      if (act) a.r_rows[d0 + tid] = r;
+      double* dst = a.J_rows + (size_t)d0 * 9;
+      for (int e = tid; e < count * 9; e += 128) { const int row = e / 9; dst[e] = stage[row * kW + 1 + (e - row * 9)]; }
+    } else if (act) {
+      const long d = a.orig[o];
+      a.r_rows[d] = r;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) a.J_rows[d * 9 + j] = J[j];
+      for (int j = 0; j < 9; ++j) a.J_rows[d * 9 + j] = J[j];
+    }
   }
 }
 
