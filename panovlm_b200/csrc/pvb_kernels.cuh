@@ -15,6 +15,9 @@
 namespace pvb {
 
 constexpr int kTile = 128;   // queries / residual rows per thread block
+#ifndef PVB_K3_MINB
+#define PVB_K3_MINB 6        // resident blocks per SM the residual kernel is compiled for: measured 4: 0.176 ms, 5: 0.163, 6: 0.153, 8: 0.156 (reduced mode, Room-shaped list)
+#endif
 
 struct WorldPose { double R[9]; double t[3]; };   // T_wl of a pose block (row-major R)
 
@@ -411,11 +414,21 @@ struct EvalArgs {
   double* partials;               // [tile][92] (may be null)
 };
 
-__global__ void __launch_bounds__(kTile) k_eval_blocks(const EvalArgs a) {
+__global__ void __launch_bounds__(kTile, PVB_K3_MINB) k_eval_blocks(const EvalArgs a) {
   __shared__ double sJ[kTile][14];   // J12 | r | cost  (stride 14 doubles)
+  __shared__ PosePrep sPrep[2];      // the tile's two pose blocks (all rows of a tile belong to one edge)
   const BlockTile t = a.tiles[blockIdx.x];
   const int i = threadIdx.x;
   const bool act = i < t.count;
+  {
+    constexpr int kD = (int)(sizeof(PosePrep) / sizeof(double));
+    if (i < 2 * kD) {
+      const int which = i / kD, k = i - which * kD;
+      const int blk = which == 0 ? a.edge_ref[t.edge] : a.edge_nei[t.edge];
+      reinterpret_cast<double*>(&sPrep[which])[k] = __ldg(reinterpret_cast<const double*>(a.prep + blk) + k);
+    }
+    __syncthreads();
+  }
   double J[12], r = 0.0, cost = 0.0;
 #pragma unroll
   for (int k = 0; k < 12; ++k) J[k] = 0.0;
@@ -424,7 +437,7 @@ __global__ void __launch_bounds__(kTile) k_eval_blocks(const EvalArgs a) {
     double c[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) c[k] = __ldg(a.consts + (size_t)k * a.n + row);
-    r = eval_block(a.type[row], a.normalize[row] != 0, c, a.prep[a.edge_ref[t.edge]], a.prep[a.edge_nei[t.edge]], J);
+    r = eval_block(a.type[row], a.normalize[row] != 0, c, sPrep[0], sPrep[1], J);
     cost = huber_correct(a.huber[row], r, J, 12);
     if (a.out_r) {
       const uint32_t o = a.orig[row];
