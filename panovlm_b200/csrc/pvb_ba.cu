@@ -23,6 +23,9 @@ namespace {
 
 constexpr int kPad = 64;        // the Cholesky works on 64-wide panels (kNB in pvb_solver.cuh)
 constexpr int kW = 11;          // work row per observation: r, J[9] (d aa | d t | d X), cost
+#ifndef PVB_K5_MINB
+#define PVB_K5_MINB 7         // resident blocks per SM the reprojection kernel is compiled for
+#endif
 
 struct PairEntry { int o1, o2; };             // contribution T_o1 * E'_o2^T to one 6x6 block of the reduced camera system
 struct PairDest { int c1, c2, begin, end; };  // block (c1 <= c2) = entries [begin, end)
@@ -62,7 +65,7 @@ struct ReprojArgs {
   double* W; double* r_rows; double* J_rows;     // W: sorted order (may be null); rows: caller's order (may be null)
 };
 
-__global__ void __launch_bounds__(128) k_reproj_rows(ReprojArgs a) {
+__global__ void __launch_bounds__(128, PVB_K5_MINB) k_reproj_rows(ReprojArgs a) {
   __shared__ double stage[128 * kW];               // the tile's work rows {r, J[9], cost}: written out with coalesced stores
   const int tid = threadIdx.x;
   const long base = (long)blockIdx.x * blockDim.x;
