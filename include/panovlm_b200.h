@@ -279,6 +279,11 @@ int pvb_unique_line_pairs(int n, const int* image_line, const int* lidar_line, c
 int pvb_build_point2plane_blocks(long n, const double* point3, const double* plane4, int ref_block, int nei_block, int angle_residual,
                                  int normalize_distance, double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize,
                                  double* huber, double* consts);           /* Optimization.cpp:506-562 */
+/* the same for the correspondences of many edges at once: correspondence i belongs to edge[i] (as pvb_frames_get_point2plane returns them),
+ * whose pose blocks are edge_ref_block[edge[i]] / edge_nei_block[edge[i]]; blocks are appended in the order of the correspondences             */
+int pvb_build_point2plane_blocks_edges(long n, const int* edge, const double* point3, const double* plane4, int n_edges, const int* edge_ref_block,
+                                       const int* edge_nei_block, int angle_residual, int normalize_distance, double weight, long at, long cap,
+                                       int* type, int* ref, int* nei, int* normalize, double* huber, double* consts);
 /* AddLidarPointToLineResidual (Optimization.cpp:443-504): Point2Line_Angle / _Meter with HuberLoss(2 deg / 0.2) */
 int pvb_build_point2line_blocks(long n, const double* point3, const double* a3, const double* b3, int ref_block, int nei_block, int angle_residual,
                                 int normalize_distance, double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize,

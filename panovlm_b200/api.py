@@ -114,7 +114,7 @@ EXPORTS = [
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
-    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text",
+    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges",
     "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates",
 ]
 
@@ -630,6 +630,17 @@ class Context:
                                                         C.c_int(int(normalize_distance)), C.c_double(weight), n, cap, *arrs)
         if m < 0:
             raise PvbError(f"pvb_build_point2plane_blocks: code {m}")
+        bl.n = m
+
+    @staticmethod
+    def build_point2plane_blocks_edges(bl, edge, point, plane, edge_ref_block, edge_nei_block, angle_residual, normalize_distance, weight):
+        e, pt, pl = _arr(edge, np.int32), _arr(point, np.float64).reshape(-1, 3), _arr(plane, np.float64).reshape(-1, 4)
+        er, en = _arr(edge_ref_block, np.int32), _arr(edge_nei_block, np.int32)
+        n, cap, *arrs = bl.args()
+        m = load_library().pvb_build_point2plane_blocks_edges(C.c_long(len(e)), _p(e), _p(pt), _p(pl), C.c_int(len(er)), _p(er), _p(en), C.c_int(int(angle_residual)),
+                                                              C.c_int(int(normalize_distance)), C.c_double(weight), n, cap, *arrs)
+        if m < 0:
+            raise PvbError(f"pvb_build_point2plane_blocks_edges: code {m}")
         bl.n = m
 
     @staticmethod

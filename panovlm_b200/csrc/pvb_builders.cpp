@@ -736,6 +736,24 @@ int pvb_build_point2plane_blocks(long n, const double* point3, const double* pla
   return (int)o.at;
 }
 
+// the same for the correspondences of MANY edges at once (pvb_frames_get_point2plane returns them edge-major with their edge index): one call per
+// outer iteration instead of one per pose-graph edge
+int pvb_build_point2plane_blocks_edges(long n, const int* edge, const double* point3, const double* plane4, int n_edges, const int* edge_ref_block,
+                                       const int* edge_nei_block, int angle_residual, int normalize_distance, double weight, long at, long cap, int* type, int* ref,
+                                       int* nei, int* normalize, double* huber, double* consts) {
+  if (n < 0 || n_edges < 0 || (n > 0 && (!edge || !point3 || !plane4 || !edge_ref_block || !edge_nei_block)) || !type || !ref || !nei || !normalize || !huber || !consts)
+    return PVB_ERR_ARG;
+  BlockOut o{at, cap, type, ref, nei, normalize, huber, consts};
+  const double hub = angle_residual ? 2 * M_PI / 180.0 : 0.2;
+  for (long i = 0; i < n; ++i) {
+    const int e = edge[i];
+    if (e < 0 || e >= n_edges) return PVB_ERR_ARG;
+    double c[12] = {point3[3 * i], point3[3 * i + 1], point3[3 * i + 2], plane4[4 * i], plane4[4 * i + 1], plane4[4 * i + 2], plane4[4 * i + 3], weight, 0, 0, 0, 0};
+    if (!push_block(o, angle_residual ? PVB_P2PLANE_ANGLE : PVB_P2PLANE_METER, edge_ref_block[e], edge_nei_block[e], normalize_distance, hub, c)) return PVB_ERR_ARG;
+  }
+  return (int)o.at;
+}
+
 int pvb_build_point2line_blocks(long n, const double* point3, const double* a3, const double* b3, int ref_block, int nei_block, int angle_residual, int normalize_distance,
                                 double weight, long at, long cap, int* type, int* ref, int* nei, int* normalize, double* huber, double* consts) {
   if (n < 0 || (n > 0 && (!point3 || !a3 || !b3)) || !type || !ref || !nei || !normalize || !huber || !consts) return PVB_ERR_ARG;

@@ -91,11 +91,8 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
         ref = np.array([e[0] for e in edges], np.int32)
         nei = np.array([e[1] for e in edges], np.int32)
         e, q, pt, pl = ctx.frames_associate_point2plane(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, 10)
-        bounds = np.searchsorted(e, np.arange(len(edges) + 1))         # correspondences come back edge-major
-        for ei in range(len(edges)):
-            lo, hi = bounds[ei], bounds[ei + 1]
-            if hi > lo:
-                Context.build_point2plane_blocks(bl, pt[lo:hi], pl[lo:hi], int(ref[ei]), int(nei[ei]), cfg.angle_residual, cfg.normalize_distance, 1.0)
+        # correspondences come back edge-major with their edge index: all blocks of the outer iteration in one builder call
+        Context.build_point2plane_blocks_edges(bl, e, pt, pl, ref, nei, cfg.angle_residual, cfg.normalize_distance, 1.0)
     return bl, all_edges
 
 

@@ -1,6 +1,7 @@
 """Host-side builders of the library (pvb_find_neighbors, pvb_build_*_blocks): pure C++ host code, no GPU needed.
 Expected values are rebuilt here in Python from the reference's description with the oracle's primitives."""
 import numpy as np
+import pytest
 
 import panovlm_b200
 from panovlm_b200 import BlockList, Context, LineFrame, synth
@@ -88,6 +89,36 @@ def test_point2plane_and_line_blocks(oracle):
     Context.build_line2line_blocks(bl2, fr, world, 4, a, b, 0, 1, False, True, 0.5)
     v = bl2.view()
     assert np.all(v["type"][len(members):] == 2) and np.all(v["huber"][len(members):] == 0.2) and np.all(v["consts"][len(members):, 9] == 0.5)
+
+
+def test_point2plane_blocks_of_many_edges_equal_the_per_edge_loop():
+    """pvb_build_point2plane_blocks_edges == AddLidarPointToPlaneResidual's loop over (i, n) pairs (Optimization.cpp:520-557), one call for all edges."""
+    rng = np.random.default_rng(5)
+    n_edges = 9
+    edge_ref, edge_nei = rng.integers(0, 6, n_edges).astype(np.int32), rng.integers(0, 6, n_edges).astype(np.int32)
+    counts = rng.integers(0, 40, n_edges)
+    counts[3] = 0                                                   # an edge without correspondences
+    edge = np.repeat(np.arange(n_edges), counts).astype(np.int32)
+    pts, pls = rng.normal(size=(len(edge), 3)), rng.normal(size=(len(edge), 4))
+    for angle, norm, w in ((True, True, 1.0), (False, False, 0.3)):
+        one = BlockList(len(edge) + 4)
+        Context.build_point2plane_blocks_edges(one, edge, pts, pls, edge_ref, edge_nei, angle, norm, w)
+        loop = BlockList(len(edge) + 4)
+        lo = 0
+        for e in range(n_edges):
+            hi = lo + counts[e]
+            if hi > lo:
+                Context.build_point2plane_blocks(loop, pts[lo:hi], pls[lo:hi], int(edge_ref[e]), int(edge_nei[e]), angle, norm, w)
+            lo = hi
+        a, b = one.view(), loop.view()
+        assert one.n == loop.n == len(edge)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    # an edge index outside the table is refused, and so is a full list
+    with pytest.raises(Exception):
+        Context.build_point2plane_blocks_edges(BlockList(100), np.array([n_edges], np.int32), pts[:1], pls[:1], edge_ref, edge_nei, True, True, 1.0)
+    with pytest.raises(Exception):
+        Context.build_point2plane_blocks_edges(BlockList(3), edge, pts, pls, edge_ref, edge_nei, True, True, 1.0)
 
 
 def test_camera_lidar_blocks_evaluate_like_the_reference_construction(oracle):
