@@ -38,12 +38,13 @@ struct BAState {
   DevBuf d_cam, d_pt, d_orig, d_bearing, d_pt_off, d_cam_off, d_cam_obs, d_prep, d_X, d_W, d_r, d_J;
   DevBuf d_C, d_gp, d_E, d_B, d_gc, d_ccost;
   DevBuf d_entries, d_dest, d_fidx, d_scc, d_scp, d_ptconst, d_Cinv, d_gsp, d_T, d_Es, d_yp;
+  DevBuf d_camblk, d_pinned;                    // joint solve: first unknown of every camera's block, pinned (constant) unknowns of free blocks
   PinBuf h_r, h_J, h_blocks, h_stage;
   bool has_rows = false, has_sys = false, pairs_built = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
   void release() {
     DevBuf* bs[] = {&d_cam, &d_pt, &d_orig, &d_bearing, &d_pt_off, &d_cam_off, &d_cam_obs, &d_prep, &d_X, &d_W, &d_r, &d_J, &d_C, &d_gp, &d_E, &d_B, &d_gc, &d_ccost,
-                    &d_entries, &d_dest, &d_fidx, &d_scc, &d_scp, &d_ptconst, &d_Cinv, &d_gsp, &d_T, &d_Es, &d_yp};
+                    &d_entries, &d_dest, &d_fidx, &d_scc, &d_scp, &d_ptconst, &d_Cinv, &d_gsp, &d_T, &d_Es, &d_yp, &d_camblk, &d_pinned};
     for (DevBuf* b : bs) b->release();
     h_r.release(); h_J.release(); h_blocks.release(); h_stage.release();
     if (ev0) cudaEventDestroy(ev0);
@@ -690,9 +691,8 @@ int pvb_joint_solve_lm(pvb_ctx* ctx, double* poses6, double* points3, const unsi
   std::vector<unsigned char> ptc(std::max<long>(np, 1), 0);
   long n_free_pts = 0;
   for (long p = 0; p < np; ++p) { ptc[p] = point_const && point_const[p] ? 1 : 0; if (!ptc[p]) ++n_free_pts; }
-  DevBuf d_camblk, d_pinned, d_diag;
-  struct Guard { DevBuf *a, *b, *c; ~Guard() { a->release(); b->release(); c->release(); } } guard{&d_camblk, &d_pinned, &d_diag};
-  CK(d_camblk.ensure((size_t)nc * 4)); CK(d_pinned.ensure(std::max<size_t>(4, pinned.size() * 4))); CK(d_diag.ensure((size_t)N * 8));
+  DevBuf& d_camblk = S->d_camblk; DevBuf& d_pinned = S->d_pinned;
+  CK(d_camblk.ensure((size_t)nc * 4)); CK(d_pinned.ensure(std::max<size_t>(4, pinned.size() * 4)));
   CK(S->d_fidx.ensure(fidx.size() * 4)); CK(S->d_scc.ensure((size_t)nc * 48)); CK(S->d_scp.ensure(std::max<size_t>(8, (size_t)np * 24))); CK(S->d_ptconst.ensure(ptc.size()));
   CK(S->d_Cinv.ensure(std::max<size_t>(8, (size_t)np * 48))); CK(S->d_gsp.ensure(std::max<size_t>(8, (size_t)np * 24))); CK(S->d_yp.ensure(std::max<size_t>(8, (size_t)np * 24)));
   CK(S->d_T.ensure(std::max<size_t>(8, (size_t)S->n_obs * 144))); CK(S->d_Es.ensure(std::max<size_t>(8, (size_t)S->n_obs * 144)));
