@@ -9,6 +9,8 @@ INDEPENDENT implementations, never from the oracle itself:
   assoc_pair.npz a small 2-frame pair (feature clouds) with the expected point-to-plane associations computed with
                  scipy cKDTree (float64 on the float32 world points) + numpy lstsq / eigh
   fast_atan2.npz dense grid of atan2 values (the polynomial must stay within 1.7e-4 rad of them)
+  reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
+                 undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
 Run from the repo root:  python tests/make_golden.py
 """
 import os
@@ -98,8 +100,45 @@ def golden_atan2():
     np.savez_compressed(os.path.join(OUT, "fast_atan2.npz"), y=y, x=x, atan2=np.arctan2(y, x))
 
 
+def golden_reproj():
+    import torch
+    from scipy.spatial.transform import Rotation
+    d = synth.make_ba_problem(n_cams=6, n_points=80, seed=20261002)
+    weight = 1.3
+    n = len(d["cam"])
+    r, J = np.zeros(n), np.zeros((n, 9))
+    for i in range(n):
+        aa = torch.tensor(d["cams"][d["cam"][i], :3], requires_grad=True)
+        t = torch.tensor(d["cams"][d["cam"][i], 3:], requires_grad=True)
+        X = torch.tensor(d["points"][d["point"][i]], requires_grad=True)
+        th = torch.linalg.norm(aa)
+        k = aa / th
+        K = torch.zeros(3, 3, dtype=torch.float64)
+        K[0, 1], K[0, 2], K[1, 0], K[1, 2], K[2, 0], K[2, 1] = -k[2], k[1], k[2], -k[0], -k[1], k[0]
+        R = torch.eye(3, dtype=torch.float64) + torch.sin(th) * K + (1 - torch.cos(th)) * (K @ K)
+        P = R @ X + t
+        s = torch.tensor(d["bearing"][i])
+        res = weight * torch.acos((P @ s) / torch.linalg.norm(P))
+        res.backward()
+        r[i] = res.item()
+        J[i] = np.concatenate([aa.grad.numpy(), t.grad.numpy(), X.grad.numpy()])
+    # a small sweep undistorted with scipy (float64), stored as the float32 the reference writes back
+    rng = np.random.default_rng(20261003)
+    m = 500
+    cloud = (rng.normal(size=(m, 4)) * 10).astype(np.float32)
+    A, E = np.eye(4), np.eye(4)
+    A[:3, :3] = Rotation.from_rotvec([0.2, -0.1, 0.3]).as_matrix(); A[:3, 3] = [1.0, 2.0, -0.5]
+    E[:3, :3] = A[:3, :3] @ Rotation.from_rotvec([0.02, 0.05, -0.03]).as_matrix(); E[:3, 3] = A[:3, 3] + [0.1, -0.05, 0.02]
+    R_se, t_se = A[:3, :3].T @ E[:3, :3], A[:3, :3].T @ (E[:3, 3] - A[:3, 3])
+    rv = Rotation.from_matrix(R_se).as_rotvec()
+    ratio = (np.arange(m, dtype=np.float32) / np.float32(m)).astype(np.float64)
+    und = np.stack([Rotation.from_rotvec(rv * q).apply(cloud[i, :3].astype(np.float64)) + q * t_se for i, q in enumerate(ratio)])
+    np.savez_compressed(os.path.join(OUT, "reproj.npz"), cam=d["cam"], point=d["point"], bearing=d["bearing"], cams=d["cams"], points=d["points"], weight=weight,
+                        residual=r, jacobian=J, sweep=cloud, T_wl=A, T_we=E, undistorted=und)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

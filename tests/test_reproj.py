@@ -272,3 +272,33 @@ def test_joint_camera_lidar_lm_matches_dense_oracle_lm(gpu_ctx, oracle, mode):
         assert np.abs(g_p - e_p).max() < 1e-4 * np.abs(e_p - d["points"]).max()
     assert np.array_equal(g_x[pose_const.astype(bool)], start[pose_const.astype(bool)])
     assert np.array_equal(g_p[pt_const.astype(bool)], d["points"][pt_const.astype(bool)])
+
+
+GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "reproj.npz")
+
+
+def test_oracle_against_committed_golden_vectors(oracle):
+    """tests/golden/reproj.npz (tests/make_golden.py: torch float64 autograd twin, scipy rotation-vector interpolation) pins the oracle."""
+    g = np.load(GOLDEN)
+    r, J, _ = oracle.Reproj(g["cam"], g["point"], g["bearing"], weight=float(g["weight"]), huber=0.0).evaluate(g["cams"], g["points"], apply_loss=False)
+    assert np.abs(r - g["residual"]).max() < 1e-10                       # acos at small angles amplifies the rounding of two different evaluation orders
+    assert (np.abs(J - g["jacobian"]).max(1) / np.abs(g["jacobian"]).max(1)).max() < 1e-8
+    und = oracle.undistort_cloud(g["T_wl"][:3, :3], g["T_wl"][:3, 3], g["T_we"][:3, :3], g["T_we"][:3, 3], g["sweep"])
+    exp = g["undistorted"].astype(np.float32)
+    ulp = np.abs(und[:, :3].view(np.int32).astype(np.int64) - exp.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1 and (ulp > 0).mean() < 0.01                    # quaternion slerp vs rotation-vector scaling: equal up to a float32 rounding flip
+    assert np.array_equal(und[:, 3], g["sweep"][:, 3])
+
+
+@pytest.mark.gpu
+def test_kernels_against_committed_golden_vectors(gpu_ctx):
+    g = np.load(GOLDEN)
+    gpu_ctx.reproj_set(g["cam"], g["point"], g["bearing"], len(g["cams"]), len(g["points"]), weight=float(g["weight"]), huber=0.0)
+    gpu_ctx.reproj_evaluate(g["cams"], g["points"], True, False)
+    r, J = gpu_ctx.reproj_rows()
+    assert (np.abs(r - g["residual"]) / np.maximum(1e-9, np.abs(g["residual"]))).max() < 1e-7        # gate: 1e-5 relative
+    assert (np.abs(J - g["jacobian"]).max(1) / np.abs(g["jacobian"]).max(1)).max() < 1e-7            # gate: 1e-6 relative
+    und = gpu_ctx.undistort_clouds(g["sweep"], np.array([0, len(g["sweep"])], np.int32), g["T_wl"][None], g["T_we"][None])
+    exp = g["undistorted"].astype(np.float32)
+    ulp = np.abs(und[:, :3].view(np.int32).astype(np.int64) - exp.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1 and (ulp > 0).mean() < 0.01
