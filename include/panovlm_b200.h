@@ -269,6 +269,11 @@ int pvb_pixel_line_neighbors(pvb_ctx* ctx, int rows, int cols, const float* line
 /* `line_lidar` (:83-97) as CSR: per image line the LiDAR points that chose it (ascending, with multiplicity), emptied below min_points (6).
  * Returns the number of entries.  Host only.                                                                                                */
 int pvb_pixel_line_candidates(int n_lines, int n_points, const int* line3, int min_points, int cap, int* line_off, int* lidar_idx);
+/* CameraLidarLineAssociate::Filter (:628-715) alone, on pairs whose LiDAR end points are in the CAMERA frame: the angle branch (great-circle
+ * planes within 5 deg, LiDAR ends inside the image line's arc, both ends within 0.4 of the image plane at radius 5; angle[i] = plane angle in
+ * degrees, :652) and the projected-length branch (100 .. 2000 px).  keep[i] = 1 when the pair survives.  Host only.                          */
+int pvb_filter_line_pairs(int rows, int cols, int n, const float* image_line4, const double* start3, const double* end3, int filter_by_angle,
+                          int filter_by_length, unsigned char* keep, float* angle);
 /* UniqueLinePair alone (host): candidates in input order -> one-to-one pairs, ascending image line                                  */
 int pvb_unique_line_pairs(int n, const int* image_line, const int* lidar_line, const float* score, int* n_out, int* out_image, int* out_lidar,
                           float* out_score);

@@ -215,6 +215,14 @@ def joint_solve_lm(blocks, reproj, poses, points, param_const=None, max_iter=20)
     return x[:poses.size].reshape(-1, 6), x[poses.size:].reshape(-1, 3), dict(zip(keys, summ.tolist()))
 
 
+def filter_line_pairs(rows, cols, image_lines, start, end, by_angle, by_length):
+    """CameraLidarLineAssociate::Filter (joint_optimization/CameraLidarLineAssociate.cpp:628-715) on camera-frame pairs."""
+    ln, s, e = _f32(image_lines).reshape(-1, 4), _f64(start).reshape(-1, 3), _f64(end).reshape(-1, 3)
+    keep, ang = np.zeros(len(ln), np.uint8), np.full(len(ln), np.float32(3.4028235e38), np.float32)
+    lib().pvo_filter_line_pairs(C.c_int(rows), C.c_int(cols), C.c_int(len(ln)), _p(ln), _p(s), _p(e), C.c_int(int(by_angle)), C.c_int(int(by_length)), _p(keep), _p(ang))
+    return keep.astype(bool), ang
+
+
 def pixel_line_neighbors(rows, cols, lines, cloud_local, T_cl):
     """First stage of the pixel-space CameraLidarLineAssociate::Associate (joint_optimization/CameraLidarLineAssociate.cpp:22-91)."""
     lines, cloud = _f32(lines).reshape(-1, 4), _f32(cloud_local).reshape(-1, 4)

@@ -376,6 +376,55 @@ struct Equirect {
   }
 };
 
+// ---- CameraLidarLineAssociate::Filter (CameraLidarLineAssociate.cpp:628-715), both branches, on pairs given in the CAMERA frame -------------
+// keep[i] = the pair survives; angle[i] receives the plane angle in DEGREES when filter_by_angle is set (:652), else it is left untouched.
+inline void FilterLinePairs(const Equirect& eq, int n, const float* image_line4, const double* start3, const double* end3, bool filter_by_angle, bool filter_by_length,
+                            unsigned char* keep, float* angle) {
+  const double zero[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i) {
+    keep[i] = 0;
+    const double* ls = start3 + 3 * i; const double* le = end3 + 3 * i;
+    if (filter_by_angle) {
+      double plane_lidar[4];
+      FormPlane3(ls, le, zero, plane_lidar);                                                         // :641
+      { const double nn = std::sqrt(Square(plane_lidar[0]) + Square(plane_lidar[1]) + Square(plane_lidar[2]) + Square(plane_lidar[3])); for (double& v : plane_lidar) v /= nn; }
+      const double px1[2] = {image_line4[4 * i], image_line4[4 * i + 1]}, px2[2] = {image_line4[4 * i + 2], image_line4[4 * i + 3]};
+      double p1[3], p2[3];
+      eq.ImageToCam(px1, 1.0, p1); eq.ImageToCam(px2, 1.0, p2);                                      // :645-646
+      double plane_img[4];
+      FormPlane3(p1, p2, zero, plane_img);
+      { const double nn = std::sqrt(Square(plane_img[0]) + Square(plane_img[1]) + Square(plane_img[2]) + Square(plane_img[3])); for (double& v : plane_img) v /= nn; }
+      const double plane_angle = PlaneAngle(plane_lidar, plane_img, true) * 180.0 / M_PI;           // :650
+      if (plane_angle > 5) continue;
+      angle[i] = (float)plane_angle;                                                                 // :652
+      const double image_line_angle = VectorAngle3D(p1, p2) / 2.0;
+      double sp[3], ep[3];
+      ProjectPointToPlane(ls, plane_img, sp, true);
+      ProjectPointToPlane(le, plane_img, ep, true);
+      const double mid[3] = {(p1[0] + p2[0]) / 2.0, (p1[1] + p2[1]) / 2.0, (p1[2] + p2[2]) / 2.0};
+      if (VectorAngle3D(sp, mid) > image_line_angle) continue;                                       // :660
+      if (VectorAngle3D(ep, mid) > image_line_angle) continue;
+      const double ns = std::sqrt(Square(ls[0]) + Square(ls[1]) + Square(ls[2])), ne = std::sqrt(Square(le[0]) + Square(le[1]) + Square(le[2]));
+      const double a5[3] = {ls[0] / ns * 5, ls[1] / ns * 5, ls[2] / ns * 5}, b5[3] = {le[0] / ne * 5, le[1] / ne * 5, le[2] / ne * 5};   // :665-666
+      const float distance = (float)std::min(PointToPlaneDistance(plane_img, a5, true), PointToPlaneDistance(plane_img, b5, true));
+      if (distance > 0.4) continue;                                                                  // :669
+    }
+    if (filter_by_length) {                                                                          // :673-692
+      const float a[3] = {(float)ls[0], (float)ls[1], (float)ls[2]}, b[3] = {(float)le[0], (float)le[1], (float)le[2]};
+      float pa[2], pb[2]; eq.CamToImage(a, pa); eq.CamToImage(b, pb);
+      auto seg = eq.BreakToSegments(pa, pb, 100);
+      float len = 0;
+      for (size_t k = 0; k + 1 < seg.size(); ++k) {
+        if (std::abs(seg[k].first - seg[k + 1].first) > 0.8 * eq.cols) continue;
+        const float dx = seg[k].first - seg[k + 1].first, dy = seg[k].second - seg[k + 1].second;
+        len += std::sqrt(dx * dx + dy * dy);
+      }
+      if (len < 100.f || len > 2000.f) continue;
+    }
+    keep[i] = 1;
+  }
+}
+
 // ---- pixel-space Associate, first stage (CameraLidarLineAssociate.cpp:22-91): the fallback for frames without LiDAR segments ----------
 // image lines -> sub-line mid points (BreakToSegments(line, 70), seam pieces skipped, :38-54); every LiDAR point -> camera frame
 // (pcl::transformPointCloud, float32) -> pixel (CamToImage, float + FastAtan2, :75-76) -> its 3 nearest mid points (cv::flann exact search,

@@ -380,6 +380,12 @@ int pvo_pixel_sub_lines(int rows, int cols, const float* lines, int L, int cap, 
   return (int)s2l.size();
 }
 
+void pvo_filter_line_pairs(int rows, int cols, int n, const float* image_line4, const double* start3, const double* end3, int by_angle, int by_length, unsigned char* keep,
+                           float* angle) {
+  Equirect eq{rows, cols};
+  FilterLinePairs(eq, n, image_line4, start3, end3, by_angle != 0, by_length != 0, keep, angle);
+}
+
 void* pvo_kdtree_build(const float* pts, int n) { KdTree* t = new KdTree(); t->Build(pts, n, 4); return t; }
 void pvo_kdtree_free(void* t) { delete (KdTree*)t; }
 

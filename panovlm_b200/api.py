@@ -114,7 +114,7 @@ EXPORTS = [
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
-    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges",
+    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges", "pvb_filter_line_pairs",
     "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates",
 ]
 
@@ -424,6 +424,16 @@ class Context:
         self._ck(self._L.pvb_pixel_line_neighbors(self._h, C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), _p(cloud), C.c_int(n), _p(_arr(T_cl, np.float64)),
                                                   _p(line3), _p(d2), _p(px)))
         return line3, d2, px
+
+    @staticmethod
+    def filter_line_pairs(rows, cols, image_lines, start, end, by_angle, by_length):
+        ln, s_, e_ = _arr(image_lines, np.float32).reshape(-1, 4), _arr(start, np.float64).reshape(-1, 3), _arr(end, np.float64).reshape(-1, 3)
+        keep, ang = np.zeros(len(ln), np.uint8), np.full(len(ln), np.float32(3.4028235e38), np.float32)
+        rc = load_library().pvb_filter_line_pairs(C.c_int(rows), C.c_int(cols), C.c_int(len(ln)), _p(ln), _p(s_), _p(e_), C.c_int(int(by_angle)), C.c_int(int(by_length)),
+                                                  _p(keep), _p(ang))
+        if rc < 0:
+            raise PvbError(f"pvb_filter_line_pairs: code {rc}")
+        return keep.astype(bool), ang
 
     @staticmethod
     def pixel_line_candidates(n_lines, line3, min_points=6):

@@ -535,6 +535,62 @@ int pvb_camera_lidar_associate(pvb_ctx* ctx, int rows, int cols, const float* li
   return PVB_OK;
 }
 
+// ---- CameraLidarLineAssociate::Filter (joint_optimization/CameraLidarLineAssociate.cpp:628-715) on pairs in the camera frame -----------------
+namespace {
+// projected length (px) of a camera-frame LiDAR line: CamToImage of both ends, BreakToSegments(100), seam pieces skipped (:676-687)
+float projected_length(int rows, int cols, const double* s3, const double* e3) {
+  float ua, va, ub, vb;
+  cam_to_image_f32((float)s3[0], (float)s3[1], (float)s3[2], rows, cols, ua, va);
+  cam_to_image_f32((float)e3[0], (float)e3[1], (float)e3[2], rows, cols, ub, vb);
+  const float a[2] = {ua, va}, b[2] = {ub, vb};
+  const auto seg = break_to_segments(rows, cols, a, b, 100);
+  float len = 0;
+  for (size_t i = 0; i + 1 < seg.size(); ++i) {
+    if (std::abs(seg[i].first - seg[i + 1].first) > 0.8 * cols) continue;
+    const float dx = seg[i].first - seg[i + 1].first, dy = seg[i].second - seg[i + 1].second;
+    len += std::sqrt(dx * dx + dy * dy);
+  }
+  return len;
+}
+}  // namespace
+
+int pvb_filter_line_pairs(int rows, int cols, int n, const float* image_line4, const double* start3, const double* end3, int filter_by_angle, int filter_by_length,
+                          unsigned char* keep, float* angle) {
+  if (rows <= 0 || cols <= 0 || n < 0 || (n > 0 && (!image_line4 || !start3 || !end3 || !keep)) || (filter_by_angle && n > 0 && !angle)) return PVB_ERR_ARG;
+  for (int i = 0; i < n; ++i) {
+    const double* ls = start3 + 3 * (size_t)i; const double* le = end3 + 3 * (size_t)i;
+    bool ok = true;
+    if (filter_by_angle) {
+      // the two great-circle planes: LiDAR line and image line, each through the sphere centre, normalised as 4-vectors (:641-649)
+      double pl_lidar[4], pl_img[4], p1[3], p2[3];
+      plane_through_origin(ls, le, pl_lidar); normalize4(pl_lidar);
+      image_to_cam_f64(image_line4[4 * i], image_line4[4 * i + 1], rows, cols, p1);
+      image_to_cam_f64(image_line4[4 * i + 2], image_line4[4 * i + 3], rows, cols, p2);
+      plane_through_origin(p1, p2, pl_img); normalize4(pl_img);
+      const double deg = plane_angle(pl_lidar, pl_img, true) * 180.0 / M_PI;
+      ok = !(deg > 5);                                                                                // :651
+      if (ok) {
+        angle[i] = (float)deg;
+        const double half_arc = vector_angle(p1, p2) / 2.0;
+        const double mid[3] = {(p1[0] + p2[0]) / 2.0, (p1[1] + p2[1]) / 2.0, (p1[2] + p2[2]) / 2.0};
+        double sp[3], ep[3];
+        project_to_plane(ls, pl_img, sp); project_to_plane(le, pl_img, ep);
+        ok = !(vector_angle(sp, mid) > half_arc) && !(vector_angle(ep, mid) > half_arc);              // :660-663
+      }
+      if (ok) {                                                                                       // both ends pushed to radius 5 must stay within 0.4 of the image plane (:665-670)
+        const double ns = std::sqrt(sq(ls[0]) + sq(ls[1]) + sq(ls[2])), ne = std::sqrt(sq(le[0]) + sq(le[1]) + sq(le[2]));
+        const double a5[3] = {ls[0] / ns * 5, ls[1] / ns * 5, ls[2] / ns * 5}, b5[3] = {le[0] / ne * 5, le[1] / ne * 5, le[2] / ne * 5};
+        const double da = std::fabs(pl_img[0] * a5[0] + pl_img[1] * a5[1] + pl_img[2] * a5[2] + pl_img[3]);
+        const double db = std::fabs(pl_img[0] * b5[0] + pl_img[1] * b5[1] + pl_img[2] * b5[2] + pl_img[3]);
+        ok = !((float)std::min(da, db) > 0.4);
+      }
+    }
+    if (ok && filter_by_length) { const float len = projected_length(rows, cols, ls, le); ok = !(len < 100.f || len > 2000.f); }   // :688-692
+    keep[i] = ok ? 1 : 0;
+  }
+  return PVB_OK;
+}
+
 // ---- pixel-space Associate, first stage (joint_optimization/CameraLidarLineAssociate.cpp:22-102) -----------------------------------------
 // image lines -> sub-line mid points: BreakToSegments(line, 70), pieces across the +-pi seam skipped (:38-54)
 int pvb_pixel_sub_lines(int rows, int cols, const float* lines4, int n_lines, int cap, float* mid2, int* sub_to_line) {

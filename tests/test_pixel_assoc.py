@@ -91,3 +91,35 @@ def test_pixel_line_neighbors_kernel_is_bit_exact(gpu_ctx, oracle):
     l3, dd, _ = gpu_ctx.pixel_line_neighbors(ROWS, COLS, np.array([[100.0, 100.0, 120.0, 110.0]], np.float32), fr["cloud"][:100], T)
     o3, od, _ = oracle.pixel_line_neighbors(ROWS, COLS, np.array([[100.0, 100.0, 120.0, 110.0]], np.float32), fr["cloud"][:100], T)
     assert np.array_equal(l3, o3) and np.all(l3[:, 1:] == -1) and np.array_equal(dd, od)
+
+
+def test_filter_line_pairs_matches_oracle_and_geometry(oracle):
+    """CameraLidarLineAssociate::Filter (:628-715): both branches against the oracle, and the angle branch against its geometric meaning."""
+    fr, T, rng = _scene(34)
+    ends_cam = fr["end_points"].reshape(-1, 2, 3) @ T[:3, :3].T + T[:3, 3]
+    S = len(ends_cam)
+    px = oracle.cam_to_image(ROWS, COLS, ends_cam.reshape(-1, 3)).reshape(-1, 4)
+    # every LiDAR segment paired with (a) its own projection, (b) the projection stretched beyond both ends, (c) a tilted line, (d) a far away line
+    own = px + rng.normal(0, 1.0, px.shape)
+    centre = (px[:, :2] + px[:, 2:]) / 2
+    stretched = np.concatenate([centre + 1.6 * (px[:, :2] - centre), centre + 1.6 * (px[:, 2:] - centre)], axis=1)
+    tilted = stretched + np.concatenate([np.full((S, 1), 400.0), np.zeros((S, 3))], axis=1)
+    far = stretched + 700.0
+    lines = np.concatenate([own, stretched, tilted, far]).astype(np.float32)
+    start = np.tile(ends_cam[:, 0], (4, 1)); end = np.tile(ends_cam[:, 1], (4, 1))
+    for by_angle, by_length in ((True, True), (True, False), (False, True), (False, False)):
+        k_o, a_o = oracle.filter_line_pairs(ROWS, COLS, lines, start, end, by_angle, by_length)
+        k_p, a_p = panovlm_b200.Context.filter_line_pairs(ROWS, COLS, lines, start, end, by_angle, by_length)
+        assert np.array_equal(k_o, k_p) and np.array_equal(a_o, a_p)
+        if not by_angle and not by_length:
+            assert k_p.all()
+    k, ang = panovlm_b200.Context.filter_line_pairs(ROWS, COLS, lines, start, end, True, False)
+    assert k[S:2 * S].mean() > 0.8                               # a longer image line that contains the LiDAR line passes
+    assert not k[3 * S:].any()                                   # a line hundreds of pixels away fails
+    assert np.all(ang[k] <= 5.0) and k[2 * S:3 * S].mean() < 0.5           # one end moved by 400 px: the great-circle planes differ by more than 5 deg
+    # length branch: a segment projected shorter than 100 px is dropped
+    short = np.array([[0.0, 0.0, 5.0]]), np.array([[0.02, 0.0, 5.0]])
+    kk, _ = panovlm_b200.Context.filter_line_pairs(ROWS, COLS, np.array([[2880.0, 1440.0, 2900.0, 1440.0]], np.float32), short[0], short[1], False, True)
+    assert not kk[0]
+    k0, a0 = panovlm_b200.Context.filter_line_pairs(ROWS, COLS, np.zeros((0, 4), np.float32), np.zeros((0, 3)), np.zeros((0, 3)), True, True)
+    assert len(k0) == 0
