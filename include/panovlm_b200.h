@@ -120,6 +120,15 @@ int pvb_frames_associate_point2plane(pvb_ctx* ctx, const double* poses, int n_ed
 /* correspondences of the last association, edge-major, query order within an edge (the reference's push_back
  * order): edge index, query index in nei.surfFlat, point in the nei sensor frame, plane in the ref sensor frame */
 int pvb_frames_get_point2plane(const pvb_ctx* ctx, long cap, int* edge, int* query, double* point3, double* plane4);
+/* AddLidarPointToPlaneResidual (util/Optimization.cpp:506-562) without a host round trip: the association above, then the accepted
+ * correspondences are compacted on the device (prefix sum) and written as residual blocks straight into the blocks-mode buffers -
+ * equivalent to pvb_frames_get_point2plane + pvb_build_point2plane_blocks_edges + pvb_blocks_set, edge-major in the reference's order.
+ * Frame f uses pose block block_offset + f of n_pose_blocks (joint problems keep the cameras in front).  n_extra host-built blocks
+ * (line-to-line, camera-LiDAR, ...; arrays as pvb_blocks_set, may be 0 / NULL) are appended behind them.  *n_blocks = total.          */
+int pvb_frames_point2plane_blocks(pvb_ctx* ctx, const double* poses, int n_edges, const int* ref, const int* nei, const pvb_assoc_params* prm,
+                                  int angle_residual, int normalize_distance, double weight, int block_offset, int n_pose_blocks, long n_extra,
+                                  const int* x_type, const int* x_ref, const int* x_nei, const int* x_normalize, const double* x_huber,
+                                  const double* x_consts, long* n_blocks);
 /* debug/parity view of the k-NN itself for one edge: indices into ref.surfLessFlat and float32 squared distances */
 int pvb_frames_knn(pvb_ctx* ctx, const double* poses, int ref, int nei, const pvb_assoc_params* prm, int* idx, float* d2);
 

@@ -114,7 +114,7 @@ EXPORTS = [
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
-    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges", "pvb_filter_line_pairs",
+    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges", "pvb_filter_line_pairs", "pvb_frames_point2plane_blocks",
     "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates",
 ]
 
@@ -262,6 +262,23 @@ class Context:
         e, q, pt, pl = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros((m, 3)), np.zeros((m, 4))
         self._ck(self._L.pvb_frames_get_point2plane(self._h, C.c_long(m), _p(e), _p(q), _p(pt), _p(pl)))
         return e, q, pt, pl
+
+    def frames_point2plane_blocks(self, poses, ref, nei, plane_tolerance, dist_threshold, angle_residual, normalize_distance, weight, n_pose_blocks, block_offset=0,
+                                  extra=None, k=10, cell_size=0.0):
+        """Association + residual blocks of all edges on the device (AddLidarPointToPlaneResidual); `extra`: a BlockList.view() of host-built blocks."""
+        prm = _AssocParams(plane_tolerance, dist_threshold, k, cell_size)
+        ref, nei = _arr(ref, np.int32), _arr(nei, np.int32)
+        n = C.c_long()
+        if extra is not None and len(extra["type"]):
+            xt, xr, xn, xz = (_arr(extra[key], np.int32) for key in ("type", "ref", "nei", "normalize"))
+            xh, xc = _arr(extra["huber"], np.float64), _arr(extra["consts"], np.float64).reshape(-1, 12)
+            args = (C.c_long(len(xt)), _p(xt), _p(xr), _p(xn), _p(xz), _p(xh), _p(xc))
+        else:
+            args = (C.c_long(0), None, None, None, None, None, None)
+        self._ck(self._L.pvb_frames_point2plane_blocks(self._h, _p(_arr(poses, np.float64)), C.c_int(len(ref)), _p(ref), _p(nei), C.byref(prm), C.c_int(int(angle_residual)),
+                                                       C.c_int(int(normalize_distance)), C.c_double(weight), C.c_int(block_offset), C.c_int(n_pose_blocks), *args, C.byref(n)))
+        self._n_blocks, self._nb = n.value, int(n_pose_blocks)
+        return n.value
 
     def frames_knn(self, poses, ref, nei, n_query, dist_threshold, k=10, cell_size=0.0):
         poses = _arr(poses, np.float64)

@@ -464,6 +464,35 @@ __global__ void __launch_bounds__(kTile, PVB_K3_MINB) k_eval_blocks(const EvalAr
   }
 }
 
+// ---- B1 on the device: the accepted correspondences of an association become residual blocks without leaving HBM ------------------------
+// flags (one byte per query slot) -> 32-bit flags for the prefix sum that compacts them
+__global__ void __launch_bounds__(256) k_flags_to_u32(const unsigned char* __restrict__ valid, long long n, uint32_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) out[i] = i < n ? (valid[i] ? 1u : 0u) : 0u;          // one extra element: its exclusive sum is the total
+}
+__global__ void __launch_bounds__(256) k_gather_u32(const uint32_t* __restrict__ src, const int* __restrict__ idx, int n, uint32_t* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+// slot s (valid) -> block row pos[s]: Point2Plane_Angle / _Meter with the reference's Huber width (util/Optimization.cpp:513-517, 541-557),
+// constants SoA consts[k * n_total + row] = point (0..2) | plane (3..6) | weight (7)
+__global__ void __launch_bounds__(256) k_blocks_from_point2plane(const unsigned char* __restrict__ valid, const uint32_t* __restrict__ pos, long long n_slots,
+                                                                 const double* __restrict__ point, const double* __restrict__ plane, int type, int normalize, double huber,
+                                                                 double weight, long long n_total, int* __restrict__ b_type, int* __restrict__ b_norm,
+                                                                 double* __restrict__ b_huber, double* __restrict__ b_consts, uint32_t* __restrict__ b_orig) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !valid[s]) return;
+  const long long r = pos[s];
+  b_type[r] = type; b_norm[r] = normalize; b_huber[r] = huber; b_orig[r] = (uint32_t)r;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) b_consts[(size_t)k * n_total + r] = point[s * 3 + k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) b_consts[(size_t)(3 + k) * n_total + r] = plane[s * 4 + k];
+  b_consts[(size_t)7 * n_total + r] = weight;
+#pragma unroll
+  for (int k = 8; k < 12; ++k) b_consts[(size_t)k * n_total + r] = 0.0;
+}
+
 // ---- K4: sum the per-tile partials of each edge / frame in tile order --------------------------------------------------
 // Stage 1: block (group, chunk) sums its share of the group's partial rows (8 slices x 32 value lanes, slices added in
 // order) into chunk_out[group][chunk][NV]; stage 2 (k_sum_chunks) adds the chunks in order.  Every order is fixed =>

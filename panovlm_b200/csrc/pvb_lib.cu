@@ -739,6 +739,106 @@ int pvb_frames_associate_point2plane(pvb_ctx* ctx, const double* poses, int n_ed
   return PVB_OK;
 }
 
+// AddLidarPointToPlaneResidual without the host round trip: associate, compact the accepted correspondences with a prefix sum and write the
+// residual blocks (edge-major, query order inside an edge = the reference's push_back order) straight into the blocks-mode buffers; host-built
+// extra blocks (line-to-line, camera-LiDAR, ...) are appended behind them as further edges.
+int pvb_frames_point2plane_blocks(pvb_ctx* ctx, const double* poses, int n_edges, const int* ref, const int* nei, const pvb_assoc_params* prm, int angle_residual,
+                                  int normalize_distance, double weight, int block_offset, int n_pose_blocks, long n_extra, const int* x_type, const int* x_ref,
+                                  const int* x_nei, const int* x_normalize, const double* x_huber, const double* x_consts, long* n_blocks) {
+  if (!ctx || !poses || n_edges < 0 || (n_edges > 0 && (!ref || !nei)) || n_extra < 0 || (n_extra > 0 && (!x_type || !x_ref || !x_nei || !x_normalize || !x_huber || !x_consts)))
+    return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_frames_point2plane_blocks: bad arguments") : PVB_ERR_ARG;
+  if (block_offset < 0 || n_pose_blocks < block_offset + ctx->n_frames) return ctx->fail(PVB_ERR_ARG, "pvb_frames_point2plane_blocks: %d pose blocks do not hold %d frames at offset %d", n_pose_blocks, ctx->n_frames, block_offset);
+  if (!ctx->g_edge_ref.empty()) return ctx->fail(PVB_ERR_STATE, "pvb_frames_point2plane_blocks: not available with a global edge list (sharded pose graph)");
+  const int nb = n_pose_blocks;
+  for (long i = 0; i < n_extra; ++i) {
+    if (x_ref[i] < 0 || x_ref[i] >= nb || x_nei[i] < 0 || x_nei[i] >= nb) return ctx->fail(PVB_ERR_ARG, "extra block %ld: pose index out of range", i);
+    if (x_type[i] < 0 || x_type[i] > PVB_LINE2LINE_ANGLE) return ctx->fail(PVB_ERR_ARG, "extra block %ld: unknown residual type %d", i, x_type[i]);
+  }
+  CK(cudaSetDevice(ctx->device));
+  long long slots = 0; std::vector<int> sb;
+  int rc = frames_run(ctx, poses, n_edges, ref, nei, prm, false, &slots, &sb); if (rc) return rc;
+  // ---- compaction of the accepted slots: pos[s] = row of slot s, pos[slots] = their number
+  CK(ctx->m_a.ensure((size_t)(slots + 1) * 4)); CK(ctx->m_b.ensure((size_t)(slots + 1) * 4)); CK(ctx->m_c.ensure((size_t)(n_edges + 1) * 4)); CK(ctx->m_d.ensure((size_t)(n_edges + 1) * 4));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
+  k_flags_to_u32<<<(unsigned)((slots + 256) / 256), 256, 0, ctx->stream>>>(ctx->f_valid.as<unsigned char>(), slots, ctx->m_a.as<uint32_t>());
+  CKL();
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->m_a.as<uint32_t>(), ctx->m_b.as<uint32_t>(), (int)(slots + 1), ctx->stream);
+  CK(ctx->m_e.ensure(tmp));
+  size_t tb = ctx->m_e.cap;
+  CK(cub::DeviceScan::ExclusiveSum(ctx->m_e.p, tb, ctx->m_a.as<uint32_t>(), ctx->m_b.as<uint32_t>(), (int)(slots + 1), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_c.p, sb.data(), (size_t)(n_edges + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_gather_u32<<<(n_edges + 256) / 256, 256, 0, ctx->stream>>>(ctx->m_b.as<uint32_t>(), ctx->m_c.as<int>(), n_edges + 1, ctx->m_d.as<uint32_t>());
+  CKL();
+  std::vector<uint32_t> row_begin(n_edges + 1);                      // first row of every association edge
+  CK(cudaMemcpyAsync(row_begin.data(), ctx->m_d.p, (size_t)(n_edges + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const long long n_dev = row_begin[n_edges], n = n_dev + n_extra;
+  ctx->a_edge.clear(); ctx->a_query.clear(); ctx->a_point.clear(); ctx->a_plane.clear();     // the correspondences stay on the device in this path
+  // ---- edges and tiles: the association edges in their order, then the extra blocks grouped by (ref, nei) like pvb_blocks_set
+  ctx->bn = n; ctx->nb = nb; ctx->b_has_rows = ctx->b_has_sys = false;
+  ctx->edge_ref.clear(); ctx->edge_nei.clear(); ctx->edge_tile_begin.clear();
+  std::vector<BlockTile> tiles;
+  for (int e = 0; e < n_edges; ++e) {
+    ctx->edge_ref.push_back(block_offset + ref[e]); ctx->edge_nei.push_back(block_offset + nei[e]); ctx->edge_tile_begin.push_back((int)tiles.size());
+    for (long long s0 = row_begin[e]; s0 < row_begin[e + 1]; s0 += kTile) tiles.push_back(BlockTile{e, (int)s0, (int)std::min<long long>(kTile, row_begin[e + 1] - s0), 0});
+  }
+  std::vector<uint32_t> order(n_extra);
+  for (long i = 0; i < n_extra; ++i) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (long long)x_ref[a] * nb + x_nei[a] < (long long)x_ref[b] * nb + x_nei[b]; });
+  for (long i = 0; i < n_extra;) {
+    long j = i;
+    const int er = x_ref[order[i]], en = x_nei[order[i]];
+    while (j < n_extra && x_ref[order[j]] == er && x_nei[order[j]] == en) ++j;
+    const int e = (int)ctx->edge_ref.size();
+    ctx->edge_ref.push_back(er); ctx->edge_nei.push_back(en); ctx->edge_tile_begin.push_back((int)tiles.size());
+    for (long s0 = i; s0 < j; s0 += kTile) tiles.push_back(BlockTile{e, (int)(n_dev + s0), (int)std::min<long>(kTile, j - s0), 0});
+    i = j;
+  }
+  ctx->edge_tile_begin.push_back((int)tiles.size());
+  ctx->b_tiles = (int)tiles.size();
+  ctx->b_orig.clear();
+  const int ne = (int)ctx->edge_ref.size();
+  CK(ctx->b_tile.ensure(std::max<size_t>(16, tiles.size() * sizeof(BlockTile))));
+  CK(ctx->b_eref.ensure(std::max<size_t>(16, (size_t)ne * 4))); CK(ctx->b_enei.ensure(std::max<size_t>(16, (size_t)ne * 4)));
+  CK(ctx->b_tbegin.ensure((size_t)(ne + 1) * 4));
+  CK(ctx->b_type.ensure(std::max<size_t>(16, (size_t)n * 4))); CK(ctx->b_norm.ensure(std::max<size_t>(16, (size_t)n * 4)));
+  CK(ctx->b_huber.ensure(std::max<size_t>(16, (size_t)n * 8))); CK(ctx->b_consts.ensure(std::max<size_t>(16, (size_t)n * 96)));
+  CK(ctx->b_orig_d.ensure(std::max<size_t>(16, (size_t)n * 4)));
+  CK(ctx->b_r.ensure(std::max<size_t>(16, (size_t)n * 8))); CK(ctx->b_J.ensure(std::max<size_t>(16, (size_t)n * 96)));
+  CK(ctx->b_part.ensure(std::max<size_t>(16, tiles.size() * 92 * 8))); CK(ctx->b_esys.ensure(std::max<size_t>(16, (size_t)ne * 92 * 8)));
+  CK(ctx->h_esys.ensure(std::max<size_t>(16, (size_t)ne * 92 * 8)));
+  if (n_dev > 0) {
+    k_blocks_from_point2plane<<<(unsigned)((slots + 255) / 256), 256, 0, ctx->stream>>>(ctx->f_valid.as<unsigned char>(), ctx->m_b.as<uint32_t>(), slots, ctx->f_point.as<double>(),
+        ctx->f_plane.as<double>(), angle_residual ? PVB_P2PLANE_ANGLE : PVB_P2PLANE_METER, normalize_distance, angle_residual ? 2 * M_PI / 180.0 : 0.2, weight, n,
+        ctx->b_type.as<int>(), ctx->b_norm.as<int>(), ctx->b_huber.as<double>(), ctx->b_consts.as<double>(), ctx->b_orig_d.as<uint32_t>());
+    CKL();
+  }
+  std::vector<int> s_type(n_extra), s_norm(n_extra); std::vector<double> s_huber(n_extra), s_consts((size_t)n_extra * 12); std::vector<uint32_t> s_orig(n_extra);
+  for (long r = 0; r < n_extra; ++r) {
+    const uint32_t o = order[r];
+    s_type[r] = x_type[o]; s_norm[r] = x_normalize[o]; s_huber[r] = x_huber[o]; s_orig[r] = (uint32_t)(n_dev + o);
+    for (int k = 0; k < 12; ++k) s_consts[(size_t)k * n_extra + r] = x_consts[(size_t)o * 12 + k];
+  }
+  if (n_extra > 0) {
+    CK(cudaMemcpyAsync(ctx->b_type.as<int>() + n_dev, s_type.data(), (size_t)n_extra * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_norm.as<int>() + n_dev, s_norm.data(), (size_t)n_extra * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_huber.as<double>() + n_dev, s_huber.data(), (size_t)n_extra * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_orig_d.as<uint32_t>() + n_dev, s_orig.data(), (size_t)n_extra * 4, cudaMemcpyHostToDevice, ctx->stream));
+    for (int k = 0; k < 12; ++k)
+      CK(cudaMemcpyAsync(ctx->b_consts.as<double>() + (size_t)k * n + n_dev, s_consts.data() + (size_t)k * n_extra, (size_t)n_extra * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->b_tile.p, tiles.data(), tiles.size() * sizeof(BlockTile), cudaMemcpyHostToDevice, ctx->stream));
+  if (ne > 0) {
+    CK(cudaMemcpyAsync(ctx->b_eref.p, ctx->edge_ref.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_enei.p, ctx->edge_nei.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(ctx->b_tbegin.p, ctx->edge_tile_begin.data(), (size_t)(ne + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (n_blocks) *n_blocks = (long)n;
+  return PVB_OK;
+}
+
 int pvb_frames_get_point2plane(const pvb_ctx* ctx, long cap, int* edge, int* query, double* point3, double* plane4) {
   if (!ctx) return PVB_ERR_ARG;
   const long n = std::min<long>(cap, (long)ctx->a_edge.size());

@@ -52,12 +52,30 @@ def build_problem(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa
     return out, pairs, (bl_cl.n, bl_ll.n)
 
 
-def optimize(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa_to_R):
-    """One call of CameraLidarOptimizer::Optimize: build the three residual families at the current estimate and solve."""
+def optimize(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa_to_R, device_blocks=True):
+    """One call of CameraLidarOptimizer::Optimize: build the three residual families at the current estimate and solve.
+    device_blocks: the LiDAR point-to-plane correspondences become residual blocks on the device (Context.frames_point2plane_blocks); only the
+    camera-LiDAR blocks and the other LiDAR families are built on the host and appended."""
     n = len(data["frames"])
-    v, pairs, counts = build_problem(ctx, data, cams, lidars, points, cfg, aa_to_R)
     poses = np.concatenate([cams, lidars])
-    ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], 2 * n)
+    if device_blocks and cfg.lidar.point_to_plane:
+        frames = data["frames"]
+        pairs = associate_lines(ctx, frames, data["image_lines"], cams, lidars, data["rows"], data["cols"], aa_to_R)
+        bl_cl = BlockList(2 * sum(len(p[0]) for p in pairs.values()) + 16)
+        for (ci, li), (il, ll, s, e, ang) in pairs.items():
+            if len(il):
+                Context.build_camera_lidar_blocks(bl_cl, data["rows"], data["cols"], data["image_lines"][ci][il], s, e, np.ones(len(il), np.float32), ci, n + li,
+                                                  cfg.camera_lidar_weight)
+        bl_ll, _, mine = odometry.build_problem(ctx, frames, lidars, cfg.lidar, aa_to_R, host_point2plane=False)
+        a, b = bl_cl.view(), bl_ll.view()
+        extra = {k: np.concatenate([a[k], b[k] + n if k in ("ref", "nei") else b[k]]) for k in ("type", "ref", "nei", "normalize", "huber", "consts")}
+        ref, nei = np.array([e[0] for e in mine], np.int32), np.array([e[1] for e in mine], np.int32)
+        n_total = ctx.frames_point2plane_blocks(lidars, ref, nei, cfg.lidar.plane_tolerance, cfg.lidar.plane_dis_threshold, cfg.lidar.angle_residual,
+                                                cfg.lidar.normalize_distance, 1.0, 2 * n, block_offset=n, extra=extra)
+        v, counts = None, (bl_cl.n, n_total - bl_cl.n)
+    else:
+        v, pairs, counts = build_problem(ctx, data, cams, lidars, points, cfg, aa_to_R)
+        ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], 2 * n)
     ctx.reproj_set(data["cam"], data["point"], data["bearing"], n, len(points), weight=cfg.camera_weight, huber=4.0 * np.pi / 180.0)   # :431-432
     const = np.zeros((2 * n, 6), np.uint8)
     const[:n, :3] = 0 if cfg.refine_camera_rotation else 1                               # :466-476

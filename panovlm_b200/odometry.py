@@ -48,10 +48,12 @@ def pose_graph_edges(poses, cfg: OdometryConfig, aa_to_R):
     return [(i, j) for i in range(n) for j in neighbors[i] if 0 <= j < n and j != i]
 
 
-def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, frame_range=None):
+def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, frame_range=None, host_point2plane=True):
     """One outer iteration's residual blocks (the Add*Residual calls of RefinePose); returns a BlockList and the GLOBAL edge list.
     frame_range = (lo, hi): only the edges whose reference frame lies in [lo, hi) are associated and turned into blocks (one rank's shard of a
-    pose graph split across GPUs); the clouds of all frames stay available as halo."""
+    pose graph split across GPUs); the clouds of all frames stay available as halo.
+    host_point2plane = False leaves the point-to-plane family to Context.frames_point2plane_blocks (association and blocks without a host round trip):
+    the BlockList then only holds the other families and the edge list of the shard is returned as third value."""
     n = len(frames)
     R_wl, t_wl = world_from_pose_blocks(poses, aa_to_R)
     all_edges = pose_graph_edges(poses, cfg, aa_to_R)
@@ -87,6 +89,8 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
                 Context.build_line2line_blocks(bl, lf[j], world[j], nl[k], a[k], b[k], i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
     if cfg.point_to_plane:                                          # AddLidarPointToPlaneResidual (Optimization.cpp:506-562)
         ctx.frames_set([f["surfLessFlat"] for f in frames], [f["surfFlat"] for f in frames])
+    if not host_point2plane:
+        return bl, all_edges, edges
     if cfg.point_to_plane and edges:
         ref = np.array([e[0] for e in edges], np.int32)
         nei = np.array([e[1] for e in edges], np.int32)
@@ -96,11 +100,19 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
     return bl, all_edges
 
 
-def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R):
-    """RefinePose: build the problem at `poses`, fix the first frame, solve (LidarOdometry.cpp:15-114)."""
-    bl, edges = build_problem(ctx, frames, poses, cfg, aa_to_R)
-    v = bl.view()
-    ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
+def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, device_blocks=True):
+    """RefinePose: build the problem at `poses`, fix the first frame, solve (LidarOdometry.cpp:15-114).  device_blocks: the point-to-plane
+    correspondences become residual blocks on the device (no download / rebuild / upload); the other families are built on the host and appended."""
+    if device_blocks and cfg.point_to_plane:
+        bl, edges, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, host_point2plane=False)
+        ref, nei = np.array([e[0] for e in mine], np.int32), np.array([e[1] for e in mine], np.int32)
+        n_total = ctx.frames_point2plane_blocks(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, cfg.angle_residual, cfg.normalize_distance, 1.0,
+                                                len(frames), extra=bl.view())
+        bl.n = n_total
+    else:
+        bl, edges = build_problem(ctx, frames, poses, cfg, aa_to_R)
+        v = bl.view()
+        ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
     mask = np.zeros(len(frames), np.uint8); mask[0] = 1
     new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
     summary["n_blocks"], summary["n_edges"] = bl.n, len(edges)

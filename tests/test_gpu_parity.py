@@ -651,6 +651,62 @@ def test_odometry_outer_iteration_matches_oracle_loop(gpu_ctx, oracle):
     assert np.abs(p_gpu - truth).max() < np.abs(start - truth).max()
 
 
+def test_point2plane_blocks_built_on_the_device_equal_the_host_builders(gpu_ctx, oracle):
+    """pvb_frames_point2plane_blocks == pvb_frames_associate_point2plane + pvb_build_point2plane_blocks_edges + pvb_blocks_set: same rows bit for bit,
+    extra host blocks appended behind them, pose-block offset (joint layout), and the same RefinePose result through either path."""
+    from panovlm_b200 import BlockList, Context, odometry, synth
+    from scipy.spatial.transform import Rotation
+    frames = synth.make_sequence(5, n_az=600)
+    rng = np.random.default_rng(4)
+    R0 = [f["R_wl"] @ Rotation.from_rotvec(rng.normal(0, 0.01, 3) * (i > 0)).as_matrix() for i, f in enumerate(frames)]
+    t0 = [f["t_wl"] + rng.normal(0, 0.03, 3) * (i > 0) for i, f in enumerate(frames)]
+    poses = odometry.pose_blocks_from_world(R0, t0, oracle.R_to_aa)
+    cfg = odometry.OdometryConfig(line_to_line=False)
+    edges = odometry.pose_graph_edges(poses, cfg, oracle.aa_to_R)
+    ref, nei = np.array([e[0] for e in edges], np.int32), np.array([e[1] for e in edges], np.int32)
+    gpu_ctx.frames_set([f["surfLessFlat"] for f in frames], [f["surfFlat"] for f in frames])
+    # host path
+    e, q, pt, pl = gpu_ctx.frames_associate_point2plane(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, 10)
+    bl = BlockList(len(e) + 8)
+    Context.build_point2plane_blocks_edges(bl, e, pt, pl, ref, nei, True, True, 1.0)
+    v = bl.view()
+    gpu_ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
+    gpu_ctx.blocks_evaluate(poses, True, True)
+    r_h, J_h = gpu_ctx.blocks_rows()
+    H_h, g_h, c_h = gpu_ctx.blocks_dense_system()
+    # device path
+    n = gpu_ctx.frames_point2plane_blocks(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, True, True, 1.0, len(frames))
+    assert n == len(e) > 1000
+    gpu_ctx.blocks_evaluate(poses, True, True)
+    r_d, J_d = gpu_ctx.blocks_rows()
+    H_d, g_d, c_d = gpu_ctx.blocks_dense_system()
+    assert np.array_equal(r_h, r_d) and np.array_equal(J_h, J_d)
+    assert np.abs(H_h - H_d).max() <= 1e-12 * np.abs(H_h).max() and abs(c_h - c_d) <= 1e-12 * c_h
+    # extra host blocks behind the device rows + pose-block offset 3 (the joint layout keeps other blocks in front)
+    x = cases.random_blocks(7, 300, nb=len(frames) + 3)
+    n2 = gpu_ctx.frames_point2plane_blocks(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, True, True, 1.0, len(frames) + 3, block_offset=3,
+                                           extra=dict(type=x["type"], ref=x["ref"], nei=x["nei"], normalize=x["normalize"], huber=x["huber"], consts=x["consts"]))
+    assert n2 == n + 300
+    big = np.concatenate([x["poses"][:3], poses])
+    gpu_ctx.blocks_evaluate(big, True, True)
+    r2, J2 = gpu_ctx.blocks_rows()
+    assert np.array_equal(r2[:n], r_h) and np.array_equal(J2[:n], J_h)
+    xb = oracle.Blocks(x["type"], x["ref"], x["nei"], x["consts"], x["huber"], x["normalize"])
+    xr, xJ, _ = xb.evaluate(big, apply_loss=True)
+    assert (np.abs(r2[n:] - xr) / np.maximum(1e-9, np.abs(xr))).max() < 1e-7 and np.abs(J2[n:] - xJ).max() < 1e-6 * np.abs(xJ).max()
+    # RefinePose through either path
+    cfg2 = odometry.OdometryConfig()
+    p_dev, s_dev = odometry.refine_pose(gpu_ctx, frames, poses, cfg2, oracle.aa_to_R, device_blocks=True)
+    p_host, s_host = odometry.refine_pose(gpu_ctx, frames, poses, cfg2, oracle.aa_to_R, device_blocks=False)
+    assert s_dev["n_blocks"] == s_host["n_blocks"] and s_dev["iterations"] == s_host["iterations"] and s_dev["successful"] == s_host["successful"]
+    assert abs(s_dev["final_cost"] - s_host["final_cost"]) < 1e-9 * s_host["final_cost"]
+    assert np.abs(p_dev - p_host).max() < 1e-9
+    # no edges at all: only the extra blocks remain
+    n3 = gpu_ctx.frames_point2plane_blocks(poses, ref[:0], nei[:0], cfg.plane_tolerance, cfg.plane_dis_threshold, True, True, 1.0, len(frames) + 3, block_offset=3,
+                                           extra=dict(type=x["type"], ref=x["ref"], nei=x["nei"], normalize=x["normalize"], huber=x["huber"], consts=x["consts"]))
+    assert n3 == 300
+
+
 def test_frames_point2line_matches_oracle(gpu_ctx, oracle):
     """AssociatePoint2Line (5-NN + PCA line) for consecutive frames, both directions, non-trivial poses."""
     from panovlm_b200 import Context, BlockList, synth

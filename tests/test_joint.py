@@ -13,7 +13,13 @@ def test_joint_optimize_matches_oracle(gpu_ctx, oracle, refine_structure):
     d = synth.make_joint_problem(n_frames=6, n_points=200, n_az=600)
     n = 6
     cfg = joint.JointConfig(refine_structure=refine_structure, max_lm_iterations=12)
-    cams, lidars, points, summ, (v, const, pt_const) = joint.optimize(gpu_ctx, d, d["cams"], d["lidars"], d["points"], cfg, oracle.aa_to_R)
+    cams, lidars, points, summ, (v, const, pt_const) = joint.optimize(gpu_ctx, d, d["cams"], d["lidars"], d["points"], cfg, oracle.aa_to_R, device_blocks=False)
+    # the same call with the point-to-plane blocks built on the device: same problem (rows in another order), same answer up to rounding
+    cams2, lidars2, points2, summ2, _ = joint.optimize(gpu_ctx, d, d["cams"], d["lidars"], d["points"], cfg, oracle.aa_to_R, device_blocks=True)
+    for k in ("iterations", "successful", "unsuccessful", "termination", "n_camera_lidar_blocks", "n_lidar_blocks"):
+        assert summ[k] == summ2[k], (k, summ, summ2)
+    assert abs(summ["final_cost"] - summ2["final_cost"]) < 1e-9 * summ["final_cost"]
+    assert np.abs(np.concatenate([cams2, lidars2]) - np.concatenate([cams, lidars])).max() < 1e-8 and np.abs(points2 - points).max() < 1e-8
     assert summ["n_line_pairs"] >= 10 and summ["n_camera_lidar_blocks"] == 2 * summ["n_line_pairs"] and summ["n_lidar_blocks"] > 1000
     # the same problem through the oracle's dense LM
     blk = oracle.Blocks(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"])
