@@ -70,6 +70,14 @@ for name, kind in (("device", api.SOLVER_DEVICE), ("host", api.SOLVER_HOST)):
     s["n_blocks"] = bl.n
     out[f"lm_{name}"] = s
     out[f"pose_err_after_{name}"] = float(np.abs(new_poses - odometry.pose_blocks_from_world([f["R_wl"] for f in frames], [f["t_wl"] for f in frames], R_to_aa)).max())
+# one whole RefinePose (association + residual blocks + LM) with the blocks built on the host vs on the device
+ctx.blocks_set_linear_solver(api.SOLVER_DEVICE)
+for name, dev in (("host_blocks", False), ("device_blocks", True)):
+    for rep in range(2):
+        t = time.time()
+        p2, s2 = odometry.refine_pose(ctx, frames, poses, cfg, aa_to_R, device_blocks=dev)
+        out[f"refine_pose_{name}_s"] = time.time() - t
+    out[f"refine_pose_{name}_final_cost"] = s2["final_cost"]
 # the device Cholesky alone at this size
 rng2 = np.random.default_rng(2)
 nn = 6 * (n - 1)
