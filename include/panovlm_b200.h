@@ -197,6 +197,17 @@ int pvb_angle_votes(pvb_ctx* ctx, int rows, int cols, const float* lines4, int n
 int pvb_find_neighbors(int n_frames, const double* t_wl, const unsigned char* pose_valid, const unsigned char* frame_valid,
                        int neighbor_size, int* out_offsets, int* out_neighbors, int cap);
 
+/* CameraLidarOptimizer::NeighborEachFrame (joint_optimization/CameraLidarOptimizer.cpp:551-610): per image the LiDAR frames its lines are
+ * associated with - a temporal window of neighbor_size indices, or the neighbor_size nearest LiDAR centres (+ previous / next index).
+ * t_wc / t_wl: camera / LiDAR positions (n x 3); CSR output as pvb_find_neighbors; returns the number of entries or < 0.  Host only.       */
+int pvb_neighbor_each_frame(int n_frames, int n_lidars, int neighbor_size, int temporal, const double* t_wc, const unsigned char* frame_pose_valid,
+                            const double* t_wl, const unsigned char* lidar_pose_valid, const unsigned char* lidar_valid, int* out_offsets,
+                            int* out_neighbors, int cap);
+/* CameraLidarOptimizer::LidarMaskByTrack (:612-642) after GenerateTracks (pvb_generate_line_tracks): mask[seg_off[f] + line] = 1 for every
+ * LiDAR line that belongs to a track.  Host only.                                                                                      */
+int pvb_lidar_mask_by_track(int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int n_lidars, const int* seg_off,
+                            unsigned char* mask);
+
 typedef struct {
   const float* corner_local; int n_corner;      /* cornerLessSharp, n x 4, sensor frame                                 */
   const int* p2s_off; const int* p2s_ids;       /* point_to_segment as CSR (sensors/Velodyne.h:89)                       */

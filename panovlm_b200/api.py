@@ -114,7 +114,7 @@ EXPORTS = [
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
-    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges", "pvb_filter_line_pairs", "pvb_frames_point2plane_blocks",
+    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges", "pvb_filter_line_pairs", "pvb_frames_point2plane_blocks", "pvb_neighbor_each_frame", "pvb_lidar_mask_by_track",
     "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates",
 ]
 
@@ -376,6 +376,33 @@ class Context:
         if m < 0:
             raise PvbError(f"pvb_find_neighbors: code {m}")
         return [out[off[i]:off[i + 1]].tolist() for i in range(n)]
+
+    @staticmethod
+    def neighbor_each_frame(n_frames, n_lidars, neighbor_size, temporal, t_wc=None, frame_pose_valid=None, t_wl=None, lidar_pose_valid=None, lidar_valid=None):
+        tc = None if t_wc is None else _arr(t_wc, np.float64).reshape(-1, 3)
+        tl = None if t_wl is None else _arr(t_wl, np.float64).reshape(-1, 3)
+        fpv = None if frame_pose_valid is None else _arr(frame_pose_valid, np.uint8)
+        lpv = None if lidar_pose_valid is None else _arr(lidar_pose_valid, np.uint8)
+        lv = None if lidar_valid is None else _arr(lidar_valid, np.uint8)
+        off, out = np.zeros(n_frames + 1, np.int32), np.zeros(max(1, n_frames * (neighbor_size + 2)), np.int32)
+        m = load_library().pvb_neighbor_each_frame(C.c_int(n_frames), C.c_int(n_lidars), C.c_int(neighbor_size), C.c_int(int(temporal)), _p(tc), _p(fpv), _p(tl), _p(lpv),
+                                                   _p(lv), _p(off), _p(out), C.c_int(len(out)))
+        if m < 0:
+            raise PvbError(f"pvb_neighbor_each_frame: code {m}")
+        return [out[off[i]:off[i + 1]].tolist() for i in range(n_frames)]
+
+    @staticmethod
+    def lidar_mask_by_track(tracks, n_segments_per_lidar):
+        """tracks: list of (m, 2) arrays of (frame, line) features as returned by generate_line_tracks; returns one bool mask per LiDAR frame."""
+        track_off = np.concatenate([[0], np.cumsum([len(t) for t in tracks])]).astype(np.int32)
+        feats = np.concatenate([np.asarray(t, np.int32).reshape(-1, 2) for t in tracks]) if len(tracks) else np.zeros((0, 2), np.int32)
+        ff, fl = _arr(feats[:, 0], np.int32), _arr(feats[:, 1], np.int32)
+        seg_off = np.concatenate([[0], np.cumsum(n_segments_per_lidar)]).astype(np.int32)
+        mask = np.zeros(max(1, int(seg_off[-1])), np.uint8)
+        rc = load_library().pvb_lidar_mask_by_track(C.c_int(len(track_off) - 1), _p(track_off), _p(ff), _p(fl), C.c_int(len(seg_off) - 1), _p(seg_off), _p(mask))
+        if rc < 0:
+            raise PvbError(f"pvb_lidar_mask_by_track: code {rc}")
+        return [mask[seg_off[i]:seg_off[i + 1]].astype(bool) for i in range(len(seg_off) - 1)]
 
     def transform_cloud(self, xyzi, R, t):
         a = _arr(xyzi, np.float32).reshape(-1, 4)

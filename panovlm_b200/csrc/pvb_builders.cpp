@@ -213,6 +213,57 @@ int pvb_find_neighbors(int n, const double* t_wl, const unsigned char* pose_vali
   return total;
 }
 
+// CameraLidarOptimizer::NeighborEachFrame (joint_optimization/CameraLidarOptimizer.cpp:551-610): the LiDAR frames every image is associated with.
+// temporal: a window of neighbor_size LiDAR indices around the image index, shifted to stay inside [0, n_lidars) (:556-567);
+// otherwise the neighbor_size LiDARs nearest to the camera centre (float32 k-NN over the LiDARs with a valid pose and valid data) plus the previous /
+// next LiDAR index when they are not among them (:591-596); images without a valid pose get no neighbour.
+int pvb_neighbor_each_frame(int n_frames, int n_lidars, int neighbor_size, int temporal, const double* t_wc, const unsigned char* frame_pose_valid, const double* t_wl,
+                            const unsigned char* lidar_pose_valid, const unsigned char* lidar_valid, int* out_offsets, int* out_neighbors, int cap) {
+  if (n_frames < 0 || n_lidars < 0 || neighbor_size < 0 || !out_offsets || (cap > 0 && !out_neighbors) || (!temporal && n_frames > 0 && (!t_wc || (n_lidars > 0 && !t_wl)))) return PVB_ERR_ARG;
+  int total = 0;
+  out_offsets[0] = 0;
+  std::vector<int> centre_lidar; std::vector<float> centre;
+  if (!temporal)
+    for (int i = 0; i < n_lidars; ++i)
+      if ((!lidar_pose_valid || lidar_pose_valid[i]) && (!lidar_valid || lidar_valid[i])) { centre_lidar.push_back(i); for (int k = 0; k < 3; ++k) centre.push_back((float)t_wl[3 * i + k]); }
+  const int m = (int)centre_lidar.size();
+  for (int f = 0; f < n_frames; ++f) {
+    std::vector<int> nb;
+    if (temporal) {
+      int lo = std::max(0, f - neighbor_size / 2);
+      const int hi = std::min(n_lidars, lo + neighbor_size);
+      lo = std::max(0, hi - neighbor_size);
+      for (int l = lo; l < hi; ++l) nb.push_back(l);
+    } else if (!frame_pose_valid || frame_pose_valid[f]) {
+      const float q[3] = {(float)t_wc[3 * f], (float)t_wc[3 * f + 1], (float)t_wc[3 * f + 2]};
+      std::vector<std::pair<float, int>> d(m);
+      for (int j = 0; j < m; ++j) d[j] = {sqdist_f32(q[0], q[1], q[2], centre[3 * j], centre[3 * j + 1], centre[3 * j + 2]), j};
+      std::sort(d.begin(), d.end());
+      for (int j = 0; j < std::min(neighbor_size, m); ++j) nb.push_back(centre_lidar[d[j].second]);
+      const std::set<int> have(nb.begin(), nb.end());
+      if (have.count(f - 1) == 0 && f - 1 >= 0) nb.push_back(f - 1);
+      if (have.count(f + 1) == 0 && f + 1 < n_lidars) nb.push_back(f + 1);
+    }
+    for (int v : nb) { if (total >= cap) return PVB_ERR_NOMEM; out_neighbors[total++] = v; }
+    out_offsets[f + 1] = total;
+  }
+  return total;
+}
+
+// CameraLidarOptimizer::LidarMaskByTrack (:612-642), the part after GenerateTracks: a LiDAR line takes part in the camera-LiDAR association only when it
+// belongs to a line track.  seg_off: n_lidars + 1 offsets of every frame's segments in `mask`.
+int pvb_lidar_mask_by_track(int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int n_lidars, const int* seg_off, unsigned char* mask) {
+  if (n_tracks < 0 || n_lidars < 0 || !seg_off || (n_tracks > 0 && (!track_off || !feat_frame || !feat_line)) || (n_lidars > 0 && seg_off[n_lidars] > 0 && !mask)) return PVB_ERR_ARG;
+  std::fill(mask, mask + seg_off[n_lidars], (unsigned char)0);
+  for (int t = 0; t < n_tracks; ++t)
+    for (int k = track_off[t]; k < track_off[t + 1]; ++k) {
+      const int fr = feat_frame[k], ln = feat_line[k];
+      if (fr < 0 || fr >= n_lidars || ln < 0 || seg_off[fr] + ln >= seg_off[fr + 1]) return PVB_ERR_ARG;
+      mask[seg_off[fr] + ln] = 1;
+    }
+  return PVB_OK;
+}
+
 int pvb_line2line_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, double dist_threshold, int* n_out, int* nei_line, int* ref_line,
                             double* point_a3, double* point_b3) {
   if (!ctx || !ref || !nei || !n_out) return PVB_ERR_ARG;

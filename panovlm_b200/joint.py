@@ -25,14 +25,23 @@ def _T_from_block(block, aa_to_R):
     return T
 
 
-def associate_lines(ctx: Context, frames, image_lines, cams, lidars, rows, cols, aa_to_R):
-    """AssociateLineMulti with neighbor_size_joint = 1 (CameraLidarOptimizer.cpp:330-384): image i against LiDAR i at T_cl = T_cw T_wl (:347-353)."""
+def associate_lines(ctx: Context, frames, image_lines, cams, lidars, rows, cols, aa_to_R, neighbors=None, lidar_masks=None, image_masks=None):
+    """AssociateLineMulti (CameraLidarOptimizer.cpp:330-384): image i against every LiDAR of neighbors[i] at T_cl = T_cw T_wl (:347-353), optionally
+    restricted to the LiDAR lines / image lines that belong to tracks (lidar_masks from Context.lidar_mask_by_track, :339-342).  neighbors = None:
+    neighbor_size_joint = 1 in temporal mode, i.e. LiDAR i (Context.neighbor_each_frame gives the general lists)."""
     pairs = {}
-    for i, f in enumerate(frames):
-        T_cl = _T_from_block(cams[i], aa_to_R) @ np.linalg.inv(_T_from_block(lidars[i], aa_to_R))
-        lf = LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], np.eye(3), np.zeros(3))
-        il, ll, s, e, ang = ctx.camera_lidar_associate(rows, cols, image_lines[i], lf, T_cl, True, True)
-        pairs[(i, i)] = (il, ll, s, e, ang)
+    n = len(frames)
+    if neighbors is None:
+        neighbors = Context.neighbor_each_frame(n, n, 1, True)
+    for i in range(n):
+        T_cw = _T_from_block(cams[i], aa_to_R)
+        for li in neighbors[i]:
+            f = frames[li]
+            T_cl = T_cw @ np.linalg.inv(_T_from_block(lidars[li], aa_to_R))
+            lf = LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], np.eye(3), np.zeros(3))
+            il, ll, s, e, ang = ctx.camera_lidar_associate(rows, cols, image_lines[i], lf, T_cl, True, True, None if image_masks is None else image_masks[i],
+                                                           None if lidar_masks is None else lidar_masks[li])
+            pairs[(i, li)] = (il, ll, s, e, ang)
     return pairs
 
 

@@ -256,3 +256,44 @@ def test_unique_line_pairs_matches_oracle_and_is_one_to_one(oracle):
     assert [x.tolist() for x in Context.unique_line_pairs([1, 2, 1], [0, 1, 1], [0.3, 0.5, 0.4])[:2]] == [[1], [0]]            # case 2: L2-B dropped
     assert [x.tolist() for x in Context.unique_line_pairs([1, 2, 1], [0, 1, 1], [0.5, 0.3, 0.4])[:2]] == [[2], [1]]            # case 3: L1-A dropped
     assert [x.tolist() for x in Context.unique_line_pairs([1, 2, 1], [0, 1, 1], [0.3, 0.5, 0.9])[:2]] == [[1, 2], [0, 1]]      # case 4: unchanged
+
+
+def test_neighbor_each_frame_and_lidar_mask_match_restatement():
+    """NeighborEachFrame / LidarMaskByTrack (joint_optimization/CameraLidarOptimizer.cpp:551-642) against a Python restatement."""
+    rng = np.random.default_rng(8)
+    # temporal windows (:556-567)
+    for n_frames, n_lidars, size in ((10, 10, 1), (10, 10, 4), (7, 5, 3), (3, 2, 6), (0, 0, 2)):
+        got = Context.neighbor_each_frame(n_frames, n_lidars, size, True)
+        for f in range(n_frames):
+            lo = max(0, f - size // 2); hi = min(n_lidars, lo + size); lo = max(0, hi - size)
+            assert got[f] == list(range(lo, hi))
+    # spatial: float32 k-NN over the usable LiDAR centres + previous / next index (:570-606)
+    n = 40
+    t_wl = np.cumsum(rng.normal(0, 0.5, (n, 3)), axis=0)
+    t_wc = t_wl + rng.normal(0, 0.05, (n, 3))
+    lpv, lv, fpv = (rng.random(n) > 0.15).astype(np.uint8), (rng.random(n) > 0.1).astype(np.uint8), (rng.random(n) > 0.1).astype(np.uint8)
+    got = Context.neighbor_each_frame(n, n, 5, False, t_wc, fpv, t_wl, lpv, lv)
+    usable = [i for i in range(n) if lpv[i] and lv[i]]
+    C32 = t_wl[usable].astype(np.float32)
+    for f in range(n):
+        if not fpv[f]:
+            assert got[f] == []
+            continue
+        q = t_wc[f].astype(np.float32)
+        d = (C32 - q) ** 2
+        d2 = (d[:, 0] + d[:, 1]) + d[:, 2]
+        order = np.lexsort((np.arange(len(usable)), d2))[:5]
+        exp = [usable[j] for j in order]
+        have = set(exp)
+        if f - 1 >= 0 and f - 1 not in have:
+            exp.append(f - 1)
+        if f + 1 < n and f + 1 not in have:
+            exp.append(f + 1)
+        assert got[f] == exp
+    # LidarMaskByTrack: lines that belong to a track are switched on
+    tracks = [np.array([[0, 2], [1, 0], [3, 1]]), np.array([[1, 3], [2, 0]])]
+    masks = Context.lidar_mask_by_track(tracks, [4, 5, 1, 2])
+    assert [m.tolist() for m in masks] == [[False, False, True, False], [True, False, False, True, False], [True], [False, True]]
+    assert [m.tolist() for m in Context.lidar_mask_by_track([], [2, 0])] == [[False, False], []]
+    with pytest.raises(Exception):
+        Context.lidar_mask_by_track([np.array([[0, 9]])], [4])
