@@ -321,6 +321,10 @@ int pvb_build_line2line_blocks(const pvb_line_frame* nei, const float* nei_corne
 int pvb_build_camera_lidar_blocks(int rows, int cols, int n_pairs, const float* image_line4, const double* start3, const double* end3,
                                   const float* pair_weight, int cam_block, int lidar_block, double weight, long at, long cap, int* type, int* ref,
                                   int* nei, int* normalize, double* huber, double* consts);
+/* calibration mode, CameraLidarOptimizer::Optimize(line_pairs, T_cl) (joint_optimization/CameraLidarOptimizer.cpp:32-64): per pair
+ * Plane2Plane_Relative + HuberLoss(2 deg) and PlaneRelativeIOUResidual (weight 2, no loss) on the ONE relative pose block (aa_cl, t_cl)    */
+int pvb_build_calibration_blocks(int rows, int cols, int n_pairs, const float* image_line4, const double* start3, const double* end3, int pose_block,
+                                 long at, long cap, int* type, int* ref, int* nei, int* normalize, double* huber, double* consts);
 /* pcl::transformPointCloud of one cloud on the device (sensors/Velodyne.cpp:1790-1806): n x 4 float32 in, n x 4 out     */
 int pvb_transform_cloud(pvb_ctx* ctx, const float* xyzi, long n, const double* R9, const double* t3, float* out);
 

@@ -215,6 +215,15 @@ def joint_solve_lm(blocks, reproj, poses, points, param_const=None, max_iter=20)
     return x[:poses.size].reshape(-1, 6), x[poses.size:].reshape(-1, 3), dict(zip(keys, summ.tolist()))
 
 
+def build_calibration_blocks(rows, cols, image_lines, start, end):
+    """The two residual blocks per line pair of the calibration-mode Optimize (joint_optimization/CameraLidarOptimizer.cpp:32-64)."""
+    ln, s, e = _f32(image_lines).reshape(-1, 4), _f64(start).reshape(-1, 3), _f64(end).reshape(-1, 3)
+    n = len(ln)
+    typ, hub, consts = np.zeros(2 * n, np.int32), np.zeros(2 * n), np.zeros((2 * n, 12))
+    lib().pvo_build_calibration_blocks(C.c_int(rows), C.c_int(cols), C.c_int(n), _p(ln), _p(s), _p(e), _p(typ), _p(hub), _p(consts))
+    return typ, hub, consts
+
+
 def filter_line_pairs(rows, cols, image_lines, start, end, by_angle, by_length):
     """CameraLidarLineAssociate::Filter (joint_optimization/CameraLidarLineAssociate.cpp:628-715) on camera-frame pairs."""
     ln, s, e = _f32(image_lines).reshape(-1, 4), _f64(start).reshape(-1, 3), _f64(end).reshape(-1, 3)

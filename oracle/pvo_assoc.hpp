@@ -425,6 +425,42 @@ inline void FilterLinePairs(const Equirect& eq, int n, const float* image_line4,
   }
 }
 
+// ---- calibration mode: the residual blocks of CameraLidarOptimizer::Optimize(line_pairs, T_cl) (CameraLidarOptimizer.cpp:32-64) -------------
+// Per line pair two blocks on the ONE relative pose (aa_cl, t_cl): Plane2Plane_Relative (HuberLoss(2 deg)) and PlaneRelativeIOUResidual (no loss,
+// weight 2).  The image line's end points go through ImageToCam(cv::Point2f, 5.f) in float and the plane normal is a float cross product (:50-56).
+// consts layout = the oracle's block types 6 / 7 (pvo_solver.hpp); out arrays hold 2 * n rows.
+inline void BuildCalibrationBlocks(const Equirect& eq, int n, const float* image_line4, const double* start3, const double* end3, int* type, double* huber, double* consts) {
+  for (int i = 0; i < n; ++i) {
+    const float px1[2] = {image_line4[4 * i], image_line4[4 * i + 1]}, px2[2] = {image_line4[4 * i + 2], image_line4[4 * i + 3]};
+    float p1[3], p2[3];
+    eq.ImageToCam(px1, 5.0f, p1); eq.ImageToCam(px2, 5.0f, p2);                                 // :50-51
+    const float p3[3] = {0, 0, 0};
+    const double a = ((p2[1] - p1[1]) * (p3[2] - p1[2]) - (p2[2] - p1[2]) * (p3[1] - p1[1]));      // :54-56, float arithmetic
+    const double b = ((p2[2] - p1[2]) * (p3[0] - p1[0]) - (p2[0] - p1[0]) * (p3[2] - p1[2]));
+    const double c = ((p2[0] - p1[0]) * (p3[1] - p1[1]) - (p2[1] - p1[1]) * (p3[0] - p1[0]));
+    const double nn = std::sqrt(a * a + b * b + c * c);
+    const double* ls = start3 + 3 * i; const double* le = end3 + 3 * i;
+    double* c1 = consts + 24 * i; double* c2 = c1 + 12;
+    for (int k = 0; k < 24; ++k) c1[k] = 0.0;
+    // Plane2Plane_Relative::Create(Vector3d(a,b,c), lidar_line_end, lidar_line_start): ctor normalises the plane (CostFunction.h:305), weight 1
+    c1[0] = a / nn; c1[1] = b / nn; c1[2] = c / nn;
+    for (int k = 0; k < 3; ++k) { c1[3 + k] = le[k]; c1[6 + k] = ls[k]; }
+    c1[9] = 1.0;
+    type[2 * i] = 6; huber[2 * i] = 2.0 * M_PI / 180.0;                                           // :36, :59
+    // PlaneRelativeIOUResidual::Create(Vector4d(a,b,c,0), (start + end)/2, p1, p2, 2): plane / |n|, angle and middle in float (CostFunction.h:524-529)
+    c2[0] = a / nn; c2[1] = b / nn; c2[2] = c / nn; c2[3] = 0.0 / nn;
+    for (int k = 0; k < 3; ++k) c2[4 + k] = (ls[k] + le[k]) / 2.0;
+    float dot = p1[0] * p2[0] + p1[1] * p2[1] + p1[2] * p2[2];
+    const float n1 = std::sqrt(p1[0] * p1[0] + p1[1] * p1[1] + p1[2] * p1[2]), n2 = std::sqrt(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
+    dot /= (n1 * n2);
+    const float ang = dot >= 1.0f ? 0.0f : (dot <= -1.0f ? (float)M_PI : std::acos(dot));
+    c2[10] = (double)(ang / 2.f);
+    for (int k = 0; k < 3; ++k) c2[7 + k] = (double)((p1[k] + p2[k]) / 2.f);
+    c2[11] = 2.0;
+    type[2 * i + 1] = 7; huber[2 * i + 1] = 0.0;                                                   // :63 loss == nullptr
+  }
+}
+
 // ---- pixel-space Associate, first stage (CameraLidarLineAssociate.cpp:22-91): the fallback for frames without LiDAR segments ----------
 // image lines -> sub-line mid points (BreakToSegments(line, 70), seam pieces skipped, :38-54); every LiDAR point -> camera frame
 // (pcl::transformPointCloud, float32) -> pixel (CamToImage, float + FastAtan2, :75-76) -> its 3 nearest mid points (cv::flann exact search,

@@ -386,6 +386,11 @@ void pvo_filter_line_pairs(int rows, int cols, int n, const float* image_line4, 
   FilterLinePairs(eq, n, image_line4, start3, end3, by_angle != 0, by_length != 0, keep, angle);
 }
 
+void pvo_build_calibration_blocks(int rows, int cols, int n, const float* image_line4, const double* start3, const double* end3, int* type, double* huber, double* consts) {
+  Equirect eq{rows, cols};
+  BuildCalibrationBlocks(eq, n, image_line4, start3, end3, type, huber, consts);
+}
+
 void* pvo_kdtree_build(const float* pts, int n) { KdTree* t = new KdTree(); t->Build(pts, n, 4); return t; }
 void pvo_kdtree_free(void* t) { delete (KdTree*)t; }
 

@@ -114,7 +114,7 @@ EXPORTS = [
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
-    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges", "pvb_filter_line_pairs", "pvb_frames_point2plane_blocks", "pvb_neighbor_each_frame", "pvb_lidar_mask_by_track",
+    "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges", "pvb_filter_line_pairs", "pvb_frames_point2plane_blocks", "pvb_neighbor_each_frame", "pvb_lidar_mask_by_track", "pvb_build_calibration_blocks",
     "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates",
 ]
 
@@ -726,6 +726,15 @@ class Context:
                                                          C.c_double(weight), n, cap, *arrs)
         if m < 0:
             raise PvbError(f"pvb_build_camera_lidar_blocks: code {m}")
+        bl.n = m
+
+    @staticmethod
+    def build_calibration_blocks(bl, rows, cols, image_lines, start, end, pose_block=0):
+        ln, s, e = _arr(image_lines, np.float32).reshape(-1, 4), _arr(start, np.float64).reshape(-1, 3), _arr(end, np.float64).reshape(-1, 3)
+        n, cap, *arrs = bl.args()
+        m = load_library().pvb_build_calibration_blocks(C.c_int(rows), C.c_int(cols), C.c_int(len(ln)), _p(ln), _p(s), _p(e), C.c_int(pose_block), n, cap, *arrs)
+        if m < 0:
+            raise PvbError(f"pvb_build_calibration_blocks: code {m}")
         bl.n = m
 
     # ---- D/E/F

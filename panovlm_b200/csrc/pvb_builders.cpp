@@ -784,6 +784,36 @@ int pvb_undistort_end_poses(int n, const double* poses16, const unsigned char* p
   return PVB_OK;
 }
 
+// Calibration mode: the blocks of CameraLidarOptimizer::Optimize(line_pairs, T_cl) (joint_optimization/CameraLidarOptimizer.cpp:32-64) on ONE
+// relative pose block.  Float path of the reference kept: ImageToCam(cv::Point2f, 5.f) and a float cross product for the image plane (:50-56),
+// float half angle and middle of the image line inside PlaneRelativeIOUResidual's constructor (base/CostFunction.h:524-529).
+int pvb_build_calibration_blocks(int rows, int cols, int n_pairs, const float* line4, const double* start3, const double* end3, int pose_block, long at, long cap,
+                                 int* type, int* ref, int* nei, int* normalize, double* huber, double* consts) {
+  if (rows <= 0 || cols <= 0 || n_pairs < 0 || (n_pairs > 0 && (!line4 || !start3 || !end3)) || !type || !ref || !nei || !normalize || !huber || !consts) return PVB_ERR_ARG;
+  BlockOut o{at, cap, type, ref, nei, normalize, huber, consts};
+  for (int i = 0; i < n_pairs; ++i) {
+    float u[3], v[3];
+    image_to_cam_f32(line4[4 * i], line4[4 * i + 1], rows, cols, 5.0f, u);
+    image_to_cam_f32(line4[4 * i + 2], line4[4 * i + 3], rows, cols, 5.0f, v);
+    // (v - u) x (0 - u) in float, promoted afterwards
+    const float w0 = 0.f - u[0], w1 = 0.f - u[1], w2 = 0.f - u[2];
+    const double nx = (v[1] - u[1]) * w2 - (v[2] - u[2]) * w1;
+    const double ny = (v[2] - u[2]) * w0 - (v[0] - u[0]) * w2;
+    const double nz = (v[0] - u[0]) * w1 - (v[1] - u[1]) * w0;
+    const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+    const double* s = start3 + 3 * (size_t)i; const double* e = end3 + 3 * (size_t)i;
+    const double c1[12] = {nx / len, ny / len, nz / len, e[0], e[1], e[2], s[0], s[1], s[2], 1.0, 0, 0};       // Plane2Plane_Relative(plane, end, start), HuberLoss(2 deg)
+    if (!push_block(o, PVB_PLANE2PLANE_RELATIVE, pose_block, pose_block, 1, 2.0 * M_PI / 180.0, c1)) return PVB_ERR_NOMEM;
+    float cs = u[0] * v[0] + u[1] * v[1] + u[2] * v[2];
+    cs /= (std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) * std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
+    const float arc = cs >= 1.0f ? 0.0f : (cs <= -1.0f ? (float)M_PI : std::acos(cs));
+    const double c2[12] = {nx / len, ny / len, nz / len, 0.0 / len, (s[0] + e[0]) / 2.0, (s[1] + e[1]) / 2.0, (s[2] + e[2]) / 2.0,
+                           (double)((u[0] + v[0]) / 2.f), (double)((u[1] + v[1]) / 2.f), (double)((u[2] + v[2]) / 2.f), (double)(arc / 2.f), 2.0};
+    if (!push_block(o, PVB_PLANE_RELATIVE_IOU, pose_block, pose_block, 1, 0.0, c2)) return PVB_ERR_NOMEM;      // loss == nullptr, weight 2 (:61-63)
+  }
+  return (int)o.at;
+}
+
 // ---- pose text files (util/FileIO.cpp:11-73 ReadPoseT, :168-191 ExportPoseT): the wire format either side of the path -----------------
 // One line per frame: [name ]r00 r01 r02 tx r10 r11 r12 ty r20 r21 r22 tz, written with the default ostream precision (6 significant digits,
 // "%g" - the reference's own precision loss, kept so that files stay interchangeable); a line holding "inf" / "nan" marks a frame without pose.

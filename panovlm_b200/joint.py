@@ -96,3 +96,39 @@ def optimize(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa_to_R
     new_poses, new_points, summary = ctx.joint_solve_lm(poses, points, const, pt_const, cfg.max_lm_iterations)
     summary.update(n_camera_lidar_blocks=counts[0], n_lidar_blocks=counts[1], n_reproj=len(data["cam"]), n_line_pairs=sum(len(p[0]) for p in pairs.values()))
     return new_poses[:n], new_poses[n:], new_points, summary, (v, const, pt_const)
+
+
+def calibrate(ctx: Context, frames, image_lines, rows, cols, T_cl_init, aa_to_R, R_to_aa, max_iterations=35):
+    """Calibration mode of CameraLidarOptimizer::JointOptimize (CameraLidarOptimizer.cpp:195-233): one relative pose T_cl for all (image i, LiDAR i)
+    pairs.  Per iteration: AssociateLineSingle at the current T_cl (:301-317, AssociateByAngle with its defaults: one-to-one pairs), the residual blocks of
+    Optimize(line_pairs, T_cl) (:32-64) on the single pose block, LM with max_num_iterations = 50 (:68), stop when the rotation changed by less than
+    0.1 deg and the translation by less than 0.01 (:229)."""
+    T = np.array(T_cl_init, dtype=np.float64)
+    lfs = [LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], np.eye(3), np.zeros(3)) for f in frames]
+
+    def associate(T_cl):
+        return [ctx.camera_lidar_associate(rows, cols, image_lines[i], lfs[i], T_cl, True, False) for i in range(len(frames))]
+
+    pairs = associate(T)
+    log = []
+    for it in range(max_iterations):
+        bl = BlockList(2 * sum(len(p[0]) for p in pairs) + 4)
+        for i, (il, ll, s, e, ang) in enumerate(pairs):
+            if len(il):
+                Context.build_calibration_blocks(bl, rows, cols, image_lines[i][il], s, e, 0)
+        v = bl.view()
+        ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], 1)
+        pose = np.concatenate([R_to_aa(T[:3, :3]), T[:3, 3]])[None, :]
+        new_pose, summary = ctx.blocks_solve_lm(pose, None, 50)
+        T_new = np.eye(4)
+        T_new[:3, :3] = aa_to_R(new_pose[0, :3])
+        T_new[:3, 3] = new_pose[0, 3:]
+        rot_change = np.float32(np.arccos(np.clip((np.trace(T[:3, :3].T @ T_new[:3, :3]) - 1) / 2.0, -1.0, 1.0))) * np.float32(180.0 / np.pi)
+        trans_change = np.float32(np.linalg.norm(T[:3, 3] - T_new[:3, 3]))
+        T = T_new
+        pairs = associate(T)
+        summary.update(n_pairs=bl.n // 2, rotation_change_deg=float(rot_change), translation_change=float(trans_change))
+        log.append(summary)
+        if rot_change < 0.1 and trans_change < 0.01:
+            break
+    return T, log

@@ -297,3 +297,26 @@ def test_neighbor_each_frame_and_lidar_mask_match_restatement():
     assert [m.tolist() for m in Context.lidar_mask_by_track([], [2, 0])] == [[False, False], []]
     with pytest.raises(Exception):
         Context.lidar_mask_by_track([np.array([[0, 9]])], [4])
+
+
+def test_calibration_blocks_match_oracle(oracle):
+    """pvb_build_calibration_blocks == the block construction of the calibration-mode Optimize (CameraLidarOptimizer.cpp:32-64)."""
+    rng = np.random.default_rng(9)
+    n = 40
+    lines = np.stack([rng.uniform(0, 5760, n), rng.uniform(200, 2600, n), rng.uniform(0, 5760, n), rng.uniform(200, 2600, n)], axis=1).astype(np.float32)
+    start, end = rng.normal(0, 3, (n, 3)), rng.normal(0, 3, (n, 3))
+    typ, hub, consts = oracle.build_calibration_blocks(2880, 5760, lines, start, end)
+    bl = BlockList(2 * n + 2)
+    Context.build_calibration_blocks(bl, 2880, 5760, lines, start, end, 0)
+    v = bl.view()
+    assert bl.n == 2 * n
+    assert np.array_equal(v["type"], typ) and np.array_equal(v["huber"], hub) and np.all(v["ref"] == 0) and np.all(v["nei"] == 0)
+    assert np.array_equal(v["consts"], consts)
+    # geometric meaning: the plane normal is perpendicular to both image rays, the half arc is half the angle between them
+    p = oracle.image_to_cam(2880, 5760, lines.reshape(-1, 2).astype(np.float64)).reshape(n, 2, 3) if hasattr(oracle, "image_to_cam") else None
+    if p is not None:
+        assert np.abs(np.sum(consts[0::2, :3] * p[:, 0], 1)).max() < 1e-5 and np.abs(np.sum(consts[0::2, :3] * p[:, 1], 1)).max() < 1e-5
+    assert np.all(consts[0::2, 9] == 1.0) and np.all(consts[1::2, 11] == 2.0) and np.all(consts[1::2, 3] == 0.0)
+    assert np.array_equal(consts[0::2, 3:6], end) and np.array_equal(consts[0::2, 6:9], start)
+    with pytest.raises(Exception):
+        Context.build_calibration_blocks(BlockList(3), 2880, 5760, lines, start, end, 0)
