@@ -132,3 +132,25 @@ def calibrate(ctx: Context, frames, image_lines, rows, cols, T_cl_init, aa_to_R,
         if rot_change < 0.1 and trans_change < 0.01:
             break
     return T, log
+
+
+def joint_optimize(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa_to_R, num_iteration_joint=5, optimize_fn=None):
+    """Mapping mode of CameraLidarOptimizer::JointOptimize (CameraLidarOptimizer.cpp:236-287): Optimize (which re-associates the lines at the current
+    estimate) repeated up to num_iteration_joint times with the reference's two early exits - the cost changed by less than 1 % (:271, compared with the
+    previous iteration; the first comparison divides by last_cost = 0 and never fires) or fewer than 5 successful LM steps in two consecutive
+    iterations (:276; last_step starts at INT32_MAX)."""
+    optimize_fn = optimize_fn or optimize
+    last_cost, last_step = 0.0, 2 ** 31 - 1
+    log = []
+    for it in range(num_iteration_joint):
+        cams, lidars, points, summary, _ = optimize_fn(ctx, data, cams, lidars, points, cfg, aa_to_R)
+        log.append(summary)
+        curr_cost, curr_step = summary["final_cost"], summary["successful"]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rel = np.abs(np.float64(curr_cost) - last_cost) / np.float64(last_cost)
+        if rel < 0.01:
+            break
+        if curr_step < 5 and last_step < 5:
+            break
+        last_cost, last_step = curr_cost, curr_step
+    return cams, lidars, points, log
