@@ -567,107 +567,6 @@ __device__ __forceinline__ double vector_angle_nf(const double* a, const double*
   return acos(c);
 }
 
-// ---- K2p split variant (PVB_SPLIT, off by default): the neighbour search and the FP64 tail of the fused kernel as two launches -----------------
-// k_knn_positions: query -> world, exact K-NN on the grid (pruned walk): integer / FP32 only, so it can be compiled for more resident blocks than the
-// fused kernel; writes the K record positions of every query as [tile][K][kTile] (coalesced), 0xFFFFFFFF in slot 0 when the search fails.
-// k_plane_tail: class test, plane fit, collinearity, tolerance, residual + Jacobian, per-warp 6x6 partial - the statements of k_associate after the
-// search, on the stored positions.  Results are identical to the fused kernel (same functions, same order).
-template <int K, int MINB>
-__global__ void __launch_bounds__(kTile, MINB) k_knn_positions(const AssocArgs a, uint32_t* __restrict__ nn_pos) {
-  const QueryTile t = a.tiles[blockIdx.x];
-  const Pair pr = a.pairs[t.pair];
-  const int i = threadIdx.x;
-  uint32_t* out = nn_pos + (size_t)blockIdx.x * K * kTile + i;
-  if (i >= t.count) { out[0] = 0xFFFFFFFFu; return; }
-  const GridDesc& g = a.grids[pr.target_cloud];
-  const uint32_t* cs = a.cell_start + g.cell_base;
-  const F4* srt = a.sorted;
-  const WorldPose& wn = a.wpose[pr.nei_block];
-  const F4 q = ldg_f4(a.q_local + t.start + i);
-  float qx, qy, qz;
-  transform_point_f32(wn.R, wn.t, q.x, q.y, q.z, qx, qy, qz);
-  auto cells = [cs](long long c) { return (long long)__ldg(cs + c); };
-  auto loadg = [srt](long long p) { return ldg_f4(srt + p); };
-  const int rmax = (int)ceil(a.thr / g.h);
-  const int found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, a.prm.sq_thr, a.prm.r0 < 1 ? 1 : a.prm.r0, rmax, [&](int j, uint32_t pos, uint32_t) { out[(size_t)j * kTile] = pos; });
-  if (found < K) out[0] = 0xFFFFFFFFu;
-}
-
-template <int K, bool REDUCE, bool REF_ID>
-__global__ void __launch_bounds__(kTile, 5) k_plane_tail(const AssocArgs a, const uint32_t* __restrict__ nn_pos) {
-  __shared__ double sJ[REDUCE ? kTile : 1][8];
-  __shared__ uint32_t s_win[K][kTile];
-  const QueryTile t = a.tiles[blockIdx.x];
-  const Pair pr = a.pairs[t.pair];
-  const int i = threadIdx.x;
-  const bool act = i < t.count;
-  bool valid = false;
-  double p_local[3] = {0, 0, 0}, plane[4] = {0, 0, 0, 0};
-  double r = 0.0, cost = 0.0, J[12];
-#pragma unroll
-  for (int k = 0; k < 12; ++k) J[k] = 0.0;
-  uint32_t qi = 0;
-  const F4* srt = a.sorted;
-  const WorldPose& wn = a.wpose[pr.nei_block];
-  const WorldPose& wr = a.wpose[pr.ref_block];
-  if (act) {
-    const uint32_t* in = nn_pos + (size_t)blockIdx.x * K * kTile + i;
-#pragma unroll
-    for (int j = 0; j < K; ++j) s_win[j][i] = in[(size_t)j * kTile];
-    const F4 q = ldg_f4(a.q_local + t.start + i);
-    float qx, qy, qz;
-    transform_point_f32(wn.R, wn.t, q.x, q.y, q.z, qx, qy, qz);
-    const int gq = t.start + i;
-    qi = a.q_orig ? a.q_orig[gq] : (uint32_t)(t.out_base + i);
-    auto loadg = [srt](long long p) { return ldg_f4(srt + p); };
-    auto win = [&](int j) { return s_win[j][i]; };
-    AssocParams prm = a.prm;
-    valid = s_win[0][i] != 0xFFFFFFFFu &&
-            plane_from_neighbours<K, REF_ID>(loadg, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win);
-    if (valid && (REDUCE || a.out_res)) {
-      double c[8] = {p_local[0], p_local[1], p_local[2], plane[0], plane[1], plane[2], plane[3], a.weight};
-      double q3[3], P[3], g3[3];
-      transform_nei_to_ref(a.prep[pr.ref_block], a.prep[pr.nei_block], c, q3, P);
-      r = tail_point_plane(a.residual_type, a.normalize != 0, c, P, g3);
-      accumulate_row(a.prep[pr.ref_block], a.prep[pr.nei_block], q3, P, g3, J);
-      cost = huber_correct(a.huber, r, J, 12);
-    }
-    if (a.out_valid) a.out_valid[qi] = valid ? 1 : 0;
-    if (a.out_point && valid) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) a.out_point[(size_t)qi * 3 + k] = p_local[k];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) a.out_plane[(size_t)qi * 4 + k] = plane[k];
-    }
-    if (a.out_res) {
-      a.out_res[qi] = r;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) a.out_jac6[(size_t)qi * 6 + k] = J[6 + k];
-    }
-  }
-  if (REDUCE) {      // per-warp reduction, identical to k_associate's
-    const int w = i >> 5, lane = i & 31;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) sJ[i][k] = valid ? J[6 + k] : 0.0;
-    sJ[i][6] = valid ? r : 0.0;
-    sJ[i][7] = valid ? cost : 0.0;
-    const unsigned b = __ballot_sync(0xffffffffu, valid);
-    __syncwarp();
-    double* out = a.partials + ((size_t)blockIdx.x * (kTile / 32) + w) * 29;
-    if (lane < 28) {
-      int ia = 0, ib = 0; double acc = 0.0;
-      if (lane < 21) { int o = lane; ia = 0; while (o >= 6 - ia) { o -= 6 - ia; ++ia; } ib = ia + o; }
-      else if (lane < 27) { ia = lane - 21; ib = 6; }
-      const double (*rows)[8] = &sJ[w * 32];
-      if (lane < 27) { for (int row = 0; row < 32; ++row) acc += rows[row][ia] * rows[row][ib]; }
-      else { for (int row = 0; row < 32; ++row) acc += rows[row][7]; }
-      out[lane] = acc;
-    } else if (lane == 28) {
-      out[28] = (double)__popc(b);
-    }
-  }
-}
-
 // ---- K2l: line-to-line vote matrix ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_line_votes(const double* __restrict__ ref_lines, int S_ref, const F4* __restrict__ pts, int n_pts,
                                                     const int* __restrict__ p2s_off, const int* __restrict__ p2s_ids, double thr, int* __restrict__ M) {

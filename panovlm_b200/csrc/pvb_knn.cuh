@@ -410,76 +410,6 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
   return true;
 }
 
-// The part of associate_point2plane that follows the neighbour search (class test, streaming plane fit, collinearity, tolerance, query -> neighbour
-// frame), as a function of its own: the split variant of the fused kernel (k_knn_positions + k_plane_tail, PVB_SPLIT) runs the integer / FP32 search
-// and this FP64 tail as two launches with different register budgets.  Same statements in the same order as above => same results bit for bit.
-template <int K, bool REF_ID, typename Load, typename WinGet>
-PVB_HD bool plane_from_neighbours(const Load& load, const AssocParams& prm, float qx, float qy, float qz, uint32_t qcls, const double* R_ref, const double* t_ref,
-                                  const double* R_nei, const double* t_nei, double p_local[3], double plane[4], const WinGet& win) {
-  // neighbours -> reference sensor frame (:587), streamed: Gram matrix for the LSQ plane and the scatter matrix
-  PlaneAcc acc; plane_acc_clear(acc);
-  int same = 0;
-#pragma unroll 1
-  for (int j = 0; j < K; ++j) {
-    const F4 p = load((long long)win(j));
-    same += ((f2u(p.w) & 31u) == qcls) ? 1 : 0;                  // :586 pt.intensity == point.intensity
-    const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
-    double pl[3];
-    if (REF_ID) { pl[0] = pw[0]; pl[1] = pw[1]; pl[2] = pw[2]; } else world2local(R_ref, t_ref, pw, pl);
-    plane_acc_add(acc, pl);
-  }
-  if (same < K) return false;                                    // :590
-  if (collinear_from_gram(acc, K, prm.collinear_tol)) return false;   // :594-596
-  Chol3 L;
-  double x[3];
-  if (chol3_factor(acc, L)) {
-    { const double rhs[3] = {-acc.h0, -acc.h1, -acc.h2}; chol3_solve(L, rhs, x); }   // :593 FormPlane: A x = -1
-    // one refinement step: t = A^T (b - A x)
-    double t[3] = {0.0, 0.0, 0.0};
-#pragma unroll 1
-    for (int j = 0; j < K; ++j) {
-      const F4 p = load((long long)win(j));
-      const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
-      double pl[3];
-      if (REF_ID) { pl[0] = pw[0]; pl[1] = pw[1]; pl[2] = pw[2]; } else world2local(R_ref, t_ref, pw, pl);
-      const double rj = -1.0 - (pl[0] * x[0] + pl[1] * x[1] + pl[2] * x[2]);
-      t[0] += pl[0] * rj; t[1] += pl[1] * rj; t[2] += pl[2] * rj;
-    }
-    double dx[3];
-    chol3_solve(L, t, dx);
-    x[0] += dx[0]; x[1] += dx[1]; x[2] += dx[2];
-  } else {                                                       // rank-deficient neighbour set: Eigen's basic solution
-    double A[K * 3];
-#pragma unroll 1
-    for (int j = 0; j < K; ++j) {
-      const F4 p = load((long long)win(j));
-      const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
-      if (REF_ID) { A[j * 3] = pw[0]; A[j * 3 + 1] = pw[1]; A[j * 3 + 2] = pw[2]; } else world2local(R_ref, t_ref, pw, &A[j * 3]);
-    }
-    lstsq_minus_one_rolled(K, A, x);
-  }
-  const double nrm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-  const double d = 1.0 / nrm;
-  const double n0 = x[0] / nrm, n1 = x[1] / nrm, n2 = x[2] / nrm;
-  if (prm.plane_tol > 0) {                                       // Geometry.hpp:364-371
-    bool ok = true;
-#pragma unroll 1
-    for (int j = 0; j < K; ++j) {
-      const F4 p = load((long long)win(j));
-      const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
-      double pl[3];
-      if (REF_ID) { pl[0] = pw[0]; pl[1] = pw[1]; pl[2] = pw[2]; } else world2local(R_ref, t_ref, pw, pl);
-      ok = ok && !(fabs(n0 * pl[0] + n1 * pl[1] + n2 * pl[2] + d) > prm.plane_tol);
-    }
-    if (!ok) return false;
-  }
-  plane[0] = n0; plane[1] = n1; plane[2] = n2; plane[3] = d;
-  const double qw[3] = {(double)qx, (double)qy, (double)qz};
-  world2local(R_nei, t_nei, qw, p_local);                        // :598-599
-  return true;
-}
-
-
 // Per-query body of AssociatePoint2Line (lidar_mapping/LidarFeatureAssociate.cpp:478-548): 5 nearest corner points of
 // the reference frame (world, float32), PCA line test in the WORLD frame, synthetic end points c +- 0.1 d moved to the
 // reference sensor frame, query moved to the neighbour's sensor frame.

@@ -141,21 +141,6 @@ int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_ide
   a.stats = nullptr;
   a.prm.r0 = ctx->tune_r0;
   if (stage && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
-  if (ctx->tune_split > 0 && !dbg && !stage) {
-    // split variant (PVB_SPLIT = resident blocks per SM the search kernel is compiled for: 8, 10 or 12): search, then the FP64 tail
-    CK(ctx->d_nnpos.ensure((size_t)n_tiles * k * kTile * 4));
-    uint32_t* pos = ctx->d_nnpos.as<uint32_t>();
-#define PVB_SPLIT_A(KK) do { if (ctx->tune_split >= 12) k_knn_positions<KK, 12><<<n_tiles, kTile, 0, ctx->stream>>>(a, pos); \
-                             else if (ctx->tune_split >= 10) k_knn_positions<KK, 10><<<n_tiles, kTile, 0, ctx->stream>>>(a, pos); \
-                             else k_knn_positions<KK, 8><<<n_tiles, kTile, 0, ctx->stream>>>(a, pos); } while (0)
-#define PVB_SPLIT_B(KK) do { if (ref_identity) k_plane_tail<KK, REDUCE, true><<<n_tiles, kTile, 0, ctx->stream>>>(a, pos); \
-                             else k_plane_tail<KK, REDUCE, false><<<n_tiles, kTile, 0, ctx->stream>>>(a, pos); } while (0)
-    if (k == 10) { PVB_SPLIT_A(10); CKL(); PVB_SPLIT_B(10); } else { PVB_SPLIT_A(5); CKL(); PVB_SPLIT_B(5); }
-#undef PVB_SPLIT_A
-#undef PVB_SPLIT_B
-    CKL();
-    return PVB_OK;
-  }
 #define PVB_LAUNCH(KK, MB, DBG, ST) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, ST, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, ST, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
 #define PVB_MINB_SWITCH(KK, ST) do { if (minb >= 6) PVB_LAUNCH(KK, 6, false, ST); else if (minb == 5) PVB_LAUNCH(KK, 5, false, ST); else PVB_LAUNCH(KK, 4, false, ST); } while (0)
 #define PVB_DISPATCH(KK)                                                                                   \
@@ -188,7 +173,6 @@ int pvb_create(int device, pvb_ctx** out) {
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->bev0); cudaEventCreate(&ctx->bev1);
   if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e);
   if (const char* e = getenv("PVB_STAGE")) ctx->tune_stage = atoi(e) != 0;
-  if (const char* e = getenv("PVB_SPLIT")) ctx->tune_split = atoi(e);
   if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
   if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = std::max(0.1, atof(e));
@@ -204,7 +188,7 @@ void pvb_destroy(pvb_ctx* ctx) {
   DevBuf* dbs[] = {&ctx->d_prep, &ctx->d_wpose, &ctx->b_tile, &ctx->b_eref, &ctx->b_enei, &ctx->b_type, &ctx->b_norm, &ctx->b_huber, &ctx->b_consts, &ctx->b_orig_d, &ctx->b_r, &ctx->b_J,
                    &ctx->b_part, &ctx->b_esys, &ctx->b_tbegin, &ctx->f_pairs, &ctx->f_qtiles, &ctx->f_valid, &ctx->f_point, &ctx->f_plane, &ctx->f_nn_idx, &ctx->f_nn_d2,
                    &ctx->d_q_sorted, &ctx->d_q_orig, &ctx->d_pairs, &ctx->d_qtiles, &ctx->d_part, &ctx->d_sys, &ctx->d_tbegin, &ctx->d_valid, &ctx->d_point, &ctx->d_plane,
-                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e, &ctx->b_chunk, &ctx->d_chunk, &ctx->d_stats, &ctx->d_nnpos};
+                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e, &ctx->b_chunk, &ctx->d_chunk, &ctx->d_stats};
   for (DevBuf* b : dbs) b->release();
   PinBuf* pbs[] = {&ctx->h_pose, &ctx->h_r, &ctx->h_J, &ctx->h_esys, &ctx->fh_valid, &ctx->fh_point, &ctx->fh_plane, &ctx->dh_sys, &ctx->mh_a};
   for (PinBuf* b : pbs) b->release();

@@ -11,8 +11,7 @@
 using namespace pvb;
 
 // per-query association on a host-built grid (counting sort), K = 10 or 5
-static int g_prune = 1;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned walk from a 3x3x3 (default device path) / 5x5x5 block,
-                          // 3: the split variant (neighbour search and plane tail as two separate functions, PVB_SPLIT on the device)
+static int g_prune = 1;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned walk from a 3x3x3 (default device path) / 5x5x5 block
 template <int K>
 static void associate_all(const float* tgt, int n, const double* R_ref, const double* t_ref, const float* qry, int m, const double* R_nei, const double* t_nei,
                           double h, float thr, double plane_tol, unsigned char* valid, double* p_local, double* plane, int* nn_idx, float* nn_d2) {
@@ -52,11 +51,6 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
     auto no_map = [](int, int, uint32_t&, uint32_t&) {};
 #define PVBH_ASSOC(MODE) associate_point2plane<K, false, MODE>(g, cells, load, load, no_map, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei, \
                                                                p_local + 3 * i, plane + 4 * i, win, set_win, range_set, range_get)
-    if (g_prune == 3) {
-      const int found = knn_select_pruned<K>(g, cells, load, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], prm.sq_thr, 1, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); });
-      valid[i] = (found == K && plane_from_neighbours<K, false>(load, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei, p_local + 3 * i,
-                                                                plane + 4 * i, win)) ? 1 : 0;
-    } else
     valid[i] = (g_prune == 0 ? PVBH_ASSOC(false) : PVBH_ASSOC(true)) ? 1 : 0;
 #undef PVBH_ASSOC
     std::vector<std::pair<std::pair<float, uint32_t>, int>> nn;

@@ -45,10 +45,10 @@ def test_zero_rows_and_golden_functors(harness):
         assert (np.abs(J - g["jacobian"]) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1, keepdims=True))).max() < 1e-7
 
 
-@pytest.mark.parametrize("prune", [1, 2, 0, 3])
+@pytest.mark.parametrize("prune", [1, 2, 0])
 def test_grid_knn_and_association_equal_oracle(oracle, harness, prune):
     """prune = 1 / 2: the pruned walk starting from a 3x3x3 (default device path) / 5x5x5 block (rows / cells beyond the running K-th distance
-    are skipped); 0: the exhaustive block walk; 3: the split variant (search and plane tail as two functions, PVB_SPLIT on the device)."""
+    are skipped); 0: the exhaustive block walk."""
     harness.pvbh_set_prune(C.c_int(prune))
     g = np.load(os.path.join(G, "assoc_pair.npz"))
     refw, neiw = np.ascontiguousarray(g["ref_world"]), np.ascontiguousarray(g["nei_world"])
