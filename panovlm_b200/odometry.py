@@ -146,16 +146,21 @@ def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_
     return new_poses, summary
 
 
-def estimate_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, max_iteration=7):
-    """EstimatePose's outer loop with its early exits (LidarOdometry.cpp:166-183)."""
-    last_cost, small_steps, log = None, 0, []
+def estimate_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, max_iteration=7, refine_fn=None):
+    """EstimatePose's outer loop with its early exits (LidarOdometry.cpp:166-183): RefinePose up to max_iteration times; stop when the cost changed by
+    less than 1 % of the PREVIOUS cost (the first comparison divides by last_cost = 0 and never fires) or when two consecutive iterations took fewer
+    than 5 successful LM steps (last_step starts at INT16_MAX)."""
+    refine_fn = refine_fn or refine_pose
+    last_cost, last_step, log = 0.0, 2 ** 15 - 1, []
     for it in range(max_iteration):
-        poses, s = refine_pose(ctx, frames, poses, cfg, aa_to_R)
+        poses, s = refine_fn(ctx, frames, poses, cfg, aa_to_R)
         log.append(s)
-        if last_cost is not None and abs(last_cost - s["final_cost"]) / max(s["final_cost"], 1e-300) < 0.01:
+        curr_cost, curr_step = s["final_cost"], s["successful"]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rel = np.abs(np.float64(curr_cost) - last_cost) / np.float64(last_cost)
+        if rel < 0.01:
             break
-        small_steps = small_steps + 1 if s["successful"] < 5 else 0
-        if small_steps >= 2:
+        if curr_step < 5 and last_step < 5:
             break
-        last_cost = s["final_cost"]
+        last_cost, last_step = curr_cost, curr_step
     return poses, log
