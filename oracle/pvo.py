@@ -36,6 +36,21 @@ def lib():
     return _LIB
 
 
+def ref_lib():
+    """oracle/_ref/libpvo_ref.so: the reference's own base/Math.h compiled where it lies (make -C oracle ref); None when it has not been built."""
+    path = os.path.join(_HERE, "_ref", "libpvo_ref.so")
+    return C.CDLL(path) if os.path.exists(path) else None
+
+
+def ref_fast_atan2(y, x):
+    """FastAtan2 of the REFERENCE (base/Math.h:15-29) through oracle/_ref."""
+    L = ref_lib()
+    y, x = np.ascontiguousarray(y), np.ascontiguousarray(x)
+    out = np.empty_like(y)
+    (L.ref_fast_atan2_f if y.dtype == np.float32 else L.ref_fast_atan2_d)(C.c_long(y.size), _p(y), _p(x), _p(out))
+    return out
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 

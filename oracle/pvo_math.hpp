@@ -9,7 +9,8 @@
 //
 // PARITY STATUS: *unpinned by the reference's own tests* — the reference ships no unit tests, golden
 // vectors or KATs for this path and cannot be compiled here (Eigen/Ceres/PCL
-// absent).  The oracle is instead pinned against independent implementations (scipy Rotation,
+// absent), except base/Math.h: FastAtan2 below is pinned bit for bit against the reference's own code (oracle/_ref, `make -C oracle ref`,
+// tests/golden/ref_fast_atan2.npz).  Everything else is pinned against independent implementations (scipy Rotation,
 // torch float64 autograd, numpy lstsq/eigh, scipy cKDTree, central finite differences) in
 // tests/test_oracle_*.py and the committed fixtures under tests/golden/.
 #pragma once

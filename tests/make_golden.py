@@ -9,6 +9,8 @@ INDEPENDENT implementations, never from the oracle itself:
   assoc_pair.npz a small 2-frame pair (feature clouds) with the expected point-to-plane associations computed with
                  scipy cKDTree (float64 on the float32 world points) + numpy lstsq / eigh
   fast_atan2.npz dense grid of atan2 values (the polynomial must stay within 1.7e-4 rad of them)
+  ref_fast_atan2.npz  outputs of the REFERENCE'S OWN FastAtan2 (base/Math.h compiled where it lies, oracle/_ref, `make -C oracle ref`) in float32 and
+                 float64 on a dense angle sweep, random points and the axis / signed-zero / extreme-ratio cases: the one fixture produced by reference code
   reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
                  undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
 Run from the repo root:  python tests/make_golden.py
@@ -137,8 +139,22 @@ def golden_reproj():
                         residual=r, jacobian=J, sweep=cloud, T_wl=A, T_we=E, undistorted=und)
 
 
+def golden_ref_math():
+    from oracle import pvo
+    if pvo.ref_lib() is None:
+        print("oracle/_ref not built (no /root/reference here): ref_fast_atan2.npz left as committed")
+        return
+    rng = np.random.default_rng(20261004)
+    ang = np.linspace(-np.pi, np.pi, 6001)
+    r = rng.uniform(0.05, 80, size=ang.shape)
+    y = np.concatenate([r * np.sin(ang), rng.normal(0, 10, 6000), [0, 0, 1, -1, 0, -0.0, 0.0, 1e-30, 1e30, -1e-30, 5, 5, -5, -5]])
+    x = np.concatenate([r * np.cos(ang), rng.normal(0, 10, 6000), [0, 1, 0, 0, -1, -1, -0.0, 1e30, 1e-30, -1e30, 5, -5, 5, -5]])
+    yf, xf = y.astype(np.float32), x.astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "ref_fast_atan2.npz"), y=y, x=x, out_f64=pvo.ref_fast_atan2(y, x), yf=yf, xf=xf, out_f32=pvo.ref_fast_atan2(yf, xf))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

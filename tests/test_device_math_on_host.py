@@ -181,3 +181,17 @@ def test_pruned_block_walk_is_exact_on_random_surface_clouds(oracle, harness):
             inside = d2[r] < d2[r, K - 1]
             assert set(idx[r][inside]) <= set(ni[r]), (trial, r)
         assert np.all(ni[~full][:, K - 1] == -1)
+
+
+def test_product_fast_atan2_equals_the_reference_code_outputs(harness):
+    """The product's fast_atan2_f32 / fast_atan2_f64 (compiled for the host) against the outputs of the reference's own base/Math.h
+    (tests/golden/ref_fast_atan2.npz, produced through oracle/_ref): bit for bit."""
+    g = np.load(os.path.join(G, "ref_fast_atan2.npz"))
+    yf, xf = np.ascontiguousarray(g["yf"]), np.ascontiguousarray(g["xf"])
+    out = np.zeros_like(yf)
+    harness.pvbh_fast_atan2_f(C.c_long(len(yf)), p(yf), p(xf), p(out))
+    assert np.array_equal(out, g["out_f32"])
+    y, x = np.ascontiguousarray(g["y"]), np.ascontiguousarray(g["x"])
+    outd = np.zeros_like(y)
+    harness.pvbh_fast_atan2_d(C.c_long(len(y)), p(y), p(x), p(outd))
+    assert np.array_equal(outd, g["out_f64"])

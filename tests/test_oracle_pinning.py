@@ -104,6 +104,21 @@ def test_form_plane_and_line_match_numpy(oracle):
     assert ok and abs(abs(line[3:] @ np.ones(3) / np.sqrt(3)) - 1) < 1e-6
 
 
+def test_fast_atan2_is_bit_identical_to_the_reference_code(oracle):
+    """tests/golden/ref_fast_atan2.npz holds the outputs of the reference's own base/Math.h (compiled where it lies into oracle/_ref by
+    `make -C oracle ref`): the oracle's restatement must reproduce them bit for bit in float32 and float64; when oracle/_ref is present (this
+    container, and the GPU box through the snapshot) the comparison is repeated live on a million random inputs."""
+    g = np.load(os.path.join(G, "ref_fast_atan2.npz"))
+    assert np.array_equal(oracle.fast_atan2(g["y"], g["x"]), g["out_f64"])
+    assert np.array_equal(oracle.fast_atan2(g["yf"], g["xf"]), g["out_f32"])
+    if oracle.ref_lib() is not None:
+        rng = np.random.default_rng(77)
+        for dt in (np.float32, np.float64):
+            y, x = (rng.normal(size=1_000_000) * 20).astype(dt), (rng.normal(size=1_000_000) * 20).astype(dt)
+            assert np.array_equal(oracle.fast_atan2(y, x), oracle.ref_fast_atan2(y, x))
+            assert np.array_equal(oracle.ref_fast_atan2(g["y"].astype(dt), g["x"].astype(dt)), g["out_f64"] if dt == np.float64 else g["out_f32"])
+
+
 def test_fast_atan2_error_bound_and_branches(oracle):
     g = np.load(os.path.join(G, "fast_atan2.npz"))
     got = oracle.fast_atan2(g["y"], g["x"])
