@@ -4,7 +4,8 @@ ctypes front-end of ``oracle/libpvo_oracle.so`` (the CPU restatement of PanoVLM'
 ``pvo_math.hpp``).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this module; nothing under ``panovlm_b200/`` does.
 Parity status: unpinned by the reference's own tests (it has none) — pinned against scipy / numpy /
-torch-autograd in ``tests/test_oracle_*.py``.
+torch-autograd in ``tests/test_oracle_*.py`` and, for the functor / geometry / projection layers, against the reference's own
+source compiled with stand-in container types (``oracle/_ref``, ``oracle/shim``, ``tests/test_reference_pinning.py``).
 """
 import ctypes as C
 import os
@@ -458,3 +459,61 @@ def dense_icp_eval(target_world, src_local, src_off, poses_lw, plane_tol, dist_t
                              C.c_double(plane_tol), C.c_float(dist_thr), C.c_int(k), C.c_double(huber), C.c_double(weight), C.c_int(mode),
                              tree.h if tree is not None else None, _p(out), _p(times), C.byref(nassoc))
     return out, times, nassoc.value
+
+
+# ---- oracle/_ref/libpvo_ref_path.so: the reference's own CostFunction.h / Geometry.hpp / Equirectangular.{h,cpp} compiled where they lie, with the
+# stand-in container types of oracle/shim (make -C oracle ref).  Checker of the checker: used by tests/ and tests/make_golden.py only. ----
+REF_PAIRWISE_P2PLANE, REF_PAIRWISE_P2LINE, REF_REPROJ_1ANGLE, REF_PLANE_IOU_CAMERA = 9, 10, 11, 12
+
+
+def ref_path_lib():
+    path = os.path.join(_HERE, "_ref", "libpvo_ref_path.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_eval_functors.restype = C.c_long
+    for f in ("ref_point_to_line_distance3d", "ref_point_to_plane_distance", "ref_vector_angle3d", "ref_plane_angle"):
+        getattr(L, f).restype = C.c_double
+    return L
+
+
+def ref_eval_functors(type, normalize, raw, params, jac=True, consts=True):
+    """The reference's functors through `Functor::Create(...)->Evaluate()`.  raw: n x 16 constructor arguments, params: n x 12 (blocks of 3 in call
+    order).  Returns r[n], J[n x 12] (blocks in call order), consts[n x 12] (members after the constructor, oracle block layout)."""
+    type = _i32(type)
+    n = len(type)
+    normalize = _i32(np.broadcast_to(normalize, n))
+    raw, params = _f64(raw).reshape(n, 16), _f64(params).reshape(n, 12)
+    r = np.zeros(n)
+    J = np.zeros((n, 12)) if jac else None
+    c = np.zeros((n, 12)) if consts else None
+    rc = ref_path_lib().ref_eval_functors(C.c_long(n), _p(type), _p(normalize), _p(raw), _p(params), _p(r), _p(J), _p(c))
+    assert rc == 0, f"reference functor evaluation failed at row {-1 - rc}"
+    return r, J, c
+
+
+def image_to_cam_f(rows, cols, px, r):
+    px = _f32(px).reshape(-1, 2)
+    out = np.zeros((len(px), 3), np.float32)
+    lib().pvo_image_to_cam_f(C.c_int(rows), C.c_int(cols), C.c_long(len(px)), _p(px), C.c_float(r), _p(out))
+    return out
+
+
+def break_to_segments(rows, cols, line4, seg_length):
+    """Equirectangular::BreakToSegments (sensors/Equirectangular.cpp:20-58) of one image line."""
+    buf = np.zeros((512, 2), np.float32)
+    k = lib().pvo_break_to_segments(C.c_int(rows), C.c_int(cols), _p(_f32(line4)), C.c_float(seg_length), C.c_int(512), _p(buf))
+    assert k >= 0
+    return buf[:k].copy()
+
+
+def form_plane3(p1, p2, p3):
+    out = np.zeros(4)
+    lib().pvo_form_plane3(_p(_f64(p1)), _p(_f64(p2)), _p(_f64(p3)), _p(out))
+    return out
+
+
+def geometry_helpers(point, line6, plane4):
+    out, proj = np.zeros(5), np.zeros((2, 3))
+    lib().pvo_geometry_helpers(_p(_f64(point)), _p(_f64(line6)), _p(_f64(plane4)), _p(out), _p(proj))
+    return out, proj

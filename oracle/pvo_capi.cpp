@@ -43,6 +43,28 @@ void pvo_fast_atan2_d(long n, const double* y, const double* x, double* out) { f
 void pvo_image_to_cam_d(int rows, int cols, long n, const double* px, double* cam) { Equirect eq{rows, cols}; for (long i = 0; i < n; ++i) eq.ImageToCam(px + 2 * i, 1.0, cam + 3 * i); }
 void pvo_cam_to_image_d(int rows, int cols, long n, const double* cam, double* px) { Equirect eq{rows, cols}; for (long i = 0; i < n; ++i) eq.CamToImage(cam + 3 * i, px + 2 * i); }
 void pvo_cam_to_image_f(int rows, int cols, long n, const float* cam, float* px) { Equirect eq{rows, cols}; for (long i = 0; i < n; ++i) eq.CamToImage(cam + 3 * i, px + 2 * i); }
+void pvo_image_to_cam_f(int rows, int cols, long n, const float* px, float r, float* cam) { Equirect eq{rows, cols}; for (long i = 0; i < n; ++i) eq.ImageToCam(px + 2 * i, r, cam + 3 * i); }
+int pvo_break_to_segments(int rows, int cols, const float* line4, float seg_length, int cap, float* out2) {
+  Equirect eq{rows, cols};
+  const auto s = eq.BreakToSegments(line4, line4 + 2, seg_length);
+  if ((int)s.size() > cap) return -1;
+  for (size_t i = 0; i < s.size(); ++i) { out2[2 * i] = s[i].first; out2[2 * i + 1] = s[i].second; }
+  return (int)s.size();
+}
+void pvo_form_plane3(const double* p1, const double* p2, const double* p3, double* out4) { FormPlane3(p1, p2, p3, out4); }
+// out5 = PointToLineDistance3D(point, line6), PointToPlaneDistance(plane4, point, false), the same with the plane normalised by |n| and normalized = true,
+// VectorAngle3D(point, line6[0:3]), PlaneAngle(point, line6[0:3]); proj6 = ProjectPointToPlane(point, plane4, false / true as above)
+void pvo_geometry_helpers(const double* point, const double* line6, const double* plane4, double* out5, double* proj6) {
+  double pn[4]; const double nn = std::sqrt(plane4[0] * plane4[0] + plane4[1] * plane4[1] + plane4[2] * plane4[2]);
+  for (int i = 0; i < 4; ++i) pn[i] = i < 3 ? plane4[i] / nn : plane4[i];
+  out5[0] = PointToLineDistance3D(point, line6);
+  out5[1] = PointToPlaneDistance(plane4, point, false);
+  out5[2] = PointToPlaneDistance(pn, point, true);
+  out5[3] = VectorAngle3D(point, line6, false);
+  out5[4] = PlaneAngle(point, line6, false);
+  ProjectPointToPlane(point, plane4, proj6, false);
+  ProjectPointToPlane(point, pn, proj6 + 3, true);
+}
 
 // ---- residual blocks ------------------------------------------------------------------------------------
 // blocks are passed as parallel arrays: type/ref/nei/normalize (int32), huber (f64), consts (n x 12 f64).

@@ -9,8 +9,10 @@
 //
 // PARITY STATUS: *unpinned by the reference's own tests* — the reference ships no unit tests, golden
 // vectors or KATs for this path and cannot be compiled here (Eigen/Ceres/PCL
-// absent), except base/Math.h: FastAtan2 below is pinned bit for bit against the reference's own code (oracle/_ref, `make -C oracle ref`,
-// tests/golden/ref_fast_atan2.npz).  Everything else is pinned against independent implementations (scipy Rotation,
+// absent).  Two pieces of the reference's own source DO run here (oracle/_ref, `make -C oracle ref`): base/Math.h as it is (FastAtan2: bit for bit,
+// tests/golden/ref_fast_atan2.npz) and base/CostFunction.h + base/Geometry.hpp + sensors/Equirectangular.{h,cpp} compiled with the stand-in Eigen / Ceres /
+// OpenCV types of oracle/shim (functor residuals and Jacobians, projection, BreakToSegments: bit-identical to this restatement; FormPlane / FormLine: same
+// decisions; tests/test_reference_pinning.py, tests/golden/ref_functors.npz, ref_geometry.npz).  Everything else is pinned against independent implementations (scipy Rotation,
 // torch float64 autograd, numpy lstsq/eigh, scipy cKDTree, central finite differences) in
 // tests/test_oracle_*.py and the committed fixtures under tests/golden/.
 #pragma once

@@ -11,6 +11,11 @@ INDEPENDENT implementations, never from the oracle itself:
   fast_atan2.npz dense grid of atan2 values (the polynomial must stay within 1.7e-4 rad of them)
   ref_fast_atan2.npz  outputs of the REFERENCE'S OWN FastAtan2 (base/Math.h compiled where it lies, oracle/_ref, `make -C oracle ref`) in float32 and
                  float64 on a dense angle sweep, random points and the axis / signed-zero / extreme-ratio cases: the one fixture produced by reference code
+  ref_functors.npz  residuals + Jacobians + post-constructor constants of all nine functors of the path evaluated by the REFERENCE'S OWN
+                 base/CostFunction.h through `Functor::Create(...)->Evaluate()` (compiled where it lies with the stand-in Eigen / Ceres / OpenCV types of
+                 oracle/shim: oracle/_ref/libpvo_ref_path.so), same keys as functors.npz so the kernel tests read it the same way
+  ref_geometry.npz  FormPlane / FormLine / SlerpPose / PointToLineDistance3D ... of the reference's base/Geometry.hpp and the projection functions of
+                 sensors/Equirectangular.{h,cpp} (CamToImage float / double, ImageToCam, BreakToSegments incl. seam crossings), same build
   reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
                  undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
 Run from the repo root:  python tests/make_golden.py
@@ -153,8 +158,109 @@ def golden_ref_math():
     np.savez_compressed(os.path.join(OUT, "ref_fast_atan2.npz"), y=y, x=x, out_f64=pvo.ref_fast_atan2(y, x), yf=yf, xf=xf, out_f32=pvo.ref_fast_atan2(yf, xf))
 
 
+def golden_ref_path():
+    from oracle import pvo
+    L = pvo.ref_path_lib()
+    if L is None:
+        print("oracle/_ref/libpvo_ref_path.so not built (no /root/reference here): ref_functors.npz / ref_geometry.npz left as committed")
+        return
+    import ctypes as C
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    c = cases.ref_functor_cases(20261017, 600)
+    r, J, consts = pvo.ref_eval_functors(c["type"], c["normalize"], c["raw"], c["params"])
+    assert np.all(np.isfinite(r)) and np.all(np.isfinite(J))
+    c["consts"] = consts
+    np.savez_compressed(os.path.join(OUT, "ref_functors.npz"), residual=r, jacobian=cases.ref_jacobian_to_block_layout(c["type"], J), jacobian_call_order=J, **c)
+    # pairwise functors and the reprojection functor (2 and 3 parameter blocks)
+    rng = np.random.default_rng(20261018)
+    n = 200
+    typ = np.repeat([pvo.REF_PAIRWISE_P2PLANE, pvo.REF_PAIRWISE_P2LINE, pvo.REF_REPROJ_1ANGLE, pvo.REF_PLANE_IOU_CAMERA], n).astype(np.int32)
+    raw, params = np.zeros((4 * n, 16)), np.zeros((4 * n, 12))
+    nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    raw[:n, :3] = rng.normal(0, 3, (n, 3)); raw[:n, 3:6] = nrm; raw[:n, 6] = rng.normal(0, 2, n); raw[:n, 7] = rng.uniform(0.5, 2, n)
+    raw[n:2 * n, :9] = rng.normal(0, 3, (n, 9)); raw[n:2 * n, 9] = rng.uniform(0.5, 2, n)
+    raw[2 * n:3 * n, :3] = rng.normal(0, 1, (n, 3)); raw[2 * n:3 * n, 3] = rng.uniform(0.5, 2, n)
+    raw[3 * n:, :4] = rng.normal(0, 1, (n, 4)); raw[3 * n:, 4:7] = rng.normal(0, 3, (n, 3)); raw[3 * n:, 7:13] = rng.normal(0, 1, (n, 6)); raw[3 * n:, 13] = rng.uniform(0.5, 2, n)
+    params[:, :3] = rng.normal(0, 0.5, (4 * n, 3)); params[:, 3:6] = rng.normal(0, 1, (4 * n, 3))
+    params[2 * n:3 * n, 6:9] = rng.normal(0, 4, (n, 3))
+    params[3 * n:, 6:9] = rng.normal(0, 0.5, (n, 3)); params[3 * n:, 9:] = rng.normal(0, 1, (n, 3))
+    params[::9, :3] = 0.0
+    r2, J2, c2 = pvo.ref_eval_functors(typ, 0, raw, params)
+    assert np.all(np.isfinite(r2)) and np.all(np.isfinite(J2))
+    # geometry helpers
+    out = dict(pw_type=typ, pw_raw=raw, pw_params=params, pw_residual=r2, pw_jacobian=J2, pw_consts=c2)
+    m = 300
+    planes, lines, line_ok = np.zeros((m, 4)), np.zeros((m, 6)), np.zeros(m)
+    pts_all = np.zeros((m, 10, 3)); counts = np.zeros(m, np.int32)
+    tol_p, tol_l, thr_l = np.zeros(m), np.zeros(m), np.zeros(m)
+    for i in range(m):
+        k = int(rng.integers(3, 11)); counts[i] = k
+        kind = i % 4
+        base = rng.normal(0, 5, 3); u = rng.normal(size=3); u /= np.linalg.norm(u); v = np.cross(u, rng.normal(size=3)); v /= np.linalg.norm(v)
+        if kind == 0:   pts = base + rng.normal(0, 1, (k, 1)) * u + rng.normal(0, 1, (k, 1)) * v + rng.normal(0, 0.005, (k, 3))     # plane
+        elif kind == 1: pts = base + rng.normal(0, 1, (k, 1)) * u + rng.normal(0, 0.01, (k, 3))                                       # line
+        elif kind == 2: pts = base + rng.normal(0, 1, (k, 3))                                                                         # blob
+        else:           pts = base + rng.normal(0, 1, (k, 1)) * u                                                                     # exactly collinear: rank deficient
+        pts_all[i, :k] = pts
+        tol_p[i] = [0.0, 0.02, 0.05][i % 3]; tol_l[i] = [3.0, 10.0][i % 2]; thr_l[i] = [0.0, 0.05][(i // 2) % 2]
+        L.ref_form_plane(C.c_int(k), p(np.ascontiguousarray(pts)), C.c_double(tol_p[i]), p(planes[i:i + 1]))
+        L.ref_form_line(C.c_int(k), p(np.ascontiguousarray(pts)), C.c_double(tol_l[i]), C.c_double(thr_l[i]), p(lines[i:i + 1]))
+    out.update(fp_points=pts_all, fp_counts=counts, fp_tol=tol_p, fp_plane=planes, fl_tol=tol_l, fl_thr=thr_l, fl_line=lines)
+    q = rng.normal(0, 3, (m, 16))
+    s = np.zeros((m, 5)); proj = np.zeros((m, 2, 3)); plane3 = np.zeros((m, 4))
+    for i in range(m):
+        pt, ln, pl = q[i, :3].copy(), q[i, 3:9].copy(), q[i, 9:13].copy()
+        s[i, 0] = L.ref_point_to_line_distance3d(p(pt), p(ln))
+        for nz in (0, 1):
+            pln = pl.copy()
+            if nz: pln[:3] /= np.linalg.norm(pln[:3])
+            s[i, 1 + nz] = L.ref_point_to_plane_distance(p(pln), p(pt), C.c_int(nz))
+            L.ref_project_point_to_plane(p(pt), p(pln), p(proj[i, nz:nz + 1]), C.c_int(nz))
+        s[i, 3] = L.ref_vector_angle3d(p(pt), p(ln[:3].copy()), C.c_int(0))
+        s[i, 4] = L.ref_plane_angle(p(pt), p(ln[:3].copy()), C.c_int(0))
+        L.ref_form_plane3(p(pt), p(ln[:3].copy()), p(ln[3:].copy()), p(plane3[i:i + 1]))
+    out.update(g_in=q, g_scalar=s, g_project=proj, g_plane3=plane3)
+    from scipy.spatial.transform import Rotation
+    n_s = 80
+    w1, w2, ratio, so = np.zeros((n_s, 4, 4)), np.zeros((n_s, 4, 4)), rng.uniform(0, 1, n_s), np.zeros((n_s, 4, 4))
+    for i in range(n_s):
+        for w in (w1, w2):
+            w[i] = np.eye(4); w[i, :3, :3] = Rotation.from_rotvec(rng.normal(0, [0.05, 1.0, 2.5][i % 3], 3)).as_matrix(); w[i, :3, 3] = rng.normal(0, 2, 3)
+        if i % 10 == 0: w2[i] = w1[i]
+        L.ref_slerp_pose(p(w1[i]), p(w2[i]), C.c_double(ratio[i]), p(so[i]))
+    out.update(slerp_w1=w1, slerp_w2=w2, slerp_ratio=ratio, slerp_out=so)
+    # projection
+    rows, cols = 2880, 5760
+    cam_f = np.concatenate([rng.normal(0, 5, (4000, 3)), [[0, 0, 1], [0, 0, -1], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [1e-8, 0, -1], [-1e-8, 0, -1]]]).astype(np.float32)
+    px_f = np.zeros((len(cam_f), 2), np.float32); L.ref_cam_to_image_f(C.c_int(rows), C.c_int(cols), C.c_long(len(cam_f)), p(cam_f), p(px_f))
+    cam_d = cam_f.astype(np.float64) + rng.normal(0, 1e-3, cam_f.shape)
+    px_d, px_e = np.zeros((len(cam_d), 2)), np.zeros((len(cam_d), 2))
+    L.ref_cam_to_image_d(C.c_int(rows), C.c_int(cols), C.c_long(len(cam_d)), p(cam_d), p(px_d))
+    L.ref_cam_to_image_eigen_d(C.c_int(rows), C.c_int(cols), C.c_long(len(cam_d)), p(cam_d), p(px_e))
+    pix = np.stack([rng.uniform(0, cols, 2000), rng.uniform(0, rows, 2000)], axis=1)
+    pix[:4] = [[0, 0], [cols, rows], [cols / 2, rows / 2], [cols - 1, 0]]
+    i2c_d, i2c_e = np.zeros((len(pix), 3)), np.zeros((len(pix), 3))
+    L.ref_image_to_cam_d(C.c_int(rows), C.c_int(cols), C.c_long(len(pix)), p(pix), C.c_double(1.0), p(i2c_d))
+    L.ref_image_to_cam_eigen_d(C.c_int(rows), C.c_int(cols), C.c_long(len(pix)), p(pix), C.c_double(1.0), p(i2c_e))
+    pix_f = pix.astype(np.float32); i2c_f = np.zeros((len(pix), 3), np.float32)
+    L.ref_image_to_cam_f(C.c_int(rows), C.c_int(cols), C.c_long(len(pix)), p(pix_f), C.c_float(5.0), p(i2c_f))
+    n_l = 300
+    ln = np.stack([rng.uniform(0, cols, n_l), rng.uniform(0, rows, n_l), rng.uniform(0, cols, n_l), rng.uniform(0, rows, n_l)], axis=1).astype(np.float32)
+    ln[::5, 0] = rng.uniform(0, 300, len(ln[::5])); ln[::5, 2] = rng.uniform(cols - 300, cols, len(ln[::5]))     # seam crossings
+    seg_len = np.where(np.arange(n_l) % 2 == 0, 70.0, 100.0).astype(np.float32)
+    seg_off, seg_xy = [0], []
+    for i in range(n_l):
+        buf = np.zeros((256, 2), np.float32)
+        k = L.ref_break_to_segments(C.c_int(rows), C.c_int(cols), p(ln[i]), C.c_float(seg_len[i]), C.c_int(256), p(buf))
+        assert k > 0
+        seg_xy.append(buf[:k].copy()); seg_off.append(seg_off[-1] + k)
+    out.update(rows=rows, cols=cols, cam_f=cam_f, px_f=px_f, cam_d=cam_d, px_d=px_d, px_eigen_d=px_e, pix=pix, i2c_d=i2c_d, i2c_eigen_d=i2c_e, pix_f=pix_f, i2c_f5=i2c_f,
+               bts_lines=ln, bts_seg_len=seg_len, bts_off=np.array(seg_off, np.int32), bts_xy=np.concatenate(seg_xy))
+    np.savez_compressed(os.path.join(OUT, "ref_geometry.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

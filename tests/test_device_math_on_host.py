@@ -37,7 +37,7 @@ def test_zero_rows_and_golden_functors(harness):
     c = cases.on_plane_blocks()
     r, J, _ = _eval(harness, c, 0)
     assert np.all(r == 0) and np.all(J == 0)
-    for name in ("functors.npz", "functors_f6.npz"):
+    for name in ("functors.npz", "functors_f6.npz", "ref_functors.npz"):      # the last one: outputs of the reference's own CostFunction.h (oracle/_ref)
         g = dict(np.load(os.path.join(G, name)))
         g["nb"] = int(g["nb"])
         r, J, _ = _eval(harness, g, 0)

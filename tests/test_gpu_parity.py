@@ -38,7 +38,7 @@ def test_blocks_rows_match_oracle(gpu_ctx, oracle, gen):
 
 
 def test_blocks_golden_functors_and_zero_rows(gpu_ctx):
-    for name in ("functors.npz", "functors_f6.npz"):
+    for name in ("functors.npz", "functors_f6.npz", "ref_functors.npz"):      # the last one: outputs of the reference's own CostFunction.h (oracle/_ref)
         g = np.load(os.path.join(G, name))
         gpu_ctx.blocks_set(g["type"], g["ref"], g["nei"], g["consts"], 0.0, g["normalize"], int(g["nb"]))
         gpu_ctx.blocks_evaluate(g["poses"], True, False)

@@ -1,0 +1,215 @@
+"""The oracle (and the product's host-side math) against the REFERENCE'S OWN source code.
+
+`make -C oracle ref` compiles base/CostFunction.h, base/Geometry.hpp, base/Math.h and sensors/Equirectangular.{h,cpp} where they lie under
+/root/reference into oracle/_ref/libpvo_ref_path.so; Eigen / Ceres / OpenCV / PCL / glog are not installed here, so oracle/shim/ provides stand-ins
+for the value types those files use.  What that pins is the reference's formulas, branch thresholds, argument order and constructor
+normalisations - not Eigen's or Ceres' arithmetic.  The outputs are committed as tests/golden/ref_functors.npz and ref_geometry.npz
+(tests/make_golden.py: golden_ref_path), which is what these tests read, so they run wherever the repository goes; when the library itself is present
+the comparison is repeated live on fresh random inputs."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None  # noqa: E731
+
+
+def _oracle_blocks(oracle, c, consts):
+    b = oracle.Blocks(c["type"], c["ref"], c["nei"], consts, 0.0, c["normalize"])
+    return b.evaluate(c["poses"], apply_loss=False)
+
+
+def test_oracle_functors_equal_the_reference_functors(oracle):
+    """All nine functors of the path (F1-F3, F5, F6): residual and Jacobian of the oracle's restatement == the reference's own templates run through
+    ceres::CostFunction::Evaluate (Jet<12> / Jet<6>).  The gate is 1e-12 relative; measured: bit-identical."""
+    g = np.load(os.path.join(G, "ref_functors.npz"))
+    assert set(np.unique(g["type"]).tolist()) == set(range(9))
+    r, J, _ = _oracle_blocks(oracle, g, g["consts"])
+    assert (np.abs(r - g["residual"]) / np.maximum(1e-9, np.abs(g["residual"]))).max() < 1e-12
+    assert (np.abs(J - g["jacobian"]).max(1) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1))).max() < 1e-12
+    # the branches the reference has must be present in the fixture: zero residuals of the angle types (< 1e-3 => 0) and of the IOU hinge
+    assert np.any((g["residual"] == 0) & (g["type"] == 8)) and np.any((g["residual"] == 0) & np.isin(g["type"], (5, 7)))
+    if oracle.ref_path_lib() is not None:                                  # live, fresh inputs
+        c = cases.ref_functor_cases(99, 4000)
+        r_ref, J_ref, k_ref = oracle.ref_eval_functors(c["type"], c["normalize"], c["raw"], c["params"])
+        r, J, _ = _oracle_blocks(oracle, c, k_ref)
+        assert (np.abs(r - r_ref) / np.maximum(1e-9, np.abs(r_ref))).max() < 1e-12
+        J_ref = cases.ref_jacobian_to_block_layout(c["type"], J_ref)
+        assert (np.abs(J - J_ref).max(1) / np.maximum(1e-9, np.abs(J_ref).max(1))).max() < 1e-12
+
+
+def test_constructor_normalisations_equal_the_reference(oracle):
+    """The constants a block carries are the functor's members AFTER its constructor ran (plane_ref.normalize(), (a - b).normalized(),
+    plane / |n|, the float32 half arc of PlaneRelativeIOUResidual).  The fixture holds the reference's; rebuild them here from the raw arguments."""
+    g = np.load(os.path.join(G, "ref_functors.npz"))
+    raw, k, t = g["raw"], g["consts"], g["type"]
+    unit = lambda v: v / np.linalg.norm(v, axis=1, keepdims=True)  # noqa: E731
+    m = np.isin(t, (0, 1))
+    assert np.array_equal(k[m, :8], raw[m, :8])                                                            # no normalisation: the caller's job
+    m = np.isin(t, (2, 3))
+    assert np.array_equal(k[m, :6], raw[m, :6]) and np.abs(k[m, 6:9] - unit(raw[m, 3:6] - raw[m, 6:9])).max() < 1e-15 and np.array_equal(k[m, 9], raw[m, 9])
+    m = np.isin(t, (4, 6))
+    assert np.abs(k[m, :3] - unit(raw[m, :3])).max() < 1e-15 and np.array_equal(k[m, 3:10], raw[m, 3:10])
+    m = t == 5
+    assert np.abs(k[m, :4] - raw[m, :4] / np.linalg.norm(raw[m, :3], axis=1, keepdims=True)).max() < 1e-15 and np.array_equal(k[m, 4:12], raw[m, 4:12])
+    m = t == 8
+    assert np.abs(k[m, :3] - unit(raw[m, :3])).max() < 1e-15 and np.abs(k[m, 3:6] - unit(raw[m, 3:6])).max() < 1e-15
+    m = t == 7                                                                                             # float32 constructor path (:518-529)
+    s, e = raw[m, 7:10].astype(np.float32), raw[m, 10:13].astype(np.float32)
+    cosang = (s * e).sum(1, dtype=np.float32) / (np.sqrt((s * s).sum(1, dtype=np.float32)) * np.sqrt((e * e).sum(1, dtype=np.float32)))
+    assert np.abs(k[m, 10] - np.arccos(cosang.astype(np.float32)).astype(np.float32) / np.float32(2)).max() < 1e-6
+    assert np.array_equal(k[m, 7:10], ((s + e) / np.float32(2)).astype(np.float64)) and np.array_equal(k[m, 11], raw[m, 13])
+
+
+def test_pairwise_and_reprojection_functors_equal_the_reference(oracle):
+    """F4 (PairWisePoint2Plane_Meter / PairWisePoint2Line_Meter: one relative pose, P = R p + t) is the 4-block functor with the neighbour block at
+    identity - not bit-identical (the 4-block form goes through RotationMatrixToAngleAxis), gate 1e-9; PanoramaReprojResidual_1Angle against the
+    oracle's Jet<9> evaluation; PlaneIOUResidual's camera-LiDAR constructor against the LiDAR-LiDAR one fed with its documented constants."""
+    g = np.load(os.path.join(G, "ref_geometry.npz"))
+    t, raw, prm, r_ref, J_ref, k_ref = (g[x] for x in ("pw_type", "pw_raw", "pw_params", "pw_residual", "pw_jacobian", "pw_consts"))
+    for ref_type, block_type in ((oracle.REF_PAIRWISE_P2PLANE, oracle.P2PLANE_METER), (oracle.REF_PAIRWISE_P2LINE, oracle.P2LINE_METER)):
+        m = t == ref_type
+        n = int(m.sum())
+        poses = np.zeros((n + 1, 6)); poses[:n] = prm[m, :6]
+        b = oracle.Blocks(np.full(n, block_type), np.arange(n), n, k_ref[m], 0.0, 0)
+        r, J, _ = b.evaluate(poses, apply_loss=False)
+        assert (np.abs(r - r_ref[m]) / np.maximum(1e-9, np.abs(r_ref[m]))).max() < 1e-9
+        assert (np.abs(J[:, :6] - J_ref[m, :6]).max(1) / np.maximum(1e-9, np.abs(J_ref[m, :6]).max(1))).max() < 1e-7
+    m = t == oracle.REF_REPROJ_1ANGLE
+    n = int(m.sum())
+    rp = oracle.Reproj(np.arange(n), np.arange(n), k_ref[m, :3], weight=1.0)
+    r, J = rp.evaluate(prm[m, :6], prm[m, 6:9], apply_loss=False)[:2]
+    w = k_ref[m, 3]
+    assert (np.abs(r * w - r_ref[m]) / np.maximum(1e-9, np.abs(r_ref[m]))).max() < 1e-12
+    assert (np.abs(J[:, :9] * w[:, None] - J_ref[m, :9]).max(1) / np.maximum(1e-9, np.abs(J_ref[m, :9]).max(1))).max() < 1e-12
+    m = t == oracle.REF_PLANE_IOU_CAMERA                                     # CostFunction.h:442-451
+    s, e = raw[m, 7:10], raw[m, 10:13]
+    ang = np.arccos(np.clip((s * e).sum(1) / np.linalg.norm(s, axis=1) / np.linalg.norm(e, axis=1), -1, 1)) / 2
+    assert np.abs(k_ref[m, 10] - ang).max() < 1e-12 and np.abs(k_ref[m, 7:10] - (s + e) / 2).max() < 1e-15
+    assert np.abs(k_ref[m, :4] - raw[m, :4] / np.linalg.norm(raw[m, :3], axis=1, keepdims=True)).max() < 1e-15
+    n = int(m.sum())
+    poses = np.concatenate([prm[m, :6], prm[m, 6:]])
+    b = oracle.Blocks(np.full(n, oracle.PLANE_IOU), np.arange(n), n + np.arange(n), k_ref[m], 0.0, 0)
+    r, J, _ = b.evaluate(poses, apply_loss=False)
+    assert (np.abs(r - r_ref[m]) / np.maximum(1e-9, np.abs(r_ref[m]))).max() < 1e-12
+    assert (np.abs(J - J_ref[m]).max(1) / np.maximum(1e-9, np.abs(J_ref[m]).max(1))).max() < 1e-12
+
+
+def test_geometry_helpers_equal_the_reference(oracle):
+    """base/Geometry.hpp: FormPlane (3 points and least squares + tolerance), FormLine (PCA + ratio / distance tests), PointToLineDistance3D,
+    PointToPlaneDistance, ProjectPointToPlane, VectorAngle3D, PlaneAngle, SlerpPose.  Accept / reject decisions must be identical; values agree to
+    1e-9 (the QR / eigen solver / quaternion arithmetic behind them is the shim's in the fixture and the oracle's own here)."""
+    g = np.load(os.path.join(G, "ref_geometry.npz"))
+    n_rej_p = n_rej_l = 0
+    for i in range(len(g["fp_counts"])):
+        pts = g["fp_points"][i, :g["fp_counts"][i]]
+        pl = oracle.form_plane(pts, float(g["fp_tol"][i]))
+        ref = g["fp_plane"][i]
+        if i % 4 == 3:
+            continue                      # exactly collinear points: a rank-deficient system, the answer depends on the QR's rank decision
+        assert np.all(ref == 0) == np.all(pl == 0), i
+        n_rej_p += int(np.all(ref == 0))
+        assert np.abs(pl - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), i
+        ok, ln = oracle.form_line(pts, float(g["fl_tol"][i]), float(g["fl_thr"][i]))
+        ref = g["fl_line"][i]
+        assert ok == bool(np.any(ref != 0)), i
+        n_rej_l += int(not ok)
+        if ok:
+            sgn = np.sign(np.dot(ln[3:], ref[3:]))                # an eigenvector's sign is the solver's choice
+            assert np.abs(ln[:3] - ref[:3]).max() < 1e-12 and np.abs(sgn * ln[3:] - ref[3:]).max() < 1e-9, i
+    assert n_rej_p > 20 and n_rej_l > 20                          # both outcomes are exercised
+    for i in range(len(g["g_in"])):
+        q = g["g_in"][i]
+        out, proj = oracle.geometry_helpers(q[:3], q[3:9], q[9:13])
+        assert np.abs(out - g["g_scalar"][i]).max() <= 1e-13 * max(1.0, np.abs(g["g_scalar"][i]).max()), i
+        assert np.abs(proj - g["g_project"][i]).max() < 1e-12, i
+        assert np.abs(oracle.form_plane3(q[:3], q[3:6], q[6:9]) - g["g_plane3"][i]).max() < 1e-12 * max(1.0, np.abs(g["g_plane3"][i]).max()), i
+    for i in range(len(g["slerp_ratio"])):
+        out = oracle.slerp_pose(g["slerp_w1"][i], g["slerp_w2"][i], float(g["slerp_ratio"][i]))
+        assert np.abs(out - g["slerp_out"][i]).max() < 1e-12, i
+
+
+def test_equirectangular_projection_equals_the_reference(oracle):
+    """sensors/Equirectangular.h / .cpp: CamToImage in float32 (the bulk path: FastAtan2, float arithmetic) must be BIT-IDENTICAL; the double paths
+    (cv::Point and Eigen overloads) and ImageToCam agree to the last bits; BreakToSegments gives the same polyline incl. the seam split."""
+    g = np.load(os.path.join(G, "ref_geometry.npz"))
+    rows, cols = int(g["rows"]), int(g["cols"])
+    assert np.array_equal(oracle.cam_to_image(rows, cols, g["cam_f"]), g["px_f"])
+    assert np.array_equal(oracle.cam_to_image(rows, cols, g["cam_d"]), g["px_d"])
+    assert np.abs(g["px_eigen_d"] - g["px_d"]).max() < 1e-9                                  # the two overloads of the reference agree with each other
+    assert np.abs(oracle.image_to_cam(rows, cols, g["pix"]) - g["i2c_d"]).max() < 1e-15
+    assert np.abs(g["i2c_eigen_d"] - g["i2c_d"]).max() < 1e-15
+    assert np.array_equal(oracle.image_to_cam_f(rows, cols, g["pix_f"], 5.0), g["i2c_f5"])
+    n_seam = 0
+    for i in range(len(g["bts_lines"])):
+        ref = g["bts_xy"][g["bts_off"][i]:g["bts_off"][i + 1]]
+        got = oracle.break_to_segments(rows, cols, g["bts_lines"][i], float(g["bts_seg_len"][i]))
+        assert got.shape == ref.shape and np.array_equal(got, ref), i
+        n_seam += int(np.any(np.abs(np.diff(ref[:, 0])) > 0.8 * cols))
+    assert n_seam > 10
+    if oracle.ref_path_lib() is not None:
+        L = oracle.ref_path_lib()
+        rng = np.random.default_rng(5)
+        cam = rng.normal(0, 10, (500_000, 3)).astype(np.float32)
+        px = np.zeros((len(cam), 2), np.float32)
+        L.ref_cam_to_image_f(C.c_int(rows), C.c_int(cols), C.c_long(len(cam)), p(cam), p(px))
+        assert np.array_equal(oracle.cam_to_image(rows, cols, cam), px)
+
+
+def test_product_host_math_equals_the_reference_functors(harness):
+    """The product's analytic residual / Jacobian code (pvb_math.cuh compiled for the host) against the reference-compiled fixture directly:
+    BASELINE.json's gates (1e-5 residual, 1e-6 Jacobian; measured ~1e-9)."""
+    g = np.load(os.path.join(G, "ref_functors.npz"))
+    n = len(g["type"])
+    r, J, cost = np.zeros(n), np.zeros((n, 12)), np.zeros(n)
+    harness.pvbh_eval_blocks(C.c_long(n), p(g["type"]), p(g["ref"]), p(g["nei"]), p(g["normalize"]), p(np.zeros(n)), p(np.ascontiguousarray(g["consts"])),
+                             p(np.ascontiguousarray(g["poses"])), C.c_int(int(g["nb"])), C.c_int(0), p(r), p(J), p(cost))
+    assert (np.abs(r - g["residual"]) / np.maximum(1e-9, np.abs(g["residual"]))).max() < 1e-8
+    keep = np.abs(g["residual"]) > 1e-12                  # at r == 0 the sign of abs' is a subgradient
+    assert (np.abs(J - g["jacobian"]).max(1) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1)))[keep].max() < 1e-7
+
+
+def test_product_builders_carry_the_reference_constructor_constants(oracle):
+    """pvb_build_point2line_blocks / pvb_build_camera_lidar_blocks / pvb_build_calibration_blocks against constants produced by the reference's
+    constructors (fixture) and by the reference construction sequence of util/Optimization.cpp:585-600 / CameraLidarOptimizer.cpp:45-63 replayed
+    with the reference-checked primitives."""
+    from panovlm_b200 import BlockList, Context
+    g = np.load(os.path.join(G, "ref_functors.npz"))
+    m = np.isin(g["type"], (2, 3))
+    raw, k = g["raw"][m], g["consts"][m]
+    bl = BlockList(len(raw) + 1)
+    Context.build_point2line_blocks(bl, raw[:, :3], raw[:, 3:6], raw[:, 6:9], 0, 1, False, False, 1.0)
+    v = bl.view()
+    assert np.array_equal(v["consts"][:, :6], k[:, :6]) and np.abs(v["consts"][:, 6:9] - k[:, 6:9]).max() < 1e-15
+    m = np.isin(g["type"], (4, 5))
+    if oracle.ref_path_lib() is None:
+        return
+    # B4 with the reference's own constructors: plane through the two image rays, Plane2Plane_Global(plane.head(3), end, start, w_pair * w),
+    # PlaneIOUResidual(plane, (end + start) / 2, (p1 + p2) / 2, angle(p1, p2), 2 w)
+    rows, cols, n = 2880, 5760, 60
+    rng = np.random.default_rng(31)
+    lines = np.stack([rng.uniform(0, cols, n), rng.uniform(0, rows, n), rng.uniform(0, cols, n), rng.uniform(0, rows, n)], axis=1).astype(np.float32)
+    start, end = rng.normal(0, 3, (n, 3)), rng.normal(0, 3, (n, 3))
+    pw = rng.uniform(0.5, 2, n).astype(np.float32)
+    L = oracle.ref_path_lib()
+    px = lines.astype(np.float64).reshape(-1, 2)
+    cam = np.zeros((2 * n, 3))
+    L.ref_image_to_cam_eigen_d(C.c_int(rows), C.c_int(cols), C.c_long(2 * n), p(px), C.c_double(1.0), p(cam))
+    p1, p2 = cam[0::2], cam[1::2]
+    raw = np.zeros((2 * n, 16)); typ = np.tile([4, 5], n).astype(np.int32)
+    for i in range(n):
+        plane = np.zeros(4)
+        L.ref_form_plane3(p(np.ascontiguousarray(p1[i])), p(np.ascontiguousarray(p2[i])), p(np.zeros(3)), p(plane))
+        ang = L.ref_vector_angle3d(p(np.ascontiguousarray(p1[i])), p(np.ascontiguousarray(p2[i])), C.c_int(1))
+        raw[2 * i, :3] = plane[:3]; raw[2 * i, 3:6] = end[i]; raw[2 * i, 6:9] = start[i]; raw[2 * i, 9] = float(pw[i]) * 25.0
+        raw[2 * i + 1, :4] = plane; raw[2 * i + 1, 4:7] = (end[i] + start[i]) / 2.0; raw[2 * i + 1, 7:10] = (p1[i] + p2[i]) / 2.0; raw[2 * i + 1, 10] = ang; raw[2 * i + 1, 11] = 2.0 * 25.0
+    _, _, k_ref = oracle.ref_eval_functors(typ, 0, raw, np.zeros((2 * n, 12)), jac=False)
+    bl = BlockList(2 * n + 1)
+    Context.build_camera_lidar_blocks(bl, rows, cols, lines, start, end, pw, 0, 1, 25.0)
+    v = bl.view()
+    assert np.array_equal(v["type"], typ)
+    assert np.abs(v["consts"] - k_ref).max() < 1e-12
