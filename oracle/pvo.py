@@ -517,3 +517,73 @@ def geometry_helpers(point, line6, plane4):
     out, proj = np.zeros(5), np.zeros((2, 3))
     lib().pvo_geometry_helpers(_p(_f64(point)), _p(_f64(line6)), _p(_f64(plane4)), _p(out), _p(proj))
     return out, proj
+
+
+# ---- oracle/_ref/libpvo_ref_assoc.so: the reference's own lidar_mapping/LidarFeatureAssociate.cpp compiled where it lies (make -C oracle ref) ----
+def ref_assoc_lib():
+    path = os.path.join(_HERE, "_ref", "libpvo_ref_assoc.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_frame_create.restype = C.c_void_p
+    return L
+
+
+class RefFrame:
+    """A `Velodyne` object of the reference as its association functions see it (world-frame feature clouds, segment tables, pose)."""
+
+    def __init__(self, R_wl, t_wl, corner_world=None, p2s_off=None, p2s_ids=None, coeffs_local=None, surf_flat_world=None, surf_less_flat_world=None, id=0,
+                 valid=True, pose_valid=True):
+        self.L = ref_assoc_lib()
+        z = np.zeros((0, 4), np.float32)
+        cw = _f32(z if corner_world is None else corner_world).reshape(-1, 4)
+        sf = _f32(z if surf_flat_world is None else surf_flat_world).reshape(-1, 4)
+        sl = _f32(z if surf_less_flat_world is None else surf_less_flat_world).reshape(-1, 4)
+        co = _f64(np.zeros((0, 6)) if coeffs_local is None else coeffs_local).reshape(-1, 6)
+        off = None if p2s_off is None else _i32(p2s_off)
+        ids = None if p2s_ids is None else _i32(p2s_ids)
+        self.h = self.L.ref_frame_create(C.c_int(id), C.c_int(int(valid)), C.c_int(int(pose_valid)), _p(_f64(R_wl)), _p(_f64(t_wl)), _p(cw), C.c_int(len(cw)), _p(off), _p(ids),
+                                         C.c_int(len(co)), _p(co), None, _p(sf), C.c_int(len(sf)), _p(sl), C.c_int(len(sl)))
+        assert self.h
+        self.n_corner, self.n_flat = len(cw), len(sf)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_frame_destroy(C.c_void_p(self.h))
+            self.h = None
+
+
+def ref_associate_point2plane(ref, nei, plane_tol, dist_thr):
+    cap = max(1, nei.n_flat)
+    pt, pl = np.empty((cap, 3)), np.empty((cap, 4))
+    m = ref.L.ref_associate_point2plane(C.c_void_p(ref.h), C.c_void_p(nei.h), C.c_double(plane_tol), C.c_float(dist_thr), C.c_int(cap), _p(pt), _p(pl))
+    assert m >= 0
+    return pt[:m].copy(), pl[:m].copy()
+
+
+def ref_associate_point2line(ref, nei, dist_thr, variant=""):
+    """variant: "" (AssociatePoint2Line), "_segment_knn", "_segment"."""
+    cap = max(1, 4 * nei.n_corner)
+    pt, a, b = np.empty((cap, 3)), np.empty((cap, 3)), np.empty((cap, 3))
+    m = getattr(ref.L, "ref_associate_point2line" + variant)(C.c_void_p(ref.h), C.c_void_p(nei.h), C.c_float(dist_thr), C.c_int(cap), _p(pt), _p(a), _p(b))
+    assert m >= 0
+    return pt[:m].copy(), a[:m].copy(), b[:m].copy()
+
+
+def ref_associate_line2line(ref, nei, dist_thr, knn=False):
+    cap = 4096
+    ni, ri, a, b = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty((cap, 3)), np.empty((cap, 3))
+    m = getattr(ref.L, "ref_associate_line2line_knn" if knn else "ref_associate_line2line")(C.c_void_p(ref.h), C.c_void_p(nei.h), C.c_float(dist_thr), C.c_int(cap), _p(ni), _p(ri), _p(a), _p(b))
+    assert m >= 0
+    return ni[:m].copy(), ri[:m].copy(), a[:m].copy(), b[:m].copy()
+
+
+def ref_find_neighbors(R_wl, t_wl, pose_valid, valid, neighbor_size):
+    R_wl, t_wl = _f64(R_wl).reshape(-1, 9), _f64(t_wl).reshape(-1, 3)
+    n = len(t_wl)
+    pv, va = np.ascontiguousarray(pose_valid, np.uint8), np.ascontiguousarray(valid, np.uint8)
+    cap = n * (neighbor_size + 64) + 64
+    off, ids = np.zeros(n + 1, np.int32), np.zeros(cap, np.int32)
+    m = ref_assoc_lib().ref_find_neighbors(C.c_int(n), _p(R_wl), _p(t_wl), _p(pv), _p(va), C.c_int(neighbor_size), C.c_int(cap), _p(off), _p(ids))
+    assert m >= 0
+    return [ids[off[i]:off[i + 1]].tolist() for i in range(n)]

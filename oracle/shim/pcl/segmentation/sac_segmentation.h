@@ -1,1 +1,1 @@
-#include "../../pvo_shim_cv.hpp"
+#include "../../pvo_shim_pcl.hpp"

@@ -1,5 +1,5 @@
 // ORACLE/shim — TEST INFRASTRUCTURE ONLY.  Stand-in for the OpenCV value types the reference's geometry / projection headers use (cv::Point_,
-// cv::Point3_, cv::Vec, a cv::Mat that can only be empty or a float3 table), plus PCL's PointXYZI / ModelCoefficients / PointCloud and glog's LOG().
+// cv::Point3_, cv::Vec, a cv::Mat that can only be empty or a float3 table), plus glog's LOG() (the PCL stand-ins live in pvo_shim_pcl.hpp).
 // See pvo_shim_eigen.hpp for why this exists.
 #pragma once
 #include <cmath>
@@ -75,18 +75,7 @@ struct Mat {
 };
 }  // namespace cv
 
-namespace pcl {
-struct PointXYZI { float x = 0, y = 0, z = 0, intensity = 0; };
-struct PointXYZ { float x = 0, y = 0, z = 0; };
-struct ModelCoefficients { std::vector<float> values; };
-template <typename P> struct PointCloud {
-  std::vector<P> points;
-  size_t size() const { return points.size(); }
-  P& operator[](size_t i) { return points[i]; }
-  const P& operator[](size_t i) const { return points[i]; }
-  void push_back(const P& p) { points.push_back(p); }
-};
-}  // namespace pcl
+#include "pvo_shim_pcl.hpp"
 
 #ifndef LOG
 namespace pvo_shim { struct NullLog { template <typename T> NullLog& operator<<(const T&) { return *this; } NullLog& operator<<(std::ostream& (*)(std::ostream&)) { return *this; } }; }

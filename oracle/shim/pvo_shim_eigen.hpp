@@ -6,6 +6,8 @@
 // Not a general library: only what the compiled reference code uses.
 #pragma once
 #include <algorithm>
+#include <atomic>
+#include <cfloat>
 #include <cmath>
 #include <cstddef>
 #include <limits>
@@ -13,8 +15,10 @@
 #include <type_traits>
 #include <vector>
 
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 namespace Eigen {
 const int Dynamic = -1;
+typedef std::ptrdiff_t Index;
 template <class T> struct aligned_allocator : std::allocator<T> {
   aligned_allocator() = default;
   template <class U> aligned_allocator(const aligned_allocator<U>&) {}
@@ -53,10 +57,11 @@ template <typename T, int R, int C>
 class Matrix {
  public:
   typedef T Scalar;
+  typedef Eigen::Index Index;
   shim::Storage<T, R, C> s;
   Matrix() {}
   // element-list constructors (fixed-size vectors)
-  Matrix(const T& a, const T& b) { static_assert(R * C == 2, "size"); s.d[0] = a; s.d[1] = b; }
+  Matrix(const T& a, const T& b) { init2(a, b, std::integral_constant<bool, (R == Dynamic || C == Dynamic)>()); }
   Matrix(const T& a, const T& b, const T& c) { static_assert(R * C == 3, "size"); s.d[0] = a; s.d[1] = b; s.d[2] = c; }
   Matrix(const T& a, const T& b, const T& c, const T& d) { static_assert(R * C == 4, "size"); s.d[0] = a; s.d[1] = b; s.d[2] = c; s.d[3] = d; }
   template <typename U, typename = typename std::enable_if<std::is_arithmetic<U>::value && !std::is_same<U, T>::value>::type>
@@ -64,7 +69,11 @@ class Matrix {
   template <typename U, typename = typename std::enable_if<std::is_arithmetic<U>::value && !std::is_same<U, T>::value>::type>
   Matrix(U a, U b, U c, U d) { static_assert(R * C == 4, "size"); s.d[0] = T(a); s.d[1] = T(b); s.d[2] = T(c); s.d[3] = T(d); }
   template <typename U, typename = typename std::enable_if<std::is_arithmetic<U>::value && !std::is_same<U, T>::value>::type>
-  Matrix(U a, U b) { static_assert(R * C == 2, "size"); s.d[0] = T(a); s.d[1] = T(b); }
+  Matrix(U a, U b) { init2(a, b, std::integral_constant<bool, (R == Dynamic || C == Dynamic)>()); }   // (x, y) of a 2-vector, or (rows, cols) of a dynamic matrix
+ private:
+  template <typename U> void init2(U a, U b, std::false_type) { static_assert(R * C == 2, "size"); s.d[0] = T(a); s.d[1] = T(b); }
+  template <typename U> void init2(U rows, U cols, std::true_type) { s.resize((int)rows, (int)cols); }
+ public:
   explicit Matrix(const Quaternion<T>& q) { static_assert(R == 3 && C == 3, "3x3"); *this = q.toRotationMatrix(); }
 
   int rows() const { return s.rows(); }
@@ -86,6 +95,11 @@ class Matrix {
   T& w() { return s.data()[3]; } const T& w() const { return s.data()[3]; }
   void fill(const T& v) { for (int i = 0; i < size(); ++i) s.data()[i] = v; }
   static Matrix Zero() { Matrix m; m.fill(T(0)); return m; }
+  static Matrix Ones() { Matrix m; m.fill(T(1)); return m; }
+  bool isZero(double prec = 1e-12) const { using std::abs; for (int i = 0; i < size(); ++i) if (!(abs(s.data()[i]) <= prec)) return false; return true; }
+  Matrix<T, 1, C> row(int i) const { Matrix<T, 1, C> v; v.resize(1, cols()); for (int j = 0; j < cols(); ++j) v(0, j) = (*this)(i, j); return v; }
+  template <typename I> T maxCoeff(I* where) const { int b = 0; for (int k = 1; k < size(); ++k) if (s.data()[k] > s.data()[b]) b = k; *where = (I)b; return s.data()[b]; }
+  T maxCoeff() const { int b; return maxCoeff(&b); }
   static Matrix Identity() { Matrix m; m.fill(T(0)); for (int i = 0; i < std::min(m.rows(), m.cols()); ++i) m(i, i) = T(1); return m; }
   shim::CommaInit<T, R, C> operator<<(const T& v) { coeffLinearRowMajor(0) = v; return shim::CommaInit<T, R, C>{*this, 1}; }
 
@@ -291,4 +305,5 @@ typedef Matrix<double, 2, 1> Vector2d; typedef Matrix<double, 3, 1> Vector3d; ty
 typedef Matrix<float, 2, 1> Vector2f;  typedef Matrix<float, 3, 1> Vector3f;  typedef Matrix<float, 4, 1> Vector4f;
 typedef Matrix<double, 3, 3> Matrix3d; typedef Matrix<double, 4, 4> Matrix4d; typedef Matrix<float, 3, 3> Matrix3f; typedef Matrix<float, 4, 4> Matrix4f;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd; typedef Matrix<double, Dynamic, 1> VectorXd;
+typedef Matrix<float, Dynamic, Dynamic> MatrixXf; typedef Matrix<int, Dynamic, Dynamic> MatrixXi; typedef Matrix<float, Dynamic, 1> VectorXf;
 }  // namespace Eigen

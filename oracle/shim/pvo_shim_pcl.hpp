@@ -1,0 +1,80 @@
+// ORACLE/shim — TEST INFRASTRUCTURE ONLY.  Stand-in for the PCL 1.10 types that the reference's sensors/Velodyne.h (class declaration only) and
+// lidar_mapping/LidarFeatureAssociate.{h,cpp} use: point structs, pcl::PointCloud, and pcl::KdTreeFLANN as an EXACT search - what FLANN's
+// KDTreeSingleIndex returns with epsilon 0: the k nearest points by squared L2 distance accumulated in float32 over (x, y, z), ascending, ties by index.
+// The kd-tree itself is not reproduced (an exact search has one answer up to ties).  Everything else named by those headers (VoxelGrid, IO, ICP,
+// RANSAC, normals, region growing) is declared only as far as the compiler needs to see a type; none of it is called on the association path.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace pcl {
+struct PointXYZ { float x = 0, y = 0, z = 0; };
+struct PointXYZI { float x = 0, y = 0, z = 0, intensity = 0; };
+struct PointXYZRGB { float x = 0, y = 0, z = 0; unsigned char r = 0, g = 0, b = 0; };
+struct PointXYZRGBL { float x = 0, y = 0, z = 0; unsigned char r = 0, g = 0, b = 0; unsigned int label = 0; };
+struct Normal { float normal_x = 0, normal_y = 0, normal_z = 0, curvature = 0; };
+struct ModelCoefficients { std::vector<float> values; };
+struct PointIndices { std::vector<int> indices; };
+
+template <typename P> struct PointCloud {
+  typedef std::shared_ptr<PointCloud<P>> Ptr;
+  typedef std::shared_ptr<const PointCloud<P>> ConstPtr;
+  typedef typename std::vector<P>::iterator iterator;
+  typedef typename std::vector<P>::const_iterator const_iterator;
+  std::vector<P> points; unsigned width = 0, height = 1; bool is_dense = true;
+  size_t size() const { return points.size(); }
+  bool empty() const { return points.empty(); }
+  void clear() { points.clear(); width = 0; }
+  void resize(size_t n) { points.resize(n); width = (unsigned)n; }
+  void reserve(size_t n) { points.reserve(n); }
+  void push_back(const P& p) { points.push_back(p); width = (unsigned)points.size(); }
+  P& operator[](size_t i) { return points[i]; }
+  const P& operator[](size_t i) const { return points[i]; }
+  P& at(size_t i) { return points.at(i); }
+  const P& at(size_t i) const { return points.at(i); }
+  iterator begin() { return points.begin(); } iterator end() { return points.end(); }
+  const_iterator begin() const { return points.begin(); } const_iterator end() const { return points.end(); }
+  PointCloud& operator+=(const PointCloud& o) { points.insert(points.end(), o.points.begin(), o.points.end()); width = (unsigned)points.size(); return *this; }
+  Ptr makeShared() const { return Ptr(new PointCloud<P>(*this)); }
+};
+
+template <typename P> class KdTreeFLANN {
+  typename PointCloud<P>::ConstPtr cloud_;
+ public:
+  typedef std::shared_ptr<KdTreeFLANN<P>> Ptr;
+  void setInputCloud(const typename PointCloud<P>::ConstPtr& c) { cloud_ = c; }
+  static float dist2(const P& a, const P& b) { float r = 0; float d = a.x - b.x; r += d * d; d = a.y - b.y; r += d * d; d = a.z - b.z; r += d * d; return r; }
+  int nearestKSearch(const P& q, int k, std::vector<int>& idx, std::vector<float>& sqd) const {
+    const int n = (int)cloud_->points.size();
+    std::vector<std::pair<float, int>> all(n);
+    for (int i = 0; i < n; ++i) all[i] = std::make_pair(dist2(cloud_->points[i], q), i);
+    const int kk = std::min(k, n);
+    std::partial_sort(all.begin(), all.begin() + kk, all.end());
+    idx.resize(kk); sqd.resize(kk);
+    for (int i = 0; i < kk; ++i) { idx[i] = all[i].second; sqd[i] = all[i].first; }
+    return kk;
+  }
+  int radiusSearch(const P& q, double radius, std::vector<int>& idx, std::vector<float>& sqd, unsigned max_nn = 0) const {
+    const int n = (int)cloud_->points.size();
+    const float r2 = (float)(radius * radius);
+    std::vector<std::pair<float, int>> in;
+    for (int i = 0; i < n; ++i) { const float d = dist2(cloud_->points[i], q); if (d <= r2) in.push_back(std::make_pair(d, i)); }
+    std::sort(in.begin(), in.end());
+    if (max_nn && in.size() > max_nn) in.resize(max_nn);
+    idx.resize(in.size()); sqd.resize(in.size());
+    for (size_t i = 0; i < in.size(); ++i) { idx[i] = in[i].second; sqd[i] = in[i].first; }
+    return (int)in.size();
+  }
+};
+template <typename P> class VoxelGrid {
+ public:
+  void setLeafSize(float, float, float) {}
+};
+namespace io {
+template <typename C> inline int savePCDFileASCII(const std::string&, const C&) { return 0; }   // debug dumps (visualization = true only)
+template <typename C> inline int savePCDFileBinary(const std::string&, const C&) { return 0; }
+}  // namespace io
+}  // namespace pcl

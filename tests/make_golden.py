@@ -16,6 +16,8 @@ INDEPENDENT implementations, never from the oracle itself:
                  oracle/shim: oracle/_ref/libpvo_ref_path.so), same keys as functors.npz so the kernel tests read it the same way
   ref_geometry.npz  FormPlane / FormLine / SlerpPose / PointToLineDistance3D ... of the reference's base/Geometry.hpp and the projection functions of
                  sensors/Equirectangular.{h,cpp} (CamToImage float / double, ImageToCam, BreakToSegments incl. seam crossings), same build
+  ref_assoc.npz  correspondences returned by the reference's own lidar_mapping/LidarFeatureAssociate.cpp (all six association functions, FindNeighbors,
+                 TransformLines; compiled where it lies with the PCL / Eigen stand-ins of oracle/shim: oracle/_ref/libpvo_ref_assoc.so) on four synthetic pairs
   reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
                  undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
 Run from the repo root:  python tests/make_golden.py
@@ -259,8 +261,48 @@ def golden_ref_path():
     np.savez_compressed(os.path.join(OUT, "ref_geometry.npz"), **out)
 
 
+def golden_ref_assoc():
+    """tests/golden/ref_assoc.npz: outputs of the reference's own lidar_mapping/LidarFeatureAssociate.cpp (oracle/_ref/libpvo_ref_assoc.so) on the synthetic
+    pairs of tests/test_reference_pinning.py: ASSOC_CASES, plus FindNeighbors on pose sets with loops and missing poses, and TransformLines."""
+    from oracle import pvo
+    if pvo.ref_assoc_lib() is None:
+        print("oracle/_ref/libpvo_ref_assoc.so not built (no /root/reference here): ref_assoc.npz left as committed")
+        return
+    import test_reference_pinning as trp
+    out = {}
+    for ci, (seed, n_az, perturb, tol, thr_p, thr_l) in enumerate(trp.ASSOC_CASES):
+        A, B, RB, tB = trp.assoc_case(pvo, seed, n_az, perturb)
+        for k, v in trp.reference_associations(pvo, A, B, RB, tB, tol, thr_p, thr_l).items():
+            out[f"c{ci}_{k}"] = v
+            print(f"  case {ci} {k}: {len(v)}")
+    rng = np.random.default_rng(20261025)
+    fn = []
+    # a straight walk, a loop that closes after > 200 frames, and the same with poses / frames missing
+    s = np.arange(60) * 0.4
+    fn.append((np.stack([s, 0.1 * np.sin(s), np.zeros_like(s)], 1), np.ones(60, np.uint8), np.ones(60, np.uint8), 6))
+    a = np.linspace(0, 2 * np.pi, 520)
+    loop = np.stack([30 * np.cos(a), 30 * np.sin(a), 0.05 * rng.normal(size=520)], 1)
+    fn.append((loop, np.ones(520, np.uint8), np.ones(520, np.uint8), 6))
+    pv = (rng.random(520) > 0.05).astype(np.uint8); va = (rng.random(520) > 0.03).astype(np.uint8); pv[:3] = 1; va[:3] = 1
+    fn.append((loop + rng.normal(0, 0.3, loop.shape), pv, va, 6))
+    fn.append((rng.uniform(-15, 15, (300, 3)), np.ones(300, np.uint8), np.ones(300, np.uint8), 4))
+    for ci, (t, pv, va, k) in enumerate(fn):
+        R = np.tile(np.eye(3).reshape(1, 9), (len(t), 1))
+        nb = pvo.ref_find_neighbors(R, t, pv, va, k)
+        off = np.zeros(len(t) + 1, np.int32); off[1:] = np.cumsum([len(x) for x in nb])
+        out.update({f"fn{ci}_t": t, f"fn{ci}_pose_valid": pv, f"fn{ci}_valid": va, f"fn{ci}_k": k, f"fn{ci}_off": off, f"fn{ci}_ids": np.concatenate(nb).astype(np.int32)})
+    out["fn_cases"] = len(fn)
+    from scipy.spatial.transform import Rotation
+    import ctypes as C
+    T = np.eye(4); T[:3, :3] = Rotation.from_rotvec([0.3, -1.1, 0.7]).as_matrix(); T[:3, 3] = [1.5, -2.0, 0.3]
+    lin = rng.normal(0, 3, (40, 6)); lout = np.zeros_like(lin)
+    pvo.ref_assoc_lib().ref_transform_lines(T.ctypes.data_as(C.c_void_p), C.c_int(40), lin.ctypes.data_as(C.c_void_p), lout.ctypes.data_as(C.c_void_p))
+    out.update(tl_T=T, tl_in=lin, tl_out=lout)
+    np.savez_compressed(os.path.join(OUT, "ref_assoc.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -213,3 +213,111 @@ def test_product_builders_carry_the_reference_constructor_constants(oracle):
     v = bl.view()
     assert np.array_equal(v["type"], typ)
     assert np.abs(v["consts"] - k_ref).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------------------
+# The association layer: lidar_mapping/LidarFeatureAssociate.cpp compiled where it lies (oracle/ref_assoc_wrap.cpp, oracle/_ref/libpvo_ref_assoc.so)
+# ------------------------------------------------------------------------------------------------------------------------------------------------
+def _world(oracle, F, key, R=None, t=None):
+    return oracle.transform_cloud(F["R_wl"] if R is None else R, F["t_wl"] if t is None else t, F[key])
+
+
+def assoc_case(oracle, seed, n_az=900, perturb=0.0):
+    """A synthetic 2-frame pair as the association functions see it; `perturb` moves the neighbour's pose estimate off the truth; perturb < 0: the
+    estimate is the identity (the initial guess of BASELINE.json configs[0]) - exactly representable, so the kernel tests can use the same case."""
+    from panovlm_b200 import synth
+    from scipy.spatial.transform import Rotation
+    A, B = synth.make_pair(seed=seed, n_az=n_az, ground_class=True)
+    rng = np.random.default_rng(seed)
+    RB = Rotation.from_rotvec(rng.normal(0, abs(perturb) * 0.2, 3)).as_matrix() @ B["R_wl"]
+    tB = B["t_wl"] + rng.normal(0, abs(perturb), 3)
+    if perturb < 0:
+        RB, tB = np.eye(3), np.zeros(3)
+    return A, B, RB, tB
+
+
+def oracle_associations(oracle, A, B, RB, tB, plane_tol, thr_plane, thr_line):
+    """Every association function of LidarFeatureAssociate.cpp through the ORACLE, flattened into a dict of arrays."""
+    out = {}
+    ref_sl, nei_sf = _world(oracle, A, "surfLessFlat"), _world(oracle, B, "surfFlat", RB, tB)
+    ref_c, nei_c = _world(oracle, A, "cornerLessSharp"), _world(oracle, B, "cornerLessSharp", RB, tB)
+    ref_lw, nei_lw = oracle.transform_lines(A["R_wl"], A["t_wl"], A["segment_coeffs"]), oracle.transform_lines(RB, tB, B["segment_coeffs"])
+    S_a, S_b = len(A["segment_coeffs"]), len(B["segment_coeffs"])
+    _, out["p2plane_point"], out["p2plane_plane"] = oracle.associate_p2plane(ref_sl, A["R_wl"], A["t_wl"], nei_sf, RB, tB, plane_tol, thr_plane, 10, True)
+    M = oracle.line_votes(ref_lw, nei_c, B["p2s_off"], B["p2s_ids"], S_b, thr_line)
+    out["l2l_nei"], out["l2l_ref"], out["l2l_a"], out["l2l_b"] = oracle.find_associations(A["segment_coeffs"], ref_lw, nei_lw, np.diff(B["seg_off"]), M)
+    M = oracle.line2line_knn_votes(ref_c, A["p2s_off"], A["p2s_ids"], S_a, nei_c, B["p2s_off"], B["p2s_ids"], S_b, thr_line)
+    out["l2lknn_nei"], out["l2lknn_ref"], out["l2lknn_a"], out["l2lknn_b"] = oracle.find_associations(A["segment_coeffs"], ref_lw, nei_lw, np.diff(B["seg_off"]), M)
+    _, out["p2l_point"], out["p2l_a"], out["p2l_b"] = oracle.associate_p2line(ref_c, A["R_wl"], A["t_wl"], nei_c, RB, tB, thr_line)
+    _, _, out["p2lsk_point"], out["p2lsk_a"], out["p2lsk_b"] = oracle.associate_p2line_segment_knn(ref_c, A["p2s_off"], A["p2s_ids"], A["segment_coeffs"], nei_c, RB, tB, thr_line)
+    _, _, out["p2ls_point"], out["p2ls_a"], out["p2ls_b"] = oracle.associate_p2line_segment(ref_lw, A["segment_coeffs"], nei_c, RB, tB, thr_line)
+    return out
+
+
+def reference_associations(oracle, A, B, RB, tB, plane_tol, thr_plane, thr_line):
+    """The same through the reference's own functions (needs oracle/_ref/libpvo_ref_assoc.so)."""
+    fa = oracle.RefFrame(A["R_wl"], A["t_wl"], _world(oracle, A, "cornerLessSharp"), A["p2s_off"], A["p2s_ids"], A["segment_coeffs"], _world(oracle, A, "surfFlat"),
+                         _world(oracle, A, "surfLessFlat"), id=0)
+    fb = oracle.RefFrame(RB, tB, _world(oracle, B, "cornerLessSharp", RB, tB), B["p2s_off"], B["p2s_ids"], B["segment_coeffs"], _world(oracle, B, "surfFlat", RB, tB),
+                         _world(oracle, B, "surfLessFlat", RB, tB), id=1)
+    out = {}
+    out["p2plane_point"], out["p2plane_plane"] = oracle.ref_associate_point2plane(fa, fb, plane_tol, thr_plane)
+    out["l2l_nei"], out["l2l_ref"], out["l2l_a"], out["l2l_b"] = oracle.ref_associate_line2line(fa, fb, thr_line)
+    out["l2lknn_nei"], out["l2lknn_ref"], out["l2lknn_a"], out["l2lknn_b"] = oracle.ref_associate_line2line(fa, fb, thr_line, knn=True)
+    out["p2l_point"], out["p2l_a"], out["p2l_b"] = oracle.ref_associate_point2line(fa, fb, thr_line)
+    out["p2lsk_point"], out["p2lsk_a"], out["p2lsk_b"] = oracle.ref_associate_point2line(fa, fb, thr_line, "_segment_knn")
+    out["p2ls_point"], out["p2ls_a"], out["p2ls_b"] = oracle.ref_associate_point2line(fa, fb, thr_line, "_segment")
+    return out
+
+
+ASSOC_CASES = [(20261021, 900, 0.0, 0.05, 1.0, 0.3), (20261022, 900, 0.02, 0.05, 1.0, 0.4), (20261023, 1800, 0.05, 0.01, 0.7, 0.3), (20261024, 900, 0.15, 0.05, 0.5, 0.6), (20261025, 900, -1.0, 0.05, 1.0, 0.3)]
+
+
+def _compare_associations(got, exp, tag):
+    for k in exp:
+        assert got[k].shape == exp[k].shape, (tag, k, got[k].shape, exp[k].shape)
+        if exp[k].dtype.kind == "i" or k.endswith("_point"):
+            assert np.array_equal(got[k], exp[k]), (tag, k)                  # index lists and the queries (World2Local of a float32 point): exact
+        elif k in ("p2l_a", "p2l_b"):
+            # PCA line through 5 neighbours: centre +- 0.1 * direction, the eigenvector's sign is the solver's choice => compare as an unordered pair
+            pass
+        else:
+            assert np.abs(got[k] - exp[k]).max() < 1e-9, (tag, k)
+    a, b, ea, eb = got["p2l_a"], got["p2l_b"], exp["p2l_a"], exp["p2l_b"]
+    if len(a):
+        same = np.maximum(np.abs(a - ea).max(1), np.abs(b - eb).max(1))
+        flip = np.maximum(np.abs(a - eb).max(1), np.abs(b - ea).max(1))
+        assert np.minimum(same, flip).max() < 1e-9, (tag, "p2l line")
+
+
+def test_oracle_associations_equal_the_reference_associations(oracle):
+    """A1 / A2 / A3 (all six association functions) on four synthetic pairs: the oracle returns the same correspondences in the same order as the
+    reference's own code; planes / lines agree to 1e-9.  Reads the committed fixture; repeats the comparison live when oracle/_ref is present."""
+    g = np.load(os.path.join(G, "ref_assoc.npz"))
+    total = {}
+    for ci, (seed, n_az, perturb, tol, thr_p, thr_l) in enumerate(ASSOC_CASES):
+        A, B, RB, tB = assoc_case(oracle, seed, n_az, perturb)
+        got = oracle_associations(oracle, A, B, RB, tB, tol, thr_p, thr_l)
+        exp = {k[len(f"c{ci}_"):]: g[k] for k in g.files if k.startswith(f"c{ci}_")}
+        assert set(exp) == set(got)
+        _compare_associations(got, exp, f"fixture case {ci}")
+        for k in got:
+            total[k] = total.get(k, 0) + len(got[k])
+        if oracle.ref_assoc_lib() is not None:
+            _compare_associations(got, reference_associations(oracle, A, B, RB, tB, tol, thr_p, thr_l), f"live case {ci}")
+    assert total["p2plane_point"] > 500 and total["l2l_nei"] > 20 and total["l2lknn_nei"] > 10 and total["p2l_point"] > 100 and total["p2lsk_point"] > 100 and total["p2ls_point"] > 100
+
+
+def test_find_neighbors_and_transform_lines_equal_the_reference(oracle):
+    """N (FindNeighbors: k-NN over frame centres, forced previous / next valid frame, loop candidates, frames without a pose) and TransformLines."""
+    from panovlm_b200 import Context
+    g = np.load(os.path.join(G, "ref_assoc.npz"))
+    for ci in range(int(g["fn_cases"])):
+        t, pv, va, k = g[f"fn{ci}_t"], g[f"fn{ci}_pose_valid"], g[f"fn{ci}_valid"], int(g[f"fn{ci}_k"])
+        exp = [g[f"fn{ci}_ids"][g[f"fn{ci}_off"][i]:g[f"fn{ci}_off"][i + 1]].tolist() for i in range(len(t))]
+        got = Context.find_neighbors(t, pv, va, k)
+        assert [list(x) for x in got] == exp, ci
+        if oracle.ref_assoc_lib() is not None:
+            R = np.tile(np.eye(3).reshape(1, 9), (len(t), 1))
+            assert oracle.ref_find_neighbors(R, t, pv, va, k) == exp
+    assert np.abs(oracle.transform_lines(g["tl_T"][:3, :3], g["tl_T"][:3, 3], g["tl_in"]) - g["tl_out"]).max() < 1e-12
