@@ -587,3 +587,31 @@ def ref_find_neighbors(R_wl, t_wl, pose_valid, valid, neighbor_size):
     m = ref_assoc_lib().ref_find_neighbors(C.c_int(n), _p(R_wl), _p(t_wl), _p(pv), _p(va), C.c_int(neighbor_size), C.c_int(cap), _p(off), _p(ids))
     assert m >= 0
     return [ids[off[i]:off[i + 1]].tolist() for i in range(n)]
+
+
+# ---- oracle/_ref/libpvo_ref_camlidar.so: the reference's own CameraLidarLineAssociate.cpp + ProjectLidar2PanoramaDepth (make -C oracle ref) ----
+def ref_camlidar_lib():
+    path = os.path.join(_HERE, "_ref", "libpvo_ref_camlidar.so")
+    return C.CDLL(path) if os.path.exists(path) else None
+
+
+def ref_associate_by_angle(rows, cols, lines, cloud_local, p2s_off, p2s_ids, coeffs, end_points, T_cl, multiple_association=True, image_mask=None, lidar_mask=None):
+    lines, cloud = _f32(lines).reshape(-1, 4), _f32(cloud_local).reshape(-1, 4)
+    coeffs = _f64(coeffs).reshape(-1, 6)
+    S = len(coeffs)
+    cap = max(1, len(lines) * S)
+    oi, ol = np.empty(cap, dtype=np.int32), np.empty(cap, dtype=np.int32)
+    os_, oe, oa = np.empty((cap, 3)), np.empty((cap, 3)), np.empty(cap, dtype=np.float32)
+    m = ref_camlidar_lib().ref_associate_by_angle(
+        C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), _p(cloud), C.c_int(len(cloud)), _p(_i32(p2s_off)), _p(_i32(p2s_ids)), C.c_int(S), _p(coeffs),
+        _p(_f64(end_points)), _p(_f64(T_cl)), C.c_int(int(multiple_association)), _p(np.ascontiguousarray(image_mask, np.uint8)) if image_mask is not None else None,
+        _p(np.ascontiguousarray(lidar_mask, np.uint8)) if lidar_mask is not None else None, C.c_int(cap), _p(oi), _p(ol), _p(os_), _p(oe), _p(oa))
+    assert m >= 0
+    return oi[:m].copy(), ol[:m].copy(), os_[:m].copy(), oe[:m].copy(), oa[:m].copy()
+
+
+def ref_project_depth(cloud, rows, cols, T_cl, size=3):
+    cloud = _f32(cloud).reshape(-1, 4)
+    img = np.zeros((rows, cols), dtype=np.uint16)
+    ref_camlidar_lib().ref_project_lidar2panorama_depth(_p(cloud), C.c_long(len(cloud)), C.c_int(rows), C.c_int(cols), _p(_f64(T_cl)), C.c_int(size), _p(img))
+    return img

@@ -1,0 +1,74 @@
+// ORACLE/_ref — TEST INFRASTRUCTURE ONLY.  C entry points around the REFERENCE'S OWN joint_optimization/CameraLidarLineAssociate.cpp
+// (AssociateByAngle with its Filter(false, true) and UniqueLinePair tails) and the template ProjectLidar2PanoramaDepth of util/Visualization.h, compiled from
+// the files where they lie under /root/reference (never copied) together with every header they include (Visualization.h, Frame.h, Velodyne.h,
+// Equirectangular.h, Geometry.hpp, Serialization.h, DepthCompletion.h, SIFT.h ...).  None of OpenCV / PCL / Eigen / Boost / CGAL / glog exists in this
+// image; oracle/shim/ provides stand-ins (value types, an exact float32 k-NN behind cv::flann::Index, pcl::transformPointCloud as double math + float
+// store, no-op drawing / IO).  pcl::SACSegmentation is NOT reproduced (shim: no inliers), so the pixel-space Associate() overloads, whose result
+// depends on PCL's RANSAC, are compiled but not exported.  Functions the reference defines in other translation units and only calls from debug
+// branches (drawing, Frame accessors) are given empty bodies below so that the library loads.
+// Built by `make -C oracle ref` into oracle/_ref/libpvo_ref_camlidar.so; used by tests/test_reference_pinning.py and tests/make_golden.py only.
+#include <algorithm>
+#include <cassert>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+#include REF_CAMERA_LIDAR_LINE_ASSOCIATE_CPP
+#include REF_EQUIRECT_CPP            // sensors/Equirectangular.cpp: BreakToSegments, used by Filter's length branch
+
+// defined by the reference in util/Visualization.cpp / sensors/Frame.cpp and reached only from debug / visualisation branches: empty bodies so the library loads
+cv::Vec3b Gray2Color(uchar) { return cv::Vec3b(); }
+cv::Mat DrawLinePairsOnImage(const cv::Mat& img_gray, const vector<CameraLidarLinePair>&, const Eigen::Matrix4d&, const int, const bool) { return img_gray; }
+const cv::Mat Frame::GetImageGray() const { return cv::Mat(); }
+
+extern "C" {
+// AssociateByAngle.  lines: L x 4 float (image line end points, pixels); cloud_local: n x 4 float = cornerLessSharp in the LiDAR frame; point -> segment
+// sets (CSR); S segments with coefficients (S x 6) and projected end points (2 S x 3, LiDAR frame); T_cl row-major 4x4; masks may be null.
+// Outputs per pair: image_line_id, lidar_line_id, start / end (LiDAR frame, as the function leaves them), score (`angle` member).  Returns the count or -1.
+int ref_associate_by_angle(int rows, int cols, const float* lines, int L, const float* cloud_local, int n, const int* p2s_off, const int* p2s_ids, int S,
+                           const double* coeffs, const double* end_points, const double* T_cl_rowmajor, int multiple_association, const unsigned char* image_mask,
+                           const unsigned char* lidar_mask, int cap, int* image_line_id, int* lidar_line_id, double* start3, double* end3, float* score) {
+  std::vector<cv::Vec4f> ln;
+  for (int i = 0; i < L; ++i) ln.push_back(cv::Vec4f(lines[4 * i], lines[4 * i + 1], lines[4 * i + 2], lines[4 * i + 3]));
+  pcl::PointCloud<pcl::PointXYZI> cloud;
+  for (int i = 0; i < n; ++i) { pcl::PointXYZI p; p.x = cloud_local[4 * i]; p.y = cloud_local[4 * i + 1]; p.z = cloud_local[4 * i + 2]; p.intensity = cloud_local[4 * i + 3]; cloud.push_back(p); }
+  std::vector<std::set<int>> p2s(n);
+  for (int i = 0; i < n; ++i) for (int k = p2s_off[i]; k < p2s_off[i + 1]; ++k) p2s[i].insert(p2s_ids[k]);
+  std::vector<pcl::PointCloud<pcl::PointXYZI>> seg(S);
+  for (int i = 0; i < n; ++i) for (int s : p2s[i]) seg[s].push_back(cloud.points[i]);
+  eigen_vector<Vector6d> co;
+  for (int s = 0; s < S; ++s) { Vector6d c; for (int k = 0; k < 6; ++k) c[k] = coeffs[6 * s + k]; co.push_back(c); }
+  eigen_vector<Eigen::Vector3d> ends;
+  for (int i = 0; i < 2 * S; ++i) ends.push_back(Eigen::Vector3d(end_points[3 * i], end_points[3 * i + 1], end_points[3 * i + 2]));
+  Eigen::Matrix4d T; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T(i, j) = T_cl_rowmajor[4 * i + j];
+  std::vector<bool> im, lm;
+  if (image_mask) im.assign(image_mask, image_mask + L);
+  if (lidar_mask) lm.assign(lidar_mask, lidar_mask + S);
+  CameraLidarLineAssociate a(rows, cols);
+  a.AssociateByAngle(ln, seg, co, cloud, p2s, ends, T, multiple_association != 0, im, lm);
+  const std::vector<CameraLidarLinePair> pairs = a.GetAssociatedPairs();
+  if ((int)pairs.size() > cap) return -1;
+  for (size_t i = 0; i < pairs.size(); ++i) {
+    image_line_id[i] = pairs[i].image_line_id; lidar_line_id[i] = pairs[i].lidar_line_id; score[i] = pairs[i].angle;
+    for (int k = 0; k < 3; ++k) { start3[3 * i + k] = pairs[i].lidar_line_start[k]; end3[3 * i + k] = pairs[i].lidar_line_end[k]; }
+  }
+  return (int)pairs.size();
+}
+
+// ProjectLidar2PanoramaDepth<pcl::PointXYZI> (util/Visualization.h:407-441): rows x cols uint16 image
+void ref_project_lidar2panorama_depth(const float* cloud_xyzi, long n, int rows, int cols, const double* T_cl_rowmajor, int size, unsigned short* image) {
+  pcl::PointCloud<pcl::PointXYZI> cloud;
+  for (long i = 0; i < n; ++i) { pcl::PointXYZI p; p.x = cloud_xyzi[4 * i]; p.y = cloud_xyzi[4 * i + 1]; p.z = cloud_xyzi[4 * i + 2]; p.intensity = cloud_xyzi[4 * i + 3]; cloud.push_back(p); }
+  Eigen::Matrix4d T; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T(i, j) = T_cl_rowmajor[4 * i + j];
+  const cv::Mat img = ProjectLidar2PanoramaDepth(cloud, rows, cols, T, (size_t)size);
+  for (int i = 0; i < rows; ++i) for (int j = 0; j < cols; ++j) image[(size_t)i * cols + j] = img.at<uint16_t>(i, j);
+}
+}

@@ -2,12 +2,19 @@
 // cv::Point3_, cv::Vec, a cv::Mat that can only be empty or a float3 table), plus glog's LOG() (the PCL stand-ins live in pvo_shim_pcl.hpp).
 // See pvo_shim_eigen.hpp for why this exists.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <iostream>
+#include <string>
 #include <vector>
 
+#include <cassert>
+typedef unsigned char uchar; typedef unsigned short ushort;   // OpenCV declares these at global scope
+#define CV_GRAY2BGR 8
+#define CV_BGR2GRAY 6
 #define CV_32FC3 21
 #define CV_16U 2
+#define CV_16UC1 2
 namespace cv {
 template <typename T> struct Point_ {
   T x, y;
@@ -64,15 +71,68 @@ typedef Point3_<int> Point3i; typedef Point3_<float> Point3f; typedef Point3_<do
 typedef Vec<float, 2> Vec2f; typedef Vec<float, 3> Vec3f; typedef Vec<float, 4> Vec4f; typedef Vec<float, 6> Vec6f;
 typedef Vec<double, 2> Vec2d; typedef Vec<double, 3> Vec3d; typedef Vec<double, 4> Vec4d; typedef Vec<double, 6> Vec6d;
 typedef Vec<int, 2> Vec2i; typedef Vec<int, 3> Vec3i; typedef Vec<int, 4> Vec4i;
-// only what Equirectangular's optional pixel -> bearing table needs
+typedef Vec<uchar, 3> Vec3b;
+struct Scalar { double val[4]; Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; } double& operator[](int i) { return val[i]; } const double& operator[](int i) const { return val[i]; } };
+struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
+struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
+struct DMatch { int queryIdx = -1, trainIdx = -1, imgIdx = -1; float distance = 0; };
+namespace line_descriptor { struct KeyLine { float angle = 0; int class_id = 0, octave = 0; Point2f pt; float response = 0, size = 0, startPointX = 0, startPointY = 0, endPointX = 0, endPointY = 0,
+  sPointInOctaveX = 0, sPointInOctaveY = 0, ePointInOctaveX = 0, ePointInOctaveY = 0, lineLength = 0; int numOfPixels = 0; }; }
+// a dense 2-D array of `type` elements (CV_8U, CV_16U, CV_32F, CV_8UC3, CV_32FC3 ...): enough for zeros / at<T> / clone / empty / convertTo-free code
+#define CV_8U 0
+#define CV_8UC1 0
+#define CV_8UC3 16
+#define CV_32F 5
+#define CV_32FC1 5
+#define CV_64F 6
 struct Mat {
-  int rows = 0, cols = 0; std::vector<Vec3f> d;
-  static Mat zeros(int r, int c, int) { Mat m; m.rows = r; m.cols = c; m.d.assign((size_t)r * c, Vec3f()); return m; }
+  int rows = 0, cols = 0, type_ = 0; std::vector<unsigned char> d;
+  static int elem(int type) { const int depth = type & 7, ch = (type >> 3) + 1; const int sz[] = {1, 1, 2, 2, 4, 4, 8, 2}; return sz[depth] * ch; }
+  Mat() {}
+  Mat(int r, int c, int type) : rows(r), cols(c), type_(type), d((size_t)r * c * elem(type), 0) {}
+  Mat(int r, int c, int type, const Scalar&) : rows(r), cols(c), type_(type), d((size_t)r * c * elem(type), 0) {}
+  static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
   bool empty() const { return d.empty(); }
-  template <typename V> V& at(int i, int j) { return d[(size_t)i * cols + j]; }
-  template <typename V> const V& at(int i, int j) const { return d[(size_t)i * cols + j]; }
-  template <typename V> const V& at(const Point2i& p) const { return d[(size_t)p.y * cols + p.x]; }
+  bool isContinuous() const { return true; }
+  size_t elemSize() const { return (size_t)elem(type_); }
+  void create(int r, int c, int type) { *this = Mat(r, c, type); }
+  unsigned char* ptr(int i = 0) { return d.data() + (size_t)i * cols * elem(type_); }
+  const unsigned char* ptr(int i = 0) const { return d.data() + (size_t)i * cols * elem(type_); }
+  Mat clone() const { return *this; }
+  int type() const { return type_; }
+  int channels() const { return (type_ >> 3) + 1; }
+  Size size() const { return Size(cols, rows); }
+  template <typename V> V& at(int i, int j) { return *reinterpret_cast<V*>(d.data() + ((size_t)i * cols + j) * sizeof(V)); }
+  template <typename V> const V& at(int i, int j) const { return *reinterpret_cast<const V*>(d.data() + ((size_t)i * cols + j) * sizeof(V)); }
+  template <typename V> V& at(const Point2i& p) { return at<V>(p.y, p.x); }
+  template <typename V> const V& at(const Point2i& p) const { return at<V>(p.y, p.x); }
+  template <typename V> V* ptr(int i) { return reinterpret_cast<V*>(d.data() + (size_t)i * cols * elem(type_)); }
 };
+// drawing / IO named by the reference's debug branches (visualization flags off in every test): no-ops
+inline bool imwrite(const std::string&, const Mat&) { return true; }
+inline void cvtColor(const Mat& a, Mat& b, int) { b = a; }
+enum { COLOR_GRAY2BGR = 8, COLOR_BGR2GRAY = 6, COLOR_GRAY2RGB = 8 };
+inline void circle(Mat&, Point2i, int, const Scalar&, int = 1) {}
+inline void line(Mat&, Point2i, Point2i, const Scalar&, int = 1) {}
+namespace flann {
+struct KDTreeIndexParams { explicit KDTreeIndexParams(int = 4) {} };
+struct SearchParams { explicit SearchParams(int = 32, float = 0, bool = true) {} };
+// cv::flann::Index over the rows of a CV_32F matrix; SearchParams(-1) = unlimited checks = exact search: float32 squared L2, ascending
+struct Index {
+  Mat feat;
+  Index() {}
+  Index(const Mat& features, const KDTreeIndexParams&) : feat(features) {}
+  void knnSearch(const std::vector<float>& q, std::vector<int>& idx, std::vector<float>& dist, int knn, const SearchParams&) const {
+    const int n = feat.rows, dim = feat.cols;
+    std::vector<std::pair<float, int>> all(n);
+    for (int i = 0; i < n; ++i) { float s = 0; for (int k = 0; k < dim; ++k) { const float df = feat.at<float>(i, k) - q[k]; s += df * df; } all[i] = std::make_pair(s, i); }
+    const int kk = std::min(knn, n);
+    std::partial_sort(all.begin(), all.begin() + kk, all.end());
+    idx.assign(knn, -1); dist.assign(knn, 0.f);
+    for (int i = 0; i < kk; ++i) { idx[i] = all[i].second; dist[i] = all[i].first; }
+  }
+};
+}  // namespace flann
 }  // namespace cv
 
 #include "pvo_shim_pcl.hpp"

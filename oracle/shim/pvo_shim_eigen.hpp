@@ -16,6 +16,7 @@
 #include <vector>
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#define EIGEN_ALIGN16
 namespace Eigen {
 const int Dynamic = -1;
 typedef std::ptrdiff_t Index;
@@ -25,6 +26,7 @@ template <class T> struct aligned_allocator : std::allocator<T> {
   template <class U> struct rebind { typedef aligned_allocator<U> other; };
 };
 template <typename T> class Quaternion;
+template <typename T> class AngleAxis;
 template <typename T, int R, int C> class Matrix;
 
 namespace shim {
@@ -75,6 +77,7 @@ class Matrix {
   template <typename U> void init2(U rows, U cols, std::true_type) { s.resize((int)rows, (int)cols); }
  public:
   explicit Matrix(const Quaternion<T>& q) { static_assert(R == 3 && C == 3, "3x3"); *this = q.toRotationMatrix(); }
+  explicit Matrix(const AngleAxis<T>& a) { static_assert(R == 3 && C == 3, "3x3"); *this = a.toRotationMatrix(); }
 
   int rows() const { return s.rows(); }
   int cols() const { return s.cols(); }
@@ -119,6 +122,11 @@ class Matrix {
     Matrix<T, BR, BC> b; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) b(i, j) = (*this)(i0 + i, j0 + j); return b;
   }
   template <int BR, int BC> shim::BlockRef<T, BR, BC, R, C> block(int i0, int j0) { return shim::BlockRef<T, BR, BC, R, C>(*this, i0, j0); }
+  Matrix<T, (R == Dynamic ? Dynamic : R + 1), 1> homogeneous() const { static_assert(C == 1, "vector"); Matrix<T, (R == Dynamic ? Dynamic : R + 1), 1> h; h.resize(rows() + 1, 1); for (int i = 0; i < rows(); ++i) h(i) = (*this)(i); h(rows()) = T(1); return h; }
+  template <typename U> Matrix<U, R, C> cast() const { Matrix<U, R, C> m; m.resize(rows(), cols()); for (int i = 0; i < size(); ++i) m.data()[i] = U(s.data()[i]); return m; }
+  template <int N> Matrix<T, N, 1> head() const { Matrix<T, N, 1> h; for (int i = 0; i < N; ++i) h(i) = (*this)(i); return h; }
+  Matrix<T, Dynamic, 1> head(int n) const { Matrix<T, Dynamic, 1> h; h.resize(n, 1); for (int i = 0; i < n; ++i) h(i) = (*this)(i); return h; }
+  Matrix<T, (R == Dynamic ? Dynamic : R - 1), 1> hnormalized() const { static_assert(C == 1, "vector"); Matrix<T, (R == Dynamic ? Dynamic : R - 1), 1> h; h.resize(rows() - 1, 1); for (int i = 0; i + 1 < rows(); ++i) h(i) = (*this)(i) / (*this)(rows() - 1); return h; }
   Matrix inverse() const;  // square, fixed size: Gauss-Jordan with partial pivoting (Eigen uses cofactors for <= 4x4; equal up to rounding)
   shim::ColPivQR<T, C> colPivHouseholderQr() const { return shim::ColPivQR<T, C>(*this); }
 };
@@ -301,9 +309,29 @@ class Quaternion {
   }
 };
 
+// Eigen::AngleAxis -> rotation matrix (Rodrigues, Eigen's toRotationMatrix formula); axis expected normalised
+template <typename T>
+class AngleAxis {
+  T angle_; Matrix<T, 3, 1> axis_;
+ public:
+  AngleAxis(const T& angle, const Matrix<T, 3, 1>& axis) : angle_(angle), axis_(axis) {}
+  Matrix<T, 3, 3> toRotationMatrix() const {
+    using std::sin; using std::cos;
+    Matrix<T, 3, 3> res; const T s = sin(angle_), c = cos(angle_);
+    const Matrix<T, 3, 1> sin_axis = axis_ * s, cos1_axis = axis_ * (T(1) - c);
+    T tmp;
+    tmp = cos1_axis.x() * axis_.y(); res(0, 1) = tmp - sin_axis.z(); res(1, 0) = tmp + sin_axis.z();
+    tmp = cos1_axis.x() * axis_.z(); res(0, 2) = tmp + sin_axis.y(); res(2, 0) = tmp - sin_axis.y();
+    tmp = cos1_axis.y() * axis_.z(); res(1, 2) = tmp - sin_axis.x(); res(2, 1) = tmp + sin_axis.x();
+    res(0, 0) = cos1_axis.x() * axis_.x() + c; res(1, 1) = cos1_axis.y() * axis_.y() + c; res(2, 2) = cos1_axis.z() * axis_.z() + c;
+    return res;
+  }
+};
+typedef AngleAxis<double> AngleAxisd; typedef AngleAxis<float> AngleAxisf;
 typedef Matrix<double, 2, 1> Vector2d; typedef Matrix<double, 3, 1> Vector3d; typedef Matrix<double, 4, 1> Vector4d;
 typedef Matrix<float, 2, 1> Vector2f;  typedef Matrix<float, 3, 1> Vector3f;  typedef Matrix<float, 4, 1> Vector4f;
 typedef Matrix<double, 3, 3> Matrix3d; typedef Matrix<double, 4, 4> Matrix4d; typedef Matrix<float, 3, 3> Matrix3f; typedef Matrix<float, 4, 4> Matrix4f;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd; typedef Matrix<double, Dynamic, 1> VectorXd;
+typedef Matrix<int, 3, 1> Vector3i; typedef Matrix<int, 2, 1> Vector2i;
 typedef Matrix<float, Dynamic, Dynamic> MatrixXf; typedef Matrix<int, Dynamic, Dynamic> MatrixXi; typedef Matrix<float, Dynamic, 1> VectorXf;
 }  // namespace Eigen

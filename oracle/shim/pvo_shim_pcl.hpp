@@ -17,7 +17,7 @@ struct PointXYZRGB { float x = 0, y = 0, z = 0; unsigned char r = 0, g = 0, b = 
 struct PointXYZRGBL { float x = 0, y = 0, z = 0; unsigned char r = 0, g = 0, b = 0; unsigned int label = 0; };
 struct Normal { float normal_x = 0, normal_y = 0, normal_z = 0, curvature = 0; };
 struct ModelCoefficients { std::vector<float> values; };
-struct PointIndices { std::vector<int> indices; };
+struct PointIndices { typedef std::shared_ptr<PointIndices> Ptr; std::vector<int> indices; };
 
 template <typename P> struct PointCloud {
   typedef std::shared_ptr<PointCloud<P>> Ptr;
@@ -73,6 +73,31 @@ template <typename P> class VoxelGrid {
  public:
   void setLeafSize(float, float, float) {}
 };
+// pcl::transformPointCloud(in, out, Matrix4): PCL 1.10 computes x' = T(0,0) x + T(0,1) y + T(0,2) z + T(0,3) in the MATRIX's scalar type and stores float32;
+// the other fields are copied.  M is any 4x4 type with operator()(i, j).
+template <typename P, typename M> inline void transformPointCloud(const PointCloud<P>& in, PointCloud<P>& out, const M& T) {
+  PointCloud<P> tmp = in;
+  for (size_t i = 0; i < in.points.size(); ++i) {
+    const P& p = in.points[i];
+    tmp.points[i].x = static_cast<float>(T(0, 0) * p.x + T(0, 1) * p.y + T(0, 2) * p.z + T(0, 3));
+    tmp.points[i].y = static_cast<float>(T(1, 0) * p.x + T(1, 1) * p.y + T(1, 2) * p.z + T(1, 3));
+    tmp.points[i].z = static_cast<float>(T(2, 0) * p.x + T(2, 1) * p.y + T(2, 2) * p.z + T(2, 3));
+  }
+  out = tmp;
+}
+// pcl::SACSegmentation (RANSAC line fit behind CameraLidarLineAssociate::FitLineRANSAC, the fallback for frames without LiDAR segments): NOT reproduced -
+// its sample sequence depends on PCL's internal random generator.  segment() reports no inliers, so FitLineRANSAC returns false.
+enum { SACMODEL_LINE = 1, SAC_RANSAC = 0 };
+template <typename P> class SACSegmentation {
+ public:
+  void setOptimizeCoefficients(bool) {} void setModelType(int) {} void setMethodType(int) {} void setDistanceThreshold(double) {}
+  void setInputCloud(const typename PointCloud<P>::ConstPtr&) {}
+  void segment(PointIndices& inliers, ModelCoefficients&) { inliers.indices.clear(); }
+};
+template <typename P, typename V> inline unsigned compute3DCentroid(const PointCloud<P>&, const PointIndices&, V&) { return 0; }
+template <typename P, typename V, typename M> inline unsigned computeCovarianceMatrix(const PointCloud<P>&, const PointIndices&, const V&, M&) { return 0; }
+template <typename M, typename V> inline void eigen33(const M&, V&) {}
+template <typename M, typename S, typename V> inline void computeCorrespondingEigenVector(const M&, const S&, V&) {}
 namespace io {
 template <typename C> inline int savePCDFileASCII(const std::string&, const C&) { return 0; }   // debug dumps (visualization = true only)
 template <typename C> inline int savePCDFileBinary(const std::string&, const C&) { return 0; }

@@ -18,6 +18,8 @@ INDEPENDENT implementations, never from the oracle itself:
                  sensors/Equirectangular.{h,cpp} (CamToImage float / double, ImageToCam, BreakToSegments incl. seam crossings), same build
   ref_assoc.npz  correspondences returned by the reference's own lidar_mapping/LidarFeatureAssociate.cpp (all six association functions, FindNeighbors,
                  TransformLines; compiled where it lies with the PCL / Eigen stand-ins of oracle/shim: oracle/_ref/libpvo_ref_assoc.so) on four synthetic pairs
+  ref_camlidar.npz  (image line, LiDAR segment) pairs of the reference's own CameraLidarLineAssociate::AssociateByAngle (+ Filter + UniqueLinePair, masks) and uint16
+                 depth images of its ProjectLidar2PanoramaDepth (oracle/_ref/libpvo_ref_camlidar.so)
   reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
                  undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
 Run from the repo root:  python tests/make_golden.py
@@ -301,8 +303,30 @@ def golden_ref_assoc():
     np.savez_compressed(os.path.join(OUT, "ref_assoc.npz"), **out)
 
 
+def golden_ref_camlidar():
+    """tests/golden/ref_camlidar.npz: pair lists of the reference's own CameraLidarLineAssociate::AssociateByAngle (+ Filter + UniqueLinePair) and depth images of
+    its ProjectLidar2PanoramaDepth (oracle/_ref/libpvo_ref_camlidar.so) on the case of tests/test_reference_pinning.py: camlidar_case."""
+    from oracle import pvo
+    if pvo.ref_camlidar_lib() is None:
+        print("oracle/_ref/libpvo_ref_camlidar.so not built (no /root/reference here): ref_camlidar.npz left as committed")
+        return
+    import test_reference_pinning as trp
+    A, rows, cols, T, lines = trp.camlidar_case()
+    out = dict(lines=lines, T_cl=T)
+    n_seg = len(A["segment_coeffs"])
+    for name, multi, masked in trp.CAMLIDAR_VARIANTS:
+        im, lm = trp._camlidar_masks(out, len(lines), n_seg) if masked else (None, None)
+        r = pvo.ref_associate_by_angle(rows, cols, lines, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], A["segment_coeffs"], A["end_points"], T, multi, im, lm)
+        for k, v in zip(("image", "lidar", "start", "end", "score"), r):
+            out[f"{name}_{k}"] = v
+        print(f"  {name}: {len(r[0])} pairs")
+    out["depth_720"] = pvo.ref_project_depth(A["cloud"], 720, 1440, T, 3)
+    out["depth_360"] = pvo.ref_project_depth(A["cloud"], 360, 720, T, 4)
+    np.savez_compressed(os.path.join(OUT, "ref_camlidar.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -321,3 +321,57 @@ def test_find_neighbors_and_transform_lines_equal_the_reference(oracle):
             R = np.tile(np.eye(3).reshape(1, 9), (len(t), 1))
             assert oracle.ref_find_neighbors(R, t, pv, va, k) == exp
     assert np.abs(oracle.transform_lines(g["tl_T"][:3, :3], g["tl_T"][:3, 3], g["tl_in"]) - g["tl_out"]).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------------------
+# Camera-LiDAR line association (A4) and the depth splat (P): joint_optimization/CameraLidarLineAssociate.cpp and util/Visualization.h compiled where
+# they lie (oracle/ref_camlidar_wrap.cpp, oracle/_ref/libpvo_ref_camlidar.so)
+# ------------------------------------------------------------------------------------------------------------------------------------------------
+def camlidar_case(oracle_mod=None):
+    """One frame with LiDAR segments, image lines = projections of the segments' end points + noise, clutter lines and near-duplicates (so that
+    UniqueLinePair has conflicts to resolve), a T_cl off the identity, and masks that exclude one image line and one segment."""
+    from panovlm_b200 import synth
+    from scipy.spatial.transform import Rotation
+    A, _ = synth.make_pair(seed=20261030, n_az=1800, ground_class=True)
+    rows, cols = 2880, 5760
+    T = np.eye(4); T[:3, :3] = Rotation.from_rotvec([0.01, 0.02, -0.01]).as_matrix(); T[:3, 3] = [0.03, -0.05, 0.02]
+    rng = np.random.default_rng(9)
+    ends_cam = A["end_points"].reshape(-1, 3) @ T[:3, :3].T + T[:3, 3]
+    lon = np.arctan2(ends_cam[:, 0], ends_cam[:, 2]); lat = -np.arctan2(ends_cam[:, 1], np.hypot(ends_cam[:, 0], ends_cam[:, 2]))
+    px = np.stack([cols * (0.5 + lon / (2 * np.pi)), rows * (0.5 - lat / np.pi)], axis=1).reshape(-1, 4) + rng.normal(0, 2, (len(A["end_points"]), 4))
+    clutter = np.stack([rng.uniform(0, cols, 30), rng.uniform(0, rows, 30), rng.uniform(0, cols, 30), rng.uniform(0, rows, 30)], axis=1)
+    lines = np.concatenate([px, clutter, px + 1.5]).astype(np.float32)
+    return A, rows, cols, T, lines
+
+
+CAMLIDAR_VARIANTS = [("multi", True, False), ("unique", False, False), ("masked", True, True)]
+
+
+def _camlidar_masks(g, n_lines, n_seg):
+    im = np.ones(n_lines, np.uint8); im[int(g["multi_image"][0])] = 0
+    lm = np.ones(n_seg, np.uint8); lm[int(g["multi_lidar"][-1])] = 0
+    return im, lm
+
+
+def test_camera_lidar_association_and_depth_splat_equal_the_reference(oracle):
+    """A4: AssociateByAngle + Filter(false, true) + UniqueLinePair of the reference == the oracle: same (image line, LiDAR segment) pairs in the same order,
+    float32 scores bit-identical, end points to 1e-12; masks honoured.  P: ProjectLidar2PanoramaDepth gives the identical uint16 image (last writer wins)."""
+    g = np.load(os.path.join(G, "ref_camlidar.npz"))
+    A, rows, cols, T, lines = camlidar_case()
+    assert np.array_equal(lines, g["lines"])
+    sizes = np.diff(A["seg_off"])
+    for name, multi, masked in CAMLIDAR_VARIANTS:
+        im, lm = _camlidar_masks(g, len(lines), len(sizes)) if masked else (None, None)
+        got = oracle.associate_by_angle(rows, cols, lines, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], sizes, A["end_points"], T, True, multi, im, lm)
+        assert np.array_equal(got[0], g[name + "_image"]) and np.array_equal(got[1], g[name + "_lidar"]) and np.array_equal(got[4], g[name + "_score"]), name
+        assert np.abs(got[2] - g[name + "_start"]).max() < 1e-12 and np.abs(got[3] - g[name + "_end"]).max() < 1e-12, name
+        if oracle.ref_camlidar_lib() is not None:
+            ref = oracle.ref_associate_by_angle(rows, cols, lines, A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], A["segment_coeffs"], A["end_points"], T, multi, im, lm)
+            assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1], got[1]) and np.array_equal(ref[4], got[4]), name
+    assert len(g["unique_image"]) < len(g["multi_image"]) and len(g["masked_image"]) < len(g["multi_image"]) and len(g["unique_image"]) >= 10
+    for key, r_, c_, size in (("depth_720", 720, 1440, 3), ("depth_360", 360, 720, 4)):
+        img, _ = oracle.project_depth(A["cloud"], r_, c_, T, size=size)
+        assert np.array_equal(img, g[key]) and (img > 0).sum() > 20000, key
+    if oracle.ref_camlidar_lib() is not None:
+        img, _ = oracle.project_depth(A["cloud"], rows, cols, T, size=3)
+        assert np.array_equal(img, oracle.ref_project_depth(A["cloud"], rows, cols, T, 3))

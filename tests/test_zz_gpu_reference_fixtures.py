@@ -65,3 +65,26 @@ def test_projection_kernel_equals_the_reference_projection(gpu_ctx):
     cam = np.concatenate([g["cam_f"], np.zeros((len(g["cam_f"]), 1), np.float32)], axis=1)
     out = gpu_ctx.project_equirect(cam, np.eye(4), int(g["rows"]), int(g["cols"]))
     assert np.array_equal(out[:, :2], g["px_f"])
+
+
+def test_camera_lidar_kernel_equals_the_reference_association(gpu_ctx):
+    """k_angle_votes + tail (A4) == the reference's AssociateByAngle + Filter(false, true) + UniqueLinePair: pair lists, float32 scores, masks."""
+    from test_reference_pinning import CAMLIDAR_VARIANTS, _camlidar_masks, camlidar_case
+    g = np.load(os.path.join(G, "ref_camlidar.npz"))
+    A, rows, cols, T, lines = camlidar_case()
+    fr = _line_frame(A, A["R_wl"], A["t_wl"])
+    n_seg = len(A["segment_coeffs"])
+    for name, multi, masked in CAMLIDAR_VARIANTS:
+        im, lm = _camlidar_masks(g, len(lines), n_seg) if masked else (None, None)
+        il, ll, s, e, ang = gpu_ctx.camera_lidar_associate(rows, cols, lines, fr, T, True, multi, im, lm)
+        assert np.array_equal(il, g[name + "_image"]) and np.array_equal(ll, g[name + "_lidar"]) and np.array_equal(ang, g[name + "_score"]), name
+        assert np.abs(s - g[name + "_start"]).max() < 1e-12 and np.abs(e - g[name + "_end"]).max() < 1e-12, name
+
+
+def test_depth_splat_kernel_equals_the_reference_image(gpu_ctx):
+    """k_project + k_splat_finalize (P) == ProjectLidar2PanoramaDepth of the reference: identical uint16 images (window clipping, last writer wins)."""
+    from test_reference_pinning import camlidar_case
+    g = np.load(os.path.join(G, "ref_camlidar.npz"))
+    A, _, _, T, _ = camlidar_case()
+    for key, rows, cols, size in (("depth_720", 720, 1440, 3), ("depth_360", 360, 720, 4)):
+        assert np.array_equal(gpu_ctx.project_depth_image(A["cloud"], T, rows, cols, size), g[key]), key
