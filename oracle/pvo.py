@@ -615,3 +615,14 @@ def ref_project_depth(cloud, rows, cols, T_cl, size=3):
     img = np.zeros((rows, cols), dtype=np.uint16)
     ref_camlidar_lib().ref_project_lidar2panorama_depth(_p(cloud), C.c_long(len(cloud)), C.c_int(rows), C.c_int(cols), _p(_f64(T_cl)), C.c_int(size), _p(img))
     return img
+
+
+def ref_generate_line_tracks(frames, neighbor_size, min_track_length):
+    """LidarLineMatch::GenerateTracks of the reference over a list of RefFrame; returns a list of (m, 2) arrays of (frame, line)."""
+    n = len(frames)
+    arr = (C.c_void_p * n)(*[f.h for f in frames])
+    cap = 1 << 20
+    off, ff, fl = np.zeros(cap + 1, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    m = frames[0].L.ref_generate_line_tracks(C.c_int(n), arr, C.c_int(neighbor_size), C.c_int(min_track_length), C.c_int(cap), _p(off), _p(ff), _p(fl))
+    assert m >= 0
+    return [np.stack([ff[off[t]:off[t + 1]], fl[off[t]:off[t + 1]]], axis=1) for t in range(m)]

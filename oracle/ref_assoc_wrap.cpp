@@ -25,6 +25,8 @@
 #include <chrono>
 #define private public          // the wrapper sets Velodyne::world (set by Transform2LidarWorld, sensors/Velodyne.cpp:1807) after filling world-frame clouds
 #include REF_LIDAR_FEATURE_ASSOCIATE_CPP
+#include REF_TRACKS_CPP                   // util/Tracks.cpp: TrackBuilder (union-find over (frame, line) features), Filter, ExportTracks
+#include REF_LIDAR_LINE_MATCH_CPP         // lidar_mapping/LidarLineMatch.cpp: GenerateTracks = FindNeighbors + AssociateLine2Line(nei, i, 0.3) + TrackBuilder
 #undef private
 
 // ---- class Velodyne: the members the association code needs (sensors/Velodyne.cpp, restated) ----
@@ -128,6 +130,24 @@ void ref_transform_lines(const double* T_rowmajor16, int n, const double* lines6
   const eigen_vector<Vector6d> out = TransformLines(in, T);
   for (int i = 0; i < n; ++i) for (int k = 0; k < 6; ++k) out6[6 * i + k] = out[i][k];
 }
+// LidarLineMatch::GenerateTracks over frames made by ref_frame_create (copied into a std::vector<Velodyne>).  Output: track t = features
+// [off[t], off[t + 1]) as (frame, line) pairs in the set's order.  Returns the number of tracks, or -1 when cap is too small.
+int ref_generate_line_tracks(int n, void* const* frames, int neighbor_size, int min_track_length, int cap, int* off, int* feat_frame, int* feat_line) {
+  std::vector<Velodyne> lidars;
+  for (int i = 0; i < n; ++i) lidars.push_back(*static_cast<const Velodyne*>(frames[i]));
+  LidarLineMatch m(lidars);
+  m.SetNeighborSize(neighbor_size);
+  m.SetMinTrackLength(min_track_length);
+  m.GenerateTracks();
+  const std::vector<LineTrack>& tr = m.GetTracks();
+  int total = 0; off[0] = 0;
+  for (size_t t = 0; t < tr.size(); ++t) {
+    for (const auto& f : tr[t].feature_pairs) { if (total >= cap) return -1; feat_frame[total] = (int)f.first; feat_line[total] = (int)f.second; ++total; }
+    off[t + 1] = total;
+  }
+  return (int)tr.size();
+}
+
 // FindNeighbors over n frames given by pose (R row-major 9, t 3), pose_valid and valid flags; CSR output (off[n + 1], ids[cap]); returns total or -1
 int ref_find_neighbors(int n, const double* R_wl, const double* t_wl, const unsigned char* pose_valid, const unsigned char* valid, int neighbor_size, int cap, int* off, int* ids) {
   std::vector<Velodyne> lidars(n);

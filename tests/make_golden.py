@@ -300,6 +300,11 @@ def golden_ref_assoc():
     lin = rng.normal(0, 3, (40, 6)); lout = np.zeros_like(lin)
     pvo.ref_assoc_lib().ref_transform_lines(T.ctypes.data_as(C.c_void_p), C.c_int(40), lin.ctypes.data_as(C.c_void_p), lout.ctypes.data_as(C.c_void_p))
     out.update(tl_T=T, tl_in=lin, tl_out=lout)
+    for ci, (nf, n_az, k, min_len, no_pose) in enumerate(trp.TRACK_CASES):          # LidarLineMatch::GenerateTracks
+        tr = trp.reference_line_tracks(pvo, trp.track_case(nf, n_az), k, min_len, no_pose)
+        off = np.zeros(len(tr) + 1, np.int32); off[1:] = np.cumsum([len(t) for t in tr])
+        out[f"tr{ci}_off"] = off; out[f"tr{ci}_feat"] = np.concatenate(tr).astype(np.int32)
+        print(f"  tracks case {ci}: {len(tr)} tracks, {off[-1]} features")
     np.savez_compressed(os.path.join(OUT, "ref_assoc.npz"), **out)
 
 

@@ -375,3 +375,61 @@ def test_camera_lidar_association_and_depth_splat_equal_the_reference(oracle):
     if oracle.ref_camlidar_lib() is not None:
         img, _ = oracle.project_depth(A["cloud"], rows, cols, T, size=3)
         assert np.array_equal(img, oracle.ref_project_depth(A["cloud"], rows, cols, T, 3))
+
+
+# ---- LiDAR line tracks: lidar_mapping/LidarLineMatch.cpp + util/Tracks.cpp (GenerateTracks = FindNeighbors + AssociateLine2Line + TrackBuilder) ----
+TRACK_CASES = [(8, 600, 4, 3, None), (8, 600, 4, 2, 2), (12, 600, 2, 3, None), (12, 600, 6, 4, 5)]      # frames, n_az, neighbor_size, min_track_length, frame without pose
+
+
+def track_case(n_frames, n_az):
+    from panovlm_b200 import synth
+    return synth.make_sequence(n_frames, n_az=n_az)
+
+
+def oracle_line_tracks(oracle, frames, neighbor_size, min_len, no_pose, builder=None):
+    """The oracle's pipeline for GenerateTracks; `builder` swaps the union-find stage (the product's host pvb_line_tracks_build)."""
+    from panovlm_b200 import Context
+    n = len(frames)
+    R_wl, t_wl = [f["R_wl"] for f in frames], np.array([f["t_wl"] for f in frames])
+    pv = np.ones(n, np.uint8)
+    if no_pose is not None:
+        pv[no_pose] = 0
+    nbrs = Context.find_neighbors(t_wl, pv, None, neighbor_size)
+    corner_w = [oracle.transform_cloud(R_wl[i], t_wl[i], f["cornerLessSharp"]) for i, f in enumerate(frames)]
+    lines_w = [oracle.transform_lines(R_wl[i], t_wl[i], f["segment_coeffs"]) for i, f in enumerate(frames)]
+    pa, pb, off, ma, mb = [], [], [0], [], []
+    for i in range(n):
+        if not pv[i]:
+            continue
+        for nb in nbrs[i]:
+            if not (0 <= nb < n) or not pv[nb]:
+                continue                                   # the synthetic cases never pair a valid frame with a pose-less neighbour's clouds
+            M = oracle.line_votes(lines_w[nb], corner_w[i], frames[i]["p2s_off"], frames[i]["p2s_ids"], len(frames[i]["segment_coeffs"]), 0.3)
+            on, orf, _, _ = oracle.find_associations(frames[nb]["segment_coeffs"], lines_w[nb], lines_w[i], np.diff(frames[i]["seg_off"]), M)
+            for x, y in sorted(set(zip(on.tolist(), orf.tolist()))):
+                ma.append(x); mb.append(y)
+            pa.append(i); pb.append(nb); off.append(len(ma))
+    return (builder or oracle.line_tracks)(pa, pb, off, ma, mb, min_len, True)
+
+
+def reference_line_tracks(oracle, frames, neighbor_size, min_len, no_pose):
+    rf = []
+    for i, f in enumerate(frames):
+        cw = oracle.transform_cloud(f["R_wl"], f["t_wl"], f["cornerLessSharp"])
+        rf.append(oracle.RefFrame(f["R_wl"], f["t_wl"], cw, f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], id=i, pose_valid=(i != no_pose)))
+    return oracle.ref_generate_line_tracks(rf, neighbor_size, min_len)
+
+
+def test_line_tracks_equal_the_reference_generate_tracks(oracle):
+    from panovlm_b200 import Context
+    g = np.load(os.path.join(G, "ref_assoc.npz"))
+    for ci, (nf, n_az, k, min_len, no_pose) in enumerate(TRACK_CASES):
+        frames = track_case(nf, n_az)
+        exp = [g[f"tr{ci}_feat"][g[f"tr{ci}_off"][t]:g[f"tr{ci}_off"][t + 1]] for t in range(len(g[f"tr{ci}_off"]) - 1)]
+        assert len(exp) >= 5
+        for builder in (None, Context.line_tracks_build):
+            got = oracle_line_tracks(oracle, frames, k, min_len, no_pose, builder)
+            assert len(got) == len(exp) and all(np.array_equal(a, b) for a, b in zip(got, exp)), (ci, builder)
+        if oracle.ref_assoc_lib() is not None:
+            ref = reference_line_tracks(oracle, frames, k, min_len, no_pose)
+            assert len(ref) == len(exp) and all(np.array_equal(a, b) for a, b in zip(ref, exp)), ci

@@ -88,3 +88,19 @@ def test_depth_splat_kernel_equals_the_reference_image(gpu_ctx):
     A, _, _, T, _ = camlidar_case()
     for key, rows, cols, size in (("depth_720", 720, 1440, 3), ("depth_360", 360, 720, 4)):
         assert np.array_equal(gpu_ctx.project_depth_image(A["cloud"], T, rows, cols, size), g[key]), key
+
+
+def test_generate_line_tracks_equals_the_reference_tracks(gpu_ctx):
+    """pvb_generate_line_tracks (device vote matrices per pair + host union-find) == LidarLineMatch::GenerateTracks of the reference."""
+    from panovlm_b200 import Context
+    from test_reference_pinning import TRACK_CASES, track_case
+    g = np.load(os.path.join(G, "ref_assoc.npz"))
+    for ci, (nf, n_az, k, min_len, no_pose) in enumerate(TRACK_CASES):
+        frames = track_case(nf, n_az)
+        exp = [g[f"tr{ci}_feat"][g[f"tr{ci}_off"][t]:g[f"tr{ci}_off"][t + 1]] for t in range(len(g[f"tr{ci}_off"]) - 1)]
+        pv = np.ones(nf, np.uint8)
+        if no_pose is not None:
+            pv[no_pose] = 0
+        nbrs = Context.find_neighbors(np.array([f["t_wl"] for f in frames]), pv, None, k)
+        got = gpu_ctx.generate_line_tracks([_line_frame(f, f["R_wl"], f["t_wl"]) for f in frames], nbrs, pv, 0.3, min_len)
+        assert len(got) == len(exp) and all(np.array_equal(a, b) for a, b in zip(got, exp)), ci
