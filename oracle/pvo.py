@@ -626,3 +626,34 @@ def ref_generate_line_tracks(frames, neighbor_size, min_track_length):
     m = frames[0].L.ref_generate_line_tracks(C.c_int(n), arr, C.c_int(neighbor_size), C.c_int(min_track_length), C.c_int(cap), _p(off), _p(ff), _p(fl))
     assert m >= 0
     return [np.stack([ff[off[t]:off[t + 1]], fl[off[t]:off[t + 1]]], axis=1) for t in range(m)]
+
+
+def ref_refine_pose_blocks(frames, point_to_plane=True, line_to_line=True, point_to_line=False, use_segment=True, angle_residual=True, normalize_distance=True,
+                           plane_dis_threshold=1.0, line_dis_threshold=0.3, plane_tolerance=0.05):
+    """The residual blocks one LidarOdometry::RefinePose registers, built by the reference's own util/Optimization.cpp builders over a list of RefFrame and
+    evaluated once (raw residual / 1x12 Jacobian).  Returns dict(ref, nei, huber, residual, jacobian, poses)."""
+    n = len(frames)
+    arr = (C.c_void_p * n)(*[f.h for f in frames])
+    cap = 1 << 21
+    rf, nf, hb, r, J, poses = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap), np.zeros(cap), np.zeros((cap, 12)), np.zeros((n, 6))
+    L = frames[0].L
+    L.ref_refine_pose_blocks.restype = C.c_long
+    m = L.ref_refine_pose_blocks(C.c_int(n), arr, C.c_int(int(point_to_plane)), C.c_int(int(line_to_line)), C.c_int(int(point_to_line)), C.c_int(int(use_segment)),
+                                 C.c_int(int(angle_residual)), C.c_int(int(normalize_distance)), C.c_double(plane_dis_threshold), C.c_double(line_dis_threshold),
+                                 C.c_double(plane_tolerance), C.c_long(cap), _p(rf), _p(nf), _p(hb), _p(r), _p(J), _p(poses))
+    assert m >= 0, m
+    return dict(ref=rf[:m].copy(), nei=nf[:m].copy(), huber=hb[:m].copy(), residual=r[:m].copy(), jacobian=J[:m].copy(), poses=poses)
+
+
+def ref_camera_lidar_blocks(rows, cols, image_lines, start, end, pair_weight, R_wc, t_wc, R_wl, t_wl, weight):
+    """AddCameraLidarResidual of the reference for one (image, LiDAR) frame pair: raw residuals / Jacobians of the 2 n blocks + the two pose blocks."""
+    ln, s, e = _f32(image_lines).reshape(-1, 4), _f64(start).reshape(-1, 3), _f64(end).reshape(-1, 3)
+    n = len(ln)
+    pw = None if pair_weight is None else _f32(pair_weight)
+    r, J, poses = np.zeros(2 * n), np.zeros((2 * n, 12)), np.zeros((2, 6))
+    L = ref_assoc_lib()
+    L.ref_camera_lidar_blocks.restype = C.c_long
+    m = L.ref_camera_lidar_blocks(C.c_int(rows), C.c_int(cols), C.c_int(n), _p(ln), _p(s), _p(e), _p(pw), _p(_f64(R_wc)), _p(_f64(t_wc)), _p(_f64(R_wl)), _p(_f64(t_wl)),
+                                  C.c_double(weight), C.c_long(2 * n), _p(r), _p(J), _p(poses))
+    assert m == 2 * n, m
+    return r, J, poses

@@ -27,6 +27,7 @@
 #include REF_LIDAR_FEATURE_ASSOCIATE_CPP
 #include REF_TRACKS_CPP                   // util/Tracks.cpp: TrackBuilder (union-find over (frame, line) features), Filter, ExportTracks
 #include REF_LIDAR_LINE_MATCH_CPP         // lidar_mapping/LidarLineMatch.cpp: GenerateTracks = FindNeighbors + AssociateLine2Line(nei, i, 0.3) + TrackBuilder
+#include REF_OPTIMIZATION_CPP             // util/Optimization.cpp: the residual-block builders (AddLidarPointToPlaneResidual ...); ceres::Problem = the shim's recorder
 #undef private
 
 // ---- class Velodyne: the members the association code needs (sensors/Velodyne.cpp, restated) ----
@@ -52,6 +53,29 @@ const bool Velodyne::IsPoseValid() const {                                      
   return false;
 }
 const bool Velodyne::IsInWorldCoordinate() const { return world; }                                                                           // :1901-1904
+
+// ---- class Frame: the members util/Optimization.cpp calls (sensors/Frame.cpp, restated) ----
+Frame::Frame(int _rows, int _cols, int _id, const std::string _name) : id(_id), name(_name), rows(_rows), cols(_cols), scale(0) {                // :10-16
+  R_wc = Eigen::Matrix3d::Zero();
+  t_wc = std::numeric_limits<double>::infinity() * Eigen::Vector3d::Ones();
+  gps = std::numeric_limits<double>::infinity() * Eigen::Vector3d::Ones();
+}
+Frame::~Frame() {}                                                                                                                               // :227-229
+void Frame::SetPose(const Eigen::Matrix3d _R_wc, const Eigen::Vector3d _t_wc) { R_wc = _R_wc; t_wc = _t_wc; }                                    // :52-56
+const Eigen::Matrix4d Frame::GetPose() const {                                                                                                   // :129-135
+  Eigen::Matrix4d T_wc = Eigen::Matrix4d::Identity();
+  T_wc.block<3, 3>(0, 0) = R_wc;
+  T_wc.block<3, 1>(0, 3) = t_wc;
+  return T_wc;
+}
+const std::vector<cv::KeyPoint>& Frame::GetKeyPoints() const { return keypoints_all; }                                                           // :137-140
+const int Frame::GetImageRows() const { return rows; }                                                                                           // :188-191
+const int Frame::GetImageCols() const { return cols; }                                                                                           // :193-196
+const bool Frame::IsPoseValid() const {                                                                                                          // :203-208
+  if (!std::isinf(t_wc(0)) && !std::isnan(t_wc(0)) && !std::isinf(t_wc(1)) && !std::isnan(t_wc(1)) && !std::isinf(t_wc(2)) && !std::isnan(t_wc(2)) && !R_wc.isZero())
+    return true;
+  return false;
+}
 
 namespace {
 void fill_cloud(pcl::PointCloud<PointType>& c, const float* xyzi, int n) {
@@ -146,6 +170,99 @@ int ref_generate_line_tracks(int n, void* const* frames, int neighbor_size, int 
     off[t + 1] = total;
   }
   return (int)tr.size();
+}
+
+// The residual blocks of one LidarOdometry::RefinePose call, as the reference's own builders register them.  The preamble is RefinePose's
+// (lidar_mapping/LidarOdometry.cpp:23-64, restated here because LidarOdometry.cpp itself needs the whole pipeline): pose blocks (aa_lw, t_lw) from
+// GetPose().inverse() + ceres::RotationMatrixToAngleAxis, FindNeighbors(lidars, 6), then - in this order - AddLidarPointToLineResidual (if point_to_line),
+// GenerateTracks(4, 3) + AddLidarLineToLineResidual2 (if line_to_line && use_segment), AddLidarPointToPlaneResidual (if point_to_plane), every builder called
+// with RefinePose's arguments (default weight).  The recorded blocks are then evaluated ONCE through ceres::CostFunction::Evaluate at those pose blocks.
+// Per block: reference / neighbour frame (from the parameter pointers), Huber parameter a (0 = loss nullptr), raw residual, raw 1x12 Jacobian.
+// poses_out: n x 6 pose blocks.  Returns the number of blocks, -1 when cap is too small, -2 on an Evaluate failure.
+long ref_refine_pose_blocks(int n, void* const* frames, int point_to_plane, int line_to_line, int point_to_line, int use_segment, int angle_residual, int normalize_distance,
+                            double plane_dis_threshold, double line_dis_threshold, double plane_tolerance, long cap, int* ref_frame, int* nei_frame, double* huber_a,
+                            double* residual, double* jac12, double* poses_out) {
+  std::vector<Velodyne> lidars;
+  for (int i = 0; i < n; ++i) lidars.push_back(*static_cast<const Velodyne*>(frames[i]));
+  eigen_vector<Eigen::Vector3d> angleAxis_lw_list(lidars.size(), Eigen::Vector3d::Ones());
+  eigen_vector<Eigen::Vector3d> t_lw_list(lidars.size(), Eigen::Vector3d::Ones());
+  for (size_t i = 0; i < lidars.size(); i++) {                                                     // LidarOdometry.cpp:25-33
+    if (!lidars[i].IsPoseValid() || !lidars[i].valid) continue;
+    Eigen::Matrix4d T_lw = lidars[i].GetPose().inverse();
+    Eigen::Matrix3d R_lw = T_lw.block<3, 3>(0, 0);
+    ceres::RotationMatrixToAngleAxis(R_lw.data(), angleAxis_lw_list[i].data());
+    t_lw_list[i] = T_lw.block<3, 1>(0, 3);
+  }
+  std::vector<std::vector<int>> neighbors_all = FindNeighbors(lidars, 6);                          // :35
+  ceres::Problem problem;
+  if (point_to_line)                                                                                // :38-40
+    AddLidarPointToLineResidual(neighbors_all, lidars, angleAxis_lw_list, t_lw_list, problem, line_dis_threshold, use_segment != 0, angle_residual != 0, normalize_distance != 0);
+  if (line_to_line && use_segment) {                                                                // :41-53
+    LidarLineMatch matcher(lidars);
+    matcher.SetNeighborSize(4);
+    matcher.SetMinTrackLength(3);
+    matcher.GenerateTracks();
+    AddLidarLineToLineResidual2(neighbors_all, lidars, angleAxis_lw_list, t_lw_list, problem, matcher.GetTracks(), line_dis_threshold, angle_residual != 0, normalize_distance != 0);
+  }
+  if (point_to_plane)                                                                               // :54-57
+    AddLidarPointToPlaneResidual(neighbors_all, lidars, angleAxis_lw_list, t_lw_list, problem, plane_dis_threshold, plane_tolerance, angle_residual != 0, normalize_distance != 0);
+  for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) { poses_out[6 * i + k] = angleAxis_lw_list[i][k]; poses_out[6 * i + 3 + k] = t_lw_list[i][k]; }
+  if ((long)problem.blocks.size() > cap) return -1;
+  for (size_t b = 0; b < problem.blocks.size(); ++b) {
+    const ceres::Problem::Block& blk = problem.blocks[b];
+    if (blk.params.size() != 4) return -2;
+    ref_frame[b] = (int)((Eigen::Vector3d*)blk.params[0] - &angleAxis_lw_list[0]);
+    nei_frame[b] = (int)((Eigen::Vector3d*)blk.params[2] - &angleAxis_lw_list[0]);
+    if (blk.params[1] != t_lw_list[ref_frame[b]].data() || blk.params[3] != t_lw_list[nei_frame[b]].data()) return -2;
+    const ceres::HuberLoss* h = dynamic_cast<const ceres::HuberLoss*>(blk.loss);
+    huber_a[b] = h ? h->a() : 0.0;
+    double jb[4][3]; double* jp[4] = {jb[0], jb[1], jb[2], jb[3]};
+    if (!blk.cost->Evaluate(blk.params.data(), residual + b, jp)) return -2;
+    std::memcpy(jac12 + 12 * b, jb, sizeof(jb));
+  }
+  return (long)problem.blocks.size();
+}
+
+// AddCameraLidarResidual (util/Optimization.cpp:564-607) for ONE (image, LiDAR) pair of frames: n line pairs (image line in pixels, LiDAR segment start / end
+// in the LiDAR frame, pair weight), camera pose T_wc and LiDAR pose T_wl (rotation row-major), global weight.  The pose blocks are built as
+// CameraLidarOptimizer::Optimize does (inverse pose + RotationMatrixToAngleAxis).  Two blocks per pair, in registration order: raw residual, raw 1x12
+// Jacobian (camera block = reference, LiDAR block = neighbour).  poses_out: 2 x 6 = (aa_cw, t_cw), (aa_lw, t_lw).  Returns the block count or < 0.
+long ref_camera_lidar_blocks(int rows, int cols, int n, const float* image_line4, const double* start3, const double* end3, const float* pair_weight, const double* R_wc,
+                             const double* t_wc, const double* R_wl, const double* t_wl, double weight, long cap, double* residual, double* jac12, double* poses_out) {
+  std::vector<Frame> frames; frames.push_back(Frame(rows, cols, 0, "frame"));
+  std::vector<Velodyne> lidars(1); lidars[0].id = 0;
+  Eigen::Matrix3d Rc, Rl;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { Rc(i, j) = R_wc[3 * i + j]; Rl(i, j) = R_wl[3 * i + j]; }
+  frames[0].SetPose(Rc, Eigen::Vector3d(t_wc[0], t_wc[1], t_wc[2]));
+  lidars[0].SetPose(Rl, Eigen::Vector3d(t_wl[0], t_wl[1], t_wl[2]));
+  eigen_vector<Eigen::Vector3d> aa_cw(1), t_cw(1), aa_lw(1), t_lw(1);
+  { Eigen::Matrix4d T = frames[0].GetPose().inverse(); Eigen::Matrix3d R = T.block<3, 3>(0, 0); ceres::RotationMatrixToAngleAxis(R.data(), aa_cw[0].data()); t_cw[0] = T.block<3, 1>(0, 3); }
+  { Eigen::Matrix4d T = lidars[0].GetPose().inverse(); Eigen::Matrix3d R = T.block<3, 3>(0, 0); ceres::RotationMatrixToAngleAxis(R.data(), aa_lw[0].data()); t_lw[0] = T.block<3, 1>(0, 3); }
+  eigen_map<std::pair<size_t, size_t>, std::vector<CameraLidarLinePair>> line_pairs;
+  std::vector<CameraLidarLinePair>& v = line_pairs[std::pair<size_t, size_t>(0, 0)];
+  for (int i = 0; i < n; ++i) {
+    CameraLidarLinePair lp;
+    lp.image_id = 0; lp.lidar_id = 0;
+    lp.image_line = cv::Vec4f(image_line4[4 * i], image_line4[4 * i + 1], image_line4[4 * i + 2], image_line4[4 * i + 3]);
+    lp.lidar_line_start = Eigen::Vector3d(start3[3 * i], start3[3 * i + 1], start3[3 * i + 2]);
+    lp.lidar_line_end = Eigen::Vector3d(end3[3 * i], end3[3 * i + 1], end3[3 * i + 2]);
+    lp.weight = pair_weight ? pair_weight[i] : 1.f;
+    v.push_back(lp);
+  }
+  ceres::Problem problem;
+  ceres::LossFunction* loss = new ceres::HuberLoss(3.0 * M_PI / 180.0);
+  AddCameraLidarResidual(frames, lidars, aa_cw, t_cw, aa_lw, t_lw, line_pairs, loss, problem, weight);
+  for (int k = 0; k < 3; ++k) { poses_out[k] = aa_cw[0][k]; poses_out[3 + k] = t_cw[0][k]; poses_out[6 + k] = aa_lw[0][k]; poses_out[9 + k] = t_lw[0][k]; }
+  if ((long)problem.blocks.size() > cap) return -1;
+  for (size_t b = 0; b < problem.blocks.size(); ++b) {
+    const ceres::Problem::Block& blk = problem.blocks[b];
+    if (blk.params.size() != 4 || blk.params[0] != aa_cw[0].data() || blk.params[1] != t_cw[0].data() || blk.params[2] != aa_lw[0].data() || blk.params[3] != t_lw[0].data()) return -2;
+    double jb[4][3]; double* jp[4] = {jb[0], jb[1], jb[2], jb[3]};
+    if (!blk.cost->Evaluate(blk.params.data(), residual + b, jp)) return -2;
+    std::memcpy(jac12 + 12 * b, jb, sizeof(jb));
+  }
+  delete loss;
+  return (long)problem.blocks.size();
 }
 
 // FindNeighbors over n frames given by pose (R row-major 9, t 3), pose_valid and valid flags; CSR output (off[n + 1], ids[cap]); returns total or -1

@@ -7,7 +7,9 @@
 #include <cfloat>
 #include <cmath>
 #include <limits>
+#include <algorithm>
 #include <memory>
+#include <string>
 #include <vector>
 
 namespace ceres {
@@ -159,7 +161,22 @@ class CostFunction {
  protected:
   std::vector<int> sizes_; int num_residuals_ = 0;
 };
-class LossFunction;
+// rho(s), rho'(s), rho''(s) of the squared residual norm s (ceres/loss_function.h)
+class LossFunction {
+ public:
+  virtual ~LossFunction() {}
+  virtual void Evaluate(double sq_norm, double out[3]) const = 0;
+};
+class HuberLoss : public LossFunction {
+  const double a_, b_;
+ public:
+  explicit HuberLoss(double a) : a_(a), b_(a * a) {}
+  double a() const { return a_; }
+  void Evaluate(double s, double rho[3]) const override {
+    if (s > b_) { const double r = std::sqrt(s); rho[0] = 2.0 * a_ * r - b_; rho[1] = std::max(std::numeric_limits<double>::min(), a_ / r); rho[2] = -rho[1] / (2.0 * s); }
+    else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+  }
+};
 
 template <typename Functor, int kNumResiduals, int... Ns>
 class AutoDiffCostFunction : public CostFunction {
@@ -187,4 +204,42 @@ class AutoDiffCostFunction : public CostFunction {
     return true;
   }
 };
+
+// ---- ceres::Problem as a RECORDER: it keeps the residual blocks exactly as the caller registered them (cost function, loss function or null, parameter block
+// pointers in call order) and the constant-block marks, so a test can replay them.  ceres::Solve is NOT reproduced: it returns without touching the parameters
+// and reports an unusable solution, which is what the stand-in deserves.
+enum LinearSolverType { DENSE_NORMAL_CHOLESKY, DENSE_QR, SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR, CGNR };
+enum PreconditionerType { IDENTITY, JACOBI, SCHUR_JACOBI, CLUSTER_JACOBI, CLUSTER_TRIDIAGONAL };
+enum SparseLinearAlgebraLibraryType { SUITE_SPARSE, CX_SPARSE, EIGEN_SPARSE, ACCELERATE_SPARSE, NO_SPARSE };
+inline bool IsSparseLinearAlgebraLibraryTypeAvailable(SparseLinearAlgebraLibraryType) { return false; }
+class Problem {
+ public:
+  struct Block { CostFunction* cost; LossFunction* loss; std::vector<double*> params; };
+  std::vector<Block> blocks;
+  std::vector<double*> constant_blocks;
+  template <typename... P> void* AddResidualBlock(CostFunction* cost, LossFunction* loss, P*... p) { blocks.push_back(Block{cost, loss, std::vector<double*>{p...}}); return nullptr; }
+  void AddParameterBlock(double*, int) {}
+  void SetParameterBlockConstant(double* p) { constant_blocks.push_back(p); }
+  void SetParameterBlockVariable(double*) {}
+  int NumResidualBlocks() const { return (int)blocks.size(); }
+  int NumResiduals() const { int n = 0; for (const Block& b : blocks) n += b.cost->num_residuals(); return n; }
+  ~Problem() { for (Block& b : blocks) delete b.cost; }   // Ceres owns the cost functions (loss functions are shared between blocks: left to leak here)
+};
+class Solver {
+ public:
+  struct Options {
+    bool minimizer_progress_to_stdout = false, update_state_every_iteration = false;
+    int num_threads = 1, max_num_iterations = 50, max_linear_solver_iterations = 500;
+    LinearSolverType linear_solver_type = SPARSE_NORMAL_CHOLESKY; PreconditionerType preconditioner_type = JACOBI;
+    SparseLinearAlgebraLibraryType sparse_linear_algebra_library_type = NO_SPARSE;
+    double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+  };
+  struct Summary {
+    double initial_cost = -1, final_cost = -1; int num_successful_steps = 0, num_unsuccessful_steps = 0;
+    bool IsSolutionUsable() const { return false; }
+    std::string BriefReport() const { return "oracle/shim: ceres::Solve is not reproduced"; }
+    std::string FullReport() const { return BriefReport(); }
+  };
+};
+inline void Solve(const Solver::Options&, Problem*, Solver::Summary*) {}
 }  // namespace ceres

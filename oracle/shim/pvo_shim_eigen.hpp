@@ -76,6 +76,8 @@ class Matrix {
   template <typename U> void init2(U a, U b, std::false_type) { static_assert(R * C == 2, "size"); s.d[0] = T(a); s.d[1] = T(b); }
   template <typename U> void init2(U rows, U cols, std::true_type) { s.resize((int)rows, (int)cols); }
  public:
+  template <int R2, int C2, typename = typename std::enable_if<(R2 != R || C2 != C) && (R2 == Dynamic || C2 == Dynamic || R == Dynamic || C == Dynamic)>::type>
+  Matrix(const Matrix<T, R2, C2>& o) { s.resize(o.rows(), o.cols()); for (int i = 0; i < o.size() && i < size(); ++i) s.data()[i] = o.data()[i]; }   // dynamic <-> fixed of the same shape
   explicit Matrix(const Quaternion<T>& q) { static_assert(R == 3 && C == 3, "3x3"); *this = q.toRotationMatrix(); }
   explicit Matrix(const AngleAxis<T>& a) { static_assert(R == 3 && C == 3, "3x3"); *this = a.toRotationMatrix(); }
 
@@ -159,6 +161,10 @@ template <typename T, int R, int C, typename S, typename = typename std::enable_
 inline Matrix<T, R, C> operator*(const S& k, const Matrix<T, R, C>& a) { Matrix<T, R, C> m = a; for (int i = 0; i < a.size(); ++i) m.data()[i] = T(k) * a.data()[i]; return m; }
 template <typename T, int R, int C, typename S, typename = typename std::enable_if<std::is_convertible<S, T>::value && !std::is_class<typename std::remove_reference<S>::type>::value || std::is_same<S, T>::value>::type>
 inline Matrix<T, R, C> operator/(const Matrix<T, R, C>& a, const S& k) { Matrix<T, R, C> m = a; for (int i = 0; i < a.size(); ++i) m.data()[i] = a.data()[i] / T(k); return m; }
+template <typename T, int R, int C, typename S, typename = typename std::enable_if<std::is_convertible<S, T>::value && !std::is_class<typename std::remove_reference<S>::type>::value || std::is_same<S, T>::value>::type>
+inline Matrix<T, R, C>& operator/=(Matrix<T, R, C>& a, const S& k) { a = a / k; return a; }
+template <typename T, int R, int C, typename S, typename = typename std::enable_if<std::is_convertible<S, T>::value && !std::is_class<typename std::remove_reference<S>::type>::value || std::is_same<S, T>::value>::type>
+inline Matrix<T, R, C>& operator*=(Matrix<T, R, C>& a, const S& k) { a = a * k; return a; }
 template <typename T, int R, int K, int C>
 inline Matrix<T, R, C> operator*(const Matrix<T, R, K>& a, const Matrix<T, K, C>& b) {
   Matrix<T, R, C> m; m.resize(a.rows(), b.cols());

@@ -20,6 +20,8 @@ INDEPENDENT implementations, never from the oracle itself:
                  TransformLines; compiled where it lies with the PCL / Eigen stand-ins of oracle/shim: oracle/_ref/libpvo_ref_assoc.so) on four synthetic pairs
   ref_camlidar.npz  (image line, LiDAR segment) pairs of the reference's own CameraLidarLineAssociate::AssociateByAngle (+ Filter + UniqueLinePair, masks) and uint16
                  depth images of its ProjectLidar2PanoramaDepth (oracle/_ref/libpvo_ref_camlidar.so)
+  ref_builders.npz  the residual blocks (frame pairs, loss, raw residual, raw Jacobian, in registration order) that the reference's own util/Optimization.cpp builders
+                 register for one RefinePose in five configurations, and AddCameraLidarResidual for one frame pair (ceres::Problem = a recorder, oracle/shim)
   reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
                  undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
 Run from the repo root:  python tests/make_golden.py
@@ -330,8 +332,37 @@ def golden_ref_camlidar():
     np.savez_compressed(os.path.join(OUT, "ref_camlidar.npz"), **out)
 
 
+def golden_ref_builders():
+    """tests/golden/ref_builders.npz: the residual blocks registered by the reference's own util/Optimization.cpp builders (oracle/_ref/libpvo_ref_assoc.so; ceres::Problem
+    replaced by a recorder) for the RefinePose configurations of tests/test_reference_pinning.py: BUILDER_CASES, each block evaluated once through
+    ceres::CostFunction::Evaluate; plus AddCameraLidarResidual for one (image, LiDAR) pair of frames."""
+    from oracle import pvo
+    if pvo.ref_assoc_lib() is None:
+        print("oracle/_ref/libpvo_ref_assoc.so not built (no /root/reference here): ref_builders.npz left as committed")
+        return
+    import test_reference_pinning as trp
+    from scipy.spatial.transform import Rotation
+    frames, Rs, ts = trp.builder_case()
+    out = {}
+    for ci, kw in enumerate(trp.BUILDER_CASES):
+        r = trp.reference_refine_blocks(pvo, frames, Rs, ts, **kw)
+        for k, v in r.items():
+            out[f"b{ci}_{k}"] = v.astype(np.int16) if k in ("ref", "nei") else (v[::trp.JAC_STRIDE] if k == "jacobian" else v)   # every 8th Jacobian row keeps the file small
+        print(f"  builders case {ci}: {len(r['residual'])} blocks, {int((r['huber'] == 0).sum())} without loss")
+    rng = np.random.default_rng(20261031)
+    rows, cols, n = 2880, 5760, 80
+    lines = np.stack([rng.uniform(0, cols, n), rng.uniform(200, rows - 200, n), rng.uniform(0, cols, n), rng.uniform(200, rows - 200, n)], axis=1).astype(np.float32)
+    start, end = rng.normal(0, 3, (n, 3)), rng.normal(0, 3, (n, 3))
+    pw = rng.uniform(0.5, 2, n).astype(np.float32)
+    R_wc, t_wc = Rotation.from_rotvec([0.2, -0.4, 0.1]).as_matrix(), np.array([1.0, -0.5, 0.3])
+    R_wl, t_wl = Rotation.from_rotvec([0.25, -0.35, 0.12]).as_matrix(), np.array([1.1, -0.45, 0.2])
+    r, J, poses = pvo.ref_camera_lidar_blocks(rows, cols, lines, start, end, pw, R_wc, t_wc, R_wl, t_wl, 25.0)
+    out.update(cl_rows=rows, cl_cols=cols, cl_lines=lines, cl_start=start, cl_end=end, cl_pair_weight=pw, cl_weight=25.0, cl_poses=poses, cl_residual=r, cl_jacobian=J)
+    np.savez_compressed(os.path.join(OUT, "ref_builders.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar(); golden_ref_builders()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

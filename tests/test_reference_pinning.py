@@ -433,3 +433,118 @@ def test_line_tracks_equal_the_reference_generate_tracks(oracle):
         if oracle.ref_assoc_lib() is not None:
             ref = reference_line_tracks(oracle, frames, k, min_len, no_pose)
             assert len(ref) == len(exp) and all(np.array_equal(a, b) for a, b in zip(ref, exp)), ci
+
+
+# ---- Residual-block builders: util/Optimization.cpp (AddLidarPointToPlaneResidual, AddLidarLineToLineResidual2, AddLidarPointToLineResidual,
+# AddCameraLidarResidual) compiled where it lies; ceres::Problem is a recorder (oracle/shim/pvo_shim_ceres.hpp) ----
+JAC_STRIDE = 8          # the fixture keeps every 8th Jacobian row of the block lists
+BUILDER_CASES = [dict(), dict(angle_residual=False, normalize_distance=False), dict(point_to_line=True, line_to_line=False, use_segment=True),
+                 dict(point_to_line=True, line_to_line=False, point_to_plane=False, use_segment=False, line_dis_threshold=0.4), dict(plane_tolerance=0.01, line_dis_threshold=0.4)]
+
+
+def builder_case(n_frames=6, n_az=600, seed=3):
+    from panovlm_b200 import synth
+    from scipy.spatial.transform import Rotation
+    frames = synth.make_sequence(n_frames, n_az=n_az)
+    rng = np.random.default_rng(seed)
+    Rs = [f["R_wl"] @ Rotation.from_rotvec(rng.normal(0, 0.01, 3)).as_matrix() for f in frames]
+    ts = [f["t_wl"] + rng.normal(0, 0.03, 3) for f in frames]
+    return frames, Rs, ts
+
+
+def product_refine_blocks(oracle, frames, Rs, ts, point_to_plane=True, line_to_line=True, point_to_line=False, use_segment=True, angle_residual=True,
+                          normalize_distance=True, plane_dis_threshold=1.0, line_dis_threshold=0.3, plane_tolerance=0.05):
+    """The block list of one RefinePose built from the ORACLE's associations and the PRODUCT's host builders (pvb_build_*_blocks, pvb_find_neighbors,
+    pvb_line_tracks_build / pvb_line_tracks_gate), in the reference's registration order."""
+    from panovlm_b200 import BlockList, Context, LineFrame
+    n = len(frames)
+    t_arr = np.array(ts)
+    nbrs = Context.find_neighbors(t_arr, None, None, 6)
+    edges = [(i, j) for i in range(n) for j in nbrs[i] if 0 <= j < n and j != i]
+    corner_w = [oracle.transform_cloud(Rs[i], ts[i], f["cornerLessSharp"]) for i, f in enumerate(frames)]
+    tgt_w = [oracle.transform_cloud(Rs[i], ts[i], f["surfLessFlat"]) for i, f in enumerate(frames)]
+    qry_w = [oracle.transform_cloud(Rs[i], ts[i], f["surfFlat"]) for i, f in enumerate(frames)]
+    lines_w = [oracle.transform_lines(Rs[i], ts[i], f["segment_coeffs"]) for i, f in enumerate(frames)]
+    lf = [LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], Rs[i], ts[i]) for i, f in enumerate(frames)]
+    bl = BlockList(200000)
+
+    def l2l(i, j, thr):
+        fj = frames[j]
+        M = oracle.line_votes(lines_w[i], corner_w[j], fj["p2s_off"], fj["p2s_ids"], len(fj["segment_coeffs"]), thr)
+        return oracle.find_associations(frames[i]["segment_coeffs"], lines_w[i], lines_w[j], np.diff(fj["seg_off"]), M)
+    if point_to_line:
+        for (i, j) in edges:
+            if abs(i - j) > 1:
+                continue
+            if use_segment:
+                _, _, pt, a, b = oracle.associate_p2line_segment_knn(corner_w[i], frames[i]["p2s_off"], frames[i]["p2s_ids"], frames[i]["segment_coeffs"], corner_w[j], Rs[j], ts[j], line_dis_threshold)
+            else:
+                _, pt, a, b = oracle.associate_p2line(corner_w[i], Rs[i], ts[i], corner_w[j], Rs[j], ts[j], line_dis_threshold)
+            if len(pt):
+                Context.build_point2line_blocks(bl, pt, a, b, i, j, angle_residual, normalize_distance, 1.0)
+    if line_to_line and use_segment:
+        tn = Context.find_neighbors(t_arr, None, None, 4)
+        pa, pb, off, ma, mb = [], [], [0], [], []
+        for i in range(n):
+            for nb in tn[i]:
+                on, orf, _, _ = l2l(nb, i, 0.3)
+                for x, y in sorted(set(zip(on.tolist(), orf.tolist()))):
+                    ma.append(x); mb.append(y)
+                pa.append(i); pb.append(nb); off.append(len(ma))
+        tracks = Context.line_tracks_build(pa, pb, off, ma, mb, 3, True)
+        for (i, j) in edges:
+            on, orf, oa, ob = l2l(i, j, line_dis_threshold)
+            keep = Context.line_tracks_gate(tracks, i, j, orf, on)
+            assert np.array_equal(keep, oracle.line_track_gate(tracks, i, j, orf, on))
+            for k in np.nonzero(keep)[0]:
+                Context.build_line2line_blocks(bl, lf[j], corner_w[j], int(on[k]), oa[k], ob[k], i, j, angle_residual, normalize_distance, 1.0)
+    if point_to_plane:
+        for (i, j) in edges:
+            _, pt, pl = oracle.associate_p2plane(tgt_w[i], Rs[i], ts[i], qry_w[j], Rs[j], ts[j], plane_tolerance, plane_dis_threshold, 10, True)
+            if len(pt):
+                Context.build_point2plane_blocks(bl, pt, pl, i, j, angle_residual, normalize_distance, 1.0)
+    return bl.view()
+
+
+def reference_refine_blocks(oracle, frames, Rs, ts, **kw):
+    rf = [oracle.RefFrame(Rs[i], ts[i], oracle.transform_cloud(Rs[i], ts[i], f["cornerLessSharp"]), f["p2s_off"], f["p2s_ids"], f["segment_coeffs"],
+                          oracle.transform_cloud(Rs[i], ts[i], f["surfFlat"]), oracle.transform_cloud(Rs[i], ts[i], f["surfLessFlat"]), id=i) for i, f in enumerate(frames)]
+    return oracle.ref_refine_pose_blocks(rf, **kw)
+
+
+def test_residual_block_lists_equal_the_reference_builders(oracle):
+    """B1 / B2 / B3: the blocks the reference's own builders register for one RefinePose (which frame pairs, which functor, which loss - nullptr for the
+    angle line residuals -, which constants, in which order) == the list built by the product's host builders from the oracle's associations: same
+    (reference, neighbour) frames and Huber parameters, raw residuals and Jacobians equal to 1e-9 when both lists are evaluated at the same pose blocks."""
+    g = np.load(os.path.join(G, "ref_builders.npz"))
+    frames, Rs, ts = builder_case()
+    for ci, kw in enumerate(BUILDER_CASES):
+        v = product_refine_blocks(oracle, frames, Rs, ts, **kw)
+        exp = {k[len(f"b{ci}_"):]: g[k] for k in g.files if k.startswith(f"b{ci}_")}
+        assert len(v["type"]) == len(exp["residual"]) > 1000, (ci, len(v["type"]), len(exp["residual"]))
+        assert np.array_equal(v["ref"], exp["ref"]) and np.array_equal(v["nei"], exp["nei"]), ci
+        assert np.abs(v["huber"] - exp["huber"]).max() < 1e-15, ci
+        b = oracle.Blocks(v["type"], v["ref"], v["nei"], v["consts"], 0.0, v["normalize"])
+        r, J, _ = b.evaluate(exp["poses"], apply_loss=False)
+        # planes / lines differ by ~1e-14 between the two QR / eigen implementations; acos near 1 amplifies that by 1 / r for small angle residuals
+        assert np.all(np.abs(r - exp["residual"]) <= 1e-9 * np.abs(exp["residual"]) + 1e-11), ci
+        assert np.all(np.abs(J[::JAC_STRIDE] - exp["jacobian"]).max(1) <= 1e-6 * np.abs(exp["jacobian"]).max(1) + 1e-9), ci
+        if oracle.ref_assoc_lib() is not None and ci == 0:
+            live = reference_refine_blocks(oracle, frames, Rs, ts, **kw)
+            assert np.array_equal(live["ref"], exp["ref"]) and np.array_equal(live["residual"], exp["residual"])
+
+
+def test_camera_lidar_blocks_equal_the_reference_builder(oracle):
+    """B4: AddCameraLidarResidual of the reference == pvb_build_camera_lidar_blocks (Plane2Plane_Global + PlaneIOUResidual per pair, weights, constants)."""
+    from panovlm_b200 import BlockList, Context
+    g = np.load(os.path.join(G, "ref_builders.npz"))
+    bl = BlockList(2 * len(g["cl_lines"]) + 1)
+    Context.build_camera_lidar_blocks(bl, int(g["cl_rows"]), int(g["cl_cols"]), g["cl_lines"], g["cl_start"], g["cl_end"], g["cl_pair_weight"], 0, 1, float(g["cl_weight"]))
+    v = bl.view()
+    assert np.allclose(v["huber"], 3 * np.pi / 180)
+    b = oracle.Blocks(v["type"], v["ref"], v["nei"], v["consts"], 0.0, v["normalize"])
+    r, J, _ = b.evaluate(g["cl_poses"], apply_loss=False)
+    assert len(r) == len(g["cl_residual"]) == 2 * len(g["cl_lines"])
+    assert (np.abs(r - g["cl_residual"]) / np.maximum(1e-6, np.abs(g["cl_residual"]))).max() < 1e-9
+    assert (np.abs(J - g["cl_jacobian"]).max(1) / np.maximum(1e-6, np.abs(g["cl_jacobian"]).max(1))).max() < 1e-8
+    assert (g["cl_residual"] > 0).sum() > len(r) // 2
