@@ -657,3 +657,20 @@ def ref_camera_lidar_blocks(rows, cols, image_lines, start, end, pair_weight, R_
                                   C.c_double(weight), C.c_long(2 * n), _p(r), _p(J), _p(poses))
     assert m == 2 * n, m
     return r, J, poses
+
+
+def ref_camera_residual_blocks(rows, cols, R_wc, t_wc, pose_valid, kp_off, kp_xy, track_off, feat_frame, feat_index, points3, weight=1.0):
+    """AddCameraResidual (ANGLE_RESIDUAL_1) of the reference: returns dict(cam, track, residual, jacobian (n x 9), cams (n_frames x 6 pose blocks))."""
+    R_wc, t_wc = _f64(R_wc).reshape(-1, 9), _f64(t_wc).reshape(-1, 3)
+    nf = len(t_wc)
+    pv = np.ascontiguousarray(pose_valid, np.uint8)
+    kp_off, track_off, feat_frame, feat_index = _i32(kp_off), _i32(track_off), _i32(feat_frame), _i32(feat_index)
+    kp_xy, points3 = _f32(kp_xy).reshape(-1, 2), _f64(points3).reshape(-1, 3)
+    cap = len(feat_frame)
+    cam, trk, r, J, cams = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap), np.zeros((cap, 9)), np.zeros((nf, 6))
+    L = ref_assoc_lib()
+    L.ref_camera_residual_blocks.restype = C.c_long
+    m = L.ref_camera_residual_blocks(C.c_int(rows), C.c_int(cols), C.c_int(nf), _p(R_wc), _p(t_wc), _p(pv), _p(kp_off), _p(kp_xy), C.c_int(len(track_off) - 1), _p(track_off),
+                                     _p(feat_frame), _p(feat_index), _p(points3), C.c_double(weight), C.c_long(cap), _p(cam), _p(trk), _p(r), _p(J), _p(cams))
+    assert m >= 0, m
+    return dict(cam=cam[:m].copy(), track=trk[:m].copy(), residual=r[:m].copy(), jacobian=J[:m].copy(), cams=cams)

@@ -265,6 +265,48 @@ long ref_camera_lidar_blocks(int rows, int cols, int n, const float* image_line4
   return (long)problem.blocks.size();
 }
 
+// AddCameraResidual (util/Optimization.cpp:172-222) with residual_type = ANGLE_RESIDUAL_1 (PanoramaReprojResidual_1Angle, the type SfMGlobalBA and the joint
+// stage use): n_frames cameras (pose T_wc, rotation row-major; pose_valid = 0 leaves the constructor's "no pose" state) with their key points (CSR: kp_off,
+// kp_xy float pixels), tracks (CSR: track_off, (feat_frame, feat_index)) with their 3-D points, weight.  Pose blocks as SfMGlobalBA builds them (:13-30:
+// inverse pose + RotationMatrixToAngleAxis).  Per registered block, in registration order: camera, track, raw residual, raw 1x9 Jacobian (aa, t, X).
+long ref_camera_residual_blocks(int rows, int cols, int n_frames, const double* R_wc, const double* t_wc, const unsigned char* pose_valid, const int* kp_off, const float* kp_xy,
+                                int n_tracks, const int* track_off, const int* feat_frame, const int* feat_index, const double* points3, double weight, long cap,
+                                int* cam, int* track, double* residual, double* jac9, double* cams_out) {
+  std::vector<Frame> frames;
+  for (int f = 0; f < n_frames; ++f) {
+    frames.push_back(Frame(rows, cols, f, "frame"));
+    if (pose_valid[f]) { Eigen::Matrix3d R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R(i, j) = R_wc[9 * f + 3 * i + j]; frames[f].SetPose(R, Eigen::Vector3d(t_wc[3 * f], t_wc[3 * f + 1], t_wc[3 * f + 2])); }
+    for (int k = kp_off[f]; k < kp_off[f + 1]; ++k) { cv::KeyPoint kp; kp.pt = cv::Point2f(kp_xy[2 * k], kp_xy[2 * k + 1]); frames[f].keypoints_all.push_back(kp); }
+  }
+  eigen_vector<Eigen::Vector3d> aa(n_frames, Eigen::Vector3d::Zero()), tt(n_frames, Eigen::Vector3d::Zero());
+  for (int f = 0; f < n_frames; ++f) {
+    if (!frames[f].IsPoseValid()) continue;
+    Eigen::Matrix4d T = frames[f].GetPose().inverse(); Eigen::Matrix3d R = T.block<3, 3>(0, 0);
+    ceres::RotationMatrixToAngleAxis(R.data(), aa[f].data()); tt[f] = T.block<3, 1>(0, 3);
+  }
+  std::vector<PointTrack> structure;
+  for (int t = 0; t < n_tracks; ++t) {
+    std::set<std::pair<uint32_t, uint32_t>> fp;
+    for (int k = track_off[t]; k < track_off[t + 1]; ++k) fp.insert(std::make_pair((uint32_t)feat_frame[k], (uint32_t)feat_index[k]));
+    structure.push_back(PointTrack(t, fp, Eigen::Vector3d(points3[3 * t], points3[3 * t + 1], points3[3 * t + 2])));
+  }
+  ceres::Problem problem;
+  AddCameraResidual(frames, aa, tt, structure, problem, ANGLE_RESIDUAL_1, weight);
+  for (int f = 0; f < n_frames; ++f) for (int k = 0; k < 3; ++k) { cams_out[6 * f + k] = aa[f][k]; cams_out[6 * f + 3 + k] = tt[f][k]; }
+  if ((long)problem.blocks.size() > cap) return -1;
+  for (size_t b = 0; b < problem.blocks.size(); ++b) {
+    const ceres::Problem::Block& blk = problem.blocks[b];
+    if (blk.params.size() != 3) return -2;
+    cam[b] = (int)((Eigen::Vector3d*)blk.params[0] - &aa[0]);
+    track[b] = -1;
+    for (int t = 0; t < n_tracks; ++t) if (blk.params[2] == structure[t].point_3d.data()) { track[b] = t; break; }
+    double jb[3][3]; double* jp[3] = {jb[0], jb[1], jb[2]};
+    if (!blk.cost->Evaluate(blk.params.data(), residual + b, jp)) return -2;
+    std::memcpy(jac9 + 9 * b, jb, sizeof(jb));
+  }
+  return (long)problem.blocks.size();
+}
+
 // FindNeighbors over n frames given by pose (R row-major 9, t 3), pose_valid and valid flags; CSR output (off[n + 1], ids[cap]); returns total or -1
 int ref_find_neighbors(int n, const double* R_wl, const double* t_wl, const unsigned char* pose_valid, const unsigned char* valid, int neighbor_size, int cap, int* off, int* ids) {
   std::vector<Velodyne> lidars(n);

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <iostream>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cassert>
@@ -16,11 +17,14 @@ typedef unsigned char uchar; typedef unsigned short ushort;   // OpenCV declares
 #define CV_16U 2
 #define CV_16UC1 2
 namespace cv {
+// cv::saturate_cast: floating point -> integer rounds to nearest (cvRound = lrint, ties to even); everything else is a plain conversion
+template <typename To, typename From> inline typename std::enable_if<std::is_integral<To>::value && std::is_floating_point<From>::value, To>::type saturate_cast(From v) { return (To)std::lrint(v); }
+template <typename To, typename From> inline typename std::enable_if<!(std::is_integral<To>::value && std::is_floating_point<From>::value), To>::type saturate_cast(From v) { return (To)v; }
 template <typename T> struct Point_ {
   T x, y;
   Point_() : x(0), y(0) {}
   Point_(T a, T b) : x(a), y(b) {}
-  template <typename U> Point_(const Point_<U>& o) : x(T(o.x)), y(T(o.y)) {}  // NOLINT
+  template <typename U> Point_(const Point_<U>& o) : x(saturate_cast<T>(o.x)), y(saturate_cast<T>(o.y)) {}  // NOLINT: OpenCV's implicit Point_ conversion
   T dot(const Point_& o) const { return x * o.x + y * o.y; }
 };
 template <typename T> inline Point_<T> operator+(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x + b.x, a.y + b.y); }
@@ -47,7 +51,7 @@ template <typename T> struct Point3_ {
   T x, y, z;
   Point3_() : x(0), y(0), z(0) {}
   Point3_(T a, T b, T c) : x(a), y(b), z(c) {}
-  template <typename U> Point3_(const Point3_<U>& o) : x(T(o.x)), y(T(o.y)), z(T(o.z)) {}  // NOLINT
+  template <typename U> Point3_(const Point3_<U>& o) : x(saturate_cast<T>(o.x)), y(saturate_cast<T>(o.y)), z(saturate_cast<T>(o.z)) {}  // NOLINT
   Point3_(const Vec<T, 3>& v) : x(v[0]), y(v[1]), z(v[2]) {}  // NOLINT
   operator Vec<T, 3>() const { return Vec<T, 3>(x, y, z); }
   T dot(const Point3_& o) const { return x * o.x + y * o.y + z * o.z; }

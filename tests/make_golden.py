@@ -358,6 +358,10 @@ def golden_ref_builders():
     R_wl, t_wl = Rotation.from_rotvec([0.25, -0.35, 0.12]).as_matrix(), np.array([1.1, -0.45, 0.2])
     r, J, poses = pvo.ref_camera_lidar_blocks(rows, cols, lines, start, end, pw, R_wc, t_wc, R_wl, t_wl, 25.0)
     out.update(cl_rows=rows, cl_cols=cols, cl_lines=lines, cl_start=start, cl_end=end, cl_pair_weight=pw, cl_weight=25.0, cl_poses=poses, cl_residual=r, cl_jacobian=J)
+    rows, cols, R, t, pv, kp_off, xy, track_off, ff, fi, pts = trp.camera_residual_case()          # AddCameraResidual (ANGLE_RESIDUAL_1)
+    cr = pvo.ref_camera_residual_blocks(rows, cols, R, t, pv, kp_off, xy, track_off, ff, fi, pts, 0.7)
+    out.update(cr_cam=cr["cam"], cr_track=cr["track"], cr_residual=cr["residual"], cr_jacobian=cr["jacobian"], cr_cams=cr["cams"], cr_weight=0.7)
+    print(f"  camera residual blocks: {len(cr['cam'])} of {len(ff)} features")
     np.savez_compressed(os.path.join(OUT, "ref_builders.npz"), **out)
 
 

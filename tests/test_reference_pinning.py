@@ -548,3 +548,42 @@ def test_camera_lidar_blocks_equal_the_reference_builder(oracle):
     assert (np.abs(r - g["cl_residual"]) / np.maximum(1e-6, np.abs(g["cl_residual"]))).max() < 1e-9
     assert (np.abs(J - g["cl_jacobian"]).max(1) / np.maximum(1e-6, np.abs(g["cl_jacobian"]).max(1))).max() < 1e-8
     assert (g["cl_residual"] > 0).sum() > len(r) // 2
+
+
+def camera_residual_case():
+    """6 panoramas (2 without a pose), 400 key points each - a share of them exactly on half-integer pixel coordinates, where the implicit
+    cv::Point2f -> cv::Point2i conversion of `eq.ImageToCam(keypoint.pt)` (Optimization.cpp:203) rounds ties to even -, 150 tracks of 2-5 features."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(20261101)
+    rows, cols, nf, nk = 2880, 5760, 6, 400
+    R = np.stack([Rotation.from_rotvec(rng.normal(0, 0.4, 3)).as_matrix() for _ in range(nf)]); t = rng.normal(0, 2, (nf, 3))
+    pv = np.ones(nf, np.uint8); pv[[2, 4]] = 0
+    xy = np.stack([rng.uniform(0, cols - 1, nf * nk), rng.uniform(0, rows - 1, nf * nk)], axis=1)
+    xy[::7] = np.floor(xy[::7]) + 0.5
+    xy = xy.astype(np.float32)
+    kp_off = np.arange(nf + 1, dtype=np.int32) * nk
+    track_off, ff, fi = [0], [], []
+    for _ in range(150):
+        fr = np.sort(rng.choice(nf, int(rng.integers(2, 6)), replace=False))
+        for f in fr:
+            ff.append(int(f)); fi.append(int(rng.integers(0, nk)))
+        track_off.append(len(ff))
+    pts = rng.normal(0, 6, (150, 3))
+    return rows, cols, R, t, pv, kp_off, xy, np.array(track_off, np.int32), np.array(ff, np.int32), np.array(fi, np.int32), pts
+
+
+def test_reprojection_observations_equal_the_reference_builder(oracle):
+    """(f) rank 3: AddCameraResidual of the reference (ANGLE_RESIDUAL_1) == pvb_build_reproj_observations + the oracle's PanoramaReprojResidual_1Angle:
+    same (camera, track) list - features of frames without a pose skipped -, bearings from the ROUNDED pixel, raw residuals and 1x9 Jacobians."""
+    from panovlm_b200 import Context
+    g = np.load(os.path.join(G, "ref_builders.npz"))
+    rows, cols, R, t, pv, kp_off, xy, track_off, ff, fi, pts = camera_residual_case()
+    cam, point, bearing = Context.build_reproj_observations(rows, cols, track_off, ff, xy[kp_off[ff] + fi], pv)
+    assert np.array_equal(cam, g["cr_cam"]) and np.array_equal(point, g["cr_track"]) and 200 < len(cam) < len(ff)
+    rp = oracle.Reproj(cam, point, bearing, weight=float(g["cr_weight"]))
+    r, J = rp.evaluate(g["cr_cams"], pts, apply_loss=False)[:2]
+    assert np.all(np.abs(r - g["cr_residual"]) <= 1e-9 * np.abs(g["cr_residual"]) + 1e-12)
+    assert np.all(np.abs(J[:, :9] - g["cr_jacobian"]).max(1) <= 1e-7 * np.abs(g["cr_jacobian"]).max(1) + 1e-10)
+    if oracle.ref_assoc_lib() is not None:
+        live = oracle.ref_camera_residual_blocks(rows, cols, R, t, pv, kp_off, xy, track_off, ff, fi, pts, float(g["cr_weight"]))
+        assert np.array_equal(live["cam"], cam) and np.array_equal(live["residual"], g["cr_residual"])
