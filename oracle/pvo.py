@@ -533,7 +533,8 @@ class RefFrame:
     """A `Velodyne` object of the reference as its association functions see it (world-frame feature clouds, segment tables, pose)."""
 
     def __init__(self, R_wl, t_wl, corner_world=None, p2s_off=None, p2s_ids=None, coeffs_local=None, surf_flat_world=None, surf_less_flat_world=None, id=0,
-                 valid=True, pose_valid=True):
+                 valid=True, pose_valid=True, local=False):
+        """local=True: the clouds are given in the SENSOR frame and the reference's own Transform2LidarWorld() moves them."""
         self.L = ref_assoc_lib()
         z = np.zeros((0, 4), np.float32)
         cw = _f32(z if corner_world is None else corner_world).reshape(-1, 4)
@@ -543,9 +544,23 @@ class RefFrame:
         off = None if p2s_off is None else _i32(p2s_off)
         ids = None if p2s_ids is None else _i32(p2s_ids)
         self.h = self.L.ref_frame_create(C.c_int(id), C.c_int(int(valid)), C.c_int(int(pose_valid)), _p(_f64(R_wl)), _p(_f64(t_wl)), _p(cw), C.c_int(len(cw)), _p(off), _p(ids),
-                                         C.c_int(len(co)), _p(co), None, _p(sf), C.c_int(len(sf)), _p(sl), C.c_int(len(sl)))
+                                         C.c_int(len(co)), _p(co), None, _p(sf), C.c_int(len(sf)), _p(sl), C.c_int(len(sl)), C.c_int(0 if local else 1))
         assert self.h
         self.n_corner, self.n_flat = len(cw), len(sf)
+
+    def cloud(self, which):
+        """which: "corner" / "flat" / "less_flat": the frame's cloud as the reference holds it now (n x 4 float32)."""
+        k = {"corner": 0, "flat": 1, "less_flat": 2}[which]
+        out = np.zeros((1 << 16, 4), np.float32)
+        m = self.L.ref_frame_get_cloud(C.c_void_p(self.h), C.c_int(k), C.c_int(len(out)), _p(out))
+        assert m >= 0
+        return out[:m].copy()
+
+    def to_local(self):
+        self.L.ref_frame_to_local(C.c_void_p(self.h))
+
+    def to_world(self):
+        self.L.ref_frame_to_world(C.c_void_p(self.h))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -674,3 +689,11 @@ def ref_camera_residual_blocks(rows, cols, R_wc, t_wc, pose_valid, kp_off, kp_xy
                                      _p(feat_frame), _p(feat_index), _p(points3), C.c_double(weight), C.c_long(cap), _p(cam), _p(trk), _p(r), _p(J), _p(cams))
     assert m >= 0, m
     return dict(cam=cam[:m].copy(), track=trk[:m].copy(), residual=r[:m].copy(), jacobian=J[:m].copy(), cams=cams)
+
+
+def ref_undistort_cloud(R_wl, t_wl, R_we, t_we, cloud):
+    """Velodyne::UndistortCloud of the reference on one raw sweep (n x 4 float32)."""
+    cloud = _f32(cloud).reshape(-1, 4)
+    out = np.empty_like(cloud)
+    ok = ref_assoc_lib().ref_undistort_cloud(_p(_f64(R_wl)), _p(_f64(t_wl)), _p(_f64(R_we)), _p(_f64(t_we)), _p(cloud), C.c_long(len(cloud)), _p(out))
+    return bool(ok), out

@@ -3,13 +3,15 @@
 // AssociatePoint2LineSegment, AssociateLine2LineKNN), compiled from the file where it lies under /root/reference (never copied) together with the
 // headers it includes (LidarFeatureAssociate.h, sensors/Velodyne.h and its sub-headers, base/Geometry.hpp ...).  PCL / Eigen / OpenCV / glog / Boost are
 // absent from this image: oracle/shim/ provides stand-ins - an Eigen-like matrix, and pcl::KdTreeFLANN as an exact float32 search (shim/pvo_shim_pcl.hpp).
-// sensors/Velodyne.cpp (1900 lines of feature extraction on real PCL algorithms) cannot be compiled that way; the EIGHT small member functions of
-// class Velodyne that the association code calls are therefore defined below, each a restatement of the cited lines of sensors/Velodyne.cpp.
+// sensors/Velodyne.cpp is compiled too (its feature-extraction members call into translation units that are not: those entry points abort, see below), so
+// the Velodyne class - poses, World2Local, Transform2LidarWorld / Transform2Local, UndistortCloud - is the reference's own.
 // What this pins: the control flow, thresholds, class test, vote rules, conflict resolution and output order of the reference's association functions.
 // Built by `make -C oracle ref` into oracle/_ref/libpvo_ref_assoc.so; used by tests/test_reference_pinning.py and tests/make_golden.py only.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -24,35 +26,26 @@
 #include <atomic>
 #include <chrono>
 #define private public          // the wrapper sets Velodyne::world (set by Transform2LidarWorld, sensors/Velodyne.cpp:1807) after filling world-frame clouds
+#include REF_VELODYNE_CPP                 // sensors/Velodyne.cpp: the class itself (poses, Transform2LidarWorld / Transform2Local, World2Local, UndistortCloud ...)
 #include REF_LIDAR_FEATURE_ASSOCIATE_CPP
 #include REF_TRACKS_CPP                   // util/Tracks.cpp: TrackBuilder (union-find over (frame, line) features), Filter, ExportTracks
 #include REF_LIDAR_LINE_MATCH_CPP         // lidar_mapping/LidarLineMatch.cpp: GenerateTracks = FindNeighbors + AssociateLine2Line(nei, i, 0.3) + TrackBuilder
 #include REF_OPTIMIZATION_CPP             // util/Optimization.cpp: the residual-block builders (AddLidarPointToPlaneResidual ...); ceres::Problem = the shim's recorder
 #undef private
 
-// ---- class Velodyne: the members the association code needs (sensors/Velodyne.cpp, restated) ----
-Velodyne::Velodyne() : world(false), scanPeriod(0.1), valid(true), N_SCANS(0), id(-1) {                                   // :61-79
-  R_wl = Eigen::Matrix3d::Zero();
-  t_wl = std::numeric_limits<double>::infinity() * Eigen::Vector3d::Ones();
-  T_wc_wl = Eigen::Matrix4d::Identity();
-  cloudCurvature = NULL; cloudSortInd = NULL; cloudState = NULL; left_neighbor = NULL; right_neighbor = NULL;
+// ---- defined by the reference in translation units that are NOT compiled here (ground segmentation, LiDAR line / plane extraction, drawing) and reached only from
+// Velodyne's feature-extraction members, which no entry point of this library calls: bodies that abort loudly, so that nothing can silently depend on them ----
+static void not_compiled(const char* what) { std::fprintf(stderr, "oracle/_ref: %s belongs to a reference file that is not part of this build\n", what); std::abort(); }
+cv::Vec3b Gray2Color(uchar) { not_compiled("Gray2Color (util/Visualization.cpp)"); return cv::Vec3b(); }
+std::vector<std::vector<int>> PlaneSegmentation2(const pcl::PointCloud<pcl::PointXYZI>::Ptr, const Eigen::Matrix<float, Eigen::Dynamic, Eigen::Dynamic>&,
+                                                 const std::vector<std::pair<size_t, size_t>>&, const std::vector<std::vector<int>>&, int, int) {
+  not_compiled("PlaneSegmentation2 (sensors/LidarPlaneExtraction.cpp)"); return {};
 }
-Velodyne::~Velodyne() {}                                                                                                    // :81-89 (clears the clouds)
-const Eigen::Vector3d Velodyne::World2Local(Eigen::Vector3d point_w) const { return R_wl.transpose() * point_w - R_wl.transpose() * t_wl; }   // :1850-1853
-const Eigen::Vector3d Velodyne::Local2World(Eigen::Vector3d point_local) const { return R_wl * point_local + t_wl; }                          // :1856-1859
-void Velodyne::SetPose(const Eigen::Matrix3d _R_wl, const Eigen::Vector3d _t_wl) { R_wl = _R_wl; t_wl = _t_wl; }                              // :1867-1871
-const Eigen::Matrix4d Velodyne::GetPose() const {                                                                                            // :1886-1892
-  Eigen::Matrix4d T_wl = Eigen::Matrix4d::Identity();
-  T_wl.block<3, 3>(0, 0) = R_wl;
-  T_wl.block<3, 1>(0, 3) = t_wl;
-  return T_wl;
+void ExtractLineFeatures(const pcl::PointCloud<pcl::PointXYZI>&, const std::vector<std::pair<size_t, size_t>>&, std::vector<pcl::PointCloud<pcl::PointXYZI>>&, eigen_vector<Vector6d>&) {
+  not_compiled("ExtractLineFeatures (sensors/LidarLineExtraction.cpp)");
 }
-const bool Velodyne::IsPoseValid() const {                                                                                                   // :1894-1899
-  if (!std::isinf(t_wl(0)) && !std::isnan(t_wl(0)) && !std::isinf(t_wl(1)) && !std::isnan(t_wl(1)) && !std::isinf(t_wl(2)) && !std::isnan(t_wl(2)) && !R_wl.isZero())
-    return true;
-  return false;
-}
-const bool Velodyne::IsInWorldCoordinate() const { return world; }                                                                           // :1901-1904
+GroundSegmentation::GroundSegmentation(const GroundSegmentationParams& p) : params_(p) { not_compiled("GroundSegmentation (sensors/ground_segmentation.cpp)"); }
+void GroundSegmentation::segment(const PointCloud&, std::vector<int>&) { not_compiled("GroundSegmentation::segment"); }
 
 // ---- class Frame: the members util/Optimization.cpp calls (sensors/Frame.cpp, restated) ----
 Frame::Frame(int _rows, int _cols, int _id, const std::string _name) : id(_id), name(_name), rows(_rows), cols(_cols), scale(0) {                // :10-16
@@ -85,21 +78,22 @@ void fill_cloud(pcl::PointCloud<PointType>& c, const float* xyzi, int n) {
 }  // namespace
 
 extern "C" {
-// A frame as the association code sees it: pose (R row-major, t; pose_valid = 0 leaves the constructor's "no pose" state), the three feature clouds
-// ALREADY in the world frame (float32 x, y, z, intensity = what Transform2LidarWorld leaves), the point -> segment sets of cornerLessSharp (CSR),
-// the segment coefficients in the SENSOR frame and the number of points of every segment.
-void* ref_frame_create(int id, int valid, int pose_valid, const double* R_wl, const double* t_wl, const float* corner_world, int n_corner, const int* p2s_off,
-                       const int* p2s_ids, int S, const double* coeffs_local, const int* seg_sizes, const float* surf_flat_world, int n_flat,
-                       const float* surf_less_flat_world, int n_less) {
+// A frame as the association code sees it: pose (R row-major, t; pose_valid = 0 leaves the constructor's "no pose" state), the three feature clouds (float32
+// x, y, z, intensity), the point -> segment sets of cornerLessSharp (CSR), the segment coefficients in the SENSOR frame.  clouds_in_world = 0: the clouds are
+// given in the SENSOR frame and the reference's own Velodyne::Transform2LidarWorld() moves them (the state RefinePose starts from, LidarOdometry.cpp:17-21);
+// clouds_in_world = 1: they are already world-frame and only the flag is set.
+void* ref_frame_create(int id, int valid, int pose_valid, const double* R_wl, const double* t_wl, const float* corner, int n_corner, const int* p2s_off,
+                       const int* p2s_ids, int S, const double* coeffs_local, const int* seg_sizes, const float* surf_flat, int n_flat,
+                       const float* surf_less_flat, int n_less, int clouds_in_world) {
   Velodyne* v = new Velodyne();
   v->id = id; v->valid = valid != 0;
   if (pose_valid) {
     Eigen::Matrix3d R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R(i, j) = R_wl[3 * i + j];
     v->SetPose(R, Eigen::Vector3d(t_wl[0], t_wl[1], t_wl[2]));
   }
-  fill_cloud(v->cornerLessSharp, corner_world, n_corner);
-  fill_cloud(v->surfFlat, surf_flat_world, n_flat);
-  fill_cloud(v->surfLessFlat, surf_less_flat_world, n_less);
+  fill_cloud(v->cornerLessSharp, corner, n_corner);
+  fill_cloud(v->surfFlat, surf_flat, n_flat);
+  fill_cloud(v->surfLessFlat, surf_less_flat, n_less);
   v->point_to_segment.resize(n_corner);
   if (p2s_off) for (int i = 0; i < n_corner; ++i) for (int k = p2s_off[i]; k < p2s_off[i + 1]; ++k) v->point_to_segment[i].insert(p2s_ids[k]);
   v->edge_segmented.resize(S);
@@ -111,8 +105,31 @@ void* ref_frame_create(int id, int valid, int pose_valid, const double* R_wl, co
   // gives explicit sizes they must agree
   for (int i = 0; i < n_corner; ++i) for (int s : v->point_to_segment[i]) v->edge_segmented[s].push_back(v->cornerLessSharp.points[i]);
   if (seg_sizes) for (int s = 0; s < S; ++s) if ((int)v->edge_segmented[s].size() != seg_sizes[s]) { delete v; return nullptr; }
-  v->world = 1;
+  if (clouds_in_world) v->world = 1;
+  else if (pose_valid) v->Transform2LidarWorld();
   return v;
+}
+// which: 0 cornerLessSharp, 1 surfFlat, 2 surfLessFlat; out: n x 4 float.  Returns the point count.
+int ref_frame_get_cloud(const void* f, int which, int cap, float* out) {
+  const Velodyne* v = static_cast<const Velodyne*>(f);
+  const pcl::PointCloud<PointType>& c = which == 0 ? v->cornerLessSharp : (which == 1 ? v->surfFlat : v->surfLessFlat);
+  if ((int)c.size() > cap) return -1;
+  for (size_t i = 0; i < c.size(); ++i) { out[4 * i] = c.points[i].x; out[4 * i + 1] = c.points[i].y; out[4 * i + 2] = c.points[i].z; out[4 * i + 3] = c.points[i].intensity; }
+  return (int)c.size();
+}
+// Velodyne::Transform2Local() after Transform2LidarWorld(): the round trip the joint stage makes every outer iteration (CameraLidarOptimizer.cpp:416, 535-536)
+void ref_frame_to_local(void* f) { static_cast<Velodyne*>(f)->Transform2Local(); }
+void ref_frame_to_world(void* f) { static_cast<Velodyne*>(f)->Transform2LidarWorld(); }
+// Velodyne::UndistortCloud(R_we, t_we) (sensors/Velodyne.cpp:1642-1674) on a raw sweep: cloud n x 4 float in, undistorted cloud out.  Returns 1 / 0 like the member.
+int ref_undistort_cloud(const double* R_wl, const double* t_wl, const double* R_we, const double* t_we, const float* cloud, long n, float* out) {
+  Velodyne v;
+  Eigen::Matrix3d Rl, Re;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { Rl(i, j) = R_wl[3 * i + j]; Re(i, j) = R_we[3 * i + j]; }
+  v.SetPose(Rl, Eigen::Vector3d(t_wl[0], t_wl[1], t_wl[2]));
+  fill_cloud(v.cloud, cloud, (int)n);
+  const bool ok = v.UndistortCloud(Re, Eigen::Vector3d(t_we[0], t_we[1], t_we[2]));
+  for (long i = 0; i < n; ++i) { out[4 * i] = v.cloud.points[i].x; out[4 * i + 1] = v.cloud.points[i].y; out[4 * i + 2] = v.cloud.points[i].z; out[4 * i + 3] = v.cloud.points[i].intensity; }
+  return ok ? 1 : 0;
 }
 void ref_frame_destroy(void* f) { delete static_cast<Velodyne*>(f); }
 

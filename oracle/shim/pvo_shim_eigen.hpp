@@ -304,6 +304,13 @@ class Quaternion {
     if (d < T(0)) s1 = -s1;
     return Quaternion(s0 * w_ + s1 * o.w_, s0 * x_ + s1 * o.x_, s0 * y_ + s1 * o.y_, s0 * z_ + s1 * o.z_);
   }
+  // q * v: Eigen's _transformVector: uv = 2 * (vec x v); v + w * uv + vec x uv
+  Matrix<T, 3, 1> operator*(const Matrix<T, 3, 1>& v) const {
+    const Matrix<T, 3, 1> u(x_, y_, z_);
+    Matrix<T, 3, 1> uv = u.cross(v);
+    uv = uv + uv;
+    return v + uv * w_ + u.cross(uv);
+  }
   Matrix<T, 3, 3> toRotationMatrix() const {
     Matrix<T, 3, 3> r;
     const T tx = T(2) * x_, ty = T(2) * y_, tz = T(2) * z_;
@@ -334,6 +341,7 @@ class AngleAxis {
   }
 };
 typedef AngleAxis<double> AngleAxisd; typedef AngleAxis<float> AngleAxisf;
+typedef Quaternion<double> Quaterniond; typedef Quaternion<float> Quaternionf;
 typedef Matrix<double, 2, 1> Vector2d; typedef Matrix<double, 3, 1> Vector3d; typedef Matrix<double, 4, 1> Vector4d;
 typedef Matrix<float, 2, 1> Vector2f;  typedef Matrix<float, 3, 1> Vector3f;  typedef Matrix<float, 4, 1> Vector4f;
 typedef Matrix<double, 3, 3> Matrix3d; typedef Matrix<double, 4, 4> Matrix4d; typedef Matrix<float, 3, 3> Matrix3f; typedef Matrix<float, 4, 4> Matrix4f;

@@ -6,6 +6,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
@@ -31,6 +32,8 @@ template <typename P> struct PointCloud {
   void resize(size_t n) { points.resize(n); width = (unsigned)n; }
   void reserve(size_t n) { points.reserve(n); }
   void push_back(const P& p) { points.push_back(p); width = (unsigned)points.size(); }
+  template <typename... A> void emplace_back(A&&... a) { points.emplace_back(std::forward<A>(a)...); width = (unsigned)points.size(); }
+  void swap(PointCloud& o) { points.swap(o.points); std::swap(width, o.width); std::swap(height, o.height); std::swap(is_dense, o.is_dense); }
   P& operator[](size_t i) { return points[i]; }
   const P& operator[](size_t i) const { return points[i]; }
   P& at(size_t i) { return points.at(i); }
@@ -69,10 +72,33 @@ template <typename P> class KdTreeFLANN {
     return (int)in.size();
   }
 };
+// pcl::VoxelGrid / RANSAC plane model / NaN removal: named by the feature-extraction code of sensors/Velodyne.cpp, which is NOT on the compiled path and is not
+// reproduced: filter() copies its input, the RANSAC finds nothing.
 template <typename P> class VoxelGrid {
+  typename PointCloud<P>::ConstPtr in_;
  public:
   void setLeafSize(float, float, float) {}
+  void setInputCloud(const typename PointCloud<P>::ConstPtr& c) { in_ = c; }
+  void filter(PointCloud<P>& out) { if (in_) out = *in_; }
 };
+template <typename P> class SampleConsensusModelPlane {
+ public:
+  typedef std::shared_ptr<SampleConsensusModelPlane<P>> Ptr;
+  explicit SampleConsensusModelPlane(const typename PointCloud<P>::ConstPtr&) {}
+};
+template <typename P> class RandomSampleConsensus {
+ public:
+  explicit RandomSampleConsensus(const typename SampleConsensusModelPlane<P>::Ptr&) {}
+  void setDistanceThreshold(double) {}
+  bool computeModel() { return false; }
+  void getInliers(std::vector<int>& v) { v.clear(); }
+  template <typename V> void getModelCoefficients(V&) {}
+};
+template <typename P> inline void removeNaNFromPointCloud(const PointCloud<P>& in, PointCloud<P>& out, std::vector<int>& index) {
+  PointCloud<P> tmp; index.clear();
+  for (size_t i = 0; i < in.points.size(); ++i) { const P& p = in.points[i]; if (std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z)) { tmp.push_back(p); index.push_back((int)i); } }
+  out = tmp;
+}
 // pcl::transformPointCloud(in, out, Matrix4): PCL 1.10 computes x' = T(0,0) x + T(0,1) y + T(0,2) z + T(0,3) in the MATRIX's scalar type and stores float32;
 // the other fields are copied.  M is any 4x4 type with operator()(i, j).
 template <typename P, typename M> inline void transformPointCloud(const PointCloud<P>& in, PointCloud<P>& out, const M& T) {
@@ -101,5 +127,8 @@ template <typename M, typename S, typename V> inline void computeCorrespondingEi
 namespace io {
 template <typename C> inline int savePCDFileASCII(const std::string&, const C&) { return 0; }   // debug dumps (visualization = true only)
 template <typename C> inline int savePCDFileBinary(const std::string&, const C&) { return 0; }
+template <typename C> inline int savePCDFile(const std::string&, const C&) { return 0; }
+template <typename C> inline int loadPCDFile(const std::string&, C&) { return -1; }   // no file IO in the stand-in
+template <typename C> inline int loadPLYFile(const std::string&, C&) { return -1; }
 }  // namespace io
 }  // namespace pcl

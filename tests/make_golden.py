@@ -22,6 +22,7 @@ INDEPENDENT implementations, never from the oracle itself:
                  depth images of its ProjectLidar2PanoramaDepth (oracle/_ref/libpvo_ref_camlidar.so)
   ref_builders.npz  the residual blocks (frame pairs, loss, raw residual, raw Jacobian, in registration order) that the reference's own util/Optimization.cpp builders
                  register for one RefinePose in five configurations, and AddCameraLidarResidual for one frame pair (ceres::Problem = a recorder, oracle/shim)
+  ref_velodyne.npz  float32 clouds after the reference's own Transform2LidarWorld / Transform2Local and UndistortCloud (sensors/Velodyne.cpp compiled where it lies)
   reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
                  undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
 Run from the repo root:  python tests/make_golden.py
@@ -365,8 +366,28 @@ def golden_ref_builders():
     np.savez_compressed(os.path.join(OUT, "ref_builders.npz"), **out)
 
 
+def golden_ref_velodyne():
+    """tests/golden/ref_velodyne.npz: clouds moved by the reference's own Velodyne::Transform2LidarWorld / Transform2Local and undistorted by its UndistortCloud
+    (sensors/Velodyne.cpp compiled where it lies, oracle/_ref/libpvo_ref_assoc.so)."""
+    from oracle import pvo
+    if pvo.ref_assoc_lib() is None:
+        print("oracle/_ref/libpvo_ref_assoc.so not built (no /root/reference here): ref_velodyne.npz left as committed")
+        return
+    import test_reference_pinning as trp
+    cloud, R_wl, t_wl, sweeps = trp.velodyne_case()
+    f = pvo.RefFrame(R_wl, t_wl, surf_less_flat_world=cloud, local=True)
+    out = dict(world=f.cloud("less_flat"))
+    f.to_local()
+    out["local_again"] = f.cloud("less_flat")
+    for k, (R_we, t_we) in enumerate(sweeps):
+        ok, und = pvo.ref_undistort_cloud(R_wl, t_wl, R_we, t_we, cloud)
+        assert ok
+        out[f"undistorted{k}"] = und
+    np.savez_compressed(os.path.join(OUT, "ref_velodyne.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar(); golden_ref_builders()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar(); golden_ref_builders(); golden_ref_velodyne()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

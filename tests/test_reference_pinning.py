@@ -256,10 +256,9 @@ def oracle_associations(oracle, A, B, RB, tB, plane_tol, thr_plane, thr_line):
 
 def reference_associations(oracle, A, B, RB, tB, plane_tol, thr_plane, thr_line):
     """The same through the reference's own functions (needs oracle/_ref/libpvo_ref_assoc.so)."""
-    fa = oracle.RefFrame(A["R_wl"], A["t_wl"], _world(oracle, A, "cornerLessSharp"), A["p2s_off"], A["p2s_ids"], A["segment_coeffs"], _world(oracle, A, "surfFlat"),
-                         _world(oracle, A, "surfLessFlat"), id=0)
-    fb = oracle.RefFrame(RB, tB, _world(oracle, B, "cornerLessSharp", RB, tB), B["p2s_off"], B["p2s_ids"], B["segment_coeffs"], _world(oracle, B, "surfFlat", RB, tB),
-                         _world(oracle, B, "surfLessFlat", RB, tB), id=1)
+    # sensor-frame clouds: the reference's own Velodyne::Transform2LidarWorld() brings them to the world frame (T1)
+    fa = oracle.RefFrame(A["R_wl"], A["t_wl"], A["cornerLessSharp"], A["p2s_off"], A["p2s_ids"], A["segment_coeffs"], A["surfFlat"], A["surfLessFlat"], id=0, local=True)
+    fb = oracle.RefFrame(RB, tB, B["cornerLessSharp"], B["p2s_off"], B["p2s_ids"], B["segment_coeffs"], B["surfFlat"], B["surfLessFlat"], id=1, local=True)
     out = {}
     out["p2plane_point"], out["p2plane_plane"] = oracle.ref_associate_point2plane(fa, fb, plane_tol, thr_plane)
     out["l2l_nei"], out["l2l_ref"], out["l2l_a"], out["l2l_b"] = oracle.ref_associate_line2line(fa, fb, thr_line)
@@ -415,8 +414,7 @@ def oracle_line_tracks(oracle, frames, neighbor_size, min_len, no_pose, builder=
 def reference_line_tracks(oracle, frames, neighbor_size, min_len, no_pose):
     rf = []
     for i, f in enumerate(frames):
-        cw = oracle.transform_cloud(f["R_wl"], f["t_wl"], f["cornerLessSharp"])
-        rf.append(oracle.RefFrame(f["R_wl"], f["t_wl"], cw, f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], id=i, pose_valid=(i != no_pose)))
+        rf.append(oracle.RefFrame(f["R_wl"], f["t_wl"], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], id=i, pose_valid=(i != no_pose), local=True))
     return oracle.ref_generate_line_tracks(rf, neighbor_size, min_len)
 
 
@@ -507,8 +505,8 @@ def product_refine_blocks(oracle, frames, Rs, ts, point_to_plane=True, line_to_l
 
 
 def reference_refine_blocks(oracle, frames, Rs, ts, **kw):
-    rf = [oracle.RefFrame(Rs[i], ts[i], oracle.transform_cloud(Rs[i], ts[i], f["cornerLessSharp"]), f["p2s_off"], f["p2s_ids"], f["segment_coeffs"],
-                          oracle.transform_cloud(Rs[i], ts[i], f["surfFlat"]), oracle.transform_cloud(Rs[i], ts[i], f["surfLessFlat"]), id=i) for i, f in enumerate(frames)]
+    rf = [oracle.RefFrame(Rs[i], ts[i], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["surfFlat"], f["surfLessFlat"], id=i, local=True)
+          for i, f in enumerate(frames)]
     return oracle.ref_refine_pose_blocks(rf, **kw)
 
 
@@ -587,3 +585,29 @@ def test_reprojection_observations_equal_the_reference_builder(oracle):
     if oracle.ref_assoc_lib() is not None:
         live = oracle.ref_camera_residual_blocks(rows, cols, R, t, pv, kp_off, xy, track_off, ff, fi, pts, float(g["cr_weight"]))
         assert np.array_equal(live["cam"], cam) and np.array_equal(live["residual"], g["cr_residual"])
+
+
+# ---- class Velodyne itself: sensors/Velodyne.cpp compiled where it lies (T1 Transform2LidarWorld / Transform2Local, T2 World2Local, UndistortCloud) ----
+def velodyne_case():
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(20261102)
+    cloud = np.concatenate([rng.normal(0, 8, (6000, 3)), rng.uniform(0, 1, (6000, 1))], axis=1).astype(np.float32)
+    R_wl = Rotation.from_rotvec([0.1, -0.3, 0.2]).as_matrix(); t_wl = np.array([1.0, 2.0, -0.5])
+    sweeps = [(R_wl @ Rotation.from_rotvec([0.02, 0.05, -0.03]).as_matrix(), t_wl + np.array([0.3, -0.1, 0.05])),      # ordinary motion
+              (R_wl, t_wl + np.array([0.2, 0.0, 0.0])),                                                               # pure translation: slerp's |d| >= 1 - eps branch
+              (R_wl @ Rotation.from_rotvec([0.0, 2.9, 0.0]).as_matrix(), t_wl)]                                      # large rotation
+    return cloud, R_wl, t_wl, sweeps
+
+
+def test_transform_and_undistortion_equal_the_reference(oracle):
+    """T1: the float32 world clouds left by the reference's Transform2LidarWorld (pcl::transformPointCloud with a double matrix) and the sensor-frame clouds
+    after Transform2Local are BIT-IDENTICAL to the oracle's transform; (f) rank 4: Velodyne::UndistortCloud (Quaternion slerp per point) likewise."""
+    g = np.load(os.path.join(G, "ref_velodyne.npz"))
+    cloud, R_wl, t_wl, sweeps = velodyne_case()
+    assert np.array_equal(oracle.transform_cloud(R_wl, t_wl, cloud), g["world"])
+    assert np.array_equal(oracle.transform_cloud(R_wl.T, -R_wl.T @ t_wl, g["world"]), g["local_again"])
+    for k, (R_we, t_we) in enumerate(sweeps):
+        assert np.array_equal(oracle.undistort_cloud(R_wl, t_wl, R_we, t_we, cloud), g[f"undistorted{k}"]), k
+    if oracle.ref_assoc_lib() is not None:
+        f = oracle.RefFrame(R_wl, t_wl, surf_less_flat_world=cloud, local=True)
+        assert np.array_equal(f.cloud("less_flat"), g["world"])

@@ -104,3 +104,25 @@ def test_generate_line_tracks_equals_the_reference_tracks(gpu_ctx):
         nbrs = Context.find_neighbors(np.array([f["t_wl"] for f in frames]), pv, None, k)
         got = gpu_ctx.generate_line_tracks([_line_frame(f, f["R_wl"], f["t_wl"]) for f in frames], nbrs, pv, 0.3, min_len)
         assert len(got) == len(exp) and all(np.array_equal(a, b) for a, b in zip(got, exp)), ci
+
+
+def test_transform_and_undistort_kernels_equal_the_reference_clouds(gpu_ctx):
+    """k_transform_simple (T1) bit for bit against the cloud left by the reference's Transform2LidarWorld; k_undistort against its UndistortCloud, with the
+    tolerance of tests/test_undistort.py (device sin vs glibc: at most one float32 rounding flip on <= 1e-4 of the values)."""
+    from test_reference_pinning import velodyne_case
+    g = np.load(os.path.join(G, "ref_velodyne.npz"))
+    cloud, R_wl, t_wl, sweeps = velodyne_case()
+    assert np.array_equal(gpu_ctx.transform_cloud(cloud, R_wl, t_wl), g["world"])
+    T_wl = np.eye(4); T_wl[:3, :3] = R_wl; T_wl[:3, 3] = t_wl
+    n = len(cloud)
+    off = (np.arange(len(sweeps) + 1) * n).astype(np.int32)
+    T_we = np.stack([np.block([[R, t[:, None]], [np.zeros((1, 3)), np.ones((1, 1))]]) for R, t in sweeps])
+    out = gpu_ctx.undistort_clouds(np.concatenate([cloud] * len(sweeps)), off, np.stack([T_wl] * len(sweeps)), T_we)
+    bad = 0
+    for k in range(len(sweeps)):
+        got, ref = out[off[k]:off[k + 1]], g[f"undistorted{k}"]
+        assert np.array_equal(got[:, 3], ref[:, 3])
+        d = np.abs(got[:, :3].view(np.int32).astype(np.int64) - ref[:, :3].view(np.int32).astype(np.int64))
+        assert d.max() <= 1, k
+        bad += int((d > 0).sum())
+    assert bad <= 1e-4 * 3 * off[-1] + 2
