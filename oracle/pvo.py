@@ -534,7 +534,8 @@ class RefFrame:
 
     def __init__(self, R_wl, t_wl, corner_world=None, p2s_off=None, p2s_ids=None, coeffs_local=None, surf_flat_world=None, surf_less_flat_world=None, id=0,
                  valid=True, pose_valid=True, local=False):
-        """local=True: the clouds are given in the SENSOR frame and the reference's own Transform2LidarWorld() moves them."""
+        """local=True: the clouds are given in the SENSOR frame and the reference's own Transform2LidarWorld() moves them; local="keep": sensor-frame clouds
+        that stay there (for the entry points that run the reference's own pipeline stages, which transform the frames themselves)."""
         self.L = ref_assoc_lib()
         z = np.zeros((0, 4), np.float32)
         cw = _f32(z if corner_world is None else corner_world).reshape(-1, 4)
@@ -544,7 +545,7 @@ class RefFrame:
         off = None if p2s_off is None else _i32(p2s_off)
         ids = None if p2s_ids is None else _i32(p2s_ids)
         self.h = self.L.ref_frame_create(C.c_int(id), C.c_int(int(valid)), C.c_int(int(pose_valid)), _p(_f64(R_wl)), _p(_f64(t_wl)), _p(cw), C.c_int(len(cw)), _p(off), _p(ids),
-                                         C.c_int(len(co)), _p(co), None, _p(sf), C.c_int(len(sf)), _p(sl), C.c_int(len(sl)), C.c_int(0 if local else 1))
+                                         C.c_int(len(co)), _p(co), None, _p(sf), C.c_int(len(sf)), _p(sl), C.c_int(len(sl)), C.c_int(2 if local == "keep" else (0 if local else 1)))
         assert self.h
         self.n_corner, self.n_flat = len(cw), len(sf)
 
@@ -645,19 +646,21 @@ def ref_generate_line_tracks(frames, neighbor_size, min_track_length):
 
 def ref_refine_pose_blocks(frames, point_to_plane=True, line_to_line=True, point_to_line=False, use_segment=True, angle_residual=True, normalize_distance=True,
                            plane_dis_threshold=1.0, line_dis_threshold=0.3, plane_tolerance=0.05):
-    """The residual blocks one LidarOdometry::RefinePose registers, built by the reference's own util/Optimization.cpp builders over a list of RefFrame and
-    evaluated once (raw residual / 1x12 Jacobian).  Returns dict(ref, nei, huber, residual, jacobian, poses)."""
+    """The problem that the reference's own LidarOdometry::RefinePose hands to ceres::Solve (recorded by the stand-in's solve hook) over a list of RefFrame, every block
+    evaluated once (raw residual / 1x12 Jacobian).  Returns dict(ref, nei, huber, residual, jacobian, poses, info = [max_num_iterations, linear_solver_type,
+    number of constant blocks, first valid frame])."""
     n = len(frames)
     arr = (C.c_void_p * n)(*[f.h for f in frames])
     cap = 1 << 21
     rf, nf, hb, r, J, poses = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap), np.zeros(cap), np.zeros((cap, 12)), np.zeros((n, 6))
+    info = np.zeros(4, np.int32)
     L = frames[0].L
     L.ref_refine_pose_blocks.restype = C.c_long
     m = L.ref_refine_pose_blocks(C.c_int(n), arr, C.c_int(int(point_to_plane)), C.c_int(int(line_to_line)), C.c_int(int(point_to_line)), C.c_int(int(use_segment)),
                                  C.c_int(int(angle_residual)), C.c_int(int(normalize_distance)), C.c_double(plane_dis_threshold), C.c_double(line_dis_threshold),
-                                 C.c_double(plane_tolerance), C.c_long(cap), _p(rf), _p(nf), _p(hb), _p(r), _p(J), _p(poses))
+                                 C.c_double(plane_tolerance), C.c_long(cap), _p(rf), _p(nf), _p(hb), _p(r), _p(J), _p(poses), _p(info))
     assert m >= 0, m
-    return dict(ref=rf[:m].copy(), nei=nf[:m].copy(), huber=hb[:m].copy(), residual=r[:m].copy(), jacobian=J[:m].copy(), poses=poses)
+    return dict(ref=rf[:m].copy(), nei=nf[:m].copy(), huber=hb[:m].copy(), residual=r[:m].copy(), jacobian=J[:m].copy(), poses=poses, info=info)
 
 
 def ref_camera_lidar_blocks(rows, cols, image_lines, start, end, pair_weight, R_wc, t_wc, R_wl, t_wl, weight):
@@ -697,3 +700,48 @@ def ref_undistort_cloud(R_wl, t_wl, R_we, t_we, cloud):
     out = np.empty_like(cloud)
     ok = ref_assoc_lib().ref_undistort_cloud(_p(_f64(R_wl)), _p(_f64(t_wl)), _p(_f64(R_we)), _p(_f64(t_we)), _p(cloud), C.c_long(len(cloud)), _p(out))
     return bool(ok), out
+
+
+def ref_undistort_lidars(R_wl, t_wl, pose_valid, valid, off, clouds, gap_time=0.0):
+    """LidarOdometry::UndistortLidars of the reference: returns the sweeps (concatenated, n x 4 float32) as it leaves them."""
+    R_wl, t_wl = _f64(R_wl).reshape(-1, 9), _f64(t_wl).reshape(-1, 3)
+    clouds, off = _f32(clouds).reshape(-1, 4), _i32(off)
+    out = np.empty_like(clouds)
+    ref_assoc_lib().ref_undistort_lidars(C.c_int(len(t_wl)), _p(R_wl), _p(t_wl), _p(np.ascontiguousarray(pose_valid, np.uint8)), _p(np.ascontiguousarray(valid, np.uint8)),
+                                         _p(off), _p(clouds), C.c_float(gap_time), _p(out))
+    return out
+
+
+def ref_export_pose_t(path, R, t, names=None):
+    R, t = _f64(R).reshape(-1, 9), _f64(t).reshape(-1, 3)
+    arr = None if names is None else (C.c_char_p * len(R))(*[nm.encode() for nm in names])
+    ref_assoc_lib().ref_export_pose_t(str(path).encode(), C.c_int(len(R)), _p(R), _p(t), arr)
+
+
+def ref_read_pose_t(path, with_invalid=False, cap=4096):
+    R, t, names = np.zeros((cap, 9)), np.zeros((cap, 3)), C.create_string_buffer(256 * cap)
+    m = ref_assoc_lib().ref_read_pose_t(str(path).encode(), C.c_int(int(with_invalid)), C.c_int(cap), _p(R), _p(t), names)
+    assert m >= 0, m
+    return R[:m].reshape(-1, 3, 3).copy(), t[:m].copy(), [names.raw[256 * i:256 * (i + 1)].split(b"\0")[0].decode() for i in range(m)]
+
+
+def ref_neighbor_each_frame(R_wc, t_wc, frame_pose_valid, R_wl, t_wl, lidar_pose_valid, lidar_valid, neighbor_size, temporal):
+    R_wc, t_wc, R_wl, t_wl = _f64(R_wc).reshape(-1, 9), _f64(t_wc).reshape(-1, 3), _f64(R_wl).reshape(-1, 9), _f64(t_wl).reshape(-1, 3)
+    nf, nl = len(t_wc), len(t_wl)
+    cap = nf * (neighbor_size + 4) + 16
+    off, ids = np.zeros(nf + 1, np.int32), np.zeros(cap, np.int32)
+    m = ref_assoc_lib().ref_neighbor_each_frame(C.c_int(nf), _p(R_wc), _p(t_wc), _p(np.ascontiguousarray(frame_pose_valid, np.uint8)), C.c_int(nl), _p(R_wl), _p(t_wl),
+                                                _p(np.ascontiguousarray(lidar_pose_valid, np.uint8)), _p(np.ascontiguousarray(lidar_valid, np.uint8)), C.c_int(neighbor_size),
+                                                C.c_int(int(temporal)), C.c_int(cap), _p(off), _p(ids))
+    assert m >= 0
+    return [ids[off[i]:off[i + 1]].tolist() for i in range(nf)]
+
+
+def ref_lidar_mask_by_track(frames, min_track_length=3, neighbor_size=3):
+    n = len(frames)
+    arr = (C.c_void_p * n)(*[f.h for f in frames])
+    cap = 1 << 16
+    off, mask = np.zeros(n + 1, np.int32), np.zeros(cap, np.uint8)
+    m = frames[0].L.ref_lidar_mask_by_track(C.c_int(n), arr, C.c_int(min_track_length), C.c_int(neighbor_size), C.c_int(cap), _p(off), _p(mask))
+    assert m >= 0
+    return [mask[off[i]:off[i + 1]].astype(bool) for i in range(n)]

@@ -8,29 +8,52 @@
 // What this pins: the control flow, thresholds, class test, vote rules, conflict resolution and output order of the reference's association functions.
 // Built by `make -C oracle ref` into oracle/_ref/libpvo_ref_assoc.so; used by tests/test_reference_pinning.py and tests/make_golden.py only.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
+#include <iomanip>
 #include <iostream>
 #include <iterator>
+#include <list>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <numeric>
+#include <queue>
+#include <random>
 #include <set>
 #include <sstream>
 #include <stack>
 #include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
 #include <vector>
-#include <atomic>
-#include <chrono>
-#define private public          // the wrapper sets Velodyne::world (set by Transform2LidarWorld, sensors/Velodyne.cpp:1807) after filling world-frame clouds
-#include REF_VELODYNE_CPP                 // sensors/Velodyne.cpp: the class itself (poses, Transform2LidarWorld / Transform2Local, World2Local, UndistortCloud ...)
-#include REF_LIDAR_FEATURE_ASSOCIATE_CPP
-#include REF_TRACKS_CPP                   // util/Tracks.cpp: TrackBuilder (union-find over (frame, line) features), Filter, ExportTracks
-#include REF_LIDAR_LINE_MATCH_CPP         // lidar_mapping/LidarLineMatch.cpp: GenerateTracks = FindNeighbors + AssociateLine2Line(nei, i, 0.3) + TrackBuilder
-#include REF_OPTIMIZATION_CPP             // util/Optimization.cpp: the residual-block builders (AddLidarPointToPlaneResidual ...); ceres::Problem = the shim's recorder
+#include <omp.h>
+#define private public          // the wrapper reads / fills private members (Velodyne::world, Frame::keypoints_all, CameraLidarOptimizer's private stages)
+#define REF(path) REF_STR(REFERENCE_ROOT/path)
+#define REF_STR(x) REF_STR2(x)
+#define REF_STR2(x) #x
+#include REF(base/common.cpp)                                  // SplitString, IterateFiles (the file system stand-in lists nothing)
+#include REF(base/ProcessBar.cpp)
+#include REF(sensors/Velodyne.cpp)                             // the class itself: poses, Transform2LidarWorld / Transform2Local, World2Local, UndistortCloud ...
+#include REF(sensors/Frame.cpp)
+#include REF(sensors/Equirectangular.cpp)
+#include REF(lidar_mapping/LidarFeatureAssociate.cpp)
+#include REF(util/Tracks.cpp)                                  // TrackBuilder (union-find over (frame, line) features), Filter, ExportTracks
+#include REF(lidar_mapping/LidarLineMatch.cpp)                 // GenerateTracks = FindNeighbors + AssociateLine2Line(nei, i, 0.3) + TrackBuilder
+#include REF(util/Optimization.cpp)                            // the residual-block builders; ceres::Problem = the shim's recorder
+#include REF(util/FileIO.cpp)                                  // ReadPoseT / ExportPoseT (pose text files)
+#include REF(sfm/Structure.cpp)
+#include REF(lidar_mapping/LidarOdometry.cpp)                  // RefinePose, UndistortLidars
+#include REF(joint_optimization/CameraLidarLineAssociate.cpp)
+#include REF(joint_optimization/CameraLidarOptimizer.cpp)      // NeighborEachFrame, LidarMaskByTrack, AssociateLineMulti, Optimize
 #undef private
 
 // ---- defined by the reference in translation units that are NOT compiled here (ground segmentation, LiDAR line / plane extraction, drawing) and reached only from
@@ -47,28 +70,11 @@ void ExtractLineFeatures(const pcl::PointCloud<pcl::PointXYZI>&, const std::vect
 GroundSegmentation::GroundSegmentation(const GroundSegmentationParams& p) : params_(p) { not_compiled("GroundSegmentation (sensors/ground_segmentation.cpp)"); }
 void GroundSegmentation::segment(const PointCloud&, std::vector<int>&) { not_compiled("GroundSegmentation::segment"); }
 
-// ---- class Frame: the members util/Optimization.cpp calls (sensors/Frame.cpp, restated) ----
-Frame::Frame(int _rows, int _cols, int _id, const std::string _name) : id(_id), name(_name), rows(_rows), cols(_cols), scale(0) {                // :10-16
-  R_wc = Eigen::Matrix3d::Zero();
-  t_wc = std::numeric_limits<double>::infinity() * Eigen::Vector3d::Ones();
-  gps = std::numeric_limits<double>::infinity() * Eigen::Vector3d::Ones();
-}
-Frame::~Frame() {}                                                                                                                               // :227-229
-void Frame::SetPose(const Eigen::Matrix3d _R_wc, const Eigen::Vector3d _t_wc) { R_wc = _R_wc; t_wc = _t_wc; }                                    // :52-56
-const Eigen::Matrix4d Frame::GetPose() const {                                                                                                   // :129-135
-  Eigen::Matrix4d T_wc = Eigen::Matrix4d::Identity();
-  T_wc.block<3, 3>(0, 0) = R_wc;
-  T_wc.block<3, 1>(0, 3) = t_wc;
-  return T_wc;
-}
-const std::vector<cv::KeyPoint>& Frame::GetKeyPoints() const { return keypoints_all; }                                                           // :137-140
-const int Frame::GetImageRows() const { return rows; }                                                                                           // :188-191
-const int Frame::GetImageCols() const { return cols; }                                                                                           // :193-196
-const bool Frame::IsPoseValid() const {                                                                                                          // :203-208
-  if (!std::isinf(t_wc(0)) && !std::isnan(t_wc(0)) && !std::isinf(t_wc(1)) && !std::isnan(t_wc(1)) && !std::isinf(t_wc(2)) && !std::isnan(t_wc(2)) && !R_wc.isZero())
-    return true;
-  return false;
-}
+// ---- class PanoramaLine (util/PanoramaLine.cpp is image line DETECTION on real OpenCV algorithms and is not compiled): the three trivial members the joint stage needs
+// to carry already-detected lines around.  Everything else of that file, and the other non-compiled files, are abort placeholders in ref_unresolved_stubs.c ----
+PanoramaLine::~PanoramaLine() {}
+void PanoramaLine::SetName(const std::string& _name) { name = _name; }
+const std::vector<cv::Vec4f>& PanoramaLine::GetLines() const { return lines; }
 
 namespace {
 void fill_cloud(pcl::PointCloud<PointType>& c, const float* xyzi, int n) {
@@ -81,7 +87,7 @@ extern "C" {
 // A frame as the association code sees it: pose (R row-major, t; pose_valid = 0 leaves the constructor's "no pose" state), the three feature clouds (float32
 // x, y, z, intensity), the point -> segment sets of cornerLessSharp (CSR), the segment coefficients in the SENSOR frame.  clouds_in_world = 0: the clouds are
 // given in the SENSOR frame and the reference's own Velodyne::Transform2LidarWorld() moves them (the state RefinePose starts from, LidarOdometry.cpp:17-21);
-// clouds_in_world = 1: they are already world-frame and only the flag is set.
+// clouds_in_world = 1: they are already world-frame and only the flag is set; 2: sensor-frame clouds, left there (RefinePose / LidarMaskByTrack move them themselves).
 void* ref_frame_create(int id, int valid, int pose_valid, const double* R_wl, const double* t_wl, const float* corner, int n_corner, const int* p2s_off,
                        const int* p2s_ids, int S, const double* coeffs_local, const int* seg_sizes, const float* surf_flat, int n_flat,
                        const float* surf_less_flat, int n_less, int clouds_in_world) {
@@ -105,8 +111,8 @@ void* ref_frame_create(int id, int valid, int pose_valid, const double* R_wl, co
   // gives explicit sizes they must agree
   for (int i = 0; i < n_corner; ++i) for (int s : v->point_to_segment[i]) v->edge_segmented[s].push_back(v->cornerLessSharp.points[i]);
   if (seg_sizes) for (int s = 0; s < S; ++s) if ((int)v->edge_segmented[s].size() != seg_sizes[s]) { delete v; return nullptr; }
-  if (clouds_in_world) v->world = 1;
-  else if (pose_valid) v->Transform2LidarWorld();
+  if (clouds_in_world == 1) v->world = 1;
+  else if (clouds_in_world == 0 && pose_valid) v->Transform2LidarWorld();       // 2: sensor-frame clouds stay where they are (the caller's pipeline moves them)
   return v;
 }
 // which: 0 cornerLessSharp, 1 surfFlat, 2 surfLessFlat; out: n x 4 float.  Returns the point count.
@@ -189,55 +195,149 @@ int ref_generate_line_tracks(int n, void* const* frames, int neighbor_size, int 
   return (int)tr.size();
 }
 
-// The residual blocks of one LidarOdometry::RefinePose call, as the reference's own builders register them.  The preamble is RefinePose's
-// (lidar_mapping/LidarOdometry.cpp:23-64, restated here because LidarOdometry.cpp itself needs the whole pipeline): pose blocks (aa_lw, t_lw) from
-// GetPose().inverse() + ceres::RotationMatrixToAngleAxis, FindNeighbors(lidars, 6), then - in this order - AddLidarPointToLineResidual (if point_to_line),
-// GenerateTracks(4, 3) + AddLidarLineToLineResidual2 (if line_to_line && use_segment), AddLidarPointToPlaneResidual (if point_to_plane), every builder called
-// with RefinePose's arguments (default weight).  The recorded blocks are then evaluated ONCE through ceres::CostFunction::Evaluate at those pose blocks.
-// Per block: reference / neighbour frame (from the parameter pointers), Huber parameter a (0 = loss nullptr), raw residual, raw 1x12 Jacobian.
-// poses_out: n x 6 pose blocks.  Returns the number of blocks, -1 when cap is too small, -2 on an Evaluate failure.
+// ---- what ceres::Solve sees: a snapshot taken by the stand-in's solve hook (the solver itself is not reproduced) ----
+namespace {
+struct Snapshot {
+  std::vector<int> ref, nei; std::vector<double> huber, residual, jac; std::vector<const double*> constant; std::vector<double> poses;
+  int n_frames = 0, first_valid = 0, max_num_iterations = 0, linear_solver = -1; long status = 0;
+};
+Snapshot* g_snap = nullptr;
+// RefinePose's problem: 4-block residuals over (aa_lw[i], t_lw[i]); the first valid frame's two blocks are constant (LidarOdometry.cpp:58-64), which gives the
+// base addresses of the two pose lists (contiguous eigen_vector<Vector3d>)
+void lidar_hook(const ceres::Solver::Options& o, ceres::Problem* p, ceres::Solver::Summary* s) {
+  Snapshot& S = *g_snap;
+  S.max_num_iterations = o.max_num_iterations; S.linear_solver = (int)o.linear_solver_type;
+  S.constant = p->constant_blocks;
+  if (p->constant_blocks.size() != 2) { S.status = -3; return; }
+  const Eigen::Vector3d* aa = (const Eigen::Vector3d*)p->constant_blocks[0] - S.first_valid;
+  const Eigen::Vector3d* tt = (const Eigen::Vector3d*)p->constant_blocks[1] - S.first_valid;
+  S.poses.resize(6 * S.n_frames);
+  for (int i = 0; i < S.n_frames; ++i) for (int k = 0; k < 3; ++k) { S.poses[6 * i + k] = aa[i][k]; S.poses[6 * i + 3 + k] = tt[i][k]; }
+  for (const ceres::Problem::Block& blk : p->blocks) {
+    if (blk.params.size() != 4) { S.status = -2; return; }
+    const int r = (int)((const Eigen::Vector3d*)blk.params[0] - aa), n = (int)((const Eigen::Vector3d*)blk.params[2] - aa);
+    if (r < 0 || r >= S.n_frames || n < 0 || n >= S.n_frames || blk.params[1] != (const double*)(tt + r) || blk.params[3] != (const double*)(tt + n)) { S.status = -2; return; }
+    S.ref.push_back(r); S.nei.push_back(n);
+    const ceres::HuberLoss* h = dynamic_cast<const ceres::HuberLoss*>(blk.loss);
+    S.huber.push_back(h ? h->a() : 0.0);
+    double res, jb[4][3]; double* jp[4] = {jb[0], jb[1], jb[2], jb[3]};
+    if (!blk.cost->Evaluate(blk.params.data(), &res, jp)) { S.status = -2; return; }
+    S.residual.push_back(res); S.jac.insert(S.jac.end(), &jb[0][0], &jb[0][0] + 12);
+  }
+  s->usable = true; s->final_cost = 0; s->num_successful_steps = 0;      // keeps RefinePose off its failure branch (which writes debug files)
+}
+Config make_config(int point_to_plane, int line_to_line, int point_to_line, int angle_residual, int normalize_distance, float plane_dis_threshold, float line_dis_threshold,
+                   float plane_tolerance) {
+  Config c;                                             // base/Config.h defaults; the fields below are the ones RefinePose reads (config/*.txt: lines 67-76)
+  c.point_to_plane_residual = point_to_plane != 0; c.line_to_line_residual = line_to_line != 0; c.point_to_line_residual = point_to_line != 0;
+  c.angle_residual = angle_residual != 0; c.normalize_distance = normalize_distance != 0;
+  c.point_to_plane_dis_threshold = plane_dis_threshold; c.point_to_line_dis_threshold = line_dis_threshold; c.lidar_plane_tolerance = plane_tolerance;
+  c.num_threads = 1;
+  return c;
+}
+}  // namespace
+
+// The residual blocks of one LidarOdometry::RefinePose call: the reference's OWN RefinePose (lidar_mapping/LidarOdometry.cpp:15-114) runs - pose blocks, FindNeighbors(6),
+// GenerateTracks(4, 3), the builders, SetParameterBlockConstant of the first valid frame, SetOptionsLidar - and the stand-in's ceres::Solve hook records the problem it
+// is handed, evaluating every block once through ceres::CostFunction::Evaluate.  The thresholds travel as `float`, as they do in base/Config.h.
+// Per block: reference / neighbour frame, Huber parameter a (0 = loss nullptr), raw residual, raw 1x12 Jacobian.  poses_out: n x 6 pose blocks; info4 = {max_num_iterations,
+// linear_solver_type, number of constant blocks, first valid frame}.  Returns the number of blocks, -1 when cap is too small, -2 / -3 on an inconsistency.
 long ref_refine_pose_blocks(int n, void* const* frames, int point_to_plane, int line_to_line, int point_to_line, int use_segment, int angle_residual, int normalize_distance,
                             double plane_dis_threshold, double line_dis_threshold, double plane_tolerance, long cap, int* ref_frame, int* nei_frame, double* huber_a,
-                            double* residual, double* jac12, double* poses_out) {
+                            double* residual, double* jac12, double* poses_out, int* info4) {
   std::vector<Velodyne> lidars;
   for (int i = 0; i < n; ++i) lidars.push_back(*static_cast<const Velodyne*>(frames[i]));
-  eigen_vector<Eigen::Vector3d> angleAxis_lw_list(lidars.size(), Eigen::Vector3d::Ones());
-  eigen_vector<Eigen::Vector3d> t_lw_list(lidars.size(), Eigen::Vector3d::Ones());
-  for (size_t i = 0; i < lidars.size(); i++) {                                                     // LidarOdometry.cpp:25-33
-    if (!lidars[i].IsPoseValid() || !lidars[i].valid) continue;
-    Eigen::Matrix4d T_lw = lidars[i].GetPose().inverse();
-    Eigen::Matrix3d R_lw = T_lw.block<3, 3>(0, 0);
-    ceres::RotationMatrixToAngleAxis(R_lw.data(), angleAxis_lw_list[i].data());
-    t_lw_list[i] = T_lw.block<3, 1>(0, 3);
+  for (Velodyne& l : lidars) if (l.IsInWorldCoordinate()) l.Transform2Local();                 // RefinePose itself moves them to the world frame (:17-21)
+  const Config config = make_config(point_to_plane, line_to_line, point_to_line, angle_residual, normalize_distance, (float)plane_dis_threshold, (float)line_dis_threshold,
+                                    (float)plane_tolerance);
+  LidarOdometry odo(lidars, config);
+  Snapshot S; S.n_frames = n;
+  for (S.first_valid = 0; S.first_valid < n; ++S.first_valid) if (lidars[S.first_valid].IsPoseValid() && lidars[S.first_valid].valid) break;
+  g_snap = &S; ceres::solve_hook() = lidar_hook;
+  double cost = 0; int steps = 0;
+  odo.RefinePose(cost, steps, use_segment != 0);
+  ceres::solve_hook() = nullptr; g_snap = nullptr;
+  if (S.status < 0) return S.status;
+  if ((long)S.residual.size() > cap) return -1;
+  for (size_t b = 0; b < S.residual.size(); ++b) { ref_frame[b] = S.ref[b]; nei_frame[b] = S.nei[b]; huber_a[b] = S.huber[b]; residual[b] = S.residual[b]; }
+  if (!S.jac.empty()) std::memcpy(jac12, S.jac.data(), S.jac.size() * sizeof(double));
+  if (!S.poses.empty()) std::memcpy(poses_out, S.poses.data(), S.poses.size() * sizeof(double));
+  info4[0] = S.max_num_iterations; info4[1] = S.linear_solver; info4[2] = (int)S.constant.size(); info4[3] = S.first_valid;
+  return (long)S.residual.size();
+}
+
+// LidarOdometry::UndistortLidars (lidar_mapping/LidarOdometry.cpp:189-263): sweep-end pose selection (next / previous frame with a pose, SlerpPose with the
+// duration ratio) + Velodyne::UndistortCloud per frame.  n frames with pose (R row-major 9, t 3), pose_valid / valid flags, raw sweeps concatenated (off[n + 1],
+// n_points x 4 float).  out: the sweeps as the reference leaves them in `lidars[i].cloud`.
+void ref_undistort_lidars(int n, const double* R_wl, const double* t_wl, const unsigned char* pose_valid, const unsigned char* valid, const int* off, const float* clouds,
+                          float gap_time, float* out) {
+  std::vector<Velodyne> lidars(n);
+  for (int f = 0; f < n; ++f) {
+    lidars[f].id = f; lidars[f].valid = valid[f] != 0;
+    if (pose_valid[f]) { Eigen::Matrix3d R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R(i, j) = R_wl[9 * f + 3 * i + j]; lidars[f].SetPose(R, Eigen::Vector3d(t_wl[3 * f], t_wl[3 * f + 1], t_wl[3 * f + 2])); }
+    fill_cloud(lidars[f].cloud, clouds + 4 * (size_t)off[f], off[f + 1] - off[f]);
   }
-  std::vector<std::vector<int>> neighbors_all = FindNeighbors(lidars, 6);                          // :35
-  ceres::Problem problem;
-  if (point_to_line)                                                                                // :38-40
-    AddLidarPointToLineResidual(neighbors_all, lidars, angleAxis_lw_list, t_lw_list, problem, line_dis_threshold, use_segment != 0, angle_residual != 0, normalize_distance != 0);
-  if (line_to_line && use_segment) {                                                                // :41-53
-    LidarLineMatch matcher(lidars);
-    matcher.SetNeighborSize(4);
-    matcher.SetMinTrackLength(3);
-    matcher.GenerateTracks();
-    AddLidarLineToLineResidual2(neighbors_all, lidars, angleAxis_lw_list, t_lw_list, problem, matcher.GetTracks(), line_dis_threshold, angle_residual != 0, normalize_distance != 0);
+  Config config; config.num_threads = 1;
+  LidarOdometry odo(lidars, config);
+  odo.UndistortLidars(gap_time);
+  const std::vector<Velodyne>& res = odo.GetLidarData();
+  for (int f = 0; f < n; ++f) for (int i = 0; i < off[f + 1] - off[f]; ++i) {
+    const PointType& p = res[f].cloud.points[i]; float* o = out + 4 * ((size_t)off[f] + i);
+    o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = p.intensity;
   }
-  if (point_to_plane)                                                                               // :54-57
-    AddLidarPointToPlaneResidual(neighbors_all, lidars, angleAxis_lw_list, t_lw_list, problem, plane_dis_threshold, plane_tolerance, angle_residual != 0, normalize_distance != 0);
-  for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) { poses_out[6 * i + k] = angleAxis_lw_list[i][k]; poses_out[6 * i + 3 + k] = t_lw_list[i][k]; }
-  if ((long)problem.blocks.size() > cap) return -1;
-  for (size_t b = 0; b < problem.blocks.size(); ++b) {
-    const ceres::Problem::Block& blk = problem.blocks[b];
-    if (blk.params.size() != 4) return -2;
-    ref_frame[b] = (int)((Eigen::Vector3d*)blk.params[0] - &angleAxis_lw_list[0]);
-    nei_frame[b] = (int)((Eigen::Vector3d*)blk.params[2] - &angleAxis_lw_list[0]);
-    if (blk.params[1] != t_lw_list[ref_frame[b]].data() || blk.params[3] != t_lw_list[nei_frame[b]].data()) return -2;
-    const ceres::HuberLoss* h = dynamic_cast<const ceres::HuberLoss*>(blk.loss);
-    huber_a[b] = h ? h->a() : 0.0;
-    double jb[4][3]; double* jp[4] = {jb[0], jb[1], jb[2], jb[3]};
-    if (!blk.cost->Evaluate(blk.params.data(), residual + b, jp)) return -2;
-    std::memcpy(jac12 + 12 * b, jb, sizeof(jb));
+}
+
+// ExportPoseT / ReadPoseT (util/FileIO.cpp:11-73, 168-191): pose text files.  names may be null (no name column).
+void ref_export_pose_t(const char* path, int n, const double* R9, const double* t3, const char* const* names) {
+  eigen_vector<Eigen::Matrix3d> Rl; eigen_vector<Eigen::Vector3d> tl; std::vector<std::string> nl;
+  for (int f = 0; f < n; ++f) {
+    Eigen::Matrix3d R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R(i, j) = R9[9 * f + 3 * i + j];
+    Rl.push_back(R); tl.push_back(Eigen::Vector3d(t3[3 * f], t3[3 * f + 1], t3[3 * f + 2]));
+    if (names) nl.push_back(names[f]);
   }
-  return (long)problem.blocks.size();
+  ExportPoseT(path, Rl, tl, nl);
+}
+int ref_read_pose_t(const char* path, int with_invalid, int cap, double* R9, double* t3, char* names_256) {
+  eigen_vector<Eigen::Matrix3d> Rl; eigen_vector<Eigen::Vector3d> tl; std::vector<std::string> nl;
+  if (!ReadPoseT(path, with_invalid != 0, Rl, tl, nl)) return -1;
+  if ((int)Rl.size() > cap) return -2;
+  for (size_t f = 0; f < Rl.size(); ++f) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R9[9 * f + 3 * i + j] = Rl[f](i, j);
+    for (int k = 0; k < 3; ++k) t3[3 * f + k] = tl[f][k];
+    std::snprintf(names_256 + 256 * f, 256, "%s", nl[f].c_str());
+  }
+  return (int)Rl.size();
+}
+
+// CameraLidarOptimizer::NeighborEachFrame (joint_optimization/CameraLidarOptimizer.cpp:551-607) and LidarMaskByTrack (:609-642), called on an optimizer object
+// built from n_frames camera poses and the LiDAR frames.  CSR outputs.
+int ref_neighbor_each_frame(int n_frames, const double* R_wc, const double* t_wc, const unsigned char* frame_pose_valid, int n_lidars, const double* R_wl, const double* t_wl,
+                            const unsigned char* lidar_pose_valid, const unsigned char* lidar_valid, int neighbor_size, int temporal, int cap, int* off, int* ids) {
+  std::vector<Frame> frames; std::vector<Velodyne> lidars(n_lidars);
+  for (int f = 0; f < n_frames; ++f) {
+    frames.push_back(Frame(2880, 5760, f, "frame"));
+    if (frame_pose_valid[f]) { Eigen::Matrix3d R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R(i, j) = R_wc[9 * f + 3 * i + j]; frames[f].SetPose(R, Eigen::Vector3d(t_wc[3 * f], t_wc[3 * f + 1], t_wc[3 * f + 2])); }
+  }
+  for (int f = 0; f < n_lidars; ++f) {
+    lidars[f].id = f; lidars[f].valid = lidar_valid[f] != 0;
+    if (lidar_pose_valid[f]) { Eigen::Matrix3d R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R(i, j) = R_wl[9 * f + 3 * i + j]; lidars[f].SetPose(R, Eigen::Vector3d(t_wl[3 * f], t_wl[3 * f + 1], t_wl[3 * f + 2])); }
+  }
+  Config config; config.num_threads = 1;
+  CameraLidarOptimizer opt(Eigen::Matrix4d::Identity(), lidars, frames, config);
+  const std::vector<std::vector<int>> nb = opt.NeighborEachFrame(neighbor_size, temporal != 0);
+  int total = 0; off[0] = 0;
+  for (int f = 0; f < n_frames; ++f) { for (int v : nb[f]) { if (total >= cap) return -1; ids[total++] = v; } off[f + 1] = total; }
+  return total;
+}
+int ref_lidar_mask_by_track(int n, void* const* lidar_frames, int min_track_length, int neighbor_size, int cap, int* off, unsigned char* mask) {
+  std::vector<Velodyne> lidars; std::vector<Frame> frames;
+  for (int i = 0; i < n; ++i) lidars.push_back(*static_cast<const Velodyne*>(lidar_frames[i]));
+  Config config; config.num_threads = 1;
+  CameraLidarOptimizer opt(Eigen::Matrix4d::Identity(), lidars, frames, config);
+  const std::vector<std::vector<bool>> m = opt.LidarMaskByTrack(min_track_length, neighbor_size);
+  int total = 0; off[0] = 0;
+  for (int f = 0; f < n; ++f) { for (bool v : m[f]) { if (total >= cap) return -1; mask[total++] = v ? 1 : 0; } off[f + 1] = total; }
+  return total;
 }
 
 // AddCameraLidarResidual (util/Optimization.cpp:564-607) for ONE (image, LiDAR) pair of frames: n line pairs (image line in pixels, LiDAR segment start / end

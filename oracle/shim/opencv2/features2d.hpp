@@ -1,0 +1,1 @@
+#include "../pvo_shim_cv.hpp"

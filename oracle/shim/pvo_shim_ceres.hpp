@@ -216,10 +216,10 @@ class Problem {
  public:
   struct Block { CostFunction* cost; LossFunction* loss; std::vector<double*> params; };
   std::vector<Block> blocks;
-  std::vector<double*> constant_blocks;
+  std::vector<const double*> constant_blocks;
   template <typename... P> void* AddResidualBlock(CostFunction* cost, LossFunction* loss, P*... p) { blocks.push_back(Block{cost, loss, std::vector<double*>{p...}}); return nullptr; }
   void AddParameterBlock(double*, int) {}
-  void SetParameterBlockConstant(double* p) { constant_blocks.push_back(p); }
+  void SetParameterBlockConstant(const double* p) { constant_blocks.push_back(p); }
   void SetParameterBlockVariable(double*) {}
   int NumResidualBlocks() const { return (int)blocks.size(); }
   int NumResiduals() const { int n = 0; for (const Block& b : blocks) n += b.cost->num_residuals(); return n; }
@@ -236,10 +236,15 @@ class Solver {
   };
   struct Summary {
     double initial_cost = -1, final_cost = -1; int num_successful_steps = 0, num_unsuccessful_steps = 0;
-    bool IsSolutionUsable() const { return false; }
+    bool usable = false;
+    bool IsSolutionUsable() const { return usable; }
     std::string BriefReport() const { return "oracle/shim: ceres::Solve is not reproduced"; }
     std::string FullReport() const { return BriefReport(); }
   };
 };
-inline void Solve(const Solver::Options&, Problem*, Solver::Summary*) {}
+// ceres::Solve: the solver is NOT reproduced.  A test harness may install a hook that LOOKS at the problem the caller assembled (and fills the summary);
+// without a hook the call returns an unusable summary and leaves the parameters alone.
+typedef void (*SolveHook)(const Solver::Options&, Problem*, Solver::Summary*);
+inline SolveHook& solve_hook() { static SolveHook h = nullptr; return h; }
+inline void Solve(const Solver::Options& o, Problem* p, Solver::Summary* s) { if (solve_hook()) solve_hook()(o, p, s); }
 }  // namespace ceres

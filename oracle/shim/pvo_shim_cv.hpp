@@ -4,6 +4,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <fstream>
 #include <iostream>
 #include <string>
 #include <type_traits>
@@ -12,6 +13,9 @@
 #include <cassert>
 typedef unsigned char uchar; typedef unsigned short ushort;   // OpenCV declares these at global scope
 #define CV_GRAY2BGR 8
+#define CV_LOAD_IMAGE_GRAYSCALE 0
+#define CV_LOAD_IMAGE_COLOR 1
+#define CV_LOAD_IMAGE_UNCHANGED -1
 #define CV_BGR2GRAY 6
 #define CV_32FC3 21
 #define CV_16U 2
@@ -103,6 +107,9 @@ struct Mat {
   unsigned char* ptr(int i = 0) { return d.data() + (size_t)i * cols * elem(type_); }
   const unsigned char* ptr(int i = 0) const { return d.data() + (size_t)i * cols * elem(type_); }
   Mat clone() const { return *this; }
+  void release() { d.clear(); rows = cols = 0; }
+  void convertTo(Mat& out, int, double = 1, double = 0) const { out = *this; }     // image arithmetic is only named by image IO helpers: not reproduced
+  Mat& operator*=(double) { return *this; } Mat& operator/=(double) { return *this; } Mat& operator-=(double) { return *this; } Mat& operator+=(double) { return *this; }
   int type() const { return type_; }
   int channels() const { return (type_ >> 3) + 1; }
   Size size() const { return Size(cols, rows); }
@@ -114,9 +121,14 @@ struct Mat {
 };
 // drawing / IO named by the reference's debug branches (visualization flags off in every test): no-ops
 inline bool imwrite(const std::string&, const Mat&) { return true; }
+inline Mat imread(const std::string&, int = 1) { return Mat(); }          // no file IO in the stand-in
+inline Mat operator+(const Mat& a, double) { return a; }
+inline Mat operator*(const Mat& a, double) { return a; }
 inline void cvtColor(const Mat& a, Mat& b, int) { b = a; }
 enum { COLOR_GRAY2BGR = 8, COLOR_BGR2GRAY = 6, COLOR_GRAY2RGB = 8 };
 inline void circle(Mat&, Point2i, int, const Scalar&, int = 1) {}
+inline void pyrUp(const Mat& a, Mat& b) { b = a; }      // image pyramids: named by Frame's image loaders only, not reproduced
+inline void pyrDown(const Mat& a, Mat& b) { b = a; }
 inline void line(Mat&, Point2i, Point2i, const Scalar&, int = 1) {}
 namespace flann {
 struct KDTreeIndexParams { explicit KDTreeIndexParams(int = 4) {} };

@@ -101,6 +101,7 @@ class Matrix {
   void fill(const T& v) { for (int i = 0; i < size(); ++i) s.data()[i] = v; }
   static Matrix Zero() { Matrix m; m.fill(T(0)); return m; }
   static Matrix Ones() { Matrix m; m.fill(T(1)); return m; }
+  T trace() const { T t = (*this)(0, 0); for (int i = 1; i < std::min(rows(), cols()); ++i) t = t + (*this)(i, i); return t; }
   bool isZero(double prec = 1e-12) const { using std::abs; for (int i = 0; i < size(); ++i) if (!(abs(s.data()[i]) <= prec)) return false; return true; }
   Matrix<T, 1, C> row(int i) const { Matrix<T, 1, C> v; v.resize(1, cols()); for (int j = 0; j < cols(); ++j) v(0, j) = (*this)(i, j); return v; }
   template <typename I> T maxCoeff(I* where) const { int b = 0; for (int k = 1; k < size(); ++k) if (s.data()[k] > s.data()[b]) b = k; *where = (I)b; return s.data()[b]; }

@@ -13,7 +13,7 @@
 
 namespace pcl {
 struct PointXYZ { float x = 0, y = 0, z = 0; };
-struct PointXYZI { float x = 0, y = 0, z = 0, intensity = 0; };
+struct PointXYZI { float x = 0, y = 0, z = 0, intensity = 0; PointXYZI() {} explicit PointXYZI(float i) : intensity(i) {} };
 struct PointXYZRGB { float x = 0, y = 0, z = 0; unsigned char r = 0, g = 0, b = 0; };
 struct PointXYZRGBL { float x = 0, y = 0, z = 0; unsigned char r = 0, g = 0, b = 0; unsigned int label = 0; };
 struct Normal { float normal_x = 0, normal_y = 0, normal_z = 0, curvature = 0; };

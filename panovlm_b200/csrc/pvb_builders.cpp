@@ -3,6 +3,7 @@
 // the host (small integer / per-segment work): lidar_mapping/LidarFeatureAssociate.cpp:19-111, 120-197 and
 // joint_optimization/CameraLidarLineAssociate.cpp:415-475, 628-715.  Only public pvb_* entry points are used for the
 // device work (vote matrices, cloud transforms).
+#include <limits>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -768,16 +769,17 @@ int pvb_undistort_end_poses(int n, const double* poses16, const unsigned char* p
       int nxt = i + 1;
       while (nxt < n && !pose_valid[nxt] && !frame_valid[nxt]) ++nxt;
       if (nxt == n) continue;
-      if (!slerp_pose(cur, poses16 + (size_t)nxt * 16, sweep / ((nxt - i) * period), dst)) return PVB_ERR_ARG;
+      // a neighbour that is valid but has no pose (R = 0, t = inf) is NOT stepped over by the reference; its SlerpPose then runs on a singular matrix and the
+      // sweep comes out as NaN (pinned against the reference's own UndistortLidars, tests/test_reference_pinning.py) - reproduced, not repaired
+      if (!slerp_pose(cur, poses16 + (size_t)nxt * 16, sweep / ((nxt - i) * period), dst)) std::fill(dst, dst + 16, std::numeric_limits<double>::quiet_NaN());
     } else {
       // last frame: extrapolate from an earlier frame (:229-240); the loop tests frame i's own `valid` flag and index 0 is rejected (:232)
       int prv = i - 1;
       while (prv >= 0 && !pose_valid[prv] && !frame_valid[i]) --prv;
       if (prv <= 0) continue;
       double mid[16], inv_cur[16], rel[16];
-      if (!slerp_pose(poses16 + (size_t)prv * 16, cur, 1.0 - sweep / ((prv - i) * period), mid) || !inverse4(cur, inv_cur)) return PVB_ERR_ARG;
-      mul4(inv_cur, mid, rel);
-      mul4(cur, rel, dst);
+      if (!slerp_pose(poses16 + (size_t)prv * 16, cur, 1.0 - sweep / ((prv - i) * period), mid) || !inverse4(cur, inv_cur)) std::fill(dst, dst + 16, std::numeric_limits<double>::quiet_NaN());
+      else { mul4(inv_cur, mid, rel); mul4(cur, rel, dst); }
     }
     has_end[i] = 1;
   }

@@ -308,6 +308,18 @@ def golden_ref_assoc():
         off = np.zeros(len(tr) + 1, np.int32); off[1:] = np.cumsum([len(t) for t in tr])
         out[f"tr{ci}_off"] = off; out[f"tr{ci}_feat"] = np.concatenate(tr).astype(np.int32)
         print(f"  tracks case {ci}: {len(tr)} tracks, {off[-1]} features")
+        frames_ci = trp.track_case(nf, n_az)                                              # CameraLidarOptimizer::LidarMaskByTrack with the same parameters
+        rf = [pvo.RefFrame(f["R_wl"], f["t_wl"], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], id=i, pose_valid=(i != no_pose), local="keep")
+              for i, f in enumerate(frames_ci)]
+        masks = pvo.ref_lidar_mask_by_track(rf, min_len, k)
+        moff = np.zeros(len(masks) + 1, np.int32); moff[1:] = np.cumsum([len(m) for m in masks])
+        out[f"lm{ci}_off"] = moff; out[f"lm{ci}_mask"] = np.concatenate(masks).astype(np.uint8)
+    t_wc, fpv, t_wl, lpv, lva = trp.neighbor_each_frame_case()                             # CameraLidarOptimizer::NeighborEachFrame
+    I = np.tile(np.eye(3).reshape(1, 9), (len(t_wc), 1))
+    for ci, (k, temporal) in enumerate(((3, True), (1, True), (4, False), (2, False))):
+        nb = pvo.ref_neighbor_each_frame(I, t_wc, fpv, I, t_wl, lpv, lva, k, temporal)
+        off = np.zeros(len(nb) + 1, np.int32); off[1:] = np.cumsum([len(x) for x in nb])
+        out[f"nef{ci}_off"] = off; out[f"nef{ci}_ids"] = np.concatenate([np.asarray(x, np.int32) for x in nb]) if off[-1] else np.zeros(0, np.int32)
     np.savez_compressed(os.path.join(OUT, "ref_assoc.npz"), **out)
 
 
@@ -383,6 +395,26 @@ def golden_ref_velodyne():
         ok, und = pvo.ref_undistort_cloud(R_wl, t_wl, R_we, t_we, cloud)
         assert ok
         out[f"undistorted{k}"] = und
+    T, pv, va, off, clouds = trp.undistort_lidars_case()                                  # LidarOdometry::UndistortLidars
+    for gi, gap in enumerate((0.0, 0.02)):
+        out[f"ul_out{gi}"] = pvo.ref_undistort_lidars(T[:, :3, :3], T[:, :3, 3], pv, va, off, clouds, gap)
+        print(f"  UndistortLidars gap {gap}: {int((out[f'ul_out{gi}'] != clouds).any(1).sum())} of {len(clouds)} points moved")
+    # pose text files (util/FileIO.cpp: ExportPoseT / ReadPoseT)
+    import tempfile
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(20261105)
+    n = 9
+    R = np.stack([Rotation.from_rotvec(rng.normal(size=3)).as_matrix() for _ in range(n)]); t = rng.normal(size=(n, 3)) * 100
+    t[3] = np.inf; R[3] = 0; t[6, 1] = 1e-7; t[7] = [123456.789, -0.000012345, 1e10]
+    names = [f"frame_{i:04d}.pcd" for i in range(n)]
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "poses.txt")
+        pvo.ref_export_pose_t(path, R, t, names)
+        text = open(path, "rb").read()
+        ra = pvo.ref_read_pose_t(path, True); rv = pvo.ref_read_pose_t(path, False)
+    out.update(pt_R=R, pt_t=t, pt_names=np.array(names), pt_text=np.frombuffer(text, np.uint8), pt_read_all_R=ra[0], pt_read_all_t=ra[1], pt_read_all_names=np.array(ra[2]),
+               pt_read_valid_R=rv[0], pt_read_valid_t=rv[1], pt_read_valid_names=np.array(rv[2]))
+    print(text.decode().splitlines()[3], "|", len(ra[2]), "read with invalid,", len(rv[2]), "without")
     np.savez_compressed(os.path.join(OUT, "ref_velodyne.npz"), **out)
 
 

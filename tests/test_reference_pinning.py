@@ -505,7 +505,7 @@ def product_refine_blocks(oracle, frames, Rs, ts, point_to_plane=True, line_to_l
 
 
 def reference_refine_blocks(oracle, frames, Rs, ts, **kw):
-    rf = [oracle.RefFrame(Rs[i], ts[i], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["surfFlat"], f["surfLessFlat"], id=i, local=True)
+    rf = [oracle.RefFrame(Rs[i], ts[i], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["surfFlat"], f["surfLessFlat"], id=i, local="keep")
           for i, f in enumerate(frames)]
     return oracle.ref_refine_pose_blocks(rf, **kw)
 
@@ -611,3 +611,100 @@ def test_transform_and_undistortion_equal_the_reference(oracle):
     if oracle.ref_assoc_lib() is not None:
         f = oracle.RefFrame(R_wl, t_wl, surf_less_flat_world=cloud, local=True)
         assert np.array_equal(f.cloud("less_flat"), g["world"])
+
+
+# ---- loop level: LidarOdometry::UndistortLidars, pose text files (util/FileIO.cpp), CameraLidarOptimizer::NeighborEachFrame / LidarMaskByTrack ----
+def undistort_lidars_case():
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(20261103)
+    n, per = 9, 700
+    T = np.tile(np.eye(4), (n, 1, 1))
+    for f in range(1, n):
+        d = np.eye(4); d[:3, :3] = Rotation.from_rotvec(rng.normal(0, 0.05, 3)).as_matrix(); d[:3, 3] = rng.normal(0, 0.2, 3) + [0.4, 0, 0]
+        T[f] = T[f - 1] @ d
+    pv = np.ones(n, np.uint8); pv[[3, 7]] = 0
+    va = np.ones(n, np.uint8); va[[3, 5]] = 0
+    # a frame without a pose holds R = 0, t = inf (Velodyne's constructor state, what ReadPoseT stores for an `inf` line).  Frame 3 has neither pose nor data and is
+    # stepped over; frame 7 has no pose but IS valid, so the reference's `!IsPoseValid() && !valid` test stops there and its neighbours slerp towards a non-pose:
+    # their sweeps come out as NaN - reproduced, not fixed
+    T[pv == 0, :3, :3] = 0.0; T[pv == 0, :3, 3] = np.inf
+    off = (np.arange(n + 1) * per).astype(np.int32)
+    clouds = np.concatenate([rng.normal(0, 10, (n * per, 3)), rng.uniform(0, 1, (n * per, 1))], axis=1).astype(np.float32)
+    return T, pv, va, off, clouds
+
+
+def test_undistort_lidars_equals_the_reference_loop(oracle):
+    """(f) rank 4: the reference's own LidarOdometry::UndistortLidars (sweep-end pose from the next / previous frame with a pose, SlerpPose with the duration
+    ratio, UndistortCloud) == pvb_undistort_end_poses + the oracle's UndistortCloud: float32 sweeps bit-identical, frames without an end pose untouched."""
+    from panovlm_b200 import Context
+    g = np.load(os.path.join(G, "ref_velodyne.npz"))
+    T, pv, va, off, clouds = undistort_lidars_case()
+    for gi, gap in enumerate((0.0, 0.02)):
+        e_pose, e_has = Context.undistort_end_poses(T, pv, va, gap)
+        o_pose, o_has = oracle.undistort_end_poses(T, pv, va, gap)
+        assert np.array_equal(e_has, o_has) and 0 < e_has.sum() < len(T)
+        out = clouds.copy()
+        for f in range(len(T)):
+            if e_has[f]:
+                out[off[f]:off[f + 1]] = oracle.undistort_cloud(T[f][:3, :3], T[f][:3, 3], e_pose[f][:3, :3], e_pose[f][:3, 3], clouds[off[f]:off[f + 1]])
+        assert np.array_equal(out, g[f"ul_out{gi}"], equal_nan=True), gap
+        moved = (out != clouds).any(1).reshape(len(T), -1).any(1)
+        assert np.isnan(out).any() and np.isfinite(out[off[0]:off[2]]).all() and not moved[3] and not moved[5] and not moved[7]
+        if oracle.ref_assoc_lib() is not None:
+            assert np.array_equal(oracle.ref_undistort_lidars(T[:, :3, :3], T[:, :3, 3], pv, va, off, clouds, gap), g[f"ul_out{gi}"], equal_nan=True)
+
+
+def test_pose_text_files_equal_the_reference_io(oracle, tmp_path):
+    """ExportPoseT / ReadPoseT of the reference (util/FileIO.cpp) against pvb_write_poses_text / pvb_read_poses_text: the committed file written by the reference is
+    reproduced byte for byte (6 significant digits, `inf` lines for frames without a pose), and both readers return the same poses from it."""
+    from panovlm_b200 import Context
+    g = np.load(os.path.join(G, "ref_velodyne.npz"))
+    R, t, names = g["pt_R"], g["pt_t"], [str(x) for x in g["pt_names"]]
+    text = bytes(g["pt_text"]).decode()
+    path = tmp_path / "poses.txt"
+    Context.write_poses_text(path, R, t, names)
+    assert path.read_text() == text
+    for with_invalid in (True, False):
+        R2, t2, valid, nm = Context.read_poses_text(path, with_invalid=with_invalid)
+        key = "pt_read_all" if with_invalid else "pt_read_valid"
+        assert np.array_equal(np.asarray(R2).reshape(-1, 9), g[key + "_R"].reshape(-1, 9)) and np.array_equal(np.asarray(t2), g[key + "_t"]) and list(nm) == [str(x) for x in g[key + "_names"]]
+    if oracle.ref_assoc_lib() is not None:
+        p2 = tmp_path / "ref.txt"
+        oracle.ref_export_pose_t(p2, R, t, names)
+        assert p2.read_text() == text
+        Rr, tr, nr = oracle.ref_read_pose_t(path, True)
+        assert np.array_equal(Rr.reshape(-1, 9), g["pt_read_all_R"].reshape(-1, 9)) and nr == [str(x) for x in g["pt_read_all_names"]]
+
+
+def neighbor_each_frame_case():
+    rng = np.random.default_rng(20261104)
+    n = 40
+    s = np.arange(n) * 0.5
+    t_wl = np.stack([s, 0.3 * np.sin(s), np.zeros(n)], 1) + rng.normal(0, 0.02, (n, 3))
+    t_wc = t_wl + rng.normal(0, 0.05, (n, 3))
+    fpv = np.ones(n, np.uint8); fpv[[4, 17]] = 0
+    lpv = np.ones(n, np.uint8); lpv[[9, 30]] = 0
+    lva = np.ones(n, np.uint8); lva[21] = 0
+    return t_wc, fpv, t_wl, lpv, lva
+
+
+def test_neighbor_each_frame_and_lidar_mask_equal_the_reference(oracle):
+    """CameraLidarOptimizer::NeighborEachFrame (temporal window / spatial k-NN + forced i-1, i+1) and LidarMaskByTrack (segments that belong to a LiDAR line track)
+    of the reference == pvb_neighbor_each_frame / pvb_lidar_mask_by_track."""
+    from panovlm_b200 import Context
+    g = np.load(os.path.join(G, "ref_assoc.npz"))
+    t_wc, fpv, t_wl, lpv, lva = neighbor_each_frame_case()
+    n = len(t_wc)
+    I = np.tile(np.eye(3).reshape(1, 9), (n, 1))
+    for ci, (k, temporal) in enumerate(((3, True), (1, True), (4, False), (2, False))):
+        exp = [g[f"nef{ci}_ids"][g[f"nef{ci}_off"][i]:g[f"nef{ci}_off"][i + 1]].tolist() for i in range(n)]
+        got = Context.neighbor_each_frame(n, n, k, temporal, t_wc, fpv, t_wl, lpv, lva)
+        assert [list(x) for x in got] == exp, (k, temporal)
+        if oracle.ref_assoc_lib() is not None:
+            assert oracle.ref_neighbor_each_frame(I, t_wc, fpv, I, t_wl, lpv, lva, k, temporal) == exp
+    for ci, (nf, n_az, k, min_len, no_pose) in enumerate(TRACK_CASES):
+        frames = track_case(nf, n_az)
+        tracks = [g[f"tr{ci}_feat"][g[f"tr{ci}_off"][t]:g[f"tr{ci}_off"][t + 1]] for t in range(len(g[f"tr{ci}_off"]) - 1)]
+        exp = [g[f"lm{ci}_mask"][g[f"lm{ci}_off"][i]:g[f"lm{ci}_off"][i + 1]].astype(bool) for i in range(nf)]
+        got = Context.lidar_mask_by_track(tracks, [len(f["segment_coeffs"]) for f in frames])
+        assert all(np.array_equal(a, b) for a, b in zip(got, exp)) and sum(int(m.sum()) for m in exp) > 20, ci
