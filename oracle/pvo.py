@@ -533,7 +533,7 @@ class RefFrame:
     """A `Velodyne` object of the reference as its association functions see it (world-frame feature clouds, segment tables, pose)."""
 
     def __init__(self, R_wl, t_wl, corner_world=None, p2s_off=None, p2s_ids=None, coeffs_local=None, surf_flat_world=None, surf_less_flat_world=None, id=0,
-                 valid=True, pose_valid=True, local=False):
+                 valid=True, pose_valid=True, local=False, end_points=None):
         """local=True: the clouds are given in the SENSOR frame and the reference's own Transform2LidarWorld() moves them; local="keep": sensor-frame clouds
         that stay there (for the entry points that run the reference's own pipeline stages, which transform the frames themselves)."""
         self.L = ref_assoc_lib()
@@ -545,7 +545,7 @@ class RefFrame:
         off = None if p2s_off is None else _i32(p2s_off)
         ids = None if p2s_ids is None else _i32(p2s_ids)
         self.h = self.L.ref_frame_create(C.c_int(id), C.c_int(int(valid)), C.c_int(int(pose_valid)), _p(_f64(R_wl)), _p(_f64(t_wl)), _p(cw), C.c_int(len(cw)), _p(off), _p(ids),
-                                         C.c_int(len(co)), _p(co), None, _p(sf), C.c_int(len(sf)), _p(sl), C.c_int(len(sl)), C.c_int(2 if local == "keep" else (0 if local else 1)))
+                                         C.c_int(len(co)), _p(co), None, _p(sf), C.c_int(len(sf)), _p(sl), C.c_int(len(sl)), C.c_int(2 if local == "keep" else (0 if local else 1)), _p(None if end_points is None else _f64(end_points)))
         assert self.h
         self.n_corner, self.n_flat = len(cw), len(sf)
 
@@ -745,3 +745,32 @@ def ref_lidar_mask_by_track(frames, min_track_length=3, neighbor_size=3):
     m = frames[0].L.ref_lidar_mask_by_track(C.c_int(n), arr, C.c_int(min_track_length), C.c_int(neighbor_size), C.c_int(cap), _p(off), _p(mask))
     assert m >= 0
     return [mask[off[i]:off[i + 1]].astype(bool) for i in range(n)]
+
+
+def ref_joint_optimize_blocks(rows, cols, R_wc, t_wc, image_lines, keypoints, lidar_frames, track_off, feat_frame, feat_index, points3, T_cl_init, neighbor_size_joint=1,
+                              camera_weight=1.0, lidar_weight=0.01, camera_lidar_weight=25.0, point_to_plane=True, line_to_line=True, point_to_line=False, angle_residual=True,
+                              normalize_distance=True, plane_dis_threshold=1.0, line_dis_threshold=0.3, plane_tolerance=0.05, refine=(True, True, True, True, True)):
+    """The problem the reference's own mapping-mode CameraLidarOptimizer::Optimize hands to ceres::Solve (line pairs from its AssociateLineMulti).  image_lines / keypoints:
+    one array per camera frame.  Returns dict(n_params, a, b, huber, residual, jacobian, const_part, poses, n_line_pairs)."""
+    R_wc, t_wc = _f64(R_wc).reshape(-1, 9), _f64(t_wc).reshape(-1, 3)
+    nc, nl = len(t_wc), len(lidar_frames)
+    line_off = np.concatenate([[0], np.cumsum([len(x) for x in image_lines])]).astype(np.int32)
+    lines = _f32(np.concatenate([np.asarray(x, np.float32).reshape(-1, 4) for x in image_lines]))
+    kp_off = np.concatenate([[0], np.cumsum([len(x) for x in keypoints])]).astype(np.int32)
+    kp = _f32(np.concatenate([np.asarray(x, np.float32).reshape(-1, 2) for x in keypoints]))
+    arr = (C.c_void_p * nl)(*[f.h for f in lidar_frames])
+    track_off, feat_frame, feat_index, points3 = _i32(track_off), _i32(feat_frame), _i32(feat_index), _f64(points3).reshape(-1, 3)
+    cap, ccap = 1 << 21, 1 << 16
+    npar, a, b, hb, r, J = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap), np.zeros(cap), np.zeros((cap, 12))
+    cpart, ncst, poses, nlp = np.zeros(ccap, np.int32), C.c_int(), np.zeros((nc + nl, 6)), C.c_int()
+    L = lidar_frames[0].L
+    L.ref_joint_optimize_blocks.restype = C.c_long
+    m = L.ref_joint_optimize_blocks(C.c_int(rows), C.c_int(cols), C.c_int(nc), _p(R_wc), _p(t_wc), _p(line_off), _p(lines), _p(kp_off), _p(kp), C.c_int(nl), arr,
+                                    C.c_int(len(track_off) - 1), _p(track_off), _p(feat_frame), _p(feat_index), _p(points3), _p(_f64(T_cl_init)), C.c_int(neighbor_size_joint),
+                                    C.c_double(camera_weight), C.c_double(lidar_weight), C.c_double(camera_lidar_weight), C.c_int(int(point_to_plane)), C.c_int(int(line_to_line)),
+                                    C.c_int(int(point_to_line)), C.c_int(int(angle_residual)), C.c_int(int(normalize_distance)), C.c_double(plane_dis_threshold),
+                                    C.c_double(line_dis_threshold), C.c_double(plane_tolerance), *[C.c_int(int(x)) for x in refine], C.c_long(cap), _p(npar), _p(a), _p(b), _p(hb),
+                                    _p(r), _p(J), C.c_int(ccap), _p(cpart), C.byref(ncst), _p(poses), C.byref(nlp))
+    assert m >= 0, m
+    return dict(n_params=npar[:m].copy(), a=a[:m].copy(), b=b[:m].copy(), huber=hb[:m].copy(), residual=r[:m].copy(), jacobian=J[:m].copy(), const_part=cpart[:ncst.value].copy(),
+                poses=poses, n_line_pairs=nlp.value)

@@ -72,6 +72,7 @@ void GroundSegmentation::segment(const PointCloud&, std::vector<int>&) { not_com
 
 // ---- class PanoramaLine (util/PanoramaLine.cpp is image line DETECTION on real OpenCV algorithms and is not compiled): the three trivial members the joint stage needs
 // to carry already-detected lines around.  Everything else of that file, and the other non-compiled files, are abort placeholders in ref_unresolved_stubs.c ----
+PanoramaLine::PanoramaLine() : id(-1), rows(0), cols(0) {}
 PanoramaLine::~PanoramaLine() {}
 void PanoramaLine::SetName(const std::string& _name) { name = _name; }
 const std::vector<cv::Vec4f>& PanoramaLine::GetLines() const { return lines; }
@@ -90,7 +91,7 @@ extern "C" {
 // clouds_in_world = 1: they are already world-frame and only the flag is set; 2: sensor-frame clouds, left there (RefinePose / LidarMaskByTrack move them themselves).
 void* ref_frame_create(int id, int valid, int pose_valid, const double* R_wl, const double* t_wl, const float* corner, int n_corner, const int* p2s_off,
                        const int* p2s_ids, int S, const double* coeffs_local, const int* seg_sizes, const float* surf_flat, int n_flat,
-                       const float* surf_less_flat, int n_less, int clouds_in_world) {
+                       const float* surf_less_flat, int n_less, int clouds_in_world, const double* end_points) {
   Velodyne* v = new Velodyne();
   v->id = id; v->valid = valid != 0;
   if (pose_valid) {
@@ -107,6 +108,7 @@ void* ref_frame_create(int id, int valid, int pose_valid, const double* R_wl, co
     Vector6d c; for (int k = 0; k < 6; ++k) c[k] = coeffs_local[6 * s + k];
     v->segment_coeffs.push_back(c);
   }
+  if (end_points) for (int i = 0; i < 2 * S; ++i) v->end_points.push_back(Eigen::Vector3d(end_points[3 * i], end_points[3 * i + 1], end_points[3 * i + 2]));   // sensor frame, projected on the line
   // the points of a segment = the cornerLessSharp points whose set holds it (Velodyne::EdgeToLine fills both from the same lists); when the caller
   // gives explicit sizes they must agree
   for (int i = 0; i < n_corner; ++i) for (int s : v->point_to_segment[i]) v->edge_segmented[s].push_back(v->cornerLessSharp.points[i]);
@@ -307,6 +309,115 @@ int ref_read_pose_t(const char* path, int with_invalid, int cap, double* R9, dou
     std::snprintf(names_256 + 256 * f, 256, "%s", nl[f].c_str());
   }
   return (int)Rl.size();
+}
+
+// The problem that the reference's OWN mapping-mode CameraLidarOptimizer::Optimize (joint_optimization/CameraLidarOptimizer.cpp:387-548) hands to ceres::Solve, with the line
+// pairs coming from its own AssociateLineMulti(neighbor_size_joint, temporal = true, no track masks) (:330-384).  Inputs: n camera frames (pose T_wc, image lines CSR,
+// key points CSR), the LiDAR frames (ref_frame_create with clouds_in_world = 2 and end points), structure tracks (CSR of (frame, key point)) with their 3-D points,
+// T_cl_init, the weights / switches of base/Config.h.  Per recorded block: n_params (4: pose-pose, 3: reprojection), a / b = pose-block indices in the layout
+// [cameras 0..n) | LiDARs n..n+m) (4-block) or (camera, track) (3-block), Huber a, raw residual, raw Jacobian (12 or 9 entries of 12).  const_part: for every constant
+// parameter block an id: pose block b rotation -> 2 b, translation -> 2 b + 1, track t -> 2 (n + m) + t.  poses_out: (n + m) x 6.
+namespace {
+struct JointSnapshot {
+  int n_cams = 0, n_lidars = 0; const std::vector<PointTrack>* structure = nullptr;
+  std::vector<int> n_params, a, b, const_part; std::vector<double> huber, residual, jac, poses; long status = 0;
+};
+JointSnapshot* g_joint = nullptr;
+void joint_hook(const ceres::Solver::Options&, ceres::Problem* p, ceres::Solver::Summary* s) {
+  JointSnapshot& S = *g_joint;
+  typedef const Eigen::Vector3d* V;
+  const size_t nc = p->constant_blocks.size();
+  if (nc < 2) { S.status = -3; return; }
+  const V caa = (V)p->constant_blocks[nc - 2], ctt = (V)p->constant_blocks[nc - 1];            // :490-491: camera 0 is made constant last
+  auto in = [](V base, int n, const double* q) { return (V)q >= base && (V)q < base + n; };
+  V laa = nullptr, ltt = nullptr;                                                               // the LiDAR lists: lowest addresses seen outside the camera lists
+  for (const ceres::Problem::Block& blk : p->blocks) if (blk.params.size() == 4) for (int k = 0; k < 4; ++k) {
+    const double* q = blk.params[k];
+    if (in(caa, S.n_cams, q) || in(ctt, S.n_cams, q)) continue;
+    V& base = (k % 2 == 0) ? laa : ltt;
+    if (!base || (V)q < base) base = (V)q;
+  }
+  auto pose_index = [&](const double* q, int part) -> int {                                       // part 0: rotation list, 1: translation list
+    if (in(part ? ctt : caa, S.n_cams, q)) return (int)((V)q - (part ? ctt : caa));
+    V base = part ? ltt : laa;
+    if (base && in(base, S.n_lidars, q)) return S.n_cams + (int)((V)q - base);
+    return -1;
+  };
+  for (const ceres::Problem::Block& blk : p->blocks) {
+    const int np = (int)blk.params.size();
+    int ia = -1, ib = -1;
+    if (np == 4) {
+      ia = pose_index(blk.params[0], 0); ib = pose_index(blk.params[2], 0);
+      if (ia < 0 || ib < 0 || pose_index(blk.params[1], 1) != ia || pose_index(blk.params[3], 1) != ib) { S.status = -2; return; }
+    } else if (np == 3) {
+      ia = pose_index(blk.params[0], 0);
+      for (size_t t = 0; t < S.structure->size(); ++t) if (blk.params[2] == (*S.structure)[t].point_3d.data()) { ib = (int)t; break; }
+      if (ia < 0 || ib < 0 || pose_index(blk.params[1], 1) != ia) { S.status = -2; return; }
+    } else { S.status = -2; return; }
+    const ceres::HuberLoss* h = dynamic_cast<const ceres::HuberLoss*>(blk.loss);
+    double res, jb[4][3] = {{0}}; double* jp[4] = {jb[0], jb[1], jb[2], jb[3]};
+    if (!blk.cost->Evaluate(blk.params.data(), &res, jp)) { S.status = -2; return; }
+    S.n_params.push_back(np); S.a.push_back(ia); S.b.push_back(ib); S.huber.push_back(h ? h->a() : 0.0); S.residual.push_back(res);
+    S.jac.insert(S.jac.end(), &jb[0][0], &jb[0][0] + 12);
+  }
+  for (const double* q : p->constant_blocks) {
+    int id = -1, k;
+    if ((k = pose_index(q, 0)) >= 0) id = 2 * k;
+    else if ((k = pose_index(q, 1)) >= 0) id = 2 * k + 1;
+    else for (size_t t = 0; t < S.structure->size(); ++t) if (q == (*S.structure)[t].point_3d.data()) { id = 2 * (S.n_cams + S.n_lidars) + (int)t; break; }
+    S.const_part.push_back(id);
+  }
+  S.poses.assign(6 * (S.n_cams + S.n_lidars), 0.0);
+  for (int i = 0; i < S.n_cams; ++i) for (int k = 0; k < 3; ++k) { S.poses[6 * i + k] = caa[i][k]; S.poses[6 * i + 3 + k] = ctt[i][k]; }
+  if (laa && ltt) for (int i = 0; i < S.n_lidars; ++i) for (int k = 0; k < 3; ++k) { S.poses[6 * (S.n_cams + i) + k] = laa[i][k]; S.poses[6 * (S.n_cams + i) + 3 + k] = ltt[i][k]; }
+  s->usable = true; s->final_cost = 0;
+}
+}  // namespace
+
+long ref_joint_optimize_blocks(int rows, int cols, int n_cams, const double* R_wc, const double* t_wc, const int* line_off, const float* lines4, const int* kp_off, const float* kp_xy,
+                               int n_lidars, void* const* lidar_frames, int n_tracks, const int* track_off, const int* feat_frame, const int* feat_index, const double* points3,
+                               const double* T_cl_init16, int neighbor_size_joint, double camera_weight, double lidar_weight, double camera_lidar_weight, int point_to_plane,
+                               int line_to_line, int point_to_line, int angle_residual, int normalize_distance, double plane_dis_threshold, double line_dis_threshold,
+                               double plane_tolerance, int refine_camera_rotation, int refine_camera_trans, int refine_lidar_rotation, int refine_lidar_trans, int refine_structure,
+                               long cap, int* n_params, int* a, int* b, double* huber_a, double* residual, double* jac12, int const_cap, int* const_part, int* n_const,
+                               double* poses_out, int* n_line_pairs) {
+  std::vector<Frame> frames; std::vector<Velodyne> lidars; std::vector<PanoramaLine> image_lines(n_cams);
+  for (int f = 0; f < n_cams; ++f) {
+    frames.push_back(Frame(rows, cols, f, "frame"));
+    Eigen::Matrix3d R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R(i, j) = R_wc[9 * f + 3 * i + j];
+    frames[f].SetPose(R, Eigen::Vector3d(t_wc[3 * f], t_wc[3 * f + 1], t_wc[3 * f + 2]));
+    for (int k = kp_off[f]; k < kp_off[f + 1]; ++k) { cv::KeyPoint kp; kp.pt = cv::Point2f(kp_xy[2 * k], kp_xy[2 * k + 1]); frames[f].keypoints_all.push_back(kp); }
+    image_lines[f].id = f; image_lines[f].rows = rows; image_lines[f].cols = cols;
+    for (int k = line_off[f]; k < line_off[f + 1]; ++k) image_lines[f].lines.push_back(cv::Vec4f(lines4[4 * k], lines4[4 * k + 1], lines4[4 * k + 2], lines4[4 * k + 3]));
+  }
+  for (int i = 0; i < n_lidars; ++i) lidars.push_back(*static_cast<const Velodyne*>(lidar_frames[i]));
+  std::vector<PointTrack> structure;
+  structure.reserve(n_tracks);
+  for (int t = 0; t < n_tracks; ++t) {
+    std::set<std::pair<uint32_t, uint32_t>> fp;
+    for (int k = track_off[t]; k < track_off[t + 1]; ++k) fp.insert(std::make_pair((uint32_t)feat_frame[k], (uint32_t)feat_index[k]));
+    structure.push_back(PointTrack(t, fp, Eigen::Vector3d(points3[3 * t], points3[3 * t + 1], points3[3 * t + 2])));
+  }
+  Config config = make_config(point_to_plane, line_to_line, point_to_line, angle_residual, normalize_distance, (float)plane_dis_threshold, (float)line_dis_threshold, (float)plane_tolerance);
+  config.camera_weight = camera_weight; config.lidar_weight = lidar_weight; config.camera_lidar_weight = camera_lidar_weight; config.neighbor_size_joint = neighbor_size_joint;
+  Eigen::Matrix4d T_cl; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T_cl(i, j) = T_cl_init16[4 * i + j];
+  CameraLidarOptimizer opt(T_cl, lidars, frames, config);
+  opt.image_lines_all = image_lines;
+  const eigen_map<std::pair<size_t, size_t>, std::vector<CameraLidarLinePair>> line_pairs = opt.AssociateLineMulti(neighbor_size_joint, true, false, false);
+  *n_line_pairs = 0; for (const auto& kv : line_pairs) *n_line_pairs += (int)kv.second.size();
+  JointSnapshot S; S.n_cams = n_cams; S.n_lidars = n_lidars; S.structure = &structure;
+  g_joint = &S; ceres::solve_hook() = joint_hook;
+  double cost = 0; int steps = 0;
+  opt.Optimize(line_pairs, structure, refine_camera_rotation != 0, refine_camera_trans != 0, refine_lidar_rotation != 0, refine_lidar_trans != 0, refine_structure != 0, cost, steps);
+  ceres::solve_hook() = nullptr; g_joint = nullptr;
+  if (S.status < 0) return S.status;
+  if ((long)S.residual.size() > cap || (int)S.const_part.size() > const_cap) return -1;
+  for (size_t k = 0; k < S.residual.size(); ++k) { n_params[k] = S.n_params[k]; a[k] = S.a[k]; b[k] = S.b[k]; huber_a[k] = S.huber[k]; residual[k] = S.residual[k]; }
+  if (!S.jac.empty()) std::memcpy(jac12, S.jac.data(), S.jac.size() * sizeof(double));
+  for (size_t k = 0; k < S.const_part.size(); ++k) const_part[k] = S.const_part[k];
+  *n_const = (int)S.const_part.size();
+  std::memcpy(poses_out, S.poses.data(), S.poses.size() * sizeof(double));
+  return (long)S.residual.size();
 }
 
 // CameraLidarOptimizer::NeighborEachFrame (joint_optimization/CameraLidarOptimizer.cpp:551-607) and LidarMaskByTrack (:609-642), called on an optimizer object

@@ -68,6 +68,15 @@ class BlockList:
         n = self.n
         return dict(type=self.type[:n], ref=self.ref[:n], nei=self.nei[:n], normalize=self.normalize[:n], huber=self.huber[:n], consts=self.consts[:n])
 
+    def extend(self, blocks):
+        """Append blocks given as a dict of parallel arrays (the layout view() returns)."""
+        m = len(blocks["type"])
+        if self.n + m > self.cap:
+            raise PvbError("BlockList.extend: capacity exceeded")
+        for k in ("type", "ref", "nei", "normalize", "huber", "consts"):
+            getattr(self, k)[self.n:self.n + m] = blocks[k]
+        self.n += m
+
 
 class _AssocParams(C.Structure):
     _fields_ = [("plane_tolerance", C.c_double), ("dist_threshold", C.c_float), ("k", C.c_int), ("cell_size", C.c_double)]

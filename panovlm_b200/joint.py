@@ -18,6 +18,35 @@ class JointConfig:
         self.max_lm_iterations = max_lm_iterations
 
 
+def joint_lidar_config(lidar: odometry.OdometryConfig):
+    """The LiDAR-LiDAR builders as CameraLidarOptimizer::Optimize calls them (CameraLidarOptimizer.cpp:436-458) - which is NOT how RefinePose calls them:
+    * AddLidarPointToLineResidual is called WITHOUT its `use_segment` argument (:441-443), so every later argument lands one slot early: use_segment <- angle_residual,
+      angle_residual <- normalize_distance, normalized_distance <- (lidar_weight != 0), weight <- default 1.0;
+    * AddLidarLineToLineResidual2 runs whenever line_to_line_residual is set (no `use_segment` gate) and gets no weight (1.0);
+    * AddLidarPointToPlaneResidual gets weight = lidar_weight.
+    Returns (config for the point-to-line family, config for the other two).  Pinned against the reference's own Optimize (tests/test_reference_pinning.py)."""
+    import copy
+    main = copy.copy(lidar)
+    main.plane_weight, main.point_to_line = lidar.lidar_weight, False
+    p2l = copy.copy(lidar)
+    p2l.point_to_plane, p2l.line_to_line = False, False
+    p2l.use_segment, p2l.angle_residual, p2l.normalize_distance, p2l.point_line_weight = bool(lidar.angle_residual), bool(lidar.normalize_distance), lidar.lidar_weight != 0, 1.0
+    return p2l, main
+
+
+def _lidar_blocks(ctx, frames, lidars, lidar_cfg, aa_to_R, host_point2plane=True):
+    """The LiDAR-LiDAR blocks of the joint stage in the reference's registration order: point-to-line (if enabled), then line-to-line, then point-to-plane."""
+    p2l, main = joint_lidar_config(lidar_cfg)
+    res = odometry.build_problem(ctx, frames, lidars, main, aa_to_R, host_point2plane=host_point2plane)
+    if lidar_cfg.point_to_line:
+        pre, _ = odometry.build_problem(ctx, frames, lidars, p2l, aa_to_R)
+        a, b = pre.view(), res[0].view()
+        merged = BlockList(pre.n + res[0].n + 1)
+        merged.extend({k: np.concatenate([a[k], b[k]]) for k in a})
+        res = (merged,) + tuple(res[1:])
+    return res, main
+
+
 def _T_from_block(block, aa_to_R):
     T = np.eye(4)
     T[:3, :3] = aa_to_R(block[:3])
@@ -55,7 +84,7 @@ def build_problem(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa
         if len(il):
             Context.build_camera_lidar_blocks(bl_cl, data["rows"], data["cols"], data["image_lines"][ci][il], s, e, np.ones(len(il), np.float32), ci, n + li,
                                               cfg.camera_lidar_weight)
-    bl_ll, _ = odometry.build_problem(ctx, frames, lidars, cfg.lidar, aa_to_R)            # steps 4: the LiDAR-LiDAR blocks of RefinePose
+    (bl_ll, _), _ = _lidar_blocks(ctx, frames, lidars, cfg.lidar, aa_to_R)                # step 4: the LiDAR-LiDAR blocks, called as Optimize calls the builders
     a, b = bl_cl.view(), bl_ll.view()
     out = {k: np.concatenate([a[k], b[k] + n if k in ("ref", "nei") else b[k]]) for k in ("type", "ref", "nei", "normalize", "huber", "consts")}
     return out, pairs, (bl_cl.n, bl_ll.n)
@@ -75,12 +104,12 @@ def optimize(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa_to_R
             if len(il):
                 Context.build_camera_lidar_blocks(bl_cl, data["rows"], data["cols"], data["image_lines"][ci][il], s, e, np.ones(len(il), np.float32), ci, n + li,
                                                   cfg.camera_lidar_weight)
-        bl_ll, _, mine = odometry.build_problem(ctx, frames, lidars, cfg.lidar, aa_to_R, host_point2plane=False)
+        (bl_ll, _, mine), main_cfg = _lidar_blocks(ctx, frames, lidars, cfg.lidar, aa_to_R, host_point2plane=False)
         a, b = bl_cl.view(), bl_ll.view()
         extra = {k: np.concatenate([a[k], b[k] + n if k in ("ref", "nei") else b[k]]) for k in ("type", "ref", "nei", "normalize", "huber", "consts")}
         ref, nei = np.array([e[0] for e in mine], np.int32), np.array([e[1] for e in mine], np.int32)
         n_total = ctx.frames_point2plane_blocks(lidars, ref, nei, cfg.lidar.plane_tolerance, cfg.lidar.plane_dis_threshold, cfg.lidar.angle_residual,
-                                                cfg.lidar.normalize_distance, 1.0, 2 * n, block_offset=n, extra=extra)
+                                                cfg.lidar.normalize_distance, main_cfg.plane_weight, 2 * n, block_offset=n, extra=extra)
         v, counts = None, (bl_cl.n, n_total - bl_cl.n)
     else:
         v, pairs, counts = build_problem(ctx, data, cams, lidars, points, cfg, aa_to_R)

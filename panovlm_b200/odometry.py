@@ -20,6 +20,10 @@ class OdometryConfig:
         self.plane_dis_threshold, self.line_dis_threshold, self.plane_tolerance = plane_dis_threshold, line_dis_threshold, plane_tolerance
         self.lidar_weight, self.neighbor_size, self.max_lm_iterations = lidar_weight, neighbor_size, max_lm_iterations
         self.line_tracks, self.track_neighbor_size, self.min_track_length = line_tracks, track_neighbor_size, min_track_length   # LidarOdometry.cpp:47-50
+        # weight handed to the point-to-plane / point-to-line builders.  RefinePose passes none (default 1.0, LidarOdometry.cpp:38-57: lidar_weight is NOT used there);
+        # the joint stage passes config.lidar_weight to the point-to-plane builder (CameraLidarOptimizer.cpp:455-458) - see joint.joint_lidar_config.  The angle
+        # functors ignore their weight (base/CostFunction.h:714-717, 916-920), so this only matters with angle_residual = False.
+        self.plane_weight, self.point_line_weight = 1.0, 1.0
 
 
 def pose_blocks_from_world(R_wl, t_wl, R_to_aa):
@@ -68,7 +72,7 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
         if cfg.use_segment:                                         # AssociatePoint2LineSegmentKNN (:482)
             for (i, j) in near:
                 _, _, pt, a, b = ctx.point2line_segment_knn_associate(lf[i], lf[j], cfg.line_dis_threshold)
-                Context.build_point2line_blocks(bl, pt, a, b, i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
+                Context.build_point2line_blocks(bl, pt, a, b, i, j, cfg.angle_residual, cfg.normalize_distance, cfg.point_line_weight)
         elif near:                                                  # AssociatePoint2Line (:484)
             ctx.frames_set_corners([f["cornerLessSharp"] for f in frames])
             e, _, pt, a, b = ctx.frames_associate_point2line(poses, np.array([x[0] for x in near], np.int32), np.array([x[1] for x in near], np.int32), cfg.line_dis_threshold)
@@ -76,7 +80,7 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
             for ei, (i, j) in enumerate(near):
                 lo, hi = bounds[ei], bounds[ei + 1]
                 if hi > lo:
-                    Context.build_point2line_blocks(bl, pt[lo:hi], a[lo:hi], b[lo:hi], i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
+                    Context.build_point2line_blocks(bl, pt[lo:hi], a[lo:hi], b[lo:hi], i, j, cfg.angle_residual, cfg.normalize_distance, cfg.point_line_weight)
     if cfg.line_to_line:                                            # AddLidarLineToLineResidual2 (Optimization.cpp:329-441)
         world = [ctx.transform_cloud(f["cornerLessSharp"], R_wl[i], t_wl[i]) for i, f in enumerate(frames)]
         tracks = None
@@ -96,7 +100,7 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
         nei = np.array([e[1] for e in edges], np.int32)
         e, q, pt, pl = ctx.frames_associate_point2plane(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, 10)
         # correspondences come back edge-major with their edge index: all blocks of the outer iteration in one builder call
-        Context.build_point2plane_blocks_edges(bl, e, pt, pl, ref, nei, cfg.angle_residual, cfg.normalize_distance, 1.0)
+        Context.build_point2plane_blocks_edges(bl, e, pt, pl, ref, nei, cfg.angle_residual, cfg.normalize_distance, cfg.plane_weight)
     return bl, all_edges
 
 
@@ -106,7 +110,7 @@ def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, devic
     if device_blocks and cfg.point_to_plane:
         bl, edges, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, host_point2plane=False)
         ref, nei = np.array([e[0] for e in mine], np.int32), np.array([e[1] for e in mine], np.int32)
-        n_total = ctx.frames_point2plane_blocks(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, cfg.angle_residual, cfg.normalize_distance, 1.0,
+        n_total = ctx.frames_point2plane_blocks(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, cfg.angle_residual, cfg.normalize_distance, cfg.plane_weight,
                                                 len(frames), extra=bl.view())
         bl.n = n_total
     else:

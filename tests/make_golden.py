@@ -23,6 +23,7 @@ INDEPENDENT implementations, never from the oracle itself:
   ref_builders.npz  the residual blocks (frame pairs, loss, raw residual, raw Jacobian, in registration order) that the reference's own util/Optimization.cpp builders
                  register for one RefinePose in five configurations, and AddCameraLidarResidual for one frame pair (ceres::Problem = a recorder, oracle/shim)
   ref_velodyne.npz  float32 clouds after the reference's own Transform2LidarWorld / Transform2Local and UndistortCloud (sensors/Velodyne.cpp compiled where it lies)
+  ref_joint.npz  the problem of the joint stage (configs[2]) as the reference's own AssociateLineMulti + Optimize assemble it, recorded at ceres::Solve
   reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
                  undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
 Run from the repo root:  python tests/make_golden.py
@@ -418,8 +419,26 @@ def golden_ref_velodyne():
     np.savez_compressed(os.path.join(OUT, "ref_velodyne.npz"), **out)
 
 
+def golden_ref_joint():
+    """tests/golden/ref_joint.npz: the problem the reference's own CameraLidarOptimizer::AssociateLineMulti + mapping-mode Optimize hand to ceres::Solve (recorded by the
+    stand-in's solve hook, every block evaluated once) for tests/test_reference_pinning.py: JOINT_CASES."""
+    from oracle import pvo
+    if pvo.ref_assoc_lib() is None:
+        print("oracle/_ref/libpvo_ref_assoc.so not built (no /root/reference here): ref_joint.npz left as committed")
+        return
+    import test_reference_pinning as trp
+    d = trp.joint_case()
+    out = {}
+    for ci, kw in enumerate(trp.JOINT_CASES):
+        r = trp.reference_joint_blocks(pvo, d, **kw)
+        for k, v in r.items():
+            out[f"j{ci}_{k}"] = (np.asarray(v).astype(np.int16) if k in ("a", "b", "n_params") else (v[::trp.JAC_STRIDE] if k == "jacobian" else v))
+        print(f"  joint case {ci}: {len(r['residual'])} blocks ({int((r['n_params'] == 3).sum())} reprojection), {r['n_line_pairs']} line pairs, constant parts {r['const_part'][:6].tolist()}...")
+    np.savez_compressed(os.path.join(OUT, "ref_joint.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar(); golden_ref_builders(); golden_ref_velodyne()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar(); golden_ref_builders(); golden_ref_velodyne(); golden_ref_joint()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

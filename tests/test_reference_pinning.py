@@ -451,7 +451,8 @@ def builder_case(n_frames=6, n_az=600, seed=3):
 
 
 def product_refine_blocks(oracle, frames, Rs, ts, point_to_plane=True, line_to_line=True, point_to_line=False, use_segment=True, angle_residual=True,
-                          normalize_distance=True, plane_dis_threshold=1.0, line_dis_threshold=0.3, plane_tolerance=0.05):
+                          normalize_distance=True, plane_dis_threshold=1.0, line_dis_threshold=0.3, plane_tolerance=0.05, plane_weight=1.0, p2l=None, block_offset=0,
+                          l2l_needs_segment=True):
     """The block list of one RefinePose built from the ORACLE's associations and the PRODUCT's host builders (pvb_build_*_blocks, pvb_find_neighbors,
     pvb_line_tracks_build / pvb_line_tracks_gate), in the reference's registration order."""
     from panovlm_b200 import BlockList, Context, LineFrame
@@ -471,16 +472,17 @@ def product_refine_blocks(oracle, frames, Rs, ts, point_to_plane=True, line_to_l
         M = oracle.line_votes(lines_w[i], corner_w[j], fj["p2s_off"], fj["p2s_ids"], len(fj["segment_coeffs"]), thr)
         return oracle.find_associations(frames[i]["segment_coeffs"], lines_w[i], lines_w[j], np.diff(fj["seg_off"]), M)
     if point_to_line:
+        p_seg, p_angle, p_norm, p_w = p2l if p2l is not None else (use_segment, angle_residual, normalize_distance, 1.0)
         for (i, j) in edges:
             if abs(i - j) > 1:
                 continue
-            if use_segment:
+            if p_seg:
                 _, _, pt, a, b = oracle.associate_p2line_segment_knn(corner_w[i], frames[i]["p2s_off"], frames[i]["p2s_ids"], frames[i]["segment_coeffs"], corner_w[j], Rs[j], ts[j], line_dis_threshold)
             else:
                 _, pt, a, b = oracle.associate_p2line(corner_w[i], Rs[i], ts[i], corner_w[j], Rs[j], ts[j], line_dis_threshold)
             if len(pt):
-                Context.build_point2line_blocks(bl, pt, a, b, i, j, angle_residual, normalize_distance, 1.0)
-    if line_to_line and use_segment:
+                Context.build_point2line_blocks(bl, pt, a, b, i + block_offset, j + block_offset, p_angle, p_norm, p_w)
+    if line_to_line and (use_segment or not l2l_needs_segment):
         tn = Context.find_neighbors(t_arr, None, None, 4)
         pa, pb, off, ma, mb = [], [], [0], [], []
         for i in range(n):
@@ -495,12 +497,12 @@ def product_refine_blocks(oracle, frames, Rs, ts, point_to_plane=True, line_to_l
             keep = Context.line_tracks_gate(tracks, i, j, orf, on)
             assert np.array_equal(keep, oracle.line_track_gate(tracks, i, j, orf, on))
             for k in np.nonzero(keep)[0]:
-                Context.build_line2line_blocks(bl, lf[j], corner_w[j], int(on[k]), oa[k], ob[k], i, j, angle_residual, normalize_distance, 1.0)
+                Context.build_line2line_blocks(bl, lf[j], corner_w[j], int(on[k]), oa[k], ob[k], i + block_offset, j + block_offset, angle_residual, normalize_distance, 1.0)
     if point_to_plane:
         for (i, j) in edges:
             _, pt, pl = oracle.associate_p2plane(tgt_w[i], Rs[i], ts[i], qry_w[j], Rs[j], ts[j], plane_tolerance, plane_dis_threshold, 10, True)
             if len(pt):
-                Context.build_point2plane_blocks(bl, pt, pl, i, j, angle_residual, normalize_distance, 1.0)
+                Context.build_point2plane_blocks(bl, pt, pl, i + block_offset, j + block_offset, angle_residual, normalize_distance, plane_weight)
     return bl.view()
 
 
@@ -708,3 +710,123 @@ def test_neighbor_each_frame_and_lidar_mask_equal_the_reference(oracle):
         exp = [g[f"lm{ci}_mask"][g[f"lm{ci}_off"][i]:g[f"lm{ci}_off"][i + 1]].astype(bool) for i in range(nf)]
         got = Context.lidar_mask_by_track(tracks, [len(f["segment_coeffs"]) for f in frames])
         assert all(np.array_equal(a, b) for a, b in zip(got, exp)) and sum(int(m.sum()) for m in exp) > 20, ci
+
+
+# ---- the joint problem (BASELINE.json configs[2]): CameraLidarOptimizer::AssociateLineMulti + mapping-mode Optimize of the reference, recorded at ceres::Solve ----
+JOINT_CASES = [dict(),                                                                                   # Room.txt: angle residuals, line-to-line + point-to-plane
+               dict(angle_residual=False, normalize_distance=False, point_to_line=True, lidar_weight=0.1, refine=(True, False, True, True, False))]
+
+
+def joint_case():
+    from panovlm_b200 import synth
+    frames, Rs, ts = builder_case(n_frames=5, n_az=600, seed=8)
+    rng = np.random.default_rng(20261106)
+    rows, cols = 2880, 5760
+    T_cl = np.eye(4); T_cl[:3, :3] = synth.rotvec_to_R(np.array([0.01, 0.02, -0.01])); T_cl[:3, 3] = [0.03, -0.05, 0.02]
+    R_wc, t_wc, image_lines = [], [], []
+    for f in frames:
+        T_wl = np.eye(4); T_wl[:3, :3] = f["R_wl"]; T_wl[:3, 3] = f["t_wl"]
+        T_wc = T_wl @ np.linalg.inv(T_cl)
+        R_wc.append(T_wc[:3, :3]); t_wc.append(T_wc[:3, 3])
+        ends_cam = f["end_points"].reshape(-1, 3) @ T_cl[:3, :3].T + T_cl[:3, 3]
+        px = synth.pixel_of(ends_cam, rows, cols).reshape(-1, 4) + rng.normal(0, 2.0, (len(f["end_points"]), 4))
+        cl = np.stack([rng.uniform(0, cols, 15), rng.uniform(0, rows, 15), rng.uniform(0, cols, 15), rng.uniform(0, rows, 15)], axis=1)
+        image_lines.append(np.concatenate([px, cl]).astype(np.float32))
+    n_pts, nf = 120, len(frames)
+    pts = rng.uniform([-3, -2, -1], [3, 2, 1], (n_pts, 3)) * 1.5
+    keypoints = [[] for _ in range(nf)]
+    track_off, ff, fi = [0], [], []
+    for p_ in range(n_pts):
+        for c in np.sort(rng.choice(nf, int(rng.integers(2, 5)), replace=False)):
+            Pc = R_wc[c].T @ (pts[p_] - t_wc[c])
+            uv = synth.pixel_of(Pc[None], rows, cols)[0] + rng.normal(0, 1.0, 2)
+            ff.append(int(c)); fi.append(len(keypoints[c])); keypoints[c].append(uv)
+        track_off.append(len(ff))
+    keypoints = [np.array(k, np.float32).reshape(-1, 2) for k in keypoints]
+    return dict(frames=frames, Rs=Rs, ts=ts, rows=rows, cols=cols, T_cl=T_cl, R_wc=np.array(R_wc), t_wc=np.array(t_wc), image_lines=image_lines, keypoints=keypoints,
+                track_off=np.array(track_off, np.int32), feat_frame=np.array(ff, np.int32), feat_index=np.array(fi, np.int32), points=pts + rng.normal(0, 0.03, pts.shape))
+
+
+def reference_joint_blocks(oracle, d, **kw):
+    rf = [oracle.RefFrame(d["Rs"][i], d["ts"][i], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["surfFlat"], f["surfLessFlat"], id=i, local="keep",
+                          end_points=f["end_points"]) for i, f in enumerate(d["frames"])]
+    return oracle.ref_joint_optimize_blocks(d["rows"], d["cols"], d["R_wc"], d["t_wc"], d["image_lines"], d["keypoints"], rf, d["track_off"], d["feat_frame"], d["feat_index"],
+                                            d["points"], d["T_cl"], **kw)
+
+
+def product_joint_blocks(oracle, d, camera_weight=1.0, lidar_weight=0.01, camera_lidar_weight=25.0, point_to_plane=True, line_to_line=True, point_to_line=False,
+                         angle_residual=True, normalize_distance=True, plane_dis_threshold=1.0, line_dis_threshold=0.3, plane_tolerance=0.05, refine=None):
+    """The joint problem in the reference's registration order, from the oracle's associations and the product's host functions: camera-LiDAR blocks, reprojection
+    observations, then the LiDAR-LiDAR families called as Optimize calls them (panovlm_b200.joint.joint_lidar_config)."""
+    from panovlm_b200 import BlockList, Context, joint, odometry
+    frames, n = d["frames"], len(d["frames"])
+    # base/Config.h keeps the weights and thresholds as `float`: what reaches the builders is double(float(value))
+    camera_weight, lidar_weight, camera_lidar_weight = (float(np.float32(x)) for x in (camera_weight, lidar_weight, camera_lidar_weight))
+    bl = BlockList(4096)
+    n_pairs = 0
+    for i, nbrs in enumerate(Context.neighbor_each_frame(n, n, 1, True)):
+        T_wc = np.eye(4); T_wc[:3, :3] = d["R_wc"][i]; T_wc[:3, 3] = d["t_wc"][i]
+        for li in nbrs:
+            f = frames[li]
+            T_wl = np.eye(4); T_wl[:3, :3] = d["Rs"][li]; T_wl[:3, 3] = d["ts"][li]
+            T_cl = np.linalg.inv(T_wc) @ T_wl
+            il, ll, s_, e_, ang = oracle.associate_by_angle(d["rows"], d["cols"], d["image_lines"][i], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], np.diff(f["seg_off"]),
+                                                            f["end_points"], T_cl, True, True)
+            n_pairs += len(il)
+            if len(il):
+                Context.build_camera_lidar_blocks(bl, d["rows"], d["cols"], d["image_lines"][i][il], s_, e_, np.ones(len(il), np.float32), i, n + li, camera_lidar_weight)
+    cl = {k: v.copy() for k, v in bl.view().items()}
+    kp_off = np.concatenate([[0], np.cumsum([len(k) for k in d["keypoints"]])])
+    xy = np.concatenate(d["keypoints"])[kp_off[d["feat_frame"]] + d["feat_index"]]
+    cam, point, bearing = Context.build_reproj_observations(d["rows"], d["cols"], d["track_off"], d["feat_frame"], xy, None)
+    cfg = odometry.OdometryConfig(point_to_plane=point_to_plane, line_to_line=line_to_line, point_to_line=point_to_line, angle_residual=angle_residual,
+                                  normalize_distance=normalize_distance, lidar_weight=lidar_weight)
+    p2l_cfg, main_cfg = joint.joint_lidar_config(cfg)
+    ll = product_refine_blocks(oracle, frames, d["Rs"], d["ts"], point_to_plane=point_to_plane, line_to_line=line_to_line, point_to_line=point_to_line, use_segment=True,
+                               angle_residual=angle_residual, normalize_distance=normalize_distance, plane_dis_threshold=float(np.float32(plane_dis_threshold)),
+                               line_dis_threshold=float(np.float32(line_dis_threshold)), plane_tolerance=float(np.float32(plane_tolerance)), plane_weight=main_cfg.plane_weight,
+                               p2l=(p2l_cfg.use_segment, p2l_cfg.angle_residual, p2l_cfg.normalize_distance, p2l_cfg.point_line_weight), block_offset=n, l2l_needs_segment=False)
+    return cl, (cam, point, bearing), ll, n_pairs
+
+
+def test_joint_problem_equals_the_reference_optimize(oracle):
+    """configs[2]: the whole problem the reference's mapping-mode Optimize hands to the solver - AssociateLineMulti's line pairs, AddCameraLidarResidual, AddCameraResidual,
+    the three LiDAR builders with the joint stage's (shifted) arguments and weights, the constant blocks - against the product's host functions fed by the oracle."""
+    g = np.load(os.path.join(G, "ref_joint.npz"))
+    d = joint_case()
+    n = len(d["frames"])
+    for ci, kw in enumerate(JOINT_CASES):
+        exp = {k[len(f"j{ci}_"):]: g[k] for k in g.files if k.startswith(f"j{ci}_")}
+        cl, (cam, point, bearing), ll, n_pairs = product_joint_blocks(oracle, d, **kw)
+        n_cl, n_rp, n_ll = len(cl["type"]), len(cam), len(ll["type"])
+        assert n_pairs == int(exp["n_line_pairs"]) >= 10 and n_cl == 2 * n_pairs
+        assert len(exp["residual"]) == n_cl + n_rp + n_ll, (ci, len(exp["residual"]), n_cl, n_rp, n_ll)
+        npar = exp["n_params"]
+        assert np.all(npar[:n_cl] == 4) and np.all(npar[n_cl:n_cl + n_rp] == 3) and np.all(npar[n_cl + n_rp:] == 4)
+        four = {k: np.concatenate([cl[k], ll[k]]) for k in cl}
+        m4 = npar == 4
+        assert np.array_equal(four["ref"], exp["a"][m4]) and np.array_equal(four["nei"], exp["b"][m4]) and np.abs(four["huber"] - exp["huber"][m4]).max() < 1e-15, ci
+        assert np.array_equal(cam, exp["a"][~m4]) and np.array_equal(point, exp["b"][~m4]) and np.allclose(exp["huber"][~m4], 4 * np.pi / 180)
+        b = oracle.Blocks(four["type"], four["ref"], four["nei"], four["consts"], 0.0, four["normalize"])
+        r, J, _ = b.evaluate(exp["poses"], apply_loss=False)
+        rp = oracle.Reproj(cam, point, bearing, weight=float(np.float32(kw.get("camera_weight", 1.0))))
+        r3, J3 = rp.evaluate(exp["poses"][:n], d["points"], apply_loss=False)[:2]
+        r_all, J_all = np.zeros(len(npar)), np.zeros((len(npar), 12))
+        r_all[m4], J_all[m4] = r, J
+        r_all[~m4] = r3; J_all[~m4, :9] = J3[:, :9]
+        assert np.all(np.abs(r_all - exp["residual"]) <= 1e-9 * np.abs(exp["residual"]) + 5e-11), ci      # 5e-11: acos near 1 on a 3e-5 rad residual
+        assert np.all(np.abs(J_all[::JAC_STRIDE] - exp["jacobian"]).max(1) <= 1e-6 * np.abs(exp["jacobian"]).max(1) + 1e-9), ci
+        # constant parameter blocks: the refine_* switches (rotation 2 b, translation 2 b + 1, track 2 (n + m) + t), then camera 0 (:462-491)
+        refine = kw.get("refine", (True, True, True, True, True))
+        want = []
+        if not refine[4]:
+            want += [4 * n + t for t in range(len(d["points"]))]
+        for i in range(n):
+            want += ([2 * i] if not refine[0] else []) + ([2 * i + 1] if not refine[1] else [])
+        for i in range(n):
+            want += ([2 * (n + i)] if not refine[2] else []) + ([2 * (n + i) + 1] if not refine[3] else [])
+        want += [0, 1]
+        assert exp["const_part"].tolist() == want, ci
+    if oracle.ref_assoc_lib() is not None:
+        live = reference_joint_blocks(oracle, d, **JOINT_CASES[0])
+        assert np.array_equal(live["residual"], g["j0_residual"]) and np.array_equal(live["a"], g["j0_a"])
