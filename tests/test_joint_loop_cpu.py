@@ -71,3 +71,35 @@ def test_estimate_pose_early_exits():
     fn, calls = scripted([100.0, 50.0, 25.0], [4, 4, 9])
     odometry.estimate_pose(None, None, z, None, None, 7, fn)
     assert calls["n"] == 2
+
+
+def test_joint_stage_calls_the_lidar_builders_like_the_reference(monkeypatch):
+    """CameraLidarOptimizer::Optimize passes the LiDAR builders other arguments than RefinePose does (CameraLidarOptimizer.cpp:436-458; pinned against the
+    reference's own Optimize in test_reference_pinning.py): joint_lidar_config derives the two configurations, _lidar_blocks keeps the reference's registration order
+    (point-to-line first) and the return shape of odometry.build_problem for both values of host_point2plane."""
+    import numpy as np
+    from panovlm_b200 import BlockList, joint, odometry
+    cfg = odometry.OdometryConfig(point_to_line=True, angle_residual=False, normalize_distance=True, lidar_weight=0.1)
+    p2l, main = joint.joint_lidar_config(cfg)
+    assert (p2l.use_segment, p2l.angle_residual, p2l.normalize_distance, p2l.point_line_weight) == (False, True, True, 1.0)       # every argument one slot early
+    assert not p2l.point_to_plane and not p2l.line_to_line and p2l.point_to_line
+    assert main.plane_weight == 0.1 and not main.point_to_line and main.line_to_line and main.point_to_plane
+    assert cfg.plane_weight == 1.0 and cfg.point_to_line                                                                          # the caller's config is untouched
+    zero = joint.joint_lidar_config(odometry.OdometryConfig(point_to_line=True, lidar_weight=0.0))[0]
+    assert zero.normalize_distance is False                                                                                       # bool(lidar_weight)
+    calls = []
+
+    def fake_build(ctx, frames, poses, c, aa_to_R, frame_range=None, host_point2plane=True):
+        calls.append((c.point_to_line, c.point_to_plane, host_point2plane))
+        bl = BlockList(8)
+        k = 2 if c.point_to_line else 3
+        bl.extend(dict(type=np.full(k, 3 if c.point_to_line else 1, np.int32), ref=np.zeros(k, np.int32), nei=np.ones(k, np.int32), normalize=np.ones(k, np.int32),
+                       huber=np.zeros(k), consts=np.zeros((k, 12))))
+        return (bl, [(0, 1)]) if host_point2plane else (bl, [(0, 1)], [(0, 1)])
+    monkeypatch.setattr(odometry, "build_problem", fake_build)
+    (bl, edges), m = joint._lidar_blocks(None, None, None, cfg, None)
+    assert bl.view()["type"].tolist() == [3, 3, 1, 1, 1] and edges == [(0, 1)] and m.plane_weight == 0.1
+    (bl, edges, mine), _ = joint._lidar_blocks(None, None, None, cfg, None, host_point2plane=False)
+    assert bl.n == 5 and mine == [(0, 1)]
+    (bl, edges), _ = joint._lidar_blocks(None, None, None, odometry.OdometryConfig(), None)
+    assert bl.n == 3 and calls[-1] == (False, True, True)
