@@ -333,7 +333,10 @@ int pvb_transform_cloud(pvb_ctx* ctx, const float* xyzi, long n, const double* R
 int pvb_slerp_pose(const double* pose_w1_16, const double* pose_w2_16, double ratio, double* out16);
 /* The pose of the END of every sweep as LidarOdometry::UndistortLidars chooses it (lidar_mapping/LidarOdometry.cpp:203-243, sweep 0.1 s
  * + gap_time between sweeps): interpolated towards the next usable frame, extrapolated for the last frame; has_end[i] = 0 where the
- * reference saves the raw cloud (`goto save_undistort`).  poses16: n x 16; pose_valid / frame_valid: IsPoseValid() / valid. Host only. */
+ * reference saves the raw cloud (`goto save_undistort`).  poses16: n x 16; pose_valid / frame_valid: IsPoseValid() / valid. Host only.
+ * A frame without a pose is expected as the reference stores it (R = 0, t = inf).  Like the reference, the search only steps over frames that
+ * have NEITHER a pose NOR valid data (`!IsPoseValid() && !valid`, :220, :231): next to a valid frame without a pose the end pose is NaN
+ * (has_end = 1) and the undistorted sweep comes out as NaN - identical to LidarOdometry::UndistortLidars (tests/golden/ref_velodyne.npz).   */
 int pvb_undistort_end_poses(int n, const double* poses16, const unsigned char* pose_valid, const unsigned char* frame_valid, float gap_time,
                             double* out_pose16, unsigned char* has_end);
 /* Pose text files (util/FileIO.cpp:11-73 ReadPoseT, :168-191 ExportPoseT): one line per frame, [name ]r00 r01 r02 tx r10 r11 r12 ty r20 r21 r22 tz
