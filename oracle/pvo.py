@@ -774,3 +774,19 @@ def ref_joint_optimize_blocks(rows, cols, R_wc, t_wc, image_lines, keypoints, li
     assert m >= 0, m
     return dict(n_params=npar[:m].copy(), a=a[:m].copy(), b=b[:m].copy(), huber=hb[:m].copy(), residual=r[:m].copy(), jacobian=J[:m].copy(), const_part=cpart[:ncst.value].copy(),
                 poses=poses, n_line_pairs=nlp.value)
+
+
+def ref_calibration_blocks(rows, cols, image_lines, lidar_frames, T_cl):
+    """Calibration mode of the reference: AssociateLineSingle(T_cl) + Optimize(line_pairs, T_cl) recorded at ceres::Solve.  Returns dict(huber, residual, jacobian (n x 6),
+    pose (aa_cl, t_cl), info = [line pairs, max_num_iterations, linear_solver_type])."""
+    n = len(lidar_frames)
+    line_off = np.concatenate([[0], np.cumsum([len(x) for x in image_lines])]).astype(np.int32)
+    lines = _f32(np.concatenate([np.asarray(x, np.float32).reshape(-1, 4) for x in image_lines]))
+    arr = (C.c_void_p * n)(*[f.h for f in lidar_frames])
+    cap = 1 << 16
+    hb, r, J, pose, info = np.zeros(cap), np.zeros(cap), np.zeros((cap, 6)), np.zeros(6), np.zeros(3, np.int32)
+    L = lidar_frames[0].L
+    L.ref_calibration_blocks.restype = C.c_long
+    m = L.ref_calibration_blocks(C.c_int(rows), C.c_int(cols), C.c_int(n), _p(line_off), _p(lines), arr, _p(_f64(T_cl)), C.c_long(cap), _p(hb), _p(r), _p(J), _p(pose), _p(info))
+    assert m >= 0, m
+    return dict(huber=hb[:m].copy(), residual=r[:m].copy(), jacobian=J[:m].copy(), pose=pose, info=info)

@@ -420,6 +420,54 @@ long ref_joint_optimize_blocks(int rows, int cols, int n_cams, const double* R_w
   return (long)S.residual.size();
 }
 
+// Calibration mode: the reference's own AssociateLineSingle(T_cl) (joint_optimization/CameraLidarOptimizer.cpp:300-328: image i against LiDAR i, AssociateByAngle with its
+// defaults = one-to-one pairs) followed by Optimize(line_pairs, T_cl) (:32-96: Plane2Plane_Relative with HuberLoss(2 deg) + PlaneRelativeIOUResidual without a loss on ONE
+// relative pose block), recorded at ceres::Solve.  Per block: Huber a, raw residual, raw 1x6 Jacobian (aa_cl, t_cl); pose6 = the pose block; info3 = {number of line
+// pairs, max_num_iterations, linear_solver_type}.  Returns the number of blocks or < 0.
+namespace {
+struct CalibSnapshot { std::vector<double> huber, residual, jac, pose; int max_it = 0, solver = -1; long status = 0; };
+CalibSnapshot* g_calib = nullptr;
+void calib_hook(const ceres::Solver::Options& o, ceres::Problem* p, ceres::Solver::Summary* s) {
+  CalibSnapshot& S = *g_calib;
+  S.max_it = o.max_num_iterations; S.solver = (int)o.linear_solver_type;
+  for (const ceres::Problem::Block& blk : p->blocks) {
+    if (blk.params.size() != 2 || blk.params[0] != p->blocks[0].params[0] || blk.params[1] != p->blocks[0].params[1]) { S.status = -2; return; }
+    const ceres::HuberLoss* h = dynamic_cast<const ceres::HuberLoss*>(blk.loss);
+    double res, jb[2][3]; double* jp[2] = {jb[0], jb[1]};
+    if (!blk.cost->Evaluate(blk.params.data(), &res, jp)) { S.status = -2; return; }
+    S.huber.push_back(h ? h->a() : 0.0); S.residual.push_back(res); S.jac.insert(S.jac.end(), &jb[0][0], &jb[0][0] + 6);
+  }
+  if (!p->blocks.empty()) { S.pose.assign(p->blocks[0].params[0], p->blocks[0].params[0] + 3); S.pose.insert(S.pose.end(), p->blocks[0].params[1], p->blocks[0].params[1] + 3); }
+  s->usable = true;
+}
+}  // namespace
+long ref_calibration_blocks(int rows, int cols, int n, const int* line_off, const float* lines4, void* const* lidar_frames, const double* T_cl16, long cap, double* huber_a,
+                            double* residual, double* jac6, double* pose6, int* info3) {
+  std::vector<Frame> frames; std::vector<Velodyne> lidars; std::vector<PanoramaLine> image_lines(n);
+  for (int f = 0; f < n; ++f) {
+    frames.push_back(Frame(rows, cols, f, "frame"));
+    image_lines[f].id = f; image_lines[f].rows = rows; image_lines[f].cols = cols;
+    for (int k = line_off[f]; k < line_off[f + 1]; ++k) image_lines[f].lines.push_back(cv::Vec4f(lines4[4 * k], lines4[4 * k + 1], lines4[4 * k + 2], lines4[4 * k + 3]));
+    lidars.push_back(*static_cast<const Velodyne*>(lidar_frames[f]));
+  }
+  Config config; config.num_threads = 1;
+  Eigen::Matrix4d T_cl; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T_cl(i, j) = T_cl16[4 * i + j];
+  CameraLidarOptimizer opt(T_cl, lidars, frames, config);
+  opt.image_lines_all = image_lines;
+  const eigen_map<std::pair<size_t, size_t>, std::vector<CameraLidarLinePair>> line_pairs = opt.AssociateLineSingle(T_cl);
+  info3[0] = 0; for (const auto& kv : line_pairs) info3[0] += (int)kv.second.size();
+  CalibSnapshot S; g_calib = &S; ceres::solve_hook() = calib_hook;
+  opt.Optimize(line_pairs, T_cl);
+  ceres::solve_hook() = nullptr; g_calib = nullptr;
+  if (S.status < 0) return S.status;
+  if ((long)S.residual.size() > cap) return -1;
+  for (size_t k = 0; k < S.residual.size(); ++k) { huber_a[k] = S.huber[k]; residual[k] = S.residual[k]; }
+  if (!S.jac.empty()) std::memcpy(jac6, S.jac.data(), S.jac.size() * sizeof(double));
+  if (S.pose.size() == 6) std::memcpy(pose6, S.pose.data(), 48);
+  info3[1] = S.max_it; info3[2] = S.solver;
+  return (long)S.residual.size();
+}
+
 // CameraLidarOptimizer::NeighborEachFrame (joint_optimization/CameraLidarOptimizer.cpp:551-607) and LidarMaskByTrack (:609-642), called on an optimizer object
 // built from n_frames camera poses and the LiDAR frames.  CSR outputs.
 int ref_neighbor_each_frame(int n_frames, const double* R_wc, const double* t_wc, const unsigned char* frame_pose_valid, int n_lidars, const double* R_wl, const double* t_wl,

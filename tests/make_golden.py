@@ -434,6 +434,12 @@ def golden_ref_joint():
         for k, v in r.items():
             out[f"j{ci}_{k}"] = (np.asarray(v).astype(np.int16) if k in ("a", "b", "n_params") else (v[::trp.JAC_STRIDE] if k == "jacobian" else v))
         print(f"  joint case {ci}: {len(r['residual'])} blocks ({int((r['n_params'] == 3).sum())} reprojection), {r['n_line_pairs']} line pairs, constant parts {r['const_part'][:6].tolist()}...")
+    T = d["T_cl"].copy(); T[:3, 3] += [0.02, -0.01, 0.015]                               # calibration mode: AssociateLineSingle + Optimize(line_pairs, T_cl)
+    rf = [pvo.RefFrame(np.eye(3), np.zeros(3), f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], id=i, local="keep", end_points=f["end_points"])
+          for i, f in enumerate(d["frames"])]
+    c = pvo.ref_calibration_blocks(d["rows"], d["cols"], d["image_lines"], rf, T)
+    out.update({f"cal_{k}": v for k, v in c.items()})
+    print(f"  calibration: {len(c['residual'])} blocks from {c['info'][0]} line pairs, options {c['info'][1:].tolist()}")
     np.savez_compressed(os.path.join(OUT, "ref_joint.npz"), **out)
 
 

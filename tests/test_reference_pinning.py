@@ -830,3 +830,35 @@ def test_joint_problem_equals_the_reference_optimize(oracle):
     if oracle.ref_assoc_lib() is not None:
         live = reference_joint_blocks(oracle, d, **JOINT_CASES[0])
         assert np.array_equal(live["residual"], g["j0_residual"]) and np.array_equal(live["a"], g["j0_a"])
+
+
+def test_calibration_problem_equals_the_reference_optimize(oracle):
+    """Calibration mode: the reference's AssociateLineSingle(T_cl) + Optimize(line_pairs, T_cl) recorded at ceres::Solve == one-to-one AssociateByAngle of the oracle +
+    pvb_build_calibration_blocks (Plane2Plane_Relative in degrees with Huber 2 deg, PlaneRelativeIOUResidual with weight 2 and no loss, the float32 image-plane path)."""
+    from panovlm_b200 import BlockList, Context
+    g = np.load(os.path.join(G, "ref_joint.npz"))
+    d = joint_case()
+    T = d["T_cl"].copy(); T[:3, 3] += [0.02, -0.01, 0.015]
+    bl = BlockList(2048)
+    n_pairs = 0
+    for i, f in enumerate(d["frames"]):
+        il, ll, s_, e_, _ = oracle.associate_by_angle(d["rows"], d["cols"], d["image_lines"][i], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], np.diff(f["seg_off"]), f["end_points"],
+                                                      T, True, False)
+        n_pairs += len(il)
+        if len(il):
+            Context.build_calibration_blocks(bl, d["rows"], d["cols"], d["image_lines"][i][il], s_, e_, 0)
+    v = bl.view()
+    assert n_pairs == int(g["cal_info"][0]) >= 20 and len(v["type"]) == len(g["cal_residual"]) == 2 * n_pairs
+    assert int(g["cal_info"][1]) == 50                                                       # options.max_num_iterations (:69)
+    assert np.abs(v["huber"] - g["cal_huber"]).max() < 1e-15 and np.all(g["cal_huber"][1::2] == 0) and np.allclose(g["cal_huber"][0::2], 2 * np.pi / 180)
+    pose = np.concatenate([oracle.R_to_aa(T[:3, :3]), T[:3, 3]])
+    assert np.abs(pose - g["cal_pose"]).max() < 1e-15
+    b = oracle.Blocks(v["type"], 0, 0, v["consts"], 0.0, v["normalize"])
+    r, J, _ = b.evaluate(g["cal_pose"].reshape(1, 6), apply_loss=False)
+    assert np.all(np.abs(r - g["cal_residual"]) <= 1e-9 * np.abs(g["cal_residual"]) + 1e-9)             # residuals in degrees (Plane2Plane_Relative)
+    assert np.all(np.abs(J[:, :6] - g["cal_jacobian"]).max(1) <= 1e-6 * np.abs(g["cal_jacobian"]).max(1) + 1e-7)
+    if oracle.ref_assoc_lib() is not None:
+        rf = [oracle.RefFrame(np.eye(3), np.zeros(3), f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], id=i, local="keep", end_points=f["end_points"])
+              for i, f in enumerate(d["frames"])]
+        live = oracle.ref_calibration_blocks(d["rows"], d["cols"], d["image_lines"], rf, T)
+        assert np.array_equal(live["residual"], g["cal_residual"])
