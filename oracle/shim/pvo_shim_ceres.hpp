@@ -162,6 +162,17 @@ class CostFunction {
   std::vector<int> sizes_; int num_residuals_ = 0;
 };
 // rho(s), rho'(s), rho''(s) of the squared residual norm s (ceres/loss_function.h)
+// ceres::SizedCostFunction / ceres::EvaluationCallback: the two classes a user-side bridge derives from (include/panovlm_b200_ceres_adapter.hpp)
+template <int kNumResiduals, int... Ns>
+class SizedCostFunction : public CostFunction {
+ public:
+  SizedCostFunction() { const int n[] = {Ns...}; sizes_.assign(n, n + sizeof...(Ns)); num_residuals_ = kNumResiduals; }
+};
+class EvaluationCallback {
+ public:
+  virtual ~EvaluationCallback() {}
+  virtual void PrepareForEvaluation(bool evaluate_jacobians, bool new_evaluation_point) = 0;
+};
 class LossFunction {
  public:
   virtual ~LossFunction() {}
@@ -214,6 +225,10 @@ enum SparseLinearAlgebraLibraryType { SUITE_SPARSE, CX_SPARSE, EIGEN_SPARSE, ACC
 inline bool IsSparseLinearAlgebraLibraryTypeAvailable(SparseLinearAlgebraLibraryType) { return false; }
 class Problem {
  public:
+  struct Options { EvaluationCallback* evaluation_callback = nullptr; };
+  Options options;
+  Problem() {}
+  explicit Problem(const Options& o) : options(o) {}
   struct Block { CostFunction* cost; LossFunction* loss; std::vector<double*> params; };
   std::vector<Block> blocks;
   std::vector<const double*> constant_blocks;

@@ -46,3 +46,16 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"oracle|pvo_", open(os.path.join(dp, f), errors="ignore").read()):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_ceres_adapter_builds_against_the_ceres_surface_and_fails_loudly_without_a_device():
+    """include/panovlm_b200_ceres_adapter.hpp (ceres::EvaluationCallback + ceres::SizedCostFunction<1,3,3,3,3> rows) compiles and links against the ceres surface
+    (oracle/shim stand-in: Ceres itself is not installed) and libpanovlm_b200.so; without a CUDA device the bridge cannot even get a context: no CPU fallback."""
+    import ctypes
+    import numpy as np
+    import torch
+    from conftest import build_adapter_harness
+    L = ctypes.CDLL(build_adapter_harness())
+    assert hasattr(L, "adapter_run")
+    if not torch.cuda.is_available():
+        assert L.adapter_run(0, ctypes.c_long(0), None, None, None, None, None, None, 1, np.zeros(6).ctypes.data_as(ctypes.c_void_p), 0, None, None) == -1

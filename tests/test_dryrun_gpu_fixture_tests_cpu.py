@@ -61,7 +61,7 @@ def test_gpu_fixture_tests_dry_run(monkeypatch):
     import test_zz_gpu_reference_fixtures as z
     monkeypatch.setattr(panovlm_b200, "LineFrame", FakeLF)
     ctx = FakeCtx()
-    names = [n for n in dir(z) if n.startswith("test_")]
+    names = [n for n in dir(z) if n.startswith("test_") and n != "test_ceres_bridge_serves_the_device_rows_through_the_ceres_surface"]   # that one needs the real library
     assert len(names) == 7
     for name in names:
         getattr(z, name)(ctx)

@@ -126,3 +126,29 @@ def test_transform_and_undistort_kernels_equal_the_reference_clouds(gpu_ctx):
         assert d.max() <= 1, k
         bad += int((d > 0).sum())
     assert bad <= 1e-4 * 3 * off[-1] + 2
+
+
+def test_ceres_bridge_serves_the_device_rows_through_the_ceres_surface(gpu_ctx, oracle):
+    """(b) boundary: include/panovlm_b200_ceres_adapter.hpp driven the way Ceres drives it (tests/adapter_harness.cpp): AddBlocks registers one SizedCostFunction per
+    block on the callers' pose lists with loss == nullptr, PrepareForEvaluation launches ONE device evaluation, every CostFunction::Evaluate then returns the row the
+    kernel wrote (loss-corrected), null Jacobian blocks are skipped.  Compared with the oracle's one-functor-at-a-time evaluation."""
+    import ctypes as C
+    import cases
+    from conftest import build_adapter_harness
+    L = C.CDLL(build_adapter_harness())
+    p = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)  # noqa: E731
+    c = cases.random_blocks(5, 3000)
+    n = len(c["type"])
+    blk = oracle.Blocks(c["type"], c["ref"], c["nei"], c["consts"], c["huber"], c["normalize"])
+    r_o, J_o, _ = blk.evaluate(c["poses"], apply_loss=True)
+    keep = [np.ascontiguousarray(c[k], np.int32) for k in ("type", "ref", "nei", "normalize")] + [np.ascontiguousarray(c[k], np.float64) for k in ("huber", "consts", "poses")]
+    for null_block in (0, 1):
+        r, J = np.zeros(n), np.zeros((n, 12))
+        rc = L.adapter_run(0, C.c_long(n), p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]), p(keep[4]), p(keep[5]), C.c_int(c["nb"]), p(keep[6]), C.c_int(null_block), p(r), p(J))
+        assert rc == 0, rc
+        assert (np.abs(r - r_o) / np.maximum(1e-9, np.abs(r_o))).max() < 1e-5
+        J_exp = J_o.copy()
+        if null_block:
+            for i in range(n):
+                J_exp[i, 3 * (i % 4):3 * (i % 4) + 3] = 0
+        assert (np.abs(J - J_exp).max(1) / np.maximum(1e-9, np.abs(J_o).max(1))).max() < 1e-6
