@@ -862,3 +862,38 @@ def test_calibration_problem_equals_the_reference_optimize(oracle):
               for i, f in enumerate(d["frames"])]
         live = oracle.ref_calibration_blocks(d["rows"], d["cols"], d["image_lines"], rf, T)
         assert np.array_equal(live["residual"], g["cal_residual"])
+
+
+def test_dense_icp_evaluation_equals_the_reference_pieces(oracle):
+    """BASELINE.json configs[4] / the bench and smoke() path: the oracle's dense ICP evaluation (association + plane fit + Point2Plane_Meter + Huber + per-frame 6x6
+    reduce) rebuilt from the REFERENCE'S OWN pieces - Transform2LidarWorld, AssociatePoint2Plane and Point2Plane_Meter::Create(...)->Evaluate() (oracle/_ref) - with Ceres'
+    corrector for HuberLoss applied here.  Runs only where oracle/_ref is present (this container); the kernels are checked against this oracle function on the GPU."""
+    if oracle.ref_assoc_lib() is None or oracle.ref_path_lib() is None:
+        pytest.skip("oracle/_ref is not built here")
+    from panovlm_b200 import synth
+    d = synth.make_dense_sweep(n_target=20000, n_frames=3, pts_per_frame=1500, seed=11)
+    tol, thr, hub, w = 0.05, 1.0, 0.2, 0.7
+    sys_o, _, n_o = oracle.dense_icp_eval(d["target"], d["src_local"], d["src_off"], d["poses_lw_init"], tol, thr, 10, hub, w, 1)
+    tgt = oracle.RefFrame(np.eye(3), np.zeros(3), surf_less_flat_world=d["target"])
+    total = 0
+    for f in range(3):
+        src = d["src_local"][d["src_off"][f]:d["src_off"][f + 1]]
+        p = d["poses_lw_init"][f]
+        R_wl = oracle.aa_to_R(p[:3]).T
+        fr = oracle.RefFrame(R_wl, -R_wl @ p[3:], surf_flat_world=src, local=True)
+        pt, pl = oracle.ref_associate_point2plane(tgt, fr, tol, thr)
+        m = len(pt)
+        total += m
+        raw = np.zeros((m, 16)); raw[:, :3] = pt; raw[:, 3:7] = pl; raw[:, 7] = w
+        prm = np.zeros((m, 12)); prm[:, 6:] = p
+        r, J, _ = oracle.ref_eval_functors(np.zeros(m, np.int32), 0, raw, prm)
+        s = r * r
+        out = s > hub * hub                                             # ceres::HuberLoss + Corrector: rho' = a / |r| beyond a, rho'' < 0 => plain sqrt(rho') scaling
+        scale = np.where(out, np.sqrt(hub / np.maximum(np.abs(r), 1e-300)), 1.0)
+        cost = np.where(out, 2 * hub * np.abs(r) - hub * hub, s).sum() * 0.5
+        Jc, rc = J[:, 6:] * scale[:, None], r * scale
+        H, g = Jc.T @ Jc, Jc.T @ rc
+        exp = np.concatenate([H[np.triu_indices(6)], g, [cost, m]])
+        assert sys_o[f, 28] == m and m > 500
+        assert np.abs(sys_o[f] - exp).max() < 1e-9 * np.abs(exp).max(), f
+    assert total == n_o
