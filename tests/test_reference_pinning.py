@@ -532,6 +532,10 @@ def test_residual_block_lists_equal_the_reference_builders(oracle):
         if oracle.ref_assoc_lib() is not None and ci == 0:
             live = reference_refine_blocks(oracle, frames, Rs, ts, **kw)
             assert np.array_equal(live["ref"], exp["ref"]) and np.array_equal(live["residual"], exp["residual"])
+            # what RefinePose hands to ceres::Solve besides the blocks: SetOptionsLidar's max_num_iterations = 20 (util/Optimization.cpp:663; OdometryConfig.max_lm_iterations),
+            # DENSE_SCHUR below 100 frames (:645-647), and exactly two constant parameter blocks = the first valid frame's (LidarOdometry.cpp:58-64; is_const[0] in refine_pose)
+            from panovlm_b200 import odometry
+            assert live["info"].tolist() == [odometry.OdometryConfig().max_lm_iterations, 3, 2, 0]
 
 
 def test_camera_lidar_blocks_equal_the_reference_builder(oracle):
