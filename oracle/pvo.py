@@ -790,3 +790,15 @@ def ref_calibration_blocks(rows, cols, image_lines, lidar_frames, T_cl):
     m = L.ref_calibration_blocks(C.c_int(rows), C.c_int(cols), C.c_int(n), _p(line_off), _p(lines), arr, _p(_f64(T_cl)), C.c_long(cap), _p(hb), _p(r), _p(J), _p(pose), _p(info))
     assert m >= 0, m
     return dict(huber=hb[:m].copy(), residual=r[:m].copy(), jacobian=J[:m].copy(), pose=pose, info=info)
+
+
+def ref_pixel_associate_candidates(rows, cols, lines, cloud_local, T_cl):
+    """First stage of the reference's pixel-space Associate(): the candidate point lists (camera-frame float32 x, y, z) handed to the RANSAC fit, one per image line with
+    at least 6 candidates, in ascending line order."""
+    lines, cloud = _f32(lines).reshape(-1, 4), _f32(cloud_local).reshape(-1, 4)
+    cap_l, cap_p = len(lines) + 1, 3 * len(cloud) + 16
+    off, xyz = np.zeros(cap_l + 1, np.int32), np.zeros((cap_p, 3), np.float32)
+    m = ref_camlidar_lib().ref_pixel_associate_candidates(C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), _p(cloud), C.c_int(len(cloud)), _p(_f64(T_cl)),
+                                                          C.c_int(cap_l), C.c_long(cap_p), _p(off), _p(xyz))
+    assert m >= 0
+    return [xyz[off[k]:off[k + 1]].copy() for k in range(m)]

@@ -63,6 +63,32 @@ int ref_associate_by_angle(int rows, int cols, const float* lines, int L, const 
   return (int)pairs.size();
 }
 
+// The deterministic FIRST stage of the pixel-space Associate(lines, point_cloud, T_cl) (:22-102): cloud -> camera frame -> CamToImage pixel -> 3 nearest sub-line mid points
+// (BreakToSegments(line, 70), 60 px gate) -> per image line the list of LiDAR points, lists shorter than 6 dropped.  The reference then hands every list to
+// FitLineRANSAC -> pcl::SACSegmentation; the stand-in records what it receives (camera-frame x, y, z, in the order of the line -> points map) and reports no inliers,
+// so nothing after the RANSAC runs.  Output: CSR of the recorded lists.  Returns the number of lists or -1.
+int ref_pixel_associate_candidates(int rows, int cols, const float* lines, int L, const float* cloud_local, int n, const double* T_cl_rowmajor, int cap_lists, long cap_points,
+                                   int* off, float* xyz) {
+  std::vector<cv::Vec4f> ln;
+  for (int i = 0; i < L; ++i) ln.push_back(cv::Vec4f(lines[4 * i], lines[4 * i + 1], lines[4 * i + 2], lines[4 * i + 3]));
+  pcl::PointCloud<pcl::PointXYZI> cloud;
+  for (int i = 0; i < n; ++i) { pcl::PointXYZI p; p.x = cloud_local[4 * i]; p.y = cloud_local[4 * i + 1]; p.z = cloud_local[4 * i + 2]; p.intensity = cloud_local[4 * i + 3]; cloud.push_back(p); }
+  Eigen::Matrix4d T; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T(i, j) = T_cl_rowmajor[4 * i + j];
+  std::vector<std::vector<float>> rec;
+  pcl::sac_recorder() = &rec;
+  CameraLidarLineAssociate a(rows, cols);
+  a.Associate(ln, cloud, T);
+  pcl::sac_recorder() = nullptr;
+  if ((int)rec.size() > cap_lists) return -1;
+  long total = 0; off[0] = 0;
+  for (size_t k = 0; k < rec.size(); ++k) {
+    if (total + (long)rec[k].size() / 3 > cap_points) return -1;
+    std::memcpy(xyz + 3 * total, rec[k].data(), rec[k].size() * sizeof(float));
+    total += (long)rec[k].size() / 3; off[k + 1] = (int)total;
+  }
+  return (int)rec.size();
+}
+
 // ProjectLidar2PanoramaDepth<pcl::PointXYZI> (util/Visualization.h:407-441): rows x cols uint16 image
 void ref_project_lidar2panorama_depth(const float* cloud_xyzi, long n, int rows, int cols, const double* T_cl_rowmajor, int size, unsigned short* image) {
   pcl::PointCloud<pcl::PointXYZI> cloud;

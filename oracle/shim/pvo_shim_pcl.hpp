@@ -114,10 +114,17 @@ template <typename P, typename M> inline void transformPointCloud(const PointClo
 // pcl::SACSegmentation (RANSAC line fit behind CameraLidarLineAssociate::FitLineRANSAC, the fallback for frames without LiDAR segments): NOT reproduced -
 // its sample sequence depends on PCL's internal random generator.  segment() reports no inliers, so FitLineRANSAC returns false.
 enum { SACMODEL_LINE = 1, SAC_RANSAC = 0 };
+// A test harness may ask the stand-in to RECORD the clouds it is handed (the candidate points of every image line = the result of the first, deterministic
+// stage of CameraLidarLineAssociate::Associate): sac_recorder() points at a vector of (x, y, z) lists, or is null.
+inline std::vector<std::vector<float>>*& sac_recorder() { static std::vector<std::vector<float>>* r = nullptr; return r; }
 template <typename P> class SACSegmentation {
  public:
   void setOptimizeCoefficients(bool) {} void setModelType(int) {} void setMethodType(int) {} void setDistanceThreshold(double) {}
-  void setInputCloud(const typename PointCloud<P>::ConstPtr&) {}
+  void setInputCloud(const typename PointCloud<P>::ConstPtr& c) {
+    if (!sac_recorder()) return;
+    std::vector<float> xyz; for (const P& p : c->points) { xyz.push_back(p.x); xyz.push_back(p.y); xyz.push_back(p.z); }
+    sac_recorder()->push_back(xyz);
+  }
   void segment(PointIndices& inliers, ModelCoefficients&) { inliers.indices.clear(); }
 };
 template <typename P, typename V> inline unsigned compute3DCentroid(const PointCloud<P>&, const PointIndices&, V&) { return 0; }

@@ -341,6 +341,9 @@ def golden_ref_camlidar():
         for k, v in zip(("image", "lidar", "start", "end", "score"), r):
             out[f"{name}_{k}"] = v
         print(f"  {name}: {len(r[0])} pairs")
+    cand = pvo.ref_pixel_associate_candidates(rows, cols, lines, A["cloud"][::4], T)          # first stage of the pixel-space Associate()
+    out["px_off"] = np.concatenate([[0], np.cumsum([len(c) for c in cand])]).astype(np.int32); out["px_xyz"] = np.concatenate(cand)
+    print(f"  pixel-space candidates: {len(cand)} lines, {out['px_off'][-1]} points")
     out["depth_720"] = pvo.ref_project_depth(A["cloud"], 720, 1440, T, 3)
     out["depth_360"] = pvo.ref_project_depth(A["cloud"], 360, 720, T, 4)
     np.savez_compressed(os.path.join(OUT, "ref_camlidar.npz"), **out)

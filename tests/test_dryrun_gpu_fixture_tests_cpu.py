@@ -49,6 +49,7 @@ class FakeCtx:
                 pa.append(i); pb.append(nb); off.append(len(ma))
         return pvo.line_tracks(pa, pb, off, ma, mb, min_len, True)
     def transform_cloud(self, c, R, t): return pvo.transform_cloud(R, t, c)
+    def pixel_line_neighbors(self, rows, cols, lines, cloud, T): return pvo.pixel_line_neighbors(rows, cols, lines, cloud, T)
     def undistort_clouds(self, cloud, off, T_wl, T_we, has=None):
         out = cloud.copy()
         for f in range(len(off) - 1):
@@ -62,6 +63,6 @@ def test_gpu_fixture_tests_dry_run(monkeypatch):
     monkeypatch.setattr(panovlm_b200, "LineFrame", FakeLF)
     ctx = FakeCtx()
     names = [n for n in dir(z) if n.startswith("test_") and n != "test_ceres_bridge_serves_the_device_rows_through_the_ceres_surface"]   # that one needs the real library
-    assert len(names) == 7
+    assert len(names) == 8
     for name in names:
         getattr(z, name)(ctx)

@@ -128,6 +128,21 @@ def test_transform_and_undistort_kernels_equal_the_reference_clouds(gpu_ctx):
     assert bad <= 1e-4 * 3 * off[-1] + 2
 
 
+def test_pixel_knn_kernel_equals_the_reference_first_stage(gpu_ctx):
+    """k_pixel_knn3 (A5, first stage) + pvb_pixel_line_candidates == the candidate lists the reference's own pixel-space Associate() hands to its RANSAC fit."""
+    from panovlm_b200 import Context
+    from test_reference_pinning import camlidar_case
+    g = np.load(os.path.join(G, "ref_camlidar.npz"))
+    A, rows, cols, T, lines = camlidar_case()
+    cloud = A["cloud"][::4]
+    line3, _, _ = gpu_ctx.pixel_line_neighbors(rows, cols, lines, cloud, T)
+    off, idx = Context.pixel_line_candidates(len(lines), line3, 6)
+    cam = gpu_ctx.transform_cloud(cloud, T[:3, :3], T[:3, 3])[:, :3]
+    got = [cam[idx[off[l]:off[l + 1]]] for l in range(len(lines)) if off[l + 1] > off[l]]
+    exp = [g["px_xyz"][g["px_off"][k]:g["px_off"][k + 1]] for k in range(len(g["px_off"]) - 1)]
+    assert len(got) == len(exp) >= 10 and all(np.array_equal(a, b) for a, b in zip(got, exp))
+
+
 def test_ceres_bridge_serves_the_device_rows_through_the_ceres_surface(gpu_ctx, oracle):
     """(b) boundary: include/panovlm_b200_ceres_adapter.hpp driven the way Ceres drives it (tests/adapter_harness.cpp): AddBlocks registers one SizedCostFunction per
     block on the callers' pose lists with loss == nullptr, PrepareForEvaluation launches ONE device evaluation, every CostFunction::Evaluate then returns the row the
