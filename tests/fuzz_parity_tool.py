@@ -1,4 +1,5 @@
-"""Randomised GPU-vs-oracle parity sweep of the fused association path (development / validation tool).
+"""TEST INFRASTRUCTURE (lives under tests/ because it calls the oracle; not collected by pytest - run it by hand on a GPU box: python tests/fuzz_parity_tool.py [n]).
+Randomised GPU-vs-oracle parity sweep of the fused association path (development / validation tool).
 Random scene sizes, rigid placements of the world (negative coordinates, clamped grids), cell sizes (ring-2+ paths),
 thresholds, k, tolerances, residual types, with and without TMA staging.  Exits non-zero on the first mismatch."""
 import json

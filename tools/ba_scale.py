@@ -41,12 +41,6 @@ launches0 = ctx.kernel_launches
 t0 = time.perf_counter()
 c, p, s = ctx.reproj_solve_lm(d["cams"], d["points"], cam_const, None, max_iterations=20)
 out["lm"] = {"seconds": time.perf_counter() - t0, "summary": s, "kernel_launches": ctx.kernel_launches - launches0, "unknowns": int(6 * (n_cams - 1) + 3 * n_points)}
-# CPU oracle: one Jet<9> autodiff functor at a time (what Ceres does), all host threads
-from oracle import pvo  # noqa: E402
-R = pvo.Reproj(d["cam"], d["point"], d["bearing"], huber=huber)
-t0 = time.perf_counter()
-for _ in range(3):
-    R.evaluate(d["cams"], d["points"])
-cpu_s = (time.perf_counter() - t0) / 3
-out["cpu_oracle"] = {"evaluate_s": cpu_s, "evals_per_s": n_obs / cpu_s, "threads": pvo.num_threads()}
+# the CPU leg of this comparison (the oracle's one-Jet<9>-at-a-time evaluation of the same observations) lives in tests/ba_cpu_baseline_tool.py: only tests/, smoke() and
+# bench.py's cpu_baseline leg may call the oracle
 print(json.dumps(out))
