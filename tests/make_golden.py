@@ -24,6 +24,7 @@ INDEPENDENT implementations, never from the oracle itself:
                  register for one RefinePose in five configurations, and AddCameraLidarResidual for one frame pair (ceres::Problem = a recorder, oracle/shim)
   ref_velodyne.npz  float32 clouds after the reference's own Transform2LidarWorld / Transform2Local and UndistortCloud (sensors/Velodyne.cpp compiled where it lies)
   ref_joint.npz  the problem of the joint stage (configs[2]) as the reference's own AssociateLineMulti + Optimize assemble it, recorded at ceres::Solve
+  ref_dense.npz  per-frame 6x6 systems of a small dense ICP evaluation (the bench / smoke path) rebuilt from the reference's own association + functor code
   reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
                  undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
 Run from the repo root:  python tests/make_golden.py
@@ -446,8 +447,23 @@ def golden_ref_joint():
     np.savez_compressed(os.path.join(OUT, "ref_joint.npz"), **out)
 
 
+def golden_ref_dense():
+    """tests/golden/ref_dense.npz: per-frame normal equations of the dense ICP evaluation (configs[4] shape, small) rebuilt from the reference's own pieces
+    (tests/test_reference_pinning.py: dense_systems_from_reference_pieces)."""
+    from oracle import pvo
+    if pvo.ref_assoc_lib() is None or pvo.ref_path_lib() is None:
+        print("oracle/_ref not built (no /root/reference here): ref_dense.npz left as committed")
+        return
+    import test_reference_pinning as trp
+    c = trp.DENSE_CASE
+    d = synth.make_dense_sweep(n_target=c["n_target"], n_frames=c["n_frames"], pts_per_frame=c["pts_per_frame"], seed=c["seed"])
+    sysm = trp.dense_systems_from_reference_pieces(pvo, d, c["plane_tol"], c["dist_thr"], c["huber"], c["weight"])
+    print("  dense systems:", sysm[:, 28].astype(int).tolist(), "accepted queries per frame")
+    np.savez_compressed(os.path.join(OUT, "ref_dense.npz"), systems=sysm)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar(); golden_ref_builders(); golden_ref_velodyne(); golden_ref_joint()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar(); golden_ref_builders(); golden_ref_velodyne(); golden_ref_joint(); golden_ref_dense()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -48,6 +48,10 @@ class FakeCtx:
                 for x, y in sorted(set(zip(on.tolist(), orf.tolist()))): ma.append(x); mb.append(y)
                 pa.append(i); pb.append(nb); off.append(len(ma))
         return pvo.line_tracks(pa, pb, off, ma, mb, min_len, True)
+    def dense_set_target(self, t): self.dt = t
+    def dense_set_sources(self, s, off): self.ds, self.doff = s, off
+    def dense_params(self, tol, thr, k, typ, normalize, huber, weight): return (tol, thr, k, huber, weight)
+    def dense_evaluate(self, poses, prm): return pvo.dense_icp_eval(self.dt, self.ds, self.doff, poses, prm[0], prm[1], prm[2], prm[3], prm[4], 1)[0]
     def transform_cloud(self, c, R, t): return pvo.transform_cloud(R, t, c)
     def pixel_line_neighbors(self, rows, cols, lines, cloud, T): return pvo.pixel_line_neighbors(rows, cols, lines, cloud, T)
     def undistort_clouds(self, cloud, off, T_wl, T_we, has=None):
@@ -63,6 +67,6 @@ def test_gpu_fixture_tests_dry_run(monkeypatch):
     monkeypatch.setattr(panovlm_b200, "LineFrame", FakeLF)
     ctx = FakeCtx()
     names = [n for n in dir(z) if n.startswith("test_") and n != "test_ceres_bridge_serves_the_device_rows_through_the_ceres_surface"]   # that one needs the real library
-    assert len(names) == 8
+    assert len(names) == 9
     for name in names:
         getattr(z, name)(ctx)

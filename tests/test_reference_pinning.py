@@ -868,55 +868,46 @@ def test_calibration_problem_equals_the_reference_optimize(oracle):
         assert np.array_equal(live["residual"], g["cal_residual"])
 
 
-def test_dense_icp_evaluation_equals_the_reference_pieces(oracle):
-    """BASELINE.json configs[4] / the bench and smoke() path: the oracle's dense ICP evaluation (association + plane fit + Point2Plane_Meter + Huber + per-frame 6x6
-    reduce) rebuilt from the REFERENCE'S OWN pieces - Transform2LidarWorld, AssociatePoint2Plane and Point2Plane_Meter::Create(...)->Evaluate() (oracle/_ref) - with Ceres'
-    corrector for HuberLoss applied here.  Runs only where oracle/_ref is present (this container); the kernels are checked against this oracle function on the GPU."""
-    if oracle.ref_assoc_lib() is None or oracle.ref_path_lib() is None:
-        pytest.skip("oracle/_ref is not built here")
-    from panovlm_b200 import synth
-    d = synth.make_dense_sweep(n_target=20000, n_frames=3, pts_per_frame=1500, seed=11)
-    tol, thr, hub, w = 0.05, 1.0, 0.2, 0.7
-    sys_o, _, n_o = oracle.dense_icp_eval(d["target"], d["src_local"], d["src_off"], d["poses_lw_init"], tol, thr, 10, hub, w, 1)
+DENSE_CASE = dict(n_target=20000, n_frames=3, pts_per_frame=1500, seed=11, plane_tol=0.05, dist_thr=1.0, huber=0.2, weight=0.7)
+
+
+def dense_systems_from_reference_pieces(oracle, d, tol, thr, hub, w):
+    """Per-frame [H upper (21) | g (6) | cost | count] of the dense ICP evaluation built from the reference's own Transform2LidarWorld, AssociatePoint2Plane and
+    Point2Plane_Meter::Create(...)->Evaluate(), with Ceres' corrector for HuberLoss written out (rho' = a / |r| beyond a; rho'' < 0 => plain sqrt(rho') scaling)."""
     tgt = oracle.RefFrame(np.eye(3), np.zeros(3), surf_less_flat_world=d["target"])
-    total = 0
-    for f in range(3):
+    out = np.zeros((len(d["src_off"]) - 1, 29))
+    for f in range(len(out)):
         src = d["src_local"][d["src_off"][f]:d["src_off"][f + 1]]
         p = d["poses_lw_init"][f]
         R_wl = oracle.aa_to_R(p[:3]).T
         fr = oracle.RefFrame(R_wl, -R_wl @ p[3:], surf_flat_world=src, local=True)
         pt, pl = oracle.ref_associate_point2plane(tgt, fr, tol, thr)
         m = len(pt)
-        total += m
         raw = np.zeros((m, 16)); raw[:, :3] = pt; raw[:, 3:7] = pl; raw[:, 7] = w
         prm = np.zeros((m, 12)); prm[:, 6:] = p
         r, J, _ = oracle.ref_eval_functors(np.zeros(m, np.int32), 0, raw, prm)
-        s = r * r
-        out = s > hub * hub                                             # ceres::HuberLoss + Corrector: rho' = a / |r| beyond a, rho'' < 0 => plain sqrt(rho') scaling
-        scale = np.where(out, np.sqrt(hub / np.maximum(np.abs(r), 1e-300)), 1.0)
-        cost = np.where(out, 2 * hub * np.abs(r) - hub * hub, s).sum() * 0.5
+        s_ = r * r
+        outl = s_ > hub * hub
+        scale = np.where(outl, np.sqrt(hub / np.maximum(np.abs(r), 1e-300)), 1.0)
+        cost = np.where(outl, 2 * hub * np.abs(r) - hub * hub, s_).sum() * 0.5
         Jc, rc = J[:, 6:] * scale[:, None], r * scale
         H, g = Jc.T @ Jc, Jc.T @ rc
-        exp = np.concatenate([H[np.triu_indices(6)], g, [cost, m]])
-        assert sys_o[f, 28] == m and m > 500
-        assert np.abs(sys_o[f] - exp).max() < 1e-9 * np.abs(exp).max(), f
-    assert total == n_o
+        out[f] = np.concatenate([H[np.triu_indices(6)], g, [cost, m]])
+    return out
 
 
-def test_pixel_space_candidates_equal_the_reference_first_stage(oracle):
-    """A5, first stage: the candidate lists the reference's own pixel-space Associate() hands to its RANSAC fit (recorded by the SACSegmentation stand-in) == the oracle's
-    pixel_line_neighbors + the product's host pvb_pixel_line_candidates: same lines get a list, same LiDAR points in the same order (duplicates included)."""
-    from panovlm_b200 import Context
-    g = np.load(os.path.join(G, "ref_camlidar.npz"))
-    A, rows, cols, T, lines = camlidar_case()
-    cloud = A["cloud"][::4]
-    line3, _, _ = oracle.pixel_line_neighbors(rows, cols, lines, cloud, T)
-    off, idx = Context.pixel_line_candidates(len(lines), line3, 6)
-    cam = oracle.transform_cloud(T[:3, :3], T[:3, 3], cloud)[:, :3]
-    got = [cam[idx[off[l]:off[l + 1]]] for l in range(len(lines)) if off[l + 1] > off[l]]
-    exp = [g["px_xyz"][g["px_off"][k]:g["px_off"][k + 1]] for k in range(len(g["px_off"]) - 1)]
-    assert len(got) == len(exp) >= 10 and sum(len(x) for x in exp) > 300
-    assert all(np.array_equal(a, b) for a, b in zip(got, exp))
-    if oracle.ref_camlidar_lib() is not None:
-        live = oracle.ref_pixel_associate_candidates(rows, cols, lines, cloud, T)
-        assert len(live) == len(exp) and all(np.array_equal(a, b) for a, b in zip(live, exp))
+def test_dense_icp_evaluation_equals_the_reference_pieces(oracle):
+    """BASELINE.json configs[4] / the bench and smoke() path: the oracle's dense ICP evaluation (association + plane fit + Point2Plane_Meter + Huber + per-frame 6x6
+    reduce) against per-frame systems rebuilt from the REFERENCE'S OWN pieces (dense_systems_from_reference_pieces; committed as tests/golden/ref_dense.npz, rebuilt live when
+    oracle/_ref is present).  The kernels read the same fixture in tests/test_zz_gpu_reference_fixtures.py."""
+    from panovlm_b200 import synth
+    c = DENSE_CASE
+    d = synth.make_dense_sweep(n_target=c["n_target"], n_frames=c["n_frames"], pts_per_frame=c["pts_per_frame"], seed=c["seed"])
+    g = np.load(os.path.join(G, "ref_dense.npz"))
+    sys_o, _, n_o = oracle.dense_icp_eval(d["target"], d["src_local"], d["src_off"], d["poses_lw_init"], c["plane_tol"], c["dist_thr"], 10, c["huber"], c["weight"], 1)
+    exp = g["systems"]
+    assert np.array_equal(sys_o[:, 28], exp[:, 28]) and n_o == exp[:, 28].sum() and np.all(exp[:, 28] > 500)
+    assert np.abs(sys_o - exp).max() < 1e-9 * np.abs(exp).max()
+    if oracle.ref_assoc_lib() is not None and oracle.ref_path_lib() is not None:
+        live = dense_systems_from_reference_pieces(oracle, d, c["plane_tol"], c["dist_thr"], c["huber"], c["weight"])
+        assert np.array_equal(live, exp)

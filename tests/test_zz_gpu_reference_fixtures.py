@@ -143,6 +143,23 @@ def test_pixel_knn_kernel_equals_the_reference_first_stage(gpu_ctx):
     assert len(got) == len(exp) >= 10 and all(np.array_equal(a, b) for a, b in zip(got, exp))
 
 
+def test_dense_kernel_equals_the_systems_built_from_the_reference_pieces(gpu_ctx):
+    """k_associate<10, reduce> in dense mode (the bench / smoke path, configs[4]) against per-frame normal equations rebuilt from the reference's OWN Transform2LidarWorld,
+    AssociatePoint2Plane and Point2Plane_Meter (tests/golden/ref_dense.npz): identical association counts, systems / gradients / costs to 1e-8 (smoke()'s gate)."""
+    import panovlm_b200
+    from panovlm_b200 import synth
+    from test_reference_pinning import DENSE_CASE as c
+    g = np.load(os.path.join(G, "ref_dense.npz"))
+    d = synth.make_dense_sweep(n_target=c["n_target"], n_frames=c["n_frames"], pts_per_frame=c["pts_per_frame"], seed=c["seed"])
+    gpu_ctx.dense_set_target(d["target"])
+    gpu_ctx.dense_set_sources(d["src_local"], d["src_off"])
+    prm = gpu_ctx.dense_params(c["plane_tol"], c["dist_thr"], 10, panovlm_b200.P2PLANE_METER, 1, c["huber"], c["weight"])
+    s_gpu = gpu_ctx.dense_evaluate(d["poses_lw_init"], prm)
+    exp = g["systems"]
+    assert np.array_equal(s_gpu[:, 28], exp[:, 28])
+    assert np.abs(s_gpu - exp).max() < 1e-8 * np.abs(exp).max()
+
+
 def test_ceres_bridge_serves_the_device_rows_through_the_ceres_surface(gpu_ctx, oracle):
     """(b) boundary: include/panovlm_b200_ceres_adapter.hpp driven the way Ceres drives it (tests/adapter_harness.cpp): AddBlocks registers one SizedCostFunction per
     block on the callers' pose lists with loss == nullptr, PrepareForEvaluation launches ONE device evaluation, every CostFunction::Evaluate then returns the row the
