@@ -911,3 +911,22 @@ def test_dense_icp_evaluation_equals_the_reference_pieces(oracle):
     if oracle.ref_assoc_lib() is not None and oracle.ref_path_lib() is not None:
         live = dense_systems_from_reference_pieces(oracle, d, c["plane_tol"], c["dist_thr"], c["huber"], c["weight"])
         assert np.array_equal(live, exp)
+
+
+def test_pixel_space_candidates_equal_the_reference_first_stage(oracle):
+    """A5, first stage: the candidate lists the reference's own pixel-space Associate() hands to its RANSAC fit (recorded by the SACSegmentation stand-in) == the oracle's
+    pixel_line_neighbors + the product's host pvb_pixel_line_candidates: same lines get a list, same LiDAR points in the same order (duplicates included)."""
+    from panovlm_b200 import Context
+    g = np.load(os.path.join(G, "ref_camlidar.npz"))
+    A, rows, cols, T, lines = camlidar_case()
+    cloud = A["cloud"][::4]
+    line3, _, _ = oracle.pixel_line_neighbors(rows, cols, lines, cloud, T)
+    off, idx = Context.pixel_line_candidates(len(lines), line3, 6)
+    cam = oracle.transform_cloud(T[:3, :3], T[:3, 3], cloud)[:, :3]
+    got = [cam[idx[off[l]:off[l + 1]]] for l in range(len(lines)) if off[l + 1] > off[l]]
+    exp = [g["px_xyz"][g["px_off"][k]:g["px_off"][k + 1]] for k in range(len(g["px_off"]) - 1)]
+    assert len(got) == len(exp) >= 10 and sum(len(x) for x in exp) > 300
+    assert all(np.array_equal(a, b) for a, b in zip(got, exp))
+    if oracle.ref_camlidar_lib() is not None:
+        live = oracle.ref_pixel_associate_candidates(rows, cols, lines, cloud, T)
+        assert len(live) == len(exp) and all(np.array_equal(a, b) for a, b in zip(live, exp))
