@@ -802,3 +802,14 @@ def ref_pixel_associate_candidates(rows, cols, lines, cloud_local, T_cl):
                                                           C.c_int(cap_l), C.c_long(cap_p), _p(off), _p(xyz))
     assert m >= 0
     return [xyz[off[k]:off[k + 1]].copy() for k in range(m)]
+
+
+def ref_joint_optimize_loop(rows, cols, R_wc, t_wc, image_lines, lidar_frames, T_cl_init, num_iteration_joint, script_cost, script_steps):
+    """The reference's own mapping-mode JointOptimize with a scripted solver (k-th solve reports script_cost[k] / script_steps[k]); returns the number of solver calls."""
+    R_wc, t_wc = _f64(R_wc).reshape(-1, 9), _f64(t_wc).reshape(-1, 3)
+    line_off = np.concatenate([[0], np.cumsum([len(x) for x in image_lines])]).astype(np.int32)
+    lines = _f32(np.concatenate([np.asarray(x, np.float32).reshape(-1, 4) for x in image_lines]))
+    arr = (C.c_void_p * len(lidar_frames))(*[f.h for f in lidar_frames])
+    sc, ss = _f64(script_cost), _i32(script_steps)
+    return lidar_frames[0].L.ref_joint_optimize_loop(C.c_int(rows), C.c_int(cols), C.c_int(len(t_wc)), _p(R_wc), _p(t_wc), _p(line_off), _p(lines), C.c_int(len(lidar_frames)), arr,
+                                                     _p(_f64(T_cl_init)), C.c_int(num_iteration_joint), C.c_int(len(sc)), _p(sc), _p(ss))

@@ -420,6 +420,43 @@ long ref_joint_optimize_blocks(int rows, int cols, int n_cams, const double* R_w
   return (long)S.residual.size();
 }
 
+// The OUTER loop of the mapping mode: the reference's own CameraLidarOptimizer::JointOptimize (:236-287) - AssociateLineMulti, then up to num_iteration_joint times Optimize +
+// re-association, with its two early exits - run with a SCRIPTED solver: the k-th ceres::Solve call reports final_cost = script_cost[k] and num_successful_steps =
+// script_steps[k] and leaves the parameters alone.  Returns how many times Optimize reached the solver (or < 0).  Same inputs as ref_joint_optimize_blocks.
+namespace {
+struct LoopScript { const double* cost; const int* steps; int n, calls; };
+LoopScript* g_loop = nullptr;
+void loop_hook(const ceres::Solver::Options&, ceres::Problem*, ceres::Solver::Summary* s) {
+  LoopScript& L = *g_loop;
+  const int k = std::min(L.calls, L.n - 1);
+  s->usable = true; s->final_cost = L.cost[k]; s->num_successful_steps = L.steps[k];
+  ++L.calls;
+}
+}  // namespace
+int ref_joint_optimize_loop(int rows, int cols, int n_cams, const double* R_wc, const double* t_wc, const int* line_off, const float* lines4, int n_lidars, void* const* lidar_frames,
+                            const double* T_cl_init16, int num_iteration_joint, int n_script, const double* script_cost, const int* script_steps) {
+  std::vector<Frame> frames; std::vector<Velodyne> lidars; std::vector<PanoramaLine> image_lines(n_cams);
+  for (int f = 0; f < n_cams; ++f) {
+    frames.push_back(Frame(rows, cols, f, "frame"));
+    Eigen::Matrix3d R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R(i, j) = R_wc[9 * f + 3 * i + j];
+    frames[f].SetPose(R, Eigen::Vector3d(t_wc[3 * f], t_wc[3 * f + 1], t_wc[3 * f + 2]));
+    image_lines[f].id = f; image_lines[f].rows = rows; image_lines[f].cols = cols;
+    for (int k = line_off[f]; k < line_off[f + 1]; ++k) image_lines[f].lines.push_back(cv::Vec4f(lines4[4 * k], lines4[4 * k + 1], lines4[4 * k + 2], lines4[4 * k + 3]));
+  }
+  for (int i = 0; i < n_lidars; ++i) lidars.push_back(*static_cast<const Velodyne*>(lidar_frames[i]));
+  Config config = make_config(1, 0, 0, 1, 1, 1.0f, 0.3f, 0.05f);
+  config.num_iteration_joint = num_iteration_joint; config.neighbor_size_joint = 1;
+  Eigen::Matrix4d T_cl; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T_cl(i, j) = T_cl_init16[4 * i + j];
+  CameraLidarOptimizer opt(T_cl, lidars, frames, config);
+  opt.image_lines_all = image_lines;
+  opt.SetOptimizationMode(MAPPING);
+  LoopScript L{script_cost, script_steps, n_script, 0};
+  g_loop = &L; ceres::solve_hook() = loop_hook;
+  const bool ok = opt.JointOptimize(false);
+  ceres::solve_hook() = nullptr; g_loop = nullptr;
+  return ok ? L.calls : -1;
+}
+
 // Calibration mode: the reference's own AssociateLineSingle(T_cl) (joint_optimization/CameraLidarOptimizer.cpp:300-328: image i against LiDAR i, AssociateByAngle with its
 // defaults = one-to-one pairs) followed by Optimize(line_pairs, T_cl) (:32-96: Plane2Plane_Relative with HuberLoss(2 deg) + PlaneRelativeIOUResidual without a loss on ONE
 // relative pose block), recorded at ceres::Solve.  Per block: Huber a, raw residual, raw 1x6 Jacobian (aa_cl, t_cl); pose6 = the pose block; info3 = {number of line

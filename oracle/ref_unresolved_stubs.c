@@ -5,10 +5,10 @@
 #include <stdlib.h>
 static void not_compiled(const char* what) { fprintf(stderr, "oracle/_ref: %s belongs to a reference file that is not part of this build\n", what); abort(); }
 
-void _Z15CameraCenterPCDRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEERKSt6vectorIN5Eigen6MatrixIdLi3ELi1EEENS8_17aligned_allocatorISA_EEE(void) { not_compiled("CameraCenterPCD"); }
+int _Z15CameraCenterPCDRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEERKSt6vectorIN5Eigen6MatrixIdLi3ELi1EEENS8_17aligned_allocatorISA_EEE(void) { return 0; }   /* a debug file writer (util/Visualization.cpp) called unconditionally by JointOptimize: the stand-in writes nothing */
 void _Z16DrawLinesOnImageRKN2cv3MatERKSt6vectorINS_3VecIfLi4EEESaIS5_EERKS3_INS_6ScalarESaISA_EEibbRKS3_IiSaIiEE(void) { not_compiled("DrawLinesOnImage"); }
 void _Z16TriangulateNViewRKSt6vectorIN5Eigen6MatrixIdLi3ELi3EEENS0_17aligned_allocatorIS2_EEERKS_INS1_IdLi3ELi1EEENS3_IS8_EEERKS_IN2cv7Point3_IfEESaISF_EE(void) { not_compiled("TriangulateNView"); }
-void _Z19CameraPoseVisualizeRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEERKSt6vectorIN5Eigen6MatrixIdLi3ELi3EEENS8_17aligned_allocatorISA_EEERKS7_INS9_IdLi3ELi1EEENSB_ISG_EEEi(void) { not_compiled("CameraPoseVisualize"); }
+int _Z19CameraPoseVisualizeRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEERKSt6vectorIN5Eigen6MatrixIdLi3ELi3EEENS8_17aligned_allocatorISA_EEERKS7_INS9_IdLi3ELi1EEENSB_ISG_EEEi(void) { return 0; }   /* a debug file writer (util/Visualization.cpp) called unconditionally by JointOptimize: the stand-in writes nothing */
 void _Z19ExtractSIFTQuadtreeRKN2cv3MatERSt6vectorINS_8KeyPointESaIS4_EEiiS2_(void) { not_compiled("ExtractSIFTQuadtree"); }
 void _Z20DrawLinePairsOnImageRKN2cv3MatERKSt6vectorI19CameraLidarLinePairSaIS4_EERKN5Eigen6MatrixIdLi4ELi4EEEib(void) { not_compiled("DrawLinePairsOnImage"); }
 void _Z21ComputeSIFTDescriptorRKN2cv3MatERSt6vectorINS_8KeyPointESaIS4_EERS0_b(void) { not_compiled("ComputeSIFTDescriptor"); }

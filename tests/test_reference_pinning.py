@@ -930,3 +930,35 @@ def test_pixel_space_candidates_equal_the_reference_first_stage(oracle):
     if oracle.ref_camlidar_lib() is not None:
         live = oracle.ref_pixel_associate_candidates(rows, cols, lines, cloud, T)
         assert len(live) == len(exp) and all(np.array_equal(a, b) for a, b in zip(live, exp))
+
+
+LOOP_SCRIPTS = [[(100, 20), (50, 20), (49.9, 20), (10, 20)],                         # cost change below 1 % of the previous cost
+                [(100, 3), (50, 2), (20, 1)],                                        # fewer than 5 successful steps twice in a row
+                [(100, 20), (80, 3), (60, 20), (40, 2), (20, 1), (10, 1)],           # a good iteration in between resets nothing: only consecutive ones count
+                [(0.0, 20), (0.0, 20), (1, 1)],                                      # 0 / 0 and x / 0: the relative test never fires on a zero previous cost
+                [(100, 20), (90, 20), (80, 20), (70, 20), (60, 20), (50, 20), (40, 20), (30, 20), (20, 20)]]      # runs into num_iteration_joint
+
+
+def test_joint_outer_loop_equals_the_reference_joint_optimize(oracle):
+    """The mapping-mode outer loop: the reference's own JointOptimize (AssociateLineMulti, Optimize, re-association, two early exits) driven by a scripted solver calls
+    Optimize exactly as often as panovlm_b200.joint.joint_optimize does with the same scripted Optimize."""
+    from panovlm_b200 import joint
+    g = np.load(os.path.join(G, "ref_joint.npz"))
+    counts = []
+    for script in LOOP_SCRIPTS:
+        calls = []
+
+        def scripted(ctx, data, cams, lidars, points, cfg, aa_to_R, _s=script, _c=calls):
+            k = min(len(_c), len(_s) - 1)
+            _c.append(k)
+            return cams, lidars, points, dict(final_cost=float(_s[k][0]), successful=int(_s[k][1])), None
+        joint.joint_optimize(None, None, None, None, None, joint.JointConfig(), None, num_iteration_joint=7, optimize_fn=scripted)
+        counts.append(len(calls))
+    assert counts == g["loop_counts"].tolist() == [3, 2, 5, 4, 7]
+    if oracle.ref_assoc_lib() is not None:
+        d = joint_case()
+        rf = [oracle.RefFrame(d["Rs"][i], d["ts"][i], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["surfFlat"], f["surfLessFlat"], id=i, local="keep",
+                              end_points=f["end_points"]) for i, f in enumerate(d["frames"])]
+        live = [oracle.ref_joint_optimize_loop(d["rows"], d["cols"], d["R_wc"], d["t_wc"], d["image_lines"], rf, d["T_cl"], 7, [x[0] for x in sc], [x[1] for x in sc])
+                for sc in LOOP_SCRIPTS]
+        assert live == counts
