@@ -1,6 +1,7 @@
 // ORACLE/_ref — TEST INFRASTRUCTURE ONLY.  C entry points around the REFERENCE'S OWN base/Math.h (FastAtan2, Square), compiled from the file where it
 // lies under /root/reference (never copied into this repository): the one source file of the hot path that needs nothing but the standard library.
-// Everything else on the path pulls in Eigen / Ceres / PCL / OpenCV / Boost headers and cannot be built here.
+// Everything else on the path pulls in Eigen / Ceres / PCL / OpenCV / Boost headers: those files are compiled against the stand-ins of oracle/shim (ref_path_wrap.cpp,
+// ref_assoc_wrap.cpp, ref_camlidar_wrap.cpp).
 // Built by `make -C oracle ref` into oracle/_ref/libpvo_ref.so with the reference's own flags (CMakeLists.txt:4-13: -std=gnu++14 -fopenmp, Release =
 // -O3 -DNDEBUG, no -march: plain x86-64, so no FMA contraction).  Used to pin the oracle's restatement of FastAtan2 bit for bit
 // (tests/test_oracle_pinning.py) and to generate tests/golden/ref_fast_atan2.npz (tests/make_golden.py).
