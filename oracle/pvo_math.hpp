@@ -7,14 +7,15 @@
 // jet.h / loss_function.h, Eigen 3.4 QR + eigen solver, PCL 1.10 + FLANN) is restated from the
 // libraries' documented behaviour.
 //
-// PARITY STATUS: *unpinned by the reference's own tests* — the reference ships no unit tests, golden
-// vectors or KATs for this path and cannot be compiled here (Eigen/Ceres/PCL
-// absent).  Two pieces of the reference's own source DO run here (oracle/_ref, `make -C oracle ref`): base/Math.h as it is (FastAtan2: bit for bit,
-// tests/golden/ref_fast_atan2.npz) and base/CostFunction.h + base/Geometry.hpp + sensors/Equirectangular.{h,cpp} compiled with the stand-in Eigen / Ceres /
-// OpenCV types of oracle/shim (functor residuals and Jacobians, projection, BreakToSegments: bit-identical to this restatement; FormPlane / FormLine: same
-// decisions; tests/test_reference_pinning.py, tests/golden/ref_functors.npz, ref_geometry.npz).  Everything else is pinned against independent implementations (scipy Rotation,
-// torch float64 autograd, numpy lstsq/eigh, scipy cKDTree, central finite differences) in
-// tests/test_oracle_*.py and the committed fixtures under tests/golden/.
+// PARITY STATUS: *unpinned by the reference's own tests* - the reference ships no unit tests, golden vectors or KATs for this path and cannot be
+// built as a whole here (Eigen / Ceres / PCL / OpenCV / Boost absent).  What DOES run here is the reference's own SOURCE (oracle/_ref, `make -C oracle ref`): base/Math.h
+// as it is, and 14 translation units (CostFunction.h / Geometry.hpp / Equirectangular, Velodyne.cpp, LidarFeatureAssociate.cpp, LidarLineMatch.cpp, Tracks.cpp,
+// Optimization.cpp, LidarOdometry.cpp, CameraLidarLineAssociate.cpp, CameraLidarOptimizer.cpp, FileIO.cpp, Frame.cpp ...) compiled where they lie against the stand-in
+// container / solver types of oracle/shim.  This restatement is bit-identical to it for FastAtan2, all functors (residuals and Jacobians), the projection, BreakToSegments,
+// Transform2LidarWorld and UndistortCloud, and returns the same correspondences, tracks, pairs and residual-block lists in the same order
+// (tests/test_reference_pinning.py, tests/golden/ref_*.npz).  Not pinned anywhere: the arithmetic INSIDE Eigen, Ceres and FLANN and the Ceres solver,
+// which are restated from documentation; those parts are checked against independent implementations (scipy Rotation, torch float64 autograd, numpy lstsq / eigh, scipy
+// cKDTree, central finite differences) in tests/test_oracle_*.py and the other fixtures under tests/golden/.
 #pragma once
 #include <algorithm>
 #include <cfloat>
