@@ -813,3 +813,15 @@ def ref_joint_optimize_loop(rows, cols, R_wc, t_wc, image_lines, lidar_frames, T
     sc, ss = _f64(script_cost), _i32(script_steps)
     return lidar_frames[0].L.ref_joint_optimize_loop(C.c_int(rows), C.c_int(cols), C.c_int(len(t_wc)), _p(R_wc), _p(t_wc), _p(line_off), _p(lines), C.c_int(len(lidar_frames)), arr,
                                                      _p(_f64(T_cl_init)), C.c_int(num_iteration_joint), C.c_int(len(sc)), _p(sc), _p(ss))
+
+
+def ref_calibration_loop(rows, cols, image_lines, lidar_frames, T_cl, deltas6):
+    """The reference's own calibration-mode JointOptimize with a scripted solver (the k-th solve adds deltas6[k] to (aa_cl, t_cl)); returns (solver calls, T_cl result)."""
+    n = len(lidar_frames)
+    line_off = np.concatenate([[0], np.cumsum([len(x) for x in image_lines])]).astype(np.int32)
+    lines = _f32(np.concatenate([np.asarray(x, np.float32).reshape(-1, 4) for x in image_lines]))
+    arr = (C.c_void_p * n)(*[f.h for f in lidar_frames])
+    d6 = _f64(deltas6).reshape(-1, 6)
+    T_out = np.zeros((4, 4))
+    m = lidar_frames[0].L.ref_calibration_loop(C.c_int(rows), C.c_int(cols), C.c_int(n), _p(line_off), _p(lines), arr, _p(_f64(T_cl)), C.c_int(len(d6)), _p(d6), _p(T_out))
+    return m, T_out

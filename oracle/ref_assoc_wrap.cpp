@@ -505,6 +505,41 @@ long ref_calibration_blocks(int rows, int cols, int n, const int* line_off, cons
   return (long)S.residual.size();
 }
 
+// The OUTER loop of the calibration mode: the reference's own JointOptimize (:195-233: AssociateLineSingle, up to 35 x [Optimize(line_pairs, T_cl), rotation / translation
+// change, re-association], exit when the rotation changed by < 0.1 deg AND the translation by < 0.01) with a SCRIPTED solver: the k-th ceres::Solve adds delta6[k] to the
+// relative pose block (aa_cl, t_cl); after the script ends it adds nothing.  Returns the number of solver calls; T_out16 = GetResult().
+namespace {
+struct CalibScript { const double* delta6; int n, calls; };
+CalibScript* g_cscript = nullptr;
+void calib_loop_hook(const ceres::Solver::Options&, ceres::Problem* p, ceres::Solver::Summary* s) {
+  CalibScript& C = *g_cscript;
+  if (C.calls < C.n && !p->blocks.empty()) for (int k = 0; k < 3; ++k) { p->blocks[0].params[0][k] += C.delta6[6 * C.calls + k]; p->blocks[0].params[1][k] += C.delta6[6 * C.calls + 3 + k]; }
+  ++C.calls; s->usable = true;
+}
+}  // namespace
+int ref_calibration_loop(int rows, int cols, int n, const int* line_off, const float* lines4, void* const* lidar_frames, const double* T_cl16, int n_script, const double* delta6,
+                         double* T_out16) {
+  std::vector<Frame> frames; std::vector<Velodyne> lidars; std::vector<PanoramaLine> image_lines(n);
+  for (int f = 0; f < n; ++f) {
+    frames.push_back(Frame(rows, cols, f, "frame"));
+    image_lines[f].id = f; image_lines[f].rows = rows; image_lines[f].cols = cols;
+    for (int k = line_off[f]; k < line_off[f + 1]; ++k) image_lines[f].lines.push_back(cv::Vec4f(lines4[4 * k], lines4[4 * k + 1], lines4[4 * k + 2], lines4[4 * k + 3]));
+    lidars.push_back(*static_cast<const Velodyne*>(lidar_frames[f]));
+  }
+  Config config; config.num_threads = 1;
+  Eigen::Matrix4d T_cl; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T_cl(i, j) = T_cl16[4 * i + j];
+  CameraLidarOptimizer opt(T_cl, lidars, frames, config);
+  opt.image_lines_all = image_lines;
+  opt.SetOptimizationMode(CALIBRATION);
+  CalibScript C{delta6, n_script, 0};
+  g_cscript = &C; ceres::solve_hook() = calib_loop_hook;
+  const bool ok = opt.JointOptimize(false);
+  ceres::solve_hook() = nullptr; g_cscript = nullptr;
+  const Eigen::Matrix4d T = opt.GetResult();
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T_out16[4 * i + j] = T(i, j);
+  return ok ? C.calls : -1;
+}
+
 // CameraLidarOptimizer::NeighborEachFrame (joint_optimization/CameraLidarOptimizer.cpp:551-607) and LidarMaskByTrack (:609-642), called on an optimizer object
 // built from n_frames camera poses and the LiDAR frames.  CSR outputs.
 int ref_neighbor_each_frame(int n_frames, const double* R_wc, const double* t_wc, const unsigned char* frame_pose_valid, int n_lidars, const double* R_wl, const double* t_wl,

@@ -127,16 +127,21 @@ def optimize(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa_to_R
     return new_poses[:n], new_poses[n:], new_points, summary, (v, const, pt_const)
 
 
-def calibrate(ctx: Context, frames, image_lines, rows, cols, T_cl_init, aa_to_R, R_to_aa, max_iterations=35):
+def calibrate(ctx: Context, frames, image_lines, rows, cols, T_cl_init, aa_to_R, R_to_aa, max_iterations=35, associate_fn=None, solve_fn=None):
     """Calibration mode of CameraLidarOptimizer::JointOptimize (CameraLidarOptimizer.cpp:195-233): one relative pose T_cl for all (image i, LiDAR i)
     pairs.  Per iteration: AssociateLineSingle at the current T_cl (:301-317, AssociateByAngle with its defaults: one-to-one pairs), the residual blocks of
     Optimize(line_pairs, T_cl) (:32-64) on the single pose block, LM with max_num_iterations = 50 (:68), stop when the rotation changed by less than
-    0.1 deg and the translation by less than 0.01 (:229)."""
+    0.1 deg and the translation by less than 0.01 (:229).
+    associate_fn(T_cl) -> per frame (image line ids, LiDAR line ids, start, end, score) and solve_fn(blocks, pose) -> (new pose, summary) replace the device association
+    and the device LM (used by the CPU test that runs this loop next to the reference's own JointOptimize with a scripted solver)."""
     T = np.array(T_cl_init, dtype=np.float64)
-    lfs = [LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], np.eye(3), np.zeros(3)) for f in frames]
+    if associate_fn is None:
+        lfs = [LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], np.eye(3), np.zeros(3)) for f in frames]
 
-    def associate(T_cl):
-        return [ctx.camera_lidar_associate(rows, cols, image_lines[i], lfs[i], T_cl, True, False) for i in range(len(frames))]
+        def associate(T_cl):
+            return [ctx.camera_lidar_associate(rows, cols, image_lines[i], lfs[i], T_cl, True, False) for i in range(len(frames))]
+    else:
+        associate = associate_fn
 
     pairs = associate(T)
     log = []
@@ -146,9 +151,12 @@ def calibrate(ctx: Context, frames, image_lines, rows, cols, T_cl_init, aa_to_R,
             if len(il):
                 Context.build_calibration_blocks(bl, rows, cols, image_lines[i][il], s, e, 0)
         v = bl.view()
-        ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], 1)
         pose = np.concatenate([R_to_aa(T[:3, :3]), T[:3, 3]])[None, :]
-        new_pose, summary = ctx.blocks_solve_lm(pose, None, 50)
+        if solve_fn is None:
+            ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], 1)
+            new_pose, summary = ctx.blocks_solve_lm(pose, None, 50)
+        else:
+            new_pose, summary = solve_fn(v, pose)
         T_new = np.eye(4)
         T_new[:3, :3] = aa_to_R(new_pose[0, :3])
         T_new[:3, 3] = new_pose[0, 3:]

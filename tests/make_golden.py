@@ -444,6 +444,10 @@ def golden_ref_joint():
     c = pvo.ref_calibration_blocks(d["rows"], d["cols"], d["image_lines"], rf, T)
     out.update({f"cal_{k}": v for k, v in c.items()})
     print(f"  calibration: {len(c['residual'])} blocks from {c['info'][0]} line pairs, options {c['info'][1:].tolist()}")
+    rf3 = rf[:3]                                                                          # calibration-mode JointOptimize with a scripted solver
+    res = [pvo.ref_calibration_loop(d["rows"], d["cols"], d["image_lines"][:3], rf3, T, sc) for sc in trp.CALIB_SCRIPTS]
+    out["cal_loop_calls"] = np.array([r_[0] for r_ in res], np.int32); out["cal_loop_T"] = np.stack([r_[1] for r_ in res])
+    print("  calibration loop solver calls per script:", out["cal_loop_calls"].tolist())
     rf2 = [pvo.RefFrame(d["Rs"][i], d["ts"][i], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["surfFlat"], f["surfLessFlat"], id=i, local="keep",
                         end_points=f["end_points"]) for i, f in enumerate(d["frames"])]
     out["loop_counts"] = np.array([pvo.ref_joint_optimize_loop(d["rows"], d["cols"], d["R_wc"], d["t_wc"], d["image_lines"], rf2, d["T_cl"], 7, [x[0] for x in sc],

@@ -962,3 +962,39 @@ def test_joint_outer_loop_equals_the_reference_joint_optimize(oracle):
         live = [oracle.ref_joint_optimize_loop(d["rows"], d["cols"], d["R_wc"], d["t_wc"], d["image_lines"], rf, d["T_cl"], 7, [x[0] for x in sc], [x[1] for x in sc])
                 for sc in LOOP_SCRIPTS]
         assert live == counts
+
+
+CALIB_SCRIPTS = [np.zeros((0, 6)),                                                                        # nothing moves: one iteration
+                 np.array([[0.01, 0, 0, 0.02, 0, 0], [0.004, 0, 0, 0, 0.02, 0], [1e-5, 0, 0, 1e-4, 0, 0]]),  # two real updates, then below both thresholds
+                 np.array([[1e-4, 0, 0, 0.02, 0, 0], [1e-4, 0, 0, 0.005, 0, 0]]),                          # rotation already small, translation decides
+                 np.array([[0.002, 0, 0, 0, 0, 0]] * 4 + [[0.0015, 0, 0, 0, 0, 0]])]                       # 0.115 deg steps stay above 0.1 deg, 0.086 deg ends it
+
+
+def test_calibration_outer_loop_equals_the_reference_joint_optimize(oracle):
+    """Calibration mode, outer loop: the reference's own JointOptimize (AssociateLineSingle, Optimize(line_pairs, T_cl), float32 rotation / translation change, exit below
+    0.1 deg AND 0.01) with a scripted solver (the k-th solve adds a scripted delta to the pose block) against panovlm_b200.joint.calibrate running the same script:
+    same number of iterations, same final T_cl."""
+    from panovlm_b200 import joint
+    g = np.load(os.path.join(G, "ref_joint.npz"))
+    d = joint_case()
+    frames = d["frames"][:3]
+    T0 = d["T_cl"].copy(); T0[:3, 3] += [0.02, -0.01, 0.015]
+
+    def associate(T_cl):
+        return [oracle.associate_by_angle(d["rows"], d["cols"], d["image_lines"][i], f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], np.diff(f["seg_off"]), f["end_points"], T_cl,
+                                          True, False) for i, f in enumerate(frames)]
+    for si, script in enumerate(CALIB_SCRIPTS):
+        calls = []
+
+        def solve(blocks, pose, _s=script, _c=calls):
+            k = len(_c); _c.append(k)
+            return pose + (_s[k][None, :] if k < len(_s) else 0.0), dict(final_cost=0.0, successful=0)
+        T, log = joint.calibrate(None, frames, d["image_lines"], d["rows"], d["cols"], T0, oracle.aa_to_R, oracle.R_to_aa, associate_fn=associate, solve_fn=solve)
+        assert len(log) == int(g["cal_loop_calls"][si]), (si, len(log))
+        assert np.abs(T - g["cal_loop_T"][si]).max() < 1e-12, si
+    assert g["cal_loop_calls"].tolist() == [1, 3, 2, 5]
+    if oracle.ref_assoc_lib() is not None:
+        rf = [oracle.RefFrame(np.eye(3), np.zeros(3), f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], id=i, local="keep", end_points=f["end_points"])
+              for i, f in enumerate(frames)]
+        m, To = oracle.ref_calibration_loop(d["rows"], d["cols"], d["image_lines"][:3], rf, T0, CALIB_SCRIPTS[1])
+        assert m == 3 and np.array_equal(To, g["cal_loop_T"][1])
