@@ -289,6 +289,15 @@ int pvb_pixel_line_neighbors(pvb_ctx* ctx, int rows, int cols, const float* line
 /* `line_lidar` (:83-97) as CSR: per image line the LiDAR points that chose it (ascending, with multiplicity), emptied below min_points (6).
  * Returns the number of entries.  Host only.                                                                                                */
 int pvb_pixel_line_candidates(int n_lines, int n_points, const int* line3, int min_points, int cap, int* line_off, int* lidar_idx);
+/* FitLineRANSAC (:717-752) + the end-point tail of the pixel-space Associate (:117-137) for ONE candidate list (camera-frame points, `stride` floats per
+ * point, x y z first).  PARITY UNPINNED for the sample-consensus part: the reference calls pcl::SACSegmentation (a system dependency that is neither in the
+ * reference tree nor installed here); this restates PCL 1.10's RANSAC over SACMODEL_LINE (boost mt19937 seeded 12345, uniform_int(0, INT_MAX), index shuffle
+ * sampling, adaptive iteration count) with the reference's settings: dist_threshold 0.1, PCL defaults max_iterations 50, probability 0.99.  The reference's
+ * own code after it is restated as written: float32 centroid / covariance of the inliers, direction = eigenvector of the largest eigenvalue (pcl::eigen33),
+ * farthest inlier pair (whose POSITIONS in the inlier list index the candidate list, :136-137), ProjectPoint2Line3D in double.
+ * Returns the number of inliers; fewer than 3 = no line (the reference's `false`; outputs untouched).  inliers: ascending, at most `cap`.  Host only.        */
+int pvb_pixel_fit_line(const float* xyz, int n, int stride, double dist_threshold, int max_iterations, double probability, float* coeff6, int cap, int* inliers,
+                       double* start3, double* end3);
 /* CameraLidarLineAssociate::Filter (:628-715) alone, on pairs whose LiDAR end points are in the CAMERA frame: the angle branch (great-circle
  * planes within 5 deg, LiDAR ends inside the image line's arc, both ends within 0.4 of the image plane at radius 5; angle[i] = plane angle in
  * degrees, :652) and the projected-length branch (100 .. 2000 px).  keep[i] = 1 when the pair survives.  Host only.                          */

@@ -124,7 +124,7 @@ EXPORTS = [
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
     "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges", "pvb_filter_line_pairs", "pvb_frames_point2plane_blocks", "pvb_neighbor_each_frame", "pvb_lidar_mask_by_track", "pvb_build_calibration_blocks",
-    "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates",
+    "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates", "pvb_pixel_fit_line",
 ]
 
 
@@ -496,6 +496,44 @@ class Context:
         if m < 0:
             raise PvbError(f"pvb_pixel_line_candidates: code {m}")
         return off, idx[:m].copy()
+
+    @staticmethod
+    def pixel_fit_line(xyz, dist_threshold=0.1, max_iterations=50, probability=0.99):
+        """FitLineRANSAC + end points for one candidate list (CameraLidarLineAssociate.cpp:105-144, 717-752; the RANSAC restates PCL 1.10, parity unpinned).
+        Returns None when fewer than 3 inliers, else (coeff6 float32, inlier indices, start, end)."""
+        a = _arr(xyz, np.float32)
+        a = a.reshape(-1, a.shape[-1] if a.ndim == 2 else 3)
+        coeff, inl, s_, e_ = np.zeros(6, np.float32), np.zeros(max(1, len(a)), np.int32), np.zeros(3), np.zeros(3)
+        m = load_library().pvb_pixel_fit_line(_p(a), C.c_int(len(a)), C.c_int(a.shape[1]), C.c_double(dist_threshold), C.c_int(max_iterations), C.c_double(probability),
+                                              _p(coeff), C.c_int(len(inl)), _p(inl), _p(s_), _p(e_))
+        if m < 0:
+            raise PvbError(f"pvb_pixel_fit_line: code {m}")
+        return None if m < 3 else (coeff, inl[:m].copy(), s_, e_)
+
+    def pixel_associate(self, rows, cols, lines, cloud_local, T_cl):
+        """CameraLidarLineAssociate::Associate(lines, cloud, T_cl) (CameraLidarLineAssociate.cpp:22-188), the fallback for frames without LiDAR segments: projected LiDAR
+        points -> 3 nearest image sub-lines (device) -> per image line the candidate points (>= 6) -> line fit (pixel_fit_line; its RANSAC is parity-unpinned) ->
+        Filter(true, true) -> end points back in the LiDAR frame.  Returns (image line ids, start (n,3), end (n,3), angle float32) in ascending image line order."""
+        lines = _arr(lines, np.float32).reshape(-1, 4)
+        T = _arr(T_cl, np.float64).reshape(4, 4)
+        cloud = _arr(cloud_local, np.float32).reshape(-1, 4)
+        line3, _, _ = self.pixel_line_neighbors(rows, cols, lines, cloud, T)
+        off, idx = Context.pixel_line_candidates(len(lines), line3, 6)
+        cam = self.transform_cloud(cloud, T[:3, :3], T[:3, 3])                       # pcl::transformPointCloud(point_cloud, cloud, T_cl) (:26)
+        ids, s_, e_ = [], [], []
+        for li in range(len(lines)):
+            if off[li + 1] > off[li]:
+                fit = Context.pixel_fit_line(cam[idx[off[li]:off[li + 1]]])
+                if fit is not None:
+                    ids.append(li); s_.append(fit[2]); e_.append(fit[3])
+        ids, s_, e_ = np.array(ids, np.int32), np.array(s_, np.float64).reshape(-1, 3), np.array(e_, np.float64).reshape(-1, 3)
+        keep, ang = Context.filter_line_pairs(rows, cols, lines[ids], s_, e_, True, True)
+        T_lc = np.linalg.inv(T)                                                       # :182-187
+
+        def back(p):                                                                  # (T_lc * p.homogeneous()).hnormalized()
+            h = np.c_[p, np.ones(len(p))] @ T_lc.T
+            return h[:, :3] / h[:, 3:]
+        return ids[keep], back(s_[keep]), back(e_[keep]), ang[keep]
 
     def joint_solve_lm(self, poses, points, pose_param_const=None, point_const=None, max_iterations=20):
         poses, points = _arr(poses, np.float64).copy().reshape(-1, 6), _arr(points, np.float64).copy().reshape(-1, 3)

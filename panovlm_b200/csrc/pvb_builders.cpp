@@ -700,6 +700,183 @@ int pvb_pixel_line_candidates(int n_lines, int n_points, const int* line3, int m
   return line_off[n_lines];
 }
 
+// ---- FitLineRANSAC + the end-point tail of the pixel-space Associate (joint_optimization/CameraLidarLineAssociate.cpp:105-144, 717-752) ------------
+// PARITY UNPINNED for the sample-consensus part: the reference calls pcl::SACSegmentation (SACMODEL_LINE, SAC_RANSAC, threshold 0.1, PCL's defaults
+// max_iterations = 50, probability = 0.99, random = false); PCL is a system dependency (libpcl-dev of the reference's Dockerfile, not in /root/reference, not
+// installed here), so what follows restates PCL 1.10's published algorithm (sample_consensus/ransac.hpp, sac_model.h, sac_model_line.hpp, common/centroid.hpp,
+// common/eigen.hpp) without an answer to compare with.  Everything of the reference's OWN code around it (:117-137) is restated as written.
+namespace {
+// boost::mt19937 seeded with 12345 + boost::uniform_int<>(0, INT_MAX): the bucket method divides the 32-bit output by 2 (SampleConsensusModel::rnd())
+struct Mt19937 {
+  uint32_t mt[624]; int at;
+  explicit Mt19937(uint32_t seed) { mt[0] = seed; for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i; at = 624; }
+  uint32_t next() {
+    if (at >= 624) {
+      for (int i = 0; i < 624; ++i) {
+        const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      at = 0;
+    }
+    uint32_t y = mt[at++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+  }
+};
+
+// squared float32 distance of point p to the line (a, unit d): |(a - p) x d|^2 (Vector4f::cross3, sac_model_line.hpp countWithinDistance / selectWithinDistance)
+inline float line_sqdist_f32(const float* a, const float* d, const float* p) {
+  const float vx = a[0] - p[0], vy = a[1] - p[1], vz = a[2] - p[2];
+  const float cx = vy * d[2] - vz * d[1], cy = vz * d[0] - vx * d[2], cz = vx * d[1] - vy * d[0];
+  return cx * cx + cy * cy + cz * cz;
+}
+inline void normalize3_f32(float* v) {                                   // Eigen: if (squaredNorm > 0) v /= sqrt(squaredNorm)
+  const float z = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  if (z > 0.f) { const float n = std::sqrt(z); v[0] /= n; v[1] /= n; v[2] /= n; }
+}
+
+// pcl::computeRoots2 / computeRoots / eigen33(mat, evals) / computeCorrespondingEigenVector in float32 (common/impl/eigen.hpp)
+void roots2_f32(float b, float c, float* r) {
+  r[0] = 0.f;
+  float d = b * b - 4.0f * c;
+  if (d < 0.f) d = 0.f;
+  const float sd = std::sqrt(d);
+  r[2] = 0.5f * (b + sd); r[1] = 0.5f * (b - sd);
+}
+void roots3_f32(const float m[3][3], float* r) {
+  const float c0 = m[0][0] * m[1][1] * m[2][2] + 2.f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] - m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+  const float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] - m[1][2] * m[1][2];
+  const float c2 = m[0][0] + m[1][1] + m[2][2];
+  if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) { roots2_f32(c2, c1, r); return; }
+  const float inv3 = 1.0f / 3.0f, sqrt3 = std::sqrt(3.0f);
+  const float c2_3 = c2 * inv3;
+  float a_3 = (c1 - c2 * c2_3) * inv3;
+  if (a_3 > 0.f) a_3 = 0.f;
+  const float half_b = 0.5f * (c0 + c2_3 * (2.f * c2_3 * c2_3 - c1));
+  float q = half_b * half_b + a_3 * a_3 * a_3;
+  if (q > 0.f) q = 0.f;
+  const float rho = std::sqrt(-a_3), theta = std::atan2(std::sqrt(-q), half_b) * inv3, ct = std::cos(theta), st = std::sin(theta);
+  r[0] = c2_3 + 2.f * rho * ct;
+  r[1] = c2_3 - rho * (ct + sqrt3 * st);
+  r[2] = c2_3 - rho * (ct - sqrt3 * st);
+  if (r[0] >= r[1]) std::swap(r[0], r[1]);
+  if (r[1] >= r[2]) { std::swap(r[1], r[2]); if (r[0] >= r[1]) std::swap(r[0], r[1]); }
+  if (r[0] <= 0.f) roots2_f32(c2, c1, r);
+}
+inline float max_abs33(const float m[3][3]) { float s = 0.f; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s = std::max(s, std::fabs(m[i][j])); return s; }
+void largest_eigenvector_f32(const float cov[3][3], float* vec) {
+  float scale = max_abs33(cov);
+  if (scale <= std::numeric_limits<float>::min()) scale = 1.f;
+  float sm[3][3], ev[3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sm[i][j] = cov[i][j] / scale;
+  roots3_f32(sm, ev);
+  const float lambda = ev[2] * scale;                                   // eigen33(mat, evals): evals *= scale
+  // computeCorrespondingEigenVector(mat, lambda): its own scaling, (mat / scale - lambda / scale * I), largest of the three row cross products
+  for (int i = 0; i < 3; ++i) sm[i][i] -= lambda / scale;
+  float c[3][3];
+  const int pr[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+  float len[3];
+  for (int k = 0; k < 3; ++k) {
+    const float* a = sm[pr[k][0]]; const float* b = sm[pr[k][1]];
+    c[k][0] = a[1] * b[2] - a[2] * b[1]; c[k][1] = a[2] * b[0] - a[0] * b[2]; c[k][2] = a[0] * b[1] - a[1] * b[0];
+    len[k] = c[k][0] * c[k][0] + c[k][1] * c[k][1] + c[k][2] * c[k][2];
+  }
+  const int best = (len[0] >= len[1] && len[0] >= len[2]) ? 0 : ((len[1] >= len[0] && len[1] >= len[2]) ? 1 : 2);
+  const float n = std::sqrt(len[best]);
+  for (int j = 0; j < 3; ++j) vec[j] = c[best][j] / n;
+}
+}  // namespace
+
+int pvb_pixel_fit_line(const float* xyz, int n, int stride, double dist_threshold, int max_iterations, double probability, float* coeff6, int cap, int* inliers,
+                       double* start3, double* end3) {
+  if (n < 0 || stride < 3 || (n > 0 && !xyz) || !coeff6 || (cap > 0 && !inliers) || !start3 || !end3 || max_iterations < 0 || !(probability > 0.0 && probability < 1.0))
+    return PVB_ERR_ARG;
+  auto P = [&](int i) { return xyz + (size_t)i * stride; };
+  if (n < 2) return 0;                                                   // getSamples: fewer points than the sample size -> no model
+  // --- RandomSampleConsensus::computeModel over SampleConsensusModelLine
+  Mt19937 gen(12345u);
+  std::vector<int> shuffled(n);
+  for (int i = 0; i < n; ++i) shuffled[i] = i;
+  const double sqr_thr = dist_threshold * dist_threshold, log_p = std::log(1.0 - probability), one_over_n = 1.0 / (double)n;
+  const double eps = std::numeric_limits<double>::epsilon();
+  int iterations = 0, best = -std::numeric_limits<int>::max();
+  unsigned skipped = 0; const unsigned max_skip = (unsigned)max_iterations * 10u;
+  double k = std::numeric_limits<double>::max();
+  float best_model[6]; bool have = false;
+  while ((double)iterations < k && skipped < max_skip) {
+    int s0 = -1, s1 = -1;
+    for (int check = 0; check < 1000; ++check) {                         // getSamples: drawIndexSample until isSampleGood (max_sample_checks_)
+      for (int i = 0; i < 2; ++i) std::swap(shuffled[i], shuffled[i + (int)((gen.next() >> 1) % (uint32_t)(n - i))]);
+      const float* a = P(shuffled[0]); const float* b = P(shuffled[1]);
+      if (a[0] != b[0] || a[1] != b[1] || a[2] != b[2]) { s0 = shuffled[0]; s1 = shuffled[1]; break; }
+    }
+    if (s0 < 0) break;                                                   // "No samples could be selected"
+    const float* a = P(s0); const float* b = P(s1);
+    const float fe = std::numeric_limits<float>::epsilon();
+    if (std::fabs(a[0] - b[0]) <= fe && std::fabs(a[1] - b[1]) <= fe && std::fabs(a[2] - b[2]) <= fe) { ++skipped; continue; }
+    float model[6] = {a[0], a[1], a[2], b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    normalize3_f32(model + 3);
+    float dir[3] = {model[3], model[4], model[5]};
+    normalize3_f32(dir);                                                 // countWithinDistance normalises the direction once more
+    int count = 0;
+    for (int i = 0; i < n; ++i) if ((double)line_sqdist_f32(model, dir, P(i)) < sqr_thr) ++count;
+    if (count > best) {
+      best = count; have = true;
+      std::memcpy(best_model, model, sizeof model);
+      const double w = (double)best * one_over_n;
+      double p_no_outliers = 1.0 - w * w;                                // pow(w, sample size = 2)
+      p_no_outliers = std::max(eps, p_no_outliers);
+      p_no_outliers = std::min(1.0 - eps, p_no_outliers);
+      k = log_p / std::log(p_no_outliers);
+    }
+    ++iterations;
+    if (iterations > max_iterations) break;
+  }
+  if (!have) return 0;
+  std::vector<int> in;
+  {
+    float dir[3] = {best_model[3], best_model[4], best_model[5]};
+    normalize3_f32(dir);
+    for (int i = 0; i < n; ++i) if ((double)line_sqdist_f32(best_model, dir, P(i)) < sqr_thr) in.push_back(i);
+  }
+  const int m = (int)in.size();
+  if (m < 3) return m;                                                   // FitLineRANSAC :729 -> false
+  if (m > cap) return PVB_ERR_NOMEM;
+  // --- FitLineRANSAC :731-749: centroid + (unnormalised) covariance of the inliers in float32, direction = eigenvector of the largest eigenvalue
+  float cen[3] = {0.f, 0.f, 0.f};
+  for (int i : in) { cen[0] += P(i)[0]; cen[1] += P(i)[1]; cen[2] += P(i)[2]; }
+  for (int j = 0; j < 3; ++j) cen[j] /= (float)m;
+  float cov[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  for (int i : in) {
+    float px = P(i)[0] - cen[0]; float py = P(i)[1] - cen[1]; float pz = P(i)[2] - cen[2];
+    cov[1][1] += py * py; cov[1][2] += py * pz; cov[2][2] += pz * pz;
+    py *= px; pz *= px; px *= px;
+    cov[0][0] += px; cov[0][1] += py; cov[0][2] += pz;
+  }
+  cov[1][0] = cov[0][1]; cov[2][0] = cov[0][2]; cov[2][1] = cov[1][2];
+  for (int j = 0; j < 3; ++j) coeff6[j] = cen[j];
+  largest_eigenvector_f32(cov, coeff6 + 3);
+  for (int i = 0; i < m; ++i) inliers[i] = in[i];
+  // --- Associate :117-137: the two inliers farthest apart (float32 squared distance, first maximum) ... whose POSITIONS in the inlier list are then used as
+  // indices into the candidate cloud (`line_points[start]`, not `line_points[inliers[start]]`) - reproduced as written
+  int start = 0, end = 0; float max_d = -1.f;
+  for (int i = 0; i < m; ++i)
+    for (int j = i + 1; j < m; ++j) {
+      const float* a = P(in[i]); const float* b = P(in[j]);
+      const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+      const float d = dx * dx + dy * dy + dz * dz;
+      if (d > max_d) { max_d = d; start = i; end = j; }
+    }
+  const double x0 = coeff6[0], y0 = coeff6[1], z0 = coeff6[2], nx = coeff6[3], ny = coeff6[4], nz = coeff6[5];     // ProjectPoint2Line3D<double>, base/Geometry.hpp:151-161
+  const int ends[2] = {start, end}; double* out[2] = {start3, end3};
+  for (int e = 0; e < 2; ++e) {
+    const float* p = P(ends[e]);
+    const double kk = (nx * ((double)p[0] - x0) + ny * ((double)p[1] - y0) + nz * ((double)p[2] - z0)) / (nx * nx + ny * ny + nz * nz);
+    out[e][0] = kk * nx + x0; out[e][1] = kk * ny + y0; out[e][2] = kk * nz + z0;
+  }
+  return m;
+}
+
 // ---- pose interpolation around the sweep undistortion (base/Geometry.hpp:572-583, lidar_mapping/LidarOdometry.cpp:203-243) -------------
 namespace {
 // 4x4 inverse by Gauss-Jordan elimination with partial pivoting (the reference calls Eigen's general Matrix4d::inverse())

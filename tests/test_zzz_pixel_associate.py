@@ -1,0 +1,57 @@
+"""Context.pixel_associate = CameraLidarLineAssociate::Associate(lines, cloud, T_cl) (CameraLidarLineAssociate.cpp:22-188) end to end.  The first stage is pinned
+against the reference's own code (tests/test_zz_gpu_reference_fixtures.py::test_pixel_knn_kernel_equals_the_reference_first_stage); the line fit's RANSAC restates
+PCL and is parity-unpinned (tests/test_pixel_fit_line.py).  Here: the composition (CPU, the oracle standing in for the two device calls) and the same call on the
+device (named to run after every other GPU test: first run on a B200 = the round-end run)."""
+import numpy as np
+import pytest
+
+from panovlm_b200 import Context
+from test_reference_pinning import camlidar_case
+
+
+class _OracleBackedCtx(Context):
+    def __init__(self, pvo):                                                         # no device: the two device calls go to the oracle
+        self._pvo = pvo
+
+    def pixel_line_neighbors(self, rows, cols, lines, cloud, T):
+        return self._pvo.pixel_line_neighbors(rows, cols, lines, cloud, T)
+
+    def transform_cloud(self, c, R, t):
+        return self._pvo.transform_cloud(R, t, c)
+
+    def __del__(self):
+        pass
+
+
+def _case():
+    A, rows, cols, T, lines = camlidar_case()
+    return rows, cols, lines, A["cloud"][::4], T
+
+
+def _check(out, rows, cols, lines, cloud, T):
+    ids, s, e, ang = out
+    assert len(ids) >= 3 and np.all(np.diff(ids) > 0) and s.shape == e.shape == (len(ids), 3) and ang.dtype == np.float32
+    assert np.all(ang < 5.0)                                                          # Filter: great-circle planes within 5 degrees (:652-655)
+    # both ends lie on a line through the LiDAR cloud: some cloud point within the RANSAC threshold (0.1 m) + slack of each end's neighbourhood
+    d_s = np.linalg.norm(cloud[None, :, :3] - s[:, None, :], axis=2).min(1)
+    d_e = np.linalg.norm(cloud[None, :, :3] - e[:, None, :], axis=2).min(1)
+    assert d_s.max() < 1.0 and d_e.max() < 1.0
+    assert np.all(np.linalg.norm(s - e, axis=1) > 0.1)
+
+
+def test_pixel_associate_composition_on_the_oracle(oracle):
+    rows, cols, lines, cloud, T = _case()
+    ctx = _OracleBackedCtx(oracle)
+    out = ctx.pixel_associate(rows, cols, lines, cloud, T)
+    _check(out, rows, cols, lines, cloud, T)
+    again = ctx.pixel_associate(rows, cols, lines, cloud, T)
+    assert all(np.array_equal(a, b) for a, b in zip(out, again))
+
+
+@pytest.mark.gpu
+def test_pixel_associate_on_the_device_equals_the_oracle_backed_composition(gpu_ctx, oracle):
+    rows, cols, lines, cloud, T = _case()
+    got = gpu_ctx.pixel_associate(rows, cols, lines, cloud, T)
+    exp = _OracleBackedCtx(oracle).pixel_associate(rows, cols, lines, cloud, T)
+    assert all(np.array_equal(a, b) for a, b in zip(got, exp))                        # first stage and transform are bit-exact, the rest is the same host code
+    _check(got, rows, cols, lines, cloud, T)
