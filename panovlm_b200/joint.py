@@ -67,6 +67,10 @@ def associate_lines(ctx: Context, frames, image_lines, cams, lidars, rows, cols,
         for li in neighbors[i]:
             f = frames[li]
             T_cl = T_cw @ np.linalg.inv(_T_from_block(lidars[li], aa_to_R))
+            if len(f["segment_coeffs"]) == 0:                            # no LiDAR segments: the pixel-space Associate(lines, cornerLessSharp, T_cl) (:366-367)
+                il, s, e, ang = ctx.pixel_associate(rows, cols, image_lines[i], f["cornerLessSharp"], T_cl)
+                pairs[(i, li)] = (il, np.full(len(il), -1, np.int32), s, e, ang)
+                continue
             lf = LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], np.eye(3), np.zeros(3))
             il, ll, s, e, ang = ctx.camera_lidar_associate(rows, cols, image_lines[i], lf, T_cl, True, True, None if image_masks is None else image_masks[i],
                                                            None if lidar_masks is None else lidar_masks[li])

@@ -55,3 +55,17 @@ def test_pixel_associate_on_the_device_equals_the_oracle_backed_composition(gpu_
     exp = _OracleBackedCtx(oracle).pixel_associate(rows, cols, lines, cloud, T)
     assert all(np.array_equal(a, b) for a, b in zip(got, exp))                        # first stage and transform are bit-exact, the rest is the same host code
     _check(got, rows, cols, lines, cloud, T)
+
+
+def test_associate_lines_takes_the_pixel_path_for_frames_without_segments(oracle):
+    """AssociateLineMulti (CameraLidarOptimizer.cpp:360-367): a LiDAR frame whose edge_segmented is empty goes through Associate(lines, cornerLessSharp, T_cl)."""
+    from panovlm_b200 import joint
+    A, rows, cols, T, lines = camlidar_case()
+    frame = dict(cornerLessSharp=A["cloud"][::4], p2s_off=np.zeros(1, np.int32), p2s_ids=np.zeros(0, np.int32), segment_coeffs=np.zeros((0, 6)), end_points=np.zeros((0, 6)))
+    cam = np.concatenate([oracle.R_to_aa(T[:3, :3]), T[:3, 3]])[None, :]
+    ctx = _OracleBackedCtx(oracle)
+    pairs = joint.associate_lines(ctx, [frame], [lines], cam, np.zeros((1, 6)), rows, cols, oracle.aa_to_R)
+    il, ll, s, e, ang = pairs[(0, 0)]
+    exp = ctx.pixel_associate(rows, cols, lines, frame["cornerLessSharp"], T)
+    assert np.array_equal(il, exp[0]) and np.all(ll == -1) and len(il) >= 3
+    assert np.abs(s - exp[1]).max() < 1e-9 and np.abs(e - exp[2]).max() < 1e-9          # T_cl rebuilt from the angle-axis block
