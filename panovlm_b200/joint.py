@@ -140,10 +140,18 @@ def calibrate(ctx: Context, frames, image_lines, rows, cols, T_cl_init, aa_to_R,
     and the device LM (used by the CPU test that runs this loop next to the reference's own JointOptimize with a scripted solver)."""
     T = np.array(T_cl_init, dtype=np.float64)
     if associate_fn is None:
-        lfs = [LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], np.eye(3), np.zeros(3)) for f in frames]
+        lfs = [LineFrame(f["cornerLessSharp"], f["p2s_off"], f["p2s_ids"], f["segment_coeffs"], f["end_points"], np.eye(3), np.zeros(3)) if len(f["segment_coeffs"]) else None
+               for f in frames]
 
-        def associate(T_cl):
-            return [ctx.camera_lidar_associate(rows, cols, image_lines[i], lfs[i], T_cl, True, False) for i in range(len(frames))]
+        def associate(T_cl):                                                   # AssociateLineSingle (:301-317); frames without LiDAR segments take the pixel-space Associate (:313-314)
+            out = []
+            for i, f in enumerate(frames):
+                if len(f["segment_coeffs"]) == 0:
+                    il, s, e, ang = ctx.pixel_associate(rows, cols, image_lines[i], f["cornerLessSharp"], T_cl)
+                    out.append((il, np.full(len(il), -1, np.int32), s, e, ang))
+                else:
+                    out.append(ctx.camera_lidar_associate(rows, cols, image_lines[i], lfs[i], T_cl, True, False))
+            return out
     else:
         associate = associate_fn
 
