@@ -7,8 +7,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace pcl {
@@ -112,11 +114,13 @@ template <typename P, typename M> inline void transformPointCloud(const PointClo
   out = tmp;
 }
 // pcl::SACSegmentation (RANSAC line fit behind CameraLidarLineAssociate::FitLineRANSAC, the fallback for frames without LiDAR segments): NOT reproduced -
-// its sample sequence depends on PCL's internal random generator.  segment() reports no inliers, so FitLineRANSAC returns false.
+// its sample sequence depends on PCL's internal random generator.  segment() reports no inliers (FitLineRANSAC returns false) unless a harness scripts them.
 enum { SACMODEL_LINE = 1, SAC_RANSAC = 0 };
 // A test harness may ask the stand-in to RECORD the clouds it is handed (the candidate points of every image line = the result of the first, deterministic
 // stage of CameraLidarLineAssociate::Associate): sac_recorder() points at a vector of (x, y, z) lists, or is null.
 inline std::vector<std::vector<float>>*& sac_recorder() { static std::vector<std::vector<float>>* r = nullptr; return r; }
+// sac_script(): (inlier lists in call order, next call) or null - see SACSegmentation::segment
+inline std::pair<std::vector<std::vector<int>>, size_t>*& sac_script() { static std::pair<std::vector<std::vector<int>>, size_t>* r = nullptr; return r; }
 template <typename P> class SACSegmentation {
  public:
   void setOptimizeCoefficients(bool) {} void setModelType(int) {} void setMethodType(int) {} void setDistanceThreshold(double) {}
@@ -125,12 +129,83 @@ template <typename P> class SACSegmentation {
     std::vector<float> xyz; for (const P& p : c->points) { xyz.push_back(p.x); xyz.push_back(p.y); xyz.push_back(p.z); }
     sac_recorder()->push_back(xyz);
   }
-  void segment(PointIndices& inliers, ModelCoefficients&) { inliers.indices.clear(); }
+  // Scripted mode (sac_script() set by a harness): the k-th call reports the k-th scripted inlier list and a 6-value coefficient vector (the caller overwrites
+  // it), so that the REFERENCE'S OWN code after the RANSAC runs (FitLineRANSAC :729-751, Associate :117-187).  Otherwise: no inliers.
+  void segment(PointIndices& inliers, ModelCoefficients& coeff) {
+    inliers.indices.clear();
+    if (!sac_script()) return;
+    size_t& k = sac_script()->second;
+    if (k < sac_script()->first.size()) inliers.indices = sac_script()->first[k];
+    ++k;
+    coeff.values.assign(6, 0.f);
+  }
 };
-template <typename P, typename V> inline unsigned compute3DCentroid(const PointCloud<P>&, const PointIndices&, V&) { return 0; }
-template <typename P, typename V, typename M> inline unsigned computeCovarianceMatrix(const PointCloud<P>&, const PointIndices&, const V&, M&) { return 0; }
-template <typename M, typename V> inline void eigen33(const M&, V&) {}
-template <typename M, typename S, typename V> inline void computeCorrespondingEigenVector(const M&, const S&, V&) {}
+// stand-ins for pcl/common/centroid.hpp and pcl/common/eigen.hpp (PCL 1.10's published float32 algorithms restated; only operator[] / operator()(i, j) of the
+// vector / matrix types are used).  They serve the scripted mode above; PCL itself is not available here.
+template <typename P, typename V> inline unsigned compute3DCentroid(const PointCloud<P>& cloud, const PointIndices& ind, V& c) {
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int i : ind.indices) { sx += cloud.points[i].x; sy += cloud.points[i].y; sz += cloud.points[i].z; }
+  const float n = static_cast<float>(ind.indices.size());
+  c[0] = sx / n; c[1] = sy / n; c[2] = sz / n; c[3] = 1.f;
+  return static_cast<unsigned>(ind.indices.size());
+}
+template <typename P, typename V, typename M> inline unsigned computeCovarianceMatrix(const PointCloud<P>& cloud, const PointIndices& ind, const V& c, M& cov) {
+  float m00 = 0.f, m01 = 0.f, m02 = 0.f, m11 = 0.f, m12 = 0.f, m22 = 0.f;
+  for (int i : ind.indices) {
+    float x = cloud.points[i].x - c[0], y = cloud.points[i].y - c[1], z = cloud.points[i].z - c[2];
+    m11 += y * y; m12 += y * z; m22 += z * z;
+    y *= x; z *= x; x *= x;
+    m00 += x; m01 += y; m02 += z;
+  }
+  cov(0, 0) = m00; cov(0, 1) = m01; cov(0, 2) = m02; cov(1, 0) = m01; cov(1, 1) = m11; cov(1, 2) = m12; cov(2, 0) = m02; cov(2, 1) = m12; cov(2, 2) = m22;
+  return static_cast<unsigned>(ind.indices.size());
+}
+namespace shim_detail {
+inline void roots2(float b, float c, float* r) { r[0] = 0.f; float d = b * b - 4.0f * c; if (d < 0.f) d = 0.f; const float sd = std::sqrt(d); r[2] = 0.5f * (b + sd); r[1] = 0.5f * (b - sd); }
+inline void roots3(const float m[3][3], float* r) {
+  const float c0 = m[0][0] * m[1][1] * m[2][2] + 2.f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] - m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+  const float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] - m[1][2] * m[1][2];
+  const float c2 = m[0][0] + m[1][1] + m[2][2];
+  if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) { roots2(c2, c1, r); return; }
+  const float inv3 = 1.0f / 3.0f, sqrt3 = std::sqrt(3.0f), c2_3 = c2 * inv3;
+  float a_3 = (c1 - c2 * c2_3) * inv3; if (a_3 > 0.f) a_3 = 0.f;
+  const float half_b = 0.5f * (c0 + c2_3 * (2.f * c2_3 * c2_3 - c1));
+  float q = half_b * half_b + a_3 * a_3 * a_3; if (q > 0.f) q = 0.f;
+  const float rho = std::sqrt(-a_3), theta = std::atan2(std::sqrt(-q), half_b) * inv3, ct = std::cos(theta), st = std::sin(theta);
+  r[0] = c2_3 + 2.f * rho * ct; r[1] = c2_3 - rho * (ct + sqrt3 * st); r[2] = c2_3 - rho * (ct - sqrt3 * st);
+  if (r[0] >= r[1]) std::swap(r[0], r[1]);
+  if (r[1] >= r[2]) { std::swap(r[1], r[2]); if (r[0] >= r[1]) std::swap(r[0], r[1]); }
+  if (r[0] <= 0.f) roots2(c2, c1, r);
+}
+template <typename M> inline float scaled(const M& mat, float sm[3][3]) {
+  float scale = 0.f;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) scale = std::max(scale, std::fabs(static_cast<float>(mat(i, j))));
+  if (scale <= std::numeric_limits<float>::min()) scale = 1.f;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sm[i][j] = static_cast<float>(mat(i, j)) / scale;
+  return scale;
+}
+}  // namespace shim_detail
+template <typename M, typename V> inline void eigen33(const M& mat, V& evals) {
+  float sm[3][3], r[3];
+  const float scale = shim_detail::scaled(mat, sm);
+  shim_detail::roots3(sm, r);
+  for (int k = 0; k < 3; ++k) evals[k] = r[k] * scale;
+}
+template <typename M, typename S, typename V> inline void computeCorrespondingEigenVector(const M& mat, const S& eigenvalue, V& vec) {
+  float sm[3][3];
+  const float scale = shim_detail::scaled(mat, sm);
+  for (int i = 0; i < 3; ++i) sm[i][i] -= static_cast<float>(eigenvalue) / scale;
+  const int pr[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+  float c[3][3], len[3];
+  for (int k = 0; k < 3; ++k) {
+    const float* a = sm[pr[k][0]]; const float* b = sm[pr[k][1]];
+    c[k][0] = a[1] * b[2] - a[2] * b[1]; c[k][1] = a[2] * b[0] - a[0] * b[2]; c[k][2] = a[0] * b[1] - a[1] * b[0];
+    len[k] = c[k][0] * c[k][0] + c[k][1] * c[k][1] + c[k][2] * c[k][2];
+  }
+  const int best = (len[0] >= len[1] && len[0] >= len[2]) ? 0 : ((len[1] >= len[0] && len[1] >= len[2]) ? 1 : 2);
+  const float n = std::sqrt(len[best]);
+  for (int j = 0; j < 3; ++j) vec[j] = c[best][j] / n;
+}
 namespace io {
 template <typename C> inline int savePCDFileASCII(const std::string&, const C&) { return 0; }   // debug dumps (visualization = true only)
 template <typename C> inline int savePCDFileBinary(const std::string&, const C&) { return 0; }

@@ -471,8 +471,39 @@ def golden_ref_dense():
     np.savez_compressed(os.path.join(OUT, "ref_dense.npz"), systems=sysm)
 
 
+def pixel_fit_script(pvo, rows, cols, lines, cloud, T):
+    """The inlier lists the product's pvb_pixel_fit_line reports for the candidate lists of the pixel-space Associate() (empty when it finds no line)."""
+    from panovlm_b200 import Context
+    line3, _, _ = pvo.pixel_line_neighbors(rows, cols, lines, cloud, T)
+    off, idx = Context.pixel_line_candidates(len(lines), line3, 6)
+    cam = pvo.transform_cloud(T[:3, :3], T[:3, 3], cloud)
+    script = []
+    for li in range(len(lines)):
+        if off[li + 1] > off[li]:
+            fit = Context.pixel_fit_line(cam[idx[off[li]:off[li + 1]]])
+            script.append(np.zeros(0, np.int32) if fit is None else fit[1])
+    return script
+
+
+def golden_ref_pixel_fit():
+    """tests/golden/ref_pixel_fit.npz: the reference's own pixel-space Associate() (CameraLidarLineAssociate.cpp:22-188) run with the RANSAC's inliers SCRIPTED to what
+    the product's pvb_pixel_fit_line reports (PCL is not available; oracle/shim's SACSegmentation replays the script) - everything after the RANSAC is the reference's code."""
+    from oracle import pvo
+    if pvo.ref_camlidar_lib() is None:
+        print("oracle/_ref not built (no /root/reference here): ref_pixel_fit.npz left as committed")
+        return
+    import test_reference_pinning as trp
+    A, rows, cols, T, lines = trp.camlidar_case()
+    cloud = A["cloud"][::4]
+    script = pixel_fit_script(pvo, rows, cols, lines, cloud, T)
+    il, s, e, ang = pvo.ref_pixel_associate_scripted(rows, cols, lines, cloud, T, script)
+    print(f"  scripted pixel-space Associate: {len(script)} candidate lists, {sum(len(x) >= 3 for x in script)} fits, {len(il)} pairs after Filter(true, true)")
+    np.savez_compressed(os.path.join(OUT, "ref_pixel_fit.npz"), inl_off=np.concatenate([[0], np.cumsum([len(x) for x in script])]).astype(np.int32),
+                        inl_idx=np.concatenate(script).astype(np.int32), image_line=il, start=s, end=e, angle=ang)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar(); golden_ref_builders(); golden_ref_velodyne(); golden_ref_joint(); golden_ref_dense()
+    golden_functors(); golden_functors_f6(); golden_rotations(); golden_assoc(); golden_atan2(); golden_reproj(); golden_ref_math(); golden_ref_path(); golden_ref_assoc(); golden_ref_camlidar(); golden_ref_builders(); golden_ref_velodyne(); golden_ref_joint(); golden_ref_dense(); golden_ref_pixel_fit()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -69,3 +69,22 @@ def test_associate_lines_takes_the_pixel_path_for_frames_without_segments(oracle
     exp = ctx.pixel_associate(rows, cols, lines, frame["cornerLessSharp"], T)
     assert np.array_equal(il, exp[0]) and np.all(ll == -1) and len(il) >= 3
     assert np.abs(s - exp[1]).max() < 1e-9 and np.abs(e - exp[2]).max() < 1e-9          # T_cl rebuilt from the angle-axis block
+
+
+def test_everything_after_the_ransac_equals_the_reference_own_code(oracle):
+    """tests/golden/ref_pixel_fit.npz = the reference's own Associate() (oracle/_ref) with the RANSAC's inliers scripted to the product's (tests/make_golden.py:
+    golden_ref_pixel_fit).  Pins what follows the RANSAC against the reference's code: the < 3 test, the refit, the farthest pair with its position-as-index quirk
+    (:136-137), ProjectPoint2Line3D, Filter(true, true), the transform back to the LiDAR frame."""
+    import os
+    from make_golden import pixel_fit_script
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pixel_fit.npz"))
+    rows, cols, lines, cloud, T = _case()
+    script = pixel_fit_script(oracle, rows, cols, lines, cloud, T)
+    assert np.array_equal(np.concatenate(script), g["inl_idx"]) and np.array_equal(np.cumsum([len(x) for x in script]), g["inl_off"][1:])     # the script is in sync
+    ids, s, e, ang = _OracleBackedCtx(oracle).pixel_associate(rows, cols, lines, cloud, T)
+    assert len(ids) == len(g["angle"]) >= 10 and np.array_equal(lines[ids], g["image_line"])
+    assert np.array_equal(ang, g["angle"])
+    assert np.abs(s - g["start"]).max() < 1e-9 and np.abs(e - g["end"]).max() < 1e-9
+    if oracle.ref_camlidar_lib() is not None:                                                # live, where oracle/_ref is built
+        il, s2, e2, a2 = oracle.ref_pixel_associate_scripted(rows, cols, lines, cloud, T, script)
+        assert np.array_equal(il, g["image_line"]) and np.array_equal(s2, g["start"]) and np.array_equal(e2, g["end"]) and np.array_equal(a2, g["angle"])
