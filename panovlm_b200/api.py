@@ -519,6 +519,8 @@ class Context:
         cloud = _arr(cloud_local, np.float32).reshape(-1, 4)
         line3, _, _ = self.pixel_line_neighbors(rows, cols, lines, cloud, T)
         off, idx = Context.pixel_line_candidates(len(lines), line3, 6)
+        if off[-1] == 0:                                                              # no image line collected 6 candidates
+            return np.zeros(0, np.int32), np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0, np.float32)
         cam = self.transform_cloud(cloud, T[:3, :3], T[:3, 3])                       # pcl::transformPointCloud(point_cloud, cloud, T_cl) (:26)
         ids, s_, e_ = [], [], []
         for li in range(len(lines)):
