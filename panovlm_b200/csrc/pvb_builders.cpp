@@ -703,8 +703,10 @@ int pvb_pixel_line_candidates(int n_lines, int n_points, const int* line3, int m
 // ---- FitLineRANSAC + the end-point tail of the pixel-space Associate (joint_optimization/CameraLidarLineAssociate.cpp:105-144, 717-752) ------------
 // PARITY UNPINNED for the sample-consensus part: the reference calls pcl::SACSegmentation (SACMODEL_LINE, SAC_RANSAC, threshold 0.1, PCL's defaults
 // max_iterations = 50, probability = 0.99, random = false); PCL is a system dependency (libpcl-dev of the reference's Dockerfile, not in /root/reference, not
-// installed here), so what follows restates PCL 1.10's published algorithm (sample_consensus/ransac.hpp, sac_model.h, sac_model_line.hpp, common/centroid.hpp,
-// common/eigen.hpp) without an answer to compare with.  Everything of the reference's OWN code around it (:117-137) is restated as written.
+// installed here), so what follows restates PCL's published sequential algorithm (sample_consensus/ransac.hpp, sac_model.h, sac_model_line.hpp, common/centroid.hpp,
+// common/eigen.hpp as of PCL 1.10 - 1.12; the Dockerfile does not pin a version) without an answer to compare with.  Version note: isSampleGood is written as an exact
+// comparison in some releases and as an epsilon comparison in others; both reject a duplicated point, and a pair closer than float epsilon in all three coordinates is
+// rejected by computeModelCoefficients below at the cost of the same two generator draws, so the sample sequence is the same.  Everything of the reference's OWN code around it (:117-137) is restated as written.
 namespace {
 // boost::mt19937 seeded with 12345 + boost::uniform_int<>(0, INT_MAX): the bucket method divides the 32-bit output by 2 (SampleConsensusModel::rnd())
 struct Mt19937 {
