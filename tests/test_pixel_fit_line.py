@@ -139,3 +139,12 @@ def test_no_line_cases():
     coeff, inl, s, e = Context.pixel_fit_line(P)
     assert np.array_equal(inl, np.arange(5)) and np.allclose(np.abs(coeff[3:]), [1, 0, 0], atol=1e-6) and np.allclose(coeff[:3], [2, 0, 0])
     assert np.allclose(s, [0, 0, 0]) and np.allclose(e, [4, 0, 0])
+
+
+def test_stride_of_a_pcl_point_gives_the_same_fit():
+    """pcl::PointXYZI is 8 floats wide (x y z 1 | intensity + padding): the INTEGRATION.md binding passes stride 8."""
+    P, _, _ = _cloud(3)
+    wide = np.zeros((len(P), 8), f32)
+    wide[:, :3], wide[:, 3], wide[:, 4] = P, 1.0, 7.0
+    a, b = Context.pixel_fit_line(P), Context.pixel_fit_line(wide)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
