@@ -298,6 +298,10 @@ int pvb_pixel_line_candidates(int n_lines, int n_points, const int* line3, int m
  * Returns the number of inliers; fewer than 3 = no line (the reference's `false`; outputs untouched).  inliers: ascending, at most `cap`.  Host only.        */
 int pvb_pixel_fit_line(const float* xyz, int n, int stride, double dist_threshold, int max_iterations, double probability, float* coeff6, int cap, int* inliers,
                        double* start3, double* end3);
+/* The fit of every candidate list of one image (the loop of Associate :88-146) on all host threads: list l = cloud_cam[lidar_idx[line_off[l] .. line_off[l+1])]
+ * (camera-frame cloud, 4 floats per point; CSR from pvb_pixel_line_candidates).  n_inliers[l] < 3 = no line for image line l; coeff6 / start3 / end3 are per line. */
+int pvb_pixel_fit_lines(const float* cloud_cam, int n_points, int n_lines, const int* line_off, const int* lidar_idx, double dist_threshold, int max_iterations,
+                        double probability, int* n_inliers, float* coeff6, double* start3, double* end3);
 /* CameraLidarLineAssociate::Filter (:628-715) alone, on pairs whose LiDAR end points are in the CAMERA frame: the angle branch (great-circle
  * planes within 5 deg, LiDAR ends inside the image line's arc, both ends within 0.4 of the image plane at radius 5; angle[i] = plane angle in
  * degrees, :652) and the projected-length branch (100 .. 2000 px).  keep[i] = 1 when the pair survives.  Host only.                          */

@@ -124,7 +124,7 @@ EXPORTS = [
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
     "pvb_reproj_solve_lm", "pvb_build_reproj_observations", "pvb_joint_solve_lm",
     "pvb_blocks_set_edge_list", "pvb_blocks_set_reduce_hook", "pvb_write_poses_text", "pvb_read_poses_text", "pvb_build_point2plane_blocks_edges", "pvb_filter_line_pairs", "pvb_frames_point2plane_blocks", "pvb_neighbor_each_frame", "pvb_lidar_mask_by_track", "pvb_build_calibration_blocks",
-    "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates", "pvb_pixel_fit_line",
+    "pvb_pixel_sub_lines", "pvb_pixel_knn3", "pvb_pixel_line_neighbors", "pvb_pixel_line_candidates", "pvb_pixel_fit_line", "pvb_pixel_fit_lines",
 ]
 
 
@@ -510,6 +510,18 @@ class Context:
             raise PvbError(f"pvb_pixel_fit_line: code {m}")
         return None if m < 3 else (coeff, inl[:m].copy(), s_, e_)
 
+    @staticmethod
+    def pixel_fit_lines(cloud_cam, line_off, lidar_idx, dist_threshold=0.1, max_iterations=50, probability=0.99):
+        """pixel_fit_line for every candidate list of one image (CSR from pixel_line_candidates) on all host threads: (inlier counts, start (L,3), end (L,3))."""
+        cam, off, idx = _arr(cloud_cam, np.float32).reshape(-1, 4), _arr(line_off, np.int32), _arr(lidar_idx, np.int32)
+        L = len(off) - 1
+        n_in, coeff, s_, e_ = np.zeros(L, np.int32), np.zeros((L, 6), np.float32), np.zeros((L, 3)), np.zeros((L, 3))
+        rc = load_library().pvb_pixel_fit_lines(_p(cam), C.c_int(len(cam)), C.c_int(L), _p(off), _p(idx), C.c_double(dist_threshold), C.c_int(max_iterations), C.c_double(probability),
+                                                _p(n_in), _p(coeff), _p(s_), _p(e_))
+        if rc < 0:
+            raise PvbError(f"pvb_pixel_fit_lines: code {rc}")
+        return n_in, s_, e_
+
     def pixel_associate(self, rows, cols, lines, cloud_local, T_cl):
         """CameraLidarLineAssociate::Associate(lines, cloud, T_cl) (CameraLidarLineAssociate.cpp:22-188), the fallback for frames without LiDAR segments: projected LiDAR
         points -> 3 nearest image sub-lines (device) -> per image line the candidate points (>= 6) -> line fit (pixel_fit_line; its RANSAC is parity-unpinned) ->
@@ -522,13 +534,9 @@ class Context:
         if off[-1] == 0:                                                              # no image line collected 6 candidates
             return np.zeros(0, np.int32), np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0, np.float32)
         cam = self.transform_cloud(cloud, T[:3, :3], T[:3, 3])                       # pcl::transformPointCloud(point_cloud, cloud, T_cl) (:26)
-        ids, s_, e_ = [], [], []
-        for li in range(len(lines)):
-            if off[li + 1] > off[li]:
-                fit = Context.pixel_fit_line(cam[idx[off[li]:off[li + 1]]])
-                if fit is not None:
-                    ids.append(li); s_.append(fit[2]); e_.append(fit[3])
-        ids, s_, e_ = np.array(ids, np.int32), np.array(s_, np.float64).reshape(-1, 3), np.array(e_, np.float64).reshape(-1, 3)
+        n_in, s_, e_ = Context.pixel_fit_lines(cam, off, idx)
+        ids = np.flatnonzero(n_in >= 3).astype(np.int32)
+        s_, e_ = s_[ids], e_[ids]
         keep, ang = Context.filter_line_pairs(rows, cols, lines[ids], s_, e_, True, True)
         T_lc = np.linalg.inv(T)                                                       # :182-187
 

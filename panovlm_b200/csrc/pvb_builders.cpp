@@ -879,6 +879,32 @@ int pvb_pixel_fit_line(const float* xyz, int n, int stride, double dist_threshol
   return m;
 }
 
+// All candidate lists of one image (the loop of Associate :88-146): list l = points cloud_cam[lidar_idx[line_off[l] .. line_off[l+1])] (pvb_pixel_line_candidates);
+// every reference call builds a fresh SACSegmentation (seed 12345), so the fits are independent and run on all host threads.  n_inliers[l] < 3: no line.
+int pvb_pixel_fit_lines(const float* cloud_cam, int n_points, int n_lines, const int* line_off, const int* lidar_idx, double dist_threshold, int max_iterations,
+                        double probability, int* n_inliers, float* coeff6, double* start3, double* end3) {
+  if (n_lines < 0 || n_points < 0 || !line_off || (n_lines > 0 && (!n_inliers || !coeff6 || !start3 || !end3)) || (n_points > 0 && !cloud_cam)) return PVB_ERR_ARG;
+  if (n_lines > 0 && line_off[n_lines] > 0 && !lidar_idx) return PVB_ERR_ARG;
+  for (int l = 0; l < n_lines; ++l) if (line_off[l + 1] < line_off[l]) return PVB_ERR_ARG;
+  for (int i = 0; i < (n_lines ? line_off[n_lines] : 0); ++i) if (lidar_idx[i] < 0 || lidar_idx[i] >= n_points) return PVB_ERR_ARG;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic)
+  for (int l = 0; l < n_lines; ++l) {
+    const int m = line_off[l + 1] - line_off[l];
+    n_inliers[l] = 0;
+    if (m == 0) continue;
+    std::vector<float> pts((size_t)m * 3);
+    for (int i = 0; i < m; ++i) std::memcpy(&pts[(size_t)i * 3], cloud_cam + (size_t)lidar_idx[line_off[l] + i] * 4, 12);
+    std::vector<int> inl(m);
+    const int rc = pvb_pixel_fit_line(pts.data(), m, 3, dist_threshold, max_iterations, probability, coeff6 + (size_t)l * 6, m, inl.data(), start3 + (size_t)l * 3, end3 + (size_t)l * 3);
+    if (rc < 0) {
+#pragma omp atomic write
+      bad = rc;
+    } else n_inliers[l] = rc;
+  }
+  return bad < 0 ? bad : PVB_OK;
+}
+
 // ---- pose interpolation around the sweep undistortion (base/Geometry.hpp:572-583, lidar_mapping/LidarOdometry.cpp:203-243) -------------
 namespace {
 // 4x4 inverse by Gauss-Jordan elimination with partial pivoting (the reference calls Eigen's general Matrix4d::inverse())
