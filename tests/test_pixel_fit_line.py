@@ -148,3 +148,23 @@ def test_stride_of_a_pcl_point_gives_the_same_fit():
     wide[:, :3], wide[:, 3], wide[:, 4] = P, 1.0, 7.0
     a, b = Context.pixel_fit_line(P), Context.pixel_fit_line(wide)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_batched_fit_equals_the_per_list_calls_and_checks_its_arguments():
+    from panovlm_b200 import PvbError
+    clouds = [_cloud(s)[0] for s in range(4)]
+    cam = np.zeros((sum(len(c) for c in clouds), 4), f32)
+    cam[:, :3] = np.concatenate(clouds)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(cam))                                                         # lists address the cloud through an index array
+    inv = np.argsort(perm)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in clouds]), [sum(len(c) for c in clouds)]]).astype(np.int32)      # last list empty
+    n_in, s, e = Context.pixel_fit_lines(cam[perm], off, inv.astype(np.int32))
+    assert n_in[-1] == 0
+    for l, c in enumerate(clouds):
+        _, inl, s1, e1 = Context.pixel_fit_line(c)
+        assert n_in[l] == len(inl) and np.array_equal(s[l], s1) and np.array_equal(e[l], e1)
+    with pytest.raises(PvbError):
+        Context.pixel_fit_lines(cam, np.array([0, 3], np.int32), np.array([0, 1, len(cam)], np.int32))                   # index out of range
+    with pytest.raises(PvbError):
+        Context.pixel_fit_lines(cam, np.array([0, 3, 2], np.int32), np.array([0, 1, 2], np.int32))                       # offsets not ascending
