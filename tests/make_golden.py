@@ -24,6 +24,8 @@ INDEPENDENT implementations, never from the oracle itself:
                  register for one RefinePose in five configurations, and AddCameraLidarResidual for one frame pair (ceres::Problem = a recorder, oracle/shim)
   ref_velodyne.npz  float32 clouds after the reference's own Transform2LidarWorld / Transform2Local and UndistortCloud (sensors/Velodyne.cpp compiled where it lies)
   ref_joint.npz  the problem of the joint stage (configs[2]) as the reference's own AssociateLineMulti + Optimize assemble it, recorded at ceres::Solve
+  ref_pixel_fit.npz  the pairs of the reference's own pixel-space Associate() run to its end with the RANSAC's inliers scripted to what pvb_pixel_fit_line reports
+                 (PCL is not available: oracle/shim's SACSegmentation replays the script; everything after the RANSAC is the reference's code)
   ref_dense.npz  per-frame 6x6 systems of a small dense ICP evaluation (the bench / smoke path) rebuilt from the reference's own association + functor code
   reproj.npz     residuals + 1x9 Jacobians of PanoramaReprojResidual_1Angle from a torch float64 autograd twin (Rodrigues closed form), and the
                  undistortion of a small sweep with scipy.spatial.transform (rotation vector scaling instead of quaternion slerp)
