@@ -88,3 +88,23 @@ def test_everything_after_the_ransac_equals_the_reference_own_code(oracle):
     if oracle.ref_camlidar_lib() is not None:                                                # live, where oracle/_ref is built
         il, s2, e2, a2 = oracle.ref_pixel_associate_scripted(rows, cols, lines, cloud, T, script)
         assert np.array_equal(il, g["image_line"]) and np.array_equal(s2, g["start"]) and np.array_equal(e2, g["end"]) and np.array_equal(a2, g["angle"])
+
+
+def test_calibration_loop_takes_the_pixel_path_for_frames_without_segments(oracle):
+    """AssociateLineSingle (CameraLidarOptimizer.cpp:309-314): with edge_segmented empty the pairs of the calibration problem come from Associate(lines, cornerLessSharp, T_cl);
+    two residual blocks per pair on the one pose block (Optimize(line_pairs, T_cl) :32-64).  The solver is scripted (no device)."""
+    from panovlm_b200 import joint
+    A, rows, cols, T, lines = camlidar_case()
+    frame = dict(cornerLessSharp=A["cloud"][::4], p2s_off=np.zeros(1, np.int32), p2s_ids=np.zeros(0, np.int32), segment_coeffs=np.zeros((0, 6)), end_points=np.zeros((0, 6)))
+    ctx = _OracleBackedCtx(oracle)
+    seen = []
+
+    def solve(v, pose):
+        seen.append(v)
+        return pose.copy(), dict(final_cost=1.0, successful=1)
+
+    T_out, log = joint.calibrate(ctx, [frame], [lines], rows, cols, T, oracle.aa_to_R, oracle.R_to_aa, max_iterations=3, solve_fn=solve)
+    n_pairs = len(ctx.pixel_associate(rows, cols, lines, frame["cornerLessSharp"], T)[0])
+    assert len(log) == 1 and log[0]["n_pairs"] == n_pairs >= 10                       # pose unchanged by the scripted solver: the loop stops after one iteration
+    assert len(seen[0]["type"]) == 2 * n_pairs and np.all(seen[0]["ref"] == 0)
+    assert np.abs(T_out - T).max() < 1e-12
