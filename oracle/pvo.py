@@ -6,6 +6,9 @@ ctypes front-end of ``oracle/libpvo_oracle.so`` (the CPU restatement of PanoVLM'
 Parity status: unpinned by the reference's own tests (it has none) — pinned against scipy / numpy /
 torch-autograd in ``tests/test_oracle_*.py`` and, for the functor / geometry / projection layers, against the reference's own
 source compiled with stand-in container types (``oracle/_ref``, ``oracle/shim``, ``tests/test_reference_pinning.py``).
+The RANSAC line fit of the pixel-space fallback (pcl::SACSegmentation) has no restatement here - PARITY UNPINNED: PCL is not available; the product's
+``pvb_pixel_fit_line`` is checked against a numpy twin in ``tests/test_pixel_fit_line.py`` and everything after the RANSAC against the reference's own code
+run with scripted inliers (``ref_pixel_associate_scripted``).
 """
 import ctypes as C
 import os
