@@ -807,6 +807,16 @@ def ref_pixel_associate_candidates(rows, cols, lines, cloud_local, T_cl):
     return [xyz[off[k]:off[k + 1]].copy() for k in range(m)]
 
 
+def ref_set_sac_script(inlier_lists):
+    """Scripts (None: clears) the RANSAC answers inside libpvo_ref_assoc.so - see oracle/ref_assoc_wrap.cpp; returns the number of calls answered by the previous script."""
+    L = ref_assoc_lib()
+    if inlier_lists is None:
+        return L.ref_set_sac_script(C.c_int(-1), None, None)
+    off = np.concatenate([[0], np.cumsum([len(x) for x in inlier_lists])]).astype(np.int32)
+    idx = _i32(np.concatenate([np.asarray(x, np.int32) for x in inlier_lists] + [np.zeros(0, np.int32)]))
+    return L.ref_set_sac_script(C.c_int(len(inlier_lists)), _p(off), _p(idx))
+
+
 def ref_pixel_associate_scripted(rows, cols, lines, cloud_local, T_cl, inlier_lists):
     """The reference's whole pixel-space Associate() with the RANSAC's inliers scripted (inlier_lists[k] = indices into the k-th candidate list, in the order of
     ref_pixel_associate_candidates).  Returns (image_line4 float32, start (n,3), end (n,3), angle float32) of the surviving pairs."""

@@ -478,6 +478,18 @@ void calib_hook(const ceres::Solver::Options& o, ceres::Problem* p, ceres::Solve
   s->usable = true;
 }
 }  // namespace
+// Scripts the answers of the pcl::SACSegmentation stand-in inside THIS library (oracle/shim/pvo_shim_pcl.hpp: the k-th segment() call reports inlier list k), so that the
+// pixel-space Associate() behind AssociateLineSingle / AssociateLineMulti (frames without LiDAR segments) runs to its end.  n_lists < 0 clears the script; returns the
+// number of segment() calls answered since the script was set.
+int ref_set_sac_script(int n_lists, const int* off, const int* idx) {
+  static std::pair<std::vector<std::vector<int>>, size_t> script;
+  const int answered = (int)script.second;
+  script.first.clear(); script.second = 0;
+  if (n_lists < 0) { pcl::sac_script() = nullptr; return answered; }
+  for (int k = 0; k < n_lists; ++k) script.first.push_back(std::vector<int>(idx + off[k], idx + off[k + 1]));
+  pcl::sac_script() = &script;
+  return answered;
+}
 long ref_calibration_blocks(int rows, int cols, int n, const int* line_off, const float* lines4, void* const* lidar_frames, const double* T_cl16, long cap, double* huber_a,
                             double* residual, double* jac6, double* pose6, int* info3) {
   std::vector<Frame> frames; std::vector<Velodyne> lidars; std::vector<PanoramaLine> image_lines(n);

@@ -487,6 +487,18 @@ def pixel_fit_script(pvo, rows, cols, lines, cloud, T):
     return script
 
 
+def pixel_calibration_from_reference(pvo, rows, cols, lines, cloud, T, script):
+    """The reference's own AssociateLineSingle + Optimize(line_pairs, T_cl) (recorded at ceres::Solve) on ONE frame without LiDAR segments, RANSAC answers scripted."""
+    rf = pvo.RefFrame(np.eye(3), np.zeros(3), cloud, np.zeros(len(cloud) + 1, np.int32), np.zeros(0, np.int32), np.zeros((0, 6)), id=0, local="keep", end_points=np.zeros((0, 6)))
+    pvo.ref_set_sac_script(script)
+    try:
+        cal = pvo.ref_calibration_blocks(rows, cols, [lines], [rf], T)
+    finally:
+        answered = pvo.ref_set_sac_script(None)
+    assert answered == len(script), (answered, len(script))
+    return cal
+
+
 def golden_ref_pixel_fit():
     """tests/golden/ref_pixel_fit.npz: the reference's own pixel-space Associate() (CameraLidarLineAssociate.cpp:22-188) run with the RANSAC's inliers SCRIPTED to what
     the product's pvb_pixel_fit_line reports (PCL is not available; oracle/shim's SACSegmentation replays the script) - everything after the RANSAC is the reference's code."""
@@ -500,7 +512,11 @@ def golden_ref_pixel_fit():
     script = pixel_fit_script(pvo, rows, cols, lines, cloud, T)
     il, s, e, ang = pvo.ref_pixel_associate_scripted(rows, cols, lines, cloud, T, script)
     print(f"  scripted pixel-space Associate: {len(script)} candidate lists, {sum(len(x) >= 3 for x in script)} fits, {len(il)} pairs after Filter(true, true)")
-    np.savez_compressed(os.path.join(OUT, "ref_pixel_fit.npz"), inl_off=np.concatenate([[0], np.cumsum([len(x) for x in script])]).astype(np.int32),
+    # the same frame through the reference's calibration mode: AssociateLineSingle takes Associate(lines, cornerLessSharp, T_cl) when edge_segmented is empty (:313-314)
+    cal = pixel_calibration_from_reference(pvo, rows, cols, lines, cloud, T, script)
+    print(f"  calibration mode over the pixel path: {int(cal['info'][0])} pairs, {len(cal['residual'])} residual blocks")
+    np.savez_compressed(os.path.join(OUT, "ref_pixel_fit.npz"), cal_residual=cal["residual"], cal_jacobian=cal["jacobian"], cal_huber=cal["huber"], cal_pose=cal["pose"],
+                        cal_info=cal["info"], inl_off=np.concatenate([[0], np.cumsum([len(x) for x in script])]).astype(np.int32),
                         inl_idx=np.concatenate(script).astype(np.int32), image_line=il, start=s, end=e, angle=ang)
 
 

@@ -108,3 +108,27 @@ def test_calibration_loop_takes_the_pixel_path_for_frames_without_segments(oracl
     assert len(log) == 1 and log[0]["n_pairs"] == n_pairs >= 10                       # pose unchanged by the scripted solver: the loop stops after one iteration
     assert len(seen[0]["type"]) == 2 * n_pairs and np.all(seen[0]["ref"] == 0)
     assert np.abs(T_out - T).max() < 1e-12
+
+
+def test_calibration_problem_over_the_pixel_path_equals_the_reference_optimize(oracle):
+    """The reference's own AssociateLineSingle + Optimize(line_pairs, T_cl) on a frame WITHOUT LiDAR segments (RANSAC answers scripted, recorded at ceres::Solve;
+    tests/golden/ref_pixel_fit.npz cal_*) == Context.pixel_associate + pvb_build_calibration_blocks: same pairs, residuals (degrees) and Jacobians of the one pose block."""
+    import os
+    from panovlm_b200 import BlockList
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pixel_fit.npz"))
+    rows, cols, lines, cloud, T = _case()
+    il, s, e, _ = _OracleBackedCtx(oracle).pixel_associate(rows, cols, lines, cloud, T)
+    bl = BlockList(2 * len(il) + 4)
+    Context.build_calibration_blocks(bl, rows, cols, lines[il], s, e, 0)
+    v = bl.view()
+    assert len(il) == int(g["cal_info"][0]) and len(v["type"]) == len(g["cal_residual"]) == 2 * len(il)
+    assert np.abs(v["huber"] - g["cal_huber"]).max() < 1e-15
+    pose = np.concatenate([oracle.R_to_aa(T[:3, :3]), T[:3, 3]])
+    assert np.abs(pose - g["cal_pose"]).max() < 1e-15
+    r, J, _ = oracle.Blocks(v["type"], 0, 0, v["consts"], 0.0, v["normalize"]).evaluate(g["cal_pose"].reshape(1, 6), apply_loss=False)
+    assert np.all(np.abs(r - g["cal_residual"]) <= 1e-9 * np.abs(g["cal_residual"]) + 1e-9)
+    assert np.all(np.abs(J[:, :6] - g["cal_jacobian"]).max(1) <= 1e-6 * np.abs(g["cal_jacobian"]).max(1) + 1e-7)
+    if oracle.ref_assoc_lib() is not None:                                               # live, where oracle/_ref is built
+        from make_golden import pixel_calibration_from_reference, pixel_fit_script
+        live = pixel_calibration_from_reference(oracle, rows, cols, lines, cloud, T, pixel_fit_script(oracle, rows, cols, lines, cloud, T))
+        assert np.array_equal(live["residual"], g["cal_residual"]) and np.array_equal(live["jacobian"], g["cal_jacobian"])
