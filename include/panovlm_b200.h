@@ -163,6 +163,14 @@ int pvb_dense_evaluate(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_par
  * it is a caller-owned device buffer (n_frames x 29 doubles) the result is written to; otherwise it receives the
  * context's own buffer.                                                                                            */
 int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_params* prm, double** dev_sys29);
+/* Search-radius hints of the dense path.  Every evaluation stores, per source point, its world position and the squared
+ * distance of its K-th neighbour; the next evaluation bounds that point's search by sqrt(tau_old) + |q - q_old| (the K old
+ * neighbours still lie within it).  A hint only shortens the walk - a search that finds fewer than K points below it starts
+ * again without it - so results never depend on it.  enable = 0 ignores the stored hints (they are still rewritten);
+ * pvb_dense_reset_hints forgets them (the next evaluation is a cold search).  Hints are forgotten whenever the target or the
+ * layout of the source frames changes.                                                                              */
+int pvb_dense_set_hints(pvb_ctx* ctx, int enable);
+int pvb_dense_reset_hints(pvb_ctx* ctx);
 /* debug: out2[0] = tiles of the fused kernel staged through TMA so far, out2[1] = tiles that used the global-memory path */
 int pvb_debug_counters(pvb_ctx* ctx, unsigned long long* out2);
 /* device time (CUDA events on the context's stream) of the fused associate+residual kernel of the last dense evaluate */

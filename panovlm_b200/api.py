@@ -348,6 +348,12 @@ class Context:
         self._ck(self._L.pvb_dense_evaluate_device(self._h, _p(poses), C.byref(prm), C.byref(ptr)))
         return ptr.value
 
+    def dense_set_hints(self, enable=True):
+        self._ck(self._L.pvb_dense_set_hints(self._h, C.c_int(1 if enable else 0)))
+
+    def dense_reset_hints(self):
+        self._ck(self._L.pvb_dense_reset_hints(self._h))
+
     def debug_counters(self):
         out = (C.c_ulonglong * 2)()
         self._ck(self._L.pvb_debug_counters(self._h, out))

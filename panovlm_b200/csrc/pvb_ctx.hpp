@@ -63,7 +63,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 6, tune_stage = 0, tune_r0 = 1; double tune_cellcap = 4.0, tune_hscale = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
+  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_mode = 2, tune_hints = 1; double tune_cellcap = 4.0, tune_hscale = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
@@ -88,6 +88,7 @@ struct pvb_ctx {
   std::vector<int> a_edge, a_query; std::vector<double> a_point, a_plane;
   // ---- dense mode
   CloudSet d_tgt, d_src; TargetIndex d_index; int d_frames = 0;
+  DevBuf d_hint;                                                       // search-radius hints of the dense queries (launch order), see AssocArgs::hint
   DevBuf d_q_sorted, d_q_orig, d_pairs, d_qtiles, d_part, d_sys, d_tbegin, d_valid, d_point, d_plane, d_res, d_jac;
   PinBuf dh_sys;
   int d_ntiles = 0; double d_cell = 0;

@@ -150,6 +150,10 @@ struct AssocArgs {
   int* out_nn_idx; float* out_nn_d2;                                 // idem, K per query (debug / parity)
   double* partials;                                                  // [tile][warp][29]
   unsigned long long* stats;                                         // optional: [0] tiles staged through TMA, [1] tiles on the global path
+  // search-radius hints of the buffered single-pass search (MODE 2), one record per query in launch order: {x, y, z of the query in the world
+  // frame at the last evaluation, its K-th squared distance then (float; not finite = no hint)}.  Read and rewritten in place; may be null.
+  F4* hint;
+  int use_hint;                                                      // 0: ignore the stored hints (they are still rewritten)
 };
 
 // ---- TMA staging helpers (sm_90+/sm_100a): 1-D bulk copies global -> shared completing on an mbarrier ---------------------
@@ -176,10 +180,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 constexpr int kStageRows = 64;     // (y,z) rows of a tile's cell box that can be staged
 constexpr int kStageCap = 768;     // staged records per tile (12 KB of shared memory)
 
-template <int K, bool REDUCE, int MINB, bool DEBUG_NN, bool STAGE, bool REF_ID>
+constexpr int kListCap = 24;       // per-query candidate list of the buffered single-pass search (8 B per entry)
+
+// MODE: 0 = TMA-staged tile + exhaustive walk, 1 = pruned two-pass walk, 2 = buffered single pass with search-radius hints (default)
+template <int K, bool REDUCE, int MINB, bool DEBUG_NN, int MODE, bool REF_ID>
 __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
+  constexpr bool STAGE = MODE == 0;
+  constexpr int LC = kListCap;
   __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
-  __shared__ uint32_t s_win[K][kTile];           // record positions of each query's K neighbours
+  __shared__ uint32_t s_win[MODE == 2 ? 1 : K][kTile];           // record positions of each query's K neighbours (MODE 2: slots 0..K-1 of the list)
+  __shared__ uint2 s_list[MODE == 2 ? LC : 1][kTile];            // MODE 2: (d2 bits, record position) of the candidates below the running limit
   __shared__ uint32_t s_rng[18][kTile];          // the <= 9 (lo, hi) row ranges of each query's 3x3x3 cell block
   __shared__ __align__(16) F4 s_pts[STAGE ? kStageCap : 1];          // the tile's candidate rows, copied by TMA
   __shared__ uint32_t s_row_lo[STAGE ? kStageRows : 1], s_row_base[STAGE ? kStageRows : 1];
@@ -274,28 +284,44 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
         hi = nlo + (hi - lo); lo = nlo;
       }
     };
-    auto win = [&](int j) { return s_win[j][i]; };
-    auto set_win = [&](int j, uint32_t pos) { s_win[j][i] = pos; };
+    auto win = [&](int j) { return MODE == 2 ? s_list[j][i].y : s_win[j][i]; };
+    auto set_win = [&](int j, uint32_t pos) { if (MODE == 2) s_list[j][i].y = pos; else s_win[j][i] = pos; };
     auto range_set = [&](int k, uint32_t lo, uint32_t hi) { s_rng[2 * k][i] = lo; s_rng[2 * k + 1][i] = hi; };
     auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = s_rng[2 * k][i]; hi = s_rng[2 * k + 1][i]; };
+    auto lput = [&](int n, uint32_t key, uint32_t pos) { s_list[n][i] = make_uint2(key, pos); };
+    auto lkey = [&](int n) { return s_list[n][i].x; };
+    auto lpos = [&](int n) { return s_list[n][i].y; };
+    auto lmove = [&](int dst, int src) { s_list[dst][i] = s_list[src][i]; };
     AssocParams prm = a.prm;
     prm.rmax = (int)ceil(a.thr / g.h);
     if (DEBUG_NN && a.out_nn_idx) {
 #pragma unroll
-      for (int j = 0; j < K; ++j) s_win[j][i] = 0xFFFFFFFFu;
+      for (int j = 0; j < K; ++j) set_win(j, 0xFFFFFFFFu);
     }
-    valid = associate_point2plane<K, REF_ID, !STAGE>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
-                                     range_get);
+    // search-radius hint: K target points lay within sqrt(tau_old) of q_old => within sqrt(tau_old) + |q - q_old| of q
+    uint32_t lim_hint = 0u, tau = 0x7F800000u;
+    if (MODE == 2 && a.hint && a.use_hint) {
+      const F4 hq = ldg_f4(a.hint + gq);
+      if (hq.w >= 0.f && hq.w < 3.0e38f) {
+        const double dx = (double)qx - (double)hq.x, dy = (double)qy - (double)hq.y, dz = (double)qz - (double)hq.z;
+        const double rad = (sqrt((double)hq.w) + sqrt(dx * dx + dy * dy + dz * dz)) * (1.0 + 1e-5) + 1e-9;
+        const double lim2 = rad * rad;
+        if (lim2 < (double)prm.sq_thr) lim_hint = f2u((float)lim2) + 2u;      // +1 ulp for the float rounding, +1 to make the bound exclusive
+      }
+    }
+    valid = associate_point2plane<K, REF_ID, MODE, LC>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
+                                     range_get, lim_hint, &tau, lput, lkey, lpos, lmove);
+    if (MODE == 2 && a.hint) { F4 ho; ho.x = qx; ho.y = qy; ho.z = qz; ho.w = u2f(tau); reinterpret_cast<float4*>(a.hint)[gq] = make_float4(ho.x, ho.y, ho.z, ho.w); }
     auto load = loadg;     // the debug view below is only built without staging
     if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
       for (int j = 0; j < K; ++j) {
-        const uint32_t pj = s_win[j][i];
+        const uint32_t pj = win(j);
         if (pj == 0xFFFFFFFFu) { a.out_nn_idx[(size_t)qi * K + (K - 1 - j)] = -1; a.out_nn_d2[(size_t)qi * K + (K - 1 - j)] = INFINITY; continue; }
         const F4 rj = load((long long)pj);
         const float dj = sqdist_f32(qx, qy, qz, rj.x, rj.y, rj.z);
         int rank = 0;
         for (int m = 0; m < K; ++m) {
-          const uint32_t pm = s_win[m][i];
+          const uint32_t pm = win(m);
           if (pm == 0xFFFFFFFFu || m == j) continue;
           const F4 rm = load((long long)pm);
           const float dm = sqdist_f32(qx, qy, qz, rm.x, rm.y, rm.z);

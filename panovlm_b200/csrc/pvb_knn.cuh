@@ -322,6 +322,138 @@ PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const L
   return n_out;
 }
 
+// ---- buffered single-pass variant (default path since round 2) -----------------------------------------------------------------
+// One walk over the block instead of two: every candidate whose squared distance is below the running limit is appended to a small
+// per-query list (key = d2 bits, payload = record position; LC entries, caller-provided storage); when the list is full it is cut
+// back to its K smallest entries (value-only min/max network over the list, then an in-place compaction) and the limit drops to the
+// K-th of them, which also prunes the rows / cells still to come.  The final cut leaves the K nearest in list slots 0..K-1.
+// Ties at the K-th distance are resolved by visiting order exactly like the two-pass variants (a later candidate must be strictly
+// closer to displace an earlier one), so the selected set is identical to theirs.
+//
+// Search-radius hint: `lim_hint` (0 = none) is an exclusive upper bound (d2 bit pattern) that the caller claims holds for the K-th
+// squared distance, e.g. from the previous evaluation of the same query: K target points lay within sqrt(tau_old) of q_old, so they
+// lie within sqrt(tau_old) + |q - q_old| of q.  The hint only shortens the walk: when fewer than K candidates are found below it
+// (a stale hint) the search restarts without it, so the result never depends on the hint being right.
+//   lput(n, key, pos) / lkey(i) / lpos(i) / lmove(dst, src): list storage;  returns K (found; *tau_out = K-th key) or 0.
+template <int K, int LC, typename LKey, typename LPos, typename LMove>
+PVB_HD uint32_t list_cut_to_k(int& n, const LKey& lkey, const LPos& lpos, const LMove& lmove) {
+  uint32_t keys[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) keys[j] = 0xFFFFFFFFu;
+#pragma unroll 2
+  for (int i = 0; i < n; ++i) topk_values_insert<K>(keys, lkey(i));
+  const uint32_t tau = keys[K - 1];
+  int n_lt = 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) n_lt += keys[j] < tau ? 1 : 0;
+  const int eq_needed = K - n_lt;
+  int eq_taken = 0, out = 0;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t kb = lkey(i);
+    bool take = kb < tau;
+    if (kb == tau && eq_taken < eq_needed) { take = true; ++eq_taken; }
+    if (take) { if (out != i) lmove(out, i); ++out; }
+  }
+  n = out;
+  return tau;
+}
+
+template <int K, int LC, typename CellLoader, typename Load, typename LPut, typename LKey, typename LPos, typename LMove>
+PVB_HD int knn_select_buffered(const GridDesc& g, const CellLoader& cells, const Load& load, float qx, float qy, float qz, float sq_thr, int rmax, uint32_t lim_hint,
+                               const LPut& lput, const LKey& lkey, const LPos& lpos, const LMove& lmove, uint32_t* tau_out) {
+  static_assert(LC >= K + 2, "list capacity");
+  const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
+  const double fx = ((double)qx - g.origin[0]) * g.inv_h, fy = ((double)qy - g.origin[1]) * g.inv_h, fz = ((double)qz - g.origin[2]) * g.inv_h;
+  const int cx = cell_coord((double)qx, g.origin[0], g.inv_h, g.dims[0]);
+  const int cy = cell_coord((double)qy, g.origin[1], g.inv_h, g.dims[1]);
+  const int cz = cell_coord((double)qz, g.origin[2], g.inv_h, g.dims[2]);
+  double gap_lo[3], gap_hi[3], slack = 0.5;
+  {
+    const double f[3] = {fx - cx, fy - cy, fz - cz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double lo = f[a] < 0.0 ? 0.0 : f[a], hi = 1.0 - f[a] < 0.0 ? 0.0 : 1.0 - f[a];
+      gap_lo[a] = lo * g.h; gap_hi[a] = hi * g.h;
+      const double m = lo < hi ? lo : hi;
+      slack = m < slack ? m : slack;
+    }
+  }
+  FaceGaps fg;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { fg.lo[a] = (float)(gap_lo[a] * gap_lo[a] * (1.0 - 1e-5)); fg.hi[a] = (float)(gap_hi[a] * gap_hi[a] * (1.0 - 1e-5)); }
+  if (rmax < 1) rmax = 1;
+  // block radius (cells) that covers the hinted search radius: every point closer than (r + slack) * h lies in the (2r+1)^3 block
+  int rb = 1;
+  bool hinted = lim_hint != 0u && lim_hint < init;
+  if (hinted) {
+    const double lim = (double)u2f(lim_hint);
+    const double reach1 = (1.0 + slack) * g.h, reach2 = (2.0 + slack) * g.h;
+    if (lim < reach1 * reach1 * (1.0 - 1e-6)) rb = 1;
+    else if (lim < reach2 * reach2 * (1.0 - 1e-6) && rmax >= 2) rb = 2;
+    else hinted = false;
+  }
+  int n = 0;
+  uint32_t lim = hinted ? lim_hint : init;         // accept d2 bits < lim
+  // limit_key view for the pruned walk (it skips a row / cell when its bound key is > limit_key): lim - 1
+  uint32_t limit_key = lim - 1u;
+  auto body = [&](long long i) {
+    const F4 c = load(i);
+    const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
+    if (kb < lim) {
+      lput(n, kb, (uint32_t)i); ++n;
+      if (n == LC) { lim = list_cut_to_k<K, LC>(n, lkey, lpos, lmove); limit_key = lim == 0u ? 0u : lim - 1u; }
+    }
+  };
+  for (;;) {
+    walk_block_pruned<K>(g, cells, cx, cy, cz, fg, gap_lo, gap_hi, rb, limit_key, body);
+    if (n >= K || !hinted) break;
+    hinted = false; n = 0; rb = 1; lim = init; limit_key = lim - 1u;     // stale hint: search again without it
+  }
+  if (n > K) { lim = list_cut_to_k<K, LC>(n, lkey, lpos, lmove); limit_key = lim == 0u ? 0u : lim - 1u; }
+  else if (n == K) {
+    uint32_t mx = 0u;
+#pragma unroll
+    for (int j = 0; j < K; ++j) { const uint32_t v = lkey(j); mx = v > mx ? v : mx; }
+    lim = mx; limit_key = lim == 0u ? 0u : lim - 1u;
+  }
+  // lim == K-th key when n == K.  Done when the block covers it; otherwise widen ring by ring (rare)
+  bool done = false;
+  if (n == K) {
+    const double reach = ((double)rb + slack) * g.h;
+    done = (double)u2f(lim) < reach * reach * (1.0 - 1e-6);
+  }
+  if (!done) {
+    uint32_t kth = n == K ? lim : init;              // the K-th smallest so far (exclusive bound for ties handled by the cut)
+    for (int r = rb + 1; r <= rmax; ++r) {
+      for_each_range(g, cells, cx, cy, cz, r, false, [&](long long lo, long long hi) {
+        for (long long i = lo; i < hi; ++i) {
+          const F4 c = load(i);
+          const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
+          if (kb < kth) {
+            lput(n, kb, (uint32_t)i); ++n;
+            if (n == LC) kth = list_cut_to_k<K, LC>(n, lkey, lpos, lmove);
+          }
+        }
+      });
+      if (n > K) kth = list_cut_to_k<K, LC>(n, lkey, lpos, lmove);
+      else if (n == K) {
+        uint32_t mx = 0u;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { const uint32_t v = lkey(j); mx = v > mx ? v : mx; }
+        kth = mx;
+      }
+      if (n == K) {      // ring r covers every point closer than (r + slack) * h
+        const double reach = ((double)r + slack) * g.h;
+        if ((double)u2f(kth) < reach * reach * (1.0 - 1e-6)) break;
+      }
+    }
+    lim = kth;
+  }
+  if (n < K) return 0;
+  if (tau_out) *tau_out = lim;
+  return K;
+}
+
 struct AssocParams {
   float sq_thr;           // point_to_plane_dis_threshold^2 computed in float (LidarFeatureAssociate.cpp:557)
   int rmax;               // ceil(thr / h)
@@ -336,16 +468,35 @@ struct AssocParams {
 // caller's per-query neighbour slots (shared memory on the device).
 // REF_ID: the reference frame's pose is exactly the identity (rigid target map): World2Local of a neighbour is then the
 // neighbour itself bit for bit (x*1 + y*0 + z*0 - 0), so the 3 x K matrix-vector products per query are skipped.
-template <int K, bool REF_ID, bool PRUNE, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+// MODE: 0 = exhaustive walk over stored row ranges (TMA-staged variant), 1 = pruned two-pass walk, 2 = buffered single pass (default; uses the
+// list accessors and the search-radius hint, see knn_select_buffered; the K nearest end up in list slots 0..K-1 = win(0..K-1)).
+template <int K, bool REF_ID, int MODE, int LC = K + 2, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet,
+          typename LPut, typename LKey, typename LPos, typename LMove>
 PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const Load1& load1, const LoadG& loadg, const RowMap& row_map, const AssocParams& prm,
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
-                                  double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get) {
+                                  double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get,
+                                  uint32_t lim_hint, uint32_t* tau_out, const LPut& lput, const LKey& lkey, const LPos& lpos, const LMove& lmove) {
   int ring = 1;
   int found;
-  if (PRUNE) { found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }); ring = 2; }
+  if (MODE == 2) { found = knn_select_buffered<K, LC>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.rmax, lim_hint, lput, lkey, lpos, lmove, tau_out); ring = 2; }
+  else if (MODE == 1) { found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }); ring = 2; }
   else found = knn_select<K>(g, cells, load1, loadg, row_map, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
   if (found < K) return false;                                   // :578
+  {
+    // canonical neighbour order = ascending record position: the plane fit below sums over the neighbours, and the order the search
+    // found them in depends on the walk (block radius, ring expansion, hints); sorting makes the result independent of all of that
+    uint32_t wp[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) wp[j] = win(j);
+#pragma unroll
+    for (int a = 1; a < K; ++a) {
+#pragma unroll
+      for (int b = a; b >= 1; --b) { const uint32_t lo = wp[b - 1] < wp[b] ? wp[b - 1] : wp[b], hi = wp[b - 1] < wp[b] ? wp[b] : wp[b - 1]; wp[b - 1] = lo; wp[b] = hi; }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) set_win(j, wp[j]);
+  }
   auto load = [&](long long pos) { return ring == 1 ? load1(pos) : loadg(pos); };   // neighbour positions live in the space they were found in (k-th beyond the threshold) + quirk C.6 guard
   // neighbours -> reference sensor frame (:587), streamed: Gram matrix for the LSQ plane and the scatter matrix
   PlaneAcc acc; plane_acc_clear(acc);

@@ -133,20 +133,23 @@ int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_
 template <bool REDUCE>
 int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_identity = false) {
   if (n_tiles == 0) return PVB_OK;
-  // tuning knobs (PVB_MINB: resident blocks per SM the register allocation targets; PVB_STAGE: 1 = stage each tile's candidate
-  // rows in shared memory with TMA bulk copies, 0 = read them through L1/L2).  Defaults: fastest measured on B200.
-  const int minb = ctx->tune_minb, stage = ctx->tune_stage;
+  // tuning knobs (PVB_MINB: resident blocks per SM the register allocation targets; PVB_MODE: 2 = buffered single-pass search with search-radius
+  // hints (default), 1 = pruned two-pass walk, 0 = stage each tile's candidate rows in shared memory with TMA bulk copies + exhaustive walk;
+  // PVB_STAGE=1 is the old spelling of PVB_MODE=0).  Defaults: fastest measured on B200.
+  const int minb = ctx->tune_minb, mode = ctx->tune_stage ? 0 : ctx->tune_mode;
   const bool dbg = a.out_nn_idx != nullptr;
   if (k != 5 && k != 10) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
   a.stats = nullptr;
   a.prm.r0 = ctx->tune_r0;
-  if (stage && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
-#define PVB_LAUNCH(KK, MB, DBG, ST) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, ST, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, ST, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
-#define PVB_MINB_SWITCH(KK, ST) do { if (minb >= 6) PVB_LAUNCH(KK, 6, false, ST); else if (minb == 5) PVB_LAUNCH(KK, 5, false, ST); else PVB_LAUNCH(KK, 4, false, ST); } while (0)
+  a.use_hint = ctx->tune_hints;
+  if (mode == 0 && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
+#define PVB_LAUNCH(KK, MB, DBG, MD) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, MD, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, MD, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
+#define PVB_MINB_SWITCH(KK, MD) do { if (minb >= 6) PVB_LAUNCH(KK, 6, false, MD); else if (minb == 5) PVB_LAUNCH(KK, 5, false, MD); else PVB_LAUNCH(KK, 4, false, MD); } while (0)
 #define PVB_DISPATCH(KK)                                                                                   \
-  if (dbg) PVB_LAUNCH(KK, 4, true, false);                                                                 \
-  else if (stage) PVB_MINB_SWITCH(KK, true);                                                               \
-  else PVB_MINB_SWITCH(KK, false);
+  if (dbg) { if (mode == 1) PVB_LAUNCH(KK, 4, true, 1); else PVB_LAUNCH(KK, 4, true, 2); }                 \
+  else if (mode == 0) PVB_LAUNCH(KK, 6, false, 0);                                                         \
+  else if (mode == 1) PVB_LAUNCH(KK, 6, false, 1);                                                         \
+  else PVB_MINB_SWITCH(KK, 2);
   if (k == 10) { PVB_DISPATCH(10) } else { PVB_DISPATCH(5) }
 #undef PVB_DISPATCH
 #undef PVB_MINB_SWITCH
@@ -173,6 +176,8 @@ int pvb_create(int device, pvb_ctx** out) {
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->bev0); cudaEventCreate(&ctx->bev1);
   if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e);
   if (const char* e = getenv("PVB_STAGE")) ctx->tune_stage = atoi(e) != 0;
+  if (const char* e = getenv("PVB_MODE")) ctx->tune_mode = std::min(2, std::max(0, atoi(e)));
+  if (const char* e = getenv("PVB_HINTS")) ctx->tune_hints = atoi(e) != 0;
   if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
   if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = std::max(0.1, atof(e));
@@ -704,6 +709,7 @@ static int frames_run(pvb_ctx* ctx, const double* poses, int n_edges, const int*
   a.q_local = ctx->f_qry.local.as<F4>(); a.q_orig = nullptr; a.tiles = ctx->f_qtiles.as<QueryTile>(); a.pairs = ctx->f_pairs.as<Pair>();
   a.grids = ctx->f_index.grids.as<GridDesc>(); a.cell_start = ctx->f_index.cell_start.as<uint32_t>(); a.sorted = ctx->f_index.sorted.as<F4>();
   a.wpose = ctx->d_wpose.as<WorldPose>(); a.prep = ctx->d_prep.as<PosePrep>();
+  a.hint = nullptr;      // pose-graph pairs: every query set is searched once per outer iteration, no hints
   a.prm.sq_thr = prm->dist_threshold * prm->dist_threshold; a.prm.rmax = 1; a.prm.plane_tol = prm->plane_tolerance; a.prm.collinear_tol = 3.0;
   a.thr = (double)prm->dist_threshold;
   a.residual_type = PVB_P2PLANE_METER; a.normalize = 0; a.huber = 0; a.weight = 1;
@@ -952,6 +958,7 @@ int pvb_dense_set_target(pvb_ctx* ctx, const float* xyzc, long n, double cell_si
   rc = build_target_index(ctx, ctx->d_tgt, ctx->d_index, cell_size); if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   // the unsorted world copy and sort scratch are not needed after the build
+  if (ctx->d_hint.p && ctx->d_src.n_points > 0) CK(cudaMemsetAsync(ctx->d_hint.p, 0x7f, (size_t)ctx->d_src.n_points * sizeof(F4), ctx->stream));   // hints belong to the old target
   ctx->d_index.world.release(); ctx->d_index.keys.release(); ctx->d_index.keys_alt.release(); ctx->d_index.vals.release(); ctx->d_index.vals_alt.release(); ctx->d_index.hist.release();
   return PVB_OK;
 }
@@ -993,6 +1000,8 @@ static int dense_prepare_layout(pvb_ctx* ctx, const int* offsets, int n_frames) 
   CK(ctx->m_a.ensure(std::max<size_t>(16, (size_t)n * 8))); CK(ctx->m_b.ensure(std::max<size_t>(16, (size_t)n * 8)));
   CK(ctx->m_c.ensure(std::max<size_t>(16, (size_t)n * 4))); CK(ctx->m_d.ensure(std::max<size_t>(16, (size_t)n * 4)));
   CK(ctx->d_q_sorted.ensure(std::max<size_t>(16, (size_t)n * sizeof(F4)))); CK(ctx->d_q_orig.ensure(std::max<size_t>(16, (size_t)n * 4)));
+  CK(ctx->d_hint.ensure(std::max<size_t>(16, (size_t)n * sizeof(F4))));
+  CK(cudaMemsetAsync(ctx->d_hint.p, 0x7f, (size_t)n * sizeof(F4), ctx->stream));      // 0x7f7f7f7f = 3.39e38: "no hint"
   CK(ctx->d_pairs.ensure(pairs.size() * sizeof(Pair))); CK(ctx->d_qtiles.ensure(std::max<size_t>(16, tiles.size() * sizeof(QueryTile)))); CK(ctx->d_tbegin.ensure(tbegin.size() * 4));
   CK(ctx->d_part.ensure(std::max<size_t>(16, tiles.size() * (kTile / 32) * 29 * 8))); CK(ctx->d_sys.ensure((size_t)n_frames * 29 * 8)); CK(ctx->dh_sys.ensure((size_t)n_frames * 29 * 8));
   size_t tb = 0;
@@ -1052,6 +1061,7 @@ static int dense_args(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_para
   a.q_local = ctx->d_q_sorted.as<F4>(); a.q_orig = ctx->d_q_orig.as<uint32_t>(); a.tiles = ctx->d_qtiles.as<QueryTile>(); a.pairs = ctx->d_pairs.as<Pair>();
   a.grids = ctx->d_index.grids.as<GridDesc>(); a.cell_start = ctx->d_index.cell_start.as<uint32_t>(); a.sorted = ctx->d_index.sorted.as<F4>();
   a.wpose = ctx->d_wpose.as<WorldPose>(); a.prep = ctx->d_prep.as<PosePrep>();
+  a.hint = ctx->d_hint.as<F4>();
   a.prm.sq_thr = prm->dist_threshold * prm->dist_threshold; a.prm.rmax = 1; a.prm.plane_tol = prm->plane_tolerance; a.prm.collinear_tol = 3.0;
   a.thr = (double)prm->dist_threshold;
   a.residual_type = prm->residual_type; a.normalize = prm->normalize; a.huber = prm->huber; a.weight = prm->weight;
@@ -1087,6 +1097,14 @@ int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_de
   k_sum_chunks<29><<<ctx->d_frames, 32, 0, ctx->stream>>>(ctx->d_chunk.as<double>(), dst);
   CKL();
   if (dev_sys) *dev_sys = dst;
+  return PVB_OK;
+}
+
+int pvb_dense_set_hints(pvb_ctx* ctx, int enable) { if (!ctx) return PVB_ERR_ARG; ctx->tune_hints = enable != 0; return PVB_OK; }
+int pvb_dense_reset_hints(pvb_ctx* ctx) {
+  if (!ctx) return PVB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->d_hint.p && ctx->d_src.n_points > 0) CK(cudaMemsetAsync(ctx->d_hint.p, 0x7f, (size_t)ctx->d_src.n_points * sizeof(F4), ctx->stream));
   return PVB_OK;
 }
 

@@ -11,7 +11,9 @@
 using namespace pvb;
 
 // per-query association on a host-built grid (counting sort), K = 10 or 5
-static int g_prune = 1;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned walk from a 3x3x3 (default device path) / 5x5x5 block
+static int g_prune = 1;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned two-pass walk from a 3x3x3 / 5x5x5 block, 3: buffered single pass (default device path)
+static const float* g_hint = nullptr;   // mode 3: per query {x, y, z, tau} search-radius hints (the device kernel's formula), or null
+static float* g_hint_out = nullptr;     // mode 3: the hints the device kernel would store
 template <int K>
 static void associate_all(const float* tgt, int n, const double* R_ref, const double* t_ref, const float* qry, int m, const double* R_nei, const double* t_nei,
                           double h, float thr, double plane_tol, unsigned char* valid, double* p_local, double* plane, int* nn_idx, float* nn_d2) {
@@ -49,10 +51,34 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
     auto range_set = [&](int k, uint32_t lo, uint32_t hi) { rng[2 * k] = lo; rng[2 * k + 1] = hi; };
     auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = rng[2 * k]; hi = rng[2 * k + 1]; };
     auto no_map = [](int, int, uint32_t&, uint32_t&) {};
-#define PVBH_ASSOC(MODE) associate_point2plane<K, false, MODE>(g, cells, load, load, no_map, prm, qry[i * 4], qry[i * 4 + 1], qry[i * 4 + 2], qcls, R_ref, t_ref, R_nei, t_nei, \
-                                                               p_local + 3 * i, plane + 4 * i, win, set_win, range_set, range_get)
-    valid[i] = (g_prune == 0 ? PVBH_ASSOC(false) : PVBH_ASSOC(true)) ? 1 : 0;
+    constexpr int LC = 24;
+    uint32_t lk[LC], lp[LC];
+    auto lput = [&](int nn_, uint32_t key, uint32_t pos) { lk[nn_] = key; lp[nn_] = pos; };
+    auto lkey = [&](int nn_) { return lk[nn_]; };
+    auto lpos = [&](int nn_) { return lp[nn_]; };
+    auto lmove = [&](int dst, int src) { lk[dst] = lk[src]; lp[dst] = lp[src]; };
+    auto win2 = [&](int j) { return lp[j]; };
+    auto set_win2 = [&](int j, uint32_t pos) { lp[j] = pos; };
+    const float qx = qry[i * 4], qy = qry[i * 4 + 1], qz = qry[i * 4 + 2];
+    uint32_t lim_hint = 0u, tau = 0x7F800000u;
+    if (g_prune == 3 && g_hint) {        // same arithmetic as k_associate (pvb_kernels.cuh)
+      const float* hq = g_hint + 4 * i;
+      if (hq[3] >= 0.f && hq[3] < 3.0e38f) {
+        const double dx = (double)qx - (double)hq[0], dy = (double)qy - (double)hq[1], dz = (double)qz - (double)hq[2];
+        const double rad = (sqrt((double)hq[3]) + sqrt(dx * dx + dy * dy + dz * dz)) * (1.0 + 1e-5) + 1e-9;
+        const double lim2 = rad * rad;
+        if (lim2 < (double)prm.sq_thr) lim_hint = f2u((float)lim2) + 2u;
+      }
+    }
+#define PVBH_ASSOC(MODE, W, SW) associate_point2plane<K, false, MODE, LC>(g, cells, load, load, no_map, prm, qx, qy, qz, qcls, R_ref, t_ref, R_nei, t_nei, \
+                                                               p_local + 3 * i, plane + 4 * i, W, SW, range_set, range_get, lim_hint, &tau, lput, lkey, lpos, lmove)
+    if (g_prune == 3) { for (int j = 0; j < K; ++j) lp[j] = 0xFFFFFFFFu; }
+    valid[i] = (g_prune == 0 ? PVBH_ASSOC(0, win, set_win) : (g_prune == 3 ? PVBH_ASSOC(2, win2, set_win2) : PVBH_ASSOC(1, win, set_win))) ? 1 : 0;
 #undef PVBH_ASSOC
+    if (g_prune == 3) {
+      for (int j = 0; j < K; ++j) wpos[j] = tau == 0x7F800000u ? 0xFFFFFFFFu : lp[j];
+      if (g_hint_out) { g_hint_out[4 * i] = qx; g_hint_out[4 * i + 1] = qy; g_hint_out[4 * i + 2] = qz; g_hint_out[4 * i + 3] = u2f(tau); }
+    }
     std::vector<std::pair<std::pair<float, uint32_t>, int>> nn;
     for (int j = 0; j < K; ++j) {
       if (wpos[j] == 0xFFFFFFFFu) continue;
@@ -100,6 +126,7 @@ static void associate_lines(const float* tgt, int n, const double* R_ref, const 
 
 extern "C" {
 void pvbh_set_prune(int on) { g_prune = on; }
+void pvbh_set_hints(const float* hint_in, float* hint_out) { g_hint = hint_in; g_hint_out = hint_out; }
 
 
 void pvbh_associate_lines(const float* tgt, int n, const double* R_ref, const double* t_ref, const float* qry, int m, const double* R_nei, const double* t_nei,

@@ -45,11 +45,12 @@ def test_zero_rows_and_golden_functors(harness):
         assert (np.abs(J - g["jacobian"]) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1, keepdims=True))).max() < 1e-7
 
 
-@pytest.mark.parametrize("prune", [1, 2, 0])
+@pytest.mark.parametrize("prune", [3, 1, 2, 0])
 def test_grid_knn_and_association_equal_oracle(oracle, harness, prune):
-    """prune = 1 / 2: the pruned walk starting from a 3x3x3 (default device path) / 5x5x5 block (rows / cells beyond the running K-th distance
-    are skipped); 0: the exhaustive block walk."""
+    """prune = 3: the buffered single-pass search (default device path); 1 / 2: the pruned two-pass walk starting from a 3x3x3 / 5x5x5 block
+    (rows / cells beyond the running K-th distance are skipped); 0: the exhaustive block walk."""
     harness.pvbh_set_prune(C.c_int(prune))
+    harness.pvbh_set_hints(None, None)
     g = np.load(os.path.join(G, "assoc_pair.npz"))
     refw, neiw = np.ascontiguousarray(g["ref_world"]), np.ascontiguousarray(g["nei_world"])
     R_ref, t_ref, R_nei, t_nei = (np.ascontiguousarray(g[k]) for k in ("R_ref", "t_ref", "R_nei", "t_nei"))
@@ -106,6 +107,7 @@ def test_rank_deficient_neighbour_sets_follow_the_qr_basic_solution(oracle, harn
     """Neighbours with one coordinate exactly 0 in the reference frame (a floor through the origin): Eigen's rank-revealing
     QR returns a basic solution that may still pass the tolerance test; the streaming plane fit must fall back to it."""
     from panovlm_b200 import synth
+    harness.pvbh_set_prune(C.c_int(3)); harness.pvbh_set_hints(None, None)
     rng = np.random.default_rng(12)
     n = 60000
     tgt = np.concatenate([synth.sample_floor_plan(n, rng, xlim=(0, 12.0)), np.ones((n, 1))], axis=1).astype(np.float32)   # floor at z == 0, walls at x == 0 / y == 0
@@ -153,8 +155,9 @@ def test_pruned_block_walk_is_exact_on_random_surface_clouds(oracle, harness):
     below to far above the k-NN radius; the neighbour lists must equal the brute-force search bit for bit."""
     I, z = np.eye(3), np.zeros(3)
     rng = np.random.default_rng(21)
-    for trial in range(16):
-        harness.pvbh_set_prune(C.c_int(1 + trial % 2))
+    harness.pvbh_set_hints(None, None)
+    for trial in range(24):
+        harness.pvbh_set_prune(C.c_int(1 + trial % 3))
         n = int(rng.integers(400, 3000))
         uv = rng.uniform(-2, 2, (n, 2))
         which = rng.integers(0, 3, n)
@@ -181,6 +184,70 @@ def test_pruned_block_walk_is_exact_on_random_surface_clouds(oracle, harness):
             inside = d2[r] < d2[r, K - 1]
             assert set(idx[r][inside]) <= set(ni[r]), (trial, r)
         assert np.all(ni[~full][:, K - 1] == -1)
+
+
+def _fuzz_cloud(rng, n):
+    uv = rng.uniform(-2, 2, (n, 2))
+    which = rng.integers(0, 3, n)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = np.where(which == 0, uv[:, 0], np.where(which == 1, 1.5, uv[:, 0]))
+    pts[:, 1] = np.where(which == 0, uv[:, 1], np.where(which == 1, uv[:, 0], -0.7))
+    pts[:, 2] = np.where(which == 0, 0.3, uv[:, 1])
+    pts[:, :3] += rng.normal(0, 0.005, (n, 3)).astype(np.float32)
+    pts[: n // 10, :3] = pts[n // 10: 2 * (n // 10), :3][: n // 10]                # exact duplicates => distance ties
+    return pts
+
+
+def test_search_radius_hints_never_change_the_result(oracle, harness):
+    """The buffered search with hints: (a) hints written by a first evaluation and used after the queries moved (small and large moves),
+    (b) wrong hints (far too small radii, positions elsewhere) - the neighbour lists must equal the brute-force search bit for bit in
+    every case, because a hint only bounds the walk and a search that finds fewer than K below it starts again without it."""
+    I, z = np.eye(3), np.zeros(3)
+    rng = np.random.default_rng(5)
+    harness.pvbh_set_prune(C.c_int(3))
+    for trial in range(12):
+        n = int(rng.integers(1500, 6000))
+        pts = _fuzz_cloud(rng, n)
+        m = 400
+        qry = np.zeros((m, 4), np.float32)
+        qry[:, :3] = pts[rng.integers(0, n, m), :3] + rng.normal(0, 0.02, (m, 3)).astype(np.float32)
+        K = int(rng.choice([5, 10])); h = float(rng.choice([0.05, 0.1, 0.2, 0.5])); thr = float(rng.choice([0.25, 1.0]))
+
+        def run(q, hint_in, hint_out):
+            valid, pl2, pt2 = np.zeros(m, np.uint8), np.zeros((m, 4)), np.zeros((m, 3))
+            ni, nd = np.zeros((m, K), np.int32), np.zeros((m, K), np.float32)
+            harness.pvbh_set_hints(p(hint_in), p(hint_out))
+            harness.pvbh_associate(p(pts), C.c_int(n), p(I.copy()), p(z), p(q), C.c_int(m), p(I.copy()), p(z), C.c_double(h), C.c_float(thr),
+                                   C.c_double(0.05), C.c_int(K), p(valid), p(pt2), p(pl2), p(ni), p(nd))
+            harness.pvbh_set_hints(None, None)
+            return valid, pl2, ni, nd
+
+        def check(q, ni, nd):
+            idx, d2 = oracle.knn(pts, q, K, False)
+            full = d2[:, K - 1] <= np.float32(thr) * np.float32(thr)
+            assert np.array_equal(d2[full], nd[full]), (trial, h, K)
+            for r in np.nonzero(full)[0]:
+                inside = d2[r] < d2[r, K - 1]
+                assert set(idx[r][inside]) <= set(ni[r]), (trial, r)
+            assert np.all(ni[~full][:, K - 1] == -1)
+
+        hints = np.zeros((m, 4), np.float32)
+        v0, pl0, ni0, nd0 = run(qry, None, hints)
+        check(qry, ni0, nd0)
+        full = np.isfinite(hints[:, 3])
+        assert np.array_equal(hints[full, 3], nd0[full, K - 1]) and np.array_equal(hints[:, :3], qry[:, :3])
+        for move in (0.0, 0.003, 0.05, 0.4):                                        # the same queries after a pose update
+            q2 = qry.copy(); q2[:, :3] += rng.normal(0, move, (m, 3)).astype(np.float32) if move > 0 else 0
+            h2 = np.zeros((m, 4), np.float32)
+            v_h, pl_h, ni_h, nd_h = run(q2, hints, h2)
+            v_n, pl_n, ni_n, nd_n = run(q2, None, None)
+            check(q2, ni_h, nd_h)
+            assert np.array_equal(v_h, v_n) and np.array_equal(pl_h, pl_n) and np.array_equal(ni_h, ni_n) and np.array_equal(nd_h, nd_n)   # hinted == unhinted, bit for bit
+        bad = hints.copy()
+        bad[:, 3] = rng.uniform(0, 1e-4, m).astype(np.float32)                        # radii far too small
+        bad[::3, :3] = qry[::3, :3]                                                   # ... some of them at the right place
+        v_b, pl_b, ni_b, nd_b = run(qry, bad, None)
+        assert np.array_equal(v_b, v0) and np.array_equal(pl_b, pl0) and np.array_equal(ni_b, ni0) and np.array_equal(nd_b, nd0)
 
 
 def test_product_fast_atan2_equals_the_reference_code_outputs(harness):

@@ -334,6 +334,35 @@ def test_dense_gauss_newton_converges_to_true_poses(gpu_ctx, dense_small):
     assert err[:3].max() < 5e-3 and err[3:].max() < 0.15 and err[:3].max() < err0[:3].max()
 
 
+def test_dense_search_radius_hints_do_not_change_any_system(gpu_ctx, oracle, dense_small):
+    """A Gauss-Newton run with the search-radius hints of the previous evaluation (default), one with the hints ignored and one with
+    the hints reset before every evaluation give bit-identical reduced systems at every iteration; the last one also equals the oracle."""
+    d = dense_small
+    gpu_ctx.dense_set_target(d["target"])
+    gpu_ctx.dense_set_sources(d["src_local"], d["src_off"])
+    prm = gpu_ctx.dense_params(0.05, 1.0, 10, 0, 1, 0.2, 1.0)
+    runs = {}
+    for name in ("hints", "ignored", "reset"):
+        gpu_ctx.dense_reset_hints()
+        gpu_ctx.dense_set_hints(name != "ignored")
+        poses, out = d["poses_lw_init"].copy(), []
+        for it in range(5):
+            if name == "reset":
+                gpu_ctx.dense_reset_hints()
+            s = gpu_ctx.dense_evaluate(poses, prm)
+            out.append(s)
+            poses = gpu_ctx.dense_gauss_newton_step(s, poses, 1e-6)
+        runs[name] = (np.array(out), poses)
+    gpu_ctx.dense_set_hints(True)
+    assert np.array_equal(runs["hints"][0], runs["ignored"][0]) and np.array_equal(runs["hints"][0], runs["reset"][0])
+    assert np.array_equal(runs["hints"][1], runs["reset"][1])
+    # back to the initial poses with hints from the converged ones (large moves: the bound grows, the result does not change)
+    s_back = gpu_ctx.dense_evaluate(d["poses_lw_init"], prm)
+    assert np.array_equal(s_back, runs["hints"][0][0])
+    s_cpu, _, n = oracle.dense_icp_eval(d["target"], d["src_local"], d["src_off"], d["poses_lw_init"], 0.05, 1.0, 10, 0.2, 1.0, 1)
+    assert np.array_equal(s_cpu[:, 28], s_back[:, 28]) and np.abs(s_cpu - s_back).max() < 1e-8 * np.abs(s_cpu).max()
+
+
 def test_dense_full_size_properties(gpu_ctx):
     """Size-independent properties at a large size the CPU oracle cannot sweep in seconds: every source point is an
     exact copy of a target point moved by a known rigid transform => at the true pose the point-to-plane residual of
