@@ -12,8 +12,11 @@ One residual evaluation = one source point at one pose estimate (points x iterat
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm   (torchrun for N>1)
   python bench.py --impl reference ...                           the reference algorithm on the host cores (oracle port)
 
-Multi-GPU: source frames shard across ranks (each rank owns 64 frames: weak scaling), the target is replicated, the
-only exchange is the allreduce of the reduced systems.  Synthetic data, seeds fixed.
+Multi-GPU (SURVEY.md 8e / BASELINE configs[4]): the 64 source frames are sharded across the ranks (64 / N frames each: STRONG scaling, the
+default), the target is replicated, the only exchange is one NCCL allreduce of the packed 6x6/6x1 blocks of all 64 frames per step.
+`--scaling weak` gives every rank its own 64 frames instead (round-1 behaviour).  Synthetic data, seeds fixed.
+The line carries `parity`: the oracle's reduced systems of the first step (all 64 frames against the 10 M-point target, the same
+run that is timed as `cpu_baseline`) against the GPU's, and `extra.*`: the other BASELINE configs measured in the same run.
 """
 import argparse
 import json
@@ -48,6 +51,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--cell", type=float, default=0.0, help="target grid cell size in metres (0: library default)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: shard the 64 frames (strong, SURVEY 8e) or 64 frames per rank (weak)")
+    ap.add_argument("--no-configs", action="store_true", help="skip extra.pair_icp / room_refine_pose / floor_refine_pose (BASELINE configs[0,1,3])")
+    ap.add_argument("--floor-frames", type=int, default=1593)
+    ap.add_argument("--room-frames", type=int, default=454)
     return ap.parse_args()
 
 
@@ -94,11 +101,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_data(args, rank):
+def make_data(args, rank, world=1):
     from panovlm_b200 import synth
-    # the target is identical on every rank (same seed); each rank owns its own source frames
-    return synth.make_dense_sweep(n_target=args.n_target, n_frames=args.frames, pts_per_frame=args.pts_per_frame, seed=20260929,
-                                  source_seed=20260930 + 1000 * rank)
+    # the target is identical on every rank (same seed).  weak: each rank owns its own 64 source frames; strong: the same 64 frames
+    # everywhere, rank r keeps frames [r * 64 / N, (r + 1) * 64 / N)
+    weak = args.scaling == "weak"
+    d = synth.make_dense_sweep(n_target=args.n_target, n_frames=args.frames, pts_per_frame=args.pts_per_frame, seed=20260929,
+                               source_seed=20260930 + (1000 * rank if weak else 0))
+    d["frame_lo"], d["frame_hi"] = 0, args.frames
+    if not weak and world > 1:
+        lo, hi = args.frames * rank // world, args.frames * (rank + 1) // world
+        o0, o1 = int(d["src_off"][lo]), int(d["src_off"][hi])
+        d["all_src_local"], d["all_src_off"], d["all_poses_lw_init"] = d["src_local"], d["src_off"], d["poses_lw_init"]
+        d["src_local"] = np.ascontiguousarray(d["src_local"][o0:o1])
+        d["src_off"] = (d["src_off"][lo:hi + 1] - o0).astype(np.int32)
+        d["poses_lw_init"] = d["poses_lw_init"][lo:hi].copy()
+        d["poses_lw_true"] = d["poses_lw_true"][lo:hi].copy()
+        d["frame_lo"], d["frame_hi"] = lo, hi
+    return d
 
 
 def use_physical_cores():
@@ -124,14 +144,14 @@ def cpu_baseline(args, d, steps=1, mode=1, tree=None, build_s=0.0):
         t0 = time.time()
         tree = pvo.KdTreeHandle(d["target"])
         build_s = time.time() - t0
-    times, n_assoc = [], 0
+    times, n_assoc, systems = [], 0, None
     for _ in range(steps):
         t0 = time.time()
-        _, tt, n_assoc = pvo.dense_icp_eval(d["target"], d["src_local"][: off[-1]], off, d["poses_lw_init"][:nf], 0.05, args.radius, args.k, 0.2, 1.0, mode, tree)
+        systems, tt, n_assoc = pvo.dense_icp_eval(d["target"], d["src_local"][: off[-1]], off, d["poses_lw_init"][:nf], 0.05, args.radius, args.k, 0.2, 1.0, mode, tree)
         times.append(time.time() - t0)
     evals = int(off[-1])
     return {"evals": evals, "seconds": float(np.median(times)), "per_step": times, "kdtree_build_s": build_s, "n_assoc": int(n_assoc),
-            "threads": pvo.num_threads(), "frames": nf, "tree": tree}
+            "threads": pvo.num_threads(), "frames": nf, "tree": tree, "systems": systems}
 
 
 def run_reference(args):
@@ -154,8 +174,8 @@ def run_reference(args):
     value = int(off[-1]) * args.steps / total
     sample = f"{nf} of {args.frames} source frames ({int(off[-1])} points) per step against the full {args.n_target}-point target, kd-tree prebuilt"
     line = {"impl": "reference", "metric": "residual_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args),
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, args.gpus),
             "cpu_baseline": {"value": value, "unit": "evals/s", "cores": pvo.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -205,12 +225,40 @@ def bench_reproj(ctx, peak_gbs, n_cams=454, n_points=200_000, seed=7):
     return out
 
 
-def config_dict(args):
-    return {"workload": f"configs[4]: dense ICP sweep, {args.n_target}-pt target, {args.frames} source frames x {args.pts_per_frame} pts per GPU, "
-                        f"k={args.k}, radius={args.radius} m, plane_tol=0.05, Point2Plane_Meter + Huber(0.2), per-frame 6x6 reduce",
-            "cell_m": args.cell, "n_target": args.n_target, "frames_per_gpu": args.frames, "pts_per_frame": args.pts_per_frame, "k": args.k, "radius_m": args.radius,
+def config_dict(args, world=1):
+    weak = args.scaling == "weak"
+    per = args.frames if weak else f"{args.frames} / {world}"
+    return {"workload": f"configs[4]: dense ICP sweep, {args.n_target}-pt target, {args.frames} source frames x {args.pts_per_frame} pts "
+                        f"{'per GPU' if weak else 'in total'}, k={args.k}, radius={args.radius} m, plane_tol=0.05, Point2Plane_Meter + Huber(0.2), per-frame 6x6 reduce",
+            "cell_m": args.cell, "n_target": args.n_target, "frames_total": args.frames * (world if weak else 1), "frames_per_gpu": per, "pts_per_frame": args.pts_per_frame,
+            "k": args.k, "radius_m": args.radius,
             "l2": "inputs (160 MB target records + 160 MB queries + cell table) exceed the 126 MB L2; no explicit flush",
-            "parallelism": "frames sharded across GPUs (weak), target replicated, one allreduce of the packed 6x6/6x1 blocks per step"}
+            "search": "exact 10-NN, buffered single pass; per-point search radius bounded by the previous step's 10th distance + displacement (exact: a stale bound "
+                      "restarts the search), warm-up steps provide the bounds of the first timed step; extra.cold_search_kernel_ms = the same launch without them",
+            "parallelism": f"frames sharded across GPUs ({args.scaling}), target replicated, one NCCL allreduce of the packed 6x6/6x1 blocks of all frames per step"}
+
+
+def kernel_sources_hash():
+    """sha256 (16 hex digits) of the sources of the fused kernel: profiles/traffic.json is only used when it was captured from these."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("pvb_kernels.cuh", "pvb_knn.cuh", "pvb_math.cuh"):
+        with open(os.path.join(ROOT, "panovlm_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def load_traffic():
+    """(dram bytes per launch, warp instructions per launch, source) of the fused kernel from the committed ncu capture, or Nones when the
+    capture does not belong to the kernel sources of this tree (tools/capture_traffic.py rewrites it)."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(tp))
+    except Exception:
+        return None, None, "no profiles/traffic.json"
+    if t.get("kernel_sources_sha256_16") != kernel_sources_hash():
+        return None, None, f"profiles/traffic.json was captured from other kernel sources ({t.get('kernel_sources_sha256_16')}): ignored"
+    return t.get("k_associate_dram_bytes_per_launch"), t.get("k_associate_warp_instructions_per_launch"), t.get("capture", "profiles/traffic.json")
 
 
 def main():
@@ -229,8 +277,13 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    d = make_data(args, rank)
-    nq = int(d["src_off"][-1])
+    weak = args.scaling == "weak"
+    d = make_data(args, rank, world)
+    nq = int(d["src_off"][-1])                                       # this rank's source points
+    nf = len(d["src_off"]) - 1                                       # this rank's frames
+    frames_total = args.frames * world if weak else args.frames
+    nq_total = nq * world if weak else args.frames * args.pts_per_frame
+    slot0 = rank * nf if weak else d["frame_lo"]                     # this rank's rows in the packed buffer of all frames
 
     ctx = panovlm_b200.Context(local)
     stream = torch.cuda.Stream()                # a real (non-legacy) stream: library work, torch events, copies and NCCL all on it
@@ -240,10 +293,9 @@ def main():
     src_pinned = torch.from_numpy(d["src_local"]).pin_memory()
     ctx.dense_set_sources_ptr(src_pinned.data_ptr(), d["src_off"])
     prm = ctx.dense_params(0.05, args.radius, args.k, panovlm_b200.P2PLANE_METER, 1, 0.2, 1.0)
-    nf = args.frames
-    sys_all = torch.zeros((world * nf, 29), dtype=torch.float64, device="cuda")     # packed normal-equation blocks of ALL ranks
-    my_ptr = sys_all.data_ptr() + rank * nf * 29 * 8
-    sys_host = torch.zeros((world * nf, 29), dtype=torch.float64).pin_memory()
+    sys_all = torch.zeros((frames_total, 29), dtype=torch.float64, device="cuda")     # packed normal-equation blocks of ALL frames
+    my_ptr = sys_all.data_ptr() + slot0 * 29 * 8
+    sys_host = torch.zeros((frames_total, 29), dtype=torch.float64).pin_memory()
 
     def gn_step(poses):
         """one Gauss-Newton iteration, inputs resident in HBM"""
@@ -254,7 +306,7 @@ def main():
             dist.all_reduce(sys_all)                  # the single exchange step: 6x6/6x1 blocks of every frame
         sys_host.copy_(sys_all, non_blocking=True)
         stream.synchronize()
-        mine = sys_host[rank * nf:(rank + 1) * nf].numpy()
+        mine = sys_host[slot0:slot0 + nf].numpy()
         return ctx.dense_gauss_newton_step(mine, poses, 1e-6), mine
 
     def barrier():
@@ -274,12 +326,14 @@ def main():
     barrier()
     l0 = ctx.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, costs = [], []
+    kernel_ms, costs, first_sys = [], [], None
     e0.record()
-    for _ in range(args.steps):
+    for it in range(args.steps):
         poses, mine = gn_step(poses)
         kernel_ms.append(ctx.dense_kernel_time_ms())
         costs.append(float(mine[:, 27].sum()))
+        if it == 0:
+            first_sys = sys_host.numpy().copy()                     # all frames' systems at the initial poses (after the allreduce)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -290,7 +344,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * nq * args.steps / (ms_max * 1e-3)
+    value = nq_total * args.steps / (ms_max * 1e-3)
 
     # ---- e2e: the same iteration through the C ABI with HOST buffers (source clouds + poses H2D, systems D2H)
     e2e = None
@@ -313,10 +367,24 @@ def main():
         te = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * nq * args.steps / (float(te.item()) * 1e-3), "unit": "evals/s",
-               "h2d_bytes_per_step": int(nq * 16 + nf * (21 + 12) * 8 * 1 + (nf + 1) * 4), "d2h_bytes_per_step": int(world * nf * 29 * 8),
+        e2e = {"value": nq_total * args.steps / (float(te.item()) * 1e-3), "unit": "evals/s",
+               "h2d_bytes_per_step": int(nq * 16 + nf * (21 + 12) * 8 * 1 + (nf + 1) * 4), "d2h_bytes_per_step": int(frames_total * 29 * 8),
                "ms_per_step": float(te.item()) / args.steps,
-               "note": "per step: source clouds (pinned host) -> device + Morton re-order, poses H2D, fused kernel, allreduce, reduced systems D2H; target map resident"}
+               "note": "per rank and step: its source clouds (pinned host) -> device + Morton re-order, poses H2D, fused kernel, allreduce, reduced systems of all frames D2H; target map resident"}
+
+    # ---- the same launch without search-radius bounds (cold search), for transparency
+    ctx.dense_reset_hints()
+    ctx.dense_evaluate_device(d["poses_lw_init"], prm, my_ptr)
+    cold_ms = ctx.dense_kernel_time_ms()
+
+    # ---- BASELINE configs[3] under the same launch: Floor RefinePose sharded over the ranks (every rank takes part)
+    floor = None
+    if not args.no_configs and not args.no_extra:
+        try:
+            from tools import bench_configs
+            floor = bench_configs.floor_refine_pose(ctx, world, rank, n_frames=args.floor_frames)
+        except Exception as e:                                   # never lose the headline line
+            floor = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -334,44 +402,46 @@ def main():
     k_ms = float(np.mean(kernel_ms))
     alg_bytes = nq * B_ALG_PER_QUERY[args.k]
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("k_associate_dram_bytes_per_launch")
-        except Exception:
-            pass
+    traffic, wi, traffic_src = load_traffic()
+    if world > 1 and not weak:
+        traffic = wi = None                                      # the capture is a full 64-frame launch
     # instruction-issue view of the same launch (the kernel is issue-bound): executed warp instructions per
     # launch from the committed ncu capture vs 4 schedulers x 148 SMs x SM clock
     issue = None
-    if os.path.exists(tp):
-        try:
-            wi = json.load(open(tp)).get("k_associate_warp_instructions_per_launch")
-            if wi:
-                issue = {"warp_instructions": wi, "achieved_ginst_s": wi / (k_ms * 1e-3) / 1e9, "peak_ginst_s": 4 * 148 * 1.965, "frac": wi / (k_ms * 1e-3) / 1e9 / (4 * 148 * 1.965)}
-        except Exception:
-            pass
-    roofline = {"bound": "hbm", "kernel": "k_associate<10,true>", "issue": issue, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "kernel_share_of_step": k_ms * args.steps / ms}
+    if wi:
+        issue = {"warp_instructions": wi, "achieved_ginst_s": wi / (k_ms * 1e-3) / 1e9, "peak_ginst_s": 4 * 148 * 1.965, "frac": wi / (k_ms * 1e-3) / 1e9 / (4 * 148 * 1.965)}
+    roofline = {"bound": "hbm", "kernel": "k_associate<10,true,...,MODE 2>", "issue": issue, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": k_ms, "kernel_ms_per_step": [round(x, 4) for x in kernel_ms], "cold_search_kernel_ms": cold_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_share_of_step": k_ms * args.steps / ms}
 
     line = {"metric": "residual_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, world), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "gn_cost_first_last": [costs[0], costs[-1]], "ms_per_gauss_newton_iter": ms_max / args.steps}
+    line["extra"] = {}
+    if floor is not None:
+        line["extra"]["floor_refine_pose_sharded"] = floor
 
     # ---- secondary kernel: K3/K4 over a Room-shaped correspondence list (configs[1] sizes: 454 pose blocks, ~3.2 k edges,
     #      1.4 M residual blocks = Point2Plane_Angle + Huber 2 deg), device time of k_eval_blocks per evaluation
     if world == 1 and not args.no_extra:
         try:
-            line["extra"] = {"k_eval_blocks": bench_blocks(ctx, peak)}
+            line["extra"]["k_eval_blocks"] = bench_blocks(ctx, peak)
         except Exception as e:                                   # never lose the headline line
-            line["extra"] = {"k_eval_blocks": {"error": str(e)}}
+            line["extra"]["k_eval_blocks"] = {"error": str(e)}
         try:
             line["extra"]["k_reproj_rows"] = bench_reproj(ctx, peak)
         except Exception as e:
             line["extra"]["k_reproj_rows"] = {"error": str(e)}
+        if not args.no_configs:
+            from tools import bench_configs
+            for name, fn in (("pair_icp", bench_configs.pair_icp), ("room_refine_pose", lambda c: bench_configs.room_refine_pose(c, n_frames=args.room_frames))):
+                try:
+                    line["extra"][name] = fn(ctx)
+                except Exception as e:
+                    line["extra"][name] = {"error": repr(e)}
 
-    # ---- CPU baseline: the oracle port timed on this box's host cores (bounded sample), N=1 only
+    # ---- CPU baseline: the oracle port timed on this box's host cores (bounded sample), N=1 only; its systems are the parity check of the GPU's first step
     if world == 1 and not args.no_cpu_baseline:
         from oracle import pvo
         use_physical_cores()
@@ -380,6 +450,12 @@ def main():
         sample = (f"{cb['frames']} of {args.frames} source frames ({cb['evals']} points, {cb['n_assoc']} accepted) against the full {args.n_target}-point target, "
                   f"kd-tree prebuilt ({cb['kdtree_build_s']:.1f} s, not counted), association + Jet<12> residuals on all threads")
         line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": cb["threads"], "kind": "port", "sample": sample, "seconds": cb["seconds"]}
+        s_cpu, s_gpu = np.asarray(cb["systems"]), first_sys[:cb["frames"]]
+        scale = float(np.abs(s_cpu).max())
+        line["parity"] = {"against": "oracle (cpu_baseline run), reduced systems of the first timed step, all source frames of the sample",
+                          "counts_equal": bool(np.array_equal(s_cpu[:, 28], s_gpu[:, 28])), "n_accepted": int(s_gpu[:, 28].sum()), "n_accepted_oracle": int(s_cpu[:, 28].sum()),
+                          "sys_max_rel": float(np.abs(s_cpu - s_gpu).max() / scale), "gate": 1e-8, "frames": int(cb["frames"])}
+        line["parity"]["ok"] = bool(line["parity"]["counts_equal"] and line["parity"]["sys_max_rel"] < 1e-8)
         cb0 = cpu_baseline(argparse.Namespace(**{**vars(args), "cpu_sample_frames": 1}), d, steps=1, mode=0, tree=cb["tree"])
         line["cpu_baseline"]["reference_faithful"] = {"value": cb0["evals"] / cb0["seconds"], "unit": "evals/s",
                                                       "note": "association serial on 1 core (util/Optimization.cpp:506-562 has no omp), evaluation on all threads; 1 frame"}

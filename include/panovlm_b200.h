@@ -60,10 +60,12 @@ void* pvb_stream(const pvb_ctx* ctx);                 /* the cudaStream_t work i
 int pvb_blocks_set(pvb_ctx* ctx, long n, const int* type, const int* ref, const int* nei, const int* normalize,
                    const double* huber, const double* consts, int n_pose_blocks);
 /* == PrepareForEvaluation: evaluates every block at `poses` (n_pose_blocks x 6, host).  want_rows: per-block
- * residual + 1x12 Jacobian rows are brought back to pinned host mirrors (original block order);
+ * residual + 1x12 Jacobian rows are brought back to pinned host mirrors (original block order); 1 = rows with the
+ * robust loss applied (Ceres' Corrector: r and J scaled by sqrt(rho')), 2 = RAW rows - the caller registers the
+ * loss with its solver (ceres::HuberLoss(huber[i])), which then also computes the robust cost itself;
  * want_system: the per-edge normal equations (12x12 upper + gradient, 92 doubles) are reduced on the device.    */
 int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int want_system);
-const double* pvb_blocks_residuals(const pvb_ctx* ctx); /* n doubles, loss-corrected                             */
+const double* pvb_blocks_residuals(const pvb_ctx* ctx); /* n doubles (loss-corrected for want_rows = 1, raw for 2)   */
 const double* pvb_blocks_jacobians(const pvb_ctx* ctx); /* n x 12 row-major [d aa_ref | d t_ref | d aa_nei | d t_nei] */
 int pvb_blocks_cost(const pvb_ctx* ctx, double* cost, long* n_residuals);
 /* device time (CUDA events) of the residual+Jacobian kernel of the last pvb_blocks_evaluate                          */
@@ -72,6 +74,9 @@ int pvb_blocks_num_edges(const pvb_ctx* ctx);
 int pvb_blocks_edges(const pvb_ctx* ctx, int* ref, int* nei);
 /* per edge: H upper-triangular row-major (78) | g (12) | cost | n_residuals  (parameter order aa_r,t_r,aa_n,t_n) */
 int pvb_blocks_edge_systems(const pvb_ctx* ctx, double* out92);
+/* the same systems where the last evaluate left them (pinned host memory, n_edges x 92 doubles; valid until the next
+ * evaluate; NULL without want_system) - what include/panovlm_b200_reduced.hpp turns into one 13-residual block per edge */
+const double* pvb_blocks_edge_systems_ptr(const pvb_ctx* ctx);
 /* dense 6nb x 6nb J^T J, J^T r assembled on the host from the edge systems of the last evaluate                 */
 int pvb_blocks_dense_system(const pvb_ctx* ctx, double* H, double* g, double* cost);
 /* the ceres::Solve(SetOptionsLidar(...)) step (LidarOdometry.cpp:78-80): trust-region LM over the registered
@@ -381,11 +386,12 @@ int pvb_undistort_clouds(pvb_ctx* ctx, const float* xyzi, const int* offsets, in
 int pvb_reproj_set(pvb_ctx* ctx, long n_obs, const int* cam, const int* point, const double* bearing3, double weight, double huber, int n_cams,
                    long n_points);
 /* == PrepareForEvaluation for these blocks.  want_rows: residual + 1x9 Jacobian row [d aa_cw | d t_cw | d point] per observation in the
- * caller's order (pinned host mirrors); want_system: the blocks of the normal equations are reduced on the device — per camera
+ * caller's order (pinned host mirrors; 1 = loss-corrected, 2 = raw rows for a solver that applies the loss itself - not together with
+ * want_system); want_system: the blocks of the normal equations are reduced on the device — per camera
  * J_c^T J_c (upper 6x6, 21) and gradient (6), per point J_p^T J_p (upper 3x3, 6) and gradient (3), per observation the 6x3 coupling
  * block J_c^T J_p.                                                                                                                  */
 int pvb_reproj_evaluate(pvb_ctx* ctx, const double* cams6, const double* points3, int want_rows, int want_system);
-const double* pvb_reproj_residuals(const pvb_ctx* ctx);   /* n_obs doubles, loss-corrected              */
+const double* pvb_reproj_residuals(const pvb_ctx* ctx);   /* n_obs doubles (loss-corrected / raw)       */
 const double* pvb_reproj_jacobians(const pvb_ctx* ctx);   /* n_obs x 9 row-major                        */
 int pvb_reproj_cost(const pvb_ctx* ctx, double* cost);
 /* the reduced blocks of the last evaluate (any pointer may be NULL): cam_H21 n_cams x 21, cam_g6 n_cams x 6, pt_H6 n_points x 6,

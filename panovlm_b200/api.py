@@ -100,6 +100,7 @@ def load_library():
     L.pvb_last_error.restype = C.c_char_p
     L.pvb_kernel_launches.restype = C.c_long
     L.pvb_stream.restype = C.c_void_p
+    L.pvb_blocks_edge_systems_ptr.restype = C.POINTER(C.c_double)
     L.pvb_blocks_residuals.restype = C.POINTER(C.c_double)
     L.pvb_blocks_jacobians.restype = C.POINTER(C.c_double)
     L.pvb_reproj_residuals.restype = C.POINTER(C.c_double)
@@ -111,10 +112,10 @@ def load_library():
 EXPORTS = [
     "pvb_create", "pvb_destroy", "pvb_last_error", "pvb_set_stream", "pvb_synchronize", "pvb_kernel_launches", "pvb_stream",
     "pvb_blocks_set", "pvb_blocks_evaluate", "pvb_blocks_residuals", "pvb_blocks_jacobians", "pvb_blocks_cost", "pvb_blocks_kernel_time_ms", "pvb_blocks_num_edges",
-    "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_dense_system", "pvb_blocks_solve_lm",
+    "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_edge_systems_ptr", "pvb_blocks_dense_system", "pvb_blocks_solve_lm",
     "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn", "pvb_frames_set_corners", "pvb_frames_associate_point2line", "pvb_frames_get_point2line",
     "pvb_dense_set_target", "pvb_dense_set_sources", "pvb_dense_evaluate", "pvb_dense_evaluate_device", "pvb_dense_gauss_newton_step",
-    "pvb_dense_get_rows", "pvb_debug_counters", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
+    "pvb_dense_get_rows", "pvb_dense_set_hints", "pvb_dense_reset_hints", "pvb_debug_counters", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
     "pvb_find_neighbors", "pvb_line2line_associate", "pvb_camera_lidar_associate", "pvb_build_point2plane_blocks", "pvb_build_point2line_blocks", "pvb_build_line2line_blocks",
     "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
     "pvb_pair_knn5", "pvb_nearest_line", "pvb_point2line_segment_knn_associate", "pvb_point2line_segment_knn_tail", "pvb_point2line_segment_associate",

@@ -434,11 +434,13 @@ int pvb_reproj_evaluate(pvb_ctx* ctx, const double* cams6, const double* points3
   BAState* S = ctx ? ba_get(ctx, false) : nullptr;
   if (!ctx || !cams6 || (!points3 && S && S->n_pts > 0)) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_reproj_evaluate: bad arguments") : PVB_ERR_ARG;
   if (!S) return ctx->fail(PVB_ERR_STATE, "pvb_reproj_set has not been called");
+  if (want_rows == 2 && want_system) return ctx->fail(PVB_ERR_ARG, "pvb_reproj_evaluate: raw rows (want_rows = 2) and the reduced system (always loss-corrected) need two calls");
   CK(cudaSetDevice(ctx->device));
   int rc = upload_state(ctx, S, cams6, points3); if (rc) return rc;
   ReprojArgs a{};
   a.cam = S->d_cam.as<int>(); a.pt = S->d_pt.as<int>(); a.orig = S->d_orig.as<int>(); a.bearing = S->d_bearing.as<double>();
   a.prep = S->d_prep.as<PosePrep>(); a.X = S->d_X.as<double>(); a.weight = S->weight; a.huber = S->huber; a.n = S->n_obs;
+  if (want_rows == 2) a.huber = 0.0;              // raw rows: the caller registers the loss with its solver (ceres::HuberLoss)
   a.W = want_system ? S->d_W.as<double>() : nullptr;
   a.r_rows = want_rows ? S->d_r.as<double>() : nullptr; a.J_rows = want_rows ? S->d_J.as<double>() : nullptr;
   if (!want_system && !want_rows) a.W = S->d_W.as<double>();

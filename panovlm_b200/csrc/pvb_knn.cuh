@@ -18,6 +18,7 @@
 namespace pvb {
 
 struct alignas(16) F4 { float x, y, z, w; };
+struct alignas(8) U2 { uint32_t x, y; };          // candidate-list entry of the hinted search: (d2 bits, record position)
 
 struct GridDesc {
   double origin[3];
@@ -255,7 +256,8 @@ PVB_HD void walk_block_pruned(const GridDesc& g, const CellLoader& cells, int cx
 }
 
 template <int K, typename CellLoader, typename Load, typename Sink>
-PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const Load& load, float qx, float qy, float qz, float sq_thr, int r0, int rmax, const Sink& sink) {
+PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const Load& load, float qx, float qy, float qz, float sq_thr, int r0, int rmax, const Sink& sink,
+                             uint32_t* tau_out = nullptr) {
   const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
   uint32_t keys[K];
 #pragma unroll
@@ -303,6 +305,7 @@ PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const L
   }
   if (keys[K - 1] == init) return 0;
   const uint32_t tau = keys[K - 1];
+  if (tau_out) *tau_out = tau;
   int n_lt = 0;
 #pragma unroll
   for (int j = 0; j < K; ++j) n_lt += keys[j] < tau ? 1 : 0;
@@ -322,21 +325,20 @@ PVB_HD int knn_select_pruned(const GridDesc& g, const CellLoader& cells, const L
   return n_out;
 }
 
-// ---- buffered single-pass variant (default path since round 2) -----------------------------------------------------------------
-// One walk over the block instead of two: every candidate whose squared distance is below the running limit is appended to a small
-// per-query list (key = d2 bits, payload = record position; LC entries, caller-provided storage); when the list is full it is cut
-// back to its K smallest entries (value-only min/max network over the list, then an in-place compaction) and the limit drops to the
-// K-th of them, which also prunes the rows / cells still to come.  The final cut leaves the K nearest in list slots 0..K-1.
-// Ties at the K-th distance are resolved by visiting order exactly like the two-pass variants (a later candidate must be strictly
-// closer to displace an earlier one), so the selected set is identical to theirs.
-//
+// ---- hinted single-pass variant (default path since round 2) ---------------------------------------------------------------------
 // Search-radius hint: `lim_hint` (0 = none) is an exclusive upper bound (d2 bit pattern) that the caller claims holds for the K-th
 // squared distance, e.g. from the previous evaluation of the same query: K target points lay within sqrt(tau_old) of q_old, so they
-// lie within sqrt(tau_old) + |q - q_old| of q.  The hint only shortens the walk: when fewer than K candidates are found below it
-// (a stale hint) the search restarts without it, so the result never depends on the hint being right.
-//   lput(n, key, pos) / lkey(i) / lpos(i) / lmove(dst, src): list storage;  returns K (found; *tau_out = K-th key) or 0.
-template <int K, int LC, typename LKey, typename LPos, typename LMove>
-PVB_HD uint32_t list_cut_to_k(int& n, const LKey& lkey, const LPos& lpos, const LMove& lmove) {
+// lie within sqrt(tau_old) + |q - q_old| of q.  With a bound known up front ONE walk over the block is enough: every candidate below
+// the bound goes to a small per-query list (key = d2 bits, payload = record position; LC entries, caller-provided storage) with a
+// branch-free body, rows and cells beyond the bound are never touched, and the list (typically K .. K+3 entries once the poses settle)
+// is cut to its K smallest entries afterwards (value-only min/max network over the list + in-place compaction; nothing to do when it
+// holds exactly K).  The hint only shortens the walk: when fewer than K candidates are found below it (stale hint) or more than LC
+// (bound far too wide), or when there is no hint, the pruned two-pass search above runs instead, so the result never depends on the
+// hint being right.  Ties at the K-th distance are resolved by visiting order like in the two-pass search (same row order, a later
+// candidate must be strictly closer to displace an earlier one).
+//   The K nearest end up in list slots 0..K-1 (entry e at lbase[e * lstride]).
+template <int K, typename LKey, typename LMove>
+PVB_HD uint32_t list_cut_to_k(int& n, const LKey& lkey, const LMove& lmove) {
   uint32_t keys[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) keys[j] = 0xFFFFFFFFu;
@@ -358,100 +360,111 @@ PVB_HD uint32_t list_cut_to_k(int& n, const LKey& lkey, const LPos& lpos, const 
   return tau;
 }
 
-template <int K, int LC, typename CellLoader, typename Load, typename LPut, typename LKey, typename LPos, typename LMove>
-PVB_HD int knn_select_buffered(const GridDesc& g, const CellLoader& cells, const Load& load, float qx, float qy, float qz, float sq_thr, int rmax, uint32_t lim_hint,
-                               const LPut& lput, const LKey& lkey, const LPos& lpos, const LMove& lmove, uint32_t* tau_out) {
+// One walk over the (2 rb + 1)^3 block in the row order of walk_block_pruned (nearest rows first) with a FIXED exclusive limit `lim`:
+// appends every candidate with d2 bits < lim (list entries beyond LC are dropped, the count keeps running).  32-bit cell arithmetic
+// (the cell table has < 2^32 entries), four candidates in flight per iteration.
+// List storage: entry e of this query lives at lbase[e * lstride] (shared memory on the device: stride = threads per block).
+template <int LC, typename CellLoader, typename Load>
+PVB_HD int walk_block_collect(const GridDesc& g, const CellLoader& cells, const Load& load, int cx, int cy, int cz, const FaceGaps& fg, const double gap_lo[3], const double gap_hi[3],
+                              int rb, uint32_t lim, float qx, float qy, float qz, U2* lbase, int lstride) {
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  const int W = 2 * rb + 1;
+  auto far2 = [&](int a, int d) { const double v = d < 0 ? gap_lo[a] + (double)(-d - 1) * g.h : gap_hi[a] + (double)(d - 1) * g.h; return (float)(v * v * (1.0 - 1e-5)); };
+  auto bound2 = [&](int a, int d) { return d == 0 ? 0.0f : (d == -1 ? fg.lo[a] : (d == 1 ? fg.hi[a] : far2(a, d))); };
+  U2* lp = lbase;
+  U2* const lend = lbase + (long long)LC * lstride;
+#pragma unroll 1
+  for (int iz = 0; iz < W; ++iz) {
+    const int dz = (iz & 1) ? -((iz + 1) >> 1) : (iz >> 1);      // 0, -1, +1, -2, +2: nearest rows first
+    const int z = cz + dz;
+    if (z < 0 || z >= nz) continue;
+    const float bz = bound2(2, dz);
+    if (f2u(bz) >= lim) continue;
+#pragma unroll 1
+    for (int iy = 0; iy < W; ++iy) {
+      const int dy = (iy & 1) ? -((iy + 1) >> 1) : (iy >> 1);
+      const int y = cy + dy;
+      if (y < 0 || y >= ny) continue;
+      const float b2 = bound2(1, dy) + bz;                       // float sum of two margin-shrunk terms: still below the true bound
+      if (f2u(b2) >= lim) continue;
+      int xa = cx, xb = cx;
+      for (int d = 1; d <= rb; ++d) {
+        if (cx - d < 0 || f2u(b2 + bound2(0, -d)) >= lim) break;
+        xa = cx - d;
+      }
+      for (int d = 1; d <= rb; ++d) {
+        if (cx + d > nx - 1 || f2u(b2 + bound2(0, d)) >= lim) break;
+        xb = cx + d;
+      }
+      const uint32_t row = ((uint32_t)z * (uint32_t)ny + (uint32_t)y) * (uint32_t)nx;
+      const uint32_t lo = (uint32_t)cells((long long)(row + (uint32_t)xa)), hi = (uint32_t)cells((long long)(row + (uint32_t)xb + 1u));
+#pragma unroll 1
+      for (uint32_t i = lo; i < hi; i += 4u) {
+        F4 c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const uint32_t ik = i + k < hi ? i + k : hi - 1u; c[k] = load((long long)ik); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c[k].x, c[k].y, c[k].z));
+          const bool p = kb < lim && i + k < hi;
+          if (p && lp < lend) { U2 e; e.x = kb; e.y = i + k; *lp = e; }
+          lp += p ? lstride : 0;                                 // keeps counting past the capacity: the caller sees the overflow
+        }
+      }
+    }
+  }
+  return (int)((lp - lbase) / lstride);
+}
+
+template <int K, int LC, typename CellLoader, typename Load, typename WinSet>
+PVB_HD int knn_select_hinted(const GridDesc& g, const CellLoader& cells, const Load& load, float qx, float qy, float qz, float sq_thr, int r0, int rmax, uint32_t lim_hint,
+                             U2* lbase, int lstride, const WinSet& set_win, uint32_t* tau_out) {
+  auto lkey = [&](int e) { return lbase[(long long)e * lstride].x; };
+  auto lmove = [&](int dst, int src) { lbase[(long long)dst * lstride] = lbase[(long long)src * lstride]; };
   static_assert(LC >= K + 2, "list capacity");
   const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
-  const double fx = ((double)qx - g.origin[0]) * g.inv_h, fy = ((double)qy - g.origin[1]) * g.inv_h, fz = ((double)qz - g.origin[2]) * g.inv_h;
-  const int cx = cell_coord((double)qx, g.origin[0], g.inv_h, g.dims[0]);
-  const int cy = cell_coord((double)qy, g.origin[1], g.inv_h, g.dims[1]);
-  const int cz = cell_coord((double)qz, g.origin[2], g.inv_h, g.dims[2]);
-  double gap_lo[3], gap_hi[3], slack = 0.5;
-  {
-    const double f[3] = {fx - cx, fy - cy, fz - cz};
+  if (lim_hint != 0u && lim_hint < init) {
+    const double fx = ((double)qx - g.origin[0]) * g.inv_h, fy = ((double)qy - g.origin[1]) * g.inv_h, fz = ((double)qz - g.origin[2]) * g.inv_h;
+    const int cx = cell_coord((double)qx, g.origin[0], g.inv_h, g.dims[0]);
+    const int cy = cell_coord((double)qy, g.origin[1], g.inv_h, g.dims[1]);
+    const int cz = cell_coord((double)qz, g.origin[2], g.inv_h, g.dims[2]);
+    double gap_lo[3], gap_hi[3], slack = 0.5;
+    {
+      const double f[3] = {fx - cx, fy - cy, fz - cz};
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const double lo = f[a] < 0.0 ? 0.0 : f[a], hi = 1.0 - f[a] < 0.0 ? 0.0 : 1.0 - f[a];
-      gap_lo[a] = lo * g.h; gap_hi[a] = hi * g.h;
-      const double m = lo < hi ? lo : hi;
-      slack = m < slack ? m : slack;
+      for (int a = 0; a < 3; ++a) {
+        const double lo = f[a] < 0.0 ? 0.0 : f[a], hi = 1.0 - f[a] < 0.0 ? 0.0 : 1.0 - f[a];
+        gap_lo[a] = lo * g.h; gap_hi[a] = hi * g.h;
+        const double m = lo < hi ? lo : hi;
+        slack = m < slack ? m : slack;
+      }
     }
-  }
-  FaceGaps fg;
+    FaceGaps fg;
 #pragma unroll
-  for (int a = 0; a < 3; ++a) { fg.lo[a] = (float)(gap_lo[a] * gap_lo[a] * (1.0 - 1e-5)); fg.hi[a] = (float)(gap_hi[a] * gap_hi[a] * (1.0 - 1e-5)); }
-  if (rmax < 1) rmax = 1;
-  // block radius (cells) that covers the hinted search radius: every point closer than (r + slack) * h lies in the (2r+1)^3 block
-  int rb = 1;
-  bool hinted = lim_hint != 0u && lim_hint < init;
-  if (hinted) {
+    for (int a = 0; a < 3; ++a) { fg.lo[a] = (float)(gap_lo[a] * gap_lo[a] * (1.0 - 1e-5)); fg.hi[a] = (float)(gap_hi[a] * gap_hi[a] * (1.0 - 1e-5)); }
+    // block radius (cells) that covers the hinted search radius: every point closer than (r + slack) * h lies in the (2r+1)^3 block
     const double lim = (double)u2f(lim_hint);
     const double reach1 = (1.0 + slack) * g.h, reach2 = (2.0 + slack) * g.h;
+    int rb = 0;
     if (lim < reach1 * reach1 * (1.0 - 1e-6)) rb = 1;
-    else if (lim < reach2 * reach2 * (1.0 - 1e-6) && rmax >= 2) rb = 2;
-    else hinted = false;
-  }
-  int n = 0;
-  uint32_t lim = hinted ? lim_hint : init;         // accept d2 bits < lim
-  // limit_key view for the pruned walk (it skips a row / cell when its bound key is > limit_key): lim - 1
-  uint32_t limit_key = lim - 1u;
-  auto body = [&](long long i) {
-    const F4 c = load(i);
-    const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
-    if (kb < lim) {
-      lput(n, kb, (uint32_t)i); ++n;
-      if (n == LC) { lim = list_cut_to_k<K, LC>(n, lkey, lpos, lmove); limit_key = lim == 0u ? 0u : lim - 1u; }
-    }
-  };
-  for (;;) {
-    walk_block_pruned<K>(g, cells, cx, cy, cz, fg, gap_lo, gap_hi, rb, limit_key, body);
-    if (n >= K || !hinted) break;
-    hinted = false; n = 0; rb = 1; lim = init; limit_key = lim - 1u;     // stale hint: search again without it
-  }
-  if (n > K) { lim = list_cut_to_k<K, LC>(n, lkey, lpos, lmove); limit_key = lim == 0u ? 0u : lim - 1u; }
-  else if (n == K) {
-    uint32_t mx = 0u;
+    else if (lim < reach2 * reach2 * (1.0 - 1e-6)) rb = 2;
+    if (rb != 0) {
+      int n = walk_block_collect<LC>(g, cells, load, cx, cy, cz, fg, gap_lo, gap_hi, rb, lim_hint, qx, qy, qz, lbase, lstride);
+      if (n >= K && n <= LC) {
+        uint32_t tau;
+        if (n > K) tau = list_cut_to_k<K>(n, lkey, lmove);
+        else {
+          tau = 0u;
 #pragma unroll
-    for (int j = 0; j < K; ++j) { const uint32_t v = lkey(j); mx = v > mx ? v : mx; }
-    lim = mx; limit_key = lim == 0u ? 0u : lim - 1u;
-  }
-  // lim == K-th key when n == K.  Done when the block covers it; otherwise widen ring by ring (rare)
-  bool done = false;
-  if (n == K) {
-    const double reach = ((double)rb + slack) * g.h;
-    done = (double)u2f(lim) < reach * reach * (1.0 - 1e-6);
-  }
-  if (!done) {
-    uint32_t kth = n == K ? lim : init;              // the K-th smallest so far (exclusive bound for ties handled by the cut)
-    for (int r = rb + 1; r <= rmax; ++r) {
-      for_each_range(g, cells, cx, cy, cz, r, false, [&](long long lo, long long hi) {
-        for (long long i = lo; i < hi; ++i) {
-          const F4 c = load(i);
-          const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, c.x, c.y, c.z));
-          if (kb < kth) {
-            lput(n, kb, (uint32_t)i); ++n;
-            if (n == LC) kth = list_cut_to_k<K, LC>(n, lkey, lpos, lmove);
-          }
+          for (int j = 0; j < K; ++j) { const uint32_t v = lkey(j); tau = v > tau ? v : tau; }
         }
-      });
-      if (n > K) kth = list_cut_to_k<K, LC>(n, lkey, lpos, lmove);
-      else if (n == K) {
-        uint32_t mx = 0u;
-#pragma unroll
-        for (int j = 0; j < K; ++j) { const uint32_t v = lkey(j); mx = v > mx ? v : mx; }
-        kth = mx;
-      }
-      if (n == K) {      // ring r covers every point closer than (r + slack) * h
-        const double reach = ((double)r + slack) * g.h;
-        if ((double)u2f(kth) < reach * reach * (1.0 - 1e-6)) break;
+        if (tau_out) *tau_out = tau;
+        return K;
       }
     }
-    lim = kth;
   }
-  if (n < K) return 0;
-  if (tau_out) *tau_out = lim;
-  return K;
+  // no usable hint: the pruned two-pass search
+  return knn_select_pruned<K>(g, cells, load, qx, qy, qz, sq_thr, r0, rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, tau_out);
 }
 
 struct AssocParams {
@@ -468,21 +481,12 @@ struct AssocParams {
 // caller's per-query neighbour slots (shared memory on the device).
 // REF_ID: the reference frame's pose is exactly the identity (rigid target map): World2Local of a neighbour is then the
 // neighbour itself bit for bit (x*1 + y*0 + z*0 - 0), so the 3 x K matrix-vector products per query are skipped.
-// MODE: 0 = exhaustive walk over stored row ranges (TMA-staged variant), 1 = pruned two-pass walk, 2 = buffered single pass (default; uses the
-// list accessors and the search-radius hint, see knn_select_buffered; the K nearest end up in list slots 0..K-1 = win(0..K-1)).
-template <int K, bool REF_ID, int MODE, int LC = K + 2, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet,
-          typename LPut, typename LKey, typename LPos, typename LMove>
-PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const Load1& load1, const LoadG& loadg, const RowMap& row_map, const AssocParams& prm,
-                                  float qx, float qy, float qz, uint32_t qcls,
-                                  const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
-                                  double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get,
-                                  uint32_t lim_hint, uint32_t* tau_out, const LPut& lput, const LKey& lkey, const LPos& lpos, const LMove& lmove) {
-  int ring = 1;
-  int found;
-  if (MODE == 2) { found = knn_select_buffered<K, LC>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.rmax, lim_hint, lput, lkey, lpos, lmove, tau_out); ring = 2; }
-  else if (MODE == 1) { found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }); ring = 2; }
-  else found = knn_select<K>(g, cells, load1, loadg, row_map, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
-  if (found < K) return false;                                   // :578
+// Everything of AssociatePoint2Plane after the search (LidarFeatureAssociate.cpp:583-599): win(0..K-1) hold the record positions of the K nearest
+// neighbours (any order), `load` reads a record.  Same-class test, neighbours -> reference sensor frame, LSQ plane + tolerance, collinearity reject.
+template <int K, bool REF_ID, typename Load, typename WinGet, typename WinSet>
+PVB_HD bool plane_from_window(const Load& load, const AssocParams& prm, float qx, float qy, float qz, uint32_t qcls,
+                              const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
+                              double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win) {
   {
     // canonical neighbour order = ascending record position: the plane fit below sums over the neighbours, and the order the search
     // found them in depends on the walk (block radius, ring expansion, hints); sorting makes the result independent of all of that
@@ -497,7 +501,6 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
 #pragma unroll
     for (int j = 0; j < K; ++j) set_win(j, wp[j]);
   }
-  auto load = [&](long long pos) { return ring == 1 ? load1(pos) : loadg(pos); };   // neighbour positions live in the space they were found in (k-th beyond the threshold) + quirk C.6 guard
   // neighbours -> reference sensor frame (:587), streamed: Gram matrix for the LSQ plane and the scatter matrix
   PlaneAcc acc; plane_acc_clear(acc);
   int same = 0;
@@ -559,6 +562,25 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
   const double qw[3] = {(double)qx, (double)qy, (double)qz};
   world2local(R_nei, t_nei, qw, p_local);                        // :598-599
   return true;
+}
+
+
+// MODE: 0 = exhaustive walk over stored row ranges (TMA-staged variant), 1 = pruned two-pass walk, 2 = hinted single pass with the two-pass walk as
+// fallback (default; uses the list accessors and the search-radius hint, see knn_select_hinted; the K nearest end up in list slots 0..K-1 = win(0..K-1)).
+template <int K, bool REF_ID, int MODE, int LC = K + 2, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const Load1& load1, const LoadG& loadg, const RowMap& row_map, const AssocParams& prm,
+                                  float qx, float qy, float qz, uint32_t qcls,
+                                  const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
+                                  double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get,
+                                  uint32_t lim_hint, uint32_t* tau_out, U2* lbase, int lstride) {
+  int ring = 1;
+  int found;
+  if (MODE == 2) { found = knn_select_hinted<K, LC>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, lim_hint, lbase, lstride, set_win, tau_out); ring = 2; }
+  else if (MODE == 1) { found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }); ring = 2; }
+  else found = knn_select<K>(g, cells, load1, loadg, row_map, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
+  if (found < K) return false;                                   // :578
+  auto load = [&](long long pos) { return ring == 1 ? load1(pos) : loadg(pos); };   // neighbour positions live in the space they were found in (k-th beyond the threshold) + quirk C.6 guard
+  return plane_from_window<K, REF_ID>(load, prm, qx, qy, qz, qcls, R_ref, t_ref, R_nei, t_nei, p_local, plane, win, set_win);
 }
 
 // Per-query body of AssociatePoint2Line (lidar_mapping/LidarFeatureAssociate.cpp:478-548): 5 nearest corner points of

@@ -143,6 +143,20 @@ int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_ide
   a.prm.r0 = ctx->tune_r0;
   a.use_hint = ctx->tune_hints;
   if (mode == 0 && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
+  if (mode == 3) {                    // warp-cooperative search (groups of 8 queries share staged candidates)
+    constexpr size_t smem = sizeof(CoopWarp) * (kTile / 32);
+#define PVB_COOP(KK, DBG, RI) do { auto kern = k_associate_coop<KK, REDUCE, DBG, RI>; \
+      if (!ctx->coop_attr_set[(KK == 10 ? 0 : 1) * 4 + (DBG ? 2 : 0) + (RI ? 1 : 0)][REDUCE ? 1 : 0]) { \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->coop_attr_set[(KK == 10 ? 0 : 1) * 4 + (DBG ? 2 : 0) + (RI ? 1 : 0)][REDUCE ? 1 : 0] = true; } \
+      kern<<<n_tiles, kTile, smem, ctx->stream>>>(a); } while (0)
+#define PVB_COOP_K(KK) do { if (dbg) { if (ref_identity) PVB_COOP(KK, true, true); else PVB_COOP(KK, true, false); } \
+                            else { if (ref_identity) PVB_COOP(KK, false, true); else PVB_COOP(KK, false, false); } } while (0)
+    if (k == 10) PVB_COOP_K(10); else PVB_COOP_K(5);
+#undef PVB_COOP_K
+#undef PVB_COOP
+    CKL();
+    return PVB_OK;
+  }
 #define PVB_LAUNCH(KK, MB, DBG, MD) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, MD, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, MD, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
 #define PVB_MINB_SWITCH(KK, MD) do { if (minb >= 6) PVB_LAUNCH(KK, 6, false, MD); else if (minb == 5) PVB_LAUNCH(KK, 5, false, MD); else PVB_LAUNCH(KK, 4, false, MD); } while (0)
 #define PVB_DISPATCH(KK)                                                                                   \
@@ -176,7 +190,7 @@ int pvb_create(int device, pvb_ctx** out) {
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->bev0); cudaEventCreate(&ctx->bev1);
   if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e);
   if (const char* e = getenv("PVB_STAGE")) ctx->tune_stage = atoi(e) != 0;
-  if (const char* e = getenv("PVB_MODE")) ctx->tune_mode = std::min(2, std::max(0, atoi(e)));
+  if (const char* e = getenv("PVB_MODE")) ctx->tune_mode = std::min(3, std::max(0, atoi(e)));
   if (const char* e = getenv("PVB_HINTS")) ctx->tune_hints = atoi(e) != 0;
   if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
@@ -328,6 +342,7 @@ int pvb_blocks_evaluate(pvb_ctx* ctx, const double* poses, int want_rows, int wa
     a.orig = ctx->b_orig_d.as<uint32_t>(); a.n = n; a.prep = ctx->d_prep.as<PosePrep>();
     a.out_r = want_rows ? ctx->b_r.as<double>() : nullptr; a.out_J = want_rows ? ctx->b_J.as<double>() : nullptr;
     a.partials = want_system ? ctx->b_part.as<double>() : nullptr;
+    a.raw_rows = want_rows == 2 ? 1 : 0;
     CK(cudaEventRecord(ctx->bev0, ctx->stream));
     k_eval_blocks<<<ctx->b_tiles, kTile, 0, ctx->stream>>>(a);
     CKL();
@@ -396,6 +411,7 @@ int pvb_blocks_edges(const pvb_ctx* ctx, int* ref, int* nei) {
   for (size_t e = 0; e < ctx->edge_ref.size(); ++e) { ref[e] = ctx->edge_ref[e]; nei[e] = ctx->edge_nei[e]; }
   return PVB_OK;
 }
+const double* pvb_blocks_edge_systems_ptr(const pvb_ctx* ctx) { return (ctx && ctx->b_has_sys) ? ctx->h_esys.as<double>() : nullptr; }
 int pvb_blocks_edge_systems(const pvb_ctx* ctx, double* out) {
   if (!ctx || !ctx->b_has_sys) return PVB_ERR_STATE;
   memcpy(out, ctx->h_esys.p, ctx->edge_ref.size() * 92 * 8);
@@ -438,11 +454,10 @@ int pvb_blocks_dense_system(const pvb_ctx* ctx, double* H, double* g, double* co
 // factor the N x N matrix in ctx->s_A (lower triangle, in place) and solve with the right-hand side in ctx->s_rhs; *ok = 0 when a pivot fails
 constexpr size_t kTrsmSmem = 2 * kNB * (kNB + 1) * sizeof(double);
 int pvb_internal_factor_solve(pvb_ctx* ctx, int N, bool* ok) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->solver_attr_set) {       // function attributes are per device: one opt-in per context (= per device), not per process
     CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
     CK(cudaFuncSetAttribute(k_syrk_update_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
-    attr_set = true;
+    ctx->solver_attr_set = true;
   }
   CK(cudaMemsetAsync(ctx->s_fail.p, 0, 4, ctx->stream));
   CK(ctx->s_y.ensure((size_t)N * 8));

@@ -201,14 +201,19 @@ def make_pair(seed=20260925, n_az=1800, ground_class=False):
     return make_frame(RA, tA, seed + 1, n_az, ground_class), make_frame(RB, tB, seed + 2, n_az, ground_class)
 
 
-def make_sequence(n_frames, seed=20260926, n_az=1800, radius=1.2):
-    """configs[1]-like: frames along a closed loop inside the room."""
+def make_sequence(n_frames, seed=20260926, n_az=1800, radius=1.2, tilt=0.0):
+    """configs[1]-like: frames along a closed loop inside the room.
+    tilt (rad): the sensor is additionally pitched / rolled by up to `tilt` along the loop (a hand-held or backpack rig).  With tilt = 0 the
+    +-15 degree rings of a level VLP-16 at the room centre only ever see the walls and pillars - never the floor or the ceiling - so the
+    vertical translation of a frame is not observable from point-to-plane / line-to-line constraints (the optimiser is free to slide along it)."""
     rng = np.random.default_rng(seed)
     frames = []
     for i in range(n_frames):
         a = 2 * np.pi * i / n_frames
         t = np.array([radius * np.cos(a), rng.normal(0, 0.02), 0.6 * radius * np.sin(a)])
         R = rotvec_to_R(np.array([rng.normal(0, 0.01), a * 0.5 + rng.normal(0, 0.01), rng.normal(0, 0.01)]))
+        if tilt != 0.0:
+            R = R @ rotvec_to_R(np.array([tilt * np.cos(3 * a), 0.0, tilt * np.sin(2 * a + 0.7)]))
         frames.append(make_frame(R, t, seed + 10 + i, n_az))
     return frames
 

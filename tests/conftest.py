@@ -27,7 +27,7 @@ def build_adapter_harness():
     """tests/adapter_harness.cpp: the Ceres bridge of include/ driven through the ceres stand-in of oracle/shim, linked against the product library."""
     out = os.path.join(ROOT, "tests", "libpvb_adapter_harness.so")
     src = os.path.join(ROOT, "tests", "adapter_harness.cpp")
-    deps = [src, os.path.join(ROOT, "include", "panovlm_b200_ceres_adapter.hpp"), os.path.join(ROOT, "include", "panovlm_b200.h"),
+    deps = [src, os.path.join(ROOT, "include", "panovlm_b200_ceres_adapter.hpp"), os.path.join(ROOT, "include", "panovlm_b200.h"), os.path.join(ROOT, "include", "panovlm_b200_reduced.hpp"),
             os.path.join(ROOT, "oracle", "shim", "pvo_shim_ceres.hpp"), os.path.join(ROOT, "oracle", "shim", "pvo_shim_eigen.hpp")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I", os.path.join(ROOT, "oracle", "shim"), "-I", os.path.join(ROOT, "include"),

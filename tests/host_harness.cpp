@@ -52,13 +52,9 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
     auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = rng[2 * k]; hi = rng[2 * k + 1]; };
     auto no_map = [](int, int, uint32_t&, uint32_t&) {};
     constexpr int LC = 24;
-    uint32_t lk[LC], lp[LC];
-    auto lput = [&](int nn_, uint32_t key, uint32_t pos) { lk[nn_] = key; lp[nn_] = pos; };
-    auto lkey = [&](int nn_) { return lk[nn_]; };
-    auto lpos = [&](int nn_) { return lp[nn_]; };
-    auto lmove = [&](int dst, int src) { lk[dst] = lk[src]; lp[dst] = lp[src]; };
-    auto win2 = [&](int j) { return lp[j]; };
-    auto set_win2 = [&](int j, uint32_t pos) { lp[j] = pos; };
+    U2 lst[LC];
+    auto win2 = [&](int j) { return lst[j].y; };
+    auto set_win2 = [&](int j, uint32_t pos) { lst[j].y = pos; };
     const float qx = qry[i * 4], qy = qry[i * 4 + 1], qz = qry[i * 4 + 2];
     uint32_t lim_hint = 0u, tau = 0x7F800000u;
     if (g_prune == 3 && g_hint) {        // same arithmetic as k_associate (pvb_kernels.cuh)
@@ -71,12 +67,12 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
       }
     }
 #define PVBH_ASSOC(MODE, W, SW) associate_point2plane<K, false, MODE, LC>(g, cells, load, load, no_map, prm, qx, qy, qz, qcls, R_ref, t_ref, R_nei, t_nei, \
-                                                               p_local + 3 * i, plane + 4 * i, W, SW, range_set, range_get, lim_hint, &tau, lput, lkey, lpos, lmove)
-    if (g_prune == 3) { for (int j = 0; j < K; ++j) lp[j] = 0xFFFFFFFFu; }
+                                                               p_local + 3 * i, plane + 4 * i, W, SW, range_set, range_get, lim_hint, &tau, lst, 1)
+    if (g_prune == 3) { for (int j = 0; j < K; ++j) lst[j].y = 0xFFFFFFFFu; }
     valid[i] = (g_prune == 0 ? PVBH_ASSOC(0, win, set_win) : (g_prune == 3 ? PVBH_ASSOC(2, win2, set_win2) : PVBH_ASSOC(1, win, set_win))) ? 1 : 0;
 #undef PVBH_ASSOC
     if (g_prune == 3) {
-      for (int j = 0; j < K; ++j) wpos[j] = tau == 0x7F800000u ? 0xFFFFFFFFu : lp[j];
+      for (int j = 0; j < K; ++j) wpos[j] = tau == 0x7F800000u ? 0xFFFFFFFFu : lst[j].y;
       if (g_hint_out) { g_hint_out[4 * i] = qx; g_hint_out[4 * i + 1] = qy; g_hint_out[4 * i + 2] = qz; g_hint_out[4 * i + 3] = u2f(tau); }
     }
     std::vector<std::pair<std::pair<float, uint32_t>, int>> nn;

@@ -680,6 +680,40 @@ def test_odometry_outer_iteration_matches_oracle_loop(gpu_ctx, oracle):
     assert np.abs(p_gpu - truth).max() < np.abs(start - truth).max()
 
 
+def test_estimate_pose_seven_outer_iterations_match_the_oracle_end_to_end(gpu_ctx, oracle):
+    """configs[1] end to end on a 30-frame loop: the full EstimatePose (up to 7 RefinePose outer iterations with the reference's early exits, point-to-plane +
+    line-to-line + track gate, first frame fixed) through the C ABI against the same loop on the oracle: same number of outer iterations, pose deltas within
+    1e-4 relative (BASELINE.json), and the result is closer to the generator's poses than the start IN EVERY AXIS.  The sensor is tilted (synth.make_sequence):
+    with a level VLP-16 the scene holds no surface that constrains the vertical translation and both implementations slide along it (the round-1 "drift")."""
+    from panovlm_b200 import odometry, synth
+    from scipy.spatial.transform import Rotation
+    frames = synth.make_sequence(30, n_az=600, tilt=0.35)
+    rng = np.random.default_rng(1)
+    R0 = [f["R_wl"] @ Rotation.from_rotvec(rng.normal(0, 0.005, 3) * (i > 0)).as_matrix() for i, f in enumerate(frames)]
+    t0 = [f["t_wl"] + rng.normal(0, 0.02, 3) * (i > 0) for i, f in enumerate(frames)]
+    start = odometry.pose_blocks_from_world(R0, t0, oracle.R_to_aa)
+    cfg = odometry.OdometryConfig()
+    p_gpu, log_gpu = odometry.estimate_pose(gpu_ctx, frames, start, cfg, oracle.aa_to_R, max_iteration=7)
+    n_blocks = []
+
+    def oracle_refine(ctx, fr, poses, c, aa_to_R):
+        (p, s), nb = _oracle_refine(oracle, fr, poses, c)
+        n_blocks.append(nb)
+        return p, s
+    p_cpu, log_cpu = odometry.estimate_pose(None, frames, start, cfg, oracle.aa_to_R, max_iteration=7, refine_fn=oracle_refine)
+    assert len(log_gpu) == len(log_cpu) and len(log_gpu) >= 2
+    assert [s["n_blocks"] for s in log_gpu] == n_blocks
+    for sg, sc in zip(log_gpu, log_cpu):
+        assert abs(sg["final_cost"] - sc["final_cost"]) < 1e-6 * sc["final_cost"] and sg["successful"] == sc["successful"]
+    d_gpu, d_cpu = p_gpu - start, p_cpu - start
+    assert np.abs(d_gpu - d_cpu).max() < POSE_RTOL * np.abs(d_cpu).max()
+
+    def axis_err(p):
+        _, t_wl = odometry.world_from_pose_blocks(p, oracle.aa_to_R)
+        return np.abs(np.array([t - f["t_wl"] for t, f in zip(t_wl, frames)])).mean(0)
+    assert np.all(axis_err(p_gpu) < 0.6 * axis_err(start))
+
+
 def test_point2plane_blocks_built_on_the_device_equal_the_host_builders(gpu_ctx, oracle):
     """pvb_frames_point2plane_blocks == pvb_frames_associate_point2plane + pvb_build_point2plane_blocks_edges + pvb_blocks_set: same rows bit for bit,
     extra host blocks appended behind them, pose-block offset (joint layout), and the same RefinePose result through either path."""

@@ -1,0 +1,149 @@
+"""The other BASELINE.json configs as `extra.*` entries of the bench line (bench.py calls these after the headline measurement):
+  pair_icp                 configs[0]  2-frame VLP-16 scan pair, point-to-plane ICP (dense: all 28,800 points, association redone every
+                                       iteration, 20 Gauss-Newton iterations; feature mode: one RefinePose on surfFlat / surfLessFlat)
+  room_refine_pose         configs[1]  Room-shaped sequence (454 frames on a loop): EstimatePose = up to 7 RefinePose outer iterations with
+                                       point-to-plane + line-to-line residuals (config/Room.txt:67-76), first frame fixed
+  floor_refine_pose        configs[3]  Floor-shaped sequence (1593 frames): one RefinePose, reference frames sharded over the ranks of the
+                                       launch, one allreduce of the edge systems per evaluation; identical poses on every rank
+Synthetic frames (panovlm_b200.synth, seeds fixed).  Wall-clock times around device-synchronous calls; errors are against the generator's
+true poses: translation |t_wl - t_true| in metres and rotation angle of R_wl^T R_true in radians."""
+import hashlib
+import time
+
+import numpy as np
+from scipy.spatial.transform import Rotation
+
+import panovlm_b200
+from panovlm_b200 import odometry, synth
+
+
+def aa_to_R(a):
+    return Rotation.from_rotvec(a).as_matrix()
+
+
+def R_to_aa(R):
+    return Rotation.from_matrix(R).as_rotvec()
+
+
+def pose_errors(poses, frames):
+    """per-frame translation (m) and rotation (rad) errors of pose blocks against the generator's poses"""
+    R_wl, t_wl = odometry.world_from_pose_blocks(poses, aa_to_R)
+    et = np.array([np.linalg.norm(t - f["t_wl"]) for t, f in zip(t_wl, frames)])
+    er = np.array([np.linalg.norm(R_to_aa(R.T @ f["R_wl"])) for R, f in zip(R_wl, frames)])
+    return et, er
+
+
+def err_summary(poses, frames):
+    et, er = pose_errors(poses, frames)
+    _, t_wl = odometry.world_from_pose_blocks(poses, aa_to_R)
+    axis = np.abs(np.array([t - f["t_wl"] for t, f in zip(t_wl, frames)])).mean(0)
+    return {"trans_m_mean": float(et.mean()), "trans_m_max": float(et.max()), "rot_rad_mean": float(er.mean()), "rot_rad_max": float(er.max()),
+            "trans_m_mean_xyz": [float(v) for v in axis]}
+
+
+def perturbed_poses(frames, seed=1, rot=0.005, trans=0.02):
+    rng = np.random.default_rng(seed)
+    R0 = [f["R_wl"] @ Rotation.from_rotvec(rng.normal(0, rot, 3) * (i > 0)).as_matrix() for i, f in enumerate(frames)]
+    t0 = [f["t_wl"] + rng.normal(0, trans, 3) * (i > 0) for i, f in enumerate(frames)]
+    return odometry.pose_blocks_from_world(R0, t0, R_to_aa)
+
+
+def pair_icp(ctx, iterations=20):
+    A, B = synth.make_pair(seed=20260925, n_az=1800)
+    out = {"config": "configs[0]: 2-frame VLP-16 pair, frame A fixed, initial guess identity", "points_per_scan": [int(len(A["cloud"])), int(len(B["cloud"]))]}
+    truth = odometry.pose_blocks_from_world([A["R_wl"], B["R_wl"]], [A["t_wl"], B["t_wl"]], R_to_aa)
+    # (1b) dense mode: every point of B queries the full scan A, association + plane fit + residual + 6x6 reduce every iteration
+    ctx.dense_set_target(A["cloud"])
+    off = np.array([0, len(B["cloud"])], np.int32)
+    ctx.dense_set_sources(B["cloud"], off)
+    dense = {}
+    for name, rtype, huber in (("meter_huber0.2", panovlm_b200.P2PLANE_METER, 0.2), ("angle_normalised_huber2deg", panovlm_b200.P2PLANE_ANGLE, 2 * np.pi / 180)):
+        prm = ctx.dense_params(0.05, 1.0, 10, rtype, 1, huber, 1.0)
+        for rep in range(2):                       # first repetition warms buffers up
+            ctx.dense_reset_hints()
+            pose, kms, costs = np.zeros((1, 6)), [], []
+            ctx.synchronize()
+            t = time.time()
+            for it in range(iterations):
+                s = ctx.dense_evaluate(pose, prm)
+                kms.append(ctx.dense_kernel_time_ms()); costs.append(float(s[0, 27]))
+                pose = ctx.dense_gauss_newton_step(s, pose, 1e-6)
+            dt = time.time() - t
+        evals = len(B["cloud"]) * iterations
+        dense[name] = {"iterations": iterations, "seconds": dt, "ms_per_gauss_newton_iter": 1e3 * dt / iterations, "fused_kernel_ms_mean": float(np.mean(kms)),
+                       "residual_evals_per_s": evals / dt, "accepted_last": int(s[0, 28]), "cost_first_last": [costs[0], costs[-1]],
+                       "pose_error_before": err_summary(np.zeros((2, 6)), [A, B]), "pose_error_after": err_summary(np.vstack([np.zeros(6), pose[0]]), [A, B]),
+                       "pose_delta_vs_truth_max": float(np.abs(pose[0] - truth[1]).max())}
+    out["dense_icp"] = dense
+    # (1a) feature mode: one RefinePose over the pair (surfFlat of each frame against surfLessFlat of the other, + line-to-line)
+    cfg = odometry.OdometryConfig()
+    for rep in range(2):
+        ctx.synchronize()
+        t = time.time()
+        p2, s2 = odometry.refine_pose(ctx, [A, B], np.zeros((2, 6)), cfg, aa_to_R)
+        dt = time.time() - t
+    out["feature_refine_pose"] = {"seconds": dt, "summary": s2, "pose_error_after": err_summary(p2, [A, B])}
+    return out
+
+
+SENSOR_TILT = 0.35   # rad; a level VLP-16 in this room never sees floor or ceiling: vertical translation would be unobservable (synth.make_sequence)
+
+
+def room_refine_pose(ctx, n_frames=454, max_outer=7):
+    t = time.time()
+    frames = synth.make_sequence(n_frames, n_az=1800, tilt=SENSOR_TILT)
+    synth_s = time.time() - t
+    poses0 = perturbed_poses(frames)
+    ctx.blocks_set_linear_solver(panovlm_b200.api.SOLVER_DEVICE)
+    cfg = odometry.OdometryConfig()                                # config/Room.txt:67-76: point-to-plane + line-to-line, angle residuals, normalised
+    out = {"config": f"configs[1]: {n_frames} frames (sensor tilted up to {SENSOR_TILT} rad), FindNeighbors(6), point-to-plane + line-to-line (tracks gated), <= {max_outer} outer x <= 20 LM iterations, frame 0 fixed",
+           "synth_s": synth_s, "error_before": err_summary(poses0, frames)}
+    ctx.synchronize()
+    t = time.time()
+    poses, log = odometry.estimate_pose(ctx, frames, poses0, cfg, aa_to_R, max_iteration=max_outer)
+    ctx.synchronize()
+    out["estimate_pose_s"] = time.time() - t
+    out["outer_iterations"] = len(log)
+    out["per_outer"] = [{k: (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v) for k, v in s.items() if k in ("initial_cost", "final_cost", "iterations", "successful", "n_blocks", "n_edges")} for s in log]
+    out["error_after"] = err_summary(poses, frames)
+    out["lm_iterations_total"] = int(sum(s["iterations"] for s in log))
+    out["residual_evals_per_s"] = float(sum(s["n_blocks"] * (s["iterations"] + 1) for s in log) / out["estimate_pose_s"])
+    out["poses_sha"] = hashlib.sha256(np.ascontiguousarray(poses).tobytes()).hexdigest()[:16]
+    return out
+
+
+def floor_refine_pose(ctx, world, rank, n_frames=1593, n_az=600):
+    import torch
+    import torch.distributed as dist
+    t = time.time()
+    frames = synth.make_sequence(n_frames, n_az=n_az, tilt=SENSOR_TILT)
+    synth_s = time.time() - t
+    poses0 = perturbed_poses(frames)
+    ctx.blocks_set_linear_solver(panovlm_b200.api.SOLVER_DEVICE)
+    cfg = odometry.OdometryConfig(line_to_line=False)
+    res = None
+    for rep in range(2):                                   # the first pass warms up buffers and NCCL
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = time.time()
+        if world > 1:
+            poses, s = odometry.refine_pose_sharded(ctx, frames, poses0, cfg, aa_to_R, world, rank)
+        else:
+            poses, s = odometry.refine_pose(ctx, frames, poses0, cfg, aa_to_R)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.time() - t], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        res = (float(dt.item()), s)
+    out = {"config": f"configs[3]: {n_frames} frames ({n_az} azimuth steps), one RefinePose (point-to-plane), reference frames sharded over {world} GPU(s), one allreduce of the edge systems per evaluation",
+           "n_gpus": world, "synth_s": synth_s, "refine_pose_s": res[0],
+           "summary": {k: (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v) for k, v in res[1].items()},
+           "error_before": err_summary(poses0, frames), "error_after": err_summary(poses, frames)}
+    if world > 1:
+        chk = torch.tensor(poses, device="cuda")
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["poses_identical_on_all_ranks"] = bool(torch.equal(lo, hi))
+    out["poses_sha"] = hashlib.sha256(np.ascontiguousarray(poses).tobytes()).hexdigest()[:16]
+    return out
