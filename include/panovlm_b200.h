@@ -277,6 +277,20 @@ int pvb_line_tracks_gate(int n_tracks, const int* track_off, const int* feat_fra
 int pvb_generate_line_tracks(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, const unsigned char* pose_valid, const int* nbr_off, const int* nbr_ids,
                              double dist_threshold, int min_track_length, int cap_features, int* n_tracks, int* track_off, int* feat_frame, int* feat_line);
 
+/* The vote matrices of AssociateLine2Line for many frame pairs in two launches (all corner clouds -> world, all pairs' votes) and one
+ * download.  lines_world: every frame's segment lines in the world frame (TransformLines), concatenated in frame order (6 doubles each);
+ * M: pair p's n_segments(nei) x n_segments(ref) matrix at m_off[p] (m_total ints in all); world_out (may be NULL): the world-frame corner
+ * clouds concatenated in frame order (x, y, z valid).                                                                                  */
+int pvb_line_votes_batch(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, const double* lines_world, int n_pairs, const int* pair_ref, const int* pair_nei,
+                         const long long* m_off, long long m_total, double dist_threshold, int* M, float* world_out);
+/* AddLidarLineToLineResidual2 (util/Optimization.cpp:329-441) for a whole pose graph in ONE call: AssociateLine2Line of every edge
+ * (ref[e], nei[e]) from the batched device pass above, the FindAssociations tails on the host cores, the line-track gate (:383-400;
+ * tracks as pvb_generate_line_tracks returns them, n_tracks < 0: no gate) and one Point2Line block per point of every kept neighbour
+ * segment, appended edge by edge in the reference's order.  Returns the new block count (>= at) or a negative error code.              */
+int pvb_frames_line2line_blocks(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, int n_edges, const int* ref, const int* nei, double dist_threshold,
+                                int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int angle_residual, int normalize_distance,
+                                double weight, long at, long cap, int* type, int* ref_out, int* nei_out, int* normalize, double* huber, double* consts);
+
 /* CameraLidarLineAssociate::AssociateByAngle (joint_optimization/CameraLidarLineAssociate.cpp:340-475) followed by
  * Filter(false, filter_by_length) (:628-715) and, unless multiple_association, UniqueLinePair (:754-876): per (image line, LiDAR
  * segment) vote counts on the device; acceptance tests, projected-length filter, one-to-one reduction and the transform back to the

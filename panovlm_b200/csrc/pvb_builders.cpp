@@ -111,7 +111,7 @@ inline bool push_block(BlockOut& o, int type, int ref, int nei, int normalize, d
 }
 
 // FindAssociations (:120-197) on a vote matrix; shared by AssociateLine2Line and AssociateLine2LineKNN.
-int find_associations(const pvb_line_frame* ref, const pvb_line_frame* nei, const std::vector<int>& M, int* n_out, int* nei_line, int* ref_line,
+int find_associations(const pvb_line_frame* ref, const pvb_line_frame* nei, const int* M, int* n_out, int* nei_line, int* ref_line,
                              double* point_a3, double* point_b3) {
   const int Sr = ref->n_segments, Sn = nei->n_segments;
   std::vector<double> ref_w((size_t)Sr * 6), nei_w((size_t)Sn * 6);
@@ -279,7 +279,7 @@ int pvb_line2line_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_l
   std::vector<int> M((size_t)Sn * Sr, 0);
   rc = pvb_line_votes(ctx, ref_w.data(), Sr, world.data(), nei->n_corner, nei->p2s_off, nei->p2s_ids, Sn, dist_threshold, M.data());
   if (rc) return rc;
-  return find_associations(ref, nei, M, n_out, nei_line, ref_line, point_a3, point_b3);
+  return find_associations(ref, nei, M.data(), n_out, nei_line, ref_line, point_a3, point_b3);
 }
 
 // ---- segment-based variants (LidarFeatureAssociate.cpp:238-440): 5-NN / nearest line on the device, membership counting here ---------
@@ -320,7 +320,7 @@ int pvb_line2line_knn_tail(const pvb_line_frame* ref, const pvb_line_frame* nei,
       for (int e = nei->p2s_off[q]; e < nei->p2s_off[q + 1]; ++e) M[(size_t)nei->p2s_ids[e] * Sr + kv.first] += 1;   // :432-433
     }
   }
-  return find_associations(ref, nei, M, n_out, nei_line, ref_line, point_a3, point_b3);
+  return find_associations(ref, nei, M.data(), n_out, nei_line, ref_line, point_a3, point_b3);
 }
 
 int pvb_point2line_segment_knn_associate(pvb_ctx* ctx, const pvb_line_frame* ref, const pvb_line_frame* nei, float dist_threshold, long cap, long* n_out, int* query,
@@ -441,29 +441,135 @@ int pvb_line_tracks_gate(int n_tracks, const int* track_off, const int* feat_fra
   return PVB_OK;
 }
 
-// LidarLineMatch::GenerateTracks (:36-86): AssociateLine2Line(lidars[nei], lidars[i], 0.3) over the frame graph, then the track builder.
+// world-frame segment lines of every frame (TransformLines, LidarFeatureAssociate.cpp:219-236), concatenated in frame order
+static void all_lines_world(int n_frames, const pvb_line_frame* frames, std::vector<double>& lines, std::vector<int>& seg_off) {
+  seg_off.assign(n_frames + 1, 0);
+  for (int f = 0; f < n_frames; ++f) seg_off[f + 1] = seg_off[f] + frames[f].n_segments;
+  lines.assign((size_t)std::max(1, seg_off[n_frames]) * 6, 0.0);
+  for (int f = 0; f < n_frames; ++f)
+    for (int s = 0; s < frames[f].n_segments; ++s) transform_line(frames[f].R_wl, frames[f].t_wl, frames[f].segment_coeffs + 6 * s, &lines[(size_t)(seg_off[f] + s) * 6]);
+}
+
+// LidarLineMatch::GenerateTracks (:36-86): AssociateLine2Line(lidars[nei], lidars[i], 0.3) over the frame graph, then the track builder.  All vote matrices
+// come from ONE batched device pass (pvb_line_votes_batch); the FindAssociations tails run on the host cores, one pair per task.
 int pvb_generate_line_tracks(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, const unsigned char* pose_valid, const int* nbr_off, const int* nbr_ids,
                              double dist_threshold, int min_track_length, int cap_features, int* n_tracks, int* track_off, int* feat_frame, int* feat_line) {
   if (!ctx || n_frames < 0 || !n_tracks || (n_frames > 0 && (!frames || !nbr_off))) return PVB_ERR_ARG;
-  std::vector<int> pa, pb, off(1, 0), ma, mb;
-  std::vector<int> nl, rl; std::vector<double> a3, b3;
+  std::vector<int> pa, pb;                                                     // pair p: frame i = pa[p] (neighbour role), its graph neighbour n = pb[p] (reference role), :66
   for (int i = 0; i < n_frames; ++i) {
     if (pose_valid && !pose_valid[i]) continue;                                // :62
     for (int e = nbr_off[i]; e < nbr_off[i + 1]; ++e) {
       const int n = nbr_ids[e];
       if (n < 0 || n >= n_frames) return PVB_ERR_ARG;
-      const int S = std::max(1, frames[i].n_segments);
-      nl.resize(S); rl.resize(S); a3.resize(3 * (size_t)S); b3.resize(3 * (size_t)S);
-      int m = 0;
-      const int rc = pvb_line2line_associate(ctx, &frames[n], &frames[i], dist_threshold, &m, nl.data(), rl.data(), a3.data(), b3.data());   // :66 roles swapped
-      if (rc) return rc;
-      std::set<std::pair<int, int>> uniq;                                      // set<pair<neighbor_line_idx, ref_line_idx>> (:67-69)
-      for (int k = 0; k < m; ++k) uniq.insert({nl[k], rl[k]});
-      for (auto& f : uniq) { ma.push_back(f.first); mb.push_back(f.second); }
-      pa.push_back(i); pb.push_back(n); off.push_back((int)ma.size());
+      pa.push_back(i); pb.push_back(n);
     }
   }
-  return pvb_line_tracks_build((int)pa.size(), pa.data(), pb.data(), off.data(), ma.data(), mb.data(), min_track_length, 1, cap_features, n_tracks, track_off, feat_frame, feat_line);
+  const int np = (int)pa.size();
+  std::vector<long long> m_off(np + 1, 0);
+  for (int p = 0; p < np; ++p) m_off[p + 1] = m_off[p] + (long long)frames[pa[p]].n_segments * frames[pb[p]].n_segments;
+  std::vector<int> M((size_t)std::max<long long>(1, m_off[np]));
+  std::vector<double> lines; std::vector<int> seg_off;
+  all_lines_world(n_frames, frames, lines, seg_off);
+  int rc = pvb_line_votes_batch(ctx, n_frames, frames, lines.data(), np, pb.data(), pa.data(), m_off.data(), m_off[np], dist_threshold, M.data(), nullptr);
+  if (rc) return rc;
+  std::vector<std::vector<std::pair<int, int>>> matches(np);
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int p = 0; p < np; ++p) {
+    const pvb_line_frame* rf = &frames[pb[p]]; const pvb_line_frame* nf = &frames[pa[p]];
+    if (rf->n_segments == 0 || nf->n_segments == 0) continue;
+    const int S = nf->n_segments;
+    std::vector<int> nl(S), rl(S); std::vector<double> a3(3 * (size_t)S), b3(3 * (size_t)S);
+    int m = 0;
+    if (find_associations(rf, nf, M.data() + m_off[p], &m, nl.data(), rl.data(), a3.data(), b3.data()) != PVB_OK) {
+#pragma omp atomic write
+      bad = 1;
+      continue;
+    }
+    std::set<std::pair<int, int>> uniq;                                        // set<pair<neighbor_line_idx, ref_line_idx>> (:67-69)
+    for (int k = 0; k < m; ++k) uniq.insert({nl[k], rl[k]});
+    matches[p].assign(uniq.begin(), uniq.end());
+  }
+  if (bad) return PVB_ERR_ARG;
+  std::vector<int> off(1, 0), ma, mb;
+  for (int p = 0; p < np; ++p) { for (auto& f : matches[p]) { ma.push_back(f.first); mb.push_back(f.second); } off.push_back((int)ma.size()); }
+  return pvb_line_tracks_build(np, pa.data(), pb.data(), off.data(), ma.data(), mb.data(), min_track_length, 1, cap_features, n_tracks, track_off, feat_frame, feat_line);
+}
+
+// AddLidarLineToLineResidual2 (util/Optimization.cpp:329-441) for a whole pose graph in one call: AssociateLine2Line of every edge (ref[e], nei[e]) from one batched
+// device pass (world clouds + vote matrices), FindAssociations tails, the line-track gate (:383-400; n_tracks < 0: no gate) and one Point2Line block per point of every
+// kept neighbour segment (:402-435), appended edge by edge in the reference's order.  Returns the new block count or a negative error.
+int pvb_frames_line2line_blocks(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, int n_edges, const int* ref, const int* nei, double dist_threshold,
+                                int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int angle_residual, int normalize_distance, double weight,
+                                long at, long cap, int* type, int* ref_out, int* nei_out, int* normalize, double* huber, double* consts) {
+  if (!ctx || n_frames < 0 || n_edges < 0 || (n_frames > 0 && !frames) || (n_edges > 0 && (!ref || !nei)) || !type) return PVB_ERR_ARG;
+  if (n_tracks > 0 && (!track_off || !feat_frame || !feat_line)) return PVB_ERR_ARG;
+  std::vector<long long> m_off(n_edges + 1, 0);
+  for (int e = 0; e < n_edges; ++e) {
+    if (ref[e] < 0 || ref[e] >= n_frames || nei[e] < 0 || nei[e] >= n_frames) return PVB_ERR_ARG;
+    m_off[e + 1] = m_off[e] + (long long)frames[ref[e]].n_segments * frames[nei[e]].n_segments;
+  }
+  std::vector<int> M((size_t)std::max<long long>(1, m_off[n_edges]));
+  std::vector<double> lines; std::vector<int> seg_off;
+  all_lines_world(n_frames, frames, lines, seg_off);
+  std::vector<int> coff(n_frames + 1, 0);
+  for (int f = 0; f < n_frames; ++f) coff[f + 1] = coff[f] + frames[f].n_corner;
+  std::vector<float> world((size_t)std::max(1, coff[n_frames]) * 4);
+  int rc = pvb_line_votes_batch(ctx, n_frames, frames, lines.data(), n_edges, ref, nei, m_off.data(), m_off[n_edges], dist_threshold, M.data(), world.data());
+  if (rc) return rc;
+  std::vector<int> track_of;                                                   // (frame, line) -> track id, -1: none (a line belongs to at most one track)
+  if (n_tracks >= 0) {
+    track_of.assign((size_t)std::max(1, seg_off[n_frames]), -1);
+    for (int t = 0; t < n_tracks; ++t)
+      for (int k = track_off[t]; k < track_off[t + 1]; ++k) {
+        const int fr = feat_frame[k], ln = feat_line[k];
+        if (fr < 0 || fr >= n_frames || ln < 0 || ln >= frames[fr].n_segments) return PVB_ERR_ARG;
+        track_of[(size_t)seg_off[fr] + ln] = t;
+      }
+  }
+  struct Blk { double c[12]; };
+  std::vector<std::vector<Blk>> per_edge(n_edges);
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int e = 0; e < n_edges; ++e) {
+    const pvb_line_frame* rf = &frames[ref[e]]; const pvb_line_frame* nf = &frames[nei[e]];
+    if (rf->n_segments == 0 || nf->n_segments == 0) continue;                  // CheckLidarSegment (:208-216)
+    const int S = nf->n_segments;
+    std::vector<int> nl(S), rl(S); std::vector<double> a3(3 * (size_t)S), b3(3 * (size_t)S);
+    int m = 0;
+    if (find_associations(rf, nf, M.data() + m_off[e], &m, nl.data(), rl.data(), a3.data(), b3.data()) != PVB_OK) {
+#pragma omp atomic write
+      bad = 1;
+      continue;
+    }
+    const float* w = world.data() + (size_t)coff[nei[e]] * 4;
+    for (int k = 0; k < m; ++k) {
+      if (n_tracks >= 0) {                                                     // Optimization.cpp:383-400: both lines in one track
+        const int ta = track_of[(size_t)seg_off[ref[e]] + rl[k]], tb = track_of[(size_t)seg_off[nei[e]] + nl[k]];
+        if (ta < 0 || ta != tb) continue;
+      }
+      const double* a = &a3[3 * (size_t)k]; const double* b = &b3[3 * (size_t)k];
+      double d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};                   // Point2Line_*: line_direction = (a - b).normalized()
+      const double nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      for (int q = 0; q < 3; ++q) d[q] /= nn;
+      for (int i = 0; i < nf->n_corner; ++i) {
+        bool member = false;
+        for (int q = nf->p2s_off[i]; q < nf->p2s_off[i + 1]; ++q) member = member || nf->p2s_ids[q] == nl[k];
+        if (!member) continue;
+        const double pw[3] = {w[4 * i], w[4 * i + 1], w[4 * i + 2]};
+        Blk blk;
+        world2local(nf->R_wl, nf->t_wl, pw, blk.c);                            // Optimization.cpp:407 / :422
+        blk.c[3] = a[0]; blk.c[4] = a[1]; blk.c[5] = a[2]; blk.c[6] = d[0]; blk.c[7] = d[1]; blk.c[8] = d[2]; blk.c[9] = weight; blk.c[10] = blk.c[11] = 0.0;
+        per_edge[e].push_back(blk);
+      }
+    }
+  }
+  if (bad) return PVB_ERR_ARG;
+  BlockOut o{at, cap, type, ref_out, nei_out, normalize, huber, consts};
+  for (int e = 0; e < n_edges; ++e)
+    for (const Blk& blk : per_edge[e])                                         // angle residuals are added with loss == nullptr (:417), metre residuals with HuberLoss(0.2) (:430)
+      if (!push_block(o, angle_residual ? PVB_P2LINE_ANGLE : PVB_P2LINE_METER, ref[e], nei[e], normalize_distance, angle_residual ? 0.0 : 0.2, blk.c)) return PVB_ERR_NOMEM;
+  return (int)o.at;
 }
 
 // CameraLidarLineAssociate::UniqueLinePair (:754-876): reduce (image line, LiDAR line, score) candidates, processed in input order, to a

@@ -63,7 +63,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_mode = 2, tune_hints = 1; double tune_cellcap = 4.0, tune_hscale = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
+  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_mode = 2, tune_hints = 1, tune_morton_bits = 12, tune_flat = 1; double tune_cellcap = 4.0, tune_hscale = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
@@ -94,7 +94,7 @@ struct pvb_ctx {
   int d_ntiles = 0; double d_cell = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
   cudaEvent_t bev0 = nullptr, bev1 = nullptr; bool bev_valid = false;     // brackets k_eval_blocks of the last blocks evaluate
-  cudaStream_t copy_stream = nullptr; cudaEvent_t eval_done = nullptr; std::vector<cudaEvent_t> chunk_ev;
+  cudaStream_t copy_stream = nullptr, sort_stream = nullptr; cudaEvent_t eval_done = nullptr; std::vector<cudaEvent_t> chunk_ev, h2d_ev;
   std::vector<int> d_chunk_frame, d_chunk_ctile, d_chunk_qtile; bool d_chunks_pending = false;   // brackets the fused associate kernel of the last dense evaluate
   // ---- device linear solver of the LM loop (pvb_solver.cuh)
   int solver_kind = 0;                                                  // PVB_SOLVER_AUTO
@@ -104,6 +104,7 @@ struct pvb_ctx {
   int s_n = 0, s_N = 0, s_ndest = 0, s_ngdest = 0; float s_last_factor_ms = 0.f;
   // ---- misc
   DevBuf m_a, m_b, m_c, m_d, m_e;
+  DevBuf v_local, v_world, v_misc, v_M;                                 // batched line votes (pvb_line_votes_batch)
   PinBuf mh_a;
   // ---- reprojection / bundle-adjustment mode (pvb_ba.cu owns the state; released through ba_free by pvb_destroy)
   void* ba_state = nullptr; void (*ba_free)(void*) = nullptr;

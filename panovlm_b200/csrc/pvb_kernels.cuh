@@ -110,22 +110,26 @@ __global__ void __launch_bounds__(256) k_gather_f4(const F4* __restrict__ src, c
   if (i < n) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + idx[i]);
 }
 
-// Morton key of a source point in its own sensor frame (0.25 m cells, +-512 m), frame id in the high bits.
-__device__ __forceinline__ unsigned long long spread3(uint32_t v) {
-  unsigned long long x = v & 0xFFFull;
-  x = (x | (x << 16)) & 0x0000FF0000FFull; x = (x | (x << 8)) & 0x00F00F00F00Full;
-  x = (x | (x << 4)) & 0x0C30C30C30C3ull;  x = (x | (x << 2)) & 0x249249249249ull;
+// Morton key of a source point in its own sensor frame (cells of 1 / inv_cell metres inside +-512 m, `bits` bits per axis), frame id in the high bits.
+__device__ __forceinline__ unsigned long long spread3(uint32_t v) {       // <= 21 bits -> every third bit
+  unsigned long long x = v & 0x1FFFFFull;
+  x = (x | (x << 32)) & 0x001F00000000FFFFull;
+  x = (x | (x << 16)) & 0x001F0000FF0000FFull;
+  x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+  x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
   return x;
 }
-__global__ void __launch_bounds__(256) k_morton_keys(const F4* __restrict__ local, const CloudTile* __restrict__ tiles, unsigned long long* __restrict__ keys,
-                                                     uint32_t* __restrict__ vals) {
+__global__ void __launch_bounds__(256) k_morton_keys(const F4* __restrict__ local, const CloudTile* __restrict__ tiles, int first_cloud, float inv_cell, int bits,
+                                                     unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
   const CloudTile t = tiles[blockIdx.x];
   const int i = threadIdx.x;
   if (i >= t.count) return;
   const F4 p = ldg_f4(local + t.start + i);
-  auto q = [](float v) { const float f = floorf((v + 512.f) * 4.f); return (uint32_t)(f < 0.f ? 0.f : (f > 4095.f ? 4095.f : f)); };
+  const float top = (float)((1u << bits) - 1u);
+  auto q = [&](float v) { const float f = floorf((v + 512.f) * inv_cell); return (uint32_t)(f < 0.f ? 0.f : (f > top ? top : f)); };
   const unsigned long long m = spread3(q(p.x)) | (spread3(q(p.y)) << 1) | (spread3(q(p.z)) << 2);
-  keys[t.start + i] = ((unsigned long long)t.cloud << 36) | m;
+  keys[t.start + i] = ((unsigned long long)(t.cloud - first_cloud) << (3 * bits)) | m;
   vals[t.start + i] = (uint32_t)(t.start + i);
 }
 
@@ -154,6 +158,7 @@ struct AssocArgs {
   // frame at the last evaluation, its K-th squared distance then (float; not finite = no hint)}.  Read and rewritten in place; may be null.
   F4* hint;
   int use_hint;                                                      // 0: ignore the stored hints (they are still rewritten)
+  int flat_walk;                                                     // 1: the hinted walk runs over the flattened row ranges (walk_block_collect_flat)
 };
 
 // ---- TMA staging helpers (sm_90+/sm_100a): 1-D bulk copies global -> shared completing on an mbarrier ---------------------
@@ -187,9 +192,13 @@ template <int K, bool REDUCE, int MINB, bool DEBUG_NN, int MODE, bool REF_ID>
 __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
   constexpr bool STAGE = MODE == 0;
   constexpr int LC = kListCap;
-  __shared__ double sJ[REDUCE ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B)
+  __shared__ double sJ_own[(REDUCE && MODE != 2) ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B); MODE 2: aliases the warp's list
   __shared__ uint32_t s_win[MODE == 2 ? 1 : K][kTile];           // record positions of each query's K neighbours (MODE 2: slots 0..K-1 of the list)
-  __shared__ U2 s_list[MODE == 2 ? LC : 1][kTile];               // MODE 2: (d2 bits, record position) of the candidates below the hinted bound
+  // MODE 2: per warp (d2 bits, record position) of the candidates below the hinted bound, [warp][entry][lane]; its last slots double as the row table of the
+  // flattened walk and, once the warp's searches and plane fits are done, its first 2 KB as the staging rows of the warp's reduction
+  __shared__ __align__(16) U2 s_list[MODE == 2 ? kTile / 32 : 1][MODE == 2 ? LC : 1][32];
+  static_assert(MODE != 2 || sizeof(U2) * LC * 32 >= sizeof(double) * 32 * 8, "the reduction rows alias the warp's list");
+  double (*sJ)[8] = MODE == 2 ? reinterpret_cast<double (*)[8]>(&s_list[0][0][0]) : sJ_own;      // MODE 2: re-pointed per warp below
   __shared__ uint32_t s_rng[18][kTile];          // the <= 9 (lo, hi) row ranges of each query's 3x3x3 cell block
   __shared__ __align__(16) F4 s_pts[STAGE ? kStageCap : 1];          // the tile's candidate rows, copied by TMA
   __shared__ uint32_t s_row_lo[STAGE ? kStageRows : 1], s_row_base[STAGE ? kStageRows : 1];
@@ -284,8 +293,9 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
         hi = nlo + (hi - lo); lo = nlo;
       }
     };
-    auto win = [&](int j) { return MODE == 2 ? s_list[j][i].y : s_win[j][i]; };
-    auto set_win = [&](int j, uint32_t pos) { if (MODE == 2) s_list[j][i].y = pos; else s_win[j][i] = pos; };
+    U2* const my_list = &s_list[MODE == 2 ? (i >> 5) : 0][0][MODE == 2 ? (i & 31) : 0];          // entry e of this query: my_list[e * 32]
+    auto win = [&](int j) { return MODE == 2 ? my_list[j * 32].y : s_win[j][i]; };
+    auto set_win = [&](int j, uint32_t pos) { if (MODE == 2) my_list[j * 32].y = pos; else s_win[j][i] = pos; };
     auto range_set = [&](int k, uint32_t lo, uint32_t hi) { s_rng[2 * k][i] = lo; s_rng[2 * k + 1][i] = hi; };
     auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = s_rng[2 * k][i]; hi = s_rng[2 * k + 1][i]; };
     AssocParams prm = a.prm;
@@ -302,11 +312,13 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
         const double dx = (double)qx - (double)hq.x, dy = (double)qy - (double)hq.y, dz = (double)qz - (double)hq.z;
         const double rad = (sqrt((double)hq.w) + sqrt(dx * dx + dy * dy + dz * dz)) * (1.0 + 1e-5) + 1e-9;
         const double lim2 = rad * rad;
-        if (lim2 < (double)prm.sq_thr) lim_hint = f2u((float)lim2) + 2u;      // +1 ulp for the float rounding, +1 to make the bound exclusive
+        // use the bound only when the list can be expected to hold what lies below it (points on a surface: count ~ K * lim2 / tau_old);
+        // after a large pose change the bound is loose and the two-pass search is the cheaper way
+        if (lim2 < (double)prm.sq_thr && lim2 * (double)K < (double)hq.w * (0.8 * LC)) lim_hint = f2u((float)lim2) + 2u;      // +1 ulp for the float rounding, +1 to make the bound exclusive
       }
     }
     valid = associate_point2plane<K, REF_ID, MODE, LC>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
-                                     range_get, lim_hint, &tau, &s_list[0][i], kTile);
+                                     range_get, lim_hint, &tau, my_list, 32, a.flat_walk != 0);
     if (MODE == 2 && a.hint) { F4 ho; ho.x = qx; ho.y = qy; ho.z = qz; ho.w = u2f(tau); reinterpret_cast<float4*>(a.hint)[gq] = make_float4(ho.x, ho.y, ho.z, ho.w); }
     auto load = loadg;     // the debug view below is only built without staging
     if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
@@ -353,6 +365,7 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
     // staged in shared memory, then 28 lanes each own one entry of (H upper 21 | g 6 | cost); fixed summation
     // order => run-to-run identical results.  partials: [tile][warp][29].
     const int w = i >> 5, lane = i & 31;
+    if (MODE == 2) { __syncwarp(); sJ = reinterpret_cast<double (*)[8]>(&s_list[w][0][0]) - w * 32; }   // every lane of the warp is done with its list: sJ[i] = row (i & 31) of the warp's region
 #pragma unroll
     for (int k = 0; k < 6; ++k) sJ[i][k] = valid ? J[6 + k] : 0.0;
     sJ[i][6] = valid ? r : 0.0;
@@ -888,6 +901,44 @@ __global__ void __launch_bounds__(128) k_line_votes(const double* __restrict__ r
     const double dist = sqrt(dadd(dadd(dmul(e[0], e[0]), dmul(e[1], e[1])), dmul(e[2], e[2])));
     if (dist > thr) continue;
     for (int q = e0; q < e1; ++q) atomicAdd(M + (size_t)p2s_ids[q] * S_ref + s, 1);
+  }
+}
+
+// ---- K2l batched: the vote matrices of ALL frame pairs of a pose graph in one launch ----------------------------------------------------------
+// Same arithmetic per (point, line) as k_line_votes.  Inputs are the concatenation over frames of the world-frame corner clouds, their point -> segment
+// CSR lists and the world-frame segment lines; a tile = <= 128 consecutive corner points of the NEIGHBOUR frame of one pair.
+struct VotePair { int ref, nei; long long m_off; };                  // frames of the pair, offset of its S_nei x S_ref matrix in M
+struct VoteTile { int pair, start, count, pad; };                    // corner points [start, start + count) of the pair's neighbour frame (frame-relative)
+__global__ void __launch_bounds__(128) k_line_votes_batch(const VoteTile* __restrict__ tiles, const VotePair* __restrict__ pairs, const F4* __restrict__ world,
+                                                          const int* __restrict__ corner_off /*[n_frames+1]*/, const int* __restrict__ p2s_off /*[sum corners + n_frames]: per frame n+1 entries*/,
+                                                          const int* __restrict__ p2s_base /*[n_frames]: offset of the frame's ids in p2s_ids*/, const int* __restrict__ p2s_ids,
+                                                          const double* __restrict__ lines /*[sum segments][6]*/, const int* __restrict__ seg_off /*[n_frames+1]*/, double thr,
+                                                          int* __restrict__ M) {
+  extern __shared__ double s_lines[];
+  const VoteTile t = tiles[blockIdx.x];
+  const VotePair pr = pairs[t.pair];
+  const int S_ref = seg_off[pr.ref + 1] - seg_off[pr.ref];
+  const double* rl = lines + (size_t)seg_off[pr.ref] * 6;
+  for (int k = threadIdx.x; k < S_ref * 6; k += blockDim.x) s_lines[k] = rl[k];
+  __syncthreads();
+  if ((int)threadIdx.x >= t.count) return;
+  const int li = t.start + threadIdx.x;                              // point index inside the neighbour frame
+  const int gi = corner_off[pr.nei] + li;
+  const int* po = p2s_off + corner_off[pr.nei] + pr.nei;             // the frame's n + 1 CSR offsets
+  const int e0 = po[li], e1 = po[li + 1];
+  if (e0 == e1) return;
+  const F4 p = ldg_f4(world + gi);
+  const double P[3] = {(double)p.x, (double)p.y, (double)p.z};
+  const int* ids = p2s_ids + p2s_base[pr.nei];
+  int* Mp = M + pr.m_off;
+  for (int s = 0; s < S_ref; ++s) {
+    const double* l = s_lines + s * 6;   // PointToLineDistance3D (Geometry.hpp:198-211)
+    const double d0 = dsub(P[0], l[0]), d1 = dsub(P[1], l[1]), d2 = dsub(P[2], l[2]);
+    const double k = dadd(dadd(dmul(l[3], d0), dmul(l[4], d1)), dmul(l[5], d2)) / dadd(dadd(dmul(l[3], l[3]), dmul(l[4], l[4])), dmul(l[5], l[5]));
+    const double e[3] = {dsub(dadd(dmul(k, l[3]), l[0]), P[0]), dsub(dadd(dmul(k, l[4]), l[1]), P[1]), dsub(dadd(dmul(k, l[5]), l[2]), P[2])};
+    const double dist = sqrt(dadd(dadd(dmul(e[0], e[0]), dmul(e[1], e[1])), dmul(e[2], e[2])));
+    if (dist > thr) continue;
+    for (int q = e0; q < e1; ++q) atomicAdd(Mp + (size_t)ids[q] * S_ref + s, 1);
   }
 }
 

@@ -416,9 +416,72 @@ PVB_HD int walk_block_collect(const GridDesc& g, const CellLoader& cells, const 
   return (int)((lp - lbase) / lstride);
 }
 
+// The same walk for the 3x3x3 block with the candidates of all rows FLATTENED into one loop: the <= 9 surviving row ranges go to a small per-query table
+// first, then one loop runs over the concatenation, two candidates per trip.  The lanes of a warp then iterate max(total candidates) times instead of
+// sum over rows of max(row length): with rows of 0..15 records that is ~1.6x fewer trips.  Same visiting order as walk_block_collect, so the same ties
+// are resolved the same way.
+// The table lives in the LAST kRowTab slots of the candidate list itself (no extra shared memory): table entry r is read into registers when row r starts,
+// so list slot LC - kRowTab + r may be overwritten from then on; the list end moves up by one slot with every row start.  A query whose survivors outrun its
+// rows simply "overflows" earlier (count > capacity => the caller falls back to the two-pass search); once the poses settle a query has K .. K+3 survivors.
+constexpr int kRowTab = 10;          // 9 rows + a spare slot that is read (never used) after the last row
+template <int LC, typename CellLoader, typename Load>
+PVB_HD int walk_block_collect_flat(const GridDesc& g, const CellLoader& cells, const Load& load, int cx, int cy, int cz, const FaceGaps& fg, uint32_t lim, float qx, float qy, float qz,
+                                   U2* lbase, int lstride) {
+  static_assert(LC > kRowTab + 4, "list too short to hold the row table");
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  U2* const rtab = lbase + (long long)(LC - kRowTab) * lstride;
+  int nr = 0;
+  uint32_t rem = 0;
+  // the 18 cell-table look-ups of the 9 rows are independent: issue them all before the first one is needed (one memory round trip instead of nine)
+  uint32_t c_lo[9], c_hi[9];
+#pragma unroll
+  for (int o = 0; o < 9; ++o) {
+    const int iz = o / 3, iy = o - 3 * iz;
+    const int dz = (iz & 1) ? -1 : (iz >> 1), dy = (iy & 1) ? -1 : (iy >> 1);      // 0, -1, +1: nearest rows first
+    const int z = cz + dz, y = cy + dy;
+    c_lo[o] = c_hi[o] = 0u;
+    if (z < 0 || z >= nz || y < 0 || y >= ny) continue;
+    const float b2 = (dy == 0 ? 0.0f : (dy < 0 ? fg.lo[1] : fg.hi[1])) + (dz == 0 ? 0.0f : (dz < 0 ? fg.lo[2] : fg.hi[2]));
+    if (f2u(b2) >= lim) continue;
+    const int xa = (cx - 1 < 0 || f2u(b2 + fg.lo[0]) >= lim) ? cx : cx - 1;
+    const int xb = (cx + 1 > nx - 1 || f2u(b2 + fg.hi[0]) >= lim) ? cx : cx + 1;
+    const uint32_t row = ((uint32_t)z * (uint32_t)ny + (uint32_t)y) * (uint32_t)nx;
+    c_lo[o] = (uint32_t)cells((long long)(row + (uint32_t)xa)); c_hi[o] = (uint32_t)cells((long long)(row + (uint32_t)xb + 1u));
+  }
+#pragma unroll
+  for (int o = 0; o < 9; ++o)
+    if (c_hi[o] > c_lo[o]) { U2 e; e.x = c_lo[o]; e.y = c_hi[o]; rtab[(long long)nr * lstride] = e; ++nr; rem += c_hi[o] - c_lo[o]; }
+  if (rem == 0u) return 0;
+  U2* lp = lbase;
+  const U2* rt = rtab;
+  uint32_t i = rt->x, hi = rt->y;
+  U2* lend = lbase + (long long)(LC - kRowTab + 1) * lstride;      // table entry 0 is in registers: its slot is free
+  int over = 0;
+#pragma unroll 1
+  while (rem > 0u) {
+    const bool two = rem >= 2u;
+    const uint32_t ia = i;
+    ++i;
+    bool adv = i == hi;
+    if (adv) { rt += lstride; i = rt->x; hi = rt->y; }              // the slot after the last row is never used as a range (rem runs out first)
+    const uint32_t ib = two ? i : ia;
+    bool adv2 = false;
+    if (two) { ++i; adv2 = i == hi; if (adv2) { rt += lstride; i = rt->x; hi = rt->y; } }
+    const F4 ca = load((long long)ia), cb = load((long long)ib);
+    const uint32_t ka = f2u(sqdist_f32(qx, qy, qz, ca.x, ca.y, ca.z)), kb = f2u(sqdist_f32(qx, qy, qz, cb.x, cb.y, cb.z));
+    const bool pa = ka < lim, pb = two && kb < lim;
+    // the entries are written AFTER the table reads of this trip; the list end follows the rows already in registers
+    lend += (adv ? lstride : 0) + (adv2 ? lstride : 0);
+    if (pa) { if (lp < lend) { U2 e; e.x = ka; e.y = ia; *lp = e; lp += lstride; } else over = 1; }
+    if (pb) { if (lp < lend) { U2 e; e.x = kb; e.y = ib; *lp = e; lp += lstride; } else over = 1; }
+    rem -= two ? 2u : 1u;
+  }
+  return over ? LC + 1 : (int)((lp - lbase) / lstride);
+}
+
 template <int K, int LC, typename CellLoader, typename Load, typename WinSet>
 PVB_HD int knn_select_hinted(const GridDesc& g, const CellLoader& cells, const Load& load, float qx, float qy, float qz, float sq_thr, int r0, int rmax, uint32_t lim_hint,
-                             U2* lbase, int lstride, const WinSet& set_win, uint32_t* tau_out) {
+                             U2* lbase, int lstride, const WinSet& set_win, uint32_t* tau_out, bool flat = true) {
   auto lkey = [&](int e) { return lbase[(long long)e * lstride].x; };
   auto lmove = [&](int dst, int src) { lbase[(long long)dst * lstride] = lbase[(long long)src * lstride]; };
   static_assert(LC >= K + 2, "list capacity");
@@ -449,7 +512,8 @@ PVB_HD int knn_select_hinted(const GridDesc& g, const CellLoader& cells, const L
     if (lim < reach1 * reach1 * (1.0 - 1e-6)) rb = 1;
     else if (lim < reach2 * reach2 * (1.0 - 1e-6)) rb = 2;
     if (rb != 0) {
-      int n = walk_block_collect<LC>(g, cells, load, cx, cy, cz, fg, gap_lo, gap_hi, rb, lim_hint, qx, qy, qz, lbase, lstride);
+      int n = (rb == 1 && flat) ? walk_block_collect_flat<LC>(g, cells, load, cx, cy, cz, fg, lim_hint, qx, qy, qz, lbase, lstride)
+                                           : walk_block_collect<LC>(g, cells, load, cx, cy, cz, fg, gap_lo, gap_hi, rb, lim_hint, qx, qy, qz, lbase, lstride);
       if (n >= K && n <= LC) {
         uint32_t tau;
         if (n > K) tau = list_cut_to_k<K>(n, lkey, lmove);
@@ -544,8 +608,8 @@ PVB_HD bool plane_from_window(const Load& load, const AssocParams& prm, float qx
     lstsq_minus_one_rolled(K, A, x);
   }
   const double nrm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-  const double d = 1.0 / nrm;
-  const double n0 = x[0] / nrm, n1 = x[1] / nrm, n2 = x[2] / nrm;
+  const double d = 1.0 / nrm;                                     // Geometry.hpp:362-363: n = x / |x|, d = 1 / |x|
+  const double n0 = x[0] * d, n1 = x[1] * d, n2 = x[2] * d;
   if (prm.plane_tol > 0) {                                       // Geometry.hpp:364-371
     bool ok = true;
 #pragma unroll 1
@@ -572,10 +636,10 @@ PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, co
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
                                   double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get,
-                                  uint32_t lim_hint, uint32_t* tau_out, U2* lbase, int lstride) {
+                                  uint32_t lim_hint, uint32_t* tau_out, U2* lbase, int lstride, bool flat = true) {
   int ring = 1;
   int found;
-  if (MODE == 2) { found = knn_select_hinted<K, LC>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, lim_hint, lbase, lstride, set_win, tau_out); ring = 2; }
+  if (MODE == 2) { found = knn_select_hinted<K, LC>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, lim_hint, lbase, lstride, set_win, tau_out, flat); ring = 2; }
   else if (MODE == 1) { found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }); ring = 2; }
   else found = knn_select<K>(g, cells, load1, loadg, row_map, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
   if (found < K) return false;                                   // :578

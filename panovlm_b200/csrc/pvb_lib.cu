@@ -21,6 +21,7 @@ namespace {
 // scratch buffers m_a..m_e are shared with the source-upload pipeline: wait for it before reusing them elsewhere
 int quiesce_copy(pvb_ctx* ctx) {
   if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+  if (ctx->sort_stream) CK(cudaStreamSynchronize(ctx->sort_stream));
   return PVB_OK;
 }
 
@@ -141,7 +142,7 @@ int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_ide
   if (k != 5 && k != 10) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
   a.stats = nullptr;
   a.prm.r0 = ctx->tune_r0;
-  a.use_hint = ctx->tune_hints;
+  a.use_hint = ctx->tune_hints; a.flat_walk = ctx->tune_flat;
   if (mode == 0 && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
   if (mode == 3) {                    // warp-cooperative search (groups of 8 queries share staged candidates)
     constexpr size_t smem = sizeof(CoopWarp) * (kTile / 32);
@@ -192,6 +193,8 @@ int pvb_create(int device, pvb_ctx** out) {
   if (const char* e = getenv("PVB_STAGE")) ctx->tune_stage = atoi(e) != 0;
   if (const char* e = getenv("PVB_MODE")) ctx->tune_mode = std::min(3, std::max(0, atoi(e)));
   if (const char* e = getenv("PVB_HINTS")) ctx->tune_hints = atoi(e) != 0;
+  if (const char* e = getenv("PVB_FLAT")) ctx->tune_flat = atoi(e) != 0;
+  if (const char* e = getenv("PVB_MORTON_BITS")) ctx->tune_morton_bits = std::min(16, std::max(10, atoi(e)));   // bits per axis of the source re-ordering: cells of 1024 m / 2^bits
   if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
   if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = std::max(0.1, atof(e));
@@ -207,7 +210,7 @@ void pvb_destroy(pvb_ctx* ctx) {
   DevBuf* dbs[] = {&ctx->d_prep, &ctx->d_wpose, &ctx->b_tile, &ctx->b_eref, &ctx->b_enei, &ctx->b_type, &ctx->b_norm, &ctx->b_huber, &ctx->b_consts, &ctx->b_orig_d, &ctx->b_r, &ctx->b_J,
                    &ctx->b_part, &ctx->b_esys, &ctx->b_tbegin, &ctx->f_pairs, &ctx->f_qtiles, &ctx->f_valid, &ctx->f_point, &ctx->f_plane, &ctx->f_nn_idx, &ctx->f_nn_d2,
                    &ctx->d_q_sorted, &ctx->d_q_orig, &ctx->d_pairs, &ctx->d_qtiles, &ctx->d_part, &ctx->d_sys, &ctx->d_tbegin, &ctx->d_valid, &ctx->d_point, &ctx->d_plane,
-                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e, &ctx->b_chunk, &ctx->d_chunk, &ctx->d_stats};
+                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e, &ctx->v_local, &ctx->v_world, &ctx->v_misc, &ctx->v_M, &ctx->d_hint, &ctx->b_chunk, &ctx->d_chunk, &ctx->d_stats};
   for (DevBuf* b : dbs) b->release();
   PinBuf* pbs[] = {&ctx->h_pose, &ctx->h_r, &ctx->h_J, &ctx->h_esys, &ctx->fh_valid, &ctx->fh_point, &ctx->fh_plane, &ctx->dh_sys, &ctx->mh_a};
   for (PinBuf* b : pbs) b->release();
@@ -216,6 +219,8 @@ void pvb_destroy(pvb_ctx* ctx) {
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
   if (ctx->eval_done) cudaEventDestroy(ctx->eval_done);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->sort_stream) { cudaStreamSynchronize(ctx->sort_stream); cudaStreamDestroy(ctx->sort_stream); }
+  for (cudaEvent_t e : ctx->h2d_ev) cudaEventDestroy(e);
   if (ctx->bev0) cudaEventDestroy(ctx->bev0);
   if (ctx->bev1) cudaEventDestroy(ctx->bev1);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1037,30 +1042,40 @@ int pvb_dense_set_sources(pvb_ctx* ctx, const float* xyzc, const int* offsets, i
   CloudSet& cs = ctx->d_src;
   const bool same = ctx->d_frames == n_frames && (int)cs.off.size() == n_frames + 1 && std::equal(offsets, offsets + n_frames + 1, cs.off.begin());
   if (!same) { int rc = dense_prepare_layout(ctx, offsets, n_frames); if (rc) return rc; }
-  if (!ctx->copy_stream) { CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->eval_done, cudaEventDisableTiming)); }
-  cudaStream_t cp = ctx->copy_stream;
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->sort_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->eval_done, cudaEventDisableTiming));
+  }
+  // two side streams: the copy stream only moves bytes (the chunks' H2D copies run back to back at PCIe rate), the sort stream re-orders chunk c
+  // (Morton keys, radix sort, gather) as soon as its copy has landed, while chunk c + 1 is still on the wire; the evaluate waits per chunk
+  cudaStream_t cp = ctx->copy_stream, st = ctx->sort_stream;
   // the previous evaluate may still be reading the query buffers
   CK(cudaEventRecord(ctx->eval_done, ctx->stream));
   CK(cudaStreamWaitEvent(cp, ctx->eval_done, 0));
+  CK(cudaStreamWaitEvent(st, ctx->eval_done, 0));
   const int n_chunks = (int)ctx->d_chunk_frame.size() - 1;
-  int frame_bits = 1; while ((1 << frame_bits) < n_frames + 1) ++frame_bits;
+  while ((int)ctx->h2d_ev.size() < n_chunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->h2d_ev.push_back(e); }
   for (int c = 0; c < n_chunks; ++c) {
     const int f0 = ctx->d_chunk_frame[c], f1 = ctx->d_chunk_frame[c + 1];
     const long long p0 = cs.off[f0], cnt = (long long)cs.off[f1] - p0;
     if (cnt > 0) {
       CK(cudaMemcpyAsync(cs.local.as<F4>() + p0, xyzc + (size_t)p0 * 4, (size_t)cnt * sizeof(F4), cudaMemcpyHostToDevice, cp));
+      CK(cudaEventRecord(ctx->h2d_ev[c], cp));
+      CK(cudaStreamWaitEvent(st, ctx->h2d_ev[c], 0));
       const int t0 = ctx->d_chunk_ctile[c], t1 = ctx->d_chunk_ctile[c + 1];
-      // Morton re-ordering per frame (keys = frame << 36 | morton36); vals are global point indices
-      k_morton_keys<<<t1 - t0, 256, 0, cp>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, ctx->m_a.as<unsigned long long>(), ctx->m_c.as<uint32_t>());
+      // Morton re-ordering per frame (keys = (frame - first frame of the chunk) << 3 bits | morton); vals are global point indices
+      int frame_bits = 1; while ((1 << frame_bits) < f1 - f0) ++frame_bits;
+      k_morton_keys<<<t1 - t0, 256, 0, st>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, f0, (float)(1 << (ctx->tune_morton_bits - 10)), ctx->tune_morton_bits,
+                                             ctx->m_a.as<unsigned long long>(), ctx->m_c.as<uint32_t>());
       CKL();
       size_t tb = ctx->m_e.cap;
       CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<unsigned long long>() + p0, ctx->m_b.as<unsigned long long>() + p0, ctx->m_c.as<uint32_t>() + p0,
-                                         ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, 36 + frame_bits, cp));
-      k_gather_f4<<<(unsigned)((cnt + 255) / 256), 256, 0, cp>>>(cs.local.as<F4>(), ctx->m_d.as<uint32_t>() + p0, cnt, ctx->d_q_sorted.as<F4>() + p0);
+                                         ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, 3 * ctx->tune_morton_bits + frame_bits, st));
+      k_gather_f4<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(cs.local.as<F4>(), ctx->m_d.as<uint32_t>() + p0, cnt, ctx->d_q_sorted.as<F4>() + p0);
       CKL();
-      CK(cudaMemcpyAsync(ctx->d_q_orig.as<uint32_t>() + p0, ctx->m_d.as<uint32_t>() + p0, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cp));
+      CK(cudaMemcpyAsync(ctx->d_q_orig.as<uint32_t>() + p0, ctx->m_d.as<uint32_t>() + p0, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
     }
-    CK(cudaEventRecord(ctx->chunk_ev[c], cp));
+    CK(cudaEventRecord(ctx->chunk_ev[c], st));
   }
   ctx->d_chunks_pending = true;
   return PVB_OK;
@@ -1158,7 +1173,7 @@ int pvb_dense_get_rows(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_par
   CK(cudaMemsetAsync(ctx->d_valid.p, 0, n, ctx->stream)); CK(cudaMemsetAsync(ctx->d_point.p, 0, n * 24, ctx->stream)); CK(cudaMemsetAsync(ctx->d_plane.p, 0, n * 32, ctx->stream));
   a.out_valid = ctx->d_valid.as<unsigned char>(); a.out_point = ctx->d_point.as<double>(); a.out_plane = ctx->d_plane.as<double>();
   a.out_res = ctx->d_res.as<double>(); a.out_jac6 = ctx->d_jac.as<double>();
-  if (ctx->d_chunks_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->d_chunks_pending = false; }
+  if (ctx->d_chunks_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); CK(cudaStreamSynchronize(ctx->sort_stream)); ctx->d_chunks_pending = false; }
   rc = launch_associate<false>(ctx, prm->k, ctx->d_ntiles, a, true); if (rc) return rc;
   if (valid) CK(cudaMemcpyAsync(valid, ctx->d_valid.p, n, cudaMemcpyDeviceToHost, ctx->stream));
   if (point3) CK(cudaMemcpyAsync(point3, ctx->d_point.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1353,6 +1368,93 @@ int pvb_line_votes(pvb_ctx* ctx, const double* ref_lines, int S_ref, const float
   k_line_votes<<<(n_pts + 127) / 128, 128, (size_t)S_ref * 48, ctx->stream>>>(ctx->m_a.as<double>(), S_ref, ctx->m_b.as<F4>(), n_pts, ctx->m_c.as<int>(), ctx->m_d.as<int>(), thr, ctx->m_e.as<int>());
   CKL();
   CK(cudaMemcpyAsync(M, ctx->m_e.p, msz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PVB_OK;
+}
+
+// The vote matrices of AssociateLine2Line (LidarFeatureAssociate.cpp:442-476, TransformLines :219-236) for many frame pairs at once: every frame's corner cloud
+// goes to the world frame in one launch (float32 store, as Transform2LidarWorld), every pair's votes in a second one, one download.  lines_world: the frames'
+// segment lines already in the world frame (host, concatenated in frame order).  M: pair p's S_nei x S_ref matrix at m_off[p].  world_out (may be NULL): the
+// world-frame corner clouds, concatenated in frame order (the residual builders read the points from it).
+int pvb_line_votes_batch(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, const double* lines_world, int n_pairs, const int* pair_ref, const int* pair_nei,
+                         const long long* m_off, long long m_total, double thr, int* M, float* world_out) {
+  if (!ctx || n_frames < 0 || n_pairs < 0 || (n_frames > 0 && !frames) || (n_pairs > 0 && (!pair_ref || !pair_nei || !m_off || !M))) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_line_votes_batch: bad arguments") : PVB_ERR_ARG;
+  if (n_frames == 0) return PVB_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (int qrc = quiesce_copy(ctx)) return qrc;
+  std::vector<int> coff(n_frames + 1, 0), soff(n_frames + 1, 0), pbase(n_frames, 0);
+  long long n_ids = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    coff[f + 1] = coff[f] + frames[f].n_corner; soff[f + 1] = soff[f] + frames[f].n_segments;
+    pbase[f] = (int)n_ids;
+    n_ids += frames[f].n_corner > 0 ? frames[f].p2s_off[frames[f].n_corner] : 0;
+  }
+  const int nc = coff[n_frames], ns = soff[n_frames];
+  if (ns > 0 && !lines_world) return ctx->fail(PVB_ERR_ARG, "pvb_line_votes_batch: lines_world is NULL");
+  // host staging: local clouds, CSR offsets (n + 1 per frame), ids, poses
+  std::vector<F4> local((size_t)std::max(1, nc));
+  std::vector<int> poff((size_t)nc + n_frames, 0), pids((size_t)std::max<long long>(1, n_ids));
+  std::vector<WorldPose> wp(n_frames);
+  std::vector<CloudTile> ctiles; std::vector<int> cblock(n_frames);
+  for (int f = 0; f < n_frames; ++f) {
+    const pvb_line_frame& fr = frames[f];
+    if (fr.n_corner > 0) {
+      memcpy(&local[coff[f]], fr.corner_local, (size_t)fr.n_corner * 16);
+      memcpy(&poff[(size_t)coff[f] + f], fr.p2s_off, (size_t)(fr.n_corner + 1) * 4);
+      const int m = fr.p2s_off[fr.n_corner];
+      if (m > 0) memcpy(&pids[pbase[f]], fr.p2s_ids, (size_t)m * 4);
+    }
+    for (int k = 0; k < 9; ++k) wp[f].R[k] = fr.R_wl[k];
+    for (int k = 0; k < 3; ++k) wp[f].t[k] = fr.t_wl[k];
+    cblock[f] = f;
+    for (int s0 = 0; s0 < fr.n_corner; s0 += 256) ctiles.push_back(CloudTile{f, coff[f] + s0, std::min(256, fr.n_corner - s0), 0});
+  }
+  std::vector<VotePair> vp(std::max(1, n_pairs)); std::vector<VoteTile> vt;
+  int smax = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    const int r = pair_ref[p], n = pair_nei[p];
+    if (r < 0 || r >= n_frames || n < 0 || n >= n_frames) return ctx->fail(PVB_ERR_ARG, "pvb_line_votes_batch: pair %d out of range", p);
+    vp[p] = VotePair{r, n, m_off[p]};
+    if (frames[r].n_segments == 0 || frames[n].n_segments == 0) continue;      // CheckLidarSegment: nothing to vote on
+    smax = std::max(smax, frames[r].n_segments);
+    for (int s0 = 0; s0 < frames[n].n_corner; s0 += 128) vt.push_back(VoteTile{p, s0, std::min(128, frames[n].n_corner - s0), 0});
+  }
+  DevBuf& d_local = ctx->v_local; DevBuf& d_world = ctx->v_world; DevBuf& d_misc = ctx->v_misc; DevBuf& d_M = ctx->v_M;
+  // one packed upload of the small integer / double tables
+  const size_t o_coff = 0, o_soff = o_coff + (size_t)(n_frames + 1) * 4, o_pbase = o_soff + (size_t)(n_frames + 1) * 4, o_poff = o_pbase + (size_t)n_frames * 4,
+               o_pids = o_poff + poff.size() * 4, o_cblock = o_pids + pids.size() * 4, o_ctiles = (o_cblock + (size_t)n_frames * 4 + 15) / 16 * 16,
+               o_wp = o_ctiles + std::max<size_t>(1, ctiles.size()) * sizeof(CloudTile), o_lines = o_wp + (size_t)n_frames * sizeof(WorldPose),
+               o_vp = o_lines + (size_t)std::max(1, ns) * 48, o_vt = o_vp + vp.size() * sizeof(VotePair), total = o_vt + std::max<size_t>(1, vt.size()) * sizeof(VoteTile);
+  CK(ctx->mh_a.ensure(total)); CK(d_misc.ensure(total));
+  unsigned char* h = ctx->mh_a.as<unsigned char>();
+  memcpy(h + o_coff, coff.data(), (size_t)(n_frames + 1) * 4); memcpy(h + o_soff, soff.data(), (size_t)(n_frames + 1) * 4); memcpy(h + o_pbase, pbase.data(), (size_t)n_frames * 4);
+  memcpy(h + o_poff, poff.data(), poff.size() * 4); memcpy(h + o_pids, pids.data(), pids.size() * 4); memcpy(h + o_cblock, cblock.data(), (size_t)n_frames * 4);
+  if (!ctiles.empty()) memcpy(h + o_ctiles, ctiles.data(), ctiles.size() * sizeof(CloudTile));
+  memcpy(h + o_wp, wp.data(), (size_t)n_frames * sizeof(WorldPose));
+  if (ns > 0) memcpy(h + o_lines, lines_world, (size_t)ns * 48);
+  memcpy(h + o_vp, vp.data(), vp.size() * sizeof(VotePair));
+  if (!vt.empty()) memcpy(h + o_vt, vt.data(), vt.size() * sizeof(VoteTile));
+  CK(d_local.ensure(local.size() * 16)); CK(d_world.ensure(local.size() * 16)); CK(d_M.ensure(std::max<size_t>(16, (size_t)m_total * 4)));
+  CK(cudaMemcpyAsync(d_misc.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_local.p, local.data(), local.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
+  unsigned char* d = d_misc.as<unsigned char>();
+  if (!ctiles.empty()) {
+    k_transform_world<<<(unsigned)ctiles.size(), 256, 0, ctx->stream>>>(d_local.as<F4>(), reinterpret_cast<const CloudTile*>(d + o_ctiles), reinterpret_cast<const int*>(d + o_cblock),
+                                                                        reinterpret_cast<const WorldPose*>(d + o_wp), reinterpret_cast<const int*>(d + o_coff), d_world.as<F4>(), nullptr);
+    CKL();
+  }
+  if (m_total > 0) CK(cudaMemsetAsync(d_M.p, 0, (size_t)m_total * 4, ctx->stream));
+  if (!vt.empty()) {
+    const size_t smem = (size_t)smax * 48;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_line_votes_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_line_votes_batch<<<(unsigned)vt.size(), 128, smem, ctx->stream>>>(reinterpret_cast<const VoteTile*>(d + o_vt), reinterpret_cast<const VotePair*>(d + o_vp), d_world.as<F4>(),
+                                                                        reinterpret_cast<const int*>(d + o_coff), reinterpret_cast<const int*>(d + o_poff), reinterpret_cast<const int*>(d + o_pbase),
+                                                                        reinterpret_cast<const int*>(d + o_pids), reinterpret_cast<const double*>(d + o_lines), reinterpret_cast<const int*>(d + o_soff),
+                                                                        thr, d_M.as<int>());
+    CKL();
+  }
+  if (m_total > 0) CK(cudaMemcpyAsync(M, d_M.p, (size_t)m_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (world_out && nc > 0) CK(cudaMemcpyAsync(world_out, d_world.p, (size_t)nc * 16, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return PVB_OK;
 }

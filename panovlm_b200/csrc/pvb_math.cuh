@@ -356,25 +356,25 @@ PVB_HD void plane_acc_add(PlaneAcc& a, const double p[3]) {
   a.g00 += p[0] * p[0]; a.g01 += p[0] * p[1]; a.g02 += p[0] * p[2]; a.g11 += p[1] * p[1]; a.g12 += p[1] * p[2]; a.g22 += p[2] * p[2];
   a.h0 += p[0]; a.h1 += p[1]; a.h2 += p[2];
 }
-struct Chol3 { double l00, l10, l11, l20, l21, l22; };
+struct Chol3 { double l00, l10, l11, l20, l21, l22, i00, i11, i22; };      // i.. = reciprocals of the diagonal (one division each; the solves only multiply)
 PVB_HD bool chol3_factor(const PlaneAcc& a, Chol3& L) {
   if (!(a.g00 > 0.0)) return false;
-  L.l00 = sqrt(a.g00); L.l10 = a.g01 / L.l00; L.l20 = a.g02 / L.l00;
+  L.l00 = sqrt(a.g00); L.i00 = 1.0 / L.l00; L.l10 = a.g01 * L.i00; L.l20 = a.g02 * L.i00;
   const double d1 = a.g11 - L.l10 * L.l10;
   if (!(d1 > 0.0)) return false;
-  L.l11 = sqrt(d1); L.l21 = (a.g12 - L.l20 * L.l10) / L.l11;
+  L.l11 = sqrt(d1); L.i11 = 1.0 / L.l11; L.l21 = (a.g12 - L.l20 * L.l10) * L.i11;
   const double d2 = a.g22 - L.l20 * L.l20 - L.l21 * L.l21;
   if (!(d2 > 0.0)) return false;
-  L.l22 = sqrt(d2);
+  L.l22 = sqrt(d2); L.i22 = 1.0 / L.l22;
   return true;
 }
 PVB_HD void chol3_solve(const Chol3& L, const double b[3], double x[3]) {
-  const double y0 = b[0] / L.l00;
-  const double y1 = (b[1] - L.l10 * y0) / L.l11;
-  const double y2 = (b[2] - L.l20 * y0 - L.l21 * y1) / L.l22;
-  x[2] = y2 / L.l22;
-  x[1] = (y1 - L.l21 * x[2]) / L.l11;
-  x[0] = (y0 - L.l10 * x[1] - L.l20 * x[2]) / L.l00;
+  const double y0 = b[0] * L.i00;
+  const double y1 = (b[1] - L.l10 * y0) * L.i11;
+  const double y2 = (b[2] - L.l20 * y0 - L.l21 * y1) * L.i22;
+  x[2] = y2 * L.i22;
+  x[1] = (y1 - L.l21 * x[2]) * L.i11;
+  x[0] = (y0 - L.l10 * x[1] - L.l20 * x[2]) * L.i00;
 }
 // lambda_max > tol * lambda_mid of the scatter matrix (FormLine's "is a line" test)
 PVB_HD bool collinear_from_gram(const PlaneAcc& a, int n, double tol) {

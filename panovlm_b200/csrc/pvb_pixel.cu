@@ -65,6 +65,7 @@ extern "C" int pvb_pixel_knn3(pvb_ctx* ctx, int rows, int cols, const float* mid
   if (n_points == 0) return PVB_OK;
   CK(cudaSetDevice(ctx->device));
   if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));      // scratch buffers are shared with the source-upload pipeline
+  if (ctx->sort_stream) CK(cudaStreamSynchronize(ctx->sort_stream));
   CK(ctx->m_a.ensure((size_t)n_points * 16)); CK(ctx->m_b.ensure(std::max<size_t>(8, (size_t)n_mid * 8))); CK(ctx->m_c.ensure((size_t)n_points * 12));
   CK(ctx->m_d.ensure((size_t)n_points * 12)); CK(ctx->m_e.ensure((size_t)n_points * 8));
   CK(cudaMemcpyAsync(ctx->m_a.p, cloud_local, (size_t)n_points * 16, cudaMemcpyHostToDevice, ctx->stream));

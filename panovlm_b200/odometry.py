@@ -52,7 +52,7 @@ def pose_graph_edges(poses, cfg: OdometryConfig, aa_to_R):
     return [(i, j) for i in range(n) for j in neighbors[i] if 0 <= j < n and j != i]
 
 
-def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, frame_range=None, host_point2plane=True):
+def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, frame_range=None, host_point2plane=True, per_edge_line_calls=False):
     """One outer iteration's residual blocks (the Add*Residual calls of RefinePose); returns a BlockList and the GLOBAL edge list.
     frame_range = (lo, hi): only the edges whose reference frame lies in [lo, hi) are associated and turned into blocks (one rank's shard of a
     pose graph split across GPUs); the clouds of all frames stay available as halo.
@@ -82,15 +82,18 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
                 if hi > lo:
                     Context.build_point2line_blocks(bl, pt[lo:hi], a[lo:hi], b[lo:hi], i, j, cfg.angle_residual, cfg.normalize_distance, cfg.point_line_weight)
     if cfg.line_to_line:                                            # AddLidarLineToLineResidual2 (Optimization.cpp:329-441)
-        world = [ctx.transform_cloud(f["cornerLessSharp"], R_wl[i], t_wl[i]) for i, f in enumerate(frames)]
         tracks = None
         if cfg.line_tracks:                                         # LidarLineMatch::GenerateTracks (LidarLineMatch.cpp:36-86), threshold hard-coded 0.3
             tracks = ctx.generate_line_tracks(lf, Context.find_neighbors(np.array(t_wl), None, None, cfg.track_neighbor_size), None, 0.3, cfg.min_track_length)
-        for (i, j) in edges:
-            nl, rl, a, b = ctx.line2line_associate(lf[i], lf[j], cfg.line_dis_threshold)
-            keep = Context.line_tracks_gate(tracks, i, j, rl, nl) if tracks is not None else np.ones(len(nl), bool)   # Optimization.cpp:383-400
-            for k in np.nonzero(keep)[0]:
-                Context.build_line2line_blocks(bl, lf[j], world[j], nl[k], a[k], b[k], i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
+        if per_edge_line_calls:                                     # one library call per edge (the round-1 path; kept for the equivalence test)
+            world = [ctx.transform_cloud(f["cornerLessSharp"], R_wl[i], t_wl[i]) for i, f in enumerate(frames)]
+            for (i, j) in edges:
+                nl, rl, a, b = ctx.line2line_associate(lf[i], lf[j], cfg.line_dis_threshold)
+                keep = Context.line_tracks_gate(tracks, i, j, rl, nl) if tracks is not None else np.ones(len(nl), bool)   # Optimization.cpp:383-400
+                for k in np.nonzero(keep)[0]:
+                    Context.build_line2line_blocks(bl, lf[j], world[j], nl[k], a[k], b[k], i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
+        elif edges:                                                 # all edges in one call: batched device votes, tails and blocks on the host cores
+            ctx.frames_line2line_blocks(bl, lf, edges, cfg.line_dis_threshold, tracks, cfg.angle_residual, cfg.normalize_distance, 1.0)
     if cfg.point_to_plane:                                          # AddLidarPointToPlaneResidual (Optimization.cpp:506-562)
         ctx.frames_set([f["surfLessFlat"] for f in frames], [f["surfFlat"] for f in frames])
     if not host_point2plane:

@@ -35,6 +35,18 @@ def build_adapter_harness():
     return out
 
 
+def build_nccl_harness():
+    """tests/nccl_harness.cpp: a C++ multi-GPU caller (one thread + one context per GPU, ncclCommInitAll, the NCCL hook of libpanovlm_b200_nccl.so)."""
+    out = os.path.join(ROOT, "tests", "libpvb_nccl_harness.so")
+    src = os.path.join(ROOT, "tests", "nccl_harness.cpp")
+    deps = [src, os.path.join(ROOT, "include", "panovlm_b200_nccl.h"), os.path.join(ROOT, "include", "panovlm_b200.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", "-o", out, src,
+                               "-L", os.path.join(ROOT, "panovlm_b200"), "-lpanovlm_b200_nccl", "-lpanovlm_b200", "-lnccl", "-L", "/usr/local/cuda/lib64", "-lcudart",
+                               "-Wl,-rpath,$ORIGIN/../panovlm_b200"])
+    return out
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import pvo

@@ -12,6 +12,7 @@ using namespace pvb;
 
 // per-query association on a host-built grid (counting sort), K = 10 or 5
 static int g_prune = 1;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned two-pass walk from a 3x3x3 / 5x5x5 block, 3: buffered single pass (default device path)
+static int g_flat = 1;                  // mode 3: hinted walk over the flattened row ranges (device default) or the nested per-row loops
 static const float* g_hint = nullptr;   // mode 3: per query {x, y, z, tau} search-radius hints (the device kernel's formula), or null
 static float* g_hint_out = nullptr;     // mode 3: the hints the device kernel would store
 template <int K>
@@ -67,7 +68,7 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
       }
     }
 #define PVBH_ASSOC(MODE, W, SW) associate_point2plane<K, false, MODE, LC>(g, cells, load, load, no_map, prm, qx, qy, qz, qcls, R_ref, t_ref, R_nei, t_nei, \
-                                                               p_local + 3 * i, plane + 4 * i, W, SW, range_set, range_get, lim_hint, &tau, lst, 1)
+                                                               p_local + 3 * i, plane + 4 * i, W, SW, range_set, range_get, lim_hint, &tau, lst, 1, g_flat != 0)
     if (g_prune == 3) { for (int j = 0; j < K; ++j) lst[j].y = 0xFFFFFFFFu; }
     valid[i] = (g_prune == 0 ? PVBH_ASSOC(0, win, set_win) : (g_prune == 3 ? PVBH_ASSOC(2, win2, set_win2) : PVBH_ASSOC(1, win, set_win))) ? 1 : 0;
 #undef PVBH_ASSOC
@@ -122,6 +123,7 @@ static void associate_lines(const float* tgt, int n, const double* R_ref, const 
 
 extern "C" {
 void pvbh_set_prune(int on) { g_prune = on; }
+void pvbh_set_flat(int on) { g_flat = on; }
 void pvbh_set_hints(const float* hint_in, float* hint_out) { g_hint = hint_in; g_hint_out = hint_out; }
 
 

@@ -206,6 +206,7 @@ def test_search_radius_hints_never_change_the_result(oracle, harness):
     rng = np.random.default_rng(5)
     harness.pvbh_set_prune(C.c_int(3))
     for trial in range(12):
+        harness.pvbh_set_flat(C.c_int(trial % 2))                                    # flattened / nested hinted walk
         n = int(rng.integers(1500, 6000))
         pts = _fuzz_cloud(rng, n)
         m = 400
