@@ -40,6 +40,8 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+struct WorldPoseHost { double R[9]; double t[3]; };
+
 struct CloudSet {
   int n_clouds = 0; long long n_points = 0; int n_tiles = 0;
   std::vector<int> off;           // n_clouds + 1
@@ -49,10 +51,11 @@ struct CloudSet {
 
 struct TargetIndex {
   DevBuf world, sorted, keys, keys_alt, vals, vals_alt, hist, cell_start, grids, aabb, tmp;
+  DevBuf srow, sstart, srk, srw; bool has_superrows = false;      // merged super-rows of a static single-cloud target (MODE 4, dense mode)
   std::vector<GridDesc> h_grids;
   long long total_cells = 0;
   bool built = false;
-  void release() { world.release(); sorted.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release(); hist.release(); cell_start.release(); grids.release(); aabb.release(); tmp.release(); }
+  void release() { world.release(); sorted.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release(); hist.release(); cell_start.release(); grids.release(); aabb.release(); tmp.release(); srow.release(); sstart.release(); srk.release(); srw.release(); has_superrows = false; }
 };
 
 }  // namespace pvb
@@ -63,7 +66,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_mode = 2, tune_hints = 1, tune_morton_bits = 12, tune_flat = 1; double tune_cellcap = 4.0, tune_hscale = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
+  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_mode = 2, tune_dense_mode = 4, tune_static = 1, tune_hints = 1, tune_morton_bits = 12, tune_flat = 1; double tune_cellcap = 4.0, tune_hscale = 1.0, tune_dense_hscale = 1.0, tune_reorder = 1.0; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
@@ -95,7 +98,11 @@ struct pvb_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
   cudaEvent_t bev0 = nullptr, bev1 = nullptr; bool bev_valid = false;     // brackets k_eval_blocks of the last blocks evaluate
   cudaStream_t copy_stream = nullptr, sort_stream = nullptr; cudaEvent_t eval_done = nullptr; std::vector<cudaEvent_t> chunk_ev, h2d_ev;
-  std::vector<int> d_chunk_frame, d_chunk_ctile, d_chunk_qtile; bool d_chunks_pending = false;   // brackets the fused associate kernel of the last dense evaluate
+  std::vector<int> d_chunk_frame, d_chunk_ctile, d_chunk_qtile; bool d_chunks_pending = false;
+  // MODE 4: the queries are ordered by target cell under the poses of an evaluation (k_target_cell_keys); the order is redone after an upload and when a
+  // pose update may have moved a point by more than half a cell (bound from the pose change and the frame's largest sensor distance)
+  bool d_cell_order = false, d_order_pending = false, d_order_valid = false; std::vector<pvb::WorldPoseHost> d_order_wpose; DevBuf d_rmax2; PinBuf dh_rmax2; cudaEvent_t rmax_ev = nullptr, pose_ev = nullptr; bool rmax_inflight = false;
+  long d_reorders = 0;   // brackets the fused associate kernel of the last dense evaluate
   // ---- device linear solver of the LM loop (pvb_solver.cuh)
   int solver_kind = 0;                                                  // PVB_SOLVER_AUTO
   bool coop_attr_set[8][2] = {};                                        // same for the instantiations of k_associate_coop

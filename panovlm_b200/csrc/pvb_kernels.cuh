@@ -110,6 +110,72 @@ __global__ void __launch_bounds__(256) k_gather_f4(const F4* __restrict__ src, c
   if (i < n) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + idx[i]);
 }
 
+// squared distance of every target record to its K-th nearest target record (itself included) within sqrt(sq_thr), +inf when there are fewer: the static
+// search bound of MODE 4 (knn_select_superrow)
+template <int K>
+__global__ void __launch_bounds__(128) k_target_rk(GridDesc g, const uint32_t* __restrict__ cell_start, const F4* __restrict__ sorted, long long n, float sq_thr, int rmax, float* __restrict__ rk) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* cs = cell_start + g.cell_base;
+  auto cells = [cs](long long c) { return (long long)__ldg(cs + c); };
+  auto load = [sorted](long long p) { return ldg_f4(sorted + p); };
+  const F4 q = ldg_f4(sorted + i);
+  uint32_t tau = 0x7F800000u;
+  const int found = knn_select_pruned<K>(g, cells, load, q.x, q.y, q.z, sq_thr, 1, rmax, [](int, uint32_t, uint32_t) {}, &tau);
+  rk[i] = found >= K ? __uint_as_float(tau) : INFINITY;
+}
+
+// ---- merged super-rows of a static target (MODE 4): segment (row = (y, z), x) = records of the 9 cells (x, y + dy, z + dz), dz outer, dy inner ----------
+__global__ void __launch_bounds__(256) k_superrow_counts(GridDesc g, const uint32_t* __restrict__ cell_start, long long ncells, uint32_t* __restrict__ cnt) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncells) return;
+  if (c == ncells) { cnt[c] = 0u; return; }                     // the slot after the last cell (end of the last segment)
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  const int x = (int)(c % nx); const long long row = c / nx; const int y = (int)(row % ny), z = (int)(row / ny);
+  const uint32_t* cs = cell_start + g.cell_base;
+  uint32_t sum = 0u;
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int zz = z + dz; if (zz < 0 || zz >= nz) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy; if (yy < 0 || yy >= ny) continue;
+      const long long cc = ((long long)zz * ny + yy) * nx + x;
+      sum += __ldg(cs + cc + 1) - __ldg(cs + cc);
+    }
+  }
+  cnt[c] = (sum + 3u) & ~3u;                                     // segments are padded to whole groups of 4 records
+}
+// one thread per destination segment (build time only): records as groups of 4 in {x0..3}, {y0..3}, {z0..3} float4 triples, the tail of the last
+// group filled with points at +infinity (never below any bound)
+__global__ void __launch_bounds__(256) k_superrow_fill(GridDesc g, const uint32_t* __restrict__ cell_start, const F4* __restrict__ sorted, long long ncells,
+                                                       const uint32_t* __restrict__ sstart, float* __restrict__ quads, uint32_t* __restrict__ srw, const float* __restrict__ rk,
+                                                       float* __restrict__ srk) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  const int x = (int)(c % nx); const long long row = c / nx; const int y = (int)(row % ny), z = (int)(row / ny);
+  const uint32_t* cs = cell_start + g.cell_base;
+  uint32_t dst = sstart[c];
+  const uint32_t end = sstart[c + 1];
+  if (end == dst) return;
+  auto put = [&](uint32_t r, float px, float py, float pz, uint32_t w, float k) {
+    float* q = quads + (size_t)(r >> 2) * 12 + (r & 3u);
+    q[0] = px; q[4] = py; q[8] = pz; srw[r] = w; srk[r] = k;
+  };
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int zz = z + dz; if (zz < 0 || zz >= nz) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy; if (yy < 0 || yy >= ny) continue;
+      const long long cc = ((long long)zz * ny + yy) * nx + x;
+      const uint32_t lo = __ldg(cs + cc), hi = __ldg(cs + cc + 1);
+      for (uint32_t i = lo; i < hi; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(sorted) + i);          // cell_start holds positions in the sorted array of the whole cloud set
+        put(dst++, v.x, v.y, v.z, (i << 5) | (__float_as_uint(v.w) & 31u), rk[i]);
+      }
+    }
+  }
+  for (; dst < end; ++dst) put(dst, INFINITY, INFINITY, INFINITY, 0u, INFINITY);
+}
+
 // Morton key of a source point in its own sensor frame (cells of 1 / inv_cell metres inside +-512 m, `bits` bits per axis), frame id in the high bits.
 __device__ __forceinline__ unsigned long long spread3(uint32_t v) {       // <= 21 bits -> every third bit
   unsigned long long x = v & 0x1FFFFFull;
@@ -133,6 +199,34 @@ __global__ void __launch_bounds__(256) k_morton_keys(const F4* __restrict__ loca
   vals[t.start + i] = (uint32_t)(t.start + i);
 }
 
+// Target-cell key of a source point under the CURRENT pose of its frame (dense mode, MODE 4): queries sorted by (frame, cell of the target grid, x fastest)
+// put the lanes of a warp into the same few cells, so their super-row ranges coincide (same trip counts, broadcast loads).  Also the largest squared
+// distance of a frame's points from its sensor (float bits): the host bounds how far a pose update can move a point without looking at the cloud again.
+template <typename KeyT>
+__global__ void __launch_bounds__(256) k_target_cell_keys(const F4* __restrict__ local, const CloudTile* __restrict__ tiles, int first_cloud, const WorldPose* __restrict__ wpose,
+                                                          GridDesc g, int cellbits, KeyT* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ rmax2) {
+  const CloudTile t = tiles[blockIdx.x];
+  const int i = threadIdx.x;
+  float r2 = 0.f;
+  if (i < t.count) {
+    const F4 p = ldg_f4(local + t.start + i);
+    const WorldPose& wp = wpose[t.cloud + 1];                    // block 0 is the target's identity pose
+    float x, y, z;
+    transform_point_f32(wp.R, wp.t, p.x, p.y, p.z, x, y, z);
+    const int cx = cell_coord((double)x, g.origin[0], g.inv_h, g.dims[0]);
+    const int cy = cell_coord((double)y, g.origin[1], g.inv_h, g.dims[1]);
+    const int cz = cell_coord((double)z, g.origin[2], g.inv_h, g.dims[2]);
+    const unsigned long long cell = ((unsigned long long)cz * g.dims[1] + cy) * g.dims[0] + cx;
+    keys[t.start + i] = (KeyT)(((unsigned long long)(t.cloud - first_cloud) << cellbits) | cell);
+    vals[t.start + i] = (uint32_t)(t.start + i);
+    r2 = p.x * p.x + p.y * p.y + p.z * p.z;
+  }
+  uint32_t m = __float_as_uint(r2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(rmax2 + t.cloud, m);
+}
+
 // ---- K2p: fused associate (+ residual + reduce) --------------------------------------------------------------------
 struct AssocArgs {
   const F4* q_local;            // query records, local frame: x,y,z,intensity(class)  (dense mode: Morton order)
@@ -154,11 +248,17 @@ struct AssocArgs {
   int* out_nn_idx; float* out_nn_d2;                                 // idem, K per query (debug / parity)
   double* partials;                                                  // [tile][warp][29]
   unsigned long long* stats;                                         // optional: [0] tiles staged through TMA, [1] tiles on the global path
-  // search-radius hints of the buffered single-pass search (MODE 2), one record per query in launch order: {x, y, z of the query in the world
+  // search-radius hints of the buffered single-pass search (MODE 2 / 4), one record per query by OUTPUT SLOT (the query's original index in dense mode,
+  // so the hints survive a re-ordering of the queries): {x, y, z of the query in the world
   // frame at the last evaluation, its K-th squared distance then (float; not finite = no hint)}.  Read and rewritten in place; may be null.
   F4* hint;
   int use_hint;                                                      // 0: ignore the stored hints (they are still rewritten)
   int flat_walk;                                                     // 1: the hinted walk runs over the flattened row ranges (walk_block_collect_flat)
+  int use_static;                                                    // MODE 4: 1 = queries without a usable hint take the static bound of the target (srk)
+  // MODE 4: merged super-rows of a static target (knn_select_superrow): records with w = (position in `sorted` << 5) | class, and the start of
+  // every (row, x cell) segment, indexed like cell_start (GridDesc::cell_base applies)
+  const float4* srow; const uint32_t* sstart; const uint32_t* srw; const float* srk;      // srow: groups of 4 records as {x0..3},{y0..3},{z0..3}; srw[r] = (position << 5) | class;
+  float one;                                                         // srk[r]: squared distance of record r to its 10th nearest target point (static bound); one = 1.0f (see DevSuperRow::sqdist4)
 };
 
 // ---- TMA staging helpers (sm_90+/sm_100a): 1-D bulk copies global -> shared completing on an mbarrier ---------------------
@@ -186,20 +286,56 @@ constexpr int kStageRows = 64;     // (y,z) rows of a tile's cell box that can b
 constexpr int kStageCap = 768;     // staged records per tile (12 KB of shared memory)
 
 constexpr int kListCap = 24;       // per-query candidate list of the buffered single-pass search (8 B per entry)
+#ifndef PVB_LC4
+#define PVB_LC4 32
+#endif
+constexpr int kListCap4 = PVB_LC4;      // the same for MODE 4 (room for the ~1.7 K survivors of the static bound before a compaction)
 
-// MODE: 0 = TMA-staged tile + exhaustive walk, 1 = pruned two-pass walk, 2 = buffered single pass with search-radius hints (default)
+// MODE: 0 = TMA-staged tile + exhaustive walk, 1 = pruned two-pass walk, 2 = buffered single pass with search-radius hints (frames mode default),
+//       4 = buffered single pass over the merged super-rows of a static target (dense mode default)
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+struct DevSuperRow {
+  const uint32_t* st; const float4* quads; const uint32_t* wp; const float* rkp; float one;
+  __device__ __forceinline__ float rk(uint32_t r) const { return __ldg(rkp + r); }
+  __device__ __forceinline__ uint32_t w(uint32_t r) const { return __ldg(wp + r); }
+  __device__ __forceinline__ uint32_t start(long long i) const { return __ldg(st + i); }
+  // squared distances of the 4 records of group G to q: packed FP32x2 arithmetic, two candidates per instruction.  Every operation rounds like the scalar
+  // one (sub.rn / mul.rn per half); the additions are fma(a, one, b) with `one` = 1.0f read from the kernel arguments: a * 1 is exact, so the result is
+  // the correctly rounded a + b, and ptxas cannot contract it with the multiplication that produced `a` (it does contract mul.rn.f32x2 + add.rn.f32x2
+  // into FFMA2, which would change the last bit; tools/micro/packed_sqdist_check.cu compares 4 M distances with the scalar __fmul_rn / __fadd_rn path).
+  struct Quad { float4 X, Y, Z; };
+  __device__ __forceinline__ Quad load3(uint32_t G) const { Quad q; q.X = __ldg(quads + 3u * G); q.Y = __ldg(quads + 3u * G + 1u); q.Z = __ldg(quads + 3u * G + 2u); return q; }
+  __device__ __forceinline__ void sqdist4(const Quad& c, float qx, float qy, float qz, uint32_t (&kb)[4]) const {
+    const float4 X = c.X, Y = c.Y, Z = c.Z;
+    const unsigned long long QX = f2_pack(qx, qx), QY = f2_pack(qy, qy), QZ = f2_pack(qz, qz), ONE = f2_pack(one, one);
+    const unsigned long long dx0 = f2_sub(f2_pack(X.x, X.y), QX), dx1 = f2_sub(f2_pack(X.z, X.w), QX);
+    const unsigned long long dy0 = f2_sub(f2_pack(Y.x, Y.y), QY), dy1 = f2_sub(f2_pack(Y.z, Y.w), QY);
+    const unsigned long long dz0 = f2_sub(f2_pack(Z.x, Z.y), QZ), dz1 = f2_sub(f2_pack(Z.z, Z.w), QZ);
+    const unsigned long long s0 = f2_fma(f2_fma(f2_mul(dx0, dx0), ONE, f2_mul(dy0, dy0)), ONE, f2_mul(dz0, dz0));
+    const unsigned long long s1 = f2_fma(f2_fma(f2_mul(dx1, dx1), ONE, f2_mul(dy1, dy1)), ONE, f2_mul(dz1, dz1));
+    float d0, d1, d2, d3;
+    f2_unpack(s0, d0, d1); f2_unpack(s1, d2, d3);
+    kb[0] = __float_as_uint(d0); kb[1] = __float_as_uint(d1); kb[2] = __float_as_uint(d2); kb[3] = __float_as_uint(d3);
+  }
+};
 template <int K, bool REDUCE, int MINB, bool DEBUG_NN, int MODE, bool REF_ID>
 __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
   constexpr bool STAGE = MODE == 0;
-  constexpr int LC = kListCap;
-  __shared__ double sJ_own[(REDUCE && MODE != 2) ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B); MODE 2: aliases the warp's list
-  __shared__ uint32_t s_win[MODE == 2 ? 1 : K][kTile];           // record positions of each query's K neighbours (MODE 2: slots 0..K-1 of the list)
+  constexpr bool LIST = MODE == 2 || MODE == 4;      // per-query candidate list in shared memory
+  constexpr int LC = MODE == 4 ? kListCap4 : kListCap;
+  __shared__ double sJ_own[(REDUCE && !LIST) ? kTile : 1][8];   // per row: J6 (nei pose) | r | cost   (row stride 8 doubles = 64 B); MODE 2: aliases the warp's list
+  __shared__ uint32_t s_win[LIST ? 1 : K][kTile];           // record positions of each query's K neighbours (MODE 2: slots 0..K-1 of the list)
   // MODE 2: per warp (d2 bits, record position) of the candidates below the hinted bound, [warp][entry][lane]; its last slots double as the row table of the
   // flattened walk and, once the warp's searches and plane fits are done, its first 2 KB as the staging rows of the warp's reduction
-  __shared__ __align__(16) U2 s_list[MODE == 2 ? kTile / 32 : 1][MODE == 2 ? LC : 1][32];
-  static_assert(MODE != 2 || sizeof(U2) * LC * 32 >= sizeof(double) * 32 * 8, "the reduction rows alias the warp's list");
-  double (*sJ)[8] = MODE == 2 ? reinterpret_cast<double (*)[8]>(&s_list[0][0][0]) : sJ_own;      // MODE 2: re-pointed per warp below
-  __shared__ uint32_t s_rng[18][kTile];          // the <= 9 (lo, hi) row ranges of each query's 3x3x3 cell block
+  __shared__ __align__(16) U2 s_list[LIST ? kTile / 32 : 1][LIST ? LC : 1][32];
+  static_assert(!LIST || LC * 8 >= K * 16, "the neighbour records alias the warp's list");
+  static_assert(!LIST || sizeof(U2) * LC * 32 >= sizeof(double) * 32 * 8, "the reduction rows alias the warp's list");
+  double (*sJ)[8] = LIST ? reinterpret_cast<double (*)[8]>(&s_list[0][0][0]) : sJ_own;      // MODE 2: re-pointed per warp below
+  __shared__ uint32_t s_rng[18][(MODE == 0) ? kTile : 1];          // the <= 9 (lo, hi) row ranges of each query's 3x3x3 cell block
   __shared__ __align__(16) F4 s_pts[STAGE ? kStageCap : 1];          // the tile's candidate rows, copied by TMA
   __shared__ uint32_t s_row_lo[STAGE ? kStageRows : 1], s_row_base[STAGE ? kStageRows : 1];
   __shared__ int s_box[6];
@@ -209,7 +345,9 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
   const Pair pr = a.pairs[t.pair];
   const int i = threadIdx.x;
   const bool act = i < t.count;
-  bool valid = false;
+  bool valid = false, dyn_tight = false;
+  int found = 0;
+  uint32_t lim_hint = 0u, tau = 0x7F800000u;
   double p_local[3] = {0, 0, 0}, plane[4] = {0, 0, 0, 0};
   double r = 0.0, cost = 0.0, J[12];
 #pragma unroll
@@ -293,11 +431,11 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
         hi = nlo + (hi - lo); lo = nlo;
       }
     };
-    U2* const my_list = &s_list[MODE == 2 ? (i >> 5) : 0][0][MODE == 2 ? (i & 31) : 0];          // entry e of this query: my_list[e * 32]
-    auto win = [&](int j) { return MODE == 2 ? my_list[j * 32].y : s_win[j][i]; };
-    auto set_win = [&](int j, uint32_t pos) { if (MODE == 2) my_list[j * 32].y = pos; else s_win[j][i] = pos; };
-    auto range_set = [&](int k, uint32_t lo, uint32_t hi) { s_rng[2 * k][i] = lo; s_rng[2 * k + 1][i] = hi; };
-    auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { lo = s_rng[2 * k][i]; hi = s_rng[2 * k + 1][i]; };
+    U2* const my_list = &s_list[LIST ? (i >> 5) : 0][0][LIST ? (i & 31) : 0];          // entry e of this query: my_list[e * 32]
+    auto win = [&](int j) { return LIST ? my_list[j * 32].y : s_win[j][i]; };
+    auto set_win = [&](int j, uint32_t pos) { if (LIST) my_list[j * 32].y = pos; else s_win[j][i] = pos; };
+    auto range_set = [&](int k, uint32_t lo, uint32_t hi) { if (MODE == 0) { s_rng[2 * k][i] = lo; s_rng[2 * k + 1][i] = hi; } };
+    auto range_get = [&](int k, uint32_t& lo, uint32_t& hi) { if (MODE == 0) { lo = s_rng[2 * k][i]; hi = s_rng[2 * k + 1][i]; } else { lo = hi = 0u; } };
     AssocParams prm = a.prm;
     prm.rmax = (int)ceil(a.thr / g.h);
     if (DEBUG_NN && a.out_nn_idx) {
@@ -305,21 +443,71 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
       for (int j = 0; j < K; ++j) set_win(j, 0xFFFFFFFFu);
     }
     // search-radius hint: K target points lay within sqrt(tau_old) of q_old => within sqrt(tau_old) + |q - q_old| of q
-    uint32_t lim_hint = 0u, tau = 0x7F800000u;
-    if (MODE == 2 && a.hint && a.use_hint) {
-      const F4 hq = ldg_f4(a.hint + gq);
+    if (LIST && a.hint && a.use_hint) {
+      const F4 hq = ldg_f4(a.hint + qi);
       if (hq.w >= 0.f && hq.w < 3.0e38f) {
         const double dx = (double)qx - (double)hq.x, dy = (double)qy - (double)hq.y, dz = (double)qz - (double)hq.z;
         const double rad = (sqrt((double)hq.w) + sqrt(dx * dx + dy * dy + dz * dz)) * (1.0 + 1e-5) + 1e-9;
         const double lim2 = rad * rad;
-        // use the bound only when the list can be expected to hold what lies below it (points on a surface: count ~ K * lim2 / tau_old);
-        // after a large pose change the bound is loose and the two-pass search is the cheaper way
-        if (lim2 < (double)prm.sq_thr && lim2 * (double)K < (double)hq.w * (0.8 * LC)) lim_hint = f2u((float)lim2) + 2u;      // +1 ulp for the float rounding, +1 to make the bound exclusive
+        // the bound is "tight" when the list can be expected to hold what lies below it (points on a surface: count ~ K * lim2 / tau_old); after a large
+        // pose change it is loose: MODE 2 then takes the two-pass search, MODE 4 also looks for the static bound of the target and keeps the smaller one
+        if (lim2 < (double)prm.sq_thr) {
+          dyn_tight = lim2 * (double)K < (double)hq.w * (0.8 * LC);
+          if (dyn_tight || MODE == 4) lim_hint = f2u((float)lim2) + 2u;      // +1 ulp for the float rounding, +1 to make the bound exclusive
+        }
       }
     }
-    valid = associate_point2plane<K, REF_ID, MODE, LC>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
-                                     range_get, lim_hint, &tau, my_list, 32, a.flat_walk != 0);
-    if (MODE == 2 && a.hint) { F4 ho; ho.x = qx; ho.y = qy; ho.z = qz; ho.w = u2f(tau); reinterpret_cast<float4*>(a.hint)[gq] = make_float4(ho.x, ho.y, ho.z, ho.w); }
+    if (MODE == 2) {
+      // a warp whose lanes took different search paths pays for both: the bounded single pass is only taken when every active lane of the warp has a usable
+      // bound (after a large pose change most warps fall back as a whole and cost what the two-pass search costs, not the sum).  MODE 4 has the static
+      // bound of the target for the lanes without one, so every lane takes the single pass.
+      const unsigned am = __activemask();
+      if (__ballot_sync(am, lim_hint == 0u)) lim_hint = 0u;
+    }
+    if (!LIST) {
+      DevSuperRow sr{};
+      valid = associate_point2plane<K, REF_ID, MODE, LC>(g, cells, load1, loadg, row_map, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, range_set,
+                                       range_get, lim_hint, &tau, my_list, 32, a.flat_walk != 0, sr);
+    } else if (MODE == 2) {
+      DevSuperRow sr{};
+      found = search_list_modes<K, MODE, LC, SingleLane>(g, cells, loadg, prm, true, qx, qy, qz, set_win, lim_hint, dyn_tight, &tau, my_list, 32, a.flat_walk != 0, sr, false);
+    }
+  }
+  if (MODE == 4) {      // warp-synchronous search: every lane of the warp takes part (inactive lanes with an empty range)
+    auto cells = [cs](long long c) { return (long long)__ldg(cs + c); };
+    auto loadg = [srt](long long p) { return ldg_f4(srt + p); };
+    U2* const my_list = &s_list[LIST ? (i >> 5) : 0][0][LIST ? (i & 31) : 0];
+    auto set_win = [&](int j, uint32_t pos) { my_list[j * 32].y = pos; };
+    AssocParams prm = a.prm;
+    prm.rmax = (int)ceil(a.thr / g.h);
+    DevSuperRow sr; sr.st = a.sstart + g.cell_base; sr.quads = a.srow; sr.wp = a.srw; sr.rkp = a.srk; sr.one = a.one;
+    found = search_list_modes<K, MODE, LC, WarpLanes>(g, cells, loadg, prm, act, qx, qy, qz, set_win, lim_hint, dyn_tight, &tau, my_list, 32, false, sr, a.use_static != 0);
+  }
+  if (LIST && act && a.hint) reinterpret_cast<float4*>(a.hint)[qi] = make_float4(qx, qy, qz, u2f(tau));
+  // list modes: every lane of the warp leaves its search here; the K positions move to registers and the warp's list region becomes the store of the
+  // neighbours' records ([j][lane], 16 B each: K * 16 <= LC * 8), fetched once per query and read by the three passes of the plane fit
+  uint32_t wp[LIST ? K : 1];
+  if (LIST) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < K; ++j) wp[j] = (act && found >= K) ? s_list[i >> 5][j][i & 31].y : 0xFFFFFFFFu;
+    __syncwarp();
+  }
+  if (act) {
+    auto loadg = [srt](long long p) { return ldg_f4(srt + p); };
+    AssocParams prm = a.prm;
+    auto win = [&](int j) { return LIST ? wp[LIST ? j : 0] : s_win[j][i]; };
+    if (LIST && found >= K) {
+      struct SmemNb {
+        F4* base;
+        __device__ __forceinline__ void sync() {}
+        __device__ __forceinline__ void put(int j, const F4& v) { reinterpret_cast<float4*>(base)[j * 32] = make_float4(v.x, v.y, v.z, v.w); }
+        __device__ __forceinline__ F4 get(int j) const { const float4 v = reinterpret_cast<const float4*>(base)[j * 32]; F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+      } nb;
+      nb.base = reinterpret_cast<F4*>(&s_list[i >> 5][0][0]) + (i & 31);
+      auto set_wp = [&](int j, uint32_t pos) { wp[LIST ? j : 0] = pos; };
+      valid = plane_from_window<K, REF_ID>(loadg, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_wp, nb);
+    }
     auto load = loadg;     // the debug view below is only built without staging
     if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
       for (int j = 0; j < K; ++j) {
@@ -365,7 +553,7 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
     // staged in shared memory, then 28 lanes each own one entry of (H upper 21 | g 6 | cost); fixed summation
     // order => run-to-run identical results.  partials: [tile][warp][29].
     const int w = i >> 5, lane = i & 31;
-    if (MODE == 2) { __syncwarp(); sJ = reinterpret_cast<double (*)[8]>(&s_list[w][0][0]) - w * 32; }   // every lane of the warp is done with its list: sJ[i] = row (i & 31) of the warp's region
+    if (LIST) { __syncwarp(); sJ = reinterpret_cast<double (*)[8]>(&s_list[w][0][0]) - w * 32; }   // every lane of the warp is done with its list: sJ[i] = row (i & 31) of the warp's region
 #pragma unroll
     for (int k = 0; k < 6; ++k) sJ[i][k] = valid ? J[6 + k] : 0.0;
     sJ[i][6] = valid ? r : 0.0;
@@ -408,11 +596,6 @@ struct CoopWarp {                   // shared memory of one warp
 };
 static_assert(sizeof(float) * 3 * 4 * kGCP >= sizeof(uint32_t) * kListCap * 32 + sizeof(double) * 32 * 8, "keys and the reduction rows alias the candidate arrays");
 
-__device__ __forceinline__ unsigned long long f2_pack(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // All 32 lanes call.  part: this lane has a usable bound (rad = search radius in metres, lim = exclusive bound on the K-th squared distance as float bits).
 // Returns true when the lane's K nearest are in W.lpos[0..K-1][lane] (any order) and *tau_out = bits of the K-th squared distance.
@@ -577,7 +760,7 @@ __global__ void __launch_bounds__(kTile, 4) k_associate_coop(const AssocArgs a) 
   // search-radius hint: K target points lay within sqrt(tau_old) of q_old => within sqrt(tau_old) + |q - q_old| of q
   bool part = false; double rad = 0.0; uint32_t lim = 0u, tau = 0x7F800000u;
   if (act && a.hint && a.use_hint) {
-    const F4 hq = ldg_f4(a.hint + gq);
+    const F4 hq = ldg_f4(a.hint + qi);
     if (hq.w >= 0.f && hq.w < 3.0e38f) {
       const double dx = (double)qx - (double)hq.x, dy = (double)qy - (double)hq.y, dz = (double)qz - (double)hq.z;
       rad = (sqrt((double)hq.w) + sqrt(dx * dx + dy * dy + dz * dz)) * (1.0 + 1e-5) + 1e-9;
@@ -598,8 +781,8 @@ __global__ void __launch_bounds__(kTile, 4) k_associate_coop(const AssocArgs a) 
       }
       found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int jj, uint32_t pos, uint32_t) { set_win(jj, pos); }, &tau) >= K;
     }
-    if (a.hint) reinterpret_cast<float4*>(a.hint)[gq] = make_float4(qx, qy, qz, u2f(tau));
-    if (found) valid = plane_from_window<K, REF_ID>(loadg, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win);
+    if (a.hint) reinterpret_cast<float4*>(a.hint)[qi] = make_float4(qx, qy, qz, u2f(tau));
+    if (found) { LocalNbStore<K> nb; valid = plane_from_window<K, REF_ID>(loadg, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, nb); }
     if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
       for (int jj = 0; jj < K; ++jj) {
         const uint32_t pj = found ? win(jj) : 0xFFFFFFFFu;

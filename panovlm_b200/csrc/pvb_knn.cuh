@@ -531,6 +531,153 @@ PVB_HD int knn_select_hinted(const GridDesc& g, const CellLoader& cells, const L
   return knn_select_pruned<K>(g, cells, load, qx, qy, qz, sq_thr, r0, rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, tau_out);
 }
 
+// ---- super-row variant (MODE 4, dense mode default since round 2) ------------------------------------------------------------------
+// The 3x3x3 block walk above touches up to 9 row ranges per query (18 cell-table look-ups, per-lane row bookkeeping: the integer overhead was
+// ~2/3 of the walk's instructions).  For a STATIC target the 9 rows (y +- 1, z +- 1) around a row can be merged once, at index-build time:
+// super-row (y, z) holds, for every x cell, the records of the 9 cells (x, y + dy, z + dz) back to back (dz outer, dy inner), x ascending.
+// The 27-cell neighbourhood of a query in cell (cx, cy, cz) is then ONE contiguous range of the super-row array,
+//     [sstart[row * nx + cx - 1], sstart[row * nx + cx + 2])        with row = cz * ny + cy,
+// found with a few table look-ups and walked by one loop with no bookkeeping.  The array is ~9x the target (1.9 GB for 10 M points): HBM
+// capacity and bandwidth traded for instruction issue slots, which is what limits this kernel.
+// Layout (SR): every (row, x) segment is padded to a multiple of 4 records with points at +infinity; group G = records 4G .. 4G+3 is stored as
+// three float4 {x0..x3}, {y0..y3}, {z0..z3} (48 B), so one 128-bit load feeds two packed FP32x2 operations (two candidates per instruction);
+// w(r) = (position in the cell-sorted array << 5) | class and rk(r) (below) live in parallel arrays that are only read for the few survivors.
+//   sr.start(i): sstart[i] of this cloud's table (record units, multiples of 4);  sr.load3(G) / sr.sqdist4(quad, q, kb[4]): float32 bit patterns of the squared
+//   distances of group G's records to q (flann::L2_Simple: non-fused, x then y then z);  sr.w(r), sr.rk(r).
+// The function is WARP-SYNCHRONOUS on the device (W = WarpLanes): all 32 lanes call it (inactive lanes with active = false), loops run to the longest
+// range of the warp, and the list is compacted for every lane at once when any lane's list is about to overflow (cut to the K smallest, the
+// bound tightens to the K-th) - so ANY bound works, even none, with one walk.  On the host (W = SingleLane) the same code runs per query.
+// Bounds on the K-th squared distance (exclusive, float bits):
+//   * lim_dyn: from the previous evaluation of the query (see k_associate), 0 = none; dyn_tight: the caller expects few survivors below it;
+//   * static (use_static, taken when the dynamic one is absent or loose): sr.rk(p) is the squared distance from target point p to ITS K_build-th
+//     nearest target point (p included, K_build >= K, computed once when the index is built), so K target points lie within sqrt(rk(p)) + |q - p| of
+//     the query for ANY p; p = the nearest record of the query's own x segment (one short scan).  On surface-like clouds ~1.7 K survivors.
+// Exactness: the range covers every point within (1 + slack) * h of the query (slack = distance to the nearest face of the query's own
+// cell in cells); the x - 1 / x + 1 cells are skipped only when their nearest face is beyond the bound.  When fewer than K candidates are found
+// or the K-th distance is not below that reach (sparse neighbourhood, wrong hint) `fallback` is set and the caller runs the generic ring search.
+struct SingleLane {
+  PVB_HD static bool any(bool p) { return p; }
+  PVB_HD static uint32_t max_u32(uint32_t v) { return v; }
+};
+#ifdef __CUDACC__
+struct WarpLanes {
+  __device__ __forceinline__ static bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+  __device__ __forceinline__ static uint32_t max_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+};
+#endif
+struct NoSuperRow {
+  PVB_HD float rk(uint32_t) const { return 0.f; }
+  PVB_HD uint32_t w(uint32_t) const { return 0u; }
+  PVB_HD uint32_t start(long long) const { return 0u; }
+  struct Quad { int none; };
+  PVB_HD Quad load3(uint32_t) const { return Quad{0}; }
+  PVB_HD void sqdist4(const Quad&, float, float, float, uint32_t (&kb)[4]) const { kb[0] = kb[1] = kb[2] = kb[3] = 0x7F800000u; }
+};
+
+template <int K, int LC, typename W, typename SR>
+PVB_HD int knn_select_superrow(const GridDesc& g, const SR& sr, bool active, float qx, float qy, float qz, float sq_thr, uint32_t lim_dyn, bool dyn_tight, bool use_static,
+                               U2* lbase, int lstride, uint32_t* tau_out, bool& fallback) {
+  static_assert(LC >= K + 4, "list capacity");
+  fallback = false;
+  auto lkey = [&](int e) { return lbase[(long long)e * lstride].x; };
+  auto lmove = [&](int dst, int src) { lbase[(long long)dst * lstride] = lbase[(long long)src * lstride]; };
+  const uint32_t init = f2u(sq_thr) + 1u;          // every d2 <= sq_thr is below it
+  const int nx = g.dims[0], ny = g.dims[1];
+  const double fx = ((double)qx - g.origin[0]) * g.inv_h, fy = ((double)qy - g.origin[1]) * g.inv_h, fz = ((double)qz - g.origin[2]) * g.inv_h;
+  const int cx = cell_coord((double)qx, g.origin[0], g.inv_h, g.dims[0]);
+  const int cy = cell_coord((double)qy, g.origin[1], g.inv_h, g.dims[1]);
+  const int cz = cell_coord((double)qz, g.origin[2], g.inv_h, g.dims[2]);
+  double slack = 0.5, gx_lo = 0.0, gx_hi = 0.0;
+  {
+    const double f[3] = {fx - cx, fy - cy, fz - cz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double lo = f[a] < 0.0 ? 0.0 : f[a], hi = 1.0 - f[a] < 0.0 ? 0.0 : 1.0 - f[a];
+      if (a == 0) { gx_lo = lo * g.h; gx_hi = hi * g.h; }
+      const double m = lo < hi ? lo : hi;
+      slack = m < slack ? m : slack;
+    }
+  }
+  // squared distance (float, shrunk by a safety margin) to the faces of the query's cell along x = lower bound for the cells beyond them
+  const uint32_t b_lo = f2u((float)(gx_lo * gx_lo * (1.0 - 1e-5))), b_hi = f2u((float)(gx_hi * gx_hi * (1.0 - 1e-5)));
+  const double reach1 = (1.0 + slack) * g.h;
+  const double r1sq = reach1 * reach1 * (1.0 - 1e-6);
+  const uint32_t base = ((uint32_t)cz * (uint32_t)ny + (uint32_t)cy) * (uint32_t)nx + (uint32_t)cx;
+  const bool has_l = cx > 0, has_r = cx < nx - 1;
+  uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u;
+  if (active) {
+    s1 = sr.start((long long)base); s2 = sr.start((long long)(base + 1u));
+    s0 = has_l ? sr.start((long long)(base - 1u)) : s1; s3 = has_r ? sr.start((long long)(base + 2u)) : s2;
+  }
+  uint32_t lim = (lim_dyn != 0u && lim_dyn < init) ? lim_dyn : init;
+  // ---- static bound: nearest record of the query's own x segment + that record's K-th neighbour distance
+  const bool need_static = active && use_static && !(lim < init && dyn_tight);
+  if (W::any(need_static)) {
+    const uint32_t a0 = need_static ? s1 : 0u, a1 = need_static ? s2 : 0u;
+    const uint32_t it_n = W::max_u32((a1 - a0) >> 2);
+    uint32_t best = 0x7F800000u, bestp = 0u, i = a0;
+    typename SR::Quad cur = sr.load3(i < a1 ? (i >> 2) : 0u);
+#pragma unroll 1
+    for (uint32_t it = 0; it < it_n; ++it, i += 4u) {
+      const bool in = i < a1;
+      const typename SR::Quad nxt = sr.load3(i + 4u < a1 ? ((i + 4u) >> 2) : 0u);      // the next group is in flight while this one is evaluated
+      uint32_t kb[4];
+      sr.sqdist4(cur, qx, qy, qz, kb);
+      cur = nxt;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const bool b = in && kb[k] < best; bestp = b ? i + (uint32_t)k : bestp; best = b ? kb[k] : best; }
+    }
+    if (need_static && best < 0x7F800000u) {
+      const float rk = sr.rk(bestp);
+      if (rk >= 0.f && rk < 3.0e38f) {
+        const double rad = (sqrt((double)u2f(best)) + sqrt((double)rk)) * (1.0 + 1e-5) + 1e-9;
+        const double lim2 = rad * rad;
+        if (lim2 < (double)sq_thr) { const uint32_t ls = f2u((float)lim2) + 2u; lim = ls < lim ? ls : lim; }      // +1 ulp for the float rounding, +1 to make the bound exclusive
+      }
+    }
+  }
+  // ---- one walk over the range: everything below the bound goes to the list; the warp compacts its lists together when one is about to overflow
+  uint32_t lo = (has_l && b_lo < lim) ? s0 : s1, hi = (has_r && b_hi < lim) ? s3 : s2;
+  if (!active) lo = hi = 0u;
+  const uint32_t it_n = W::max_u32((hi - lo) >> 2);
+  int n = 0;
+  {
+    uint32_t i = lo;
+    typename SR::Quad cur = sr.load3(i < hi ? (i >> 2) : 0u);
+#pragma unroll 1
+    for (uint32_t it = 0; it < it_n; ++it, i += 4u) {
+      const bool in = i < hi;
+      const typename SR::Quad nxt = sr.load3(i + 4u < hi ? ((i + 4u) >> 2) : 0u);      // the next group is in flight while this one is evaluated
+      uint32_t kb[4];
+      sr.sqdist4(cur, qx, qy, qz, kb);
+      cur = nxt;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool p = in && kb[k] < lim;
+        if (p) { U2 e; e.x = kb[k]; e.y = i + (uint32_t)k; lbase[(long long)n * lstride] = e; }
+        n += p ? 1 : 0;
+      }
+      if (W::any(n > LC - 4)) {
+        if (n > K) { const uint32_t t = list_cut_to_k<K>(n, lkey, lmove); lim = t < lim ? t : lim; }
+      }
+    }
+  }
+  if (!active) return 0;
+  if (n < K) { fallback = true; return 0; }
+  uint32_t tau;
+  if (n > K) tau = list_cut_to_k<K>(n, lkey, lmove);
+  else {
+    tau = 0u;
+#pragma unroll
+    for (int j = 0; j < K; ++j) { const uint32_t v = lkey(j); tau = v > tau ? v : tau; }
+  }
+  if (!((double)u2f(tau) < r1sq)) { fallback = true; return 0; }
+#pragma unroll
+  for (int j = 0; j < K; ++j) lbase[(long long)j * lstride].y = sr.w(lbase[(long long)j * lstride].y) >> 5;      // record -> position in the cell-sorted array
+  if (tau_out) *tau_out = tau;
+  return K;
+}
+
 struct AssocParams {
   float sq_thr;           // point_to_plane_dis_threshold^2 computed in float (LidarFeatureAssociate.cpp:557)
   int rmax;               // ceil(thr / h)
@@ -547,10 +694,20 @@ struct AssocParams {
 // neighbour itself bit for bit (x*1 + y*0 + z*0 - 0), so the 3 x K matrix-vector products per query are skipped.
 // Everything of AssociatePoint2Plane after the search (LidarFeatureAssociate.cpp:583-599): win(0..K-1) hold the record positions of the K nearest
 // neighbours (any order), `load` reads a record.  Same-class test, neighbours -> reference sensor frame, LSQ plane + tolerance, collinearity reject.
-template <int K, bool REF_ID, typename Load, typename WinGet, typename WinSet>
+// The K neighbour records are fetched ONCE (K independent gathers in flight) into a small store and read from there by the three passes of the fit
+// (Gram matrix, refinement step, tolerance test); on the device the store is the warp's shared-memory list region (see k_associate), here a local array.
+template <int K>
+struct LocalNbStore {
+  F4 r[K];
+  PVB_HD void sync() {}
+  PVB_HD void put(int j, const F4& v) { r[j] = v; }
+  PVB_HD F4 get(int j) const { return r[j]; }
+};
+
+template <int K, bool REF_ID, typename Load, typename WinGet, typename WinSet, typename NB>
 PVB_HD bool plane_from_window(const Load& load, const AssocParams& prm, float qx, float qy, float qz, uint32_t qcls,
                               const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
-                              double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win) {
+                              double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, NB& nb) {
   {
     // canonical neighbour order = ascending record position: the plane fit below sums over the neighbours, and the order the search
     // found them in depends on the walk (block radius, ring expansion, hints); sorting makes the result independent of all of that
@@ -564,13 +721,16 @@ PVB_HD bool plane_from_window(const Load& load, const AssocParams& prm, float qx
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) set_win(j, wp[j]);
+    nb.sync();
+#pragma unroll
+    for (int j = 0; j < K; ++j) nb.put(j, load((long long)wp[j]));
   }
   // neighbours -> reference sensor frame (:587), streamed: Gram matrix for the LSQ plane and the scatter matrix
   PlaneAcc acc; plane_acc_clear(acc);
   int same = 0;
 #pragma unroll 1
   for (int j = 0; j < K; ++j) {
-    const F4 p = load((long long)win(j));
+    const F4 p = nb.get(j);
     same += ((f2u(p.w) & 31u) == qcls) ? 1 : 0;                  // :586 pt.intensity == point.intensity
     const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
     double pl[3];
@@ -587,7 +747,7 @@ PVB_HD bool plane_from_window(const Load& load, const AssocParams& prm, float qx
     double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll 1
     for (int j = 0; j < K; ++j) {
-      const F4 p = load((long long)win(j));
+      const F4 p = nb.get(j);
       const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
       double pl[3];
       if (REF_ID) { pl[0] = pw[0]; pl[1] = pw[1]; pl[2] = pw[2]; } else world2local(R_ref, t_ref, pw, pl);
@@ -601,7 +761,7 @@ PVB_HD bool plane_from_window(const Load& load, const AssocParams& prm, float qx
     double A[K * 3];
 #pragma unroll 1
     for (int j = 0; j < K; ++j) {
-      const F4 p = load((long long)win(j));
+      const F4 p = nb.get(j);
       const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
       if (REF_ID) { A[j * 3] = pw[0]; A[j * 3 + 1] = pw[1]; A[j * 3 + 2] = pw[2]; } else world2local(R_ref, t_ref, pw, &A[j * 3]);
     }
@@ -614,7 +774,7 @@ PVB_HD bool plane_from_window(const Load& load, const AssocParams& prm, float qx
     bool ok = true;
 #pragma unroll 1
     for (int j = 0; j < K; ++j) {
-      const F4 p = load((long long)win(j));
+      const F4 p = nb.get(j);
       const double pw[3] = {(double)p.x, (double)p.y, (double)p.z};
       double pl[3];
       if (REF_ID) { pl[0] = pw[0]; pl[1] = pw[1]; pl[2] = pw[2]; } else world2local(R_ref, t_ref, pw, pl);
@@ -629,22 +789,40 @@ PVB_HD bool plane_from_window(const Load& load, const AssocParams& prm, float qx
 }
 
 
+// The search of the list modes alone (MODE 2: per-row walk, MODE 4: merged super-rows): the K nearest end up in list slots 0..K-1 (.y = position in the
+// cell-sorted array); returns K, or 0 when the K-th nearest is beyond the threshold.  MODE 4 on the device: called by ALL lanes of the warp (W = WarpLanes).
+template <int K, int MODE, int LC, typename W, typename CellLoader, typename LoadG, typename WinSet, typename SR>
+PVB_HD int search_list_modes(const GridDesc& g, const CellLoader& cells, const LoadG& loadg, const AssocParams& prm, bool active, float qx, float qy, float qz, const WinSet& set_win,
+                             uint32_t lim_hint, bool dyn_tight, uint32_t* tau_out, U2* lbase, int lstride, bool flat, const SR& sr, bool use_static = true) {
+  if (MODE == 4) {
+    bool fb = false;
+    const int found = knn_select_superrow<K, LC, W>(g, sr, active, qx, qy, qz, prm.sq_thr, lim_hint, dyn_tight, use_static, lbase, lstride, tau_out, fb);
+    if (!fb) return found;
+    return knn_select_hinted<K, LC>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, dyn_tight ? lim_hint : 0u, lbase, lstride, set_win, tau_out, false);
+  }
+  if (!active) return 0;
+  return knn_select_hinted<K, LC>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, lim_hint, lbase, lstride, set_win, tau_out, flat);
+}
+
 // MODE: 0 = exhaustive walk over stored row ranges (TMA-staged variant), 1 = pruned two-pass walk, 2 = hinted single pass with the two-pass walk as
-// fallback (default; uses the list accessors and the search-radius hint, see knn_select_hinted; the K nearest end up in list slots 0..K-1 = win(0..K-1)).
-template <int K, bool REF_ID, int MODE, int LC = K + 2, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet>
+// fallback (uses the list accessors and the search-radius hint, see knn_select_hinted; the K nearest end up in list slots 0..K-1 = win(0..K-1)),
+// 4 = the same over the merged super-rows of a static target (knn_select_superrow; dense mode default).
+template <int K, bool REF_ID, int MODE, int LC = K + 2, typename CellLoader, typename Load1, typename LoadG, typename RowMap, typename WinGet, typename WinSet, typename RangeSet, typename RangeGet,
+          typename SR = NoSuperRow>
 PVB_HD bool associate_point2plane(const GridDesc& g, const CellLoader& cells, const Load1& load1, const LoadG& loadg, const RowMap& row_map, const AssocParams& prm,
                                   float qx, float qy, float qz, uint32_t qcls,
                                   const double* R_ref, const double* t_ref, const double* R_nei, const double* t_nei,
                                   double p_local[3], double plane[4], const WinGet& win, const WinSet& set_win, const RangeSet& range_set, const RangeGet& range_get,
-                                  uint32_t lim_hint, uint32_t* tau_out, U2* lbase, int lstride, bool flat = true) {
+                                  uint32_t lim_hint, uint32_t* tau_out, U2* lbase, int lstride, bool flat = true, const SR& sr = SR(), bool use_static = true) {
   int ring = 1;
   int found;
-  if (MODE == 2) { found = knn_select_hinted<K, LC>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, lim_hint, lbase, lstride, set_win, tau_out, flat); ring = 2; }
+  if (MODE == 4 || MODE == 2) { found = search_list_modes<K, MODE, LC, SingleLane>(g, cells, loadg, prm, true, qx, qy, qz, set_win, lim_hint, lim_hint != 0u, tau_out, lbase, lstride, flat, sr, use_static); ring = 2; }
   else if (MODE == 1) { found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }); ring = 2; }
   else found = knn_select<K>(g, cells, load1, loadg, row_map, qx, qy, qz, prm.sq_thr, prm.rmax, [&](int j, uint32_t pos, uint32_t) { set_win(j, pos); }, range_set, range_get, ring);
   if (found < K) return false;                                   // :578
   auto load = [&](long long pos) { return ring == 1 ? load1(pos) : loadg(pos); };   // neighbour positions live in the space they were found in (k-th beyond the threshold) + quirk C.6 guard
-  return plane_from_window<K, REF_ID>(load, prm, qx, qy, qz, qcls, R_ref, t_ref, R_nei, t_nei, p_local, plane, win, set_win);
+  LocalNbStore<K> nb;
+  return plane_from_window<K, REF_ID>(load, prm, qx, qy, qz, qcls, R_ref, t_ref, R_nei, t_nei, p_local, plane, win, set_win, nb);
 }
 
 // Per-query body of AssociatePoint2Line (lidar_mapping/LidarFeatureAssociate.cpp:478-548): 5 nearest corner points of

@@ -67,7 +67,8 @@ int set_cloudset(pvb_ctx* ctx, CloudSet& cs, const std::vector<const float*>& pt
 }
 
 // world transform + cell-sorted layout of every cloud of `cs` (poses already uploaded to ctx->d_wpose)
-int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_hint) {
+int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_hint, double hscale = 0.0) {
+  if (hscale <= 0.0) hscale = ctx->tune_hscale;
   const long long n = cs.n_points;
   ti.built = false;
   if (n == 0 || cs.n_clouds == 0) { ti.h_grids.assign(cs.n_clouds, GridDesc{}); ti.built = true; return PVB_OK; }
@@ -91,7 +92,7 @@ int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_
     if (cnt == 0) { g.dims[0] = g.dims[1] = g.dims[2] = 1; g.h = 1.0; g.inv_h = 1.0; g.origin[0] = g.origin[1] = g.origin[2] = 0; cells += 2; continue; }
     double lo[3], ext[3];
     for (int k = 0; k < 3; ++k) { lo[k] = unordered_f32(init[(size_t)c * 6 + k]); ext[k] = std::max(1e-3, (double)unordered_f32(init[(size_t)c * 6 + 3 + k]) - lo[k]); }
-    double h = cell_hint > 0 ? cell_hint : ctx->tune_hscale * std::cbrt(ext[0] * ext[1] * ext[2] / (double)cnt);
+    double h = cell_hint > 0 ? cell_hint : hscale * std::cbrt(ext[0] * ext[1] * ext[2] / (double)cnt);
     h = std::max(h, 0.02);
     for (;;) {
       double nc = 1; for (int k = 0; k < 3; ++k) nc *= std::floor(ext[k] / h) + 1;
@@ -131,18 +132,55 @@ int build_target_index(pvb_ctx* ctx, CloudSet& cs, TargetIndex& ti, double cell_
   return PVB_OK;
 }
 
+// merged super-rows of a single-cloud index (MODE 4, see knn_select_superrow): 9x the records, one contiguous range per 27-cell neighbourhood
+int build_superrows(pvb_ctx* ctx, TargetIndex& ti) {
+  ti.has_superrows = false;
+  if (!ti.built || ti.h_grids.size() != 1 || ti.h_grids[0].n_points <= 0) return PVB_OK;
+  const GridDesc g = ti.h_grids[0];
+  const long long ncells = (long long)g.dims[0] * g.dims[1] * g.dims[2];
+  if (10ll * g.n_points >= (1ll << 32)) return PVB_OK;                         // positions are 32-bit
+  CK(ti.hist.ensure((size_t)(ncells + 1) * 4));
+  CK(ti.sstart.ensure((size_t)(ncells + 1) * 4));
+  const unsigned nb = (unsigned)((ncells + 1 + 255) / 256);
+  k_superrow_counts<<<nb, 256, 0, ctx->stream>>>(g, ti.cell_start.as<uint32_t>(), ncells, ti.hist.as<uint32_t>());
+  CKL();
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, ti.hist.as<uint32_t>(), ti.sstart.as<uint32_t>(), (int)(ncells + 1), ctx->stream);
+  CK(ti.tmp.ensure(tb));
+  tb = ti.tmp.cap;
+  CK(cub::DeviceScan::ExclusiveSum(ti.tmp.p, tb, ti.hist.as<uint32_t>(), ti.sstart.as<uint32_t>(), (int)(ncells + 1), ctx->stream));
+  uint32_t total = 0;
+  CK(cudaMemcpyAsync(&total, ti.sstart.as<uint32_t>() + ncells, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(ti.srow.ensure(std::max<size_t>(64, (size_t)total * 12)));
+  CK(ti.srk.ensure(std::max<size_t>(16, (size_t)total * 4))); CK(ti.srw.ensure(std::max<size_t>(16, (size_t)total * 4)));
+  // static search bound: every target point's distance to its 10th nearest target point (within 1.5 cells: a looser bound could not be used anyway)
+  CK(ti.vals.ensure((size_t)g.n_points * 4));
+  const float rk_thr = (float)(1.5 * g.h);
+  k_target_rk<10><<<(unsigned)((g.n_points + 127) / 128), 128, 0, ctx->stream>>>(g, ti.cell_start.as<uint32_t>(), ti.sorted.as<F4>(), (long long)g.n_points, rk_thr * rk_thr, 2, ti.vals.as<float>());
+  CKL();
+  k_superrow_fill<<<(unsigned)((ncells + 255) / 256), 256, 0, ctx->stream>>>(g, ti.cell_start.as<uint32_t>(), ti.sorted.as<F4>(), ncells, ti.sstart.as<uint32_t>(), ti.srow.as<float>(),
+                                                                            ti.srw.as<uint32_t>(), ti.vals.as<float>(), ti.srk.as<float>());
+  CKL();
+  ti.has_superrows = true;
+  return PVB_OK;
+}
+
 template <bool REDUCE>
 int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_identity = false) {
   if (n_tiles == 0) return PVB_OK;
   // tuning knobs (PVB_MINB: resident blocks per SM the register allocation targets; PVB_MODE: 2 = buffered single-pass search with search-radius
   // hints (default), 1 = pruned two-pass walk, 0 = stage each tile's candidate rows in shared memory with TMA bulk copies + exhaustive walk;
   // PVB_STAGE=1 is the old spelling of PVB_MODE=0).  Defaults: fastest measured on B200.
-  const int minb = ctx->tune_minb, mode = ctx->tune_stage ? 0 : ctx->tune_mode;
+  const int minb = ctx->tune_minb;
+  int mode = ctx->tune_stage ? 0 : ctx->tune_mode;
+  if (a.srow && a.sstart && a.out_nn_idx == nullptr) mode = 4;      // the caller's index has merged super-rows (dense mode)
+  else if (mode == 4) mode = 2;
   const bool dbg = a.out_nn_idx != nullptr;
   if (k != 5 && k != 10) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
   a.stats = nullptr;
   a.prm.r0 = ctx->tune_r0;
-  a.use_hint = ctx->tune_hints; a.flat_walk = ctx->tune_flat;
+  a.use_hint = ctx->tune_hints; a.flat_walk = ctx->tune_flat; a.use_static = ctx->tune_static;
   if (mode == 0 && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
   if (mode == 3) {                    // warp-cooperative search (groups of 8 queries share staged candidates)
     constexpr size_t smem = sizeof(CoopWarp) * (kTile / 32);
@@ -159,11 +197,12 @@ int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_ide
     return PVB_OK;
   }
 #define PVB_LAUNCH(KK, MB, DBG, MD) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, MD, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, MD, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
-#define PVB_MINB_SWITCH(KK, MD) do { if (minb >= 6) PVB_LAUNCH(KK, 6, false, MD); else if (minb == 5) PVB_LAUNCH(KK, 5, false, MD); else PVB_LAUNCH(KK, 4, false, MD); } while (0)
+#define PVB_MINB_SWITCH(KK, MD) do { (void)minb; PVB_LAUNCH(KK, 6, false, MD); } while (0)      // 6 resident blocks per SM measured fastest (4 / 5 were compiled in round 1: profiles/r1f_sweep.log)
 #define PVB_DISPATCH(KK)                                                                                   \
   if (dbg) { if (mode == 1) PVB_LAUNCH(KK, 4, true, 1); else PVB_LAUNCH(KK, 4, true, 2); }                 \
   else if (mode == 0) PVB_LAUNCH(KK, 6, false, 0);                                                         \
   else if (mode == 1) PVB_LAUNCH(KK, 6, false, 1);                                                         \
+  else if (mode == 4) PVB_MINB_SWITCH(KK, 4);                                                              \
   else PVB_MINB_SWITCH(KK, 2);
   if (k == 10) { PVB_DISPATCH(10) } else { PVB_DISPATCH(5) }
 #undef PVB_DISPATCH
@@ -191,13 +230,16 @@ int pvb_create(int device, pvb_ctx** out) {
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->bev0); cudaEventCreate(&ctx->bev1);
   if (const char* e = getenv("PVB_MINB")) ctx->tune_minb = atoi(e);
   if (const char* e = getenv("PVB_STAGE")) ctx->tune_stage = atoi(e) != 0;
-  if (const char* e = getenv("PVB_MODE")) ctx->tune_mode = std::min(3, std::max(0, atoi(e)));
+  if (const char* e = getenv("PVB_MODE")) { ctx->tune_dense_mode = std::min(4, std::max(0, atoi(e))); ctx->tune_mode = ctx->tune_dense_mode == 4 ? 2 : ctx->tune_dense_mode; }
   if (const char* e = getenv("PVB_HINTS")) ctx->tune_hints = atoi(e) != 0;
   if (const char* e = getenv("PVB_FLAT")) ctx->tune_flat = atoi(e) != 0;
   if (const char* e = getenv("PVB_MORTON_BITS")) ctx->tune_morton_bits = std::min(16, std::max(10, atoi(e)));   // bits per axis of the source re-ordering: cells of 1024 m / 2^bits
   if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
-  if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = std::max(0.1, atof(e));
+  if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = ctx->tune_dense_hscale = std::max(0.1, atof(e));
+  if (const char* e = getenv("PVB_STATIC")) ctx->tune_static = atoi(e) != 0;
+  if (const char* e = getenv("PVB_REORDER")) ctx->tune_reorder = std::max(0.0, atof(e));      // re-order the dense queries when a pose update may move a point by more than this many cells
+  if (const char* e = getenv("PVB_DENSE_HSCALE")) ctx->tune_dense_hscale = std::max(0.1, atof(e));
   if (ctx->d_stats.ensure(16) == cudaSuccess) cudaMemset(ctx->d_stats.p, 0, 16);
   *out = ctx;
   return PVB_OK;
@@ -218,6 +260,9 @@ void pvb_destroy(pvb_ctx* ctx) {
   ctx->fh_la.release(); ctx->fh_lb.release(); ctx->d_tgt.release(); ctx->d_src.release(); ctx->d_index.release();
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
   if (ctx->eval_done) cudaEventDestroy(ctx->eval_done);
+  if (ctx->rmax_ev) cudaEventDestroy(ctx->rmax_ev);
+  if (ctx->pose_ev) cudaEventDestroy(ctx->pose_ev);
+  ctx->d_rmax2.release(); ctx->dh_rmax2.release();
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->sort_stream) { cudaStreamSynchronize(ctx->sort_stream); cudaStreamDestroy(ctx->sort_stream); }
   for (cudaEvent_t e : ctx->h2d_ev) cudaEventDestroy(e);
@@ -975,7 +1020,11 @@ int pvb_dense_set_target(pvb_ctx* ctx, const float* xyzc, long n, double cell_si
   const double zero6[6] = {0, 0, 0, 0, 0, 0};
   rc = upload_poses(ctx, zero6, 1, false); if (rc) return rc;      // target frame == world
   ctx->d_cell = cell_size;
-  rc = build_target_index(ctx, ctx->d_tgt, ctx->d_index, cell_size); if (rc) return rc;
+  const bool sr = ctx->tune_dense_mode == 4 && !ctx->tune_stage;
+  rc = build_target_index(ctx, ctx->d_tgt, ctx->d_index, cell_size, sr ? ctx->tune_dense_hscale : ctx->tune_hscale); if (rc) return rc;
+  ctx->d_index.srow.release(); ctx->d_index.sstart.release(); ctx->d_index.srk.release(); ctx->d_index.srw.release(); ctx->d_index.has_superrows = false;
+  ctx->d_order_valid = false;                                  // the query order belongs to the old grid
+  if (sr) { rc = build_superrows(ctx, ctx->d_index); if (rc) return rc; }
   CK(cudaStreamSynchronize(ctx->stream));
   // the unsorted world copy and sort scratch are not needed after the build
   if (ctx->d_hint.p && ctx->d_src.n_points > 0) CK(cudaMemsetAsync(ctx->d_hint.p, 0x7f, (size_t)ctx->d_src.n_points * sizeof(F4), ctx->stream));   // hints belong to the old target
@@ -1055,9 +1104,16 @@ int pvb_dense_set_sources(pvb_ctx* ctx, const float* xyzc, const int* offsets, i
   CK(cudaStreamWaitEvent(st, ctx->eval_done, 0));
   const int n_chunks = (int)ctx->d_chunk_frame.size() - 1;
   while ((int)ctx->h2d_ev.size() < n_chunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->h2d_ev.push_back(e); }
+  // MODE 4 orders the queries by TARGET cell, which needs the poses: only the copies are queued here, the ordering runs at the next evaluate (dense_order_queries)
+  ctx->d_cell_order = ctx->tune_dense_mode == 4 && !ctx->tune_stage && ctx->d_index.has_superrows;
   for (int c = 0; c < n_chunks; ++c) {
     const int f0 = ctx->d_chunk_frame[c], f1 = ctx->d_chunk_frame[c + 1];
     const long long p0 = cs.off[f0], cnt = (long long)cs.off[f1] - p0;
+    if (cnt > 0 && ctx->d_cell_order) {
+      CK(cudaMemcpyAsync(cs.local.as<F4>() + p0, xyzc + (size_t)p0 * 4, (size_t)cnt * sizeof(F4), cudaMemcpyHostToDevice, cp));
+      CK(cudaEventRecord(ctx->h2d_ev[c], cp));
+      continue;
+    }
     if (cnt > 0) {
       CK(cudaMemcpyAsync(cs.local.as<F4>() + p0, xyzc + (size_t)p0 * 4, (size_t)cnt * sizeof(F4), cudaMemcpyHostToDevice, cp));
       CK(cudaEventRecord(ctx->h2d_ev[c], cp));
@@ -1078,6 +1134,82 @@ int pvb_dense_set_sources(pvb_ctx* ctx, const float* xyzc, const int* offsets, i
     CK(cudaEventRecord(ctx->chunk_ev[c], st));
   }
   ctx->d_chunks_pending = true;
+  ctx->d_order_pending = ctx->d_cell_order;
+  return PVB_OK;
+}
+
+// MODE 4: (re-)order the queries of every frame by target cell under the poses just uploaded (ctx->h_pose / d_wpose).  Runs chunk by chunk on the sort
+// stream (after the chunk's H2D copy when the upload is fresh) and signals chunk_ev[c]; the evaluate then launches chunk by chunk as for a fresh upload.
+// Returns *did = false when the present order is still good: no upload since, and no frame's pose moved a point by more than half a cell.
+static int dense_order_queries(pvb_ctx* ctx, bool* did) {
+  *did = false;
+  if (!ctx->d_cell_order) return PVB_OK;
+  CloudSet& cs = ctx->d_src;
+  const int nf = ctx->d_frames;
+  const GridDesc g = ctx->d_index.h_grids[0];
+  const WorldPose* hw = reinterpret_cast<const WorldPose*>(ctx->h_pose.as<PosePrep>() + (nf + 1)) + 1;      // staging of upload_poses: block 0 = identity
+  bool need = ctx->d_order_pending || !ctx->d_order_valid || (int)ctx->d_order_wpose.size() != nf;
+  if (!need) {
+    if (ctx->rmax_inflight) { if (cudaEventQuery(ctx->rmax_ev) == cudaSuccess) ctx->rmax_inflight = false; else need = true; }
+    const float* r2 = ctx->dh_rmax2.as<float>();
+    for (int f = 0; f < nf && !need; ++f) {
+      double fr = 0, dt = 0;
+      for (int k = 0; k < 9; ++k) { const double d = hw[f].R[k] - ctx->d_order_wpose[f].R[k]; fr += d * d; }
+      for (int k = 0; k < 3; ++k) { const double d = hw[f].t[k] - ctx->d_order_wpose[f].t[k]; dt += d * d; }
+      if (std::sqrt(fr) * std::sqrt((double)r2[f]) + std::sqrt(dt) > ctx->tune_reorder * g.h) need = true;
+      if (need && getenv("PVB_DEBUG_ORDER")) fprintf(stderr, "[pvb] re-order: frame %d dR %.3g rmax %.3g dt %.3g h %.3g\n", f, std::sqrt(fr), std::sqrt((double)r2[f]), std::sqrt(dt), g.h);
+    }
+  }
+  if (!need) return PVB_OK;
+  if (getenv("PVB_DEBUG_ORDER")) fprintf(stderr, "[pvb] re-order #%ld: pending %d valid %d inflight %d\n", ctx->d_reorders, (int)ctx->d_order_pending, (int)ctx->d_order_valid, (int)ctx->rmax_inflight);
+  if (!ctx->rmax_ev) { CK(cudaEventCreateWithFlags(&ctx->rmax_ev, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->pose_ev, cudaEventDisableTiming)); }
+  const bool fresh = ctx->d_order_pending;
+  // fresh upload: chunk by chunk on the sort stream behind the chunks' H2D copies (the evaluate launches per chunk); pose update: ONE sort of all frames on the
+  // main stream, one launch afterwards
+  cudaStream_t st = fresh ? ctx->sort_stream : ctx->stream;
+  CK(ctx->d_rmax2.ensure((size_t)nf * 4)); CK(ctx->dh_rmax2.ensure((size_t)nf * 4));
+  if (fresh) {
+    CK(cudaEventRecord(ctx->pose_ev, ctx->stream));                // the poses of this evaluate
+    CK(cudaStreamWaitEvent(st, ctx->pose_ev, 0));
+  }
+  CK(cudaMemsetAsync(ctx->d_rmax2.p, 0, (size_t)nf * 4, st));
+  long long ncells = (long long)g.dims[0] * g.dims[1] * g.dims[2];
+  int cellbits = 1; while ((1ll << cellbits) < ncells) ++cellbits;
+  const int n_chunks = fresh ? (int)ctx->d_chunk_frame.size() - 1 : 1;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int f0 = fresh ? ctx->d_chunk_frame[c] : 0, f1 = fresh ? ctx->d_chunk_frame[c + 1] : nf;
+    const long long p0 = cs.off[f0], cnt = (long long)cs.off[f1] - p0;
+    if (cnt > 0) {
+      if (fresh) CK(cudaStreamWaitEvent(st, ctx->h2d_ev[c], 0));
+      const int t0 = fresh ? ctx->d_chunk_ctile[c] : 0, t1 = fresh ? ctx->d_chunk_ctile[c + 1] : cs.n_tiles;
+      int frame_bits = 1; while ((1 << frame_bits) < f1 - f0) ++frame_bits;
+      size_t tb = ctx->m_e.cap;
+      if (cellbits + frame_bits <= 32) {
+        k_target_cell_keys<uint32_t><<<t1 - t0, 256, 0, st>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, f0, ctx->d_wpose.as<WorldPose>(), g, cellbits,
+                                                              ctx->m_a.as<uint32_t>(), ctx->m_c.as<uint32_t>(), ctx->d_rmax2.as<uint32_t>());
+        CKL();
+        CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<uint32_t>() + p0, ctx->m_b.as<uint32_t>() + p0, ctx->m_c.as<uint32_t>() + p0,
+                                           ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, cellbits + frame_bits, st));
+      } else {
+        k_target_cell_keys<unsigned long long><<<t1 - t0, 256, 0, st>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, f0, ctx->d_wpose.as<WorldPose>(), g, cellbits,
+                                                                        ctx->m_a.as<unsigned long long>(), ctx->m_c.as<uint32_t>(), ctx->d_rmax2.as<uint32_t>());
+        CKL();
+        CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<unsigned long long>() + p0, ctx->m_b.as<unsigned long long>() + p0, ctx->m_c.as<uint32_t>() + p0,
+                                           ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, cellbits + frame_bits, st));
+      }
+      k_gather_f4<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(cs.local.as<F4>(), ctx->m_d.as<uint32_t>() + p0, cnt, ctx->d_q_sorted.as<F4>() + p0);
+      CKL();
+      CK(cudaMemcpyAsync(ctx->d_q_orig.as<uint32_t>() + p0, ctx->m_d.as<uint32_t>() + p0, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (fresh) CK(cudaEventRecord(ctx->chunk_ev[c], st));
+  }
+  CK(cudaMemcpyAsync(ctx->dh_rmax2.p, ctx->d_rmax2.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->rmax_ev, st));
+  ctx->rmax_inflight = true;
+  ctx->d_order_wpose.resize(nf);
+  for (int f = 0; f < nf; ++f) { memcpy(ctx->d_order_wpose[f].R, hw[f].R, 72); memcpy(ctx->d_order_wpose[f].t, hw[f].t, 24); }
+  ctx->d_order_pending = false; ctx->d_order_valid = true; ctx->d_chunks_pending = fresh; ctx->d_reorders++;
+  *did = true;
   return PVB_OK;
 }
 
@@ -1092,6 +1224,8 @@ static int dense_args(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_para
   a.grids = ctx->d_index.grids.as<GridDesc>(); a.cell_start = ctx->d_index.cell_start.as<uint32_t>(); a.sorted = ctx->d_index.sorted.as<F4>();
   a.wpose = ctx->d_wpose.as<WorldPose>(); a.prep = ctx->d_prep.as<PosePrep>();
   a.hint = ctx->d_hint.as<F4>();
+  if (ctx->d_index.has_superrows && ctx->tune_dense_mode == 4 && !ctx->tune_stage) { a.srow = ctx->d_index.srow.as<float4>(); a.sstart = ctx->d_index.sstart.as<uint32_t>(); a.srw = ctx->d_index.srw.as<uint32_t>(); a.srk = ctx->d_index.srk.as<float>(); }
+  a.one = 1.0f;
   a.prm.sq_thr = prm->dist_threshold * prm->dist_threshold; a.prm.rmax = 1; a.prm.plane_tol = prm->plane_tolerance; a.prm.collinear_tol = 3.0;
   a.thr = (double)prm->dist_threshold;
   a.residual_type = prm->residual_type; a.normalize = prm->normalize; a.huber = prm->huber; a.weight = prm->weight;
@@ -1104,6 +1238,7 @@ int pvb_dense_evaluate_device(pvb_ctx* ctx, const double* poses_lw, const pvb_de
   AssocArgs a; int rc = dense_args(ctx, poses_lw, prm, a); if (rc) return rc;
   a.partials = ctx->d_part.as<double>();
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  { bool did = false; rc = dense_order_queries(ctx, &did); if (rc) return rc; }
   if (ctx->d_chunks_pending) {            // fresh upload: consume it chunk by chunk as the copy stream delivers
     const int n_chunks = (int)ctx->d_chunk_frame.size() - 1;
     for (int c = 0; c < n_chunks; ++c) {
@@ -1173,6 +1308,7 @@ int pvb_dense_get_rows(pvb_ctx* ctx, const double* poses_lw, const pvb_dense_par
   CK(cudaMemsetAsync(ctx->d_valid.p, 0, n, ctx->stream)); CK(cudaMemsetAsync(ctx->d_point.p, 0, n * 24, ctx->stream)); CK(cudaMemsetAsync(ctx->d_plane.p, 0, n * 32, ctx->stream));
   a.out_valid = ctx->d_valid.as<unsigned char>(); a.out_point = ctx->d_point.as<double>(); a.out_plane = ctx->d_plane.as<double>();
   a.out_res = ctx->d_res.as<double>(); a.out_jac6 = ctx->d_jac.as<double>();
+  { bool did = false; rc = dense_order_queries(ctx, &did); if (rc) return rc; }
   if (ctx->d_chunks_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); CK(cudaStreamSynchronize(ctx->sort_stream)); ctx->d_chunks_pending = false; }
   rc = launch_associate<false>(ctx, prm->k, ctx->d_ntiles, a, true); if (rc) return rc;
   if (valid) CK(cudaMemcpyAsync(valid, ctx->d_valid.p, n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -11,7 +11,8 @@
 using namespace pvb;
 
 // per-query association on a host-built grid (counting sort), K = 10 or 5
-static int g_prune = 1;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned two-pass walk from a 3x3x3 / 5x5x5 block, 3: buffered single pass (default device path)
+static int g_prune = 1;   // 0: exhaustive block walk (TMA-staged variant), 1 / 2: pruned two-pass walk from a 3x3x3 / 5x5x5 block, 3: buffered single pass (frames mode default), 4: the same over merged super-rows (dense mode default)
+static int g_static = 1;                // mode 4: queries without a usable hint take the static bound of the target
 static int g_flat = 1;                  // mode 3: hinted walk over the flattened row ranges (device default) or the nested per-row loops
 static const float* g_hint = nullptr;   // mode 3: per query {x, y, z, tau} search-radius hints (the device kernel's formula), or null
 static float* g_hint_out = nullptr;     // mode 3: the hints the device kernel would store
@@ -41,6 +42,54 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
   }
   auto cells = [&](long long c) { return (long long)start[c]; };
   auto load = [&](long long i) { return sorted[i]; };
+  // merged super-rows (mode 4), built like k_superrow_counts / k_superrow_fill
+  struct HostSuperRow {
+    std::vector<uint32_t> st, wv; std::vector<float> quads, rkv;
+    float rk(uint32_t r) const { return rkv[r]; }
+    uint32_t w(uint32_t r) const { return wv[r]; }
+    uint32_t start(long long i) const { return st[i]; }
+    struct Quad { float v[12]; };
+    Quad load3(uint32_t G) const { Quad q; memcpy(q.v, quads.data() + (size_t)G * 12, 48); return q; }
+    void sqdist4(const Quad& c, float qx, float qy, float qz, uint32_t (&kb)[4]) const {
+      for (int k = 0; k < 4; ++k) kb[k] = f2u(sqdist_f32(qx, qy, qz, c.v[k], c.v[4 + k], c.v[8 + k]));
+    }
+  } sr;
+  if (g_prune == 4) {
+    const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+    // static bound of every target record like k_target_rk: squared distance to its 10th nearest target point (itself included) within 1.5 cells, else +inf
+    std::vector<float> rk(n);
+    { const float rthr = (float)(1.5 * h); const float rthr2 = rthr * rthr; std::vector<float> dd(n);
+      for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) dd[j] = sqdist_f32(sorted[i].x, sorted[i].y, sorted[i].z, sorted[j].x, sorted[j].y, sorted[j].z);
+        if (n >= 10) { std::nth_element(dd.begin(), dd.begin() + 9, dd.end()); rk[i] = dd[9] <= rthr2 ? dd[9] : INFINITY; } else rk[i] = INFINITY;
+      } }
+    // merged super-rows like k_superrow_counts / k_superrow_fill: segments padded to groups of 4 with points at +infinity
+    sr.st.assign(ncell + 1, 0u);
+    for (int pass = 0; pass < 2; ++pass) {
+      uint32_t run = 0;
+      auto put = [&](uint32_t r, float px, float py, float pz, uint32_t w, float k) {
+        float* q = sr.quads.data() + (size_t)(r >> 2) * 12 + (r & 3u);
+        q[0] = px; q[4] = py; q[8] = pz; sr.wv[r] = w; sr.rkv[r] = k;
+      };
+      for (long long c = 0; c < ncell; ++c) {
+        const int x = (int)(c % nx); const long long row = c / nx; const int y = (int)(row % ny), z = (int)(row / ny);
+        if (pass == 0) sr.st[c] = run;
+        for (int dz = -1; dz <= 1; ++dz) {
+          const int zz = z + dz; if (zz < 0 || zz >= nz) continue;
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy; if (yy < 0 || yy >= ny) continue;
+            const long long cc = ((long long)zz * ny + yy) * nx + x;
+            for (int i = start[cc]; i < start[cc + 1]; ++i) {
+              if (pass == 1) put(run, sorted[i].x, sorted[i].y, sorted[i].z, ((uint32_t)i << 5) | (f2u(sorted[i].w) & 31u), rk[i]);
+              ++run;
+            }
+          }
+        }
+        while (run & 3u) { if (pass == 1) put(run, INFINITY, INFINITY, INFINITY, 0u, INFINITY); ++run; }
+      }
+      if (pass == 0) { sr.st[ncell] = run; sr.quads.assign((size_t)std::max<uint32_t>(run, 4u) * 3, 0.f); sr.wv.assign(run, 0u); sr.rkv.assign(run, 0.f); }
+    }
+  }
   AssocParams prm; prm.sq_thr = thr * thr; prm.rmax = (int)std::ceil((double)thr / h); prm.plane_tol = plane_tol; prm.collinear_tol = 3.0; prm.r0 = g_prune == 2 ? 2 : 1;
   for (int i = 0; i < m; ++i) {
     uint32_t wpos[K];
@@ -58,7 +107,7 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
     auto set_win2 = [&](int j, uint32_t pos) { lst[j].y = pos; };
     const float qx = qry[i * 4], qy = qry[i * 4 + 1], qz = qry[i * 4 + 2];
     uint32_t lim_hint = 0u, tau = 0x7F800000u;
-    if (g_prune == 3 && g_hint) {        // same arithmetic as k_associate (pvb_kernels.cuh)
+    if (g_prune >= 3 && g_hint) {        // same arithmetic as k_associate (pvb_kernels.cuh)
       const float* hq = g_hint + 4 * i;
       if (hq[3] >= 0.f && hq[3] < 3.0e38f) {
         const double dx = (double)qx - (double)hq[0], dy = (double)qy - (double)hq[1], dz = (double)qz - (double)hq[2];
@@ -69,10 +118,14 @@ static void associate_all(const float* tgt, int n, const double* R_ref, const do
     }
 #define PVBH_ASSOC(MODE, W, SW) associate_point2plane<K, false, MODE, LC>(g, cells, load, load, no_map, prm, qx, qy, qz, qcls, R_ref, t_ref, R_nei, t_nei, \
                                                                p_local + 3 * i, plane + 4 * i, W, SW, range_set, range_get, lim_hint, &tau, lst, 1, g_flat != 0)
-    if (g_prune == 3) { for (int j = 0; j < K; ++j) lst[j].y = 0xFFFFFFFFu; }
+    if (g_prune >= 3) { for (int j = 0; j < K; ++j) lst[j].y = 0xFFFFFFFFu; }
+    if (g_prune == 4)
+      valid[i] = associate_point2plane<K, false, 4, LC>(g, cells, load, load, no_map, prm, qx, qy, qz, qcls, R_ref, t_ref, R_nei, t_nei, p_local + 3 * i, plane + 4 * i, win2, set_win2,
+                                                        range_set, range_get, lim_hint, &tau, lst, 1, false, sr, g_static != 0) ? 1 : 0;
+    else
     valid[i] = (g_prune == 0 ? PVBH_ASSOC(0, win, set_win) : (g_prune == 3 ? PVBH_ASSOC(2, win2, set_win2) : PVBH_ASSOC(1, win, set_win))) ? 1 : 0;
 #undef PVBH_ASSOC
-    if (g_prune == 3) {
+    if (g_prune >= 3) {
       for (int j = 0; j < K; ++j) wpos[j] = tau == 0x7F800000u ? 0xFFFFFFFFu : lst[j].y;
       if (g_hint_out) { g_hint_out[4 * i] = qx; g_hint_out[4 * i + 1] = qy; g_hint_out[4 * i + 2] = qz; g_hint_out[4 * i + 3] = u2f(tau); }
     }
@@ -124,6 +177,7 @@ static void associate_lines(const float* tgt, int n, const double* R_ref, const 
 extern "C" {
 void pvbh_set_prune(int on) { g_prune = on; }
 void pvbh_set_flat(int on) { g_flat = on; }
+void pvbh_set_static(int on) { g_static = on; }
 void pvbh_set_hints(const float* hint_in, float* hint_out) { g_hint = hint_in; g_hint_out = hint_out; }
 
 

@@ -45,9 +45,9 @@ def test_zero_rows_and_golden_functors(harness):
         assert (np.abs(J - g["jacobian"]) / np.maximum(1e-9, np.abs(g["jacobian"]).max(1, keepdims=True))).max() < 1e-7
 
 
-@pytest.mark.parametrize("prune", [3, 1, 2, 0])
+@pytest.mark.parametrize("prune", [4, 3, 1, 2, 0])
 def test_grid_knn_and_association_equal_oracle(oracle, harness, prune):
-    """prune = 3: the buffered single-pass search (default device path); 1 / 2: the pruned two-pass walk starting from a 3x3x3 / 5x5x5 block
+    """prune = 4: the buffered single-pass search over merged super-rows (dense mode default); 3: the buffered single-pass search (frames mode default); 1 / 2: the pruned two-pass walk starting from a 3x3x3 / 5x5x5 block
     (rows / cells beyond the running K-th distance are skipped); 0: the exhaustive block walk."""
     harness.pvbh_set_prune(C.c_int(prune))
     harness.pvbh_set_hints(None, None)
@@ -156,8 +156,9 @@ def test_pruned_block_walk_is_exact_on_random_surface_clouds(oracle, harness):
     I, z = np.eye(3), np.zeros(3)
     rng = np.random.default_rng(21)
     harness.pvbh_set_hints(None, None)
-    for trial in range(24):
-        harness.pvbh_set_prune(C.c_int(1 + trial % 3))
+    for trial in range(40):
+        harness.pvbh_set_prune(C.c_int(1 + trial % 4))
+        harness.pvbh_set_static(C.c_int((trial // 4) % 2))                              # mode 4 with / without the static bound of the target
         n = int(rng.integers(400, 3000))
         uv = rng.uniform(-2, 2, (n, 2))
         which = rng.integers(0, 3, n)
@@ -204,8 +205,8 @@ def test_search_radius_hints_never_change_the_result(oracle, harness):
     every case, because a hint only bounds the walk and a search that finds fewer than K below it starts again without it."""
     I, z = np.eye(3), np.zeros(3)
     rng = np.random.default_rng(5)
-    harness.pvbh_set_prune(C.c_int(3))
-    for trial in range(12):
+    for trial in range(16):
+        harness.pvbh_set_prune(C.c_int(3 + (trial // 2) % 2))                              # per-row walk / merged super-rows
         harness.pvbh_set_flat(C.c_int(trial % 2))                                    # flattened / nested hinted walk
         n = int(rng.integers(1500, 6000))
         pts = _fuzz_cloud(rng, n)
