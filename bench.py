@@ -233,8 +233,10 @@ def config_dict(args, world=1):
             "cell_m": args.cell, "n_target": args.n_target, "frames_total": args.frames * (world if weak else 1), "frames_per_gpu": per, "pts_per_frame": args.pts_per_frame,
             "k": args.k, "radius_m": args.radius,
             "l2": "inputs (160 MB target records + 160 MB queries + cell table) exceed the 126 MB L2; no explicit flush",
-            "search": "exact 10-NN, buffered single pass; per-point search radius bounded by the previous step's 10th distance + displacement (exact: a stale bound "
-                      "restarts the search), warm-up steps provide the bounds of the first timed step; extra.cold_search_kernel_ms = the same launch without them",
+            "search": "exact 10-NN, one buffered pass over the merged super-rows of the static target (queries ordered by target cell, re-ordered after large pose updates: "
+                      "the re-ordering is inside kernel_ms of the steps that need it); per-point search radius bounded by the previous step's 10th distance + displacement, "
+                      "else by the target's own 10-NN radius at the nearest target point (static bound), else by list compaction - every bound is exact; warm-up steps "
+                      "provide the bounds of the first timed step; roofline.cold_search_kernel_ms = the same launch without them",
             "parallelism": f"frames sharded across GPUs ({args.scaling}), target replicated, one NCCL allreduce of the packed 6x6/6x1 blocks of all frames per step"}
 
 
@@ -350,6 +352,17 @@ def main():
     e2e = None
     if not args.no_e2e:
         poses_e = d["poses_lw_init"].copy()
+        # the copy rate of this box's pinned host memory -> HBM path (the e2e step moves nq * 16 bytes over it)
+        h2d_gbs = None
+        try:
+            dst = torch.empty(src_pinned.numel(), dtype=src_pinned.dtype, device="cuda").view(src_pinned.shape)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dst.copy_(src_pinned, non_blocking=True); torch.cuda.synchronize()
+            g0.record(); dst.copy_(src_pinned, non_blocking=True); g1.record(); torch.cuda.synchronize()
+            h2d_gbs = src_pinned.numel() * 4 / (g0.elapsed_time(g1) * 1e-3) / 1e9
+            del dst
+        except Exception:
+            pass
 
         def e2e_step(p):
             ctx.dense_set_sources_ptr(src_pinned.data_ptr(), d["src_off"])       # H2D of this step's source clouds + re-ordering
@@ -370,7 +383,9 @@ def main():
         e2e = {"value": nq_total * args.steps / (float(te.item()) * 1e-3), "unit": "evals/s",
                "h2d_bytes_per_step": int(nq * 16 + nf * (21 + 12) * 8 * 1 + (nf + 1) * 4), "d2h_bytes_per_step": int(frames_total * 29 * 8),
                "ms_per_step": float(te.item()) / args.steps,
-               "note": "per rank and step: its source clouds (pinned host) -> device + Morton re-order, poses H2D, fused kernel, allreduce, reduced systems of all frames D2H; target map resident"}
+               "h2d_gbs_measured": h2d_gbs, "h2d_floor_ms_per_step": (nq * 16 / (h2d_gbs * 1e9) * 1e3) if h2d_gbs else None,
+               "note": "per rank and step: its source clouds (pinned host) -> device + ordering by target cell (chunked, overlapped with the copies), poses H2D, fused kernel per chunk, "
+                       "allreduce, reduced systems of all frames D2H; target map resident.  h2d_floor_ms_per_step = this step's input bytes / the pinned-memory copy rate measured in this run"}
 
     # ---- the same launch without search-radius bounds (cold search), for transparency
     ctx.dense_reset_hints()
@@ -410,7 +425,7 @@ def main():
     issue = None
     if wi:
         issue = {"warp_instructions": wi, "achieved_ginst_s": wi / (k_ms * 1e-3) / 1e9, "peak_ginst_s": 4 * 148 * 1.965, "frac": wi / (k_ms * 1e-3) / 1e9 / (4 * 148 * 1.965)}
-    roofline = {"bound": "hbm", "kernel": "k_associate<10,true,...,MODE 2>", "issue": issue, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_associate<10,true,...,MODE 4> (merged super-rows, warp-synchronous single pass)", "issue": issue, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": k_ms, "kernel_ms_per_step": [round(x, 4) for x in kernel_ms], "cold_search_kernel_ms": cold_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_share_of_step": k_ms * args.steps / ms}
 

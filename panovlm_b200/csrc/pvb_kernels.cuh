@@ -287,7 +287,7 @@ constexpr int kStageCap = 768;     // staged records per tile (12 KB of shared m
 
 constexpr int kListCap = 24;       // per-query candidate list of the buffered single-pass search (8 B per entry)
 #ifndef PVB_LC4
-#define PVB_LC4 32
+#define PVB_LC4 24
 #endif
 constexpr int kListCap4 = PVB_LC4;      // the same for MODE 4 (room for the ~1.7 K survivors of the static bound before a compaction)
 
@@ -945,19 +945,37 @@ __global__ void __launch_bounds__(kTile, PVB_K3_MINB) k_eval_blocks(const EvalAr
     if (a.raw_rows) cost = huber_correct(a.huber[row], r, J, 12);
   }
   if (a.partials) {
+    // every warp sums its own 32 rows (3 of the 92 entries per lane: three independent accumulation chains of 32 instead of one of 128 per thread, and
+    // no idle warp), then 92 threads add the four warp sums in warp order: the order of every sum is fixed => run-to-run identical results
+    __shared__ double sW[kTile / 32][92];
 #pragma unroll
     for (int k = 0; k < 12; ++k) sJ[i][k] = J[k];
     sJ[i][12] = r; sJ[i][13] = cost;
-    __syncthreads();
-    if (i < 92) {
-      int ia = 0, ib = 0; double acc = 0.0;
-      if (i < 78) { int o = i; while (o >= 12 - ia) { o -= 12 - ia; ++ia; } ib = ia + o; }
-      else if (i < 90) { ia = i - 78; ib = 12; }
-      if (i < 90) { for (int row = 0; row < kTile; ++row) acc += sJ[row][ia] * sJ[row][ib]; }
-      else if (i == 90) { for (int row = 0; row < kTile; ++row) acc += sJ[row][13]; }
-      else acc = (double)t.count;
-      a.partials[(size_t)blockIdx.x * 92 + i] = acc;
+    __syncwarp();
+    const int w = i >> 5, lane = i & 31;
+    const double (*rows)[14] = &sJ[w * 32];
+    int ia[3], ib[3];
+#pragma unroll
+    for (int e3 = 0; e3 < 3; ++e3) {
+      const int e = lane + 32 * e3;
+      ia[e3] = 13; ib[e3] = 13;                                  // e >= 90: the cost column (entry 90; entries 91.. are not stored)
+      if (e < 78) { int o = e, a0 = 0; while (o >= 12 - a0) { o -= 12 - a0; ++a0; } ia[e3] = a0; ib[e3] = a0 + o; }
+      else if (e < 90) { ia[e3] = e - 78; ib[e3] = 12; }
     }
+    double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll 4
+    for (int row = 0; row < 32; ++row) {
+#pragma unroll
+      for (int e3 = 0; e3 < 3; ++e3) {
+        const double va = rows[row][ia[e3]], vb = lane + 32 * e3 < 90 ? rows[row][ib[e3]] : 1.0;
+        acc[e3] += va * vb;
+      }
+    }
+#pragma unroll
+    for (int e3 = 0; e3 < 3; ++e3) if (lane + 32 * e3 < 91) sW[w][lane + 32 * e3] = acc[e3];
+    __syncthreads();
+    if (i < 91) a.partials[(size_t)blockIdx.x * 92 + i] = ((sW[0][i] + sW[1][i]) + sW[2][i]) + sW[3][i];
+    else if (i == 91) a.partials[(size_t)blockIdx.x * 92 + 91] = (double)t.count;
   }
 }
 

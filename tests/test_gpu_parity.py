@@ -363,6 +363,38 @@ def test_dense_search_radius_hints_do_not_change_any_system(gpu_ctx, oracle, den
     assert np.array_equal(s_cpu[:, 28], s_back[:, 28]) and np.abs(s_cpu - s_back).max() < 1e-8 * np.abs(s_cpu).max()
 
 
+def test_dense_exact_distance_ties_at_the_kth_neighbour(gpu_ctx, oracle):
+    """Exact float32 ties at the K-th distance: a third of the target points are exact duplicates of other target points, so for
+    many queries the 10th and 11th neighbour are equally far.  FLANN's choice among them is implementation-defined, the oracle takes the smaller index, the
+    kernels take their visiting order - but tied duplicates carry the same coordinates, so the accepted set, the fitted planes and the reduced systems must
+    still agree (1e-9), in every search mode of the dense path (cold search, bounds from the previous evaluation, static bounds only)."""
+    from panovlm_b200 import synth
+    d = synth.make_dense_sweep(n_target=120_000, n_frames=3, pts_per_frame=4000, seed=23)
+    tgt = d["target"].copy()
+    rng = np.random.default_rng(7)
+    dup = rng.choice(len(tgt), len(tgt) // 3, replace=False)
+    src_of = rng.choice(np.setdiff1d(np.arange(len(tgt)), dup), len(dup))
+    tgt[dup] = tgt[src_of]                                                             # exact duplicates (same class too)
+    gpu_ctx.dense_set_target(tgt)
+    gpu_ctx.dense_set_sources(d["src_local"], d["src_off"])
+    prm = gpu_ctx.dense_params(0.05, 1.0, 10, 0, 1, 0.2, 1.0)
+    idx, d2 = oracle.knn(tgt, oracle.transform_cloud(*_world_pose(oracle, d["poses_lw_init"][0]), d["src_local"][: d["src_off"][1]]), 11, False)
+    assert (d2[:, 9] == d2[:, 10]).mean() > 0.05                                       # the case is really exercised
+    s_cpu, _, n = oracle.dense_icp_eval(tgt, d["src_local"], d["src_off"], d["poses_lw_init"], 0.05, 1.0, 10, 0.2, 1.0, 1)
+    for hints in (True, False):
+        gpu_ctx.dense_reset_hints(); gpu_ctx.dense_set_hints(hints)
+        for rep in range(2):                                                           # second evaluation: bounds from the first one
+            s_gpu = gpu_ctx.dense_evaluate(d["poses_lw_init"], prm)
+            assert np.array_equal(s_cpu[:, 28], s_gpu[:, 28]) and n == s_gpu[:, 28].sum()
+            assert np.abs(s_cpu - s_gpu).max() < 1e-9 * np.abs(s_cpu).max()
+    gpu_ctx.dense_set_hints(True)
+
+
+def _world_pose(oracle, pose_lw):
+    R_wl = oracle.aa_to_R(pose_lw[:3]).T
+    return R_wl, -R_wl @ pose_lw[3:]
+
+
 def test_dense_full_size_properties(gpu_ctx):
     """Size-independent properties at a large size the CPU oracle cannot sweep in seconds: every source point is an
     exact copy of a target point moved by a known rigid transform => at the true pose the point-to-plane residual of
