@@ -35,6 +35,14 @@ __device__ __forceinline__ F4 ldg_f4(const F4* p) {
   F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
 }
 
+// two small host-mapped arrays -> device (pose staging, see upload_poses)
+__global__ void __launch_bounds__(256) k_copy_words(const unsigned long long* __restrict__ a, long long na, unsigned long long* __restrict__ da,
+                                                    const unsigned long long* __restrict__ b, long long nb, unsigned long long* __restrict__ db) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < na) da[i] = a[i];
+  else if (i < na + nb) db[i - na] = b[i - na];
+}
+
 // ---- T1: local -> world (float32) for every point of every cloud; w = (index in cloud << 5) | class ----------
 __global__ void __launch_bounds__(256) k_transform_world(const F4* __restrict__ local, const CloudTile* __restrict__ tiles,
                                                          const int* __restrict__ cloud_block, const WorldPose* __restrict__ wpose,
