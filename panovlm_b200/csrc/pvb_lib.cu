@@ -825,7 +825,6 @@ int pvb_frames_point2plane_blocks(pvb_ctx* ctx, const double* poses, int n_edges
   if (!ctx || !poses || n_edges < 0 || (n_edges > 0 && (!ref || !nei)) || n_extra < 0 || (n_extra > 0 && (!x_type || !x_ref || !x_nei || !x_normalize || !x_huber || !x_consts)))
     return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_frames_point2plane_blocks: bad arguments") : PVB_ERR_ARG;
   if (block_offset < 0 || n_pose_blocks < block_offset + ctx->n_frames) return ctx->fail(PVB_ERR_ARG, "pvb_frames_point2plane_blocks: %d pose blocks do not hold %d frames at offset %d", n_pose_blocks, ctx->n_frames, block_offset);
-  if (!ctx->g_edge_ref.empty()) return ctx->fail(PVB_ERR_STATE, "pvb_frames_point2plane_blocks: not available with a global edge list (sharded pose graph)");
   const int nb = n_pose_blocks;
   for (long i = 0; i < n_extra; ++i) {
     if (x_ref[i] < 0 || x_ref[i] >= nb || x_nei[i] < 0 || x_nei[i] >= nb) return ctx->fail(PVB_ERR_ARG, "extra block %ld: pose index out of range", i);
@@ -856,21 +855,53 @@ int pvb_frames_point2plane_blocks(pvb_ctx* ctx, const double* poses, int n_edges
   ctx->bn = n; ctx->nb = nb; ctx->b_has_rows = ctx->b_has_sys = false;
   ctx->edge_ref.clear(); ctx->edge_nei.clear(); ctx->edge_tile_begin.clear();
   std::vector<BlockTile> tiles;
-  for (int e = 0; e < n_edges; ++e) {
-    ctx->edge_ref.push_back(block_offset + ref[e]); ctx->edge_nei.push_back(block_offset + nei[e]); ctx->edge_tile_begin.push_back((int)tiles.size());
-    for (long long s0 = row_begin[e]; s0 < row_begin[e + 1]; s0 += kTile) tiles.push_back(BlockTile{e, (int)s0, (int)std::min<long long>(kTile, row_begin[e + 1] - s0), 0});
-  }
   std::vector<uint32_t> order(n_extra);
   for (long i = 0; i < n_extra; ++i) order[i] = (uint32_t)i;
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (long long)x_ref[a] * nb + x_nei[a] < (long long)x_ref[b] * nb + x_nei[b]; });
-  for (long i = 0; i < n_extra;) {
-    long j = i;
-    const int er = x_ref[order[i]], en = x_nei[order[i]];
-    while (j < n_extra && x_ref[order[j]] == er && x_nei[order[j]] == en) ++j;
-    const int e = (int)ctx->edge_ref.size();
-    ctx->edge_ref.push_back(er); ctx->edge_nei.push_back(en); ctx->edge_tile_begin.push_back((int)tiles.size());
-    for (long s0 = i; s0 < j; s0 += kTile) tiles.push_back(BlockTile{e, (int)(n_dev + s0), (int)std::min<long>(kTile, j - s0), 0});
-    i = j;
+  if (ctx->g_edge_ref.empty()) {
+    for (int e = 0; e < n_edges; ++e) {
+      ctx->edge_ref.push_back(block_offset + ref[e]); ctx->edge_nei.push_back(block_offset + nei[e]); ctx->edge_tile_begin.push_back((int)tiles.size());
+      for (long long s0 = row_begin[e]; s0 < row_begin[e + 1]; s0 += kTile) tiles.push_back(BlockTile{e, (int)s0, (int)std::min<long long>(kTile, row_begin[e + 1] - s0), 0});
+    }
+    for (long i = 0; i < n_extra;) {
+      long j = i;
+      const int er = x_ref[order[i]], en = x_nei[order[i]];
+      while (j < n_extra && x_ref[order[j]] == er && x_nei[order[j]] == en) ++j;
+      const int e = (int)ctx->edge_ref.size();
+      ctx->edge_ref.push_back(er); ctx->edge_nei.push_back(en); ctx->edge_tile_begin.push_back((int)tiles.size());
+      for (long s0 = i; s0 < j; s0 += kTile) tiles.push_back(BlockTile{e, (int)(n_dev + s0), (int)std::min<long>(kTile, j - s0), 0});
+      i = j;
+    }
+  } else {
+    // sharded pose graph: the GLOBAL edge list is the reduction layout (every rank sums into the same n_edges x 92 buffer); this rank's association
+    // edges and extra blocks are filed under their global edge, edges of other ranks keep an empty tile range
+    const size_t ng = ctx->g_edge_ref.size();
+    auto find_edge = [&](int er, int en) -> long {
+      size_t lo = 0, hi = ng;                                     // the list is sorted by (ref, nei) (pvb_blocks_set_edge_list)
+      while (lo < hi) { const size_t mid = (lo + hi) / 2; if (ctx->g_edge_ref[mid] < er || (ctx->g_edge_ref[mid] == er && ctx->g_edge_nei[mid] < en)) lo = mid + 1; else hi = mid; }
+      return (lo < ng && ctx->g_edge_ref[lo] == er && ctx->g_edge_nei[lo] == en) ? (long)lo : -1;
+    };
+    std::vector<std::pair<long, BlockTile>> filed;
+    for (int e = 0; e < n_edges; ++e) {
+      const long ge = find_edge(block_offset + ref[e], block_offset + nei[e]);
+      if (ge < 0) return ctx->fail(PVB_ERR_ARG, "association edge %d -> %d is not in the edge list set by pvb_blocks_set_edge_list", ref[e], nei[e]);
+      for (long long s0 = row_begin[e]; s0 < row_begin[e + 1]; s0 += kTile) filed.push_back({ge, BlockTile{(int)ge, (int)s0, (int)std::min<long long>(kTile, row_begin[e + 1] - s0), 0}});
+    }
+    for (long i = 0; i < n_extra;) {
+      long j = i;
+      const int er = x_ref[order[i]], en = x_nei[order[i]];
+      while (j < n_extra && x_ref[order[j]] == er && x_nei[order[j]] == en) ++j;
+      const long ge = find_edge(er, en);
+      if (ge < 0) return ctx->fail(PVB_ERR_ARG, "extra block edge %d -> %d is not in the edge list set by pvb_blocks_set_edge_list", er, en);
+      for (long s0 = i; s0 < j; s0 += kTile) filed.push_back({ge, BlockTile{(int)ge, (int)(n_dev + s0), (int)std::min<long>(kTile, j - s0), 0}});
+      i = j;
+    }
+    std::stable_sort(filed.begin(), filed.end(), [](const std::pair<long, BlockTile>& a, const std::pair<long, BlockTile>& b) { return a.first < b.first; });
+    size_t f = 0;
+    for (size_t ge = 0; ge < ng; ++ge) {
+      ctx->edge_ref.push_back(ctx->g_edge_ref[ge]); ctx->edge_nei.push_back(ctx->g_edge_nei[ge]); ctx->edge_tile_begin.push_back((int)tiles.size());
+      while (f < filed.size() && filed[f].first == (long)ge) tiles.push_back(filed[f++].second);
+    }
   }
   ctx->edge_tile_begin.push_back((int)tiles.size());
   ctx->b_tiles = (int)tiles.size();

@@ -126,7 +126,7 @@ def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, devic
     return new_poses, summary
 
 
-def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, world, rank, group=None):
+def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, world, rank, group=None, device_blocks=True):
     """RefinePose on one rank of a pose graph sharded across GPUs (BASELINE.json configs[3]): contiguous ranges of reference frames
     balanced by the query count of their edges, association + residual blocks of the rank's own edges only, the GLOBAL edge list as reduction layout
     and ONE allreduce of the edge systems per evaluation (panovlm_b200.dist.install_allreduce_hook).  Every rank returns the same poses."""
@@ -136,13 +136,21 @@ def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_
     for (i, j) in all_edges:
         weights[i] += len(frames[j]["surfFlat"]) + 4 * len(frames[j]["cornerLessSharp"])
     bounds = pd.shard_frames_by_weight(weights, world)
-    bl, _ = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=(int(bounds[rank]), int(bounds[rank + 1])))
+    fr = (int(bounds[rank]), int(bounds[rank + 1]))
     er, en = pd.global_edge_list([e[0] for e in all_edges], [e[1] for e in all_edges])
-    v = bl.view()
     ctx.blocks_set_edge_list(er, en)
     hook = pd.install_allreduce_hook(ctx, group)
     try:
-        ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
+        if device_blocks and cfg.point_to_plane:
+            # the rank's own point-to-plane correspondences become residual blocks on the device, filed under the GLOBAL edge list (no download / rebuild / upload)
+            bl, _, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=fr, host_point2plane=False)
+            ref, nei = np.array([e[0] for e in mine], np.int32), np.array([e[1] for e in mine], np.int32)
+            bl.n = ctx.frames_point2plane_blocks(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, cfg.angle_residual, cfg.normalize_distance, cfg.plane_weight,
+                                                 len(frames), extra=bl.view())
+        else:
+            bl, _ = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=fr)
+            v = bl.view()
+            ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
         mask = np.zeros(len(frames), np.uint8); mask[0] = 1
         new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
     finally:

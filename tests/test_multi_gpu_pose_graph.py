@@ -163,3 +163,56 @@ def test_sharded_pose_graph_lm_equals_single_process(gpu_ctx):
     # with one empty rank the sum has a single non-zero term: bit-identical to the single process
     for kind in (api.SOLVER_HOST, api.SOLVER_DEVICE):
         assert np.array_equal(out[0][("one_rank_empty", kind)][0], single[kind][0])
+
+
+def _seq_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import panovlm_b200
+    from panovlm_b200 import odometry, synth
+    from oracle import pvo
+    torch.cuda.set_device(0)
+    ctx = panovlm_b200.Context(0)
+    frames, poses0, cfg = _sequence()
+    res = {}
+    for dev in (True, False):
+        res[dev] = odometry.refine_pose_sharded(ctx, frames, poses0, cfg, pvo.aa_to_R, world, rank, device_blocks=dev)
+    out[rank] = res
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def _sequence():
+    from panovlm_b200 import odometry, synth
+    from oracle import pvo
+    from scipy.spatial.transform import Rotation
+    frames = synth.make_sequence(10, n_az=360, tilt=0.3)
+    rng = np.random.default_rng(3)
+    R0 = [f["R_wl"] @ Rotation.from_rotvec(rng.normal(0, 0.005, 3) * (i > 0)).as_matrix() for i, f in enumerate(frames)]
+    t0 = [f["t_wl"] + rng.normal(0, 0.02, 3) * (i > 0) for i, f in enumerate(frames)]
+    return frames, odometry.pose_blocks_from_world(R0, t0, pvo.R_to_aa), odometry.OdometryConfig(line_to_line=True)
+
+
+@pytest.mark.gpu
+def test_sharded_refine_pose_with_device_built_blocks(gpu_ctx, oracle):
+    """RefinePose sharded over 2 ranks (reference frames split by weight): the point-to-plane correspondences of a rank's own edges become residual blocks on the
+    device and are filed under the GLOBAL edge list (pvb_frames_point2plane_blocks with pvb_blocks_set_edge_list), the line blocks built on the host are appended.
+    Both ranks end at bit-identical poses; they equal the host-built sharded run and the single-process RefinePose to rounding (same rows, different tile splits)."""
+    from panovlm_b200 import odometry
+    frames, poses0, cfg = _sequence()
+    ps, ss = odometry.refine_pose(gpu_ctx, frames, poses0, cfg, oracle.aa_to_R)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_seq_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for dev in (True, False):
+        (p0, s0), (p1, s1) = out[0][dev], out[1][dev]
+        assert np.array_equal(p0, p1) and s0["allreduces"] == s1["allreduces"] > 0
+        assert s0["n_blocks_local"] + s1["n_blocks_local"] == ss["n_blocks"]
+        for k in ("iterations", "successful", "unsuccessful", "termination"):
+            assert s0[k] == ss[k]
+        assert abs(s0["final_cost"] - ss["final_cost"]) < 1e-9 * ss["final_cost"]
+        assert np.abs(p0 - ps).max() < 1e-8 * max(1e-12, np.abs(ps - poses0).max())
+    # device-built and host-built shards hold the same rows in a different tile split: equal to rounding
+    assert np.abs(out[0][True][0] - out[0][False][0]).max() < 1e-8 * np.abs(ps - poses0).max()
