@@ -229,10 +229,19 @@ __global__ void __launch_bounds__(256) k_target_cell_keys(const F4* __restrict__
     vals[t.start + i] = (uint32_t)(t.start + i);
     r2 = p.x * p.x + p.y * p.y + p.z * p.z;
   }
-  uint32_t m = __float_as_uint(r2);
+  if (rmax2) {                                                   // only after an upload (the cloud does not change with the poses); one atomic per block:
+    __shared__ uint32_t s_m[8];                                  // same-address atomics of every warp made this kernel 4x slower than its memory traffic
+    uint32_t m = __float_as_uint(r2);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(rmax2 + t.cloud, m);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 1; w < 8; ++w) m = max(m, s_m[w]);
+      if (m) atomicMax(rmax2 + t.cloud, m);
+    }
+  }
 }
 
 // ---- K2p: fused associate (+ residual + reduce) --------------------------------------------------------------------
@@ -262,6 +271,7 @@ struct AssocArgs {
   F4* hint;
   int use_hint;                                                      // 0: ignore the stored hints (they are still rewritten)
   int flat_walk;                                                     // 1: the hinted walk runs over the flattened row ranges (walk_block_collect_flat)
+  double tight_frac;                                                 // MODE 4: a bound counts as tight when the predicted survivors stay below this share of the list
   int use_static;                                                    // MODE 4: 1 = queries without a usable hint take the static bound of the target (srk)
   // MODE 4: merged super-rows of a static target (knn_select_superrow): records with w = (position in `sorted` << 5) | class, and the start of
   // every (row, x cell) segment, indexed like cell_start (GridDesc::cell_base applies)
@@ -460,7 +470,7 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
         // the bound is "tight" when the list can be expected to hold what lies below it (points on a surface: count ~ K * lim2 / tau_old); after a large
         // pose change it is loose: MODE 2 then takes the two-pass search, MODE 4 also looks for the static bound of the target and keeps the smaller one
         if (lim2 < (double)prm.sq_thr) {
-          dyn_tight = lim2 * (double)K < (double)hq.w * (0.8 * LC);
+          dyn_tight = lim2 * (double)K < (double)hq.w * ((MODE == 4 ? a.tight_frac : 0.8) * LC);      // MODE 4: a looser bound is still used, together with the static one
           if (dyn_tight || MODE == 4) lim_hint = f2u((float)lim2) + 2u;      // +1 ulp for the float rounding, +1 to make the bound exclusive
         }
       }

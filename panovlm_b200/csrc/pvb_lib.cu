@@ -186,7 +186,7 @@ int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_ide
   if (k != 5 && k != 10) return ctx->fail(PVB_ERR_ARG, "k must be 5 or 10 (got %d)", k);
   a.stats = nullptr;
   a.prm.r0 = ctx->tune_r0;
-  a.use_hint = ctx->tune_hints; a.flat_walk = ctx->tune_flat; a.use_static = ctx->tune_static;
+  a.use_hint = ctx->tune_hints; a.flat_walk = ctx->tune_flat; a.use_static = ctx->tune_static; a.tight_frac = ctx->tune_tight;
   if (mode == 0 && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
   if (mode == 3) {                    // warp-cooperative search (groups of 8 queries share staged candidates)
     constexpr size_t smem = sizeof(CoopWarp) * (kTile / 32);
@@ -243,6 +243,7 @@ int pvb_create(int device, pvb_ctx** out) {
   if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
   if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = ctx->tune_dense_hscale = std::max(0.1, atof(e));
+  if (const char* e = getenv("PVB_TIGHT")) ctx->tune_tight = atof(e);
   if (const char* e = getenv("PVB_STATIC")) ctx->tune_static = atoi(e) != 0;
   if (const char* e = getenv("PVB_REORDER")) ctx->tune_reorder = std::max(0.0, atof(e));      // re-order the dense queries when a pose update may move a point by more than this many cells
   if (const char* e = getenv("PVB_DENSE_HSCALE")) ctx->tune_dense_hscale = std::max(0.1, atof(e));
@@ -1209,7 +1210,8 @@ static int dense_order_queries(pvb_ctx* ctx, bool* did) {
     CK(cudaEventRecord(ctx->pose_ev, ctx->stream));                // the poses of this evaluate
     CK(cudaStreamWaitEvent(st, ctx->pose_ev, 0));
   }
-  CK(cudaMemsetAsync(ctx->d_rmax2.p, 0, (size_t)nf * 4, st));
+  if (fresh) CK(cudaMemsetAsync(ctx->d_rmax2.p, 0, (size_t)nf * 4, st));
+  uint32_t* const rmax_dst = fresh ? ctx->d_rmax2.as<uint32_t>() : nullptr;
   long long ncells = (long long)g.dims[0] * g.dims[1] * g.dims[2];
   int cellbits = 1; while ((1ll << cellbits) < ncells) ++cellbits;
   const int n_chunks = fresh ? (int)ctx->d_chunk_frame.size() - 1 : 1;
@@ -1223,13 +1225,13 @@ static int dense_order_queries(pvb_ctx* ctx, bool* did) {
       size_t tb = ctx->m_e.cap;
       if (cellbits + frame_bits <= 32) {
         k_target_cell_keys<uint32_t><<<t1 - t0, 256, 0, st>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, f0, ctx->d_wpose.as<WorldPose>(), g, cellbits,
-                                                              ctx->m_a.as<uint32_t>(), ctx->m_c.as<uint32_t>(), ctx->d_rmax2.as<uint32_t>());
+                                                              ctx->m_a.as<uint32_t>(), ctx->m_c.as<uint32_t>(), rmax_dst);
         CKL();
         CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<uint32_t>() + p0, ctx->m_b.as<uint32_t>() + p0, ctx->m_c.as<uint32_t>() + p0,
                                            ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, cellbits + frame_bits, st));
       } else {
         k_target_cell_keys<unsigned long long><<<t1 - t0, 256, 0, st>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, f0, ctx->d_wpose.as<WorldPose>(), g, cellbits,
-                                                                        ctx->m_a.as<unsigned long long>(), ctx->m_c.as<uint32_t>(), ctx->d_rmax2.as<uint32_t>());
+                                                                        ctx->m_a.as<unsigned long long>(), ctx->m_c.as<uint32_t>(), rmax_dst);
         CKL();
         CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<unsigned long long>() + p0, ctx->m_b.as<unsigned long long>() + p0, ctx->m_c.as<uint32_t>() + p0,
                                            ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, cellbits + frame_bits, st));
@@ -1240,9 +1242,11 @@ static int dense_order_queries(pvb_ctx* ctx, bool* did) {
     }
     if (fresh) CK(cudaEventRecord(ctx->chunk_ev[c], st));
   }
-  CK(cudaMemcpyAsync(ctx->dh_rmax2.p, ctx->d_rmax2.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(ctx->rmax_ev, st));
-  ctx->rmax_inflight = true;
+  if (fresh) {
+    CK(cudaMemcpyAsync(ctx->dh_rmax2.p, ctx->d_rmax2.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->rmax_ev, st));
+    ctx->rmax_inflight = true;
+  }
   ctx->d_order_wpose.resize(nf);
   for (int f = 0; f < nf; ++f) { memcpy(ctx->d_order_wpose[f].R, hw[f].R, 72); memcpy(ctx->d_order_wpose[f].t, hw[f].t, 24); }
   ctx->d_order_pending = false; ctx->d_order_valid = true; ctx->d_chunks_pending = fresh; ctx->d_reorders++;
