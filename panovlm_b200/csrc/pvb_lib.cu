@@ -611,6 +611,7 @@ static int solve_lm_device(pvb_ctx* ctx, double* poses, const unsigned char* is_
   };
   double cost = 0;
   rc = evaluate(poses, &cost); if (rc) return rc;
+  bool stale = false;
   S = LMSummary(); S.initial_cost = cost;
   if (n == 0) { S.final_cost = cost; S.termination = 2; return PVB_OK; }
   double* hv = ctx->sh_vec.as<double>();
@@ -650,6 +651,7 @@ static int solve_lm_device(pvb_ctx* ctx, double* poses, const unsigned char* is_
     sn = std::sqrt(sn); xn = std::sqrt(xn);
     double new_cost = 0;
     rc = evaluate(cand.data(), &new_cost); if (rc) return rc;
+    stale = true;                                               // the device now holds the CANDIDATE's edge systems
     if (sn <= opt.parameter_tolerance * (xn + opt.parameter_tolerance)) { S.termination = 3; break; }
     const double change = cost - new_cost;
     if (std::fabs(change) <= opt.function_tolerance * cost) { S.termination = 1; break; }
@@ -658,6 +660,7 @@ static int solve_lm_device(pvb_ctx* ctx, double* poses, const unsigned char* is_
       std::copy(cand.begin(), cand.end(), poses);
       cost = new_cost;
       rc = solver_assemble(ctx, gs); if (rc) return rc;        // edge systems of the accepted point are already on the device
+      stale = false;
       S.successful++;
       radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
       decrease = 2.0;
@@ -668,6 +671,9 @@ static int solve_lm_device(pvb_ctx* ctx, double* poses, const unsigned char* is_
     }
   }
   S.final_cost = cost;
+  // a loop that ends on a rejected / terminating candidate leaves that candidate's systems behind: they do not describe the returned poses, so
+  // pvb_blocks_cost / pvb_blocks_edge_systems / pvb_blocks_dense_system report "no evaluation" until the caller evaluates again
+  if (stale) ctx->b_has_sys = ctx->b_has_rows = false;
   return PVB_OK;
 }
 

@@ -10,7 +10,7 @@ from .api import BlockList, Context, LineFrame
 
 class JointConfig:
     def __init__(self, camera_weight=1.0, camera_lidar_weight=1.0, lidar=None, refine_camera_rotation=True, refine_camera_trans=True, refine_lidar_rotation=True,
-                 refine_lidar_trans=True, refine_structure=True, max_lm_iterations=20):
+                 refine_lidar_trans=True, refine_structure=True, max_lm_iterations=50):      # SetOptionsSfM leaves Ceres' default max_num_iterations = 50 (util/Optimization.cpp:611-636)
         self.camera_weight, self.camera_lidar_weight = camera_weight, camera_lidar_weight        # config/Room.txt:81-83
         self.lidar = lidar or odometry.OdometryConfig(line_to_line=False)
         self.refine_camera_rotation, self.refine_camera_trans = refine_camera_rotation, refine_camera_trans
@@ -126,7 +126,12 @@ def optimize(ctx: Context, data, cams, lidars, points, cfg: JointConfig, aa_to_R
     const[n:, 3:] = 0 if cfg.refine_lidar_trans else 1
     const[0] = 1                                                                         # :490-491 camera 0 constant
     pt_const = None if cfg.refine_structure else np.ones(len(points), np.uint8)          # :462-465
-    new_poses, new_points, summary = ctx.joint_solve_lm(poses, points, const, pt_const, cfg.max_lm_iterations)
+    if const.all() and pt_const is None:
+        # Optimize(refine_* = false, refine_structure = true) is a structure-only bundle adjustment in the reference: every pose block constant, the points free
+        _, new_points, summary = ctx.reproj_solve_lm(cams, points, np.ones((n, 6), np.uint8), None, cfg.max_lm_iterations)
+        new_poses = poses.copy()
+    else:
+        new_poses, new_points, summary = ctx.joint_solve_lm(poses, points, const, pt_const, cfg.max_lm_iterations)
     summary.update(n_camera_lidar_blocks=counts[0], n_lidar_blocks=counts[1], n_reproj=len(data["cam"]), n_line_pairs=sum(len(p[0]) for p in pairs.values()))
     return new_poses[:n], new_poses[n:], new_points, summary, (v, const, pt_const)
 
