@@ -86,9 +86,13 @@ int pvb_blocks_solve_lm(pvb_ctx* ctx, double* poses, const unsigned char* is_con
 /* where the linear algebra of the LM step runs — the analogue of SetOptionsLidar's linear_solver_type choice
  * (util/Optimization.cpp:647-662): HOST = dense Cholesky on the host cores; DEVICE = the edge systems stay in HBM, dense assembly,
  * Jacobi scaling, damping, blocked FP64 Cholesky and the triangular solves are kernels (pvb_solver.cuh), only 6N-vectors cross PCIe;
- * AUTO (default) = DEVICE from 256 free unknowns.                                                                                   */
-enum { PVB_SOLVER_AUTO = 0, PVB_SOLVER_HOST = 1, PVB_SOLVER_DEVICE = 2 };
+ * PCG = the same matrix as 6x6 blocks (no dense matrix, no factorisation) + block-Jacobi preconditioned conjugate gradients on the
+ * device, converged to rounding (relative residual 1e-12) - the counterpart of the reference's sparse / iterative solvers for large pose
+ * graphs; AUTO (default) = DEVICE from 256 free unknowns, PCG above 500 pose blocks (SetOptionsLidar: sparse from 50, iterative from 2000).  */
+enum { PVB_SOLVER_AUTO = 0, PVB_SOLVER_HOST = 1, PVB_SOLVER_DEVICE = 2, PVB_SOLVER_PCG = 3 };
 int pvb_blocks_set_linear_solver(pvb_ctx* ctx, int kind);
+/* statistics of the PCG solver since the context was created: number of solves and total CG iterations */
+int pvb_blocks_pcg_stats(const pvb_ctx* ctx, long* solves, long* iterations);
 /* the device Cholesky solve alone: x = A^-1 b, A symmetric positive definite n x n row-major (parity / timing entry);
  * factor_ms (may be NULL) = device time of factorisation + substitution                                                             */
 int pvb_cholesky_solve(pvb_ctx* ctx, const double* A, int n, const double* b, double* x, float* factor_ms);

@@ -11,7 +11,7 @@ import numpy as np
 
 P2PLANE_METER, P2PLANE_ANGLE, P2LINE_METER, P2LINE_ANGLE, PLANE2PLANE_GLOBAL, PLANE_IOU = range(6)
 PLANE2PLANE_RELATIVE, PLANE_RELATIVE_IOU, LINE2LINE_ANGLE = 6, 7, 8
-SOLVER_AUTO, SOLVER_HOST, SOLVER_DEVICE = 0, 1, 2   # pvb_blocks_set_linear_solver
+SOLVER_AUTO, SOLVER_HOST, SOLVER_DEVICE, SOLVER_PCG = 0, 1, 2, 3   # pvb_blocks_set_linear_solver
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -112,7 +112,7 @@ def load_library():
 EXPORTS = [
     "pvb_create", "pvb_destroy", "pvb_last_error", "pvb_set_stream", "pvb_synchronize", "pvb_kernel_launches", "pvb_stream",
     "pvb_blocks_set", "pvb_blocks_evaluate", "pvb_blocks_residuals", "pvb_blocks_jacobians", "pvb_blocks_cost", "pvb_blocks_kernel_time_ms", "pvb_blocks_num_edges",
-    "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_edge_systems_ptr", "pvb_blocks_dense_system", "pvb_blocks_solve_lm",
+    "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_edge_systems_ptr", "pvb_blocks_dense_system", "pvb_blocks_solve_lm", "pvb_blocks_pcg_stats",
     "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn", "pvb_frames_set_corners", "pvb_frames_associate_point2line", "pvb_frames_get_point2line",
     "pvb_dense_set_target", "pvb_dense_set_sources", "pvb_dense_evaluate", "pvb_dense_evaluate_device", "pvb_dense_gauss_newton_step",
     "pvb_dense_get_rows", "pvb_dense_set_hints", "pvb_dense_reset_hints", "pvb_debug_counters", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
@@ -241,6 +241,12 @@ class Context:
         self._ck(self._L.pvb_blocks_solve_lm(self._h, _p(poses), _p(mask), C.c_int(max_iterations), _p(s)))
         keys = ["initial_cost", "final_cost", "iterations", "successful", "unsuccessful", "termination"]
         return poses, dict(zip(keys, s.tolist()))
+
+    def blocks_pcg_stats(self):
+        """(number of PCG solves, total CG iterations) since the context was created"""
+        a, b = C.c_long(0), C.c_long(0)
+        self._ck(self._L.pvb_blocks_pcg_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def blocks_set_linear_solver(self, kind):
         self._ck(self._L.pvb_blocks_set_linear_solver(self._h, C.c_int(kind)))

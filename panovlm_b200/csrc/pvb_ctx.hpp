@@ -108,6 +108,9 @@ struct pvb_ctx {
   bool coop_attr_set[8][2] = {};                                        // same for the instantiations of k_associate_coop
   bool solver_attr_set = false;                                         // dynamic shared memory opt-in of the solver kernels done on this context's device
   DevBuf s_H, s_A, s_g, s_sc, s_rhs, s_y, s_term, s_con, s_seg, s_gcon, s_gseg, s_fail; PinBuf sh_vec;
+  // block-sparse PCG form of the step (pvb_solver.cuh): BSR structure + values, CG vectors, per-CTA partial sums, device scalars
+  DevBuf s_bsr_rowptr, s_bsr_col, s_bsr_diag, s_bsr_val, s_px, s_pr, s_pz, s_pp, s_pq, s_dmp, s_minv, s_part, s_scal; int s_nfb = 0, s_nblk = 0;
+  bool pcg_active = false; double pcg_tol = 1e-12; int pcg_max_it = 4000; long pcg_iterations = 0, pcg_solves = 0;
   int s_n = 0, s_N = 0, s_ndest = 0, s_ngdest = 0; float s_last_factor_ms = 0.f;
   // ---- misc
   DevBuf m_a, m_b, m_c, m_d, m_e;

@@ -299,4 +299,201 @@ __global__ void __launch_bounds__(256) k_model_terms(const double* __restrict__ 
   if (lane == 0) term[row] = y[row] * (g[row] * sc[row] + 0.5 * s);
 }
 
+// ---- block-sparse form of the same step: preconditioned conjugate gradients (SetOptionsLidar's policy above 2000 frames is an iterative solver,
+//      util/Optimization.cpp:652-658; here also selectable for any size, converged to rounding) ------------------------------------------------------
+// The reduced pose-graph matrix is kept as 6x6 blocks (BSR, full symmetric storage, rows and columns = free pose blocks, blocks of a row sorted by
+// column): one block per distinct (row block, column block) pair, the sum of its edge contributions in ascending edge order - exactly the blocks
+// k_assemble_H scatters into the dense matrix, without the dense matrix (37 MB instead of 730 MB for Floor, and no O(n^3) factorisation).
+// System of a trust-region step: (S H S + D) y = -S g with S = diag(sc) (Jacobi scaling), D = clamp(diag(S H S), 1e-6, 1e32) / radius.
+// Preconditioner: block Jacobi (the inverse of every damped 6x6 diagonal block).  Every sum runs in a fixed order (per-CTA partials added in CTA
+// order by every thread) => bit-reproducible, and identical on every rank of a sharded run.
+constexpr int kPcgThreads = 192;            // 32 block rows per CTA: a block row never straddles two CTAs
+
+__global__ void __launch_bounds__(64) k_assemble_bsr(const HContrib* __restrict__ con, const int* __restrict__ seg, const double* __restrict__ esys, double* __restrict__ val) {
+  const int t = threadIdx.x;
+  if (t >= 36) return;
+  const int i = t / 6, j = t % 6;
+  const int s0 = seg[blockIdx.x], s1 = seg[blockIdx.x + 1];
+  double acc = 0.0;
+  for (int s = s0; s < s1; ++s) {
+    const HContrib c = con[s];
+    const int a = ((c.kind >> 1) & 1) * 6 + i, b = (c.kind & 1) * 6 + j;
+    acc += esys[(size_t)c.edge * 92 + (a <= b ? upper12(a, b) : upper12(b, a))];
+  }
+  val[(size_t)blockIdx.x * 36 + t] = acc;
+}
+
+__global__ void k_bsr_jacobi_scale(const double* __restrict__ val, const int* __restrict__ diag, int n, double* __restrict__ sc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sc[i] = 1.0 / (1.0 + sqrt(val[(size_t)diag[i / 6] * 36 + (i % 6) * 7]));
+}
+
+// per LM iteration: rhs = -g sc, damping D, inverse of the damped scaled diagonal blocks (one thread per block row; Gauss-Jordan on the SPD 6x6 block)
+__global__ void k_bsr_prepare_step(const double* __restrict__ val, const int* __restrict__ diag, const double* __restrict__ g, const double* __restrict__ sc, int nfb, double radius,
+                                   double* __restrict__ rhs, double* __restrict__ dmp, double* __restrict__ minv, int* __restrict__ fail) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nfb) return;
+  double M[6][6], I[6][6];
+  const double* v = val + (size_t)diag[b] * 36;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) { M[i][j] = v[i * 6 + j] * sc[6 * b + i] * sc[6 * b + j]; I[i][j] = i == j ? 1.0 : 0.0; }
+  for (int i = 0; i < 6; ++i) {
+    const double d = fmin(fmax(M[i][i], 1e-6), 1e32) / radius;
+    dmp[6 * b + i] = d; M[i][i] += d;
+    rhs[6 * b + i] = -g[6 * b + i] * sc[6 * b + i];
+  }
+  for (int k = 0; k < 6; ++k) {                                   // SPD: no pivoting needed
+    const double piv = M[k][k];
+    if (!(piv > 0.0)) { *fail = 1; return; }
+    const double ip = 1.0 / piv;
+    for (int j = 0; j < 6; ++j) { M[k][j] *= ip; I[k][j] *= ip; }
+    for (int i = 0; i < 6; ++i) {
+      if (i == k) continue;
+      const double f = M[i][k];
+      for (int j = 0; j < 6; ++j) { M[i][j] -= f * M[k][j]; I[i][j] -= f * I[k][j]; }
+    }
+  }
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) minv[(size_t)b * 36 + i * 6 + j] = I[i][j];
+}
+
+// Sum over the CTA with a fixed-shape tree (deterministic: the shape depends on blockDim only); result in every thread.  sm: >= 512 doubles.
+__device__ __forceinline__ double cta_sum_tree(double v, double* sm) {
+  const int t = threadIdx.x, bd = blockDim.x;
+  __syncthreads();
+  sm[t] = v;
+  __syncthreads();
+#pragma unroll
+  for (int s = 256; s > 0; s >>= 1) {
+    if (t < s && t + s < bd) sm[t] += sm[t + s];
+    __syncthreads();
+  }
+  return sm[0];
+}
+// Grid-wide total of per-CTA partial sums without a second launch and without every thread re-reading all partials: every CTA stores its partial, the CTA
+// that arrives LAST (atomic counter) adds all of them with the same fixed-shape tree - the result does not depend on which CTA is last - and publishes it.
+// Up to two totals at once.  Returns nothing: consumers are the NEXT kernel on the stream.
+__device__ __forceinline__ void grid_total(double p0, double p1, double* part0, double* part1, int n_cta, unsigned* counter, double* out0, double* out1, double* sm) {
+  __shared__ int s_last;
+  const int t = threadIdx.x, bd = blockDim.x;
+  if (t == 0) {
+    part0[blockIdx.x] = p0;
+    if (part1) part1[blockIdx.x] = p1;
+    __threadfence();
+    s_last = atomicAdd(counter, 1u) == (unsigned)(n_cta - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double a = 0.0, b = 0.0;
+  for (int c = t; c < n_cta; c += bd) { a += reinterpret_cast<volatile double*>(part0)[c]; if (part1) b += reinterpret_cast<volatile double*>(part1)[c]; }
+  a = cta_sum_tree(a, sm);
+  if (part1) b = cta_sum_tree(b, sm);
+  if (t == 0) { *out0 = a; if (part1) *out1 = b; *counter = 0u; }
+}
+
+// Device scalars of the CG loop (doubles): [0], [1] = r.z after the latest two updates (update number k writes slot k & 1; the initial one is number 0),
+// [2] = r.r after the latest update, [3] = p.q of the latest product.
+// One CG iteration = two launches.
+// (1) k_pcg_spmv (iteration it = 0, 1, ...): direction + matrix-vector product.  beta = rz[it & 1] / rz[(it + 1) & 1] (it == 0: beta = 0; plain != 0: beta = 0,
+//     no scalars touched: q = S H S z, used for the model terms); the new direction p = z + beta p_old is formed on the fly for the gathered entries and stored
+//     for the CTA's own rows (p ping-pongs between two buffers, so no launch separates "update p" from "use all of p"); q = (S H S + D) p.
+//     One warp per block row (see the kernel).  [3] = p.q.
+// (2) k_pcg_update: alpha = rz[it & 1] / [3]; x += alpha p; r -= alpha q; z = Minv r; rz[(it + 1) & 1] = r.z, [2] = r.r.
+constexpr int kSpmvRows = 4;                // one warp per block row, 4 rows per CTA
+__global__ void __launch_bounds__(kSpmvRows * 32) k_pcg_spmv(int plain, int it, int nfb, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                             const double* __restrict__ val, const double* __restrict__ sc, const double* __restrict__ dmp, double* scal,
+                                                             const double* __restrict__ z, const double* __restrict__ p_old, double* __restrict__ p_new, double* __restrict__ q,
+                                                             double* part_pq, unsigned* counter) {
+  __shared__ double sm[512];
+  __shared__ double swarp[kSpmvRows];
+  double beta = 0.0;
+  if (!plain && it > 0) {
+    const double rz = scal[it & 1], rz_old = scal[(it + 1) & 1];
+    beta = rz_old > 0.0 ? rz / rz_old : 0.0;
+  }
+  const bool mix = !plain && it > 0;                             // it == 0: p_old is uninitialised memory (0 * NaN)
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kSpmvRows + w;
+  // lane l multiplies the blocks d0 + l, d0 + l + 32, ... of its row (a whole 6x6 block per lane: 18 independent 16-byte loads + 6 gathered vector entries, so a
+  // row of ~40 blocks is two short dependent steps instead of a chain of 40), then the 6 outputs are summed over the lanes with a fixed-shape butterfly
+  double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (b < nfb) {
+    const int d1 = rowptr[b + 1];
+    for (int d = rowptr[b] + lane; d < d1; d += 32) {
+      const int c = 6 * col[d];
+      double pv[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) pv[j] = sc[c + j] * (mix ? z[c + j] + beta * p_old[c + j] : z[c + j]);
+      const double2* v = reinterpret_cast<const double2*>(val + (size_t)d * 36);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double2 v0 = v[3 * i], v1 = v[3 * i + 1], v2 = v[3 * i + 2];
+        out[i] += ((((v0.x * pv[0] + v0.y * pv[1]) + v1.x * pv[2]) + v1.y * pv[3]) + v2.x * pv[4]) + v2.y * pv[5];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) out[i] += __shfl_xor_sync(0xffffffffu, out[i], o);
+  }
+  double pq = 0.0;
+  if (b < nfb && lane < 6) {
+    const int row = 6 * b + lane;
+    double s = out[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) s = lane == i ? out[i] : s;
+    s *= sc[row];
+    const double pv = mix ? z[row] + beta * p_old[row] : z[row];
+    if (!plain) { p_new[row] = pv; s += dmp[row] * pv; }
+    q[row] = s;
+    pq = pv * s;
+  }
+  if (plain) return;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) pq += __shfl_xor_sync(0xffffffffu, pq, o);      // lanes 0..5 hold values, 6 and 7 zeros: lane 0 gets the sum of the row
+  if (lane == 0) swarp[w] = pq;
+  __syncthreads();
+  const double cta = ((swarp[0] + swarp[1]) + swarp[2]) + swarp[3];
+  grid_total(cta, 0.0, part_pq, nullptr, (int)gridDim.x, counter, scal + 3, nullptr, sm);
+}
+
+__global__ void __launch_bounds__(kPcgThreads) k_pcg_update(int first, int it, int n, const double* __restrict__ rhs, const double* __restrict__ minv, double* scal,
+                                                            double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, const double* __restrict__ p,
+                                                            const double* __restrict__ q, double* part_rz, double* part_rr, unsigned* counter) {
+  __shared__ double sm[512];
+  __shared__ double sr[kPcgThreads];
+  const int i = blockIdx.x * kPcgThreads + threadIdx.x;
+  double alpha = 0.0;
+  if (!first) {
+    const double pq = scal[3], rz = scal[it & 1];
+    alpha = (pq > 0.0 && rz > 0.0) ? rz / pq : 0.0;             // breakdown / converged to zero: freeze
+  }
+  double ri = 0.0;
+  if (i < n) {
+    if (first) { ri = rhs[i]; x[i] = 0.0; }
+    else { ri = r[i] - alpha * q[i]; x[i] += alpha * p[i]; }
+    r[i] = ri;
+  }
+  sr[threadIdx.x] = ri;
+  __syncthreads();
+  double zi = 0.0;
+  if (i < n) {
+    const int b = i / 6, k = i - 6 * b, t0 = threadIdx.x - k;
+    const double* m = minv + (size_t)b * 36 + k * 6;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) zi += m[j] * sr[t0 + j];
+    z[i] = zi;
+  }
+  const double s1 = cta_sum_tree(ri * zi, sm);
+  const double s2 = cta_sum_tree(ri * ri, sm);
+  grid_total(s1, s2, part_rz, part_rr, (int)gridDim.x, counter, scal + (first ? 0 : ((it + 1) & 1)), scal + 2, sm);
+}
+
+// model-cost terms from the block-sparse matrix: term[i] = y_i (g_i sc_i + 0.5 (S H S y)_i), hy = S H S y from k_bsr_spmv
+__global__ void k_bsr_model_terms(const double* __restrict__ g, const double* __restrict__ sc, const double* __restrict__ y, const double* __restrict__ hy, int n, double* __restrict__ term) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) term[i] = y[i] * (g[i] * sc[i] + 0.5 * hy[i]);
+}
+
 }  // namespace pvb

@@ -5,6 +5,8 @@ matrices (kernel) + tails (host C++), LiDAR line tracks and their gate (LidarLin
 track length 3 as LidarOdometry.cpp:47-50, util/Optimization.cpp:383-400), residual-block builders (host C++), Levenberg-Marquardt
 with device evaluation.
 """
+import time
+
 import numpy as np
 
 from .api import BlockList, Context, LineFrame
@@ -121,7 +123,9 @@ def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, devic
         v = bl.view()
         ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
     mask = np.zeros(len(frames), np.uint8); mask[0] = 1
+    t_lm = time.time()
     new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
+    summary["lm_s"] = time.time() - t_lm
     summary["n_blocks"], summary["n_edges"] = bl.n, len(edges)
     return new_poses, summary
 
@@ -152,7 +156,9 @@ def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_
             v = bl.view()
             ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
         mask = np.zeros(len(frames), np.uint8); mask[0] = 1
+        t_lm = time.time()
         new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
+        summary["lm_s"] = time.time() - t_lm
     finally:
         pd.remove_allreduce_hook(ctx)
         ctx.blocks_set_edge_list(None)

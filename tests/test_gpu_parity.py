@@ -165,12 +165,21 @@ def test_lm_device_solver_on_a_large_pose_graph(gpu_ctx, oracle):
     gpu_ctx.blocks_set(typ, ref, nei, consts, hub, 1, nb)
     out = {}
     try:
-        for kind in (api.SOLVER_HOST, api.SOLVER_DEVICE, api.SOLVER_AUTO):
+        for kind in (api.SOLVER_HOST, api.SOLVER_DEVICE, api.SOLVER_AUTO, api.SOLVER_PCG, api.SOLVER_PCG):
             gpu_ctx.blocks_set_linear_solver(kind)
-            out[kind] = gpu_ctx.blocks_solve_lm(start, is_const=mask, max_iterations=8)
+            out.setdefault(kind, []).append(gpu_ctx.blocks_solve_lm(start, is_const=mask, max_iterations=8))
     finally:
         gpu_ctx.blocks_set_linear_solver(api.SOLVER_AUTO)
+    (Pp, sp), (Pp2, sp2) = out[api.SOLVER_PCG]
+    out = {k: v[0] for k, v in out.items()}
     Ph, sh = out[api.SOLVER_HOST]; Pd, sd = out[api.SOLVER_DEVICE]; Pa, sa = out[api.SOLVER_AUTO]
+    # block-sparse PCG (no dense matrix, no factorisation), converged to rounding: same LM trajectory as the Cholesky solvers, deterministic
+    assert (sp["iterations"], sp["successful"], sp["termination"]) == (sh["iterations"], sh["successful"], sh["termination"])
+    assert abs(sp["final_cost"] - sh["final_cost"]) < 1e-9 * sh["final_cost"]
+    assert np.abs((Pp - start) - (Ph - start)).max() < 1e-7 * np.abs(Ph - start).max()
+    assert np.array_equal(Pp, Pp2) and sp == sp2
+    solves, cg_its = gpu_ctx.blocks_pcg_stats()
+    assert solves >= 2 * sp["iterations"] - 2 and cg_its > 0
     assert sh["final_cost"] < 0.2 * sh["initial_cost"]
     assert (sd["iterations"], sd["successful"], sd["termination"]) == (sh["iterations"], sh["successful"], sh["termination"])
     assert abs(sd["final_cost"] - sh["final_cost"]) < 1e-9 * sh["final_cost"]

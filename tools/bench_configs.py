@@ -119,25 +119,37 @@ def floor_refine_pose(ctx, world, rank, n_frames=1593, n_az=600):
     frames = synth.make_sequence(n_frames, n_az=n_az, tilt=SENSOR_TILT)
     synth_s = time.time() - t
     poses0 = perturbed_poses(frames)
-    ctx.blocks_set_linear_solver(panovlm_b200.api.SOLVER_DEVICE)
     cfg = odometry.OdometryConfig(line_to_line=False)
-    res = None
-    for rep in range(2):                                   # the first pass warms up buffers and NCCL
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t = time.time()
-        if world > 1:
-            poses, s = odometry.refine_pose_sharded(ctx, frames, poses0, cfg, aa_to_R, world, rank)
-        else:
-            poses, s = odometry.refine_pose(ctx, frames, poses0, cfg, aa_to_R)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.time() - t], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        res = (float(dt.item()), s)
+    runs = {}
+    # dense: the device Cholesky (what AUTO takes up to 2000 frames, like the reference's exact SPARSE_SCHUR); pcg: the block-sparse preconditioned CG converged
+    # to rounding (what AUTO takes above 2000 frames) - no dense matrix, nothing replicated that grows with n^3
+    for name, kind in (("dense", panovlm_b200.api.SOLVER_DEVICE), ("pcg", panovlm_b200.api.SOLVER_PCG)):
+        ctx.blocks_set_linear_solver(kind)
+        st0 = ctx.blocks_pcg_stats()
+        for rep in range(2):                                   # the first pass warms up buffers and NCCL
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t = time.time()
+            if world > 1:
+                poses, s = odometry.refine_pose_sharded(ctx, frames, poses0, cfg, aa_to_R, world, rank)
+            else:
+                poses, s = odometry.refine_pose(ctx, frames, poses0, cfg, aa_to_R)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.time() - t], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            runs[name] = (float(dt.item()), s, poses)
+        st1 = ctx.blocks_pcg_stats()
+        if name == "pcg":
+            runs["pcg_stats"] = {"solves": (st1[0] - st0[0]) // 2, "cg_iterations": (st1[1] - st0[1]) // 2}
+    ctx.blocks_set_linear_solver(panovlm_b200.api.SOLVER_AUTO)
+    res = runs["pcg"]                                        # what AUTO takes at this size (above 500 pose blocks)
+    poses = res[2]
     out = {"config": f"configs[3]: {n_frames} frames ({n_az} azimuth steps), one RefinePose (point-to-plane), reference frames sharded over {world} GPU(s), one allreduce of the edge systems per evaluation",
-           "n_gpus": world, "synth_s": synth_s, "refine_pose_s": res[0],
+           "n_gpus": world, "synth_s": synth_s, "refine_pose_s": res[0], "refine_pose_dense_cholesky_s": runs["dense"][0], "linear_solver": "block-sparse PCG (AUTO above 500 pose blocks)", "pcg": runs["pcg_stats"],
+           "lm_s": {"dense": runs["dense"][1].get("lm_s"), "pcg": runs["pcg"][1].get("lm_s")},
+           "pcg_vs_dense": {"max_pose_difference": float(np.abs(runs["pcg"][2] - runs["dense"][2]).max()), "same_lm_steps": all(runs["pcg"][1][k] == runs["dense"][1][k] for k in ("iterations", "successful", "unsuccessful", "termination"))},
            "summary": {k: (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v) for k, v in res[1].items()},
            "error_before": err_summary(poses0, frames), "error_after": err_summary(poses, frames)}
     if world > 1:
