@@ -178,10 +178,11 @@ int pvb_find_neighbors(int n, const double* t_wl, const unsigned char* pose_vali
   for (int i = 0; i < n; ++i)
     if (pv(i) && fv(i)) { centre_frame.push_back(i); for (int k = 0; k < 3; ++k) centre.push_back((float)t_wl[3 * i + k]); }
   const int m = (int)centre_frame.size();
-  int total = 0;
-  out_offsets[0] = 0;
+  // every frame's list is independent (a sort of all centre distances per frame): frames in parallel on the host cores, lists concatenated in frame order
+  std::vector<std::vector<int>> lists(n);
+#pragma omp parallel for schedule(dynamic, 16)
   for (int i = 0; i < n; ++i) {
-    std::vector<int> neighbors;
+    std::vector<int>& neighbors = lists[i];
     if (pv(i)) {
       const float q[3] = {(float)t_wl[3 * i], (float)t_wl[3 * i + 1], (float)t_wl[3 * i + 2]};
       std::vector<std::pair<float, int>> d(m);
@@ -208,7 +209,11 @@ int pvb_find_neighbors(int n, const double* t_wl, const unsigned char* pose_vali
     } else {
       for (int j = -neighbor_size / 2; j <= neighbor_size / 2; ++j) neighbors.push_back(i - j);   // :103-106 (may be out of range; callers filter)
     }
-    for (int v : neighbors) { if (total >= cap) return PVB_ERR_ARG; out_neighbors[total++] = v; }
+  }
+  int total = 0;
+  out_offsets[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    for (int v : lists[i]) { if (total >= cap) return PVB_ERR_ARG; out_neighbors[total++] = v; }
     out_offsets[i + 1] = total;
   }
   return total;

@@ -54,7 +54,7 @@ def pose_graph_edges(poses, cfg: OdometryConfig, aa_to_R):
     return [(i, j) for i in range(n) for j in neighbors[i] if 0 <= j < n and j != i]
 
 
-def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, frame_range=None, host_point2plane=True, per_edge_line_calls=False):
+def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, frame_range=None, host_point2plane=True, per_edge_line_calls=False, all_edges=None):
     """One outer iteration's residual blocks (the Add*Residual calls of RefinePose); returns a BlockList and the GLOBAL edge list.
     frame_range = (lo, hi): only the edges whose reference frame lies in [lo, hi) are associated and turned into blocks (one rank's shard of a
     pose graph split across GPUs); the clouds of all frames stay available as halo.
@@ -62,7 +62,8 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
     the BlockList then only holds the other families and the edge list of the shard is returned as third value."""
     n = len(frames)
     R_wl, t_wl = world_from_pose_blocks(poses, aa_to_R)
-    all_edges = pose_graph_edges(poses, cfg, aa_to_R)
+    if all_edges is None:
+        all_edges = pose_graph_edges(poses, cfg, aa_to_R)
     edges = all_edges if frame_range is None else [(i, j) for (i, j) in all_edges if frame_range[0] <= i < frame_range[1]]
     cap = sum(len(frames[j]["surfFlat"]) for _, j in edges) + sum(len(frames[j]["cornerLessSharp"]) for _, j in edges) * 6 + 16
     bl = BlockList(cap)
@@ -147,12 +148,12 @@ def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_
     try:
         if device_blocks and cfg.point_to_plane:
             # the rank's own point-to-plane correspondences become residual blocks on the device, filed under the GLOBAL edge list (no download / rebuild / upload)
-            bl, _, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=fr, host_point2plane=False)
+            bl, _, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=fr, host_point2plane=False, all_edges=all_edges)
             ref, nei = np.array([e[0] for e in mine], np.int32), np.array([e[1] for e in mine], np.int32)
             bl.n = ctx.frames_point2plane_blocks(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, cfg.angle_residual, cfg.normalize_distance, cfg.plane_weight,
                                                  len(frames), extra=bl.view())
         else:
-            bl, _ = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=fr)
+            bl, _ = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=fr, all_edges=all_edges)
             v = bl.view()
             ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
         mask = np.zeros(len(frames), np.uint8); mask[0] = 1
