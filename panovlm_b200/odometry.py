@@ -113,6 +113,7 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
 def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, device_blocks=True):
     """RefinePose: build the problem at `poses`, fix the first frame, solve (LidarOdometry.cpp:15-114).  device_blocks: the point-to-plane
     correspondences become residual blocks on the device (no download / rebuild / upload); the other families are built on the host and appended."""
+    t0 = time.time()
     if device_blocks and cfg.point_to_plane:
         bl, edges, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, host_point2plane=False)
         ref, nei = np.array([e[0] for e in mine], np.int32), np.array([e[1] for e in mine], np.int32)
@@ -127,6 +128,7 @@ def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, devic
     t_lm = time.time()
     new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
     summary["lm_s"] = time.time() - t_lm
+    summary["build_s"] = t_lm - t0
     summary["n_blocks"], summary["n_edges"] = bl.n, len(edges)
     return new_poses, summary
 
@@ -136,7 +138,9 @@ def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_
     balanced by the query count of their edges, association + residual blocks of the rank's own edges only, the GLOBAL edge list as reduction layout
     and ONE allreduce of the edge systems per evaluation (panovlm_b200.dist.install_allreduce_hook).  Every rank returns the same poses."""
     from . import dist as pd
+    t0 = time.time()
     all_edges = pose_graph_edges(poses, cfg, aa_to_R)
+    t_edges = time.time() - t0
     weights = np.zeros(len(frames))
     for (i, j) in all_edges:
         weights[i] += len(frames[j]["surfFlat"]) + 4 * len(frames[j]["cornerLessSharp"])
@@ -160,6 +164,7 @@ def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_
         t_lm = time.time()
         new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
         summary["lm_s"] = time.time() - t_lm
+        summary["edges_s"], summary["build_s"] = t_edges, t_lm - t0 - t_edges
     finally:
         pd.remove_allreduce_hook(ctx)
         ctx.blocks_set_edge_list(None)
