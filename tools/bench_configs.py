@@ -98,13 +98,14 @@ def room_refine_pose(ctx, n_frames=454, max_outer=7):
     cfg = odometry.OdometryConfig()                                # config/Room.txt:67-76: point-to-plane + line-to-line, angle residuals, normalised
     out = {"config": f"configs[1]: {n_frames} frames (sensor tilted up to {SENSOR_TILT} rad), FindNeighbors(6), point-to-plane + line-to-line (tracks gated), <= {max_outer} outer x <= 20 LM iterations, frame 0 fixed",
            "synth_s": synth_s, "error_before": err_summary(poses0, frames)}
-    ctx.synchronize()
-    t = time.time()
-    poses, log = odometry.estimate_pose(ctx, frames, poses0, cfg, aa_to_R, max_iteration=max_outer)
-    ctx.synchronize()
-    out["estimate_pose_s"] = time.time() - t
+    for rep in range(2):                                   # the first pass pays for buffer allocation and first-use initialisation (reported separately)
+        ctx.synchronize()
+        t = time.time()
+        poses, log = odometry.estimate_pose(ctx, frames, poses0, cfg, aa_to_R, max_iteration=max_outer)
+        ctx.synchronize()
+        out["estimate_pose_s" if rep else "estimate_pose_first_call_s"] = time.time() - t
     out["outer_iterations"] = len(log)
-    out["per_outer"] = [{k: (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v) for k, v in s.items() if k in ("initial_cost", "final_cost", "iterations", "successful", "n_blocks", "n_edges")} for s in log]
+    out["per_outer"] = [{k: (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v) for k, v in s.items() if k in ("initial_cost", "final_cost", "iterations", "successful", "n_blocks", "n_edges", "build_s", "lm_s")} for s in log]
     out["error_after"] = err_summary(poses, frames)
     out["lm_iterations_total"] = int(sum(s["iterations"] for s in log))
     out["residual_evals_per_s"] = float(sum(s["n_blocks"] * (s["iterations"] + 1) for s in log) / out["estimate_pose_s"])
