@@ -5,6 +5,7 @@
 // device work (vote matrices, cloud transforms).
 #include <limits>
 #include <algorithm>
+#include <omp.h>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -168,6 +169,9 @@ void push_segment_assoc(const pvb_line_frame* ref, const pvb_line_frame* nei, in
 
 extern "C" {
 
+static inline uint32_t bits_of(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float float_of(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
 int pvb_find_neighbors(int n, const double* t_wl, const unsigned char* pose_valid, const unsigned char* frame_valid, int neighbor_size,
                        int* out_offsets, int* out_neighbors, int cap) {
   if (n <= 0 || !t_wl || !out_offsets || !out_neighbors || neighbor_size < 1) return PVB_ERR_ARG;
@@ -180,14 +184,21 @@ int pvb_find_neighbors(int n, const double* t_wl, const unsigned char* pose_vali
   const int m = (int)centre_frame.size();
   // every frame's list is independent (a sort of all centre distances per frame): frames in parallel on the host cores, lists concatenated in frame order
   std::vector<std::vector<int>> lists(n);
-#pragma omp parallel for schedule(dynamic, 16)
+  // (an explicit thread count: launchers such as torchrun export OMP_NUM_THREADS=1, which would make this loop serial on every rank)
+  const int n_threads = std::max(1, std::min(8, omp_get_num_procs()));
+#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
   for (int i = 0; i < n; ++i) {
     std::vector<int>& neighbors = lists[i];
     if (pv(i)) {
       const float q[3] = {(float)t_wl[3 * i], (float)t_wl[3 * i + 1], (float)t_wl[3 * i + 2]};
-      std::vector<std::pair<float, int>> d(m);
-      for (int j = 0; j < m; ++j) d[j] = {sqdist_f32(q[0], q[1], q[2], centre[3 * j], centre[3 * j + 1], centre[3 * j + 2]), j};
-      std::sort(d.begin(), d.end());
+      // (squared distance, index) packed into one 64-bit key: non-negative floats order like their bit patterns, so sorting the keys is the
+      // lexicographic sort of the pairs at half the cost
+      std::vector<unsigned long long> keys(m);
+      for (int j = 0; j < m; ++j) keys[j] = ((unsigned long long)bits_of(sqdist_f32(q[0], q[1], q[2], centre[3 * j], centre[3 * j + 1], centre[3 * j + 2])) << 32) | (unsigned)j;
+      std::sort(keys.begin(), keys.end());
+      struct DI { float first; int second; };
+      std::vector<DI> d(m);
+      for (int j = 0; j < m; ++j) { d[j].first = float_of((uint32_t)(keys[j] >> 32)); d[j].second = (int)(keys[j] & 0xFFFFFFFFu); }
       const int k = std::min(neighbor_size, m);
       for (int j = 0; j < k; ++j) neighbors.push_back(d[j].second);
       if (!neighbors.empty()) neighbors.erase(neighbors.begin());              // the first is the frame itself (:52)

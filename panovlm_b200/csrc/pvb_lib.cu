@@ -1186,7 +1186,8 @@ static int dense_prepare_layout(pvb_ctx* ctx, const int* offsets, int n_frames) 
   const long long n = cs.n_points;
   std::vector<CloudTile> ctiles; std::vector<int> blocks(n_frames);
   std::vector<Pair> pairs(n_frames); std::vector<QueryTile> tiles; std::vector<int> tbegin(n_frames + 1, 0);
-  const int n_chunks = std::min(n_frames, 8);
+  // chunks of the upload pipeline: at most 8, and not smaller than ~1 M points (a chunk's ordering is ~8 launches: below that size their fixed cost outweighs the overlap)
+  const int n_chunks = (int)std::max<long long>(1, std::min<long long>(std::min(n_frames, 8), (long long)cs.off[n_frames] / 1000000));
   ctx->d_chunk_frame.assign(n_chunks + 1, 0); ctx->d_chunk_ctile.assign(n_chunks + 1, 0); ctx->d_chunk_qtile.assign(n_chunks + 1, 0);
   for (int c = 0; c <= n_chunks; ++c) ctx->d_chunk_frame[c] = (int)((long long)n_frames * c / n_chunks);
   int chunk = 0;

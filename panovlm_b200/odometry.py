@@ -39,6 +39,11 @@ def pose_blocks_from_world(R_wl, t_wl, R_to_aa):
 
 
 def world_from_pose_blocks(poses, aa_to_R):
+    if hasattr(aa_to_R, "batch"):                 # optional vectorised form of the same map: aa_to_R.batch(aa[n, 3]) -> R[n, 3, 3]
+        poses = np.asarray(poses, dtype=np.float64)
+        R = np.transpose(np.asarray(aa_to_R.batch(poses[:, :3])), (0, 2, 1))
+        t = -np.einsum("nij,nj->ni", R, poses[:, 3:])
+        return list(R), list(t)
     R_wl, t_wl = [], []
     for p in poses:
         R = aa_to_R(p[:3]).T

@@ -21,6 +21,9 @@ def aa_to_R(a):
     return Rotation.from_rotvec(a).as_matrix()
 
 
+aa_to_R.batch = lambda aa: Rotation.from_rotvec(aa).as_matrix()      # all pose blocks at once (odometry.world_from_pose_blocks)
+
+
 def R_to_aa(R):
     return Rotation.from_matrix(R).as_rotvec()
 
