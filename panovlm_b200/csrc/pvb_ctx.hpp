@@ -105,7 +105,6 @@ struct pvb_ctx {
   long d_reorders = 0;   // brackets the fused associate kernel of the last dense evaluate
   // ---- device linear solver of the LM loop (pvb_solver.cuh)
   int solver_kind = 0;                                                  // PVB_SOLVER_AUTO
-  bool coop_attr_set[8][2] = {};                                        // same for the instantiations of k_associate_coop
   bool solver_attr_set = false;                                         // dynamic shared memory opt-in of the solver kernels done on this context's device
   DevBuf s_H, s_A, s_g, s_sc, s_rhs, s_y, s_term, s_con, s_seg, s_gcon, s_gseg, s_fail; PinBuf sh_vec;
   // block-sparse PCG form of the step (pvb_solver.cuh): BSR structure + values, CG vectors, per-CTA partial sums, device scalars

@@ -1,6 +1,8 @@
 // panovlm_b200 — sm_100a kernels of the hot path.  HBM-bound integer/float/double work: no tensor cores.
 //   k_transform_world      T1  Velodyne::Transform2LidarWorld per cloud (float32 store) + per-cloud AABB
-//   k_cell_hist/k_scatter      cell-sorted target layout (uniform grid, x fastest)
+//   k_cell_keys (+ cub sort / scan), k_gather_f4   cell-sorted target layout (uniform grid, x fastest)
+//   k_superrow_counts / k_superrow_fill / k_target_rk   merged super-rows + static search bounds of a static target (dense mode)
+//   k_target_cell_keys     query order by target cell (dense mode)
 //   k_associate<K,...>     K2p fused: query -> world, exact k-NN on the grid, class test, plane fit, collinearity,
 //                              [emit correspondence] [residual + Jacobian rows] [per-tile 6x6 normal-equation partial]
 //   k_eval_blocks          K3  residual + analytic Jacobian over a correspondence list (+ per-tile 12x12 partial)
@@ -584,278 +586,6 @@ __global__ void __launch_bounds__(kTile, MINB) k_associate(const AssocArgs a) {
       if (lane < 21) { int o = lane; ia = 0; while (o >= 6 - ia) { o -= 6 - ia; ++ia; } ib = ia + o; }
       else if (lane < 27) { ia = lane - 21; ib = 6; }
       const double (*rows)[8] = &sJ[w * 32];
-      if (lane < 27) { for (int row = 0; row < 32; ++row) acc += rows[row][ia] * rows[row][ib]; }
-      else { for (int row = 0; row < 32; ++row) acc += rows[row][7]; }
-      out[lane] = acc;
-    } else if (lane == 28) {
-      out[28] = (double)__popc(b);
-    }
-  }
-}
-
-// ---- K2p, warp-cooperative form (MODE 3): groups of 8 neighbouring queries share their candidates through shared memory -------------------
-// The per-lane walks of k_associate keep 13 of 32 lanes busy: every lane has its own <= 9 row ranges of different lengths.  Here the 32 queries of a
-// warp (consecutive in the fine Morton order of the upload, so spatially compact) form 4 groups of 8.  A group takes the union of its queries'
-// search boxes [q - R, q + R] (R = the per-query radius bound from the hint of the previous evaluation), looks the (y, z) rows of that box up once
-// (8 lanes x <= 4 rows), and its 8 lanes copy the rows' records into the group's shared-memory buffer as structure-of-arrays (x[], y[], z[], position[]),
-// <= kGC candidates per chunk.  Then every lane scans ITS group's buffer: 128-bit shared loads (the 8 lanes of a group read the same address: broadcast;
-// the 4 groups hit different banks), packed FP32x2 arithmetic (FADD2 / FMUL2 / FFMA2: two candidates per instruction), all 32 lanes busy, same trip
-// count for everybody.  The packed arithmetic uses fused multiply-adds, so it is only a FILTER: a candidate passes when its approximate squared distance
-// is below the bound inflated by 1e-6; the exact non-fused float32 distance (flann::L2_Simple) is recomputed for the few survivors (K .. K+3 once the poses
-// settle) and the K smallest are selected exactly as in the per-lane search.  Queries without a hint, groups whose box spans more than 32 rows, queries with
-// more than LC survivors or fewer than K below their bound fall back to the per-lane two-pass search (knn_select_pruned) - results never depend on the path.
-constexpr int kGC = 128;            // staged candidates per group and chunk
-constexpr int kGCP = kGC + 8;       // + 8 floats: room for the sentinels of the last 8-wide step and a 32-byte bank shift between the groups' arrays
-struct CoopWarp {                   // shared memory of one warp
-  float gx[4][kGCP], gy[4][kGCP], gz[4][kGCP];
-  uint32_t gpos[4][kGC];
-  uint32_t rowlo[4][32], rowoff[4][36];
-  uint32_t lpos[kListCap][32];      // survivors: record positions, [entry][lane]
-};
-static_assert(sizeof(float) * 3 * 4 * kGCP >= sizeof(uint32_t) * kListCap * 32 + sizeof(double) * 32 * 8, "keys and the reduction rows alias the candidate arrays");
-
-
-// All 32 lanes call.  part: this lane has a usable bound (rad = search radius in metres, lim = exclusive bound on the K-th squared distance as float bits).
-// Returns true when the lane's K nearest are in W.lpos[0..K-1][lane] (any order) and *tau_out = bits of the K-th squared distance.
-template <int K>
-__device__ __forceinline__ bool coop_search(const GridDesc& g, const uint32_t* __restrict__ cs, const F4* __restrict__ srt, CoopWarp& W, bool part, float qx, float qy, float qz,
-                                            double rad, uint32_t lim, uint32_t* tau_out) {
-  constexpr unsigned FULL = 0xffffffffu;
-  constexpr int LC = kListCap;
-  const int lane = threadIdx.x & 31, grp = lane >> 3, j = lane & 7;
-  // ---- the group's box: union of [q - rad, q + rad] over its participating lanes (rounded outwards)
-  float lo[3], hi[3];
-  {
-    const float q[3] = {qx, qy, qz};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      lo[a] = part ? __double2float_rd((double)q[a] - rad) : INFINITY;
-      hi[a] = part ? __double2float_ru((double)q[a] + rad) : -INFINITY;
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(FULL, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(FULL, hi[a], o)); }
-    }
-  }
-  int c0[3] = {0, 0, 0}, c1[3] = {0, 0, 0}, nrows = 0, ny = 1;
-  if (hi[0] >= lo[0]) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { c0[a] = cell_coord((double)lo[a], g.origin[a], g.inv_h, g.dims[a]); c1[a] = cell_coord((double)hi[a], g.origin[a], g.inv_h, g.dims[a]); }
-    ny = c1[1] - c0[1] + 1;
-    nrows = ny * (c1[2] - c0[2] + 1);
-    if (nrows > 32) { nrows = 0; part = false; }            // group-uniform: an 8-run that straddles a jump of the curve
-  }
-  // ---- row ranges: lane j of the group looks rows j, j + 8, j + 16, j + 24 up; exclusive prefix of their lengths in row order
-  uint32_t total = 0;
-#pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const int r = j + 8 * m;
-    uint32_t lo_r = 0, len = 0;
-    if (r < nrows) {
-      const int yy = r % ny, zz = r / ny;
-      const uint32_t row = ((uint32_t)(c0[2] + zz) * (uint32_t)g.dims[1] + (uint32_t)(c0[1] + yy)) * (uint32_t)g.dims[0];
-      lo_r = __ldg(cs + row + (uint32_t)c0[0]);
-      len = __ldg(cs + row + (uint32_t)c1[0] + 1u) - lo_r;
-    }
-    uint32_t incl = len;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o, 8); if (j >= o) incl += t; }
-    if (r < nrows) { W.rowlo[grp][r] = lo_r; W.rowoff[grp][r] = total + incl - len; }
-    total += __shfl_sync(FULL, incl, 7, 8);
-  }
-  if (j == 0) W.rowoff[grp][nrows] = total;
-  uint32_t maxtotal = total;
-  int nrmax = nrows;
-#pragma unroll
-  for (int o = 8; o < 32; o <<= 1) { maxtotal = max(maxtotal, __shfl_xor_sync(FULL, maxtotal, o)); nrmax = max(nrmax, __shfl_xor_sync(FULL, nrmax, o)); }
-  __syncwarp();
-  // ---- chunks of <= kGC candidates per group: stage, then scan
-  const float limscan = part ? u2f(lim) * 1.000001f : -1.0f;
-  const unsigned long long QX = f2_pack(qx, qx), QY = f2_pack(qy, qy), QZ = f2_pack(qz, qz);
-  uint32_t* lp = &W.lpos[0][lane];
-  uint32_t* const lend = lp + LC * 32;
-  float* const gx = W.gx[grp]; float* const gy = W.gy[grp]; float* const gz = W.gz[grp];
-  uint32_t* const gp = W.gpos[grp];
-  for (uint32_t b0 = 0; b0 < maxtotal; b0 += kGC) {
-    for (int r = 0; r < nrmax; ++r) {
-      if (r < nrows) {
-        const uint32_t o = W.rowoff[grp][r], e = W.rowoff[grp][r + 1];
-        const uint32_t a = max(o, b0), b = min(e, b0 + (uint32_t)kGC);
-        const uint32_t base = W.rowlo[grp][r];
-        for (uint32_t k = a + j; k < b; k += 8) {
-          const F4 rec = ldg_f4(srt + base + (k - o));
-          const uint32_t idx = k - b0;
-          gx[idx] = rec.x; gy[idx] = rec.y; gz[idx] = rec.z; gp[idx] = base + (k - o);
-        }
-      }
-    }
-    const uint32_t cnt = total > b0 ? min(total - b0, (uint32_t)kGC) : 0u;
-    uint32_t cmax = cnt;
-#pragma unroll
-    for (int o = 8; o < 32; o <<= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-    const uint32_t cmax8 = (cmax + 7u) & ~7u;
-    for (uint32_t k = cnt + j; k < cmax8; k += 8) gx[k] = INFINITY;          // sentinels: never below any bound
-    __syncwarp();
-    for (uint32_t c = 0; c < cmax8; c += 8) {
-#pragma unroll
-      for (int h4 = 0; h4 < 2; ++h4) {
-        const float4 X = *reinterpret_cast<const float4*>(gx + c + 4 * h4);
-        const float4 Y = *reinterpret_cast<const float4*>(gy + c + 4 * h4);
-        const float4 Z = *reinterpret_cast<const float4*>(gz + c + 4 * h4);
-        const unsigned long long dx0 = f2_sub(f2_pack(X.x, X.y), QX), dx1 = f2_sub(f2_pack(X.z, X.w), QX);
-        const unsigned long long dy0 = f2_sub(f2_pack(Y.x, Y.y), QY), dy1 = f2_sub(f2_pack(Y.z, Y.w), QY);
-        const unsigned long long dz0 = f2_sub(f2_pack(Z.x, Z.y), QZ), dz1 = f2_sub(f2_pack(Z.z, Z.w), QZ);
-        const unsigned long long s0 = f2_fma(dz0, dz0, f2_fma(dy0, dy0, f2_mul(dx0, dx0)));
-        const unsigned long long s1 = f2_fma(dz1, dz1, f2_fma(dy1, dy1, f2_mul(dx1, dx1)));
-        float d[4];
-        f2_unpack(s0, d[0], d[1]); f2_unpack(s1, d[2], d[3]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool p = d[k] < limscan;
-          if (p && lp < lend) *lp = gp[c + 4 * h4 + k];
-          lp += p ? 32 : 0;                                                    // keeps counting past the capacity
-        }
-      }
-    }
-    __syncwarp();
-  }
-  // ---- survivors: exact float32 distances, exact count below the bound, cut to the K smallest
-  int n = (int)((lp - &W.lpos[0][lane]) >> 5);
-  uint32_t* keys = reinterpret_cast<uint32_t*>(&W.gx[0][0]) + lane;            // [entry][lane], aliases the candidate arrays (all lanes are past the scan)
-  bool ok = part && n >= K && n <= LC;
-  if (ok) {
-    int below = 0;
-    for (int e = 0; e < n; ++e) {
-      const F4 rec = ldg_f4(srt + W.lpos[e][lane]);
-      const uint32_t kb = f2u(sqdist_f32(qx, qy, qz, rec.x, rec.y, rec.z));
-      keys[e * 32] = kb;
-      below += kb < lim ? 1 : 0;
-    }
-    ok = below >= K;
-  }
-  if (ok) {
-    uint32_t tau;
-    auto lkey = [&](int e) { return keys[e * 32]; };
-    auto lmove = [&](int dst, int src) { keys[dst * 32] = keys[src * 32]; W.lpos[dst][lane] = W.lpos[src][lane]; };
-    if (n > K) tau = list_cut_to_k<K>(n, lkey, lmove);
-    else {
-      tau = 0u;
-#pragma unroll
-      for (int e = 0; e < K; ++e) { const uint32_t v = keys[e * 32]; tau = v > tau ? v : tau; }
-    }
-    *tau_out = tau;
-  }
-  return ok;
-}
-
-template <int K, bool REDUCE, bool DEBUG_NN, bool REF_ID>
-__global__ void __launch_bounds__(kTile, 4) k_associate_coop(const AssocArgs a) {
-  extern __shared__ __align__(16) unsigned char coop_smem[];
-  CoopWarp& W = reinterpret_cast<CoopWarp*>(coop_smem)[threadIdx.x >> 5];
-  const QueryTile t = a.tiles[blockIdx.x];
-  const Pair pr = a.pairs[t.pair];
-  const int i = threadIdx.x, lane = i & 31;
-  const bool act = i < t.count;
-  bool valid = false;
-  double p_local[3] = {0, 0, 0}, plane[4] = {0, 0, 0, 0};
-  double r = 0.0, cost = 0.0, J[12];
-#pragma unroll
-  for (int k = 0; k < 12; ++k) J[k] = 0.0;
-  const GridDesc& g = a.grids[pr.target_cloud];
-  const uint32_t* cs = a.cell_start + g.cell_base;
-  const F4* srt = a.sorted;
-  const WorldPose& wn = a.wpose[pr.nei_block];
-  const WorldPose& wr = a.wpose[pr.ref_block];
-  const int gq = t.start + i;
-  F4 q; q.x = q.y = q.z = q.w = 0.f;
-  float qx = 0.f, qy = 0.f, qz = 0.f;
-  uint32_t qi = 0;
-  if (act) {
-    q = ldg_f4(a.q_local + gq);
-    transform_point_f32(wn.R, wn.t, q.x, q.y, q.z, qx, qy, qz);
-    qi = a.q_orig ? a.q_orig[gq] : (uint32_t)(t.out_base + i);
-  }
-  AssocParams prm = a.prm;
-  prm.rmax = (int)ceil(a.thr / g.h);
-  // search-radius hint: K target points lay within sqrt(tau_old) of q_old => within sqrt(tau_old) + |q - q_old| of q
-  bool part = false; double rad = 0.0; uint32_t lim = 0u, tau = 0x7F800000u;
-  if (act && a.hint && a.use_hint) {
-    const F4 hq = ldg_f4(a.hint + qi);
-    if (hq.w >= 0.f && hq.w < 3.0e38f) {
-      const double dx = (double)qx - (double)hq.x, dy = (double)qy - (double)hq.y, dz = (double)qz - (double)hq.z;
-      rad = (sqrt((double)hq.w) + sqrt(dx * dx + dy * dy + dz * dz)) * (1.0 + 1e-5) + 1e-9;
-      const double lim2 = rad * rad;
-      if (lim2 < (double)prm.sq_thr) { lim = f2u((float)lim2) + 2u; part = true; rad *= 1.0 + 1e-6; }
-    }
-  }
-  bool found = coop_search<K>(g, cs, srt, W, part, qx, qy, qz, rad, lim, &tau);
-  auto win = [&](int jj) { return W.lpos[jj][lane]; };
-  auto set_win = [&](int jj, uint32_t pos) { W.lpos[jj][lane] = pos; };
-  auto loadg = [srt](long long p) { return ldg_f4(srt + p); };
-  if (act) {
-    if (!found) {                        // per-lane fallback: the pruned two-pass search
-      auto cells = [cs](long long c) { return (long long)__ldg(cs + c); };
-      if (DEBUG_NN && a.out_nn_idx) {
-#pragma unroll
-        for (int jj = 0; jj < K; ++jj) set_win(jj, 0xFFFFFFFFu);
-      }
-      found = knn_select_pruned<K>(g, cells, loadg, qx, qy, qz, prm.sq_thr, prm.r0 < 1 ? 1 : prm.r0, prm.rmax, [&](int jj, uint32_t pos, uint32_t) { set_win(jj, pos); }, &tau) >= K;
-    }
-    if (a.hint) reinterpret_cast<float4*>(a.hint)[qi] = make_float4(qx, qy, qz, u2f(tau));
-    if (found) { LocalNbStore<K> nb; valid = plane_from_window<K, REF_ID>(loadg, prm, qx, qy, qz, (uint32_t)q.w & 31u, wr.R, wr.t, wn.R, wn.t, p_local, plane, win, set_win, nb); }
-    if (DEBUG_NN && a.out_nn_idx) {     // debug / parity view: neighbours ordered by (d2, record position)
-      for (int jj = 0; jj < K; ++jj) {
-        const uint32_t pj = found ? win(jj) : 0xFFFFFFFFu;
-        if (pj == 0xFFFFFFFFu) { a.out_nn_idx[(size_t)qi * K + (K - 1 - jj)] = -1; a.out_nn_d2[(size_t)qi * K + (K - 1 - jj)] = INFINITY; continue; }
-        const F4 rj = loadg((long long)pj);
-        const float dj = sqdist_f32(qx, qy, qz, rj.x, rj.y, rj.z);
-        int rank = 0;
-        for (int m = 0; m < K; ++m) {
-          const uint32_t pm = win(m);
-          if (m == jj) continue;
-          const F4 rm = loadg((long long)pm);
-          const float dm = sqdist_f32(qx, qy, qz, rm.x, rm.y, rm.z);
-          rank += (dm < dj || (dm == dj && pm < pj)) ? 1 : 0;
-        }
-        a.out_nn_idx[(size_t)qi * K + rank] = (int)(f2u(rj.w) >> 5);
-        a.out_nn_d2[(size_t)qi * K + rank] = dj;
-      }
-    }
-    if (valid && (REDUCE || a.out_res)) {
-      double c[8] = {p_local[0], p_local[1], p_local[2], plane[0], plane[1], plane[2], plane[3], a.weight};
-      double qq[3], P[3], gg[3];
-      transform_nei_to_ref(a.prep[pr.ref_block], a.prep[pr.nei_block], c, qq, P);
-      r = tail_point_plane(a.residual_type, a.normalize != 0, c, P, gg);
-      accumulate_row(a.prep[pr.ref_block], a.prep[pr.nei_block], qq, P, gg, J);
-      cost = huber_correct(a.huber, r, J, 12);
-    }
-    if (a.out_valid) a.out_valid[qi] = valid ? 1 : 0;
-    if (a.out_point && valid) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) a.out_point[(size_t)qi * 3 + k] = p_local[k];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) a.out_plane[(size_t)qi * 4 + k] = plane[k];
-    }
-    if (a.out_res) {
-      a.out_res[qi] = r;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) a.out_jac6[(size_t)qi * 6 + k] = J[6 + k];
-    }
-  }
-  if (REDUCE) {
-    // per-warp reduction as in k_associate; the row staging aliases the candidate arrays (every lane of the warp is past the search)
-    __syncwarp();
-    double (*rows)[8] = reinterpret_cast<double (*)[8]>(&W.gx[0][0]);
-    const int w = i >> 5;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) rows[lane][k] = valid ? J[6 + k] : 0.0;
-    rows[lane][6] = valid ? r : 0.0;
-    rows[lane][7] = valid ? cost : 0.0;
-    const unsigned b = __ballot_sync(0xffffffffu, valid);
-    __syncwarp();
-    double* out = a.partials + ((size_t)blockIdx.x * (kTile / 32) + w) * 29;
-    if (lane < 28) {
-      int ia = 0, ib = 0; double acc = 0.0;
-      if (lane < 21) { int o = lane; ia = 0; while (o >= 6 - ia) { o -= 6 - ia; ++ia; } ib = ia + o; }
-      else if (lane < 27) { ia = lane - 21; ib = 6; }
       if (lane < 27) { for (int row = 0; row < 32; ++row) acc += rows[row][ia] * rows[row][ib]; }
       else { for (int row = 0; row < 32; ++row) acc += rows[row][7]; }
       out[lane] = acc;

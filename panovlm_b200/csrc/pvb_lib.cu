@@ -188,20 +188,7 @@ int launch_associate(pvb_ctx* ctx, int k, int n_tiles, AssocArgs a, bool ref_ide
   a.prm.r0 = ctx->tune_r0;
   a.use_hint = ctx->tune_hints; a.flat_walk = ctx->tune_flat; a.use_static = ctx->tune_static; a.tight_frac = ctx->tune_tight;
   if (mode == 0 && !dbg) { CK(ctx->d_stats.ensure(16)); a.stats = ctx->d_stats.as<unsigned long long>(); }
-  if (mode == 3) {                    // warp-cooperative search (groups of 8 queries share staged candidates)
-    constexpr size_t smem = sizeof(CoopWarp) * (kTile / 32);
-#define PVB_COOP(KK, DBG, RI) do { auto kern = k_associate_coop<KK, REDUCE, DBG, RI>; \
-      if (!ctx->coop_attr_set[(KK == 10 ? 0 : 1) * 4 + (DBG ? 2 : 0) + (RI ? 1 : 0)][REDUCE ? 1 : 0]) { \
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->coop_attr_set[(KK == 10 ? 0 : 1) * 4 + (DBG ? 2 : 0) + (RI ? 1 : 0)][REDUCE ? 1 : 0] = true; } \
-      kern<<<n_tiles, kTile, smem, ctx->stream>>>(a); } while (0)
-#define PVB_COOP_K(KK) do { if (dbg) { if (ref_identity) PVB_COOP(KK, true, true); else PVB_COOP(KK, true, false); } \
-                            else { if (ref_identity) PVB_COOP(KK, false, true); else PVB_COOP(KK, false, false); } } while (0)
-    if (k == 10) PVB_COOP_K(10); else PVB_COOP_K(5);
-#undef PVB_COOP_K
-#undef PVB_COOP
-    CKL();
-    return PVB_OK;
-  }
+  if (mode == 3) mode = 2;            // (the warp-cooperative experiment of round 2 was 2x slower than MODE 2 and has been removed)
 #define PVB_LAUNCH(KK, MB, DBG, MD) do { if (ref_identity) k_associate<KK, REDUCE, MB, DBG, MD, true><<<n_tiles, kTile, 0, ctx->stream>>>(a); else k_associate<KK, REDUCE, MB, DBG, MD, false><<<n_tiles, kTile, 0, ctx->stream>>>(a); } while (0)
 #define PVB_MINB_SWITCH(KK, MD) do { (void)minb; PVB_LAUNCH(KK, 6, false, MD); } while (0)      // 6 resident blocks per SM measured fastest (4 / 5 were compiled in round 1: profiles/r1f_sweep.log)
 #define PVB_DISPATCH(KK)                                                                                   \
