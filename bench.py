@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--cell", type=float, default=0.0, help="target grid cell size in metres (0: library default)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: shard the 64 frames (strong, SURVEY 8e) or 64 frames per rank (weak)")
-    ap.add_argument("--no-configs", action="store_true", help="skip extra.pair_icp / room_refine_pose / floor_refine_pose (BASELINE configs[0,1,3])")
+    ap.add_argument("--no-configs", action="store_true", help="skip extra.pair_icp / room_refine_pose / room_joint / floor_refine_pose_sharded (BASELINE configs[0,1,2,3])")
     ap.add_argument("--floor-frames", type=int, default=1593)
     ap.add_argument("--room-frames", type=int, default=454)
     return ap.parse_args()
@@ -450,7 +450,8 @@ def main():
             line["extra"]["k_reproj_rows"] = {"error": str(e)}
         if not args.no_configs:
             from tools import bench_configs
-            for name, fn in (("pair_icp", bench_configs.pair_icp), ("room_refine_pose", lambda c: bench_configs.room_refine_pose(c, n_frames=args.room_frames))):
+            for name, fn in (("pair_icp", bench_configs.pair_icp), ("room_refine_pose", lambda c: bench_configs.room_refine_pose(c, n_frames=args.room_frames)),
+                             ("room_joint", lambda c: bench_configs.room_joint(c, n_frames=args.room_frames))):
                 try:
                     line["extra"][name] = fn(ctx)
                 except Exception as e:

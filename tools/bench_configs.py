@@ -116,6 +116,39 @@ def room_refine_pose(ctx, n_frames=454, max_outer=7):
     return out
 
 
+def room_joint(ctx, n_frames=454, n_points=100_000, n_az=900):
+    """BASELINE configs[2]: joint camera-LiDAR refinement of a Room-shaped sequence - equirectangular line association of every (image, LiDAR) pair,
+    camera-LiDAR + LiDAR-LiDAR + reprojection residual blocks, one CameraLidarOptimizer::Optimize call (LM over camera poses, LiDAR poses and structure points)."""
+    from panovlm_b200 import joint
+    t = time.time()
+    d = synth.make_joint_problem(n_frames=n_frames, n_points=n_points, n_az=n_az, clutter=100, track_len=(3, 10))
+    out = {"config": f"configs[2]: {n_frames} frames, 5760x2880 panoramas, {n_points} structure points, neighbor_size_joint = 1, one Optimize call (<= 50 LM iterations)",
+           "synth_s": time.time() - t}
+    ctx.blocks_set_linear_solver(panovlm_b200.api.SOLVER_DEVICE)
+    cfg = joint.JointConfig()
+    for rep in range(2):                                       # the first pass pays for buffer allocation
+        ctx.synchronize()
+        t = time.time()
+        pairs = joint.associate_lines(ctx, d["frames"], d["image_lines"], d["cams"], d["lidars"], d["rows"], d["cols"], aa_to_R)
+        ctx.synchronize()
+        out["associate_lines_s"] = time.time() - t
+        l0 = ctx.kernel_launches
+        t = time.time()
+        cams, lidars, points, summ, _ = joint.optimize(ctx, d, d["cams"], d["lidars"], d["points"], cfg, aa_to_R)
+        ctx.synchronize()
+        out["optimize_s"] = time.time() - t
+        out["kernel_launches"] = int(ctx.kernel_launches - l0)
+    ctx.blocks_set_linear_solver(panovlm_b200.api.SOLVER_AUTO)
+    out["n_line_pairs"] = int(sum(len(p[0]) for p in pairs.values()))
+    out["summary"] = {k: (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v) for k, v in summ.items()}
+    out["unknowns"] = int(12 * n_frames - 6 + 3 * n_points)
+    n_res = summ.get("n_camera_lidar_blocks", 0) + summ.get("n_lidar_blocks", 0) + summ.get("n_reproj", 0)
+    out["residual_evals_per_s"] = float(n_res * (summ["iterations"] + 1) / out["optimize_s"])
+    out["lidar_t_err_before_after"] = [float(np.abs(d["lidars"][:, 3:] - d["lidars_gt"][:, 3:]).mean()), float(np.abs(lidars[:, 3:] - d["lidars_gt"][:, 3:]).mean())]
+    out["camera_t_err_before_after"] = [float(np.abs(d["cams"][:, 3:] - d["cams_gt"][:, 3:]).mean()), float(np.abs(cams[:, 3:] - d["cams_gt"][:, 3:]).mean())]
+    return out
+
+
 def floor_refine_pose(ctx, world, rank, n_frames=1593, n_az=600):
     import torch
     import torch.distributed as dist
