@@ -66,7 +66,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_mode = 2, tune_dense_mode = 4, tune_static = 1, tune_hints = 1, tune_morton_bits = 12, tune_flat = 1; double tune_cellcap = 4.0, tune_hscale = 1.0, tune_dense_hscale = 1.0, tune_reorder = 1.0, tune_tight = 0.8; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
+  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_mode = 2, tune_dense_mode = 4, tune_static = 1, tune_key64 = 0, tune_hints = 1, tune_morton_bits = 12, tune_flat = 1; double tune_cellcap = 4.0, tune_hscale = 1.0, tune_dense_hscale = 1.0, tune_reorder = 1.0, tune_tight = 0.8; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode

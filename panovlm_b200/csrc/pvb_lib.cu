@@ -230,6 +230,7 @@ int pvb_create(int device, pvb_ctx** out) {
   if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
   if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = ctx->tune_dense_hscale = std::max(0.1, atof(e));
+  if (const char* e = getenv("PVB_KEY64")) ctx->tune_key64 = atoi(e) != 0;      // force the 64-bit cell keys of very large grids (test hook)
   if (const char* e = getenv("PVB_TIGHT")) ctx->tune_tight = atof(e);
   if (const char* e = getenv("PVB_STATIC")) ctx->tune_static = atoi(e) != 0;
   if (const char* e = getenv("PVB_REORDER")) ctx->tune_reorder = std::max(0.0, atof(e));      // re-order the dense queries when a pose update may move a point by more than this many cells
@@ -1313,7 +1314,7 @@ static int dense_order_queries(pvb_ctx* ctx, bool* did) {
       const int t0 = fresh ? ctx->d_chunk_ctile[c] : 0, t1 = fresh ? ctx->d_chunk_ctile[c + 1] : cs.n_tiles;
       int frame_bits = 1; while ((1 << frame_bits) < f1 - f0) ++frame_bits;
       size_t tb = ctx->m_e.cap;
-      if (cellbits + frame_bits <= 32) {
+      if (cellbits + frame_bits <= 32 && !ctx->tune_key64) {
         k_target_cell_keys<uint32_t><<<t1 - t0, 256, 0, st>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, f0, ctx->d_wpose.as<WorldPose>(), g, cellbits,
                                                               ctx->m_a.as<uint32_t>(), ctx->m_c.as<uint32_t>(), rmax_dst);
         CKL();

@@ -404,6 +404,47 @@ def _world_pose(oracle, pose_lw):
     return R_wl, -R_wl @ pose_lw[3:]
 
 
+def test_dense_query_order_and_search_states_never_change_a_system(oracle, dense_small):
+    """Dense mode orders the queries by target cell and re-orders them after uploads and large pose updates; the search takes bounds from the previous evaluation,
+    from the target's own 10-NN radii, or none.  None of it may change a result: the same Gauss-Newton run with (a) the defaults, (b) re-ordering at every pose
+    change (PVB_REORDER=0), (c) never re-ordering after the first evaluation, (d) 64-bit cell keys, (e) no static bounds, (f) the per-row walk of MODE 2 and (g) the
+    two-pass search of MODE 1 gives the same accepted counts and reduced systems equal to rounding (the order of the queries changes the order of the per-warp sums),
+    and all equal the oracle at the first pose."""
+    import panovlm_b200
+    d = dense_small
+    s_cpu, _, n = oracle.dense_icp_eval(d["target"], d["src_local"], d["src_off"], d["poses_lw_init"], 0.05, 1.0, 10, 0.2, 1.0, 1)
+    runs = {}
+    for name, env in (("default", {}), ("always", {"PVB_REORDER": "0"}), ("never", {"PVB_REORDER": "1e9"}), ("key64", {"PVB_KEY64": "1"}), ("nostatic", {"PVB_STATIC": "0"}),
+                      ("mode2", {"PVB_MODE": "2"}), ("mode1", {"PVB_MODE": "1"})):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            ctx = panovlm_b200.Context(0)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        ctx.dense_set_target(d["target"])
+        ctx.dense_set_sources(d["src_local"], d["src_off"])
+        prm = ctx.dense_params(0.05, 1.0, 10, 0, 1, 0.2, 1.0)
+        poses, out = d["poses_lw_init"].copy(), []
+        for it in range(4):
+            s = ctx.dense_evaluate(poses, prm)
+            out.append(s)
+            poses = ctx.dense_gauss_newton_step(s, poses, 1e-6)
+        out.append(ctx.dense_evaluate(d["poses_lw_init"], prm))          # back to the start: a large pose change with stale bounds
+        runs[name] = np.array(out)
+        ctx.close()
+    ref = runs["default"]
+    assert np.array_equal(s_cpu[:, 28], ref[0][:, 28]) and np.abs(s_cpu - ref[0]).max() < 1e-8 * np.abs(s_cpu).max()
+    for name, r in runs.items():
+        assert np.array_equal(r[..., 28], ref[..., 28]), name
+        assert np.abs(r - ref).max() < 1e-9 * np.abs(ref).max(), name
+    assert np.array_equal(ref[0][:, 28], ref[4][:, 28]) and np.abs(ref[0] - ref[4]).max() < 1e-9 * np.abs(ref[0]).max()
+
+
 def test_dense_full_size_properties(gpu_ctx):
     """Size-independent properties at a large size the CPU oracle cannot sweep in seconds: every source point is an
     exact copy of a target point moved by a known rigid transform => at the true pose the point-to-plane residual of
