@@ -182,6 +182,9 @@ int pvb_dense_set_hints(pvb_ctx* ctx, int enable);
 int pvb_dense_reset_hints(pvb_ctx* ctx);
 /* debug: out2[0] = tiles of the fused kernel staged through TMA so far, out2[1] = tiles that used the global-memory path */
 int pvb_debug_counters(pvb_ctx* ctx, unsigned long long* out2);
+/* dense mode: how often the queries were sorted by target cell, and how often a fresh upload re-used the previous permutation (same layout, poses near those of the
+ * last sort, order still local when last measured) */
+int pvb_dense_order_stats(const pvb_ctx* ctx, long* sorts, long* reuses);
 /* device time (CUDA events on the context's stream) of the fused associate+residual kernel of the last dense evaluate */
 int pvb_dense_kernel_time_ms(pvb_ctx* ctx, float* ms);
 /* Gauss-Newton/LM step per frame from the reduced 6x6 systems (host, 64 tiny solves): poses updated in place.   */

@@ -115,7 +115,7 @@ EXPORTS = [
     "pvb_blocks_edges", "pvb_blocks_edge_systems", "pvb_blocks_edge_systems_ptr", "pvb_blocks_dense_system", "pvb_blocks_solve_lm", "pvb_blocks_pcg_stats",
     "pvb_frames_set", "pvb_frames_associate_point2plane", "pvb_frames_get_point2plane", "pvb_frames_knn", "pvb_frames_set_corners", "pvb_frames_associate_point2line", "pvb_frames_get_point2line",
     "pvb_dense_set_target", "pvb_dense_set_sources", "pvb_dense_evaluate", "pvb_dense_evaluate_device", "pvb_dense_gauss_newton_step",
-    "pvb_dense_get_rows", "pvb_dense_set_hints", "pvb_dense_reset_hints", "pvb_debug_counters", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
+    "pvb_dense_get_rows", "pvb_dense_set_hints", "pvb_dense_reset_hints", "pvb_debug_counters", "pvb_dense_order_stats", "pvb_dense_kernel_time_ms", "pvb_project_equirect", "pvb_project_depth_image", "pvb_line_votes", "pvb_angle_votes",
     "pvb_find_neighbors", "pvb_line2line_associate", "pvb_camera_lidar_associate", "pvb_build_point2plane_blocks", "pvb_build_point2line_blocks", "pvb_build_line2line_blocks",
     "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
     "pvb_pair_knn5", "pvb_nearest_line", "pvb_point2line_segment_knn_associate", "pvb_point2line_segment_knn_tail", "pvb_point2line_segment_associate",
@@ -358,6 +358,12 @@ class Context:
 
     def dense_set_hints(self, enable=True):
         self._ck(self._L.pvb_dense_set_hints(self._h, C.c_int(1 if enable else 0)))
+
+    def dense_order_stats(self):
+        """(sorts of the queries by target cell, fresh uploads that re-used the previous permutation)"""
+        a, b = C.c_long(0), C.c_long(0)
+        self._ck(self._L.pvb_dense_order_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def dense_reset_hints(self):
         self._ck(self._L.pvb_dense_reset_hints(self._h))

@@ -66,7 +66,7 @@ struct pvb_ctx {
   cudaStream_t stream = nullptr; bool own_stream = true;
   std::string err;
   long launches = 0;
-  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_mode = 2, tune_dense_mode = 4, tune_static = 1, tune_key64 = 0, tune_hints = 1, tune_morton_bits = 12, tune_flat = 1; double tune_cellcap = 4.0, tune_hscale = 1.0, tune_dense_hscale = 1.0, tune_reorder = 1.0, tune_tight = 0.8; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
+  int tune_minb = 6, tune_stage = 0, tune_r0 = 1, tune_mode = 2, tune_dense_mode = 4, tune_static = 1, tune_key64 = 0, tune_chunks = 8, tune_chunk_min = 1000000, tune_hints = 1, tune_morton_bits = 12, tune_flat = 1; double tune_cellcap = 4.0, tune_hscale = 1.0, tune_dense_hscale = 1.0, tune_reorder = 1.0, tune_tight = 0.8; DevBuf d_stats;   // fastest measured on B200 (tools/sweep_variants.py, profiles/r1f_sweep.log)
   // pose staging
   PinBuf h_pose; DevBuf d_prep, d_wpose;
   // ---- blocks mode
@@ -102,7 +102,11 @@ struct pvb_ctx {
   // MODE 4: the queries are ordered by target cell under the poses of an evaluation (k_target_cell_keys); the order is redone after an upload and when a
   // pose update may have moved a point by more than half a cell (bound from the pose change and the frame's largest sensor distance)
   bool d_cell_order = false, d_order_pending = false, d_order_valid = false; std::vector<pvb::WorldPoseHost> d_order_wpose; DevBuf d_rmax2; PinBuf dh_rmax2; cudaEvent_t rmax_ev = nullptr, pose_ev = nullptr; bool rmax_inflight = false;
-  long d_reorders = 0;   // brackets the fused associate kernel of the last dense evaluate
+  long d_reorders = 0, d_order_reuses = 0;
+  // a fresh upload with the layout of the previous one re-uses the previous permutation (gather only, no keys / sort) while the poses stay close to those of the
+  // last sort and the measured locality of the order (k_order_locality, read back one evaluation later) stays near the value seen right after that sort
+  bool d_perm_valid = false, loc_inflight = false, loc_was_sort = false, loc_known = false; double loc_sorted_frac = 0.0, loc_last_frac = 1.0; int reuse_holdoff = 0, reuse_backoff = 1;
+  DevBuf d_loc; PinBuf dh_loc; cudaEvent_t loc_ev = nullptr; int tune_reuse = 1;   // brackets the fused associate kernel of the last dense evaluate
   // ---- device linear solver of the LM loop (pvb_solver.cuh)
   int solver_kind = 0;                                                  // PVB_SOLVER_AUTO
   bool solver_attr_set = false;                                         // dynamic shared memory opt-in of the solver kernels done on this context's device

@@ -246,6 +246,30 @@ __global__ void __launch_bounds__(256) k_target_cell_keys(const F4* __restrict__
   }
 }
 
+// Locality of a query order (dense mode): number of adjacent pairs (j - 1, j) of the same frame whose target cells are NOT neighbours (differ by more than one
+// cell along an axis).  keys[] are the target-cell keys by ORIGINAL index (k_target_cell_keys), order[] the permutation in use.  After a sort the count is
+// the number of jumps of the occupied-cell sequence; a re-used permutation whose count stays near that value still groups the lanes of a warp spatially.
+template <typename KeyT>
+__global__ void __launch_bounds__(256) k_order_locality(const KeyT* __restrict__ keys, const uint32_t* __restrict__ order, long long cnt, GridDesc g, int cellbits,
+                                                        unsigned int* __restrict__ counter) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool far = false;
+  if (j > 0 && j < cnt) {
+    const unsigned long long a = (unsigned long long)keys[order[j]], b = (unsigned long long)keys[order[j - 1]];
+    if ((a >> cellbits) == (b >> cellbits)) {
+      const unsigned long long mask = (1ull << cellbits) - 1ull;
+      const long long ca = (long long)(a & mask), cb = (long long)(b & mask);
+      const int nx = g.dims[0], ny = g.dims[1];
+      const int xa = (int)(ca % nx), xb = (int)(cb % nx);
+      const long long ra = ca / nx, rb = cb / nx;
+      const int ya = (int)(ra % ny), yb = (int)(rb % ny), za = (int)(ra / ny), zb = (int)(rb / ny);
+      far = abs(xa - xb) > 1 || abs(ya - yb) > 1 || abs(za - zb) > 1;
+    }
+  }
+  const int n = __syncthreads_count(far ? 1 : 0);
+  if (threadIdx.x == 0 && n) atomicAdd(counter, (unsigned int)n);
+}
+
 // ---- K2p: fused associate (+ residual + reduce) --------------------------------------------------------------------
 struct AssocArgs {
   const F4* q_local;            // query records, local frame: x,y,z,intensity(class)  (dense mode: Morton order)

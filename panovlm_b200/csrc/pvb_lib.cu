@@ -230,6 +230,9 @@ int pvb_create(int device, pvb_ctx** out) {
   if (const char* e = getenv("PVB_R0")) ctx->tune_r0 = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("PVB_CELLCAP")) ctx->tune_cellcap = std::max(1.0, atof(e));
   if (const char* e = getenv("PVB_HSCALE")) ctx->tune_hscale = ctx->tune_dense_hscale = std::max(0.1, atof(e));
+  if (const char* e = getenv("PVB_REUSE")) ctx->tune_reuse = atoi(e) != 0;      // fresh uploads may keep the previous query permutation
+  if (const char* e = getenv("PVB_CHUNKS")) ctx->tune_chunks = std::max(1, atoi(e));
+  if (const char* e = getenv("PVB_CHUNK_MIN")) ctx->tune_chunk_min = std::max(1, atoi(e));
   if (const char* e = getenv("PVB_KEY64")) ctx->tune_key64 = atoi(e) != 0;      // force the 64-bit cell keys of very large grids (test hook)
   if (const char* e = getenv("PVB_TIGHT")) ctx->tune_tight = atof(e);
   if (const char* e = getenv("PVB_STATIC")) ctx->tune_static = atoi(e) != 0;
@@ -256,6 +259,8 @@ void pvb_destroy(pvb_ctx* ctx) {
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
   if (ctx->eval_done) cudaEventDestroy(ctx->eval_done);
   if (ctx->rmax_ev) cudaEventDestroy(ctx->rmax_ev);
+  if (ctx->loc_ev) cudaEventDestroy(ctx->loc_ev);
+  ctx->d_loc.release(); ctx->dh_loc.release();
   if (ctx->pose_ev) cudaEventDestroy(ctx->pose_ev);
   ctx->d_rmax2.release(); ctx->dh_rmax2.release();
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -1151,7 +1156,7 @@ int pvb_dense_set_target(pvb_ctx* ctx, const float* xyzc, long n, double cell_si
   const bool sr = ctx->tune_dense_mode == 4 && !ctx->tune_stage;
   rc = build_target_index(ctx, ctx->d_tgt, ctx->d_index, cell_size, sr ? ctx->tune_dense_hscale : ctx->tune_hscale); if (rc) return rc;
   ctx->d_index.srow.release(); ctx->d_index.sstart.release(); ctx->d_index.srk.release(); ctx->d_index.srw.release(); ctx->d_index.has_superrows = false;
-  ctx->d_order_valid = false;                                  // the query order belongs to the old grid
+  ctx->d_order_valid = false; ctx->d_perm_valid = false; ctx->loc_known = false;      // the query order belongs to the old grid
   if (sr) { rc = build_superrows(ctx, ctx->d_index); if (rc) return rc; }
   CK(cudaStreamSynchronize(ctx->stream));
   // the unsorted world copy and sort scratch are not needed after the build
@@ -1174,8 +1179,8 @@ static int dense_prepare_layout(pvb_ctx* ctx, const int* offsets, int n_frames) 
   const long long n = cs.n_points;
   std::vector<CloudTile> ctiles; std::vector<int> blocks(n_frames);
   std::vector<Pair> pairs(n_frames); std::vector<QueryTile> tiles; std::vector<int> tbegin(n_frames + 1, 0);
-  // chunks of the upload pipeline: at most 8, and not smaller than ~1 M points (a chunk's ordering is ~8 launches: below that size their fixed cost outweighs the overlap)
-  const int n_chunks = (int)std::max<long long>(1, std::min<long long>(std::min(n_frames, 8), (long long)cs.off[n_frames] / 1000000));
+  // chunks of the upload pipeline: at most tune_chunks, and not smaller than ~tune_chunk_min points (a chunk's ordering is ~8 launches: below that size their fixed cost outweighs the overlap)
+  const int n_chunks = (int)std::max<long long>(1, std::min<long long>(std::min(n_frames, ctx->tune_chunks), (long long)cs.off[n_frames] / ctx->tune_chunk_min));
   ctx->d_chunk_frame.assign(n_chunks + 1, 0); ctx->d_chunk_ctile.assign(n_chunks + 1, 0); ctx->d_chunk_qtile.assign(n_chunks + 1, 0);
   for (int c = 0; c <= n_chunks; ++c) ctx->d_chunk_frame[c] = (int)((long long)n_frames * c / n_chunks);
   int chunk = 0;
@@ -1193,6 +1198,7 @@ static int dense_prepare_layout(pvb_ctx* ctx, const int* offsets, int n_frames) 
   cs.n_tiles = (int)ctiles.size();
   ctx->d_ntiles = (int)tiles.size();
   ctx->d_frames = n_frames;
+  ctx->d_perm_valid = false; ctx->d_order_valid = false; ctx->loc_known = false; ctx->loc_inflight = false;      // a new layout: the old permutation means nothing
   CK(cs.local.ensure(std::max<size_t>(16, (size_t)n * sizeof(F4))));
   CK(cs.tiles.ensure(std::max<size_t>(16, ctiles.size() * sizeof(CloudTile))));
   CK(ctx->m_a.ensure(std::max<size_t>(16, (size_t)n * 8))); CK(ctx->m_b.ensure(std::max<size_t>(16, (size_t)n * 8)));
@@ -1277,20 +1283,39 @@ static int dense_order_queries(pvb_ctx* ctx, bool* did) {
   const int nf = ctx->d_frames;
   const GridDesc g = ctx->d_index.h_grids[0];
   const WorldPose* hw = reinterpret_cast<const WorldPose*>(ctx->h_pose.as<PosePrep>() + (nf + 1)) + 1;      // staging of upload_poses: block 0 = identity
-  bool need = ctx->d_order_pending || !ctx->d_order_valid || (int)ctx->d_order_wpose.size() != nf;
-  if (!need) {
-    if (ctx->rmax_inflight) { if (cudaEventQuery(ctx->rmax_ev) == cudaSuccess) ctx->rmax_inflight = false; else need = true; }
+  // have the poses moved a point of some frame by more than tune_reorder cells since the last SORT?  (bound from the pose change and the frame's largest sensor distance)
+  auto poses_moved = [&]() -> bool {
+    if (!ctx->d_order_valid || (int)ctx->d_order_wpose.size() != nf) return true;
+    if (ctx->rmax_inflight) { if (cudaEventQuery(ctx->rmax_ev) == cudaSuccess) ctx->rmax_inflight = false; else return true; }
     const float* r2 = ctx->dh_rmax2.as<float>();
-    for (int f = 0; f < nf && !need; ++f) {
+    for (int f = 0; f < nf; ++f) {
       double fr = 0, dt = 0;
       for (int k = 0; k < 9; ++k) { const double d = hw[f].R[k] - ctx->d_order_wpose[f].R[k]; fr += d * d; }
       for (int k = 0; k < 3; ++k) { const double d = hw[f].t[k] - ctx->d_order_wpose[f].t[k]; dt += d * d; }
-      if (std::sqrt(fr) * std::sqrt((double)r2[f]) + std::sqrt(dt) > ctx->tune_reorder * g.h) need = true;
-      if (need && getenv("PVB_DEBUG_ORDER")) fprintf(stderr, "[pvb] re-order: frame %d dR %.3g rmax %.3g dt %.3g h %.3g\n", f, std::sqrt(fr), std::sqrt((double)r2[f]), std::sqrt(dt), g.h);
+      if (std::sqrt(fr) * std::sqrt((double)r2[f]) + std::sqrt(dt) > ctx->tune_reorder * g.h) {
+        if (getenv("PVB_DEBUG_ORDER")) fprintf(stderr, "[pvb] re-order: frame %d dR %.3g rmax %.3g dt %.3g h %.3g\n", f, std::sqrt(fr), std::sqrt((double)r2[f]), std::sqrt(dt), g.h);
+        return true;
+      }
     }
+    return false;
+  };
+  const bool moved = poses_moved();
+  if (!ctx->d_order_pending && !moved) return PVB_OK;
+  // locality of the order used by the previous fresh upload (measured on the device, read back here)
+  if (ctx->loc_inflight && cudaEventQuery(ctx->loc_ev) == cudaSuccess) {
+    ctx->loc_inflight = false; ctx->loc_known = true;
+    const double frac = (double)*ctx->dh_loc.as<unsigned int>() / (double)std::max<long long>(1, cs.n_points);
+    ctx->loc_last_frac = frac;
+    if (ctx->loc_was_sort) { ctx->loc_sorted_frac = frac; }
+    else if (frac > ctx->loc_sorted_frac + 0.05) { ctx->reuse_holdoff = ctx->reuse_backoff; ctx->reuse_backoff = std::min(64, 2 * ctx->reuse_backoff); }      // the data changed: sort, and wait longer before trusting an old order again
+    else ctx->reuse_backoff = 1;
   }
-  if (!need) return PVB_OK;
-  if (getenv("PVB_DEBUG_ORDER")) fprintf(stderr, "[pvb] re-order #%ld: pending %d valid %d inflight %d\n", ctx->d_reorders, (int)ctx->d_order_pending, (int)ctx->d_order_valid, (int)ctx->rmax_inflight);
+  // a fresh upload may keep the previous permutation (gather only): same layout, poses near those of the last sort, and the order was still local when last measured
+  bool reuse = ctx->d_order_pending && ctx->tune_reuse && ctx->d_perm_valid && !moved && ctx->loc_known && !ctx->loc_inflight &&
+               ctx->loc_last_frac <= ctx->loc_sorted_frac + 0.05 && ctx->reuse_holdoff == 0;
+  if (ctx->d_order_pending && !reuse && ctx->reuse_holdoff > 0) --ctx->reuse_holdoff;
+  if (getenv("PVB_DEBUG_ORDER")) fprintf(stderr, "[pvb] re-order #%ld: pending %d valid %d moved %d reuse %d locality %.3f (sorted %.3f)\n", ctx->d_reorders, (int)ctx->d_order_pending, (int)ctx->d_order_valid, (int)moved, (int)reuse, ctx->loc_last_frac, ctx->loc_sorted_frac);
+  if (!ctx->loc_ev) { CK(cudaEventCreateWithFlags(&ctx->loc_ev, cudaEventDisableTiming)); CK(ctx->d_loc.ensure(16)); CK(ctx->dh_loc.ensure(16)); }
   if (!ctx->rmax_ev) { CK(cudaEventCreateWithFlags(&ctx->rmax_ev, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->pose_ev, cudaEventDisableTiming)); }
   const bool fresh = ctx->d_order_pending;
   // fresh upload: chunk by chunk on the sort stream behind the chunks' H2D copies (the evaluate launches per chunk); pose update: ONE sort of all frames on the
@@ -1301,7 +1326,7 @@ static int dense_order_queries(pvb_ctx* ctx, bool* did) {
     CK(cudaEventRecord(ctx->pose_ev, ctx->stream));                // the poses of this evaluate
     CK(cudaStreamWaitEvent(st, ctx->pose_ev, 0));
   }
-  if (fresh) CK(cudaMemsetAsync(ctx->d_rmax2.p, 0, (size_t)nf * 4, st));
+  if (fresh) { CK(cudaMemsetAsync(ctx->d_rmax2.p, 0, (size_t)nf * 4, st)); CK(cudaMemsetAsync(ctx->d_loc.p, 0, 4, st)); }
   uint32_t* const rmax_dst = fresh ? ctx->d_rmax2.as<uint32_t>() : nullptr;
   long long ncells = (long long)g.dims[0] * g.dims[1] * g.dims[2];
   int cellbits = 1; while ((1ll << cellbits) < ncells) ++cellbits;
@@ -1314,22 +1339,30 @@ static int dense_order_queries(pvb_ctx* ctx, bool* did) {
       const int t0 = fresh ? ctx->d_chunk_ctile[c] : 0, t1 = fresh ? ctx->d_chunk_ctile[c + 1] : cs.n_tiles;
       int frame_bits = 1; while ((1 << frame_bits) < f1 - f0) ++frame_bits;
       size_t tb = ctx->m_e.cap;
+      const unsigned lb = (unsigned)((cnt + 255) / 256);
       if (cellbits + frame_bits <= 32 && !ctx->tune_key64) {
         k_target_cell_keys<uint32_t><<<t1 - t0, 256, 0, st>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, f0, ctx->d_wpose.as<WorldPose>(), g, cellbits,
                                                               ctx->m_a.as<uint32_t>(), ctx->m_c.as<uint32_t>(), rmax_dst);
         CKL();
-        CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<uint32_t>() + p0, ctx->m_b.as<uint32_t>() + p0, ctx->m_c.as<uint32_t>() + p0,
-                                           ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, cellbits + frame_bits, st));
+        if (!reuse) {
+          CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<uint32_t>() + p0, ctx->m_b.as<uint32_t>() + p0, ctx->m_c.as<uint32_t>() + p0,
+                                             ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, cellbits + frame_bits, st));
+          CK(cudaMemcpyAsync(ctx->d_q_orig.as<uint32_t>() + p0, ctx->m_d.as<uint32_t>() + p0, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        if (fresh) { k_order_locality<uint32_t><<<lb, 256, 0, st>>>(ctx->m_a.as<uint32_t>(), ctx->d_q_orig.as<uint32_t>() + p0, cnt, g, cellbits, ctx->d_loc.as<unsigned int>()); CKL(); }
       } else {
         k_target_cell_keys<unsigned long long><<<t1 - t0, 256, 0, st>>>(cs.local.as<F4>(), cs.tiles.as<CloudTile>() + t0, f0, ctx->d_wpose.as<WorldPose>(), g, cellbits,
                                                                         ctx->m_a.as<unsigned long long>(), ctx->m_c.as<uint32_t>(), rmax_dst);
         CKL();
-        CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<unsigned long long>() + p0, ctx->m_b.as<unsigned long long>() + p0, ctx->m_c.as<uint32_t>() + p0,
-                                           ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, cellbits + frame_bits, st));
+        if (!reuse) {
+          CK(cub::DeviceRadixSort::SortPairs(ctx->m_e.p, tb, ctx->m_a.as<unsigned long long>() + p0, ctx->m_b.as<unsigned long long>() + p0, ctx->m_c.as<uint32_t>() + p0,
+                                             ctx->m_d.as<uint32_t>() + p0, (int)cnt, 0, cellbits + frame_bits, st));
+          CK(cudaMemcpyAsync(ctx->d_q_orig.as<uint32_t>() + p0, ctx->m_d.as<uint32_t>() + p0, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        if (fresh) { k_order_locality<unsigned long long><<<lb, 256, 0, st>>>(ctx->m_a.as<unsigned long long>(), ctx->d_q_orig.as<uint32_t>() + p0, cnt, g, cellbits, ctx->d_loc.as<unsigned int>()); CKL(); }
       }
-      k_gather_f4<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(cs.local.as<F4>(), ctx->m_d.as<uint32_t>() + p0, cnt, ctx->d_q_sorted.as<F4>() + p0);
+      k_gather_f4<<<lb, 256, 0, st>>>(cs.local.as<F4>(), ctx->d_q_orig.as<uint32_t>() + p0, cnt, ctx->d_q_sorted.as<F4>() + p0);
       CKL();
-      CK(cudaMemcpyAsync(ctx->d_q_orig.as<uint32_t>() + p0, ctx->m_d.as<uint32_t>() + p0, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
     }
     if (fresh) CK(cudaEventRecord(ctx->chunk_ev[c], st));
   }
@@ -1338,9 +1371,17 @@ static int dense_order_queries(pvb_ctx* ctx, bool* did) {
     CK(cudaEventRecord(ctx->rmax_ev, st));
     ctx->rmax_inflight = true;
   }
-  ctx->d_order_wpose.resize(nf);
-  for (int f = 0; f < nf; ++f) { memcpy(ctx->d_order_wpose[f].R, hw[f].R, 72); memcpy(ctx->d_order_wpose[f].t, hw[f].t, 24); }
-  ctx->d_order_pending = false; ctx->d_order_valid = true; ctx->d_chunks_pending = fresh; ctx->d_reorders++;
+  if (fresh) {
+    CK(cudaMemcpyAsync(ctx->dh_loc.p, ctx->d_loc.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->loc_ev, st));
+    ctx->loc_inflight = true; ctx->loc_was_sort = !reuse;
+  }
+  if (!reuse) {
+    ctx->d_order_wpose.resize(nf);
+    for (int f = 0; f < nf; ++f) { memcpy(ctx->d_order_wpose[f].R, hw[f].R, 72); memcpy(ctx->d_order_wpose[f].t, hw[f].t, 24); }
+    ctx->d_reorders++;
+  } else ctx->d_order_reuses++;
+  ctx->d_order_pending = false; ctx->d_order_valid = true; ctx->d_perm_valid = true; ctx->d_chunks_pending = fresh;
   *did = true;
   return PVB_OK;
 }
@@ -1402,6 +1443,13 @@ int pvb_dense_reset_hints(pvb_ctx* ctx) {
   if (!ctx) return PVB_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (ctx->d_hint.p && ctx->d_src.n_points > 0) CK(cudaMemsetAsync(ctx->d_hint.p, 0x7f, (size_t)ctx->d_src.n_points * sizeof(F4), ctx->stream));
+  return PVB_OK;
+}
+
+int pvb_dense_order_stats(const pvb_ctx* ctx, long* sorts, long* reuses) {
+  if (!ctx) return PVB_ERR_ARG;
+  if (sorts) *sorts = ctx->d_reorders;
+  if (reuses) *reuses = ctx->d_order_reuses;
   return PVB_OK;
 }
 

@@ -445,6 +445,35 @@ def test_dense_query_order_and_search_states_never_change_a_system(oracle, dense
     assert np.array_equal(ref[0][:, 28], ref[4][:, 28]) and np.abs(ref[0] - ref[4]).max() < 1e-9 * np.abs(ref[0]).max()
 
 
+def test_dense_fresh_uploads_may_reuse_the_previous_query_order(oracle, dense_small):
+    """A fresh upload with the layout of the previous one keeps the previous permutation (no sort) while the poses stay near those of the last sort and the order is
+    still local; new data under the same layout is detected by the locality measurement of the step that used the stale order, and sorted again.  Every evaluation
+    equals the oracle (counts exactly, systems to rounding) whatever order was used."""
+    import panovlm_b200
+    d = dense_small
+    ctx = panovlm_b200.Context(0)
+    ctx.dense_set_target(d["target"])
+    prm = ctx.dense_params(0.05, 1.0, 10, 0, 1, 0.2, 1.0)
+    rng = np.random.default_rng(1)
+    other = d["src_local"].copy()
+    for f in range(len(d["src_off"]) - 1):                                     # different points under the same layout: every frame's points shuffled
+        lo, hi = d["src_off"][f], d["src_off"][f + 1]
+        other[lo:hi] = other[lo:hi][rng.permutation(hi - lo)]
+    s_cpu, _, _ = oracle.dense_icp_eval(d["target"], d["src_local"], d["src_off"], d["poses_lw_init"], 0.05, 1.0, 10, 0.2, 1.0, 1)
+    s_oth, _, _ = oracle.dense_icp_eval(d["target"], other, d["src_off"], d["poses_lw_init"], 0.05, 1.0, 10, 0.2, 1.0, 1)
+    log = []
+    for step, (src, ref) in enumerate([(d["src_local"], s_cpu)] * 4 + [(other, s_oth)] * 4 + [(d["src_local"], s_cpu)] * 2):
+        ctx.dense_set_sources(src, d["src_off"])
+        s = ctx.dense_evaluate(d["poses_lw_init"], prm)
+        assert np.array_equal(ref[:, 28], s[:, 28]) and np.abs(ref - s).max() < 1e-8 * np.abs(ref).max(), step
+        log.append(ctx.dense_order_stats())
+    sorts = np.diff([0] + [x[0] for x in log]); reuses = np.diff([0] + [x[1] for x in log])
+    assert sorts[0] == 1 and reuses[1:4].sum() >= 2                                 # the same data again: the permutation is kept
+    assert sorts[4:8].sum() >= 1                                                     # new data under the old order is noticed and sorted
+    assert (sorts + reuses == 1).all()
+    ctx.close()
+
+
 def test_dense_full_size_properties(gpu_ctx):
     """Size-independent properties at a large size the CPU oracle cannot sweep in seconds: every source point is an
     exact copy of a target point moved by a known rigid transform => at the true pose the point-to-plane residual of
