@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu --tb=short > gpurun_out/r2w_gputests.log 2>&1; tail -4 gpurun_out/r2w_gputests.log
-timeout 900 python tools/capture_traffic.py gpurun_out/r2w_traffic steady 2>&1 | tail -1
-cp gpurun_out/r2w_traffic.json profiles/traffic.json
-timeout 900 python bench.py > gpurun_out/r2w_bench_n1.json 2> gpurun_out/r2w_bench_n1.err; tail -c 300 gpurun_out/r2w_bench_n1.err
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2w_bench_reference.json 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r2w_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra > /dev/null 2>&1
-python tools/launch_summary.py gpurun_out/r2w_launches.csv > gpurun_out/r2w_launches_summary.txt 2>&1; head -8 gpurun_out/r2w_launches_summary.txt
+timeout 1500 python -m pytest tests -x -q -m gpu --tb=short > gpurun_out/r2y_gputests.log 2>&1; tail -4 gpurun_out/r2y_gputests.log
+timeout 900 python tools/capture_traffic.py gpurun_out/r2y_traffic steady 2>&1 | tail -1
+cp gpurun_out/r2y_traffic.json profiles/traffic.json
+timeout 900 python bench.py > gpurun_out/r2y_bench_n1.json 2> gpurun_out/r2y_bench_n1.err; tail -c 300 gpurun_out/r2y_bench_n1.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2y_bench_reference.json 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r2y_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra > /dev/null 2>&1
+python tools/launch_summary.py gpurun_out/r2y_launches.csv > gpurun_out/r2y_launches_summary.txt 2>&1; head -8 gpurun_out/r2y_launches_summary.txt
 python __graft_entry__.py smoke 2>&1 | tail -1
