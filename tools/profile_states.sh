@@ -1,3 +1,4 @@
+# ncu --set full of ONE full-grid launch of the dense fused kernel in the steady / cold state of a Gauss-Newton run (tools/profile_dense.py), summaries + per-source-line view.
 mkdir -p gpurun_out
 SYM='_ZN3pvb11k_associateILi10ELb1ELi6ELb0ELi4ELb1EEEvNS_9AssocArgsE'
 for st in steady cold; do
