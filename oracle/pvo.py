@@ -831,6 +831,26 @@ def ref_pixel_associate_scripted(rows, cols, lines, cloud_local, T_cl, inlier_li
     return il[:m].copy(), s[:m].copy(), e[:m].copy(), ang[:m].copy()
 
 
+def ref_pixel_associate_segmented_scripted(rows, cols, lines, segments, T_cl, inlier_lists):
+    """The reference's segmented pixel-space Associate(lines, segmented_cloud, T_cl) (CameraLidarLineAssociate.cpp:191-338) with the RANSAC's inliers scripted
+    (inlier_lists[k] = indices into the majority segment of the k-th image line that reaches the fit).  Returns (image_line4, start, end, angle) of the surviving pairs,
+    or None when the script does not match the number of fits."""
+    lines = _f32(lines).reshape(-1, 4)
+    segs = [_f32(x).reshape(-1, 4) for x in segments]
+    seg_off = np.concatenate([[0], np.cumsum([len(x) for x in segs])]).astype(np.int32)
+    cloud = _f32(np.concatenate(segs + [np.zeros((0, 4), np.float32)]))
+    off = np.concatenate([[0], np.cumsum([len(x) for x in inlier_lists])]).astype(np.int32)
+    idx = _i32(np.concatenate([np.asarray(x, np.int32) for x in inlier_lists] + [np.zeros(0, np.int32)]))
+    cap = len(lines) + 1
+    il, s, e, ang = np.zeros((cap, 4), np.float32), np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros(cap, np.float32)
+    m = ref_camlidar_lib().ref_pixel_associate_segmented_scripted(C.c_int(rows), C.c_int(cols), _p(lines), C.c_int(len(lines)), _p(cloud), C.c_int(len(segs)), _p(seg_off),
+                                                                  _p(_f64(T_cl)), C.c_int(len(inlier_lists)), _p(off), _p(idx), C.c_int(cap), _p(il), _p(s), _p(e), _p(ang))
+    if m == -2:
+        return None
+    assert m >= 0, m
+    return il[:m].copy(), s[:m].copy(), e[:m].copy(), ang[:m].copy()
+
+
 def ref_joint_optimize_loop(rows, cols, R_wc, t_wc, image_lines, lidar_frames, T_cl_init, num_iteration_joint, script_cost, script_steps):
     """The reference's own mapping-mode JointOptimize with a scripted solver (k-th solve reports script_cost[k] / script_steps[k]); returns the number of solver calls."""
     R_wc, t_wc = _f64(R_wc).reshape(-1, 9), _f64(t_wc).reshape(-1, 3)

@@ -118,6 +118,35 @@ int ref_pixel_associate_scripted(int rows, int cols, const float* lines, int L, 
   return (int)pairs.size();
 }
 
+// The SEGMENTED overload, Associate(lines, segmented_cloud, T_cl) (CameraLidarLineAssociate.cpp:191-338; no live caller in the reference, the call sites are
+// commented out), run the same way: segment k = points [seg_off[k], seg_off[k+1]) of cloud_local (LiDAR frame), the k-th FitLineRANSAC call (one per image line whose
+// candidates pass the 6-point and the 70 % single-segment tests; it fits the WHOLE majority segment, in the LiDAR frame) answers with inlier list k.
+int ref_pixel_associate_segmented_scripted(int rows, int cols, const float* lines, int L, const float* cloud_local, int n_seg, const int* seg_off, const double* T_cl_rowmajor,
+                                           int n_lists, const int* inl_off, const int* inl_idx, int cap, float* image_line4, double* start3, double* end3, float* angle) {
+  std::vector<cv::Vec4f> ln;
+  for (int i = 0; i < L; ++i) ln.push_back(cv::Vec4f(lines[4 * i], lines[4 * i + 1], lines[4 * i + 2], lines[4 * i + 3]));
+  std::vector<pcl::PointCloud<pcl::PointXYZI>> segs(n_seg);
+  for (int k = 0; k < n_seg; ++k)
+    for (int i = seg_off[k]; i < seg_off[k + 1]; ++i) { pcl::PointXYZI p; p.x = cloud_local[4 * i]; p.y = cloud_local[4 * i + 1]; p.z = cloud_local[4 * i + 2]; p.intensity = cloud_local[4 * i + 3]; segs[k].push_back(p); }
+  Eigen::Matrix4d T; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T(i, j) = T_cl_rowmajor[4 * i + j];
+  std::pair<std::vector<std::vector<int>>, size_t> script;
+  for (int k = 0; k < n_lists; ++k) script.first.push_back(std::vector<int>(inl_idx + inl_off[k], inl_idx + inl_off[k + 1]));
+  script.second = 0;
+  pcl::sac_script() = &script;
+  CameraLidarLineAssociate a(rows, cols);
+  a.Associate(ln, segs, T);
+  pcl::sac_script() = nullptr;
+  if ((int)script.second != n_lists) return -2 - (int)script.second * 0;            // the script must match the number of FitLineRANSAC calls
+  const std::vector<CameraLidarLinePair> pairs = a.GetAssociatedPairs();
+  if ((int)pairs.size() > cap) return -1;
+  for (size_t i = 0; i < pairs.size(); ++i) {
+    for (int k = 0; k < 4; ++k) image_line4[4 * i + k] = pairs[i].image_line[k];
+    for (int k = 0; k < 3; ++k) { start3[3 * i + k] = pairs[i].lidar_line_start[k]; end3[3 * i + k] = pairs[i].lidar_line_end[k]; }
+    angle[i] = pairs[i].angle;
+  }
+  return (int)pairs.size();
+}
+
 // ProjectLidar2PanoramaDepth<pcl::PointXYZI> (util/Visualization.h:407-441): rows x cols uint16 image
 void ref_project_lidar2panorama_depth(const float* cloud_xyzi, long n, int rows, int cols, const double* T_cl_rowmajor, int size, unsigned short* image) {
   pcl::PointCloud<pcl::PointXYZI> cloud;

@@ -565,6 +565,58 @@ class Context:
             return h[:, :3] / h[:, 3:]
         return ids[keep], back(s_[keep]), back(e_[keep]), ang[keep]
 
+    @staticmethod
+    def segmented_fit_lists(n_lines, cand_off, cand_idx, seg_of_point, seg_off):
+        """The per-line tests of the segmented Associate() between its k-NN stage and its line fit (CameraLidarLineAssociate.cpp:265-292): an image line with at least 6
+        candidate points goes on when at least 70 % of them belong to ONE LiDAR segment (the first segment with the largest count); the fit then takes ALL points of that
+        segment.  Returns (image line ids, majority segment per line, CSR offsets, point indices) of the lists to fit."""
+        n_seg = len(seg_off) - 1
+        ids, segs, off, idx = [], [], [0], []
+        for li in range(n_lines):
+            c = cand_idx[cand_off[li]:cand_off[li + 1]]
+            if len(c) == 0:
+                continue
+            cnt = np.bincount(seg_of_point[c], minlength=n_seg)
+            mp = int(np.argmax(cnt))                                                  # max_element: the first maximum
+            if cnt[mp] < 0.7 * len(c):
+                continue
+            ids.append(li); segs.append(mp)
+            idx.append(np.arange(seg_off[mp], seg_off[mp + 1], dtype=np.int32)); off.append(off[-1] + int(seg_off[mp + 1] - seg_off[mp]))
+        return (np.array(ids, np.int32), np.array(segs, np.int32), np.array(off, np.int32),
+                np.concatenate(idx).astype(np.int32) if idx else np.zeros(0, np.int32))
+
+    def pixel_associate_segmented(self, rows, cols, lines, segments, T_cl):
+        """CameraLidarLineAssociate::Associate(lines, segmented_cloud, T_cl) (CameraLidarLineAssociate.cpp:191-338; the reference's call sites of this overload are commented
+        out, it is built for completeness): every point carries its segment index, projected points -> 3 nearest image sub-lines (device) -> per image line the candidate
+        points (>= 6) -> 70 % single-segment test -> line fit of the WHOLE majority segment -> Filter(true, true) -> T_lc.  As written in the reference the fit runs on the
+        segment in the LiDAR frame (`segmented_cloud[max_position]`, not the transformed copy), so Filter sees LiDAR-frame end points as if they were camera-frame ones and
+        the final T_lc moves them once more; this is reproduced, not corrected.  Returns (image line ids, start (n,3), end (n,3), angle float32)."""
+        lines = _arr(lines, np.float32).reshape(-1, 4)
+        T = _arr(T_cl, np.float64).reshape(4, 4)
+        segs = [_arr(x, np.float32).reshape(-1, 4) for x in segments]
+        empty = (np.zeros(0, np.int32), np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0, np.float32))
+        if not segs or sum(len(x) for x in segs) == 0:
+            return empty
+        seg_off = np.concatenate([[0], np.cumsum([len(x) for x in segs])]).astype(np.int32)
+        base = np.ascontiguousarray(np.concatenate(segs))
+        seg_of_point = np.repeat(np.arange(len(segs), dtype=np.int32), [len(x) for x in segs])
+        cloud = base.copy(); cloud[:, 3] = seg_of_point                                # :196-204 p.intensity = i
+        line3, _, _ = self.pixel_line_neighbors(rows, cols, lines, cloud, T)
+        off, idx = Context.pixel_line_candidates(len(lines), line3, 6)
+        ids, _, f_off, f_idx = Context.segmented_fit_lists(len(lines), off, idx, seg_of_point, seg_off)
+        if len(ids) == 0:
+            return empty
+        n_in, s_, e_ = Context.pixel_fit_lines(base, f_off, f_idx)
+        ok = n_in >= 3
+        ids, s_, e_ = ids[ok], s_[ok], e_[ok]
+        keep, ang = Context.filter_line_pairs(rows, cols, lines[ids], s_, e_, True, True)
+        T_lc = np.linalg.inv(T)                                                       # :331-336
+
+        def back(p):
+            h = np.c_[p, np.ones(len(p))] @ T_lc.T
+            return h[:, :3] / h[:, 3:]
+        return ids[keep], back(s_[keep]), back(e_[keep]), ang[keep]
+
     def joint_solve_lm(self, poses, points, pose_param_const=None, point_const=None, max_iterations=20):
         poses, points = _arr(poses, np.float64).copy().reshape(-1, 6), _arr(points, np.float64).copy().reshape(-1, 3)
         cc = None if pose_param_const is None else _arr(pose_param_const, np.uint8)

@@ -487,6 +487,34 @@ def pixel_fit_script(pvo, rows, cols, lines, cloud, T):
     return script
 
 
+def segments_of(A):
+    """The LiDAR segments of a synthetic frame as separate clouds (edge_segmented of the reference): points of cornerLessSharp by their first segment id."""
+    off, ids = A["p2s_off"], A["p2s_ids"]
+    n_seg = len(A["segment_coeffs"])
+    pts = A["cornerLessSharp"]
+    first = np.array([ids[off[i]] if off[i + 1] > off[i] else -1 for i in range(len(pts))])
+    return [np.ascontiguousarray(pts[first == k]) for k in range(n_seg)]
+
+
+def pixel_fit_script_segmented(pvo, rows, cols, lines, segments, T):
+    """The inlier lists pvb_pixel_fit_line reports for the fits of the SEGMENTED pixel-space Associate() (one per image line that passes the 6-point and 70 % tests: the
+    whole majority segment, LiDAR frame)."""
+    from panovlm_b200 import Context
+    segs = [np.asarray(x, np.float32).reshape(-1, 4) for x in segments]
+    seg_off = np.concatenate([[0], np.cumsum([len(x) for x in segs])]).astype(np.int32)
+    base = np.concatenate(segs)
+    seg_of_point = np.repeat(np.arange(len(segs), dtype=np.int32), [len(x) for x in segs])
+    cloud = base.copy(); cloud[:, 3] = seg_of_point
+    line3, _, _ = pvo.pixel_line_neighbors(rows, cols, lines, cloud, T)
+    off, idx = Context.pixel_line_candidates(len(lines), line3, 6)
+    ids, _, f_off, f_idx = Context.segmented_fit_lists(len(lines), off, idx, seg_of_point, seg_off)
+    script = []
+    for k in range(len(ids)):
+        fit = Context.pixel_fit_line(base[f_idx[f_off[k]:f_off[k + 1]]])
+        script.append(np.zeros(0, np.int32) if fit is None else fit[1])
+    return script
+
+
 def pixel_calibration_from_reference(pvo, rows, cols, lines, cloud, T, script):
     """The reference's own AssociateLineSingle + Optimize(line_pairs, T_cl) (recorded at ceres::Solve) on ONE frame without LiDAR segments, RANSAC answers scripted."""
     rf = pvo.RefFrame(np.eye(3), np.zeros(3), cloud, np.zeros(len(cloud) + 1, np.int32), np.zeros(0, np.int32), np.zeros((0, 6)), id=0, local="keep", end_points=np.zeros((0, 6)))
@@ -515,7 +543,15 @@ def golden_ref_pixel_fit():
     # the same frame through the reference's calibration mode: AssociateLineSingle takes Associate(lines, cornerLessSharp, T_cl) when edge_segmented is empty (:313-314)
     cal = pixel_calibration_from_reference(pvo, rows, cols, lines, cloud, T, script)
     print(f"  calibration mode over the pixel path: {int(cal['info'][0])} pairs, {len(cal['residual'])} residual blocks")
-    np.savez_compressed(os.path.join(OUT, "ref_pixel_fit.npz"), cal_residual=cal["residual"], cal_jacobian=cal["jacobian"], cal_huber=cal["huber"], cal_pose=cal["pose"],
+    # the segmented overload (:191-338) on the same frame, its segments as separate clouds
+    segs = segments_of(A)
+    script_seg = pixel_fit_script_segmented(pvo, rows, cols, lines, segs, T)
+    out_seg = pvo.ref_pixel_associate_segmented_scripted(rows, cols, lines, segs, T, script_seg)
+    assert out_seg is not None, "the script of the segmented Associate() does not match the reference's number of fits"
+    print(f"  scripted segmented Associate: {len(segs)} segments, {len(script_seg)} fits, {len(out_seg[0])} pairs after Filter(true, true)")
+    np.savez_compressed(os.path.join(OUT, "ref_pixel_fit.npz"), seg_inl_off=np.concatenate([[0], np.cumsum([len(x) for x in script_seg])]).astype(np.int32),
+                        seg_inl_idx=np.concatenate(script_seg + [np.zeros(0, np.int32)]).astype(np.int32), seg_image_line=out_seg[0], seg_start=out_seg[1], seg_end=out_seg[2],
+                        seg_angle=out_seg[3], cal_residual=cal["residual"], cal_jacobian=cal["jacobian"], cal_huber=cal["huber"], cal_pose=cal["pose"],
                         cal_info=cal["info"], inl_off=np.concatenate([[0], np.cumsum([len(x) for x in script])]).astype(np.int32),
                         inl_idx=np.concatenate(script).astype(np.int32), image_line=il, start=s, end=e, angle=ang)
 

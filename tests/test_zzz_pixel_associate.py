@@ -132,3 +132,43 @@ def test_calibration_problem_over_the_pixel_path_equals_the_reference_optimize(o
         from make_golden import pixel_calibration_from_reference, pixel_fit_script
         live = pixel_calibration_from_reference(oracle, rows, cols, lines, cloud, T, pixel_fit_script(oracle, rows, cols, lines, cloud, T))
         assert np.array_equal(live["residual"], g["cal_residual"]) and np.array_equal(live["jacobian"], g["cal_jacobian"])
+
+
+def _segments():
+    from make_golden import segments_of
+    A, rows, cols, T, lines = camlidar_case()
+    return rows, cols, lines, segments_of(A), T
+
+
+def test_segmented_associate_equals_the_reference_own_code(oracle):
+    """Context.pixel_associate_segmented = the SEGMENTED overload Associate(lines, segmented_cloud, T_cl) (CameraLidarLineAssociate.cpp:191-338; the reference's own call
+    sites of it are commented out).  tests/golden/ref_pixel_fit.npz seg_* = that function of the reference (oracle/_ref) with the RANSAC's inliers scripted to the product's:
+    the script is in sync (the same image lines reach the fit: 6-point test, 70 % single-segment test, first-maximum rule), and everything after the RANSAC is the
+    reference's code - including its quirk of fitting the segment in the LiDAR frame and applying T_lc afterwards anyway."""
+    import os
+    from make_golden import pixel_fit_script_segmented
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pixel_fit.npz"))
+    rows, cols, lines, segs, T = _segments()
+    script = pixel_fit_script_segmented(oracle, rows, cols, lines, segs, T)
+    assert len(script) == len(g["seg_inl_off"]) - 1 >= 10
+    assert np.array_equal(np.concatenate(script), g["seg_inl_idx"]) and np.array_equal(np.cumsum([len(x) for x in script]), g["seg_inl_off"][1:])
+    ids, s, e, ang = _OracleBackedCtx(oracle).pixel_associate_segmented(rows, cols, lines, segs, T)
+    assert len(ids) == len(g["seg_angle"]) >= 3 and np.array_equal(lines[ids], g["seg_image_line"])
+    assert np.array_equal(ang, g["seg_angle"])
+    assert np.abs(s - g["seg_start"]).max() < 1e-9 and np.abs(e - g["seg_end"]).max() < 1e-9
+    if oracle.ref_camlidar_lib() is not None:                                                # live, where oracle/_ref is built
+        live = oracle.ref_pixel_associate_segmented_scripted(rows, cols, lines, segs, T, script)
+        assert live is not None and np.array_equal(live[0], g["seg_image_line"]) and np.array_equal(live[1], g["seg_start"]) and np.array_equal(live[3], g["seg_angle"])
+        # a script of the wrong length is noticed: the number of fits is part of what is pinned
+        assert oracle.ref_pixel_associate_segmented_scripted(rows, cols, lines, segs, T, script[:-1]) is None
+    # no segments / empty segments
+    out = _OracleBackedCtx(oracle).pixel_associate_segmented(rows, cols, lines, [], T)
+    assert len(out[0]) == 0 and out[1].shape == (0, 3)
+
+
+@pytest.mark.gpu
+def test_segmented_associate_on_the_device_equals_the_oracle_backed_composition(gpu_ctx, oracle):
+    rows, cols, lines, segs, T = _segments()
+    got = gpu_ctx.pixel_associate_segmented(rows, cols, lines, segs, T)
+    exp = _OracleBackedCtx(oracle).pixel_associate_segmented(rows, cols, lines, segs, T)
+    assert len(got[0]) >= 3 and all(np.array_equal(a, b) for a, b in zip(got, exp))
