@@ -51,6 +51,14 @@ def world_from_pose_blocks(poses, aa_to_R):
     return R_wl, t_wl
 
 
+def first_valid_frame(frames):
+    """RefinePose holds the pose blocks of the FIRST VALID frame constant (LidarOdometry.cpp:59-76), not blindly those of frame 0: `if(!lidars[i].IsPoseValid() || !lidars[i].valid) continue;`.  A frame dict may carry valid = False / pose_valid = False."""
+    for i, f in enumerate(frames):
+        if f.get("valid", True) and f.get("pose_valid", True):
+            return i
+    return 0
+
+
 def pose_graph_edges(poses, cfg: OdometryConfig, aa_to_R):
     """FindNeighbors (LidarFeatureAssociate.cpp:19-111) -> the (reference frame, neighbour frame) pairs of one outer iteration."""
     n = len(poses)
@@ -129,7 +137,7 @@ def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, devic
         bl, edges = build_problem(ctx, frames, poses, cfg, aa_to_R)
         v = bl.view()
         ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
-    mask = np.zeros(len(frames), np.uint8); mask[0] = 1
+    mask = np.zeros(len(frames), np.uint8); mask[first_valid_frame(frames)] = 1
     t_lm = time.time()
     new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
     summary["lm_s"] = time.time() - t_lm
@@ -165,7 +173,7 @@ def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_
             bl, _ = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=fr, all_edges=all_edges)
             v = bl.view()
             ctx.blocks_set(v["type"], v["ref"], v["nei"], v["consts"], v["huber"], v["normalize"], len(frames))
-        mask = np.zeros(len(frames), np.uint8); mask[0] = 1
+        mask = np.zeros(len(frames), np.uint8); mask[first_valid_frame(frames)] = 1
         t_lm = time.time()
         new_poses, summary = ctx.blocks_solve_lm(poses, mask, cfg.max_lm_iterations)
         summary["lm_s"] = time.time() - t_lm

@@ -320,3 +320,11 @@ def test_calibration_blocks_match_oracle(oracle):
     assert np.array_equal(consts[0::2, 3:6], end) and np.array_equal(consts[0::2, 6:9], start)
     with pytest.raises(Exception):
         Context.build_calibration_blocks(BlockList(3), 2880, 5760, lines, start, end, 0)
+
+
+def test_refine_pose_holds_the_first_valid_frame_constant():
+    """LidarOdometry.cpp:59-66: the constant pose blocks are those of the first frame with a valid pose AND valid data, not of frame 0."""
+    from panovlm_b200 import odometry
+    assert odometry.first_valid_frame([{}, {}, {}]) == 0
+    assert odometry.first_valid_frame([{"valid": False}, {"pose_valid": False}, {"valid": True}, {}]) == 2
+    assert odometry.first_valid_frame([{"valid": False}]) == 0
