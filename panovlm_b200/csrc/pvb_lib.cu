@@ -566,13 +566,19 @@ static int solver_prepare(pvb_ctx* ctx, const unsigned char* is_const) {
   gseg.push_back((int)gcon.size());
   ctx->s_ndest = (int)seg.size() - 1; ctx->s_ngdest = (int)gseg.size() - 1;
   const size_t N = (size_t)ctx->s_N;
+  if (ctx->pcg_active) {
+    // a free pose block without any residual has no diagonal block to precondition with: such (degenerate) graphs take the dense path, whose damping keeps them solvable
+    std::vector<char> has_diag(nf, 0);
+    for (int d = 0; d < ctx->s_ndest; ++d) { const HContrib& c = con[seg[d]]; if (c.dest_r == c.dest_c) has_diag[c.dest_r] = 1; }
+    for (int b = 0; b < nf; ++b) if (!has_diag[b]) { ctx->pcg_active = false; break; }
+  }
   if (!ctx->pcg_active) { CK(ctx->s_H.ensure(N * N * 8)); CK(ctx->s_A.ensure(N * N * 8)); }
   else {
     // block-sparse form: one 6x6 block per destination (row block, column block), rows sorted (the order of `con`)
     const int nd = ctx->s_ndest;
     std::vector<int> rowptr(nf + 1, 0), col(nd), diag(nf, -1);
     for (int d = 0; d < nd; ++d) { const HContrib& c = con[seg[d]]; rowptr[c.dest_r + 1]++; col[d] = c.dest_c; if (c.dest_r == c.dest_c) diag[c.dest_r] = d; }
-    for (int b = 0; b < nf; ++b) { rowptr[b + 1] += rowptr[b]; if (diag[b] < 0) return ctx->fail(PVB_ERR_STATE, "free pose block without a residual: the normal equations are singular"); }
+    for (int b = 0; b < nf; ++b) rowptr[b + 1] += rowptr[b];
     ctx->s_nfb = nf; ctx->s_nblk = nd;
     const int ncta = (ctx->s_n + kPcgThreads - 1) / kPcgThreads;
     CK(ctx->s_bsr_rowptr.ensure((size_t)(nf + 1) * 4)); CK(ctx->s_bsr_col.ensure(std::max<size_t>(16, (size_t)nd * 4))); CK(ctx->s_bsr_diag.ensure((size_t)nf * 4));

@@ -190,6 +190,26 @@ def test_lm_device_solver_on_a_large_pose_graph(gpu_ctx, oracle):
     assert np.abs((Pd - start) - (P1 - start)).max() < POSE_RTOL * np.abs(P1 - start).max()
 
 
+def test_pcg_solver_request_on_a_graph_with_an_isolated_frame_takes_the_dense_path(gpu_ctx):
+    """A free pose block without any residual has no diagonal block for the block-Jacobi preconditioner: the PCG request falls back to the damped dense
+    factorisation for such a (degenerate) graph instead of failing, and the isolated pose stays where it was."""
+    from panovlm_b200 import api
+    nb = 12
+    typ, ref, nei, consts, hub, start, mask = _pose_graph_problem(nb - 1, 4000, seed=9)
+    start = np.concatenate([start, [[0.1, -0.2, 0.05, 1.0, 2.0, 3.0]]]); mask = np.concatenate([mask, [0]]).astype(np.uint8)
+    gpu_ctx.blocks_set(typ, ref, nei, consts, hub, 1, nb)
+    out = {}
+    try:
+        for kind in (api.SOLVER_DEVICE, api.SOLVER_PCG):
+            gpu_ctx.blocks_set_linear_solver(kind)
+            out[kind] = gpu_ctx.blocks_solve_lm(start, is_const=mask, max_iterations=6)
+    finally:
+        gpu_ctx.blocks_set_linear_solver(api.SOLVER_AUTO)
+    assert np.array_equal(out[api.SOLVER_DEVICE][0], out[api.SOLVER_PCG][0]) and out[api.SOLVER_DEVICE][1] == out[api.SOLVER_PCG][1]
+    assert np.array_equal(out[api.SOLVER_PCG][0][nb - 1], start[nb - 1])
+    assert out[api.SOLVER_PCG][1]["final_cost"] < 0.5 * out[api.SOLVER_PCG][1]["initial_cost"]
+
+
 # ---------------------------------------------------------------- B. frames: T1 + K2p (emit)
 def _pair_frames(seed=20260925, n_az=900, ground=True):
     from panovlm_b200 import synth
