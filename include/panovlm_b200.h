@@ -297,6 +297,15 @@ int pvb_line_votes_batch(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frame
 int pvb_frames_line2line_blocks(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, int n_edges, const int* ref, const int* nei, double dist_threshold,
                                 int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int angle_residual, int normalize_distance,
                                 double weight, long at, long cap, int* type, int* ref_out, int* nei_out, int* normalize, double* huber, double* consts);
+/* The same family with the tails on the device as well (csrc/pvb_lines.cuh): the vote matrices stay in HBM, FindAssociations
+ * (lidar_mapping/LidarFeatureAssociate.cpp:120-197) and the track gate run as one thread per edge, and the Point2Line blocks are written by the
+ * device straight into the block arrays when the NEXT pvb_frames_point2plane_blocks call sizes them (placed after that call's extra blocks,
+ * one reduction edge per pose-graph edge; with pvb_blocks_set_edge_list: filed under the global edges).  Only the per-edge block counts come
+ * back to the host.  The block constants are bit-identical to pvb_frames_line2line_blocks'.  *n_blocks = the line blocks that wait; they are
+ * dropped by the next pvb_line_votes_batch / pvb_generate_line_tracks call or consumed by the next pvb_frames_point2plane_blocks.           */
+int pvb_frames_line2line_blocks_device(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, int n_edges, const int* ref, const int* nei, double dist_threshold,
+                                       int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int angle_residual, int normalize_distance,
+                                       double weight, long* n_blocks);
 
 /* CameraLidarLineAssociate::AssociateByAngle (joint_optimization/CameraLidarLineAssociate.cpp:340-475) followed by
  * Filter(false, filter_by_length) (:628-715) and, unless multiple_association, UniqueLinePair (:754-876): per (image line, LiDAR

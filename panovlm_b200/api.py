@@ -120,7 +120,7 @@ EXPORTS = [
     "pvb_build_camera_lidar_blocks", "pvb_transform_cloud",
     "pvb_pair_knn5", "pvb_nearest_line", "pvb_point2line_segment_knn_associate", "pvb_point2line_segment_knn_tail", "pvb_point2line_segment_associate",
     "pvb_line2line_knn_associate", "pvb_line2line_knn_tail", "pvb_line_tracks_build", "pvb_line_tracks_gate", "pvb_generate_line_tracks",
-    "pvb_line_votes_batch", "pvb_frames_line2line_blocks",
+    "pvb_line_votes_batch", "pvb_frames_line2line_blocks", "pvb_frames_line2line_blocks_device",
     "pvb_blocks_set_linear_solver", "pvb_cholesky_solve", "pvb_unique_line_pairs",
     "pvb_slerp_pose", "pvb_undistort_end_poses", "pvb_undistort_clouds",
     "pvb_reproj_set", "pvb_reproj_evaluate", "pvb_reproj_residuals", "pvb_reproj_jacobians", "pvb_reproj_cost", "pvb_reproj_blocks", "pvb_reproj_kernel_time_ms",
@@ -781,6 +781,25 @@ class Context:
         if m < 0:
             raise PvbError(f"pvb_frames_line2line_blocks: code {m}: {self._L.pvb_last_error(self._h).decode()}")
         bl.n = m
+
+    def frames_line2line_blocks_device(self, frames, edges, dist_threshold, tracks, angle_residual, normalize_distance, weight):
+        """AddLidarLineToLineResidual2 with the tails on the device too: the blocks wait in HBM for the next frames_point2plane_blocks call, which places
+        them in the block arrays.  Returns the number of waiting line blocks."""
+        arr = (_LineFrame * len(frames))(*[f.c for f in frames])
+        ref, nei = _arr([e[0] for e in edges], np.int32), _arr([e[1] for e in edges], np.int32)
+        if tracks is None:
+            nt, toff, ff, fl = -1, None, None, None
+        else:
+            nt = len(tracks)
+            toff = np.zeros(nt + 1, np.int32)
+            toff[1:] = np.cumsum([len(t) for t in tracks])
+            feats = np.concatenate(tracks) if tracks else np.zeros((0, 2), np.int32)
+            ff, fl = _arr(feats[:, 0], np.int32), _arr(feats[:, 1], np.int32)
+        n = C.c_long()
+        self._ck(self._L.pvb_frames_line2line_blocks_device(self._h, C.c_int(len(frames)), arr, C.c_int(len(edges)), _p(ref), _p(nei), C.c_double(dist_threshold), C.c_int(nt),
+                                                            _p(toff) if toff is not None else None, _p(ff) if ff is not None else None, _p(fl) if fl is not None else None,
+                                                            C.c_int(int(angle_residual)), C.c_int(int(normalize_distance)), C.c_double(weight), C.byref(n)))
+        return n.value
 
     @staticmethod
     def point2line_segment_knn_tail(ref, nei, idx5):

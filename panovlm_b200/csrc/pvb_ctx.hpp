@@ -118,6 +118,16 @@ struct pvb_ctx {
   // ---- misc
   DevBuf m_a, m_b, m_c, m_d, m_e;
   DevBuf v_local, v_world, v_misc, v_M;                                 // batched line votes (pvb_line_votes_batch)
+  // device tails of the line-to-line family (pvb_frames_line2line_blocks_device): where the tables of the last vote pass lie in v_misc, the tail's own tables
+  // (lt_misc) and scratch, and the blocks that wait for the next pvb_frames_point2plane_blocks to place them in the block arrays
+  struct LineLayout { bool valid = false; int n_frames = 0, n_pairs = 0; size_t o_coff = 0, o_soff = 0, o_pbase = 0, o_poff = 0, o_pids = 0, o_wp = 0, o_lines = 0, o_vp = 0; } line_layout;
+  struct LinePending {
+    bool pending = false; long long total = 0, slots = 0;
+    std::vector<int> ref, nei, cnt;                                     // the edges (frame indices) and their block counts
+    int type = 0, normalize = 0; double huber = 0.0, weight = 1.0;
+    size_t o_hoff = 0, o_slot = 0, o_coeffs = 0;                        // offsets inside lt_misc
+  } line_pending;
+  DevBuf lt_misc, lt_hold, lt_kbase, lt_cnt, lt_base;
   PinBuf mh_a;
   // ---- reprojection / bundle-adjustment mode (pvb_ba.cu owns the state; released through ba_free by pvb_destroy)
   void* ba_state = nullptr; void (*ba_free)(void*) = nullptr;

@@ -13,6 +13,7 @@
 #include "pvb_host.hpp"
 #include "pvb_kernels.cuh"
 #include "pvb_solver.cuh"
+#include "pvb_lines.cuh"
 
 using namespace pvb;
 
@@ -250,7 +251,7 @@ void pvb_destroy(pvb_ctx* ctx) {
   DevBuf* dbs[] = {&ctx->d_prep, &ctx->d_wpose, &ctx->b_tile, &ctx->b_eref, &ctx->b_enei, &ctx->b_type, &ctx->b_norm, &ctx->b_huber, &ctx->b_consts, &ctx->b_orig_d, &ctx->b_r, &ctx->b_J,
                    &ctx->b_part, &ctx->b_esys, &ctx->b_tbegin, &ctx->f_pairs, &ctx->f_qtiles, &ctx->f_valid, &ctx->f_point, &ctx->f_plane, &ctx->f_nn_idx, &ctx->f_nn_d2,
                    &ctx->d_q_sorted, &ctx->d_q_orig, &ctx->d_pairs, &ctx->d_qtiles, &ctx->d_part, &ctx->d_sys, &ctx->d_tbegin, &ctx->d_valid, &ctx->d_point, &ctx->d_plane,
-                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e, &ctx->v_local, &ctx->v_world, &ctx->v_misc, &ctx->v_M, &ctx->d_hint, &ctx->b_chunk, &ctx->d_chunk, &ctx->d_stats};
+                   &ctx->d_res, &ctx->d_jac, &ctx->m_a, &ctx->m_b, &ctx->m_c, &ctx->m_d, &ctx->m_e, &ctx->v_local, &ctx->v_world, &ctx->v_misc, &ctx->v_M, &ctx->lt_misc, &ctx->lt_hold, &ctx->lt_kbase, &ctx->lt_cnt, &ctx->lt_base, &ctx->d_hint, &ctx->b_chunk, &ctx->d_chunk, &ctx->d_stats};
   for (DevBuf* b : dbs) b->release();
   PinBuf* pbs[] = {&ctx->h_pose, &ctx->h_r, &ctx->h_J, &ctx->h_esys, &ctx->fh_valid, &ctx->fh_point, &ctx->fh_plane, &ctx->dh_sys, &ctx->mh_a};
   for (PinBuf* b : pbs) b->release();
@@ -951,7 +952,20 @@ int pvb_frames_point2plane_blocks(pvb_ctx* ctx, const double* poses, int n_edges
   std::vector<uint32_t> row_begin(n_edges + 1);                      // first row of every association edge
   CK(cudaMemcpyAsync(row_begin.data(), ctx->m_d.p, (size_t)(n_edges + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  const long long n_dev = row_begin[n_edges], n = n_dev + n_extra;
+  // line-to-line blocks left on the device by pvb_frames_line2line_blocks_device: placed after the host extras, one reduction edge per pose-graph edge that has any
+  pvb_ctx::LinePending& LP = ctx->line_pending;
+  const bool lx = LP.pending && ctx->line_layout.valid;
+  const long long n_lx = lx ? LP.total : 0;
+  std::vector<long long> lx_base;                                    // first line block of every line edge (relative to the first line block)
+  if (lx) {
+    lx_base.assign(LP.cnt.size(), 0);
+    long long run = 0;
+    for (size_t e = 0; e < LP.cnt.size(); ++e) {
+      if (block_offset + LP.ref[e] >= nb || block_offset + LP.nei[e] >= nb) return ctx->fail(PVB_ERR_ARG, "pvb_frames_point2plane_blocks: line edge %d -> %d exceeds %d pose blocks", LP.ref[e], LP.nei[e], nb);
+      lx_base[e] = run; run += LP.cnt[e];
+    }
+  }
+  const long long n_dev = row_begin[n_edges], n = n_dev + n_extra + n_lx, lx_at = n_dev + n_extra;
   ctx->a_edge.clear(); ctx->a_query.clear(); ctx->a_point.clear(); ctx->a_plane.clear();     // the correspondences stay on the device in this path
   // ---- edges and tiles: the association edges in their order, then the extra blocks grouped by (ref, nei) like pvb_blocks_set
   ctx->bn = n; ctx->nb = nb; ctx->b_has_rows = ctx->b_has_sys = false;
@@ -974,6 +988,13 @@ int pvb_frames_point2plane_blocks(pvb_ctx* ctx, const double* poses, int n_edges
       for (long s0 = i; s0 < j; s0 += kTile) tiles.push_back(BlockTile{e, (int)(n_dev + s0), (int)std::min<long>(kTile, j - s0), 0});
       i = j;
     }
+    if (lx)
+      for (size_t le = 0; le < LP.cnt.size(); ++le) {
+        if (LP.cnt[le] == 0) continue;
+        const int e = (int)ctx->edge_ref.size();
+        ctx->edge_ref.push_back(block_offset + LP.ref[le]); ctx->edge_nei.push_back(block_offset + LP.nei[le]); ctx->edge_tile_begin.push_back((int)tiles.size());
+        for (long long s0 = 0; s0 < LP.cnt[le]; s0 += kTile) tiles.push_back(BlockTile{e, (int)(lx_at + lx_base[le] + s0), (int)std::min<long long>(kTile, LP.cnt[le] - s0), 0});
+      }
   } else {
     // sharded pose graph: the GLOBAL edge list is the reduction layout (every rank sums into the same n_edges x 92 buffer); this rank's association
     // edges and extra blocks are filed under their global edge, edges of other ranks keep an empty tile range
@@ -998,6 +1019,13 @@ int pvb_frames_point2plane_blocks(pvb_ctx* ctx, const double* poses, int n_edges
       for (long s0 = i; s0 < j; s0 += kTile) filed.push_back({ge, BlockTile{(int)ge, (int)(n_dev + s0), (int)std::min<long>(kTile, j - s0), 0}});
       i = j;
     }
+    if (lx)
+      for (size_t le = 0; le < LP.cnt.size(); ++le) {
+        if (LP.cnt[le] == 0) continue;
+        const long ge = find_edge(block_offset + LP.ref[le], block_offset + LP.nei[le]);
+        if (ge < 0) return ctx->fail(PVB_ERR_ARG, "line edge %d -> %d is not in the edge list set by pvb_blocks_set_edge_list", LP.ref[le], LP.nei[le]);
+        for (long long s0 = 0; s0 < LP.cnt[le]; s0 += kTile) filed.push_back({ge, BlockTile{(int)ge, (int)(lx_at + lx_base[le] + s0), (int)std::min<long long>(kTile, LP.cnt[le] - s0), 0}});
+      }
     std::stable_sort(filed.begin(), filed.end(), [](const std::pair<long, BlockTile>& a, const std::pair<long, BlockTile>& b) { return a.first < b.first; });
     size_t f = 0;
     for (size_t ge = 0; ge < ng; ++ge) {
@@ -1038,6 +1066,20 @@ int pvb_frames_point2plane_blocks(pvb_ctx* ctx, const double* poses, int n_edges
     for (int k = 0; k < 12; ++k)
       CK(cudaMemcpyAsync(ctx->b_consts.as<double>() + (size_t)k * n + n_dev, s_consts.data() + (size_t)k * n_extra, (size_t)n_extra * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
+  if (n_lx > 0) {
+    const pvb_ctx::LineLayout& L = ctx->line_layout;
+    CK(ctx->lt_base.ensure(lx_base.size() * 8));
+    CK(cudaMemcpyAsync(ctx->lt_base.p, lx_base.data(), lx_base.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned char* d = ctx->v_misc.as<unsigned char>();
+    const unsigned char* t = ctx->lt_misc.as<unsigned char>();
+    k_line_blocks_emit<<<(unsigned)LP.slots, 128, 0, ctx->stream>>>(reinterpret_cast<const int*>(t + LP.o_slot), reinterpret_cast<const int*>(t + LP.o_hoff), ctx->lt_hold.as<int>(), ctx->lt_kbase.as<int>(),
+        ctx->lt_base.as<long long>(), reinterpret_cast<const VotePair*>(d + L.o_vp), reinterpret_cast<const int*>(d + L.o_soff), reinterpret_cast<const double*>(t + LP.o_coeffs),
+        reinterpret_cast<const int*>(d + L.o_coff), reinterpret_cast<const int*>(d + L.o_poff), reinterpret_cast<const int*>(d + L.o_pbase), reinterpret_cast<const int*>(d + L.o_pids),
+        ctx->v_world.as<F4>(), reinterpret_cast<const WorldPose*>(d + L.o_wp), LP.type, LP.normalize, LP.huber, LP.weight, n, lx_at,
+        ctx->b_type.as<int>(), ctx->b_norm.as<int>(), ctx->b_huber.as<double>(), ctx->b_consts.as<double>(), ctx->b_orig_d.as<uint32_t>());
+    CKL();
+  }
+  LP.pending = false;                                                // consumed (or dropped: a pending list never outlives the next block build)
   if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->b_tile.p, tiles.data(), tiles.size() * sizeof(BlockTile), cudaMemcpyHostToDevice, ctx->stream));
   if (ne > 0) {
     CK(cudaMemcpyAsync(ctx->b_eref.p, ctx->edge_ref.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1700,7 +1742,8 @@ int pvb_line_votes(pvb_ctx* ctx, const double* ref_lines, int S_ref, const float
 // world-frame corner clouds, concatenated in frame order (the residual builders read the points from it).
 int pvb_line_votes_batch(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, const double* lines_world, int n_pairs, const int* pair_ref, const int* pair_nei,
                          const long long* m_off, long long m_total, double thr, int* M, float* world_out) {
-  if (!ctx || n_frames < 0 || n_pairs < 0 || (n_frames > 0 && !frames) || (n_pairs > 0 && (!pair_ref || !pair_nei || !m_off || !M))) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_line_votes_batch: bad arguments") : PVB_ERR_ARG;
+  if (!ctx || n_frames < 0 || n_pairs < 0 || (n_frames > 0 && !frames) || (n_pairs > 0 && (!pair_ref || !pair_nei || !m_off))) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_line_votes_batch: bad arguments") : PVB_ERR_ARG;
+  ctx->line_layout.valid = false; ctx->line_pending.pending = false;   // the tables the device tail reads are about to be rewritten
   if (n_frames == 0) return PVB_OK;
   CK(cudaSetDevice(ctx->device));
   if (int qrc = quiesce_copy(ctx)) return qrc;
@@ -1775,9 +1818,97 @@ int pvb_line_votes_batch(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frame
                                                                         thr, d_M.as<int>());
     CKL();
   }
-  if (m_total > 0) CK(cudaMemcpyAsync(M, d_M.p, (size_t)m_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (M && m_total > 0) CK(cudaMemcpyAsync(M, d_M.p, (size_t)m_total * 4, cudaMemcpyDeviceToHost, ctx->stream));   // M == NULL: the matrices stay on the device (device tail)
   if (world_out && nc > 0) CK(cudaMemcpyAsync(world_out, d_world.p, (size_t)nc * 16, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->line_layout = pvb_ctx::LineLayout{true, n_frames, n_pairs, o_coff, o_soff, o_pbase, o_poff, o_pids, o_wp, o_lines, o_vp};
+  return PVB_OK;
+}
+
+// AddLidarLineToLineResidual2 (util/Optimization.cpp:329-441) for a whole pose graph with the tails on the device (pvb_lines.cuh): the vote pass above with the
+// matrices left in HBM, FindAssociations + track gate per edge (k_line_assoc), and - when the next pvb_frames_point2plane_blocks sizes the block arrays - one
+// Point2Line block per member point of every kept neighbour segment (k_line_blocks_emit).  Only the per-edge block COUNTS come back to the host.
+int pvb_frames_line2line_blocks_device(pvb_ctx* ctx, int n_frames, const pvb_line_frame* frames, int n_edges, const int* ref, const int* nei, double dist_threshold,
+                                       int n_tracks, const int* track_off, const int* feat_frame, const int* feat_line, int angle_residual, int normalize_distance,
+                                       double weight, long* n_blocks) {
+  if (!ctx || n_frames < 0 || n_edges < 0 || (n_frames > 0 && !frames) || (n_edges > 0 && (!ref || !nei))) return ctx ? ctx->fail(PVB_ERR_ARG, "pvb_frames_line2line_blocks_device: bad arguments") : PVB_ERR_ARG;
+  if (n_tracks > 0 && (!track_off || !feat_frame || !feat_line)) return ctx->fail(PVB_ERR_ARG, "pvb_frames_line2line_blocks_device: tracks are NULL");
+  if (n_blocks) *n_blocks = 0;
+  ctx->line_pending.pending = false;
+  if (n_frames == 0 || n_edges == 0) return PVB_OK;
+  std::vector<int> soff(n_frames + 1, 0);
+  for (int f = 0; f < n_frames; ++f) soff[f + 1] = soff[f] + frames[f].n_segments;
+  const int ns = soff[n_frames];
+  std::vector<long long> m_off(n_edges + 1, 0); std::vector<int> h_off(n_edges + 1, 0);
+  for (int e = 0; e < n_edges; ++e) {
+    if (ref[e] < 0 || ref[e] >= n_frames || nei[e] < 0 || nei[e] >= n_frames) return ctx->fail(PVB_ERR_ARG, "pvb_frames_line2line_blocks_device: edge %d out of range", e);
+    m_off[e + 1] = m_off[e] + (long long)frames[ref[e]].n_segments * frames[nei[e]].n_segments;
+    h_off[e + 1] = h_off[e] + frames[ref[e]].n_segments;
+  }
+  const int H = h_off[n_edges];
+  if (ns == 0 || H == 0) return PVB_OK;
+  // world-frame segment lines (TransformLines, LidarFeatureAssociate.cpp:219-236), the local coefficients, segment sizes and the track of every line
+  std::vector<double> lines((size_t)ns * 6), coeffs((size_t)ns * 6);
+  std::vector<int> seg_size(ns, 0), member(ns, 0), track_of(ns, -1), slot_edge(H);
+  for (int f = 0; f < n_frames; ++f) {
+    const pvb_line_frame& fr = frames[f];
+    for (int s = 0; s < fr.n_segments; ++s) {
+      const double* in = fr.segment_coeffs + 6 * s; double* out = &lines[(size_t)(soff[f] + s) * 6];
+      for (int r = 0; r < 3; ++r) {
+        out[r] = fr.R_wl[r * 3] * in[0] + fr.R_wl[r * 3 + 1] * in[1] + fr.R_wl[r * 3 + 2] * in[2] + fr.t_wl[r];
+        out[3 + r] = fr.R_wl[r * 3] * in[3] + fr.R_wl[r * 3 + 1] * in[4] + fr.R_wl[r * 3 + 2] * in[5];
+      }
+      memcpy(&coeffs[(size_t)(soff[f] + s) * 6], in, 48);
+    }
+    for (int i = 0; i < fr.n_corner; ++i) {
+      for (int q = fr.p2s_off[i]; q < fr.p2s_off[i + 1]; ++q) {
+        const int id = fr.p2s_ids[q];
+        if (id < 0 || id >= fr.n_segments) return ctx->fail(PVB_ERR_ARG, "pvb_frames_line2line_blocks_device: frame %d point %d names segment %d of %d", f, i, id, fr.n_segments);
+        seg_size[soff[f] + id]++;
+        bool first = true;                                             // a point is a member once, however often it lists the segment
+        for (int q2 = fr.p2s_off[i]; q2 < q; ++q2) first = first && fr.p2s_ids[q2] != id;
+        if (first) member[soff[f] + id]++;
+      }
+    }
+  }
+  if (n_tracks >= 0)
+    for (int t = 0; t < n_tracks; ++t)
+      for (int k = track_off[t]; k < track_off[t + 1]; ++k) {
+        const int fr = feat_frame[k], ln = feat_line[k];
+        if (fr < 0 || fr >= n_frames || ln < 0 || ln >= frames[fr].n_segments) return ctx->fail(PVB_ERR_ARG, "pvb_frames_line2line_blocks_device: track %d names line %d of frame %d", t, ln, fr);
+        track_of[soff[fr] + ln] = t;
+      }
+  for (int e = 0; e < n_edges; ++e) for (int k = h_off[e]; k < h_off[e + 1]; ++k) slot_edge[k] = e;
+  int rc = pvb_line_votes_batch(ctx, n_frames, frames, lines.data(), n_edges, ref, nei, m_off.data(), m_off[n_edges], dist_threshold, nullptr, nullptr);
+  if (rc) return rc;
+  const pvb_ctx::LineLayout& L = ctx->line_layout;
+  if (!L.valid) return ctx->fail(PVB_ERR_STATE, "pvb_frames_line2line_blocks_device: the vote pass left no tables");
+  // the tail's own tables in one upload: seg_size | member | track_of | h_off | slot_edge | local coefficients
+  const size_t o_size = 0, o_member = o_size + (size_t)ns * 4, o_track = o_member + (size_t)ns * 4, o_hoff = o_track + (size_t)ns * 4, o_slot = o_hoff + (size_t)(n_edges + 1) * 4,
+               o_coeffs = (o_slot + (size_t)H * 4 + 15) / 16 * 16, total = o_coeffs + (size_t)ns * 48;
+  std::vector<unsigned char> hbuf(total);
+  memcpy(&hbuf[o_size], seg_size.data(), (size_t)ns * 4); memcpy(&hbuf[o_member], member.data(), (size_t)ns * 4); memcpy(&hbuf[o_track], track_of.data(), (size_t)ns * 4);
+  memcpy(&hbuf[o_hoff], h_off.data(), (size_t)(n_edges + 1) * 4); memcpy(&hbuf[o_slot], slot_edge.data(), (size_t)H * 4); memcpy(&hbuf[o_coeffs], coeffs.data(), (size_t)ns * 48);
+  CK(ctx->lt_misc.ensure(total)); CK(ctx->lt_hold.ensure((size_t)H * 4)); CK(ctx->lt_kbase.ensure((size_t)H * 4)); CK(ctx->lt_cnt.ensure((size_t)n_edges * 4));
+  CK(cudaMemcpyAsync(ctx->lt_misc.p, hbuf.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned char* d = ctx->v_misc.as<unsigned char>();
+  const unsigned char* t = ctx->lt_misc.as<unsigned char>();
+  k_line_assoc<<<(n_edges + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const VotePair*>(d + L.o_vp), n_edges, ctx->v_M.as<int>(), reinterpret_cast<const int*>(d + L.o_soff),
+                                                              reinterpret_cast<const double*>(d + L.o_lines), reinterpret_cast<const int*>(t + o_size), reinterpret_cast<const int*>(t + o_member),
+                                                              n_tracks >= 0 ? reinterpret_cast<const int*>(t + o_track) : nullptr, reinterpret_cast<const int*>(t + o_hoff),
+                                                              ctx->lt_hold.as<int>(), ctx->lt_kbase.as<int>(), ctx->lt_cnt.as<int>());
+  CKL();
+  pvb_ctx::LinePending& P = ctx->line_pending;
+  P.cnt.assign(n_edges, 0);
+  CK(cudaMemcpyAsync(P.cnt.data(), ctx->lt_cnt.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  P.ref.assign(ref, ref + n_edges); P.nei.assign(nei, nei + n_edges);
+  P.total = 0;
+  for (int e = 0; e < n_edges; ++e) P.total += P.cnt[e];
+  P.slots = H; P.type = angle_residual ? PVB_P2LINE_ANGLE : PVB_P2LINE_METER; P.normalize = normalize_distance; P.huber = angle_residual ? 0.0 : 0.2; P.weight = weight;
+  P.o_hoff = o_hoff; P.o_slot = o_slot; P.o_coeffs = o_coeffs;
+  P.pending = P.total > 0;
+  if (n_blocks) *n_blocks = (long)P.total;
   return PVB_OK;
 }
 

@@ -12,6 +12,11 @@ import numpy as np
 from .api import BlockList, Context, LineFrame
 
 
+# the line-to-line tails and blocks on the device (pvb_frames_line2line_blocks_device) instead of the host cores; same block constants either way
+# (tests/test_device_line_blocks.py).  The sharded mirror keeps the host tails: its device variant has not been run on more than one GPU.
+DEVICE_LINE_BLOCKS = True
+
+
 class OdometryConfig:
     def __init__(self, point_to_plane=True, line_to_line=True, point_to_line=False, use_segment=True, angle_residual=True, normalize_distance=True, plane_dis_threshold=1.0,
                  line_dis_threshold=0.3, plane_tolerance=0.05, lidar_weight=0.01, neighbor_size=6, max_lm_iterations=20, line_tracks=True,
@@ -67,12 +72,15 @@ def pose_graph_edges(poses, cfg: OdometryConfig, aa_to_R):
     return [(i, j) for i in range(n) for j in neighbors[i] if 0 <= j < n and j != i]
 
 
-def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, frame_range=None, host_point2plane=True, per_edge_line_calls=False, all_edges=None):
+def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, frame_range=None, host_point2plane=True, per_edge_line_calls=False, all_edges=None,
+                  device_line_blocks=False):
     """One outer iteration's residual blocks (the Add*Residual calls of RefinePose); returns a BlockList and the GLOBAL edge list.
     frame_range = (lo, hi): only the edges whose reference frame lies in [lo, hi) are associated and turned into blocks (one rank's shard of a
     pose graph split across GPUs); the clouds of all frames stay available as halo.
     host_point2plane = False leaves the point-to-plane family to Context.frames_point2plane_blocks (association and blocks without a host round trip):
-    the BlockList then only holds the other families and the edge list of the shard is returned as third value."""
+    the BlockList then only holds the other families and the edge list of the shard is returned as third value.
+    device_line_blocks (with host_point2plane = False): the line-to-line tails and blocks stay on the device as well (Context.frames_line2line_blocks_device);
+    the blocks wait in HBM for the frames_point2plane_blocks call of the caller."""
     n = len(frames)
     R_wl, t_wl = world_from_pose_blocks(poses, aa_to_R)
     if all_edges is None:
@@ -108,6 +116,8 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
                 keep = Context.line_tracks_gate(tracks, i, j, rl, nl) if tracks is not None else np.ones(len(nl), bool)   # Optimization.cpp:383-400
                 for k in np.nonzero(keep)[0]:
                     Context.build_line2line_blocks(bl, lf[j], world[j], nl[k], a[k], b[k], i, j, cfg.angle_residual, cfg.normalize_distance, 1.0)
+        elif edges and device_line_blocks and not host_point2plane and cfg.point_to_plane:   # votes, tails and blocks on the device
+            ctx.frames_line2line_blocks_device(lf, edges, cfg.line_dis_threshold, tracks, cfg.angle_residual, cfg.normalize_distance, 1.0)
         elif edges:                                                 # all edges in one call: batched device votes, tails and blocks on the host cores
             ctx.frames_line2line_blocks(bl, lf, edges, cfg.line_dis_threshold, tracks, cfg.angle_residual, cfg.normalize_distance, 1.0)
     if cfg.point_to_plane:                                          # AddLidarPointToPlaneResidual (Optimization.cpp:506-562)
@@ -123,12 +133,12 @@ def build_problem(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, fra
     return bl, all_edges
 
 
-def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, device_blocks=True):
+def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, device_blocks=True, device_line_blocks=DEVICE_LINE_BLOCKS):
     """RefinePose: build the problem at `poses`, fix the first frame, solve (LidarOdometry.cpp:15-114).  device_blocks: the point-to-plane
     correspondences become residual blocks on the device (no download / rebuild / upload); the other families are built on the host and appended."""
     t0 = time.time()
     if device_blocks and cfg.point_to_plane:
-        bl, edges, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, host_point2plane=False)
+        bl, edges, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, host_point2plane=False, device_line_blocks=device_line_blocks)
         ref, nei = np.array([e[0] for e in mine], np.int32), np.array([e[1] for e in mine], np.int32)
         n_total = ctx.frames_point2plane_blocks(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, cfg.angle_residual, cfg.normalize_distance, cfg.plane_weight,
                                                 len(frames), extra=bl.view())
@@ -146,7 +156,7 @@ def refine_pose(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, devic
     return new_poses, summary
 
 
-def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, world, rank, group=None, device_blocks=True):
+def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_R, world, rank, group=None, device_blocks=True, device_line_blocks=False):
     """RefinePose on one rank of a pose graph sharded across GPUs (BASELINE.json configs[3]): contiguous ranges of reference frames
     balanced by the query count of their edges, association + residual blocks of the rank's own edges only, the GLOBAL edge list as reduction layout
     and ONE allreduce of the edge systems per evaluation (panovlm_b200.dist.install_allreduce_hook).  Every rank returns the same poses."""
@@ -165,7 +175,7 @@ def refine_pose_sharded(ctx: Context, frames, poses, cfg: OdometryConfig, aa_to_
     try:
         if device_blocks and cfg.point_to_plane:
             # the rank's own point-to-plane correspondences become residual blocks on the device, filed under the GLOBAL edge list (no download / rebuild / upload)
-            bl, _, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=fr, host_point2plane=False, all_edges=all_edges)
+            bl, _, mine = build_problem(ctx, frames, poses, cfg, aa_to_R, frame_range=fr, host_point2plane=False, all_edges=all_edges, device_line_blocks=device_line_blocks)
             ref, nei = np.array([e[0] for e in mine], np.int32), np.array([e[1] for e in mine], np.int32)
             bl.n = ctx.frames_point2plane_blocks(poses, ref, nei, cfg.plane_tolerance, cfg.plane_dis_threshold, cfg.angle_residual, cfg.normalize_distance, cfg.plane_weight,
                                                  len(frames), extra=bl.view())
